@@ -1,0 +1,193 @@
+/* uggpu.h -- C-ABI of libuggpu.so, the B200 (sm_100a) device layer behind the
+ * `gpuls` numproc family (ug_b200/host/gpuls_np.cc).
+ *
+ * No UG type crosses this boundary: plain pointers, ints and doubles only.
+ * Every function returns 0 on success (NUM_OK, np/np.h:66) and a non-zero code on
+ * failure; uggpu_last_error() then describes it.  Error codes reuse the reference's
+ * NUM_* values (np/np.h:65-75) where one applies.  There is NO CPU fallback: if no
+ * CUDA device is usable, uggpu_ctx_create fails.
+ *
+ * Data model (SURVEY.md 8a'): a context holds a hierarchy of levels 0..top.  A level
+ * has n block rows (one per UG VECTOR in FIRSTVECTOR->SUCCVC order), block size bs
+ * (components per vector, 1..UGGPU_MAX_BS), per-row flags copied from the VECTOR
+ * control words, any number of matrices (one per MATDATA_DESC, "mat" handle) in
+ * BSR with the entries of a row in VSTART->MNEXT order (diagonal first), any number
+ * of vectors (one per VECDATA_DESC, "vec" handle, dense double[n*bs]), and the
+ * standard prolongation P (rows = this level, cols = level-1) together with the
+ * restriction R (rows = level-1, cols = this level, entries in fine NODE list order).
+ *
+ * Every operation is asynchronous on the context's stream except the ones that
+ * return host values (reductions, downloads, solve), which synchronise before
+ * returning -- the reference's callers read VVALUEs / LRESULT immediately.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference root).
+ */
+#ifndef UGGPU_H
+#define UGGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGGPU_MAX_BS      3    /* components per vector handled by the block kernels          */
+#define UGGPU_MAX_LEVELS  32   /* MAXLEVEL, gm/gm.h                                           */
+#define UGGPU_MAX_COMP    40   /* MAX_VEC_COMP, np/udm/udm.h: length of a VEC_SCALAR          */
+
+/* loop modes, np/np.h:184-185 */
+#define UGGPU_ON_SURFACE  (-1)
+#define UGGPU_ALL_VECTORS 0
+
+/* bits of the per-row `ctl` byte (gm/gm.h:2264-2279 FINE_GRID_DOF / NEW_DEFECT) */
+#define UGGPU_CTL_NEW_DEFECT    1u
+#define UGGPU_CTL_FINE_GRID_DOF 2u
+
+/* return codes (np/np.h:65-75) */
+#define UGGPU_OK               0
+#define UGGPU_OUT_OF_MEM       1
+#define UGGPU_DESC_MISMATCH    3
+#define UGGPU_BLOCK_TOO_LARGE  4
+#define UGGPU_SMALL_DIAG       6
+#define UGGPU_NO_COARSER_GRID  7
+#define UGGPU_ERROR            9
+#define UGGPU_CUDA_ERROR      20
+
+typedef struct uggpu_ctx uggpu_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int  uggpu_ctx_create(int device, uggpu_ctx **out);
+int  uggpu_ctx_destroy(uggpu_ctx *ctx);
+const char *uggpu_last_error(void);
+int  uggpu_sync(uggpu_ctx *ctx);
+/* FULLREFINELEVEL(mg) (gm/gm.h) used by the ON_SURFACE loops, np/algebra/vecloop.ct:22 */
+int  uggpu_set_fullrefinelevel(uggpu_ctx *ctx, int level);
+/* number of kernels launched by this context since creation (bench `gpu_launches`) */
+int64_t uggpu_launch_count(uggpu_ctx *ctx);
+/* bytes of device memory currently held by the context */
+int64_t uggpu_device_bytes(uggpu_ctx *ctx);
+
+/* ---- hierarchy upload = "PreProcess flattens VECTOR/MATRIX lists" ------------------------
+ * (the reference's own precedent: np/amglib/amg_ug.cc:207-390 AMGSolverPreProcess)       */
+int uggpu_level_create(uggpu_ctx *ctx, int level, int n, int bs);
+int uggpu_level_destroy(uggpu_ctx *ctx, int level);
+int uggpu_level_n(uggpu_ctx *ctx, int level);
+int uggpu_level_bs(uggpu_ctx *ctx, int level);
+/* vclass/vnclass: VCLASS/VNCLASS 0..3 (gm/gm.h:2224-2232); ctl: UGGPU_CTL_*; skip: VECSKIP bits.
+ * NULL pointers select the defaults of a uniformly refined grid: class 3, nclass 3 (0 on the
+ * top level is irrelevant to the kernels), ctl = both bits, skip = 0. */
+int uggpu_level_set_flags(uggpu_ctx *ctx, int level, const uint8_t *vclass, const uint8_t *vnclass,
+                          const uint8_t *ctl, const uint32_t *skip);
+/* rowptr[n+1], col[nnz] (int32, 0-based), val[nnz*bs*bs] row-major blocks; host pointers. */
+int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, const int32_t *col,
+                  const double *val);
+int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const double *val);
+int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val);
+int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat);
+int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
+/* Standard (geometric) transfer stencils between `level` and level-1 (np/algebra/transgrid.cc:117-336):
+ * P: p_rowptr[n_fine+1], p_col (coarse row), p_w (GNs weight, zeros dropped, corner order);
+ * R: r_rowptr[n_coarse+1], r_col (fine row), r_w, entries in FIRSTNODE(fine)->SUCCN order and only
+ *    for fine vectors with VCLASS >= NEWDEF_CLASS (transgrid.cc:153). */
+int uggpu_transfer_set(uggpu_ctx *ctx, int level,
+                       const int32_t *p_rowptr, const int32_t *p_col, const double *p_w,
+                       const int32_t *r_rowptr, const int32_t *r_col, const double *r_w);
+
+/* ---- vectors (VECDATA_DESC on one level) ------------------------------------------------ */
+int uggpu_vec_alloc(uggpu_ctx *ctx, int level, int vec);          /* AllocVDFromVD, np/udm/udm.h:476 */
+int uggpu_vec_free(uggpu_ctx *ctx, int level, int vec);           /* FreeVD, udm.h:520 */
+int uggpu_vec_upload(uggpu_ctx *ctx, int level, int vec, const double *host);   /* n*bs doubles */
+int uggpu_vec_download(uggpu_ctx *ctx, int level, int vec, double *host);
+/* raw device pointer of a vector (for callers that already hold device data, e.g. the bench) */
+int uggpu_vec_devptr(uggpu_ctx *ctx, int level, int vec, void **dptr);
+
+/* ---- BLAS level 1, np/np.h:190-226, np/algebra/ugblas.cc:2291-3251 ----------------------------- */
+int uggpu_dset     (uggpu_ctx*, int fl, int tl, int mode, int x, double a);
+int uggpu_dcopy    (uggpu_ctx*, int fl, int tl, int mode, int x, int y);
+int uggpu_dscal    (uggpu_ctx*, int fl, int tl, int mode, int x, double a);
+int uggpu_dscalx   (uggpu_ctx*, int fl, int tl, int mode, int x, const double *a /* [bs] */);
+int uggpu_dadd     (uggpu_ctx*, int fl, int tl, int mode, int x, int y);
+int uggpu_dsub     (uggpu_ctx*, int fl, int tl, int mode, int x, int y);
+int uggpu_dminusadd(uggpu_ctx*, int fl, int tl, int mode, int x, int y);
+int uggpu_daxpy    (uggpu_ctx*, int fl, int tl, int mode, int x, double a, int y);
+int uggpu_daxpyx   (uggpu_ctx*, int fl, int tl, int mode, int x, const double *a, int y);
+int uggpu_ddot     (uggpu_ctx*, int fl, int tl, int mode, int x, int y, double *a);
+int uggpu_ddotx    (uggpu_ctx*, int fl, int tl, int mode, int x, int y, double *a /* [bs] */);
+int uggpu_dnrm2    (uggpu_ctx*, int fl, int tl, int mode, int x, double *a);
+int uggpu_dnrm2x   (uggpu_ctx*, int fl, int tl, int mode, int x, double *a /* [bs] */);
+
+/* ---- BLAS level 2, np/np.h:238-243, ugblas.cc:3782-4042 ------------------------------------------ */
+int uggpu_dmatmul      (uggpu_ctx*, int fl, int tl, int mode, int x, int M, int y);  /* x  = M y */
+int uggpu_dmatmul_add  (uggpu_ctx*, int fl, int tl, int mode, int x, int M, int y);  /* x += M y */
+int uggpu_dmatmul_minus(uggpu_ctx*, int fl, int tl, int mode, int x, int M, int y);  /* x -= M y */
+
+/* ---- smoother, np/np.h:430 l_jac (np/algebra/ugiter.cc:271-335) ------------------------------------ */
+int uggpu_l_jac(uggpu_ctx*, int level, int v, int M, int d);
+/* Smoother() of np/procs/iter.cc:817-842 with Step = JacobiStep: x = damp * Diag(A)^-1 b ; b -= A x */
+int uggpu_jac_smooth(uggpu_ctx*, int level, int x, int b, int A, const double *damp /* [bs] */);
+
+/* ---- grid transfer, np/np.h:475-489 (np/algebra/transgrid.cc:462,529) ------------------------------- */
+/* StandardRestrict(GRID_ON_LEVEL(level), to, from, damp): fine `level` -> level-1 */
+int uggpu_restrict(uggpu_ctx*, int level, int to, int from, const double *damp /* [bs] */);
+/* StandardInterpolateCorrection(GRID_ON_LEVEL(level), to, from, damp): level-1 -> fine `level` */
+int uggpu_interpolate_correction(uggpu_ctx*, int level, int to, int from, const double *damp);
+
+/* ---- multigrid cycle, np/procs/iter.cc:7741-7949 Lmgc ------------------------------------------------ */
+/* Base solver hook: called with the stream drained when the recursion reaches baselevel.  It must
+ * turn the defect b into (correction c, updated defect b) on that level exactly like
+ * NP_LINEAR_SOLVER::Solver (np/procs/ls.h:79-132), using uggpu_vec_download/upload.  NULL selects
+ * the built-in device solver `ls $I lu` (dense LU without pivoting in vector-index order,
+ * np/algebra/ugiter.cc:3657 l_lrdecomp + :4444 l_luiter, iterated like ls.cc:637-749). */
+typedef int (*uggpu_base_solver_fn)(void *user, uggpu_ctx *ctx, int level, int c, int b, int A);
+
+typedef struct uggpu_lmgc_cfg {
+  int    nu1, nu2, gamma;            /* $n1 $n2 $g     (iter.cc:7637-7642)                     */
+  int    baselevel;                  /* $b                                                      */
+  double smooth_damp[UGGPU_MAX_BS];  /* jac $damp      (iter.cc:771)                            */
+  double cycle_damp[UGGPU_MAX_BS];   /* lmgc $damp     (iter.cc:7665) passed to the prolongation */
+  int    t;                          /* vector handle of the temporary np->t (iter.cc:7810)     */
+  int    base_maxit;                 /* base `ls $m`                                            */
+  double base_reduction;             /* base `ls $red`                                          */
+  double base_abslimit;              /* base `ls $abslimit` (default 1e-10, npscan)             */
+  uggpu_base_solver_fn base_solver;  /* NULL = built-in device LU                               */
+  void  *base_user;
+  int    fused;                      /* 0: one kernel per reference call (op-for-op mirror);
+                                        1: fused kernels (identical results, fewer passes)      */
+} uggpu_lmgc_cfg;
+
+int uggpu_lmgc_preprocess(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int A);   /* LmgcPreProcess iter.cc:7707 */
+int uggpu_lmgc(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int c, int b, int A); /* Lmgc          iter.cc:7741 */
+
+/* ---- linear solver, np/procs/ls.cc:562-749 ------------------------------------------------------------ */
+typedef struct uggpu_lresult {       /* LRESULT, np/procs/ls.h:72-77 */
+  int    error_code;
+  int    converged;
+  int    number_of_linear_iterations;
+  double first_defect[UGGPU_MAX_BS];
+  double last_defect[UGGPU_MAX_BS];
+} uggpu_lresult;
+
+/* LinearDefect ls.cc:562: b -= A x on levels bl..level, ON_SURFACE */
+int uggpu_ls_defect(uggpu_ctx*, int bl, int level, int x, int b, int A);
+/* LinearResiduum ls.cc:577: last_defect = dnrm2x(bl..level, ON_SURFACE, b) */
+int uggpu_ls_residuum(uggpu_ctx*, int bl, int level, int b, uggpu_lresult *res);
+/* LinearSolver ls.cc:637 with Iter = lmgc, Update = LSUpdate (ls.cc:869).  `res->last_defect`
+ * must hold the residuum on entry (as in the reference, where Residuum is called first).
+ * history (may be NULL) receives last_defect[0..bs) after every iteration: history[it*bs+i]. */
+int uggpu_ls_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x, int b, int A, int c,
+                   int maxiter, const double *abslimit, const double *reduction,
+                   uggpu_lresult *res, double *history);
+
+/* ---- synthetic hierarchies generated on the device (bench input only; no reference analogue:
+ * UG's grid manager needs ~2.5 kB per unknown) -------------------------------------------- */
+/* P1 Poisson on the unit cube, structured nx*ny*nz cells on level 0, each cell split into the six
+ * tetrahedra around diagonal 0-6, uniformly refined `top` times.  Creates
+ * levels 0..top with matrix handle A, Dirichlet identity rows (VECSKIP) and the standard P/R. */
+int uggpu_synth_poisson3d(uggpu_ctx*, int nx, int ny, int nz, int top, int A);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGGPU_H */

@@ -1,0 +1,638 @@
+// oracle/ug_driver.cc -- TEST INFRASTRUCTURE ONLY (golden-vector generator, reference runner and
+// CPU-baseline timer).  Never linked into the product; only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may execute the binary built from it.
+//
+// Links against the UNMODIFIED reference compiled from /root/reference (oracle/Makefile) and drives
+// it exactly as SURVEY.md Appendix A/B documents: builds a hierarchy through UG's own commands,
+// assembles P1/Q1 Poisson or 3x3 linear elasticity into MVALUEs, then
+//   --dump F   writes the flattened hierarchy (via the product's PreProcess flattening code,
+//              ug_b200/host/gpuls_flatten.cc) plus, with --ops, the result of every individual
+//              reference call on the hot path (dmatmul*, BLAS-1, l_jac, Smoother, StandardRestrict,
+//              StandardInterpolateCorrection, Lmgc) and, with --solve, the defect history and
+//              iterates of `ls`+`lmgc`+`jac`+`transfer`.  These dumps ARE the golden vectors
+//              (the reference ships none).
+//   --time     times the reference V-cycle and kernels on this host (CPU baseline, 1 core).
+//   --gpu      additionally runs the same script with the gpuls numproc family (drop-in test) and
+//              compares against the CPU classes in-process.
+#include "config.h"
+#include <cstdio>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <ctime>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "initug.h"
+#include "gm.h"
+#include "np.h"
+#include "std_domain.h"
+#include "cmdline.h"
+#include "ugm.h"
+#include "algebra.h"
+#include "shapes.h"
+#include "evm.h"
+#include "numproc.h"
+#include "iter.h"
+#include "ls.h"
+#include "transfer.h"
+#include "transgrid.h"
+#include "ugdevices.h"
+#include "refine.h"
+
+#include "gpuls_flatten.h"
+#ifdef WITH_GPULS
+#include "gpuls_np.h"
+#endif
+
+USING_UG_NAMESPACES
+using namespace PPIF;
+
+// ------------------------------------------------------------------------------------------------
+// dump file: sequence of records  [u32 namelen][name][u8 dtype][u64 count][raw]   (magic "UGH1\n")
+// dtype: 0=i32 1=f64 2=u8 3=u32
+struct Dump {
+  FILE *f = NULL;
+  void open(const char *path) { f = fopen(path, "wb"); if (!f) { perror(path); exit(2); } fwrite("UGH1\n", 1, 5, f); }
+  void rec(const std::string &name, int dtype, const void *p, size_t count, size_t esz) {
+    if (!f) return;
+    uint32_t nl = (uint32_t)name.size(); uint8_t dt = (uint8_t)dtype; uint64_t c = count;
+    fwrite(&nl, 4, 1, f); fwrite(name.data(), 1, nl, f); fwrite(&dt, 1, 1, f); fwrite(&c, 8, 1, f);
+    if (count) fwrite(p, esz, count, f);
+  }
+  void i32(const std::string &n, const std::vector<int32_t> &v) { rec(n, 0, v.data(), v.size(), 4); }
+  void f64(const std::string &n, const std::vector<double> &v) { rec(n, 1, v.data(), v.size(), 8); }
+  void u8(const std::string &n, const std::vector<uint8_t> &v) { rec(n, 2, v.data(), v.size(), 1); }
+  void u32(const std::string &n, const std::vector<uint32_t> &v) { rec(n, 3, v.data(), v.size(), 4); }
+  void scalar_i(const std::string &n, int v) { int32_t x = v; rec(n, 0, &x, 1, 4); }
+  void scalar_d(const std::string &n, double v) { rec(n, 1, &v, 1, 8); }
+  void close() { if (f) fclose(f); f = NULL; }
+};
+static Dump D;
+
+static void cmd(const char *fmt, ...)
+{
+  char b[2048];
+  va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+  if (ExecCommand(b)) { fprintf(stderr, "UG command failed: %s\n", b); exit(3); }
+}
+
+static double now()
+{
+  struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static INT BndCond(void *, void *, DOUBLE *, DOUBLE *v, INT *t) { v[0] = 0; *t = 1; return 0; }
+
+// ------------------------------------------------------------------------------------------------
+struct Opt {
+  std::string grid = (DIM == 3) ? "tet" : "tri";
+  int bs = 1, refine = 3, adapt = 0, nu1 = 2, nu2 = 2, gamma = 1, cycles = 10, reps = 5;
+  double damp = (DIM == 3) ? 0.6 : 0.8;
+  std::string dump, gpu;
+  bool ops = false, solve = false, timeit = false, quiet = true;
+};
+
+static MULTIGRID *mg;
+static VECDATA_DESC *vx, *vb, *vc, *vt;
+static MATDATA_DESC *mA;
+static int BS;
+
+static std::string L(const char *what, int lev) { char b[128]; snprintf(b, sizeof b, "L%d/%s", lev, what); return b; }
+
+// deterministic test vectors: k * 2^-20 from a 64-bit LCG, seed mixes level+tag
+static void fill_lcg(const VECDATA_DESC *vd, int lev, uint64_t seed)
+{
+  uint64_t s = 12345ull + seed * 0x9E3779B97F4A7C15ull + (uint64_t)lev * 1000003ull;
+  for (VECTOR *v = FIRSTVECTOR(GRID_ON_LEVEL(mg, lev)); v != NULL; v = SUCCVC(v))
+    for (int i = 0; i < BS; i++) {
+      s = s * 6364136223846793005ull + 1442695040888963407ull;
+      int64_t k = (int64_t)((s >> 33) & 0xFFFFF) - 0x80000;
+      VVALUE(v, VD_CMP_OF_TYPE(vd, VTYPE(v), i)) = (double)k * (1.0 / 1048576.0);
+    }
+}
+
+static std::vector<double> gather(const VECDATA_DESC *vd, int lev)
+{
+  std::vector<double> h((size_t)NVEC(GRID_ON_LEVEL(mg, lev)) * BS);
+  gpuls::GatherVector(mg, lev, vd, BS, h.data());
+  return h;
+}
+static void dumpvec(const std::string &name, const VECDATA_DESC *vd, int lev) { D.f64(L(name.c_str(), lev), gather(vd, lev)); }
+
+// ------------------------------------------------------------------------------------------------
+// element matrices
+static const double HEXLOC[8][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1}};
+static const double QUADLOC[4][2] = {{0,0},{1,0},{1,1},{0,1}};
+
+// shape function gradients in reference coordinates for tensor-product elements
+static void tp_shape(int nc, const double *xi, double *N, double (*dN)[DIM])
+{
+  for (int i = 0; i < nc; i++) {
+    double f[DIM], df[DIM];
+    for (int d = 0; d < DIM; d++) {
+      double a = (DIM == 3) ? HEXLOC[i][d] : QUADLOC[i][d % 2];
+      f[d] = a ? xi[d] : 1.0 - xi[d];
+      df[d] = a ? 1.0 : -1.0;
+    }
+    N[i] = 1.0;
+    for (int d = 0; d < DIM; d++) N[i] *= f[d];
+    for (int d = 0; d < DIM; d++) {
+      dN[i][d] = df[d];
+      for (int e = 0; e < DIM; e++) if (e != d) dN[i][d] *= f[e];
+    }
+  }
+}
+
+static double det_inv(const double J[DIM][DIM], double Ji[DIM][DIM])
+{
+#if DIM == 2
+  double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+  return det;
+#else
+  double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det; Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+  Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  return det;
+#endif
+}
+
+// Quadrature points: simplex -> centroid rule is exact for P1 stiffness; tensor elements -> 2-point Gauss.
+// Returns gradients G[q][i][d], weights*detJ W[q], shape values N[q][i].
+struct QP { double w; double N[8]; double G[8][DIM]; };
+static int element_qps(ELEMENT *e, QP *qp)
+{
+  int nc = CORNERS_OF_ELEM(e);
+  double X[8][DIM];
+  for (int i = 0; i < nc; i++) for (int d = 0; d < DIM; d++) X[i][d] = CVECT(MYVERTEX(CORNER(e, i)))[d];
+  if (nc == DIM + 1) {
+    // barycentric: N_0 = 1 - sum xi, N_i = xi_{i-1}
+    double J[DIM][DIM], Ji[DIM][DIM];
+    for (int d = 0; d < DIM; d++) for (int k = 0; k < DIM; k++) J[k][d] = X[k + 1][d] - X[0][d];  // J[k][d] = dx_d/dxi_k
+    double det = det_inv(J, Ji);
+    double vol = fabs(det) / ((DIM == 3) ? 6.0 : 2.0);
+    qp[0].w = vol;
+    for (int i = 0; i < nc; i++) qp[0].N[i] = 1.0 / nc;
+    for (int d = 0; d < DIM; d++) {
+      double s = 0;
+      for (int k = 0; k < DIM; k++) { qp[0].G[k + 1][d] = Ji[d][k]; s += Ji[d][k]; }  // grad_x xi_k
+      qp[0].G[0][d] = -s;
+    }
+    return 1;
+  }
+  const double g[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+  int nq = 0;
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < ((DIM == 3) ? 2 : 1); c++) {
+    double xi[3] = {g[a], g[b], g[c]};
+    double dN[8][DIM], J[DIM][DIM], Ji[DIM][DIM];
+    tp_shape(nc, xi, qp[nq].N, dN);
+    for (int k = 0; k < DIM; k++) for (int d = 0; d < DIM; d++) { J[k][d] = 0; for (int i = 0; i < nc; i++) J[k][d] += dN[i][k] * X[i][d]; }
+    double det = det_inv(J, Ji);
+    qp[nq].w = fabs(det) / ((DIM == 3) ? 8.0 : 4.0);
+    for (int i = 0; i < nc; i++) for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < DIM; k++) s += Ji[d][k] * dN[i][k]; qp[nq].G[i][d] = s; }
+    nq++;
+  }
+  return nq;
+}
+
+static void assemble(void)
+{
+  int t0 = 0;
+  const double E = 1.0, nu = 0.3, lam = E * nu / ((1 + nu) * (1 - 2 * nu)), mu = E / (2 * (1 + nu));
+  for (int l = 0; l <= TOPLEVEL(mg); l++) {
+    GRID *g = GRID_ON_LEVEL(mg, l);
+    for (VECTOR *v = FIRSTVECTOR(g); v; v = SUCCVC(v)) {
+      t0 = VTYPE(v);
+      VECSKIP(v) = 0;
+      for (int i = 0; i < BS; i++) {
+        VVALUE(v, VD_CMP_OF_TYPE(vx, t0, i)) = 0; VVALUE(v, VD_CMP_OF_TYPE(vb, t0, i)) = 0;
+        VVALUE(v, VD_CMP_OF_TYPE(vc, t0, i)) = 0; VVALUE(v, VD_CMP_OF_TYPE(vt, t0, i)) = 0;
+      }
+      for (MATRIX *m = VSTART(v); m; m = MNEXT(m))
+        for (int k = 0; k < BS * BS; k++) MVALUE(m, MD_MCMP_OF_RT_CT(mA, t0, t0, k)) = 0;
+    }
+    QP qp[8];
+    for (ELEMENT *e = FIRSTELEMENT(g); e; e = SUCCE(e)) {
+      int nc = CORNERS_OF_ELEM(e);
+      int nq = element_qps(e, qp);
+      for (int i = 0; i < nc; i++) {
+        VECTOR *vi = NVECTOR(CORNER(e, i));
+        for (int q = 0; q < nq; q++) {
+          if (BS == 1) VVALUE(vi, VD_CMP_OF_TYPE(vb, t0, 0)) += qp[q].w * qp[q].N[i];
+          else VVALUE(vi, VD_CMP_OF_TYPE(vb, t0, BS - 1)) += -qp[q].w * qp[q].N[i];  // gravity on last comp
+        }
+        for (int j = 0; j < nc; j++) {
+          VECTOR *vj = NVECTOR(CORNER(e, j));
+          MATRIX *m = GetMatrix(vi, vj);
+          if (!m) { fprintf(stderr, "missing connection\n"); exit(4); }
+          for (int q = 0; q < nq; q++) {
+            const double *gi = qp[q].G[i], *gj = qp[q].G[j];
+            double dot = 0; for (int d = 0; d < DIM; d++) dot += gi[d] * gj[d];
+            if (BS == 1) MVALUE(m, MD_MCMP_OF_RT_CT(mA, t0, t0, 0)) += qp[q].w * dot;
+            else
+              for (int a = 0; a < BS; a++) for (int b = 0; b < BS; b++) {
+                double k = lam * gi[a] * gj[b] + mu * gi[b] * gj[a] + ((a == b) ? mu * dot : 0.0);
+                MVALUE(m, MD_MCMP_OF_RT_CT(mA, t0, t0, a * BS + b)) += qp[q].w * k;
+              }
+          }
+        }
+      }
+    }
+    // Dirichlet: identity rows + skip flags on boundary vertices (Appendix B)
+    for (NODE *n = FIRSTNODE(g); n; n = SUCCN(n))
+      if (OBJT(MYVERTEX(n)) == BVOBJ) {
+        VECTOR *v = NVECTOR(n);
+        VECSKIP(v) = (1u << BS) - 1;
+        for (int i = 0; i < BS; i++) VVALUE(v, VD_CMP_OF_TYPE(vb, t0, i)) = 0;
+        for (MATRIX *m = VSTART(v); m; m = MNEXT(m))
+          for (int k = 0; k < BS * BS; k++) MVALUE(m, MD_MCMP_OF_RT_CT(mA, t0, t0, k)) = 0;
+        for (int i = 0; i < BS; i++) MVALUE(VSTART(v), MD_MCMP_OF_RT_CT(mA, t0, t0, i * BS + i)) = 1.0;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static void build_hierarchy(const Opt &o)
+{
+  CreateBoundaryValueProblem("theBVP", BndCond, 0, NULL, 0, NULL);
+#if DIM == 3
+  cmd("configure theBVP $d Hexahedron");
+#else
+  cmd("configure theBVP $d Quadrilateral");
+#endif
+  cmd("newformat F $V n%d: vt 8 $M implicit(vt): mt 2 $I n%d", o.bs, o.bs * o.bs);
+  cmd("new themg $b theBVP $f F $h 30000M");
+  mg = GetMultigrid((char *)"themg");
+#if DIM == 3
+  if (o.grid == "tet") {
+    cmd("ie 0 1 2 6"); cmd("ie 0 2 3 6"); cmd("ie 0 3 7 6"); cmd("ie 0 7 4 6"); cmd("ie 0 4 5 6"); cmd("ie 0 5 1 6");
+  } else cmd("ie 0 1 2 3 4 5 6 7");
+#else
+  if (o.grid == "tri") { cmd("ie 0 1 2"); cmd("ie 0 2 3"); } else cmd("ie 0 1 2 3");
+#endif
+  cmd("fixcoarsegrid");
+  for (int i = 0; i < o.refine; i++) cmd("refine $a");
+  for (int r = 0; r < o.adapt; r++) {
+    for (int l = 0; l <= TOPLEVEL(mg); l++)
+      for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l)); e; e = SUCCE(e)) {
+        if (!EstimateHere(e)) continue;
+        int nc = CORNERS_OF_ELEM(e); bool in = true;
+        for (int d = 0; d < DIM; d++) { double c = 0; for (int i = 0; i < nc; i++) c += CVECT(MYVERTEX(CORNER(e, i)))[d]; if (c / nc > 0.5) in = false; }
+        if (in) MarkForRefinement(e, RED, 0);
+      }
+    cmd("refine");
+  }
+  cmd("createvector sol rhs cor tmp");
+  cmd("creatematrix MAT");
+  vx = GetVecDataDescByName(mg, (char *)"sol"); vb = GetVecDataDescByName(mg, (char *)"rhs");
+  vc = GetVecDataDescByName(mg, (char *)"cor"); vt = GetVecDataDescByName(mg, (char *)"tmp");
+  mA = GetMatDataDescByName(mg, (char *)"MAT");
+  if (!vx || !vb || !vc || !vt || !mA) { fprintf(stderr, "descriptor lookup failed\n"); exit(5); }
+  BS = o.bs;
+  assemble();
+}
+
+static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const char *lmgc, const char *transfer, const char *ls, int maxit)
+{
+  cmd("npcreate %ssmooth $c %s", pfx, jac);      cmd("npinit %ssmooth $damp %.17g", pfx, o.damp);
+  cmd("npcreate %sbaseit $c lu", pfx);           cmd("npinit %sbaseit", pfx);
+  cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
+  cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer", pfx);
+  cmd("npcreate %slmgc $c %s", pfx, lmgc);
+  cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma);
+  cmd("npcreate %smgs $c %s", pfx, ls);
+  cmd("npinit %smgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I %slmgc $display %s", pfx, maxit, pfx, o.quiet ? "no" : "full");
+}
+
+// ------------------------------------------------------------------------------------------------
+static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
+{
+  int top = TOPLEVEL(mg);
+  fl.resize(top + 1);
+  D.scalar_i("dim", DIM); D.scalar_i("bs", BS); D.scalar_i("toplevel", top);
+  D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg));
+  D.scalar_d("damp", o.damp); D.scalar_i("nu1", o.nu1); D.scalar_i("nu2", o.nu2); D.scalar_i("gamma", o.gamma);
+  for (int l = 0; l <= top; l++) {
+    if (gpuls::FlattenFlags(mg, l, vx, fl[l])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
+    if (gpuls::FlattenMatrix(mg, l, mA, fl[l])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
+  }
+  for (int l = 1; l <= top; l++)
+    if (gpuls::FlattenTransfer(mg, l, fl[l])) { fprintf(stderr, "FlattenTransfer failed\n"); exit(6); }
+  for (int l = 0; l <= top; l++) {
+    gpuls::FlatLevel &f = fl[l];
+    D.scalar_i(L("n", l), f.n);
+    D.i32(L("rowptr", l), f.rowptr); D.i32(L("col", l), f.col); D.f64(L("val", l), f.val);
+    D.u8(L("vclass", l), f.vclass); D.u8(L("vnclass", l), f.vnclass); D.u8(L("ctl", l), f.ctl); D.u32(L("skip", l), f.skip);
+    if (l > 0) {
+      D.i32(L("p_rowptr", l), f.p_rowptr); D.i32(L("p_col", l), f.p_col); D.f64(L("p_w", l), f.p_w);
+      D.i32(L("r_rowptr", l), f.r_rowptr); D.i32(L("r_col", l), f.r_col); D.f64(L("r_w", l), f.r_w);
+      D.i32(L("node_row", l), f.node_row);
+    }
+    dumpvec("rhs", vb, l);
+    // vertex coordinates in row order (lets tests relate UG's ordering to the synthetic generator)
+    std::vector<double> xyz((size_t)f.n * DIM);
+    for (NODE *n = FIRSTNODE(GRID_ON_LEVEL(mg, l)); n; n = SUCCN(n))
+      for (int d = 0; d < DIM; d++) xyz[(size_t)VINDEX(NVECTOR(n)) * DIM + d] = CVECT(MYVERTEX(n))[d];
+    D.f64(L("xyz", l), xyz);
+  }
+}
+
+// every individual reference call on the hot path, inputs and outputs dumped
+static void dump_ops(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  VEC_SCALAR damp, one, a3;
+  for (int i = 0; i < MAX_VEC_COMP; i++) { damp[i] = o.damp; one[i] = 1.0; a3[i] = 0.25 + 0.5 * i; }
+  NP_ITER *smooth = (NP_ITER *)GetNumProcByName(mg, "smooth", ITER_CLASS_NAME);
+  INT result = 0, bl = 0;
+  for (int l = 0; l <= top; l++) {
+    GRID *g = GRID_ON_LEVEL(mg, l);
+    fill_lcg(vx, l, 1); fill_lcg(vb, l, 2); fill_lcg(vc, l, 3); fill_lcg(vt, l, 4);
+    dumpvec("in/x", vx, l); dumpvec("in/b", vb, l); dumpvec("in/c", vc, l); dumpvec("in/t", vt, l);
+    // BLAS-2 (ALL_VECTORS, single level)
+    dmatmul(mg, l, l, ALL_VECTORS, vt, mA, vx);       dumpvec("dmatmul", vt, l);
+    dmatmul_add(mg, l, l, ALL_VECTORS, vt, mA, vb);   dumpvec("dmatmul_add", vt, l);
+    dmatmul_minus(mg, l, l, ALL_VECTORS, vt, mA, vc); dumpvec("dmatmul_minus", vt, l);
+    // BLAS-1 chain on t (each result depends on the previous one; inputs x,b,c stay fixed)
+    fill_lcg(vt, l, 4);
+    dcopy(mg, l, l, ALL_VECTORS, vt, vx);             dumpvec("dcopy", vt, l);
+    dscal(mg, l, l, ALL_VECTORS, vt, 0.75);           dumpvec("dscal", vt, l);
+    dscalx(mg, l, l, ALL_VECTORS, vt, a3);            dumpvec("dscalx", vt, l);
+    dadd(mg, l, l, ALL_VECTORS, vt, vb);              dumpvec("dadd", vt, l);
+    dsub(mg, l, l, ALL_VECTORS, vt, vc);              dumpvec("dsub", vt, l);
+    dminusadd(mg, l, l, ALL_VECTORS, vt, vb);         dumpvec("dminusadd", vt, l);
+    daxpy(mg, l, l, ALL_VECTORS, vt, -1.375, vx);     dumpvec("daxpy", vt, l);
+    daxpyx(mg, l, l, ALL_VECTORS, vt, a3, vc);        dumpvec("daxpyx", vt, l);
+    DOUBLE s; VEC_SCALAR sx;
+    ddot(mg, l, l, ALL_VECTORS, vx, vb, &s);          D.scalar_d(L("ddot", l), s);
+    dnrm2(mg, l, l, ALL_VECTORS, vx, &s);             D.scalar_d(L("dnrm2", l), s);
+    ddotx(mg, l, l, ALL_VECTORS, vx, vb, sx);         D.rec(L("ddotx", l), 1, sx, BS, 8);
+    dnrm2x(mg, l, l, ALL_VECTORS, vx, sx);            D.rec(L("dnrm2x", l), 1, sx, BS, 8);
+    dset(mg, l, l, ALL_VECTORS, vt, 0.5);             dumpvec("dset", vt, l);
+    // l_jac and the damped Jacobi smoother step in defect-correction form
+    fill_lcg(vt, l, 4);
+    if (l_jac(g, vt, mA, vb) != NUM_OK) { fprintf(stderr, "l_jac failed\n"); exit(7); }
+    dumpvec("l_jac", vt, l);
+    if (l > 0) {
+      fill_lcg(vt, l, 4);
+      (*smooth->PreProcess)(smooth, l, vx, vb, mA, &bl, &result);
+      if ((*smooth->Iter)(smooth, l, vt, vb, mA, &result)) { fprintf(stderr, "smoother failed\n"); exit(7); }
+      dumpvec("smooth/t", vt, l); dumpvec("smooth/b", vb, l);
+      (*smooth->PostProcess)(smooth, l, vx, vb, mA, &result);
+      fill_lcg(vb, l, 2);
+    }
+  }
+  // grid transfer: restrict x (fine) into c (coarse, pre-filled), prolong x (coarse) into t (fine)
+  for (int l = 1; l <= top; l++) {
+    fill_lcg(vx, l, 1); fill_lcg(vx, l - 1, 1); fill_lcg(vc, l - 1, 3); fill_lcg(vt, l, 4);
+    // `to` and `from` are the same descriptor in Lmgc (b,b); use the same here: c on both levels
+    fill_lcg(vc, l, 5);
+    dumpvec("restrict/in_fine", vc, l); dumpvec("restrict/in_coarse", vc, l - 1);
+    if (StandardRestrict(GRID_ON_LEVEL(mg, l), vc, vc, a3) != NUM_OK) { fprintf(stderr, "restrict failed\n"); exit(8); }
+    dumpvec("restrict/out", vc, l - 1);
+    if (StandardInterpolateCorrection(GRID_ON_LEVEL(mg, l), vt, vx, a3) != NUM_OK) { fprintf(stderr, "interpolate failed\n"); exit(8); }
+    dumpvec("interpolate/in_coarse", vx, l - 1); dumpvec("interpolate/out", vt, l);
+  }
+  D.rec("ops/a3", 1, a3, BS, 8);
+  // surface-mode loops over all levels (matter on adaptive hierarchies)
+  {
+    int fr = FULLREFINELEVEL(mg);
+    for (int l = 0; l <= top; l++) { fill_lcg(vx, l, 11); fill_lcg(vb, l, 12); fill_lcg(vt, l, 13); }
+    for (int l = 0; l <= top; l++) { dumpvec("surf/in_x", vx, l); dumpvec("surf/in_b", vb, l); }
+    dmatmul_minus(mg, fr, top, ON_SURFACE, vb, mA, vx);
+    for (int l = 0; l <= top; l++) dumpvec("surf/dmatmul_minus", vb, l);
+    VEC_SCALAR sx; DOUBLE s;
+    dnrm2x(mg, fr, top, ON_SURFACE, vb, sx); D.rec("surf/dnrm2x", 1, sx, BS, 8);
+    ddot(mg, fr, top, ON_SURFACE, vb, vx, &s); D.scalar_d("surf/ddot", s);
+    dset(mg, fr, top, ON_SURFACE, vt, 2.5);
+    for (int l = 0; l <= top; l++) dumpvec("surf/dset", vt, l);
+    daxpy(mg, fr, top, ON_SURFACE, vt, 0.5, vx);
+    for (int l = 0; l <= top; l++) dumpvec("surf/daxpy", vt, l);
+  }
+}
+
+static void restore_problem(void)
+{
+  // rhs and sol back to the assembled state (assemble() also rewrites the matrix: same values)
+  assemble();
+}
+
+// one Lmgc cycle through the numproc interface + the full `ls` solve
+static void dump_solve(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  INT result = 0, bl = 0;
+  restore_problem();
+  NP_ITER *lmgc = (NP_ITER *)GetNumProcByName(mg, "lmgc", ITER_CLASS_NAME);
+  // --- a single cycle on the raw right-hand side (c = 0 on entry)
+  (*lmgc->PreProcess)(lmgc, top, vx, vb, mA, &bl, &result);
+  dset(mg, 0, top, ALL_VECTORS, vc, 0.0);
+  if ((*lmgc->Iter)(lmgc, top, vc, vb, mA, &result)) { fprintf(stderr, "Lmgc failed\n"); exit(9); }
+  for (int l = 0; l <= top; l++) { dumpvec("lmgc/c", vc, l); dumpvec("lmgc/b", vb, l); }
+  (*lmgc->PostProcess)(lmgc, top, vx, vb, mA, &result);
+  // --- full solve, history after every iteration (maxit = cycles, limits unreachable)
+  restore_problem();
+  NP_LINEAR_SOLVER *ls = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "mgs", LINEAR_SOLVER_CLASS_NAME);
+  LRESULT lr; memset(&lr, 0, sizeof lr);
+  (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+  (*ls->Defect)(ls, top, vx, vb, mA, &result);
+  (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
+  D.rec("solve/first_defect", 1, lr.last_defect, BS, 8);
+  for (int l = 0; l <= top; l++) dumpvec("solve/b_first", vb, l);
+  (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
+  // iterate one cycle at a time to record the history: maxit=1 solver calls are NOT equivalent
+  // (first_defect handling), so we call Solver once with maxit=cycles and read PCR-independent
+  // results; the per-iteration history comes from re-running with increasing maxit on fresh data.
+  std::vector<double> hist;
+  for (int k = 1; k <= o.cycles; k++) {
+    restore_problem();
+    cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", k);
+    (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+    (*ls->Defect)(ls, top, vx, vb, mA, &result);
+    (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
+    VEC_SCALAR abslimit, red;
+    for (int i = 0; i < MAX_VEC_COMP; i++) { abslimit[i] = 1e-30; red[i] = 1e-30; }
+    if ((*ls->Solver)(ls, top, vx, vb, mA, abslimit, red, &lr)) { fprintf(stderr, "Solver failed\n"); exit(9); }
+    for (int i = 0; i < BS; i++) hist.push_back(lr.last_defect[i]);
+    (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
+    if (k == 1 || k == 2 || k == 5 || k == o.cycles) {
+      char nm[64];
+      for (int l = 0; l <= top; l++) {
+        snprintf(nm, sizeof nm, "solve/x_after_%d", k); dumpvec(nm, vx, l);
+        snprintf(nm, sizeof nm, "solve/b_after_%d", k); dumpvec(nm, vb, l);
+      }
+    }
+  }
+  D.f64("solve/history", hist);
+  D.scalar_i("solve/cycles", o.cycles);
+  printf("history:");
+  for (size_t i = 0; i < hist.size(); i++) printf(" %.10e", hist[i]);
+  printf("\n");
+}
+
+// CPU baseline: time the reference's own solver (1 core; UG is single-threaded)
+static void time_reference(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  INT result = 0, bl = 0;
+  long n = NVEC(GRID_ON_LEVEL(mg, top));
+  restore_problem();
+  NP_LINEAR_SOLVER *ls = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "mgs", LINEAR_SOLVER_CLASS_NAME);
+  cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", o.cycles);
+  LRESULT lr; memset(&lr, 0, sizeof lr);
+  (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+  (*ls->Defect)(ls, top, vx, vb, mA, &result);
+  (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
+  VEC_SCALAR abslimit, red;
+  for (int i = 0; i < MAX_VEC_COMP; i++) { abslimit[i] = 1e-30; red[i] = 1e-30; }
+  double t0 = now();
+  (*ls->Solver)(ls, top, vx, vb, mA, abslimit, red, &lr);
+  double t1 = now();
+  (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
+  int its = lr.number_of_linear_iterations ? lr.number_of_linear_iterations : o.cycles;
+  double tcyc = (t1 - t0) / its;
+  // kernel timings
+  double best_mm = 1e30, best_dot = 1e30;
+  for (int r = 0; r < o.reps; r++) {
+    double a = now(); dmatmul_minus(mg, top, top, ALL_VECTORS, vb, mA, vx); double b = now();
+    DOUBLE s; ddot(mg, top, top, ALL_VECTORS, vb, vx, &s); double c = now();
+    if (b - a < best_mm) best_mm = b - a;
+    if (c - b < best_dot) best_dot = c - b;
+  }
+  long nnz = 0;
+  for (VECTOR *v = FIRSTVECTOR(GRID_ON_LEVEL(mg, top)); v; v = SUCCVC(v)) for (MATRIX *m = VSTART(v); m; m = MNEXT(m)) nnz++;
+  printf("{\"kind\": \"reference\", \"cores\": 1, \"dim\": %d, \"bs\": %d, \"levels\": %d, \"unknowns\": %ld, \"nnz\": %ld, "
+         "\"cycles\": %d, \"s_per_cycle\": %.6e, \"vcycle_unknowns_per_s\": %.6e, \"dmatmul_minus_s\": %.6e, \"ddot_s\": %.6e, "
+         "\"last_defect\": %.10e}\n",
+         DIM, BS, top + 1, n * BS, nnz, its, tcyc, n * BS / tcyc, best_mm, best_dot, lr.last_defect[0]);
+}
+
+#ifdef WITH_GPULS
+static int run_gpu(const Opt &o);
+#endif
+
+int main(int argc, char **argv)
+{
+  Opt o;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto nxt = [&]() { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return std::string(argv[++i]); };
+    if (a == "--grid") o.grid = nxt(); else if (a == "--bs") o.bs = atoi(nxt().c_str());
+    else if (a == "--refine") o.refine = atoi(nxt().c_str()); else if (a == "--adapt") o.adapt = atoi(nxt().c_str());
+    else if (a == "--nu1") o.nu1 = atoi(nxt().c_str()); else if (a == "--nu2") o.nu2 = atoi(nxt().c_str());
+    else if (a == "--gamma") o.gamma = atoi(nxt().c_str()); else if (a == "--cycles") o.cycles = atoi(nxt().c_str());
+    else if (a == "--reps") o.reps = atoi(nxt().c_str());
+    else if (a == "--damp") o.damp = atof(nxt().c_str()); else if (a == "--dump") o.dump = nxt();
+    else if (a == "--ops") o.ops = true; else if (a == "--solve") o.solve = true; else if (a == "--time") o.timeit = true;
+    else if (a == "--verbose") o.quiet = false; else if (a == "--gpu") o.gpu = nxt();
+    else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
+  }
+  int ac = 1; char *av0 = argv[0]; char **av = &av0;
+  // keep UG's banner noise out of stdout: results are printed by this driver only
+  FILE *saved = stdout;
+  (void)saved;
+  if (InitUg(&ac, &av)) { fprintf(stderr, "InitUg failed\n"); return 1; }
+#ifdef WITH_GPULS
+  if (!o.gpu.empty()) { if (gpuls::LoadDeviceLibrary(o.gpu.c_str())) { fprintf(stderr, "cannot load %s\n", o.gpu.c_str()); return 1; } if (InitGpuLS()) { fprintf(stderr, "InitGpuLS failed\n"); return 1; } }
+#endif
+  double t0 = now();
+  build_hierarchy(o);
+  double t1 = now();
+  int top = TOPLEVEL(mg);
+  printf("hierarchy: dim=%d grid=%s bs=%d levels=%d fullrefinelevel=%d n=[", DIM, o.grid.c_str(), BS, top + 1, (int)FULLREFINELEVEL(mg));
+  for (int l = 0; l <= top; l++) printf("%s%d", l ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
+  printf("] build_s=%.2f\n", t1 - t0);
+  make_numprocs(o, "", "jac", "lmgc", "transfer", "ls", o.cycles);
+  std::vector<gpuls::FlatLevel> fl;
+  if (!o.dump.empty()) {
+    D.open(o.dump.c_str());
+    dump_hierarchy(o, fl);
+    if (o.ops) dump_ops(o);
+    if (o.solve) dump_solve(o);
+    D.close();
+  }
+  if (o.timeit) time_reference(o);
+#ifdef WITH_GPULS
+  if (!o.gpu.empty()) return run_gpu(o);
+#endif
+  return 0;
+}
+
+#ifdef WITH_GPULS
+// Drop-in test: identical numproc script with the gpuls classes; compare with the CPU classes.
+static double maxrel(const std::vector<double> &a, const std::vector<double> &b)
+{
+  double num = 0, den = 0;
+  for (size_t i = 0; i < a.size(); i++) { num = fmax(num, fabs(a[i] - b[i])); den = fmax(den, fabs(a[i])); }
+  return den > 0 ? num / den : num;
+}
+
+static int run_gpu(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  INT result = 0, bl = 0;
+  VEC_SCALAR abslimit, red;
+  for (int i = 0; i < MAX_VEC_COMP; i++) { abslimit[i] = 1e-30; red[i] = 1e-30; }
+  int fails = 0;
+  // 1. CPU reference run
+  restore_problem();
+  cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", o.cycles);
+  NP_LINEAR_SOLVER *ls = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "mgs", LINEAR_SOLVER_CLASS_NAME);
+  LRESULT lr; memset(&lr, 0, sizeof lr);
+  (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+  (*ls->Defect)(ls, top, vx, vb, mA, &result);
+  (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
+  double c0 = now();
+  (*ls->Solver)(ls, top, vx, vb, mA, abslimit, red, &lr);
+  double c1 = now();
+  (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
+  std::vector<std::vector<double> > xr(top + 1), br(top + 1);
+  for (int l = 0; l <= top; l++) { xr[l] = gather(vx, l); br[l] = gather(vb, l); }
+  LRESULT lr_cpu = lr;
+
+  // 2. every gpuls configuration: (a) all four GPU classes, device base solver; (b) GPU classes with the
+  //    CPU base solver numproc; (c) CPU ls + gpulmgc; (d) CPU ls + CPU lmgc + gpujac + gputransfer
+  struct Cfg { const char *name, *jac, *lmgc, *transfer, *ls; const char *extra; double tol; };
+  const Cfg cfgs[] = {
+    {"gpuls+gpulmgc+gpujac+gputransfer (host base solver)", "gpujac", "gpulmgc", "gputransfer", "gpuls", "", 0.0},
+    {"gpuls+gpulmgc, device base solver", "gpujac", "gpulmgc", "gputransfer", "gpuls", " $devbase", 1e-12},
+    {"ls+gpulmgc", "gpujac", "gpulmgc", "gputransfer", "ls", "", 0.0},
+    {"ls+lmgc+gpujac+gputransfer", "gpujac", "lmgc", "gputransfer", "ls", "", 0.0},
+  };
+  int k = 0;
+  for (const Cfg &c : cfgs) {
+    char pfx[16]; snprintf(pfx, sizeof pfx, "g%d", k++);
+    make_numprocs(o, pfx, c.jac, c.lmgc, c.transfer, c.ls, o.cycles);
+    if (c.extra[0]) cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d%s", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, c.extra);
+    restore_problem();
+    std::string name = std::string(pfx) + "mgs";
+    NP_LINEAR_SOLVER *g = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, name.c_str(), LINEAR_SOLVER_CLASS_NAME);
+    memset(&lr, 0, sizeof lr);
+    if ((*g->PreProcess)(g, top, vx, vb, mA, &bl, &result)) { printf("FAIL %s: PreProcess\n", c.name); fails++; continue; }
+    (*g->Defect)(g, top, vx, vb, mA, &result);
+    (*g->Residuum)(g, bl, top, vx, vb, mA, &lr);
+    double g0 = now();
+    if ((*g->Solver)(g, top, vx, vb, mA, abslimit, red, &lr)) { printf("FAIL %s: Solver\n", c.name); fails++; continue; }
+    double g1 = now();
+    (*g->PostProcess)(g, top, vx, vb, mA, &result);
+    double ex = 0, eb = 0;
+    for (int l = 0; l <= top; l++) { ex = fmax(ex, maxrel(xr[l], gather(vx, l))); eb = fmax(eb, maxrel(br[l], gather(vb, l))); }
+    double ed = 0;
+    for (int i = 0; i < BS; i++) ed = fmax(ed, fabs(lr.last_defect[i] - lr_cpu.last_defect[i]) / lr_cpu.last_defect[i]);
+    bool ok = ex <= c.tol && eb <= c.tol && ed <= 1e-12 && lr.number_of_linear_iterations == lr_cpu.number_of_linear_iterations;
+    printf("%s %s: its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e b=%.3e defect=%.3e  t_gpu=%.4fs t_cpu=%.4fs\n", ok ? "PASS" : "FAIL", c.name,
+           (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_cpu.last_defect[0], ex, eb, ed, g1 - g0, c1 - c0);
+    if (!ok) fails++;
+  }
+  printf("gpuls drop-in: %d failure(s)\n", fails);
+  return fails ? 10 : 0;
+}
+#endif
