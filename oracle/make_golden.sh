@@ -1,0 +1,21 @@
+#!/bin/bash
+# oracle/make_golden.sh -- TEST INFRASTRUCTURE.  Regenerates tests/golden/*.ugh by running the
+# UNMODIFIED reference (oracle/_ref/ugoracle{2,3}, built by oracle/Makefile from /root/reference).
+# The reference ships no golden vectors for this path, so these dumps --
+# outputs of the reference itself on seeded inputs -- are the pinned fixtures.
+set -e
+cd "$(dirname "$0")"
+make -s -j8 ref
+G=../tests/golden
+mkdir -p $G
+# C1 (BASELINE.json configs[0]) scaled to a committable size: 2D P1, unit square, 4 refinements
+./_ref/ugoracle2 --grid tri  --refine 4 --damp 0.8 --cycles 10 --dump $G/c1_tri2d_r4.ugh  --ops --solve > /dev/null
+# C2 family: 3D P1 tets, 3 refinements (9^3 = 729 unknowns)
+./_ref/ugoracle3 --grid tet  --refine 3 --damp 0.6 --cycles 10 --dump $G/c2_tet3d_r3.ugh  --ops --solve > /dev/null
+# C4 family: Q1 hexes, 3x3 blocks (linear elasticity), 2 refinements (125 nodes)
+./_ref/ugoracle3 --grid hex  --bs 3 --refine 2 --damp 0.6 --cycles 10 --dump $G/c4_hex3d_bs3_r2.ugh --ops --solve > /dev/null
+# C5 family: adaptively refined tets (2 uniform + 2 local refinements): partial levels, classes < 3
+./_ref/ugoracle3 --grid tet  --refine 2 --adapt 2 --damp 0.6 --cycles 10 --dump $G/c5_tet3d_adapt.ugh --ops --solve > /dev/null
+# quads with scalar unknowns (Q1 in 2D), W-cycle
+./_ref/ugoracle2 --grid quad --refine 3 --damp 0.8 --gamma 2 --cycles 6 --dump $G/q1_quad2d_r3_w.ugh --ops --solve > /dev/null
+ls -la $G

@@ -406,7 +406,7 @@ static void dump_ops(const Opt &o)
   {
     int fr = FULLREFINELEVEL(mg);
     for (int l = 0; l <= top; l++) { fill_lcg(vx, l, 11); fill_lcg(vb, l, 12); fill_lcg(vt, l, 13); }
-    for (int l = 0; l <= top; l++) { dumpvec("surf/in_x", vx, l); dumpvec("surf/in_b", vb, l); }
+    for (int l = 0; l <= top; l++) { dumpvec("surf/in_x", vx, l); dumpvec("surf/in_b", vb, l); dumpvec("surf/in_t", vt, l); }
     dmatmul_minus(mg, fr, top, ON_SURFACE, vb, mA, vx);
     for (int l = 0; l <= top; l++) dumpvec("surf/dmatmul_minus", vb, l);
     VEC_SCALAR sx; DOUBLE s;

@@ -1,0 +1,301 @@
+/* oracle/ugport.c -- TEST INFRASTRUCTURE ONLY: see ugport.h.
+ *
+ * Sequential, one statement per reference statement where it matters for rounding; compile with
+ * -ffp-contract=off.  Each function cites the reference lines it restates (paths relative to the
+ * reference root, UG 3.12.1).
+ */
+#include "ugport.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NEWDEF_CLASS 2   /* gm/algebra.h:70 */
+#define ACTIVE_CLASS 3   /* gm/algebra.h:71 */
+#define CTL_NEW_DEFECT 1u
+#define CTL_FINE_GRID_DOF 2u
+
+static int row_on(const ugport_level *L, int rowmode, int r)
+{
+  if (rowmode == 0) return 1;
+  if (rowmode == 1) return (L->ctl[r] & CTL_NEW_DEFECT) != 0;    /* vecloop.ct:31 */
+  return (L->ctl[r] & CTL_FINE_GRID_DOF) != 0;                   /* vecloop.ct:24 */
+}
+
+/* np/algebra/matloop.ct:74-100 with T_MOD_SCAL ugblas.cc:4007 (scalar) and MATMUL_nn_SUCC
+ * ugblas.h:161-282 (blocks): per entry e_i = (m_i0*y_0 + m_i1*y_1) + m_i2*y_2 ; s_i += e_i */
+void ugport_dmatmul(const ugport_level *L, int op, int rowmode, double *x, const double *y)
+{
+  int bs = L->bs, bb = bs * bs;
+  for (int r = 0; r < L->n; r++) {
+    if (!row_on(L, rowmode, r)) continue;
+    double s[UGPORT_MAX_BS] = {0.0, 0.0, 0.0};
+    for (int e = L->rowptr[r]; e < L->rowptr[r + 1]; e++) {
+      const double *m = L->val + (size_t)e * bb;
+      const double *w = y + (size_t)L->col[e] * bs;
+      for (int i = 0; i < bs; i++) {
+        double acc = m[i * bs] * w[0];
+        for (int j = 1; j < bs; j++) acc = acc + m[i * bs + j] * w[j];
+        s[i] += acc;
+      }
+    }
+    for (int i = 0; i < bs; i++) {
+      double *xi = x + (size_t)r * bs + i;
+      if (op == 0) { if (bs == 1) *xi = s[i]; else { *xi = 0.0; *xi += s[i]; } }  /* matmode.ct:76 T_CLEAR_X */
+      else if (op == 1) *xi += s[i];
+      else *xi -= s[i];
+    }
+  }
+}
+
+#define VLOOP(body) \
+  for (int r = 0; r < L->n; r++) { if (!row_on(L, rowmode, r)) continue; \
+    for (int i = 0; i < L->bs; i++) { size_t k = (size_t)r * L->bs + i; body; } }
+
+void ugport_dset(const ugport_level *L, int rowmode, double *x, double a) { VLOOP(x[k] = a) }
+void ugport_dcopy(const ugport_level *L, int rowmode, double *x, const double *y) { VLOOP(x[k] = y[k]) }
+void ugport_dscal(const ugport_level *L, int rowmode, double *x, double a) { VLOOP(x[k] *= a) }
+void ugport_dscalx(const ugport_level *L, int rowmode, double *x, const double *a) { VLOOP(x[k] *= a[i]) }
+void ugport_dadd(const ugport_level *L, int rowmode, double *x, const double *y) { VLOOP(x[k] += y[k]) }
+void ugport_dsub(const ugport_level *L, int rowmode, double *x, const double *y) { VLOOP(x[k] -= y[k]) }
+void ugport_dminusadd(const ugport_level *L, int rowmode, double *x, const double *y) { VLOOP(x[k] = y[k] - x[k]) }
+void ugport_daxpy(const ugport_level *L, int rowmode, double *x, double a, const double *y) { VLOOP(x[k] += a * y[k]) }
+void ugport_daxpyx(const ugport_level *L, int rowmode, double *x, const double *a, const double *y) { VLOOP(x[k] += a[i] * y[k]) }
+void ugport_ddot_acc(const ugport_level *L, int rowmode, const double *x, const double *y, double *sum) { VLOOP(*sum += x[k] * y[k]) }
+void ugport_ddotx_acc(const ugport_level *L, int rowmode, const double *x, const double *y, double *sum) { VLOOP(sum[i] += x[k] * y[k]) }
+void ugport_dnrm2_acc(const ugport_level *L, int rowmode, const double *x, double *sum) { VLOOP(double s = x[k]; *sum += s * s) }
+void ugport_dnrm2x_acc(const ugport_level *L, int rowmode, const double *x, double *sum) { VLOOP(double s = x[k]; sum[i] += s * s) }
+
+/* np/algebra/block.cc:104-142 SolveSmallBlock, n = 1,2,3 */
+static int solve_small_block(int n, double *sol, const double *mat, const double *rhs)
+{
+  if (n == 1) { sol[0] = rhs[0] / mat[0]; return 0; }
+  if (n == 2) {
+    double det = mat[0] * mat[3] - mat[1] * mat[2];
+    if (det == 0.0) return 1;
+    det = 1.0 / det;
+    sol[0] = (rhs[0] * mat[3] - rhs[1] * mat[1]) * det;
+    sol[1] = (rhs[1] * mat[0] - rhs[0] * mat[2]) * det;
+    return 0;
+  }
+  double M3div0 = mat[3] / mat[0];
+  double M6div0 = mat[6] / mat[0];
+  double aux = (mat[7] - M6div0 * mat[1]) / (mat[4] - M3div0 * mat[1]);
+  sol[2] = (rhs[2] - M6div0 * rhs[0] - aux * (rhs[1] - M3div0 * rhs[0]))
+           / (mat[8] - M6div0 * mat[2] - aux * (mat[5] - M3div0 * mat[2]));
+  sol[1] = (rhs[1] - mat[3] / mat[0] * rhs[0] - (mat[5] - M3div0 * mat[2]) * sol[2])
+           / (mat[4] - M3div0 * mat[1]);
+  sol[0] = (rhs[0] - mat[1] * sol[1] - mat[2] * sol[2]) / mat[0];
+  return 0;
+}
+
+/* np/algebra/ugiter.cc:271-335 */
+int ugport_l_jac(const ugport_level *L, double *v, const double *d)
+{
+  int bs = L->bs, bb = bs * bs;
+  for (int r = 0; r < L->n; r++) {
+    double *vr = v + (size_t)r * bs;
+    if (L->vclass[r] < ACTIVE_CLASS) { for (int i = 0; i < bs; i++) vr[i] = 0.0; continue; }
+    double s[UGPORT_MAX_BS];
+    for (int i = 0; i < bs; i++) s[i] = d[(size_t)r * bs + i];
+    if (solve_small_block(bs, vr, L->val + (size_t)L->rowptr[r] * bb, s)) return 6; /* NUM_SMALL_DIAG */
+  }
+  return 0;
+}
+
+/* np/procs/iter.cc:817-842 Smoother with JacobiStep :911 */
+int ugport_jac_smooth(const ugport_level *L, double *x, double *b, const double *damp)
+{
+  int err = ugport_l_jac(L, x, b);
+  if (err) return err;
+  ugport_dscalx(L, 0, x, damp);
+  ugport_dmatmul(L, 2, 0, b, x);
+  return 0;
+}
+
+/* np/algebra/transgrid.cc:117-189.  R rows list the contributions to one coarse vector in fine NODE
+ * list order, so the serial sum below performs the same additions in the same order as the
+ * reference's scatter loop. */
+void ugport_restrict(const ugport_level *fine, const ugport_level *coarse, double *to, const double *from, const double *damp)
+{
+  int bs = fine->bs;
+  for (int r = 0; r < coarse->n; r++) {
+    double *tr = to + (size_t)r * bs;
+    if (coarse->vnclass[r] >= NEWDEF_CLASS) for (int i = 0; i < bs; i++) tr[i] = 0.0;   /* :143-147 */
+    uint32_t skip = coarse->skip[r];
+    for (int e = fine->r_rowptr[r]; e < fine->r_rowptr[r + 1]; e++) {
+      const double *f = from + (size_t)fine->r_col[e] * bs;
+      double w = fine->r_w[e];
+      for (int j = 0; j < bs; j++)
+        if (!(skip & (1u << j))) {
+          double s = damp[j] * f[j];            /* :164 / :173 */
+          tr[j] += w * s;                       /* :165 (w = 1) / :187 */
+        }
+    }
+  }
+}
+
+/* np/algebra/transgrid.cc:235-307 */
+void ugport_interpolate(const ugport_level *fine, const ugport_level *coarse, double *to, const double *from, const double *damp)
+{
+  int bs = fine->bs;
+  (void)coarse;
+  for (int r = 0; r < fine->n; r++) {
+    double *tr = to + (size_t)r * bs;
+    for (int i = 0; i < bs; i++) tr[i] = 0.0;                                  /* :264-268 */
+    uint32_t skip = fine->skip[r];
+    for (int j = 0; j < bs; j++) {
+      if (skip & (1u << j)) continue;
+      for (int e = fine->p_rowptr[r]; e < fine->p_rowptr[r + 1]; e++)
+        tr[j] += fine->p_w[e] * damp[j] * from[(size_t)fine->p_col[e] * bs + j];   /* :305 ; corner :290 */
+    }
+  }
+}
+
+/* Dense LU of the base level in vector-index order, right-looking, no pivoting: the arithmetic of
+ * l_lrdecomp (ugiter.cc:3657-3760, scalar) / its block variant, on a dense copy so that fill-in
+ * needs no extra connections.  Stores the inverse diagonal (StoreInverse, ugiter.cc:139).
+ * Rows with VCLASS < ACTIVE_CLASS are excluded like in the reference. */
+double *ugport_base_factor(const ugport_level *L)
+{
+  int N = L->n * L->bs, bs = L->bs, bb = bs * bs;
+  double *lu = (double *)calloc((size_t)N * N, sizeof(double));
+  for (int r = 0; r < L->n; r++)
+    for (int e = L->rowptr[r]; e < L->rowptr[r + 1]; e++)
+      for (int i = 0; i < bs; i++) for (int j = 0; j < bs; j++)
+        lu[(size_t)(r * bs + i) * N + L->col[e] * bs + j] = L->val[(size_t)e * bb + i * bs + j];
+  for (int i = 0; i < N; i++) {
+    if (L->vclass[i / bs] < ACTIVE_CLASS) continue;
+    double inv = 1.0 / lu[(size_t)i * N + i];
+    lu[(size_t)i * N + i] = inv;
+    for (int j = i + 1; j < N; j++) {
+      if (L->vclass[j / bs] < ACTIVE_CLASS) continue;
+      double piv = lu[(size_t)j * N + i] * inv;
+      lu[(size_t)j * N + i] = piv;
+      if (piv == 0.0) continue;
+      for (int k = i + 1; k < N; k++) {
+        if (L->vclass[k / bs] < ACTIVE_CLASS) continue;
+        lu[(size_t)j * N + k] -= piv * lu[(size_t)i * N + k];
+      }
+    }
+  }
+  return lu;
+}
+void ugport_base_free(double *lu) { free(lu); }
+
+/* l_luiter ugiter.cc:4444-4520 on the dense factors (sums in index order) */
+static void base_lu_solve(const ugport_level *L, const double *lu, double *v, const double *d)
+{
+  int N = L->n * L->bs, bs = L->bs;
+  for (int i = 0; i < N; i++) {
+    if (L->vclass[i / bs] < ACTIVE_CLASS) { v[i] = 0.0; continue; }
+    double sum = 0.0;
+    for (int j = 0; j < i; j++) if (L->vclass[j / bs] >= ACTIVE_CLASS) sum += lu[(size_t)i * N + j] * v[j];
+    v[i] = d[i] - sum;
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    if (L->vclass[i / bs] < ACTIVE_CLASS) continue;
+    double sum = 0.0;
+    for (int j = i + 1; j < N; j++) if (L->vclass[j / bs] >= ACTIVE_CLASS) sum += lu[(size_t)i * N + j] * v[j];
+    v[i] = (v[i] - sum) * lu[(size_t)i * N + i];
+  }
+}
+
+static int sc_cmp(const double *x, const double *y, int n)   /* npscan.cc:1027 */
+{
+  for (int i = 0; i < n; i++) if (fabs(x[i]) >= fabs(y[i])) return 0;
+  return 1;
+}
+
+/* base `ls $I lu`: LinearResiduum + LinearSolver (ls.cc:577,637) with Iter = Smoother/ILUStep (damp 1) */
+static void base_solve(const ugport_level *L, const ugport_cfg *cfg, const double *lu, double *c, double *b, double *t)
+{
+  int bs = L->bs, N = L->n * bs;
+  double first[UGPORT_MAX_BS], last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS], absl[UGPORT_MAX_BS];
+  memset(last, 0, sizeof last);
+  ugport_dnrm2x_acc(L, 1, b, last);           /* Residuum at tl = base level: NEW_DEFECT rows (vecloop.ct:30-38) */
+  for (int i = 0; i < bs; i++) { last[i] = sqrt(last[i]); first[i] = last[i]; absl[i] = cfg->base_abslimit;
+    reach[i] = first[i] * cfg->base_reduction; if (reach[i] == 0.0) reach[i] = cfg->base_reduction; }
+  if (sc_cmp(first, absl, bs)) return;
+  double *cc = (double *)malloc(sizeof(double) * N);
+  for (int it = 0; it < cfg->base_maxit; it++) {
+    (void)t;
+    base_lu_solve(L, lu, cc, b);                 /* dset(c,0); Iter: c' = LU^-1 b; dscalx(1); b -= A c' */
+    ugport_dmatmul(L, 2, 0, b, cc);
+    for (int k = 0; k < N; k++) c[k] += cc[k];   /* LSUpdate ls.cc:869 */
+    memset(last, 0, sizeof last);
+    ugport_dnrm2x_acc(L, 1, b, last);
+    for (int i = 0; i < bs; i++) last[i] = sqrt(last[i]);
+    if (sc_cmp(last, absl, bs) || sc_cmp(last, reach, bs)) break;
+  }
+  free(cc);
+}
+
+/* np/procs/iter.cc:7741-7949 */
+int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu, int level, double **c, double **b, double **t)
+{
+  const ugport_level *L = &lv[level];
+  double one[UGPORT_MAX_BS] = {1.0, 1.0, 1.0};
+  if (level <= cfg->baselevel) { base_solve(L, cfg, lu, c[level], b[level], t[level]); return 0; }
+  for (int i = 0; i < cfg->nu1; i++) {
+    int err = ugport_jac_smooth(L, t[level], b[level], cfg->smooth_damp);
+    if (err) return err;
+    ugport_dadd(L, 0, c[level], t[level]);
+  }
+  ugport_restrict(L, &lv[level - 1], b[level - 1], b[level], one);           /* :7843, Factor_One */
+  ugport_dset(&lv[level - 1], 0, c[level - 1], 0.0);                         /* :7873 */
+  for (int g = 0; g < cfg->gamma; g++) {
+    int err = ugport_lmgc(lv, cfg, lu, level - 1, c, b, t);
+    if (err) return err;
+  }
+  ugport_interpolate(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);  /* :7886 */
+  ugport_dadd(L, 0, c[level], t[level]);                                     /* :7903 */
+  ugport_dmatmul(L, 2, 0, b[level], t[level]);                               /* :7905 */
+  for (int i = 0; i < cfg->nu2; i++) {
+    int err = ugport_jac_smooth(L, t[level], b[level], cfg->smooth_damp);
+    if (err) return err;
+    ugport_dadd(L, 0, c[level], t[level]);
+  }
+  return 0;
+}
+
+/* ls.cc:562: dmatmul_minus(bl..level, ON_SURFACE); surface loops: matloop.ct:22-73 */
+void ugport_ls_defect(const ugport_level *lv, int fr, int bl, int level, double **x, double **b)
+{
+  (void)bl;
+  for (int l = fr; l < level; l++) ugport_dmatmul(&lv[l], 2, 2, b[l], x[l]);
+  ugport_dmatmul(&lv[level], 2, 1, b[level], x[level]);
+}
+
+/* ls.cc:577: dnrm2x(bl..level, ON_SURFACE) -- one running sum across levels, then sqrt */
+void ugport_ls_residuum(const ugport_level *lv, int fr, int bl, int level, double **b, double *defect)
+{
+  (void)bl;
+  int bs = lv[level].bs;
+  for (int i = 0; i < bs; i++) defect[i] = 0.0;
+  for (int l = fr; l < level; l++) ugport_dnrm2x_acc(&lv[l], 2, b[l], defect);
+  ugport_dnrm2x_acc(&lv[level], 1, b[level], defect);
+  for (int i = 0; i < bs; i++) defect[i] = sqrt(defect[i]);
+}
+
+/* ls.cc:637-749 with Update = LSUpdate (:869, dadd on levels baselevel..level) */
+int ugport_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int level, double **x, double **b, double **c, double **t,
+                 int maxiter, const double *abslimit, const double *reduction, double *first_defect, double *history)
+{
+  int bs = lv[level].bs, bl = cfg->baselevel, it, done = 0;
+  double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS];
+  double *lu = ugport_base_factor(&lv[bl]);
+  ugport_ls_residuum(lv, fr, bl, level, b, last);
+  for (int i = 0; i < bs; i++) { first_defect[i] = last[i]; reach[i] = last[i] * reduction[i]; if (reach[i] == 0.0) reach[i] = reduction[i]; }
+  if (sc_cmp(last, abslimit, bs)) { ugport_base_free(lu); return 0; }
+  for (it = 0; it < maxiter; it++) {
+    ugport_dset(&lv[level], 0, c[level], 0.0);
+    if (ugport_lmgc(lv, cfg, lu, level, c, b, t)) { ugport_base_free(lu); return -1; }
+    for (int l = bl; l <= level; l++) ugport_dadd(&lv[l], 0, x[l], c[l]);
+    ugport_ls_residuum(lv, fr, bl, level, b, last);
+    if (history) for (int i = 0; i < bs; i++) history[it * bs + i] = last[i];
+    done = it + 1;
+    if (sc_cmp(last, abslimit, bs) || sc_cmp(last, reach, bs)) break;
+  }
+  ugport_base_free(lu);
+  return done;
+}

@@ -1,0 +1,45 @@
+"""The CPU restatement (oracle/ugport.c) against the golden dumps of the compiled reference.
+
+Everything is required to be BIT-exact, reductions included: the restatement is sequential and
+follows the reference's statement order, and both are compiled with -ffp-contract=off.
+"""
+import numpy as np
+
+from oracle.ugport import PortBackend
+from replay import replay_ops, replay_solve
+
+
+def test_port_ops_bitexact(golden):
+    be = PortBackend(golden)
+    n = replay_ops(be, golden, exact=True, exact_red=True)
+    assert n > 20
+
+
+def test_port_cycle_and_solve_bitexact(golden):
+    be = PortBackend(golden)
+    n = replay_solve(be, golden, exact=True, red_tol=0.0)
+    assert n > 10
+
+
+def test_golden_invariants(golden):
+    """Invariants the reference's own checkers assert (np/algebra/npcheck.cc:118-154)."""
+    for l, lv in enumerate(golden.levels):
+        assert lv.rowptr[0] == 0 and lv.rowptr[-1] == lv.col.size
+        assert np.array_equal(lv.col[lv.rowptr[:-1]], np.arange(lv.n)), "diagonal first"
+        new_defect = (lv.ctl & 1) != 0
+        fine_dof = (lv.ctl & 2) != 0
+        assert np.array_equal(new_defect, lv.vclass >= 2)
+        assert np.array_equal(fine_dof, (lv.vclass >= 2) & (lv.vnclass <= 1))
+        if l > 0:
+            assert lv.p_rowptr[-1] == lv.p_col.size == lv.p_w.size
+            # R is P restricted to fine rows with VCLASS >= NEWDEF_CLASS, transposed
+            keep = np.repeat(lv.vclass >= 2, np.diff(lv.p_rowptr))
+            assert lv.r_col.size == int(keep.sum())
+            rows = np.repeat(np.arange(lv.n), np.diff(lv.p_rowptr))[keep]
+            pt = sorted(zip(lv.p_col[keep].tolist(), rows.tolist(), lv.p_w[keep].tolist()))
+            rr = np.repeat(np.arange(golden.levels[l - 1].n), np.diff(lv.r_rowptr))
+            rt = sorted(zip(rr.tolist(), lv.r_col.tolist(), lv.r_w.tolist()))
+            assert pt == rt
+            # partition of unity of the P1/Q1 interpolation weights
+            s = np.add.reduceat(lv.p_w, lv.p_rowptr[:-1])
+            assert np.allclose(s, 1.0, atol=1e-14)
