@@ -62,6 +62,8 @@ int  uggpu_ctx_create(int device, uggpu_ctx **out);
 int  uggpu_ctx_destroy(uggpu_ctx *ctx);
 const char *uggpu_last_error(void);
 int  uggpu_sync(uggpu_ctx *ctx);
+/* the context's CUDA stream (cudaStream_t as void*), so that callers can time with events on it */
+int  uggpu_stream(uggpu_ctx *ctx, void **stream);
 /* FULLREFINELEVEL(mg) (gm/gm.h) used by the ON_SURFACE loops, np/algebra/vecloop.ct:22 */
 int  uggpu_set_fullrefinelevel(uggpu_ctx *ctx, int level);
 /* number of kernels launched by this context since creation (bench `gpu_launches`) */
@@ -81,11 +83,14 @@ int uggpu_level_bs(uggpu_ctx *ctx, int level);
 int uggpu_level_set_flags(uggpu_ctx *ctx, int level, const uint8_t *vclass, const uint8_t *vnclass,
                           const uint8_t *ctl, const uint32_t *skip);
 /* rowptr[n+1], col[nnz] (int32, 0-based), val[nnz*bs*bs] row-major blocks; host pointers. */
+int uggpu_level_get_flags(uggpu_ctx *ctx, int level, uint8_t *vclass, uint8_t *vnclass, uint8_t *ctl, uint32_t *skip);
 int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, const int32_t *col,
                   const double *val);
 int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const double *val);
 int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val);
 int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat);
+/* entries actually stored on the device (SELL-32 slices padded to their longest row) */
+int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat);
 int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
 /* Standard (geometric) transfer stencils between `level` and level-1 (np/algebra/transgrid.cc:117-336):
  * P: p_rowptr[n_fine+1], p_col (coarse row), p_w (GNs weight, zeros dropped, corner order);
@@ -94,6 +99,10 @@ int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
 int uggpu_transfer_set(uggpu_ctx *ctx, int level,
                        const int32_t *p_rowptr, const int32_t *p_col, const double *p_w,
                        const int32_t *r_rowptr, const int32_t *r_col, const double *r_w);
+
+/* which: 0 = P, 1 = R; any output pointer may be NULL */
+int uggpu_transfer_get(uggpu_ctx *ctx, int level, int which, int32_t *rowptr, int32_t *col, double *w);
+int64_t uggpu_transfer_nnz(uggpu_ctx *ctx, int level, int which);
 
 /* ---- vectors (VECDATA_DESC on one level) ------------------------------------------------ */
 int uggpu_vec_alloc(uggpu_ctx *ctx, int level, int vec);          /* AllocVDFromVD, np/udm/udm.h:476 */
@@ -182,10 +191,15 @@ int uggpu_ls_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x, 
 
 /* ---- synthetic hierarchies generated on the device (bench input only; no reference analogue:
  * UG's grid manager needs ~2.5 kB per unknown) -------------------------------------------- */
-/* P1 Poisson on the unit cube, structured nx*ny*nz cells on level 0, each cell split into the six
- * tetrahedra around diagonal 0-6, uniformly refined `top` times.  Creates
- * levels 0..top with matrix handle A, Dirichlet identity rows (VECSKIP) and the standard P/R. */
-int uggpu_synth_poisson3d(uggpu_ctx*, int nx, int ny, int nz, int top, int A);
+#define UGGPU_SYNTH_P1_SIMPLEX    0   /* P1 Poisson on Kuhn triangles (nz = 0) / tetrahedra, scalar          */
+#define UGGPU_SYNTH_Q1_POISSON    1   /* Q1 Poisson on cubes, scalar, 27-point rows                          */
+#define UGGPU_SYNTH_Q1_ELASTICITY 2   /* Q1 linear elasticity on cubes, 3x3 blocks (E = 1, nu = 0.3)         */
+/* Structured nx*ny*nz cubic cells on level 0 of the unit square (nz = 0) or cube, uniformly refined `top` times.
+ * Creates levels 0..top with matrix handle A, the per-row flags of a uniformly refined UG multigrid, Dirichlet
+ * identity rows (VECSKIP) on the whole boundary and the standard P/R; sets FULLREFINELEVEL = top. */
+int uggpu_synth_hierarchy(uggpu_ctx*, int kind, int nx, int ny, int nz, int top, int A);
+/* load vector of the constant right-hand side 1 (0 on Dirichlet rows) into vector `vec` of `level` */
+int uggpu_synth_rhs(uggpu_ctx*, int level, int vec);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,365 @@
+// cycle.cu -- the multigrid cycle Lmgc (np/procs/iter.cc:7741-7949), its base-level solver `ls $I lu`
+// (np/procs/ls.cc:637-749 around l_lrdecomp/l_luiter, np/algebra/ugiter.cc:3657,4444) and the outer linear
+// solver LinearDefect/LinearResiduum/LinearSolver (np/procs/ls.cc:562-749), all device-resident.
+//
+// Two schedules produce bit-identical vectors:
+//   fused = 0  one kernel per reference call, in the reference's order (the op-for-op mirror);
+//   fused = 1  per level and cycle: 1 Jacobi-diagonal pass (fused into the restriction on coarse levels),
+//              nu1 + 1 + nu2 fused smoothing-step kernels (spmv.cu k_smooth_k), 1 restriction, 1 prolongation;
+//              on the solver's top level the last step also applies x += c and accumulates the defect norm.
+#include "uggpu_internal.h"
+
+#include <cmath>
+#include <cstring>
+
+// ---- dense LU of the base level ---------------------------------------------------------------------------------
+#define LU_THREADS 1024
+#define LU_MAX_N 2048
+
+__global__ void k_lu_scatter(SellView A, int bs, int N, double *__restrict__ lu)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n) return;
+  int bb = bs * bs, lane = r & 31;
+  int64_t sp = A.slice_ptr[r >> 5];
+  int len = A.rowlen[r];
+  for (int j = 0; j < len; j++) {
+    int c = A.col[sp + (int64_t)j * 32 + lane];
+    for (int i = 0; i < bs; i++)
+      for (int k = 0; k < bs; k++)
+        lu[(size_t)(c * bs + k) * N + (r * bs + i)] = A.val[(sp + (int64_t)j * 32) * bb + (int64_t)(i * bs + k) * 32 + lane];
+  }
+}
+
+// Right-looking LU without pivoting in vector-index order; element (i,j) at lu[j*N+i]; the inverse of the
+// diagonal is stored (StoreInverse, ugiter.cc:139).  Rows/columns of vectors with VCLASS < ACTIVE_CLASS are left out.
+// Every element receives its updates for i = 0,1,2,... in the same order as a sequential elimination.
+__global__ void __launch_bounds__(LU_THREADS) k_lu_factor(int N, int bs, const uint8_t *__restrict__ vclass, double *__restrict__ lu)
+{
+  __shared__ double sinv;
+  const int tid = threadIdx.x;
+  for (int i = 0; i < N; i++) {
+    if (vclass[i / bs] < 3) continue;
+    if (tid == 0) { double inv = 1.0 / lu[(size_t)i * N + i]; lu[(size_t)i * N + i] = inv; sinv = inv; }
+    __syncthreads();
+    const double inv = sinv;
+    for (int j = i + 1 + tid; j < N; j += LU_THREADS)
+      if (vclass[j / bs] >= 3) lu[(size_t)i * N + j] = lu[(size_t)i * N + j] * inv;
+    __syncthreads();
+    const int m = N - i - 1;
+    for (int idx = tid; idx < m * m; idx += LU_THREADS) {
+      int j = i + 1 + idx % m, k = i + 1 + idx / m;
+      if (vclass[j / bs] < 3 || vclass[k / bs] < 3) continue;
+      double piv = lu[(size_t)i * N + j];
+      if (piv == 0.0) continue;
+      lu[(size_t)k * N + j] = lu[(size_t)k * N + j] - piv * lu[(size_t)k * N + i];
+    }
+    __syncthreads();
+  }
+}
+
+// v = (LU)^-1 d  (l_luiter ugiter.cc:4444): forward sums accumulate column by column (ascending j, the order of a
+// sequential row sum), backward sums are formed in ascending j by one thread from products computed in parallel.
+__global__ void __launch_bounds__(LU_THREADS) k_lu_solve(int N, int bs, const uint8_t *__restrict__ vclass, const double *__restrict__ lu,
+                                                         double *__restrict__ v, const double *__restrict__ d)
+{
+  __shared__ double vs[LU_MAX_N];
+  __shared__ double prod[LU_MAX_N];
+  __shared__ uint8_t act[LU_MAX_N];
+  const int tid = threadIdx.x;
+  constexpr int Q = LU_MAX_N / LU_THREADS;
+  double sum[Q];
+#pragma unroll
+  for (int q = 0; q < Q; q++) sum[q] = 0.0;
+  for (int i = tid; i < N; i += LU_THREADS) act[i] = vclass[i / bs] >= 3;
+  __syncthreads();
+  for (int j = 0; j < N; j++) {
+    if ((j % LU_THREADS) == tid) vs[j] = act[j] ? d[j] - sum[j / LU_THREADS] : 0.0;
+    __syncthreads();
+    if (!act[j]) continue;
+    const double vj = vs[j];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+      int i = tid + q * LU_THREADS;
+      if (i > j && i < N && act[i]) sum[q] += lu[(size_t)j * N + i] * vj;
+    }
+  }
+  __syncthreads();
+  for (int i = N - 1; i >= 0; i--) {
+    if (!act[i]) continue;
+    for (int j = i + 1 + tid; j < N; j += LU_THREADS)
+      if (act[j]) prod[j] = lu[(size_t)j * N + i] * vs[j];
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int j = i + 1; j < N; j++) if (act[j]) s += prod[j];
+      vs[i] = (vs[i] - s) * lu[(size_t)i * N + i];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += LU_THREADS) v[i] = vs[i];
+}
+
+static int ensure_vec(uggpu_ctx *ctx, int level, int vec) { return uggpu_vec_alloc(ctx, level, vec); }
+
+extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int A)
+{
+  if (!ctx || !cfg) return uggpu_fail(UGGPU_ERROR, "null argument");
+  int bl = cfg->baselevel;
+  if (bl > level) return uggpu_fail(UGGPU_ERROR, "baselevel %d above level %d", bl, level);
+  for (int l = bl; l <= level; l++) {
+    if (!get_level(ctx, l)) return UGGPU_ERROR;
+    if (!get_mat(ctx, l, A)) return UGGPU_DESC_MISMATCH;
+    if (l > bl && (!ctx->lev[l].P.valid() || !ctx->lev[l].R.valid()))
+      return uggpu_fail(UGGPU_NO_COARSER_GRID, "level %d has no transfer stencils", l);
+    UG_TRY(ensure_vec(ctx, l, cfg->t));
+    UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_B));
+  }
+  if (cfg->base_solver == nullptr) {
+    Level *L = &ctx->lev[bl];
+    int N = L->n * L->bs;
+    if (N > LU_MAX_N) return uggpu_fail(UGGPU_OUT_OF_MEM, "base level has %d unknowns; the device LU handles at most %d (use a coarser base level or a host base solver)", N, LU_MAX_N);
+    if (L->lu) UG_TRY(dfree(ctx, L->lu, (size_t)L->luN * L->luN));
+    L->luN = N; L->luA = A;
+    UG_TRY(dalloc(ctx, &L->lu, (size_t)N * N));
+    if (N > 0) {
+      CUDA_TRY(cudaMemsetAsync(L->lu, 0, (size_t)N * N * sizeof(double), ctx->stream));
+      SellMat *M = get_mat(ctx, bl, A);
+      k_lu_scatter<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(view(*M), L->bs, N, L->lu);
+      KCHECK(ctx);
+      k_lu_factor<<<1, LU_THREADS, 0, ctx->stream>>>(N, L->bs, L->vclass, L->lu);
+      KCHECK(ctx);
+    }
+    UG_TRY(ensure_vec(ctx, bl, UGGPU_VEC_TMP_C));
+  }
+  return 0;
+}
+
+static int sc_cmp(const double *x, const double *y, int n)   // npscan.cc:1027
+{
+  for (int i = 0; i < n; i++) if (fabs(x[i]) >= fabs(y[i])) return 0;
+  return 1;
+}
+
+// dnrm2x of one level (rowmode) -> out[bs]
+static int level_norm(uggpu_ctx *ctx, int level, int rowmode, const double *x, double *out)
+{
+  int bs = ctx->lev[level].bs;
+  UG_TRY(k_reduce(ctx, level, rowmode, RED_NRM2, x, x, 0));
+  UG_TRY(fetch_results(ctx, 1));
+  for (int i = 0; i < bs; i++) out[i] = sqrt(ctx->hres[i]);
+  return 0;
+}
+
+// base level: NP_LINEAR_SOLVER `ls $I lu` = LinearResiduum + LinearSolver (ls.cc:577,637) with Iter = LU (damp 1)
+static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
+{
+  if (cfg->base_solver) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int rc = cfg->base_solver(cfg->base_user, ctx, level, c, b, A);
+    if (rc) return uggpu_fail(rc, "host base solver returned %d", rc);
+    return 0;
+  }
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (!L->lu || L->luA != A) return uggpu_fail(UGGPU_ERROR, "base level %d not factored: call uggpu_lmgc_preprocess first", level);
+  int bs = L->bs;
+  double *cp = get_vec(ctx, level, c), *bp = get_vec(ctx, level, b), *cc = get_vec(ctx, level, UGGPU_VEC_TMP_C);
+  if (!cp || !bp || !cc) return UGGPU_DESC_MISMATCH;
+  if (L->n == 0) return 0;
+  double first[UGGPU_MAX_BS], last[UGGPU_MAX_BS], reach[UGGPU_MAX_BS], absl[UGGPU_MAX_BS];
+  UG_TRY(level_norm(ctx, level, 1, bp, last));
+  for (int i = 0; i < bs; i++) {
+    first[i] = last[i]; absl[i] = cfg->base_abslimit;
+    reach[i] = first[i] * cfg->base_reduction;
+    if (reach[i] == 0.0) reach[i] = cfg->base_reduction;
+  }
+  if (sc_cmp(first, absl, bs)) return 0;
+  Damp none = mkdamp(nullptr, 0);
+  for (int it = 0; it < cfg->base_maxit; it++) {
+    k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
+    KCHECK(ctx);
+    UG_TRY(k_dmatmul(ctx, level, 2, 0, b, A, UGGPU_VEC_TMP_C));
+    UG_TRY(k_vec_op(ctx, level, 0, VOP_ADD, cp, cc, none));
+    UG_TRY(level_norm(ctx, level, 1, bp, last));
+    if (sc_cmp(last, absl, bs) || sc_cmp(last, reach, bs)) break;
+  }
+  return 0;
+}
+
+// ---- Lmgc ---------------------------------------------------------------------------------------------------------------
+struct TopFuse {       // work of the enclosing LinearSolver iteration folded into the cycle's kernels (fused schedule only)
+  int level = -1;      // solver level; -1: none
+  int x = 0;           // x += c (LSUpdate ls.cc:869) on `level`
+  bool c_zero = false; // c is known to be 0 on entry (dset ls.cc:695 skipped)
+  bool norm = false;   // accumulate ||b||^2 over NEW_DEFECT rows of `level` into result slot 0
+  bool done_x = false, done_norm = false;
+};
+
+static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
+{
+  if (level <= cfg->baselevel) return base_solve(ctx, cfg, level, c, b, A);
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  const int t = cfg->t;
+  double one[UGGPU_MAX_BS] = {1.0, 1.0, 1.0};
+  for (int i = 0; i < cfg->nu1; i++) {
+    UG_TRY(uggpu_jac_smooth(ctx, level, t, b, A, cfg->smooth_damp));
+    UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
+  }
+  UG_TRY(uggpu_restrict(ctx, level, b, b, one));                                   // iter.cc:7843, Factor_One
+  UG_TRY(uggpu_dset(ctx, level - 1, level - 1, UGGPU_ALL_VECTORS, c, 0.0));        // :7873
+  for (int g = 0; g < cfg->gamma; g++) UG_TRY(lmgc_unfused(ctx, cfg, level - 1, c, b, A));
+  UG_TRY(uggpu_interpolate_correction(ctx, level, t, c, cfg->cycle_damp));         // :7886
+  UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));                  // :7903
+  UG_TRY(uggpu_dmatmul_minus(ctx, level, level, UGGPU_ALL_VECTORS, b, A, t));      // :7905
+  for (int i = 0; i < cfg->nu2; i++) {
+    UG_TRY(uggpu_jac_smooth(ctx, level, t, b, A, cfg->smooth_damp));
+    UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
+  }
+  return 0;
+}
+
+// t_ready: the temporary cfg->t of this level already holds damp * Diag(A)^-1 b (written by the restriction above)
+static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf)
+{
+  if (level <= cfg->baselevel) return base_solve(ctx, cfg, level, c, b, A);
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  const int bs = L->bs;
+  double *tA = get_vec(ctx, level, cfg->t), *tB = get_vec(ctx, level, UGGPU_VEC_TMP_B);
+  double *cp = get_vec(ctx, level, c), *bp = get_vec(ctx, level, b);
+  if (!tA || !tB || !cp || !bp) return UGGPU_DESC_MISMATCH;
+  const Damp sd = mkdamp(cfg->smooth_damp, bs), cd = mkdamp(cfg->cycle_damp, bs), one = mkdamp(nullptr, 0);
+  const bool top = tf && tf->level == level;
+  bool c_zero = top && tf->c_zero;
+  double *xp = nullptr;
+  if (top) { xp = get_vec(ctx, level, tf->x); if (!xp) return UGGPU_DESC_MISMATCH; }
+  double *cur = tA, *oth = tB;
+
+  if (cfg->nu1 > 0) {
+    if (!t_ready) UG_TRY(k_jac(ctx, level, A, cur, bp, sd));
+    for (int i = 0; i < cfg->nu1; i++) {
+      int flags = (c_zero ? SF_CSET : SF_CADD) | (i < cfg->nu1 - 1 ? SF_TOUT : 0);
+      UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, nullptr, 0));
+      c_zero = false;
+      double *sw = cur; cur = oth; oth = sw;
+    }
+  }
+  // restriction (+ first Jacobi correction and c = 0 of the coarse level)
+  {
+    const int lc = level - 1;
+    double *bc = get_vec(ctx, lc, b), *cc = get_vec(ctx, lc, c), *tc = get_vec(ctx, lc, cfg->t);
+    if (!bc || !cc || !tc) return UGGPU_DESC_MISMATCH;
+    const bool fuse = lc > cfg->baselevel && cfg->nu1 > 0;
+    UG_TRY(k_restrict(ctx, level, bc, bp, one, fuse, A, tc, cc, sd));
+    if (!fuse) UG_TRY(k_vec_op(ctx, lc, 0, VOP_SET, cc, nullptr, Damp{{0.0, 0.0, 0.0}}));   // dset(c,0) iter.cc:7873
+    for (int g = 0; g < cfg->gamma; g++) UG_TRY(lmgc_fused(ctx, cfg, lc, c, b, A, fuse && g == 0, nullptr));
+    UG_TRY(k_interpolate(ctx, level, tA, cc, cd));
+  }
+  // c += t ; b -= A t ; first post-smoothing correction
+  {
+    const bool last = cfg->nu2 == 0;
+    int flags = (c_zero ? SF_CSET : SF_CADD) | (last ? 0 : SF_TOUT);
+    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; }
+    UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0));
+    c_zero = false;
+    cur = tB; oth = tA;
+  }
+  for (int i = 0; i < cfg->nu2; i++) {
+    const bool last = i == cfg->nu2 - 1;
+    int flags = SF_CADD | (last ? 0 : SF_TOUT);
+    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; }
+    UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0));
+    double *sw = cur; cur = oth; oth = sw;
+  }
+  return 0;
+}
+
+static int lmgc_check(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b)
+{
+  if (!ctx || !cfg) return uggpu_fail(UGGPU_ERROR, "null argument");
+  if (cfg->nu1 < 0 || cfg->nu2 < 0 || cfg->gamma < 1) return uggpu_fail(UGGPU_ERROR, "lmgc: bad nu1/nu2/gamma");
+  for (int l = cfg->baselevel; l <= level; l++) {
+    if (!get_level(ctx, l)) return UGGPU_ERROR;
+    UG_TRY(ensure_vec(ctx, l, c));
+    UG_TRY(ensure_vec(ctx, l, b));
+    UG_TRY(ensure_vec(ctx, l, cfg->t));
+    UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_B));
+  }
+  return 0;
+}
+
+extern "C" int uggpu_lmgc(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
+{
+  UG_TRY(lmgc_check(ctx, cfg, level, c, b));
+  if (cfg->fused) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
+  else UG_TRY(lmgc_unfused(ctx, cfg, level, c, b, A));
+  return check_device_error(ctx);
+}
+
+// ---- linear solver -------------------------------------------------------------------------------------------------------
+extern "C" int uggpu_ls_defect(uggpu_ctx *ctx, int bl, int level, int x, int b, int A)
+{
+  (void)bl;   // ON_SURFACE loops start at FULLREFINELEVEL whatever fl is (matloop.ct:22)
+  return uggpu_dmatmul_minus(ctx, bl, level, UGGPU_ON_SURFACE, b, A, x);
+}
+
+extern "C" int uggpu_ls_residuum(uggpu_ctx *ctx, int bl, int level, int b, uggpu_lresult *res)
+{
+  if (!res) return uggpu_fail(UGGPU_ERROR, "null result");
+  double s[UGGPU_MAX_BS]; int bs;
+  UG_TRY(reduce_loop(ctx, bl, level, UGGPU_ON_SURFACE, RED_NRM2, b, b, s, &bs));
+  for (int i = 0; i < bs; i++) res->last_defect[i] = sqrt(s[i]);
+  return 0;
+}
+
+extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level, int x, int b, int A, int c,
+                              int maxiter, const double *abslimit, const double *reduction, uggpu_lresult *res, double *history)
+{
+  if (!res || !abslimit || !reduction) return uggpu_fail(UGGPU_ERROR, "null argument");
+  UG_TRY(lmgc_check(ctx, cfg, level, c, b));
+  Level *L = get_level(ctx, level);
+  const int bs = L->bs;
+  for (int l = bl; l <= level; l++) if (!get_vec(ctx, l, x)) return UGGPU_DESC_MISMATCH;
+  double reach[UGGPU_MAX_BS];
+  res->error_code = 0; res->converged = 0; res->number_of_linear_iterations = 0;
+  for (int i = 0; i < bs; i++) {
+    res->first_defect[i] = res->last_defect[i];
+    reach[i] = res->last_defect[i] * reduction[i];
+    if (reach[i] == 0.0) reach[i] = reduction[i];              // ls.cc:663-667
+  }
+  if (sc_cmp(res->last_defect, abslimit, bs)) { res->converged = 1; return 0; }
+  const Damp none = mkdamp(nullptr, 0);
+  const bool surface_is_top = ctx->fullrefinelevel >= level;   // no lower-level terms in the ON_SURFACE norm
+  for (int it = 0; it < maxiter; it++) {
+    bool done_x = false, done_norm = false;
+    if (cfg->fused && level > cfg->baselevel) {
+      TopFuse tf;
+      tf.level = level; tf.x = x; tf.c_zero = true; tf.norm = surface_is_top;
+      UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, &tf));
+      done_x = tf.done_x; done_norm = tf.done_norm;
+    } else {
+      UG_TRY(uggpu_dset(ctx, level, level, UGGPU_ALL_VECTORS, c, 0.0));     // ls.cc:695
+      if (cfg->fused) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
+      else UG_TRY(lmgc_unfused(ctx, cfg, level, c, b, A));
+    }
+    // LSUpdate (ls.cc:869): x += c on levels bl..level
+    for (int l = bl; l <= level; l++) {
+      if (l == level && done_x) continue;
+      UG_TRY(k_vec_op(ctx, l, 0, VOP_ADD, get_vec(ctx, l, x), get_vec(ctx, l, c), none));
+    }
+    if (done_norm) {
+      UG_TRY(fetch_results(ctx, 1));
+      for (int i = 0; i < bs; i++) res->last_defect[i] = sqrt(ctx->hres[i]);
+    } else {
+      UG_TRY(uggpu_ls_residuum(ctx, bl, level, b, res));
+    }
+    if (history) for (int i = 0; i < bs; i++) history[it * bs + i] = res->last_defect[i];
+    res->number_of_linear_iterations = it + 1;
+    if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) { res->converged = 1; break; }
+  }
+  int rc = check_device_error(ctx);
+  if (rc) res->error_code = rc;
+  return rc;
+}

@@ -1,0 +1,140 @@
+// uggpu_internal.h -- shared declarations of libuggpu.so (sm_100a device layer of the gpuls numprocs).
+//
+// Device data layout (DESIGN.md "data layout in HBM"):
+//  * vectors: dense double[n*bs], entry (row r, component i) at r*bs+i; row r = position of the UG VECTOR
+//    in FIRSTVECTOR->SUCCVC order.
+//  * matrices (A per MATDATA_DESC, and the transfer stencils P and R): SELL-32 -- rows are cut into slices of
+//    32 consecutive rows (one warp), a slice stores its entries "column-major": entry j of lane l at
+//    slice_ptr[s] + j*32 + l.  Entry order inside a row is the canonical one (VSTART->MNEXT, diagonal
+//    first), so one thread walking j = 0..len-1 performs the reference's additions in the reference's
+//    order while the warp's loads are perfectly coalesced.  Blocks (bs>1) are stored component-planar:
+//    component k of entry e at val[(slice_ptr[s] + j*32)*bb + k*32 + l].
+#ifndef UGGPU_INTERNAL_H
+#define UGGPU_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "uggpu.h"
+
+#define SLICE 32
+
+struct SellMat {
+  int      n = 0;          // rows
+  int      bb = 1;         // doubles per entry (bs*bs for A, 1 for transfer weights)
+  int64_t  nnz = 0;        // true entries
+  int64_t  padded = 0;     // stored entries (multiple of 32 per slice)
+  int      maxlen = 0;
+  int64_t *slice_ptr = nullptr;   // [nslices+1], entry offsets
+  uint16_t *rowlen = nullptr;     // [n]
+  int32_t *col = nullptr;         // [padded]
+  double  *val = nullptr;         // [padded*bb]
+  bool valid() const { return n > 0 && col != nullptr; }
+};
+
+struct SellView {          // what a kernel needs (passed by value)
+  int n;
+  const int64_t *slice_ptr;
+  const uint16_t *rowlen;
+  const int32_t *col;
+  const double *val;
+};
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.rowlen, m.col, m.val}; }
+
+struct Level {
+  bool exists = false;
+  int n = 0, bs = 0;
+  uint8_t *vclass = nullptr, *vnclass = nullptr, *ctl = nullptr;
+  uint32_t *skip = nullptr;
+  bool uniform_flags = true;     // every row class 3 / both ctl bits (lets kernels skip flag reads? no: flags are always read)
+  std::map<int, SellMat> mats;
+  std::map<int, double *> vecs;
+  SellMat P, R;                  // P: rows = this level, cols = level-1;  R: rows = level-1, cols = this level
+  // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
+  double *lu = nullptr;
+  int luN = 0, luA = -1;
+};
+
+struct uggpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Level lev[UGGPU_MAX_LEVELS];
+  int fullrefinelevel = 0;
+  int64_t launches = 0;
+  int64_t bytes = 0;
+  // reduction scratch
+  double *partials = nullptr;  size_t partials_cap = 0;   // device
+  double *dres = nullptr;                                  // device results [UGGPU_MAX_LEVELS*4*UGGPU_MAX_BS]
+  double *hres = nullptr;                                  // pinned host mirror
+  int *derr = nullptr;                                     // device error word
+  int *herr = nullptr;                                     // pinned
+  int sm_count = 148;
+  // multi-GPU (comm.cu)
+  void *comm = nullptr;
+};
+
+// ---- error plumbing -------------------------------------------------------------------------------
+int uggpu_fail(int code, const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return uggpu_fail(UGGPU_CUDA_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define UG_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+#define KCHECK(ctx) do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
+
+// ---- helpers (ctx.cu) -------------------------------------------------------------------------------
+int dev_alloc(uggpu_ctx *ctx, void **p, size_t bytes);
+int dev_free(uggpu_ctx *ctx, void *p, size_t bytes);
+template <class T> static inline int dalloc(uggpu_ctx *ctx, T **p, size_t count) { return dev_alloc(ctx, (void **)p, count * sizeof(T)); }
+template <class T> static inline int dfree(uggpu_ctx *ctx, T *&p, size_t count) { int rc = dev_free(ctx, (void *)p, count * sizeof(T)); p = nullptr; return rc; }
+Level *get_level(uggpu_ctx *ctx, int level);                 // NULL + error if absent
+double *get_vec(uggpu_ctx *ctx, int level, int vec);         // NULL + error if absent
+SellMat *get_mat(uggpu_ctx *ctx, int level, int mat);
+int ensure_partials(uggpu_ctx *ctx, size_t count);
+int check_device_error(uggpu_ctx *ctx);                      // sync + read the device error word
+
+// ---- SELL (sell.cu) -----------------------------------------------------------------------------------
+// Builds a SELL-32 matrix from device CSR (rowptr int64[n+1], col, val[nnz*bb] row-major blocks).
+int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr, const int32_t *d_col, const double *d_val, SellMat *out);
+int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, const int32_t *col, const double *val, SellMat *out);
+int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val);
+int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t *col, double *val);
+int sell_free(uggpu_ctx *ctx, SellMat *m);
+
+// ---- kernels used across files --------------------------------------------------------------------------
+struct Damp { double a[UGGPU_MAX_BS]; };
+static inline Damp mkdamp(const double *d, int bs) { Damp r; for (int i = 0; i < UGGPU_MAX_BS; i++) r.a[i] = (d && i < bs) ? d[i] : 1.0; return r; }
+
+// rowmode: 0 all rows, 1 NEW_DEFECT rows, 2 FINE_GRID_DOF rows (vecloop.ct:22-49)
+int k_dmatmul(uggpu_ctx *ctx, int level, int op, int rowmode, int x, int M, int y);
+int k_vec_op(uggpu_ctx *ctx, int level, int rowmode, int op, double *x, const double *y, Damp a);
+int k_reduce(uggpu_ctx *ctx, int level, int rowmode, int kind, const double *x, const double *y, int slot);
+int fetch_results(uggpu_ctx *ctx, int nslots);   // dres -> hres, synchronises
+int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot);   // ctx->partials -> dres[slot]
+struct LoopItem { int level, rowmode; };
+// (level, rowmode) pairs of one reference loop over levels fl..tl in `mode` (vecloop.ct:22-49)
+int surface_loop(uggpu_ctx *ctx, int fl, int tl, int mode, std::vector<LoopItem> &out);
+int reduce_loop(uggpu_ctx *ctx, int fl, int tl, int mode, int kind, int x, int y, double *sums, int *bs_out);
+
+enum { VOP_SET, VOP_COPY, VOP_SCALX, VOP_ADD, VOP_SUB, VOP_MINUSADD, VOP_AXPYX };
+enum { RED_DOT, RED_NRM2 };
+
+// smoother step flags (spmv.cu, DESIGN.md "fused kernels")
+enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16 };
+int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout,
+                  Damp damp, double *x, int norm_slot);
+int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp);   // v = damp * Diag(A)^-1 d (class-masked)
+// transfer.cu: fine `level` -> level-1; with fuse: also tout = sdamp*Diag(A_{level-1})^-1 to, czero = 0 on level-1
+int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp);
+int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp);
+// internal temporary vector handles (never visible through the C-ABI callers' handle space)
+#define UGGPU_VEC_TMP_A (-1001)
+#define UGGPU_VEC_TMP_B (-1002)
+#define UGGPU_VEC_TMP_C (-1003)
+
+#endif
