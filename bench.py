@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- V(2,2)-cycle throughput of the gpuls hot path on B200 (BASELINE.json metric).
+
+One "step" = one iteration of the linear solver `ls` with `lmgc` V(2,2) damped-Jacobi as Iter, i.e. exactly the body
+of LinearSolver's loop (np/procs/ls.cc:693-708): c = 0; c = Lmgc(b) (b updated to the new defect); x += c;
+||b||_2 -- on a synthetic 3D P1 Poisson hierarchy (BASELINE.json configs[1]: unit cube, tetrahedra, base 4x4x4 cells,
+7 uniform refinements = 8 levels, 513^3 = 135 005 697 fine unknowns).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference [...]                        the unmodified reference on the host CPU (oracle/_ref)
+
+Prints ONE JSON line (rank 0).  `value` = fine unknowns * K / device time of K steps with everything resident in HBM;
+`e2e` = the same through the C-ABI with HOST vectors (x, b uploaded and downloaded inside the timed region, as
+NP_LINEAR_SOLVER::Solver does with UG's VECTOR lists); `roofline` = the dominant kernel (fused smoothing step on the
+finest level) timed with CUDA events around each of its launches inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vcycle_unknowns_per_s"
+UNIT = "unknowns/s"
+
+
+def workload_name(cells, top, n):
+    return (f"3D P1 Poisson, unit cube, Kuhn tetrahedra, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
+            f"{n} fine unknowns, V(2,2) Jacobi damp 0.6, base solver ls+lu")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference_cpu(refine: int, cycles: int):
+    """Times the UNMODIFIED reference (oracle/_ref/ugoracle3: UG's own ls+lmgc+jac+transfer numprocs on its VECTOR/
+    MATRIX lists) on this host.  UG is single-threaded (its only parallel mode is MPI, not installed): 1 core."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ugoracle3")
+    if not os.path.exists(exe):
+        return None
+    out = subprocess.run([exe, "--grid", "tet", "--refine", str(refine), "--damp", "0.6", "--time", "--cycles", str(cycles), "--reps", "3"],
+                         capture_output=True, text=True, timeout=1500)
+    for line in out.stdout.splitlines():
+        if line.startswith('{"kind"'):
+            return json.loads(line)
+    raise RuntimeError("reference run produced no result line:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+
+
+def run_port_cpu(cells: int, top: int, cycles: int):
+    """Fallback CPU baseline when oracle/_ref is absent: the plain-C restatement (oracle/ugport.c) on a synthetic
+    hierarchy downloaded from the device generator."""
+    import numpy as np
+    from ug_b200 import capi
+    from oracle.ugport import PortBackend
+    ctx = capi.Context(0)
+    ctx.call("uggpu_synth_hierarchy", capi.SYNTH_P1_SIMPLEX, cells, cells, cells, top, ctx.handle("A"))
+    hier = ctx.download_hierarchy(top)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    rhs = ctx.get(top, "b")
+    ctx.close()
+    be = PortBackend(hier)
+    for l, lv in enumerate(hier.levels):
+        be.put(l, "x", np.zeros(lv.n)); be.put(l, "b", rhs if l == top else np.zeros(lv.n))
+    cfg = dict(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6)
+    t0 = time.perf_counter()
+    its, _, _ = be.solve(top, "x", "b", cfg, cycles)
+    dt = time.perf_counter() - t0
+    n = hier.levels[-1].n
+    return {"kind": "port", "cores": 1, "unknowns": n, "cycles": its, "s_per_cycle": dt / its, "vcycle_unknowns_per_s": n * its / dt}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cycles = max(1, min(args.steps, 20))
+    r = run_reference_cpu(args.cpu_refine, cycles)
+    kind = "reference"
+    if r is None:
+        r = run_port_cpu(1, 5, cycles)
+        kind = "port"
+    n = r["unknowns"]
+    sample = (f"{'UG 3.12.1 ls+lmgc+jac+transfer' if kind == 'reference' else 'oracle/ugport.c'}: {r['cycles']} V(2,2) cycles on a "
+              f"{r.get('levels', '?')}-level unit-cube tet hierarchy with {n} fine unknowns (largest the host builds in ~10 s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["vcycle_unknowns_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["cycles"], "warmup": 0, "ms_per_step": r["s_per_cycle"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.cells, args.top, (args.cells * 2 ** args.top + 1) ** 3),
+                   "measured_on": sample},
+        "cpu_baseline": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [s.strip() for s in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def our_arm(args):
+    import numpy as np
+    import torch
+    from ug_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the gpuls path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cells, top = args.cells, args.top
+    ctx = capi.Context(local)
+    A = ctx.handle("A")
+    t0 = time.perf_counter()
+    ctx.call("uggpu_synth_hierarchy", capi.SYNTH_P1_SIMPLEX, cells, cells, cells, top, A)
+    n = ctx.level_n(top)
+    for name in ("x", "b", "c"):
+        for l in range(top + 1):
+            ctx.alloc(l, name)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6, fused=1)
+    ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+    ctx.sync()
+    setup_s = time.perf_counter() - t0
+    X, B, Cc = ctx.handle("x"), ctx.handle("b"), ctx.handle("c")
+    res = capi.LResult()
+    ctx.call("uggpu_ls_defect", 0, top, X, B, A)
+    ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
+    first = res.last_defect[0]
+    absl, red = capi._vs([1e-300]), capi._vs([1e-300])
+
+    def step():
+        ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, X, B, A, Cc, 1, absl, red, C.byref(res), None)
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    hist = []
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.call("uggpu_prof_enable", 1)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        hist.append(res.last_defect[0])
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    # per-kernel event times of the timed region
+    prof = {}
+    kinds = {"smooth": 0, "jac": 1, "restrict": 2, "interpolate": 3, "vecop": 4, "reduce": 5, "dmatmul": 6, "base": 7}
+    cnt, kms, kby = C.c_int64(), C.c_double(), C.c_double()
+    for name, k in kinds.items():
+        ctx.call("uggpu_prof_summary", k, -1, C.byref(cnt), C.byref(kms), C.byref(kby))
+        prof[name] = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+    ctx.call("uggpu_prof_summary", 0, top, C.byref(cnt), C.byref(kms), C.byref(kby))
+    dom = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+    ctx.call("uggpu_prof_enable", 0)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end: host vectors in, host vectors out, every step -------------------------------------------------
+    xh = torch.zeros(n, dtype=torch.float64).pin_memory()
+    bh = torch.empty(n, dtype=torch.float64).pin_memory()
+    ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
+    ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
+
+    def e2e_step():
+        ctx.call("uggpu_vec_upload", top, X, C.c_void_p(xh.data_ptr()))
+        ctx.call("uggpu_vec_upload", top, B, C.c_void_p(bh.data_ptr()))
+        ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
+        step()
+        ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
+        ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    dev_bytes = ctx.device_bytes()
+
+    if rank != 0:
+        return 0
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("k_smooth_k_dram_bytes_per_launch")
+    total_alg = sum(v["alg_bytes"] for v in prof.values())
+    n_total = n * world
+    value = n_total * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(cells, top, n), "parallelism": f"dp{world}", "cache": "inputs larger than L2 (matrix 24 GB per sweep)",
+                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2),
+                   "defect": [first, hist[-1]] if hist else None},
+        "roofline": {"bound": "hbm", "kernel": "k_smooth_k<1,*> (fused smoothing step, finest level)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
+                     "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
+                     "share_of_step": dom["ms"] / ms,
+                     "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
+        "kernels": prof,
+        "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n + 8,
+                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        r = run_reference_cpu(args.cpu_refine, 5)
+        kind = "reference"
+        if r is None:
+            r = run_port_cpu(1, 5, 5)
+            kind = "port"
+        line["cpu_baseline"] = {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": 1, "kind": kind,
+                                "sample": f"{r['cycles']} V(2,2) cycles, {r['unknowns']} fine unknowns, "
+                                          + ("unmodified UG 3.12.1 numprocs (oracle/_ref/ugoracle3), single-threaded" if kind == "reference" else "oracle/ugport.c")}
+    print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=4, help="base cells per direction")
+    ap.add_argument("--top", type=int, default=7, help="number of uniform refinements (levels - 1)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-refine", type=int, default=6, help="refinements of the host-side reference run (6 -> 274 625 unknowns)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+    return our_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

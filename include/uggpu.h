@@ -71,6 +71,19 @@ int64_t uggpu_launch_count(uggpu_ctx *ctx);
 /* bytes of device memory currently held by the context */
 int64_t uggpu_device_bytes(uggpu_ctx *ctx);
 
+/* ---- per-kernel timing (CUDA events on the context's stream around every launch while enabled) -------------
+ * kinds; level/kind -1 = all.  alg_bytes = algorithmic (compulsory) bytes of the matching launches, SURVEY.md 8(d). */
+#define UGGPU_K_SMOOTH      0   /* fused smoothing step (dmatmul_minus + dadd + next l_jac [+ x update, norm]) */
+#define UGGPU_K_JAC         1
+#define UGGPU_K_RESTRICT    2
+#define UGGPU_K_INTERPOLATE 3
+#define UGGPU_K_VECOP       4
+#define UGGPU_K_REDUCE      5
+#define UGGPU_K_DMATMUL     6
+#define UGGPU_K_BASE        7
+int uggpu_prof_enable(uggpu_ctx *ctx, int on);   /* also clears the records */
+int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes);
+
 /* ---- hierarchy upload = "PreProcess flattens VECTOR/MATRIX lists" ------------------------
  * (the reference's own precedent: np/amglib/amg_ug.cc:207-390 AMGSolverPreProcess)       */
 int uggpu_level_create(uggpu_ctx *ctx, int level, int n, int bs);

@@ -1,0 +1,144 @@
+"""Synthetic hierarchies (ug_b200/csrc/synth.cu): (1) the 2D generator reproduces, entry by entry up to the row
+permutation, the hierarchy the unmodified reference builds (golden c1); (2) on synthetic 3D hierarchies the CUDA
+path is bit-identical to the oracle port, at sizes the port finishes in seconds; (3) size-independent properties
+at a larger size (constant-preserving prolongation, R = P^T, symmetric A on free rows, monotone defect history)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from ug_b200 import capi
+from ug_b200.hierarchy import Hierarchy
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _synth(cells, dim, top):
+    ctx = capi.Context(0)
+    ctx.call("uggpu_synth_hierarchy", capi.SYNTH_P1_SIMPLEX, cells, cells, cells if dim == 3 else 0, top, ctx.handle("A"))
+    return ctx
+
+
+def _coords(cells, dim, level):
+    nn = cells * 2 ** level + 1
+    idx = np.arange(nn ** dim)
+    xs = [(idx // nn ** d) % nn for d in range(dim)]
+    return np.stack(xs, 1), nn
+
+
+def test_synth2d_equals_reference_hierarchy():
+    gold = Hierarchy.from_ugh(os.path.join(GOLD, "c1_tri2d_r4.ugh"))
+    ctx = _synth(1, 2, gold.top)
+    syn = ctx.download_hierarchy(gold.top)
+    perm = []     # perm[l][gold row] = synthetic row
+    for l, (g, s) in enumerate(zip(gold.levels, syn.levels)):
+        xy, nn = _coords(1, 2, l)
+        gij = np.rint(g.xyz.reshape(-1, 2) * (nn - 1)).astype(int)
+        p = gij[:, 0] + nn * gij[:, 1]
+        assert sorted(p.tolist()) == list(range(s.n))
+        perm.append(p)
+        assert g.n == s.n and g.nnz == s.nnz
+        for k in ("vclass", "vnclass", "ctl", "skip"):
+            assert np.array_equal(getattr(g, k), getattr(s, k)[p]), (l, k)
+        ge = {(p[r], p[g.col[e]]): g.val[e] for r in range(g.n) for e in range(g.rowptr[r], g.rowptr[r + 1])}
+        se = {(r, s.col[e]): s.val[e] for r in range(s.n) for e in range(s.rowptr[r], s.rowptr[r + 1])}
+        assert ge.keys() == se.keys()
+        assert max(abs(ge[k] - se[k]) for k in ge) < 1e-14
+        assert np.array_equal(s.col[s.rowptr[:-1]], np.arange(s.n))      # diagonal first
+        ctx.call("uggpu_synth_rhs", l, ctx.handle("b"))
+        assert np.allclose(ctx.get(l, "b")[p], g.rhs, rtol=1e-14, atol=0)
+        if l > 0:
+            pc = perm[l - 1]
+            for pre in ("p", "r"):
+                grp, gc, gw = (getattr(g, pre + k) for k in ("_rowptr", "_col", "_w"))
+                srp, sc, sw = (getattr(s, pre + k) for k in ("_rowptr", "_col", "_w"))
+                rowp, colp = (p, pc) if pre == "p" else (pc, p)
+                gs = {(rowp[r], colp[gc[e]]): gw[e] for r in range(grp.size - 1) for e in range(grp[r], grp[r + 1])}
+                ss = {(r, sc[e]): sw[e] for r in range(srp.size - 1) for e in range(srp[r], srp[r + 1])}
+                assert gs == ss, (l, pre)
+    ctx.close()
+
+
+@pytest.mark.parametrize("cells,dim,top", [(2, 3, 3), (1, 3, 4), (3, 2, 4)])
+def test_synth_solve_bitexact_vs_port(cells, dim, top):
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    ctx = _synth(cells, dim, top)
+    hier = ctx.download_hierarchy(top)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    rhs = ctx.get(top, "b")
+    ctx.close()
+    cfg = dict(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6 if dim == 3 else 0.8)
+    out = []
+    for be in (GpuBackend(hier, fused=1), GpuBackend(hier, fused=0), PortBackend(hier)):
+        for l, lv in enumerate(hier.levels):
+            be.put(l, "x", np.zeros(lv.n)); be.put(l, "b", rhs if l == top else np.zeros(lv.n))
+        be.ls_defect(0, top, "x", "b")
+        its, first, hist = be.solve(top, "x", "b", cfg, 6)
+        out.append((its, hist, [be.get(l, "x") for l in range(top + 1)], [be.get(l, "b") for l in range(top + 1)]))
+        if hasattr(be, "close"):
+            be.close()
+    ref = out[-1]
+    assert ref[0] == 6 and ref[1][-1] < 0.2 * ref[1][0]
+    for its, hist, xs, bs in out[:-1]:
+        assert its == ref[0]
+        assert np.max(np.abs(hist - ref[1]) / ref[1]) < 1e-12
+        for l in range(top + 1):
+            assert np.array_equal(xs[l], ref[2][l]), l
+            assert np.array_equal(bs[l], ref[3][l]), l
+
+
+def test_synth_properties_large():
+    """65^3 = 274 625 unknowns: properties that do not need the CPU checker."""
+    cells, top = 2, 5
+    ctx = _synth(cells, 3, top)
+    n = ctx.level_n(top)
+    assert n == 65 ** 3
+    A = ctx.handle("A")
+    one = capi._vs([1.0])
+    # prolongation preserves constants on free rows, is zero on Dirichlet rows
+    ctx.put(top - 1, "c", np.ones(ctx.level_n(top - 1)))
+    ctx.alloc(top, "t")
+    ctx.call("uggpu_interpolate_correction", top, ctx.handle("t"), ctx.handle("c"), one)
+    t = ctx.get(top, "t")
+    skip = np.zeros(n, np.uint32)
+    ctx.call("uggpu_level_get_flags", top, None, None, None, skip.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(t, (skip == 0).astype(float))
+    # <R u, v> = <u, P v> for v supported on free coarse rows (adjointness of restriction and prolongation)
+    rng = np.random.default_rng(7)
+    u = rng.integers(-8, 8, n).astype(float) * (skip == 0)
+    skc = np.zeros(ctx.level_n(top - 1), np.uint32)
+    ctx.call("uggpu_level_get_flags", top - 1, None, None, None, skc.ctypes.data_as(C.c_void_p))
+    v = rng.integers(-8, 8, skc.size).astype(float) * (skc == 0)
+    ctx.put(top, "u", u); ctx.put(top - 1, "v", v); ctx.alloc(top - 1, "u"); ctx.alloc(top, "v")
+    ctx.call("uggpu_restrict", top, ctx.handle("u"), ctx.handle("u"), one)
+    ctx.call("uggpu_interpolate_correction", top, ctx.handle("v"), ctx.handle("v"), one)
+    assert np.dot(ctx.get(top - 1, "u"), v) == np.dot(u, ctx.get(top, "v"))     # dyadic weights, small integers: exact
+    # A is symmetric on the free rows: <A u, w> = <u, A w>
+    w = rng.integers(-8, 8, n).astype(float) * (skip == 0)
+    ctx.put(top, "w", w); ctx.alloc(top, "Au"); ctx.alloc(top, "Aw")
+    ctx.call("uggpu_dmatmul", top, top, 0, ctx.handle("Au"), A, ctx.handle("u"))
+    ctx.call("uggpu_dmatmul", top, top, 0, ctx.handle("Aw"), A, ctx.handle("w"))
+    lhs, rhs = np.dot(ctx.get(top, "Au") * (skip == 0), w), np.dot(u, ctx.get(top, "Aw") * (skip == 0))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    # V-cycles converge with a level-independent rate (h-independence of multigrid)
+    for name in ("x", "b", "c"):
+        for l in range(top + 1):
+            ctx.alloc(l, name)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    cfg = ctx.lmgc_cfg(smooth_damp=0.6, fused=1)
+    ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+    res = capi.LResult()
+    ctx.call("uggpu_ls_residuum", 0, top, ctx.handle("b"), C.byref(res))
+    hist = np.zeros(8)
+    ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, ctx.handle("x"), ctx.handle("b"), A, ctx.handle("c"), 8,
+             capi._vs([1e-300]), capi._vs([1e-300]), C.byref(res), hist.ctypes.data_as(C.POINTER(C.c_double)))
+    rates = hist[1:] / hist[:-1]
+    assert np.all(rates < 0.75) and res.number_of_linear_iterations == 8
+    # the defect the solver reports is the defect of the iterate it returns: b0 - A x == b (up to rounding)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("w"))
+    ctx.call("uggpu_dmatmul_minus", top, top, 0, ctx.handle("w"), A, ctx.handle("x"))
+    assert np.max(np.abs(ctx.get(top, "w") - ctx.get(top, "b"))) < 1e-12 * np.max(np.abs(hist[0]))
+    ctx.close()

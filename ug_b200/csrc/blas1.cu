@@ -63,6 +63,7 @@ static int launch_vop(uggpu_ctx *ctx, Level *L, int rowmode, double *x, const do
 {
   size_t cnt = (size_t)L->n * L->bs;
   if (cnt == 0) return 0;
+  ProfScope ps(ctx, UGGPU_K_VECOP, (int)(L - ctx->lev), 8.0 * cnt * (1.0 + (VopTraits<OP>::reads_x ? 1.0 : 0.0) + (VopTraits<OP>::reads_y ? 1.0 : 0.0)));
   if (rowmode == 0) {
     size_t pairs = (cnt + 1) / 2;
     k_vop_all<OP><<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(cnt, L->bs, x, y, a);
@@ -169,6 +170,7 @@ static int launch_red(uggpu_ctx *ctx, Level *L, int rowmode, int kind, const dou
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   UG_TRY(ensure_partials(ctx, (size_t)blocks * BS));
+  ProfScope ps(ctx, UGGPU_K_REDUCE, (int)(L - ctx->lev), 8.0 * BS * L->n * (kind == RED_DOT ? 2.0 : 1.0));
   if (kind == RED_DOT) k_red_rows<BS, RED_DOT><<<blocks, RED_THREADS, 0, ctx->stream>>>(L->n, bit, L->ctl, x, y, ctx->partials);
   else k_red_rows<BS, RED_NRM2><<<blocks, RED_THREADS, 0, ctx->stream>>>(L->n, bit, L->ctl, x, y, ctx->partials);
   KCHECK(ctx);

@@ -378,3 +378,54 @@ extern "C" int uggpu_vec_devptr(uggpu_ctx *ctx, int level, int vec, void **dptr)
   *dptr = p;
   return 0;
 }
+
+// ---- per-kernel profiling ------------------------------------------------------------------------------------------
+static cudaEvent_t prof_event(uggpu_ctx *ctx)
+{
+  cudaEvent_t e;
+  if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(uggpu_ctx *c, int kind, int level, double bytes) : ctx(c), on(c->prof)
+{
+  if (!on) return;
+  rec.kind = kind; rec.level = level; rec.bytes = bytes;
+  rec.e0 = prof_event(ctx); rec.e1 = prof_event(ctx);
+  cudaEventRecord(rec.e0, ctx->stream);
+}
+
+ProfScope::~ProfScope()
+{
+  if (!on) return;
+  cudaEventRecord(rec.e1, ctx->stream);
+  ctx->prof_recs.push_back(rec);
+}
+
+extern "C" int uggpu_prof_enable(uggpu_ctx *ctx, int on)
+{
+  if (!ctx) return uggpu_fail(UGGPU_ERROR, "null context");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (auto &r : ctx->prof_recs) { ctx->prof_pool.push_back(r.e0); ctx->prof_pool.push_back(r.e1); }
+  ctx->prof_recs.clear();
+  ctx->prof = on != 0;
+  return 0;
+}
+
+extern "C" int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes)
+{
+  if (!ctx) return uggpu_fail(UGGPU_ERROR, "null context");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int64_t cnt = 0; double t = 0.0, by = 0.0;
+  for (auto &r : ctx->prof_recs) {
+    if ((kind >= 0 && r.kind != kind) || (level >= 0 && r.level != level)) continue;
+    float e = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&e, r.e0, r.e1));
+    cnt++; t += e; by += r.bytes;
+  }
+  if (launches) *launches = cnt;
+  if (ms) *ms = t;
+  if (alg_bytes) *alg_bytes = by;
+  return 0;
+}

@@ -177,8 +177,11 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   if (sc_cmp(first, absl, bs)) return 0;
   Damp none = mkdamp(nullptr, 0);
   for (int it = 0; it < cfg->base_maxit; it++) {
-    k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
-    KCHECK(ctx);
+    {
+      ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
+      k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
+      KCHECK(ctx);
+    }
     UG_TRY(k_dmatmul(ctx, level, 2, 0, b, A, UGGPU_VEC_TMP_C));
     UG_TRY(k_vec_op(ctx, level, 0, VOP_ADD, cp, cc, none));
     UG_TRY(level_norm(ctx, level, 1, bp, last));

@@ -97,6 +97,8 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   uint8_t bit = rowmode == 0 ? 0 : (rowmode == 1 ? UGGPU_CTL_NEW_DEFECT : UGGPU_CTL_FINE_GRID_DOF);
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   SellView v = view(*A);
+  const double nb = 8.0 * BS * L->n;
+  ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), (double)A->nnz * (8.0 * BS * BS + 4.0) + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
   if (op == 0) k_dmatmul_k<BS, 0><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
   else if (op == 1) k_dmatmul_k<BS, 1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
   else k_dmatmul_k<BS, 2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
@@ -167,6 +169,7 @@ int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp dam
   if (L->n == 0) return 0;
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   SellView vw = view(*M);
+  ProfScope ps(ctx, UGGPU_K_JAC, level, (double)L->n * (8.0 * L->bs * L->bs + 16.0 * L->bs));
   switch (L->bs) {
     case 1: k_jac_k<1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr); break;
     case 2: k_jac_k<2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr); break;
@@ -287,6 +290,10 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const doub
 {
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)blocks * BS));
+  const double nb = 8.0 * BS * L->n;
+  // algorithmic bytes: entries, row lengths, gathered operand once, b read+write, c, tout, x
+  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), (double)A->nnz * (8.0 * BS * BS + 4.0) + 4.0 * (L->n + 1.0) + 3.0 * nb
+               + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
   k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr);
   KCHECK(ctx);
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot));

@@ -131,6 +131,8 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
     if (!M) return UGGPU_DESC_MISMATCH;
     Av = view(*M);
   }
+ const double nbf = 8.0 * F->bs * F->n, nbc = 8.0 * F->bs * C->n;
+  ProfScope ps(ctx, UGGPU_K_RESTRICT, level, (double)F->R.nnz * 12.0 + 4.0 * (C->n + 1.0) + nbf + nbc + (fuse ? (double)C->n * 8.0 * F->bs * F->bs + 2.0 * nbc : 0.0));
 #define RS(BSV)                                                                                                                        \
   if (fuse) k_restrict_k<BSV, true><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr); \
   else k_restrict_k<BSV, false><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr)
@@ -152,6 +154,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   if (!F->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (F->n == 0) return 0;
   int blocks = (F->n + TR_THREADS - 1) / TR_THREADS;
+  ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, (double)F->P.nnz * 12.0 + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
   switch (F->bs) {
     case 1: k_interpolate_k<1><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;
     case 2: k_interpolate_k<2><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;

@@ -72,8 +72,21 @@ struct uggpu_ctx {
   int *derr = nullptr;                                     // device error word
   int *herr = nullptr;                                     // pinned
   int sm_count = 148;
+  // per-kernel event timing (uggpu_prof_*): records are resolved lazily after a synchronise
+  bool prof = false;
+  struct ProfRec { int kind, level; double bytes; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
   // multi-GPU (comm.cu)
   void *comm = nullptr;
+};
+
+// RAII bracket around one kernel launch: two events on the context's stream when profiling is on
+struct ProfScope {
+  uggpu_ctx *ctx; bool on;
+  uggpu_ctx::ProfRec rec;
+  ProfScope(uggpu_ctx *c, int kind, int level, double bytes);
+  ~ProfScope();
 };
 
 // ---- error plumbing -------------------------------------------------------------------------------
