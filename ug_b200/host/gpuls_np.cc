@@ -1,0 +1,737 @@
+// gpuls_np.cc -- see gpuls_np.h.  Host-side product code of the `gpuls` numproc family (no CUDA, no oracle).
+//
+// Structure mirrors the reference classes one to one (file:line in the comments); the BLAS/iter/transfer calls of
+// the CPU classes are replaced by calls through the C-ABI of include/uggpu.h on a device mirror of the multigrid:
+//   * PreProcess flattens UG's VECTOR/MATRIX lists of the levels involved (gpuls_flatten.cc) and uploads them once;
+//     PostProcess releases the device resources (the pattern of np/amglib/amg_ug.cc:207-390,599-615);
+//   * every entry point is synchronous: its vector arguments are gathered from the VVALUEs and uploaded on entry,
+//     results are downloaded and scattered back before it returns, because UG callers read VVALUEs immediately;
+//   * linear_solver.gpuls + iter.gpulmgc keep the whole solve resident: x, b go up once, all iterations run on the
+//     device (uggpu_ls_solve), x, b, c come back once.
+#include "config.h"
+#include "gpuls_np.h"
+#include "gpuls_flatten.h"
+
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "numproc.h"
+#include "npscan.h"
+#include "pcr.h"
+#include "iter.h"
+#include "ls.h"
+#include "transfer.h"
+#include "ugdevices.h"
+#include "ugstruct.h"
+#include "misc.h"
+#include "general.h"
+
+#include "uggpu.h"
+
+USING_UG_NAMESPACES
+
+// ---- the device library, bound at run time -------------------------------------------------------------------------
+#define UGGPU_FUNCS(X)                                                                                                                          \
+  X(uggpu_ctx_create) X(uggpu_ctx_destroy) X(uggpu_last_error) X(uggpu_set_fullrefinelevel) X(uggpu_level_create) X(uggpu_level_set_flags)     \
+  X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
+  X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
+  X(uggpu_ls_solve) X(uggpu_launch_count)
+
+namespace {
+struct Api {
+#define X(f) decltype(&::f) f = nullptr;
+  UGGPU_FUNCS(X)
+#undef X
+  void *dl = nullptr;
+} api;
+std::string g_load_error;
+}
+
+int gpuls::LoadDeviceLibrary(const char *path)
+{
+  if (api.dl) return 0;
+  const char *cand[3] = {path, getenv("UGGPU_LIB"), "libuggpu.so"};
+  for (const char *p : cand) {
+    if (!p || !*p) continue;
+    api.dl = dlopen(p, RTLD_NOW | RTLD_LOCAL);
+    if (api.dl) break;
+    g_load_error = dlerror();
+  }
+  if (!api.dl) return 1;
+#define X(f) api.f = (decltype(api.f))dlsym(api.dl, #f); if (!api.f) { g_load_error = "missing symbol " #f; dlclose(api.dl); api.dl = nullptr; return 2; }
+  UGGPU_FUNCS(X)
+#undef X
+  return 0;
+}
+const char *gpuls::LastLoadError() { return g_load_error.c_str(); }
+
+// ---- device mirror of one multigrid -------------------------------------------------------------------------------------
+namespace {
+
+struct Mirror {
+  MULTIGRID *mg = nullptr;
+  uggpu_ctx *ctx = nullptr;
+  int refs = 0;
+  int bs = 0;
+  const VECDATA_DESC *xdesc = nullptr;
+  std::vector<gpuls::FlatLevel> fl;
+  std::vector<char> have_level, have_transfer;
+  std::map<const void *, int> handles;
+  std::vector<double> buf;
+
+  int handle(const void *desc)
+  {
+    auto it = handles.find(desc);
+    if (it != handles.end()) return it->second;
+    int h = (int)handles.size() + 1;
+    handles[desc] = h;
+    return h;
+  }
+};
+
+std::map<MULTIGRID *, Mirror> g_mirrors;
+
+int dev_fail(const char *where)
+{
+  UserWriteF("gpuls: %s failed: %s\n", where, api.uggpu_last_error ? api.uggpu_last_error() : "device library not loaded");
+  return 1;
+}
+#define DEV(call) do { if (api.call) return dev_fail(#call); } while (0)
+
+Mirror *Acquire(MULTIGRID *mg)
+{
+  if (!api.dl && gpuls::LoadDeviceLibrary(NULL)) {
+    UserWriteF("gpuls: cannot load the device library (%s); there is no CPU fallback\n", g_load_error.c_str());
+    return NULL;
+  }
+  Mirror &m = g_mirrors[mg];
+  if (m.refs == 0) {
+    m.mg = mg;
+    int dev = 0;
+    if (const char *s = getenv("UGGPU_DEVICE")) dev = atoi(s);
+    if (api.uggpu_ctx_create(dev, &m.ctx)) { dev_fail("uggpu_ctx_create"); g_mirrors.erase(mg); return NULL; }
+    m.fl.assign(MAXLEVEL, gpuls::FlatLevel());
+    m.have_level.assign(MAXLEVEL, 0);
+    m.have_transfer.assign(MAXLEVEL, 0);
+    m.handles.clear();
+  }
+  m.refs++;
+  return &m;
+}
+
+void Release(MULTIGRID *mg)
+{
+  auto it = g_mirrors.find(mg);
+  if (it == g_mirrors.end()) return;
+  if (--it->second.refs > 0) return;
+  if (it->second.ctx) api.uggpu_ctx_destroy(it->second.ctx);
+  g_mirrors.erase(it);
+}
+
+Mirror *Find(MULTIGRID *mg)
+{
+  auto it = g_mirrors.find(mg);
+  return it == g_mirrors.end() ? NULL : &it->second;
+}
+
+// flatten + upload matrix A and the row flags of `level` (once per PreProcess bracket)
+int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC *A)
+{
+  if (m->have_level[level]) return 0;
+  gpuls::FlatLevel &f = m->fl[level];
+  if (gpuls::FlattenFlags(m->mg, level, x, f)) { UserWriteF("gpuls: level %d is not a pure nodal vector format\n", level); return 1; }
+  if (f.bs > UGGPU_MAX_BS) { UserWriteF("gpuls: %d components per vector exceed UGGPU_MAX_BS\n", f.bs); return 1; }
+  if (gpuls::FlattenMatrix(m->mg, level, A, f)) { UserWrite("gpuls: cannot flatten the matrix\n"); return 1; }
+  m->bs = f.bs;
+  m->xdesc = x;
+  DEV(uggpu_level_create(m->ctx, level, f.n, f.bs));
+  DEV(uggpu_level_set_flags(m->ctx, level, f.vclass.data(), f.vnclass.data(), f.ctl.data(), f.skip.data()));
+  DEV(uggpu_mat_set(m->ctx, level, m->handle(A), f.rowptr.data(), f.col.data(), f.val.data()));
+  DEV(uggpu_set_fullrefinelevel(m->ctx, FULLREFINELEVEL(m->mg)));
+  m->have_level[level] = 1;
+  return 0;
+}
+
+int EnsureTransfer(Mirror *m, int level)
+{
+  if (m->have_transfer[level]) return 0;
+  if (level < 1 || !m->have_level[level] || !m->have_level[level - 1]) return 1;
+  gpuls::FlatLevel &f = m->fl[level];
+  if (gpuls::FlattenTransfer(m->mg, level, f)) { UserWriteF("gpuls: cannot flatten the standard transfer of level %d\n", level); return 1; }
+  DEV(uggpu_transfer_set(m->ctx, level, f.p_rowptr.data(), f.p_col.data(), f.p_w.data(), f.r_rowptr.data(), f.r_col.data(), f.r_w.data()));
+  m->have_transfer[level] = 1;
+  return 0;
+}
+
+int Upload(Mirror *m, int level, const VECDATA_DESC *vd)
+{
+  const gpuls::FlatLevel &f = m->fl[level];
+  m->buf.resize((size_t)f.n * f.bs + 1);
+  gpuls::GatherVector(m->mg, level, vd, f.bs, m->buf.data());
+  DEV(uggpu_vec_upload(m->ctx, level, m->handle(vd), m->buf.data()));
+  return 0;
+}
+
+int Download(Mirror *m, int level, const VECDATA_DESC *vd)
+{
+  const gpuls::FlatLevel &f = m->fl[level];
+  m->buf.resize((size_t)f.n * f.bs + 1);
+  DEV(uggpu_vec_download(m->ctx, level, m->handle(vd), m->buf.data()));
+  gpuls::ScatterVector(m->mg, level, vd, f.bs, m->buf.data());
+  return 0;
+}
+
+void VsToArray(const VEC_SCALAR vs, int bs, double *out) { for (int i = 0; i < UGGPU_MAX_BS; i++) out[i] = i < bs ? vs[i] : 1.0; }
+
+// =========================================================================================================================
+// iter.gpujac  (reference: NP_SMOOTHER iter.cc:152-177, SmootherInit :763, Smoother :817, JacobiPreProcess/Step :894-925)
+// =========================================================================================================================
+struct NP_GPUJAC {
+  NP_ITER iter;
+  VEC_SCALAR damp;
+  Mirror *m;
+  INT acquired;        // PreProcess is called once per level (iter.cc:7719): one mirror reference each
+};
+
+INT GpuJacInit(NP_BASE *theNP, INT argc, char **argv)
+{
+  NP_GPUJAC *np = (NP_GPUJAC *)theNP;
+  for (int i = 0; i < MAX_VEC_COMP; i++) np->damp[i] = 1.0;
+  sc_read(np->damp, NP_FMT(np), np->iter.b, "damp", argc, argv);          // iter.cc:771
+  return NPIterInit(&np->iter, argc, argv);
+}
+
+INT GpuJacDisplay(NP_BASE *theNP)
+{
+  NP_GPUJAC *np = (NP_GPUJAC *)theNP;
+  NPIterDisplay(&np->iter);
+  UserWrite("configuration parameters:\n");
+  if (sc_disp(np->damp, np->iter.b, "damp")) REP_ERR_RETURN(1);
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "device", "B200 via libuggpu");
+  return 0;
+}
+
+INT GpuJacPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *baselevel, INT *result)
+{
+  NP_GPUJAC *np = (NP_GPUJAC *)theNP;
+  Mirror *m = Acquire(NP_MG(theNP));
+  if (m == NULL) NP_RETURN(1, result[0]);
+  np->m = m;
+  np->acquired++;
+  if (EnsureLevel(np->m, level, x, A)) NP_RETURN(1, result[0]);
+  *baselevel = level;                                                      // iter.cc:908
+  return 0;
+}
+
+// one damped Jacobi step in defect-correction form: x = damp * Diag(A)^-1 b ; b -= A x   (Smoother iter.cc:817-842)
+INT GpuJacIter(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUJAC *np = (NP_GPUJAC *)theNP;
+  NPIT_A(theNP) = A; NPIT_c(theNP) = x; NPIT_b(theNP) = b;
+  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  if (m == NULL || !m->have_level[level]) { UserWrite("gpujac: Iter without PreProcess\n"); NP_RETURN(1, result[0]); }
+  double damp[UGGPU_MAX_BS];
+  VsToArray(np->damp, m->bs, damp);
+  if (Upload(m, level, b)) NP_RETURN(1, result[0]);
+  if (api.uggpu_vec_alloc(m->ctx, level, m->handle(x))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+  if (api.uggpu_jac_smooth(m->ctx, level, m->handle(x), m->handle(b), m->handle(A), damp)) NP_RETURN(dev_fail("uggpu_jac_smooth"), result[0]);
+  if (Download(m, level, x) || Download(m, level, b)) NP_RETURN(1, result[0]);
+  return 0;
+}
+
+INT GpuJacPostProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUJAC *np = (NP_GPUJAC *)theNP;
+  if (np->acquired > 0) {
+    Release(NP_MG(theNP));
+    if (--np->acquired == 0) np->m = NULL;
+  }
+  return 0;
+}
+
+INT GpuJacConstruct(NP_BASE *theNP)
+{
+  theNP->Init = GpuJacInit;
+  theNP->Display = GpuJacDisplay;
+  theNP->Execute = NPIterExecute;
+  NP_ITER *np = (NP_ITER *)theNP;
+  np->PreProcess = GpuJacPreProcess;
+  np->Iter = GpuJacIter;
+  np->PostProcess = GpuJacPostProcess;
+  return 0;
+}
+
+// =========================================================================================================================
+// transfer.gputransfer  (reference: NP_STANDARD_TRANSFER transfer.cc:115-133, standard mode only)
+// =========================================================================================================================
+struct NP_GPUTRANSFER {
+  NP_TRANSFER transfer;
+  Mirror *m;
+  INT fl, tl;
+};
+
+INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
+{
+  if (ReadArgvOption("M", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("L", argc, argv) || ReadArgvOption("D", argc, argv)) {
+    UserWrite("gputransfer: only the standard (geometric) transfer is on the GPU path; $M $S $L $D are not supported\n");
+    return NP_NOT_ACTIVE;
+  }
+  return NPTransferInit((NP_TRANSFER *)theNP, argc, argv);                // transfer.cc:593
+}
+
+INT GpuTransferDisplay(NP_BASE *theNP)
+{
+  NPTransferDisplay((NP_TRANSFER *)theNP);
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "Restrict", "StandardRestrict (device)");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", "StandardInterpolateCorrection (device)");
+  return 0;
+}
+
+// TransferPreProcess transfer.cc:643: nothing to do in the sequential standard mode; here: build the device stencils
+INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  np->m = Acquire(NP_MG(theNP));
+  if (np->m == NULL) NP_RETURN(1, result[0]);
+  np->fl = *fl; np->tl = tl;
+  for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) NP_RETURN(1, result[0]);
+  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l)) NP_RETURN(1, result[0]);
+  return 0;
+}
+
+// RestrictDefect transfer.cc:724: fine `level` -> level-1
+INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: RestrictDefect without PreProcess (or level < 1: matrix-dependent transfer is not on the GPU path)\n"); NP_RETURN(1, result[0]); }
+  double d[UGGPU_MAX_BS];
+  VsToArray(damp, m->bs, d);
+  // the coarse vector is an input too: rows with VNCLASS < NEWDEF_CLASS keep their values (transgrid.cc:143-147)
+  if (Upload(m, level, from) || Upload(m, level - 1, to)) NP_RETURN(1, result[0]);
+  if (api.uggpu_restrict(m->ctx, level, m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_restrict"), result[0]);
+  if (Download(m, level - 1, to)) NP_RETURN(1, result[0]);
+  result[0] = 0;
+  return 0;
+}
+
+// InterpolateCorrection transfer.cc:747: level-1 -> fine `level`
+INT GpuInterpolateCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: InterpolateCorrection without PreProcess\n"); NP_RETURN(1, result[0]); }
+  double d[UGGPU_MAX_BS];
+  VsToArray(damp, m->bs, d);
+  if (Upload(m, level - 1, from)) NP_RETURN(1, result[0]);
+  if (api.uggpu_vec_alloc(m->ctx, level, m->handle(to))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+  if (api.uggpu_interpolate_correction(m->ctx, level, m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_interpolate_correction"), result[0]);
+  if (Download(m, level, to)) NP_RETURN(1, result[0]);
+  result[0] = 0;
+  return 0;
+}
+
+INT GpuTransferPostProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  if (np->m) Release(NP_MG(theNP));
+  np->m = NULL;
+  return 0;
+}
+
+INT GpuTransferConstruct(NP_BASE *theNP)
+{
+  theNP->Init = GpuTransferInit;
+  theNP->Display = GpuTransferDisplay;
+  theNP->Execute = NPTransferExecute;
+  NP_TRANSFER *np = (NP_TRANSFER *)theNP;
+  np->PreProcess = GpuTransferPreProcess;
+  np->PreProcessProject = NULL;
+  np->PreProcessSolution = NULL;
+  np->InterpolateCorrection = GpuInterpolateCorrection;
+  np->RestrictDefect = GpuRestrictDefect;
+  np->InterpolateNewVectors = NULL;      // nested-iteration hooks: not on the cycle path; callers test for NULL
+  np->ProjectSolution = NULL;
+  np->AdaptCorrection = NULL;            // iter.cc:7944 tests for NULL
+  np->PostProcess = GpuTransferPostProcess;
+  np->PostProcessProject = NULL;
+  np->PostProcessSolution = NULL;
+  return 0;
+}
+
+// =========================================================================================================================
+// iter.gpulmgc  (reference: NP_LMGC iter.cc:411-429, LmgcInit :7613, LmgcPreProcess :7707, Lmgc :7741, LmgcPostProcess :7951)
+// =========================================================================================================================
+struct NP_GPULMGC {
+  NP_ITER iter;
+  INT gamma, nu1, nu2, baselevel;
+  NP_TRANSFER *Transfer;
+  NP_ITER *PreSmooth, *PostSmooth;
+  NP_LINEAR_SOLVER *BaseSolver;
+  VECDATA_DESC *t;
+  VEC_SCALAR damp;
+  INT devbase, unfused;
+  Mirror *m;
+  INT level;                    // level of the PreProcess bracket
+  // descriptors of the cycle in flight (for the host base-solver callback)
+  VECDATA_DESC *cur_c, *cur_b;
+  MATDATA_DESC *cur_A;
+  int t_handle;
+};
+
+INT GpuLmgcInit(NP_BASE *theNP, INT argc, char **argv)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)theNP;
+  char post[VALUELEN], pre[VALUELEN], base[VALUELEN];
+  np->t = ReadArgvVecDesc(theNP->mg, "t", argc, argv);
+  np->Transfer = (NP_TRANSFER *)ReadArgvNumProc(theNP->mg, "T", TRANSFER_CLASS_NAME, argc, argv);
+  for (int i = 1; i < argc; i++)
+    if (argv[i][0] == 'S') {
+      if (sscanf(argv[i], "S %s %s %s", pre, post, base) != 3) continue;
+      np->PreSmooth = (NP_ITER *)GetNumProcByName(theNP->mg, pre, ITER_CLASS_NAME);
+      np->PostSmooth = (NP_ITER *)GetNumProcByName(theNP->mg, post, ITER_CLASS_NAME);
+      np->BaseSolver = (NP_LINEAR_SOLVER *)GetNumProcByName(theNP->mg, base, LINEAR_SOLVER_CLASS_NAME);
+      break;
+    }
+  if (ReadArgvINT("g", &(np->gamma), argc, argv)) np->gamma = 1;
+  if (ReadArgvINT("n1", &(np->nu1), argc, argv)) np->nu1 = 1;
+  if (ReadArgvINT("n2", &(np->nu2), argc, argv)) np->nu2 = 1;
+  if (ReadArgvINT("b", &(np->baselevel), argc, argv)) np->baselevel = 0;
+  if (np->baselevel < 0) {                                                // iter.cc:7645-7651
+    int i;
+    for (i = FULLREFINELEVEL(NP_MG(theNP)); i > 0; i--)
+      if (NVEC(GRID_ON_LEVEL(NP_MG(theNP), i)) <= -np->baselevel) break;
+    np->baselevel = i;
+  }
+  np->devbase = ReadArgvOption("devbase", argc, argv);
+  np->unfused = ReadArgvOption("unfused", argc, argv);
+  if (np->Transfer == NULL || np->PreSmooth == NULL || np->PostSmooth == NULL) REP_ERR_RETURN(NP_NOT_ACTIVE);
+  if (np->BaseSolver == NULL && !np->devbase) REP_ERR_RETURN(NP_NOT_ACTIVE);
+  if (np->PreSmooth->Iter != GpuJacIter || np->PostSmooth->Iter != GpuJacIter) {
+    UserWrite("gpulmgc: $S pre and post smoother must be of class gpujac (damped Jacobi is the smoother on the GPU path)\n");
+    return NP_NOT_ACTIVE;
+  }
+  if (np->Transfer->RestrictDefect != GpuRestrictDefect) {
+    UserWrite("gpulmgc: $T must be of class gputransfer\n");
+    return NP_NOT_ACTIVE;
+  }
+  if (np->gamma < 1) { UserWrite("gpulmgc: $g must be >= 1\n"); return NP_NOT_ACTIVE; }
+  INT ret = NPIterInit(&np->iter, argc, argv);
+  if (sc_read(np->damp, NP_FMT(np), np->iter.b, "damp", argc, argv))
+    for (int i = 0; i < MAX_VEC_COMP; i++) np->damp[i] = 1.0;
+  return ret;
+}
+
+INT GpuLmgcDisplay(NP_BASE *theNP)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)theNP;
+  NPIterDisplay(&np->iter);
+  UserWrite("configuration parameters:\n");
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "g", (int)np->gamma);
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "n1", (int)np->nu1);
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "n2", (int)np->nu2);
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "baselevel", (int)np->baselevel);
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "T", np->Transfer ? ENVITEM_NAME(np->Transfer) : "---");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "pre", np->PreSmooth ? ENVITEM_NAME(np->PreSmooth) : "---");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "post", np->PostSmooth ? ENVITEM_NAME(np->PostSmooth) : "---");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "base", np->devbase ? "device LU" : (np->BaseSolver ? ENVITEM_NAME(np->BaseSolver) : "---"));
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "schedule", np->unfused ? "one kernel per call" : "fused");
+  if (sc_disp(np->damp, np->iter.b, "damp")) REP_ERR_RETURN(1);
+  return 0;
+}
+
+// base level: exactly what Lmgc does there (iter.cc:7760-7800), on the host numproc, between a download and an upload
+int HostBaseSolver(void *user, uggpu_ctx *ctx, int level, int c, int b, int A)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)user;
+  Mirror *m = np->m;
+  LRESULT lresult;
+  if (Download(m, level, np->cur_c) || Download(m, level, np->cur_b)) return 1;
+  if ((*np->BaseSolver->Residuum)(np->BaseSolver, MIN(level, np->baselevel), level, np->cur_c, np->cur_b, np->cur_A, &lresult)) return 1;
+  if ((*np->BaseSolver->Solver)(np->BaseSolver, level, np->cur_c, np->cur_b, np->cur_A, np->BaseSolver->abslimit, np->BaseSolver->reduction, &lresult)) return 1;
+  if (Upload(m, level, np->cur_c) || Upload(m, level, np->cur_b)) return 1;
+  return 0;
+}
+
+void FillCfg(NP_GPULMGC *np, uggpu_lmgc_cfg *cfg)
+{
+  Mirror *m = np->m;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->nu1 = np->nu1; cfg->nu2 = np->nu2; cfg->gamma = np->gamma; cfg->baselevel = np->baselevel;
+  VsToArray(((NP_GPUJAC *)np->PreSmooth)->damp, m->bs, cfg->smooth_damp);
+  VsToArray(np->damp, m->bs, cfg->cycle_damp);
+  cfg->t = np->t_handle;
+  cfg->fused = np->unfused ? 0 : 1;
+  if (np->devbase) {
+    cfg->base_solver = NULL;
+    // the parameters of the reference's `ls $I lu` base solver if one is given, else its documented defaults
+    cfg->base_maxit = 10; cfg->base_reduction = 1e-8; cfg->base_abslimit = 1e-10;
+    if (np->BaseSolver) { cfg->base_reduction = np->BaseSolver->reduction[0]; cfg->base_abslimit = np->BaseSolver->abslimit[0]; }
+  } else {
+    cfg->base_solver = HostBaseSolver;
+    cfg->base_user = np;
+  }
+}
+
+INT GpuLmgcPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *baselevel, INT *result)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)theNP;
+  np->m = Acquire(NP_MG(theNP));
+  if (np->m == NULL) NP_RETURN(1, result[0]);
+  np->level = level;
+  // same order as LmgcPreProcess iter.cc:7714-7738
+  if ((*np->Transfer->PreProcess)(np->Transfer, &(np->baselevel), level, x, b, A, result)) REP_ERR_RETURN(1);
+  for (int i = np->baselevel + 1; i <= level; i++)
+    if ((*np->PreSmooth->PreProcess)(np->PreSmooth, i, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+  if (np->PreSmooth != np->PostSmooth)
+    for (int i = np->baselevel + 1; i <= level; i++)
+      if ((*np->PostSmooth->PreProcess)(np->PostSmooth, i, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+  *baselevel = MIN(np->baselevel, level);
+  if (!np->devbase && np->BaseSolver->PreProcess != NULL)
+    if ((*np->BaseSolver->PreProcess)(np->BaseSolver, *baselevel, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+  if (((NP_GPUJAC *)np->PreSmooth)->damp[0] != ((NP_GPUJAC *)np->PostSmooth)->damp[0]) {
+    UserWrite("gpulmgc: pre and post smoother must use the same damping\n");
+    NP_RETURN(1, result[0]);
+  }
+  np->t_handle = np->m->handle(&np->t);      // the temporary np->t of Lmgc (iter.cc:7810) lives on the device only
+  uggpu_lmgc_cfg cfg;
+  FillCfg(np, &cfg);
+  if (api.uggpu_lmgc_preprocess(np->m->ctx, &cfg, level, np->m->handle(A))) NP_RETURN(dev_fail("uggpu_lmgc_preprocess"), result[0]);
+  return 0;
+}
+
+// Lmgc iter.cc:7741: c (in/out) and b (in/out) on `level`; the levels below are work space whose final contents the
+// reference leaves in the VECTORs, so they are downloaded too.
+INT GpuLmgcIter(NP_ITER *theNP, INT level, VECDATA_DESC *c, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)theNP;
+  NPIT_A(theNP) = A; NPIT_c(theNP) = c; NPIT_b(theNP) = b;
+  Mirror *m = np->m;
+  if (m == NULL) { UserWrite("gpulmgc: Iter without PreProcess\n"); NP_RETURN(1, result[0]); }
+  np->cur_c = c; np->cur_b = b; np->cur_A = A;
+  uggpu_lmgc_cfg cfg;
+  FillCfg(np, &cfg);
+  const int bl = MIN(np->baselevel, level);
+  for (int l = bl; l <= level; l++)
+    if (Upload(m, l, c) || Upload(m, l, b)) NP_RETURN(1, result[0]);
+  if (api.uggpu_lmgc(m->ctx, &cfg, level, m->handle(c), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_lmgc"), result[0]);
+  for (int l = bl; l <= level; l++)
+    if (Download(m, l, c) || Download(m, l, b)) NP_RETURN(1, result[0]);
+  return 0;
+}
+
+INT GpuLmgcPostProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPULMGC *np = (NP_GPULMGC *)theNP;
+  // reverse order of LmgcPostProcess iter.cc:7951-7984
+  if (!np->devbase && np->BaseSolver->PostProcess != NULL)
+    if ((*np->BaseSolver->PostProcess)(np->BaseSolver, np->baselevel, x, b, A, result)) REP_ERR_RETURN(1);
+  if (np->PreSmooth != np->PostSmooth)
+    for (int i = level; i >= np->baselevel + 1; i--)
+      if ((*np->PostSmooth->PostProcess)(np->PostSmooth, i, x, b, A, result)) REP_ERR_RETURN(1);
+  for (int i = level; i >= np->baselevel + 1; i--)
+    if ((*np->PreSmooth->PostProcess)(np->PreSmooth, i, x, b, A, result)) REP_ERR_RETURN(1);
+  if ((*np->Transfer->PostProcess)(np->Transfer, &(np->baselevel), level, x, b, A, result)) REP_ERR_RETURN(1);
+  if (np->m) Release(NP_MG(theNP));
+  np->m = NULL;
+  return 0;
+}
+
+INT GpuLmgcConstruct(NP_BASE *theNP)
+{
+  theNP->Init = GpuLmgcInit;
+  theNP->Display = GpuLmgcDisplay;
+  theNP->Execute = NPIterExecute;
+  NP_ITER *np = (NP_ITER *)theNP;
+  np->PreProcess = GpuLmgcPreProcess;
+  np->Iter = GpuLmgcIter;
+  np->PostProcess = GpuLmgcPostProcess;
+  return 0;
+}
+
+// =========================================================================================================================
+// linear_solver.gpuls  (reference: NP_LS ls.cc:79-108, LinearSolverInit :771, PreProcess :539, Defect :562, Residuum :577,
+//                       LinearSolver :637-749 with Update = LSUpdate :869)
+// =========================================================================================================================
+struct NP_GPULS {
+  NP_LINEAR_SOLVER ls;
+  NP_ITER *Iter;
+  INT maxiter, baselevel, display;
+  VECDATA_DESC *c;
+  Mirror *m;
+};
+
+INT GpuLsInit(NP_BASE *theNP, INT argc, char **argv)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  if (ReadArgvINT("m", &(np->maxiter), argc, argv)) REP_ERR_RETURN(NP_NOT_ACTIVE);
+  np->display = ReadArgvDisplay(argc, argv);
+  np->Iter = (NP_ITER *)ReadArgvNumProc(theNP->mg, "I", ITER_CLASS_NAME, argc, argv);
+  if (np->Iter == NULL) REP_ERR_RETURN(NP_NOT_ACTIVE);
+  if (np->Iter->Iter != GpuLmgcIter) {
+    UserWrite("gpuls: $I must be of class gpulmgc (the device-resident solve has no host iteration)\n");
+    return NP_NOT_ACTIVE;
+  }
+  np->baselevel = 0;
+  np->c = ReadArgvVecDesc(theNP->mg, "c", argc, argv);
+  return NPLinearSolverInit(&np->ls, argc, argv);
+}
+
+INT GpuLsDisplay(NP_BASE *theNP)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  NPLinearSolverDisplay(&np->ls);
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "m", (int)np->maxiter);
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "baselevel", (int)np->baselevel);
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "Iter", np->Iter ? ENVITEM_NAME(np->Iter) : "---");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "DispMode", np->display == PCR_NO_DISPLAY ? "NO_DISPLAY" : (np->display == PCR_RED_DISPLAY ? "RED_DISPLAY" : "FULL_DISPLAY"));
+  return 0;
+}
+
+INT GpuLsPreProcess(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *baselevel, INT *result)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  NPLS_A(theNP) = A; NPLS_x(theNP) = x; NPLS_b(theNP) = b;
+  np->m = Acquire(NP_MG(theNP));
+  if (np->m == NULL) NP_RETURN(1, result[0]);
+  if ((*np->Iter->PreProcess)(np->Iter, level, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+  np->baselevel = MIN(*baselevel, level);
+  // ON_SURFACE loops touch levels FULLREFINELEVEL..level
+  for (int l = MIN(np->baselevel, (INT)FULLREFINELEVEL(NP_MG(theNP))); l <= level; l++)
+    if (EnsureLevel(np->m, l, x, A)) NP_RETURN(1, result[0]);
+  return 0;
+}
+
+INT GpuLsDefect(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  Mirror *m = np->m;
+  if (m == NULL) { UserWrite("gpuls: Defect without PreProcess\n"); NP_RETURN(1, result[0]); }
+  const int bl = MIN(FULLREFINELEVEL(NP_MG(theNP)), MAX(0, np->baselevel));   // ls.cc:570
+  const int fr = MIN((INT)FULLREFINELEVEL(NP_MG(theNP)), level);
+  for (int l = fr; l <= level; l++)
+    if (Upload(m, l, x) || Upload(m, l, b)) NP_RETURN(1, result[0]);
+  if (api.uggpu_ls_defect(m->ctx, bl, level, m->handle(x), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_ls_defect"), result[0]);
+  for (int l = fr; l <= level; l++)
+    if (Download(m, l, b)) NP_RETURN(1, result[0]);
+  return *result;
+}
+
+INT GpuLsResiduum(NP_LINEAR_SOLVER *theNP, INT bl, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, LRESULT *lresult)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  Mirror *m = np->m;
+  if (m == NULL) { UserWrite("gpuls: Residuum without PreProcess\n"); NP_RETURN(1, lresult->error_code); }
+  const int fr = MIN((INT)FULLREFINELEVEL(NP_MG(theNP)), level);
+  for (int l = fr; l <= level; l++)
+    if (Upload(m, l, b)) NP_RETURN(1, lresult->error_code);
+  uggpu_lresult r;
+  memset(&r, 0, sizeof r);
+  if (api.uggpu_ls_residuum(m->ctx, bl, level, m->handle(b), &r)) NP_RETURN(dev_fail("uggpu_ls_residuum"), lresult->error_code);
+  for (int i = 0; i < m->bs; i++) lresult->last_defect[i] = r.last_defect[i];
+  return 0;
+}
+
+// LinearSolver ls.cc:637-749, all iterations on the device
+INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, VEC_SCALAR abslimit, VEC_SCALAR reduction, LRESULT *lresult)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  NP_GPULMGC *mgc = (NP_GPULMGC *)np->Iter;
+  Mirror *m = np->m;
+  INT PrintID = 0;
+  char text[DISPLAY_WIDTH + 4];
+  if (m == NULL || mgc->m == NULL) { UserWrite("gpuls: Solver without PreProcess\n"); NP_RETURN(1, lresult->error_code); }
+  const int bs = m->bs, bl = np->baselevel;
+  for (int i = 0; i < VD_NCOMP(x); i++) { NPLS_red(theNP)[i] = reduction[i]; NPLS_abs(theNP)[i] = abslimit[i]; }
+  if (AllocVDFromVD(NP_MG(theNP), bl, level, x, &np->c)) NP_RETURN(1, lresult->error_code);   // ls.cc:662
+  CenterInPattern(text, DISPLAY_WIDTH, ENVITEM_NAME(np), '*', "\n");
+  if (np->display > PCR_NO_DISPLAY)
+    if (PreparePCR(x, np->display, text, &PrintID)) NP_RETURN(1, lresult->error_code);
+  clock_t clock_start = clock();
+
+  // up: x and b (all cycle levels: the reference's x += c and the cycle's work vectors live on them), c = np->c
+  for (int l = bl; l <= level; l++) {
+    if (Upload(m, l, x) || Upload(m, l, b)) NP_RETURN(1, lresult->error_code);
+    if (api.uggpu_vec_alloc(m->ctx, l, m->handle(np->c))) NP_RETURN(dev_fail("uggpu_vec_alloc"), lresult->error_code);
+  }
+  mgc->cur_c = np->c; mgc->cur_b = b; mgc->cur_A = A;
+  uggpu_lmgc_cfg cfg;
+  FillCfg(mgc, &cfg);
+  uggpu_lresult r;
+  memset(&r, 0, sizeof r);
+  double absl[UGGPU_MAX_BS], red[UGGPU_MAX_BS];
+  for (int i = 0; i < UGGPU_MAX_BS; i++) { absl[i] = abslimit[i < bs ? i : 0]; red[i] = reduction[i < bs ? i : 0]; r.last_defect[i] = i < bs ? lresult->last_defect[i] : 0.0; }
+  std::vector<double> history((size_t)MAX(np->maxiter, 1) * bs, 0.0);
+  if (api.uggpu_ls_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
+    NP_RETURN(dev_fail("uggpu_ls_solve"), lresult->error_code);
+  // down: x, b, c on every cycle level (what the CPU classes leave in the VECTORs)
+  for (int l = bl; l <= level; l++)
+    if (Download(m, l, x) || Download(m, l, b) || Download(m, l, np->c)) NP_RETURN(1, lresult->error_code);
+
+  for (int i = 0; i < bs; i++) { lresult->first_defect[i] = r.first_defect[i]; lresult->last_defect[i] = r.last_defect[i]; }
+  lresult->converged = r.converged;
+  lresult->number_of_linear_iterations = r.number_of_linear_iterations;
+  lresult->error_code = r.error_code;
+  double ti = (double)(clock() - clock_start) / CLOCKS_PER_SEC;
+  if (np->display > PCR_NO_DISPLAY) {
+    VEC_SCALAR d;
+    for (int i = 0; i < MAX_VEC_COMP; i++) d[i] = 0.0;
+    for (int i = 0; i < bs; i++) d[i] = r.first_defect[i];
+    if (DoPCR(PrintID, d, PCR_CRATE_SD)) NP_RETURN(1, lresult->error_code);
+    for (int it = 0; it < r.number_of_linear_iterations; it++) {
+      for (int i = 0; i < bs; i++) d[i] = history[(size_t)it * bs + i];
+      if (DoPCR(PrintID, d, PCR_CRATE_SD)) NP_RETURN(1, lresult->error_code);
+    }
+    if (DoPCR(PrintID, lresult->last_defect, PCR_AVERAGE)) NP_RETURN(1, lresult->error_code);
+    if (PostPCR(PrintID, ":ls:avg")) NP_RETURN(1, lresult->error_code);
+    if (SetStringValue(":ls:avg:iter", (DOUBLE)(r.number_of_linear_iterations + (r.converged ? 0 : 1)))) NP_RETURN(1, lresult->error_code);
+    if (lresult->number_of_linear_iterations != 0)
+      UserWriteF("LS  : L=%2d N=%2d TSOLVE=%10.4g TIT=%10.4g\n", level, lresult->number_of_linear_iterations, ti, ti / lresult->number_of_linear_iterations);
+    else
+      UserWriteF("LS  : L=%2d N=%2d TSOLVE=%10.4g\n", level, lresult->number_of_linear_iterations, ti);
+  }
+  if (FreeVD(NP_MG(theNP), bl, level, np->c)) REP_ERR_RETURN(1);
+  return 0;
+}
+
+INT GpuLsPostProcess(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPULS *np = (NP_GPULS *)theNP;
+  if (np->Iter->PostProcess != NULL)
+    if ((*np->Iter->PostProcess)(np->Iter, level, x, b, A, result)) NP_RETURN(1, result[0]);
+  np->baselevel = MAX(BOTTOMLEVEL(theNP->base.mg), np->baselevel);
+  if (np->m) Release(NP_MG(theNP));
+  np->m = NULL;
+  return 0;
+}
+
+INT GpuLsConstruct(NP_BASE *theNP)
+{
+  theNP->Init = GpuLsInit;
+  theNP->Display = GpuLsDisplay;
+  theNP->Execute = NPLinearSolverExecute;
+  NP_LINEAR_SOLVER *np = (NP_LINEAR_SOLVER *)theNP;
+  np->PreProcess = GpuLsPreProcess;
+  np->Defect = GpuLsDefect;
+  np->Residuum = GpuLsResiduum;
+  np->Solver = GpuLsSolver;
+  np->PostProcess = GpuLsPostProcess;
+  return 0;
+}
+
+}  // namespace
+
+INT NS_DIM_PREFIX InitGpuLS(void)
+{
+  if (CreateClass(ITER_CLASS_NAME ".gpujac", sizeof(NP_GPUJAC), GpuJacConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(TRANSFER_CLASS_NAME ".gputransfer", sizeof(NP_GPUTRANSFER), GpuTransferConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ITER_CLASS_NAME ".gpulmgc", sizeof(NP_GPULMGC), GpuLmgcConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpuls", sizeof(NP_GPULS), GpuLsConstruct)) REP_ERR_RETURN(__LINE__);
+  return 0;
+}

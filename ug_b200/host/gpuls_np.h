@@ -1,0 +1,32 @@
+// gpuls_np.h -- the `gpuls` numproc family: drop-in GPU replacements for UG's CPU numprocs on the multigrid
+// hot path.  Compiled against the UG headers (-D_2 / -D_3) by the application that links libug; reaches the GPU
+// only through the C-ABI of include/uggpu.h, bound at run time with dlopen (no CUDA headers here).
+//
+//   class name (npcreate $c ...)   abstract base                replaces (reference)
+//   iter.gpujac                    NP_ITER   (iter.h:68)        iter.jac          iter.cc:894-942
+//   transfer.gputransfer           NP_TRANSFER (transfer.h:79)  transfer.transfer transfer.cc:553-897 (standard mode)
+//   iter.gpulmgc                   NP_ITER                      iter.lmgc         iter.cc:7613-7980
+//   linear_solver.gpuls            NP_LINEAR_SOLVER (ls.h:79)   linear_solver.ls  ls.cc:539-905
+//
+// Same option letters as the CPU classes ($A $x $b $c $damp $S $T $n1 $n2 $g $b $t $m $I $red $abslimit $display),
+// plus on gpulmgc: $devbase (solve the base level on the device instead of calling the BaseSolver numproc) and
+// $unfused (one kernel per reference call).  Usage: call InitGpuLS() once after InitUg(), then e.g.
+//   npcreate smooth $c gpujac; npcreate transfer $c gputransfer; npcreate lmgc $c gpulmgc; npcreate mgs $c gpuls;
+#ifndef GPULS_NP_H
+#define GPULS_NP_H
+
+#include "gm.h"
+#include "np.h"
+
+namespace gpuls {
+// dlopen()s libuggpu.so (path may be NULL: $UGGPU_LIB, then "libuggpu.so" on the loader path). 0 = ok.
+int LoadDeviceLibrary(const char *path);
+const char *LastLoadError();
+}
+
+START_UGDIM_NAMESPACE
+// registers the four classes (np/udm/numproc.h:108 CreateClass); 0 = ok
+INT InitGpuLS(void);
+END_UGDIM_NAMESPACE
+
+#endif
