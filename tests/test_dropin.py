@@ -1,0 +1,34 @@
+"""Drop-in test of the `gpuls` numproc family inside the UNMODIFIED reference: oracle/_ref/ugoracle{2,3} link libug
+(compiled from /root/reference) with ug_b200/host/gpuls_np.cc, register iter.gpujac / transfer.gputransfer /
+iter.gpulmgc / linear_solver.gpuls via InitGpuLS(), run the SAME numproc script once with the CPU classes and once
+with every GPU/CPU mix, and compare the VVALUEs UG holds afterwards (bit-exact when the base solver is the CPU numproc,
+1e-12 with the device LU) and LRESULT.  The binaries are built where /root/reference exists (oracle/Makefile) and
+travel to the GPU box; the test is skipped if they are absent."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
+
+CASES = [
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle2", ["--grid", "tri", "--refine", "5", "--damp", "0.8", "--cycles", "6"]),
+    ("ugoracle2", ["--grid", "quad", "--refine", "3", "--damp", "0.8", "--gamma", "2", "--cycles", "5"]),
+]
+
+
+@pytest.mark.parametrize("exe,args", CASES, ids=["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W"])
+def test_gpuls_numprocs_inside_ug(exe, args):
+    path = os.path.join(ROOT, "oracle", "_ref", exe)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
+    assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
+    assert sum(l.startswith("PASS") for l in lines) == 4, lines
+    assert lines[-1] == "gpuls drop-in: 0 failure(s)"
