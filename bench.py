@@ -164,8 +164,23 @@ def our_arm(args):
     ctx = capi.Context(local)
     A = ctx.handle("A")
     t0 = time.perf_counter()
-    ctx.call("uggpu_synth_hierarchy", capi.SYNTH_P1_SIMPLEX, cells, cells, cells, top, A)
+    # weak scaling: every GPU gets a box of cells^3 base cells (513^3-type fine grid per GPU); the rank array follows
+    # UG's RCB of a structured grid (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2)
+    P = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
+    if P is None:
+        raise SystemExit(f"bench.py: unsupported GPU count {world} (1, 2, 4 or 8)")
+    if world > 1:
+        import torch.distributed as dist
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            ctx.call_noctx("uggpu_comm_unique_id", idbuf)
+        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        ctx.call("uggpu_comm_init", world, rank, C.c_char_p(bytes(t.cpu().tolist())))
+    ctx.call("uggpu_synth_hierarchy_part", capi.SYNTH_P1_SIMPLEX, cells * P[0], cells * P[1], cells * P[2], top, A,
+             P[0], P[1], P[2], rank, C.c_int64(args.replicate_below))
     n = ctx.level_n(top)
+    n_global = int(ctx.L.uggpu_level_n_global(ctx.h, top))
     for name in ("x", "b", "c"):
         for l in range(top + 1):
             ctx.alloc(l, name)
@@ -266,13 +281,20 @@ def our_arm(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("k_smooth_k_dram_bytes_per_launch")
     total_alg = sum(v["alg_bytes"] for v in prof.values())
-    n_total = n * world
+    n_total = n_global
     value = n_total * args.steps / (ms * 1e-3)
+    exchanges = int(ctx.L.uggpu_comm_exchanges(ctx.h))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(cells, top, n), "parallelism": f"dp{world}", "cache": "inputs larger than L2 (matrix 24 GB per sweep)",
+        "config": {"workload": workload_name(cells, top, n) if world == 1 else
+                   (f"3D P1 Poisson, box of {P[0]}x{P[1]}x{P[2]} unit cubes (one per GPU), Kuhn tetrahedra, base {cells * P[0]}x{cells * P[1]}x{cells * P[2]} cells, "
+                    f"{top + 1} levels, {n_global} fine unknowns ({n} on rank 0), V(2,2) Jacobi damp 0.6, base solver ls+lu"),
+                   "parallelism": f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + NCCL halo copies, "
+                                  f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
+                   "halo_exchanges_total": exchanges,
+                   "cache": "inputs larger than L2 (matrix 24 GB per sweep)",
                    "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2),
                    "defect": [first, hist[-1]] if hist else None},
         "roofline": {"bound": "hbm", "kernel": "k_smooth_k<1,*> (fused smoothing step, finest level)", "achieved": achieved, "peak": peak,
@@ -282,7 +304,7 @@ def our_arm(args):
                      "share_of_step": dom["ms"] / ms,
                      "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
         "kernels": prof,
-        "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n + 8,
+        "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": (16 * n + 8) * world,
                 "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -312,6 +334,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-refine", type=int, default=6, help="refinements of the host-side reference run (6 -> 274 625 unknowns)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicate-below", type=int, default=300000,
+                    help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -214,6 +214,31 @@ int uggpu_synth_hierarchy(uggpu_ctx*, int kind, int nx, int ny, int nz, int top,
 /* load vector of the constant right-hand side 1 (0 on Dirichlet rows) into vector `vec` of `level` */
 int uggpu_synth_rhs(uggpu_ctx*, int level, int vec);
 
+/* ---- multi-GPU: one context (one process) per GPU, NCCL over NVLink ---------------------------------------------------
+ * Replaces, for the hot path, the ppif/DDD call sites of SURVEY.md 2.2: the interface exchange of
+ * l_vector_consistent (np/algebra/ugblas.cc:398) becomes a halo copy inside the SpMV-type entry points, the global
+ * sums of ddot/dnrm2 (UG_GlobalSumNDOUBLE, parallel/dddif/support.cc:526) an ncclAllReduce inside the reductions,
+ * coarse-level agglomeration (np/procs/amgtransfer.cc:246) a replicated coarse hierarchy.  All of it is implicit:
+ * the entry points above behave identically on a partitioned hierarchy. */
+int uggpu_comm_unique_id(void *out128);                       /* rank 0: ncclGetUniqueId; broadcast the 128 bytes   */
+int uggpu_comm_init(uggpu_ctx *ctx, int nranks, int rank, const void *id128);
+int uggpu_comm_destroy(uggpu_ctx *ctx);
+int uggpu_comm_size(uggpu_ctx *ctx);
+int uggpu_comm_rank(uggpu_ctx *ctx);
+int64_t uggpu_comm_exchanges(uggpu_ctx *ctx);                 /* halo exchanges issued so far                        */
+/* As uggpu_synth_hierarchy on a px*py*pz rank array (element partition into equal boxes of base cells = RCB of
+ * parallel/dddif/lbrcb.cc:250 on a structured grid; sons inherit, lbrcb.cc:376; shared vectors are owned by the lowest
+ * rank, priority.cc:200).  This rank generates the rows it owns plus ghost columns.  Levels with at most
+ * `replicate_below` rows (and level 0) are held completely by every rank. */
+int uggpu_synth_hierarchy_part(uggpu_ctx*, int kind, int nx, int ny, int nz, int top, int A,
+                               int px, int py, int pz, int rank, int64_t replicate_below);
+int64_t uggpu_level_n_global(uggpu_ctx *ctx, int level);      /* rows of the level over all ranks                    */
+int uggpu_level_is_partitioned(uggpu_ctx *ctx, int level);
+int uggpu_synth_global_ids(uggpu_ctx *ctx, int level, int64_t *ids /* [uggpu_level_n] */);
+/* host-only views of the partition arithmetic (no GPU needed; used by the CPU tests of the multi-rank logic) */
+int uggpu_part_describe(int dim, int cx, int cy, int cz, int px, int py, int pz, int rank, int32_t *out, int cap);
+int uggpu_part_local_index(int dim, int cx, int cy, int cz, int px, int py, int pz, int rank, int x, int y, int z);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,12 @@ class Context:
             raise UggpuError(f"{fn} -> {rc}: {self.L.uggpu_last_error().decode()}")
         return rc
 
+    def call_noctx(self, fn: str, *args):
+        rc = getattr(self.L, fn)(*args)
+        if rc:
+            raise UggpuError(f"{fn} -> {rc}: {self.L.uggpu_last_error().decode()}")
+        return rc
+
     # ---- handles: descriptor names -> small ints (what VECDATA_DESC/MATDATA_DESC pointers are to the numprocs)
     def handle(self, name: str) -> int:
         if name not in self._names:

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_final(size_t count, const d
   block_reduce_store<BS>(acc, out);
 }
 
-int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot)
+int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot, int level)
 {
   double *out = ctx->dres + (size_t)slot * UGGPU_MAX_BS;
   switch (bs) {
@@ -158,6 +158,8 @@ int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot)
     default: k_red_final<3><<<1, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, out); break;
   }
   KCHECK(ctx);
+  // global sum over the ranks (UG_GlobalSumNDOUBLE, parallel/dddif/support.cc:526) where the rows are partitioned
+  if (ctx->comm && level >= 0 && ctx->lev[level].partitioned) UG_TRY(allreduce_sum(ctx, out, (size_t)bs));
   return 0;
 }
 
@@ -174,7 +176,7 @@ static int launch_red(uggpu_ctx *ctx, Level *L, int rowmode, int kind, const dou
   if (kind == RED_DOT) k_red_rows<BS, RED_DOT><<<blocks, RED_THREADS, 0, ctx->stream>>>(L->n, bit, L->ctl, x, y, ctx->partials);
   else k_red_rows<BS, RED_NRM2><<<blocks, RED_THREADS, 0, ctx->stream>>>(L->n, bit, L->ctl, x, y, ctx->partials);
   KCHECK(ctx);
-  return reduce_partials_final(ctx, BS, (size_t)blocks, slot);
+  return reduce_partials_final(ctx, BS, (size_t)blocks, slot, (int)(L - ctx->lev));
 }
 
 int k_reduce(uggpu_ctx *ctx, int level, int rowmode, int kind, const double *x, const double *y, int slot)

@@ -124,6 +124,7 @@ extern "C" int uggpu_ctx_destroy(uggpu_ctx *ctx)
   if (ctx == nullptr) return 0;
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStreamSynchronize(ctx->stream);
+  uggpu_comm_destroy(ctx);
   for (int l = 0; l < UGGPU_MAX_LEVELS; l++)
     if (ctx->lev[l].exists) uggpu_level_destroy(ctx, l);
   if (ctx->partials) dfree(ctx, ctx->partials, ctx->partials_cap);
@@ -199,7 +200,8 @@ extern "C" int uggpu_level_destroy(uggpu_ctx *ctx, int level)
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   size_t n = (size_t)L->n;
   for (auto &kv : L->mats) sell_free(ctx, &kv.second);
-  for (auto &kv : L->vecs) { double *p = kv.second; dfree(ctx, p, n * L->bs); }
+  for (auto &kv : L->vecs) { double *p = kv.second; dfree(ctx, p, vec_count(L)); }
+  level_free_part(ctx, L);
   sell_free(ctx, &L->P);
   sell_free(ctx, &L->R);
   if (L->lu) dfree(ctx, L->lu, (size_t)L->luN * L->luN);
@@ -330,7 +332,7 @@ extern "C" int uggpu_vec_alloc(uggpu_ctx *ctx, int level, int vec)
   if (!L) return UGGPU_ERROR;
   if (L->vecs.count(vec)) return 0;
   double *p = nullptr;
-  size_t cnt = (size_t)L->n * L->bs;
+  size_t cnt = vec_count(L);
   UG_TRY(dalloc(ctx, &p, cnt));
   CUDA_TRY(cudaMemsetAsync(p, 0, (cnt ? cnt : 2) * sizeof(double), ctx->stream));
   L->vecs[vec] = p;
@@ -345,7 +347,7 @@ extern "C" int uggpu_vec_free(uggpu_ctx *ctx, int level, int vec)
   if (it == L->vecs.end()) return 0;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   double *p = it->second;
-  UG_TRY(dfree(ctx, p, (size_t)L->n * L->bs));
+  UG_TRY(dfree(ctx, p, vec_count(L)));
   L->vecs.erase(it);
   return 0;
 }

@@ -254,7 +254,8 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     const int lc = level - 1;
     double *bc = get_vec(ctx, lc, b), *cc = get_vec(ctx, lc, c), *tc = get_vec(ctx, lc, cfg->t);
     if (!bc || !cc || !tc) return UGGPU_DESC_MISMATCH;
-    const bool fuse = lc > cfg->baselevel && cfg->nu1 > 0;
+    // not across the gather level of a multi-GPU hierarchy: there the coarse defect is complete only after the all-reduce
+    const bool fuse = lc > cfg->baselevel && cfg->nu1 > 0 && !(ctx->comm && L->partitioned && !ctx->lev[lc].partitioned);
     UG_TRY(k_restrict(ctx, level, bc, bp, one, fuse, A, tc, cc, sd));
     if (!fuse) UG_TRY(k_vec_op(ctx, lc, 0, VOP_SET, cc, nullptr, Damp{{0.0, 0.0, 0.0}}));   // dset(c,0) iter.cc:7873
     for (int g = 0; g < cfg->gamma; g++) UG_TRY(lmgc_fused(ctx, cfg, lc, c, b, A, fuse && g == 0, nullptr));

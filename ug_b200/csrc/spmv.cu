@@ -115,6 +115,7 @@ int k_dmatmul(uggpu_ctx *ctx, int level, int op, int rowmode, int x, int M, int 
   const double *yp = get_vec(ctx, level, y);
   if (!A || !xp || !yp) return UGGPU_DESC_MISMATCH;
   if (xp == yp) return uggpu_fail(UGGPU_DESC_MISMATCH, "dmatmul: result and operand are the same vector");
+  UG_TRY(halo_exchange(ctx, level, const_cast<double *>(yp)));   // ghost columns of the operand (no-op on one GPU)
   switch (L->bs) {
     case 1: return launch_dmatmul<1>(ctx, L, A, op, rowmode, xp, yp);
     case 2: return launch_dmatmul<2>(ctx, L, A, op, rowmode, xp, yp);
@@ -296,7 +297,7 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const doub
                + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
   k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr);
   KCHECK(ctx);
-  if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot));
+  if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot, (int)(L - ctx->lev)));
   return 0;
 }
 
@@ -330,6 +331,7 @@ int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin
   if (!L || !M) return UGGPU_DESC_MISMATCH;
   if (L->n == 0) return 0;
   if ((flags & SF_TOUT) && tout == tin) return uggpu_fail(UGGPU_ERROR, "smooth step: tout aliases tin");
+  UG_TRY(halo_exchange(ctx, level, const_cast<double *>(tin)));  // ghost columns of the correction (no-op on one GPU)
   switch (L->bs) {
     case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot);
     case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot);

@@ -8,41 +8,35 @@
 // NEW_DEFECT only, the top level nclass 0 and both bits, FULLREFINELEVEL = top, Dirichlet rows are identity
 // rows with their connections kept at value 0 and all VECSKIP bits set), the standard prolongation P
 // (corner nodes weight 1, other nodes the P1/Q1 shape-function values of the father element, zeros dropped) and
-// the restriction R with entries in ascending fine-row order.
+// the restriction R with entries in ascending (global) fine-row order.
 //
-// Meshes: structured nx x ny (x nz) cells on the unit square/cube, rows numbered lexicographically (x fastest).
+// Meshes: structured nx x ny (x nz) cubic cells of size h0 = 1/nx on the box [0,1] x [0,ny/nx] (x [0,nz/nx]), rows
+// numbered lexicographically (x fastest).
 //   P1 simplices: every cell is cut into the 2 (6) Kuhn simplices around the diagonal 0-2 (0-6) (the coarse grids of
 //     SURVEY.md Appendix A); finer levels are again Kuhn triangulations (Bey refinement), so every interior row has the
 //     7 (15) connections along the directions {0,1}^d \ 0 and their negatives.  In 2D this is exactly the mesh UG's
 //     own refinement produces (tests/test_synth.py matches it entry by entry against the golden dump); in 3D UG's
 //     regular rule picks varying octahedron diagonals and ends with 14.6 connections per row on average instead of 15.
 //     P1 Laplace on a Kuhn mesh: diagonal 2d h^(d-2), axis neighbours -h^(d-2), diagonal neighbours 0 (stored).
-//   Q1 cubes (scalar Poisson or 3x3 linear elasticity, E = 1, nu = 0.3): rows assembled on the device from the 8x8
-//     (24x24) element matrix integrated on the host with 2x2x2 Gauss points; 27 block connections per interior row.
+//
+// Multi-GPU: with a Px x Py x Pz rank array (uggpu_synth_hierarchy_part) every rank generates only the rows it owns
+// plus ghost columns (part.h); levels with at most `replicate_below` rows are generated completely on every rank.
+// The arithmetic per row is the same as on one GPU, so partitioned and unpartitioned solves agree bit for bit.
 #include "uggpu_internal.h"
+#include "part.h"
 
 #include <cmath>
 #include <cstring>
 #include <vector>
 
-struct SynthGrid {
+struct SynthParams {
   int dim;
-  int nn[3];        // nodes per direction on this level
-  int nc[3];        // nodes per direction on the next coarser level (transfer only)
   double hpow;      // h^(dim-2)
   double hvol;      // h^dim
 };
 
-__device__ __forceinline__ void node_coords(const SynthGrid &g, int r, int (&x)[3])
-{
-  x[0] = r % g.nn[0];
-  int q = r / g.nn[0];
-  x[1] = q % g.nn[1];
-  x[2] = q / g.nn[1];
-}
 __device__ __forceinline__ bool in_grid(const int (&nn)[3], const int (&x)[3]) { return x[0] >= 0 && x[0] < nn[0] && x[1] >= 0 && x[1] < nn[1] && x[2] >= 0 && x[2] < nn[2]; }
-__device__ __forceinline__ int node_index(const int (&nn)[3], const int (&x)[3]) { return x[0] + nn[0] * (x[1] + nn[1] * x[2]); }
-__device__ __forceinline__ bool on_boundary(const SynthGrid &g, const int (&x)[3])
+__device__ __forceinline__ bool on_boundary(const PartGrid &g, const int (&x)[3])
 {
   for (int d = 0; d < g.dim; d++) if (x[d] == 0 || x[d] == g.nn[d] - 1) return true;
   return false;
@@ -55,22 +49,22 @@ __constant__ int c_kuhn2[3][3] = {{1, 0, 0}, {0, 1, 0}, {1, 1, 0}};
 #define SYNTH_MAXROW 27
 
 // one row of the P1 simplex matrix; returns its length
-__device__ int simplex_row(const SynthGrid &g, int r, int32_t *cols, double *vals)
+__device__ int simplex_row(const SynthParams &sp, const PartGrid &g, int r, int32_t *cols, double *vals)
 {
   int x[3];
-  node_coords(g, r, x);
+  part_row_coords(g, r, x);
   const bool bnd = on_boundary(g, x);
   int len = 0;
-  cols[len] = r; vals[len] = bnd ? 1.0 : 2.0 * g.dim * g.hpow; len++;
-  const int nd = g.dim == 3 ? 7 : 3;
+  cols[len] = r; vals[len] = bnd ? 1.0 : 2.0 * sp.dim * sp.hpow; len++;
+  const int nd = sp.dim == 3 ? 7 : 3;
   for (int k = 0; k < nd; k++) {
-    const int *d = g.dim == 3 ? c_kuhn3[k] : c_kuhn2[k];
+    const int *d = sp.dim == 3 ? c_kuhn3[k] : c_kuhn2[k];
     const bool axis = (d[0] + d[1] + d[2]) == 1;
     for (int sgn = 1; sgn >= -1; sgn -= 2) {
       int y[3] = {x[0] + sgn * d[0], x[1] + sgn * d[1], x[2] + sgn * d[2]};
       if (!in_grid(g.nn, y)) continue;
-      cols[len] = node_index(g.nn, y);
-      vals[len] = (bnd || !axis) ? 0.0 : -g.hpow;
+      cols[len] = part_local_index(g, y);
+      vals[len] = (bnd || !axis) ? 0.0 : -sp.hpow;
       len++;
     }
   }
@@ -78,33 +72,33 @@ __device__ int simplex_row(const SynthGrid &g, int r, int32_t *cols, double *val
 }
 
 // P row of fine node r: corner node -> (father node, 1); else midpoint of the Kuhn edge along its parity vector
-__device__ int simplex_p_row(const SynthGrid &g, int r, int32_t *cols, double *vals)
+__device__ int simplex_p_row(const PartGrid &g, const PartGrid &gc, int r, int32_t *cols, double *vals)
 {
   int x[3];
-  node_coords(g, r, x);
+  part_row_coords(g, r, x);
   int p[3] = {x[0] & 1, x[1] & 1, x[2] & 1};
   if (!(p[0] | p[1] | p[2])) {
     int X[3] = {x[0] >> 1, x[1] >> 1, x[2] >> 1};
-    cols[0] = node_index(g.nc, X); vals[0] = 1.0;
+    cols[0] = part_local_index(gc, X); vals[0] = 1.0;
     return 1;
   }
   int a[3] = {(x[0] - p[0]) >> 1, (x[1] - p[1]) >> 1, (x[2] - p[2]) >> 1};
   int b[3] = {(x[0] + p[0]) >> 1, (x[1] + p[1]) >> 1, (x[2] + p[2]) >> 1};
-  cols[0] = node_index(g.nc, a); vals[0] = 0.5;
-  cols[1] = node_index(g.nc, b); vals[1] = 0.5;
+  cols[0] = part_local_index(gc, a); vals[0] = 0.5;
+  cols[1] = part_local_index(gc, b); vals[1] = 0.5;
   return 2;
 }
 
-// R row of coarse node R: fine nodes 2X+q, q in {all components >= 0} u {all <= 0}, ascending fine index
-__device__ int simplex_r_row(const SynthGrid &g /* fine grid, nc = coarse */, int R, int32_t *cols, double *vals)
+// R row of coarse row R: fine nodes 2X+q, q in {all components >= 0} u {all <= 0}, ascending global fine index.
+// On a replicated coarse level with several ranks only the rows of the nodes this rank would own are filled: the
+// all-reduce that follows the restriction kernel adds the disjoint parts.
+__device__ int simplex_r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int R, int32_t *cols, double *vals)
 {
   int X[3];
-  X[0] = R % g.nc[0];
-  int t = R / g.nc[0];
-  X[1] = t % g.nc[1];
-  X[2] = t / g.nc[1];
+  part_row_coords(gc, R, X);
+  if (gc.replicated && gc.nranks > 1 && !box_has(gc.own, X)) return 0;
   int len = 0;
-  const int z0 = g.dim == 3 ? -1 : 0, z1 = g.dim == 3 ? 1 : 0;
+  const int z0 = sp.dim == 3 ? -1 : 0, z1 = sp.dim == 3 ? 1 : 0;
   for (int qz = z0; qz <= z1; qz++)
     for (int qy = -1; qy <= 1; qy++)
       for (int qx = -1; qx <= 1; qx++) {
@@ -112,7 +106,7 @@ __device__ int simplex_r_row(const SynthGrid &g /* fine grid, nc = coarse */, in
         if (!nonneg && !nonpos) continue;
         int y[3] = {2 * X[0] + qx, 2 * X[1] + qy, 2 * X[2] + qz};
         if (!in_grid(g.nn, y)) continue;
-        cols[len] = node_index(g.nn, y);
+        cols[len] = part_local_index(g, y);
         vals[len] = (qx | qy | qz) ? 0.5 : 1.0;
         len++;
       }
@@ -122,101 +116,125 @@ __device__ int simplex_r_row(const SynthGrid &g /* fine grid, nc = coarse */, in
 enum { GEN_A = 0, GEN_P = 1, GEN_R = 2 };
 
 template <int WHICH>
-__device__ __forceinline__ int gen_row(const SynthGrid &g, int r, int32_t *cols, double *vals)
+__device__ __forceinline__ int gen_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, int32_t *cols, double *vals)
 {
-  if (WHICH == GEN_A) return simplex_row(g, r, cols, vals);
-  if (WHICH == GEN_P) return simplex_p_row(g, r, cols, vals);
-  return simplex_r_row(g, r, cols, vals);
+  if (WHICH == GEN_A) return simplex_row(sp, g, r, cols, vals);
+  if (WHICH == GEN_P) return simplex_p_row(g, gc, r, cols, vals);
+  return simplex_r_row(sp, g, gc, r, cols, vals);
 }
 
 template <int WHICH>
-__global__ void k_synth_len(SynthGrid g, int n, uint16_t *__restrict__ rowlen, int *__restrict__ width)
+__global__ void k_synth_len(SynthParams sp, const PartGrid *__restrict__ g, const PartGrid *__restrict__ gc, int n, uint16_t *__restrict__ rowlen,
+                            int *__restrict__ width, unsigned long long *nnz)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   int32_t cols[SYNTH_MAXROW]; double vals[SYNTH_MAXROW];
   int len = 0;
-  if (r < n) { len = gen_row<WHICH>(g, r, cols, vals); rowlen[r] = (uint16_t)len; }
-  int w = len;
-  for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
-  if ((threadIdx.x & 31) == 0 && (r >> 5) < (n + 31) / 32) width[r >> 5] = w;
+  if (r < n) { len = gen_row<WHICH>(sp, *g, *gc, r, cols, vals); rowlen[r] = (uint16_t)len; }
+  int w = len, s = len;
+  for (int o = 16; o > 0; o >>= 1) { w = max(w, __shfl_xor_sync(0xffffffffu, w, o)); s += __shfl_xor_sync(0xffffffffu, s, o); }
+  if ((threadIdx.x & 31) == 0 && (r >> 5) < (n + 31) / 32) { width[r >> 5] = w; atomicAdd(nnz, (unsigned long long)s); }
 }
 
 template <int WHICH>
-__global__ void k_synth_fill(SynthGrid g, int n, const int64_t *__restrict__ slice_ptr, int32_t *__restrict__ col, double *__restrict__ val)
+__global__ void k_synth_fill(SynthParams sp, const PartGrid *__restrict__ g, const PartGrid *__restrict__ gc, int n, const int64_t *__restrict__ slice_ptr,
+                             int32_t *__restrict__ col, double *__restrict__ val)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   int s = r >> 5, lane = r & 31;
   if (s >= (n + 31) / 32) return;
   int32_t cols[SYNTH_MAXROW]; double vals[SYNTH_MAXROW];
   int len = 0;
-  if (r < n) len = gen_row<WHICH>(g, r, cols, vals);
-  const int64_t sp = slice_ptr[s];
-  const int w = (int)((slice_ptr[s + 1] - sp) >> 5);
+  if (r < n) len = gen_row<WHICH>(sp, *g, *gc, r, cols, vals);
+  const int64_t spt = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - spt) >> 5);
   const int padcol = r < n ? r : 0;
   for (int j = 0; j < w; j++) {
-    col[sp + (int64_t)j * 32 + lane] = j < len ? cols[j] : padcol;
-    val[sp + (int64_t)j * 32 + lane] = j < len ? vals[j] : 0.0;
+    col[spt + (int64_t)j * 32 + lane] = j < len ? cols[j] : padcol;
+    val[spt + (int64_t)j * 32 + lane] = j < len ? vals[j] : 0.0;
   }
 }
 
-__global__ void k_synth_flags(SynthGrid g, int n, bool top, uint8_t *vclass, uint8_t *vnclass, uint8_t *ctl, uint32_t *skip)
+__global__ void k_synth_flags(const PartGrid *__restrict__ g, int n, bool top, uint8_t *vclass, uint8_t *vnclass, uint8_t *ctl, uint32_t *skip)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
-  node_coords(g, r, x);
+  part_row_coords(*g, r, x);
   vclass[r] = 3;
   vnclass[r] = top ? 0 : 3;
   ctl[r] = top ? (UGGPU_CTL_NEW_DEFECT | UGGPU_CTL_FINE_GRID_DOF) : UGGPU_CTL_NEW_DEFECT;
-  skip[r] = on_boundary(g, x) ? 1u : 0u;
+  skip[r] = on_boundary(*g, x) ? 1u : 0u;
 }
 
-__global__ void k_synth_rhs(SynthGrid g, int n, double *b)
+__global__ void k_synth_rhs(SynthParams sp, const PartGrid *__restrict__ g, int n, double *b)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
-  node_coords(g, r, x);
-  b[r] = on_boundary(g, x) ? 0.0 : g.hvol;
+  part_row_coords(*g, r, x);
+  b[r] = on_boundary(*g, x) ? 0.0 : sp.hvol;
+}
+
+// global lexicographic id of every owned row (tests: assemble a global vector from the ranks' parts)
+__global__ void k_synth_gids(const PartGrid *__restrict__ g, int n, int64_t *ids)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int x[3];
+  part_row_coords(*g, r, x);
+  ids[r] = (int64_t)x[0] + (int64_t)g->nn[0] * ((int64_t)x[1] + (int64_t)g->nn[1] * x[2]);
+}
+
+// local indices of the rows to send, neighbour by neighbour (box order = the receiver's ghost order)
+__global__ void k_synth_sendidx(const PartGrid *__restrict__ g, int total, int32_t *idx)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int k = 0;
+  while (i >= g->nb_send_off[k + 1]) k++;
+  int x[3];
+  box_unlex(g->nb_send[k], i - g->nb_send_off[k], x);
+  idx[i] = box_lex(g->own, x);
 }
 
 template <int WHICH>
-static int synth_sell(uggpu_ctx *ctx, const SynthGrid &g, int n, SellMat *out)
+static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g, const PartGrid *d_gc, int n, SellMat *out)
 {
   cudaStream_t st = ctx->stream;
   SellMat m;
   m.n = n; m.bb = 1;
   size_t nsl = (size_t)(n + 31) / 32;
   int *d_width = nullptr;
+  unsigned long long *d_nnz = nullptr, h_nnz = 0;
   UG_TRY(dalloc(ctx, &m.rowlen, (size_t)n));
   UG_TRY(dalloc(ctx, &m.slice_ptr, nsl + 1));
   UG_TRY(dalloc(ctx, &d_width, nsl));
+  UG_TRY(dalloc(ctx, &d_nnz, 1));
+  CUDA_TRY(cudaMemsetAsync(d_nnz, 0, sizeof(unsigned long long), st));
   std::vector<int> width(nsl);
-  std::vector<int64_t> sp(nsl + 1, 0);
+  std::vector<int64_t> sp_host(nsl + 1, 0);
   int blocks = (int)((nsl * 32 + 255) / 256);
-  k_synth_len<WHICH><<<blocks, 256, 0, st>>>(g, n, m.rowlen, d_width);
-  KCHECK(ctx);
+  if (blocks > 0) {
+    k_synth_len<WHICH><<<blocks, 256, 0, st>>>(sp, d_g, d_gc, n, m.rowlen, d_width, d_nnz);
+    KCHECK(ctx);
+  }
   CUDA_TRY(cudaMemcpyAsync(width.data(), d_width, nsl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&h_nnz, d_nnz, sizeof h_nnz, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  // nnz = sum of row lengths: every slice of this structured generator is counted on the host from the widths only
-  // approximately, so the exact count is taken from a reduction over rowlen below.
-  for (size_t s = 0; s < nsl; s++) { sp[s + 1] = sp[s] + (int64_t)width[s] * 32; if (width[s] > m.maxlen) m.maxlen = width[s]; }
-  m.padded = sp[nsl];
+  m.nnz = (int64_t)h_nnz;
+  for (size_t s = 0; s < nsl; s++) { sp_host[s + 1] = sp_host[s] + (int64_t)width[s] * 32; if (width[s] > m.maxlen) m.maxlen = width[s]; }
+  m.padded = sp_host[nsl];
   UG_TRY(dfree(ctx, d_width, nsl));
-  CUDA_TRY(cudaMemcpyAsync(m.slice_ptr, sp.data(), (nsl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  UG_TRY(dfree(ctx, d_nnz, 1));
+  CUDA_TRY(cudaMemcpyAsync(m.slice_ptr, sp_host.data(), (nsl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   UG_TRY(dalloc(ctx, &m.col, (size_t)m.padded));
   UG_TRY(dalloc(ctx, &m.val, (size_t)m.padded));
-  k_synth_fill<WHICH><<<blocks, 256, 0, st>>>(g, n, m.slice_ptr, m.col, m.val);
-  KCHECK(ctx);
-  CUDA_TRY(cudaStreamSynchronize(st));
-  // exact nnz
-  {
-    std::vector<uint16_t> len((size_t)n);
-    CUDA_TRY(cudaMemcpy(len.data(), m.rowlen, (size_t)n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-    int64_t z = 0;
-    for (int i = 0; i < n; i++) z += len[i];
-    m.nnz = z;
+  if (blocks > 0) {
+    k_synth_fill<WHICH><<<blocks, 256, 0, st>>>(sp, d_g, d_gc, n, m.slice_ptr, m.col, m.val);
+    KCHECK(ctx);
   }
+  CUDA_TRY(cudaStreamSynchronize(st));
   *out = m;
   return 0;
 }
@@ -224,49 +242,78 @@ static int synth_sell(uggpu_ctx *ctx, const SynthGrid &g, int n, SellMat *out)
 struct SynthInfo { int kind, dim, cells[3], top; };
 static std::map<uggpu_ctx *, SynthInfo> g_synth;
 
-static SynthGrid make_grid(const SynthInfo &si, int level)
+static SynthParams make_params(const SynthInfo &si, int level)
 {
-  SynthGrid g;
-  g.dim = si.dim;
-  for (int d = 0; d < 3; d++) {
-    g.nn[d] = d < si.dim ? (si.cells[d] << level) + 1 : 1;
-    g.nc[d] = d < si.dim ? (level > 0 ? (si.cells[d] << (level - 1)) + 1 : 1) : 1;
-  }
+  SynthParams p;
+  p.dim = si.dim;
   double h = 1.0 / (double)(si.cells[0] << level);
-  g.hpow = si.dim == 3 ? h : 1.0;
-  g.hvol = si.dim == 3 ? h * h * h : h * h;
-  return g;
+  p.hpow = si.dim == 3 ? h : 1.0;
+  p.hvol = si.dim == 3 ? h * h * h : h * h;
+  return p;
 }
 
-extern "C" int uggpu_synth_hierarchy(uggpu_ctx *ctx, int kind, int nx, int ny, int nz, int top, int A)
+extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int ny, int nz, int top, int A,
+                                          int px, int py, int pz, int rank, int64_t replicate_below)
 {
   if (!ctx) return uggpu_fail(UGGPU_ERROR, "null context");
   if (kind != UGGPU_SYNTH_P1_SIMPLEX) return uggpu_fail(UGGPU_ERROR, "synthetic kind %d not implemented", kind);
   if (nx < 1 || ny < 1 || nz < 0 || top < 0 || top >= UGGPU_MAX_LEVELS) return uggpu_fail(UGGPU_ERROR, "bad synthetic grid %dx%dx%d top %d", nx, ny, nz, top);
-  if (nx != ny || (nz != 0 && nz != nx)) return uggpu_fail(UGGPU_ERROR, "synthetic grids use cubic cells: nx = ny (= nz)");
+  const int dim = nz > 0 ? 3 : 2;
+  if (px < 1 || py < 1 || pz < 1 || (dim == 2 && pz != 1)) return uggpu_fail(UGGPU_ERROR, "bad rank array %dx%dx%d", px, py, pz);
+  const int nranks = px * py * pz;
+  if (rank < 0 || rank >= nranks) return uggpu_fail(UGGPU_ERROR, "rank %d outside the %d-rank array", rank, nranks);
+  if (nranks > 1 && (!ctx->comm || uggpu_comm_size(ctx) != nranks))
+    return uggpu_fail(UGGPU_ERROR, "a %d-rank hierarchy needs uggpu_comm_init with %d ranks first", nranks, nranks);
   SynthInfo si;
-  si.kind = kind; si.dim = nz > 0 ? 3 : 2; si.cells[0] = nx; si.cells[1] = ny; si.cells[2] = nz; si.top = top;
+  si.kind = kind; si.dim = dim; si.cells[0] = nx; si.cells[1] = ny; si.cells[2] = nz; si.top = top;
+  const int P[3] = {px, py, pz};
   for (int l = 0; l <= top; l++) {
-    SynthGrid g = make_grid(si, l);
-    int64_t n64 = (int64_t)g.nn[0] * g.nn[1] * g.nn[2];
-    if (n64 > 2147483000LL) return uggpu_fail(UGGPU_ERROR, "level %d would have %lld rows (int32 row indices)", l, (long long)n64);
+    int cells[3] = {nx << l, ny << l, dim == 3 ? nz << l : 0};
+    int64_t n_global = (int64_t)(cells[0] + 1) * (cells[1] + 1) * (dim == 3 ? cells[2] + 1 : 1);
+    const bool replicated = nranks == 1 || n_global <= replicate_below || l == 0;
+    PartGrid *pg = new PartGrid();
+    if (part_make(pg, dim, cells, P, rank, replicated ? 1 : 0)) { delete pg; return uggpu_fail(UGGPU_ERROR, "level %d: %dx%dx%d cells do not divide over %dx%dx%d ranks", l, cells[0], cells[1], cells[2], px, py, pz); }
+    int64_t n64 = pg->n_own;
+    if (n_global > 2147483000LL && replicated) { delete pg; return uggpu_fail(UGGPU_ERROR, "level %d would have %lld rows (int32 row indices)", l, (long long)n_global); }
     int n = (int)n64;
     UG_TRY(uggpu_level_create(ctx, l, n, 1));
     Level &L = ctx->lev[l];
-    k_synth_flags<<<(n + 255) / 256, 256, 0, ctx->stream>>>(g, n, l == top, L.vclass, L.vnclass, L.ctl, L.skip);
-    KCHECK(ctx);
+    L.part = pg;
+    L.partitioned = !replicated;
+    L.nghost = replicated ? 0 : pg->n_ghost;
+    L.n_global = n_global;
+    UG_TRY(dalloc(ctx, &L.d_part, 1));
+    CUDA_TRY(cudaMemcpyAsync(L.d_part, pg, sizeof(PartGrid), cudaMemcpyHostToDevice, ctx->stream));
+    if (L.partitioned) {
+      L.send_total = pg->nb_send_off[pg->nnb];
+      UG_TRY(dalloc(ctx, &L.d_send_idx, (size_t)L.send_total));
+      if (L.send_total > 0) {
+        k_synth_sendidx<<<(L.send_total + 255) / 256, 256, 0, ctx->stream>>>(L.d_part, L.send_total, L.d_send_idx);
+        KCHECK(ctx);
+      }
+    }
+    SynthParams sp = make_params(si, l);
+    if (n > 0) {
+      k_synth_flags<<<(n + 255) / 256, 256, 0, ctx->stream>>>(L.d_part, n, l == top, L.vclass, L.vnclass, L.ctl, L.skip);
+      KCHECK(ctx);
+    }
     SellMat m;
-    UG_TRY(synth_sell<GEN_A>(ctx, g, n, &m));
+    UG_TRY(synth_sell<GEN_A>(ctx, sp, L.d_part, L.d_part, n, &m));
     L.mats[A] = m;
     if (l > 0) {
-      UG_TRY(synth_sell<GEN_P>(ctx, g, n, &L.P));
-      int ncoarse = ctx->lev[l - 1].n;
-      UG_TRY(synth_sell<GEN_R>(ctx, g, ncoarse, &L.R));
+      Level &Lc = ctx->lev[l - 1];
+      UG_TRY(synth_sell<GEN_P>(ctx, sp, L.d_part, Lc.d_part, n, &L.P));
+      UG_TRY(synth_sell<GEN_R>(ctx, sp, L.d_part, Lc.d_part, Lc.n, &L.R));
     }
   }
   ctx->fullrefinelevel = top;
   g_synth[ctx] = si;
   return 0;
+}
+
+extern "C" int uggpu_synth_hierarchy(uggpu_ctx *ctx, int kind, int nx, int ny, int nz, int top, int A)
+{
+  return uggpu_synth_hierarchy_part(ctx, kind, nx, ny, nz, top, A, 1, 1, 1, 0, 0);
 }
 
 extern "C" int uggpu_synth_rhs(uggpu_ctx *ctx, int level, int vec)
@@ -276,8 +323,38 @@ extern "C" int uggpu_synth_rhs(uggpu_ctx *ctx, int level, int vec)
   Level *L = get_level(ctx, level);
   if (!L) return UGGPU_ERROR;
   UG_TRY(uggpu_vec_alloc(ctx, level, vec));
-  SynthGrid g = make_grid(it->second, level);
-  k_synth_rhs<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(g, L->n, L->vecs[vec]);
+  if (L->n == 0) return 0;
+  SynthParams sp = make_params(it->second, level);
+  k_synth_rhs<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(sp, L->d_part, L->n, L->vecs[vec]);
   KCHECK(ctx);
+  return 0;
+}
+
+extern "C" int64_t uggpu_level_n_global(uggpu_ctx *ctx, int level)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return -1;
+  return L->part ? L->n_global : (int64_t)L->n;
+}
+
+extern "C" int uggpu_level_is_partitioned(uggpu_ctx *ctx, int level)
+{
+  Level *L = get_level(ctx, level);
+  return L ? (L->partitioned ? 1 : 0) : -1;
+}
+
+// ids[n] = global lexicographic index of every row this rank holds on `level`
+extern "C" int uggpu_synth_global_ids(uggpu_ctx *ctx, int level, int64_t *ids)
+{
+  Level *L = get_level(ctx, level);
+  if (!L || !L->d_part) return uggpu_fail(UGGPU_ERROR, "level %d is not synthetic", level);
+  if (L->n == 0) return 0;
+  int64_t *d = nullptr;
+  UG_TRY(dalloc(ctx, &d, (size_t)L->n));
+  k_synth_gids<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(L->d_part, L->n, d);
+  KCHECK(ctx);
+  CUDA_TRY(cudaMemcpyAsync(ids, d, (size_t)L->n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  UG_TRY(dfree(ctx, d, (size_t)L->n));
   return 0;
 }

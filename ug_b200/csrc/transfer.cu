@@ -123,6 +123,10 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->R.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (C->n == 0) return 0;
+  // partitioned fine level: the coarse rows this rank owns gather from fine ghost rows too
+  UG_TRY(halo_exchange(ctx, level, const_cast<double *>(from)));
+  const bool gather = ctx->comm && F->partitioned && !C->partitioned;   // first completely held (replicated) level
+  if (gather && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start not possible across the gather level");
   int blocks = (C->n + TR_THREADS - 1) / TR_THREADS;
   SellView Rv = view(F->R);
   SellView Av = Rv;
@@ -143,6 +147,9 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   }
 #undef RS
   KCHECK(ctx);
+  // every rank filled only the rows of the coarse nodes it would own (the others are 0): summing the disjoint parts
+  // is the gather of the coarse defect onto every rank (agglomeration)
+  if (gather) UG_TRY(allreduce_sum(ctx, to, (size_t)C->n * C->bs));
   return 0;
 }
 
@@ -153,6 +160,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (F->n == 0) return 0;
+  UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
   int blocks = (F->n + TR_THREADS - 1) / TR_THREADS;
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, (double)F->P.nnz * 12.0 + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
   switch (F->bs) {

@@ -56,6 +56,14 @@ struct Level {
   // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
   double *lu = nullptr;
   int luN = 0, luA = -1;
+  // multi-GPU (part.h, comm.cu): n = rows this rank owns; vectors carry nghost extra rows at the tail
+  int nghost = 0;
+  bool partitioned = false;      // rows are split over the ranks (halo exchange + global reductions apply)
+  int64_t n_global = 0;          // rows of the whole level over all ranks
+  struct PartGrid *part = nullptr;      // host copy
+  struct PartGrid *d_part = nullptr;    // device copy
+  int32_t *d_send_idx = nullptr;        // owned rows to pack, grouped by neighbour (PartGrid::nb_send_off)
+  int send_total = 0;
 };
 
 struct uggpu_ctx {
@@ -128,7 +136,7 @@ int k_dmatmul(uggpu_ctx *ctx, int level, int op, int rowmode, int x, int M, int 
 int k_vec_op(uggpu_ctx *ctx, int level, int rowmode, int op, double *x, const double *y, Damp a);
 int k_reduce(uggpu_ctx *ctx, int level, int rowmode, int kind, const double *x, const double *y, int slot);
 int fetch_results(uggpu_ctx *ctx, int nslots);   // dres -> hres, synchronises
-int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot);   // ctx->partials -> dres[slot]
+int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot, int level);   // ctx->partials -> dres[slot] (+ all-reduce on partitioned levels)
 struct LoopItem { int level, rowmode; };
 // (level, rowmode) pairs of one reference loop over levels fl..tl in `mode` (vecloop.ct:22-49)
 int surface_loop(uggpu_ctx *ctx, int fl, int tl, int mode, std::vector<LoopItem> &out);
@@ -145,6 +153,11 @@ int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp dam
 // transfer.cu: fine `level` -> level-1; with fuse: also tout = sdamp*Diag(A_{level-1})^-1 to, czero = 0 on level-1
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp);
 int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp);
+// comm.cu: all are no-ops (return 0) when the context has no communicator or the level is not partitioned
+int halo_exchange(uggpu_ctx *ctx, int level, double *v);                 // owned values -> the neighbours' ghost rows of v
+int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count);           // in place, on the context's stream
+int level_free_part(uggpu_ctx *ctx, Level *L);
+static inline size_t vec_count(const Level *L) { return ((size_t)L->n + (size_t)L->nghost) * (size_t)L->bs; }
 // internal temporary vector handles (never visible through the C-ABI callers' handle space)
 #define UGGPU_VEC_TMP_A (-1001)
 #define UGGPU_VEC_TMP_B (-1002)
