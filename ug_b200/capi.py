@@ -13,7 +13,7 @@ from typing import List
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
+LIB_PATH = os.environ.get("UGGPU_LIB") or os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
 HEADER = os.path.join(ROOT, "include", "uggpu.h")
 
 MAX_BS = 3

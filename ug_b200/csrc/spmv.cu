@@ -9,7 +9,9 @@
 // reference; tensor cores are not used (0.17-0.25 flop/byte: HBM-bound).
 #include "uggpu_internal.h"
 
+#ifndef SPMV_THREADS
 #define SPMV_THREADS 256
+#endif
 
 template <int BS>
 __device__ __forceinline__ void row_product(const SellView &A, int r, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
 #pragma unroll
       for (int i = 0; i < BS; i++) {
         double v = lane < SPMV_THREADS / 32 ? sm[lane][i] : 0.0;
-        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) partials[(size_t)blockIdx.x * BS + i] = v;
       }
     }

@@ -96,7 +96,7 @@ __device__ int simplex_r_row(const SynthParams &sp, const PartGrid &g, const Par
 {
   int X[3];
   part_row_coords(gc, R, X);
-  if (gc.replicated && gc.nranks > 1 && !box_has(gc.own, X)) return 0;
+  if (!g.replicated && gc.replicated && !box_has(gc.own, X)) return 0;   // gather level only (fine partitioned, coarse complete)
   int len = 0;
   const int z0 = sp.dim == 3 ? -1 : 0, z1 = sp.dim == 3 ? 1 : 0;
   for (int qz = z0; qz <= z1; qz++)
