@@ -10,7 +10,7 @@
 #include "uggpu_internal.h"
 
 #ifndef SPMV_THREADS
-#define SPMV_THREADS 256
+#define SPMV_THREADS 128
 #endif
 
 template <int BS>
