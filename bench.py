@@ -32,9 +32,11 @@ METRIC = "vcycle_unknowns_per_s"
 UNIT = "unknowns/s"
 
 
-def workload_name(cells, top, n):
-    return (f"3D P1 Poisson, unit cube, Kuhn tetrahedra, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
-            f"{n} fine unknowns, V(2,2) Jacobi damp 0.6, base solver ls+lu")
+def workload_name(cells, top, n, kind="p1"):
+    what = {"p1": "3D P1 Poisson, unit cube, Kuhn tetrahedra", "q1": "3D Q1 Poisson, unit cube, hexahedra (27-point rows)",
+            "elasticity": "3D Q1 linear elasticity (3x3 blocks, 27 block entries per row), unit cube, hexahedra"}[kind]
+    return (f"{what}, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
+            f"{n} fine unknowns, V(2,2) {'block-' if kind == 'elasticity' else ''}Jacobi damp 0.6, base solver ls+lu")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -177,10 +179,12 @@ def our_arm(args):
         t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
         ctx.call("uggpu_comm_init", world, rank, C.c_char_p(bytes(t.cpu().tolist())))
-    ctx.call("uggpu_synth_hierarchy_part", capi.SYNTH_P1_SIMPLEX, cells * P[0], cells * P[1], cells * P[2], top, A,
+    kind = {"p1": capi.SYNTH_P1_SIMPLEX, "q1": capi.SYNTH_Q1_POISSON, "elasticity": capi.SYNTH_Q1_ELASTICITY}[args.kind]
+    ctx.call("uggpu_synth_hierarchy_part", kind, cells * P[0], cells * P[1], cells * P[2], top, A,
              P[0], P[1], P[2], rank, C.c_int64(args.replicate_below))
-    n = ctx.level_n(top)
-    n_global = int(ctx.L.uggpu_level_n_global(ctx.h, top))
+    bs = ctx.level_bs(top)
+    n = ctx.level_n(top) * bs                      # unknowns (UG counts vector components), this rank
+    n_global = int(ctx.L.uggpu_level_n_global(ctx.h, top)) * bs
     for name in ("x", "b", "c"):
         for l in range(top + 1):
             ctx.alloc(l, name)
@@ -240,7 +244,7 @@ def our_arm(args):
         ms = float(t.item())
 
     # ---- end to end: host vectors in, host vectors out, every step -------------------------------------------------
-    xh = torch.zeros(n, dtype=torch.float64).pin_memory()
+    xh = torch.zeros(n, dtype=torch.float64).pin_memory()      # n counts components: the vectors hold n doubles
     bh = torch.empty(n, dtype=torch.float64).pin_memory()
     ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
     ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
@@ -288,16 +292,16 @@ def our_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(cells, top, n) if world == 1 else
+        "config": {"workload": workload_name(cells, top, n, args.kind) if world == 1 else
                    (f"3D P1 Poisson, box of {P[0]}x{P[1]}x{P[2]} unit cubes (one per GPU), Kuhn tetrahedra, base {cells * P[0]}x{cells * P[1]}x{cells * P[2]} cells, "
                     f"{top + 1} levels, {n_global} fine unknowns ({n} on rank 0), V(2,2) Jacobi damp 0.6, base solver ls+lu"),
                    "parallelism": f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + NCCL halo copies, "
                                   f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
                    "halo_exchanges_total": exchanges,
-                   "cache": "inputs larger than L2 (matrix 24 GB per sweep)",
+                   "cache": "inputs larger than L2 (the finest matrix alone is tens of GB per sweep)",
                    "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2),
                    "defect": [first, hist[-1]] if hist else None},
-        "roofline": {"bound": "hbm", "kernel": "k_smooth_k<1,*> (fused smoothing step, finest level)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"k_smooth_k<{bs},*> (fused smoothing step, finest level)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
                      "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
@@ -334,6 +338,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-refine", type=int, default=6, help="refinements of the host-side reference run (6 -> 274 625 unknowns)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity"],
+                    help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")
     ap.add_argument("--replicate-below", type=int, default=300000,
                     help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()

@@ -19,6 +19,10 @@
 //     regular rule picks varying octahedron diagonals and ends with 14.6 connections per row on average instead of 15.
 //     P1 Laplace on a Kuhn mesh: diagonal 2d h^(d-2), axis neighbours -h^(d-2), diagonal neighbours 0 (stored).
 //
+//   Q1 cubes (scalar Poisson or 3x3 linear elasticity, E = 1, nu = 0.3): rows assembled on the device from the 8x8
+//     (24x24) element matrix integrated on the host with 2x2x2 Gauss points; 27 block connections per interior row;
+//     UG's regular hexahedron rule produces exactly this mesh (tests/test_synth.py matches the golden dump).
+//
 // Multi-GPU: with a Px x Py x Pz rank array (uggpu_synth_hierarchy_part) every rank generates only the rows it owns
 // plus ghost columns (part.h); levels with at most `replicate_below` rows are generated completely on every rank.
 // The arithmetic per row is the same as on one GPU, so partitioned and unpartitioned solves agree bit for bit.
@@ -30,8 +34,10 @@
 #include <vector>
 
 struct SynthParams {
+  int kind;         // UGGPU_SYNTH_*
   int dim;
-  double hpow;      // h^(dim-2)
+  int bs;           // components per node
+  double hpow;      // h^(dim-2): scale of the stiffness entries
   double hvol;      // h^dim
 };
 
@@ -45,17 +51,27 @@ __device__ __forceinline__ bool on_boundary(const PartGrid &g, const int (&x)[3]
 // Kuhn directions in canonical entry order (after the diagonal): +d, -d for d = e1, e2, e3, e1+e2, e2+e3, e1+e3, e1+e2+e3
 __constant__ int c_kuhn3[7][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
 __constant__ int c_kuhn2[3][3] = {{1, 0, 0}, {0, 1, 0}, {1, 1, 0}};
+// Q1 element matrix of the unit cube (h = 1), local node a = ox + 2 oy + 4 oz, row-major (8 bs) x (8 bs); the matrix of
+// a cube of size h is h times this one (gradients ~ 1/h, volume ~ h^3)
+__constant__ double c_ke[24 * 24];
 
 #define SYNTH_MAXROW 27
 
-// one row of the P1 simplex matrix; returns its length
-__device__ int simplex_row(const SynthParams &sp, const PartGrid &g, int r, int32_t *cols, double *vals)
+struct RowGen {
+  int len;
+  int32_t cols[SYNTH_MAXROW];
+  int8_t code[SYNTH_MAXROW];   // hex matrix rows: neighbour offset (qx+1) + 3(qy+1) + 9(qz+1)
+  double w[SYNTH_MAXROW];      // scalar value of the entry (simplex matrix rows, P and R rows)
+};
+
+// one row of the P1 simplex matrix
+__device__ void simplex_row(const SynthParams &sp, const PartGrid &g, int r, RowGen &rg)
 {
   int x[3];
   part_row_coords(g, r, x);
   const bool bnd = on_boundary(g, x);
   int len = 0;
-  cols[len] = r; vals[len] = bnd ? 1.0 : 2.0 * sp.dim * sp.hpow; len++;
+  rg.cols[len] = r; rg.w[len] = bnd ? 1.0 : 2.0 * sp.dim * sp.hpow; len++;
   const int nd = sp.dim == 3 ? 7 : 3;
   for (int k = 0; k < nd; k++) {
     const int *d = sp.dim == 3 ? c_kuhn3[k] : c_kuhn2[k];
@@ -63,64 +79,134 @@ __device__ int simplex_row(const SynthParams &sp, const PartGrid &g, int r, int3
     for (int sgn = 1; sgn >= -1; sgn -= 2) {
       int y[3] = {x[0] + sgn * d[0], x[1] + sgn * d[1], x[2] + sgn * d[2]};
       if (!in_grid(g.nn, y)) continue;
-      cols[len] = part_local_index(g, y);
-      vals[len] = (bnd || !axis) ? 0.0 : -sp.hpow;
+      rg.cols[len] = part_local_index(g, y);
+      rg.w[len] = (bnd || !axis) ? 0.0 : -sp.hpow;
       len++;
     }
   }
-  return len;
+  rg.len = len;
 }
 
-// P row of fine node r: corner node -> (father node, 1); else midpoint of the Kuhn edge along its parity vector
-__device__ int simplex_p_row(const PartGrid &g, const PartGrid &gc, int r, int32_t *cols, double *vals)
+// pattern of one row of a Q1 matrix: diagonal, then the up to 26 lattice neighbours in lexicographic order
+__device__ void hex_row(const SynthParams &sp, const PartGrid &g, int r, RowGen &rg)
 {
   int x[3];
   part_row_coords(g, r, x);
-  int p[3] = {x[0] & 1, x[1] & 1, x[2] & 1};
-  if (!(p[0] | p[1] | p[2])) {
-    int X[3] = {x[0] >> 1, x[1] >> 1, x[2] >> 1};
-    cols[0] = part_local_index(gc, X); vals[0] = 1.0;
-    return 1;
-  }
-  int a[3] = {(x[0] - p[0]) >> 1, (x[1] - p[1]) >> 1, (x[2] - p[2]) >> 1};
-  int b[3] = {(x[0] + p[0]) >> 1, (x[1] + p[1]) >> 1, (x[2] + p[2]) >> 1};
-  cols[0] = part_local_index(gc, a); vals[0] = 0.5;
-  cols[1] = part_local_index(gc, b); vals[1] = 0.5;
-  return 2;
+  int len = 0;
+  rg.cols[len] = r; rg.code[len] = 13; len++;
+  for (int qz = -1; qz <= 1; qz++)
+    for (int qy = -1; qy <= 1; qy++)
+      for (int qx = -1; qx <= 1; qx++) {
+        if (!(qx | qy | qz)) continue;
+        int y[3] = {x[0] + qx, x[1] + qy, x[2] + qz};
+        if (!in_grid(g.nn, y)) continue;
+        rg.cols[len] = part_local_index(g, y);
+        rg.code[len] = (int8_t)((qx + 1) + 3 * (qy + 1) + 9 * (qz + 1));
+        len++;
+      }
+  rg.len = len;
 }
 
-// R row of coarse row R: fine nodes 2X+q, q in {all components >= 0} u {all <= 0}, ascending global fine index.
-// On a replicated coarse level with several ranks only the rows of the nodes this rank would own are filled: the
-// all-reduce that follows the restriction kernel adds the disjoint parts.
-__device__ int simplex_r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int R, int32_t *cols, double *vals)
+// bs x bs block of the Q1 matrix between node x and its neighbour `code`: sum of the element matrices of the (up to 8)
+// cells containing both, in fixed (oz, oy, ox) order; Dirichlet rows are identity rows
+__device__ void hex_block(const SynthParams &sp, const PartGrid &g, const int (&x)[3], int code, double *blk)
+{
+  const int bs = sp.bs, ld = 8 * bs;
+  for (int k = 0; k < bs * bs; k++) blk[k] = 0.0;
+  if (on_boundary(g, x)) {
+    if (code == 13) for (int i = 0; i < bs; i++) blk[i * bs + i] = 1.0;
+    return;
+  }
+  const int q[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+  for (int oz = 0; oz <= 1; oz++)
+    for (int oy = 0; oy <= 1; oy++)
+      for (int ox = 0; ox <= 1; ox++) {
+        const int o[3] = {ox, oy, oz};
+        bool ok = true;
+        int b[3];
+        for (int d = 0; d < 3; d++) {
+          int c = x[d] - o[d];
+          if (c < 0 || c > g.nn[d] - 2) ok = false;
+          b[d] = o[d] + q[d];
+          if (b[d] < 0 || b[d] > 1) ok = false;
+        }
+        if (!ok) continue;
+        const int la = ox + 2 * oy + 4 * oz, lb = b[0] + 2 * b[1] + 4 * b[2];
+        for (int i = 0; i < bs; i++)
+          for (int j = 0; j < bs; j++) blk[i * bs + j] += c_ke[(la * bs + i) * ld + lb * bs + j];
+      }
+  for (int k = 0; k < bs * bs; k++) blk[k] *= sp.hpow;
+}
+
+// P row of fine node r.  Simplices: corner node -> (father node, 1), else the midpoint of the Kuhn edge along its parity
+// vector.  Cubes: trilinear weights 2^-|p| of the 2^|p| coarse nodes around it (lexicographic).
+__device__ void p_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, RowGen &rg)
+{
+  int x[3];
+  part_row_coords(g, r, x);
+  const int p[3] = {x[0] & 1, x[1] & 1, x[2] & 1};
+  const int np = p[0] + p[1] + p[2];
+  if (np == 0) {
+    int X[3] = {x[0] >> 1, x[1] >> 1, x[2] >> 1};
+    rg.cols[0] = part_local_index(gc, X); rg.w[0] = 1.0; rg.len = 1;
+    return;
+  }
+  if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) {
+    int a[3] = {(x[0] - p[0]) >> 1, (x[1] - p[1]) >> 1, (x[2] - p[2]) >> 1};
+    int b[3] = {(x[0] + p[0]) >> 1, (x[1] + p[1]) >> 1, (x[2] + p[2]) >> 1};
+    rg.cols[0] = part_local_index(gc, a); rg.w[0] = 0.5;
+    rg.cols[1] = part_local_index(gc, b); rg.w[1] = 0.5;
+    rg.len = 2;
+    return;
+  }
+  const double w = np == 1 ? 0.5 : (np == 2 ? 0.25 : 0.125);
+  int len = 0;
+  for (int ez = 0; ez <= p[2]; ez++)
+    for (int ey = 0; ey <= p[1]; ey++)
+      for (int ex = 0; ex <= p[0]; ex++) {
+        int X[3] = {(x[0] - p[0]) / 2 + ex, (x[1] - p[1]) / 2 + ey, (x[2] - p[2]) / 2 + ez};
+        rg.cols[len] = part_local_index(gc, X); rg.w[len] = w; len++;
+      }
+  rg.len = len;
+}
+
+// R row of coarse row R: fine nodes 2X+q in ascending global fine index.  Simplices: q in {all components >= 0} u
+// {all <= 0} (the Kuhn edges at X), weight 1/2; cubes: all q in {-1,0,1}^3, weight 2^-|q|.
+// On the gather level of a multi-GPU hierarchy (fine partitioned, coarse complete) only the rows of the nodes this rank
+// would own are filled: the all-reduce that follows the restriction kernel adds the disjoint parts.
+__device__ void r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int R, RowGen &rg)
 {
   int X[3];
   part_row_coords(gc, R, X);
-  if (!g.replicated && gc.replicated && !box_has(gc.own, X)) return 0;   // gather level only (fine partitioned, coarse complete)
+  rg.len = 0;
+  if (!g.replicated && gc.replicated && !box_has(gc.own, X)) return;
   int len = 0;
   const int z0 = sp.dim == 3 ? -1 : 0, z1 = sp.dim == 3 ? 1 : 0;
   for (int qz = z0; qz <= z1; qz++)
     for (int qy = -1; qy <= 1; qy++)
       for (int qx = -1; qx <= 1; qx++) {
-        const bool nonneg = qx >= 0 && qy >= 0 && qz >= 0, nonpos = qx <= 0 && qy <= 0 && qz <= 0;
-        if (!nonneg && !nonpos) continue;
+        if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) {
+          const bool nonneg = qx >= 0 && qy >= 0 && qz >= 0, nonpos = qx <= 0 && qy <= 0 && qz <= 0;
+          if (!nonneg && !nonpos) continue;
+        }
         int y[3] = {2 * X[0] + qx, 2 * X[1] + qy, 2 * X[2] + qz};
         if (!in_grid(g.nn, y)) continue;
-        cols[len] = part_local_index(g, y);
-        vals[len] = (qx | qy | qz) ? 0.5 : 1.0;
+        const int nq = (qx != 0) + (qy != 0) + (qz != 0);
+        rg.cols[len] = part_local_index(g, y);
+        rg.w[len] = sp.kind == UGGPU_SYNTH_P1_SIMPLEX ? (nq ? 0.5 : 1.0) : (nq == 0 ? 1.0 : (nq == 1 ? 0.5 : (nq == 2 ? 0.25 : 0.125)));
         len++;
       }
-  return len;
+  rg.len = len;
 }
 
 enum { GEN_A = 0, GEN_P = 1, GEN_R = 2 };
 
 template <int WHICH>
-__device__ __forceinline__ int gen_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, int32_t *cols, double *vals)
+__device__ __forceinline__ void gen_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, RowGen &rg)
 {
-  if (WHICH == GEN_A) return simplex_row(sp, g, r, cols, vals);
-  if (WHICH == GEN_P) return simplex_p_row(g, gc, r, cols, vals);
-  return simplex_r_row(sp, g, gc, r, cols, vals);
+  if (WHICH == GEN_A) { if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) simplex_row(sp, g, r, rg); else hex_row(sp, g, r, rg); }
+  else if (WHICH == GEN_P) p_row(sp, g, gc, r, rg);
+  else r_row(sp, g, gc, r, rg);
 }
 
 template <int WHICH>
@@ -128,10 +214,10 @@ __global__ void k_synth_len(SynthParams sp, const PartGrid *__restrict__ g, cons
                             int *__restrict__ width, unsigned long long *nnz)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  int32_t cols[SYNTH_MAXROW]; double vals[SYNTH_MAXROW];
-  int len = 0;
-  if (r < n) { len = gen_row<WHICH>(sp, *g, *gc, r, cols, vals); rowlen[r] = (uint16_t)len; }
-  int w = len, s = len;
+  RowGen rg;
+  rg.len = 0;
+  if (r < n) { gen_row<WHICH>(sp, *g, *gc, r, rg); rowlen[r] = (uint16_t)rg.len; }
+  int w = rg.len, s = rg.len;
   for (int o = 16; o > 0; o >>= 1) { w = max(w, __shfl_xor_sync(0xffffffffu, w, o)); s += __shfl_xor_sync(0xffffffffu, s, o); }
   if ((threadIdx.x & 31) == 0 && (r >> 5) < (n + 31) / 32) { width[r >> 5] = w; atomicAdd(nnz, (unsigned long long)s); }
 }
@@ -143,19 +229,26 @@ __global__ void k_synth_fill(SynthParams sp, const PartGrid *__restrict__ g, con
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   int s = r >> 5, lane = r & 31;
   if (s >= (n + 31) / 32) return;
-  int32_t cols[SYNTH_MAXROW]; double vals[SYNTH_MAXROW];
-  int len = 0;
-  if (r < n) len = gen_row<WHICH>(sp, *g, *gc, r, cols, vals);
+  RowGen rg;
+  rg.len = 0;
+  if (r < n) gen_row<WHICH>(sp, *g, *gc, r, rg);
+  const bool blocks = WHICH == GEN_A && sp.kind != UGGPU_SYNTH_P1_SIMPLEX;
+  const int bb = blocks ? sp.bs * sp.bs : 1;
+  int x[3] = {0, 0, 0};
+  if (blocks && r < n) part_row_coords(*g, r, x);
   const int64_t spt = slice_ptr[s];
   const int w = (int)((slice_ptr[s + 1] - spt) >> 5);
   const int padcol = r < n ? r : 0;
   for (int j = 0; j < w; j++) {
-    col[spt + (int64_t)j * 32 + lane] = j < len ? cols[j] : padcol;
-    val[spt + (int64_t)j * 32 + lane] = j < len ? vals[j] : 0.0;
+    col[spt + (int64_t)j * 32 + lane] = j < rg.len ? rg.cols[j] : padcol;
+    double blk[UGGPU_MAX_BS * UGGPU_MAX_BS];
+    if (j < rg.len) { if (blocks) hex_block(sp, *g, x, rg.code[j], blk); else blk[0] = rg.w[j]; }
+    else for (int k = 0; k < bb; k++) blk[k] = 0.0;
+    for (int k = 0; k < bb; k++) val[(spt + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane] = blk[k];
   }
 }
 
-__global__ void k_synth_flags(const PartGrid *__restrict__ g, int n, bool top, uint8_t *vclass, uint8_t *vnclass, uint8_t *ctl, uint32_t *skip)
+__global__ void k_synth_flags(const PartGrid *__restrict__ g, int n, int bs, bool top, uint8_t *vclass, uint8_t *vnclass, uint8_t *ctl, uint32_t *skip)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -164,16 +257,22 @@ __global__ void k_synth_flags(const PartGrid *__restrict__ g, int n, bool top, u
   vclass[r] = 3;
   vnclass[r] = top ? 0 : 3;
   ctl[r] = top ? (UGGPU_CTL_NEW_DEFECT | UGGPU_CTL_FINE_GRID_DOF) : UGGPU_CTL_NEW_DEFECT;
-  skip[r] = on_boundary(*g, x) ? 1u : 0u;
+  skip[r] = on_boundary(*g, x) ? ((1u << bs) - 1u) : 0u;
 }
 
+// load vector: scalar problems f = 1; elasticity: unit gravity on the last component (as oracle/ug_driver.cc assembles it)
 __global__ void k_synth_rhs(SynthParams sp, const PartGrid *__restrict__ g, int n, double *b)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
   part_row_coords(*g, r, x);
-  b[r] = on_boundary(*g, x) ? 0.0 : sp.hvol;
+  const bool bnd = on_boundary(*g, x);
+  for (int i = 0; i < sp.bs; i++) {
+    double v = 0.0;
+    if (!bnd) { if (sp.bs == 1) v = sp.hvol; else if (i == sp.bs - 1) v = -sp.hvol; }
+    b[(size_t)r * sp.bs + i] = v;
+  }
 }
 
 // global lexicographic id of every owned row (tests: assemble a global vector from the ranks' parts)
@@ -203,7 +302,7 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
 {
   cudaStream_t st = ctx->stream;
   SellMat m;
-  m.n = n; m.bb = 1;
+  m.n = n; m.bb = (WHICH == GEN_A) ? sp.bs * sp.bs : 1;
   size_t nsl = (size_t)(n + 31) / 32;
   int *d_width = nullptr;
   unsigned long long *d_nnz = nullptr, h_nnz = 0;
@@ -229,7 +328,7 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
   UG_TRY(dfree(ctx, d_nnz, 1));
   CUDA_TRY(cudaMemcpyAsync(m.slice_ptr, sp_host.data(), (nsl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   UG_TRY(dalloc(ctx, &m.col, (size_t)m.padded));
-  UG_TRY(dalloc(ctx, &m.val, (size_t)m.padded));
+  UG_TRY(dalloc(ctx, &m.val, (size_t)m.padded * m.bb));
   if (blocks > 0) {
     k_synth_fill<WHICH><<<blocks, 256, 0, st>>>(sp, d_g, d_gc, n, m.slice_ptr, m.col, m.val);
     KCHECK(ctx);
@@ -239,12 +338,42 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
   return 0;
 }
 
+// Q1 element matrix of the unit cube with 2x2x2 Gauss points, exactly as oracle/ug_driver.cc assembles it:
+// scalar: grad N_a . grad N_b;  elasticity: lam g_a[i] g_b[j] + mu g_a[j] g_b[i] + delta_ij mu g_a . g_b  (E = 1, nu = 0.3)
+static void hex_element_matrix(int bs, double *ke /* (8 bs)^2 */)
+{
+  const double E = 1.0, nu = 0.3, lam = E * nu / ((1 + nu) * (1 - 2 * nu)), mu = E / (2 * (1 + nu));
+  const double gp[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+  const int ld = 8 * bs;
+  for (int k = 0; k < ld * ld; k++) ke[k] = 0.0;
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++) {
+    const double xi[3] = {gp[a], gp[b], gp[c]};
+    double G[8][3];
+    for (int n = 0; n < 8; n++) {
+      const int o[3] = {n & 1, (n >> 1) & 1, (n >> 2) & 1};
+      double f[3], df[3];
+      for (int d = 0; d < 3; d++) { f[d] = o[d] ? xi[d] : 1.0 - xi[d]; df[d] = o[d] ? 1.0 : -1.0; }
+      G[n][0] = df[0] * f[1] * f[2]; G[n][1] = f[0] * df[1] * f[2]; G[n][2] = f[0] * f[1] * df[2];
+    }
+    const double w = 1.0 / 8.0;
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) {
+      double dot = G[i][0] * G[j][0] + G[i][1] * G[j][1] + G[i][2] * G[j][2];
+      if (bs == 1) ke[i * ld + j] += w * dot;
+      else
+        for (int p = 0; p < 3; p++) for (int q = 0; q < 3; q++)
+          ke[(i * 3 + p) * ld + j * 3 + q] += w * (lam * G[i][p] * G[j][q] + mu * G[i][q] * G[j][p] + (p == q ? mu * dot : 0.0));
+    }
+  }
+}
+
 struct SynthInfo { int kind, dim, cells[3], top; };
 static std::map<uggpu_ctx *, SynthInfo> g_synth;
 
 static SynthParams make_params(const SynthInfo &si, int level)
 {
   SynthParams p;
+  p.kind = si.kind;
+  p.bs = si.kind == UGGPU_SYNTH_Q1_ELASTICITY ? 3 : 1;
   p.dim = si.dim;
   double h = 1.0 / (double)(si.cells[0] << level);
   p.hpow = si.dim == 3 ? h : 1.0;
@@ -256,7 +385,9 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
                                           int px, int py, int pz, int rank, int64_t replicate_below)
 {
   if (!ctx) return uggpu_fail(UGGPU_ERROR, "null context");
-  if (kind != UGGPU_SYNTH_P1_SIMPLEX) return uggpu_fail(UGGPU_ERROR, "synthetic kind %d not implemented", kind);
+  if (kind != UGGPU_SYNTH_P1_SIMPLEX && kind != UGGPU_SYNTH_Q1_POISSON && kind != UGGPU_SYNTH_Q1_ELASTICITY)
+    return uggpu_fail(UGGPU_ERROR, "synthetic kind %d not implemented", kind);
+  if (kind != UGGPU_SYNTH_P1_SIMPLEX && nz <= 0) return uggpu_fail(UGGPU_ERROR, "Q1 hierarchies are generated in 3D only");
   if (nx < 1 || ny < 1 || nz < 0 || top < 0 || top >= UGGPU_MAX_LEVELS) return uggpu_fail(UGGPU_ERROR, "bad synthetic grid %dx%dx%d top %d", nx, ny, nz, top);
   const int dim = nz > 0 ? 3 : 2;
   if (px < 1 || py < 1 || pz < 1 || (dim == 2 && pz != 1)) return uggpu_fail(UGGPU_ERROR, "bad rank array %dx%dx%d", px, py, pz);
@@ -267,6 +398,13 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
   SynthInfo si;
   si.kind = kind; si.dim = dim; si.cells[0] = nx; si.cells[1] = ny; si.cells[2] = nz; si.top = top;
   const int P[3] = {px, py, pz};
+  const int bs = kind == UGGPU_SYNTH_Q1_ELASTICITY ? 3 : 1;
+  if (kind != UGGPU_SYNTH_P1_SIMPLEX) {
+    std::vector<double> ke((size_t)(8 * bs) * (8 * bs));
+    hex_element_matrix(bs, ke.data());
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_ke, ke.data(), ke.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   for (int l = 0; l <= top; l++) {
     int cells[3] = {nx << l, ny << l, dim == 3 ? nz << l : 0};
     int64_t n_global = (int64_t)(cells[0] + 1) * (cells[1] + 1) * (dim == 3 ? cells[2] + 1 : 1);
@@ -276,7 +414,7 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
     int64_t n64 = pg->n_own;
     if (n_global > 2147483000LL && replicated) { delete pg; return uggpu_fail(UGGPU_ERROR, "level %d would have %lld rows (int32 row indices)", l, (long long)n_global); }
     int n = (int)n64;
-    UG_TRY(uggpu_level_create(ctx, l, n, 1));
+    UG_TRY(uggpu_level_create(ctx, l, n, bs));
     Level &L = ctx->lev[l];
     L.part = pg;
     L.partitioned = !replicated;
@@ -294,7 +432,7 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
     }
     SynthParams sp = make_params(si, l);
     if (n > 0) {
-      k_synth_flags<<<(n + 255) / 256, 256, 0, ctx->stream>>>(L.d_part, n, l == top, L.vclass, L.vnclass, L.ctl, L.skip);
+      k_synth_flags<<<(n + 255) / 256, 256, 0, ctx->stream>>>(L.d_part, n, bs, l == top, L.vclass, L.vnclass, L.ctl, L.skip);
       KCHECK(ctx);
     }
     SellMat m;
