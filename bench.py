@@ -40,18 +40,49 @@ def workload_name(cells, top, n, kind="p1"):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def run_reference_cpu(refine: int, cycles: int):
+def host_replicas(per_replica_gb: float = 1.0) -> int:
+    """How many independent single-threaded UG replicas this host runs at once: one per core the process may use,
+    bounded by memory (a 65^3 hierarchy needs ~0.7 GB in UG's data structures) and by 64."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        with open("/proc/meminfo") as f:
+            avail_gb = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable")) / 1e6
+    except Exception:
+        avail_gb = 8.0
+    return max(1, min(cores, int(avail_gb * 0.6 / per_replica_gb), 64))
+
+
+def run_reference_cpu(refine: int, cycles: int, replicas: int = 0):
     """Times the UNMODIFIED reference (oracle/_ref/ugoracle3: UG's own ls+lmgc+jac+transfer numprocs on its VECTOR/
-    MATRIX lists) on this host.  UG is single-threaded (its only parallel mode is MPI, not installed): 1 core."""
+    MATRIX lists) on this host.  UG is single-threaded (its only parallel mode is MPI, not installed), so all host cores
+    are used the way an MPI run would use them at best: `replicas` independent copies of the same problem run
+    concurrently (rendezvous after the hierarchy is built, oracle/ug_driver.cc --barrier) and their throughputs add up."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ugoracle3")
     if not os.path.exists(exe):
         return None
-    out = subprocess.run([exe, "--grid", "tet", "--refine", str(refine), "--damp", "0.6", "--time", "--cycles", str(cycles), "--reps", "3"],
-                         capture_output=True, text=True, timeout=1500)
-    for line in out.stdout.splitlines():
-        if line.startswith('{"kind"'):
-            return json.loads(line)
-    raise RuntimeError("reference run produced no result line:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+    replicas = replicas or host_replicas()
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([exe, "--grid", "tet", "--refine", str(refine), "--damp", "0.6", "--time", "--cycles", str(cycles),
+                                   "--reps", "1", "--barrier", d, str(replicas), str(i)],
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for i in range(replicas)]
+        outs = [p.communicate(timeout=1500) for p in procs]
+    res = []
+    for so, se in outs:
+        for line in so.splitlines():
+            if line.startswith('{"kind"'):
+                res.append(json.loads(line))
+                break
+        else:
+            raise RuntimeError("reference run produced no result line:\n" + so[-2000:] + se[-2000:])
+    r = dict(res[0])
+    r["cores"] = replicas
+    r["vcycle_unknowns_per_s"] = sum(x["vcycle_unknowns_per_s"] for x in res)
+    r["s_per_cycle"] = max(x["s_per_cycle"] for x in res)
+    r["per_core_unknowns_per_s"] = r["vcycle_unknowns_per_s"] / replicas
+    return r
 
 
 def run_port_cpu(cells: int, top: int, cycles: int):
@@ -74,7 +105,7 @@ def run_port_cpu(cells: int, top: int, cycles: int):
     its, _, _ = be.solve(top, "x", "b", cfg, cycles)
     dt = time.perf_counter() - t0
     n = hier.levels[-1].n
-    return {"kind": "port", "cores": 1, "unknowns": n, "cycles": its, "s_per_cycle": dt / its, "vcycle_unknowns_per_s": n * its / dt}
+    return {"kind": "port", "cores": 1, "levels": top + 1, "unknowns": n, "cycles": its, "s_per_cycle": dt / its, "vcycle_unknowns_per_s": n * its / dt}
 
 
 def reference_arm(args):
@@ -82,21 +113,22 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cycles = max(1, min(args.steps, 20))
-    r = run_reference_cpu(args.cpu_refine, cycles)
+    r = run_reference_cpu(args.cpu_refine, cycles, args.cpu_replicas)
     kind = "reference"
     if r is None:
         r = run_port_cpu(1, 5, cycles)
         kind = "port"
     n = r["unknowns"]
     sample = (f"{'UG 3.12.1 ls+lmgc+jac+transfer' if kind == 'reference' else 'oracle/ugport.c'}: {r['cycles']} V(2,2) cycles on a "
-              f"{r.get('levels', '?')}-level unit-cube tet hierarchy with {n} fine unknowns (largest the host builds in ~10 s)")
+              f"{r.get('levels', '?')}-level unit-cube tet hierarchy with {n} fine unknowns (largest the host builds in ~10 s), "
+              f"{r['cores']} concurrent single-threaded replica(s), throughputs added")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["vcycle_unknowns_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["cycles"], "warmup": 0, "ms_per_step": r["s_per_cycle"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.cells, args.top, (args.cells * 2 ** args.top + 1) ** 3),
                    "measured_on": sample},
-        "cpu_baseline": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -314,14 +346,15 @@ def our_arm(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
-        r = run_reference_cpu(args.cpu_refine, 5)
+        r = run_reference_cpu(args.cpu_refine, 5, args.cpu_replicas)
         kind = "reference"
         if r is None:
             r = run_port_cpu(1, 5, 5)
             kind = "port"
-        line["cpu_baseline"] = {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": 1, "kind": kind,
+        line["cpu_baseline"] = {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": r["cores"], "kind": kind,
                                 "sample": f"{r['cycles']} V(2,2) cycles, {r['unknowns']} fine unknowns, "
-                                          + ("unmodified UG 3.12.1 numprocs (oracle/_ref/ugoracle3), single-threaded" if kind == "reference" else "oracle/ugport.c")}
+                                          + (f"unmodified UG 3.12.1 numprocs (oracle/_ref/ugoracle3), {r['cores']} concurrent single-threaded "
+                                             f"replicas (UG's only parallel mode is MPI), throughputs added" if kind == "reference" else "oracle/ugport.c")}
     print(json.dumps(line))
     ctx.close()
     return 0
@@ -337,6 +370,7 @@ def main():
     ap.add_argument("--top", type=int, default=7, help="number of uniform refinements (levels - 1)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-refine", type=int, default=6, help="refinements of the host-side reference run (6 -> 274 625 unknowns)")
+    ap.add_argument("--cpu-replicas", type=int, default=0, help="concurrent single-threaded reference replicas (0 = one per host core, memory permitting)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity"],
                     help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")

@@ -104,6 +104,9 @@ int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *
 int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat);
 /* entries actually stored on the device (SELL-32 slices padded to their longest row) */
 int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat);
+/* int32 column words one pass over the matrix reads: slices whose rows all have the same column distances store one
+ * word per slice column instead of one per entry (lossless; uggpu_mat_get returns the original indices) */
+int64_t uggpu_mat_col_words(uggpu_ctx *ctx, int level, int mat);
 int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
 /* Standard (geometric) transfer stencils between `level` and level-1 (np/algebra/transgrid.cc:117-336):
  * P: p_rowptr[n_fine+1], p_col (coarse row), p_w (GNs weight, zeros dropped, corner order);

@@ -92,7 +92,8 @@ struct Opt {
   std::string grid = (DIM == 3) ? "tet" : "tri";
   int bs = 1, refine = 3, adapt = 0, nu1 = 2, nu2 = 2, gamma = 1, cycles = 10, reps = 5;
   double damp = (DIM == 3) ? 0.6 : 0.8;
-  std::string dump, gpu;
+  std::string dump, gpu, barrier_dir;   // barrier_dir: --replicas rendezvous (see time_reference)
+  int barrier_n = 0, barrier_id = 0;
   bool ops = false, solve = false, timeit = false, quiet = true;
 };
 
@@ -478,7 +479,26 @@ static void dump_solve(const Opt &o)
   printf("\n");
 }
 
-// CPU baseline: time the reference's own solver (1 core; UG is single-threaded)
+// Rendezvous of concurrently started replicas (bench.py runs one per host core, UG being single-threaded): every
+// replica drops a file when its hierarchy is built and waits for all the others, so the timed solves overlap.
+static void replica_barrier(const Opt &o)
+{
+  if (o.barrier_dir.empty() || o.barrier_n <= 1) return;
+  char nm[512];
+  snprintf(nm, sizeof nm, "%s/ready.%d", o.barrier_dir.c_str(), o.barrier_id);
+  FILE *f = fopen(nm, "w"); if (f) fclose(f);
+  for (int tries = 0; tries < 600000; tries++) {
+    int have = 0;
+    for (int i = 0; i < o.barrier_n; i++) {
+      snprintf(nm, sizeof nm, "%s/ready.%d", o.barrier_dir.c_str(), i);
+      FILE *g = fopen(nm, "r"); if (g) { fclose(g); have++; }
+    }
+    if (have >= o.barrier_n) return;
+    struct timespec ts = {0, 2000000}; nanosleep(&ts, NULL);
+  }
+}
+
+// CPU baseline: time the reference's own solver (1 core per process; UG is single-threaded)
 static void time_reference(const Opt &o)
 {
   int top = TOPLEVEL(mg);
@@ -493,6 +513,7 @@ static void time_reference(const Opt &o)
   (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
   VEC_SCALAR abslimit, red;
   for (int i = 0; i < MAX_VEC_COMP; i++) { abslimit[i] = 1e-30; red[i] = 1e-30; }
+  replica_barrier(o);
   double t0 = now();
   (*ls->Solver)(ls, top, vx, vb, mA, abslimit, red, &lr);
   double t1 = now();
@@ -530,6 +551,7 @@ int main(int argc, char **argv)
     else if (a == "--nu1") o.nu1 = atoi(nxt().c_str()); else if (a == "--nu2") o.nu2 = atoi(nxt().c_str());
     else if (a == "--gamma") o.gamma = atoi(nxt().c_str()); else if (a == "--cycles") o.cycles = atoi(nxt().c_str());
     else if (a == "--reps") o.reps = atoi(nxt().c_str());
+    else if (a == "--barrier") { o.barrier_dir = nxt(); o.barrier_n = atoi(nxt().c_str()); o.barrier_id = atoi(nxt().c_str()); }
     else if (a == "--damp") o.damp = atof(nxt().c_str()); else if (a == "--dump") o.dump = nxt();
     else if (a == "--ops") o.ops = true; else if (a == "--solve") o.solve = true; else if (a == "--time") o.timeit = true;
     else if (a == "--verbose") o.quiet = false; else if (a == "--gpu") o.gpu = nxt();

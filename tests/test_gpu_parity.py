@@ -13,9 +13,12 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
-def gpu_backend(golden, request):
+def gpu_backend(golden, request, monkeypatch):
     from backends import GpuBackend
     fused = getattr(request, "param", 1)
+    if fused == 2:      # fused schedule with the bulk-copy (TMA) staged smoothing kernel forced onto every scalar level
+        monkeypatch.setenv("UGGPU_TMA", "1"); monkeypatch.setenv("UGGPU_TMA_MIN_ROWS", "0")
+        fused = 1
     be = GpuBackend(golden, fused=fused)
     yield be
     be.close()
@@ -40,7 +43,7 @@ def test_gpu_ops_bitexact(gpu_backend, golden):
     assert n > 20
 
 
-@pytest.mark.parametrize("gpu_backend", [0, 1], indirect=True, ids=["per-call", "fused"])
+@pytest.mark.parametrize("gpu_backend", [0, 1, 2], indirect=True, ids=["per-call", "fused", "fused-tma"])
 def test_gpu_cycle_and_solve(gpu_backend, golden):
     n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
     assert n > 10

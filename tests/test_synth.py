@@ -21,6 +21,11 @@ def _synth(cells, dim, top, kind=capi.SYNTH_P1_SIMPLEX):
     return ctx
 
 
+@pytest.fixture(params=["0", "1000000000"], ids=["tma", "thread-per-row"])
+def tma_rows(request):
+    return request.param
+
+
 def _coords(cells, dim, level):
     nn = cells * 2 ** level + 1
     idx = np.arange(nn ** dim)
@@ -71,7 +76,8 @@ def test_synth_equals_reference_hierarchy(name, dim, kind):
 
 @pytest.mark.parametrize("cells,dim,top,kind", [(2, 3, 3, 0), (1, 3, 4, 0), (3, 2, 4, 0), (2, 3, 3, 1), (1, 3, 3, 2), (3, 3, 2, 2)],
                          ids=["P1-3d-17^3", "P1-3d-17^3-base1", "P1-2d-49^2", "Q1-17^3", "elast-9^3", "elast-13^3"])
-def test_synth_solve_bitexact_vs_port(cells, dim, top, kind):
+def test_synth_solve_bitexact_vs_port(cells, dim, top, kind, monkeypatch, tma_rows):
+    monkeypatch.setenv("UGGPU_TMA", "1"); monkeypatch.setenv("UGGPU_TMA_MIN_ROWS", tma_rows)     # "0": every scalar level runs the bulk-copy staged smoothing kernel
     from backends import GpuBackend
     from oracle.ugport import PortBackend
     ctx = _synth(cells, dim, top, kind)
@@ -151,3 +157,38 @@ def test_synth_properties_large():
     ctx.call("uggpu_dmatmul_minus", top, top, 0, ctx.handle("w"), A, ctx.handle("x"))
     assert np.max(np.abs(ctx.get(top, "w") - ctx.get(top, "b"))) < 1e-12 * np.max(np.abs(hist[0]))
     ctx.close()
+
+
+def test_col_compression_lossless(monkeypatch):
+    """Slices of rows with identical column distances store one word per slice column (sell.cu sell_compress_cols):
+    the decoded pattern and every result are identical to the explicit storage, only fewer column words are read."""
+    def run(compress):
+        if compress:
+            monkeypatch.delenv("UGGPU_NO_COL_COMPRESSION", raising=False)
+        else:
+            monkeypatch.setenv("UGGPU_NO_COL_COMPRESSION", "1")
+        ctx = _synth(4, 3, 4)                      # 65^3: lines of 65 rows hold slices of 32 interior rows
+        top, A = 4, ctx.handle("A")
+        hier = ctx.download_hierarchy(top)
+        words = int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
+        nnz = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A))
+        for name in ("x", "b", "c"):
+            for l in range(top + 1):
+                ctx.alloc(l, name)
+        ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+        cfg = ctx.lmgc_cfg(smooth_damp=0.6, fused=1)
+        ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+        res = capi.LResult()
+        ctx.call("uggpu_ls_residuum", 0, top, ctx.handle("b"), C.byref(res))
+        ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, ctx.handle("x"), ctx.handle("b"), A, ctx.handle("c"), 3,
+                 capi._vs([1e-300]), capi._vs([1e-300]), C.byref(res), None)
+        x, b = ctx.get(top, "x"), ctx.get(top, "b")
+        ctx.close()
+        return hier, words, nnz, x, b
+
+    h1, w1, nnz, x1, b1 = run(True)
+    h0, w0, _, x0, b0 = run(False)
+    assert w0 == nnz and w1 < 0.8 * nnz, (w0, w1, nnz)
+    for a, b in zip(h1.levels, h0.levels):
+        assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val)
+    assert np.array_equal(x1, x0) and np.array_equal(b1, b0)

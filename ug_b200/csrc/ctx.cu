@@ -276,6 +276,12 @@ extern "C" int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat)
   return m ? m->nnz : -1;
 }
 
+extern "C" int64_t uggpu_mat_col_words(uggpu_ctx *ctx, int level, int mat)
+{
+  SellMat *m = get_mat(ctx, level, mat);
+  return m ? m->col_words : -1;
+}
+
 extern "C" int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat)
 {
   SellMat *m = get_mat(ctx, level, mat);

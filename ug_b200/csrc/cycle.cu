@@ -23,8 +23,9 @@ __global__ void k_lu_scatter(SellView A, int bs, int N, double *__restrict__ lu)
   int bb = bs * bs, lane = r & 31;
   int64_t sp = A.slice_ptr[r >> 5];
   int len = A.rowlen[r];
+  const ColIter ci = col_iter(A, r);
   for (int j = 0; j < len; j++) {
-    int c = A.col[sp + (int64_t)j * 32 + lane];
+    int c = col_at(ci, j);
     for (int i = 0; i < bs; i++)
       for (int k = 0; k < bs; k++)
         lu[(size_t)(c * bs + k) * N + (r * bs + i)] = A.val[(sp + (int64_t)j * 32) * bb + (int64_t)(i * bs + k) * 32 + lane];

@@ -5,6 +5,8 @@
 // same entries are stored slice-interleaved so that thread-per-row kernels are coalesced (uggpu_internal.h).
 #include "uggpu_internal.h"
 
+#include <cstdlib>
+#include <map>
 #include <vector>
 
 __global__ void k_sell_rowlen(int n, const int64_t *__restrict__ rowptr, uint16_t *__restrict__ rowlen, int *__restrict__ width, int *err)
@@ -63,20 +65,164 @@ __global__ void k_sell_set_values(int n, int bb, const int64_t *__restrict__ row
   }
 }
 
-__global__ void k_sell_to_csr(int n, int bb, const int64_t *__restrict__ rowptr, const int64_t *__restrict__ slice_ptr,
-                              const int32_t *__restrict__ col, const double *__restrict__ val, int32_t *__restrict__ ccol, double *__restrict__ cval)
+__global__ void k_sell_to_csr(SellView A, int bb, const int64_t *__restrict__ rowptr, int32_t *__restrict__ ccol, double *__restrict__ cval)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  if (r >= A.n) return;
   int s = r >> 5, lane = r & 31;
-  int64_t sp = slice_ptr[s];
+  int64_t sp = A.slice_ptr[s];
   int64_t rp = rowptr[r];
   int len = (int)(rowptr[r + 1] - rp);
+  const ColIter ci = col_iter(A, r);
   for (int j = 0; j < len; j++) {
     int64_t src = sp + (int64_t)j * 32;
-    ccol[rp + j] = col[src + lane];
-    for (int k = 0; k < bb; k++) cval[(rp + j) * bb + k] = val[src * bb + (int64_t)k * 32 + lane];
+    ccol[rp + j] = col_at(ci, j);
+    for (int k = 0; k < bb; k++) cval[(rp + j) * bb + k] = A.val[src * bb + (int64_t)k * 32 + lane];
   }
+}
+
+// ---- column-index compression ------------------------------------------------------------------------------------------
+// One warp per slice.  flag[s] = 1 when, for every slice column j, all rows that have an entry j hold the same
+// distance col - row (and the slice is at most 32 columns wide, so that a warp can keep the distances in one register
+// per lane); cnt[s] = true entries of the slice; hash[s] = 64-bit hash of the slice's distance vector.
+__global__ void k_sell_uniform_flag(int n, const int64_t *__restrict__ slice_ptr, const uint16_t *__restrict__ rowlen, const int32_t *__restrict__ col,
+                                    uint8_t *__restrict__ flag, int *__restrict__ cnt, unsigned long long *__restrict__ hash)
+{
+  const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= (n + 31) / 32) return;
+  const int r = s * 32 + lane;
+  const int len = r < n ? rowlen[r] : 0;
+  const int64_t sp = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - sp) >> 5);
+  bool ok = true;
+  unsigned long long h = 1469598103934665603ull ^ (unsigned long long)w;
+  for (int j = 0; j < w; j++) {
+    const bool has = j < len;
+    const int d = has ? col[sp + (int64_t)j * 32 + lane] - r : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const int ref = __shfl_sync(0xffffffffu, d, m ? __ffs(m) - 1 : 0);
+    if (has && d != ref) ok = false;
+    h = (h ^ (unsigned long long)(unsigned)ref) * 1099511628211ull;
+    h ^= h >> 29;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  int c = len;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) { flag[s] = (ok && w > 0 && w <= 32) ? 1 : 0; cnt[s] = c; hash[s] = h; }
+}
+
+// writes the new column array; uniform slices that share a table write identical words to the same place
+__global__ void k_sell_compact_cols(int n, const int64_t *__restrict__ slice_ptr, const uint16_t *__restrict__ rowlen, const int32_t *__restrict__ col,
+                                    const int64_t *__restrict__ col_ptr, int32_t *__restrict__ ncol)
+{
+  const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= (n + 31) / 32) return;
+  const int r = s * 32 + lane;
+  const int len = r < n ? rowlen[r] : 0;
+  const int64_t sp = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - sp) >> 5);
+  const int64_t cp = col_ptr[s];
+  if (cp >= 0) {
+    for (int j = 0; j < w; j++) ncol[cp + (int64_t)j * 32 + lane] = col[sp + (int64_t)j * 32 + lane];
+  } else {
+    for (int j = 0; j < w; j++) {
+      const bool has = j < len;
+      const int d = has ? col[sp + (int64_t)j * 32 + lane] - r : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, has);
+      const int ref = __shfl_sync(0xffffffffu, d, m ? __ffs(m) - 1 : 0);
+      if (lane == 0) ncol[~cp + j] = ref;
+    }
+  }
+}
+
+// decodes every true entry from the new arrays and compares it with the explicit original
+__global__ void k_sell_verify_cols(int n, const int64_t *__restrict__ slice_ptr, const uint16_t *__restrict__ rowlen, const int32_t *__restrict__ col,
+                                   const int64_t *__restrict__ col_ptr, const int32_t *__restrict__ ncol, unsigned long long *__restrict__ bad)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int s = r >> 5, lane = r & 31;
+  const int64_t sp = slice_ptr[s], cp = col_ptr[s];
+  const int len = rowlen[r];
+  int wrong = 0;
+  for (int j = 0; j < len; j++) {
+    const int c = cp < 0 ? ncol[~cp + j] + r : ncol[cp + (int64_t)j * 32 + lane];
+    if (c != col[sp + (int64_t)j * 32 + lane]) wrong++;
+  }
+  if (wrong) atomicAdd(bad, (unsigned long long)wrong);
+}
+
+int sell_compress_cols(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->n <= 0 || m->col_ptr != m->slice_ptr || m->padded == 0) return 0;
+  if (getenv("UGGPU_NO_COL_COMPRESSION")) return 0;
+  cudaStream_t st = ctx->stream;
+  const size_t nsl = (size_t)(m->n + 31) / 32;
+  uint8_t *d_flag = nullptr; int *d_cnt = nullptr; unsigned long long *d_hash = nullptr;
+  UG_TRY(dalloc(ctx, &d_flag, nsl));
+  UG_TRY(dalloc(ctx, &d_cnt, nsl));
+  UG_TRY(dalloc(ctx, &d_hash, nsl + 1));       // [nsl]: mismatch counter of the verification
+  const int blocks = (int)((nsl * 32 + 255) / 256);
+  k_sell_uniform_flag<<<blocks, 256, 0, st>>>(m->n, m->slice_ptr, m->rowlen, m->col, d_flag, d_cnt, d_hash);
+  KCHECK(ctx);
+  std::vector<uint8_t> flag(nsl);
+  std::vector<int> cnt(nsl);
+  std::vector<unsigned long long> hash(nsl);
+  std::vector<int64_t> sp(nsl + 1), cp(nsl);
+  CUDA_TRY(cudaMemcpyAsync(flag.data(), d_flag, nsl, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, nsl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(hash.data(), d_hash, nsl * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(sp.data(), m->slice_ptr, (nsl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  UG_TRY(dfree(ctx, d_flag, nsl));
+  UG_TRY(dfree(ctx, d_cnt, nsl));
+  int rc = 0;
+  // slices with equal distance vectors share one table (found by hash, confirmed by the verification pass below; a
+  // hash collision makes the pass fail and the tables are then stored per slice)
+  for (int dedupe = 1; dedupe >= 0; dedupe--) {
+    std::map<unsigned long long, int64_t> tables;
+    int64_t uoff = 0, words = 0, uni = 0;
+    // tables first, explicit slices behind them (128-byte aligned)
+    for (size_t s = 0; s < nsl; s++) {
+      if (!flag[s]) continue;
+      const int64_t w = (sp[s + 1] - sp[s]) >> 5;
+      uni++;
+      if (dedupe) {
+        auto it = tables.find(hash[s]);
+        if (it != tables.end()) { cp[s] = ~it->second; continue; }
+        tables[hash[s]] = uoff;
+      }
+      cp[s] = ~uoff; uoff += (w + 3) & ~(int64_t)3; words += w;      // 16-byte granules; a shared table is read from HBM once
+    }
+    int64_t off = (uoff + 31) & ~(int64_t)31;
+    for (size_t s = 0; s < nsl; s++) {
+      if (flag[s]) continue;
+      const int64_t w = (sp[s + 1] - sp[s]) >> 5;
+      cp[s] = off; off += w * 32; words += cnt[s];
+    }
+    off += 32;                                   // a warp reads a table as 32 words
+    if (uni == 0 || off >= m->padded) break;
+    int64_t *d_cp = nullptr; int32_t *ncol = nullptr;
+    if ((rc = dalloc(ctx, &d_cp, nsl)) != 0) break;
+    if ((rc = dalloc(ctx, &ncol, (size_t)off)) != 0) { dfree(ctx, d_cp, nsl); break; }
+    cudaMemsetAsync(ncol, 0, (size_t)off * sizeof(int32_t), st);
+    cudaMemsetAsync(d_hash + nsl, 0, sizeof(unsigned long long), st);
+    cudaMemcpyAsync(d_cp, cp.data(), nsl * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    k_sell_compact_cols<<<blocks, 256, 0, st>>>(m->n, m->slice_ptr, m->rowlen, m->col, d_cp, ncol);
+    ctx->launches++;
+    k_sell_verify_cols<<<(m->n + 255) / 256, 256, 0, st>>>(m->n, m->slice_ptr, m->rowlen, m->col, d_cp, ncol, d_hash + nsl);
+    ctx->launches++;
+    unsigned long long bad = 1;
+    cudaMemcpyAsync(&bad, d_hash + nsl, sizeof bad, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = uggpu_fail(UGGPU_CUDA_ERROR, "column compression: %s", cudaGetErrorString(e)); dfree(ctx, d_cp, nsl); dfree(ctx, ncol, (size_t)off); break; }
+    if (bad) { dfree(ctx, d_cp, nsl); dfree(ctx, ncol, (size_t)off); continue; }     // hash collision: retry without sharing
+    dfree(ctx, m->col, (size_t)m->col_len);
+    m->col = ncol; m->col_len = off; m->col_ptr = d_cp; m->col_words = words; m->uniform_slices = uni;
+    break;
+  }
+  dfree(ctx, d_hash, nsl + 1);
+  return rc;
 }
 
 int sell_free(uggpu_ctx *ctx, SellMat *m)
@@ -84,9 +230,10 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   if (m->n <= 0 && !m->col) { *m = SellMat(); return 0; }
   size_t nsl = (size_t)(m->n + 31) / 32;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);
   dfree(ctx, m->rowlen, (size_t)m->n);
-  dfree(ctx, m->col, (size_t)m->padded);
+  dfree(ctx, m->col, (size_t)m->col_len);
   dfree(ctx, m->val, (size_t)m->padded * m->bb);
   *m = SellMat();
   return 0;
@@ -126,6 +273,8 @@ int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr,
     KCHECK(ctx);
   }
   CUDA_TRY(cudaStreamSynchronize(st));   // sp (host vector) must outlive the copy
+  m.col_ptr = m.slice_ptr; m.col_len = m.padded; m.col_words = m.nnz;
+  UG_TRY(sell_compress_cols(ctx, &m));
   *out = m;
   return 0;
 }
@@ -193,7 +342,7 @@ int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t 
     UG_TRY(dalloc(ctx, &d_col, nnz));
     UG_TRY(dalloc(ctx, &d_val, nnz * m->bb));
     if (m->n > 0) {
-      k_sell_to_csr<<<(m->n + 255) / 256, 256, 0, ctx->stream>>>(m->n, m->bb, d_rp, m->slice_ptr, m->col, m->val, d_col, d_val);
+      k_sell_to_csr<<<(m->n + 255) / 256, 256, 0, ctx->stream>>>(view(*m), m->bb, d_rp, d_col, d_val);
       KCHECK(ctx);
     }
     if (col) CUDA_TRY(cudaMemcpyAsync(col, d_col, nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -9,43 +9,96 @@
 // reference; tensor cores are not used (0.17-0.25 flop/byte: HBM-bound).
 #include "uggpu_internal.h"
 
+#include <cstdlib>
+
 #ifndef SPMV_THREADS
 #define SPMV_THREADS 128
 #endif
+#ifndef SPMV_UNROLL_U
+#define SPMV_UNROLL_U 4      // unroll of the uniform-slice loop (gather addresses are load-independent there)
+#endif
+#define SPMV_PRAGMA_(x) _Pragma(#x)
+#define SPMV_PRAGMA(x) SPMV_PRAGMA_(x)
 
-template <int BS>
-__device__ __forceinline__ void row_product(const SellView &A, int r, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
+// One row times y.  UNIFORM selects the column-index form of the slice (uggpu_internal.h): explicit words, one per entry,
+// or one distance per slice column shared by the 32 rows.  In the uniform form lane j holds distance j in a register (one
+// coalesced load per slice) and the loop broadcasts it with a shuffle, so the gather addresses do not depend on a load.
+template <int BS, bool UNIFORM>
+__device__ __forceinline__ void row_product_t(const SellView &A, int r, int len, int64_t cpo, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
   constexpr int BB = BS * BS;
   const int lane = r & 31;
   const int64_t sp = A.slice_ptr[r >> 5];
-  const int len = A.rowlen[r];
-  const int32_t *__restrict__ cp = A.col + sp + lane;
   const double *__restrict__ vp = A.val + sp * BB + lane;
 #pragma unroll
   for (int i = 0; i < BS; i++) s[i] = 0.0;
 #pragma unroll
   for (int k = 0; k < BB; k++) dg[k] = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < len; j++) {
-    const int c = __ldg(cp + (size_t)j * 32);
-    double m[BB], w[BS];
+  if (UNIFORM) {
+    // all 32 lanes of the warp are here (rows that do not take part have len = 0)
+    const int w = (int)((A.slice_ptr[(r >> 5) + 1] - sp) >> 5);
+    const int32_t *__restrict__ dp = A.col + ~cpo;
+    for (int j0 = 0; j0 < w; j0 += 32) {
+      const int dreg = (j0 + lane < w) ? __ldg(dp + j0 + lane) : 0;
+      const int jn = min(32, w - j0);
+SPMV_PRAGMA(unroll SPMV_UNROLL_U)
+      for (int jj = 0; jj < jn; jj++) {
+        const int j = j0 + jj;
+        const int c = r + __shfl_sync(0xffffffffu, dreg, jj);
+        if (j < len) {
+          double m[BB], wv[BS];
 #pragma unroll
-    for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
+          for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-    for (int i = 0; i < BS; i++) w[i] = y[(size_t)c * BS + i];
-    if (j == 0) {
+          for (int i = 0; i < BS; i++) wv[i] = y[(size_t)c * BS + i];
+          if (j == 0) {
 #pragma unroll
-      for (int k = 0; k < BB; k++) dg[k] = m[k];
+            for (int k = 0; k < BB; k++) dg[k] = m[k];
+          }
+#pragma unroll
+          for (int i = 0; i < BS; i++) {
+            double acc = m[i * BS] * wv[0];
+#pragma unroll
+            for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * wv[q];
+            s[i] += acc;
+          }
+        }
+      }
     }
+  } else {
+    const int32_t *__restrict__ cp = A.col + cpo + lane;
+#pragma unroll 4
+    for (int j = 0; j < len; j++) {
+      const int c = __ldg(cp + (size_t)j * 32);
+      double m[BB], w[BS];
 #pragma unroll
-    for (int i = 0; i < BS; i++) {
-      double acc = m[i * BS] * w[0];
+      for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-      for (int jj = 1; jj < BS; jj++) acc = acc + m[i * BS + jj] * w[jj];
-      s[i] += acc;
+      for (int i = 0; i < BS; i++) w[i] = y[(size_t)c * BS + i];
+      if (j == 0) {
+#pragma unroll
+        for (int k = 0; k < BB; k++) dg[k] = m[k];
+      }
+#pragma unroll
+      for (int i = 0; i < BS; i++) {
+        double acc = m[i * BS] * w[0];
+#pragma unroll
+        for (int jj = 1; jj < BS; jj++) acc = acc + m[i * BS + jj] * w[jj];
+        s[i] += acc;
+      }
     }
   }
+}
+
+// Must be entered by whole warps whose slice exists ((r & ~31) < A.n): the uniform form shuffles across the slice.
+// Rows with live == false (beyond n, or masked out by the caller) contribute nothing and get s = 0.
+template <int BS>
+__device__ __forceinline__ void row_product(const SellView &A, int r, bool live, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
+{
+  const int64_t cpo = A.col_ptr[r >> 5];
+  const int len = live ? (int)A.rowlen[r] : 0;
+  if (cpo < 0) row_product_t<BS, true>(A, r, len, cpo, y, s, dg);
+  else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);
 }
 
 // SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
@@ -79,10 +132,11 @@ template <int BS, int OP>
 __global__ void __launch_bounds__(SPMV_THREADS) k_dmatmul_k(SellView A, uint8_t bit, const uint8_t *__restrict__ ctl, double *__restrict__ x, const double *__restrict__ y)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= A.n) return;
-  if (bit && !(ctl[r] & bit)) return;
+  if ((r & ~31) >= A.n) return;
+  const bool live = r < A.n && (!bit || (ctl[r] & bit));
   double s[BS], dg[BS * BS];
-  row_product<BS>(A, r, y, s, dg);
+  row_product<BS>(A, r, live, y, s, dg);
+  if (!live) return;
 #pragma unroll
   for (int i = 0; i < BS; i++) {
     size_t k = (size_t)r * BS + i;
@@ -100,7 +154,7 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   SellView v = view(*A);
   const double nb = 8.0 * BS * L->n;
-  ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), (double)A->nnz * (8.0 * BS * BS + 4.0) + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
+  ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
   if (op == 0) k_dmatmul_k<BS, 0><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
   else if (op == 1) k_dmatmul_k<BS, 1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
   else k_dmatmul_k<BS, 2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
@@ -207,6 +261,40 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
   return 0;
 }
 
+// Software prefetch.  A thread-per-row SpMV warp lives for ~6 dependent memory round trips (offsets, then the row's entries
+// in groups of four); with every one of them an HBM miss the SMs run out of warps before HBM runs out of bandwidth (ncu:
+// long-scoreboard stalls, 59 % DRAM throughput).  Each warp therefore ends by touching, with one prefetch.global.L2 per
+// 128-byte line, the value (and explicit column) block of the slice `dist` slices ahead -- about one generation of resident
+// warps -- so that the warps of that generation find their matrix stream in L2.
+struct Prefetch {
+  int dist;        // slices ahead (0: off)
+  int nsl;         // slices of the matrix
+  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 the rows' b / c entries
+  int val_lines;   // 128-byte lines of the widest slice's value block
+  int col_lines;   // same for explicit column words
+  int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
+};
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+static Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int threads_per_block)
+{
+  Prefetch pf;
+  const char *d = getenv("UGGPU_PF_DIST"), *m = getenv("UGGPU_PF_MODE");
+  // default distance: the warps resident on the whole GPU
+  pf.dist = d ? atoi(d) : ctx->sm_count * (2048 / 32);
+  pf.mode = m ? atoi(m) : 3;
+  pf.nsl = (A->n + 31) / 32;
+  pf.val_lines = (A->maxlen * A->bb * 256 + 127) / 128;
+  pf.col_lines = A->maxlen < 32 ? A->maxlen : 32;
+  pf.val_bytes = A->padded * A->bb * (int64_t)sizeof(double);
+  pf.col_bytes = A->col_len * (int64_t)sizeof(int32_t);
+  int bs = 1; while (bs * bs < A->bb) bs++;
+  pf.vec_bytes = (int64_t)A->n * bs * (int64_t)sizeof(double);
+  if (pf.val_lines > 256) pf.dist = 0;      // very wide rows: the thread-per-row loads are long streams already
+  (void)threads_per_block;
+  return pf;
+}
+
 // ---- fused smoothing step ----------------------------------------------------------------------------------------------
 // For row r, with tin = the damped Jacobi correction of this step (already computed for ALL rows):
 //     b[r]  -= (A tin)[r]                    dmatmul_minus  iter.cc:838
@@ -219,16 +307,25 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
 template <int BS, int FLAGS>
 __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
                                                            const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
-                                                           double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err)
+                                                           double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err,
+                                                           Prefetch pf)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = r < A.n;
+  // software prefetch into L2 (see struct Prefetch): offsets of the slice pf.dist slices ahead, requested now, used at the end
+  int64_t pf_sp = -1, pf_cp = -1;
+  const int pf_slice = (r >> 5) + pf.dist;
+  if (pf.dist > 0 && pf_slice < pf.nsl) {
+    pf_sp = __ldg(A.slice_ptr + pf_slice);
+    if (pf.mode & 2) pf_cp = __ldg(A.col_ptr + pf_slice);
+  }
   double nrm[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
+  double s[BS], dg[BS * BS];
+  if ((r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
   if (active) {
-    double s[BS], dg[BS * BS], bn[BS];
-    row_product<BS>(A, r, tin, s, dg);
+    double bn[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) {
       size_t k = (size_t)r * BS + i;
@@ -267,6 +364,25 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
       }
     }
   }
+  if (pf_sp >= 0) {
+    const int lane = threadIdx.x & 31;
+    if (pf.mode & 1) {
+      const int64_t o = pf_sp * (BS * BS) * (int64_t)sizeof(double);
+      for (int l = lane; l < pf.val_lines; l += 32)
+        if (o + (int64_t)l * 128 < pf.val_bytes) prefetch_l2(reinterpret_cast<const char *>(A.val) + o + (int64_t)l * 128);
+    }
+    if ((pf.mode & 2) && pf_cp >= 0 && lane < pf.col_lines) {
+      const int64_t o = pf_cp * (int64_t)sizeof(int32_t) + (int64_t)lane * 128;
+      if (o < pf.col_bytes) prefetch_l2(reinterpret_cast<const char *>(A.col) + o);
+    }
+    if ((pf.mode & 4) && lane < 2 * BS) {
+      const int64_t o = ((int64_t)pf_slice * 32 * BS) * (int64_t)sizeof(double) + (int64_t)lane * 128;
+      if (o < pf.vec_bytes) {
+        prefetch_l2(reinterpret_cast<const char *>(b) + o);
+        if (FLAGS & SF_CADD) prefetch_l2(reinterpret_cast<const char *>(c) + o);
+      }
+    }
+  }
   if (FLAGS & SF_NORM) {
     __shared__ double sm[SPMV_THREADS / 32][UGGPU_MAX_BS];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -288,16 +404,259 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
   }
 }
 
+// ---- fused smoothing step, asynchronously staged through shared memory ----------------------------------------------
+// Same arithmetic as k_smooth_k, scalar rows.  The thread-per-row kernel above keeps every byte of the matrix stream in
+// registers while it is in flight and runs out of outstanding loads long before it runs out of HBM bandwidth (ncu: 59 %
+// DRAM throughput, 0.35 eligible warps per scheduler, everything waiting on L1TEX).  Here every warp owns two rings of
+// shared-memory buffers and works TWO slices ahead of the arithmetic:
+//   values    one cp.async.bulk (TMA) per slice -- SELL-32 keeps a slice's values contiguous -- completing on an mbarrier;
+//   operand   the gathered entries of the correction: one 8-byte cp.async per lane and entry, straight from L2/HBM into
+//             shared memory (no register is held while the load is in flight), tracked by commit groups.
+// The arithmetic then reads shared memory only.  One persistent CTA per SM; warp w of CTA c takes slices
+// (c + k * gridDim.x) * warps + w, k = 0, 1, ...
+#define TMA_VSTAGES 3
+#define TMA_XSTAGES 3
+#define TMA_MAX_WARPS 16
+#define TMA_SMEM_BUDGET (216 * 1024)
+#define TMA_PREFETCH 8
+#define TMA_MAX_WIDTH 48
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int FLAGS>
+__global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) k_smooth_tma(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+                                                                       const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
+                                                                       double *__restrict__ tout, double damp, double *__restrict__ x,
+                                                                       double *__restrict__ partials, int *err, int maxw)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warps = blockDim.x >> 5, wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsl = (A.n + 31) >> 5;
+  // ring slots (doubles): values of one slice; gathered operand of one slice + 4 rows of per-row vector entries (b, c, t, x)
+  const int vslot = maxw * 32, xslot = (maxw + 4) * 32;
+  double *vring = reinterpret_cast<double *>(smem) + (size_t)wi * (TMA_VSTAGES * vslot + TMA_XSTAGES * xslot);
+  double *xring = vring + TMA_VSTAGES * vslot;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)warps * (TMA_VSTAGES * vslot + TMA_XSTAGES * xslot) * sizeof(double)) + wi * TMA_VSTAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < TMA_VSTAGES; i++) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int stride = (int)gridDim.x * warps;                    // in slices
+  const int s_first = (int)blockIdx.x * warps + wi;
+  const int nit = s_first < nsl ? (nsl - 1 - s_first) / stride + 1 : 0;
+  const uint32_t vbase = smem_u32(vring), xbase = smem_u32(xring) + (uint32_t)lane * 8u;
+
+  // "far" registers: offsets and row length of the next slice to stage, loaded one step before they are used
+  int64_t f_sp0 = 0, f_sp1 = 0, f_cpo = 0;
+  int f_len = 0;
+  int64_t d_cpo = 0;      // distance table held in dtab (0: none; uniform slices have col_ptr < 0)
+  int dtab[32];
+  auto load_far = [&](int sl) {
+    if (sl < nsl) {
+      f_sp0 = __ldg(A.slice_ptr + sl); f_sp1 = __ldg(A.slice_ptr + sl + 1); f_cpo = __ldg(A.col_ptr + sl);
+      const int r = sl * 32 + lane;
+      f_len = r < A.n ? (int)A.rowlen[r] : 0;
+    }
+  };
+  // stage slice sl (k-th of this warp): bulk copy of its values, cp.async of its operand entries and of the row's vector
+  // entries; returns the row length
+  auto stage = [&](int k, int sl) -> int {
+    int len = 0;
+    if (sl < nsl) {
+      len = f_len;
+      const int w = (int)((f_sp1 - f_sp0) >> 5);
+      const int vs = k % TMA_VSTAGES, xs = k % TMA_XSTAGES;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[vs], (uint32_t)w * 256u);
+        if (w > 0) bulk_g2s(vring + vs * vslot, A.val + f_sp0, (uint32_t)w * 256u, &bars[vs]);
+      }
+      const int r = sl * 32 + lane;
+      const uint32_t xdst = xbase + (uint32_t)(xs * xslot) * 8u;
+      const double *__restrict__ trow = tin + r;
+      if (f_cpo < 0) {
+        if (f_cpo != d_cpo) {                 // new distance table: one coalesced load, then kept in registers (slices share tables)
+          const int dreg = __ldg(A.col + ~f_cpo + lane);      // the column array ends with 32 spare words
+#pragma unroll
+          for (int j = 0; j < 32; j++) dtab[j] = __shfl_sync(0xffffffffu, dreg, j);
+          d_cpo = f_cpo;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+          if (j < len) cp_async8(xdst + (uint32_t)j * 256u, trow + dtab[j]);
+        if (w > 16) {
+#pragma unroll
+          for (int j = 16; j < 32; j++)
+            if (j < len) cp_async8(xdst + (uint32_t)j * 256u, trow + dtab[j]);
+        }
+      } else {
+        const int32_t *__restrict__ cp = A.col + f_cpo + lane;
+#pragma unroll 8
+        for (int j = 0; j < len; j++) cp_async8(xdst + (uint32_t)j * 256u, tin + __ldg(cp + (size_t)j * 32));
+      }
+      if (r < A.n) {
+        const uint32_t rdst = xdst + (uint32_t)maxw * 256u;
+        cp_async8(rdst, b + r);
+        if ((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) cp_async8(rdst + 256u, c + r);
+        if (FLAGS & (SF_CADD | SF_CSET)) cp_async8(rdst + 512u, trow);
+        if (FLAGS & SF_XADD) cp_async8(rdst + 768u, x + r);
+      }
+    }
+    cp_async_commit();            // one group per call, empty or not: cp_async_wait<2> below counts calls
+    return len;
+  };
+
+  // the small per-slice / per-row streams (slice offsets, row lengths, flags) are pulled into L2 TMA_PREFETCH slices ahead by
+  // five lanes of one prefetch instruction, so that the loads that need them never wait for HBM
+  auto prefetch_meta = [&](int slp) {
+    if (slp < nsl && lane < 5) {
+      const void *p = lane == 0 ? (const void *)(A.slice_ptr + slp + 1) : lane == 1 ? (const void *)(A.col_ptr + slp)
+                    : lane == 2 ? (const void *)(A.rowlen + (size_t)slp * 32) : lane == 3 ? (const void *)(vclass + (size_t)slp * 32)
+                                                                                          : (const void *)(ctl + (size_t)slp * 32);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  };
+#pragma unroll 1
+  for (int k = 0; k < TMA_PREFETCH; k++) prefetch_meta(s_first + k * stride);
+  int len0, len1, len2 = 0;
+  load_far(s_first); len0 = stage(0, s_first);
+  load_far(s_first + stride); len1 = stage(1, s_first + stride);
+  load_far(s_first + 2 * stride);
+  double nacc = 0.0;
+  int sl = s_first;
+#pragma unroll 1
+  for (int it = 0; it < nit; it++, sl += stride) {
+    prefetch_meta(sl + TMA_PREFETCH * stride);
+    len2 = stage(it + 2, sl + 2 * stride);
+    load_far(sl + 3 * stride);
+    const int r = sl * 32 + lane;
+    const bool live = r < A.n;
+    int vc = 3, cb = 0;
+    if (live) {
+      if (FLAGS & SF_TOUT) vc = vclass[r];
+      if (FLAGS & SF_NORM) cb = ctl[r];
+    }
+    const int vs = it % TMA_VSTAGES, xs = it % TMA_XSTAGES;
+    cp_async_wait<2>();
+    while (!mbar_try_wait(&bars[vs], (uint32_t)((it / TMA_VSTAGES) & 1))) { }
+    const double *sval = vring + vs * vslot + lane;
+    const double *sx = xring + xs * xslot + lane;
+    double s = 0.0;
+    if (__all_sync(0xffffffffu, len0 <= 32)) {
+#pragma unroll
+      for (int j = 0; j < 16; j++)
+        if (j < len0) s += sval[j * 32] * sx[j * 32];
+      if (__any_sync(0xffffffffu, len0 > 16)) {
+#pragma unroll
+        for (int j = 16; j < 32; j++)
+          if (j < len0) s += sval[j * 32] * sx[j * 32];
+      }
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < len0; j++) s += sval[j * 32] * sx[j * 32];
+    }
+    const double dg = sval[0];
+    const double *srow = sx + maxw * 32;
+    double bv = 0.0, cv = 0.0, tv = 0.0, xv = 0.0;
+    if (live) {
+      bv = srow[0];
+      if ((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) cv = srow[32];
+      if (FLAGS & (SF_CADD | SF_CSET)) tv = srow[64];
+      if (FLAGS & SF_XADD) xv = srow[96];
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ring reads done before the next bulk write
+    if (live) {
+      const double bn = bv - s;
+      b[r] = bn;
+      if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+        double cn;
+        if (FLAGS & SF_CADD) cn = cv + tv;
+        else if (FLAGS & SF_CSET) cn = 0.0 + tv;
+        else cn = cv;
+        if (FLAGS & (SF_CADD | SF_CSET)) c[r] = cn;
+        if (FLAGS & SF_XADD) x[r] = xv + cn;
+      }
+      if (FLAGS & SF_TOUT) {
+        const double sol = vc < 3 ? 0.0 : bn / dg;
+        tout[r] = sol * damp;
+      }
+      if (FLAGS & SF_NORM) { if (cb & UGGPU_CTL_NEW_DEFECT) nacc += bn * bn; }
+    }
+    len0 = len1; len1 = len2;
+  }
+  cp_async_wait<0>();
+  if (FLAGS & SF_NORM) {
+    for (int o = 16; o > 0; o >>= 1) nacc += __shfl_down_sync(0xffffffffu, nacc, o);
+    if (lane == 0) partials[(size_t)blockIdx.x * warps + wi] = nacc;
+  }
+}
+
+// geometry of the staged kernel for matrix A; false: use the thread-per-row kernel
+static bool tma_geometry(uggpu_ctx *ctx, const Level *L, const SellMat *A, int *grid, int *warps, size_t *smem)
+{
+  // environment switches (tests, A/B runs): UGGPU_NO_TMA, UGGPU_TMA_MIN_ROWS (default 32768: smaller levels are launch-bound anyway)
+  if (!getenv("UGGPU_TMA")) return false;        // opt-in: measured slower than the prefetching thread-per-row kernel
+  const char *mr = getenv("UGGPU_TMA_MIN_ROWS");
+  const int minrows = mr ? atoi(mr) : (1 << 15);
+  if (L->bs != 1 || A->maxlen < 1 || A->maxlen > TMA_MAX_WIDTH || L->n < minrows) return false;
+  const size_t per_warp = ((size_t)TMA_VSTAGES * A->maxlen + (size_t)TMA_XSTAGES * (A->maxlen + 4)) * 256 + TMA_VSTAGES * sizeof(uint64_t);
+  int w = (int)((TMA_SMEM_BUDGET - 256) / per_warp);
+  const char *mw = getenv("UGGPU_TMA_WARPS");
+  if (mw && atoi(mw) > 0 && atoi(mw) < w) w = atoi(mw);
+  if (w > TMA_MAX_WARPS) w = TMA_MAX_WARPS;
+  if (w < 2) return false;
+  const int64_t nsl = ((int64_t)L->n + 31) / 32;
+  int64_t g = (nsl + w - 1) / w;
+  if (g > ctx->sm_count) g = ctx->sm_count;
+  *grid = (int)g; *warps = w;
+  *smem = (size_t)w * per_warp;
+  return true;
+}
+
 template <int BS, int FLAGS>
 static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot)
 {
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
+  int tgrid = 0, twarps = 0; size_t tsmem = 0;
+  const bool tma = BS == 1 && tma_geometry(ctx, L, A, &tgrid, &twarps, &tsmem);
+  if (tma) blocks = tgrid * twarps;     // one partial per warp
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)blocks * BS));
   const double nb = 8.0 * BS * L->n;
   // algorithmic bytes: entries, row lengths, gathered operand once, b read+write, c, tout, x
-  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), (double)A->nnz * (8.0 * BS * BS + 4.0) + 4.0 * (L->n + 1.0) + 3.0 * nb
+  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + 3.0 * nb
                + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
-  k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr);
+  if (tma) {
+    static bool attr_set = false;     // per instantiation
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_smooth_tma<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BUDGET)); attr_set = true; }
+    k_smooth_tma<FLAGS><<<tgrid, twarps * 32, tsmem, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr, A->maxlen);
+  } else {
+    k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                      make_prefetch(ctx, A, SPMV_THREADS));
+  }
   KCHECK(ctx);
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot, (int)(L - ctx->lev)));
   return 0;

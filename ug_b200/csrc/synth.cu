@@ -334,6 +334,8 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
     KCHECK(ctx);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
+  m.col_ptr = m.slice_ptr; m.col_len = m.padded; m.col_words = m.nnz;
+  UG_TRY(sell_compress_cols(ctx, &m));
   *out = m;
   return 0;
 }

@@ -31,11 +31,11 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   const int lane = r & 31;
   const int64_t sp = R.slice_ptr[r >> 5];
   const int len = R.rowlen[r];
-  const int32_t *__restrict__ cp = R.col + sp + lane;
+  const ColIter ci = col_iter(R, r);
   const double *__restrict__ wp = R.val + sp + lane;
 #pragma unroll 4
   for (int j = 0; j < len; j++) {
-    const int f = __ldg(cp + (size_t)j * 32);
+    const int f = col_at(ci, j);
     const double w = __ldg(wp + (size_t)j * 32);
 #pragma unroll
     for (int i = 0; i < BS; i++) {
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(TR_THREADS) k_interpolate_k(SellView P, const 
   const int lane = r & 31;
   const int64_t sp = P.slice_ptr[r >> 5];
   const int len = P.rowlen[r];
-  const int32_t *__restrict__ cp = P.col + sp + lane;
+  const ColIter ci = col_iter(P, r);
   const double *__restrict__ wp = P.val + sp + lane;
 #pragma unroll 2
   for (int j = 0; j < len; j++) {
-    const int c = __ldg(cp + (size_t)j * 32);
+    const int c = col_at(ci, j);
     const double w = __ldg(wp + (size_t)j * 32);
 #pragma unroll
     for (int i = 0; i < BS; i++)
@@ -136,7 +136,7 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
     Av = view(*M);
   }
  const double nbf = 8.0 * F->bs * F->n, nbc = 8.0 * F->bs * C->n;
-  ProfScope ps(ctx, UGGPU_K_RESTRICT, level, (double)F->R.nnz * 12.0 + 4.0 * (C->n + 1.0) + nbf + nbc + (fuse ? (double)C->n * 8.0 * F->bs * F->bs + 2.0 * nbc : 0.0));
+  ProfScope ps(ctx, UGGPU_K_RESTRICT, level, F->R.entry_bytes() + 4.0 * (C->n + 1.0) + nbf + nbc + (fuse ? (double)C->n * 8.0 * F->bs * F->bs + 2.0 * nbc : 0.0));
 #define RS(BSV)                                                                                                                        \
   if (fuse) k_restrict_k<BSV, true><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr); \
   else k_restrict_k<BSV, false><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr)
@@ -162,7 +162,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   if (F->n == 0) return 0;
   UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
   int blocks = (F->n + TR_THREADS - 1) / TR_THREADS;
-  ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, (double)F->P.nnz * 12.0 + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
+  ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
   switch (F->bs) {
     case 1: k_interpolate_k<1><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;
     case 2: k_interpolate_k<2><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;

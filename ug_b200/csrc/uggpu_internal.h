@@ -9,6 +9,12 @@
 //    first), so one thread walking j = 0..len-1 performs the reference's additions in the reference's
 //    order while the warp's loads are perfectly coalesced.  Blocks (bs>1) are stored component-planar:
 //    component k of entry e at val[(slice_ptr[s] + j*32)*bb + k*32 + l].
+//  * column indices are stored per slice in one of two lossless forms (sell.cu sell_compress_cols):
+//      explicit  col[col_ptr[s] + j*32 + l]                          (4 B per stored entry)
+//      uniform   col[~col_ptr[s] + j] + row                          (4 B per slice column)
+//    A slice is "uniform" when entry j of all its rows has the same distance to the row's own index -- the case
+//    of every slice of interior rows of a structured or uniformly refined grid.  col_ptr[s] < 0 marks the uniform
+//    form (bitwise complement of the offset).  The decoded indices are identical, only fewer bytes cross HBM.
 #ifndef UGGPU_INTERNAL_H
 #define UGGPU_INTERNAL_H
 
@@ -30,19 +36,38 @@ struct SellMat {
   int      maxlen = 0;
   int64_t *slice_ptr = nullptr;   // [nslices+1], entry offsets
   uint16_t *rowlen = nullptr;     // [n]
-  int32_t *col = nullptr;         // [padded]
+  int64_t *col_ptr = nullptr;     // [nslices]; == slice_ptr while all slices are explicit (then it is not a separate allocation)
+  int32_t *col = nullptr;         // [col_len]
+  int64_t  col_len = 0;           // int32 words in col (== padded while uncompressed)
+  int64_t  uniform_slices = 0;
   double  *val = nullptr;         // [padded*bb]
   bool valid() const { return n > 0 && col != nullptr; }
+  int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
+  // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
+  double entry_bytes() const { return 8.0 * (double)nnz * bb + 4.0 * (double)col_words; }
 };
 
 struct SellView {          // what a kernel needs (passed by value)
   int n;
   const int64_t *slice_ptr;
+  const int64_t *col_ptr;
   const uint16_t *rowlen;
   const int32_t *col;
   const double *val;
 };
-static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.rowlen, m.col, m.val}; }
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val}; }
+
+#ifdef __CUDACC__
+// column index of entry j of row r:  __ldg(ci.p + j * ci.stride) + ci.base   (warp-uniform stride/base)
+struct ColIter { const int32_t *p; int stride; int base; };
+__device__ __forceinline__ ColIter col_iter(const SellView &A, int r)
+{
+  const int64_t cp = A.col_ptr[r >> 5];
+  if (cp < 0) return ColIter{A.col + ~cp, 1, r};
+  return ColIter{A.col + cp + (r & 31), 32, 0};
+}
+__device__ __forceinline__ int col_at(const ColIter &ci, int j) { return __ldg(ci.p + (size_t)j * ci.stride) + ci.base; }
+#endif
 
 struct Level {
   bool exists = false;
@@ -126,6 +151,8 @@ int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, con
 int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val);
 int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t *col, double *val);
 int sell_free(uggpu_ctx *ctx, SellMat *m);
+// replaces the explicit column words of uniform slices by one distance per slice column (lossless); no-op when nothing is gained
+int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);
 
 // ---- kernels used across files --------------------------------------------------------------------------
 struct Damp { double a[UGGPU_MAX_BS]; };
