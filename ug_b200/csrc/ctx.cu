@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 static thread_local std::string g_last_error;
@@ -65,6 +66,32 @@ SellMat *get_mat(uggpu_ctx *ctx, int level, int mat)
   auto it = L->mats.find(mat);
   if (it == L->mats.end()) { uggpu_fail(UGGPU_DESC_MISMATCH, "matrix %d not set on level %d", mat, level); return nullptr; }
   return &it->second;
+}
+
+// Distance rule (measured on B200, 513^3, profiles/README.md): 3/4 of the warps resident on the whole GPU, i.e. the slice a
+// warp of the next generation will start with -- but never more than ~40 MB of matrix ahead (beyond ~60 MB the prefetched
+// lines are evicted from the 126 MB L2 before they are used and the kernel gets slower than without prefetch), and off when
+// that cap falls below half a generation (3x3 blocks with 27 entries: 62 KB per slice; such rows are long streams per thread
+// and reach 0.9 of the HBM peak without help).
+Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs)
+{
+  Prefetch pf;
+  const char *d = getenv("UGGPU_PF_DIST"), *m = getenv("UGGPU_PF_MODE");
+  const int64_t resident = (int64_t)ctx->sm_count * (2048 / 32);
+  const int64_t slice_bytes = (int64_t)(A->maxlen > 0 ? A->maxlen : 1) * A->bb * 256;
+  int64_t dist = resident * 3 / 4;
+  const int64_t cap = ((int64_t)40 << 20) / slice_bytes;
+  if (cap < dist) dist = cap;
+  if (dist < resident / 2) dist = 0;
+  pf.dist = d ? atoi(d) : (int)dist;
+  pf.mode = m ? atoi(m) : 7;
+  pf.nsl = (A->n + 31) / 32;
+  pf.val_lines = (A->maxlen * A->bb * 256 + 127) / 128;
+  pf.col_lines = A->maxlen < 32 ? A->maxlen : 32;
+  pf.val_bytes = A->padded * A->bb * (int64_t)sizeof(double);
+  pf.col_bytes = A->col_len * (int64_t)sizeof(int32_t);
+  pf.vec_bytes = (int64_t)A->n * bs * (int64_t)sizeof(double);     // vectors indexed by the matrix' rows
+  return pf;
 }
 
 int ensure_partials(uggpu_ctx *ctx, size_t count)

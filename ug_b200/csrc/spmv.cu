@@ -129,13 +129,17 @@ __device__ __forceinline__ int solve_small_block(const double (&mat)[BS * BS], c
 
 // ---- dmatmul family ---------------------------------------------------------------------------------------------
 template <int BS, int OP>
-__global__ void __launch_bounds__(SPMV_THREADS) k_dmatmul_k(SellView A, uint8_t bit, const uint8_t *__restrict__ ctl, double *__restrict__ x, const double *__restrict__ y)
+__global__ void __launch_bounds__(SPMV_THREADS) k_dmatmul_k(SellView A, uint8_t bit, const uint8_t *__restrict__ ctl, double *__restrict__ x, const double *__restrict__ y,
+                                                            Prefetch pf)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if ((r & ~31) >= A.n) return;
+  const PfState pfs = pf_begin(A, r, pf);
   const bool live = r < A.n && (!bit || (ctl[r] & bit));
   double s[BS], dg[BS * BS];
   row_product<BS>(A, r, live, y, s, dg);
+  pf_end<BS * BS>(A, pfs, pf);
+  if ((pf.mode & 4) && pfs.sp >= 0 && OP != 0) pf_vec<BS>(x, pfs, pf);
   if (!live) return;
 #pragma unroll
   for (int i = 0; i < BS; i++) {
@@ -155,9 +159,10 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   SellView v = view(*A);
   const double nb = 8.0 * BS * L->n;
   ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
-  if (op == 0) k_dmatmul_k<BS, 0><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
-  else if (op == 1) k_dmatmul_k<BS, 1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
-  else k_dmatmul_k<BS, 2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y);
+  const Prefetch pf = make_prefetch(ctx, A, BS);
+  if (op == 0) k_dmatmul_k<BS, 0><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
+  else if (op == 1) k_dmatmul_k<BS, 1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
+  else k_dmatmul_k<BS, 2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
   KCHECK(ctx);
   return 0;
 }
@@ -195,11 +200,18 @@ extern "C" int uggpu_dmatmul_minus(uggpu_ctx *c, int fl, int tl, int mode, int x
 // v = damp (.) Diag(A)^-1 d, v = 0 where VCLASS < ACTIVE_CLASS (ugiter.cc:300).  The diagonal block is entry 0
 // of the row, i.e. the first 32-wide column of the slice: a coalesced read.
 template <int BS>
-__global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_t *__restrict__ vclass, double *__restrict__ v, const double *__restrict__ d, Damp damp, int *err)
+__global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_t *__restrict__ vclass, double *__restrict__ v, const double *__restrict__ d, Damp damp, int *err,
+                                                        Prefetch pf)
 {
   constexpr int BB = BS * BS;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= A.n) return;
+  {     // only the diagonal blocks (the first BB columns of the slice's value block) and the defect are read
+    pf.val_lines = 2 * BB; pf.mode &= ~2;
+    const PfState pfs = pf_begin(A, r, pf);
+    pf_end<BB>(A, pfs, pf);
+    if ((pf.mode & 4) && pfs.sp >= 0) pf_vec<BS>(d, pfs, pf);
+  }
   double sol[BS];
   if (vclass[r] < 3) {
 #pragma unroll
@@ -228,9 +240,9 @@ int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp dam
   SellView vw = view(*M);
   ProfScope ps(ctx, UGGPU_K_JAC, level, (double)L->n * (8.0 * L->bs * L->bs + 16.0 * L->bs));
   switch (L->bs) {
-    case 1: k_jac_k<1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr); break;
-    case 2: k_jac_k<2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr); break;
-    default: k_jac_k<3><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr); break;
+    case 1: k_jac_k<1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
+    case 2: k_jac_k<2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
+    default: k_jac_k<3><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
   }
   KCHECK(ctx);
   return 0;
@@ -261,40 +273,6 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
   return 0;
 }
 
-// Software prefetch.  A thread-per-row SpMV warp lives for ~6 dependent memory round trips (offsets, then the row's entries
-// in groups of four); with every one of them an HBM miss the SMs run out of warps before HBM runs out of bandwidth (ncu:
-// long-scoreboard stalls, 59 % DRAM throughput).  Each warp therefore ends by touching, with one prefetch.global.L2 per
-// 128-byte line, the value (and explicit column) block of the slice `dist` slices ahead -- about one generation of resident
-// warps -- so that the warps of that generation find their matrix stream in L2.
-struct Prefetch {
-  int dist;        // slices ahead (0: off)
-  int nsl;         // slices of the matrix
-  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 the rows' b / c entries
-  int val_lines;   // 128-byte lines of the widest slice's value block
-  int col_lines;   // same for explicit column words
-  int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
-};
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-static Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int threads_per_block)
-{
-  Prefetch pf;
-  const char *d = getenv("UGGPU_PF_DIST"), *m = getenv("UGGPU_PF_MODE");
-  // default distance: the warps resident on the whole GPU
-  pf.dist = d ? atoi(d) : ctx->sm_count * (2048 / 32);
-  pf.mode = m ? atoi(m) : 3;
-  pf.nsl = (A->n + 31) / 32;
-  pf.val_lines = (A->maxlen * A->bb * 256 + 127) / 128;
-  pf.col_lines = A->maxlen < 32 ? A->maxlen : 32;
-  pf.val_bytes = A->padded * A->bb * (int64_t)sizeof(double);
-  pf.col_bytes = A->col_len * (int64_t)sizeof(int32_t);
-  int bs = 1; while (bs * bs < A->bb) bs++;
-  pf.vec_bytes = (int64_t)A->n * bs * (int64_t)sizeof(double);
-  if (pf.val_lines > 256) pf.dist = 0;      // very wide rows: the thread-per-row loads are long streams already
-  (void)threads_per_block;
-  return pf;
-}
-
 // ---- fused smoothing step ----------------------------------------------------------------------------------------------
 // For row r, with tin = the damped Jacobi correction of this step (already computed for ALL rows):
 //     b[r]  -= (A tin)[r]                    dmatmul_minus  iter.cc:838
@@ -312,13 +290,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = r < A.n;
-  // software prefetch into L2 (see struct Prefetch): offsets of the slice pf.dist slices ahead, requested now, used at the end
-  int64_t pf_sp = -1, pf_cp = -1;
-  const int pf_slice = (r >> 5) + pf.dist;
-  if (pf.dist > 0 && pf_slice < pf.nsl) {
-    pf_sp = __ldg(A.slice_ptr + pf_slice);
-    if (pf.mode & 2) pf_cp = __ldg(A.col_ptr + pf_slice);
-  }
+  const PfState pfs = pf_begin(A, r, pf);      // software prefetch into L2 (uggpu_internal.h): requested now, issued at the end
   double nrm[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
@@ -364,24 +336,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
       }
     }
   }
-  if (pf_sp >= 0) {
-    const int lane = threadIdx.x & 31;
-    if (pf.mode & 1) {
-      const int64_t o = pf_sp * (BS * BS) * (int64_t)sizeof(double);
-      for (int l = lane; l < pf.val_lines; l += 32)
-        if (o + (int64_t)l * 128 < pf.val_bytes) prefetch_l2(reinterpret_cast<const char *>(A.val) + o + (int64_t)l * 128);
-    }
-    if ((pf.mode & 2) && pf_cp >= 0 && lane < pf.col_lines) {
-      const int64_t o = pf_cp * (int64_t)sizeof(int32_t) + (int64_t)lane * 128;
-      if (o < pf.col_bytes) prefetch_l2(reinterpret_cast<const char *>(A.col) + o);
-    }
-    if ((pf.mode & 4) && lane < 2 * BS) {
-      const int64_t o = ((int64_t)pf_slice * 32 * BS) * (int64_t)sizeof(double) + (int64_t)lane * 128;
-      if (o < pf.vec_bytes) {
-        prefetch_l2(reinterpret_cast<const char *>(b) + o);
-        if (FLAGS & SF_CADD) prefetch_l2(reinterpret_cast<const char *>(c) + o);
-      }
-    }
+  pf_end<BS * BS>(A, pfs, pf);
+  if ((pf.mode & 4) && pfs.sp >= 0) {
+    pf_vec<BS>(b, pfs, pf);
+    if (FLAGS & SF_CADD) pf_vec<BS>(c, pfs, pf);
   }
   if (FLAGS & SF_NORM) {
     __shared__ double sm[SPMV_THREADS / 32][UGGPU_MAX_BS];
@@ -655,7 +613,7 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const doub
     k_smooth_tma<FLAGS><<<tgrid, twarps * 32, tsmem, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr, A->maxlen);
   } else {
     k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
-                                                                      make_prefetch(ctx, A, SPMV_THREADS));
+                                                                      make_prefetch(ctx, A, BS));
   }
   KCHECK(ctx);
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot, (int)(L - ctx->lev)));

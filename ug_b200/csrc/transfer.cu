@@ -19,10 +19,11 @@ template <int BS, bool FUSE>
 __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uint8_t *__restrict__ vnclass_c, const uint32_t *__restrict__ skip_c,
                                                            double *__restrict__ to, const double *__restrict__ from, Damp damp,
                                                            SellView Ac, const uint8_t *__restrict__ vclass_c, double *__restrict__ tout, double *__restrict__ czero,
-                                                           Damp sdamp, int *err)
+                                                           Damp sdamp, int *err, Prefetch pf)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R.n) return;
+  const PfState pfs = pf_begin(R, r, pf);
   double tr[BS];
   const bool zero = vnclass_c[r] >= 2;
 #pragma unroll
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   }
 #pragma unroll
   for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
+  pf_end<1>(R, pfs, pf);
   if (FUSE) {
     constexpr int BB = BS * BS;
     double sol[BS];
@@ -91,10 +93,11 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 // VECSKIP bit set stay 0 (:272-285).
 template <int BS>
 __global__ void __launch_bounds__(TR_THREADS) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
-                                                              const double *__restrict__ from, Damp damp)
+                                                              const double *__restrict__ from, Damp damp, Prefetch pf)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= P.n) return;
+  const PfState pfs = pf_begin(P, r, pf);
   double tr[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) tr[i] = 0.0;
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_interpolate_k(SellView P, const 
   }
 #pragma unroll
   for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
+  pf_end<1>(P, pfs, pf);
 }
 
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp)
@@ -137,9 +141,11 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   }
  const double nbf = 8.0 * F->bs * F->n, nbc = 8.0 * F->bs * C->n;
   ProfScope ps(ctx, UGGPU_K_RESTRICT, level, F->R.entry_bytes() + 4.0 * (C->n + 1.0) + nbf + nbc + (fuse ? (double)C->n * 8.0 * F->bs * F->bs + 2.0 * nbc : 0.0));
+  Prefetch pf = make_prefetch(ctx, &F->R, F->bs);
+  pf.val_lines = (F->R.maxlen * 256 + 127) / 128;     // scalar weights whatever the block size
 #define RS(BSV)                                                                                                                        \
-  if (fuse) k_restrict_k<BSV, true><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr); \
-  else k_restrict_k<BSV, false><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr)
+  if (fuse) k_restrict_k<BSV, true><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
+  else k_restrict_k<BSV, false><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf)
   switch (F->bs) {
     case 1: RS(1); break;
     case 2: RS(2); break;
@@ -163,10 +169,11 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
   int blocks = (F->n + TR_THREADS - 1) / TR_THREADS;
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
+  const Prefetch pf = make_prefetch(ctx, &F->P, F->bs);
   switch (F->bs) {
-    case 1: k_interpolate_k<1><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;
-    case 2: k_interpolate_k<2><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;
-    default: k_interpolate_k<3><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp); break;
+    case 1: k_interpolate_k<1><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
+    case 2: k_interpolate_k<2><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
+    default: k_interpolate_k<3><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
   }
   KCHECK(ctx);
   return 0;

@@ -122,6 +122,63 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// ---- software prefetch into L2 ---------------------------------------------------------------------------------------
+// A thread-per-row warp lives for ~6 dependent memory round trips (slice offsets, then the row's entries in groups of
+// four); with every one of them an HBM miss the SMs run out of warps long before HBM runs out of bandwidth (ncu on the
+// smoothing kernel: long-scoreboard stalls, 59 % DRAM throughput).  Every warp therefore ends by touching, with one
+// prefetch.global.L2 per 128-byte line, the value block (and explicit column words, and vector entries) of the slice
+// `dist` slices ahead -- one generation of resident warps -- so that that generation finds its streams in L2.
+struct Prefetch {
+  int dist;        // slices ahead (0: off)
+  int nsl;         // slices of the matrix
+  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 vector entries of the rows
+  int val_lines;   // 128-byte lines of the widest slice's value block
+  int col_lines;   // same for explicit column words
+  int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
+};
+Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs);      // ctx.cu; bs: components per row of the vectors; UGGPU_PF_DIST / UGGPU_PF_MODE override
+
+#ifdef __CUDACC__
+struct PfState { int64_t sp, cp; int slice; };
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// offsets of the far slice: requested at the start of the row's work ...
+__device__ __forceinline__ PfState pf_begin(const SellView &A, int r, const Prefetch &pf)
+{
+  PfState st{-1, -1, (r >> 5) + pf.dist};
+  if (pf.dist > 0 && st.slice < pf.nsl) {
+    st.sp = __ldg(A.slice_ptr + st.slice);
+    if (pf.mode & 2) st.cp = __ldg(A.col_ptr + st.slice);
+  }
+  return st;
+}
+// ... and used at its end: lane l touches lines l, l + 32, ... of the far slice's value block and line l of its column words
+template <int BB>
+__device__ __forceinline__ void pf_end(const SellView &A, const PfState &st, const Prefetch &pf)
+{
+  if (st.sp < 0) return;
+  const int lane = threadIdx.x & 31;
+  if (pf.mode & 1) {
+    const int64_t o = st.sp * BB * (int64_t)sizeof(double);
+    for (int l = lane; l < pf.val_lines; l += 32)
+      if (o + (int64_t)l * 128 < pf.val_bytes) prefetch_l2(reinterpret_cast<const char *>(A.val) + o + (int64_t)l * 128);
+  }
+  if ((pf.mode & 2) && st.cp >= 0 && lane < pf.col_lines) {
+    const int64_t o = st.cp * (int64_t)sizeof(int32_t) + (int64_t)lane * 128;
+    if (o < pf.col_bytes) prefetch_l2(reinterpret_cast<const char *>(A.col) + o);
+  }
+}
+// the far slice's 32 rows of a vector with BS components per row
+template <int BS>
+__device__ __forceinline__ void pf_vec(const double *v, const PfState &st, const Prefetch &pf)
+{
+  const int lane = threadIdx.x & 31;
+  if (lane < 2 * BS) {
+    const int64_t o = ((int64_t)st.slice * 32 * BS) * (int64_t)sizeof(double) + (int64_t)lane * 128;
+    if (o < pf.vec_bytes) prefetch_l2(reinterpret_cast<const char *>(v) + o);
+  }
+}
+#endif
+
 // ---- error plumbing -------------------------------------------------------------------------------
 int uggpu_fail(int code, const char *fmt, ...);
 #define CUDA_TRY(expr)                                                                                 \
