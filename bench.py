@@ -314,8 +314,10 @@ def our_arm(args):
     achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("k_smooth_k_dram_bytes_per_launch")
+    if os.path.exists(tpath):        # ncu capture of the default workload only
+        tj = json.load(open(tpath))
+        if tj.get("workload") == {"kind": args.kind, "cells": cells, "top": top} and world == 1:
+            traffic = tj.get("k_smooth_k_dram_bytes_per_launch")
     total_alg = sum(v["alg_bytes"] for v in prof.values())
     n_total = n_global
     value = n_total * args.steps / (ms * 1e-3)
