@@ -205,6 +205,21 @@ int uggpu_ls_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x, 
                    int maxiter, const double *abslimit, const double *reduction,
                    uggpu_lresult *res, double *history);
 
+/* ---- Krylov accelerators around the cycle, np/procs/ls.cc ---------------------------------------------
+ * Same conventions as uggpu_ls_solve: res->last_defect holds the residuum on entry, history[it*bs+i].
+ * ddotw np/np.h:224, np/algebra/ugblas.cc:3023: sum_i w[i] * (x_i, y_i) over the components */
+int uggpu_ddotw(uggpu_ctx*, int fl, int tl, int mode, int x, int y, const double *w /* [bs] */, double *a);
+/* class `cg`: LinearSolver ls.cc:637 with CGPrepare :976, CGUpdate :989-1027, CGClose :1159; p, t = the vector handles of
+ * NP_CG.p / NP_CG.t (ls.cc:111-124), c = the correction vector of LinearSolver */
+int uggpu_cg_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x, int b, int A, int c, int p, int t,
+                   int maxiter, const double *abslimit, const double *reduction, uggpu_lresult *res, double *history);
+/* class `bcgs`: BCGSSolver ls.cc:1864-2062 with Iter = the cycle and B = NULL; work = the handles of NP_BCGS r p v s t q
+ * (ls.cc:165-187), weight = `$weight` as given (squared internally like BCGSInit :1757), restart_every = `$R` (0: never).
+ * number_of_linear_iterations counts two per completed pass like the reference; history has one entry per pass. */
+int uggpu_bcgs_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x, int b, int A, const int *work /* [6] */,
+                     const double *weight /* [bs] */, int restart_every, int maxiter, const double *abslimit,
+                     const double *reduction, uggpu_lresult *res, double *history);
+
 /* ---- synthetic hierarchies generated on the device (bench input only; no reference analogue:
  * UG's grid manager needs ~2.5 kB per unknown) -------------------------------------------- */
 #define UGGPU_SYNTH_P1_SIMPLEX    0   /* P1 Poisson on Kuhn triangles (nz = 0) / tetrahedra, scalar          */

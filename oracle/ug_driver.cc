@@ -269,7 +269,7 @@ static void build_hierarchy(const Opt &o)
 #else
   cmd("configure theBVP $d Quadrilateral");
 #endif
-  cmd("newformat F $V n%d: vt 8 $M implicit(vt): mt 2 $I n%d", o.bs, o.bs * o.bs);
+  cmd("newformat F $V n%d: vt 16 $M implicit(vt): mt 2 $I n%d", o.bs, o.bs * o.bs);
   cmd("new themg $b theBVP $f F $h 30000M");
   mg = GetMultigrid((char *)"themg");
 #if DIM == 3
@@ -479,6 +479,52 @@ static void dump_solve(const Opt &o)
   printf("\n");
 }
 
+// Krylov accelerators of the reference around the same cycle: class `cg` (LinearSolver + CGUpdate,
+// ls.cc:989) and class `bcgs` (BCGSSolver, ls.cc:1864), $I lmgc.  As in dump_solve, run k is a fresh solve with $m k.
+static void dump_krylov(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  INT result = 0, bl = 0;
+  cmd("npcreate kcg $c cg");
+  cmd("npcreate kbcgs $c bcgs");
+  const char *names[2] = {"cg", "bcgs"};
+  const int K[2] = {6, 4};
+  for (int w = 0; w < 2; w++) {
+    std::vector<double> hist;
+    std::vector<int32_t> nits;
+    char key[64];
+    for (int k = 1; k <= K[w]; k++) {
+      restore_problem();
+      cmd("npinit k%s $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", names[w], k);
+      std::string npn = std::string("k") + names[w];
+      NP_LINEAR_SOLVER *s = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, npn.c_str(), LINEAR_SOLVER_CLASS_NAME);
+      if (!s) { fprintf(stderr, "numproc %s missing\n", npn.c_str()); exit(9); }
+      LRESULT lr; memset(&lr, 0, sizeof lr);
+      VEC_SCALAR abslimit, red;
+      for (int i = 0; i < MAX_VEC_COMP; i++) { abslimit[i] = 1e-30; red[i] = 1e-30; }
+      if ((*s->PreProcess)(s, top, vx, vb, mA, &bl, &result)) { fprintf(stderr, "%s PreProcess failed\n", names[w]); exit(9); }
+      (*s->Defect)(s, top, vx, vb, mA, &result);
+      (*s->Residuum)(s, bl, top, vx, vb, mA, &lr);
+      if (k == 1) { snprintf(key, sizeof key, "%s/first_defect", names[w]); D.rec(key, 1, lr.last_defect, BS, 8); }
+      if ((*s->Solver)(s, top, vx, vb, mA, abslimit, red, &lr)) { fprintf(stderr, "%s Solver failed\n", names[w]); exit(9); }
+      for (int i = 0; i < BS; i++) hist.push_back(lr.last_defect[i]);
+      nits.push_back(lr.number_of_linear_iterations);
+      (*s->PostProcess)(s, top, vx, vb, mA, &result);
+      if (k == 1 || k == 2 || k == K[w])
+        for (int l = 0; l <= top; l++) {
+          snprintf(key, sizeof key, "%s/x_after_%d", names[w], k); dumpvec(key, vx, l);
+          snprintf(key, sizeof key, "%s/b_after_%d", names[w], k); dumpvec(key, vb, l);
+        }
+    }
+    snprintf(key, sizeof key, "%s/history", names[w]); D.f64(key, hist);
+    snprintf(key, sizeof key, "%s/iterations", names[w]); D.i32(key, nits);
+    snprintf(key, sizeof key, "%s/K", names[w]); D.scalar_i(key, K[w]);
+    printf("%s history:", names[w]);
+    for (size_t i = 0; i < hist.size(); i++) printf(" %.6e", hist[i]);
+    printf("\n");
+  }
+}
+
 // Rendezvous of concurrently started replicas (bench.py runs one per host core, UG being single-threaded): every
 // replica drops a file when its hierarchy is built and waits for all the others, so the timed solves overlap.
 static void replica_barrier(const Opt &o)
@@ -579,6 +625,7 @@ int main(int argc, char **argv)
     dump_hierarchy(o, fl);
     if (o.ops) dump_ops(o);
     if (o.solve) dump_solve(o);
+    if (o.solve) dump_krylov(o);
     D.close();
   }
   if (o.timeit) time_reference(o);
@@ -653,6 +700,49 @@ static int run_gpu(const Opt &o)
     printf("%s %s: its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e b=%.3e defect=%.3e  t_gpu=%.4fs t_cpu=%.4fs\n", ok ? "PASS" : "FAIL", c.name,
            (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_cpu.last_defect[0], ex, eb, ed, g1 - g0, c1 - c0);
     if (!ok) fails++;
+  }
+  // 3. Krylov accelerators: the reference's `cg` / `bcgs` around its own lmgc against gpucg / gpubcgs around gpulmgc
+  //    (device-resident).  Step lengths come from parallel sums on the device: agreement to rounding (1e-9), not bitwise.
+  {
+    const char *cpu_cls[2] = {"cg", "bcgs"}, *gpu_cls[2] = {"gpucg", "gpubcgs"};
+    const int its[2] = {6, 4};
+    for (int w = 0; w < 2; w++) {
+      std::vector<std::vector<double> > xs(top + 1), bs_(top + 1);
+      LRESULT lrs[2];
+      double tm[2] = {0, 0};
+      bool okrun = true;
+      for (int side = 0; side < 2; side++) {
+        char nm[32]; snprintf(nm, sizeof nm, "kd%d%d", w, side);
+        cmd("npcreate %s $c %s", nm, side ? gpu_cls[w] : cpu_cls[w]);
+        cmd("npinit %s $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I %slmgc $display no", nm, its[w], side ? "g0" : "");
+        restore_problem();
+        NP_LINEAR_SOLVER *g = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, nm, LINEAR_SOLVER_CLASS_NAME);
+        memset(&lr, 0, sizeof lr);
+        if (!g || (*g->PreProcess)(g, top, vx, vb, mA, &bl, &result)) { printf("FAIL %s: PreProcess\n", side ? gpu_cls[w] : cpu_cls[w]); okrun = false; break; }
+        (*g->Defect)(g, top, vx, vb, mA, &result);
+        (*g->Residuum)(g, bl, top, vx, vb, mA, &lr);
+        double g0 = now();
+        if ((*g->Solver)(g, top, vx, vb, mA, abslimit, red, &lr)) { printf("FAIL %s: Solver\n", side ? gpu_cls[w] : cpu_cls[w]); okrun = false; break; }
+        tm[side] = now() - g0;
+        (*g->PostProcess)(g, top, vx, vb, mA, &result);
+        lrs[side] = lr;
+        if (side == 0) for (int l = 0; l <= top; l++) { xs[l] = gather(vx, l); bs_[l] = gather(vb, l); }
+      }
+      if (!okrun) { fails++; continue; }
+      double ex = 0, eb = 0, bscale = 0;
+      for (int l = 0; l <= top; l++) {
+        ex = fmax(ex, maxrel(xs[l], gather(vx, l)));
+        std::vector<double> gb = gather(vb, l);
+        for (size_t i = 0; i < gb.size(); i++) eb = fmax(eb, fabs(gb[i] - bs_[l][i]));
+      }
+      for (int i = 0; i < BS; i++) bscale = fmax(bscale, lrs[0].first_defect[i]);
+      eb /= bscale > 0 ? bscale : 1.0;
+      bool ok = ex <= 1e-9 && eb <= 1e-9 && lrs[0].number_of_linear_iterations == lrs[1].number_of_linear_iterations;
+      printf("%s %s vs %s: its=%d/%d last_defect=%.6e (cpu %.6e) relerr x=%.3e b=%.3e (of the first defect)  t_gpu=%.4fs t_cpu=%.4fs\n", ok ? "PASS" : "FAIL",
+             gpu_cls[w], cpu_cls[w], (int)lrs[1].number_of_linear_iterations, (int)lrs[0].number_of_linear_iterations, lrs[1].last_defect[0], lrs[0].last_defect[0],
+             ex, eb, tm[1], tm[0]);
+      if (!ok) fails++;
+    }
   }
   printf("gpuls drop-in: %d failure(s)\n", fails);
   return fails ? 10 : 0;

@@ -299,3 +299,131 @@ int ugport_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int leve
   ugport_base_free(lu);
   return done;
 }
+
+/* ---- Krylov accelerators around the cycle ------------------------------------------------------------ */
+/* loops over levels as vecloop.ct / matloop.ct do: ALL_VECTORS = every row of bl..level; ON_SURFACE = FINE_GRID_DOF rows of
+ * fullrefinelevel..level-1 and NEW_DEFECT rows of level */
+#define ALL_LOOP(stmt) for (int l = bl; l <= level; l++) { const ugport_level *L = &lv[l]; const int rm = 0; (void)rm; stmt; }
+#define SURF_LOOP(stmt) for (int l = fr; l <= level; l++) { const ugport_level *L = &lv[l]; const int rm = l < level ? 2 : 1; stmt; }
+
+static double surf_ddot(const ugport_level *lv, int fr, int level, double **x, double **y)
+{
+  double s = 0.0;
+  SURF_LOOP(ugport_ddot_acc(L, rm, x[l], y[l], &s));
+  return s;
+}
+
+/* ddotw ugblas.cc:3023-3045: per-component sums, then *s = 0; *s += w[i]*a[i] */
+static double surf_ddotw(const ugport_level *lv, int fr, int level, double **x, double **y, const double *w)
+{
+  double a[UGPORT_MAX_BS] = {0.0, 0.0, 0.0}, s = 0.0;
+  SURF_LOOP(ugport_ddotx_acc(L, rm, x[l], y[l], a));
+  for (int i = 0; i < lv[level].bs; i++) s += w[i] * a[i];
+  return s;
+}
+
+/* LinearSolver ls.cc:637-749 with Prepare/Update/Close = CGPrepare :976, CGUpdate :989-1027, CGClose :1159 (class `cg`).
+ * p, tt: work vectors np->p, np->t; t: the cycle's temporary.  Returns the iterations done, -1 on lambda == 0. */
+int ugport_cg_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int level, double **x, double **b, double **c, double **t,
+                    double **p, double **tt, int maxiter, const double *abslimit, const double *reduction, double *first_defect, double *history)
+{
+  int bs = lv[level].bs, bl = cfg->baselevel, it, done = 0;
+  double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS];
+  double *lu = ugport_base_factor(&lv[bl]);
+  ALL_LOOP(ugport_dset(L, 0, p[l], 0.0));                                        /* CGPrepare */
+  double rho = 1.0, lambda;
+  ugport_ls_residuum(lv, fr, bl, level, b, last);
+  for (int i = 0; i < bs; i++) { first_defect[i] = last[i]; reach[i] = last[i] * reduction[i]; if (reach[i] == 0.0) reach[i] = reduction[i]; }
+  if (sc_cmp(last, abslimit, bs)) { ugport_base_free(lu); return 0; }
+  for (it = 0; it < maxiter; it++) {
+    ugport_dset(&lv[level], 0, c[level], 0.0);
+    if (ugport_lmgc(lv, cfg, lu, level, c, b, t)) { ugport_base_free(lu); return -1; }
+    ALL_LOOP(ugport_dmatmul(L, 0, 0, tt[l], c[l]));                              /* t = A c         :1003 */
+    ALL_LOOP(ugport_dadd(L, 0, b[l], tt[l]));                                    /* b += t          :1005 */
+    lambda = surf_ddot(lv, fr, level, c, b);                                     /* (c,b)           :1007 */
+    ALL_LOOP(ugport_dscal(L, 0, p[l], lambda / rho));                            /* p *= lambda/rho :1009 */
+    rho = lambda;
+    ALL_LOOP(ugport_dadd(L, 0, p[l], c[l]));                                     /* p += c          :1012 */
+    ALL_LOOP(ugport_dmatmul(L, 0, 0, tt[l], p[l]));                              /* t = A p         :1014 */
+    lambda = surf_ddot(lv, fr, level, tt, p);                                    /* (t,p)           :1016 */
+    if (lambda == 0.0) { ugport_base_free(lu); return -1; }
+    ALL_LOOP(ugport_daxpy(L, 0, x[l], rho / lambda, p[l]));                      /* :1019 */
+    ALL_LOOP(ugport_daxpy(L, 0, b[l], -rho / lambda, tt[l]));                    /* :1021 */
+    ugport_ls_residuum(lv, fr, bl, level, b, last);
+    if (history) for (int i = 0; i < bs; i++) history[it * bs + i] = last[i];
+    done = it + 1;
+    if (sc_cmp(last, abslimit, bs) || sc_cmp(last, reach, bs)) break;
+  }
+  ugport_base_free(lu);
+  return done;
+}
+
+/* BCGSSolver ls.cc:1864-2062 (class `bcgs`) with Iter = the cycle, B = NULL, restart = 0.  w: the SQUARED weights
+ * (BCGSInit :1757).  work = r p v s t q.  history receives last_defect after every pass of the loop (its second
+ * residuum, or the first one if the loop ended there).  Returns number_of_linear_iterations (two per full pass). */
+int ugport_bcgs_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int level, double **x, double **b, double **t,
+                      double **r, double **p, double **v, double **s, double **tt, double **q, const double *w,
+                      int maxiter, const double *abslimit, const double *reduction, double *first_defect, double *history)
+{
+  int bs = lv[level].bs, bl = cfg->baselevel, nit = 0, eq_count = 0, restart = 1;
+  double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS], old[UGPORT_MAX_BS] = {-1.0, -1.0, -1.0};
+  double alpha = 0.0, rho_new = 0.0, beta = 0.0, tsq = 0.0, rho = 0.0, omega = 0.0;
+  double *lu = ugport_base_factor(&lv[bl]);
+  ugport_ls_residuum(lv, fr, bl, level, b, last);
+  for (int i = 0; i < bs; i++) { first_defect[i] = last[i]; reach[i] = last[i] * reduction[i]; if (reach[i] == 0.0) reach[i] = reduction[i]; }
+  int converged = sc_cmp(last, abslimit, bs);
+  for (int i = 0; i < maxiter; i++) {
+    if (converged) break;
+    if (restart) {
+      ALL_LOOP(ugport_dset(L, 0, p[l], 0.0)); ALL_LOOP(ugport_dset(L, 0, v[l], 0.0)); ALL_LOOP(ugport_dcopy(L, 0, r[l], b[l]));
+      alpha = rho = omega = 1.0;
+      restart = 0;
+    }
+    rho_new = surf_ddotw(lv, fr, level, b, r, w);                                 /* :1934 */
+    if (rho != 0.0 && omega != 0.0) beta = rho_new * alpha / rho / omega;
+    ALL_LOOP(ugport_dscal(L, 0, p[l], beta));
+    ALL_LOOP(ugport_dadd(L, 0, p[l], b[l]));
+    ALL_LOOP(ugport_daxpy(L, 0, p[l], -beta * omega, v[l]));
+    ALL_LOOP(ugport_dset(L, 0, q[l], 0.0));
+    ALL_LOOP(ugport_dcopy(L, 0, s[l], p[l]));
+    if (ugport_lmgc(lv, cfg, lu, level, q, p, t)) { ugport_base_free(lu); return -1; }     /* Iter(q, p) :1944 */
+    ALL_LOOP(ugport_dcopy(L, 0, p[l], s[l]));
+    SURF_LOOP(ugport_dmatmul(L, 0, rm, v[l], q[l]));                              /* v = A q, ON_SURFACE :1946 */
+    alpha = surf_ddotw(lv, fr, level, v, r, w);
+    if (alpha != 0.0) alpha = rho_new / alpha;
+    ALL_LOOP(ugport_daxpy(L, 0, x[l], alpha, q[l]));
+    nit++;
+    ALL_LOOP(ugport_dcopy(L, 0, s[l], b[l]));
+    ALL_LOOP(ugport_daxpy(L, 0, s[l], -alpha, v[l]));
+    ugport_ls_residuum(lv, fr, bl, level, s, last);                               /* :1975 */
+    if (sc_cmp(last, abslimit, bs) || sc_cmp(last, reach, bs)) {
+      ALL_LOOP(ugport_dcopy(L, 0, b[l], s[l]));
+      converged = 1;
+      if (history) for (int k = 0; k < bs; k++) history[i * bs + k] = last[k];
+      break;
+    }
+    ALL_LOOP(ugport_dset(L, 0, q[l], 0.0));
+    ALL_LOOP(ugport_dcopy(L, 0, tt[l], s[l]));
+    if (ugport_lmgc(lv, cfg, lu, level, q, s, t)) { ugport_base_free(lu); return -1; }     /* Iter(q, s) :1991 */
+    ALL_LOOP(ugport_dcopy(L, 0, s[l], tt[l]));
+    SURF_LOOP(ugport_dmatmul(L, 0, rm, tt[l], q[l]));                             /* t = A q :2003 */
+    tsq = surf_ddotw(lv, fr, level, tt, tt, w);
+    omega = surf_ddotw(lv, fr, level, s, tt, w);
+    if (tsq != 0.0) omega /= tsq;
+    ALL_LOOP(ugport_daxpy(L, 0, x[l], omega, q[l]));
+    ALL_LOOP(ugport_dcopy(L, 0, b[l], s[l]));
+    ALL_LOOP(ugport_daxpy(L, 0, b[l], -omega, tt[l]));
+    rho = rho_new;
+    ugport_ls_residuum(lv, fr, bl, level, b, last);
+    if (history) for (int k = 0; k < bs; k++) history[i * bs + k] = last[k];
+    nit++;
+    if (sc_cmp(last, abslimit, bs) || sc_cmp(last, reach, bs)) { converged = 1; break; }
+    int eq = 1;                                                                   /* sc_eq npscan.cc:1095, ac = 1e-4 */
+    for (int k = 0; k < bs; k++) if (last[k] < 0.0 || old[k] < 0.0 || fabs(last[k] - old[k]) > 1e-4 * sqrt(last[k] * old[k])) eq = 0;
+    eq_count = eq ? eq_count + 1 : 0;
+    for (int k = 0; k < bs; k++) old[k] = last[k];
+    if (eq_count > 4) break;
+  }
+  ugport_base_free(lu);
+  return nit;
+}

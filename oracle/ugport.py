@@ -228,3 +228,22 @@ class PortBackend:
                                   self._pp(c), self._pp(t), maxiter, self._vs([abslimit] * MAX_BS),
                                   self._vs([reduction] * MAX_BS), first, _dp(hist))
         return its, np.array(first[:self.bs]), hist[:max(its, 0) * self.bs]
+
+    def cg_solve(self, level, x, b, cfg, maxiter, abslimit=1e-30, reduction=1e-30, c="__c", t="__t", p="__p", tt="__tt"):
+        cc = self._cfg(cfg)
+        first = self._vs([0.0])
+        hist = np.zeros(maxiter * self.bs)
+        its = self.L.ugport_cg_solve(self.levels, C.byref(cc), self.h.fullrefinelevel, level, self._pp(x), self._pp(b), self._pp(c),
+                                     self._pp(t), self._pp(p), self._pp(tt), maxiter, self._vs([abslimit] * MAX_BS),
+                                     self._vs([reduction] * MAX_BS), first, _dp(hist))
+        return its, np.array(first[:self.bs]), hist[:max(its, 0) * self.bs]
+
+    def bcgs_solve(self, level, x, b, cfg, maxiter, abslimit=1e-30, reduction=1e-30, t="__t", weight=None):
+        cc = self._cfg(cfg)
+        first = self._vs([0.0])
+        hist = np.zeros(maxiter * self.bs)
+        w = self._vs([1.0] * MAX_BS if weight is None else [float(v) ** 2 for v in weight])
+        work = [self._pp("__bcgs_" + n) for n in "rpvstq"]
+        its = self.L.ugport_bcgs_solve(self.levels, C.byref(cc), self.h.fullrefinelevel, level, self._pp(x), self._pp(b), self._pp(t),
+                                       *work, w, maxiter, self._vs([abslimit] * MAX_BS), self._vs([reduction] * MAX_BS), first, _dp(hist))
+        return its, np.array(first[:self.bs]), hist[:((max(its, 0) + 1) // 2) * self.bs]

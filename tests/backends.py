@@ -124,3 +124,28 @@ class GpuBackend:
                       hist.ctypes.data_as(C.POINTER(C.c_double)))
         its = r.number_of_linear_iterations
         return its, np.array(r.first_defect[:self.bs]), hist[:its * self.bs]
+
+    def cg_solve(self, level, x, b, cfg, maxiter, abslimit=1e-30, reduction=1e-30, c="__c", t="__t", p="__p", tt="__tt"):
+        cc = self._cfg(cfg, t)
+        self.ctx.call("uggpu_lmgc_preprocess", C.byref(cc), level, self.A)
+        r = capi.LResult()
+        self.ctx.call("uggpu_ls_residuum", cc.baselevel, level, self._v(b), C.byref(r))
+        hist = np.zeros(maxiter * self.bs)
+        self.ctx.call("uggpu_cg_solve", C.byref(cc), cc.baselevel, level, self._v(x), self._v(b), self.A, self._v(c), self._v(p),
+                      self._v(tt), int(maxiter), capi._vs([abslimit]), capi._vs([reduction]), C.byref(r),
+                      hist.ctypes.data_as(C.POINTER(C.c_double)))
+        its = r.number_of_linear_iterations
+        return its, np.array(r.first_defect[:self.bs]), hist[:its * self.bs]
+
+    def bcgs_solve(self, level, x, b, cfg, maxiter, abslimit=1e-30, reduction=1e-30, t="__t", weight=None):
+        cc = self._cfg(cfg, t)
+        self.ctx.call("uggpu_lmgc_preprocess", C.byref(cc), level, self.A)
+        r = capi.LResult()
+        self.ctx.call("uggpu_ls_residuum", cc.baselevel, level, self._v(b), C.byref(r))
+        hist = np.zeros(maxiter * self.bs)
+        work = (C.c_int * 6)(*[self._v("__bcgs_" + n) for n in "rpvstq"])
+        self.ctx.call("uggpu_bcgs_solve", C.byref(cc), cc.baselevel, level, self._v(x), self._v(b), self.A, work,
+                      capi._vs([1.0] * capi.MAX_BS if weight is None else weight), 0, int(maxiter), capi._vs([abslimit]),
+                      capi._vs([reduction]), C.byref(r), hist.ctypes.data_as(C.POINTER(C.c_double)))
+        its = r.number_of_linear_iterations
+        return its, np.array(r.first_defect[:self.bs]), hist[:((its + 1) // 2) * self.bs]

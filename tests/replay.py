@@ -158,3 +158,46 @@ def replay_solve(be, hier, exact=True, vec_tol=1e-12, red_tol=1e-12, cfg_over=No
             _cmp_vec(f"L{l}/solve/b_after_{k}", be.get(l, "b"), d[f"L{l}/solve/b_after_{k}"], exact, vec_tol)
             n += 2
     return n
+
+
+def replay_krylov(be, hier, exact=True, vec_tol=1e-10, red_tol=1e-9, floor=1e-10):
+    """Mirror of dump_krylov(): class `cg` and class `bcgs` of the reference around the same cycle, fresh solves with
+    $m 1, 2, K.  With exact=False (backends whose reductions are parallel sums) vectors are compared relative to their
+    largest entry and history entries below floor * first_defect (rounding level of the converged solve) are skipped."""
+    d = hier.raw
+    top = hier.top
+    cfg = cycle_cfg(hier)
+    zeros = [np.zeros(lv.n * lv.bs) for lv in hier.levels]
+    n = 0
+    for name in ("cg", "bcgs"):
+        K = int(d[f"{name}/K"][0])
+        hist_ref = d[f"{name}/history"].reshape(K, hier.bs)
+        its_ref = d[f"{name}/iterations"]
+        first_ref = d[f"{name}/first_defect"]
+        for k in sorted({1, 2, K}):
+            for l in range(top + 1):
+                be.put(l, "x", zeros[l]); be.put(l, "b", hier.levels[l].rhs)
+            be.ls_defect(0, top, "x", "b")
+            its, first, hist = (be.cg_solve if name == "cg" else be.bcgs_solve)(top, "x", "b", cfg, k)
+            assert its == its_ref[k - 1], (name, k, its, its_ref[k - 1])
+            _cmp_red(f"{name}/first_defect", first, first_ref, 0.0 if exact else 1e-12)
+            got = hist.reshape(-1, hier.bs)[-1]
+            ref = hist_ref[k - 1]
+            if exact:
+                _cmp_red(f"{name}/history[{k}]", got, ref, 0.0)
+            else:
+                keep = ref > floor * first_ref
+                if keep.any():
+                    _cmp_red(f"{name}/history[{k}]", got[keep], ref[keep], red_tol)
+            n += 2
+            for l in range(top + 1):
+                _cmp_vec(f"L{l}/{name}/x_after_{k}", be.get(l, "x"), d[f"L{l}/{name}/x_after_{k}"], exact, vec_tol)
+                if exact:
+                    _cmp_vec(f"L{l}/{name}/b_after_{k}", be.get(l, "b"), d[f"L{l}/{name}/b_after_{k}"], True, vec_tol)
+                else:       # the defect shrinks towards rounding level: compare on the scale of the first defect
+                    gb, rb = be.get(l, "b"), d[f"L{l}/{name}/b_after_{k}"]
+                    scale = max(np.max(np.abs(d[f"L{l}/solve/b_first"])), 1e-300)
+                    if not np.max(np.abs(gb - rb)) <= vec_tol * scale:
+                        raise Mismatch(f"L{l}/{name}/b_after_{k}: abs err {np.max(np.abs(gb - rb)):.3e} > {vec_tol:.1e} * {scale:.3e}")
+                n += 2
+    return n

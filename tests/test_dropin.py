@@ -30,5 +30,5 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    assert sum(l.startswith("PASS") for l in lines) == 4, lines
+    assert sum(l.startswith("PASS") for l in lines) == 6, lines      # 4 ls/lmgc mixes + gpucg + gpubcgs
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -6,7 +6,7 @@ follows the reference's statement order, and both are compiled with -ffp-contrac
 import numpy as np
 
 from oracle.ugport import PortBackend
-from replay import replay_ops, replay_solve
+from replay import replay_krylov, replay_ops, replay_solve
 
 
 def test_port_ops_bitexact(golden):
@@ -19,6 +19,13 @@ def test_port_cycle_and_solve_bitexact(golden):
     be = PortBackend(golden)
     n = replay_solve(be, golden, exact=True, red_tol=0.0)
     assert n > 10
+
+
+def test_port_krylov_bitexact(golden):
+    """cg (ls.cc:989) and bcgs (ls.cc:1864) around the cycle: iterates, defects and histories bit for bit."""
+    be = PortBackend(golden)
+    n = replay_krylov(be, golden, exact=True)
+    assert n > 20
 
 
 def test_golden_invariants(golden):

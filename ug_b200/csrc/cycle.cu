@@ -368,3 +368,156 @@ extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
   if (rc) res->error_code = rc;
   return rc;
 }
+
+// ---- Krylov accelerators around the cycle ------------------------------------------------------------------
+// The reference's classes `cg` (LinearSolver ls.cc:637 with CGPrepare :976 / CGUpdate :989-1027 / CGClose :1159) and `bcgs`
+// (BCGSSolver ls.cc:1864-2062) with Iter = the cycle, every operation a device kernel of this library in the reference's
+// order; only the scalars (lambda, rho, alpha, omega, the defect norms) travel to the host.  Vectors agree with the reference
+// to rounding, not bit for bit: the scalars come from parallel sums.
+static int run_cycle(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
+{
+  if (cfg->fused) return lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr);
+  return lmgc_unfused(ctx, cfg, level, c, b, A);
+}
+
+static int krylov_begin(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level, int x, int b, int c, const int *work, int nwork,
+                        const double *abslimit, const double *reduction, uggpu_lresult *res, double *reach, int *bs_out)
+{
+  if (!res || !abslimit || !reduction) return uggpu_fail(UGGPU_ERROR, "null argument");
+  UG_TRY(lmgc_check(ctx, cfg, level, c, b));
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  for (int l = bl; l <= level; l++) {
+    if (!get_vec(ctx, l, x)) return UGGPU_DESC_MISMATCH;
+    for (int k = 0; k < nwork; k++) UG_TRY(ensure_vec(ctx, l, work[k]));
+  }
+  const int bs = L->bs;
+  res->error_code = 0; res->converged = 0; res->number_of_linear_iterations = 0;
+  for (int i = 0; i < bs; i++) {
+    res->first_defect[i] = res->last_defect[i];
+    reach[i] = res->last_defect[i] * reduction[i];
+    if (reach[i] == 0.0) reach[i] = reduction[i];              // sc_mul_check, ls.cc:663-667
+  }
+  *bs_out = bs;
+  return 0;
+}
+
+extern "C" int uggpu_ddotw(uggpu_ctx *ctx, int fl, int tl, int mode, int x, int y, const double *w, double *a)
+{
+  double s[UGGPU_MAX_BS]; int bs;
+  if (!w || !a) return uggpu_fail(UGGPU_ERROR, "null argument");
+  UG_TRY(reduce_loop(ctx, fl, tl, mode, RED_DOT, x, y, s, &bs));
+  *a = 0.0;
+  for (int i = 0; i < bs; i++) *a += w[i] * s[i];              // T_POST of ddotw, ugblas.cc:3044
+  return 0;
+}
+
+extern "C" int uggpu_cg_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level, int x, int b, int A, int c, int p, int t,
+                              int maxiter, const double *abslimit, const double *reduction, uggpu_lresult *res, double *history)
+{
+  double reach[UGGPU_MAX_BS]; int bs;
+  const int work[2] = {p, t};
+  UG_TRY(krylov_begin(ctx, cfg, bl, level, x, b, c, work, 2, abslimit, reduction, res, reach, &bs));
+  const int ALL = UGGPU_ALL_VECTORS, SURF = UGGPU_ON_SURFACE;
+  UG_TRY(uggpu_dset(ctx, bl, level, ALL, p, 0.0));                                  // CGPrepare
+  double rho = 1.0, lambda = 0.0;
+  if (sc_cmp(res->last_defect, abslimit, bs)) { res->converged = 1; return 0; }
+  for (int it = 0; it < maxiter; it++) {
+    UG_TRY(uggpu_dset(ctx, level, level, ALL, c, 0.0));                             // ls.cc:695
+    UG_TRY(run_cycle(ctx, cfg, level, c, b, A));
+    UG_TRY(uggpu_dmatmul(ctx, bl, level, ALL, t, A, c));                            // CGUpdate :1003
+    UG_TRY(uggpu_dadd(ctx, bl, level, ALL, b, t));
+    UG_TRY(uggpu_ddot(ctx, bl, level, SURF, c, b, &lambda));
+    UG_TRY(uggpu_dscal(ctx, bl, level, ALL, p, lambda / rho));
+    rho = lambda;
+    UG_TRY(uggpu_dadd(ctx, bl, level, ALL, p, c));
+    UG_TRY(uggpu_dmatmul(ctx, bl, level, ALL, t, A, p));
+    UG_TRY(uggpu_ddot(ctx, bl, level, SURF, t, p, &lambda));
+    if (lambda == 0.0) { res->error_code = UGGPU_ERROR; return uggpu_fail(UGGPU_ERROR, "cg: (Ap,p) = 0 in iteration %d", it); }   // :1017
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, rho / lambda, p));
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, b, -rho / lambda, t));
+    UG_TRY(uggpu_ls_residuum(ctx, bl, level, b, res));
+    if (history) for (int i = 0; i < bs; i++) history[it * bs + i] = res->last_defect[i];
+    res->number_of_linear_iterations = it + 1;
+    if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) { res->converged = 1; break; }
+  }
+  int rc = check_device_error(ctx);
+  if (rc) res->error_code = rc;
+  return rc;
+}
+
+extern "C" int uggpu_bcgs_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level, int x, int b, int A, const int *work,
+                                const double *weight, int restart_every, int maxiter, const double *abslimit, const double *reduction,
+                                uggpu_lresult *res, double *history)
+{
+  if (!work || !weight) return uggpu_fail(UGGPU_ERROR, "null argument");
+  double reach[UGGPU_MAX_BS], old[UGGPU_MAX_BS] = {-1.0, -1.0, -1.0}; int bs;
+  const int r = work[0], p = work[1], v = work[2], s = work[3], t = work[4], q = work[5];
+  UG_TRY(krylov_begin(ctx, cfg, bl, level, x, b, q, work, 6, abslimit, reduction, res, reach, &bs));
+  const int ALL = UGGPU_ALL_VECTORS, SURF = UGGPU_ON_SURFACE;
+  double w2[UGGPU_MAX_BS];
+  for (int i = 0; i < UGGPU_MAX_BS; i++) w2[i] = weight[i] * weight[i];             // BCGSInit :1757
+  double alpha = 0.0, rho_new = 0.0, beta = 0.0, tt = 0.0, rho = 0.0, omega = 0.0;
+  int restart = 1, eq_count = 0;
+  if (sc_cmp(res->last_defect, abslimit, bs)) res->converged = 1;
+  for (int i = 0; i < maxiter; i++) {
+    if (res->converged) break;
+    if ((restart_every > 0 && i % restart_every == 0) || restart) {
+      UG_TRY(uggpu_dset(ctx, bl, level, ALL, p, 0.0));
+      UG_TRY(uggpu_dset(ctx, bl, level, ALL, v, 0.0));
+      UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, r, b));
+      alpha = rho = omega = 1.0;
+      restart = 0;
+    }
+    UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, b, r, w2, &rho_new));
+    if (rho != 0.0 && omega != 0.0) beta = rho_new * alpha / rho / omega;
+    UG_TRY(uggpu_dscal(ctx, bl, level, ALL, p, beta));
+    UG_TRY(uggpu_dadd(ctx, bl, level, ALL, p, b));
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, p, -beta * omega, v));
+    UG_TRY(uggpu_dset(ctx, bl, level, ALL, q, 0.0));
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, s, p));
+    UG_TRY(run_cycle(ctx, cfg, level, q, p, A));                                    // Iter(q, p) :1944
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, p, s));
+    UG_TRY(uggpu_dmatmul(ctx, bl, level, SURF, v, A, q));
+    UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, v, r, w2, &alpha));
+    if (alpha != 0.0) alpha = rho_new / alpha;
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, alpha, q));
+    res->number_of_linear_iterations++;
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, s, b));
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, s, -alpha, v));
+    UG_TRY(uggpu_ls_residuum(ctx, bl, level, s, res));
+    if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) {
+      UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, b, s));
+      res->converged = 1;
+      if (history) for (int k = 0; k < bs; k++) history[i * bs + k] = res->last_defect[k];
+      break;
+    }
+    UG_TRY(uggpu_dset(ctx, bl, level, ALL, q, 0.0));
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, t, s));
+    UG_TRY(run_cycle(ctx, cfg, level, q, s, A));                                    // Iter(q, s) :1991
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, s, t));
+    UG_TRY(uggpu_dmatmul(ctx, bl, level, SURF, t, A, q));
+    UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, t, t, w2, &tt));
+    UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, s, t, w2, &omega));
+    if (tt != 0.0) omega /= tt;
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, omega, q));
+    UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, b, s));
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, b, -omega, t));
+    rho = rho_new;
+    UG_TRY(uggpu_ls_residuum(ctx, bl, level, b, res));
+    if (history) for (int k = 0; k < bs; k++) history[i * bs + k] = res->last_defect[k];
+    res->number_of_linear_iterations++;
+    if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) { res->converged = 1; break; }
+    int eq = 1;                                                                     // sc_eq(last, old, 1e-4), npscan.cc:1095
+    for (int k = 0; k < bs; k++) {
+      const double a = res->last_defect[k], o = old[k];
+      if (a < 0.0 || o < 0.0 || fabs(a - o) > 1e-4 * sqrt(a * o)) eq = 0;
+    }
+    eq_count = eq ? eq_count + 1 : 0;
+    for (int k = 0; k < bs; k++) old[k] = res->last_defect[k];
+    if (eq_count > 4) { res->converged = 0; break; }
+  }
+  int rc = check_device_error(ctx);
+  if (rc) res->error_code = rc;
+  return rc;
+}

@@ -41,7 +41,7 @@ USING_UG_NAMESPACES
   X(uggpu_ctx_create) X(uggpu_ctx_destroy) X(uggpu_last_error) X(uggpu_set_fullrefinelevel) X(uggpu_level_create) X(uggpu_level_set_flags)     \
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
-  X(uggpu_ls_solve) X(uggpu_launch_count)
+  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count)
 
 namespace {
 struct Api {
@@ -559,13 +559,22 @@ INT GpuLmgcConstruct(NP_BASE *theNP)
 // linear_solver.gpuls  (reference: NP_LS ls.cc:79-108, LinearSolverInit :771, PreProcess :539, Defect :562, Residuum :577,
 //                       LinearSolver :637-749 with Update = LSUpdate :869)
 // =========================================================================================================================
+// linear_solver.gpucg    (reference: class `cg`, NP_CG ls.cc:111-124, CGInit :939, CGPrepare :976, CGUpdate :989, CGClose :1159)
+// linear_solver.gpubcgs  (reference: class `bcgs`, NP_BCGS ls.cc:165-187, BCGSInit :1750, BCGSPreProcess :1805, BCGSSolver :1864)
+// share everything with gpuls except the iteration that runs on the device.
+enum { GPULS_LS = 0, GPULS_CG = 1, GPULS_BCGS = 2 };
 struct NP_GPULS {
   NP_LINEAR_SOLVER ls;
   NP_ITER *Iter;
   INT maxiter, baselevel, display;
   VECDATA_DESC *c;
   Mirror *m;
+  INT kind;                       // GPULS_*
+  INT restart;                    // bcgs $R
+  VEC_SCALAR weight;              // bcgs $weight (as given; squared on the device like BCGSInit)
+  VECDATA_DESC *w[6];             // cg: p t   bcgs: r p v s t q
 };
+const char *KindName(INT kind) { return kind == GPULS_CG ? "gpucg" : (kind == GPULS_BCGS ? "gpubcgs" : "gpuls"); }
 
 INT GpuLsInit(NP_BASE *theNP, INT argc, char **argv)
 {
@@ -575,11 +584,26 @@ INT GpuLsInit(NP_BASE *theNP, INT argc, char **argv)
   np->Iter = (NP_ITER *)ReadArgvNumProc(theNP->mg, "I", ITER_CLASS_NAME, argc, argv);
   if (np->Iter == NULL) REP_ERR_RETURN(NP_NOT_ACTIVE);
   if (np->Iter->Iter != GpuLmgcIter) {
-    UserWrite("gpuls: $I must be of class gpulmgc (the device-resident solve has no host iteration)\n");
+    UserWriteF("%s: $I must be of class gpulmgc (the device-resident solve has no host iteration)\n", KindName(np->kind));
     return NP_NOT_ACTIVE;
   }
   np->baselevel = 0;
   np->c = ReadArgvVecDesc(theNP->mg, "c", argc, argv);
+  for (int i = 0; i < 6; i++) np->w[i] = NULL;
+  if (np->kind == GPULS_CG) {
+    np->w[0] = ReadArgvVecDesc(theNP->mg, "p", argc, argv);
+    np->w[1] = ReadArgvVecDesc(theNP->mg, "t", argc, argv);
+  }
+  if (np->kind == GPULS_BCGS) {
+    const char *nm[6] = {"r", "p", "v", "s", "t", "q"};
+    for (int i = 0; i < 6; i++) np->w[i] = ReadArgvVecDesc(theNP->mg, nm[i], argc, argv);
+    if (ReadArgvINT("R", &(np->restart), argc, argv)) np->restart = 0;
+    if (np->restart < 0) REP_ERR_RETURN(NP_NOT_ACTIVE);
+    INT rc = NPLinearSolverInit(&np->ls, argc, argv);       // needs the format of x for sc_read
+    if (sc_read(np->weight, NP_FMT(np), NULL, "weight", argc, argv))
+      for (int i = 0; i < MAX_VEC_COMP; i++) np->weight[i] = 1.0;
+    return rc;
+  }
   return NPLinearSolverInit(&np->ls, argc, argv);
 }
 
@@ -668,8 +692,26 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   double absl[UGGPU_MAX_BS], red[UGGPU_MAX_BS];
   for (int i = 0; i < UGGPU_MAX_BS; i++) { absl[i] = abslimit[i < bs ? i : 0]; red[i] = reduction[i < bs ? i : 0]; r.last_defect[i] = i < bs ? lresult->last_defect[i] : 0.0; }
   std::vector<double> history((size_t)MAX(np->maxiter, 1) * bs, 0.0);
-  if (api.uggpu_ls_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
-    NP_RETURN(dev_fail("uggpu_ls_solve"), lresult->error_code);
+  const int nwork = np->kind == GPULS_CG ? 2 : (np->kind == GPULS_BCGS ? 6 : 0);
+  for (int i = 0; i < nwork; i++)          // CGPrepare / CGUpdate / BCGSPreProcess allocate these from the same pool
+    if (AllocVDFromVD(NP_MG(theNP), bl, level, x, &np->w[i])) NP_RETURN(1, lresult->error_code);
+  if (np->kind == GPULS_LS) {
+    if (api.uggpu_ls_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
+      NP_RETURN(dev_fail("uggpu_ls_solve"), lresult->error_code);
+  } else if (np->kind == GPULS_CG) {
+    if (api.uggpu_cg_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), m->handle(np->w[0]), m->handle(np->w[1]),
+                           np->maxiter, absl, red, &r, history.data()))
+      NP_RETURN(dev_fail("uggpu_cg_solve"), lresult->error_code);
+  } else {
+    int wh[6];
+    double wgt[UGGPU_MAX_BS];
+    for (int i = 0; i < 6; i++) wh[i] = m->handle(np->w[i]);
+    for (int i = 0; i < UGGPU_MAX_BS; i++) wgt[i] = i < bs ? np->weight[i] : 1.0;
+    if (api.uggpu_bcgs_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), wh, wgt, np->restart, np->maxiter, absl, red, &r, history.data()))
+      NP_RETURN(dev_fail("uggpu_bcgs_solve"), lresult->error_code);
+  }
+  for (int i = 0; i < nwork; i++)
+    if (FreeVD(NP_MG(theNP), bl, level, np->w[i])) REP_ERR_RETURN(1);
   // down: x, b, c on every cycle level (what the CPU classes leave in the VECTORs)
   for (int l = bl; l <= level; l++)
     if (Download(m, l, x) || Download(m, l, b) || Download(m, l, np->c)) NP_RETURN(1, lresult->error_code);
@@ -684,7 +726,8 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
     for (int i = 0; i < MAX_VEC_COMP; i++) d[i] = 0.0;
     for (int i = 0; i < bs; i++) d[i] = r.first_defect[i];
     if (DoPCR(PrintID, d, PCR_CRATE_SD)) NP_RETURN(1, lresult->error_code);
-    for (int it = 0; it < r.number_of_linear_iterations; it++) {
+    const int nhist = np->kind == GPULS_BCGS ? (r.number_of_linear_iterations + 1) / 2 : r.number_of_linear_iterations;
+    for (int it = 0; it < nhist; it++) {
       for (int i = 0; i < bs; i++) d[i] = history[(size_t)it * bs + i];
       if (DoPCR(PrintID, d, PCR_CRATE_SD)) NP_RETURN(1, lresult->error_code);
     }
@@ -711,8 +754,14 @@ INT GpuLsPostProcess(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDAT
   return 0;
 }
 
-INT GpuLsConstruct(NP_BASE *theNP)
+INT GpuLsConstructKind(NP_BASE *theNP, INT kind);
+INT GpuLsConstruct(NP_BASE *theNP) { return GpuLsConstructKind(theNP, GPULS_LS); }
+INT GpuCgConstruct(NP_BASE *theNP) { return GpuLsConstructKind(theNP, GPULS_CG); }
+INT GpuBcgsConstruct(NP_BASE *theNP) { return GpuLsConstructKind(theNP, GPULS_BCGS); }
+
+INT GpuLsConstructKind(NP_BASE *theNP, INT kind)
 {
+  ((NP_GPULS *)theNP)->kind = kind;
   theNP->Init = GpuLsInit;
   theNP->Display = GpuLsDisplay;
   theNP->Execute = NPLinearSolverExecute;
@@ -733,5 +782,7 @@ INT NS_DIM_PREFIX InitGpuLS(void)
   if (CreateClass(TRANSFER_CLASS_NAME ".gputransfer", sizeof(NP_GPUTRANSFER), GpuTransferConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(ITER_CLASS_NAME ".gpulmgc", sizeof(NP_GPULMGC), GpuLmgcConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpuls", sizeof(NP_GPULS), GpuLsConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpucg", sizeof(NP_GPULS), GpuCgConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpubcgs", sizeof(NP_GPULS), GpuBcgsConstruct)) REP_ERR_RETURN(__LINE__);
   return 0;
 }
