@@ -125,6 +125,10 @@ int uggpu_vec_alloc(uggpu_ctx *ctx, int level, int vec);          /* AllocVDFrom
 int uggpu_vec_free(uggpu_ctx *ctx, int level, int vec);           /* FreeVD, udm.h:520 */
 int uggpu_vec_upload(uggpu_ctx *ctx, int level, int vec, const double *host);   /* n*bs doubles */
 int uggpu_vec_download(uggpu_ctx *ctx, int level, int vec, double *host);
+/* Upload on a second stream: returns at once, the copy runs behind the work already enqueued and the first later operation
+ * that touches the vector waits for it; `host` (pinned for a truly asynchronous copy) must stay valid until then.  With the
+ * fused cycle the iterate x of uggpu_ls_solve is touched by the last kernel of a cycle only, so its upload hides behind it. */
+int uggpu_vec_upload_async(uggpu_ctx *ctx, int level, int vec, const double *host);
 /* raw device pointer of a vector (for callers that already hold device data, e.g. the bench) */
 int uggpu_vec_devptr(uggpu_ctx *ctx, int level, int vec, void **dptr);
 

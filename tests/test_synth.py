@@ -192,3 +192,37 @@ def test_col_compression_lossless(monkeypatch):
     for a, b in zip(h1.levels, h0.levels):
         assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val)
     assert np.array_equal(x1, x0) and np.array_equal(b1, b0)
+
+
+def test_async_upload_of_the_iterate():
+    """uggpu_vec_upload_async: the iterate travels on the copy stream while the cycle runs; results are those of the
+    synchronous upload, also when the vector is reused at once (upload ordered behind the kernels already enqueued)."""
+    ctx = _synth(2, 3, 4)
+    top, A = 4, ctx.handle("A")
+    for name in ("x", "b", "c"):
+        for l in range(top + 1):
+            ctx.alloc(l, name)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    b0 = ctx.get(top, "b")
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal(b0.size)
+    cfg = ctx.lmgc_cfg(smooth_damp=0.6, fused=1)
+    ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+    out = []
+    for mode in ("sync", "async", "async"):
+        ctx.put(top, "b", b0)
+        if mode == "sync":
+            ctx.put(top, "x", x0)
+        else:
+            ctx.call("uggpu_vec_upload_async", top, ctx.handle("x"), x0.ctypes.data_as(C.c_void_p))
+        res = capi.LResult()
+        ctx.call("uggpu_ls_residuum", 0, top, ctx.handle("b"), C.byref(res))
+        ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, ctx.handle("x"), ctx.handle("b"), A, ctx.handle("c"), 2,
+                 capi._vs([1e-300]), capi._vs([1e-300]), C.byref(res), None)
+        out.append((ctx.get(top, "x"), ctx.get(top, "b")))
+    for x, b in out[1:]:
+        assert np.array_equal(x, out[0][0]) and np.array_equal(b, out[0][1])
+    # a pending upload is honoured by plain vector operations and downloads too
+    ctx.call("uggpu_vec_upload_async", top, ctx.handle("x"), x0.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(ctx.get(top, "x"), x0)
+    ctx.close()

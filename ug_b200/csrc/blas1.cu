@@ -149,9 +149,38 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_final(size_t count, const d
   block_reduce_store<BS>(acc, out);
 }
 
+// middle stage for long partial lists (one partial per block of a row kernel: 10^6 at 513^3): RED_MID blocks sum contiguous
+// chunks, in a fixed order, into RED_MID partials behind the list
+#define RED_MID 128
+template <int BS>
+__global__ void __launch_bounds__(RED_THREADS) k_red_mid(size_t count, const double *__restrict__ partials, double *__restrict__ out)
+{
+  const size_t chunk = (count + RED_MID - 1) / RED_MID;
+  const size_t lo = (size_t)blockIdx.x * chunk, hi = lo + chunk < count ? lo + chunk : count;
+  double acc[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) acc[i] = 0.0;
+  for (size_t p = lo + threadIdx.x; p < hi; p += RED_THREADS)
+#pragma unroll
+    for (int i = 0; i < BS; i++) acc[i] += partials[p * BS + i];
+  block_reduce_store<BS>(acc, out + (size_t)blockIdx.x * BS);
+}
+
 int reduce_partials_final(uggpu_ctx *ctx, int bs, size_t count, int slot, int level)
 {
   double *out = ctx->dres + (size_t)slot * UGGPU_MAX_BS;
+  if (count > 16384 && ctx->partials_cap >= (count + RED_MID) * (size_t)bs) {
+    double *mid = ctx->partials + count * bs;
+    switch (bs) {
+      case 1: k_red_mid<1><<<RED_MID, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, mid); k_red_final<1><<<1, RED_THREADS, 0, ctx->stream>>>(RED_MID, mid, out); break;
+      case 2: k_red_mid<2><<<RED_MID, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, mid); k_red_final<2><<<1, RED_THREADS, 0, ctx->stream>>>(RED_MID, mid, out); break;
+      default: k_red_mid<3><<<RED_MID, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, mid); k_red_final<3><<<1, RED_THREADS, 0, ctx->stream>>>(RED_MID, mid, out); break;
+    }
+    ctx->launches++;
+    KCHECK(ctx);
+    if (ctx->comm && level >= 0 && ctx->lev[level].partitioned) UG_TRY(allreduce_sum(ctx, out, (size_t)bs));
+    return 0;
+  }
   switch (bs) {
     case 1: k_red_final<1><<<1, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, out); break;
     case 2: k_red_final<2><<<1, RED_THREADS, 0, ctx->stream>>>(count, ctx->partials, out); break;

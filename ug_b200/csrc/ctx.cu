@@ -50,13 +50,32 @@ Level *get_level(uggpu_ctx *ctx, int level)
   return &ctx->lev[level];
 }
 
-double *get_vec(uggpu_ctx *ctx, int level, int vec)
+double *get_vec_lazy(uggpu_ctx *ctx, int level, int vec)
 {
   Level *L = get_level(ctx, level);
   if (!L) return nullptr;
   auto it = L->vecs.find(vec);
   if (it == L->vecs.end()) { uggpu_fail(UGGPU_DESC_MISMATCH, "vector %d not allocated on level %d", vec, level); return nullptr; }
   return it->second;
+}
+
+// compute stream waits for an upload of the vector that is still in flight on the copy stream (uggpu_vec_upload_async)
+int vec_wait(uggpu_ctx *ctx, int level, int vec)
+{
+  Level *L = &ctx->lev[level];
+  auto it = L->pending.find(vec);
+  if (it == L->pending.end()) return 0;
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, it->second, 0));
+  CUDA_TRY(cudaEventDestroy(it->second));
+  L->pending.erase(it);
+  return 0;
+}
+
+double *get_vec(uggpu_ctx *ctx, int level, int vec)
+{
+  double *p = get_vec_lazy(ctx, level, vec);
+  if (p && !ctx->lev[level].pending.empty() && vec_wait(ctx, level, vec)) return nullptr;
+  return p;
 }
 
 SellMat *get_mat(uggpu_ctx *ctx, int level, int mat)
@@ -151,6 +170,7 @@ extern "C" int uggpu_ctx_destroy(uggpu_ctx *ctx)
   if (ctx == nullptr) return 0;
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
   uggpu_comm_destroy(ctx);
   for (int l = 0; l < UGGPU_MAX_LEVELS; l++)
     if (ctx->lev[l].exists) uggpu_level_destroy(ctx, l);
@@ -227,6 +247,8 @@ extern "C" int uggpu_level_destroy(uggpu_ctx *ctx, int level)
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   size_t n = (size_t)L->n;
   for (auto &kv : L->mats) sell_free(ctx, &kv.second);
+  for (auto &kv : L->pending) { cudaEventSynchronize(kv.second); cudaEventDestroy(kv.second); }
+  L->pending.clear();
   for (auto &kv : L->vecs) { double *p = kv.second; dfree(ctx, p, vec_count(L)); }
   level_free_part(ctx, L);
   sell_free(ctx, &L->P);
@@ -378,6 +400,7 @@ extern "C" int uggpu_vec_free(uggpu_ctx *ctx, int level, int vec)
   if (!L) return UGGPU_ERROR;
   auto it = L->vecs.find(vec);
   if (it == L->vecs.end()) return 0;
+  UG_TRY(vec_wait(ctx, level, vec));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   double *p = it->second;
   UG_TRY(dfree(ctx, p, vec_count(L)));
@@ -390,9 +413,33 @@ extern "C" int uggpu_vec_upload(uggpu_ctx *ctx, int level, int vec, const double
   Level *L = get_level(ctx, level);
   if (!L) return UGGPU_ERROR;
   if (!L->vecs.count(vec)) UG_TRY(uggpu_vec_alloc(ctx, level, vec));
+  UG_TRY(vec_wait(ctx, level, vec));
   double *p = L->vecs[vec];
   CUDA_TRY(cudaMemcpyAsync(p, host, (size_t)L->n * L->bs * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Upload that overlaps whatever the compute stream is doing: the copy runs on a second stream behind the work already
+// enqueued (so it cannot overtake kernels that still use the vector) and the first later operation that touches the
+// vector waits for it.  `host` must stay valid until then (pinned memory for a truly asynchronous copy).  Used for the
+// iterate x of a solve: only the last kernel of the first cycle needs it.
+extern "C" int uggpu_vec_upload_async(uggpu_ctx *ctx, int level, int vec, const double *host)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (!L->vecs.count(vec)) UG_TRY(uggpu_vec_alloc(ctx, level, vec));
+  UG_TRY(vec_wait(ctx, level, vec));
+  if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  cudaEvent_t before, done;
+  CUDA_TRY(cudaEventCreateWithFlags(&before, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(before, ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, before, 0));
+  CUDA_TRY(cudaEventDestroy(before));
+  CUDA_TRY(cudaMemcpyAsync(L->vecs[vec], host, (size_t)L->n * L->bs * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+  CUDA_TRY(cudaEventRecord(done, ctx->copy_stream));
+  L->pending[vec] = done;
   return 0;
 }
 

@@ -238,7 +238,8 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   const bool top = tf && tf->level == level;
   bool c_zero = top && tf->c_zero;
   double *xp = nullptr;
-  if (top) { xp = get_vec(ctx, level, tf->x); if (!xp) return UGGPU_DESC_MISMATCH; }
+  // x is only touched by the last smoothing step: an upload of it that is still in flight (uggpu_vec_upload_async) overlaps the cycle
+  if (top) { xp = get_vec_lazy(ctx, level, tf->x); if (!xp) return UGGPU_DESC_MISMATCH; }
   double *cur = tA, *oth = tB;
 
   if (cfg->nu1 > 0) {
@@ -266,7 +267,7 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   {
     const bool last = cfg->nu2 == 0;
     int flags = (c_zero ? SF_CSET : SF_CADD) | (last ? 0 : SF_TOUT);
-    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; }
+    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
     UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0));
     c_zero = false;
     cur = tB; oth = tA;
@@ -274,7 +275,7 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   for (int i = 0; i < cfg->nu2; i++) {
     const bool last = i == cfg->nu2 - 1;
     int flags = SF_CADD | (last ? 0 : SF_TOUT);
-    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; }
+    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
     UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0));
     double *sw = cur; cur = oth; oth = sw;
   }
@@ -326,7 +327,7 @@ extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
   UG_TRY(lmgc_check(ctx, cfg, level, c, b));
   Level *L = get_level(ctx, level);
   const int bs = L->bs;
-  for (int l = bl; l <= level; l++) if (!get_vec(ctx, l, x)) return UGGPU_DESC_MISMATCH;
+  for (int l = bl; l <= level; l++) if (!get_vec_lazy(ctx, l, x)) return UGGPU_DESC_MISMATCH;
   double reach[UGGPU_MAX_BS];
   res->error_code = 0; res->converged = 0; res->number_of_linear_iterations = 0;
   for (int i = 0; i < bs; i++) {

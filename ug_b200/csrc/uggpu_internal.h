@@ -77,6 +77,7 @@ struct Level {
   bool uniform_flags = true;     // every row class 3 / both ctl bits (lets kernels skip flag reads? no: flags are always read)
   std::map<int, SellMat> mats;
   std::map<int, double *> vecs;
+  std::map<int, cudaEvent_t> pending;   // vectors with an asynchronous upload in flight on the copy stream (uggpu_vec_upload_async)
   SellMat P, R;                  // P: rows = this level, cols = level-1;  R: rows = level-1, cols = this level
   // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
   double *lu = nullptr;
@@ -94,6 +95,7 @@ struct Level {
 struct uggpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // second stream for uploads that overlap the cycle (created on first use)
   Level lev[UGGPU_MAX_LEVELS];
   int fullrefinelevel = 0;
   int64_t launches = 0;
@@ -196,7 +198,9 @@ int dev_free(uggpu_ctx *ctx, void *p, size_t bytes);
 template <class T> static inline int dalloc(uggpu_ctx *ctx, T **p, size_t count) { return dev_alloc(ctx, (void **)p, count * sizeof(T)); }
 template <class T> static inline int dfree(uggpu_ctx *ctx, T *&p, size_t count) { int rc = dev_free(ctx, (void *)p, count * sizeof(T)); p = nullptr; return rc; }
 Level *get_level(uggpu_ctx *ctx, int level);                 // NULL + error if absent
-double *get_vec(uggpu_ctx *ctx, int level, int vec);         // NULL + error if absent
+double *get_vec(uggpu_ctx *ctx, int level, int vec);         // NULL + error if absent; orders the compute stream behind a pending upload of the vector
+double *get_vec_lazy(uggpu_ctx *ctx, int level, int vec);    // the pointer only: the caller calls vec_wait() before the first kernel that touches it
+int vec_wait(uggpu_ctx *ctx, int level, int vec);
 SellMat *get_mat(uggpu_ctx *ctx, int level, int mat);
 int ensure_partials(uggpu_ctx *ctx, size_t count);
 int check_device_error(uggpu_ctx *ctx);                      // sync + read the device error word
