@@ -103,7 +103,7 @@ Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs)
   if (cap < dist) dist = cap;
   if (dist < resident / 2) dist = 0;
   pf.dist = d ? atoi(d) : (int)dist;
-  pf.mode = m ? atoi(m) : 7;
+  pf.mode = m ? atoi(m) : 31;
   pf.nsl = (A->n + 31) / 32;
   pf.val_lines = (A->maxlen * A->bb * 256 + 127) / 128;
   pf.col_lines = A->maxlen < 32 ? A->maxlen : 32;
@@ -301,6 +301,7 @@ extern "C" int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *
   if (it != L->mats.end()) { UG_TRY(sell_free(ctx, &it->second)); L->mats.erase(it); }
   SellMat m;
   UG_TRY(sell_from_host_csr(ctx, L->n, L->bs * L->bs, rowptr, col, val, &m));
+  UG_TRY(sell_update_diag(ctx, &m));
   L->mats[mat] = m;
   return 0;
 }
@@ -309,7 +310,8 @@ extern "C" int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const do
 {
   SellMat *m = get_mat(ctx, level, mat);
   if (!m) return UGGPU_DESC_MISMATCH;
-  return sell_set_values_host(ctx, m, val);
+  UG_TRY(sell_set_values_host(ctx, m, val));
+  return sell_update_diag(ctx, m);
 }
 
 extern "C" int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val)

@@ -225,6 +225,28 @@ int sell_compress_cols(uggpu_ctx *ctx, SellMat *m)
   return rc;
 }
 
+__global__ void k_sell_diag(int n, int bb, const int64_t *__restrict__ slice_ptr, const uint16_t *__restrict__ rowlen, const double *__restrict__ val,
+                            double *__restrict__ diag)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsl = (n + 31) >> 5;
+  if ((r >> 5) >= nsl) return;
+  const int s = r >> 5, lane = r & 31;
+  const bool has = r < n && rowlen[r] > 0;
+  const int64_t sp = slice_ptr[s];
+  for (int k = 0; k < bb; k++) diag[((size_t)s * bb + k) * 32 + lane] = has ? val[(sp * bb) + (int64_t)k * 32 + lane] : 0.0;
+}
+
+int sell_update_diag(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->n <= 0) return 0;
+  const size_t nsl = (size_t)(m->n + 31) / 32;
+  if (!m->diag) UG_TRY(dalloc(ctx, &m->diag, nsl * 32 * m->bb));
+  k_sell_diag<<<(int)((nsl * 32 + 255) / 256), 256, 0, ctx->stream>>>(m->n, m->bb, m->slice_ptr, m->rowlen, m->val, m->diag);
+  KCHECK(ctx);
+  return 0;
+}
+
 int sell_free(uggpu_ctx *ctx, SellMat *m)
 {
   if (m->n <= 0 && !m->col) { *m = SellMat(); return 0; }
@@ -235,6 +257,7 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   dfree(ctx, m->rowlen, (size_t)m->n);
   dfree(ctx, m->col, (size_t)m->col_len);
   dfree(ctx, m->val, (size_t)m->padded * m->bb);
+  if (m->diag) dfree(ctx, m->diag, nsl * 32 * m->bb);
   *m = SellMat();
   return 0;
 }

@@ -206,19 +206,19 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_
   constexpr int BB = BS * BS;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= A.n) return;
-  {     // only the diagonal blocks (the first BB columns of the slice's value block) and the defect are read
-    pf.val_lines = 2 * BB; pf.mode &= ~2;
-    const PfState pfs = pf_begin(A, r, pf);
-    pf_end<BB>(A, pfs, pf);
-    if ((pf.mode & 4) && pfs.sp >= 0) pf_vec<BS>(d, pfs, pf);
+  const int lane = r & 31;
+  if (pf.dist > 0 && (r >> 5) + pf.dist < pf.nsl) {     // every stream of this kernel is direct-indexed: touch the far slice's lines now
+    const PfState far{0, -1, (r >> 5) + pf.dist};
+    if (lane < 2 * BB) prefetch_l2(reinterpret_cast<const char *>(A.diag) + ((size_t)far.slice * 32 * BB) * sizeof(double) + (size_t)lane * 128);
+    pf_vec<BS>(d, far, pf);
+    pf_rows<1>(vclass, far, pf);
   }
   double sol[BS];
   if (vclass[r] < 3) {
 #pragma unroll
     for (int i = 0; i < BS; i++) sol[i] = 0.0;
   } else {
-    const int64_t sp = A.slice_ptr[r >> 5];
-    const double *__restrict__ vp = A.val + sp * BB + (r & 31);
+    const double *__restrict__ vp = A.diag + ((size_t)(r >> 5) * BB) * 32 + lane;
     double m[BB], rhs[BS];
 #pragma unroll
     for (int k = 0; k < BB; k++) m[k] = vp[(size_t)k * 32];
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uin
   if ((pf.mode & 4) && pfs.sp >= 0) {
     pf_vec<BS>(b, pfs, pf);
     if (FLAGS & SF_CADD) pf_vec<BS>(c, pfs, pf);
+    if (FLAGS & SF_TOUT) pf_rows<1>(vclass, pfs, pf);
   }
   if (FLAGS & SF_NORM) {
     __shared__ double sm[SPMV_THREADS / 32][UGGPU_MAX_BS];

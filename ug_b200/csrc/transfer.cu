@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 #pragma unroll
   for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
   pf_end<1>(R, pfs, pf);
+  if ((pf.mode & 4) && pfs.sp >= 0) { pf_rows<1>(vnclass_c, pfs, pf); pf_rows<4>(skip_c, pfs, pf); if (FUSE) pf_rows<1>(vclass_c, pfs, pf); }
   if (FUSE) {
     constexpr int BB = BS * BS;
     double sol[BS];
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 #pragma unroll
       for (int i = 0; i < BS; i++) sol[i] = 0.0;
     } else {
-      const double *__restrict__ vp = Ac.val + Ac.slice_ptr[r >> 5] * BB + lane;
+      const double *__restrict__ vp = Ac.diag + ((size_t)(r >> 5) * BB) * 32 + lane;
       double m[BB];
 #pragma unroll
       for (int k = 0; k < BB; k++) m[k] = vp[(size_t)k * 32];
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_interpolate_k(SellView P, const 
 #pragma unroll
   for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
   pf_end<1>(P, pfs, pf);
+  if ((pf.mode & 4) && pfs.sp >= 0) pf_rows<4>(skip_f, pfs, pf);
 }
 
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp)

@@ -41,6 +41,9 @@ struct SellMat {
   int64_t  col_len = 0;           // int32 words in col (== padded while uncompressed)
   int64_t  uniform_slices = 0;
   double  *val = nullptr;         // [padded*bb]
+  double  *diag = nullptr;        // [nslices*32*bb] copy of entry 0 of every row (the diagonal block), same planar slice layout as val with width 1:
+                                  // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
+                                  // fused into the restriction) stream it instead of touching one column of every slice of val.  Matrices only (not P, R).
   bool valid() const { return n > 0 && col != nullptr; }
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
   // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
@@ -54,8 +57,9 @@ struct SellView {          // what a kernel needs (passed by value)
   const uint16_t *rowlen;
   const int32_t *col;
   const double *val;
+  const double *diag;
 };
-static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val}; }
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag}; }
 
 #ifdef __CUDACC__
 // column index of entry j of row r:  __ldg(ci.p + j * ci.stride) + ci.base   (warp-uniform stride/base)
@@ -133,7 +137,7 @@ struct ProfScope {
 struct Prefetch {
   int dist;        // slices ahead (0: off)
   int nsl;         // slices of the matrix
-  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 vector entries of the rows
+  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 vector entries of the rows, bit 3 slice offsets / row lengths two hops ahead, bit 4 row flags
   int val_lines;   // 128-byte lines of the widest slice's value block
   int col_lines;   // same for explicit column words
   int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
@@ -147,6 +151,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ PfState pf_begin(const SellView &A, int r, const Prefetch &pf)
 {
   PfState st{-1, -1, (r >> 5) + pf.dist};
+  // two hops: the slice offsets / row lengths of the slice 2*dist ahead are direct-indexed -> touched now, so that the loads of
+  // the far slice's offsets below (and every kernel's first loads) are L2 hits, not HBM round trips
+  const int far2 = (r >> 5) + 2 * pf.dist, lane = threadIdx.x & 31;
+  if ((pf.mode & 8) && pf.dist > 0 && far2 < pf.nsl && lane < 3)
+    prefetch_l2(lane == 0 ? (const void *)(A.slice_ptr + far2) : lane == 1 ? (const void *)(A.col_ptr + far2) : (const void *)(A.rowlen + (size_t)far2 * 32));
   if (pf.dist > 0 && st.slice < pf.nsl) {
     st.sp = __ldg(A.slice_ptr + st.slice);
     if (pf.mode & 2) st.cp = __ldg(A.col_ptr + st.slice);
@@ -178,6 +187,13 @@ __device__ __forceinline__ void pf_vec(const double *v, const PfState &st, const
     const int64_t o = ((int64_t)st.slice * 32 * BS) * (int64_t)sizeof(double) + (int64_t)lane * 128;
     if (o < pf.vec_bytes) prefetch_l2(reinterpret_cast<const char *>(v) + o);
   }
+}
+// the far slice's 32 rows of a per-row array of ELEM-byte entries (flags)
+template <int ELEM>
+__device__ __forceinline__ void pf_rows(const void *base, const PfState &st, const Prefetch &pf)
+{
+  const int lane = threadIdx.x & 31;
+  if ((pf.mode & 16) && lane < (32 * ELEM + 127) / 128 && st.slice < pf.nsl) prefetch_l2(reinterpret_cast<const char *>(base) + ((size_t)st.slice * 32 + 0) * ELEM + (size_t)lane * 128);
 }
 #endif
 
@@ -214,6 +230,8 @@ int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t 
 int sell_free(uggpu_ctx *ctx, SellMat *m);
 // replaces the explicit column words of uniform slices by one distance per slice column (lossless); no-op when nothing is gained
 int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);
+// (re)builds m->diag from the values (after the matrix is built and after every change of its values)
+int sell_update_diag(uggpu_ctx *ctx, SellMat *m);
 
 // ---- kernels used across files --------------------------------------------------------------------------
 struct Damp { double a[UGGPU_MAX_BS]; };
