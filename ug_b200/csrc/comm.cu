@@ -13,6 +13,8 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -25,17 +27,34 @@ struct Nccl {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 } nccl;
 
+#define P2P_MAX_RANKS 32
+#define P2P_FLAG_BYTES 512                // flags[rank] (8 bytes each) at the start of every window allocation
+
+// One receive window per rank, opened by its neighbours with CUDA IPC: the halo exchange of a partitioned level is then
+//   k_halo_push         my interface rows -> straight into the neighbours' windows over NVLink (peer stores), then one
+//                       release store of the exchange number into each neighbour's flag word;
+//   k_halo_wait_unpack  wait until every neighbour's number has arrived, copy the window into the ghost rows of the vector.
+// No NCCL call, no staging on the sender.  Two window halves alternate: a sender can only be one exchange ahead of a
+// receiver (it needs the receiver's flag of exchange e before it starts e+1), so half (e & 1) is free again at e+2.
+struct Peer { unsigned char *base = nullptr; int64_t half = 0; };
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   double *sendbuf = nullptr;
   size_t sendbuf_cap = 0;
   int64_t exchanges = 0, allreduces = 0;
+  // peer-memory path
+  bool p2p_tried = false, p2p = false;
+  unsigned char *win = nullptr; size_t win_bytes = 0; int64_t half = 0;   // my window: flags, then 2 * half doubles
+  Peer peers[P2P_MAX_RANKS];
+  unsigned long long seq = 0;
+  unsigned int *push_counter = nullptr;
 };
 
 int load_nccl()
@@ -49,7 +68,7 @@ int load_nccl()
   }
   if (!nccl.dl) return uggpu_fail(UGGPU_ERROR, "cannot load NCCL (libnccl.so.2): %s", dlerror());
 #define SYM(f) *(void **)(&nccl.f) = dlsym(nccl.dl, "nccl" #f); if (!nccl.f) return uggpu_fail(UGGPU_ERROR, "NCCL symbol nccl" #f " missing")
-  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(AllGather); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
   return 0;
 }
@@ -91,6 +110,9 @@ extern "C" int uggpu_comm_destroy(uggpu_ctx *ctx)
   Comm *c = (Comm *)ctx->comm;
   cudaStreamSynchronize(ctx->stream);
   if (c->sendbuf) dfree(ctx, c->sendbuf, c->sendbuf_cap);
+  for (int q = 0; q < P2P_MAX_RANKS; q++) if (c->peers[q].base) cudaIpcCloseMemHandle(c->peers[q].base);
+  if (c->win) dfree(ctx, c->win, c->win_bytes);
+  if (c->push_counter) dfree(ctx, c->push_counter, 1);
   if (c->comm) nccl.CommDestroy(c->comm);
   delete c;
   ctx->comm = nullptr;
@@ -119,11 +141,183 @@ __global__ void k_halo_pack(int total, int bs, const int32_t *__restrict__ idx, 
   buf[i] = v[(size_t)idx[e] * bs + c];
 }
 
+// ---- peer-memory halo exchange ---------------------------------------------------------------------------------------------
+struct PushArgs {
+  int nnb, bs, parity;
+  unsigned long long seq;
+  int send_off[PART_MAX_NB + 1];
+  double *dst[PART_MAX_NB];                  // neighbour's window half + its receive offset for me
+  unsigned long long *flag[PART_MAX_NB];     // neighbour's flag word for me
+};
+
+__global__ void k_halo_push(PushArgs a, int total, const int32_t *__restrict__ idx, const double *__restrict__ v, unsigned int *counter)
+{
+  const int n = total * a.bs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = i / a.bs, cpt = i - e * a.bs;
+    int k = 0;
+    while (e >= a.send_off[k + 1]) k++;
+    a.dst[k][(size_t)(e - a.send_off[k]) * a.bs + cpt] = v[(size_t)idx[e] * a.bs + cpt];
+  }
+  // the last block to finish publishes the exchange number to every neighbour (release, system scope)
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < a.nnb) {
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[threadIdx.x]), "l"(a.seq) : "memory");
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+struct WaitArgs {
+  int nnb;
+  unsigned long long seq;
+  const unsigned long long *flag[PART_MAX_NB];   // my flag words, one per neighbour
+};
+
+// every block waits for all neighbours (thread k polls neighbour k), then the grid copies the window half into the ghost rows;
+// a neighbour that does not show up within ~10 s is reported through the device error word instead of hanging the GPU
+__global__ void k_halo_wait_unpack(WaitArgs a, const double *__restrict__ win, double *__restrict__ ghost, size_t count, int *err)
+{
+  if (threadIdx.x < a.nnb) {
+    unsigned long long t0, t1, got;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(a.flag[threadIdx.x]) : "memory");
+      if (got >= a.seq) break;
+      if (*reinterpret_cast<volatile int *>(err)) break;        // an earlier exchange already failed: do not wait again
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) ghost[i] = win[i];
+}
+
+// Allocates my window, exchanges the IPC handles with ncclAllGather, opens the neighbours' windows.  Collective: every rank
+// calls it at its first halo exchange.  All ranks agree on the outcome (all-reduce of the success flags); on failure the
+// NCCL send/recv path stays in use.
+static int p2p_setup(uggpu_ctx *ctx, Comm *c)
+{
+  c->p2p_tried = true;
+  const char *mode = getenv("UGGPU_HALO");
+  int want = !(mode && strcmp(mode, "nccl") == 0) && c->nranks <= P2P_MAX_RANKS;
+  int64_t half = 0;
+  const PartGrid *gany = nullptr;
+  for (int l = 0; l < UGGPU_MAX_LEVELS; l++) {
+    Level &L = ctx->lev[l];
+    if (!L.exists || !L.partitioned || !L.part) continue;
+    gany = L.part;
+    int64_t h = (int64_t)L.nghost * L.bs;
+    if (h > half) half = h;
+  }
+  half = (half + 31) & ~(int64_t)31;
+  struct Info { cudaIpcMemHandle_t h; int64_t half; int64_t ok; };
+  static_assert(sizeof(Info) == 80, "Info layout");
+  Info mine;
+  memset(&mine, 0, sizeof mine);
+  mine.half = half; mine.ok = 0;
+  if (want && gany) {
+    c->win_bytes = P2P_FLAG_BYTES + 2 * (size_t)half * sizeof(double);
+    if (dev_alloc(ctx, (void **)&c->win, c->win_bytes) == 0 && dalloc(ctx, &c->push_counter, 1) == 0) {
+      cudaMemsetAsync(c->win, 0, c->win_bytes, ctx->stream);
+      cudaMemsetAsync(c->push_counter, 0, sizeof(unsigned int), ctx->stream);
+      if (cudaIpcGetMemHandle(&mine.h, c->win) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
+    }
+  }
+  c->half = half;
+  Info *d_send = nullptr, *d_recv = nullptr;
+  UG_TRY(dalloc(ctx, &d_send, 1));
+  UG_TRY(dalloc(ctx, &d_recv, (size_t)c->nranks));
+  CUDA_TRY(cudaMemcpyAsync(d_send, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(nccl.AllGather(d_send, d_recv, sizeof(Info), ncclChar, c->comm, ctx->stream));
+  std::vector<Info> all((size_t)c->nranks);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_recv, sizeof(Info) * c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int ok = mine.ok ? 1 : 0;
+  for (int q = 0; q < c->nranks; q++) if (!all[q].ok) ok = 0;
+  if (ok && gany) {
+    for (int k = 0; k < gany->nnb && ok; k++) {
+      const int q = gany->nb_rank[k];
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      c->peers[q].base = (unsigned char *)ptr;
+      c->peers[q].half = all[q].half;
+    }
+  }
+  // agree: 1.0 per rank that opened everything
+  double *d_ok = (double *)d_send, h_ok = ok ? 1.0 : 0.0;
+  CUDA_TRY(cudaMemcpyAsync(d_ok, &h_ok, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  c->p2p = h_ok == (double)c->nranks;
+  dfree(ctx, d_send, 1); dfree(ctx, d_recv, (size_t)c->nranks);
+  if (getenv("UGGPU_HALO_VERBOSE") && c->rank == 0)
+    fprintf(stderr, "uggpu: halo exchange over %s (%d ranks, window %lld doubles per half)\n", c->p2p ? "peer memory (CUDA IPC)" : "NCCL send/recv", c->nranks, (long long)half);
+  return 0;
+}
+
+static int halo_exchange_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v)
+{
+  const PartGrid &g = *L->part;
+  const int bs = L->bs;
+  if (L->peer_recv_off.empty()) {       // where my rows land in each neighbour's window: its receive offset for me on this level
+    int cells[3];
+    for (int d = 0; d < 3; d++) cells[d] = d < g.dim ? g.nn[d] - 1 : 0;
+    for (int k = 0; k < g.nnb; k++) {
+      PartGrid nb;
+      if (part_make(&nb, g.dim, cells, g.P, g.nb_rank[k], 0)) return uggpu_fail(UGGPU_ERROR, "halo: cannot rebuild the partition of rank %d", g.nb_rank[k]);
+      int kk = -1;
+      for (int j = 0; j < nb.nnb; j++) if (nb.nb_rank[j] == g.rank) kk = j;
+      if (kk < 0) return uggpu_fail(UGGPU_ERROR, "halo: rank %d does not list rank %d as a neighbour", g.nb_rank[k], g.rank);
+      if (nb.nb_recv_off[kk + 1] - nb.nb_recv_off[kk] != g.nb_send_off[k + 1] - g.nb_send_off[k])
+        return uggpu_fail(UGGPU_ERROR, "halo: interface sizes of ranks %d and %d differ", g.rank, g.nb_rank[k]);
+      L->peer_recv_off.push_back(nb.nb_recv_off[kk]);
+    }
+  }
+  const unsigned long long seq = ++c->seq;
+  const int parity = (int)(seq & 1ull);
+  PushArgs pa;
+  WaitArgs wa;
+  pa.nnb = wa.nnb = g.nnb; pa.bs = bs; pa.parity = parity; pa.seq = wa.seq = seq;
+  for (int k = 0; k <= g.nnb; k++) pa.send_off[k] = g.nb_send_off[k];
+  for (int k = 0; k < g.nnb; k++) {
+    const Peer &p = c->peers[g.nb_rank[k]];
+    pa.dst[k] = reinterpret_cast<double *>(p.base + P2P_FLAG_BYTES) + (size_t)parity * p.half + (size_t)L->peer_recv_off[k] * bs;
+    pa.flag[k] = reinterpret_cast<unsigned long long *>(p.base) + c->rank;
+    wa.flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + g.nb_rank[k];
+  }
+  const int tot = L->send_total * bs;
+  int pb = (tot + 255) / 256;
+  if (pb > 4 * ctx->sm_count) pb = 4 * ctx->sm_count;
+  if (pb < 1) pb = 1;
+  k_halo_push<<<pb, 256, 0, ctx->stream>>>(pa, L->send_total, L->d_send_idx, v, c->push_counter);
+  KCHECK(ctx);
+  const size_t cnt = (size_t)L->nghost * bs;
+  int wb = (int)((cnt + 255) / 256);
+  if (wb > ctx->sm_count) wb = ctx->sm_count;        // every block polls: keep them all resident
+  if (wb < 1) wb = 1;
+  k_halo_wait_unpack<<<wb, 256, 0, ctx->stream>>>(wa, reinterpret_cast<const double *>(c->win + P2P_FLAG_BYTES) + (size_t)parity * c->half,
+                                                   v + (size_t)L->n * bs, cnt, ctx->derr);
+  KCHECK(ctx);
+  c->exchanges++;
+  return 0;
+}
+
 int halo_exchange(uggpu_ctx *ctx, int level, double *v)
 {
   Level *L = &ctx->lev[level];
   if (!ctx->comm || !L->partitioned || !L->part || L->part->nnb == 0) return 0;
   Comm *c = (Comm *)ctx->comm;
+  if (!c->p2p_tried) UG_TRY(p2p_setup(ctx, c));
+  if (c->p2p) return halo_exchange_p2p(ctx, c, L, v);
   const PartGrid &g = *L->part;
   const int bs = L->bs;
   size_t need = (size_t)L->send_total * bs;

@@ -94,6 +94,7 @@ struct Level {
   struct PartGrid *d_part = nullptr;    // device copy
   int32_t *d_send_idx = nullptr;        // owned rows to pack, grouped by neighbour (PartGrid::nb_send_off)
   int send_total = 0;
+  std::vector<int> peer_recv_off;       // per neighbour: where my rows start in ITS ghost region (peer-memory halo exchange, comm.cu)
 };
 
 struct uggpu_ctx {
