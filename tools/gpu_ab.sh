@@ -1,5 +1,5 @@
 #!/bin/bash
-# generic A/B: bash tests/gpu_ab.sh <tag> "<name> ENV=.. ENV=.." ...   (runs pytest first, then one p1 bench per variant, then q1 for each)
+# generic A/B: bash tools/gpu_ab.sh <tag> "<name> ENV=.. ENV=.." ...   (runs pytest first, then one p1 bench per variant, then q1 for each)
 tag=$1; shift; out=gpurun_out; mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 for spec in "$@"; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU round: parity test, then bench with the peer-memory and the NCCL halo exchange.  bash tests/gpu_mgpu.sh <tag> <ngpus>
+# multi-GPU round: parity test, then bench with the peer-memory and the NCCL halo exchange.  bash tools/gpu_mgpu.sh <tag> <ngpus>
 tag=$1; N=$2; out=gpurun_out; mkdir -p $out
 UGGPU_HALO_VERBOSE=1 timeout 600 python -m pytest tests/test_mgpu.py -m gpu -x -q 2>&1 | tail -5
 run() { name=$1; shift

@@ -1,5 +1,5 @@
 #!/bin/bash
-# bench lines + ncu evidence for profiles/: bash tests/gpu_profile.sh <tag>
+# bench lines + ncu evidence for profiles/: bash tools/gpu_profile.sh <tag>
 tag=$1
 out=gpurun_out; mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
