@@ -92,16 +92,16 @@ SellMat *get_mat(uggpu_ctx *ctx, int level, int mat)
 // lines are evicted from the 126 MB L2 before they are used and the kernel gets slower than without prefetch), and off when
 // that cap falls below half a generation (3x3 blocks with 27 entries: 62 KB per slice; such rows are long streams per thread
 // and reach 0.9 of the HBM peak without help).
-Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs)
+Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs, int slices_per_warp)
 {
   Prefetch pf;
   const char *d = getenv("UGGPU_PF_DIST"), *m = getenv("UGGPU_PF_MODE");
   const int64_t resident = (int64_t)ctx->sm_count * (2048 / 32);
   const int64_t slice_bytes = (int64_t)(A->maxlen > 0 ? A->maxlen : 1) * A->bb * 256;
-  int64_t dist = resident * 3 / 4;
+  int64_t dist = resident * 3 / 4 * slices_per_warp;      // a resident warp holds slices_per_warp slices: one generation is that much longer
   const int64_t cap = ((int64_t)40 << 20) / slice_bytes;
   if (cap < dist) dist = cap;
-  if (dist < resident / 2) dist = 0;
+  if (dist < resident / 2 * slices_per_warp) dist = 0;
   pf.dist = d ? atoi(d) : (int)dist;
   pf.mode = m ? atoi(m) : 31;
   pf.nsl = (A->n + 31) / 32;

@@ -9,6 +9,20 @@
 #include <map>
 #include <vector>
 
+void sell_layout(const std::vector<int> &width, std::vector<int64_t> &sp, int *maxlen, int *fixed_w)
+{
+  const size_t nsl = width.size();
+  int mx = 0;
+  int64_t padded = 0;
+  for (size_t s = 0; s < nsl; s++) { if (width[s] > mx) mx = width[s]; padded += (int64_t)width[s] * 32; }
+  const int64_t fixed = (int64_t)nsl * 32 * mx;
+  const bool fix = mx > 0 && fixed <= padded + padded / 8 && !getenv("UGGPU_NO_FIXED_WIDTH");
+  sp.assign(nsl + 1, 0);
+  for (size_t s = 0; s < nsl; s++) sp[s + 1] = sp[s] + (int64_t)(fix ? mx : width[s]) * 32;
+  *maxlen = mx;
+  *fixed_w = fix ? mx : 0;
+}
+
 __global__ void k_sell_rowlen(int n, const int64_t *__restrict__ rowptr, uint16_t *__restrict__ rowlen, int *__restrict__ width, int *err)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,7 +287,7 @@ int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr,
   UG_TRY(dalloc(ctx, &m.slice_ptr, nsl + 1));
   UG_TRY(dalloc(ctx, &d_width, nsl));
   std::vector<int> width(nsl);
-  std::vector<int64_t> sp(nsl + 1, 0);
+  std::vector<int64_t> sp;
   if (n > 0) {
     int blocks = (int)((nsl * 32 + 255) / 256);
     k_sell_rowlen<<<blocks, 256, 0, st>>>(n, d_rowptr, m.rowlen, d_width, ctx->derr);
@@ -284,7 +298,7 @@ int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr,
     UG_TRY(check_device_error(ctx));
     m.nnz = last;
   }
-  for (size_t s = 0; s < nsl; s++) { sp[s + 1] = sp[s] + (int64_t)width[s] * 32; if (width[s] > m.maxlen) m.maxlen = width[s]; }
+  sell_layout(width, sp, &m.maxlen, &m.fixed_w);
   m.padded = sp[nsl];
   UG_TRY(dfree(ctx, d_width, nsl));
   CUDA_TRY(cudaMemcpyAsync(m.slice_ptr, sp.data(), (nsl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));

@@ -28,7 +28,7 @@ __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len,
 {
   constexpr int BB = BS * BS;
   const int lane = r & 31;
-  const int64_t sp = A.slice_ptr[r >> 5];
+  const int64_t sp = slice_off(A, r >> 5);
   const double *__restrict__ vp = A.val + sp * BB + lane;
 #pragma unroll
   for (int i = 0; i < BS; i++) s[i] = 0.0;
@@ -36,7 +36,7 @@ __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len,
   for (int k = 0; k < BB; k++) dg[k] = 0.0;
   if (UNIFORM) {
     // all 32 lanes of the warp are here (rows that do not take part have len = 0)
-    const int w = (int)((A.slice_ptr[(r >> 5) + 1] - sp) >> 5);
+    const int w = slice_width(A, r >> 5, sp);
     const int32_t *__restrict__ dp = A.col + ~cpo;
     for (int j0 = 0; j0 < w; j0 += 32) {
       const int dreg = (j0 + lane < w) ? __ldg(dp + j0 + lane) : 0;
@@ -95,7 +95,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 template <int BS>
 __device__ __forceinline__ void row_product(const SellView &A, int r, bool live, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
-  const int64_t cpo = A.col_ptr[r >> 5];
+  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
   const int len = live ? (int)A.rowlen[r] : 0;
   if (cpo < 0) row_product_t<BS, true>(A, r, len, cpo, y, s, dg);
   else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);

@@ -312,7 +312,7 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
   UG_TRY(dalloc(ctx, &d_nnz, 1));
   CUDA_TRY(cudaMemsetAsync(d_nnz, 0, sizeof(unsigned long long), st));
   std::vector<int> width(nsl);
-  std::vector<int64_t> sp_host(nsl + 1, 0);
+  std::vector<int64_t> sp_host;
   int blocks = (int)((nsl * 32 + 255) / 256);
   if (blocks > 0) {
     k_synth_len<WHICH><<<blocks, 256, 0, st>>>(sp, d_g, d_gc, n, m.rowlen, d_width, d_nnz);
@@ -322,7 +322,7 @@ static int synth_sell(uggpu_ctx *ctx, const SynthParams &sp, const PartGrid *d_g
   CUDA_TRY(cudaMemcpyAsync(&h_nnz, d_nnz, sizeof h_nnz, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   m.nnz = (int64_t)h_nnz;
-  for (size_t s = 0; s < nsl; s++) { sp_host[s + 1] = sp_host[s] + (int64_t)width[s] * 32; if (width[s] > m.maxlen) m.maxlen = width[s]; }
+  sell_layout(width, sp_host, &m.maxlen, &m.fixed_w);
   m.padded = sp_host[nsl];
   UG_TRY(dfree(ctx, d_width, nsl));
   UG_TRY(dfree(ctx, d_nnz, 1));

@@ -9,117 +9,226 @@
 // additions in the same order as the reference -> bit-identical results.
 #include "uggpu_internal.h"
 
+#include <cstdlib>
+
 #define TR_THREADS 256
+
+// Both kernels give every warp K consecutive slices (thread = K rows, one per slice) and issue the loads of the K rows
+// together: column words and weights of entry j of all K rows first, then the K gathers, then the arithmetic.  A transfer
+// row is short (P: 1-2 entries on simplices, at most 8 on hexahedra), so one row per thread leaves a warp with three DEPENDENT
+// round trips (slice offset -> entry -> gathered operand) of a few hundred bytes each -- latency-bound at under half of the HBM
+// bandwidth.  K independent chains per thread multiply the bytes in flight without changing any row's
+// additions or their order.
+// Fixed-width stencils (sell_layout: all uniformly refined grids) have no slice-offset load at all: two hops, and every stream
+// but the gathered operand is direct-indexed, so its far lines are touched when the warp STARTS.
+#ifndef TR_K_INTERP
+#define TR_K_INTERP 4
+#endif
+#ifndef TR_K_RESTRICT
+#define TR_K_RESTRICT 2
+#endif
+
+// L2 prefetch of the stencil entries of the slice pf.dist ahead of row r's (uggpu_internal.h), request and touch in one go
+__device__ __forceinline__ bool tr_prefetch(const SellView &T, int r, const Prefetch &pf)
+{
+  const PfState st = pf_begin(T, r, pf);
+  pf_end<1>(T, st, pf);
+  return (pf.mode & 4) && st.sp >= 0;
+}
 
 // StandardRestrict (transgrid.cc:462 -> :117): to[coarse] (zeroed where VNCLASS >= NEWDEF_CLASS) += sum w * (damp*from[fine]),
 // suppressed per component by the coarse VECSKIP bits (:161-165,:180-186).
 // Optionally fused (FUSE): the first Jacobi correction of the coarse level, tout = sdamp * Diag(Ac)^-1 to (class-masked,
 // ugiter.cc:271 + iter.cc:836) and c = 0 (dset, iter.cc:7873).
-template <int BS, bool FUSE>
+template <bool FUSE>
+__device__ __forceinline__ void restrict_prefetch(const SellView &R, int r, const Prefetch &pf, const uint8_t *vnclass_c, const uint32_t *skip_c, const uint8_t *vclass_c)
+{
+  if (tr_prefetch(R, r, pf)) {
+    const PfState far{0, -1, (r >> 5) + pf.dist};
+    pf_rows<1>(vnclass_c, far, pf); pf_rows<4>(skip_c, far, pf);
+    if (FUSE) pf_rows<1>(vclass_c, far, pf);
+  }
+}
+
+template <int BS, bool FUSE, int K>
 __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uint8_t *__restrict__ vnclass_c, const uint32_t *__restrict__ skip_c,
                                                            double *__restrict__ to, const double *__restrict__ from, Damp damp,
                                                            SellView Ac, const uint8_t *__restrict__ vclass_c, double *__restrict__ tout, double *__restrict__ czero,
                                                            Damp sdamp, int *err, Prefetch pf)
 {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R.n) return;
-  const PfState pfs = pf_begin(R, r, pf);
-  double tr[BS];
-  const bool zero = vnclass_c[r] >= 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp * K * 32 >= R.n) return;
+  int r[K], len[K];
+  uint32_t skip[K];
+  ColIter ci[K];
+  const double *wp[K];
+  double tr[K][BS];
+  int maxl = 0;
+  const bool early = R.fixed_w != 0;       // warp-uniform
 #pragma unroll
-  for (int i = 0; i < BS; i++) tr[i] = zero ? 0.0 : to[(size_t)r * BS + i];
-  const uint32_t skip = skip_c[r];
-  const int lane = r & 31;
-  const int64_t sp = R.slice_ptr[r >> 5];
-  const int len = R.rowlen[r];
-  const ColIter ci = col_iter(R, r);
-  const double *__restrict__ wp = R.val + sp + lane;
+  for (int k = 0; k < K; k++) {
+    r[k] = (int)((warp * K + k) * 32) + lane;
+    const bool live = r[k] < R.n;
+    len[k] = 0; skip[k] = 0; ci[k] = ColIter{R.col, 0, 0}; wp[k] = R.val;
+#pragma unroll
+    for (int i = 0; i < BS; i++) tr[k][i] = 0.0;
+    if (live) {
+      if (early) restrict_prefetch<FUSE>(R, r[k], pf, vnclass_c, skip_c, vclass_c);
+      const bool zero = vnclass_c[r[k]] >= 2;
+#pragma unroll
+      for (int i = 0; i < BS; i++) tr[k][i] = zero ? 0.0 : to[(size_t)r[k] * BS + i];
+      skip[k] = skip_c[r[k]];
+      len[k] = R.rowlen[r[k]];
+      ci[k] = col_iter(R, r[k]);
+      wp[k] = R.val + slice_off(R, r[k] >> 5) + lane;
+    }
+    maxl = max(maxl, len[k]);
+  }
 #pragma unroll 4
-  for (int j = 0; j < len; j++) {
-    const int f = col_at(ci, j);
-    const double w = __ldg(wp + (size_t)j * 32);
+  for (int j = 0; j < maxl; j++) {
+    int f[K];
+    double w[K], v[K][BS];
 #pragma unroll
-    for (int i = 0; i < BS; i++) {
-      if (!(skip & (1u << i))) {
-        double s = damp.a[i] * from[(size_t)f * BS + i];
-        tr[i] = tr[i] + w * s;
+    for (int k = 0; k < K; k++) {
+      const bool on = j < len[k];
+      f[k] = on ? col_at(ci[k], j) : 0;
+      w[k] = on ? __ldg(wp[k] + (size_t)j * 32) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int i = 0; i < BS; i++) v[k][i] = from[(size_t)f[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (j < len[k]) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          if (!(skip[k] & (1u << i))) {
+            double s = damp.a[i] * v[k][i];
+            tr[k][i] = tr[k][i] + w[k] * s;
+          }
+        }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
-  pf_end<1>(R, pfs, pf);
-  if ((pf.mode & 4) && pfs.sp >= 0) { pf_rows<1>(vnclass_c, pfs, pf); pf_rows<4>(skip_c, pfs, pf); if (FUSE) pf_rows<1>(vclass_c, pfs, pf); }
-  if (FUSE) {
-    constexpr int BB = BS * BS;
-    double sol[BS];
-    if (vclass_c[r] < 3) {
+  for (int k = 0; k < K; k++) {
+    if (r[k] >= R.n) continue;
 #pragma unroll
-      for (int i = 0; i < BS; i++) sol[i] = 0.0;
-    } else {
-      const double *__restrict__ vp = Ac.diag + ((size_t)(r >> 5) * BB) * 32 + lane;
-      double m[BB];
+    for (int i = 0; i < BS; i++) to[(size_t)r[k] * BS + i] = tr[k][i];
+    if (!early) restrict_prefetch<FUSE>(R, r[k], pf, vnclass_c, skip_c, vclass_c);
+    if (FUSE) {
+      constexpr int BB = BS * BS;
+      double sol[BS];
+      if (vclass_c[r[k]] < 3) {
 #pragma unroll
-      for (int k = 0; k < BB; k++) m[k] = vp[(size_t)k * 32];
-      if (BS == 1) sol[0] = tr[0] / m[0];
-      else {
-        // same closed forms as solve_small_block (spmv.cu); duplicated here to keep the kernels self-contained
-        if (BS == 2) {
-          double det = m[0] * m[3 % BB] - m[1 % BB] * m[2 % BB];
-          if (det == 0.0) { atomicExch(err, UGGPU_SMALL_DIAG); det = 1.0; }
-          det = 1.0 / det;
-          sol[0] = (tr[0] * m[3 % BB] - tr[1 % BS] * m[1 % BB]) * det;
-          sol[1 % BS] = (tr[1 % BS] * m[0] - tr[0] * m[2 % BB]) * det;
-        } else {
-          double M3div0 = m[3 % BB] / m[0];
-          double M6div0 = m[6 % BB] / m[0];
-          double aux = (m[7 % BB] - M6div0 * m[1 % BB]) / (m[4 % BB] - M3div0 * m[1 % BB]);
-          sol[2 % BS] = (tr[2 % BS] - M6div0 * tr[0] - aux * (tr[1 % BS] - M3div0 * tr[0]))
-                        / (m[8 % BB] - M6div0 * m[2 % BB] - aux * (m[5 % BB] - M3div0 * m[2 % BB]));
-          sol[1 % BS] = (tr[1 % BS] - m[3 % BB] / m[0] * tr[0] - (m[5 % BB] - M3div0 * m[2 % BB]) * sol[2 % BS])
-                        / (m[4 % BB] - M3div0 * m[1 % BB]);
-          sol[0] = (tr[0] - m[1 % BB] * sol[1 % BS] - m[2 % BB] * sol[2 % BS]) / m[0];
+        for (int i = 0; i < BS; i++) sol[i] = 0.0;
+      } else {
+        const double *__restrict__ vp = Ac.diag + ((size_t)(r[k] >> 5) * BB) * 32 + lane;
+        double m[BB];
+#pragma unroll
+        for (int q = 0; q < BB; q++) m[q] = vp[(size_t)q * 32];
+        const double (&t)[BS] = tr[k];
+        if (BS == 1) sol[0] = t[0] / m[0];
+        else {
+          // same closed forms as solve_small_block (spmv.cu); duplicated here to keep the kernels self-contained
+          if (BS == 2) {
+            double det = m[0] * m[3 % BB] - m[1 % BB] * m[2 % BB];
+            if (det == 0.0) { atomicExch(err, UGGPU_SMALL_DIAG); det = 1.0; }
+            det = 1.0 / det;
+            sol[0] = (t[0] * m[3 % BB] - t[1 % BS] * m[1 % BB]) * det;
+            sol[1 % BS] = (t[1 % BS] * m[0] - t[0] * m[2 % BB]) * det;
+          } else {
+            double M3div0 = m[3 % BB] / m[0];
+            double M6div0 = m[6 % BB] / m[0];
+            double aux = (m[7 % BB] - M6div0 * m[1 % BB]) / (m[4 % BB] - M3div0 * m[1 % BB]);
+            sol[2 % BS] = (t[2 % BS] - M6div0 * t[0] - aux * (t[1 % BS] - M3div0 * t[0]))
+                          / (m[8 % BB] - M6div0 * m[2 % BB] - aux * (m[5 % BB] - M3div0 * m[2 % BB]));
+            sol[1 % BS] = (t[1 % BS] - m[3 % BB] / m[0] * t[0] - (m[5 % BB] - M3div0 * m[2 % BB]) * sol[2 % BS])
+                          / (m[4 % BB] - M3div0 * m[1 % BB]);
+            sol[0] = (t[0] - m[1 % BB] * sol[1 % BS] - m[2 % BB] * sol[2 % BS]) / m[0];
+          }
         }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < BS; i++) {
-      tout[(size_t)r * BS + i] = sol[i] * sdamp.a[i];
-      czero[(size_t)r * BS + i] = 0.0;
+      for (int i = 0; i < BS; i++) {
+        tout[(size_t)r[k] * BS + i] = sol[i] * sdamp.a[i];
+        czero[(size_t)r[k] * BS + i] = 0.0;
+      }
     }
   }
 }
 
 // StandardInterpolateCorrection (transgrid.cc:529 -> :235): to[fine] = sum (w*damp) * from[coarse], components with the fine
 // VECSKIP bit set stay 0 (:272-285).
-template <int BS>
-__global__ void __launch_bounds__(TR_THREADS) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
+template <int BS, int K>
+__global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : 1) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
                                                               const double *__restrict__ from, Damp damp, Prefetch pf)
 {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= P.n) return;
-  const PfState pfs = pf_begin(P, r, pf);
-  double tr[BS];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp * K * 32 >= P.n) return;
+  int r[K], len[K];
+  uint32_t skip[K];
+  ColIter ci[K];
+  const double *wp[K];
+  double tr[K][BS];
+  int maxl = 0;
+  const bool early = P.fixed_w != 0;       // warp-uniform
 #pragma unroll
-  for (int i = 0; i < BS; i++) tr[i] = 0.0;
-  const uint32_t skip = skip_f[r];
-  const int lane = r & 31;
-  const int64_t sp = P.slice_ptr[r >> 5];
-  const int len = P.rowlen[r];
-  const ColIter ci = col_iter(P, r);
-  const double *__restrict__ wp = P.val + sp + lane;
+  for (int k = 0; k < K; k++) {
+    r[k] = (int)((warp * K + k) * 32) + lane;
+    const bool live = r[k] < P.n;
+    len[k] = 0; skip[k] = 0; ci[k] = ColIter{P.col, 0, 0}; wp[k] = P.val;
+#pragma unroll
+    for (int i = 0; i < BS; i++) tr[k][i] = 0.0;
+    if (live) {
+      if (early && tr_prefetch(P, r[k], pf)) pf_rows<4>(skip_f, PfState{0, -1, (r[k] >> 5) + pf.dist}, pf);
+      skip[k] = skip_f[r[k]];
+      len[k] = P.rowlen[r[k]];
+      ci[k] = col_iter(P, r[k]);
+      wp[k] = P.val + slice_off(P, r[k] >> 5) + lane;
+    }
+    maxl = max(maxl, len[k]);
+  }
 #pragma unroll 2
-  for (int j = 0; j < len; j++) {
-    const int c = col_at(ci, j);
-    const double w = __ldg(wp + (size_t)j * 32);
+  for (int j = 0; j < maxl; j++) {
+    int c[K];
+    double w[K], v[K][BS];
 #pragma unroll
-    for (int i = 0; i < BS; i++)
-      if (!(skip & (1u << i))) tr[i] = tr[i] + (w * damp.a[i]) * from[(size_t)c * BS + i];
+    for (int k = 0; k < K; k++) {
+      const bool on = j < len[k];
+      c[k] = on ? col_at(ci[k], j) : 0;
+      w[k] = on ? __ldg(wp[k] + (size_t)j * 32) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int i = 0; i < BS; i++) v[k][i] = from[(size_t)c[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (j < len[k]) {
+#pragma unroll
+        for (int i = 0; i < BS; i++)
+          if (!(skip[k] & (1u << i))) tr[k][i] = tr[k][i] + (w[k] * damp.a[i]) * v[k][i];
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < BS; i++) to[(size_t)r * BS + i] = tr[i];
-  pf_end<1>(P, pfs, pf);
-  if ((pf.mode & 4) && pfs.sp >= 0) pf_rows<4>(skip_f, pfs, pf);
+  for (int k = 0; k < K; k++) {
+    if (r[k] >= P.n) continue;
+#pragma unroll
+    for (int i = 0; i < BS; i++) to[(size_t)r[k] * BS + i] = tr[k][i];
+    if (!early && tr_prefetch(P, r[k], pf)) pf_rows<4>(skip_f, PfState{0, -1, (r[k] >> 5) + pf.dist}, pf);
+  }
+}
+
+// grid of a K-slices-per-warp kernel over n rows
+template <int K> static inline int tr_blocks(int n)
+{
+  const int64_t warps = (((int64_t)n + 31) / 32 + K - 1) / K;
+  return (int)((warps * 32 + TR_THREADS - 1) / TR_THREADS);
 }
 
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp)
@@ -133,7 +242,6 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   UG_TRY(halo_exchange(ctx, level, const_cast<double *>(from)));
   const bool gather = ctx->comm && F->partitioned && !C->partitioned;   // first completely held (replicated) level
   if (gather && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start not possible across the gather level");
-  int blocks = (C->n + TR_THREADS - 1) / TR_THREADS;
   SellView Rv = view(F->R);
   SellView Av = Rv;
   if (fuse) {
@@ -143,15 +251,19 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   }
  const double nbf = 8.0 * F->bs * F->n, nbc = 8.0 * F->bs * C->n;
   ProfScope ps(ctx, UGGPU_K_RESTRICT, level, F->R.entry_bytes() + 4.0 * (C->n + 1.0) + nbf + nbc + (fuse ? (double)C->n * 8.0 * F->bs * F->bs + 2.0 * nbc : 0.0));
-  Prefetch pf = make_prefetch(ctx, &F->R, F->bs);
-  pf.val_lines = (F->R.maxlen * 256 + 127) / 128;     // scalar weights whatever the block size
-#define RS(BSV)                                                                                                                        \
-  if (fuse) k_restrict_k<BSV, true><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
-  else k_restrict_k<BSV, false><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf)
+  // scalar rows: TR_K_RESTRICT slices per warp; block rows already carry BS independent gathers per entry and the fused 3x3 solve
+#define RS(BSV, KV)                                                                                                                    \
+  {                                                                                                                                    \
+    const Prefetch pf = make_prefetch(ctx, &F->R, F->bs, KV);                                                                          \
+    const int blocks = tr_blocks<KV>(C->n);                                                                                            \
+    if (fuse) k_restrict_k<BSV, true, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
+    else k_restrict_k<BSV, false, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
+  }
+  static const int kenv = getenv("UGGPU_TR_K_RESTRICT") ? atoi(getenv("UGGPU_TR_K_RESTRICT")) : TR_K_RESTRICT;     // A/B switch
   switch (F->bs) {
-    case 1: RS(1); break;
-    case 2: RS(2); break;
-    default: RS(3); break;
+    case 1: if (kenv >= 4) RS(1, 4) else if (kenv >= 2) RS(1, 2) else RS(1, 1) break;
+    case 2: RS(2, 1); break;
+    default: RS(3, 1); break;
   }
 #undef RS
   KCHECK(ctx);
@@ -169,14 +281,15 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   if (!F->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (F->n == 0) return 0;
   UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
-  int blocks = (F->n + TR_THREADS - 1) / TR_THREADS;
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
-  const Prefetch pf = make_prefetch(ctx, &F->P, F->bs);
+#define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV))
+  static const int kenv = getenv("UGGPU_TR_K_INTERP") ? atoi(getenv("UGGPU_TR_K_INTERP")) : TR_K_INTERP;     // A/B switch
   switch (F->bs) {
-    case 1: k_interpolate_k<1><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
-    case 2: k_interpolate_k<2><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
-    default: k_interpolate_k<3><<<blocks, TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, pf); break;
+    case 1: if (kenv >= 4) IP(1, 4); else if (kenv >= 2) IP(1, 2); else IP(1, 1); break;
+    case 2: if (kenv >= 2) IP(2, 2); else IP(2, 1); break;
+    default: if (kenv >= 2) IP(3, 2); else IP(3, 1); break;
   }
+#undef IP
   KCHECK(ctx);
   return 0;
 }

@@ -34,6 +34,7 @@ struct SellMat {
   int64_t  nnz = 0;        // true entries
   int64_t  padded = 0;     // stored entries (multiple of 32 per slice)
   int      maxlen = 0;
+  int      fixed_w = 0;    // > 0: every slice is padded to this width (slice_ptr[s] == s*32*fixed_w) and kernels compute the offset instead of loading it
   int64_t *slice_ptr = nullptr;   // [nslices+1], entry offsets
   uint16_t *rowlen = nullptr;     // [n]
   int64_t *col_ptr = nullptr;     // [nslices]; == slice_ptr while all slices are explicit (then it is not a separate allocation)
@@ -52,6 +53,7 @@ struct SellMat {
 
 struct SellView {          // what a kernel needs (passed by value)
   int n;
+  int fixed_w;
   const int64_t *slice_ptr;
   const int64_t *col_ptr;
   const uint16_t *rowlen;
@@ -59,14 +61,17 @@ struct SellView {          // what a kernel needs (passed by value)
   const double *val;
   const double *diag;
 };
-static inline SellView view(const SellMat &m) { return SellView{m.n, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag}; }
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.fixed_w, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag}; }
 
 #ifdef __CUDACC__
+// entry offset of slice s (and its width): computed for fixed-width matrices -- one dependent load less per row
+__device__ __forceinline__ int64_t slice_off(const SellView &A, int s) { return A.fixed_w ? (int64_t)s * 32 * A.fixed_w : A.slice_ptr[s]; }
+__device__ __forceinline__ int slice_width(const SellView &A, int s, int64_t sp) { return A.fixed_w ? A.fixed_w : (int)((A.slice_ptr[s + 1] - sp) >> 5); }
 // column index of entry j of row r:  __ldg(ci.p + j * ci.stride) + ci.base   (warp-uniform stride/base)
 struct ColIter { const int32_t *p; int stride; int base; };
 __device__ __forceinline__ ColIter col_iter(const SellView &A, int r)
 {
-  const int64_t cp = A.col_ptr[r >> 5];
+  const int64_t cp = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
   if (cp < 0) return ColIter{A.col + ~cp, 1, r};
   return ColIter{A.col + cp + (r & 31), 32, 0};
 }
@@ -143,7 +148,8 @@ struct Prefetch {
   int col_lines;   // same for explicit column words
   int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
 };
-Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs);      // ctx.cu; bs: components per row of the vectors; UGGPU_PF_DIST / UGGPU_PF_MODE override
+// ctx.cu; bs: components per row of the vectors; slices_per_warp: slices one warp of the kernel works on; UGGPU_PF_DIST / UGGPU_PF_MODE override
+Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs, int slices_per_warp = 1);
 
 #ifdef __CUDACC__
 struct PfState { int64_t sp, cp; int slice; };
@@ -155,11 +161,13 @@ __device__ __forceinline__ PfState pf_begin(const SellView &A, int r, const Pref
   // two hops: the slice offsets / row lengths of the slice 2*dist ahead are direct-indexed -> touched now, so that the loads of
   // the far slice's offsets below (and every kernel's first loads) are L2 hits, not HBM round trips
   const int far2 = (r >> 5) + 2 * pf.dist, lane = threadIdx.x & 31;
-  if ((pf.mode & 8) && pf.dist > 0 && far2 < pf.nsl && lane < 3)
-    prefetch_l2(lane == 0 ? (const void *)(A.slice_ptr + far2) : lane == 1 ? (const void *)(A.col_ptr + far2) : (const void *)(A.rowlen + (size_t)far2 * 32));
+  if ((pf.mode & 8) && pf.dist > 0 && far2 < pf.nsl && lane < 3) {
+    if (lane == 2) prefetch_l2(A.rowlen + (size_t)far2 * 32);
+    else if (!A.fixed_w || (lane == 1 && A.col_ptr != A.slice_ptr)) prefetch_l2(lane == 0 ? A.slice_ptr + far2 : A.col_ptr + far2);
+  }
   if (pf.dist > 0 && st.slice < pf.nsl) {
-    st.sp = __ldg(A.slice_ptr + st.slice);
-    if (pf.mode & 2) st.cp = __ldg(A.col_ptr + st.slice);
+    st.sp = A.fixed_w ? (int64_t)st.slice * 32 * A.fixed_w : __ldg(A.slice_ptr + st.slice);
+    if (pf.mode & 2) st.cp = (A.fixed_w && A.col_ptr == A.slice_ptr) ? st.sp : __ldg(A.col_ptr + st.slice);
   }
   return st;
 }
@@ -223,6 +231,10 @@ int ensure_partials(uggpu_ctx *ctx, size_t count);
 int check_device_error(uggpu_ctx *ctx);                      // sync + read the device error word
 
 // ---- SELL (sell.cu) -----------------------------------------------------------------------------------
+// Slice offsets from slice widths.  When padding every slice to the widest one costs at most 1/8 more storage the matrix is
+// laid out with that one width (*fixed_w > 0; UGGPU_NO_FIXED_WIDTH=1 disables): SELL degenerates to ELL and kernels compute
+// the offsets.  Padding is never read, so results do not depend on the choice.
+void sell_layout(const std::vector<int> &width, std::vector<int64_t> &sp, int *maxlen, int *fixed_w);
 // Builds a SELL-32 matrix from device CSR (rowptr int64[n+1], col, val[nnz*bb] row-major blocks).
 int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr, const int32_t *d_col, const double *d_val, SellMat *out);
 int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, const int32_t *col, const double *val, SellMat *out);
