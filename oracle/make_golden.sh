@@ -18,4 +18,14 @@ mkdir -p $G
 ./_ref/ugoracle3 --grid tet  --refine 2 --adapt 2 --damp 0.6 --cycles 10 --dump $G/c5_tet3d_adapt.ugh --ops --solve > /dev/null
 # quads with scalar unknowns (Q1 in 2D), W-cycle
 ./_ref/ugoracle2 --grid quad --refine 3 --damp 0.8 --gamma 2 --cycles 6 --dump $G/q1_quad2d_r3_w.ugh --ops --solve > /dev/null
+# ---- Gauss-Seidel family as smoother: reference classes gs / sgs / sor inside lmgc.  --lean: hierarchy + the
+# smoother records + the solve (every dump above also holds the l_lgs / l_ugs / l_lsor / l_usor records of its hierarchy)
+./_ref/ugoracle3 --grid tet --refine 3 --smoother gs  --damp 0.9 --cycles 6 --lean --dump $G/gs_tet3d_r3.ugh      --ops --solve > /dev/null
+./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --smoother sgs --damp 0.8 --cycles 5 --lean --dump $G/sgs_hex3d_bs3_r2.ugh --ops --solve > /dev/null
+./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --smoother sor --damp 1.1 --cycles 6 --lean --dump $G/sor_tet3d_adapt.ugh --ops --solve > /dev/null
+# base level with FREE rows (lmgc $b 2: 125 vectors, 27 of them inside): pins the order of additions of the base LU
+./_ref/ugoracle3 --grid tet --refine 3 --baselevel 2 --damp 0.6 --cycles 5 --lean --dump $G/lu_tet3d_r3_bl2.ugh --solve > /dev/null
+./_ref/ugoracle2 --grid quad --refine 3 --baselevel 2 --damp 0.8 --cycles 4 --lean --dump $G/lu_quad2d_r3_bl2.ugh --solve > /dev/null
+# ... and the block variant of l_lrdecomp / l_luiter (3x3 blocks, 27 free vectors on the base level, fill-in)
+./_ref/ugoracle3 --grid hex --bs 3 --refine 3 --baselevel 2 --damp 0.6 --cycles 3 --lean --dump $G/lu_hex3d_bs3_r3_bl2.ugh --solve > /dev/null
 ls -la $G

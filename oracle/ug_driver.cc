@@ -93,8 +93,11 @@ struct Opt {
   int bs = 1, refine = 3, adapt = 0, nu1 = 2, nu2 = 2, gamma = 1, cycles = 10, reps = 5;
   double damp = (DIM == 3) ? 0.6 : 0.8;
   std::string dump, gpu, barrier_dir;   // barrier_dir: --replicas rendezvous (see time_reference)
+  std::string smoother = "jac";         // reference smoother class used by lmgc: jac | gs | sgs | sor (iter.cc:10343-10366)
+  int baselevel = 0;                    // lmgc $b
   int barrier_n = 0, barrier_id = 0;
   bool ops = false, solve = false, timeit = false, quiet = true;
+  bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
 };
 
 static MULTIGRID *mg;
@@ -308,7 +311,7 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
   cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
   cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer", pfx);
   cmd("npcreate %slmgc $c %s", pfx, lmgc);
-  cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma);
+  cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel);
   cmd("npcreate %smgs $c %s", pfx, ls);
   cmd("npinit %smgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I %slmgc $display %s", pfx, maxit, pfx, o.quiet ? "no" : "full");
 }
@@ -321,6 +324,8 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
   D.scalar_i("dim", DIM); D.scalar_i("bs", BS); D.scalar_i("toplevel", top);
   D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg));
   D.scalar_d("damp", o.damp); D.scalar_i("nu1", o.nu1); D.scalar_i("nu2", o.nu2); D.scalar_i("gamma", o.gamma);
+  D.scalar_i("baselevel", o.baselevel);
+  D.scalar_i("smoother", o.smoother == "jac" ? 0 : o.smoother == "gs" ? 1 : o.smoother == "sgs" ? 2 : 3);
   for (int l = 0; l <= top; l++) {
     if (gpuls::FlattenFlags(mg, l, vx, fl[l])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
     if (gpuls::FlattenMatrix(mg, l, mA, fl[l])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
@@ -339,6 +344,7 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
     }
     dumpvec("rhs", vb, l);
     // vertex coordinates in row order (lets tests relate UG's ordering to the synthetic generator)
+    if (o.lean) continue;
     std::vector<double> xyz((size_t)f.n * DIM);
     for (NODE *n = FIRSTNODE(GRID_ON_LEVEL(mg, l)); n; n = SUCCN(n))
       for (int d = 0; d < DIM; d++) xyz[(size_t)VINDEX(NVECTOR(n)) * DIM + d] = CVECT(MYVERTEX(n))[d];
@@ -358,6 +364,22 @@ static void dump_ops(const Opt &o)
     GRID *g = GRID_ON_LEVEL(mg, l);
     fill_lcg(vx, l, 1); fill_lcg(vb, l, 2); fill_lcg(vc, l, 3); fill_lcg(vt, l, 4);
     dumpvec("in/x", vx, l); dumpvec("in/b", vb, l); dumpvec("in/c", vc, l); dumpvec("in/t", vt, l);
+    // Gauss-Seidel family: triangular solves in VINDEX order, ugiter.cc:412 / :735 / :1343 / :1563
+    if (l_setindex(g)) { fprintf(stderr, "l_setindex failed\n"); exit(7); }
+    fill_lcg(vt, l, 4);
+    if (l_lgs(g, vt, mA, vb, NULL) != NUM_OK) { fprintf(stderr, "l_lgs failed\n"); exit(7); }
+    dumpvec("l_lgs", vt, l);
+    fill_lcg(vt, l, 4);
+    if (l_ugs(g, vt, mA, vb) != NUM_OK) { fprintf(stderr, "l_ugs failed\n"); exit(7); }
+    dumpvec("l_ugs", vt, l);
+    fill_lcg(vt, l, 4);
+    if (l_lsor(g, vt, mA, vb, a3, NULL) != NUM_OK) { fprintf(stderr, "l_lsor failed\n"); exit(7); }
+    dumpvec("l_lsor", vt, l);
+    fill_lcg(vt, l, 4);
+    if (l_usor(g, vt, mA, vb, a3, NULL) != NUM_OK) { fprintf(stderr, "l_usor failed\n"); exit(7); }
+    dumpvec("l_usor", vt, l);
+    fill_lcg(vt, l, 4);
+    if (!o.lean) {
     // BLAS-2 (ALL_VECTORS, single level)
     dmatmul(mg, l, l, ALL_VECTORS, vt, mA, vx);       dumpvec("dmatmul", vt, l);
     dmatmul_add(mg, l, l, ALL_VECTORS, vt, mA, vb);   dumpvec("dmatmul_add", vt, l);
@@ -378,7 +400,8 @@ static void dump_ops(const Opt &o)
     ddotx(mg, l, l, ALL_VECTORS, vx, vb, sx);         D.rec(L("ddotx", l), 1, sx, BS, 8);
     dnrm2x(mg, l, l, ALL_VECTORS, vx, sx);            D.rec(L("dnrm2x", l), 1, sx, BS, 8);
     dset(mg, l, l, ALL_VECTORS, vt, 0.5);             dumpvec("dset", vt, l);
-    // l_jac and the damped Jacobi smoother step in defect-correction form
+    }
+    // l_jac and the smoother step of the configured class in defect-correction form
     fill_lcg(vt, l, 4);
     if (l_jac(g, vt, mA, vb) != NUM_OK) { fprintf(stderr, "l_jac failed\n"); exit(7); }
     dumpvec("l_jac", vt, l);
@@ -391,6 +414,8 @@ static void dump_ops(const Opt &o)
       fill_lcg(vb, l, 2);
     }
   }
+  D.rec("ops/a3", 1, a3, BS, 8);
+  if (o.lean) return;
   // grid transfer: restrict x (fine) into c (coarse, pre-filled), prolong x (coarse) into t (fine)
   for (int l = 1; l <= top; l++) {
     fill_lcg(vx, l, 1); fill_lcg(vx, l - 1, 1); fill_lcg(vc, l - 1, 3); fill_lcg(vt, l, 4);
@@ -402,7 +427,6 @@ static void dump_ops(const Opt &o)
     if (StandardInterpolateCorrection(GRID_ON_LEVEL(mg, l), vt, vx, a3) != NUM_OK) { fprintf(stderr, "interpolate failed\n"); exit(8); }
     dumpvec("interpolate/in_coarse", vx, l - 1); dumpvec("interpolate/out", vt, l);
   }
-  D.rec("ops/a3", 1, a3, BS, 8);
   // surface-mode loops over all levels (matter on adaptive hierarchies)
   {
     int fr = FULLREFINELEVEL(mg);
@@ -601,6 +625,8 @@ int main(int argc, char **argv)
     else if (a == "--damp") o.damp = atof(nxt().c_str()); else if (a == "--dump") o.dump = nxt();
     else if (a == "--ops") o.ops = true; else if (a == "--solve") o.solve = true; else if (a == "--time") o.timeit = true;
     else if (a == "--verbose") o.quiet = false; else if (a == "--gpu") o.gpu = nxt();
+    else if (a == "--smoother") o.smoother = nxt(); else if (a == "--baselevel") o.baselevel = atoi(nxt().c_str());
+    else if (a == "--lean") o.lean = true;
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;
@@ -618,14 +644,15 @@ int main(int argc, char **argv)
   printf("hierarchy: dim=%d grid=%s bs=%d levels=%d fullrefinelevel=%d n=[", DIM, o.grid.c_str(), BS, top + 1, (int)FULLREFINELEVEL(mg));
   for (int l = 0; l <= top; l++) printf("%s%d", l ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
   printf("] build_s=%.2f\n", t1 - t0);
-  make_numprocs(o, "", "jac", "lmgc", "transfer", "ls", o.cycles);
+  if (o.smoother != "jac" && o.smoother != "gs" && o.smoother != "sgs" && o.smoother != "sor") { fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str()); return 1; }
+  make_numprocs(o, "", o.smoother.c_str(), "lmgc", "transfer", "ls", o.cycles);
   std::vector<gpuls::FlatLevel> fl;
   if (!o.dump.empty()) {
     D.open(o.dump.c_str());
     dump_hierarchy(o, fl);
     if (o.ops) dump_ops(o);
     if (o.solve) dump_solve(o);
-    if (o.solve) dump_krylov(o);
+    if (o.solve && !o.lean) dump_krylov(o);
     D.close();
   }
   if (o.timeit) time_reference(o);

@@ -112,6 +112,79 @@ int ugport_jac_smooth(const ugport_level *L, double *x, double *b, const double 
   return 0;
 }
 
+/* np/algebra/ugiter.cc:412-615 (l_lgs), :735-930 (l_ugs), :1343-1560 (l_lsor), :1563-1775 (l_usor).  Row r = VINDEX.
+ * Scalar descriptors (:441-470): sum = 0; sum += m*v over the off-diagonal entries in VSTART->MNEXT order whose column is on
+ * the solved side and active; v = (d - sum)/diag, SOR: v = omega*(d - sum)/diag.  Block descriptors (:472-615): s = d;
+ * s0..s2 = 0; MATMUL_nn per entry (ugblas.h:161-213: s_i += (m_i0*w_0 + m_i1*w_1) + m_i2*w_2); s -= s0..s2;
+ * SolveSmallBlock; SOR: v_i *= omega_i (:1556). */
+static int gs_sweep(const ugport_level *L, double *v, const double *d, int upper, const double *omega)
+{
+  int bs = L->bs, bb = bs * bs, n = L->n;
+  for (int k = 0; k < n; k++) {
+    int r = upper ? n - 1 - k : k;
+    double *vr = v + (size_t)r * bs;
+    if (L->vclass[r] < ACTIVE_CLASS) { for (int i = 0; i < bs; i++) vr[i] = 0.0; continue; }
+    int e0 = L->rowptr[r];
+    if (bs == 1) {
+      double sum = 0.0;
+      for (int e = e0 + 1; e < L->rowptr[r + 1]; e++) {
+        int c = L->col[e];
+        if ((upper ? c > r : c < r) && L->vclass[c] >= ACTIVE_CLASS) sum += L->val[e] * v[c];
+      }
+      if (omega) vr[0] = omega[0] * (d[r] - sum) / L->val[e0];
+      else vr[0] = (d[r] - sum) / L->val[e0];
+      continue;
+    }
+    double s[UGPORT_MAX_BS], acc[UGPORT_MAX_BS] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < bs; i++) s[i] = d[(size_t)r * bs + i];
+    for (int e = e0 + 1; e < L->rowptr[r + 1]; e++) {
+      int c = L->col[e];
+      if (!((upper ? c > r : c < r) && L->vclass[c] >= ACTIVE_CLASS)) continue;
+      const double *m = L->val + (size_t)e * bb, *w = v + (size_t)c * bs;
+      for (int i = 0; i < bs; i++) {
+        double t = m[i * bs] * w[0];
+        for (int j = 1; j < bs; j++) t = t + m[i * bs + j] * w[j];
+        acc[i] += t;
+      }
+    }
+    for (int i = 0; i < bs; i++) s[i] -= acc[i];
+    if (solve_small_block(bs, vr, L->val + (size_t)e0 * bb, s)) return 6; /* NUM_SMALL_DIAG */
+    if (omega) for (int i = 0; i < bs; i++) vr[i] *= omega[i];
+  }
+  return 0;
+}
+int ugport_l_lgs(const ugport_level *L, double *v, const double *d) { return gs_sweep(L, v, d, 0, NULL); }
+int ugport_l_ugs(const ugport_level *L, double *v, const double *d) { return gs_sweep(L, v, d, 1, NULL); }
+int ugport_l_lsor(const ugport_level *L, double *v, const double *d, const double *omega) { return gs_sweep(L, v, d, 0, omega); }
+int ugport_l_usor(const ugport_level *L, double *v, const double *d, const double *omega) { return gs_sweep(L, v, d, 1, omega); }
+
+int ugport_smooth(const ugport_level *L, int kind, double *x, double *b, const double *damp, double *tmp)
+{
+  int err;
+  switch (kind) {
+  case UGPORT_SM_JAC: return ugport_jac_smooth(L, x, b, damp);
+  case UGPORT_SM_GS:                                        /* Smoother iter.cc:817-842 with GSStep :1039 */
+    if ((err = ugport_l_lgs(L, x, b))) return err;
+    ugport_dscalx(L, 0, x, damp);
+    ugport_dmatmul(L, 2, 0, b, x);
+    return 0;
+  case UGPORT_SM_SOR:                                       /* SORSmoother iter.cc:4786 (no dscalx: omega acts inside l_lsor) */
+    if ((err = ugport_l_lsor(L, x, b, damp))) return err;
+    ugport_dmatmul(L, 2, 0, b, x);
+    return 0;
+  case UGPORT_SM_SGS:                                       /* SGSSmoother iter.cc:1392-1456 */
+    if ((err = ugport_l_lgs(L, tmp, b))) return err;
+    ugport_dscalx(L, 0, tmp, damp);
+    ugport_dmatmul(L, 2, 0, b, tmp);
+    if ((err = ugport_l_ugs(L, x, b))) return err;
+    ugport_dscalx(L, 0, x, damp);
+    ugport_dmatmul(L, 2, 0, b, x);
+    ugport_dadd(L, 0, x, tmp);
+    return 0;
+  }
+  return 1;
+}
+
 /* np/algebra/transgrid.cc:117-189.  R rows list the contributions to one coarse vector in fine NODE
  * list order, so the serial sum below performs the same additions in the same order as the
  * reference's scatter loop. */
@@ -151,52 +224,182 @@ void ugport_interpolate(const ugport_level *fine, const ugport_level *coarse, do
   }
 }
 
-/* Dense LU of the base level in vector-index order, right-looking, no pivoting: the arithmetic of
- * l_lrdecomp (ugiter.cc:3657-3760, scalar) / its block variant, on a dense copy so that fill-in
- * needs no extra connections.  Stores the inverse diagonal (StoreInverse, ugiter.cc:139).
- * Rows with VCLASS < ACTIVE_CLASS are excluded like in the reference. */
+/* ---- base level: `lu` (np/procs/iter.cc:6443 LUPreProcess, Smoother + LUStep) -------------------------------------------
+ * l_lrdecomp (ugiter.cc:3657) eliminates on UG's per-row MATRIX LISTS and creates fill-in with CreateExtraConnection
+ * (gm/algebra.cc:1101 -> CreateConnection :969), which inserts the two new MATRIX structs at the SECOND place of both row
+ * lists (:1051-1078).  l_luiter (ugiter.cc:4444) then sums every row in list order, so the order of additions depends on the
+ * order in which fill-in appeared -- and that depends on the numbers (a zero pivot, :3741 / :3829, or a zero correction block,
+ * :3867, creates nothing).  The restatement therefore keeps the same ordered lists: row r = array of (column, block) in
+ * VSTART->MNEXT order, new entries inserted at index 1. */
+typedef struct { int col; double v[UGPORT_MAX_BS * UGPORT_MAX_BS]; } lu_ent;
+typedef struct { int len, cap; lu_ent *e; } lu_row;
+typedef struct { int n, bs; lu_row *row; } lu_fac;
+
+static lu_ent *lu_find(lu_row *r, int c)           /* GetMatrix gm/algebra.cc */
+{
+  for (int k = 0; k < r->len; k++) if (r->e[k].col == c) return &r->e[k];
+  return NULL;
+}
+static void lu_insert_second(lu_row *r, int c)     /* CreateConnection algebra.cc:1051-1078; new values are 0 */
+{
+  if (r->len == r->cap) { r->cap = r->cap ? 2 * r->cap : 8; r->e = (lu_ent *)realloc(r->e, sizeof(lu_ent) * (size_t)r->cap); }
+  memmove(&r->e[2], &r->e[1], sizeof(lu_ent) * (size_t)(r->len - 1));
+  memset(&r->e[1], 0, sizeof(lu_ent));
+  r->e[1].col = c;
+  r->len++;
+}
+
+/* InvertSmallBlock np/algebra/block.cc:272-321 (n = 1,2,3) */
+static int invert_small_block(int n, const double *mat, double *inv)
+{
+  if (n == 1) { inv[0] = 1.0 / mat[0]; return 0; }
+  if (n == 2) {
+    double det = mat[0] * mat[3] - mat[1] * mat[2];
+    if (det == 0.0) return 1;
+    double invdet = 1.0 / det;
+    inv[0] = mat[3] * invdet; inv[1] = -mat[1] * invdet; inv[2] = -mat[2] * invdet; inv[3] = mat[0] * invdet;
+    return 0;
+  }
+  double det = mat[0] * mat[4] * mat[8] + mat[1] * mat[5] * mat[6] + mat[2] * mat[3] * mat[7]
+               - mat[2] * mat[4] * mat[6] - mat[0] * mat[5] * mat[7] - mat[1] * mat[3] * mat[8];
+  if (det == 0.0) return 1;
+  double invdet = 1.0 / det;
+  inv[0] = ( mat[4] * mat[8] - mat[5] * mat[7]) * invdet;
+  inv[3] = (-mat[3] * mat[8] + mat[5] * mat[6]) * invdet;
+  inv[6] = ( mat[3] * mat[7] - mat[4] * mat[6]) * invdet;
+  inv[1] = (-mat[1] * mat[8] + mat[2] * mat[7]) * invdet;
+  inv[4] = ( mat[0] * mat[8] - mat[2] * mat[6]) * invdet;
+  inv[7] = (-mat[0] * mat[7] + mat[1] * mat[6]) * invdet;
+  inv[2] = ( mat[1] * mat[5] - mat[2] * mat[4]) * invdet;
+  inv[5] = (-mat[0] * mat[5] + mat[2] * mat[3]) * invdet;
+  inv[8] = ( mat[0] * mat[4] - mat[1] * mat[3]) * invdet;
+  return 0;
+}
+
+void ugport_base_free(double *lu)
+{
+  lu_fac *F = (lu_fac *)lu;
+  if (!F) return;
+  for (int r = 0; r < F->n; r++) free(F->row[r].e);
+  free(F->row); free(F);
+}
+
+/* l_lrdecomp ugiter.cc:3657-3880: scalar descriptors :3715-3768, block descriptors :3771-3880.  The returned handle is opaque. */
 double *ugport_base_factor(const ugport_level *L)
 {
-  int N = L->n * L->bs, bs = L->bs, bb = bs * bs;
-  double *lu = (double *)calloc((size_t)N * N, sizeof(double));
-  for (int r = 0; r < L->n; r++)
-    for (int e = L->rowptr[r]; e < L->rowptr[r + 1]; e++)
-      for (int i = 0; i < bs; i++) for (int j = 0; j < bs; j++)
-        lu[(size_t)(r * bs + i) * N + L->col[e] * bs + j] = L->val[(size_t)e * bb + i * bs + j];
-  for (int i = 0; i < N; i++) {
-    if (L->vclass[i / bs] < ACTIVE_CLASS) continue;
-    double inv = 1.0 / lu[(size_t)i * N + i];
-    lu[(size_t)i * N + i] = inv;
-    for (int j = i + 1; j < N; j++) {
-      if (L->vclass[j / bs] < ACTIVE_CLASS) continue;
-      double piv = lu[(size_t)j * N + i] * inv;
-      lu[(size_t)j * N + i] = piv;
-      if (piv == 0.0) continue;
-      for (int k = i + 1; k < N; k++) {
-        if (L->vclass[k / bs] < ACTIVE_CLASS) continue;
-        lu[(size_t)j * N + k] -= piv * lu[(size_t)i * N + k];
+  int n = L->n, bs = L->bs, bb = bs * bs;
+  lu_fac *F = (lu_fac *)calloc(1, sizeof(lu_fac));
+  F->n = n; F->bs = bs;
+  F->row = (lu_row *)calloc((size_t)(n > 0 ? n : 1), sizeof(lu_row));
+  for (int r = 0; r < n; r++) {                 /* dmatcopy(L, A): same lists */
+    lu_row *R = &F->row[r];
+    R->len = R->cap = L->rowptr[r + 1] - L->rowptr[r];
+    R->e = (lu_ent *)calloc((size_t)(R->cap > 0 ? R->cap : 1), sizeof(lu_ent));
+    for (int k = 0; k < R->len; k++) {
+      int e = L->rowptr[r] + k;
+      R->e[k].col = L->col[e];
+      memcpy(R->e[k].v, L->val + (size_t)e * bb, sizeof(double) * (size_t)bb);
+    }
+  }
+#define ACTIVE(x) (L->vclass[x] >= ACTIVE_CLASS)
+  for (int i = 0; i < n; i++) {
+    if (!ACTIVE(i)) continue;
+    lu_row *Ri = &F->row[i];
+    double inv[UGPORT_MAX_BS * UGPORT_MAX_BS];
+    if (bs == 1) inv[0] = 1.0 / Ri->e[0].v[0];
+    else if (invert_small_block(bs, Ri->e[0].v, inv)) { ugport_base_free((double *)F); return NULL; }
+    memcpy(Ri->e[0].v, inv, sizeof(double) * (size_t)bb);                     /* StoreInverse */
+    for (int a = 1; a < Ri->len; a++) {                                        /* Mij */
+      int j = Ri->e[a].col;
+      if (!(ACTIVE(j) && j > i)) continue;
+      lu_ent *Mji = lu_find(&F->row[j], i);                                    /* MADJ(Mij) */
+      double piv[UGPORT_MAX_BS * UGPORT_MAX_BS];
+      int piv_zero = 1;
+      if (bs == 1) { piv[0] = Mji->v[0] * inv[0]; piv_zero = piv[0] == 0.0; }
+      else
+        for (int i0 = 0; i0 < bs; i0++) for (int j0 = 0; j0 < bs; j0++) {
+          double sum = 0.0;
+          for (int k0 = 0; k0 < bs; k0++) sum += Mji->v[i0 * bs + k0] * inv[k0 * bs + j0];
+          piv[i0 * bs + j0] = sum;
+          if (sum != 0.0) piv_zero = 0;
+        }
+      memcpy(Mji->v, piv, sizeof(double) * (size_t)bb);
+      if (piv_zero) continue;
+      for (int c = 1; c < Ri->len; c++) {                                      /* Mik */
+        int k = Ri->e[c].col;
+        if (!(ACTIVE(k) && k > i)) continue;
+        double cor[UGPORT_MAX_BS * UGPORT_MAX_BS];
+        if (bs == 1) cor[0] = piv[0] * Ri->e[c].v[0];
+        else {
+          int cor_zero = 1;
+          for (int i0 = 0; i0 < bs; i0++) for (int j0 = 0; j0 < bs; j0++) {
+            double sum = 0.0;
+            for (int k0 = 0; k0 < bs; k0++) sum += piv[i0 * bs + k0] * Ri->e[c].v[k0 * bs + j0];
+            cor[i0 * bs + j0] = sum;
+            if (sum != 0.0) cor_zero = 0;
+          }
+          if (cor_zero) continue;
+        }
+        lu_ent *Mjk = lu_find(&F->row[j], k);
+        if (!Mjk) {                                                            /* CreateExtraConnection(g, vj, vk) */
+          lu_insert_second(&F->row[j], k);
+          lu_insert_second(&F->row[k], j);
+          Mjk = &F->row[j].e[1];
+        }
+        for (int q = 0; q < bb; q++) Mjk->v[q] -= cor[q];
       }
     }
   }
-  return lu;
+#undef ACTIVE
+  return (double *)F;
 }
-void ugport_base_free(double *lu) { free(lu); }
 
-/* l_luiter ugiter.cc:4444-4520 on the dense factors (sums in index order) */
+/* l_luiter ugiter.cc:4444-4795 on the factored lists: scalar descriptors :4470-4518, block descriptors :4522-4795 */
 static void base_lu_solve(const ugport_level *L, const double *lu, double *v, const double *d)
 {
-  int N = L->n * L->bs, bs = L->bs;
-  for (int i = 0; i < N; i++) {
-    if (L->vclass[i / bs] < ACTIVE_CLASS) { v[i] = 0.0; continue; }
-    double sum = 0.0;
-    for (int j = 0; j < i; j++) if (L->vclass[j / bs] >= ACTIVE_CLASS) sum += lu[(size_t)i * N + j] * v[j];
-    v[i] = d[i] - sum;
+  const lu_fac *F = (const lu_fac *)lu;
+  int n = F->n, bs = F->bs;
+  for (int r = 0; r < n; r++) {
+    double *vr = v + (size_t)r * bs;
+    if (L->vclass[r] < ACTIVE_CLASS) { for (int i = 0; i < bs; i++) vr[i] = 0.0; continue; }
+    const lu_row *R = &F->row[r];
+    double acc[UGPORT_MAX_BS] = {0.0, 0.0, 0.0};
+    for (int a = 1; a < R->len; a++) {
+      int c = R->e[a].col;
+      if (!(c < r && L->vclass[c] >= ACTIVE_CLASS)) continue;
+      const double *m = R->e[a].v, *w = v + (size_t)c * bs;
+      for (int i = 0; i < bs; i++) {
+        double t = m[i * bs] * w[0];
+        for (int j = 1; j < bs; j++) t = t + m[i * bs + j] * w[j];
+        acc[i] += t;
+      }
+    }
+    for (int i = 0; i < bs; i++) vr[i] = d[(size_t)r * bs + i] - acc[i];          /* Diag(L) = I */
   }
-  for (int i = N - 1; i >= 0; i--) {
-    if (L->vclass[i / bs] < ACTIVE_CLASS) continue;
-    double sum = 0.0;
-    for (int j = i + 1; j < N; j++) if (L->vclass[j / bs] >= ACTIVE_CLASS) sum += lu[(size_t)i * N + j] * v[j];
-    v[i] = (v[i] - sum) * lu[(size_t)i * N + i];
+  for (int r = n - 1; r >= 0; r--) {
+    if (L->vclass[r] < ACTIVE_CLASS) continue;
+    double *vr = v + (size_t)r * bs;
+    const lu_row *R = &F->row[r];
+    double acc[UGPORT_MAX_BS] = {0.0, 0.0, 0.0}, s[UGPORT_MAX_BS];
+    for (int a = 1; a < R->len; a++) {
+      int c = R->e[a].col;
+      if (!(c > r && L->vclass[c] >= ACTIVE_CLASS)) continue;
+      const double *m = R->e[a].v, *w = v + (size_t)c * bs;
+      for (int i = 0; i < bs; i++) {
+        double t = m[i * bs] * w[0];
+        for (int j = 1; j < bs; j++) t = t + m[i * bs + j] * w[j];
+        acc[i] += t;
+      }
+    }
+    for (int i = 0; i < bs; i++) s[i] = vr[i] - acc[i];
+    const double *inv = R->e[0].v;
+    if (bs == 1) vr[0] = s[0] * inv[0];                                             /* :4510 */
+    else
+      for (int i = 0; i < bs; i++) {                                                /* SolveInverseSmallBlock block.cc:225-253 */
+        double sum = 0.0;
+        for (int j = 0; j < bs; j++) sum += inv[i * bs + j] * s[j];
+        vr[i] = sum;
+      }
   }
 }
 
@@ -236,25 +439,27 @@ int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu,
   const ugport_level *L = &lv[level];
   double one[UGPORT_MAX_BS] = {1.0, 1.0, 1.0};
   if (level <= cfg->baselevel) { base_solve(L, cfg, lu, c[level], b[level], t[level]); return 0; }
+  double *tmp = cfg->smoother == UGPORT_SM_SGS ? (double *)malloc(sizeof(double) * (size_t)L->n * L->bs) : NULL;
   for (int i = 0; i < cfg->nu1; i++) {
-    int err = ugport_jac_smooth(L, t[level], b[level], cfg->smooth_damp);
-    if (err) return err;
+    int err = ugport_smooth(L, cfg->smoother, t[level], b[level], cfg->smooth_damp, tmp);
+    if (err) { free(tmp); return err; }
     ugport_dadd(L, 0, c[level], t[level]);
   }
   ugport_restrict(L, &lv[level - 1], b[level - 1], b[level], one);           /* :7843, Factor_One */
   ugport_dset(&lv[level - 1], 0, c[level - 1], 0.0);                         /* :7873 */
   for (int g = 0; g < cfg->gamma; g++) {
     int err = ugport_lmgc(lv, cfg, lu, level - 1, c, b, t);
-    if (err) return err;
+    if (err) { free(tmp); return err; }
   }
   ugport_interpolate(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);  /* :7886 */
   ugport_dadd(L, 0, c[level], t[level]);                                     /* :7903 */
   ugport_dmatmul(L, 2, 0, b[level], t[level]);                               /* :7905 */
   for (int i = 0; i < cfg->nu2; i++) {
-    int err = ugport_jac_smooth(L, t[level], b[level], cfg->smooth_damp);
-    if (err) return err;
+    int err = ugport_smooth(L, cfg->smoother, t[level], b[level], cfg->smooth_damp, tmp);
+    if (err) { free(tmp); return err; }
     ugport_dadd(L, 0, c[level], t[level]);
   }
+  free(tmp);
   return 0;
 }
 

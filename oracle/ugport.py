@@ -31,7 +31,11 @@ class _Level(C.Structure):
 class _Cfg(C.Structure):
     _fields_ = [("nu1", C.c_int), ("nu2", C.c_int), ("gamma", C.c_int), ("baselevel", C.c_int),
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
-                ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double)]
+                ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
+                ("smoother", C.c_int)]
+
+
+SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3}
 
 
 def build() -> str:
@@ -178,6 +182,18 @@ class PortBackend:
     def jac_smooth(self, level, x, b, damp):
         return self.L.ugport_jac_smooth(self._lp(level), _dp(self._v(x, level)), _dp(self._v(b, level)), self._vs(damp))
 
+    def l_gs(self, level, v, d, upper=False, omega=None):
+        """l_lgs / l_ugs (omega None) or l_lsor / l_usor."""
+        name = "ugport_l_" + ("u" if upper else "l") + ("gs" if omega is None else "sor")
+        args = [self._lp(level), _dp(self._v(v, level)), _dp(self._v(d, level))]
+        if omega is not None:
+            args.append(self._vs(omega))
+        return getattr(self.L, name)(*args)
+
+    def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
+        return self.L.ugport_smooth(self._lp(level), SMOOTHERS[kind], _dp(self._v(x, level)), _dp(self._v(b, level)),
+                                    self._vs(damp), _dp(self._v(tmp, level)))
+
     def restrict(self, level, to, frm, damp):
         self.L.ugport_restrict(self._lp(level), self._lp(level - 1), _dp(self._v(to, level - 1)),
                                _dp(self._v(frm, level)), self._vs(damp))
@@ -196,6 +212,7 @@ class PortBackend:
         c.base_maxit = cfg.get("base_maxit", 10)
         c.base_reduction = cfg.get("base_reduction", 1e-8)
         c.base_abslimit = cfg.get("base_abslimit", 1e-10)
+        c.smoother = SMOOTHERS[cfg.get("smoother", "jac")]
         return c
 
     def _pp(self, name):

@@ -19,6 +19,13 @@ class Mismatch(AssertionError):
     pass
 
 
+def has(hier, what):
+    """Which record groups a dump holds: 'ops' (dump_ops), 'solve' (dump_solve), 'krylov' (dump_krylov); --lean dumps of
+    oracle/ug_driver.cc leave groups out."""
+    key = {"ops": "ops/a3", "solve": "solve/history", "krylov": "cg/K"}[what]
+    return key in hier.raw
+
+
 def _cmp_vec(what, got, ref, exact, tol):
     if got.shape != ref.shape:
         raise Mismatch(f"{what}: shape {got.shape} != {ref.shape}")
@@ -61,9 +68,27 @@ def replay_ops(be, hier, exact=True, vec_tol=1e-13, red_tol=1e-13, exact_red=Fal
         _cmp_red(name, got, ref, 0.0 if exact_red else red_tol)
         n += 1
 
+    lean = "L0/dmatmul" not in d          # --lean dumps hold the smoother records only
+    kind = smoother_of(hier)
     for l in range(top + 1):
         for v in "xbct":
             be.put(l, v, d[f"L{l}/in/{v}"])
+        if f"L{l}/l_lgs" in d:            # Gauss-Seidel family
+            for name, upper, omega in (("l_lgs", False, None), ("l_ugs", True, None), ("l_lsor", False, a3), ("l_usor", True, a3)):
+                be.put(l, "t", d[f"L{l}/in/t"])
+                assert be.l_gs(l, "t", "b", upper=upper, omega=omega) == 0
+                chk(name, l, "t")
+            be.put(l, "t", d[f"L{l}/in/t"])
+        if lean:
+            be.put(l, "t", d[f"L{l}/in/t"])
+            assert be.l_jac(l, "t", "b") == 0
+            chk("l_jac", l, "t")
+            if l > 0:
+                be.put(l, "t", d[f"L{l}/in/t"])
+                assert be.smooth(l, kind, "t", "b", [damp] * 3) == 0
+                chk("smooth/t", l, "t"); chk("smooth/b", l, "b")
+                be.put(l, "b", d[f"L{l}/in/b"])
+            continue
         be.dmatmul(l, l, ALL, 0, "t", "x"); chk("dmatmul", l, "t")
         be.dmatmul(l, l, ALL, 1, "t", "b"); chk("dmatmul_add", l, "t")
         be.dmatmul(l, l, ALL, 2, "t", "c"); chk("dmatmul_minus", l, "t")
@@ -86,9 +111,11 @@ def replay_ops(be, hier, exact=True, vec_tol=1e-13, red_tol=1e-13, exact_red=Fal
         chk("l_jac", l, "t")
         if l > 0:
             be.put(l, "t", d[f"L{l}/in/t"])
-            assert be.jac_smooth(l, "t", "b", [damp] * 3) == 0
+            assert be.smooth(l, kind, "t", "b", [damp] * 3) == 0
             chk("smooth/t", l, "t"); chk("smooth/b", l, "b")
             be.put(l, "b", d[f"L{l}/in/b"])
+    if lean:
+        return n
 
     for l in range(1, top + 1):
         be.put(l, "c", d[f"L{l}/restrict/in_fine"])
@@ -116,9 +143,18 @@ def replay_ops(be, hier, exact=True, vec_tol=1e-13, red_tol=1e-13, exact_red=Fal
     return n
 
 
+SMOOTHER_NAMES = ("jac", "gs", "sgs", "sor")
+
+
+def smoother_of(hier):
+    """Smoother class the dump was written with (older dumps: jac)."""
+    return SMOOTHER_NAMES[int(hier.raw["smoother"][0])] if "smoother" in hier.raw else "jac"
+
+
 def cycle_cfg(hier, **over):
     d = hier.raw
-    cfg = dict(nu1=int(d["nu1"][0]), nu2=int(d["nu2"][0]), gamma=int(d["gamma"][0]), baselevel=0,
+    cfg = dict(nu1=int(d["nu1"][0]), nu2=int(d["nu2"][0]), gamma=int(d["gamma"][0]),
+               baselevel=int(d["baselevel"][0]) if "baselevel" in d else 0, smoother=smoother_of(hier),
                smooth_damp=float(d["damp"][0]), cycle_damp=1.0, base_maxit=10, base_reduction=1e-8,
                base_abslimit=1e-10)
     cfg.update(over)
@@ -146,8 +182,8 @@ def replay_solve(be, hier, exact=True, vec_tol=1e-12, red_tol=1e-12, cfg_over=No
             continue
         for l in range(top + 1):
             be.put(l, "x", zeros[l]); be.put(l, "b", hier.levels[l].rhs)
-        be.ls_defect(0, top, "x", "b")
-        first = be.ls_residuum(0, top, "b")
+        be.ls_defect(cfg["baselevel"], top, "x", "b")
+        first = be.ls_residuum(cfg["baselevel"], top, "b")
         _cmp_red("solve/first_defect", first, d["solve/first_defect"], red_tol); n += 1
         its, first2, hist = be.solve(top, "x", "b", cfg, k)
         assert its == k, (its, k)
