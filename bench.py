@@ -32,11 +32,12 @@ METRIC = "vcycle_unknowns_per_s"
 UNIT = "unknowns/s"
 
 
-def workload_name(cells, top, n, kind="p1"):
+def workload_name(cells, top, n, kind="p1", smoother="jac"):
     what = {"p1": "3D P1 Poisson, unit cube, Kuhn tetrahedra", "q1": "3D Q1 Poisson, unit cube, hexahedra (27-point rows)",
             "elasticity": "3D Q1 linear elasticity (3x3 blocks, 27 block entries per row), unit cube, hexahedra"}[kind]
     return (f"{what}, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
-            f"{n} fine unknowns, V(2,2) {'block-' if kind == 'elasticity' else ''}Jacobi damp 0.6, base solver ls+lu")
+            f"{n} fine unknowns, V(2,2) " + {"jac": f"{'block-' if kind == 'elasticity' else ''}Jacobi damp 0.6", "gs": "Gauss-Seidel damp 1.0",
+                                             "sgs": "symmetric Gauss-Seidel damp 1.0", "sor": "SOR omega 1.1"}[smoother] + ", base solver ls+lu")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -221,7 +222,8 @@ def our_arm(args):
         for l in range(top + 1):
             ctx.alloc(l, name)
     ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
-    cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6, fused=1)
+    sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1}[args.smoother]
+    cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=sm_damp, fused=1, smoother=args.smoother)
     ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
     ctx.sync()
     setup_s = time.perf_counter() - t0
@@ -261,13 +263,16 @@ def our_arm(args):
     launches = ctx.launch_count() - launches0
     # per-kernel event times of the timed region
     prof = {}
-    kinds = {"smooth": 0, "jac": 1, "restrict": 2, "interpolate": 3, "vecop": 4, "reduce": 5, "dmatmul": 6, "base": 7}
+    kinds = {"smooth": 0, "jac": 1, "restrict": 2, "interpolate": 3, "vecop": 4, "reduce": 5, "dmatmul": 6, "base": 7, "trisolve": 8}
     cnt, kms, kby = C.c_int64(), C.c_double(), C.c_double()
     for name, k in kinds.items():
         ctx.call("uggpu_prof_summary", k, -1, C.byref(cnt), C.byref(kms), C.byref(kby))
         prof[name] = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
-    ctx.call("uggpu_prof_summary", 0, top, C.byref(cnt), C.byref(kms), C.byref(kby))
+    # dominant kernel: the fused smoothing step (Jacobi) / the defect update dmatmul_minus (Gauss-Seidel family), finest level
+    ctx.call("uggpu_prof_summary", 0 if args.smoother == "jac" else 6, top, C.byref(cnt), C.byref(kms), C.byref(kby))
     dom = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+    ctx.call("uggpu_prof_summary", 8, top, C.byref(cnt), C.byref(kms), C.byref(kby))
+    tri = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
     ctx.call("uggpu_prof_enable", 0)
     if world > 1:
         import torch.distributed as dist
@@ -332,7 +337,7 @@ def our_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(cells, top, n, args.kind) if world == 1 else
+        "config": {"workload": workload_name(cells, top, n, args.kind, args.smoother) if world == 1 else
                    (f"3D P1 Poisson, box of {P[0]}x{P[1]}x{P[2]} unit cubes (one per GPU), Kuhn tetrahedra, base {cells * P[0]}x{cells * P[1]}x{cells * P[2]} cells, "
                     f"{top + 1} levels, {n_global} fine unknowns ({n} on rank 0), V(2,2) Jacobi damp 0.6, base solver ls+lu"),
                    "parallelism": f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + NCCL halo copies, "
@@ -341,7 +346,8 @@ def our_arm(args):
                    "cache": "inputs larger than L2 (the finest matrix alone is tens of GB per sweep)",
                    "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2),
                    "defect": [first, hist[-1]] if hist else None},
-        "roofline": {"bound": "hbm", "kernel": f"k_smooth_k<{bs},*> (fused smoothing step, finest level)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"k_smooth_k<{bs},*> (fused smoothing step, finest level)" if args.smoother == "jac" else
+                     f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
                      "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
@@ -350,6 +356,8 @@ def our_arm(args):
                      "share_of_step": dom["ms"] / ms,
                      "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
         "kernels": prof,
+        "trisolve_finest": {"launches": tri["launches"], "avg_ms": tri["ms"] / max(tri["launches"], 1),
+                            "GBps": tri["alg_bytes"] / (tri["ms"] * 1e-3) / 1e9 if tri["ms"] > 0 else 0.0} if args.smoother != "jac" else None,
         "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": (16 * n + 8) * world,
                 "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
         "gpu_launches": launches,
@@ -384,6 +392,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity"],
                     help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")
+    ap.add_argument("--smoother", default="jac", choices=["jac", "gs", "sgs", "sor"],
+                    help="smoother class of the cycle: jac = BASELINE configs (default); gs / sgs / sor: Gauss-Seidel family (SURVEY.md 8f.2, one GPU)")
     ap.add_argument("--replicate-below", type=int, default=300000,
                     help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()

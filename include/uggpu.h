@@ -81,6 +81,7 @@ int64_t uggpu_device_bytes(uggpu_ctx *ctx);
 #define UGGPU_K_REDUCE      5
 #define UGGPU_K_DMATMUL     6
 #define UGGPU_K_BASE        7
+#define UGGPU_K_TRISOLVE    8   /* level-scheduled triangular solve of the Gauss-Seidel family */
 int uggpu_prof_enable(uggpu_ctx *ctx, int on);   /* also clears the records */
 int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes);
 
@@ -157,6 +158,28 @@ int uggpu_l_jac(uggpu_ctx*, int level, int v, int M, int d);
 /* Smoother() of np/procs/iter.cc:817-842 with Step = JacobiStep: x = damp * Diag(A)^-1 b ; b -= A x */
 int uggpu_jac_smooth(uggpu_ctx*, int level, int x, int b, int A, const double *damp /* [bs] */);
 
+/* ---- Gauss-Seidel family, np/np.h:431-441 (np/algebra/ugiter.cc:412 l_lgs, :735 l_ugs, :1343 l_lsor, :1563 l_usor) --------
+ * Triangular solves in VINDEX (= row) order: v = (D+L)^-1 d / (D+U)^-1 d, with relaxation omega[bs] for the sor variants
+ * (scalar rows: omega*(d-sum)/diag; block rows: SolveSmallBlock, then v_i *= omega_i).  Rows with VCLASS < ACTIVE_CLASS get 0
+ * and are skipped as columns.  Results are bit-identical to the reference: rows are scheduled by dependency level, every row
+ * still adds the reference's terms in VSTART->MNEXT order.  uggpu_gs_preprocess builds the schedule of matrix M on `level`
+ * (GSPreProcess iter.cc:1003: l_setindex); the solves build it on first use if it is missing.  The pattern must be
+ * structurally symmetric (UG's CONNECTIONs are MATRIX pairs, gm/gm.h:653).  One GPU only. */
+int uggpu_gs_preprocess(uggpu_ctx*, int level, int M);
+int uggpu_gs_levels(uggpu_ctx*, int level, int M, int *lower, int *upper);      /* dependency levels of the two schedules (0 = not built) */
+int uggpu_l_lgs (uggpu_ctx*, int level, int v, int M, int d);
+int uggpu_l_ugs (uggpu_ctx*, int level, int v, int M, int d);
+int uggpu_l_lsor(uggpu_ctx*, int level, int v, int M, int d, const double *omega /* [bs] */);
+int uggpu_l_usor(uggpu_ctx*, int level, int v, int M, int d, const double *omega /* [bs] */);
+/* smoother classes of np/procs/iter.cc (iter.cc:10343-10366) */
+#define UGGPU_SM_JAC 0   /* jac: Smoother :817 + JacobiStep :911 */
+#define UGGPU_SM_GS  1   /* gs:  Smoother :817 + GSStep :1039    */
+#define UGGPU_SM_SGS 2   /* sgs: SGSSmoother :1392               */
+#define UGGPU_SM_SOR 3   /* sor: SORSmoother :4786 + SORStep :4744 (damp acts as omega inside l_lsor) */
+/* One smoothing step of class `kind` in defect-correction form: on entry b = defect, on exit x = correction and b = new
+ * defect.  tmp: handle of a work vector (sgs only, NP_SGS_t iter.cc:1386). */
+int uggpu_smooth(uggpu_ctx*, int level, int kind, int x, int b, int A, const double *damp /* [bs] */, int tmp);
+
 /* ---- grid transfer, np/np.h:475-489 (np/algebra/transgrid.cc:462,529) ------------------------------- */
 /* StandardRestrict(GRID_ON_LEVEL(level), to, from, damp): fine `level` -> level-1 */
 int uggpu_restrict(uggpu_ctx*, int level, int to, int from, const double *damp /* [bs] */);
@@ -184,6 +207,8 @@ typedef struct uggpu_lmgc_cfg {
   void  *base_user;
   int    fused;                      /* 0: one kernel per reference call (op-for-op mirror);
                                         1: fused kernels (identical results, fewer passes)      */
+  int    smoother;                   /* UGGPU_SM_*: class of the pre- and post-smoother ($S); the fused schedule exists for
+                                        jac, the other classes always run one kernel group per reference call */
 } uggpu_lmgc_cfg;
 
 int uggpu_lmgc_preprocess(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int A);   /* LmgcPreProcess iter.cc:7707 */

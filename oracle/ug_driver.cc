@@ -706,8 +706,8 @@ static int run_gpu(const Opt &o)
   int k = 0;
   for (const Cfg &c : cfgs) {
     char pfx[16]; snprintf(pfx, sizeof pfx, "g%d", k++);
-    make_numprocs(o, pfx, c.jac, c.lmgc, c.transfer, c.ls, o.cycles);
-    if (c.extra[0]) cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d%s", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, c.extra);
+    make_numprocs(o, pfx, (std::string("gpu") + o.smoother).c_str(), c.lmgc, c.transfer, c.ls, o.cycles);
+    if (c.extra[0]) cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d%s", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel, c.extra);
     restore_problem();
     std::string name = std::string(pfx) + "mgs";
     NP_LINEAR_SOLVER *g = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, name.c_str(), LINEAR_SOLVER_CLASS_NAME);

@@ -85,6 +85,17 @@ class GpuBackend:
     def jac_smooth(self, level, x, b, damp):
         return self.ctx.L.uggpu_jac_smooth(self.ctx.h, level, self._v(x), self._v(b), self.A, capi._vs(damp))
 
+    def l_gs(self, level, v, d, upper=False, omega=None):
+        """uggpu_l_lgs / uggpu_l_ugs (omega None) or uggpu_l_lsor / uggpu_l_usor."""
+        fn = getattr(self.ctx.L, "uggpu_l_" + ("u" if upper else "l") + ("gs" if omega is None else "sor"))
+        args = [self.ctx.h, level, self._v(v), self.A, self._v(d)]
+        if omega is not None:
+            args.append(capi._vs(omega))
+        return fn(*args)
+
+    def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
+        return self.ctx.L.uggpu_smooth(self.ctx.h, level, capi.SMOOTHERS[kind], self._v(x), self._v(b), self.A, capi._vs(damp), self._v(tmp))
+
     def restrict(self, level, to, frm, damp):
         self.ctx.call("uggpu_restrict", level, self._v(to), self._v(frm), capi._vs(damp))
 
@@ -97,7 +108,8 @@ class GpuBackend:
         c = self.ctx.lmgc_cfg(nu1=cfg["nu1"], nu2=cfg["nu2"], gamma=cfg["gamma"], baselevel=cfg.get("baselevel", 0),
                               smooth_damp=cfg["smooth_damp"], cycle_damp=cfg.get("cycle_damp", 1.0),
                               base_maxit=cfg.get("base_maxit", 10), base_reduction=cfg.get("base_reduction", 1e-8),
-                              base_abslimit=cfg.get("base_abslimit", 1e-10), fused=self.fused, t=t)
+                              base_abslimit=cfg.get("base_abslimit", 1e-10), fused=self.fused, t=t,
+                              smoother=cfg.get("smoother", "jac"))
         return c
 
     def lmgc(self, level, c, b, cfg, t="__t"):

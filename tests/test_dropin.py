@@ -19,10 +19,17 @@ CASES = [
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--damp", "0.6", "--cycles", "6"]),
     ("ugoracle2", ["--grid", "tri", "--refine", "5", "--damp", "0.8", "--cycles", "6"]),
     ("ugoracle2", ["--grid", "quad", "--refine", "3", "--damp", "0.8", "--gamma", "2", "--cycles", "5"]),
+    # Gauss-Seidel family as smoother (iter.gpugs / gpusgs / gpusor against the reference's gs / sgs / sor)
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "gs", "--damp", "0.9", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--smoother", "sgs", "--damp", "0.8", "--cycles", "4"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--smoother", "sor", "--damp", "1.1", "--cycles", "5"]),
+    # base level with free rows (lmgc $b 2)
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--baselevel", "2", "--damp", "0.6", "--cycles", "5"]),
 ]
+IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2"]
 
 
-@pytest.mark.parametrize("exe,args", CASES, ids=["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W"])
+@pytest.mark.parametrize("exe,args", CASES, ids=IDS)
 def test_gpuls_numprocs_inside_ug(exe, args):
     path = os.path.join(ROOT, "oracle", "_ref", exe)
     if not os.path.exists(path):

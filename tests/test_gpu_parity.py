@@ -49,7 +49,13 @@ def test_gpu_ops_bitexact(gpu_backend, golden):
 def test_gpu_cycle_and_solve(gpu_backend, golden):
     if not has(golden, "solve"):
         pytest.skip("dump without solve records")
-    n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
+    # Base levels with FREE rows: the device LU adds the terms of a row in index order, UG in the order of its matrix list
+    # with fill-in (pinned in the oracle port, tests/test_oracle_port.py) -- agreement to rounding, not bit for bit.
+    free_base = "baselevel" in golden.raw and int(golden.raw["baselevel"][0]) > 0
+    if free_base:
+        n = replay_solve(gpu_backend, golden, exact=False, vec_tol=1e-12, red_tol=1e-11)
+    else:
+        n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
     assert n > 10
 
 

@@ -105,6 +105,53 @@ def test_synth_solve_bitexact_vs_port(cells, dim, top, kind, monkeypatch, tma_ro
             assert np.array_equal(bs[l], ref[3][l]), l
 
 
+@pytest.mark.parametrize("cells,dim,top,kind,smoother,damp", [(2, 3, 3, 0, "gs", 0.9), (2, 3, 4, 0, "sgs", 0.8), (1, 3, 3, 2, "sor", 1.1), (2, 3, 3, 1, "sgs", 0.9),
+                                                              (3, 2, 5, 0, "sor", 1.2)],
+                         ids=["P1-17^3-gs", "P1-33^3-sgs", "elast-9^3-sor", "Q1-17^3-sgs", "P1-2d-97^2-sor"])
+def test_synth_gs_family_bitexact_vs_port(cells, dim, top, kind, smoother, damp):
+    """Gauss-Seidel family on lexicographically ordered synthetic hierarchies -- long dependency chains (a 33^3
+    Kuhn grid has 97 levels per sweep): the triangular solves alone, then the cycle with the class as smoother, bit for bit
+    against the sequential oracle port."""
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    ctx = _synth(cells, dim, top, kind)
+    hier = ctx.download_hierarchy(top)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    rhs = ctx.get(top, "b")
+    ctx.close()
+    bs = hier.bs
+    rng = np.random.default_rng(7)
+    d0 = np.round(rng.standard_normal(hier.levels[top].n * bs) * 1024) / 1024
+    omega = [0.25 + 0.5 * i for i in range(3)]
+    gpu, port = GpuBackend(hier, fused=0), PortBackend(hier)
+    for upper, om in ((False, None), (True, None), (False, omega), (True, omega)):
+        res = []
+        for be in (gpu, port):
+            be.put(top, "d", d0); be.put(top, "v", np.full(d0.size, 3.0))
+            assert be.l_gs(top, "v", "d", upper=upper, omega=om) == 0
+            res.append(be.get(top, "v"))
+        assert np.array_equal(res[0], res[1]), (upper, om)
+    lo, up = C.c_int(), C.c_int()
+    gpu.ctx.call("uggpu_gs_levels", top, gpu.A, C.byref(lo), C.byref(up))
+    nn = cells * 2 ** top
+    assert lo.value == up.value and lo.value >= nn          # at least one level per grid line
+    cfg = dict(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=damp, smoother=smoother)
+    out = []
+    for be in (gpu, port):
+        for l, lv in enumerate(hier.levels):
+            be.put(l, "x", np.zeros(lv.n * lv.bs)); be.put(l, "b", rhs if l == top else np.zeros(lv.n * lv.bs))
+        be.ls_defect(0, top, "x", "b")
+        its, first, hist = be.solve(top, "x", "b", cfg, 4)
+        out.append((its, hist, [be.get(l, "x") for l in range(top + 1)], [be.get(l, "b") for l in range(top + 1)]))
+    gpu.close()
+    (ig, hg, xg, bg), (ip, hp, xp, bp) = out
+    assert ig == ip == 4 and hp[-1] < 0.2 * hp[bs - 1]
+    assert np.max(np.abs(hg - hp) / np.maximum(hp, 1e-300)) < 1e-12
+    for l in range(top + 1):
+        assert np.array_equal(xg[l], xp[l]), l
+        assert np.array_equal(bg[l], bp[l]), l
+
+
 def test_synth_properties_large():
     """65^3 = 274 625 unknowns: properties that do not need the CPU checker."""
     cells, top = 2, 5

@@ -33,7 +33,10 @@ class LmgcCfg(C.Structure):
     _fields_ = [("nu1", C.c_int), ("nu2", C.c_int), ("gamma", C.c_int), ("baselevel", C.c_int),
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
                 ("t", C.c_int), ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
-                ("base_solver", C.c_void_p), ("base_user", C.c_void_p), ("fused", C.c_int)]
+                ("base_solver", C.c_void_p), ("base_user", C.c_void_p), ("fused", C.c_int), ("smoother", C.c_int)]
+
+
+SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3}       # UGGPU_SM_*
 
 
 class LResult(C.Structure):
@@ -193,7 +196,7 @@ class Context:
 
     # ---- cycle configuration
     def lmgc_cfg(self, nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6, cycle_damp=1.0, base_maxit=10,
-                 base_reduction=1e-8, base_abslimit=1e-10, fused=1, t="__t") -> LmgcCfg:
+                 base_reduction=1e-8, base_abslimit=1e-10, fused=1, t="__t", smoother="jac") -> LmgcCfg:
         c = LmgcCfg()
         c.nu1, c.nu2, c.gamma, c.baselevel = nu1, nu2, gamma, baselevel
         for i in range(MAX_BS):
@@ -204,4 +207,5 @@ class Context:
         c.base_solver = None
         c.base_user = None
         c.fused = int(fused)
+        c.smoother = SMOOTHERS[smoother]
         return c

@@ -115,6 +115,11 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
       return uggpu_fail(UGGPU_NO_COARSER_GRID, "level %d has no transfer stencils", l);
     UG_TRY(ensure_vec(ctx, l, cfg->t));
     UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_B));
+    if (l > bl && cfg->smoother != UGGPU_SM_JAC) {          // GSPreProcess / SGSPreProcess / SORPreProcess (iter.cc:1003,1353,4717)
+      if (cfg->smoother < UGGPU_SM_JAC || cfg->smoother > UGGPU_SM_SOR) return uggpu_fail(UGGPU_ERROR, "lmgc: unknown smoother class %d", cfg->smoother);
+      UG_TRY(uggpu_gs_preprocess(ctx, l, A));
+      if (cfg->smoother == UGGPU_SM_SGS) UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_A));
+    }
   }
   if (cfg->base_solver == nullptr) {
     Level *L = &ctx->lev[bl];
@@ -208,7 +213,7 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
   const int t = cfg->t;
   double one[UGGPU_MAX_BS] = {1.0, 1.0, 1.0};
   for (int i = 0; i < cfg->nu1; i++) {
-    UG_TRY(uggpu_jac_smooth(ctx, level, t, b, A, cfg->smooth_damp));
+    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, UGGPU_VEC_TMP_A));
     UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
   }
   UG_TRY(uggpu_restrict(ctx, level, b, b, one));                                   // iter.cc:7843, Factor_One
@@ -218,11 +223,14 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
   UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));                  // :7903
   UG_TRY(uggpu_dmatmul_minus(ctx, level, level, UGGPU_ALL_VECTORS, b, A, t));      // :7905
   for (int i = 0; i < cfg->nu2; i++) {
-    UG_TRY(uggpu_jac_smooth(ctx, level, t, b, A, cfg->smooth_damp));
+    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, UGGPU_VEC_TMP_A));
     UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
   }
   return 0;
 }
+
+// the fused schedule is built on the Jacobi step; every other smoother class runs one kernel group per reference call
+static inline bool use_fused(const uggpu_lmgc_cfg *cfg) { return cfg->fused && cfg->smoother == UGGPU_SM_JAC; }
 
 // t_ready: the temporary cfg->t of this level already holds damp * Diag(A)^-1 b (written by the restriction above)
 static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf)
@@ -299,7 +307,7 @@ static int lmgc_check(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
 extern "C" int uggpu_lmgc(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
 {
   UG_TRY(lmgc_check(ctx, cfg, level, c, b));
-  if (cfg->fused) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
+  if (use_fused(cfg)) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
   else UG_TRY(lmgc_unfused(ctx, cfg, level, c, b, A));
   return check_device_error(ctx);
 }
@@ -340,14 +348,14 @@ extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
   const bool surface_is_top = ctx->fullrefinelevel >= level;   // no lower-level terms in the ON_SURFACE norm
   for (int it = 0; it < maxiter; it++) {
     bool done_x = false, done_norm = false;
-    if (cfg->fused && level > cfg->baselevel) {
+    if (use_fused(cfg) && level > cfg->baselevel) {
       TopFuse tf;
       tf.level = level; tf.x = x; tf.c_zero = true; tf.norm = surface_is_top;
       UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, &tf));
       done_x = tf.done_x; done_norm = tf.done_norm;
     } else {
       UG_TRY(uggpu_dset(ctx, level, level, UGGPU_ALL_VECTORS, c, 0.0));     // ls.cc:695
-      if (cfg->fused) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
+      if (use_fused(cfg)) UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr));
       else UG_TRY(lmgc_unfused(ctx, cfg, level, c, b, A));
     }
     // LSUpdate (ls.cc:869): x += c on levels bl..level
@@ -377,7 +385,7 @@ extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
 // to rounding, not bit for bit: the scalars come from parallel sums.
 static int run_cycle(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
 {
-  if (cfg->fused) return lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr);
+  if (use_fused(cfg)) return lmgc_fused(ctx, cfg, level, c, b, A, false, nullptr);
   return lmgc_unfused(ctx, cfg, level, c, b, A);
 }
 

@@ -1,0 +1,516 @@
+// gs.cu -- the Gauss-Seidel family of np/algebra/ugiter.cc on the device:
+//   l_lgs :412  v = (D+L)^-1 d        l_ugs :735  v = (D+U)^-1 d        l_lsor :1343 / l_usor :1563  the same with relaxation
+// and the smoother classes built on them (np/procs/iter.cc: gs :1039, sgs :1392, sor :4744/:4786).
+//
+// The reference solves the triangle row by row in VINDEX order; row r needs the NEW values of the rows on the solved side
+// that it is connected to.  Here the rows are scheduled by dependency level (level 0: no such connection; level k: all of
+// them on levels < k) -- every row still adds exactly the reference's terms in the reference's order (VSTART->MNEXT, the
+// other side and inactive columns skipped), so the result is bit-identical, but all rows of a level run in parallel.
+//
+// PreProcess (uggpu_gs_preprocess, the analogue of GSPreProcess iter.cc:1003: l_setindex) builds, per direction:
+//   * the levels, by a topological sweep over the (structurally symmetric: CONNECTION = MATRIX pair, gm/gm.h:653) pattern;
+//   * a SECOND copy of the triangle, SELL-32 again, with the rows permuted into level order (levels padded to whole
+//     slices) and each row holding [diagonal block, entries of the solved side in list order]: a warp reads a level's rows
+//     with the same coalesced 128/256-byte loads as the SpMV kernels; column indices keep the original numbering.
+// The solve is ONE persistent kernel: warps take slices in schedule order from a ticket counter, wait until the previous
+// level's slice count is complete (one acquire poll per warp; the matrix lines of the slice are pulled into L2 meanwhile),
+// do their 32 rows, publish.  Tickets are handed out in order, so every slice a warp waits for is owned by a running warp:
+// no cooperative launch is needed and there is no deadlock; a wait that exceeds 20 s sets the device error word instead.
+#include <cub/device/device_radix_sort.cuh>       // before uggpu_internal.h: its SLICE macro is an identifier inside cub
+#include <cub/device/device_scan.cuh>
+
+#include "uggpu_internal.h"
+
+#include <cstdlib>
+#include <vector>
+
+#define TRI_THREADS 256
+
+struct TriSched {
+  int n = 0;                      // rows of the level
+  int nT = 0;                     // rows of the schedule (levels padded to multiples of 32)
+  int nlev = 0;
+  SellMat T;                      // permuted triangle
+  int32_t *perm = nullptr;        // [nT] schedule position -> row, -1 = padding
+  int32_t *slice_level = nullptr; // [nT/32]
+  int32_t *level_slices = nullptr;// [nlev]
+  unsigned int *counters = nullptr;   // [nlev + 1]: finished slices per level, then the ticket
+};
+
+static int tri_free(uggpu_ctx *ctx, TriSched *&S)
+{
+  if (!S) return 0;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  sell_free(ctx, &S->T);
+  if (S->perm) dfree(ctx, S->perm, (size_t)S->nT);
+  if (S->slice_level) dfree(ctx, S->slice_level, (size_t)S->nT / 32);
+  if (S->level_slices) dfree(ctx, S->level_slices, (size_t)S->nlev);
+  if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev + 1);
+  delete S;
+  S = nullptr;
+  return 0;
+}
+
+int sell_free_schedules(uggpu_ctx *ctx, SellMat *m)
+{
+  UG_TRY(tri_free(ctx, m->tri[0]));
+  UG_TRY(tri_free(ctx, m->tri[1]));
+  return 0;
+}
+
+// ---- schedule construction ----------------------------------------------------------------------------------------------
+// solved side of row r in direction dir: dir 0 (lower) columns c < r, dir 1 (upper) columns c > r
+__device__ __forceinline__ bool solved_side(int dir, int r, int c) { return dir == 0 ? c < r : c > r; }
+
+// indeg[r] = active connections of r on the solved side; rows without any (and all inactive rows) form level 0
+__global__ void k_tri_indeg(SellView A, const uint8_t *__restrict__ vclass, int dir, int *__restrict__ indeg, int *__restrict__ lev,
+                            int *__restrict__ frontier, int *__restrict__ count)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n) return;
+  int deg = 0;
+  if (vclass[r] >= 3) {
+    const int len = A.rowlen[r];
+    const ColIter ci = col_iter(A, r);
+    for (int j = 1; j < len; j++) {
+      const int c = col_at(ci, j);
+      if (solved_side(dir, r, c) && vclass[c] >= 3) deg++;
+    }
+  }
+  indeg[r] = deg;
+  lev[r] = deg == 0 ? 0 : -1;
+  if (deg == 0) frontier[atomicAdd(count, 1)] = r;
+}
+
+// rows finished on level `cur` release the rows that list them on their solved side (= the rows they list on the OTHER side)
+__global__ void k_tri_relax(SellView A, const uint8_t *__restrict__ vclass, int dir, const int *__restrict__ fin, int nin, int cur,
+                            int *__restrict__ indeg, int *__restrict__ lev, int *__restrict__ fout, int *__restrict__ count, int *err)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nin) return;
+  const int r = fin[i];
+  if (vclass[r] < 3) return;                 // inactive rows are nobody's dependency
+  const int len = A.rowlen[r];
+  const ColIter ci = col_iter(A, r);
+  for (int j = 1; j < len; j++) {
+    const int c = col_at(ci, j);
+    if (c == r || solved_side(dir, r, c) || vclass[c] < 3) continue;
+    const int old = atomicSub(&indeg[c], 1);
+    if (old == 1) { lev[c] = cur + 1; fout[atomicAdd(count, 1)] = c; }
+    else if (old <= 0) atomicExch(err, UGGPU_ERROR);      // c does not list r: pattern not structurally symmetric
+  }
+}
+
+__global__ void k_tri_iota(int n, int *__restrict__ a)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+__global__ void k_tri_place(int n, const int *__restrict__ key, const int *__restrict__ row, const int *__restrict__ start, const int *__restrict__ poff,
+                            int32_t *__restrict__ perm)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = key[i];
+  perm[poff[l] + (i - start[l])] = row[i];
+}
+
+// entries of schedule row p: the diagonal block + the active entries of the solved side (0 for padding and inactive rows)
+__global__ void k_tri_len(int nT, const int32_t *__restrict__ perm, SellView A, const uint8_t *__restrict__ vclass, int dir, int64_t *__restrict__ len)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nT) return;
+  const int r = perm[p];
+  int64_t n = 0;
+  if (r >= 0 && vclass[r] >= 3) {
+    n = 1;
+    const int rl = A.rowlen[r];
+    const ColIter ci = col_iter(A, r);
+    for (int j = 1; j < rl; j++) {
+      const int c = col_at(ci, j);
+      if (solved_side(dir, r, c) && vclass[c] >= 3) n++;
+    }
+  }
+  len[p] = n;
+}
+
+__global__ void k_tri_fill(int nT, int bb, const int32_t *__restrict__ perm, SellView A, const uint8_t *__restrict__ vclass, int dir,
+                           const int64_t *__restrict__ rowptr, int32_t *__restrict__ ccol, double *__restrict__ cval)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nT) return;
+  const int r = perm[p];
+  if (r < 0 || vclass[r] < 3) return;
+  const int rl = A.rowlen[r], lane = r & 31;
+  const int64_t sp = slice_off(A, r >> 5);
+  const ColIter ci = col_iter(A, r);
+  int64_t o = rowptr[p];
+  for (int j = 0; j < rl; j++) {
+    const int c = col_at(ci, j);
+    if (j > 0 && !(solved_side(dir, r, c) && vclass[c] >= 3)) continue;
+    ccol[o] = c;
+    for (int k = 0; k < bb; k++) cval[o * bb + k] = A.val[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane];
+    o++;
+  }
+}
+
+static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSched **out)
+{
+  cudaStream_t st = ctx->stream;
+  const int n = L->n;
+  TriSched *S = new TriSched();
+  S->n = n;
+  int *indeg = nullptr, *lev = nullptr, *fa = nullptr, *fb = nullptr, *d_count = nullptr;
+  int rc = 0;
+  std::vector<int> level_rows;          // rows per level
+#define TB(expr) do { if ((rc = (expr)) != 0) goto fail; } while (0)
+#define TC(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = uggpu_fail(UGGPU_CUDA_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); goto fail; } } while (0)
+  {
+    TB(dalloc(ctx, &indeg, (size_t)n)); TB(dalloc(ctx, &lev, (size_t)n));
+    TB(dalloc(ctx, &fa, (size_t)n)); TB(dalloc(ctx, &fb, (size_t)n)); TB(dalloc(ctx, &d_count, 1));
+    const SellView Av = view(*A);
+    const int blocks = (n + 255) / 256;
+    int h_count = 0;
+    TC(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+    k_tri_indeg<<<blocks, 256, 0, st>>>(Av, L->vclass, dir, indeg, lev, fa, d_count);
+    ctx->launches++;
+    TC(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TC(cudaStreamSynchronize(st));
+    int64_t total = 0;
+    int cur = 0;
+    while (h_count > 0) {
+      level_rows.push_back(h_count);
+      total += h_count;
+      const int nin = h_count;
+      TC(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+      k_tri_relax<<<(nin + 255) / 256, 256, 0, st>>>(Av, L->vclass, dir, fa, nin, cur, indeg, lev, fb, d_count, ctx->derr);
+      ctx->launches++;
+      TC(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      TC(cudaStreamSynchronize(st));
+      int *sw = fa; fa = fb; fb = sw;
+      cur++;
+    }
+    TB(check_device_error(ctx));
+    if (total != n) { rc = uggpu_fail(UGGPU_ERROR, "Gauss-Seidel schedule: %lld of %d rows could be ordered (the pattern is not structurally symmetric)", (long long)total, n); goto fail; }
+    S->nlev = (int)level_rows.size();
+    // rows sorted by (level, row): stable radix sort of the row numbers by level
+    int *key_out = fa, *row_in = fb, *row_out = indeg;      // reuse: fa/fb/indeg are free now
+    k_tri_iota<<<blocks, 256, 0, st>>>(n, row_in);
+    ctx->launches++;
+    int bits = 1;
+    while ((1 << bits) < S->nlev && bits < 31) bits++;
+    size_t tmp_bytes = 0;
+    TC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lev, key_out, row_in, row_out, n, 0, bits, st));
+    void *tmp = nullptr;
+    TB(dev_alloc(ctx, &tmp, tmp_bytes ? tmp_bytes : 1));
+    {
+      cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lev, key_out, row_in, row_out, n, 0, bits, st);
+      ctx->launches++;
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      dev_free(ctx, tmp, tmp_bytes ? tmp_bytes : 1);
+      if (e != cudaSuccess) { rc = uggpu_fail(UGGPU_CUDA_ERROR, "radix sort: %s", cudaGetErrorString(e)); goto fail; }
+    }
+    // level starts in the sorted order (= prefix sums of level_rows) and in the padded schedule
+    std::vector<int> start(S->nlev), poff(S->nlev), lsl(S->nlev);
+    int64_t acc = 0, pacc = 0;
+    for (int l = 0; l < S->nlev; l++) {
+      start[l] = (int)acc; poff[l] = (int)pacc;
+      lsl[l] = (level_rows[l] + 31) / 32;
+      acc += level_rows[l]; pacc += (int64_t)lsl[l] * 32;
+    }
+    if (pacc > 2147483647LL - 64) { rc = uggpu_fail(UGGPU_ERROR, "Gauss-Seidel schedule too long"); goto fail; }
+    S->nT = (int)pacc;
+    const int nslT = S->nT / 32;
+    std::vector<int32_t> sl((size_t)nslT);
+    for (int l = 0, s = 0; l < S->nlev; l++) for (int k = 0; k < lsl[l]; k++) sl[s++] = l;
+    int *d_start = nullptr, *d_poff = nullptr;
+    TB(dalloc(ctx, &d_start, (size_t)S->nlev)); TB(dalloc(ctx, &d_poff, (size_t)S->nlev));
+    TB(dalloc(ctx, &S->perm, (size_t)S->nT)); TB(dalloc(ctx, &S->slice_level, (size_t)nslT));
+    TB(dalloc(ctx, &S->level_slices, (size_t)S->nlev)); TB(dalloc(ctx, &S->counters, (size_t)S->nlev + 1));
+    TC(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
+    TC(cudaMemcpyAsync(d_poff, poff.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
+    TC(cudaMemcpyAsync(S->level_slices, lsl.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
+    TC(cudaMemcpyAsync(S->slice_level, sl.data(), sizeof(int32_t) * nslT, cudaMemcpyHostToDevice, st));
+    TC(cudaMemsetAsync(S->perm, 0xff, sizeof(int32_t) * (size_t)S->nT, st));
+    k_tri_place<<<blocks, 256, 0, st>>>(n, key_out, row_out, d_start, d_poff, S->perm);
+    ctx->launches++;
+    TC(cudaStreamSynchronize(st));
+    dfree(ctx, d_start, (size_t)S->nlev); dfree(ctx, d_poff, (size_t)S->nlev);
+    // the permuted triangle as CSR, then SELL
+    int64_t *d_len = nullptr, *d_rp = nullptr;
+    int32_t *ccol = nullptr; double *cval = nullptr;
+    TB(dalloc(ctx, &d_len, (size_t)S->nT + 1)); TB(dalloc(ctx, &d_rp, (size_t)S->nT + 1));
+    TC(cudaMemsetAsync(d_len, 0, sizeof(int64_t) * ((size_t)S->nT + 1), st));
+    const int tblocks = (S->nT + 255) / 256;
+    k_tri_len<<<tblocks, 256, 0, st>>>(S->nT, S->perm, Av, L->vclass, dir, d_len);
+    ctx->launches++;
+    tmp_bytes = 0;
+    TC(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_rp, S->nT + 1, st));
+    TB(dev_alloc(ctx, &tmp, tmp_bytes ? tmp_bytes : 1));
+    int64_t nnzT = 0;
+    {
+      cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_rp, S->nT + 1, st);
+      ctx->launches++;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&nnzT, d_rp + S->nT, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      dev_free(ctx, tmp, tmp_bytes ? tmp_bytes : 1);
+      if (e != cudaSuccess) { rc = uggpu_fail(UGGPU_CUDA_ERROR, "scan: %s", cudaGetErrorString(e)); goto fail; }
+    }
+    dfree(ctx, d_len, (size_t)S->nT + 1);
+    TB(dalloc(ctx, &ccol, (size_t)(nnzT > 0 ? nnzT : 1))); TB(dalloc(ctx, &cval, (size_t)(nnzT > 0 ? nnzT : 1) * A->bb));
+    k_tri_fill<<<tblocks, 256, 0, st>>>(S->nT, A->bb, S->perm, Av, L->vclass, dir, d_rp, ccol, cval);
+    ctx->launches++;
+    rc = sell_from_device_csr(ctx, S->nT, A->bb, d_rp, ccol, cval, &S->T);
+    cudaStreamSynchronize(st);
+    dfree(ctx, d_rp, (size_t)S->nT + 1); dfree(ctx, ccol, (size_t)(nnzT > 0 ? nnzT : 1)); dfree(ctx, cval, (size_t)(nnzT > 0 ? nnzT : 1) * A->bb);
+    if (rc) goto fail;
+  }
+  dfree(ctx, indeg, (size_t)n); dfree(ctx, lev, (size_t)n); dfree(ctx, fa, (size_t)n); dfree(ctx, fb, (size_t)n); dfree(ctx, d_count, 1);
+  *out = S;
+  return 0;
+fail:
+  if (indeg) dfree(ctx, indeg, (size_t)n);
+  if (lev) dfree(ctx, lev, (size_t)n);
+  if (fa) dfree(ctx, fa, (size_t)n);
+  if (fb) dfree(ctx, fb, (size_t)n);
+  if (d_count) dfree(ctx, d_count, 1);
+  tri_free(ctx, S);
+  return rc;
+#undef TB
+#undef TC
+}
+
+extern "C" int uggpu_gs_preprocess(uggpu_ctx *ctx, int level, int M)
+{
+  Level *L = get_level(ctx, level);
+  SellMat *A = get_mat(ctx, level, M);
+  if (!L || !A) return UGGPU_DESC_MISMATCH;
+  if (ctx->comm && L->partitioned) return uggpu_fail(UGGPU_ERROR, "Gauss-Seidel smoothers run on one GPU (level %d is partitioned)", level);
+  if (L->n == 0) return 0;
+  for (int dir = 0; dir < 2; dir++)
+    if (!A->tri[dir]) UG_TRY(tri_build(ctx, L, A, dir, &A->tri[dir]));
+  return 0;
+}
+
+extern "C" int uggpu_gs_levels(uggpu_ctx *ctx, int level, int M, int *lower, int *upper)
+{
+  SellMat *A = get_mat(ctx, level, M);
+  if (!A) return UGGPU_DESC_MISMATCH;
+  if (lower) *lower = A->tri[0] ? A->tri[0]->nlev : 0;
+  if (upper) *upper = A->tri[1] ? A->tri[1]->nlev : 0;
+  return 0;
+}
+
+// ---- the solve -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// SOR: 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows: solve, then
+// v_i *= omega_i :1556)
+template <int BS, int SOR>
+__global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int32_t *__restrict__ perm, const int32_t *__restrict__ slice_level,
+                                                          const int32_t *__restrict__ level_slices, unsigned int *counters, int nlev, int nsl,
+                                                          double *v, const double *__restrict__ d, Damp omega, int *err)
+{
+  constexpr int BB = BS * BS;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = (int)atomicAdd(&counters[nlev], 1u);
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s >= nsl) return;
+    const int lv = slice_level[s];
+    const int p = s * 32 + lane;
+    const int r = perm[p];
+    const int len = r >= 0 ? (int)T.rowlen[p] : 0;
+    const int64_t sp = slice_off(T, s);
+    const int w = slice_width(T, s, sp);
+    // pull the slice's values and column words into L2 while the previous level finishes
+    {
+      const char *vb = reinterpret_cast<const char *>(T.val + sp * BB);
+      const int vlines = w * BB * 2;                        // 256 bytes per component and slice column
+      for (int l = lane; l < vlines; l += 32) prefetch_l2(vb + (size_t)l * 128);
+      const int64_t cp = T.col_ptr[s];
+      if (cp >= 0 && lane < w) prefetch_l2(T.col + cp + (size_t)lane * 32);
+    }
+    if (lv > 0) {
+      if (lane == 0) {
+        const unsigned int need = (unsigned int)level_slices[lv - 1];
+        unsigned long long t0 = 0, t1;
+        int spins = 0;
+        while (ld_acquire_u32(&counters[lv - 1]) < need) {
+          if (++spins == 64) {
+            spins = 0;
+            if (*reinterpret_cast<volatile int *>(err)) break;          // an earlier wait already failed: do not wait again
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }
+          }
+          __nanosleep(40);
+        }
+        __threadfence();
+      }
+      __syncwarp();
+    }
+    if (r >= 0) {
+      if (len == 0) {                                        // VCLASS < ACTIVE_CLASS: v = 0 (ugiter.cc:447)
+#pragma unroll
+        for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, 0.0);
+      } else {
+        const ColIter ci = col_iter(T, p);
+        const double *__restrict__ vp = T.val + sp * BB + lane;
+        double dg[BB], acc[BS], rhs[BS], sol[BS];
+#pragma unroll
+        for (int k = 0; k < BB; k++) dg[k] = __ldg(vp + (size_t)k * 32);
+#pragma unroll
+        for (int i = 0; i < BS; i++) { acc[i] = 0.0; rhs[i] = d[(size_t)r * BS + i]; }
+#pragma unroll 4
+        for (int j = 1; j < len; j++) {
+          const int c = col_at(ci, j);
+          double m[BB], wv[BS];
+#pragma unroll
+          for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
+#pragma unroll
+          for (int i = 0; i < BS; i++) wv[i] = __ldcg(v + (size_t)c * BS + i);     // written by another SM during this launch: L2, not L1
+#pragma unroll
+          for (int i = 0; i < BS; i++) {
+            double t = m[i * BS] * wv[0];
+#pragma unroll
+            for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * wv[q];
+            acc[i] += t;
+          }
+        }
+        if (BS == 1) {
+          if (SOR) sol[0] = omega.a[0] * (rhs[0] - acc[0]) / dg[0];
+          else sol[0] = (rhs[0] - acc[0]) / dg[0];
+        } else {
+#pragma unroll
+          for (int i = 0; i < BS; i++) rhs[i] = rhs[i] - acc[i];
+          // SolveSmallBlock (block.cc:104-142), same closed forms as solve_small_block in spmv.cu
+          if (BS == 2) {
+            double det = dg[0] * dg[3 % BB] - dg[1 % BB] * dg[2 % BB];
+            if (det == 0.0) { atomicExch(err, UGGPU_SMALL_DIAG); det = 1.0; }
+            det = 1.0 / det;
+            sol[0] = (rhs[0] * dg[3 % BB] - rhs[1 % BS] * dg[1 % BB]) * det;
+            sol[1 % BS] = (rhs[1 % BS] * dg[0] - rhs[0] * dg[2 % BB]) * det;
+          } else {
+            double M3div0 = dg[3 % BB] / dg[0];
+            double M6div0 = dg[6 % BB] / dg[0];
+            double aux = (dg[7 % BB] - M6div0 * dg[1 % BB]) / (dg[4 % BB] - M3div0 * dg[1 % BB]);
+            sol[2 % BS] = (rhs[2 % BS] - M6div0 * rhs[0] - aux * (rhs[1 % BS] - M3div0 * rhs[0]))
+                          / (dg[8 % BB] - M6div0 * dg[2 % BB] - aux * (dg[5 % BB] - M3div0 * dg[2 % BB]));
+            sol[1 % BS] = (rhs[1 % BS] - dg[3 % BB] / dg[0] * rhs[0] - (dg[5 % BB] - M3div0 * dg[2 % BB]) * sol[2 % BS])
+                          / (dg[4 % BB] - M3div0 * dg[1 % BB]);
+            sol[0] = (rhs[0] - dg[1 % BB] * sol[1 % BS] - dg[2 % BB] * sol[2 % BS]) / dg[0];
+          }
+          if (SOR) {
+#pragma unroll
+            for (int i = 0; i < BS; i++) sol[i] = sol[i] * omega.a[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, sol[i]);
+      }
+    }
+    // publish: the warp's stores, then one release by lane 0 (the pattern of a grid barrier, per warp)
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(&counters[lv], 1u);
+    }
+  }
+}
+
+static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const double *d, const double *omega)
+{
+  Level *L = get_level(ctx, level);
+  SellMat *A = get_mat(ctx, level, M);
+  if (!L || !A) return UGGPU_DESC_MISMATCH;
+  if (v == d) return uggpu_fail(UGGPU_DESC_MISMATCH, "Gauss-Seidel solve: result and right-hand side are the same vector");
+  if (L->n == 0) return 0;
+  if (!A->tri[dir]) UG_TRY(uggpu_gs_preprocess(ctx, level, M));
+  TriSched *S = A->tri[dir];
+  const int nsl = S->nT / 32;
+  CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * ((size_t)S->nlev + 1), ctx->stream));
+  int blocks = (nsl + TRI_THREADS / 32 - 1) / (TRI_THREADS / 32);
+  const int cap = ctx->sm_count * (2048 / TRI_THREADS);
+  if (blocks > cap) blocks = cap;
+  const Damp om = mkdamp(omega, L->bs);
+  const SellView Tv = view(S->T);
+  // algorithmic bytes: the triangle's entries, row lengths and permutation, d read, v written, gathered v once
+  ProfScope ps(ctx, UGGPU_K_TRISOLVE, level, S->T.entry_bytes() + 6.0 * S->nT + 8.0 * L->bs * 3.0 * L->n);
+#define TS(BSV)                                                                                                                          \
+  if (omega) k_trisolve<BSV, 1><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->nlev, nsl, v, d, om, ctx->derr); \
+  else k_trisolve<BSV, 0><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->nlev, nsl, v, d, om, ctx->derr)
+  switch (L->bs) {
+    case 1: TS(1); break;
+    case 2: TS(2); break;
+    default: TS(3); break;
+  }
+#undef TS
+  KCHECK(ctx);
+  return 0;
+}
+
+static int tri_entry(uggpu_ctx *ctx, int level, int v, int M, int d, int dir, const double *omega)
+{
+  double *vp = get_vec(ctx, level, v);
+  const double *dp = get_vec(ctx, level, d);
+  if (!vp || !dp) return UGGPU_DESC_MISMATCH;
+  UG_TRY(tri_solve(ctx, level, M, dir, vp, dp, omega));
+  return check_device_error(ctx);
+}
+
+extern "C" int uggpu_l_lgs(uggpu_ctx *ctx, int level, int v, int M, int d) { return tri_entry(ctx, level, v, M, d, 0, nullptr); }
+extern "C" int uggpu_l_ugs(uggpu_ctx *ctx, int level, int v, int M, int d) { return tri_entry(ctx, level, v, M, d, 1, nullptr); }
+extern "C" int uggpu_l_lsor(uggpu_ctx *ctx, int level, int v, int M, int d, const double *omega)
+{
+  if (!omega) return uggpu_fail(UGGPU_ERROR, "l_lsor: null omega");
+  return tri_entry(ctx, level, v, M, d, 0, omega);
+}
+extern "C" int uggpu_l_usor(uggpu_ctx *ctx, int level, int v, int M, int d, const double *omega)
+{
+  if (!omega) return uggpu_fail(UGGPU_ERROR, "l_usor: null omega");
+  return tri_entry(ctx, level, v, M, d, 1, omega);
+}
+
+// One smoothing step of class `kind` in defect-correction form: x = correction, b updated to the new defect.
+//   UGGPU_SM_JAC  Smoother iter.cc:817 + JacobiStep :911     UGGPU_SM_GS   Smoother + GSStep :1039
+//   UGGPU_SM_SGS  SGSSmoother :1392 (tmp = NP_SGS_t)          UGGPU_SM_SOR  SORSmoother :4786 + SORStep :4744
+extern "C" int uggpu_smooth(uggpu_ctx *ctx, int level, int kind, int x, int b, int A, const double *damp, int tmp)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (kind == UGGPU_SM_JAC) return uggpu_jac_smooth(ctx, level, x, b, A, damp);
+  double *xp = get_vec(ctx, level, x), *bp = get_vec(ctx, level, b);
+  if (!xp || !bp) return UGGPU_DESC_MISMATCH;
+  const Damp dm = mkdamp(damp, L->bs);
+  switch (kind) {
+    case UGGPU_SM_GS:
+      UG_TRY(tri_solve(ctx, level, A, 0, xp, bp, nullptr));
+      UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, xp, nullptr, dm));
+      return k_dmatmul(ctx, level, 2, 0, b, A, x);
+    case UGGPU_SM_SOR:
+      UG_TRY(tri_solve(ctx, level, A, 0, xp, bp, damp));
+      return k_dmatmul(ctx, level, 2, 0, b, A, x);
+    case UGGPU_SM_SGS: {
+      UG_TRY(uggpu_vec_alloc(ctx, level, tmp));
+      double *tp = get_vec(ctx, level, tmp);
+      if (!tp) return UGGPU_DESC_MISMATCH;
+      if (tp == xp || tp == bp) return uggpu_fail(UGGPU_DESC_MISMATCH, "sgs: the work vector aliases x or b");
+      UG_TRY(tri_solve(ctx, level, A, 0, tp, bp, nullptr));
+      UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, tp, nullptr, dm));
+      UG_TRY(k_dmatmul(ctx, level, 2, 0, b, A, tmp));
+      UG_TRY(tri_solve(ctx, level, A, 1, xp, bp, nullptr));
+      UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, xp, nullptr, dm));
+      UG_TRY(k_dmatmul(ctx, level, 2, 0, b, A, x));
+      return k_vec_op(ctx, level, 0, VOP_ADD, xp, tp, mkdamp(nullptr, 0));
+    }
+  }
+  return uggpu_fail(UGGPU_ERROR, "unknown smoother class %d", kind);
+}

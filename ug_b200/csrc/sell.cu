@@ -266,6 +266,7 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   if (m->n <= 0 && !m->col) { *m = SellMat(); return 0; }
   size_t nsl = (size_t)(m->n + 31) / 32;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  UG_TRY(sell_free_schedules(ctx, m));
   if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);
   dfree(ctx, m->rowlen, (size_t)m->n);
@@ -354,6 +355,7 @@ static int device_rowptr(uggpu_ctx *ctx, const SellMat *m, std::vector<int64_t> 
 
 int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val)
 {
+  UG_TRY(sell_free_schedules(ctx, m));     // they hold the old values; rebuilt on the next Gauss-Seidel solve
   std::vector<int64_t> rp; int64_t *d_rp = nullptr; double *d_val = nullptr;
   UG_TRY(device_rowptr(ctx, m, rp, &d_rp));
   size_t cnt = (size_t)m->nnz * m->bb;

@@ -46,6 +46,7 @@ struct SellMat {
                                   // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
                                   // fused into the restriction) stream it instead of touching one column of every slice of val.  Matrices only (not P, R).
   bool valid() const { return n > 0 && col != nullptr; }
+  struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
   // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
   double entry_bytes() const { return 8.0 * (double)nnz * bb + 4.0 * (double)col_words; }
@@ -241,6 +242,7 @@ int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, con
 int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val);
 int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t *col, double *val);
 int sell_free(uggpu_ctx *ctx, SellMat *m);
+int sell_free_schedules(uggpu_ctx *ctx, SellMat *m);          // gs.cu: drops the Gauss-Seidel schedules (they hold a copy of the values)
 // replaces the explicit column words of uniform slices by one distance per slice column (lossless); no-op when nothing is gained
 int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);
 // (re)builds m->diag from the values (after the matrix is built and after every change of its values)

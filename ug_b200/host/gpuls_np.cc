@@ -41,7 +41,7 @@ USING_UG_NAMESPACES
   X(uggpu_ctx_create) X(uggpu_ctx_destroy) X(uggpu_last_error) X(uggpu_set_fullrefinelevel) X(uggpu_level_create) X(uggpu_level_set_flags)     \
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
-  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count)
+  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess)
 
 namespace {
 struct Api {
@@ -191,13 +191,20 @@ void VsToArray(const VEC_SCALAR vs, int bs, double *out) { for (int i = 0; i < U
 
 // =========================================================================================================================
 // iter.gpujac  (reference: NP_SMOOTHER iter.cc:152-177, SmootherInit :763, Smoother :817, JacobiPreProcess/Step :894-925)
+// iter.gpugs   (reference: class `gs`,  GSPreProcess :1003, GSStep :1039)          -- SURVEY.md 8f.2
+// iter.gpusgs  (reference: class `sgs`, SGSPreProcess :1353, SGSSmoother :1392)
+// iter.gpusor  (reference: class `sor`, SORPreProcess :4717, SORStep :4744, SORSmoother :4786; $damp is the relaxation omega)
+// One struct and one set of functions: `kind` (UGGPU_SM_*) is set by the constructor of the class.
 // =========================================================================================================================
 struct NP_GPUJAC {
   NP_ITER iter;
   VEC_SCALAR damp;
   Mirror *m;
   INT acquired;        // PreProcess is called once per level (iter.cc:7719): one mirror reference each
+  INT kind;            // UGGPU_SM_JAC / GS / SGS / SOR
+  int t_handle;        // sgs: the extra temporary NP_SGS_t (iter.cc:1386) lives on the device only
 };
+static const char *SmootherName(INT kind) { return kind == UGGPU_SM_GS ? "gpugs" : kind == UGGPU_SM_SGS ? "gpusgs" : kind == UGGPU_SM_SOR ? "gpusor" : "gpujac"; }
 
 INT GpuJacInit(NP_BASE *theNP, INT argc, char **argv)
 {
@@ -225,6 +232,11 @@ INT GpuJacPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b
   np->m = m;
   np->acquired++;
   if (EnsureLevel(np->m, level, x, A)) NP_RETURN(1, result[0]);
+  if (np->kind != UGGPU_SM_JAC) {
+    // l_setindex (iter.cc:1027): rows are numbered in list order by the flattening; the device builds its level schedule
+    if (api.uggpu_gs_preprocess(m->ctx, level, m->handle(A))) NP_RETURN(dev_fail("uggpu_gs_preprocess"), result[0]);
+    np->t_handle = m->handle(&np->t_handle);
+  }
   *baselevel = level;                                                      // iter.cc:908
   return 0;
 }
@@ -235,11 +247,14 @@ INT GpuJacIter(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATD
   NP_GPUJAC *np = (NP_GPUJAC *)theNP;
   NPIT_A(theNP) = A; NPIT_c(theNP) = x; NPIT_b(theNP) = b;
   Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
-  if (m == NULL || !m->have_level[level]) { UserWrite("gpujac: Iter without PreProcess\n"); NP_RETURN(1, result[0]); }
+  if (m == NULL || !m->have_level[level]) { UserWriteF("%s: Iter without PreProcess\n", SmootherName(np->kind)); NP_RETURN(1, result[0]); }
   double damp[UGGPU_MAX_BS];
   VsToArray(np->damp, m->bs, damp);
   if (Upload(m, level, b)) NP_RETURN(1, result[0]);
   if (api.uggpu_vec_alloc(m->ctx, level, m->handle(x))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+  if (np->kind != UGGPU_SM_JAC) {
+    if (api.uggpu_smooth(m->ctx, level, (int)np->kind, m->handle(x), m->handle(b), m->handle(A), damp, np->t_handle)) NP_RETURN(dev_fail("uggpu_smooth"), result[0]);
+  } else
   if (api.uggpu_jac_smooth(m->ctx, level, m->handle(x), m->handle(b), m->handle(A), damp)) NP_RETURN(dev_fail("uggpu_jac_smooth"), result[0]);
   if (Download(m, level, x) || Download(m, level, b)) NP_RETURN(1, result[0]);
   return 0;
@@ -255,7 +270,7 @@ INT GpuJacPostProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
   return 0;
 }
 
-INT GpuJacConstruct(NP_BASE *theNP)
+INT GpuSmootherConstruct(NP_BASE *theNP, INT kind)
 {
   theNP->Init = GpuJacInit;
   theNP->Display = GpuJacDisplay;
@@ -264,8 +279,13 @@ INT GpuJacConstruct(NP_BASE *theNP)
   np->PreProcess = GpuJacPreProcess;
   np->Iter = GpuJacIter;
   np->PostProcess = GpuJacPostProcess;
+  ((NP_GPUJAC *)theNP)->kind = kind;
   return 0;
 }
+INT GpuJacConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_JAC); }
+INT GpuGsConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_GS); }
+INT GpuSgsConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_SGS); }
+INT GpuSorConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_SOR); }
 
 // =========================================================================================================================
 // transfer.gputransfer  (reference: NP_STANDARD_TRANSFER transfer.cc:115-133, standard mode only)
@@ -414,7 +434,11 @@ INT GpuLmgcInit(NP_BASE *theNP, INT argc, char **argv)
   if (np->Transfer == NULL || np->PreSmooth == NULL || np->PostSmooth == NULL) REP_ERR_RETURN(NP_NOT_ACTIVE);
   if (np->BaseSolver == NULL && !np->devbase) REP_ERR_RETURN(NP_NOT_ACTIVE);
   if (np->PreSmooth->Iter != GpuJacIter || np->PostSmooth->Iter != GpuJacIter) {
-    UserWrite("gpulmgc: $S pre and post smoother must be of class gpujac (damped Jacobi is the smoother on the GPU path)\n");
+    UserWrite("gpulmgc: $S pre and post smoother must be of class gpujac, gpugs, gpusgs or gpusor\n");
+    return NP_NOT_ACTIVE;
+  }
+  if (((NP_GPUJAC *)np->PreSmooth)->kind != ((NP_GPUJAC *)np->PostSmooth)->kind) {
+    UserWrite("gpulmgc: pre and post smoother must be of the same class\n");
     return NP_NOT_ACTIVE;
   }
   if (np->Transfer->RestrictDefect != GpuRestrictDefect) {
@@ -468,6 +492,7 @@ void FillCfg(NP_GPULMGC *np, uggpu_lmgc_cfg *cfg)
   VsToArray(np->damp, m->bs, cfg->cycle_damp);
   cfg->t = np->t_handle;
   cfg->fused = np->unfused ? 0 : 1;
+  cfg->smoother = (int)((NP_GPUJAC *)np->PreSmooth)->kind;
   if (np->devbase) {
     cfg->base_solver = NULL;
     // the parameters of the reference's `ls $I lu` base solver if one is given, else its documented defaults
@@ -779,6 +804,9 @@ INT GpuLsConstructKind(NP_BASE *theNP, INT kind)
 INT NS_DIM_PREFIX InitGpuLS(void)
 {
   if (CreateClass(ITER_CLASS_NAME ".gpujac", sizeof(NP_GPUJAC), GpuJacConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ITER_CLASS_NAME ".gpugs", sizeof(NP_GPUJAC), GpuGsConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ITER_CLASS_NAME ".gpusgs", sizeof(NP_GPUJAC), GpuSgsConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ITER_CLASS_NAME ".gpusor", sizeof(NP_GPUJAC), GpuSorConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(TRANSFER_CLASS_NAME ".gputransfer", sizeof(NP_GPUTRANSFER), GpuTransferConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(ITER_CLASS_NAME ".gpulmgc", sizeof(NP_GPULMGC), GpuLmgcConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpuls", sizeof(NP_GPULS), GpuLsConstruct)) REP_ERR_RETURN(__LINE__);

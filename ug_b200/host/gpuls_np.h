@@ -4,9 +4,11 @@
 //
 //   class name (npcreate $c ...)   abstract base                replaces (reference)
 //   iter.gpujac                    NP_ITER   (iter.h:68)        iter.jac          iter.cc:894-942
+//   iter.gpugs / gpusgs / gpusor   NP_ITER                      iter.gs / sgs / sor  iter.cc:1003-1090, 1353-1490, 4717-4840
 //   transfer.gputransfer           NP_TRANSFER (transfer.h:79)  transfer.transfer transfer.cc:553-897 (standard mode)
 //   iter.gpulmgc                   NP_ITER                      iter.lmgc         iter.cc:7613-7980
 //   linear_solver.gpuls            NP_LINEAR_SOLVER (ls.h:79)   linear_solver.ls  ls.cc:539-905
+//   linear_solver.gpucg / gpubcgs  NP_LINEAR_SOLVER             linear_solver.cg / bcgs  ls.cc:939-1160, 1750-2062
 //
 // Same option letters as the CPU classes ($A $x $b $c $damp $S $T $n1 $n2 $g $b $t $m $I $red $abslimit $display),
 // plus on gpulmgc: $devbase (solve the base level on the device instead of calling the BaseSolver numproc) and
@@ -25,7 +27,7 @@ const char *LastLoadError();
 }
 
 START_UGDIM_NAMESPACE
-// registers the four classes (np/udm/numproc.h:108 CreateClass); 0 = ok
+// registers the classes (np/udm/numproc.h:108 CreateClass); 0 = ok
 INT InitGpuLS(void);
 END_UGDIM_NAMESPACE
 
