@@ -26,7 +26,9 @@ def has(hier, what):
     return key in hier.raw
 
 
-def _cmp_vec(what, got, ref, exact, tol):
+def _cmp_vec(what, got, ref, exact, tol, floor=0.0):
+    """floor: lower bound of the scale of an inexact comparison (a defect that an exact base solve leaves at rounding level has
+    no scale of its own)."""
     if got.shape != ref.shape:
         raise Mismatch(f"{what}: shape {got.shape} != {ref.shape}")
     if exact:
@@ -35,7 +37,7 @@ def _cmp_vec(what, got, ref, exact, tol):
             i = bad[0]
             raise Mismatch(f"{what}: {bad.size}/{ref.size} entries differ, first at {i}: got {got[i]!r} ref {ref[i]!r}")
     else:
-        scale = np.max(np.abs(ref)) or 1.0
+        scale = max(np.max(np.abs(ref)), floor) or 1.0
         err = np.max(np.abs(got - ref)) / scale
         if not err <= tol:
             raise Mismatch(f"{what}: max rel err {err:.3e} > {tol:.1e}")
@@ -168,12 +170,13 @@ def replay_solve(be, hier, exact=True, vec_tol=1e-12, red_tol=1e-12, cfg_over=No
     cfg = cycle_cfg(hier, **(cfg_over or {}))
     n = 0
     zeros = [np.zeros(lv.n * lv.bs) for lv in hier.levels]
+    bfloor = float(np.max(np.abs(hier.levels[top].rhs)))       # scale of the defects
     for l in range(top + 1):
         be.put(l, "b", hier.levels[l].rhs); be.put(l, "c", zeros[l])
     assert be.lmgc(top, "c", "b", cfg) == 0
-    for l in range(top + 1):
+    for l in range(cfg["baselevel"], top + 1):                  # levels below the base level are not touched by the cycle
         _cmp_vec(f"L{l}/lmgc/c", be.get(l, "c"), d[f"L{l}/lmgc/c"], exact, vec_tol)
-        _cmp_vec(f"L{l}/lmgc/b", be.get(l, "b"), d[f"L{l}/lmgc/b"], exact, vec_tol)
+        _cmp_vec(f"L{l}/lmgc/b", be.get(l, "b"), d[f"L{l}/lmgc/b"], exact, vec_tol, bfloor)
         n += 2
     cycles = int(d["solve/cycles"][0])
     hist_ref = d["solve/history"].reshape(cycles, hier.bs)
@@ -189,9 +192,9 @@ def replay_solve(be, hier, exact=True, vec_tol=1e-12, red_tol=1e-12, cfg_over=No
         assert its == k, (its, k)
         _cmp_red("solve/first_defect(solver)", first2, d["solve/first_defect"], red_tol)
         _cmp_red(f"solve/history[:{k}]", hist.reshape(k, hier.bs), hist_ref[:k], red_tol); n += 2
-        for l in range(top + 1):
+        for l in range(cfg["baselevel"], top + 1):
             _cmp_vec(f"L{l}/solve/x_after_{k}", be.get(l, "x"), d[f"L{l}/solve/x_after_{k}"], exact, vec_tol)
-            _cmp_vec(f"L{l}/solve/b_after_{k}", be.get(l, "b"), d[f"L{l}/solve/b_after_{k}"], exact, vec_tol)
+            _cmp_vec(f"L{l}/solve/b_after_{k}", be.get(l, "b"), d[f"L{l}/solve/b_after_{k}"], exact, vec_tol, bfloor)
             n += 2
     return n
 

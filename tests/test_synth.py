@@ -97,12 +97,20 @@ def test_synth_solve_bitexact_vs_port(cells, dim, top, kind, monkeypatch, tma_ro
             be.close()
     ref = out[-1]
     assert ref[0] == 6 and ref[1][-1] < 0.5 * ref[1][hier.bs - 1]
+    # 3x3 blocks with coupled FREE rows on the base level: the device LU eliminates scalar-wise in index order, the reference
+    # block-wise on its matrix lists (pinned in the oracle port) -- agreement to rounding there, bit for bit everywhere else
+    exact = not (hier.bs > 1 and cells > 2)
+    bscale = np.max(np.abs(rhs))
     for its, hist, xs, bs in out[:-1]:
         assert its == ref[0]
-        assert np.max(np.abs(hist - ref[1]) / np.maximum(ref[1], 1e-300)) < 1e-12
+        assert np.max(np.abs(hist - ref[1]) / np.maximum(ref[1], 1e-300)) < (1e-12 if exact else 1e-10)
         for l in range(top + 1):
-            assert np.array_equal(xs[l], ref[2][l]), l
-            assert np.array_equal(bs[l], ref[3][l]), l
+            if exact:
+                assert np.array_equal(xs[l], ref[2][l]), l
+                assert np.array_equal(bs[l], ref[3][l]), l
+            else:
+                assert np.max(np.abs(xs[l] - ref[2][l])) <= 1e-12 * max(np.max(np.abs(ref[2][l])), 1e-300), l
+                assert np.max(np.abs(bs[l] - ref[3][l])) <= 1e-12 * bscale, l
 
 
 @pytest.mark.parametrize("cells,dim,top,kind,smoother,damp", [(2, 3, 3, 0, "gs", 0.9), (2, 3, 4, 0, "sgs", 0.8), (1, 3, 3, 2, "sor", 1.1), (2, 3, 3, 1, "sgs", 0.9),

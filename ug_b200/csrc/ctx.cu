@@ -103,7 +103,7 @@ Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs, int slice
   if (cap < dist) dist = cap;
   if (dist < resident / 2 * slices_per_warp) dist = 0;
   pf.dist = d ? atoi(d) : (int)dist;
-  pf.mode = m ? atoi(m) : 31;
+  pf.mode = m ? atoi(m) : 63;
   pf.nsl = (A->n + 31) / 32;
   pf.val_lines = (A->maxlen * A->bb * 256 + 127) / 128;
   pf.col_lines = A->maxlen < 32 ? A->maxlen : 32;
@@ -253,7 +253,7 @@ extern "C" int uggpu_level_destroy(uggpu_ctx *ctx, int level)
   level_free_part(ctx, L);
   sell_free(ctx, &L->P);
   sell_free(ctx, &L->R);
-  if (L->lu) dfree(ctx, L->lu, (size_t)L->luN * L->luN);
+  level_free_lu(ctx, L);
   dfree(ctx, L->vclass, n); dfree(ctx, L->vnclass, n); dfree(ctx, L->ctl, n); dfree(ctx, L->skip, n);
   *L = Level();
   return 0;

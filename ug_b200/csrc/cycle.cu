@@ -10,7 +10,9 @@
 #include "uggpu_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 // ---- dense LU of the base level ---------------------------------------------------------------------------------
 #define LU_THREADS 1024
@@ -101,6 +103,133 @@ __global__ void __launch_bounds__(LU_THREADS) k_lu_solve(int N, int bs, const ui
   for (int i = tid; i < N; i += LU_THREADS) v[i] = vs[i];
 }
 
+// Scalar rows, summed in the order of UG's matrix lists.  l_lrdecomp (ugiter.cc:3657) creates fill-in with
+// CreateExtraConnection, which puts the new entries at the SECOND place of both row lists (gm/algebra.cc:1051-1078), and
+// l_luiter (ugiter.cc:4470-4518) adds a row's terms in list order -- so the order depends on when each fill-in entry appeared.
+// lu_lists() replays that on the host (integers and zero tests only) and the kernel below follows the lists: products in
+// parallel, the sum by one thread in list order.  Forward: v_i = d_i - sum_{c<i} L_ic v_c;  backward: v_i = (v_i - sum_{c>i}
+// U_ic v_c) * (1/U_ii).
+__global__ void __launch_bounds__(LU_THREADS) k_lu_solve_lists(int N, const uint8_t *__restrict__ vclass, const double *__restrict__ lu,
+                                                               const int32_t *__restrict__ lo_ptr, const int32_t *__restrict__ lo_col,
+                                                               const int32_t *__restrict__ up_ptr, const int32_t *__restrict__ up_col,
+                                                               double *__restrict__ v, const double *__restrict__ d)
+{
+  __shared__ double vs[LU_MAX_N];
+  __shared__ double prod[LU_MAX_N];
+  __shared__ uint8_t act[LU_MAX_N];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N; i += LU_THREADS) { act[i] = vclass[i] >= 3; vs[i] = 0.0; }
+  __syncthreads();
+  for (int i = 0; i < N; i++) {
+    if (!act[i]) continue;
+    const int o = lo_ptr[i], cnt = lo_ptr[i + 1] - o;
+    for (int k = tid; k < cnt; k += LU_THREADS) { const int c = lo_col[o + k]; prod[k] = lu[(size_t)c * N + i] * vs[c]; }
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int k = 0; k < cnt; k++) s += prod[k];
+      vs[i] = d[i] - s;
+    }
+    __syncthreads();
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    if (!act[i]) continue;
+    const int o = up_ptr[i], cnt = up_ptr[i + 1] - o;
+    for (int k = tid; k < cnt; k += LU_THREADS) { const int c = up_col[o + k]; prod[k] = lu[(size_t)c * N + i] * vs[c]; }
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int k = 0; k < cnt; k++) s += prod[k];
+      vs[i] = (vs[i] - s) * lu[(size_t)i * N + i];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += LU_THREADS) v[i] = vs[i];
+}
+
+int level_free_lu(uggpu_ctx *ctx, Level *L)
+{
+  if (L->lu) dfree(ctx, L->lu, (size_t)L->luN * L->luN);
+  if (L->lu_lo_ptr) dfree(ctx, L->lu_lo_ptr, (size_t)L->luN + 1);
+  if (L->lu_up_ptr) dfree(ctx, L->lu_up_ptr, (size_t)L->luN + 1);
+  if (L->lu_lo_col) dfree(ctx, L->lu_lo_col, (size_t)(L->lu_lo_nnz > 0 ? L->lu_lo_nnz : 1));
+  if (L->lu_up_col) dfree(ctx, L->lu_up_col, (size_t)(L->lu_up_nnz > 0 ? L->lu_up_nnz : 1));
+  L->luN = 0; L->luA = -1; L->lu_lo_nnz = L->lu_up_nnz = 0;
+  return 0;
+}
+
+// Replays the list operations of l_lrdecomp (scalar path ugiter.cc:3715-3768) on the pattern of M and the finished factors:
+// row lists start in VSTART->MNEXT order; at step i, for every list entry j > i whose multiplier L_ji is not zero (:3741) and
+// every list entry k > i, a missing connection (j,k) is inserted at the second place of the lists of j and of k.
+static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
+{
+  const int n = L->n;
+  std::vector<int32_t> rowptr((size_t)n + 1), col((size_t)M->nnz);
+  UG_TRY(sell_to_host_csr(ctx, M, rowptr.data(), col.data(), nullptr));
+  std::vector<uint8_t> vclass((size_t)n);
+  std::vector<double> lu((size_t)n * n);
+  CUDA_TRY(cudaMemcpyAsync(vclass.data(), L->vclass, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(lu.data(), L->lu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  // singly linked row lists in one node pool: node = (column, next); head[r] = the diagonal entry
+  std::vector<int32_t> ncol, nnext, head((size_t)n, -1);
+  ncol.reserve(col.size() * 2); nnext.reserve(col.size() * 2);
+  std::vector<uint8_t> present((size_t)n * n, 0);
+  for (int r = 0; r < n; r++) {
+    int prev = -1;
+    for (int e = rowptr[r]; e < rowptr[r + 1]; e++) {
+      const int id = (int)ncol.size();
+      ncol.push_back(col[e]); nnext.push_back(-1);
+      if (prev < 0) head[r] = id; else nnext[prev] = id;
+      prev = id;
+      present[(size_t)r * n + col[e]] = 1;
+    }
+    if (head[r] < 0 || ncol[head[r]] != r) return uggpu_fail(UGGPU_ERROR, "base level: row %d does not start with its diagonal entry", r);
+  }
+  auto active = [&](int x) { return vclass[x] >= 3; };
+  auto insert_second = [&](int r, int c) {
+    const int id = (int)ncol.size();
+    ncol.push_back(c); nnext.push_back(nnext[head[r]]);
+    nnext[head[r]] = id;
+    present[(size_t)r * n + c] = 1;
+  };
+  for (int i = 0; i < n; i++) {
+    if (!active(i)) continue;
+    for (int a = nnext[head[i]]; a >= 0; a = nnext[a]) {
+      const int j = ncol[a];
+      if (!(active(j) && j > i)) continue;
+      if (lu[(size_t)i * n + j] == 0.0) continue;            // multiplier L_ji (column-major: element (j,i) at lu[i*n+j])
+      for (int c = nnext[head[i]]; c >= 0; c = nnext[c]) {
+        const int k = ncol[c];
+        if (!(active(k) && k > i)) continue;
+        if (present[(size_t)j * n + k]) continue;
+        insert_second(j, k);
+        insert_second(k, j);
+      }
+    }
+  }
+  std::vector<int32_t> lo_ptr((size_t)n + 1, 0), up_ptr((size_t)n + 1, 0), lo_col, up_col;
+  for (int r = 0; r < n; r++) {
+    if (active(r))
+      for (int a = nnext[head[r]]; a >= 0; a = nnext[a]) {
+        const int c = ncol[a];
+        if (!active(c) || c == r) continue;
+        if (c < r) lo_col.push_back(c); else up_col.push_back(c);
+      }
+    lo_ptr[r + 1] = (int32_t)lo_col.size(); up_ptr[r + 1] = (int32_t)up_col.size();
+  }
+  L->lu_lo_nnz = (int)lo_col.size(); L->lu_up_nnz = (int)up_col.size();
+  UG_TRY(dalloc(ctx, &L->lu_lo_ptr, (size_t)n + 1)); UG_TRY(dalloc(ctx, &L->lu_up_ptr, (size_t)n + 1));
+  UG_TRY(dalloc(ctx, &L->lu_lo_col, (size_t)(L->lu_lo_nnz > 0 ? L->lu_lo_nnz : 1)));
+  UG_TRY(dalloc(ctx, &L->lu_up_col, (size_t)(L->lu_up_nnz > 0 ? L->lu_up_nnz : 1)));
+  CUDA_TRY(cudaMemcpyAsync(L->lu_lo_ptr, lo_ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(L->lu_up_ptr, up_ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (L->lu_lo_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_lo_col, lo_col.data(), sizeof(int32_t) * lo_col.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (L->lu_up_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_up_col, up_col.data(), sizeof(int32_t) * up_col.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));      // the host vectors go out of scope
+  return 0;
+}
+
 static int ensure_vec(uggpu_ctx *ctx, int level, int vec) { return uggpu_vec_alloc(ctx, level, vec); }
 
 extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int A)
@@ -125,7 +254,7 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
     Level *L = &ctx->lev[bl];
     int N = L->n * L->bs;
     if (N > LU_MAX_N) return uggpu_fail(UGGPU_OUT_OF_MEM, "base level has %d unknowns; the device LU handles at most %d (use a coarser base level or a host base solver)", N, LU_MAX_N);
-    if (L->lu) UG_TRY(dfree(ctx, L->lu, (size_t)L->luN * L->luN));
+    UG_TRY(level_free_lu(ctx, L));
     L->luN = N; L->luA = A;
     UG_TRY(dalloc(ctx, &L->lu, (size_t)N * N));
     if (N > 0) {
@@ -135,6 +264,8 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
       KCHECK(ctx);
       k_lu_factor<<<1, LU_THREADS, 0, ctx->stream>>>(N, L->bs, L->vclass, L->lu);
       KCHECK(ctx);
+      // scalar rows: the summation order of the reference's lists (block rows keep index order: DESIGN.md, base level)
+      if (L->bs == 1 && !getenv("UGGPU_LU_INDEX_ORDER")) UG_TRY(lu_lists(ctx, L, M));
     }
     UG_TRY(ensure_vec(ctx, bl, UGGPU_VEC_TMP_C));
   }
@@ -185,7 +316,8 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   for (int it = 0; it < cfg->base_maxit; it++) {
     {
       ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
-      k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
+      if (L->lu_lo_ptr) k_lu_solve_lists<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, L->vclass, L->lu, L->lu_lo_ptr, L->lu_lo_col, L->lu_up_ptr, L->lu_up_col, cc, bp);
+      else k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
       KCHECK(ctx);
     }
     UG_TRY(k_dmatmul(ctx, level, 2, 0, b, A, UGGPU_VEC_TMP_C));

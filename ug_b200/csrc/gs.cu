@@ -34,7 +34,8 @@ struct TriSched {
   int32_t *perm = nullptr;        // [nT] schedule position -> row, -1 = padding
   int32_t *slice_level = nullptr; // [nT/32]
   int32_t *level_slices = nullptr;// [nlev]
-  unsigned int *counters = nullptr;   // [nlev + 1]: finished slices per level, then the ticket
+  unsigned int *counters = nullptr;   // [32 + nlev]: ticket, finished slices per level (k_trisolve)
+  unsigned int *mail = nullptr;       // [TRI_MAIL_SLOTS * 32]: one progress word per SM, 128 bytes apart
 };
 
 static int tri_free(uggpu_ctx *ctx, TriSched *&S)
@@ -45,7 +46,8 @@ static int tri_free(uggpu_ctx *ctx, TriSched *&S)
   if (S->perm) dfree(ctx, S->perm, (size_t)S->nT);
   if (S->slice_level) dfree(ctx, S->slice_level, (size_t)S->nT / 32);
   if (S->level_slices) dfree(ctx, S->level_slices, (size_t)S->nlev);
-  if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev + 1);
+  if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev + 32);
+  if (S->mail) dfree(ctx, S->mail, (size_t)1024 * 32);
   delete S;
   S = nullptr;
   return 0;
@@ -227,7 +229,7 @@ static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSch
     int *d_start = nullptr, *d_poff = nullptr;
     TB(dalloc(ctx, &d_start, (size_t)S->nlev)); TB(dalloc(ctx, &d_poff, (size_t)S->nlev));
     TB(dalloc(ctx, &S->perm, (size_t)S->nT)); TB(dalloc(ctx, &S->slice_level, (size_t)nslT));
-    TB(dalloc(ctx, &S->level_slices, (size_t)S->nlev)); TB(dalloc(ctx, &S->counters, (size_t)S->nlev + 1));
+    TB(dalloc(ctx, &S->level_slices, (size_t)S->nlev)); TB(dalloc(ctx, &S->counters, (size_t)S->nlev + 32)); TB(dalloc(ctx, &S->mail, (size_t)1024 * 32));
     TC(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
     TC(cudaMemcpyAsync(d_poff, poff.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
     TC(cudaMemcpyAsync(S->level_slices, lsl.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
@@ -303,25 +305,39 @@ extern "C" int uggpu_gs_levels(uggpu_ctx *ctx, int level, int M, int *lower, int
 }
 
 // ---- the solve -------------------------------------------------------------------------------------------------------------
+// Synchronisation words of one schedule (TriSched::counters, zeroed before every launch):
+//   [0]                  ticket: next slice of the schedule
+//   [32 .. 32 + nlev)    finished slices per level (atomics only, nobody polls them)
+//   mail[sm * 32]        one mailbox per SM, 128 bytes apart: number of COMPLETED levels.  The warp that finishes the last slice of a
+//                        level writes that number into every mailbox; waiting warps poll only the mailbox of their own SM, so the
+//                        polls of the whole GPU spread over 100+ lines instead of hammering one (first version: every warp polled
+//                        the level counter itself -- 54 us per level at 257^3, all of it L2 same-address serialisation).
+#define TRI_MAIL_SLOTS 1024
+#define TRI_PRE 16           // column indices of a row held in registers while the warp waits
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
 {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int smid() { unsigned int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+__device__ __forceinline__ unsigned int nsmid() { unsigned int v; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v)); return v; }
 
 // SOR: 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows: solve, then
 // v_i *= omega_i :1556)
 template <int BS, int SOR>
 __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int32_t *__restrict__ perm, const int32_t *__restrict__ slice_level,
-                                                          const int32_t *__restrict__ level_slices, unsigned int *counters, int nlev, int nsl,
+                                                          const int32_t *__restrict__ level_slices, unsigned int *sync, unsigned int *mail, int nlev, int nsl,
                                                           double *v, const double *__restrict__ d, Damp omega, int *err)
 {
   constexpr int BB = BS * BS;
   const int lane = threadIdx.x & 31;
+  unsigned int *const ticket = sync, *const done = sync + 32;
+  const unsigned int *const mybox = mail + (size_t)(smid() % TRI_MAIL_SLOTS) * 32;
   for (;;) {
     int s = 0;
-    if (lane == 0) s = (int)atomicAdd(&counters[nlev], 1u);
+    if (lane == 0) s = (int)atomicAdd(ticket, 1u);
     s = __shfl_sync(0xffffffffu, s, 0);
     if (s >= nsl) return;
     const int lv = slice_level[s];
@@ -330,20 +346,33 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
     const int len = r >= 0 ? (int)T.rowlen[p] : 0;
     const int64_t sp = slice_off(T, s);
     const int w = slice_width(T, s, sp);
-    // pull the slice's values and column words into L2 while the previous level finishes
+    // everything that does not depend on other rows is fetched BEFORE the wait: the slice's values into L2, the row's column
+    // indices, diagonal block and right-hand side into registers
     {
       const char *vb = reinterpret_cast<const char *>(T.val + sp * BB);
       const int vlines = w * BB * 2;                        // 256 bytes per component and slice column
       for (int l = lane; l < vlines; l += 32) prefetch_l2(vb + (size_t)l * 128);
-      const int64_t cp = T.col_ptr[s];
-      if (cp >= 0 && lane < w) prefetch_l2(T.col + cp + (size_t)lane * 32);
     }
+    const ColIter ci = col_iter(T, p);
+    const double *__restrict__ vp = T.val + sp * BB + lane;
+    int cj[TRI_PRE];
+#pragma unroll
+    for (int j = 1; j <= TRI_PRE; j++) cj[j - 1] = j < len ? col_at(ci, j) : 0;
+    double dg[BB], rhs[BS];
+#pragma unroll
+    for (int k = 0; k < BB; k++) dg[k] = len > 0 ? __ldg(vp + (size_t)k * 32) : 1.0;
+#pragma unroll
+    for (int i = 0; i < BS; i++) rhs[i] = len > 0 ? d[(size_t)r * BS + i] : 0.0;
     if (lv > 0) {
       if (lane == 0) {
-        const unsigned int need = (unsigned int)level_slices[lv - 1];
         unsigned long long t0 = 0, t1;
         int spins = 0;
-        while (ld_acquire_u32(&counters[lv - 1]) < need) {
+        for (;;) {
+          const unsigned int cur = ld_acquire_u32(mybox);
+          if (cur >= (unsigned int)lv) break;
+          // far from its turn a warp polls rarely (a level takes at least ~1 us); next in line it polls tightly
+          const unsigned int dist = (unsigned int)lv - cur;
+          __nanosleep(dist > 1 ? min((dist - 1) * 1000u, 8000u) : 50u);
           if (++spins == 64) {
             spins = 0;
             if (*reinterpret_cast<volatile int *>(err)) break;          // an earlier wait already failed: do not wait again
@@ -351,32 +380,27 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
             if (t0 == 0) t0 = t1;
             else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }
           }
-          __nanosleep(40);
         }
         __threadfence();
       }
       __syncwarp();
     }
     if (r >= 0) {
+      double sol[BS];
       if (len == 0) {                                        // VCLASS < ACTIVE_CLASS: v = 0 (ugiter.cc:447)
 #pragma unroll
-        for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, 0.0);
+        for (int i = 0; i < BS; i++) sol[i] = 0.0;
       } else {
-        const ColIter ci = col_iter(T, p);
-        const double *__restrict__ vp = T.val + sp * BB + lane;
-        double dg[BB], acc[BS], rhs[BS], sol[BS];
+        double acc[BS];
 #pragma unroll
-        for (int k = 0; k < BB; k++) dg[k] = __ldg(vp + (size_t)k * 32);
-#pragma unroll
-        for (int i = 0; i < BS; i++) { acc[i] = 0.0; rhs[i] = d[(size_t)r * BS + i]; }
-#pragma unroll 4
-        for (int j = 1; j < len; j++) {
-          const int c = col_at(ci, j);
+        for (int i = 0; i < BS; i++) acc[i] = 0.0;
+        // entry j: the values were prefetched into L2, the operand was written by another SM during this launch (L2, not L1)
+        auto term = [&](int j, int c) {
           double m[BB], wv[BS];
 #pragma unroll
           for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-          for (int i = 0; i < BS; i++) wv[i] = __ldcg(v + (size_t)c * BS + i);     // written by another SM during this launch: L2, not L1
+          for (int i = 0; i < BS; i++) wv[i] = __ldcg(v + (size_t)c * BS + i);
 #pragma unroll
           for (int i = 0; i < BS; i++) {
             double t = m[i * BS] * wv[0];
@@ -384,7 +408,11 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
             for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * wv[q];
             acc[i] += t;
           }
-        }
+        };
+#pragma unroll
+        for (int j = 1; j <= TRI_PRE; j++)
+          if (j < len) term(j, cj[j - 1]);
+        for (int j = TRI_PRE + 1; j < len; j++) term(j, col_at(ci, j));
         if (BS == 1) {
           if (SOR) sol[0] = omega.a[0] * (rhs[0] - acc[0]) / dg[0];
           else sol[0] = (rhs[0] - acc[0]) / dg[0];
@@ -413,15 +441,25 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
             for (int i = 0; i < BS; i++) sol[i] = sol[i] * omega.a[i];
           }
         }
-#pragma unroll
-        for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, sol[i]);
       }
+#pragma unroll
+      for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, sol[i]);
     }
-    // publish: the warp's stores, then one release by lane 0 (the pattern of a grid barrier, per warp)
+    // publish: the warp's stores, then one release by lane 0 (the pattern of a grid barrier, per warp); the warp that completes
+    // the level tells every SM
     __syncwarp();
+    int last = 0;
     if (lane == 0) {
       __threadfence();
-      atomicAdd(&counters[lv], 1u);
+      last = atomicAdd(&done[lv], 1u) + 1u == (unsigned int)level_slices[lv];
+      if (last) __threadfence();
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      const unsigned int nb = min(nsmid(), (unsigned int)TRI_MAIL_SLOTS);
+      // max, not store: the stores of two consecutive levels' last warps may land in either order
+      for (unsigned int q = lane; q < nb; q += 32) atomicMax(mail + (size_t)q * 32, (unsigned int)lv + 1u);
     }
   }
 }
@@ -436,7 +474,8 @@ static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const
   if (!A->tri[dir]) UG_TRY(uggpu_gs_preprocess(ctx, level, M));
   TriSched *S = A->tri[dir];
   const int nsl = S->nT / 32;
-  CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * ((size_t)S->nlev + 1), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * ((size_t)S->nlev + 32), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(S->mail, 0, sizeof(unsigned int) * (size_t)TRI_MAIL_SLOTS * 32, ctx->stream));
   int blocks = (nsl + TRI_THREADS / 32 - 1) / (TRI_THREADS / 32);
   const int cap = ctx->sm_count * (2048 / TRI_THREADS);
   if (blocks > cap) blocks = cap;
@@ -445,8 +484,8 @@ static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const
   // algorithmic bytes: the triangle's entries, row lengths and permutation, d read, v written, gathered v once
   ProfScope ps(ctx, UGGPU_K_TRISOLVE, level, S->T.entry_bytes() + 6.0 * S->nT + 8.0 * L->bs * 3.0 * L->n);
 #define TS(BSV)                                                                                                                          \
-  if (omega) k_trisolve<BSV, 1><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->nlev, nsl, v, d, om, ctx->derr); \
-  else k_trisolve<BSV, 0><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->nlev, nsl, v, d, om, ctx->derr)
+  if (omega) k_trisolve<BSV, 1><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->mail, S->nlev, nsl, v, d, om, ctx->derr); \
+  else k_trisolve<BSV, 0><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->mail, S->nlev, nsl, v, d, om, ctx->derr)
   switch (L->bs) {
     case 1: TS(1); break;
     case 2: TS(2); break;

@@ -22,10 +22,10 @@
 // Fixed-width stencils (sell_layout: all uniformly refined grids) have no slice-offset load at all: two hops, and every stream
 // but the gathered operand is direct-indexed, so its far lines are touched when the warp STARTS.
 #ifndef TR_K_INTERP
-#define TR_K_INTERP 4
+#define TR_K_INTERP 1
 #endif
 #ifndef TR_K_RESTRICT
-#define TR_K_RESTRICT 2
+#define TR_K_RESTRICT 1
 #endif
 
 // L2 prefetch of the stencil entries of the slice pf.dist ahead of row r's (uggpu_internal.h), request and touch in one go
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   const double *wp[K];
   double tr[K][BS];
   int maxl = 0;
-  const bool early = R.fixed_w != 0;       // warp-uniform
+  const bool early = R.fixed_w != 0 && (pf.mode & 32);       // warp-uniform
 #pragma unroll
   for (int k = 0; k < K; k++) {
     r[k] = (int)((warp * K + k) * 32) + lane;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : 1) k_int
   const double *wp[K];
   double tr[K][BS];
   int maxl = 0;
-  const bool early = P.fixed_w != 0;       // warp-uniform
+  const bool early = P.fixed_w != 0 && (pf.mode & 32);       // warp-uniform
 #pragma unroll
   for (int k = 0; k < K; k++) {
     r[k] = (int)((warp * K + k) * 32) + lane;

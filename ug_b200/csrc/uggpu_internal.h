@@ -92,6 +92,9 @@ struct Level {
   // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
   double *lu = nullptr;
   int luN = 0, luA = -1;
+  // scalar levels: the rows' lower / upper entries in the order of UG's matrix lists after l_lrdecomp's fill-in (cycle.cu lu_lists)
+  int32_t *lu_lo_ptr = nullptr, *lu_lo_col = nullptr, *lu_up_ptr = nullptr, *lu_up_col = nullptr;
+  int lu_lo_nnz = 0, lu_up_nnz = 0;
   // multi-GPU (part.h, comm.cu): n = rows this rank owns; vectors carry nghost extra rows at the tail
   int nghost = 0;
   bool partitioned = false;      // rows are split over the ranks (halo exchange + global reductions apply)
@@ -144,7 +147,8 @@ struct ProfScope {
 struct Prefetch {
   int dist;        // slices ahead (0: off)
   int nsl;         // slices of the matrix
-  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 vector entries of the rows, bit 3 slice offsets / row lengths two hops ahead, bit 4 row flags
+  int mode;        // bit 0 values, bit 1 explicit column words, bit 2 vector entries of the rows, bit 3 slice offsets / row lengths two hops ahead, bit 4 row flags,
+                   // bit 5 transfer kernels on fixed-width stencils touch the far lines when the warp starts (else when it ends)
   int val_lines;   // 128-byte lines of the widest slice's value block
   int col_lines;   // same for explicit column words
   int64_t val_bytes, col_bytes, vec_bytes;   // sizes of the arrays: no line beyond them is touched
@@ -278,6 +282,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
 int halo_exchange(uggpu_ctx *ctx, int level, double *v);                 // owned values -> the neighbours' ghost rows of v
 int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count);           // in place, on the context's stream
 int level_free_part(uggpu_ctx *ctx, Level *L);
+int level_free_lu(uggpu_ctx *ctx, Level *L);                              // cycle.cu: the base-level factorisation
 static inline size_t vec_count(const Level *L) { return ((size_t)L->n + (size_t)L->nghost) * (size_t)L->bs; }
 // internal temporary vector handles (never visible through the C-ABI callers' handle space)
 #define UGGPU_VEC_TMP_A (-1001)

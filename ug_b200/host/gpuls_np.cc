@@ -476,10 +476,17 @@ int HostBaseSolver(void *user, uggpu_ctx *ctx, int level, int c, int b, int A)
   NP_GPULMGC *np = (NP_GPULMGC *)user;
   Mirror *m = np->m;
   LRESULT lresult;
-  if (Download(m, level, np->cur_c) || Download(m, level, np->cur_b)) return 1;
-  if ((*np->BaseSolver->Residuum)(np->BaseSolver, MIN(level, np->baselevel), level, np->cur_c, np->cur_b, np->cur_A, &lresult)) return 1;
-  if ((*np->BaseSolver->Solver)(np->BaseSolver, level, np->cur_c, np->cur_b, np->cur_A, np->BaseSolver->abslimit, np->BaseSolver->reduction, &lresult)) return 1;
-  if (Upload(m, level, np->cur_c) || Upload(m, level, np->cur_b)) return 1;
+  // the cycle may run on other vectors than the ones the solver was called with (bcgs: Iter(q, p) and Iter(q, s), ls.cc:1944,1990):
+  // map the handles back to their descriptors
+  VECDATA_DESC *cd = np->cur_c, *bd = np->cur_b;
+  for (auto &kv : m->handles) {
+    if (kv.second == c) cd = (VECDATA_DESC *)kv.first;
+    if (kv.second == b) bd = (VECDATA_DESC *)kv.first;
+  }
+  if (Download(m, level, cd) || Download(m, level, bd)) return 1;
+  if ((*np->BaseSolver->Residuum)(np->BaseSolver, MIN(level, np->baselevel), level, cd, bd, np->cur_A, &lresult)) return 1;
+  if ((*np->BaseSolver->Solver)(np->BaseSolver, level, cd, bd, np->cur_A, np->BaseSolver->abslimit, np->BaseSolver->reduction, &lresult)) return 1;
+  if (Upload(m, level, cd) || Upload(m, level, bd)) return 1;
   return 0;
 }
 
