@@ -20,7 +20,11 @@
 // bandwidth.  K independent chains per thread multiply the bytes in flight without changing any row's
 // additions or their order.
 // Fixed-width stencils (sell_layout: all uniformly refined grids) have no slice-offset load at all: two hops, and every stream
-// but the gathered operand is direct-indexed, so its far lines are touched when the warp STARTS.
+// but the gathered operand is direct-indexed; the interpolation touches its far lines when the warp STARTS (1.71 vs 1.74 ms at
+// 513^3), the restriction -- 15-entry rows, the warp lives longer -- when it ends (1.14 vs 1.63 ms).
+// Measured and rejected: K > 1 (interpolation 1.71 / 2.05 / 2.51 ms, restriction 1.57 / 1.81 / 2.45 ms for K = 1 / 2 / 4 at 513^3):
+// more rows per thread cost registers (occupancy) and spread the warp's gathers over more lines; K stays a template parameter
+// and an A/B switch (UGGPU_TR_K_INTERP / UGGPU_TR_K_RESTRICT), the default is 1.
 #ifndef TR_K_INTERP
 #define TR_K_INTERP 1
 #endif
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   const double *wp[K];
   double tr[K][BS];
   int maxl = 0;
-  const bool early = R.fixed_w != 0 && (pf.mode & 32);       // warp-uniform
+  const bool early = false;       // measured (513^3, B200): touching the far lines when the warp ENDS 1.14 ms, when it starts 1.63 ms
 #pragma unroll
   for (int k = 0; k < K; k++) {
     r[k] = (int)((warp * K + k) * 32) + lane;
