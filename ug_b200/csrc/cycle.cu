@@ -106,45 +106,68 @@ __global__ void __launch_bounds__(LU_THREADS) k_lu_solve(int N, int bs, const ui
 // Scalar rows, summed in the order of UG's matrix lists.  l_lrdecomp (ugiter.cc:3657) creates fill-in with
 // CreateExtraConnection, which puts the new entries at the SECOND place of both row lists (gm/algebra.cc:1051-1078), and
 // l_luiter (ugiter.cc:4470-4518) adds a row's terms in list order -- so the order depends on when each fill-in entry appeared.
-// lu_lists() replays that on the host (integers and zero tests only) and the kernel below follows the lists: products in
-// parallel, the sum by one thread in list order.  Forward: v_i = d_i - sum_{c<i} L_ic v_c;  backward: v_i = (v_i - sum_{c>i}
-// U_ic v_c) * (1/U_ii).
-__global__ void __launch_bounds__(LU_THREADS) k_lu_solve_lists(int N, const uint8_t *__restrict__ vclass, const double *__restrict__ lu,
-                                                               const int32_t *__restrict__ lo_ptr, const int32_t *__restrict__ lo_col,
-                                                               const int32_t *__restrict__ up_ptr, const int32_t *__restrict__ up_col,
-                                                               double *__restrict__ v, const double *__restrict__ d)
+// lu_lists() replays that on the host (integers and zero tests only) and packs the factors into two "row programs" (active
+// rows ascending with their L entries, active rows descending with their U entries, values gathered by k_lu_pack); the solve
+// is ONE WARP: the lanes form a row's products, lane 0 adds them in list order (a sequential sum is the reference's arithmetic),
+// and the next row's entries are already in registers while it does.  Forward: v_i = d_i - sum_{c<i} L_ic v_c;  backward:
+// v_i = (v_i - sum_{c>i} U_ic v_c) * (1/U_ii).
+#define LUS_PRE 4       // entries per lane of the next row held in registers (rows up to 128 entries are fully prefetched)
+
+struct LuProg { const int32_t *row, *ptr, *col; const double *val; int n; };
+
+__global__ void k_lu_pack(int N, const double *__restrict__ lu, const int32_t *__restrict__ row, const int32_t *__restrict__ ptr, const int32_t *__restrict__ col,
+                          double *__restrict__ val, double *__restrict__ dinv)
+{
+  const int k = blockIdx.x, r = row[k];
+  for (int e = ptr[k] + threadIdx.x; e < ptr[k + 1]; e += blockDim.x) val[e] = lu[(size_t)col[e] * N + r];
+  if (dinv && threadIdx.x == 0) dinv[k] = lu[(size_t)r * N + r];
+}
+
+template <bool BACKWARD>
+__device__ __forceinline__ void lu_sweep(const LuProg P, const double *__restrict__ rhs /* forward: d[row]; backward: dinv[k] */, double *vs, double *prod)
+{
+  const int lane = threadIdx.x;
+  if (P.n == 0) return;
+  int row_n = P.row[0], o_n = P.ptr[0], e_n = P.ptr[1];
+  double r_n = BACKWARD ? rhs[0] : rhs[row_n];
+  double nv[LUS_PRE]; int nc[LUS_PRE];
+#pragma unroll
+  for (int q = 0; q < LUS_PRE; q++) { const int e = o_n + lane + 32 * q; nv[q] = e < e_n ? P.val[e] : 0.0; nc[q] = e < e_n ? P.col[e] : 0; }
+  for (int k = 0; k < P.n; k++) {
+    const int row = row_n, o = o_n, cnt = e_n - o_n;
+    const double r = r_n;
+    double cv[LUS_PRE]; int cc[LUS_PRE];
+#pragma unroll
+    for (int q = 0; q < LUS_PRE; q++) { cv[q] = nv[q]; cc[q] = nc[q]; }
+    if (k + 1 < P.n) {                       // the next row's entries travel while this row is summed
+      row_n = P.row[k + 1]; o_n = e_n; e_n = P.ptr[k + 2];
+      r_n = BACKWARD ? rhs[k + 1] : rhs[row_n];
+#pragma unroll
+      for (int q = 0; q < LUS_PRE; q++) { const int e = o_n + lane + 32 * q; nv[q] = e < e_n ? P.val[e] : 0.0; nc[q] = e < e_n ? P.col[e] : 0; }
+    }
+#pragma unroll
+    for (int q = 0; q < LUS_PRE; q++) { const int kk = lane + 32 * q; if (kk < cnt) prod[kk] = cv[q] * vs[cc[q]]; }
+    for (int kk = lane + 32 * LUS_PRE; kk < cnt; kk += 32) prod[kk] = P.val[o + kk] * vs[P.col[o + kk]];
+    __syncwarp();
+    if (lane == 0) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int kk = 0; kk < cnt; kk++) s += prod[kk];
+      vs[row] = BACKWARD ? (vs[row] - s) * r : r - s;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) k_lu_solve_lists(int N, LuProg F, LuProg B, const double *__restrict__ dinv, double *__restrict__ v, const double *__restrict__ d)
 {
   __shared__ double vs[LU_MAX_N];
   __shared__ double prod[LU_MAX_N];
-  __shared__ uint8_t act[LU_MAX_N];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < N; i += LU_THREADS) { act[i] = vclass[i] >= 3; vs[i] = 0.0; }
-  __syncthreads();
-  for (int i = 0; i < N; i++) {
-    if (!act[i]) continue;
-    const int o = lo_ptr[i], cnt = lo_ptr[i + 1] - o;
-    for (int k = tid; k < cnt; k += LU_THREADS) { const int c = lo_col[o + k]; prod[k] = lu[(size_t)c * N + i] * vs[c]; }
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int k = 0; k < cnt; k++) s += prod[k];
-      vs[i] = d[i] - s;
-    }
-    __syncthreads();
-  }
-  for (int i = N - 1; i >= 0; i--) {
-    if (!act[i]) continue;
-    const int o = up_ptr[i], cnt = up_ptr[i + 1] - o;
-    for (int k = tid; k < cnt; k += LU_THREADS) { const int c = up_col[o + k]; prod[k] = lu[(size_t)c * N + i] * vs[c]; }
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int k = 0; k < cnt; k++) s += prod[k];
-      vs[i] = (vs[i] - s) * lu[(size_t)i * N + i];
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < N; i += LU_THREADS) v[i] = vs[i];
+  for (int i = threadIdx.x; i < N; i += 32) vs[i] = 0.0;      // rows with VCLASS < ACTIVE_CLASS stay 0 (ugiter.cc:4488)
+  __syncwarp();
+  lu_sweep<false>(F, d, vs, prod);
+  lu_sweep<true>(B, dinv, vs, prod);
+  for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
 }
 
 int level_free_lu(uggpu_ctx *ctx, Level *L)
@@ -152,9 +175,14 @@ int level_free_lu(uggpu_ctx *ctx, Level *L)
   if (L->lu) dfree(ctx, L->lu, (size_t)L->luN * L->luN);
   if (L->lu_lo_ptr) dfree(ctx, L->lu_lo_ptr, (size_t)L->luN + 1);
   if (L->lu_up_ptr) dfree(ctx, L->lu_up_ptr, (size_t)L->luN + 1);
-  if (L->lu_lo_col) dfree(ctx, L->lu_lo_col, (size_t)(L->lu_lo_nnz > 0 ? L->lu_lo_nnz : 1));
-  if (L->lu_up_col) dfree(ctx, L->lu_up_col, (size_t)(L->lu_up_nnz > 0 ? L->lu_up_nnz : 1));
-  L->luN = 0; L->luA = -1; L->lu_lo_nnz = L->lu_up_nnz = 0;
+  if (L->lu_lo_row) dfree(ctx, L->lu_lo_row, (size_t)L->luN + 1);
+  if (L->lu_up_row) dfree(ctx, L->lu_up_row, (size_t)L->luN + 1);
+  if (L->lu_dinv) dfree(ctx, L->lu_dinv, (size_t)L->luN + 1);
+  if (L->lu_lo_col) dfree(ctx, L->lu_lo_col, (size_t)L->lu_lo_nnz + 1);
+  if (L->lu_up_col) dfree(ctx, L->lu_up_col, (size_t)L->lu_up_nnz + 1);
+  if (L->lu_lo_val) dfree(ctx, L->lu_lo_val, (size_t)L->lu_lo_nnz + 1);
+  if (L->lu_up_val) dfree(ctx, L->lu_up_val, (size_t)L->lu_up_nnz + 1);
+  L->luN = 0; L->luA = -1; L->lu_lo_nnz = L->lu_up_nnz = L->lu_active = 0;
   return 0;
 }
 
@@ -208,25 +236,43 @@ static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
       }
     }
   }
-  std::vector<int32_t> lo_ptr((size_t)n + 1, 0), up_ptr((size_t)n + 1, 0), lo_col, up_col;
+  // row programs: active rows ascending with their lower entries, descending with their upper entries (list order)
+  std::vector<int32_t> f_row, f_ptr(1, 0), f_col, b_row, b_ptr(1, 0), b_col;
   for (int r = 0; r < n; r++) {
-    if (active(r))
-      for (int a = nnext[head[r]]; a >= 0; a = nnext[a]) {
-        const int c = ncol[a];
-        if (!active(c) || c == r) continue;
-        if (c < r) lo_col.push_back(c); else up_col.push_back(c);
-      }
-    lo_ptr[r + 1] = (int32_t)lo_col.size(); up_ptr[r + 1] = (int32_t)up_col.size();
+    if (!active(r)) continue;
+    f_row.push_back(r);
+    for (int a = nnext[head[r]]; a >= 0; a = nnext[a]) { const int c = ncol[a]; if (active(c) && c < r) f_col.push_back(c); }
+    f_ptr.push_back((int32_t)f_col.size());
   }
-  L->lu_lo_nnz = (int)lo_col.size(); L->lu_up_nnz = (int)up_col.size();
+  for (int r = n - 1; r >= 0; r--) {
+    if (!active(r)) continue;
+    b_row.push_back(r);
+    for (int a = nnext[head[r]]; a >= 0; a = nnext[a]) { const int c = ncol[a]; if (active(c) && c > r) b_col.push_back(c); }
+    b_ptr.push_back((int32_t)b_col.size());
+  }
+  const int na = (int)f_row.size();
+  L->lu_active = na; L->lu_lo_nnz = (int)f_col.size(); L->lu_up_nnz = (int)b_col.size();
+  UG_TRY(dalloc(ctx, &L->lu_lo_row, (size_t)n + 1)); UG_TRY(dalloc(ctx, &L->lu_up_row, (size_t)n + 1));
   UG_TRY(dalloc(ctx, &L->lu_lo_ptr, (size_t)n + 1)); UG_TRY(dalloc(ctx, &L->lu_up_ptr, (size_t)n + 1));
-  UG_TRY(dalloc(ctx, &L->lu_lo_col, (size_t)(L->lu_lo_nnz > 0 ? L->lu_lo_nnz : 1)));
-  UG_TRY(dalloc(ctx, &L->lu_up_col, (size_t)(L->lu_up_nnz > 0 ? L->lu_up_nnz : 1)));
-  CUDA_TRY(cudaMemcpyAsync(L->lu_lo_ptr, lo_ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(L->lu_up_ptr, up_ptr.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
-  if (L->lu_lo_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_lo_col, lo_col.data(), sizeof(int32_t) * lo_col.size(), cudaMemcpyHostToDevice, ctx->stream));
-  if (L->lu_up_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_up_col, up_col.data(), sizeof(int32_t) * up_col.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));      // the host vectors go out of scope
+  UG_TRY(dalloc(ctx, &L->lu_dinv, (size_t)n + 1));
+  UG_TRY(dalloc(ctx, &L->lu_lo_col, (size_t)L->lu_lo_nnz + 1)); UG_TRY(dalloc(ctx, &L->lu_up_col, (size_t)L->lu_up_nnz + 1));
+  UG_TRY(dalloc(ctx, &L->lu_lo_val, (size_t)L->lu_lo_nnz + 1)); UG_TRY(dalloc(ctx, &L->lu_up_val, (size_t)L->lu_up_nnz + 1));
+  cudaStream_t st = ctx->stream;
+  if (na) {
+    CUDA_TRY(cudaMemcpyAsync(L->lu_lo_row, f_row.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(L->lu_up_row, b_row.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(L->lu_lo_ptr, f_ptr.data(), sizeof(int32_t) * (na + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(L->lu_up_ptr, b_ptr.data(), sizeof(int32_t) * (na + 1), cudaMemcpyHostToDevice, st));
+  if (L->lu_lo_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_lo_col, f_col.data(), sizeof(int32_t) * f_col.size(), cudaMemcpyHostToDevice, st));
+  if (L->lu_up_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_up_col, b_col.data(), sizeof(int32_t) * b_col.size(), cudaMemcpyHostToDevice, st));
+  if (na) {
+    k_lu_pack<<<na, 128, 0, st>>>(n, L->lu, L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, nullptr);
+    KCHECK(ctx);
+    k_lu_pack<<<na, 128, 0, st>>>(n, L->lu, L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_dinv);
+    KCHECK(ctx);
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));      // the host vectors go out of scope
   return 0;
 }
 
@@ -316,7 +362,9 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   for (int it = 0; it < cfg->base_maxit; it++) {
     {
       ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
-      if (L->lu_lo_ptr) k_lu_solve_lists<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, L->vclass, L->lu, L->lu_lo_ptr, L->lu_lo_col, L->lu_up_ptr, L->lu_up_col, cc, bp);
+      if (L->lu_lo_ptr)
+        k_lu_solve_lists<<<1, 32, 0, ctx->stream>>>(L->luN, LuProg{L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, L->lu_active},
+                                                    LuProg{L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_active}, L->lu_dinv, cc, bp);
       else k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
       KCHECK(ctx);
     }

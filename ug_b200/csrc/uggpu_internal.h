@@ -93,8 +93,9 @@ struct Level {
   double *lu = nullptr;
   int luN = 0, luA = -1;
   // scalar levels: the rows' lower / upper entries in the order of UG's matrix lists after l_lrdecomp's fill-in (cycle.cu lu_lists)
-  int32_t *lu_lo_ptr = nullptr, *lu_lo_col = nullptr, *lu_up_ptr = nullptr, *lu_up_col = nullptr;
-  int lu_lo_nnz = 0, lu_up_nnz = 0;
+  int32_t *lu_lo_ptr = nullptr, *lu_lo_col = nullptr, *lu_up_ptr = nullptr, *lu_up_col = nullptr, *lu_lo_row = nullptr, *lu_up_row = nullptr;
+  double *lu_lo_val = nullptr, *lu_up_val = nullptr, *lu_dinv = nullptr;
+  int lu_lo_nnz = 0, lu_up_nnz = 0, lu_active = 0;
   // multi-GPU (part.h, comm.cu): n = rows this rank owns; vectors carry nghost extra rows at the tail
   int nghost = 0;
   bool partitioned = false;      // rows are split over the ranks (halo exchange + global reductions apply)
