@@ -13,18 +13,15 @@
 
 #define TR_THREADS 256
 
-// Both kernels give every warp K consecutive slices (thread = K rows, one per slice) and issue the loads of the K rows
-// together: column words and weights of entry j of all K rows first, then the K gathers, then the arithmetic.  A transfer
-// row is short (P: 1-2 entries on simplices, at most 8 on hexahedra), so one row per thread leaves a warp with three DEPENDENT
-// round trips (slice offset -> entry -> gathered operand) of a few hundred bytes each -- latency-bound at under half of the HBM
-// bandwidth.  K independent chains per thread multiply the bytes in flight without changing any row's
-// additions or their order.
-// Fixed-width stencils (sell_layout: all uniformly refined grids) have no slice-offset load at all: two hops, and every stream
-// but the gathered operand is direct-indexed; the interpolation touches its far lines when the warp STARTS (1.71 vs 1.74 ms at
-// 513^3), the restriction -- 15-entry rows, the warp lives longer -- when it ends (1.14 vs 1.63 ms).
-// Measured and rejected: K > 1 (interpolation 1.71 / 2.05 / 2.51 ms, restriction 1.57 / 1.81 / 2.45 ms for K = 1 / 2 / 4 at 513^3):
-// more rows per thread cost registers (occupancy) and spread the warp's gathers over more lines; K stays a template parameter
-// and an A/B switch (UGGPU_TR_K_INTERP / UGGPU_TR_K_RESTRICT), the default is 1.
+// Short rows (P: 1-2 entries on simplices, at most 8 on hexahedra; R: up to 15 / 27), so a warp's life is a chain of dependent
+// loads of a few hundred bytes: slice offset -> entries -> gathered operand.  What is done about it:
+//  * fixed-width stencils (sell_layout: every uniformly refined level) need no slice-offset load at all;
+//  * the head of the kernel (tr_head) is branch-free: all direct-indexed loads of a row are unconditional (indices clamped,
+//    results masked), so they leave together (restriction 1.13 -> 0.99 ms, interpolation 1.74 -> 1.62 ms at 513^3);
+//  * the far slice's lines are touched for L2 when the warp ends (uggpu_internal.h Prefetch).
+// Measured and rejected: K > 1 consecutive slices per warp with the K rows' loads batched -- interpolation 1.62 / 1.86 / 2.25 ms,
+// restriction 0.99 / 1.55 / 1.92 ms for K = 1 / 2 / 4 (more registers per thread, fewer resident warps, no gain in bytes in
+// flight).  K stays a template parameter and an A/B switch (UGGPU_TR_K_INTERP / UGGPU_TR_K_RESTRICT); the default is 1.
 #ifndef TR_K_INTERP
 #define TR_K_INTERP 1
 #endif
@@ -38,6 +35,47 @@ __device__ __forceinline__ bool tr_prefetch(const SellView &T, int r, const Pref
   const PfState st = pf_begin(T, r, pf);
   pf_end<1>(T, st, pf);
   return (pf.mode & 4) && st.sp >= 0;
+}
+
+
+// Branch-free head of a K-slices-per-warp transfer kernel: every load of the K rows is unconditional (indices clamped into
+// range, results masked afterwards), so the compiler can issue the K slices' loads back to back instead of one slice after
+// the other (the first K > 1 version wrapped each slice's head in `if (live)` around dependent loads and was SLOWER than K = 1).
+template <int K>
+struct TrHead {
+  int r[K], len[K];
+  uint32_t skip[K];
+  ColIter ci[K];
+  const double *wp[K];
+  int maxl;
+};
+template <int K>
+__device__ __forceinline__ void tr_head(const SellView &T, const uint32_t *__restrict__ skip_rows, int64_t warp, int lane, TrHead<K> &h)
+{
+  const int nsl = (T.n + 31) >> 5;
+  const bool alias = T.col_ptr == T.slice_ptr;       // no column compression on this matrix (kernel-uniform)
+  int64_t sp[K], cp[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int s = (int)min(warp * K + k, (int64_t)nsl - 1);
+    sp[k] = T.fixed_w ? (int64_t)s * 32 * T.fixed_w : T.slice_ptr[s];
+    cp[k] = alias ? sp[k] : T.col_ptr[s];
+  }
+  h.maxl = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    h.r[k] = (int)((warp * K + k) * 32) + lane;
+    const bool live = h.r[k] < T.n;
+    const int rr = live ? h.r[k] : 0;
+    const int l = T.rowlen[rr];
+    const uint32_t sk = skip_rows[rr];
+    h.len[k] = live ? l : 0;
+    h.skip[k] = sk;
+    h.wp[k] = T.val + sp[k] + lane;
+    const bool uni = cp[k] < 0;
+    h.ci[k] = ColIter{uni ? T.col + ~cp[k] : T.col + cp[k] + lane, uni ? 1 : 32, uni ? rr : 0};
+    h.maxl = max(h.maxl, h.len[k]);
+  }
 }
 
 // StandardRestrict (transgrid.cc:462 -> :117): to[coarse] (zeroed where VNCLASS >= NEWDEF_CLASS) += sum w * (damp*from[fine]),
@@ -63,31 +101,19 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp * K * 32 >= R.n) return;
-  int r[K], len[K];
-  uint32_t skip[K];
-  ColIter ci[K];
-  const double *wp[K];
-  double tr[K][BS];
-  int maxl = 0;
+  TrHead<K> h;
+  tr_head<K>(R, skip_c, warp, lane, h);
+  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci; const double *(&wp)[K] = h.wp;
+  const int maxl = h.maxl;
   const bool early = false;       // measured (513^3, B200): touching the far lines when the warp ENDS 1.14 ms, when it starts 1.63 ms
+  (void)early;
+  double tr[K][BS];
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    r[k] = (int)((warp * K + k) * 32) + lane;
-    const bool live = r[k] < R.n;
-    len[k] = 0; skip[k] = 0; ci[k] = ColIter{R.col, 0, 0}; wp[k] = R.val;
+    const int rr = r[k] < R.n ? r[k] : 0;
+    const bool zero = vnclass_c[rr] >= 2;
 #pragma unroll
-    for (int i = 0; i < BS; i++) tr[k][i] = 0.0;
-    if (live) {
-      if (early) restrict_prefetch<FUSE>(R, r[k], pf, vnclass_c, skip_c, vclass_c);
-      const bool zero = vnclass_c[r[k]] >= 2;
-#pragma unroll
-      for (int i = 0; i < BS; i++) tr[k][i] = zero ? 0.0 : to[(size_t)r[k] * BS + i];
-      skip[k] = skip_c[r[k]];
-      len[k] = R.rowlen[r[k]];
-      ci[k] = col_iter(R, r[k]);
-      wp[k] = R.val + slice_off(R, r[k] >> 5) + lane;
-    }
-    maxl = max(maxl, len[k]);
+    for (int i = 0; i < BS; i++) { const double t0 = to[(size_t)rr * BS + i]; tr[k][i] = zero ? 0.0 : t0; }
   }
 #pragma unroll 4
   for (int j = 0; j < maxl; j++) {
@@ -167,35 +193,29 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 // StandardInterpolateCorrection (transgrid.cc:529 -> :235): to[fine] = sum (w*damp) * from[coarse], components with the fine
 // VECSKIP bit set stay 0 (:272-285).
 template <int BS, int K>
-__global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : 1) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
+__global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 1 && K == 1) ? 8 : 1)) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
                                                               const double *__restrict__ from, Damp damp, Prefetch pf)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp * K * 32 >= P.n) return;
-  int r[K], len[K];
-  uint32_t skip[K];
-  ColIter ci[K];
-  const double *wp[K];
-  double tr[K][BS];
-  int maxl = 0;
-  const bool early = P.fixed_w != 0 && (pf.mode & 32);       // warp-uniform
+  const bool early = P.fixed_w != 0 && (pf.mode & 64);       // kernel-uniform; opt-in (UGGPU_PF_MODE bit 6): measured equal to touching the lines at the end (1.71 vs 1.74 ms)
+  if (early) {
 #pragma unroll
-  for (int k = 0; k < K; k++) {
-    r[k] = (int)((warp * K + k) * 32) + lane;
-    const bool live = r[k] < P.n;
-    len[k] = 0; skip[k] = 0; ci[k] = ColIter{P.col, 0, 0}; wp[k] = P.val;
+    for (int k = 0; k < K; k++) {
+      const int rk = (int)((warp * K + k) * 32) + lane;
+      if (rk < P.n && tr_prefetch(P, rk, pf)) pf_rows<4>(skip_f, PfState{0, -1, (rk >> 5) + pf.dist}, pf);
+    }
+  }
+  TrHead<K> h;
+  tr_head<K>(P, skip_f, warp, lane, h);
+  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci; const double *(&wp)[K] = h.wp;
+  const int maxl = h.maxl;
+  double tr[K][BS];
+#pragma unroll
+  for (int k = 0; k < K; k++)
 #pragma unroll
     for (int i = 0; i < BS; i++) tr[k][i] = 0.0;
-    if (live) {
-      if (early && tr_prefetch(P, r[k], pf)) pf_rows<4>(skip_f, PfState{0, -1, (r[k] >> 5) + pf.dist}, pf);
-      skip[k] = skip_f[r[k]];
-      len[k] = P.rowlen[r[k]];
-      ci[k] = col_iter(P, r[k]);
-      wp[k] = P.val + slice_off(P, r[k] >> 5) + lane;
-    }
-    maxl = max(maxl, len[k]);
-  }
 #pragma unroll 2
   for (int j = 0; j < maxl; j++) {
     int c[K];
