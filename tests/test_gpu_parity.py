@@ -49,14 +49,9 @@ def test_gpu_ops_bitexact(gpu_backend, golden):
 def test_gpu_cycle_and_solve(gpu_backend, golden):
     if not has(golden, "solve"):
         pytest.skip("dump without solve records")
-    # Base levels with FREE rows.  Scalar rows: the device LU follows the order of UG's matrix lists with fill-in (cycle.cu
-    # lu_lists) -- bit for bit.  3x3 blocks: the device eliminates scalar-wise in index order, UG block-wise on its lists (pinned
-    # in the oracle port, tests/test_oracle_port.py) -- agreement to rounding.
-    free_base = "baselevel" in golden.raw and int(golden.raw["baselevel"][0]) > 0 and golden.bs > 1
-    if free_base:
-        n = replay_solve(gpu_backend, golden, exact=False, vec_tol=1e-12, red_tol=1e-11)
-    else:
-        n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
+    # Base levels with FREE rows (lu_* fixtures): the device follows the order of UG's matrix lists with fill-in, scalar and
+    # block elimination alike (cycle.cu lu_lists) -- bit for bit.
+    n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
     assert n > 10
 
 

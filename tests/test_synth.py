@@ -97,9 +97,8 @@ def test_synth_solve_bitexact_vs_port(cells, dim, top, kind, monkeypatch, tma_ro
             be.close()
     ref = out[-1]
     assert ref[0] == 6 and ref[1][-1] < 0.5 * ref[1][hier.bs - 1]
-    # 3x3 blocks with coupled FREE rows on the base level: the device LU eliminates scalar-wise in index order, the reference
-    # block-wise on its matrix lists (pinned in the oracle port) -- agreement to rounding there, bit for bit everywhere else
-    exact = not (hier.bs > 1 and cells > 2)
+    # also with coupled FREE rows on the base level (cells > 2): the device LU follows the reference's list order, scalar and block
+    exact = True
     bscale = np.max(np.abs(rhs))
     for its, hist, xs, bs in out[:-1]:
         assert its == ref[0]

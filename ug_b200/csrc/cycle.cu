@@ -61,6 +61,104 @@ __global__ void __launch_bounds__(LU_THREADS) k_lu_factor(int N, int bs, const u
   }
 }
 
+// ---- block rows (bs = 2, 3): the block variant of l_lrdecomp (ugiter.cc:3771-3880) on a dense array of bs x bs blocks -------
+// block (row j, column k) at blk[(k*n + j)*bb .. +bb), row-major inside the block (for bs = 1 this is the scalar layout above).
+__global__ void k_lu_scatter_block(SellView A, int bs, int n, double *__restrict__ blk)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.n) return;
+  int bb = bs * bs, lane = r & 31;
+  int64_t sp = A.slice_ptr[r >> 5];
+  int len = A.rowlen[r];
+  const ColIter ci = col_iter(A, r);
+  for (int j = 0; j < len; j++) {
+    int c = col_at(ci, j);
+    for (int q = 0; q < bb; q++) blk[((size_t)c * n + r) * bb + q] = A.val[(sp + (int64_t)j * 32) * bb + (int64_t)q * 32 + lane];
+  }
+}
+
+// InvertSmallBlock, np/algebra/block.cc:272-321 (closed forms for n = 2, 3); returns non-zero for det == 0
+template <int BS>
+__device__ __forceinline__ int invert_small_block(const double *mat, double *inv)
+{
+  if (BS == 2) {
+    double det = mat[0] * mat[3] - mat[1] * mat[2];
+    if (det == 0.0) return 1;
+    double invdet = 1.0 / det;
+    inv[0] = mat[3] * invdet; inv[1] = -mat[1] * invdet; inv[2] = -mat[2] * invdet; inv[3] = mat[0] * invdet;
+    return 0;
+  }
+  double det = mat[0] * mat[4] * mat[8 % (BS * BS)] + mat[1] * mat[5 % (BS * BS)] * mat[6 % (BS * BS)] + mat[2] * mat[3] * mat[7 % (BS * BS)]
+               - mat[2] * mat[4] * mat[6 % (BS * BS)] - mat[0] * mat[5 % (BS * BS)] * mat[7 % (BS * BS)] - mat[1] * mat[3] * mat[8 % (BS * BS)];
+  if (det == 0.0) return 1;
+  double invdet = 1.0 / det;
+  constexpr int BB = BS * BS;
+  inv[0] = ( mat[4 % BB] * mat[8 % BB] - mat[5 % BB] * mat[7 % BB]) * invdet;
+  inv[3] = (-mat[3] * mat[8 % BB] + mat[5 % BB] * mat[6 % BB]) * invdet;
+  inv[6 % BB] = ( mat[3] * mat[7 % BB] - mat[4 % BB] * mat[6 % BB]) * invdet;
+  inv[1] = (-mat[1] * mat[8 % BB] + mat[2] * mat[7 % BB]) * invdet;
+  inv[4 % BB] = ( mat[0] * mat[8 % BB] - mat[2] * mat[6 % BB]) * invdet;
+  inv[7 % BB] = (-mat[0] * mat[7 % BB] + mat[1] * mat[6 % BB]) * invdet;
+  inv[2] = ( mat[1] * mat[5 % BB] - mat[2] * mat[4 % BB]) * invdet;
+  inv[5 % BB] = (-mat[0] * mat[5 % BB] + mat[2] * mat[3]) * invdet;
+  inv[8 % BB] = ( mat[0] * mat[4 % BB] - mat[1] * mat[3]) * invdet;
+  return 0;
+}
+
+// C = A * B for bs x bs blocks with the reference's summation (sum = 0; sum += a*b, ugiter.cc:3814-3822); returns true if C == 0
+template <int BS>
+__device__ __host__ __forceinline__ bool block_mul(const double *a, const double *b, double *c)
+{
+  bool zero = true;
+  for (int i0 = 0; i0 < BS; i0++)
+    for (int j0 = 0; j0 < BS; j0++) {
+      double sum = 0.0;
+      for (int k0 = 0; k0 < BS; k0++) sum += a[i0 * BS + k0] * b[k0 * BS + j0];
+      c[i0 * BS + j0] = sum;
+      if (sum != 0.0) zero = false;
+    }
+  return zero;
+}
+
+// Step i: invert the diagonal block and store the inverse (:3784-3793); every block (j,i), j > i, becomes the multiplier
+// M_ji * Inv (:3811-3826); every block (j,k), j,k > i, with a non-zero multiplier and a non-zero correction M_ji * M_ik
+// loses that correction (:3832-3877).  Blocks outside the pattern are zero, which is what the reference's "create the
+// connection when the correction is not zero" amounts to.  Each block receives its corrections for i = 0, 1, 2, ... in order.
+template <int BS>
+__global__ void __launch_bounds__(LU_THREADS) k_lu_factor_block(int n, const uint8_t *__restrict__ vclass, double *__restrict__ blk, int *err)
+{
+  constexpr int BB = BS * BS;
+  __shared__ double sinv[BB];
+  __shared__ uint8_t pz[LU_MAX_N];
+  const int tid = threadIdx.x;
+  for (int i = 0; i < n; i++) {
+    if (vclass[i] < 3) continue;
+    if (tid == 0) {
+      double *dg = blk + ((size_t)i * n + i) * BB, inv[BB];
+      if (invert_small_block<BS>(dg, inv)) { atomicExch(err, UGGPU_SMALL_DIAG); for (int q = 0; q < BB; q++) inv[q] = (q % (BS + 1)) == 0 ? 1.0 : 0.0; }
+      for (int q = 0; q < BB; q++) { dg[q] = inv[q]; sinv[q] = inv[q]; }
+    }
+    __syncthreads();
+    for (int j = i + 1 + tid; j < n; j += LU_THREADS) {
+      if (vclass[j] < 3) continue;
+      double *mji = blk + ((size_t)i * n + j) * BB, piv[BB];
+      pz[j] = block_mul<BS>(mji, sinv, piv) ? 1 : 0;
+      for (int q = 0; q < BB; q++) mji[q] = piv[q];
+    }
+    __syncthreads();
+    const int m = n - i - 1;
+    for (int idx = tid; idx < m * m; idx += LU_THREADS) {
+      const int j = i + 1 + idx % m, k = i + 1 + idx / m;
+      if (vclass[j] < 3 || vclass[k] < 3 || pz[j]) continue;
+      double cor[BB];
+      if (block_mul<BS>(blk + ((size_t)i * n + j) * BB, blk + ((size_t)k * n + i) * BB, cor)) continue;
+      double *mjk = blk + ((size_t)k * n + j) * BB;
+      for (int q = 0; q < BB; q++) mjk[q] = mjk[q] - cor[q];
+    }
+    __syncthreads();
+  }
+}
+
 // v = (LU)^-1 d  (l_luiter ugiter.cc:4444): forward sums accumulate column by column (ascending j, the order of a
 // sequential row sum), backward sums are formed in ascending j by one thread from products computed in parallel.
 __global__ void __launch_bounds__(LU_THREADS) k_lu_solve(int N, int bs, const uint8_t *__restrict__ vclass, const double *__restrict__ lu,
@@ -115,12 +213,12 @@ __global__ void __launch_bounds__(LU_THREADS) k_lu_solve(int N, int bs, const ui
 
 struct LuProg { const int32_t *row, *ptr, *col; const double *val; int n; };
 
-__global__ void k_lu_pack(int N, const double *__restrict__ lu, const int32_t *__restrict__ row, const int32_t *__restrict__ ptr, const int32_t *__restrict__ col,
+__global__ void k_lu_pack(int n, int bb, const double *__restrict__ lu, const int32_t *__restrict__ row, const int32_t *__restrict__ ptr, const int32_t *__restrict__ col,
                           double *__restrict__ val, double *__restrict__ dinv)
 {
   const int k = blockIdx.x, r = row[k];
-  for (int e = ptr[k] + threadIdx.x; e < ptr[k + 1]; e += blockDim.x) val[e] = lu[(size_t)col[e] * N + r];
-  if (dinv && threadIdx.x == 0) dinv[k] = lu[(size_t)r * N + r];
+  for (int e = ptr[k] * bb + threadIdx.x; e < ptr[k + 1] * bb; e += blockDim.x) val[e] = lu[((size_t)col[e / bb] * n + r) * bb + e % bb];
+  if (dinv && threadIdx.x < bb) dinv[k * bb + threadIdx.x] = lu[((size_t)r * n + r) * bb + threadIdx.x];
 }
 
 template <bool BACKWARD>
@@ -170,18 +268,79 @@ __global__ void __launch_bounds__(32) k_lu_solve_lists(int N, LuProg F, LuProg B
   for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
 }
 
+// Block rows: l_luiter ugiter.cc:4522-4795.  Per entry the lanes form e_i = (m_i0 w_0 + m_i1 w_1) + m_i2 w_2 (MATMUL_nn, ugblas.h:161-213),
+// lane 0 adds them in list order; forward v = d - sum (Diag(L) = I), backward v = Inv * (v - sum) (SolveInverseSmallBlock block.cc:225).
+template <int BS, bool BACKWARD>
+__device__ __forceinline__ void lu_sweep_block(const LuProg P, const double *__restrict__ d, const double *__restrict__ dinv, double *vs, double *prod)
+{
+  constexpr int BB = BS * BS;
+  const int lane = threadIdx.x;
+  for (int k = 0; k < P.n; k++) {
+    const int row = P.row[k], o = P.ptr[k], cnt = P.ptr[k + 1] - o;
+    for (int kk = lane; kk < cnt; kk += 32) {
+      const double *m = P.val + (size_t)(o + kk) * BB, *w = vs + (size_t)P.col[o + kk] * BS;
+#pragma unroll
+      for (int i = 0; i < BS; i++) {
+        double t = m[i * BS] * w[0];
+#pragma unroll
+        for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * w[q];
+        prod[kk * BS + i] = t;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double acc[BS], s[BS];
+#pragma unroll
+      for (int i = 0; i < BS; i++) acc[i] = 0.0;
+      for (int kk = 0; kk < cnt; kk++) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) acc[i] += prod[kk * BS + i];
+      }
+      if (BACKWARD) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) s[i] = vs[row * BS + i] - acc[i];
+        const double *inv = dinv + (size_t)k * BB;
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = 0; j < BS; j++) sum += inv[i * BS + j] * s[j];
+          vs[row * BS + i] = sum;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; i++) vs[row * BS + i] = d[row * BS + i] - acc[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(32) k_lu_solve_lists_block(int N, LuProg F, LuProg B, const double *__restrict__ dinv, double *__restrict__ v, const double *__restrict__ d)
+{
+  __shared__ double vs[LU_MAX_N];
+  __shared__ double prod[LU_MAX_N];
+  for (int i = threadIdx.x; i < N; i += 32) vs[i] = 0.0;
+  __syncwarp();
+  lu_sweep_block<BS, false>(F, d, dinv, vs, prod);
+  lu_sweep_block<BS, true>(B, d, dinv, vs, prod);
+  for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
+}
+
 int level_free_lu(uggpu_ctx *ctx, Level *L)
 {
+  const size_t bbf = (size_t)(L->bs > 0 ? L->bs * L->bs : 1), nrow = (size_t)(L->bs > 0 ? L->luN / L->bs : L->luN);
   if (L->lu) dfree(ctx, L->lu, (size_t)L->luN * L->luN);
-  if (L->lu_lo_ptr) dfree(ctx, L->lu_lo_ptr, (size_t)L->luN + 1);
-  if (L->lu_up_ptr) dfree(ctx, L->lu_up_ptr, (size_t)L->luN + 1);
-  if (L->lu_lo_row) dfree(ctx, L->lu_lo_row, (size_t)L->luN + 1);
-  if (L->lu_up_row) dfree(ctx, L->lu_up_row, (size_t)L->luN + 1);
-  if (L->lu_dinv) dfree(ctx, L->lu_dinv, (size_t)L->luN + 1);
+  if (L->lu_lo_ptr) dfree(ctx, L->lu_lo_ptr, nrow + 1);
+  if (L->lu_up_ptr) dfree(ctx, L->lu_up_ptr, nrow + 1);
+  if (L->lu_lo_row) dfree(ctx, L->lu_lo_row, nrow + 1);
+  if (L->lu_up_row) dfree(ctx, L->lu_up_row, nrow + 1);
+  if (L->lu_dinv) dfree(ctx, L->lu_dinv, (nrow + 1) * bbf);
   if (L->lu_lo_col) dfree(ctx, L->lu_lo_col, (size_t)L->lu_lo_nnz + 1);
   if (L->lu_up_col) dfree(ctx, L->lu_up_col, (size_t)L->lu_up_nnz + 1);
-  if (L->lu_lo_val) dfree(ctx, L->lu_lo_val, (size_t)L->lu_lo_nnz + 1);
-  if (L->lu_up_val) dfree(ctx, L->lu_up_val, (size_t)L->lu_up_nnz + 1);
+  if (L->lu_lo_val) dfree(ctx, L->lu_lo_val, ((size_t)L->lu_lo_nnz + 1) * bbf);
+  if (L->lu_up_val) dfree(ctx, L->lu_up_val, ((size_t)L->lu_up_nnz + 1) * bbf);
   L->luN = 0; L->luA = -1; L->lu_lo_nnz = L->lu_up_nnz = L->lu_active = 0;
   return 0;
 }
@@ -195,9 +354,10 @@ static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
   std::vector<int32_t> rowptr((size_t)n + 1), col((size_t)M->nnz);
   UG_TRY(sell_to_host_csr(ctx, M, rowptr.data(), col.data(), nullptr));
   std::vector<uint8_t> vclass((size_t)n);
-  std::vector<double> lu((size_t)n * n);
+  const int bs = L->bs, bb = bs * bs;
+  std::vector<double> lu((size_t)n * n * bb);
   CUDA_TRY(cudaMemcpyAsync(vclass.data(), L->vclass, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(lu.data(), L->lu, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(lu.data(), L->lu, sizeof(double) * (size_t)n * n * bb, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   // singly linked row lists in one node pool: node = (column, next); head[r] = the diagonal entry
   std::vector<int32_t> ncol, nnext, head((size_t)n, -1);
@@ -226,11 +386,19 @@ static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
     for (int a = nnext[head[i]]; a >= 0; a = nnext[a]) {
       const int j = ncol[a];
       if (!(active(j) && j > i)) continue;
-      if (lu[(size_t)i * n + j] == 0.0) continue;            // multiplier L_ji (column-major: element (j,i) at lu[i*n+j])
+      const double *lji = &lu[((size_t)i * n + j) * bb];    // multiplier block L_ji (block (j,i) at lu[(i*n+j)*bb])
+      bool pivzero = true;
+      for (int q = 0; q < bb; q++) if (lji[q] != 0.0) pivzero = false;
+      if (pivzero) continue;                                  // ugiter.cc:3741 / :3829
       for (int c = nnext[head[i]]; c >= 0; c = nnext[c]) {
         const int k = ncol[c];
         if (!(active(k) && k > i)) continue;
         if (present[(size_t)j * n + k]) continue;
+        if (bs > 1) {                                         // block path only: a zero correction creates nothing (:3867)
+          double cor[UGGPU_MAX_BS * UGGPU_MAX_BS];
+          const double *uik = &lu[((size_t)k * n + i) * bb];
+          if (bs == 2 ? block_mul<2>(lji, uik, cor) : block_mul<3>(lji, uik, cor)) continue;
+        }
         insert_second(j, k);
         insert_second(k, j);
       }
@@ -254,9 +422,9 @@ static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
   L->lu_active = na; L->lu_lo_nnz = (int)f_col.size(); L->lu_up_nnz = (int)b_col.size();
   UG_TRY(dalloc(ctx, &L->lu_lo_row, (size_t)n + 1)); UG_TRY(dalloc(ctx, &L->lu_up_row, (size_t)n + 1));
   UG_TRY(dalloc(ctx, &L->lu_lo_ptr, (size_t)n + 1)); UG_TRY(dalloc(ctx, &L->lu_up_ptr, (size_t)n + 1));
-  UG_TRY(dalloc(ctx, &L->lu_dinv, (size_t)n + 1));
+  UG_TRY(dalloc(ctx, &L->lu_dinv, ((size_t)n + 1) * bb));
   UG_TRY(dalloc(ctx, &L->lu_lo_col, (size_t)L->lu_lo_nnz + 1)); UG_TRY(dalloc(ctx, &L->lu_up_col, (size_t)L->lu_up_nnz + 1));
-  UG_TRY(dalloc(ctx, &L->lu_lo_val, (size_t)L->lu_lo_nnz + 1)); UG_TRY(dalloc(ctx, &L->lu_up_val, (size_t)L->lu_up_nnz + 1));
+  UG_TRY(dalloc(ctx, &L->lu_lo_val, ((size_t)L->lu_lo_nnz + 1) * bb)); UG_TRY(dalloc(ctx, &L->lu_up_val, ((size_t)L->lu_up_nnz + 1) * bb));
   cudaStream_t st = ctx->stream;
   if (na) {
     CUDA_TRY(cudaMemcpyAsync(L->lu_lo_row, f_row.data(), sizeof(int32_t) * na, cudaMemcpyHostToDevice, st));
@@ -267,9 +435,9 @@ static int lu_lists(uggpu_ctx *ctx, Level *L, const SellMat *M)
   if (L->lu_lo_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_lo_col, f_col.data(), sizeof(int32_t) * f_col.size(), cudaMemcpyHostToDevice, st));
   if (L->lu_up_nnz) CUDA_TRY(cudaMemcpyAsync(L->lu_up_col, b_col.data(), sizeof(int32_t) * b_col.size(), cudaMemcpyHostToDevice, st));
   if (na) {
-    k_lu_pack<<<na, 128, 0, st>>>(n, L->lu, L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, nullptr);
+    k_lu_pack<<<na, 128, 0, st>>>(n, bb, L->lu, L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, nullptr);
     KCHECK(ctx);
-    k_lu_pack<<<na, 128, 0, st>>>(n, L->lu, L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_dinv);
+    k_lu_pack<<<na, 128, 0, st>>>(n, bb, L->lu, L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_dinv);
     KCHECK(ctx);
   }
   CUDA_TRY(cudaStreamSynchronize(st));      // the host vectors go out of scope
@@ -306,12 +474,22 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
     if (N > 0) {
       CUDA_TRY(cudaMemsetAsync(L->lu, 0, (size_t)N * N * sizeof(double), ctx->stream));
       SellMat *M = get_mat(ctx, bl, A);
-      k_lu_scatter<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(view(*M), L->bs, N, L->lu);
-      KCHECK(ctx);
-      k_lu_factor<<<1, LU_THREADS, 0, ctx->stream>>>(N, L->bs, L->vclass, L->lu);
-      KCHECK(ctx);
-      // scalar rows: the summation order of the reference's lists (block rows keep index order: DESIGN.md, base level)
-      if (L->bs == 1 && !getenv("UGGPU_LU_INDEX_ORDER")) UG_TRY(lu_lists(ctx, L, M));
+      const bool lists = !getenv("UGGPU_LU_INDEX_ORDER");     // A/B switch: the first implementation (scalar elimination, sums in index order)
+      if (L->bs > 1 && lists) {
+        // block rows: the reference's block elimination on bs x bs blocks (n*n blocks of bb doubles = N*N doubles)
+        k_lu_scatter_block<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(view(*M), L->bs, L->n, L->lu);
+        KCHECK(ctx);
+        if (L->bs == 2) k_lu_factor_block<2><<<1, LU_THREADS, 0, ctx->stream>>>(L->n, L->vclass, L->lu, ctx->derr);
+        else k_lu_factor_block<3><<<1, LU_THREADS, 0, ctx->stream>>>(L->n, L->vclass, L->lu, ctx->derr);
+        KCHECK(ctx);
+      } else {
+        k_lu_scatter<<<(L->n + 255) / 256, 256, 0, ctx->stream>>>(view(*M), L->bs, N, L->lu);
+        KCHECK(ctx);
+        k_lu_factor<<<1, LU_THREADS, 0, ctx->stream>>>(N, L->bs, L->vclass, L->lu);
+        KCHECK(ctx);
+      }
+      // the summation order of the reference's matrix lists with fill-in (base level)
+      if (lists) UG_TRY(lu_lists(ctx, L, M));
     }
     UG_TRY(ensure_vec(ctx, bl, UGGPU_VEC_TMP_C));
   }
@@ -362,9 +540,12 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   for (int it = 0; it < cfg->base_maxit; it++) {
     {
       ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
-      if (L->lu_lo_ptr)
-        k_lu_solve_lists<<<1, 32, 0, ctx->stream>>>(L->luN, LuProg{L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, L->lu_active},
-                                                    LuProg{L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_active}, L->lu_dinv, cc, bp);
+      if (L->lu_lo_ptr) {
+        const LuProg F{L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, L->lu_active}, B{L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_active};
+        if (bs == 1) k_lu_solve_lists<<<1, 32, 0, ctx->stream>>>(L->luN, F, B, L->lu_dinv, cc, bp);
+        else if (bs == 2) k_lu_solve_lists_block<2><<<1, 32, 0, ctx->stream>>>(L->luN, F, B, L->lu_dinv, cc, bp);
+        else k_lu_solve_lists_block<3><<<1, 32, 0, ctx->stream>>>(L->luN, F, B, L->lu_dinv, cc, bp);
+      }
       else k_lu_solve<<<1, LU_THREADS, 0, ctx->stream>>>(L->luN, bs, L->vclass, L->lu, cc, bp);
       KCHECK(ctx);
     }
