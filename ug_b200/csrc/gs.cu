@@ -34,8 +34,10 @@ struct TriSched {
   int32_t *perm = nullptr;        // [nT] schedule position -> row, -1 = padding
   int32_t *slice_level = nullptr; // [nT/32]
   int32_t *level_slices = nullptr;// [nlev]
-  unsigned int *counters = nullptr;   // [32 + nlev]: ticket, finished slices per level (k_trisolve)
-  unsigned int *mail = nullptr;       // [TRI_MAIL_SLOTS * 32]: one progress word per SM, 128 bytes apart
+  int32_t *level_first = nullptr; // [nlev] first slice of every level
+  unsigned int *counters = nullptr;   // [nlev * 256 * 8]: finished slices per level and SM slot, one 32-byte sector each (k_trisolve)
+  unsigned long long *mail = nullptr; // [256 * 16]: one progress word per SM slot, 128 bytes apart
+  unsigned int epoch = 0;             // launches on this schedule so far
 };
 
 static int tri_free(uggpu_ctx *ctx, TriSched *&S)
@@ -46,8 +48,9 @@ static int tri_free(uggpu_ctx *ctx, TriSched *&S)
   if (S->perm) dfree(ctx, S->perm, (size_t)S->nT);
   if (S->slice_level) dfree(ctx, S->slice_level, (size_t)S->nT / 32);
   if (S->level_slices) dfree(ctx, S->level_slices, (size_t)S->nlev);
-  if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev + 32);
-  if (S->mail) dfree(ctx, S->mail, (size_t)1024 * 32);
+  if (S->level_first) dfree(ctx, S->level_first, (size_t)S->nlev);
+  if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev * 256 * 8);
+  if (S->mail) dfree(ctx, S->mail, (size_t)256 * 16);
   delete S;
   S = nullptr;
   return 0;
@@ -229,10 +232,16 @@ static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSch
     int *d_start = nullptr, *d_poff = nullptr;
     TB(dalloc(ctx, &d_start, (size_t)S->nlev)); TB(dalloc(ctx, &d_poff, (size_t)S->nlev));
     TB(dalloc(ctx, &S->perm, (size_t)S->nT)); TB(dalloc(ctx, &S->slice_level, (size_t)nslT));
-    TB(dalloc(ctx, &S->level_slices, (size_t)S->nlev)); TB(dalloc(ctx, &S->counters, (size_t)S->nlev + 32)); TB(dalloc(ctx, &S->mail, (size_t)1024 * 32));
+    TB(dalloc(ctx, &S->level_slices, (size_t)S->nlev)); TB(dalloc(ctx, &S->counters, (size_t)S->nlev * 256 * 8)); TB(dalloc(ctx, &S->mail, (size_t)256 * 16));
+    TB(dalloc(ctx, &S->level_first, (size_t)S->nlev));
+    TC(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * (size_t)S->nlev * 256 * 8, st));
+    TC(cudaMemsetAsync(S->mail, 0, sizeof(unsigned long long) * (size_t)256 * 16, st));
     TC(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
     TC(cudaMemcpyAsync(d_poff, poff.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
     TC(cudaMemcpyAsync(S->level_slices, lsl.data(), sizeof(int) * S->nlev, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> lfirst(S->nlev);
+    for (int l = 0; l < S->nlev; l++) lfirst[l] = poff[l] / 32;          // first slice of the level
+    TC(cudaMemcpyAsync(S->level_first, lfirst.data(), sizeof(int32_t) * S->nlev, cudaMemcpyHostToDevice, st));
     TC(cudaMemcpyAsync(S->slice_level, sl.data(), sizeof(int32_t) * nslT, cudaMemcpyHostToDevice, st));
     TC(cudaMemsetAsync(S->perm, 0xff, sizeof(int32_t) * (size_t)S->nT, st));
     k_tri_place<<<blocks, 256, 0, st>>>(n, key_out, row_out, d_start, d_poff, S->perm);
@@ -305,15 +314,18 @@ extern "C" int uggpu_gs_levels(uggpu_ctx *ctx, int level, int M, int *lower, int
 }
 
 // ---- the solve -------------------------------------------------------------------------------------------------------------
-// Synchronisation words of one schedule (TriSched::counters, zeroed before every launch):
-//   [0]                  ticket: next slice of the schedule
-//   [32 .. 32 + nlev)    finished slices per level (atomics only, nobody polls them)
-//   mail[sm * 32]        one mailbox per SM, 128 bytes apart: number of COMPLETED levels.  The warp that finishes the last slice of a
-//                        level writes that number into every mailbox; waiting warps poll only the mailbox of their own SM, so the
-//                        polls of the whole GPU spread over 100+ lines instead of hammering one (first version: every warp polled
-//                        the level counter itself -- 54 us per level at 257^3, all of it L2 same-address serialisation).
-#define TRI_MAIL_SLOTS 1024
-#define TRI_PRE 16           // column indices of a row held in registers while the warp waits
+// One persistent kernel per sweep, launched cooperatively (all warps co-resident) with a STATIC assignment: warp w owns slices
+// w, w + W, w + 2W, ... of the schedule.  Synchronisation words of a schedule (never reset: every launch has an epoch number):
+//   done[(lv * TRI_SLOTS + slot) * 8]   finished slices of level lv, one counter per SM slot (smid mod TRI_SLOTS), one 32-byte sector
+//                                       each: a warp that finishes a slice adds 1 with a fire-and-forget reduction -- no burst of
+//                                       same-address atomics at the end of a level;
+//   mail[slot * 16] (64 bit)            one mailbox per SM: epoch * (nlev + 1) + number of completed levels.
+// The warp that owns the FIRST slice of level lv + 1 is the monitor of level lv: instead of waiting it sums the level's counters
+// (8 acquire loads per lane) until they reach the level's slice count, then raises every mailbox (atomicMax).  All other warps
+// poll only the mailbox of their own SM, rarely while they are several levels away.
+// History at 257^3 (769 levels per sweep): every warp polling the level counter 54 us per level; mailboxes + tickets 11 us.
+#define TRI_SLOTS 256
+#define TRI_PRE 8            // column indices of a row held in registers while the warp waits
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
 {
@@ -321,34 +333,46 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned int smid() { unsigned int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
-__device__ __forceinline__ unsigned int nsmid() { unsigned int v; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v)); return v; }
+
+struct TriArgs {
+  const int32_t *perm, *slice_level, *level_slices, *level_first;
+  unsigned int *done;
+  unsigned long long *mail;
+  int nlev, nsl;
+  unsigned int epoch;         // 1, 2, 3, ... per launch on this schedule
+};
 
 // SOR: 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows: solve, then
 // v_i *= omega_i :1556)
 template <int BS, int SOR>
-__global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int32_t *__restrict__ perm, const int32_t *__restrict__ slice_level,
-                                                          const int32_t *__restrict__ level_slices, unsigned int *sync, unsigned int *mail, int nlev, int nsl,
-                                                          double *v, const double *__restrict__ d, Damp omega, int *err)
+__global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a, double *v, const double *__restrict__ d, Damp omega, int *err)
 {
   constexpr int BB = BS * BS;
   const int lane = threadIdx.x & 31;
-  unsigned int *const ticket = sync, *const done = sync + 32;
-  const unsigned int *const mybox = mail + (size_t)(smid() % TRI_MAIL_SLOTS) * 32;
-  for (;;) {
-    int s = 0;
-    if (lane == 0) s = (int)atomicAdd(ticket, 1u);
-    s = __shfl_sync(0xffffffffu, s, 0);
-    if (s >= nsl) return;
-    const int lv = slice_level[s];
+  const int W = (int)((gridDim.x * blockDim.x) >> 5);
+  const unsigned int slot = smid() & (TRI_SLOTS - 1);
+  const unsigned long long *const mybox = a.mail + (size_t)slot * 16;
+  const unsigned long long base = (unsigned long long)a.epoch * (unsigned long long)(a.nlev + 1);
+  int known = 0;               // levels 0 .. known-1 are complete, as far as this warp has seen
+  for (int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); s < a.nsl; s += W) {
+    const int lv = a.slice_level[s];
     const int p = s * 32 + lane;
-    const int r = perm[p];
+    if (s + W < a.nsl && lane < 3)          // the warp's NEXT slice: its direct-indexed lines into L2
+      prefetch_l2(lane == 0 ? (const void *)(a.perm + (size_t)(s + W) * 32) : lane == 1 ? (const void *)(T.rowlen + (size_t)(s + W) * 32) : (const void *)(a.slice_level + s + W));
+    const int r = a.perm[p];
     const int len = r >= 0 ? (int)T.rowlen[p] : 0;
     const int64_t sp = slice_off(T, s);
     const int w = slice_width(T, s, sp);
     // everything that does not depend on other rows is fetched BEFORE the wait: the slice's values into L2, the row's column
     // indices, diagonal block and right-hand side into registers
-    {
+    if (lv > known) {
       const char *vb = reinterpret_cast<const char *>(T.val + sp * BB);
       const int vlines = w * BB * 2;                        // 256 bytes per component and slice column
       for (int l = lane; l < vlines; l += 32) prefetch_l2(vb + (size_t)l * 128);
@@ -363,27 +387,56 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
     for (int k = 0; k < BB; k++) dg[k] = len > 0 ? __ldg(vp + (size_t)k * 32) : 1.0;
 #pragma unroll
     for (int i = 0; i < BS; i++) rhs[i] = len > 0 ? d[(size_t)r * BS + i] : 0.0;
-    if (lv > 0) {
-      if (lane == 0) {
-        unsigned long long t0 = 0, t1;
-        int spins = 0;
+    if (lv > known) {
+      unsigned long long t0 = 0, t1;
+      int spins = 0;
+      if (s == a.level_first[lv]) {
+        // monitor of level lv - 1
+        const unsigned int need = (unsigned int)a.level_slices[lv - 1];
+        const unsigned int want = a.epoch * need;                            // modulo 2^32, like the counters: every launch adds `need`
+        const unsigned int *cnt = a.done + (size_t)(lv - 1) * TRI_SLOTS * 8;
         for (;;) {
-          const unsigned int cur = ld_acquire_u32(mybox);
-          if (cur >= (unsigned int)lv) break;
-          // far from its turn a warp polls rarely (a level takes at least ~1 us); next in line it polls tightly
-          const unsigned int dist = (unsigned int)lv - cur;
-          __nanosleep(dist > 1 ? min((dist - 1) * 1000u, 8000u) : 50u);
-          if (++spins == 64) {
+          unsigned int sum = 0;
+#pragma unroll
+          for (int q = 0; q < TRI_SLOTS / 32; q++) sum += ld_acquire_u32(cnt + (size_t)(lane + 32 * q) * 8);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (sum == want) break;
+          int give_up = 0;
+          if (lane == 0 && ++spins == 256) {
             spins = 0;
-            if (*reinterpret_cast<volatile int *>(err)) break;          // an earlier wait already failed: do not wait again
+            if (*reinterpret_cast<volatile int *>(err)) give_up = 1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t0 == 0) t0 = t1;
-            else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }
+            else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); give_up = 1; }
           }
+          if (__shfl_sync(0xffffffffu, give_up, 0)) break;
         }
         __threadfence();
+        __syncwarp();
+        for (int q = lane; q < TRI_SLOTS; q += 32) atomicMax(a.mail + (size_t)q * 16, base + (unsigned long long)lv);
+        known = lv;
+      } else {
+        int cur = known;
+        if (lane == 0) {
+          for (;;) {
+            const unsigned long long m = ld_acquire_u64(mybox);
+            cur = m > base ? (int)(m - base) : 0;
+            if (cur >= lv) break;
+            // far from its turn a warp polls rarely (a level takes a few us); next in line it polls tightly
+            const unsigned int dist = (unsigned int)(lv - cur);
+            __nanosleep(dist > 1 ? min((dist - 1) * 1500u, 12000u) : 40u);
+            if (++spins == 64) {
+              spins = 0;
+              if (*reinterpret_cast<volatile int *>(err)) break;          // an earlier wait already failed: do not wait again
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t0 == 0) t0 = t1;
+              else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }
+            }
+          }
+        }
+        known = max(known, __shfl_sync(0xffffffffu, cur, 0));
       }
-      __syncwarp();
     }
     if (r >= 0) {
       double sol[BS];
@@ -445,23 +498,31 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, const int3
 #pragma unroll
       for (int i = 0; i < BS; i++) __stcg(v + (size_t)r * BS + i, sol[i]);
     }
-    // publish: the warp's stores, then one release by lane 0 (the pattern of a grid barrier, per warp); the warp that completes
-    // the level tells every SM
+    // publish: the warp's stores, then one release by lane 0 (the pattern of a grid barrier, per warp)
     __syncwarp();
-    int last = 0;
     if (lane == 0) {
       __threadfence();
-      last = atomicAdd(&done[lv], 1u) + 1u == (unsigned int)level_slices[lv];
-      if (last) __threadfence();
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      __threadfence();
-      const unsigned int nb = min(nsmid(), (unsigned int)TRI_MAIL_SLOTS);
-      // max, not store: the stores of two consecutive levels' last warps may land in either order
-      for (unsigned int q = lane; q < nb; q += 32) atomicMax(mail + (size_t)q * 32, (unsigned int)lv + 1u);
+      atomicAdd(a.done + ((size_t)lv * TRI_SLOTS + slot) * 8, 1u);
     }
   }
+}
+
+// co-resident blocks of a k_trisolve instantiation (cooperative launch)
+template <int BS, int SOR>
+static int tri_launch(uggpu_ctx *ctx, const SellView &Tv, const TriArgs &a, double *v, const double *d, const Damp &om)
+{
+  static int per_sm = 0;       // per instantiation
+  if (per_sm == 0) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trisolve<BS, SOR>, TRI_THREADS, 0));
+    if (per_sm < 1) return uggpu_fail(UGGPU_CUDA_ERROR, "k_trisolve does not fit on an SM");
+  }
+  int blocks = (a.nsl + TRI_THREADS / 32 - 1) / (TRI_THREADS / 32);
+  if (blocks > per_sm * ctx->sm_count) blocks = per_sm * ctx->sm_count;
+  SellView tv = Tv; TriArgs aa = a; Damp o = om; int *err = ctx->derr;
+  void *args[] = {&tv, &aa, &v, &d, &o, &err};
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_trisolve<BS, SOR>, dim3(blocks), dim3(TRI_THREADS), args, 0, ctx->stream));
+  ctx->launches++;
+  return 0;
 }
 
 static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const double *d, const double *omega)
@@ -473,27 +534,21 @@ static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const
   if (L->n == 0) return 0;
   if (!A->tri[dir]) UG_TRY(uggpu_gs_preprocess(ctx, level, M));
   TriSched *S = A->tri[dir];
-  const int nsl = S->nT / 32;
-  CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * ((size_t)S->nlev + 32), ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(S->mail, 0, sizeof(unsigned int) * (size_t)TRI_MAIL_SLOTS * 32, ctx->stream));
-  int blocks = (nsl + TRI_THREADS / 32 - 1) / (TRI_THREADS / 32);
-  const int cap = ctx->sm_count * (2048 / TRI_THREADS);
-  if (blocks > cap) blocks = cap;
+  if (++S->epoch == 0xffffffffu) {       // the epoch arithmetic of the counters is modulo 2^32: start over well before it wraps
+    CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * (size_t)S->nlev * TRI_SLOTS * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(S->mail, 0, sizeof(unsigned long long) * (size_t)TRI_SLOTS * 16, ctx->stream));
+    S->epoch = 1;
+  }
+  const TriArgs a{S->perm, S->slice_level, S->level_slices, S->level_first, S->counters, S->mail, S->nlev, S->nT / 32, S->epoch};
   const Damp om = mkdamp(omega, L->bs);
   const SellView Tv = view(S->T);
   // algorithmic bytes: the triangle's entries, row lengths and permutation, d read, v written, gathered v once
   ProfScope ps(ctx, UGGPU_K_TRISOLVE, level, S->T.entry_bytes() + 6.0 * S->nT + 8.0 * L->bs * 3.0 * L->n);
-#define TS(BSV)                                                                                                                          \
-  if (omega) k_trisolve<BSV, 1><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->mail, S->nlev, nsl, v, d, om, ctx->derr); \
-  else k_trisolve<BSV, 0><<<blocks, TRI_THREADS, 0, ctx->stream>>>(Tv, S->perm, S->slice_level, S->level_slices, S->counters, S->mail, S->nlev, nsl, v, d, om, ctx->derr)
   switch (L->bs) {
-    case 1: TS(1); break;
-    case 2: TS(2); break;
-    default: TS(3); break;
+    case 1: return omega ? tri_launch<1, 1>(ctx, Tv, a, v, d, om) : tri_launch<1, 0>(ctx, Tv, a, v, d, om);
+    case 2: return omega ? tri_launch<2, 1>(ctx, Tv, a, v, d, om) : tri_launch<2, 0>(ctx, Tv, a, v, d, om);
+    default: return omega ? tri_launch<3, 1>(ctx, Tv, a, v, d, om) : tri_launch<3, 0>(ctx, Tv, a, v, d, om);
   }
-#undef TS
-  KCHECK(ctx);
-  return 0;
 }
 
 static int tri_entry(uggpu_ctx *ctx, int level, int v, int M, int d, int dir, const double *omega)
