@@ -2,16 +2,23 @@
 # bench lines + ncu evidence for profiles/: bash tools/gpu_profile.sh <tag>
 tag=$1
 out=gpurun_out; mkdir -p $out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > $out/${tag}_bench_p1.json 2> $out/${tag}_bench_p1.err; tail -c 400 $out/${tag}_bench_p1.err
-python bench.py --kind q1 --no-cpu > $out/${tag}_bench_q1.json 2>&1
-python bench.py --kind elasticity --top 6 --no-cpu > $out/${tag}_bench_el.json 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $out/${tag}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_smooth_k -s 32 -c 3 -o $out/${tag}_smooth -f python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $out/${tag}_ncu.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py > $out/${tag}_bench_p1.json 2> $out/${tag}_bench_p1.err; tail -c 300 $out/${tag}_bench_p1.err
+timeout 600 python bench.py --kind q1 --no-cpu > $out/${tag}_bench_q1.json 2>&1
+timeout 600 python bench.py --kind elasticity --top 6 --no-cpu > $out/${tag}_bench_el.json 2>&1
+timeout 600 python bench.py --impl reference --steps 5 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $out/${tag}_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_smooth_k -s 32 -c 3 -o $out/${tag}_smooth -f python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $out/${tag}_ncu.log 2>&1
 ncu -i $out/${tag}_smooth.ncu-rep --page details > $out/${tag}_smooth_details.txt 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_interpolate_k|k_restrict_k" -s 14 -c 2 -o $out/${tag}_transfer -f python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 > $out/${tag}_ncu2.log 2>&1
+ncu -i $out/${tag}_transfer.ncu-rep --page details > $out/${tag}_transfer_details.txt 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trisolve -s 6 -c 1 -o $out/${tag}_trisolve -f python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 --top 6 --smoother gs > $out/${tag}_ncu3.log 2>&1
+ncu -i $out/${tag}_trisolve.ncu-rep --page details > $out/${tag}_trisolve_details.txt 2>&1
 for f in p1 q1 el; do python - $out/${tag}_bench_$f.json $f <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
-print(sys.argv[2], "%.3e unk/s %.2f ms/step; dom %.3f ms %.0f GB/s frac %.3f; cycle_frac %.3f e2e %.3e"%(d["value"],d["ms_per_step"],r["avg_ms"],r["achieved"],r["frac"],r["cycle_frac"],d["e2e"]["value"]), {k:round(v["ms"]/d["steps"],2) for k,v in d["kernels"].items()})
+print(sys.argv[2], "%.3e unk/s %.2f ms/step; dom %.3f ms %.0f GB/s frac %.3f; cycle_frac %.3f e2e %.3e launches %s"%(d["value"],d["ms_per_step"],r["avg_ms"],r["achieved"],r["frac"],r["cycle_frac"],d["e2e"]["value"],d["gpu_launches"]), {k:round(v["ms"]/d["steps"],2) for k,v in d["kernels"].items()}, d.get("cpu_baseline",{}).get("value"))
 PY
 done
+tail -c 600 $out/${tag}_bench_ref.json

@@ -282,8 +282,10 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
 //     partial sums of b[r]^2 over NEW_DEFECT rows          LinearResiduum ls.cc:577 (ditto)
 // Every quantity is produced by the same arithmetic operations on the same operands as in the one-kernel-
 // per-call path, so fused and unfused results are bit-identical.  tout must not alias tin (other rows gather tin).
+// scalar rows: at most 32 registers, so that 2048 threads are resident per SM (the variant with the norm partials took 40 without
+// the bound: 75 % occupancy, 4.69 instead of ~4.2 ms on the finest level)
 template <int BS, int FLAGS>
-__global__ void __launch_bounds__(SPMV_THREADS) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
                                                            const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                            double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err,
                                                            Prefetch pf)
