@@ -264,7 +264,11 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
   return 0;
 }
 
-static int halo_exchange_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v)
+int halo_exchange(uggpu_ctx *ctx, int level, double *v);
+
+// push: my interface rows into the neighbours' windows + the release of the exchange number (on the compute stream);
+// wait: poll my flag words and copy my window into the ghost rows of v (on `st`, which must be ordered behind the push).
+static int halo_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v, bool do_push, bool do_wait, cudaStream_t wait_stream)
 {
   const PartGrid &g = *L->part;
   const int bs = L->bs;
@@ -282,33 +286,70 @@ static int halo_exchange_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v)
       L->peer_recv_off.push_back(nb.nb_recv_off[kk]);
     }
   }
-  const unsigned long long seq = ++c->seq;
+  if (do_push) ++c->seq;
+  const unsigned long long seq = c->seq;
   const int parity = (int)(seq & 1ull);
-  PushArgs pa;
-  WaitArgs wa;
-  pa.nnb = wa.nnb = g.nnb; pa.bs = bs; pa.parity = parity; pa.seq = wa.seq = seq;
-  for (int k = 0; k <= g.nnb; k++) pa.send_off[k] = g.nb_send_off[k];
-  for (int k = 0; k < g.nnb; k++) {
-    const Peer &p = c->peers[g.nb_rank[k]];
-    pa.dst[k] = reinterpret_cast<double *>(p.base + P2P_FLAG_BYTES) + (size_t)parity * p.half + (size_t)L->peer_recv_off[k] * bs;
-    pa.flag[k] = reinterpret_cast<unsigned long long *>(p.base) + c->rank;
-    wa.flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + g.nb_rank[k];
+  if (do_push) {
+    PushArgs pa;
+    pa.nnb = g.nnb; pa.bs = bs; pa.parity = parity; pa.seq = seq;
+    for (int k = 0; k <= g.nnb; k++) pa.send_off[k] = g.nb_send_off[k];
+    for (int k = 0; k < g.nnb; k++) {
+      const Peer &p = c->peers[g.nb_rank[k]];
+      pa.dst[k] = reinterpret_cast<double *>(p.base + P2P_FLAG_BYTES) + (size_t)parity * p.half + (size_t)L->peer_recv_off[k] * bs;
+      pa.flag[k] = reinterpret_cast<unsigned long long *>(p.base) + c->rank;
+    }
+    const int tot = L->send_total * bs;
+    int pb = (tot + 255) / 256;
+    if (pb > 4 * ctx->sm_count) pb = 4 * ctx->sm_count;
+    if (pb < 1) pb = 1;
+    k_halo_push<<<pb, 256, 0, ctx->stream>>>(pa, L->send_total, L->d_send_idx, v, c->push_counter);
+    KCHECK(ctx);
   }
-  const int tot = L->send_total * bs;
-  int pb = (tot + 255) / 256;
-  if (pb > 4 * ctx->sm_count) pb = 4 * ctx->sm_count;
-  if (pb < 1) pb = 1;
-  k_halo_push<<<pb, 256, 0, ctx->stream>>>(pa, L->send_total, L->d_send_idx, v, c->push_counter);
-  KCHECK(ctx);
-  const size_t cnt = (size_t)L->nghost * bs;
-  int wb = (int)((cnt + 255) / 256);
-  if (wb > ctx->sm_count) wb = ctx->sm_count;        // every block polls: keep them all resident
-  if (wb < 1) wb = 1;
-  k_halo_wait_unpack<<<wb, 256, 0, ctx->stream>>>(wa, reinterpret_cast<const double *>(c->win + P2P_FLAG_BYTES) + (size_t)parity * c->half,
-                                                   v + (size_t)L->n * bs, cnt, ctx->derr);
-  KCHECK(ctx);
-  c->exchanges++;
+  if (do_wait) {
+    WaitArgs wa;
+    wa.nnb = g.nnb; wa.seq = seq;
+    for (int k = 0; k < g.nnb; k++) wa.flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + g.nb_rank[k];
+    const size_t cnt = (size_t)L->nghost * bs;
+    int wb = (int)((cnt + 255) / 256);
+    if (wb > ctx->sm_count) wb = ctx->sm_count;        // every block polls: keep them all resident
+    if (wb < 1) wb = 1;
+    k_halo_wait_unpack<<<wb, 256, 0, wait_stream>>>(wa, reinterpret_cast<const double *>(c->win + P2P_FLAG_BYTES) + (size_t)parity * c->half,
+                                                     v + (size_t)L->n * bs, cnt, ctx->derr);
+    KCHECK(ctx);
+    c->exchanges++;
+  }
   return 0;
+}
+
+static int halo_exchange_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v) { return halo_p2p(ctx, c, L, v, true, true, ctx->stream); }
+
+// Split exchange for kernels that overlap it with their interior rows (spmv.cu k_smooth_step): halo_begin pushes on the compute
+// stream and returns 1 when the second half may run on another stream (peer-memory path on a partitioned level), 0 when there is
+// nothing to exchange, and does the whole exchange itself (returning 0) on the NCCL path.  halo_finish waits + unpacks on `st`;
+// the caller orders `st` behind the push (event) and the compute stream behind `st` afterwards.
+int halo_begin(uggpu_ctx *ctx, int level, double *v, int *split)
+{
+  *split = 0;
+  Level *L = &ctx->lev[level];
+  if (!ctx->comm || !L->partitioned || !L->part || L->part->nnb == 0) return 0;
+  Comm *c = (Comm *)ctx->comm;
+  if (!c->p2p_tried) UG_TRY(p2p_setup(ctx, c));
+  // opt-in (UGGPU_OVERLAP=1): measured SLOWER than the plain exchange on the weak-scaling bench (2 GPUs, 513^3 per GPU: 33.1 vs
+  // 29.6 ms per cycle) -- an exchange costs ~25 us next to a 4 ms kernel, while the interface slices of an x-split (every 16th
+  // slice of the lexicographic order) run far below the bandwidth of the contiguous sweep.  Kept parity-tested for partitions
+  // whose interfaces are contiguous in the row order.
+  static const bool overlap = getenv("UGGPU_OVERLAP") != nullptr;
+  if (!c->p2p || !overlap) return halo_exchange(ctx, level, v);
+  UG_TRY(halo_p2p(ctx, c, L, v, true, false, ctx->stream));
+  *split = 1;
+  return 0;
+}
+
+int halo_finish(uggpu_ctx *ctx, int level, double *v, cudaStream_t st)
+{
+  Level *L = &ctx->lev[level];
+  Comm *c = (Comm *)ctx->comm;
+  return halo_p2p(ctx, c, L, v, false, true, st);
 }
 
 int halo_exchange(uggpu_ctx *ctx, int level, double *v)

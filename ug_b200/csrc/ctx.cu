@@ -171,6 +171,8 @@ extern "C" int uggpu_ctx_destroy(uggpu_ctx *ctx)
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
+  if (ctx->halo_stream) { cudaStreamSynchronize(ctx->halo_stream); cudaStreamDestroy(ctx->halo_stream); ctx->halo_stream = nullptr; }
+  for (int i = 0; i < 2; i++) if (ctx->halo_ev[i]) { cudaEventDestroy(ctx->halo_ev[i]); ctx->halo_ev[i] = nullptr; }
   uggpu_comm_destroy(ctx);
   for (int l = 0; l < UGGPU_MAX_LEVELS; l++)
     if (ctx->lev[l].exists) uggpu_level_destroy(ctx, l);

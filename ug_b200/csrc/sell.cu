@@ -267,6 +267,8 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   size_t nsl = (size_t)(m->n + 31) / 32;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   UG_TRY(sell_free_schedules(ctx, m));
+  if (m->bnd_flag) dfree(ctx, m->bnd_flag, nsl);
+  if (m->bnd_list) dfree(ctx, m->bnd_list, (size_t)(m->n_bnd > 0 ? m->n_bnd : 1));
   if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);
   dfree(ctx, m->rowlen, (size_t)m->n);

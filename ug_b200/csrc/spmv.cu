@@ -10,6 +10,7 @@
 #include "uggpu_internal.h"
 
 #include <cstdlib>
+#include <vector>
 
 #ifndef SPMV_THREADS
 #define SPMV_THREADS 128
@@ -288,9 +289,13 @@ template <int BS, int FLAGS>
 __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
                                                            const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                            double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err,
-                                                           Prefetch pf)
+                                                           Prefetch pf, const int32_t *__restrict__ list, int nlist, const uint8_t *__restrict__ skip_slice)
 {
+  // Multi-GPU overlap (launch_smooth2): the INTERIOR launch covers the whole grid and skips the slices flagged in skip_slice (a
+  // direct-indexed byte per slice: no extra hop in the row's chain of loads); the INTERFACE launch works on the slices list[w].
   int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (list) { const int w = r >> 5; r = w < nlist ? list[w] * 32 + (threadIdx.x & 31) : A.n + 32; }
+  if (skip_slice && (r & ~31) < A.n && skip_slice[r >> 5]) r = A.n + 32;
   bool active = r < A.n;
   const PfState pfs = pf_begin(A, r, pf);      // software prefetch into L2 (uggpu_internal.h): requested now, issued at the end
   double nrm[BS];
@@ -576,6 +581,42 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) k_smooth_tma(SellView A
   }
 }
 
+// ---- multi-GPU overlap: interior and interface slices ----------------------------------------------------------------------
+// flag[s] = 1 when a row of slice s has an entry in a ghost column (column index >= number of owned rows)
+__global__ void k_slice_has_ghost(SellView A, int n_owned, uint8_t *__restrict__ flag)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((r & ~31) >= A.n) return;
+  bool ghost = false;
+  if (r < A.n) {
+    const int len = A.rowlen[r];
+    const ColIter ci = col_iter(A, r);
+    for (int j = 0; j < len; j++) if (col_at(ci, j) >= n_owned) ghost = true;
+  }
+  ghost = __any_sync(0xffffffffu, ghost);
+  if ((threadIdx.x & 31) == 0) flag[r >> 5] = ghost ? 1 : 0;
+}
+
+static int build_overlap_lists(uggpu_ctx *ctx, Level *L, SellMat *A)
+{
+  const size_t nsl = (size_t)(A->n + 31) / 32;
+  uint8_t *d_flag = nullptr;
+  UG_TRY(dalloc(ctx, &d_flag, nsl));
+  k_slice_has_ghost<<<(int)((nsl * 32 + 255) / 256), 256, 0, ctx->stream>>>(view(*A), L->n, d_flag);
+  KCHECK(ctx);
+  std::vector<uint8_t> flag(nsl);
+  CUDA_TRY(cudaMemcpyAsync(flag.data(), d_flag, nsl, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  A->bnd_flag = d_flag;
+  std::vector<int32_t> bd;
+  for (size_t s = 0; s < nsl; s++) if (flag[s]) bd.push_back((int32_t)s);
+  A->n_int = (int)(nsl - bd.size()); A->n_bnd = (int)bd.size();
+  UG_TRY(dalloc(ctx, &A->bnd_list, (size_t)(A->n_bnd > 0 ? A->n_bnd : 1)));
+  if (A->n_bnd) CUDA_TRY(cudaMemcpyAsync(A->bnd_list, bd.data(), sizeof(int32_t) * bd.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // geometry of the staged kernel for matrix A; false: use the thread-per-row kernel
 static bool tma_geometry(uggpu_ctx *ctx, const Level *L, const SellMat *A, int *grid, int *warps, size_t *smem)
 {
@@ -598,12 +639,23 @@ static bool tma_geometry(uggpu_ctx *ctx, const Level *L, const SellMat *A, int *
   return true;
 }
 
+// split: the halo exchange of tin has only been STARTED (halo_begin): the interior slices run on the compute stream right away, the
+// interface slices on the halo stream behind the wait + unpack; the compute stream continues when both are done.  Every row is
+// computed by the same code on the same operands as in one launch: results do not change.
 template <int BS, int FLAGS>
-static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot)
+static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
+                          int level, int split)
 {
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   int tgrid = 0, twarps = 0; size_t tsmem = 0;
-  const bool tma = BS == 1 && tma_geometry(ctx, L, A, &tgrid, &twarps, &tsmem);
+  const bool tma = !split && BS == 1 && tma_geometry(ctx, L, A, &tgrid, &twarps, &tsmem);
+  constexpr int WPB = SPMV_THREADS / 32;
+  int bi = 0, bb = 0;
+  if (split) {
+    if (A->n_int < 0) UG_TRY(build_overlap_lists(ctx, L, A));
+    bi = (L->n + SPMV_THREADS - 1) / SPMV_THREADS; bb = (A->n_bnd + WPB - 1) / WPB;     // interior: the whole grid minus the flagged slices
+    blocks = bi + bb;
+  }
   if (tma) blocks = tgrid * twarps;     // one partial per warp
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)blocks * BS));
   const double nb = 8.0 * BS * L->n;
@@ -614,9 +666,31 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const doub
     static bool attr_set = false;     // per instantiation
     if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_smooth_tma<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BUDGET)); attr_set = true; }
     k_smooth_tma<FLAGS><<<tgrid, twarps * 32, tsmem, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr, A->maxlen);
+  } else if (split) {
+    if (!ctx->halo_stream) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_TRY(cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, hi));      // its blocks go first when SM slots free up
+      for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&ctx->halo_ev[i], cudaEventDisableTiming));
+    }
+    const Prefetch pf = make_prefetch(ctx, A, BS);
+    CUDA_TRY(cudaEventRecord(ctx->halo_ev[0], ctx->stream));                  // behind the push of halo_begin
+    if (bi > 0) {
+      k_smooth_k<BS, FLAGS><<<bi, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf, nullptr, 0, A->bnd_flag);
+      KCHECK(ctx);
+    }
+    CUDA_TRY(cudaStreamWaitEvent(ctx->halo_stream, ctx->halo_ev[0], 0));
+    UG_TRY(halo_finish(ctx, level, const_cast<double *>(tin), ctx->halo_stream));
+    if (bb > 0) {
+      k_smooth_k<BS, FLAGS><<<bb, SPMV_THREADS, 0, ctx->halo_stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x,
+                                                                        (FLAGS & SF_NORM) ? ctx->partials + (size_t)bi * BS : ctx->partials, ctx->derr, pf, A->bnd_list, A->n_bnd, nullptr);
+      ctx->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], ctx->halo_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
   } else {
     k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
-                                                                      make_prefetch(ctx, A, BS));
+                                                                      make_prefetch(ctx, A, BS), nullptr, 0, nullptr);
   }
   KCHECK(ctx);
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot, (int)(L - ctx->lev)));
@@ -624,9 +698,10 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, const SellMat *A, const doub
 }
 
 template <int BS>
-static int launch_smooth(uggpu_ctx *ctx, Level *L, const SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot)
+static int launch_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
+                         int level, int split)
 {
-#define SM_CASE(F) case F: return launch_smooth2<BS, F>(ctx, L, A, tin, b, c, tout, damp, x, norm_slot)
+#define SM_CASE(F) case F: return launch_smooth2<BS, F>(ctx, L, A, tin, b, c, tout, damp, x, norm_slot, level, split)
   switch (flags) {
     SM_CASE(0);
     SM_CASE(SF_CADD);
@@ -653,10 +728,13 @@ int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin
   if (!L || !M) return UGGPU_DESC_MISMATCH;
   if (L->n == 0) return 0;
   if ((flags & SF_TOUT) && tout == tin) return uggpu_fail(UGGPU_ERROR, "smooth step: tout aliases tin");
-  UG_TRY(halo_exchange(ctx, level, const_cast<double *>(tin)));  // ghost columns of the correction (no-op on one GPU)
+  // ghost columns of the correction (no-op on one GPU); on the peer-memory path only the push happens here and the kernel's
+  // interior slices overlap the rest of the exchange
+  int split = 0;
+  UG_TRY(halo_begin(ctx, level, const_cast<double *>(tin), &split));
   switch (L->bs) {
-    case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot);
-    case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot);
-    default: return launch_smooth<3>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot);
+    case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
+    case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
+    default: return launch_smooth<3>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
   }
 }

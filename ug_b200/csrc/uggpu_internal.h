@@ -46,6 +46,10 @@ struct SellMat {
                                   // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
                                   // fused into the restriction) stream it instead of touching one column of every slice of val.  Matrices only (not P, R).
   bool valid() const { return n > 0 && col != nullptr; }
+  // multi-GPU overlap (spmv.cu): bnd_flag[s] = 1 / bnd_list = the slices with a row that references a ghost column; built on first use
+  uint8_t *bnd_flag = nullptr;
+  int32_t *bnd_list = nullptr;
+  int n_int = -1, n_bnd = 0;
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
   // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
@@ -111,6 +115,8 @@ struct uggpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // second stream for uploads that overlap the cycle (created on first use)
+  cudaStream_t halo_stream = nullptr;   // interface rows of a partitioned level: wait for the halo + compute, next to the interior rows (created on first use)
+  cudaEvent_t halo_ev[2] = {nullptr, nullptr};
   Level lev[UGGPU_MAX_LEVELS];
   int fullrefinelevel = 0;
   int64_t launches = 0;
@@ -281,6 +287,8 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
 int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp);
 // comm.cu: all are no-ops (return 0) when the context has no communicator or the level is not partitioned
 int halo_exchange(uggpu_ctx *ctx, int level, double *v);                 // owned values -> the neighbours' ghost rows of v
+int halo_begin(uggpu_ctx *ctx, int level, double *v, int *split);        // push only; *split = 1: finish with halo_finish on another stream
+int halo_finish(uggpu_ctx *ctx, int level, double *v, cudaStream_t st);  // wait + unpack on st
 int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count);           // in place, on the context's stream
 int level_free_part(uggpu_ctx *ctx, Level *L);
 int level_free_lu(uggpu_ctx *ctx, Level *L);                              // cycle.cu: the base-level factorisation
