@@ -117,6 +117,15 @@ int uggpu_transfer_set(uggpu_ctx *ctx, int level,
                        const int32_t *p_rowptr, const int32_t *p_col, const double *p_w,
                        const int32_t *r_rowptr, const int32_t *r_col, const double *r_w);
 
+/* Transfer mode of `level` (np/procs/transfer.cc:553-573): UGGPU_TRANSFER_STANDARD (default) = StandardRestrict /
+ * StandardInterpolateCorrection (the damping enters every term, transgrid.cc:164,305); UGGPU_TRANSFER_IMAT = `transfer $M`:
+ * RestrictByMatrix / InterpolateCorrectionByMatrix (transgrid.cc:1113,1292) on stencils taken from the stored interpolation
+ * matrices -- P rows in VISTART->NEXT order, R rows in fine VECTOR list order -- where the sums are formed without the damping
+ * and the finished vector is scaled afterwards if a factor differs from 1. */
+#define UGGPU_TRANSFER_STANDARD 0
+#define UGGPU_TRANSFER_IMAT     1
+int uggpu_transfer_set_mode(uggpu_ctx *ctx, int level, int mode);
+
 /* which: 0 = P, 1 = R; any output pointer may be NULL */
 int uggpu_transfer_get(uggpu_ctx *ctx, int level, int which, int32_t *rowptr, int32_t *col, double *w);
 int64_t uggpu_transfer_nnz(uggpu_ctx *ctx, int level, int which);

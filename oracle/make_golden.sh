@@ -28,4 +28,8 @@ mkdir -p $G
 ./_ref/ugoracle2 --grid quad --refine 3 --baselevel 2 --damp 0.8 --cycles 4 --lean --dump $G/lu_quad2d_r3_bl2.ugh --solve > /dev/null
 # ... and the block variant of l_lrdecomp / l_luiter (3x3 blocks, 27 free vectors on the base level, fill-in)
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 3 --baselevel 2 --damp 0.6 --cycles 3 --lean --dump $G/lu_hex3d_bs3_r3_bl2.ugh --solve > /dev/null
+# IMAT mode of the transfer (`transfer $M`): RestrictByMatrix / InterpolateCorrectionByMatrix on the stored interpolation
+# matrices (created with CreateStandardNodeRestProl), scalar and 3x3 blocks; the transfer records use damping factors != 1
+./_ref/ugoracle2 --grid tri --refine 3 --damp 0.8 --cycles 6 --imat --dump $G/imat_tri2d_r3.ugh --ops --solve > /dev/null
+./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --damp 0.6 --cycles 6 --imat --dump $G/imat_hex3d_bs3_r2.ugh --ops --solve > /dev/null
 ls -la $G

@@ -97,6 +97,7 @@ struct Opt {
   int baselevel = 0;                    // lmgc $b
   int barrier_n = 0, barrier_id = 0;
   bool ops = false, solve = false, timeit = false, quiet = true;
+  bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
 };
 
@@ -309,7 +310,7 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
   cmd("npcreate %ssmooth $c %s", pfx, jac);      cmd("npinit %ssmooth $damp %.17g", pfx, o.damp);
   cmd("npcreate %sbaseit $c lu", pfx);           cmd("npinit %sbaseit", pfx);
   cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
-  cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer", pfx);
+  cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer%s", pfx, o.imat ? " $M" : "");
   cmd("npcreate %slmgc $c %s", pfx, lmgc);
   cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel);
   cmd("npcreate %smgs $c %s", pfx, ls);
@@ -330,8 +331,9 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
     if (gpuls::FlattenFlags(mg, l, vx, fl[l])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
     if (gpuls::FlattenMatrix(mg, l, mA, fl[l])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
   }
+  D.scalar_i("transfer_mode", o.imat ? 1 : 0);
   for (int l = 1; l <= top; l++)
-    if (gpuls::FlattenTransfer(mg, l, fl[l])) { fprintf(stderr, "FlattenTransfer failed\n"); exit(6); }
+    if (o.imat ? gpuls::FlattenTransferIMAT(mg, l, fl[l]) : gpuls::FlattenTransfer(mg, l, fl[l])) { fprintf(stderr, "FlattenTransfer failed\n"); exit(6); }
   for (int l = 0; l <= top; l++) {
     gpuls::FlatLevel &f = fl[l];
     D.scalar_i(L("n", l), f.n);
@@ -422,9 +424,9 @@ static void dump_ops(const Opt &o)
     // `to` and `from` are the same descriptor in Lmgc (b,b); use the same here: c on both levels
     fill_lcg(vc, l, 5);
     dumpvec("restrict/in_fine", vc, l); dumpvec("restrict/in_coarse", vc, l - 1);
-    if (StandardRestrict(GRID_ON_LEVEL(mg, l), vc, vc, a3) != NUM_OK) { fprintf(stderr, "restrict failed\n"); exit(8); }
+    if ((o.imat ? RestrictByMatrix(GRID_ON_LEVEL(mg, l), vc, vc, a3) : StandardRestrict(GRID_ON_LEVEL(mg, l), vc, vc, a3)) != NUM_OK) { fprintf(stderr, "restrict failed\n"); exit(8); }
     dumpvec("restrict/out", vc, l - 1);
-    if (StandardInterpolateCorrection(GRID_ON_LEVEL(mg, l), vt, vx, a3) != NUM_OK) { fprintf(stderr, "interpolate failed\n"); exit(8); }
+    if ((o.imat ? InterpolateCorrectionByMatrix(GRID_ON_LEVEL(mg, l), vt, vx, a3) : StandardInterpolateCorrection(GRID_ON_LEVEL(mg, l), vt, vx, a3)) != NUM_OK) { fprintf(stderr, "interpolate failed\n"); exit(8); }
     dumpvec("interpolate/in_coarse", vx, l - 1); dumpvec("interpolate/out", vt, l);
   }
   // surface-mode loops over all levels (matter on adaptive hierarchies)
@@ -626,7 +628,7 @@ int main(int argc, char **argv)
     else if (a == "--ops") o.ops = true; else if (a == "--solve") o.solve = true; else if (a == "--time") o.timeit = true;
     else if (a == "--verbose") o.quiet = false; else if (a == "--gpu") o.gpu = nxt();
     else if (a == "--smoother") o.smoother = nxt(); else if (a == "--baselevel") o.baselevel = atoi(nxt().c_str());
-    else if (a == "--lean") o.lean = true;
+    else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;
@@ -645,6 +647,9 @@ int main(int argc, char **argv)
   for (int l = 0; l <= top; l++) printf("%s%d", l ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
   printf("] build_s=%.2f\n", t1 - t0);
   if (o.smoother != "jac" && o.smoother != "gs" && o.smoother != "sgs" && o.smoother != "sor") { fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str()); return 1; }
+  if (o.imat)     // the interpolation matrices the $M mode works on (transgrid.cc:2363); the format reserves them ($I)
+    for (int l = 1; l <= top; l++)
+      if (CreateStandardNodeRestProl(GRID_ON_LEVEL(mg, l), BS) != NUM_OK) { fprintf(stderr, "CreateStandardNodeRestProl failed\n"); return 1; }
   make_numprocs(o, "", o.smoother.c_str(), "lmgc", "transfer", "ls", o.cycles);
   std::vector<gpuls::FlatLevel> fl;
   if (!o.dump.empty()) {

@@ -224,6 +224,66 @@ void ugport_interpolate(const ugport_level *fine, const ugport_level *coarse, do
   }
 }
 
+/* IMAT mode.  RestrictByMatrix_General transgrid.cc:1113-1240: scalar descriptors :1127-1156 (w += m*v where VECSKIP(w) == 0, then
+ * w *= damp[0] if damp[0] != 1), block descriptors :1158-1237 (per entry and component sum = 0; sum += m_ij*v_j; w_i += sum --
+ * with the blocks c*I of the standard interpolation the sum is c*v_i; components with the skip bit are left out; finally
+ * w_i *= damp_i on all rows if CheckDamp).  Both loops zero the coarse rows with VNCLASS >= NEWDEF_CLASS first and visit the fine
+ * vectors with VCLASS >= NEWDEF_CLASS in list order: that is the order of the R rows in IMAT flattening. */
+static int check_damp(int n, const double *damp) { for (int i = 0; i < n; i++) if (damp[i] != 1.0) return 1; return 0; }
+
+void ugport_restrict_imat(const ugport_level *fine, const ugport_level *coarse, double *to, const double *from, const double *damp)
+{
+  int bs = fine->bs;
+  for (int r = 0; r < coarse->n; r++) {
+    double *tr = to + (size_t)r * bs;
+    if (coarse->vnclass[r] >= NEWDEF_CLASS) for (int i = 0; i < bs; i++) tr[i] = 0.0;
+    uint32_t skip = coarse->skip[r];
+    for (int e = fine->r_rowptr[r]; e < fine->r_rowptr[r + 1]; e++) {
+      const double *f = from + (size_t)fine->r_col[e] * bs;
+      double w = fine->r_w[e];
+      if (bs == 1) { if (skip == 0) tr[0] += w * f[0]; }
+      else
+        for (int i = 0; i < bs; i++)
+          if (!(skip & (1u << i))) {
+            double sum = 0.0;
+            for (int j = 0; j < bs; j++) sum += (i == j ? w : 0.0) * f[j];
+            tr[i] += sum;
+          }
+    }
+  }
+  if (check_damp(bs, damp))
+    for (int r = 0; r < coarse->n; r++)
+      if (coarse->vnclass[r] >= NEWDEF_CLASS) for (int i = 0; i < bs; i++) to[(size_t)r * bs + i] *= damp[i];
+}
+
+/* InterpolateCorrectionByMatrix_General transgrid.cc:1292-1390: to = 0; scalar :1306-1335 (rows with the skip bit stay 0);
+ * blocks :1337-1382 (sum = 0; sum += m_ji*w_j; v_i += sum); then dscalx(to, damp) on ALL vectors if CheckDamp. */
+void ugport_interpolate_imat(const ugport_level *fine, const ugport_level *coarse, double *to, const double *from, const double *damp)
+{
+  int bs = fine->bs;
+  (void)coarse;
+  for (int r = 0; r < fine->n; r++) {
+    double *tr = to + (size_t)r * bs;
+    for (int i = 0; i < bs; i++) tr[i] = 0.0;
+    uint32_t skip = fine->skip[r];
+    if (bs == 1 && (skip & 1u)) continue;
+    for (int e = fine->p_rowptr[r]; e < fine->p_rowptr[r + 1]; e++) {
+      const double *f = from + (size_t)fine->p_col[e] * bs;
+      double w = fine->p_w[e];
+      if (bs == 1) tr[0] += w * f[0];
+      else
+        for (int i = 0; i < bs; i++)
+          if (!(skip & (1u << i))) {
+            double sum = 0.0;
+            for (int j = 0; j < bs; j++) sum += (i == j ? w : 0.0) * f[j];
+            tr[i] += sum;
+          }
+    }
+  }
+  if (check_damp(bs, damp))
+    for (int r = 0; r < fine->n; r++) for (int i = 0; i < bs; i++) to[(size_t)r * bs + i] *= damp[i];
+}
+
 /* ---- base level: `lu` (np/procs/iter.cc:6443 LUPreProcess, Smoother + LUStep) -------------------------------------------
  * l_lrdecomp (ugiter.cc:3657) eliminates on UG's per-row MATRIX LISTS and creates fill-in with CreateExtraConnection
  * (gm/algebra.cc:1101 -> CreateConnection :969), which inserts the two new MATRIX structs at the SECOND place of both row
@@ -445,13 +505,15 @@ int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu,
     if (err) { free(tmp); return err; }
     ugport_dadd(L, 0, c[level], t[level]);
   }
-  ugport_restrict(L, &lv[level - 1], b[level - 1], b[level], one);           /* :7843, Factor_One */
+  if (cfg->imat) ugport_restrict_imat(L, &lv[level - 1], b[level - 1], b[level], one);
+  else ugport_restrict(L, &lv[level - 1], b[level - 1], b[level], one);           /* :7843, Factor_One */
   ugport_dset(&lv[level - 1], 0, c[level - 1], 0.0);                         /* :7873 */
   for (int g = 0; g < cfg->gamma; g++) {
     int err = ugport_lmgc(lv, cfg, lu, level - 1, c, b, t);
     if (err) { free(tmp); return err; }
   }
-  ugport_interpolate(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);  /* :7886 */
+  if (cfg->imat) ugport_interpolate_imat(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);
+  else ugport_interpolate(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);  /* :7886 */
   ugport_dadd(L, 0, c[level], t[level]);                                     /* :7903 */
   ugport_dmatmul(L, 2, 0, b[level], t[level]);                               /* :7905 */
   for (int i = 0; i < cfg->nu2; i++) {

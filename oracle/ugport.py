@@ -32,7 +32,7 @@ class _Cfg(C.Structure):
     _fields_ = [("nu1", C.c_int), ("nu2", C.c_int), ("gamma", C.c_int), ("baselevel", C.c_int),
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
                 ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
-                ("smoother", C.c_int)]
+                ("smoother", C.c_int), ("imat", C.c_int)]
 
 
 SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3}
@@ -87,6 +87,7 @@ class PortBackend:
                 fields[k] = _p(a)
             arr[i] = _Level(lv.n, lv.bs, **fields)
         self.levels = arr
+        self.imat = bool(int(hier.raw["transfer_mode"][0])) if "transfer_mode" in getattr(hier, "raw", {}) else False
         self.vec: Dict[str, List[np.ndarray]] = {}
 
     # ---- vectors
@@ -195,11 +196,11 @@ class PortBackend:
                                     self._vs(damp), _dp(self._v(tmp, level)))
 
     def restrict(self, level, to, frm, damp):
-        self.L.ugport_restrict(self._lp(level), self._lp(level - 1), _dp(self._v(to, level - 1)),
+        (self.L.ugport_restrict_imat if self.imat else self.L.ugport_restrict)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level - 1)),
                                _dp(self._v(frm, level)), self._vs(damp))
 
     def interpolate(self, level, to, frm, damp):
-        self.L.ugport_interpolate(self._lp(level), self._lp(level - 1), _dp(self._v(to, level)),
+        (self.L.ugport_interpolate_imat if self.imat else self.L.ugport_interpolate)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level)),
                                   _dp(self._v(frm, level - 1)), self._vs(damp))
 
     # ---- cycle / solver
@@ -213,6 +214,7 @@ class PortBackend:
         c.base_reduction = cfg.get("base_reduction", 1e-8)
         c.base_abslimit = cfg.get("base_abslimit", 1e-10)
         c.smoother = SMOOTHERS[cfg.get("smoother", "jac")]
+        c.imat = 1 if self.imat else 0
         return c
 
     def _pp(self, name):

@@ -25,8 +25,10 @@ CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--smoother", "sor", "--damp", "1.1", "--cycles", "5"]),
     # base level with free rows (lmgc $b 2)
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--baselevel", "2", "--damp", "0.6", "--cycles", "5"]),
+    # transfer $M: stored interpolation matrices (RestrictByMatrix / InterpolateCorrectionByMatrix) against gputransfer $M
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--imat", "--damp", "0.6", "--cycles", "5"]),
 ]
-IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2"]
+IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)

@@ -138,6 +138,8 @@ class Context:
                 self.call("uggpu_transfer_set", l, _p(np.ascontiguousarray(lv.p_rowptr)), _p(np.ascontiguousarray(lv.p_col)),
                           _p(np.ascontiguousarray(lv.p_w)), _p(np.ascontiguousarray(lv.r_rowptr)),
                           _p(np.ascontiguousarray(lv.r_col)), _p(np.ascontiguousarray(lv.r_w)))
+                if "transfer_mode" in hier.raw:          # dumps written with `transfer $M` (oracle/ug_driver.cc --imat)
+                    self.call("uggpu_transfer_set_mode", l, int(hier.raw["transfer_mode"][0]))
         self.call("uggpu_set_fullrefinelevel", int(hier.fullrefinelevel))
 
     def download_hierarchy(self, top: int, A: str = "A"):

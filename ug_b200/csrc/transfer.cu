@@ -255,13 +255,38 @@ template <int K> static inline int tr_blocks(int n)
   return (int)((warps * 32 + TR_THREADS - 1) / TR_THREADS);
 }
 
-int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp)
+// IMAT mode, RestrictByMatrix_General transgrid.cc:1150,1225-1236: the coarse rows with VNCLASS >= NEWDEF_CLASS are scaled after the sums
+template <int BS>
+__global__ void k_scale_newdef(int n, const uint8_t *__restrict__ vnclass, double *__restrict__ v, Damp damp)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || vnclass[r] < 2) return;
+#pragma unroll
+  for (int i = 0; i < BS; i++) v[(size_t)r * BS + i] = v[(size_t)r * BS + i] * damp.a[i];
+}
+
+static bool damp_is_one(const Damp &d, int bs) { for (int i = 0; i < bs; i++) if (d.a[i] != 1.0) return false; return true; }
+
+extern "C" int uggpu_transfer_set_mode(uggpu_ctx *ctx, int level, int mode)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (mode != UGGPU_TRANSFER_STANDARD && mode != UGGPU_TRANSFER_IMAT) return uggpu_fail(UGGPU_ERROR, "unknown transfer mode %d", mode);
+  L->transfer_mode = mode;
+  return 0;
+}
+
+int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in, bool fuse, int A, double *tout, double *czero, Damp sdamp)
 {
   Level *F = get_level(ctx, level);
   Level *C = get_level(ctx, level - 1);
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->R.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (C->n == 0) return 0;
+  // IMAT mode: sums without the damping (1.0 * x is exact), the finished rows scaled afterwards
+  const bool post = F->transfer_mode == UGGPU_TRANSFER_IMAT && !damp_is_one(damp_in, F->bs);
+  if (post && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start with a damped IMAT restriction");
+  const Damp damp = F->transfer_mode == UGGPU_TRANSFER_IMAT ? mkdamp(nullptr, 0) : damp_in;
   // partitioned fine level: the coarse rows this rank owns gather from fine ghost rows too
   UG_TRY(halo_exchange(ctx, level, const_cast<double *>(from)));
   const bool gather = ctx->comm && F->partitioned && !C->partitioned;   // first completely held (replicated) level
@@ -294,16 +319,28 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   // every rank filled only the rows of the coarse nodes it would own (the others are 0): summing the disjoint parts
   // is the gather of the coarse defect onto every rank (agglomeration)
   if (gather) UG_TRY(allreduce_sum(ctx, to, (size_t)C->n * C->bs));
+  if (post) {
+    const int sb = (C->n + 255) / 256;
+    switch (F->bs) {
+      case 1: k_scale_newdef<1><<<sb, 256, 0, ctx->stream>>>(C->n, C->vnclass, to, damp_in); break;
+      case 2: k_scale_newdef<2><<<sb, 256, 0, ctx->stream>>>(C->n, C->vnclass, to, damp_in); break;
+      default: k_scale_newdef<3><<<sb, 256, 0, ctx->stream>>>(C->n, C->vnclass, to, damp_in); break;
+    }
+    KCHECK(ctx);
+  }
   return 0;
 }
 
-int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp)
+int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in)
 {
   Level *F = get_level(ctx, level);
   Level *C = get_level(ctx, level - 1);
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
   if (F->n == 0) return 0;
+  // IMAT mode (InterpolateCorrectionByMatrix_General transgrid.cc:1331,1385): sums without the damping, then dscalx on all rows
+  const bool post = F->transfer_mode == UGGPU_TRANSFER_IMAT && !damp_is_one(damp_in, F->bs);
+  const Damp damp = F->transfer_mode == UGGPU_TRANSFER_IMAT ? mkdamp(nullptr, 0) : damp_in;
   UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
 #define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV))
@@ -315,6 +352,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   }
 #undef IP
   KCHECK(ctx);
+  if (post) UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, to, nullptr, damp_in));
   return 0;
 }
 

@@ -93,6 +93,7 @@ struct Level {
   std::map<int, double *> vecs;
   std::map<int, cudaEvent_t> pending;   // vectors with an asynchronous upload in flight on the copy stream (uggpu_vec_upload_async)
   SellMat P, R;                  // P: rows = this level, cols = level-1;  R: rows = level-1, cols = this level
+  int transfer_mode = 0;         // UGGPU_TRANSFER_STANDARD / UGGPU_TRANSFER_IMAT (damping applied after the sums, transfer.cu)
   // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
   double *lu = nullptr;
   int luN = 0, luA = -1;

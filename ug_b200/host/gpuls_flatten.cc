@@ -5,6 +5,7 @@
 #include "shapes.h"
 #include "ugm.h"
 #include "algebra.h"
+#include "transgrid.h"      // CRITBIT
 
 #include <cstdio>
 
@@ -182,6 +183,47 @@ int FlattenTransfer(MULTIGRID *mg, int level, FlatLevel &out)
       int32_t pos = fill[pe[i].c]++;
       out.r_col[pos] = r;
       out.r_w[pos] = pe[i].w;
+    }
+  }
+  return 0;
+}
+
+int FlattenTransferIMAT(MULTIGRID *mg, int level, FlatLevel &out)
+{
+  if (level < 1) return 1;
+  GRID *fg = GRID_ON_LEVEL(mg, level), *cg = GRID_ON_LEVEL(mg, level - 1);
+  if (fg == NULL || cg == NULL) return 2;
+  const int nf = out.n, nc = NVEC(cg), bs = out.bs;
+  out.p_rowptr.assign(nf + 1, 0);
+  out.p_col.clear(); out.p_w.clear();
+  out.node_row.clear();
+  std::vector<int32_t> rcnt(nc + 1, 0);
+  for (VECTOR *v = FIRSTVECTOR(fg); v != NULL; v = SUCCVC(v)) {
+    const int r = VINDEX(v);
+    for (int i = 0; i < bs; i++) if (CRITBIT(v, i)) return 8;
+    for (MATRIX *m = VISTART(v); m != NULL; m = NEXT(m)) {
+      const double c = MVALUE(m, 0);
+      for (int i = 0; i < bs; i++)
+        for (int j = 0; j < bs; j++)
+          if (MVALUE(m, i * bs + j) != (i == j ? c : 0.0)) return 7;      // not c*I
+      out.p_col.push_back(VINDEX(MDEST(m)));
+      out.p_w.push_back(c);
+      if (VCLASS(v) >= NEWDEF_CLASS) rcnt[VINDEX(MDEST(m)) + 1]++;        // transgrid.cc:1142
+    }
+    out.p_rowptr[r + 1] = (int32_t)out.p_col.size();
+  }
+  out.r_rowptr.assign(nc + 1, 0);
+  for (int r = 0; r < nc; r++) out.r_rowptr[r + 1] = out.r_rowptr[r] + rcnt[r + 1];
+  out.r_col.resize(out.r_rowptr[nc]);
+  out.r_w.resize(out.r_rowptr[nc]);
+  std::vector<int32_t> fill(out.r_rowptr.begin(), out.r_rowptr.end() - 1);
+  for (VECTOR *v = FIRSTVECTOR(fg); v != NULL; v = SUCCVC(v)) {
+    if (VCLASS(v) < NEWDEF_CLASS) continue;
+    const int r = VINDEX(v);
+    for (int e = out.p_rowptr[r]; e < out.p_rowptr[r + 1]; e++) {
+      const int32_t pos = fill[out.p_col[e]]++;
+      out.r_col[pos] = r;
+      out.r_w[pos] = out.p_w[e];
     }
   }
   return 0;

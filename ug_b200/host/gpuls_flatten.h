@@ -46,6 +46,13 @@ int FlattenMatrixValues(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PRE
 // Standard P and R between `level` and level-1 (requires FlattenFlags on both levels).
 int FlattenTransfer(NS_DIM_PREFIX MULTIGRID *mg, int level, FlatLevel &out);
 
+// IMAT mode (`transfer $M`, and what RestrictDefect/InterpolateCorrection use on levels < 1, np/procs/transfer.cc:724-760): P rows
+// from the stored interpolation lists VISTART(v)->NEXT in list order, R rows in the order RestrictByMatrix_General
+// (np/algebra/transgrid.cc:1113) scatters: fine VECTOR list order, entries of a vector in list order.  Only interpolation blocks
+// of the form c*I (what CreateStandardNodeRestProl :2363 and the standard refinement store) are accepted: returns 7 otherwise,
+// 8 when a vector has CRITBITs set.
+int FlattenTransferIMAT(NS_DIM_PREFIX MULTIGRID *mg, int level, FlatLevel &out);
+
 // VVALUE gather/scatter in list order: host[r*bs+i] <-> VVALUE(v, VD_CMP_OF_TYPE(vd,VTYPE(v),i))
 void GatherVector(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PREFIX VECDATA_DESC *vd, int bs, double *host);
 void ScatterVector(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PREFIX VECDATA_DESC *vd, int bs, const double *host);

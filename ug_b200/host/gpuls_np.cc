@@ -41,7 +41,7 @@ USING_UG_NAMESPACES
   X(uggpu_ctx_create) X(uggpu_ctx_destroy) X(uggpu_last_error) X(uggpu_set_fullrefinelevel) X(uggpu_level_create) X(uggpu_level_set_flags)     \
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
-  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess)
+  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode)
 
 namespace {
 struct Api {
@@ -158,14 +158,19 @@ int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC 
   return 0;
 }
 
-int EnsureTransfer(Mirror *m, int level)
+// imat: `transfer $M` -- the stencils come from the stored interpolation matrices (gpuls_flatten.h FlattenTransferIMAT)
+int EnsureTransfer(Mirror *m, int level, int imat)
 {
-  if (m->have_transfer[level]) return 0;
+  if (m->have_transfer[level] == 1 + imat) return 0;
   if (level < 1 || !m->have_level[level] || !m->have_level[level - 1]) return 1;
   gpuls::FlatLevel &f = m->fl[level];
-  if (gpuls::FlattenTransfer(m->mg, level, f)) { UserWriteF("gpuls: cannot flatten the standard transfer of level %d\n", level); return 1; }
+  if (int rc = imat ? gpuls::FlattenTransferIMAT(m->mg, level, f) : gpuls::FlattenTransfer(m->mg, level, f)) {
+    UserWriteF("gpuls: cannot flatten the %s transfer of level %d (code %d)\n", imat ? "IMAT" : "standard", level, rc);
+    return 1;
+  }
   DEV(uggpu_transfer_set(m->ctx, level, f.p_rowptr.data(), f.p_col.data(), f.p_w.data(), f.r_rowptr.data(), f.r_col.data(), f.r_w.data()));
-  m->have_transfer[level] = 1;
+  DEV(uggpu_transfer_set_mode(m->ctx, level, imat ? UGGPU_TRANSFER_IMAT : UGGPU_TRANSFER_STANDARD));
+  m->have_transfer[level] = 1 + imat;
   return 0;
 }
 
@@ -294,12 +299,15 @@ struct NP_GPUTRANSFER {
   NP_TRANSFER transfer;
   Mirror *m;
   INT fl, tl;
+  INT imat;            // $M: IMAT_MODE (transfer.cc:564-572): RestrictByMatrix / InterpolateCorrectionByMatrix
 };
 
 INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
 {
-  if (ReadArgvOption("M", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("L", argc, argv) || ReadArgvOption("D", argc, argv)) {
-    UserWrite("gputransfer: only the standard (geometric) transfer is on the GPU path; $M $S $L $D are not supported\n");
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  np->imat = ReadArgvOption("M", argc, argv);
+  if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("L", argc, argv) || ReadArgvOption("D", argc, argv)) {
+    UserWrite("gputransfer: the standard (geometric) transfer and $M (stored interpolation matrices) are on the GPU path; $R $S $L $D are not supported\n");
     return NP_NOT_ACTIVE;
   }
   return NPTransferInit((NP_TRANSFER *)theNP, argc, argv);                // transfer.cc:593
@@ -307,9 +315,10 @@ INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
 
 INT GpuTransferDisplay(NP_BASE *theNP)
 {
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
   NPTransferDisplay((NP_TRANSFER *)theNP);
-  UserWriteF(DISPLAY_NP_FORMAT_SS, "Restrict", "StandardRestrict (device)");
-  UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", "StandardInterpolateCorrection (device)");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "Restrict", np->imat ? "RestrictByMatrix (device)" : "StandardRestrict (device)");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", np->imat ? "InterpolateCorrectionByMatrix (device)" : "StandardInterpolateCorrection (device)");
   return 0;
 }
 
@@ -321,7 +330,7 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
   if (np->m == NULL) NP_RETURN(1, result[0]);
   np->fl = *fl; np->tl = tl;
   for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) NP_RETURN(1, result[0]);
-  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l)) NP_RETURN(1, result[0]);
+  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) NP_RETURN(1, result[0]);
   return 0;
 }
 
