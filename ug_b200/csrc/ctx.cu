@@ -364,6 +364,8 @@ extern "C" int uggpu_transfer_set(uggpu_ctx *ctx, int level, const int32_t *p_ro
   UG_TRY(sell_free(ctx, &L->R));
   UG_TRY(sell_from_host_csr(ctx, L->n, 1, p_rowptr, p_col, p_w, &L->P));
   UG_TRY(sell_from_host_csr(ctx, C->n, 1, r_rowptr, r_col, r_w, &L->R));
+  UG_TRY(sell_compress_values(ctx, &L->P));
+  UG_TRY(sell_compress_values(ctx, &L->R));
   return 0;
 }
 

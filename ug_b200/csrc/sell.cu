@@ -5,7 +5,9 @@
 // same entries are stored slice-interleaved so that thread-per-row kernels are coalesced (uggpu_internal.h).
 #include "uggpu_internal.h"
 
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -239,6 +241,90 @@ int sell_compress_cols(uggpu_ctx *ctx, SellMat *m)
   return rc;
 }
 
+// ---- value dictionary of the transfer stencils ---------------------------------------------------------------------------------
+#define VT_SLOTS 1024
+#define VT_EMPTY 0xFFFFFFFFFFFFFFFFull
+// open-addressing set of the bit patterns of all stored values; overflow[0] counts the distinct ones
+__global__ void k_values_collect(int64_t count, const double *__restrict__ val, unsigned long long *tab, int *distinct)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(val[i]);
+    if (bits == VT_EMPTY) { atomicAdd(distinct, 100000); continue; }
+    unsigned h = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 54) & (VT_SLOTS - 1);
+    for (int probe = 0; probe < VT_SLOTS; probe++) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + h);
+      if (cur == bits) break;
+      if (cur == VT_EMPTY) {
+        cur = atomicCAS(tab + h, VT_EMPTY, bits);
+        if (cur == VT_EMPTY) { atomicAdd(distinct, 1); break; }
+        if (cur == bits) break;
+      }
+      h = (h + 1) & (VT_SLOTS - 1);
+      if (probe == VT_SLOTS - 1) atomicAdd(distinct, 100000);
+    }
+    if (*reinterpret_cast<volatile int *>(distinct) > 256) return;       // too many: the caller gives up
+  }
+}
+
+__global__ void k_values_encode(int64_t count, const double *__restrict__ val, const double *__restrict__ table, int nvals, uint8_t *__restrict__ code, int *bad)
+{
+  __shared__ unsigned long long st[256];
+  for (int i = threadIdx.x; i < nvals; i += blockDim.x) st[i] = (unsigned long long)__double_as_longlong(table[i]);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(val[i]);
+    int c = -1;
+    for (int k = 0; k < nvals; k++) if (st[k] == bits) { c = k; break; }
+    if (c < 0) { atomicAdd(bad, 1); c = 0; }
+    code[i] = (uint8_t)c;
+  }
+}
+
+int sell_compress_values(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->bb != 1 || m->padded <= 0 || m->vcode || getenv("UGGPU_NO_VALUE_TABLE")) return 0;
+  cudaStream_t st = ctx->stream;
+  unsigned long long *d_tab = nullptr; int *d_cnt = nullptr;
+  UG_TRY(dalloc(ctx, &d_tab, (size_t)VT_SLOTS));
+  UG_TRY(dalloc(ctx, &d_cnt, 2));
+  CUDA_TRY(cudaMemsetAsync(d_tab, 0xff, sizeof(unsigned long long) * VT_SLOTS, st));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+  int blocks = (int)((m->padded + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  k_values_collect<<<blocks, 256, 0, st>>>(m->padded, m->val, d_tab, d_cnt);
+  KCHECK(ctx);
+  std::vector<unsigned long long> tab(VT_SLOTS);
+  int cnt[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(tab.data(), d_tab, sizeof(unsigned long long) * VT_SLOTS, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  UG_TRY(dfree(ctx, d_tab, (size_t)VT_SLOTS));
+  int rc = 0;
+  if (cnt[0] >= 1 && cnt[0] <= 256) {
+    std::vector<unsigned long long> vals;
+    for (auto b : tab) if (b != VT_EMPTY) vals.push_back(b);
+    std::sort(vals.begin(), vals.end());                 // deterministic codes
+    if ((int)vals.size() == cnt[0]) {
+      double table[256];
+      for (int i = 0; i < 256; i++) { unsigned long long b = i < (int)vals.size() ? vals[i] : 0ull; memcpy(&table[i], &b, 8); }
+      uint8_t *code = nullptr; double *d_table = nullptr;
+      if ((rc = dalloc(ctx, &code, (size_t)m->padded)) == 0 && (rc = dalloc(ctx, &d_table, 256)) == 0) {
+        cudaMemcpyAsync(d_table, table, sizeof table, cudaMemcpyHostToDevice, st);
+        k_values_encode<<<blocks, 256, 0, st>>>(m->padded, m->val, d_table, (int)vals.size(), code, d_cnt + 1);
+        ctx->launches++;
+        int bad = 1;
+        cudaMemcpyAsync(&bad, d_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = uggpu_fail(UGGPU_CUDA_ERROR, "value table: %s", cudaGetErrorString(e));
+        if (rc == 0 && bad == 0) { m->vcode = code; m->vtable = d_table; m->nvals = (int)vals.size(); }
+        else { dfree(ctx, code, (size_t)m->padded); dfree(ctx, d_table, 256); }
+      }
+    }
+  }
+  dfree(ctx, d_cnt, 2);
+  return rc;
+}
+
 __global__ void k_sell_diag(int n, int bb, const int64_t *__restrict__ slice_ptr, const uint16_t *__restrict__ rowlen, const double *__restrict__ val,
                             double *__restrict__ diag)
 {
@@ -268,6 +354,8 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   UG_TRY(sell_free_schedules(ctx, m));
   if (m->bnd_flag) dfree(ctx, m->bnd_flag, nsl);
+  if (m->vcode) dfree(ctx, m->vcode, (size_t)m->padded);
+  if (m->vtable) dfree(ctx, m->vtable, 256);
   if (m->bnd_list) dfree(ctx, m->bnd_list, (size_t)(m->n_bnd > 0 ? m->n_bnd : 1));
   if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);
@@ -357,6 +445,7 @@ static int device_rowptr(uggpu_ctx *ctx, const SellMat *m, std::vector<int64_t> 
 
 int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val)
 {
+  if (m->vcode) { dfree(ctx, m->vcode, (size_t)m->padded); dfree(ctx, m->vtable, 256); m->nvals = 0; }     // stale codes
   UG_TRY(sell_free_schedules(ctx, m));     // they hold the old values; rebuilt on the next Gauss-Seidel solve
   std::vector<int64_t> rp; int64_t *d_rp = nullptr; double *d_val = nullptr;
   UG_TRY(device_rowptr(ctx, m, rp, &d_rp));

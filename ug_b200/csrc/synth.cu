@@ -445,6 +445,8 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
       Level &Lc = ctx->lev[l - 1];
       UG_TRY(synth_sell<GEN_P>(ctx, sp, L.d_part, Lc.d_part, n, &L.P));
       UG_TRY(synth_sell<GEN_R>(ctx, sp, L.d_part, Lc.d_part, Lc.n, &L.R));
+      UG_TRY(sell_compress_values(ctx, &L.P));
+      UG_TRY(sell_compress_values(ctx, &L.R));
     }
   }
   ctx->fullrefinelevel = top;

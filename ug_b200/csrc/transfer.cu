@@ -33,7 +33,14 @@
 __device__ __forceinline__ bool tr_prefetch(const SellView &T, int r, const Prefetch &pf)
 {
   const PfState st = pf_begin(T, r, pf);
-  pf_end<1>(T, st, pf);
+  if (T.vcode) {                         // one byte per entry: the slice's codes are val_lines / 8 lines
+    if (st.sp >= 0) {
+      Prefetch q = pf; q.mode &= ~1;
+      pf_end<1>(T, st, q);
+      const int lane = threadIdx.x & 31;
+      if ((pf.mode & 1) && lane * 128 < pf.val_lines * 16) prefetch_l2(T.vcode + st.sp + (size_t)lane * 128);
+    }
+  } else pf_end<1>(T, st, pf);
   return (pf.mode & 4) && st.sp >= 0;
 }
 
@@ -47,8 +54,16 @@ struct TrHead {
   uint32_t skip[K];
   ColIter ci[K];
   const double *wp[K];
+  const uint8_t *cp8[K];     // value codes (T.vcode != nullptr)
   int maxl;
 };
+// weight of entry j of row k: the stored double, or its one-byte code looked up in the matrix' value table (same bits)
+template <int K>
+__device__ __forceinline__ double tr_weight(const SellView &T, const TrHead<K> &h, int k, int j)
+{
+  if (T.vcode) return __ldg(T.vtable + __ldg(h.cp8[k] + (size_t)j * 32));
+  return __ldg(h.wp[k] + (size_t)j * 32);
+}
 template <int K>
 __device__ __forceinline__ void tr_head(const SellView &T, const uint32_t *__restrict__ skip_rows, int64_t warp, int lane, TrHead<K> &h)
 {
@@ -72,6 +87,7 @@ __device__ __forceinline__ void tr_head(const SellView &T, const uint32_t *__res
     h.len[k] = live ? l : 0;
     h.skip[k] = sk;
     h.wp[k] = T.val + sp[k] + lane;
+    h.cp8[k] = T.vcode + sp[k] + lane;
     const bool uni = cp[k] < 0;
     h.ci[k] = ColIter{uni ? T.col + ~cp[k] : T.col + cp[k] + lane, uni ? 1 : 32, uni ? rr : 0};
     h.maxl = max(h.maxl, h.len[k]);
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   if (warp * K * 32 >= R.n) return;
   TrHead<K> h;
   tr_head<K>(R, skip_c, warp, lane, h);
-  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci; const double *(&wp)[K] = h.wp;
+  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci;
   const int maxl = h.maxl;
   const bool early = false;       // measured (513^3, B200): touching the far lines when the warp ENDS 1.14 ms, when it starts 1.63 ms
   (void)early;
@@ -123,7 +139,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
     for (int k = 0; k < K; k++) {
       const bool on = j < len[k];
       f[k] = on ? col_at(ci[k], j) : 0;
-      w[k] = on ? __ldg(wp[k] + (size_t)j * 32) : 0.0;
+      w[k] = on ? tr_weight<K>(R, h, k, j) : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < K; k++)
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
   }
   TrHead<K> h;
   tr_head<K>(P, skip_f, warp, lane, h);
-  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci; const double *(&wp)[K] = h.wp;
+  int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci;
   const int maxl = h.maxl;
   double tr[K][BS];
 #pragma unroll
@@ -224,7 +240,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
     for (int k = 0; k < K; k++) {
       const bool on = j < len[k];
       c[k] = on ? col_at(ci[k], j) : 0;
-      w[k] = on ? __ldg(wp[k] + (size_t)j * 32) : 0.0;
+      w[k] = on ? tr_weight<K>(P, h, k, j) : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < K; k++)

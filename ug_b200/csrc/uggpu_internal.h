@@ -41,6 +41,11 @@ struct SellMat {
   int32_t *col = nullptr;         // [col_len]
   int64_t  col_len = 0;           // int32 words in col (== padded while uncompressed)
   int64_t  uniform_slices = 0;
+  // transfer stencils only (sell_compress_values): when the matrix holds at most 256 distinct values (the weights of a geometric
+  // transfer: 1, 1/2, 1/4, 1/8), one byte per stored entry indexes a table -- the decoded doubles are the stored ones, bit for bit
+  uint8_t *vcode = nullptr;       // [padded]
+  double  *vtable = nullptr;      // [256]
+  int      nvals = 0;
   double  *val = nullptr;         // [padded*bb]
   double  *diag = nullptr;        // [nslices*32*bb] copy of entry 0 of every row (the diagonal block), same planar slice layout as val with width 1:
                                   // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
@@ -53,7 +58,7 @@ struct SellMat {
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
   // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
-  double entry_bytes() const { return 8.0 * (double)nnz * bb + 4.0 * (double)col_words; }
+  double entry_bytes() const { return (vcode ? 1.0 : 8.0) * (double)nnz * bb + 4.0 * (double)col_words; }
 };
 
 struct SellView {          // what a kernel needs (passed by value)
@@ -65,8 +70,10 @@ struct SellView {          // what a kernel needs (passed by value)
   const int32_t *col;
   const double *val;
   const double *diag;
+  const uint8_t *vcode;      // transfer stencils with a value table (else nullptr)
+  const double *vtable;
 };
-static inline SellView view(const SellMat &m) { return SellView{m.n, m.fixed_w, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag}; }
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.fixed_w, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag, m.vcode, m.vtable}; }
 
 #ifdef __CUDACC__
 // entry offset of slice s (and its width): computed for fixed-width matrices -- one dependent load less per row
@@ -88,7 +95,6 @@ struct Level {
   int n = 0, bs = 0;
   uint8_t *vclass = nullptr, *vnclass = nullptr, *ctl = nullptr;
   uint32_t *skip = nullptr;
-  bool uniform_flags = true;     // every row class 3 / both ctl bits (lets kernels skip flag reads? no: flags are always read)
   std::map<int, SellMat> mats;
   std::map<int, double *> vecs;
   std::map<int, cudaEvent_t> pending;   // vectors with an asynchronous upload in flight on the copy stream (uggpu_vec_upload_async)
@@ -259,6 +265,8 @@ int sell_free_schedules(uggpu_ctx *ctx, SellMat *m);          // gs.cu: drops th
 int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);
 // (re)builds m->diag from the values (after the matrix is built and after every change of its values)
 int sell_update_diag(uggpu_ctx *ctx, SellMat *m);
+// scalar-entry matrices with at most 256 distinct stored values get a one-byte code per entry + a table (lossless); no-op otherwise
+int sell_compress_values(uggpu_ctx *ctx, SellMat *m);
 
 // ---- kernels used across files --------------------------------------------------------------------------
 struct Damp { double a[UGGPU_MAX_BS]; };
