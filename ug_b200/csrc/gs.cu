@@ -38,6 +38,10 @@ struct TriSched {
   unsigned int *counters = nullptr;   // [nlev * 256 * 8]: finished slices per level and SM slot, one 32-byte sector each (k_trisolve)
   unsigned long long *mail = nullptr; // [256 * 16]: one progress word per SM slot, 128 bytes apart
   unsigned int epoch = 0;             // launches on this schedule so far
+  // point-to-point mode: per slice the (at most TRI_DEPS) slices it reads from, and one completion word per slice
+  int32_t *deps = nullptr;            // [nT/32 * 32], -1 = none
+  unsigned int *sdone = nullptr;      // [nT/32]: epoch of the launch that finished the slice
+  bool p2p_ok = false;
 };
 
 static int tri_free(uggpu_ctx *ctx, TriSched *&S)
@@ -51,6 +55,8 @@ static int tri_free(uggpu_ctx *ctx, TriSched *&S)
   if (S->level_first) dfree(ctx, S->level_first, (size_t)S->nlev);
   if (S->counters) dfree(ctx, S->counters, (size_t)S->nlev * 256 * 8);
   if (S->mail) dfree(ctx, S->mail, (size_t)256 * 16);
+  if (S->deps) dfree(ctx, S->deps, (size_t)S->nT);
+  if (S->sdone) dfree(ctx, S->sdone, (size_t)S->nT / 32);
   delete S;
   S = nullptr;
   return 0;
@@ -158,6 +164,51 @@ __global__ void k_tri_fill(int nT, int bb, const int32_t *__restrict__ perm, Sel
     for (int k = 0; k < bb; k++) cval[o * bb + k] = A.val[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane];
     o++;
   }
+}
+
+// pos[row] = schedule position
+__global__ void k_tri_pos(int nT, const int32_t *__restrict__ perm, int32_t *__restrict__ pos)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nT && perm[p] >= 0) pos[perm[p]] = p;
+}
+
+// deps[s*32 .. +32): the distinct schedule slices the rows of slice s read from (one warp per slice, a 64-slot hash set in shared
+// memory); more than 32 of them -> *overflow (the schedule then keeps to whole-level waits)
+__global__ void __launch_bounds__(256) k_tri_deps(SellView T, const int32_t *__restrict__ pos, int32_t *__restrict__ deps, int *overflow)
+{
+  __shared__ int set[8][64];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nsl = T.n >> 5;
+  if (s >= nsl) return;
+  set[wib][lane] = -1; set[wib][lane + 32] = -1;
+  __syncwarp();
+  const int p = s * 32 + lane;
+  const int len = T.rowlen[p];
+  const ColIter ci = col_iter(T, p);
+  bool over = false;
+  for (int j = 1; j < len; j++) {
+    const int ds = pos[col_at(ci, j)] >> 5;
+    int h = ds & 63, probe = 0;
+    for (; probe < 64; probe++) {
+      const int old = atomicCAS(&set[wib][h], -1, ds);
+      if (old == -1 || old == ds) break;
+      h = (h + 1) & 63;
+    }
+    if (probe == 64) over = true;
+  }
+  __syncwarp();
+  int base = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int val = set[wib][half * 32 + lane];
+    const unsigned m = __ballot_sync(0xffffffffu, val >= 0);
+    const int idx = base + __popc(m & ((1u << lane) - 1u));
+    if (val >= 0) { if (idx < 32) deps[(size_t)s * 32 + idx] = val; else over = true; }
+    base += __popc(m);
+  }
+  if (__any_sync(0xffffffffu, over) && lane == 0) atomicExch(overflow, 1);
 }
 
 static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSched **out)
@@ -276,6 +327,23 @@ static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSch
     cudaStreamSynchronize(st);
     dfree(ctx, d_rp, (size_t)S->nT + 1); dfree(ctx, ccol, (size_t)(nnzT > 0 ? nnzT : 1)); dfree(ctx, cval, (size_t)(nnzT > 0 ? nnzT : 1) * A->bb);
     if (rc) goto fail;
+    // point-to-point dependencies of every slice (pos = inverse of perm; lev[] is free by now and has n entries)
+    if (!getenv("UGGPU_GS_LEVELS")) {
+      int32_t *pos = lev;
+      int *d_over = d_count;
+      TB(dalloc(ctx, &S->deps, (size_t)S->nT)); TB(dalloc(ctx, &S->sdone, (size_t)S->nT / 32));
+      TC(cudaMemsetAsync(S->deps, 0xff, sizeof(int32_t) * (size_t)S->nT, st));
+      TC(cudaMemsetAsync(S->sdone, 0, sizeof(unsigned int) * (size_t)S->nT / 32, st));
+      TC(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+      k_tri_pos<<<(S->nT + 255) / 256, 256, 0, st>>>(S->nT, S->perm, pos);
+      ctx->launches++;
+      k_tri_deps<<<(S->nT / 32 + 7) / 8, 256, 0, st>>>(view(S->T), pos, S->deps, d_over);
+      ctx->launches++;
+      int over = 1;
+      TC(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, st));
+      TC(cudaStreamSynchronize(st));
+      S->p2p_ok = over == 0;
+    }
   }
   dfree(ctx, indeg, (size_t)n); dfree(ctx, lev, (size_t)n); dfree(ctx, fa, (size_t)n); dfree(ctx, fb, (size_t)n); dfree(ctx, d_count, 1);
   *out = S;
@@ -347,11 +415,15 @@ struct TriArgs {
   unsigned long long *mail;
   int nlev, nsl;
   unsigned int epoch;         // 1, 2, 3, ... per launch on this schedule
+  const int32_t *deps;        // point-to-point mode (P2P)
+  unsigned int *sdone;
 };
 
 // SOR: 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows: solve, then
 // v_i *= omega_i :1556)
-template <int BS, int SOR>
+// P2P: a slice waits for the slices it reads from (one completion word per slice) instead of the whole previous level -- no
+// monitor, no mailbox hop, no tail at the end of every level; available when every slice reads from at most 32 others.
+template <int BS, int SOR, bool P2P>
 __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a, double *v, const double *__restrict__ d, Damp omega, int *err)
 {
   constexpr int BB = BS * BS;
@@ -387,7 +459,32 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a,
     for (int k = 0; k < BB; k++) dg[k] = len > 0 ? __ldg(vp + (size_t)k * 32) : 1.0;
 #pragma unroll
     for (int i = 0; i < BS; i++) rhs[i] = len > 0 ? d[(size_t)r * BS + i] : 0.0;
-    if (lv > known) {
+    if (P2P) {
+      // every lane watches one of the slices this one reads from; all of them poll in parallel, so a finished dependency costs
+      // one L2 round trip, not one per stage.  The acquire loads + the warp vote order the gathers below behind the writers'
+      // release (fence + flag store) without another fence.
+      const int dep = a.deps[(size_t)s * 32 + lane];
+      bool ok = dep < 0 || ld_acquire_u32(a.sdone + dep) == a.epoch;
+      if (!__all_sync(0xffffffffu, ok)) {
+        unsigned long long t0 = 0, t1;
+        int spins = 0;
+        unsigned int ns = 32;
+        do {
+          if (!ok) {
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;
+            ok = ld_acquire_u32(a.sdone + dep) == a.epoch;
+            if (++spins == 1024) {
+              spins = 0;
+              if (*reinterpret_cast<volatile int *>(err)) ok = true;          // an earlier wait already failed: do not wait again
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t0 == 0) t0 = t1;
+              else if (t1 - t0 > 20000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); ok = true; }
+            }
+          }
+        } while (!__all_sync(0xffffffffu, ok));
+      }
+    } else if (lv > known) {
       unsigned long long t0 = 0, t1;
       int spins = 0;
       if (s == a.level_first[lv]) {
@@ -502,27 +599,33 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a,
     __syncwarp();
     if (lane == 0) {
       __threadfence();
-      atomicAdd(a.done + ((size_t)lv * TRI_SLOTS + slot) * 8, 1u);
+      if (P2P) *reinterpret_cast<volatile unsigned int *>(a.sdone + s) = a.epoch;
+      else atomicAdd(a.done + ((size_t)lv * TRI_SLOTS + slot) * 8, 1u);
     }
   }
 }
 
 // co-resident blocks of a k_trisolve instantiation (cooperative launch)
-template <int BS, int SOR>
-static int tri_launch(uggpu_ctx *ctx, const SellView &Tv, const TriArgs &a, double *v, const double *d, const Damp &om)
+template <int BS, int SOR, bool P2P>
+static int tri_launch2(uggpu_ctx *ctx, const SellView &Tv, const TriArgs &a, double *v, const double *d, const Damp &om)
 {
   static int per_sm = 0;       // per instantiation
   if (per_sm == 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trisolve<BS, SOR>, TRI_THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trisolve<BS, SOR, P2P>, TRI_THREADS, 0));
     if (per_sm < 1) return uggpu_fail(UGGPU_CUDA_ERROR, "k_trisolve does not fit on an SM");
   }
   int blocks = (a.nsl + TRI_THREADS / 32 - 1) / (TRI_THREADS / 32);
   if (blocks > per_sm * ctx->sm_count) blocks = per_sm * ctx->sm_count;
   SellView tv = Tv; TriArgs aa = a; Damp o = om; int *err = ctx->derr;
   void *args[] = {&tv, &aa, &v, &d, &o, &err};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_trisolve<BS, SOR>, dim3(blocks), dim3(TRI_THREADS), args, 0, ctx->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_trisolve<BS, SOR, P2P>, dim3(blocks), dim3(TRI_THREADS), args, 0, ctx->stream));
   ctx->launches++;
   return 0;
+}
+template <int BS, int SOR>
+static int tri_launch(uggpu_ctx *ctx, const SellView &Tv, const TriArgs &a, double *v, const double *d, const Damp &om)
+{
+  return a.deps ? tri_launch2<BS, SOR, true>(ctx, Tv, a, v, d, om) : tri_launch2<BS, SOR, false>(ctx, Tv, a, v, d, om);
 }
 
 static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const double *d, const double *omega)
@@ -537,9 +640,11 @@ static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const
   if (++S->epoch == 0xffffffffu) {       // the epoch arithmetic of the counters is modulo 2^32: start over well before it wraps
     CUDA_TRY(cudaMemsetAsync(S->counters, 0, sizeof(unsigned int) * (size_t)S->nlev * TRI_SLOTS * 8, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(S->mail, 0, sizeof(unsigned long long) * (size_t)TRI_SLOTS * 16, ctx->stream));
+    if (S->sdone) CUDA_TRY(cudaMemsetAsync(S->sdone, 0, sizeof(unsigned int) * (size_t)S->nT / 32, ctx->stream));
     S->epoch = 1;
   }
-  const TriArgs a{S->perm, S->slice_level, S->level_slices, S->level_first, S->counters, S->mail, S->nlev, S->nT / 32, S->epoch};
+  const TriArgs a{S->perm, S->slice_level, S->level_slices, S->level_first, S->counters, S->mail, S->nlev, S->nT / 32, S->epoch,
+                  S->p2p_ok ? S->deps : nullptr, S->sdone};
   const Damp om = mkdamp(omega, L->bs);
   const SellView Tv = view(S->T);
   // algorithmic bytes: the triangle's entries, row lengths and permutation, d read, v written, gathered v once
