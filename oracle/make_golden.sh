@@ -32,4 +32,10 @@ mkdir -p $G
 # matrices (created with CreateStandardNodeRestProl), scalar and 3x3 blocks; the transfer records use damping factors != 1
 ./_ref/ugoracle2 --grid tri --refine 3 --damp 0.8 --cycles 6 --imat --dump $G/imat_tri2d_r3.ugh --ops --solve > /dev/null
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --damp 0.6 --cycles 6 --imat --dump $G/imat_hex3d_bs3_r2.ugh --ops --solve > /dev/null
+# ---- ILU smoother: class ilu = l_ilubthdecomp + l_luiter inside lmgc; every dump holds, per level, the decomposed
+# matrix values (canonical entry order), one l_luiter, one smoother step, and the solve.  beta != 0 exercises the diagonal modification
+./_ref/ugoracle3 --grid tet --refine 3 --smoother ilu --beta 0.25 --damp 0.9 --cycles 6 --lean --dump $G/ilu_tet3d_r3.ugh --ops --solve > /dev/null
+./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --smoother ilu --beta 0.1 --damp 0.8 --cycles 5 --lean --dump $G/ilu_hex3d_bs3_r2.ugh --ops --solve > /dev/null
+./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --smoother ilu --damp 1.0 --cycles 6 --lean --dump $G/ilu_tet3d_adapt.ugh --ops --solve > /dev/null
+./_ref/ugoracle2 --grid quad --refine 3 --smoother ilu --beta 0.5 --damp 1.0 --cycles 4 --lean --dump $G/ilu_quad2d_r3.ugh --ops --solve > /dev/null
 ls -la $G

@@ -93,7 +93,8 @@ struct Opt {
   int bs = 1, refine = 3, adapt = 0, nu1 = 2, nu2 = 2, gamma = 1, cycles = 10, reps = 5;
   double damp = (DIM == 3) ? 0.6 : 0.8;
   std::string dump, gpu, barrier_dir;   // barrier_dir: --replicas rendezvous (see time_reference)
-  std::string smoother = "jac";         // reference smoother class used by lmgc: jac | gs | sgs | sor (iter.cc:10343-10366)
+  std::string smoother = "jac";         // reference smoother class used by lmgc: jac | gs | sgs | sor | ilu (iter.cc:10343-10366)
+  double beta = 0.0;                    // ilu $beta (iter.cc:5415): diagonal modification of l_ilubthdecomp
   int baselevel = 0;                    // lmgc $b
   int barrier_n = 0, barrier_id = 0;
   bool ops = false, solve = false, timeit = false, quiet = true;
@@ -307,7 +308,9 @@ static void build_hierarchy(const Opt &o)
 
 static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const char *lmgc, const char *transfer, const char *ls, int maxit)
 {
-  cmd("npcreate %ssmooth $c %s", pfx, jac);      cmd("npinit %ssmooth $damp %.17g", pfx, o.damp);
+  cmd("npcreate %ssmooth $c %s", pfx, jac);
+  if (o.smoother == "ilu") cmd("npinit %ssmooth $damp %.17g $beta %.17g", pfx, o.damp, o.beta);
+  else cmd("npinit %ssmooth $damp %.17g", pfx, o.damp);
   cmd("npcreate %sbaseit $c lu", pfx);           cmd("npinit %sbaseit", pfx);
   cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
   cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer%s", pfx, o.imat ? " $M" : "");
@@ -326,7 +329,8 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
   D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg));
   D.scalar_d("damp", o.damp); D.scalar_i("nu1", o.nu1); D.scalar_i("nu2", o.nu2); D.scalar_i("gamma", o.gamma);
   D.scalar_i("baselevel", o.baselevel);
-  D.scalar_i("smoother", o.smoother == "jac" ? 0 : o.smoother == "gs" ? 1 : o.smoother == "sgs" ? 2 : 3);
+  D.scalar_i("smoother", o.smoother == "jac" ? 0 : o.smoother == "gs" ? 1 : o.smoother == "sgs" ? 2 : o.smoother == "sor" ? 3 : 4);
+  if (o.smoother == "ilu") D.scalar_d("ilu_beta", o.beta);
   for (int l = 0; l <= top; l++) {
     if (gpuls::FlattenFlags(mg, l, vx, fl[l])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
     if (gpuls::FlattenMatrix(mg, l, mA, fl[l])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
@@ -381,6 +385,23 @@ static void dump_ops(const Opt &o)
     if (l_usor(g, vt, mA, vb, a3, NULL) != NUM_OK) { fprintf(stderr, "l_usor failed\n"); exit(7); }
     dumpvec("l_usor", vt, l);
     fill_lcg(vt, l, 4);
+    // ILU: what ILUPreProcess / ILUStep do (iter.cc:5444-5508): L = copy of A, l_ilubthdecomp (ugiter.cc:2252) with
+    // the class's beta and no threshold, then l_luiter (:4444).  The decomposed values are dumped in the canonical entry order.
+    if (o.smoother == "ilu") {
+      MATDATA_DESC *mL = NULL;
+      VEC_SCALAR beta;
+      for (int i = 0; i < MAX_VEC_COMP; i++) beta[i] = o.beta;
+      if (AllocMDFromMD(mg, l, l, mA, &mL)) { fprintf(stderr, "AllocMDFromMD failed\n"); exit(7); }
+      if (dmatcopy(mg, l, l, ALL_VECTORS, mL, mA) != NUM_OK) { fprintf(stderr, "dmatcopy failed\n"); exit(7); }
+      if (l_ilubthdecomp(g, mL, beta, NULL, NULL, NULL) != NUM_OK) { fprintf(stderr, "l_ilubthdecomp failed\n"); exit(7); }
+      gpuls::FlatLevel fL;
+      if (gpuls::FlattenFlags(mg, l, vx, fL) || gpuls::FlattenMatrix(mg, l, mL, fL)) { fprintf(stderr, "FlattenMatrix(L) failed\n"); exit(7); }
+      D.f64(L("ilu/val", l), fL.val);
+      if (l_luiter(g, vt, mL, vb) != NUM_OK) { fprintf(stderr, "l_luiter failed\n"); exit(7); }
+      dumpvec("l_luiter", vt, l);
+      fill_lcg(vt, l, 4);
+      if (FreeMD(mg, l, l, mL)) { fprintf(stderr, "FreeMD failed\n"); exit(7); }
+    }
     if (!o.lean) {
     // BLAS-2 (ALL_VECTORS, single level)
     dmatmul(mg, l, l, ALL_VECTORS, vt, mA, vx);       dumpvec("dmatmul", vt, l);
@@ -629,6 +650,7 @@ int main(int argc, char **argv)
     else if (a == "--verbose") o.quiet = false; else if (a == "--gpu") o.gpu = nxt();
     else if (a == "--smoother") o.smoother = nxt(); else if (a == "--baselevel") o.baselevel = atoi(nxt().c_str());
     else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
+    else if (a == "--beta") o.beta = atof(nxt().c_str());
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;
@@ -646,7 +668,7 @@ int main(int argc, char **argv)
   printf("hierarchy: dim=%d grid=%s bs=%d levels=%d fullrefinelevel=%d n=[", DIM, o.grid.c_str(), BS, top + 1, (int)FULLREFINELEVEL(mg));
   for (int l = 0; l <= top; l++) printf("%s%d", l ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
   printf("] build_s=%.2f\n", t1 - t0);
-  if (o.smoother != "jac" && o.smoother != "gs" && o.smoother != "sgs" && o.smoother != "sor") { fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str()); return 1; }
+  if (o.smoother != "jac" && o.smoother != "gs" && o.smoother != "sgs" && o.smoother != "sor" && o.smoother != "ilu") { fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str()); return 1; }
   if (o.imat)     // the interpolation matrices the $M mode works on (transgrid.cc:2363); the format reserves them ($I)
     for (int l = 1; l <= top; l++)
       if (CreateStandardNodeRestProl(GRID_ON_LEVEL(mg, l), BS) != NUM_OK) { fprintf(stderr, "CreateStandardNodeRestProl failed\n"); return 1; }

@@ -172,6 +172,12 @@ int ugport_smooth(const ugport_level *L, int kind, double *x, double *b, const d
     if ((err = ugport_l_lsor(L, x, b, damp))) return err;
     ugport_dmatmul(L, 2, 0, b, x);
     return 0;
+  case UGPORT_SM_ILU:                                       /* Smoother iter.cc:817-842 with ILUStep :5478 (L->ilu: ugport_ilu_decomp) */
+    if (!L->ilu) return 1;
+    if ((err = ugport_l_luiter(L, L->ilu, x, b))) return err;
+    ugport_dscalx(L, 0, x, damp);
+    ugport_dmatmul(L, 2, 0, b, x);
+    return 0;
   case UGPORT_SM_SGS:                                       /* SGSSmoother iter.cc:1392-1456 */
     if ((err = ugport_l_lgs(L, tmp, b))) return err;
     ugport_dscalx(L, 0, tmp, damp);
@@ -333,6 +339,140 @@ static int invert_small_block(int n, const double *mat, double *inv)
   inv[2] = ( mat[1] * mat[5] - mat[2] * mat[4]) * invdet;
   inv[5] = (-mat[0] * mat[5] + mat[2] * mat[3]) * invdet;
   inv[8] = ( mat[0] * mat[4] - mat[1] * mat[3]) * invdet;
+  return 0;
+}
+
+/* ---- ILU (SURVEY.md 8f.2 rest) ---------------------------------------------------------------------------------------------
+ * l_ilubthdecomp np/algebra/ugiter.cc:2252-2640 as class `ilu` calls it (ILUPreProcess np/procs/iter.cc:5468: beta = the class's
+ * $beta, threshold = rest = oldrestthresh = NULL, so VCUSED = 0 and no connection is ever created): incomplete decomposition on
+ * the pattern of A, in place on `val` (a copy of the level's values in the same entry order), right-looking like the reference:
+ * for every active row i in index order the diagonal (block) is inverted and STORED inverted (StoreInverse, :139), every entry
+ * (j,i), j > i active, becomes the pivot M_ji * D_i^-1, and row j receives -pivot * M_ik for the active k > i of row i IN ROW i's
+ * LIST ORDER -- on the pattern as a subtraction, off the pattern as the beta-modification of D_j (scalar :2418-2420: D_j +=
+ * beta*|pivot*M_ik| entry by entry; blocks :2598-2640: row sums of |Cor| per (i,j) pair, then D_j columns scaled by
+ * 1 + beta_l*RowSum_l).  Returns 0, or -(i+1) when the diagonal of row i cannot be inverted (the reference returns -i). */
+static int csr_find(const ugport_level *L, int r, int c)          /* GetMatrix gm/algebra.cc: the diagonal is the row's first entry */
+{
+  for (int e = L->rowptr[r]; e < L->rowptr[r + 1]; e++) if (L->col[e] == c) return e;
+  return -1;
+}
+
+int ugport_ilu_decomp(const ugport_level *L, const double *beta, double *val)
+{
+  int bs = L->bs, bb = bs * bs, n = L->n;
+  memcpy(val, L->val, sizeof(double) * (size_t)L->rowptr[n] * bb);          /* dmatcopy(L, A) iter.cc:5461 */
+  for (int i = 0; i < n; i++) {
+    if (L->vclass[i] < ACTIVE_CLASS) continue;
+    int e0 = L->rowptr[i], e1 = L->rowptr[i + 1];
+    if (bs == 1) {
+      double diag = val[e0];
+      if (fabs(diag) < 2.220446049250313e-16 * 10 * 1e-20) return -(i + 1);   /* SMALL_D*1e-20, low/architecture.h:27-34 */
+      double invdiag = 1.0 / diag;
+      val[e0] = invdiag;
+      for (int e = e0 + 1; e < e1; e++) {
+        int j = L->col[e];
+        if (!(L->vclass[j] >= ACTIVE_CLASS && j > i)) continue;
+        int ji = csr_find(L, j, i);                                            /* MADJ(Mij) */
+        if (ji < 0) return 1;
+        double pivot = val[ji] * invdiag;
+        val[ji] = pivot;
+        if (pivot == 0.0) continue;
+        for (int f = e0 + 1; f < e1; f++) {
+          int k = L->col[f];
+          if (!(L->vclass[k] >= ACTIVE_CLASS && k > i)) continue;
+          int jk = csr_find(L, j, k);
+          if (jk >= 0) val[jk] -= pivot * val[f];
+          else if (beta) val[L->rowptr[j]] += beta[0] * fabs(pivot * val[f]);
+        }
+      }
+      continue;
+    }
+    double inv[9], piv[9], cor[9], rowsum[UGPORT_MAX_BS], dampf[UGPORT_MAX_BS];
+    double *Diag = val + (size_t)e0 * bb;
+    if (invert_small_block(bs, Diag, inv)) return -(i + 1);
+    for (int l = 0; l < bb; l++) Diag[l] = inv[l];
+    for (int e = e0 + 1; e < e1; e++) {
+      int j = L->col[e];
+      if (!(L->vclass[j] >= ACTIVE_CLASS && j > i)) continue;
+      for (int l = 0; l < bs; l++) rowsum[l] = 0.0;
+      int ji = csr_find(L, j, i);
+      if (ji < 0) return 1;
+      double *Piv = val + (size_t)ji * bb;
+      int pivzero = 1;
+      for (int i0 = 0; i0 < bs; i0++)
+        for (int j0 = 0; j0 < bs; j0++) {
+          double sum = 0.0;
+          for (int k0 = 0; k0 < bs; k0++) sum += Piv[i0 * bs + k0] * inv[k0 * bs + j0];
+          piv[i0 * bs + j0] = sum;
+          if (sum != 0.0) pivzero = 0;
+        }
+      for (int l = 0; l < bb; l++) Piv[l] = piv[l];
+      if (pivzero) continue;
+      for (int f = e0 + 1; f < e1; f++) {
+        int k = L->col[f];
+        if (!(L->vclass[k] >= ACTIVE_CLASS && k > i)) continue;
+        const double *Elm = val + (size_t)f * bb;
+        int corzero = 1;
+        for (int i0 = 0; i0 < bs; i0++)
+          for (int j0 = 0; j0 < bs; j0++) {
+            double sum = 0.0;
+            for (int k0 = 0; k0 < bs; k0++) sum += piv[i0 * bs + k0] * Elm[k0 * bs + j0];
+            cor[i0 * bs + j0] = sum;
+            if (sum != 0.0) corzero = 0;
+          }
+        if (corzero) continue;
+        int jk = csr_find(L, j, k);
+        if (jk >= 0) {
+          double *Mat = val + (size_t)jk * bb;
+          for (int l = 0; l < bb; l++) Mat[l] -= cor[l];
+        } else {
+          for (int l = 0; l < bs; l++)
+            for (int m = 0; m < bs; m++) rowsum[l] += fabs(cor[l * bs + m] * 1.0 * 1.0);   /* j_/k_Normalization = 1 without VD_rest */
+        }
+      }
+      if (!beta) continue;
+      for (int m = 0; m < bs; m++) dampf[m] = 1.0 + beta[m] * rowsum[m];
+      double *Djj = val + (size_t)L->rowptr[j] * bb;
+      for (int m = 0; m < bs; m++)
+        for (int l = 0; l < bs; l++) Djj[m * bs + l] *= dampf[l];
+    }
+  }
+  return 0;
+}
+
+/* l_luiter ugiter.cc:4444-4796 on the decomposed values `lval` (pattern of the level): L v = d with Diag(L) = I over the active
+ * columns c < r in list order (inactive rows get 0), then U v = v over the active c > r, the stored inverse diagonal applied by
+ * multiplication (scalar :4510; blocks SolveInverseSmallBlock block.cc:225-253). */
+int ugport_l_luiter(const ugport_level *L, const double *lval, double *v, const double *d)
+{
+  int bs = L->bs, bb = bs * bs, n = L->n;
+  for (int pass = 0; pass < 2; pass++)
+    for (int q = 0; q < n; q++) {
+      int r = pass ? n - 1 - q : q;
+      double *vr = v + (size_t)r * bs;
+      if (L->vclass[r] < ACTIVE_CLASS) { if (!pass) for (int i = 0; i < bs; i++) vr[i] = 0.0; continue; }
+      double acc[UGPORT_MAX_BS] = {0.0, 0.0, 0.0}, s[UGPORT_MAX_BS];
+      for (int e = L->rowptr[r] + 1; e < L->rowptr[r + 1]; e++) {
+        int c = L->col[e];
+        if (!((pass ? c > r : c < r) && L->vclass[c] >= ACTIVE_CLASS)) continue;
+        const double *m = lval + (size_t)e * bb, *w = v + (size_t)c * bs;
+        for (int i = 0; i < bs; i++) {
+          double t = m[i * bs] * w[0];
+          for (int j = 1; j < bs; j++) t = t + m[i * bs + j] * w[j];
+          acc[i] += t;
+        }
+      }
+      if (!pass) { for (int i = 0; i < bs; i++) vr[i] = d[(size_t)r * bs + i] - acc[i]; continue; }
+      for (int i = 0; i < bs; i++) s[i] = vr[i] - acc[i];
+      const double *inv = lval + (size_t)L->rowptr[r] * bb;
+      if (bs == 1) vr[0] = s[0] * inv[0];
+      else
+        for (int i = 0; i < bs; i++) {
+          double sum = 0.0;
+          for (int j = 0; j < bs; j++) sum += inv[i * bs + j] * s[j];
+          vr[i] = sum;
+        }
+    }
   return 0;
 }
 

@@ -25,7 +25,7 @@ class _Level(C.Structure):
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("vclass", C.c_void_p), ("vnclass", C.c_void_p), ("ctl", C.c_void_p), ("skip", C.c_void_p),
                 ("p_rowptr", C.c_void_p), ("p_col", C.c_void_p), ("p_w", C.c_void_p),
-                ("r_rowptr", C.c_void_p), ("r_col", C.c_void_p), ("r_w", C.c_void_p)]
+                ("r_rowptr", C.c_void_p), ("r_col", C.c_void_p), ("r_w", C.c_void_p), ("ilu", C.c_void_p)]
 
 
 class _Cfg(C.Structure):
@@ -35,7 +35,7 @@ class _Cfg(C.Structure):
                 ("smoother", C.c_int), ("imat", C.c_int)]
 
 
-SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3}
+SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3, "ilu": 4}
 
 
 def build() -> str:
@@ -85,10 +85,11 @@ class PortBackend:
                     a = np.ascontiguousarray(a)
                     self._keep.append(a)
                 fields[k] = _p(a)
-            arr[i] = _Level(lv.n, lv.bs, **fields)
+            arr[i] = _Level(lv.n, lv.bs, ilu=None, **fields)
         self.levels = arr
         self.imat = bool(int(hier.raw["transfer_mode"][0])) if "transfer_mode" in getattr(hier, "raw", {}) else False
         self.vec: Dict[str, List[np.ndarray]] = {}
+        self._ilu: Dict[int, tuple] = {}          # level -> (beta, decomposed values)
 
     # ---- vectors
     def _v(self, name, level):
@@ -191,6 +192,22 @@ class PortBackend:
             args.append(self._vs(omega))
         return getattr(self.L, name)(*args)
 
+    def ilu_decomp(self, level, beta):
+        """ILUPreProcess iter.cc:5444: L = copy of A, l_ilubthdecomp(L, beta); the level keeps the decomposition."""
+        lv = self.h.levels[level]
+        val = np.zeros(len(lv.col) * lv.bs * lv.bs)
+        err = self.L.ugport_ilu_decomp(self._lp(level), self._vs([beta] * MAX_BS), _dp(val))
+        if err == 0:
+            self._ilu[level] = (float(beta), val)
+            self.levels[level].ilu = _p(val)
+        return err
+
+    def ilu_values(self, level):
+        return self._ilu[level][1].copy()
+
+    def l_luiter(self, level, v, d):
+        return self.L.ugport_l_luiter(self._lp(level), _dp(self._ilu[level][1]), _dp(self._v(v, level)), _dp(self._v(d, level)))
+
     def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
         return self.L.ugport_smooth(self._lp(level), SMOOTHERS[kind], _dp(self._v(x, level)), _dp(self._v(b, level)),
                                     self._vs(damp), _dp(self._v(tmp, level)))
@@ -215,6 +232,11 @@ class PortBackend:
         c.base_abslimit = cfg.get("base_abslimit", 1e-10)
         c.smoother = SMOOTHERS[cfg.get("smoother", "jac")]
         c.imat = 1 if self.imat else 0
+        if cfg.get("smoother") == "ilu":           # what LmgcPreProcess -> ILUPreProcess does on the levels above the base level
+            beta = float(cfg.get("ilu_beta", 0.0))
+            for l in range(c.baselevel + 1, len(self.h.levels)):
+                if l not in self._ilu or self._ilu[l][0] != beta:
+                    assert self.ilu_decomp(l, beta) == 0
         return c
 
     def _pp(self, name):

@@ -81,6 +81,13 @@ def replay_ops(be, hier, exact=True, vec_tol=1e-13, red_tol=1e-13, exact_red=Fal
                 assert be.l_gs(l, "t", "b", upper=upper, omega=omega) == 0
                 chk(name, l, "t")
             be.put(l, "t", d[f"L{l}/in/t"])
+        if f"L{l}/ilu/val" in d:          # ILU: decomposition values in canonical entry order, then l_luiter
+            assert be.ilu_decomp(l, float(d["ilu_beta"][0])) == 0
+            _cmp_vec(f"L{l}/ilu/val", be.ilu_values(l), d[f"L{l}/ilu/val"], exact, vec_tol); n += 1
+            be.put(l, "t", d[f"L{l}/in/t"])
+            assert be.l_luiter(l, "t", "b") == 0
+            chk("l_luiter", l, "t")
+            be.put(l, "t", d[f"L{l}/in/t"])
         if lean:
             be.put(l, "t", d[f"L{l}/in/t"])
             assert be.l_jac(l, "t", "b") == 0
@@ -145,7 +152,7 @@ def replay_ops(be, hier, exact=True, vec_tol=1e-13, red_tol=1e-13, exact_red=Fal
     return n
 
 
-SMOOTHER_NAMES = ("jac", "gs", "sgs", "sor")
+SMOOTHER_NAMES = ("jac", "gs", "sgs", "sor", "ilu")
 
 
 def smoother_of(hier):
@@ -158,7 +165,7 @@ def cycle_cfg(hier, **over):
     cfg = dict(nu1=int(d["nu1"][0]), nu2=int(d["nu2"][0]), gamma=int(d["gamma"][0]),
                baselevel=int(d["baselevel"][0]) if "baselevel" in d else 0, smoother=smoother_of(hier),
                smooth_damp=float(d["damp"][0]), cycle_damp=1.0, base_maxit=10, base_reduction=1e-8,
-               base_abslimit=1e-10)
+               base_abslimit=1e-10, ilu_beta=float(d["ilu_beta"][0]) if "ilu_beta" in d else 0.0)
     cfg.update(over)
     return cfg
 
