@@ -185,8 +185,25 @@ int uggpu_l_usor(uggpu_ctx*, int level, int v, int M, int d, const double *omega
 #define UGGPU_SM_GS  1   /* gs:  Smoother :817 + GSStep :1039    */
 #define UGGPU_SM_SGS 2   /* sgs: SGSSmoother :1392               */
 #define UGGPU_SM_SOR 3   /* sor: SORSmoother :4786 + SORStep :4744 (damp acts as omega inside l_lsor) */
+#define UGGPU_SM_ILU 4   /* ilu: Smoother :817 + ILUStep :5478 (l_luiter on the decomposition made by ILUPreProcess :5444) */
+
+/* ---- ILU, np/np.h:236,456,466 ------------------------------------------------------------------------------
+ * dmatcopy (np/algebra/ugblas.cc, np.h:236): M = A on levels fl..tl, mode UGGPU_ALL_VECTORS only.  A missing M is created
+ * with the pattern of A (what AllocMDFromMD + dmatcopy do in ILUPreProcess iter.cc:5457-5461); an existing M must have it.
+ * l_ilubthdecomp (np/algebra/ugiter.cc:2252) as class `ilu` calls it -- beta[bs] (NULL: no diagonal modification), no threshold,
+ * no rest vector, hence no new connections: incomplete decomposition of M on its own pattern, in place; the diagonal blocks are
+ * stored inverted (StoreInverse :139).  Rows are processed by dependency level of the lower triangle, every row receiving the
+ * reference's updates in the reference's order (pivot rows ascending, their entries in VSTART->MNEXT order): bit-identical to
+ * the sequential elimination.  Returns UGGPU_SMALL_DIAG when a diagonal (block) cannot be inverted.  It also (re)builds the
+ * two triangular-solve schedules of M.  One GPU only.
+ * l_luiter (ugiter.cc:4444): v = U^-1 L^-1 d with Diag(L) = I and the stored inverse diagonal of U; inactive rows get 0. */
+int uggpu_dmatcopy(uggpu_ctx*, int fl, int tl, int mode, int M, int A);
+int uggpu_l_ilubthdecomp(uggpu_ctx*, int level, int M, const double *beta /* [bs] or NULL */);
+int uggpu_l_luiter(uggpu_ctx*, int level, int v, int M, int d);
+
 /* One smoothing step of class `kind` in defect-correction form: on entry b = defect, on exit x = correction and b = new
- * defect.  tmp: handle of a work vector (sgs only, NP_SGS_t iter.cc:1386). */
+ * defect.  tmp: sgs -- handle of a work VECTOR (NP_SGS_t iter.cc:1386); ilu -- handle of the decomposed MATRIX
+ * (NP_SMOOTHER.L iter.cc:5459); ignored by the other classes. */
 int uggpu_smooth(uggpu_ctx*, int level, int kind, int x, int b, int A, const double *damp /* [bs] */, int tmp);
 
 /* ---- grid transfer, np/np.h:475-489 (np/algebra/transgrid.cc:462,529) ------------------------------- */
@@ -218,6 +235,9 @@ typedef struct uggpu_lmgc_cfg {
                                         1: fused kernels (identical results, fewer passes)      */
   int    smoother;                   /* UGGPU_SM_*: class of the pre- and post-smoother ($S); the fused schedule exists for
                                         jac, the other classes always run one kernel group per reference call */
+  int    smoother_L;                 /* ilu: matrix handle that receives the decomposition on every level above the base
+                                        level (NP_SMOOTHER.L, allocated by ILUPreProcess iter.cc:5459)                  */
+  double ilu_beta[UGGPU_MAX_BS];     /* ilu $beta      (iter.cc:5423)                           */
 } uggpu_lmgc_cfg;
 
 int uggpu_lmgc_preprocess(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int A);   /* LmgcPreProcess iter.cc:7707 */

@@ -93,8 +93,24 @@ class GpuBackend:
             args.append(capi._vs(omega))
         return fn(*args)
 
+    # ---- ILU (uggpu_dmatcopy + uggpu_l_ilubthdecomp = ILUPreProcess iter.cc:5444, uggpu_l_luiter)
+    def ilu_decomp(self, level, beta, L="__L"):
+        self.ctx.call("uggpu_dmatcopy", level, level, 0, self.ctx.handle(L), self.A)
+        return self.ctx.L.uggpu_l_ilubthdecomp(self.ctx.h, level, self.ctx.handle(L), capi._vs([beta]))
+
+    def ilu_values(self, level, L="__L"):
+        lv = self.h.levels[level]
+        rowptr = np.zeros(lv.n + 1, np.int32); col = np.zeros(lv.col.size, np.int32); val = np.zeros(lv.col.size * lv.bs * lv.bs)
+        self.ctx.call("uggpu_mat_get", level, self.ctx.handle(L), capi._p(rowptr), capi._p(col), capi._p(val))
+        assert np.array_equal(rowptr, lv.rowptr) and np.array_equal(col, lv.col), "pattern of the decomposition differs from A"
+        return val
+
+    def l_luiter(self, level, v, d, L="__L"):
+        return self.ctx.L.uggpu_l_luiter(self.ctx.h, level, self._v(v), self.ctx.handle(L), self._v(d))
+
     def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
-        return self.ctx.L.uggpu_smooth(self.ctx.h, level, capi.SMOOTHERS[kind], self._v(x), self._v(b), self.A, capi._vs(damp), self._v(tmp))
+        t = self.ctx.handle("__L") if kind == "ilu" else self._v(tmp)        # ilu: the decomposition made by ilu_decomp
+        return self.ctx.L.uggpu_smooth(self.ctx.h, level, capi.SMOOTHERS[kind], self._v(x), self._v(b), self.A, capi._vs(damp), t)
 
     def restrict(self, level, to, frm, damp):
         self.ctx.call("uggpu_restrict", level, self._v(to), self._v(frm), capi._vs(damp))
@@ -109,7 +125,7 @@ class GpuBackend:
                               smooth_damp=cfg["smooth_damp"], cycle_damp=cfg.get("cycle_damp", 1.0),
                               base_maxit=cfg.get("base_maxit", 10), base_reduction=cfg.get("base_reduction", 1e-8),
                               base_abslimit=cfg.get("base_abslimit", 1e-10), fused=self.fused, t=t,
-                              smoother=cfg.get("smoother", "jac"))
+                              smoother=cfg.get("smoother", "jac"), ilu_beta=cfg.get("ilu_beta", 0.0))
         return c
 
     def lmgc(self, level, c, b, cfg, t="__t"):

@@ -27,8 +27,13 @@ CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--baselevel", "2", "--damp", "0.6", "--cycles", "5"]),
     # transfer $M: stored interpolation matrices (RestrictByMatrix / InterpolateCorrectionByMatrix) against gputransfer $M
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--imat", "--damp", "0.6", "--cycles", "5"]),
+    # ILU smoother (iter.gpuilu against the reference's ilu: l_ilubthdecomp with $beta + l_luiter)
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "ilu", "--beta", "0.25", "--damp", "0.9", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--smoother", "ilu", "--beta", "0.1", "--damp", "0.8", "--cycles", "4"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--smoother", "ilu", "--damp", "1.0", "--cycles", "5"]),
 ]
-IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat"]
+IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
+       "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)

@@ -159,6 +159,51 @@ def test_synth_gs_family_bitexact_vs_port(cells, dim, top, kind, smoother, damp)
         assert np.array_equal(bg[l], bp[l]), l
 
 
+@pytest.mark.parametrize("cells,dim,top,kind,beta,damp", [(2, 3, 4, 0, 0.0, 1.0), (2, 3, 3, 0, 0.35, 0.9), (1, 3, 3, 2, 0.1, 0.9), (2, 3, 3, 1, 0.2, 1.0),
+                                                          (3, 2, 5, 0, 0.5, 1.0)],
+                         ids=["P1-33^3-ilu", "P1-17^3-ilu-beta", "elast-9^3-ilu-beta", "Q1-17^3-ilu-beta", "P1-2d-97^2-ilu-beta"])
+def test_synth_ilu_bitexact_vs_port(cells, dim, top, kind, beta, damp):
+    """ILU smoother (l_ilubthdecomp + l_luiter, class ilu) on lexicographic synthetic hierarchies: the decomposed
+    matrix (every stored value), one l_luiter, then the cycle with the class as smoother -- bit for bit against the sequential
+    oracle port (which is pinned against the reference's own dumps, tests/golden/ilu_*.ugh)."""
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    ctx = _synth(cells, dim, top, kind)
+    hier = ctx.download_hierarchy(top)
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    rhs = ctx.get(top, "b")
+    ctx.close()
+    bs = hier.bs
+    rng = np.random.default_rng(11)
+    d0 = np.round(rng.standard_normal(hier.levels[top].n * bs) * 1024) / 1024
+    gpu, port = GpuBackend(hier, fused=0), PortBackend(hier)
+    res = []
+    for be in (gpu, port):
+        assert be.ilu_decomp(top, beta) == 0
+        be.put(top, "d", d0); be.put(top, "v", np.full(d0.size, 3.0))
+        assert be.l_luiter(top, "v", "d") == 0
+        res.append((be.ilu_values(top), be.get(top, "v")))
+    assert np.array_equal(res[0][0], res[1][0]), "decomposition differs"
+    assert np.array_equal(res[0][1], res[1][1]), "l_luiter differs"
+    assert not np.array_equal(res[1][0], hier.levels[top].val)
+    cfg = dict(nu1=1, nu2=1, gamma=1, baselevel=0, smooth_damp=damp, smoother="ilu", ilu_beta=beta)
+    out = []
+    for be in (gpu, port):
+        for l, lv in enumerate(hier.levels):
+            be.put(l, "x", np.zeros(lv.n * lv.bs)); be.put(l, "b", rhs if l == top else np.zeros(lv.n * lv.bs))
+        be.ls_defect(0, top, "x", "b")
+        its, first, hist = be.solve(top, "x", "b", cfg, 4)
+        out.append((its, hist, [be.get(l, "x") for l in range(top + 1)], [be.get(l, "b") for l in range(top + 1)]))
+    gpu.close()
+    (ig, hg, xg, bg), (ip, hp, xp, bp) = out
+    assert ig == ip == 4 and hp[-1] < 0.2 * hp[bs - 1]
+    assert np.max(np.abs(hg - hp) / np.maximum(hp, 1e-300)) < 1e-12
+    for l in range(top + 1):
+        assert np.array_equal(xg[l], xp[l]), l
+        assert np.array_equal(bg[l], bp[l]), l
+
+
+
 def test_synth_properties_large():
     """65^3 = 274 625 unknowns: properties that do not need the CPU checker."""
     cells, top = 2, 5

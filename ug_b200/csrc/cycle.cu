@@ -77,48 +77,7 @@ __global__ void k_lu_scatter_block(SellView A, int bs, int n, double *__restrict
   }
 }
 
-// InvertSmallBlock, np/algebra/block.cc:272-321 (closed forms for n = 2, 3); returns non-zero for det == 0
-template <int BS>
-__device__ __forceinline__ int invert_small_block(const double *mat, double *inv)
-{
-  if (BS == 2) {
-    double det = mat[0] * mat[3] - mat[1] * mat[2];
-    if (det == 0.0) return 1;
-    double invdet = 1.0 / det;
-    inv[0] = mat[3] * invdet; inv[1] = -mat[1] * invdet; inv[2] = -mat[2] * invdet; inv[3] = mat[0] * invdet;
-    return 0;
-  }
-  double det = mat[0] * mat[4] * mat[8 % (BS * BS)] + mat[1] * mat[5 % (BS * BS)] * mat[6 % (BS * BS)] + mat[2] * mat[3] * mat[7 % (BS * BS)]
-               - mat[2] * mat[4] * mat[6 % (BS * BS)] - mat[0] * mat[5 % (BS * BS)] * mat[7 % (BS * BS)] - mat[1] * mat[3] * mat[8 % (BS * BS)];
-  if (det == 0.0) return 1;
-  double invdet = 1.0 / det;
-  constexpr int BB = BS * BS;
-  inv[0] = ( mat[4 % BB] * mat[8 % BB] - mat[5 % BB] * mat[7 % BB]) * invdet;
-  inv[3] = (-mat[3] * mat[8 % BB] + mat[5 % BB] * mat[6 % BB]) * invdet;
-  inv[6 % BB] = ( mat[3] * mat[7 % BB] - mat[4 % BB] * mat[6 % BB]) * invdet;
-  inv[1] = (-mat[1] * mat[8 % BB] + mat[2] * mat[7 % BB]) * invdet;
-  inv[4 % BB] = ( mat[0] * mat[8 % BB] - mat[2] * mat[6 % BB]) * invdet;
-  inv[7 % BB] = (-mat[0] * mat[7 % BB] + mat[1] * mat[6 % BB]) * invdet;
-  inv[2] = ( mat[1] * mat[5 % BB] - mat[2] * mat[4 % BB]) * invdet;
-  inv[5 % BB] = (-mat[0] * mat[5 % BB] + mat[2] * mat[3]) * invdet;
-  inv[8 % BB] = ( mat[0] * mat[4 % BB] - mat[1] * mat[3]) * invdet;
-  return 0;
-}
-
-// C = A * B for bs x bs blocks with the reference's summation (sum = 0; sum += a*b, ugiter.cc:3814-3822); returns true if C == 0
-template <int BS>
-__device__ __host__ __forceinline__ bool block_mul(const double *a, const double *b, double *c)
-{
-  bool zero = true;
-  for (int i0 = 0; i0 < BS; i0++)
-    for (int j0 = 0; j0 < BS; j0++) {
-      double sum = 0.0;
-      for (int k0 = 0; k0 < BS; k0++) sum += a[i0 * BS + k0] * b[k0 * BS + j0];
-      c[i0 * BS + j0] = sum;
-      if (sum != 0.0) zero = false;
-    }
-  return zero;
-}
+// invert_small_block<BS>, block_mul<BS>: uggpu_internal.h (shared with the ILU decomposition in gs.cu)
 
 // Step i: invert the diagonal block and store the inverse (:3784-3793); every block (j,i), j > i, becomes the multiplier
 // M_ji * Inv (:3811-3826); every block (j,k), j,k > i, with a non-zero multiplier and a non-zero correction M_ji * M_ik
@@ -459,7 +418,13 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
     UG_TRY(ensure_vec(ctx, l, cfg->t));
     UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_B));
     if (l > bl && cfg->smoother != UGGPU_SM_JAC) {          // GSPreProcess / SGSPreProcess / SORPreProcess (iter.cc:1003,1353,4717)
-      if (cfg->smoother < UGGPU_SM_JAC || cfg->smoother > UGGPU_SM_SOR) return uggpu_fail(UGGPU_ERROR, "lmgc: unknown smoother class %d", cfg->smoother);
+      if (cfg->smoother < UGGPU_SM_JAC || cfg->smoother > UGGPU_SM_ILU) return uggpu_fail(UGGPU_ERROR, "lmgc: unknown smoother class %d", cfg->smoother);
+      if (cfg->smoother == UGGPU_SM_ILU) {               // ILUPreProcess iter.cc:5444: L = copy of A, decomposed in place
+        if (cfg->smoother_L == A) return uggpu_fail(UGGPU_DESC_MISMATCH, "lmgc: the ILU decomposition needs its own matrix handle");
+        UG_TRY(uggpu_dmatcopy(ctx, l, l, UGGPU_ALL_VECTORS, cfg->smoother_L, A));
+        UG_TRY(uggpu_l_ilubthdecomp(ctx, l, cfg->smoother_L, cfg->ilu_beta));
+        continue;
+      }
       UG_TRY(uggpu_gs_preprocess(ctx, l, A));
       if (cfg->smoother == UGGPU_SM_SGS) UG_TRY(ensure_vec(ctx, l, UGGPU_VEC_TMP_A));
     }
@@ -574,7 +539,7 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
   const int t = cfg->t;
   double one[UGGPU_MAX_BS] = {1.0, 1.0, 1.0};
   for (int i = 0; i < cfg->nu1; i++) {
-    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, UGGPU_VEC_TMP_A));
+    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, cfg->smoother == UGGPU_SM_ILU ? cfg->smoother_L : UGGPU_VEC_TMP_A));
     UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
   }
   UG_TRY(uggpu_restrict(ctx, level, b, b, one));                                   // iter.cc:7843, Factor_One
@@ -584,7 +549,7 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
   UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));                  // :7903
   UG_TRY(uggpu_dmatmul_minus(ctx, level, level, UGGPU_ALL_VECTORS, b, A, t));      // :7905
   for (int i = 0; i < cfg->nu2; i++) {
-    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, UGGPU_VEC_TMP_A));
+    UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, cfg->smoother == UGGPU_SM_ILU ? cfg->smoother_L : UGGPU_VEC_TMP_A));
     UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
   }
   return 0;

@@ -42,6 +42,7 @@ struct TriSched {
   int32_t *deps = nullptr;            // [nT/32 * 32], -1 = none
   unsigned int *sdone = nullptr;      // [nT/32]: epoch of the launch that finished the slice
   bool p2p_ok = false;
+  std::vector<int> h_poff, h_lsl;     // host copies: first schedule row and slices of every level (the ILU decomposition launches per level)
 };
 
 static int tri_free(uggpu_ctx *ctx, TriSched *&S)
@@ -277,6 +278,7 @@ static int tri_build(uggpu_ctx *ctx, Level *L, const SellMat *A, int dir, TriSch
     }
     if (pacc > 2147483647LL - 64) { rc = uggpu_fail(UGGPU_ERROR, "Gauss-Seidel schedule too long"); goto fail; }
     S->nT = (int)pacc;
+    S->h_poff = poff; S->h_lsl = lsl;
     const int nslT = S->nT / 32;
     std::vector<int32_t> sl((size_t)nslT);
     for (int l = 0, s = 0; l < S->nlev; l++) for (int k = 0; k < lsl[l]; k++) sl[s++] = l;
@@ -419,8 +421,10 @@ struct TriArgs {
   unsigned int *sdone;
 };
 
-// SOR: 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows: solve, then
-// v_i *= omega_i :1556)
+// SOR (the solve's mode): 0 = l_lgs / l_ugs, 1 = l_lsor / l_usor (scalar rows: omega*(d-sum)/diag ugiter.cc:1400; block rows:
+// solve, then v_i *= omega_i :1556), 2 = lower sweep of l_luiter (Diag(L) = I: v = d - sum, ugiter.cc:4490,4648), 3 = upper sweep
+// of l_luiter (right-hand side = v itself, stored inverse diagonal applied by multiplication :4510, SolveInverseSmallBlock
+// block.cc:225)
 // P2P: a slice waits for the slices it reads from (one completion word per slice) instead of the whole previous level -- no
 // monitor, no mailbox hop, no tail at the end of every level; available when every slice reads from at most 32 others.
 template <int BS, int SOR, bool P2P>
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a,
 #pragma unroll
     for (int k = 0; k < BB; k++) dg[k] = len > 0 ? __ldg(vp + (size_t)k * 32) : 1.0;
 #pragma unroll
-    for (int i = 0; i < BS; i++) rhs[i] = len > 0 ? d[(size_t)r * BS + i] : 0.0;
+    for (int i = 0; i < BS; i++) rhs[i] = len > 0 ? (SOR == 3 ? __ldcg(v + (size_t)r * BS + i) : d[(size_t)r * BS + i]) : 0.0;
     if (P2P) {
       // every lane watches one of the slices this one reads from; all of them poll in parallel, so a finished dependency costs
       // one L2 round trip, not one per stage.  The acquire loads + the warp vote order the gathers below behind the writers'
@@ -564,13 +568,26 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a,
           if (j < len) term(j, cj[j - 1]);
         for (int j = TRI_PRE + 1; j < len; j++) term(j, col_at(ci, j));
         if (BS == 1) {
-          if (SOR) sol[0] = omega.a[0] * (rhs[0] - acc[0]) / dg[0];
+          if (SOR == 1) sol[0] = omega.a[0] * (rhs[0] - acc[0]) / dg[0];
+          else if (SOR == 2) sol[0] = rhs[0] - acc[0];
+          else if (SOR == 3) sol[0] = (rhs[0] - acc[0]) * dg[0];
           else sol[0] = (rhs[0] - acc[0]) / dg[0];
         } else {
 #pragma unroll
           for (int i = 0; i < BS; i++) rhs[i] = rhs[i] - acc[i];
           // SolveSmallBlock (block.cc:104-142), same closed forms as solve_small_block in spmv.cu
-          if (BS == 2) {
+          if (SOR == 2) {
+#pragma unroll
+            for (int i = 0; i < BS; i++) sol[i] = rhs[i];
+          } else if (SOR == 3) {
+#pragma unroll
+            for (int i = 0; i < BS; i++) {
+              double sum = 0.0;
+#pragma unroll
+              for (int q = 0; q < BS; q++) sum += dg[i * BS + q] * rhs[q];
+              sol[i] = sum;
+            }
+          } else if (BS == 2) {
             double det = dg[0] * dg[3 % BB] - dg[1 % BB] * dg[2 % BB];
             if (det == 0.0) { atomicExch(err, UGGPU_SMALL_DIAG); det = 1.0; }
             det = 1.0 / det;
@@ -586,7 +603,7 @@ __global__ void __launch_bounds__(TRI_THREADS) k_trisolve(SellView T, TriArgs a,
                           / (dg[4 % BB] - M3div0 * dg[1 % BB]);
             sol[0] = (rhs[0] - dg[1 % BB] * sol[1 % BS] - dg[2 % BB] * sol[2 % BS]) / dg[0];
           }
-          if (SOR) {
+          if (SOR == 1) {
 #pragma unroll
             for (int i = 0; i < BS; i++) sol[i] = sol[i] * omega.a[i];
           }
@@ -628,12 +645,13 @@ static int tri_launch(uggpu_ctx *ctx, const SellView &Tv, const TriArgs &a, doub
   return a.deps ? tri_launch2<BS, SOR, true>(ctx, Tv, a, v, d, om) : tri_launch2<BS, SOR, false>(ctx, Tv, a, v, d, om);
 }
 
-static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const double *d, const double *omega)
+// lu: 0 Gauss-Seidel / SOR (omega != NULL), 2 / 3 lower / upper sweep of l_luiter (mode of k_trisolve)
+static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const double *d, const double *omega, int lu = 0)
 {
   Level *L = get_level(ctx, level);
   SellMat *A = get_mat(ctx, level, M);
   if (!L || !A) return UGGPU_DESC_MISMATCH;
-  if (v == d) return uggpu_fail(UGGPU_DESC_MISMATCH, "Gauss-Seidel solve: result and right-hand side are the same vector");
+  if (v == d && lu != 3) return uggpu_fail(UGGPU_DESC_MISMATCH, "Gauss-Seidel solve: result and right-hand side are the same vector");
   if (L->n == 0) return 0;
   if (!A->tri[dir]) UG_TRY(uggpu_gs_preprocess(ctx, level, M));
   TriSched *S = A->tri[dir];
@@ -649,11 +667,16 @@ static int tri_solve(uggpu_ctx *ctx, int level, int M, int dir, double *v, const
   const SellView Tv = view(S->T);
   // algorithmic bytes: the triangle's entries, row lengths and permutation, d read, v written, gathered v once
   ProfScope ps(ctx, UGGPU_K_TRISOLVE, level, S->T.entry_bytes() + 6.0 * S->nT + 8.0 * L->bs * 3.0 * L->n);
+  const int mode = lu ? lu : (omega ? 1 : 0);
+#define TRI_CASE(BS_) \
+  switch (mode) { case 0: return tri_launch<BS_, 0>(ctx, Tv, a, v, d, om); case 1: return tri_launch<BS_, 1>(ctx, Tv, a, v, d, om); \
+                  case 2: return tri_launch<BS_, 2>(ctx, Tv, a, v, d, om); default: return tri_launch<BS_, 3>(ctx, Tv, a, v, d, om); }
   switch (L->bs) {
-    case 1: return omega ? tri_launch<1, 1>(ctx, Tv, a, v, d, om) : tri_launch<1, 0>(ctx, Tv, a, v, d, om);
-    case 2: return omega ? tri_launch<2, 1>(ctx, Tv, a, v, d, om) : tri_launch<2, 0>(ctx, Tv, a, v, d, om);
-    default: return omega ? tri_launch<3, 1>(ctx, Tv, a, v, d, om) : tri_launch<3, 0>(ctx, Tv, a, v, d, om);
+    case 1: TRI_CASE(1)
+    case 2: TRI_CASE(2)
+    default: TRI_CASE(3)
   }
+#undef TRI_CASE
 }
 
 static int tri_entry(uggpu_ctx *ctx, int level, int v, int M, int d, int dir, const double *omega)
@@ -678,9 +701,218 @@ extern "C" int uggpu_l_usor(uggpu_ctx *ctx, int level, int v, int M, int d, cons
   return tri_entry(ctx, level, v, M, d, 1, omega);
 }
 
+// ---- ILU: l_ilubthdecomp ugiter.cc:2252 as class `ilu` calls it, l_luiter :4444 ----------------------------------
+// The reference eliminates right-looking: row i (ascending) turns every entry (j,i), j > i, into the pivot M_ji * D_i^-1 and sends
+// -pivot * M_ik into row j for the k > i of row i in row i's list order.  Seen from row j these are: for its lower neighbours i in
+// ASCENDING order, the entries of row i in list order -- a left-looking sweep that needs rows i complete, i.e. exactly the
+// dependency levels of the lower triangular solve.  One launch per level (the kernel boundary is the barrier: no spin-waits in a
+// setup step), one thread per row; the row's own entries are updated in place in the matrix's SELL storage, with separate
+// multiply and subtract like the reference's statements.  Connections are never created (no threshold, VCUSED = 0): what falls
+// off the pattern goes into the beta-modification of the diagonal (scalar :2418, blocks :2598-2640).
+template <int BS>
+__global__ void __launch_bounds__(128) k_ilu_factor_level(SellView A, double *val, const uint8_t *__restrict__ vclass,
+                                                          const int32_t *__restrict__ perm, int p0, int p1, Damp beta, int use_beta, int *err)
+{
+  constexpr int BB = BS * BS;
+  const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p1) return;
+  const int r = perm[p];
+  if (r < 0 || vclass[r] < 3) return;                       // L_VLOOP__CLASS(..., ACTIVE_CLASS): other rows stay as copied
+  const int len = A.rowlen[r];
+  const ColIter ci = col_iter(A, r);
+  double *vr = val + slice_off(A, r >> 5) * BB + (r & 31);   // component k of entry j of this row: vr[(j*BB + k)*32]
+  int last = -1;
+  for (;;) {
+    int i = 0x7fffffff, ji = -1;                            // the next lower neighbour in index order
+    for (int j = 1; j < len; j++) {
+      const int c = col_at(ci, j);
+      if (c > last && c < r && c < i && vclass[c] >= 3) { i = c; ji = j; }
+    }
+    if (ji < 0) break;
+    last = i;
+    const int leni = A.rowlen[i];
+    const ColIter cii = col_iter(A, i);
+    const double *vi = val + slice_off(A, i >> 5) * BB + (i & 31);
+    if (BS == 1) {
+      const double pivot = vr[(size_t)ji * 32] * vi[0];     // vi[0]: the stored inverse diagonal of row i
+      vr[(size_t)ji * 32] = pivot;
+      if (pivot == 0.0) continue;
+      for (int q = 1; q < leni; q++) {
+        const int k = col_at(cii, q);
+        if (!(k > i && vclass[k] >= 3)) continue;
+        const double mik = vi[(size_t)q * 32];
+        int t = -1;                                          // GetMatrix(vj, vk)
+        for (int j = 0; j < len; j++) if (col_at(ci, j) == k) { t = j; break; }
+        if (t >= 0) { const double pr = pivot * mik; vr[(size_t)t * 32] = vr[(size_t)t * 32] - pr; }
+        else if (use_beta) { const double pr = beta.a[0] * fabs(pivot * mik); vr[0] = vr[0] + pr; }
+      }
+    } else {
+      double inv[BB], pm[BB], pv[BB], cor[BB], rowsum[BS];
+#pragma unroll
+      for (int k = 0; k < BB; k++) { inv[k] = vi[(size_t)k * 32]; pv[k] = vr[((size_t)ji * BB + k) * 32]; }
+      const bool pivzero = block_mul<BS>(pv, inv, pm);
+#pragma unroll
+      for (int k = 0; k < BB; k++) vr[((size_t)ji * BB + k) * 32] = pm[k];
+      if (pivzero) continue;
+#pragma unroll
+      for (int l = 0; l < BS; l++) rowsum[l] = 0.0;
+      for (int q = 1; q < leni; q++) {
+        const int k = col_at(cii, q);
+        if (!(k > i && vclass[k] >= 3)) continue;
+        double elm[BB];
+#pragma unroll
+        for (int c = 0; c < BB; c++) elm[c] = vi[((size_t)q * BB + c) * 32];
+        if (block_mul<BS>(pm, elm, cor)) continue;           // CorIsZero
+        int t = -1;
+        for (int j = 0; j < len; j++) if (col_at(ci, j) == k) { t = j; break; }
+        if (t >= 0) {
+#pragma unroll
+          for (int c = 0; c < BB; c++) vr[((size_t)t * BB + c) * 32] = vr[((size_t)t * BB + c) * 32] - cor[c];
+        } else {
+#pragma unroll
+          for (int l = 0; l < BS; l++)
+#pragma unroll
+            for (int m = 0; m < BS; m++) rowsum[l] += fabs(cor[l * BS + m]);      // normalisation factors are 1 without a rest vector
+        }
+      }
+      if (!use_beta) continue;
+      double dampf[BS];
+#pragma unroll
+      for (int m = 0; m < BS; m++) dampf[m] = 1.0 + beta.a[m] * rowsum[m];
+#pragma unroll
+      for (int m = 0; m < BS; m++)
+#pragma unroll
+        for (int l = 0; l < BS; l++) vr[(size_t)(m * BS + l) * 32] = vr[(size_t)(m * BS + l) * 32] * dampf[l];
+    }
+  }
+  // the row's own diagonal: invert and store the inverse (:2367-2373 scalar, :2445-2452 blocks)
+  if (BS == 1) {
+    const double diag = vr[0];
+    if (fabs(diag) < 2.220446049250313e-16 * 10.0 * 1e-20) { atomicExch(err, UGGPU_SMALL_DIAG); return; }   // SMALL_D*1e-20
+    vr[0] = 1.0 / diag;
+  } else {
+    double dg[BB], inv[BB];
+#pragma unroll
+    for (int k = 0; k < BB; k++) dg[k] = vr[(size_t)k * 32];
+    if (invert_small_block<BS>(dg, inv)) { atomicExch(err, UGGPU_SMALL_DIAG); return; }
+#pragma unroll
+    for (int k = 0; k < BB; k++) vr[(size_t)k * 32] = inv[k];
+  }
+}
+
+// the values of the permuted triangle T after the matrix it was cut from changed (same entry selection and order as k_tri_fill)
+__global__ void k_tri_refresh(int nT, int bb, const int32_t *__restrict__ perm, SellView A, const double *__restrict__ aval,
+                              const uint8_t *__restrict__ vclass, int dir, SellView T, double *__restrict__ tval)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nT) return;
+  const int r = perm[p];
+  if (r < 0 || vclass[r] < 3) return;
+  const int rl = A.rowlen[r], lane = r & 31;
+  const int64_t sp = slice_off(A, r >> 5), spT = slice_off(T, p >> 5);
+  const ColIter ci = col_iter(A, r);
+  int o = 0;
+  for (int j = 0; j < rl; j++) {
+    const int c = col_at(ci, j);
+    if (j > 0 && !(solved_side(dir, r, c) && vclass[c] >= 3)) continue;
+    for (int k = 0; k < bb; k++) tval[(spT + (int64_t)o * 32) * bb + (int64_t)k * 32 + (p & 31)] = aval[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane];
+    o++;
+  }
+}
+
+// existing solve schedules of A carry their own copy of the values: bring them up to date after A's values changed
+static int tri_refresh_all(uggpu_ctx *ctx, Level *L, SellMat *A)
+{
+  for (int dir = 0; dir < 2; dir++) {
+    TriSched *T = A->tri[dir];
+    if (!T) continue;
+    k_tri_refresh<<<(T->nT + 255) / 256, 256, 0, ctx->stream>>>(T->nT, A->bb, T->perm, view(*A), A->val, L->vclass, dir, view(T->T), T->T.val);
+    KCHECK(ctx);
+    UG_TRY(sell_update_diag(ctx, &T->T));
+  }
+  return 0;
+}
+
+extern "C" int uggpu_dmatcopy(uggpu_ctx *ctx, int fl, int tl, int mode, int M, int A)
+{
+  if (mode != UGGPU_ALL_VECTORS) return uggpu_fail(UGGPU_ERROR, "dmatcopy: only ALL_VECTORS is supported");
+  if (M == A) return uggpu_fail(UGGPU_DESC_MISMATCH, "dmatcopy: source and destination are the same matrix");
+  for (int l = fl; l <= tl; l++) {
+    Level *L = get_level(ctx, l);
+    SellMat *src = get_mat(ctx, l, A);
+    if (!L || !src) return UGGPU_DESC_MISMATCH;
+    auto it = L->mats.find(M);
+    if (it != L->mats.end()) {
+      SellMat *dst = &it->second;
+      if (dst->n == src->n && dst->bb == src->bb && dst->nnz == src->nnz && dst->padded == src->padded && dst->col_len == src->col_len && dst->fixed_w == src->fixed_w) {
+        // same pattern (made by an earlier copy): the values only, also into the solve schedules M may have
+        CUDA_TRY(cudaMemcpyAsync(dst->val, src->val, sizeof(double) * (size_t)src->padded * src->bb, cudaMemcpyDeviceToDevice, ctx->stream));
+        UG_TRY(sell_update_diag(ctx, dst));
+        UG_TRY(tri_refresh_all(ctx, L, dst));
+        continue;
+      }
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      UG_TRY(sell_free(ctx, dst));
+      L->mats.erase(it);
+    }
+    SellMat m;
+    UG_TRY(sell_clone(ctx, src, &m));
+    L->mats[M] = m;
+  }
+  return 0;
+}
+
+extern "C" int uggpu_l_ilubthdecomp(uggpu_ctx *ctx, int level, int M, const double *beta)
+{
+  Level *L = get_level(ctx, level);
+  SellMat *A = get_mat(ctx, level, M);
+  if (!L || !A) return UGGPU_DESC_MISMATCH;
+  if (ctx->comm && L->partitioned) return uggpu_fail(UGGPU_ERROR, "the ILU smoother runs on one GPU (level %d is partitioned)", level);
+  if (L->n == 0) return 0;
+  if (L->bs < 1 || L->bs > 3) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "l_ilubthdecomp: block size %d", L->bs);
+  // the dependency levels of the lower triangle (l_setindex + the pattern; values do not matter)
+  if (!A->tri[0]) UG_TRY(tri_build(ctx, L, A, 0, &A->tri[0]));
+  TriSched *S = A->tri[0];
+  const SellView Av = view(*A);
+  const Damp b = mkdamp(beta, L->bs);
+  Damp bb0 = b;
+  if (!beta) for (int i = 0; i < UGGPU_MAX_BS; i++) bb0.a[i] = 0.0;
+  for (int lv = 0; lv < S->nlev; lv++) {
+    const int p0 = S->h_poff[lv], p1 = p0 + 32 * S->h_lsl[lv];
+    const int blocks = (p1 - p0 + 127) / 128;
+    switch (L->bs) {
+      case 1: k_ilu_factor_level<1><<<blocks, 128, 0, ctx->stream>>>(Av, A->val, L->vclass, S->perm, p0, p1, bb0, beta != nullptr, ctx->derr); break;
+      case 2: k_ilu_factor_level<2><<<blocks, 128, 0, ctx->stream>>>(Av, A->val, L->vclass, S->perm, p0, p1, bb0, beta != nullptr, ctx->derr); break;
+      default: k_ilu_factor_level<3><<<blocks, 128, 0, ctx->stream>>>(Av, A->val, L->vclass, S->perm, p0, p1, bb0, beta != nullptr, ctx->derr); break;
+    }
+    ctx->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  UG_TRY(check_device_error(ctx));
+  UG_TRY(sell_update_diag(ctx, A));
+  // the solve schedules carry their own copy of the values: refresh what exists, then build what is missing (from the new values)
+  UG_TRY(tri_refresh_all(ctx, L, A));
+  for (int dir = 0; dir < 2; dir++)
+    if (!A->tri[dir]) UG_TRY(tri_build(ctx, L, A, dir, &A->tri[dir]));
+  return 0;
+}
+
+extern "C" int uggpu_l_luiter(uggpu_ctx *ctx, int level, int v, int M, int d)
+{
+  double *vp = get_vec(ctx, level, v);
+  const double *dp = get_vec(ctx, level, d);
+  SellMat *A = get_mat(ctx, level, M);
+  if (!vp || !dp || !A) return UGGPU_DESC_MISMATCH;
+  if (vp == dp) return uggpu_fail(UGGPU_DESC_MISMATCH, "l_luiter: result and right-hand side are the same vector");
+  UG_TRY(tri_solve(ctx, level, M, 0, vp, dp, nullptr, 2));
+  UG_TRY(tri_solve(ctx, level, M, 1, vp, vp, nullptr, 3));
+  return check_device_error(ctx);
+}
+
 // One smoothing step of class `kind` in defect-correction form: x = correction, b updated to the new defect.
 //   UGGPU_SM_JAC  Smoother iter.cc:817 + JacobiStep :911     UGGPU_SM_GS   Smoother + GSStep :1039
 //   UGGPU_SM_SGS  SGSSmoother :1392 (tmp = NP_SGS_t)          UGGPU_SM_SOR  SORSmoother :4786 + SORStep :4744
+//   UGGPU_SM_ILU  Smoother + ILUStep :5478 (tmp = matrix handle of the decomposition)
 extern "C" int uggpu_smooth(uggpu_ctx *ctx, int level, int kind, int x, int b, int A, const double *damp, int tmp)
 {
   Level *L = get_level(ctx, level);
@@ -696,6 +928,12 @@ extern "C" int uggpu_smooth(uggpu_ctx *ctx, int level, int kind, int x, int b, i
       return k_dmatmul(ctx, level, 2, 0, b, A, x);
     case UGGPU_SM_SOR:
       UG_TRY(tri_solve(ctx, level, A, 0, xp, bp, damp));
+      return k_dmatmul(ctx, level, 2, 0, b, A, x);
+    case UGGPU_SM_ILU:                                  // Smoother iter.cc:817 + ILUStep :5478; tmp = handle of the decomposed matrix
+      if (!get_mat(ctx, level, tmp)) return UGGPU_DESC_MISMATCH;
+      UG_TRY(tri_solve(ctx, level, tmp, 0, xp, bp, nullptr, 2));
+      UG_TRY(tri_solve(ctx, level, tmp, 1, xp, xp, nullptr, 3));
+      UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, xp, nullptr, dm));
       return k_dmatmul(ctx, level, 2, 0, b, A, x);
     case UGGPU_SM_SGS: {
       UG_TRY(uggpu_vec_alloc(ctx, level, tmp));

@@ -367,6 +367,49 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   return 0;
 }
 
+// Deep copy of a matrix (pattern, layout, values, diagonal array) -- AllocMDFromMD + dmatcopy.  Schedules, interface lists and value
+// tables are not copied (the first two are rebuilt on demand, the last exists for transfer stencils only).
+int sell_clone(uggpu_ctx *ctx, const SellMat *src, SellMat *dst)
+{
+  if (src->vcode) return uggpu_fail(UGGPU_ERROR, "sell_clone: matrices with a value table cannot be copied");
+  cudaStream_t st = ctx->stream;
+  const size_t nsl = (size_t)(src->n + 31) / 32;
+  SellMat m;
+  m.n = src->n; m.bb = src->bb; m.nnz = src->nnz; m.padded = src->padded; m.maxlen = src->maxlen; m.fixed_w = src->fixed_w;
+  m.col_len = src->col_len; m.uniform_slices = src->uniform_slices; m.col_words = src->col_words;
+  int rc = 0;
+#define CL(expr) do { if (!rc) rc = (expr); } while (0)
+#define CC(expr) do { if (!rc) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) rc = uggpu_fail(UGGPU_CUDA_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); } } while (0)
+  CL(dalloc(ctx, &m.slice_ptr, nsl + 1));
+  CL(dalloc(ctx, &m.rowlen, (size_t)m.n));
+  CL(dalloc(ctx, &m.col, (size_t)m.col_len));
+  CL(dalloc(ctx, &m.val, (size_t)m.padded * m.bb));
+  if (!rc) {
+    if (src->col_ptr != src->slice_ptr) CL(dalloc(ctx, &m.col_ptr, nsl)); else m.col_ptr = m.slice_ptr;
+  }
+  if (src->diag) CL(dalloc(ctx, &m.diag, nsl * 32 * m.bb));
+  CC(cudaMemcpyAsync(m.slice_ptr, src->slice_ptr, sizeof(int64_t) * (nsl + 1), cudaMemcpyDeviceToDevice, st));
+  CC(cudaMemcpyAsync(m.rowlen, src->rowlen, sizeof(uint16_t) * (size_t)m.n, cudaMemcpyDeviceToDevice, st));
+  CC(cudaMemcpyAsync(m.col, src->col, sizeof(int32_t) * (size_t)m.col_len, cudaMemcpyDeviceToDevice, st));
+  CC(cudaMemcpyAsync(m.val, src->val, sizeof(double) * (size_t)m.padded * m.bb, cudaMemcpyDeviceToDevice, st));
+  if (!rc && src->col_ptr != src->slice_ptr) CC(cudaMemcpyAsync(m.col_ptr, src->col_ptr, sizeof(int64_t) * nsl, cudaMemcpyDeviceToDevice, st));
+  if (!rc && src->diag) CC(cudaMemcpyAsync(m.diag, src->diag, sizeof(double) * nsl * 32 * m.bb, cudaMemcpyDeviceToDevice, st));
+#undef CL
+#undef CC
+  if (rc) {
+    if (m.col_ptr == m.slice_ptr) m.col_ptr = nullptr;
+    if (m.col_ptr) dfree(ctx, m.col_ptr, nsl);
+    if (m.slice_ptr) dfree(ctx, m.slice_ptr, nsl + 1);
+    if (m.rowlen) dfree(ctx, m.rowlen, (size_t)m.n);
+    if (m.col) dfree(ctx, m.col, (size_t)m.col_len);
+    if (m.val) dfree(ctx, m.val, (size_t)m.padded * m.bb);
+    if (m.diag) dfree(ctx, m.diag, nsl * 32 * m.bb);
+    return rc;
+  }
+  *dst = m;
+  return 0;
+}
+
 int sell_from_device_csr(uggpu_ctx *ctx, int n, int bb, const int64_t *d_rowptr, const int32_t *d_col, const double *d_val, SellMat *out)
 {
   cudaStream_t st = ctx->stream;

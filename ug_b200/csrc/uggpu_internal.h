@@ -225,6 +225,53 @@ __device__ __forceinline__ void pf_rows(const void *base, const PfState &st, con
 }
 #endif
 
+#ifdef __CUDACC__
+// ---- small dense blocks (np/algebra/block.cc) ----------------------------------------------------------------------
+// InvertSmallBlock, np/algebra/block.cc:272-321 (closed forms for n = 2, 3); returns non-zero for det == 0
+template <int BS>
+__device__ __forceinline__ int invert_small_block(const double *mat, double *inv)
+{
+  if (BS == 2) {
+    double det = mat[0] * mat[3] - mat[1] * mat[2];
+    if (det == 0.0) return 1;
+    double invdet = 1.0 / det;
+    inv[0] = mat[3] * invdet; inv[1] = -mat[1] * invdet; inv[2] = -mat[2] * invdet; inv[3] = mat[0] * invdet;
+    return 0;
+  }
+  double det = mat[0] * mat[4] * mat[8 % (BS * BS)] + mat[1] * mat[5 % (BS * BS)] * mat[6 % (BS * BS)] + mat[2] * mat[3] * mat[7 % (BS * BS)]
+               - mat[2] * mat[4] * mat[6 % (BS * BS)] - mat[0] * mat[5 % (BS * BS)] * mat[7 % (BS * BS)] - mat[1] * mat[3] * mat[8 % (BS * BS)];
+  if (det == 0.0) return 1;
+  double invdet = 1.0 / det;
+  constexpr int BB = BS * BS;
+  inv[0] = ( mat[4 % BB] * mat[8 % BB] - mat[5 % BB] * mat[7 % BB]) * invdet;
+  inv[3] = (-mat[3] * mat[8 % BB] + mat[5 % BB] * mat[6 % BB]) * invdet;
+  inv[6 % BB] = ( mat[3] * mat[7 % BB] - mat[4 % BB] * mat[6 % BB]) * invdet;
+  inv[1] = (-mat[1] * mat[8 % BB] + mat[2] * mat[7 % BB]) * invdet;
+  inv[4 % BB] = ( mat[0] * mat[8 % BB] - mat[2] * mat[6 % BB]) * invdet;
+  inv[7 % BB] = (-mat[0] * mat[7 % BB] + mat[1] * mat[6 % BB]) * invdet;
+  inv[2] = ( mat[1] * mat[5 % BB] - mat[2] * mat[4 % BB]) * invdet;
+  inv[5 % BB] = (-mat[0] * mat[5 % BB] + mat[2] * mat[3]) * invdet;
+  inv[8 % BB] = ( mat[0] * mat[4 % BB] - mat[1] * mat[3]) * invdet;
+  return 0;
+}
+
+// C = A * B for bs x bs blocks with the reference's summation (sum = 0; sum += a*b, ugiter.cc:3814-3822); returns true if C == 0
+template <int BS>
+__device__ __host__ __forceinline__ bool block_mul(const double *a, const double *b, double *c)
+{
+  bool zero = true;
+  for (int i0 = 0; i0 < BS; i0++)
+    for (int j0 = 0; j0 < BS; j0++) {
+      double sum = 0.0;
+      for (int k0 = 0; k0 < BS; k0++) sum += a[i0 * BS + k0] * b[k0 * BS + j0];
+      c[i0 * BS + j0] = sum;
+      if (sum != 0.0) zero = false;
+    }
+  return zero;
+}
+
+#endif
+
 // ---- error plumbing -------------------------------------------------------------------------------
 int uggpu_fail(int code, const char *fmt, ...);
 #define CUDA_TRY(expr)                                                                                 \
@@ -260,6 +307,7 @@ int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, con
 int sell_set_values_host(uggpu_ctx *ctx, SellMat *m, const double *val);
 int sell_to_host_csr(uggpu_ctx *ctx, const SellMat *m, int32_t *rowptr, int32_t *col, double *val);
 int sell_free(uggpu_ctx *ctx, SellMat *m);
+int sell_clone(uggpu_ctx *ctx, const SellMat *src, SellMat *dst);    // deep copy: pattern, layout, values (AllocMDFromMD + dmatcopy)
 int sell_free_schedules(uggpu_ctx *ctx, SellMat *m);          // gs.cu: drops the Gauss-Seidel schedules (they hold a copy of the values)
 // replaces the explicit column words of uniform slices by one distance per slice column (lossless); no-op when nothing is gained
 int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);

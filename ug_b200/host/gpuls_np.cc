@@ -41,7 +41,8 @@ USING_UG_NAMESPACES
   X(uggpu_ctx_create) X(uggpu_ctx_destroy) X(uggpu_last_error) X(uggpu_set_fullrefinelevel) X(uggpu_level_create) X(uggpu_level_set_flags)     \
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
-  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode)
+  X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
+  X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp)
 
 namespace {
 struct Api {
@@ -199,6 +200,7 @@ void VsToArray(const VEC_SCALAR vs, int bs, double *out) { for (int i = 0; i < U
 // iter.gpugs   (reference: class `gs`,  GSPreProcess :1003, GSStep :1039)          -- SURVEY.md 8f.2
 // iter.gpusgs  (reference: class `sgs`, SGSPreProcess :1353, SGSSmoother :1392)
 // iter.gpusor  (reference: class `sor`, SORPreProcess :4717, SORStep :4744, SORSmoother :4786; $damp is the relaxation omega)
+// iter.gpuilu  (reference: class `ilu`, NP_ILU :326-330, ILUInit :5415 ($beta), ILUPreProcess :5444, ILUStep :5478)
 // One struct and one set of functions: `kind` (UGGPU_SM_*) is set by the constructor of the class.
 // =========================================================================================================================
 struct NP_GPUJAC {
@@ -206,16 +208,20 @@ struct NP_GPUJAC {
   VEC_SCALAR damp;
   Mirror *m;
   INT acquired;        // PreProcess is called once per level (iter.cc:7719): one mirror reference each
-  INT kind;            // UGGPU_SM_JAC / GS / SGS / SOR
+  INT kind;            // UGGPU_SM_JAC / GS / SGS / SOR / ILU
   int t_handle;        // sgs: the extra temporary NP_SGS_t (iter.cc:1386) lives on the device only
+  VEC_SCALAR beta;     // ilu: $beta (NP_ILU.beta iter.cc:328)
+  int L_handle;        // ilu: the decomposed copy of A (NP_SMOOTHER.L, AllocMDFromMD iter.cc:5457) lives on the device only
 };
-static const char *SmootherName(INT kind) { return kind == UGGPU_SM_GS ? "gpugs" : kind == UGGPU_SM_SGS ? "gpusgs" : kind == UGGPU_SM_SOR ? "gpusor" : "gpujac"; }
+static const char *SmootherName(INT kind) { return kind == UGGPU_SM_GS ? "gpugs" : kind == UGGPU_SM_SGS ? "gpusgs" : kind == UGGPU_SM_SOR ? "gpusor" : kind == UGGPU_SM_ILU ? "gpuilu" : "gpujac"; }
 
 INT GpuJacInit(NP_BASE *theNP, INT argc, char **argv)
 {
   NP_GPUJAC *np = (NP_GPUJAC *)theNP;
   for (int i = 0; i < MAX_VEC_COMP; i++) np->damp[i] = 1.0;
   sc_read(np->damp, NP_FMT(np), np->iter.b, "damp", argc, argv);          // iter.cc:771
+  for (int i = 0; i < MAX_VEC_COMP; i++) np->beta[i] = 0.0;
+  if (np->kind == UGGPU_SM_ILU) sc_read(np->beta, NP_FMT(np), np->iter.b, "beta", argc, argv);   // iter.cc:5422-5423
   return NPIterInit(&np->iter, argc, argv);
 }
 
@@ -225,6 +231,7 @@ INT GpuJacDisplay(NP_BASE *theNP)
   NPIterDisplay(&np->iter);
   UserWrite("configuration parameters:\n");
   if (sc_disp(np->damp, np->iter.b, "damp")) REP_ERR_RETURN(1);
+  if (np->kind == UGGPU_SM_ILU && sc_disp(np->beta, np->iter.b, "beta")) REP_ERR_RETURN(1);
   UserWriteF(DISPLAY_NP_FORMAT_SS, "device", "B200 via libuggpu");
   return 0;
 }
@@ -237,7 +244,17 @@ INT GpuJacPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b
   np->m = m;
   np->acquired++;
   if (EnsureLevel(np->m, level, x, A)) NP_RETURN(1, result[0]);
-  if (np->kind != UGGPU_SM_JAC) {
+  if (np->kind == UGGPU_SM_ILU) {
+    // ILUPreProcess iter.cc:5444-5476: L = copy of A (AllocMDFromMD + dmatcopy), l_ilubthdecomp(L, beta, no threshold)
+    double beta[UGGPU_MAX_BS];
+    for (int i = 0; i < UGGPU_MAX_BS; i++) beta[i] = i < m->bs ? np->beta[i] : 0.0;
+    np->L_handle = m->handle(&np->L_handle);
+    if (api.uggpu_dmatcopy(m->ctx, level, level, UGGPU_ALL_VECTORS, np->L_handle, m->handle(A))) NP_RETURN(dev_fail("uggpu_dmatcopy"), result[0]);
+    if (api.uggpu_l_ilubthdecomp(m->ctx, level, np->L_handle, beta)) {
+      PrintErrorMessage('E', "GpuIluPreProcess", "decomposition failed");      // iter.cc:5470
+      NP_RETURN(dev_fail("uggpu_l_ilubthdecomp"), result[0]);
+    }
+  } else if (np->kind != UGGPU_SM_JAC) {
     // l_setindex (iter.cc:1027): rows are numbered in list order by the flattening; the device builds its level schedule
     if (api.uggpu_gs_preprocess(m->ctx, level, m->handle(A))) NP_RETURN(dev_fail("uggpu_gs_preprocess"), result[0]);
     np->t_handle = m->handle(&np->t_handle);
@@ -258,7 +275,7 @@ INT GpuJacIter(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATD
   if (Upload(m, level, b)) NP_RETURN(1, result[0]);
   if (api.uggpu_vec_alloc(m->ctx, level, m->handle(x))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
   if (np->kind != UGGPU_SM_JAC) {
-    if (api.uggpu_smooth(m->ctx, level, (int)np->kind, m->handle(x), m->handle(b), m->handle(A), damp, np->t_handle)) NP_RETURN(dev_fail("uggpu_smooth"), result[0]);
+    if (api.uggpu_smooth(m->ctx, level, (int)np->kind, m->handle(x), m->handle(b), m->handle(A), damp, np->kind == UGGPU_SM_ILU ? np->L_handle : np->t_handle)) NP_RETURN(dev_fail("uggpu_smooth"), result[0]);
   } else
   if (api.uggpu_jac_smooth(m->ctx, level, m->handle(x), m->handle(b), m->handle(A), damp)) NP_RETURN(dev_fail("uggpu_jac_smooth"), result[0]);
   if (Download(m, level, x) || Download(m, level, b)) NP_RETURN(1, result[0]);
@@ -291,6 +308,7 @@ INT GpuJacConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_S
 INT GpuGsConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_GS); }
 INT GpuSgsConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_SGS); }
 INT GpuSorConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_SOR); }
+INT GpuIluConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_ILU); }
 
 // =========================================================================================================================
 // transfer.gputransfer  (reference: NP_STANDARD_TRANSFER transfer.cc:115-133, standard mode only)
@@ -443,7 +461,7 @@ INT GpuLmgcInit(NP_BASE *theNP, INT argc, char **argv)
   if (np->Transfer == NULL || np->PreSmooth == NULL || np->PostSmooth == NULL) REP_ERR_RETURN(NP_NOT_ACTIVE);
   if (np->BaseSolver == NULL && !np->devbase) REP_ERR_RETURN(NP_NOT_ACTIVE);
   if (np->PreSmooth->Iter != GpuJacIter || np->PostSmooth->Iter != GpuJacIter) {
-    UserWrite("gpulmgc: $S pre and post smoother must be of class gpujac, gpugs, gpusgs or gpusor\n");
+    UserWrite("gpulmgc: $S pre and post smoother must be of class gpujac, gpugs, gpusgs, gpusor or gpuilu\n");
     return NP_NOT_ACTIVE;
   }
   if (((NP_GPUJAC *)np->PreSmooth)->kind != ((NP_GPUJAC *)np->PostSmooth)->kind) {
@@ -509,6 +527,10 @@ void FillCfg(NP_GPULMGC *np, uggpu_lmgc_cfg *cfg)
   cfg->t = np->t_handle;
   cfg->fused = np->unfused ? 0 : 1;
   cfg->smoother = (int)((NP_GPUJAC *)np->PreSmooth)->kind;
+  if (cfg->smoother == UGGPU_SM_ILU) {
+    cfg->smoother_L = ((NP_GPUJAC *)np->PreSmooth)->L_handle;
+    for (int i = 0; i < UGGPU_MAX_BS; i++) cfg->ilu_beta[i] = i < m->bs ? ((NP_GPUJAC *)np->PreSmooth)->beta[i] : 0.0;
+  }
   if (np->devbase) {
     cfg->base_solver = NULL;
     // the parameters of the reference's `ls $I lu` base solver if one is given, else its documented defaults
@@ -823,6 +845,7 @@ INT NS_DIM_PREFIX InitGpuLS(void)
   if (CreateClass(ITER_CLASS_NAME ".gpugs", sizeof(NP_GPUJAC), GpuGsConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(ITER_CLASS_NAME ".gpusgs", sizeof(NP_GPUJAC), GpuSgsConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(ITER_CLASS_NAME ".gpusor", sizeof(NP_GPUJAC), GpuSorConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ITER_CLASS_NAME ".gpuilu", sizeof(NP_GPUJAC), GpuIluConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(TRANSFER_CLASS_NAME ".gputransfer", sizeof(NP_GPUTRANSFER), GpuTransferConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(ITER_CLASS_NAME ".gpulmgc", sizeof(NP_GPULMGC), GpuLmgcConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpuls", sizeof(NP_GPULS), GpuLsConstruct)) REP_ERR_RETURN(__LINE__);
