@@ -37,7 +37,7 @@ def workload_name(cells, top, n, kind="p1", smoother="jac"):
             "elasticity": "3D Q1 linear elasticity (3x3 blocks, 27 block entries per row), unit cube, hexahedra"}[kind]
     return (f"{what}, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
             f"{n} fine unknowns, V(2,2) " + {"jac": f"{'block-' if kind == 'elasticity' else ''}Jacobi damp 0.6", "gs": "Gauss-Seidel damp 1.0",
-                                             "sgs": "symmetric Gauss-Seidel damp 1.0", "sor": "SOR omega 1.1"}[smoother] + ", base solver ls+lu")
+                                             "sgs": "symmetric Gauss-Seidel damp 1.0", "sor": "SOR omega 1.1", "ilu": "ILU(0) beta 0 damp 1.0"}[smoother] + ", base solver ls+lu")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -222,10 +222,13 @@ def our_arm(args):
         for l in range(top + 1):
             ctx.alloc(l, name)
     ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
-    sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1}[args.smoother]
+    sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1, "ilu": 1.0}[args.smoother]
     cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=sm_damp, fused=1, smoother=args.smoother)
+    ctx.sync()
+    t_pre = time.perf_counter()
     ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
     ctx.sync()
+    preprocess_s = time.perf_counter() - t_pre      # LmgcPreProcess: base-level LU, Gauss-Seidel schedules / ILU decompositions of all levels
     setup_s = time.perf_counter() - t0
     X, B, Cc = ctx.handle("x"), ctx.handle("b"), ctx.handle("c")
     res = capi.LResult()
@@ -327,7 +330,8 @@ def our_arm(args):
             traffic = tj.get("k_smooth_k_dram_bytes_per_launch")
     # SURVEY.md 8(d) counts 4 bytes of column index per entry; the stored format fetches fewer (compressed column words)
     nnz_top, words_top = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A)), int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
-    survey_extra = 4.0 * (nnz_top - words_top) * dom["launches"]
+    vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables)
+    survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
     achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     total_alg = sum(v["alg_bytes"] for v in prof.values())
     n_total = n_global
@@ -344,14 +348,15 @@ def our_arm(args):
                                   f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
                    "halo_exchanges_total": exchanges,
                    "cache": "inputs larger than L2 (the finest matrix alone is tens of GB per sweep)",
-                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2),
+                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3),
                    "defect": [first, hist[-1]] if hist else None},
         "roofline": {"bound": "hbm", "kernel": f"k_smooth_k<{bs},*> (fused smoothing step, finest level)" if args.smoother == "jac" else
                      f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
                      "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
-                     "bytes_model": "as stored: 8 B per value, compressed column words (DESIGN.md 3), vectors once",
+                     "bytes_model": "as stored: 8 B per value fetched (slices of identical rows share value tables), compressed column words (DESIGN.md 2-3), vectors once",
+                     "value_entries_per_entry": vals_top / max(nnz_top, 1),
                      "achieved_survey_model": achieved_survey, "column_words_per_entry": words_top / max(nnz_top, 1),
                      "share_of_step": dom["ms"] / ms,
                      "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
@@ -392,8 +397,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity"],
                     help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")
-    ap.add_argument("--smoother", default="jac", choices=["jac", "gs", "sgs", "sor"],
-                    help="smoother class of the cycle: jac = BASELINE configs (default); gs / sgs / sor: Gauss-Seidel family (SURVEY.md 8f.2, one GPU)")
+    ap.add_argument("--smoother", default="jac", choices=["jac", "gs", "sgs", "sor", "ilu"],
+                    help="smoother class of the cycle: jac = BASELINE configs (default); gs / sgs / sor / ilu: Gauss-Seidel family and ILU (SURVEY.md 8f.2, one GPU)")
     ap.add_argument("--replicate-below", type=int, default=300000,
                     help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()

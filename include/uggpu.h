@@ -108,6 +108,15 @@ int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat);
 /* int32 column words one pass over the matrix reads: slices whose rows all have the same column distances store one
  * word per slice column instead of one per entry (lossless; uggpu_mat_get returns the original indices) */
 int64_t uggpu_mat_col_words(uggpu_ctx *ctx, int level, int mat);
+/* Entries whose VALUES a pass over the matrix fetches from HBM: slices of rows with uniform column distances AND bit-identical
+ * values per slice column (interior rows of a constant-coefficient operator on a structured / uniformly refined grid) read one
+ * shared table instead of their own values (lossless, verified on the device; UGGPU_NO_SHARED_VALUES=1 switches it off).
+ * Equals uggpu_mat_nnz when nothing is shared. */
+int64_t uggpu_mat_val_entries(uggpu_ctx *ctx, int level, int mat);
+/* Scalar matrices: slices (of 32 rows) that carry the matrix' DOMINANT stencil -- one pair of distance and value tables used by
+ * more than half of the slices; 0 when there is none.  Such matrices run the stencil variant of the fused smoothing kernel
+ * (tables in the kernel's constant bank; same arithmetic, same results; UGGPU_NO_STENCIL=1 switches it off). */
+int64_t uggpu_mat_stencil_slices(uggpu_ctx *ctx, int level, int mat);
 int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
 /* Standard (geometric) transfer stencils between `level` and level-1 (np/algebra/transgrid.cc:117-336):
  * P: p_rowptr[n_fine+1], p_col (coarse row), p_w (GNs weight, zeros dropped, corner order);

@@ -293,6 +293,100 @@ def test_col_compression_lossless(monkeypatch):
     assert np.array_equal(x1, x0) and np.array_equal(b1, b0)
 
 
+@pytest.mark.parametrize("kind,cells,top", [(capi.SYNTH_P1_SIMPLEX, 4, 4), (capi.SYNTH_Q1_ELASTICITY, 4, 4)], ids=["P1-65^3", "elast-65^3"])
+def test_shared_value_tables_lossless(monkeypatch, kind, cells, top):
+    """Uniform slices whose rows also hold bit-identical values read one shared value table (sell.cu sell_share_values): the
+    matrix handed back by uggpu_mat_get and every result of a solve are identical to the explicit storage -- only the values
+    fetched per sweep shrink.  After uggpu_mat_set_values with perturbed values the tables follow (or vanish)."""
+    def run(share):
+        if share:
+            monkeypatch.delenv("UGGPU_NO_SHARED_VALUES", raising=False)
+        else:
+            monkeypatch.setenv("UGGPU_NO_SHARED_VALUES", "1")
+        ctx = _synth(cells, 3, top, kind)
+        A = ctx.handle("A")
+        hier = ctx.download_hierarchy(top)
+        ve = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))
+        nnz = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A))
+        for name in ("x", "b", "c", "y"):
+            for l in range(top + 1):
+                ctx.alloc(l, name)
+        ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+        cfg = ctx.lmgc_cfg(smooth_damp=0.6, fused=1)
+        ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+        res = capi.LResult()
+        ctx.call("uggpu_ls_residuum", 0, top, ctx.handle("b"), C.byref(res))
+        ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, ctx.handle("x"), ctx.handle("b"), A, ctx.handle("c"), 3,
+                 capi._vs([1e-300]), capi._vs([1e-300]), C.byref(res), None)
+        x, b = ctx.get(top, "x"), ctx.get(top, "b")
+        # new values on the same pattern: one row in the middle changes -> its slice must fall back to explicit values
+        lv = hier.levels[top]
+        val = lv.val.copy()
+        mid = lv.n // 2
+        bb = lv.bs * lv.bs
+        val[lv.rowptr[mid] * bb:lv.rowptr[mid + 1] * bb] *= 1.5
+        ctx.call("uggpu_mat_set_values", top, A, capi._p(val))
+        ve2 = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))
+        ctx.call("uggpu_dmatmul", top, top, 0, ctx.handle("y"), A, ctx.handle("x"))
+        y = ctx.get(top, "y")
+        back = ctx.download_hierarchy(top).levels[top].val
+        ctx.close()
+        return hier, ve, ve2, nnz, x, b, y, back, val
+
+    h1, ve1, ve1b, nnz, x1, b1, y1, back1, val = run(True)
+    h0, ve0, ve0b, _, x0, b0, y0, back0, _ = run(False)
+    assert ve0 == nnz == ve0b and ve1 < 0.6 * nnz, (ve0, ve1, nnz)
+    assert ve1 < ve1b < 0.6 * nnz, (ve1, ve1b)                     # the perturbed row's slice reads its own values again
+    for a, b in zip(h1.levels, h0.levels):
+        assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val)
+    assert np.array_equal(x1, x0) and np.array_equal(b1, b0)
+    assert np.array_equal(back1, val) and np.array_equal(back0, val)
+    assert np.array_equal(y1, y0)
+
+
+@pytest.mark.parametrize("kind", [capi.SYNTH_P1_SIMPLEX, capi.SYNTH_Q1_POISSON], ids=["P1-129^3-15pt", "Q1-129^3-27pt"])
+def test_stencil_smoothing_kernel_bitexact_vs_port(monkeypatch, kind):
+    """129^3: most slices of the two finest levels carry one stencil, so the fused schedule runs the stencil variant of the smoothing
+    kernel (spmv.cu k_smooth_sten: distance and value tables as kernel parameters).  Its solve must equal, bit for bit, the
+    generic kernel's (UGGPU_NO_STENCIL=1), the one-kernel-per-call schedule's and the sequential oracle port's."""
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    top = 5
+    ctx = _synth(4, 3, top, kind)
+    hier = ctx.download_hierarchy(top)
+    A = ctx.handle("A")
+    sten = [int(ctx.L.uggpu_mat_stencil_slices(ctx.h, l, A)) for l in range(top + 1)]
+    nsl = (hier.levels[top].n + 31) // 32
+    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+    rhs = ctx.get(top, "b")
+    ctx.close()
+    assert sten[top] > 0.6 * nsl and sten[top - 1] > 0, sten          # the kernel under test is the one that runs
+    assert sten[0] == 0 and sten[1] == 0, sten
+    cfg = dict(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6)
+    out = []
+    for name in ("stencil", "generic", "per-call", "port"):
+        if name == "generic":
+            monkeypatch.setenv("UGGPU_NO_STENCIL", "1")
+        else:
+            monkeypatch.delenv("UGGPU_NO_STENCIL", raising=False)
+        be = PortBackend(hier) if name == "port" else GpuBackend(hier, fused=0 if name == "per-call" else 1)
+        for l, lv in enumerate(hier.levels):
+            be.put(l, "x", np.zeros(lv.n * lv.bs)); be.put(l, "b", rhs if l == top else np.zeros(lv.n * lv.bs))
+        be.ls_defect(0, top, "x", "b")
+        its, first, hist = be.solve(top, "x", "b", cfg, 3)
+        out.append((its, hist, [be.get(l, "x") for l in range(top + 1)], [be.get(l, "b") for l in range(top + 1)]))
+        if hasattr(be, "close"):
+            be.close()
+    ref = out[-1]
+    assert ref[0] == 3 and ref[1][-1] < 0.2 * ref[1][0]
+    for its, hist, xs, bs in out[:-1]:
+        assert its == 3
+        assert np.max(np.abs(hist - ref[1]) / ref[1]) < 1e-12
+        for l in range(top + 1):
+            assert np.array_equal(xs[l], ref[2][l]), l
+            assert np.array_equal(bs[l], ref[3][l]), l
+
+
 def test_async_upload_of_the_iterate():
     """uggpu_vec_upload_async: the iterate travels on the copy stream while the cycle runs; results are those of the
     synchronous upload, also when the vector is reused at once (upload ordered behind the kernels already enqueued)."""

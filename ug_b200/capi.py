@@ -64,7 +64,7 @@ def lib():
                              "there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
         L.uggpu_last_error.restype = C.c_char_p
-        for name in ("uggpu_launch_count", "uggpu_device_bytes", "uggpu_mat_nnz", "uggpu_mat_padded_nnz", "uggpu_transfer_nnz", "uggpu_mat_col_words"):
+        for name in ("uggpu_launch_count", "uggpu_device_bytes", "uggpu_mat_nnz", "uggpu_mat_padded_nnz", "uggpu_transfer_nnz", "uggpu_mat_col_words", "uggpu_mat_val_entries", "uggpu_mat_stencil_slices"):
             getattr(L, name).restype = C.c_int64
         L.uggpu_dset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.uggpu_dscal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]

@@ -97,7 +97,9 @@ Prefetch make_prefetch(const uggpu_ctx *ctx, const SellMat *A, int bs, int slice
   Prefetch pf;
   const char *d = getenv("UGGPU_PF_DIST"), *m = getenv("UGGPU_PF_MODE");
   const int64_t resident = (int64_t)ctx->sm_count * (2048 / 32);
-  const int64_t slice_bytes = (int64_t)(A->maxlen > 0 ? A->maxlen : 1) * A->bb * 256;
+  // slices with shared value tables (sell_share_values) have no value stream: what a slice pulls through L2 is its vector rows
+  const bool vshared = A->vt && A->vshared_slices * 2 > (int64_t)(A->n + 31) / 32;
+  const int64_t slice_bytes = vshared ? (int64_t)1024 * bs : (int64_t)(A->maxlen > 0 ? A->maxlen : 1) * A->bb * 256;
   int64_t dist = resident * 3 / 4 * slices_per_warp;      // a resident warp holds slices_per_warp slices: one generation is that much longer
   const int64_t cap = ((int64_t)40 << 20) / slice_bytes;
   if (cap < dist) dist = cap;
@@ -304,6 +306,7 @@ extern "C" int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *
   SellMat m;
   UG_TRY(sell_from_host_csr(ctx, L->n, L->bs * L->bs, rowptr, col, val, &m));
   UG_TRY(sell_update_diag(ctx, &m));
+  UG_TRY(sell_share_values(ctx, &m));
   L->mats[mat] = m;
   return 0;
 }
@@ -313,7 +316,8 @@ extern "C" int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const do
   SellMat *m = get_mat(ctx, level, mat);
   if (!m) return UGGPU_DESC_MISMATCH;
   UG_TRY(sell_set_values_host(ctx, m, val));
-  return sell_update_diag(ctx, m);
+  UG_TRY(sell_update_diag(ctx, m));
+  return sell_share_values(ctx, m);        // the tables follow the new values
 }
 
 extern "C" int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val)
@@ -333,6 +337,18 @@ extern "C" int64_t uggpu_mat_col_words(uggpu_ctx *ctx, int level, int mat)
 {
   SellMat *m = get_mat(ctx, level, mat);
   return m ? m->col_words : -1;
+}
+
+extern "C" int64_t uggpu_mat_val_entries(uggpu_ctx *ctx, int level, int mat)
+{
+  SellMat *m = get_mat(ctx, level, mat);
+  return m ? (m->val_entries >= 0 ? m->val_entries : m->nnz) : -1;
+}
+
+extern "C" int64_t uggpu_mat_stencil_slices(uggpu_ctx *ctx, int level, int mat)
+{
+  SellMat *m = get_mat(ctx, level, mat);
+  return m ? (m->sten.w > 0 ? m->sten_slices : 0) : -1;
 }
 
 extern "C" int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat)

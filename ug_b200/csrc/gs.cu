@@ -847,6 +847,7 @@ extern "C" int uggpu_dmatcopy(uggpu_ctx *ctx, int fl, int tl, int mode, int M, i
       if (dst->n == src->n && dst->bb == src->bb && dst->nnz == src->nnz && dst->padded == src->padded && dst->col_len == src->col_len && dst->fixed_w == src->fixed_w) {
         // same pattern (made by an earlier copy): the values only, also into the solve schedules M may have
         CUDA_TRY(cudaMemcpyAsync(dst->val, src->val, sizeof(double) * (size_t)src->padded * src->bb, cudaMemcpyDeviceToDevice, ctx->stream));
+        UG_TRY(sell_drop_shared_values(ctx, dst));
         UG_TRY(sell_update_diag(ctx, dst));
         UG_TRY(tri_refresh_all(ctx, L, dst));
         continue;
@@ -857,6 +858,7 @@ extern "C" int uggpu_dmatcopy(uggpu_ctx *ctx, int fl, int tl, int mode, int M, i
     }
     SellMat m;
     UG_TRY(sell_clone(ctx, src, &m));
+    UG_TRY(sell_drop_shared_values(ctx, &m));      // the copy's code words no longer point into src's value tables
     L->mats[M] = m;
   }
   return 0;
@@ -870,6 +872,7 @@ extern "C" int uggpu_l_ilubthdecomp(uggpu_ctx *ctx, int level, int M, const doub
   if (ctx->comm && L->partitioned) return uggpu_fail(UGGPU_ERROR, "the ILU smoother runs on one GPU (level %d is partitioned)", level);
   if (L->n == 0) return 0;
   if (L->bs < 1 || L->bs > 3) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "l_ilubthdecomp: block size %d", L->bs);
+  UG_TRY(sell_drop_shared_values(ctx, A));         // the values are about to change in place
   // the dependency levels of the lower triangle (l_setindex + the pattern; values do not matter)
   if (!A->tri[0]) UG_TRY(tri_build(ctx, L, A, 0, &A->tri[0]));
   TriSched *S = A->tri[0];

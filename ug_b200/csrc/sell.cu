@@ -241,6 +241,188 @@ int sell_compress_cols(uggpu_ctx *ctx, SellMat *m)
   return rc;
 }
 
+// ---- shared value tables of uniform slices (matrices) ------------------------------------------------------------------------
+// One warp per slice with uniform column distances.  vflag[s] = 1 when, for every slice column j and block component k, all rows
+// that have an entry j hold the same bit pattern; cnt[s] = true entries of the slice; hash[s] = 64-bit hash of the value vector.
+__global__ void k_sell_vuniform_flag(int n, int bb, const int64_t *__restrict__ slice_ptr, const int64_t *__restrict__ col_ptr, const uint16_t *__restrict__ rowlen,
+                                     const double *__restrict__ val, uint8_t *__restrict__ vflag, int *__restrict__ cnt, unsigned long long *__restrict__ hash)
+{
+  const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= (n + 31) / 32) return;
+  const int r = s * 32 + lane;
+  const int len = r < n ? rowlen[r] : 0;
+  const int64_t sp = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - sp) >> 5);
+  int c = len;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  bool ok = col_ptr[s] < 0;
+  unsigned long long h = 1469598103934665603ull ^ (unsigned long long)(w * 16 + bb);
+  if (ok)
+    for (int j = 0; j < w; j++) {
+      const bool has = j < len;
+      const unsigned m = __ballot_sync(0xffffffffu, has);
+      const int src = m ? __ffs(m) - 1 : 0;
+      for (int k = 0; k < bb; k++) {
+        const unsigned long long bits = has ? (unsigned long long)__double_as_longlong(val[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane]) : 0ull;
+        const unsigned long long ref = __shfl_sync(0xffffffffu, bits, src);
+        if (has && bits != ref) ok = false;
+        h = (h ^ ref) * 1099511628211ull;
+        h ^= h >> 29;
+      }
+    }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) { vflag[s] = ok && w > 0 ? 1 : 0; cnt[s] = c; hash[s] = h; }
+}
+
+// slices that share a table write identical doubles to the same place
+__global__ void k_sell_fill_vt(int n, int bb, const int64_t *__restrict__ slice_ptr, const int64_t *__restrict__ col_ptr, const uint16_t *__restrict__ rowlen,
+                               const double *__restrict__ val, double *__restrict__ vt)
+{
+  const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= (n + 31) / 32) return;
+  const int64_t cp = col_ptr[s];
+  if (cp >= 0 || UG_VALTAB(cp) < 0) return;
+  const int64_t vo = UG_VALTAB(cp);
+  const int r = s * 32 + lane;
+  const int len = r < n ? rowlen[r] : 0;
+  const int64_t sp = slice_ptr[s];
+  const int w = (int)((slice_ptr[s + 1] - sp) >> 5);
+  for (int j = 0; j < w; j++) {
+    const bool has = j < len;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const int src = m ? __ffs(m) - 1 : 0;
+    if (lane == src && has)
+      for (int k = 0; k < bb; k++) vt[vo + (int64_t)j * bb + k] = val[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane];
+  }
+}
+
+// decodes every true entry of the slices with shared values from the tables and compares the bits with the explicit values
+__global__ void k_sell_verify_vt(int n, int bb, const int64_t *__restrict__ slice_ptr, const int64_t *__restrict__ col_ptr, const uint16_t *__restrict__ rowlen,
+                                 const double *__restrict__ val, const double *__restrict__ vt, unsigned long long *__restrict__ bad)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int s = r >> 5, lane = r & 31;
+  const int64_t cp = col_ptr[s];
+  if (cp >= 0 || UG_VALTAB(cp) < 0) return;
+  const int64_t vo = UG_VALTAB(cp), sp = slice_ptr[s];
+  const int len = rowlen[r];
+  int wrong = 0;
+  for (int j = 0; j < len; j++)
+    for (int k = 0; k < bb; k++)
+      if (__double_as_longlong(vt[vo + (int64_t)j * bb + k]) != __double_as_longlong(val[(sp + (int64_t)j * 32) * bb + (int64_t)k * 32 + lane])) wrong++;
+  if (wrong) atomicAdd(bad, (unsigned long long)wrong);
+}
+
+__global__ void k_sell_strip_vt(int nsl, int64_t *__restrict__ col_ptr)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nsl && col_ptr[s] < 0) col_ptr[s] = ~UG_COLTAB(col_ptr[s]);
+}
+
+int sell_drop_shared_values(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->n <= 0 || m->col_ptr == m->slice_ptr || !m->col_ptr) return 0;
+  const int nsl = (m->n + 31) / 32;
+  k_sell_strip_vt<<<(nsl + 255) / 256, 256, 0, ctx->stream>>>(nsl, m->col_ptr);
+  KCHECK(ctx);
+  if (m->vt) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); UG_TRY(dfree(ctx, m->vt, (size_t)m->vt_len)); }
+  m->vt_len = 0; m->vshared_slices = 0; m->val_entries = -1;
+  m->sten.w = 0; m->sten_slices = 0;
+  return 0;
+}
+
+int sell_share_values(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->n <= 0 || m->col_ptr == m->slice_ptr || m->uniform_slices == 0 || m->vcode) return 0;
+  UG_TRY(sell_drop_shared_values(ctx, m));
+  if (getenv("UGGPU_NO_SHARED_VALUES")) return 0;
+  cudaStream_t st = ctx->stream;
+  const size_t nsl = (size_t)(m->n + 31) / 32;
+  uint8_t *d_flag = nullptr; int *d_cnt = nullptr; unsigned long long *d_hash = nullptr;
+  UG_TRY(dalloc(ctx, &d_flag, nsl));
+  UG_TRY(dalloc(ctx, &d_cnt, nsl));
+  UG_TRY(dalloc(ctx, &d_hash, nsl + 1));       // [nsl]: mismatch counter of the verification
+  const int blocks = (int)((nsl * 32 + 255) / 256);
+  k_sell_vuniform_flag<<<blocks, 256, 0, st>>>(m->n, m->bb, m->slice_ptr, m->col_ptr, m->rowlen, m->val, d_flag, d_cnt, d_hash);
+  KCHECK(ctx);
+  std::vector<uint8_t> flag(nsl);
+  std::vector<int> cnt(nsl);
+  std::vector<unsigned long long> hash(nsl);
+  std::vector<int64_t> sp(nsl + 1), cp(nsl), ncp(nsl);
+  CUDA_TRY(cudaMemcpyAsync(flag.data(), d_flag, nsl, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, nsl * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(hash.data(), d_hash, nsl * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(sp.data(), m->slice_ptr, (nsl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(cp.data(), m->col_ptr, nsl * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  UG_TRY(dfree(ctx, d_flag, nsl));
+  UG_TRY(dfree(ctx, d_cnt, nsl));
+  int rc = 0;
+  for (int dedupe = 1; dedupe >= 0; dedupe--) {
+    std::map<unsigned long long, int64_t> tables;
+    int64_t voff = 0, entries = 0, shared = 0;
+    for (size_t s = 0; s < nsl; s++) {
+      ncp[s] = cp[s];
+      if (!flag[s]) { entries += cnt[s]; continue; }
+      const int64_t w = (sp[s + 1] - sp[s]) >> 5;
+      shared++;
+      int64_t vo;
+      auto it = dedupe ? tables.find(hash[s]) : tables.end();
+      if (it != tables.end()) vo = it->second;
+      else {
+        vo = voff; voff += (w * m->bb + 1) & ~(int64_t)1; entries += w;      // 16-byte granules; a shared table crosses HBM once
+        if (dedupe) tables[hash[s]] = vo;
+      }
+      ncp[s] = ~(UG_COLTAB(cp[s]) | ((vo + 1) << 32));
+    }
+    if (shared == 0 || voff >= ((int64_t)1 << 30)) break;
+    // worth it only if most of the value stream disappears
+    if (entries * 4 > m->nnz * 3) break;
+    double *vt = nullptr; int64_t *d_cp = nullptr;
+    if ((rc = dalloc(ctx, &vt, (size_t)voff)) != 0) break;
+    if ((rc = dalloc(ctx, &d_cp, nsl)) != 0) { dfree(ctx, vt, (size_t)voff); break; }
+    cudaMemsetAsync(vt, 0, (size_t)voff * sizeof(double), st);
+    cudaMemsetAsync(d_hash + nsl, 0, sizeof(unsigned long long), st);
+    cudaMemcpyAsync(d_cp, ncp.data(), nsl * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    k_sell_fill_vt<<<blocks, 256, 0, st>>>(m->n, m->bb, m->slice_ptr, d_cp, m->rowlen, m->val, vt);
+    ctx->launches++;
+    k_sell_verify_vt<<<(m->n + 255) / 256, 256, 0, st>>>(m->n, m->bb, m->slice_ptr, d_cp, m->rowlen, m->val, vt, d_hash + nsl);
+    ctx->launches++;
+    unsigned long long bad = 1;
+    cudaMemcpyAsync(&bad, d_hash + nsl, sizeof bad, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = uggpu_fail(UGGPU_CUDA_ERROR, "shared value tables: %s", cudaGetErrorString(e)); dfree(ctx, vt, (size_t)voff); dfree(ctx, d_cp, nsl); break; }
+    if (bad) { dfree(ctx, vt, (size_t)voff); dfree(ctx, d_cp, nsl); continue; }      // hash collision: retry without sharing between slices
+    dfree(ctx, m->col_ptr, nsl);
+    m->col_ptr = d_cp; m->vt = vt; m->vt_len = voff; m->vshared_slices = shared; m->val_entries = entries;
+    // scalar matrices: the code word most slices carry = the dominant stencil (kernel-parameter tables of the stencil kernel, spmv.cu)
+    if (m->bb == 1) {
+      std::map<int64_t, int64_t> freq;
+      for (size_t s = 0; s < nsl; s++) if (flag[s]) freq[ncp[s]]++;
+      int64_t best = 0, bestn = 0;
+      for (auto &kv : freq) if (kv.second > bestn) { best = kv.first; bestn = kv.second; }
+      size_t s0 = 0;
+      while (s0 < nsl && ncp[s0] != best) s0++;
+      const int64_t w = s0 < nsl ? (sp[s0 + 1] - sp[s0]) >> 5 : 0;
+      if (bestn * 2 > (int64_t)nsl && w >= 1 && w <= 32) {
+        int32_t dist[32]; double vals[32];
+        cudaMemcpyAsync(dist, m->col + UG_COLTAB(best), sizeof(int32_t) * w, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(vals, vt + UG_VALTAB(best), sizeof(double) * w, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) == cudaSuccess) {
+          Sten sn; memset(&sn, 0, sizeof sn);
+          sn.code = best; sn.w = (int)w; sn.maxd = 0;
+          for (int j = 0; j < w; j++) { sn.dbytes[j] = (long long)dist[j] * 8; sn.v[j] = vals[j]; if (dist[j] > sn.maxd) sn.maxd = dist[j]; }
+          m->sten = sn; m->sten_slices = bestn;
+        }
+      }
+    }
+    break;
+  }
+  dfree(ctx, d_hash, nsl + 1);
+  return rc;
+}
+
 // ---- value dictionary of the transfer stencils ---------------------------------------------------------------------------------
 #define VT_SLOTS 1024
 #define VT_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -356,6 +538,7 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   if (m->bnd_flag) dfree(ctx, m->bnd_flag, nsl);
   if (m->vcode) dfree(ctx, m->vcode, (size_t)m->padded);
   if (m->vtable) dfree(ctx, m->vtable, 256);
+  if (m->vt) dfree(ctx, m->vt, (size_t)m->vt_len);
   if (m->bnd_list) dfree(ctx, m->bnd_list, (size_t)(m->n_bnd > 0 ? m->n_bnd : 1));
   if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);

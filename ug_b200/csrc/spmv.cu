@@ -18,13 +18,24 @@
 #ifndef SPMV_UNROLL_U
 #define SPMV_UNROLL_U 4      // unroll of the uniform-slice loop (gather addresses are load-independent there)
 #endif
+#ifndef SPMV_MINBLOCKS
+#define SPMV_MINBLOCKS (2048 / SPMV_THREADS)   // scalar rows: resident blocks per SM the smoothing kernel is compiled for (register bound)
+#endif
+#ifndef SPMV_FULL
+#define SPMV_FULL 1          // 1: slices with shared values whose rows all have the full width run a predicate-free loop
+#endif
+#ifndef SPMV_EARLY
+#define SPMV_EARLY 0         // 1: the row's own b, c, tin entries are requested before the row product (scalar rows)
+#endif
 #define SPMV_PRAGMA_(x) _Pragma(#x)
 #define SPMV_PRAGMA(x) SPMV_PRAGMA_(x)
 
 // One row times y.  UNIFORM selects the column-index form of the slice (uggpu_internal.h): explicit words, one per entry,
 // or one distance per slice column shared by the 32 rows.  In the uniform form lane j holds distance j in a register (one
 // coalesced load per slice) and the loop broadcasts it with a shuffle, so the gather addresses do not depend on a load.
-template <int BS, bool UNIFORM>
+// VSHARED (uniform slices only): the slice's values come from a shared table, one block per slice column (sell.cu
+// sell_share_values) -- a warp-uniform, L1-resident load instead of 256 bytes of HBM stream per component and column.
+template <int BS, bool UNIFORM, bool VSHARED = false>
 __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len, int64_t cpo, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
   constexpr int BB = BS * BS;
@@ -38,7 +49,36 @@ __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len,
   if (UNIFORM) {
     // all 32 lanes of the warp are here (rows that do not take part have len = 0)
     const int w = slice_width(A, r >> 5, sp);
-    const int32_t *__restrict__ dp = A.col + ~cpo;
+    const int32_t *__restrict__ dp = A.col + UG_COLTAB(cpo);
+    const double *__restrict__ tp = VSHARED ? A.vt + UG_VALTAB(cpo) : nullptr;
+#if SPMV_FULL
+    // all 32 rows have the slice's full width (every slice of interior rows): no per-lane predicate inside the loop, so the
+    // compiler is free to batch the loop's loads
+    if (VSHARED && w <= 32 && __all_sync(0xffffffffu, len == w)) {
+      const int dreg = lane < w ? __ldg(dp + lane) : 0;
+SPMV_PRAGMA(unroll SPMV_UNROLL_U)
+      for (int j = 0; j < w; j++) {
+        const int c = r + __shfl_sync(0xffffffffu, dreg, j);
+        double m[BB], wv[BS];
+#pragma unroll
+        for (int k = 0; k < BB; k++) m[k] = __ldg(tp + (size_t)j * BB + k);
+#pragma unroll
+        for (int i = 0; i < BS; i++) wv[i] = y[(size_t)c * BS + i];
+        if (j == 0) {
+#pragma unroll
+          for (int k = 0; k < BB; k++) dg[k] = m[k];
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double acc = m[i * BS] * wv[0];
+#pragma unroll
+          for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * wv[q];
+          s[i] += acc;
+        }
+      }
+      return;
+    }
+#endif
     for (int j0 = 0; j0 < w; j0 += 32) {
       const int dreg = (j0 + lane < w) ? __ldg(dp + j0 + lane) : 0;
       const int jn = min(32, w - j0);
@@ -49,7 +89,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
         if (j < len) {
           double m[BB], wv[BS];
 #pragma unroll
-          for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
+          for (int k = 0; k < BB; k++) m[k] = VSHARED ? __ldg(tp + (size_t)j * BB + k) : __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
           for (int i = 0; i < BS; i++) wv[i] = y[(size_t)c * BS + i];
           if (j == 0) {
@@ -98,8 +138,10 @@ __device__ __forceinline__ void row_product(const SellView &A, int r, bool live,
 {
   const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
   const int len = live ? (int)A.rowlen[r] : 0;
-  if (cpo < 0) row_product_t<BS, true>(A, r, len, cpo, y, s, dg);
-  else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);
+  if (cpo < 0) {
+    if (A.vt && UG_VALTAB(cpo) >= 0) row_product_t<BS, true, true>(A, r, len, cpo, y, s, dg);
+    else row_product_t<BS, true>(A, r, len, cpo, y, s, dg);
+  } else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);
 }
 
 // SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
@@ -286,7 +328,7 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
 // scalar rows: at most 32 registers, so that 2048 threads are resident per SM (the variant with the norm partials took 40 without
 // the bound: 75 % occupancy, 4.69 instead of ~4.2 ms on the finest level)
 template <int BS, int FLAGS>
-__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? SPMV_MINBLOCKS : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
                                                            const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                            double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err,
                                                            Prefetch pf, const int32_t *__restrict__ list, int nlist, const uint8_t *__restrict__ skip_slice)
@@ -302,13 +344,20 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
   double s[BS], dg[BS * BS];
+  // scalar rows: the row's own entries of b, c, tin are requested first, so that their (HBM or L2) round trip runs next to the gathers
+  double eb = 0.0, ec = 0.0, et = 0.0;
+  if (SPMV_EARLY && BS == 1 && active) {
+    eb = b[r];
+    if ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ec = c[r];
+    if (FLAGS & (SF_CADD | SF_CSET)) et = tin[r];
+  }
   if ((r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
   if (active) {
     double bn[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) {
       size_t k = (size_t)r * BS + i;
-      bn[i] = b[k] - s[i];
+      bn[i] = ((SPMV_EARLY && BS == 1) ? eb : b[k]) - s[i];
       b[k] = bn[i];
     }
     if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
@@ -316,9 +365,11 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 
       for (int i = 0; i < BS; i++) {
         size_t k = (size_t)r * BS + i;
         double cn;
-        if (FLAGS & SF_CADD) cn = c[k] + tin[k];
-        else if (FLAGS & SF_CSET) cn = 0.0 + tin[k];
-        else cn = c[k];
+        const double tk = (SPMV_EARLY && BS == 1) ? et : ((FLAGS & (SF_CADD | SF_CSET)) ? tin[k] : 0.0);
+        const double ck = (SPMV_EARLY && BS == 1) ? ec : ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET) ? c[k] : 0.0);
+        if (FLAGS & SF_CADD) cn = ck + tk;
+        else if (FLAGS & SF_CSET) cn = 0.0 + tk;
+        else cn = ck;
         if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
         if (FLAGS & SF_XADD) x[k] = x[k] + cn;
       }
@@ -366,6 +417,103 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? 2048 / SPMV_THREADS : 
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) partials[(size_t)blockIdx.x * BS + i] = v;
       }
+    }
+  }
+}
+
+// ---- fused smoothing step, stencil variant (scalar rows) -------------------------------------------------------------------
+// Same arithmetic as k_smooth_k.  On a matrix whose slices mostly carry ONE stencil (Sten: the dominant pair of column-distance
+// and value tables, sell_share_values) the thread-per-row kernel is no longer limited by HBM but by instruction issue: ncu on the
+// 513^3 level showed ~490 warp instructions per slice, 2/3 of them bookkeeping (generic prefetch, 64-bit slice arithmetic, the
+// paths for other storage forms).  Here the stencil arrives as a kernel parameter and its width W is a template parameter (15:
+// P1 on simplices, 27: Q1 on hexahedra), so the loop over its columns is unrolled without predicates, every distance and value
+// is a constant-bank operand (no table load, no shuffle), the row's own b, c, tin entries are requested before the gathers, and
+// the prefetch touches only what such a slice streams (b, c, and the rows of tin first reached through the largest distance).
+// Slices with another code word, or with rows shorter than the stencil, take row_product.
+template <int FLAGS>
+__device__ __forceinline__ double smooth_tail(int r, double sum, double dg, double eb, double ec, double et, uint8_t vc, const uint8_t *__restrict__ ctl,
+                                              double *__restrict__ b, double *__restrict__ c, double *__restrict__ tout, double damp, double *__restrict__ x)
+{
+  const double bn = eb - sum;
+  b[r] = bn;
+  if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+    double cn;
+    if (FLAGS & SF_CADD) cn = ec + et;
+    else if (FLAGS & SF_CSET) cn = 0.0 + et;
+    else cn = ec;
+    if (FLAGS & (SF_CADD | SF_CSET)) c[r] = cn;
+    if (FLAGS & SF_XADD) x[r] = x[r] + cn;
+  }
+  if (FLAGS & SF_TOUT) {
+    const double sol = vc < 3 ? 0.0 : bn / dg;                 // l_jac: 0 below ACTIVE_CLASS (ugiter.cc:300)
+    tout[r] = sol * damp;
+  }
+  if (FLAGS & SF_NORM) {
+    if (ctl[r] & UGGPU_CTL_NEW_DEFECT) return bn * bn;
+  }
+  return 0.0;
+}
+
+template <int FLAGS, int W>
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MINBLOCKS) k_smooth_sten(const __grid_constant__ Sten st, SellView A, const uint8_t *__restrict__ vclass,
+                                                                              const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b,
+                                                                              double *__restrict__ c, double *__restrict__ tout, double damp, double *__restrict__ x,
+                                                                              double *__restrict__ partials, int *err, int pf_dist, int nsl)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5;
+  const bool active = r < A.n;
+  double nrm = 0.0;
+  if (s < nsl) {                                               // whole warps
+    const long long cpo = __ldg(A.col_ptr + s);
+    const int len = active ? (int)A.rowlen[r] : 0;
+    if (cpo == st.code && __all_sync(0xffffffffu, len == W)) {
+      // the row's own entries first: their round trip runs next to the gathers
+      const double eb = b[r];
+      const double ec = ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ? c[r] : 0.0;
+      const double et = (FLAGS & (SF_CADD | SF_CSET)) ? tin[r] : 0.0;
+      const uint8_t vc = (FLAGS & SF_TOUT) ? vclass[r] : (uint8_t)3;
+      const char *yb = reinterpret_cast<const char *>(tin + r);
+      double sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        const double y = __ldg(reinterpret_cast<const double *>(yb + st.dbytes[j]));
+        const double p = st.v[j] * y;
+        sum += p;
+      }
+      nrm = smooth_tail<FLAGS>(r, sum, st.v[0], eb, ec, et, vc, ctl, b, c, tout, damp, x);
+    } else {
+      double s1[1], d1[1];
+      row_product<1>(A, r, active, tin, s1, d1);
+      if (active) {
+        const double eb = b[r];
+        const double ec = ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ? c[r] : 0.0;
+        const double et = (FLAGS & (SF_CADD | SF_CSET)) ? tin[r] : 0.0;
+        const uint8_t vc = (FLAGS & SF_TOUT) ? vclass[r] : (uint8_t)3;
+        nrm = smooth_tail<FLAGS>(r, s1[0], d1[0], eb, ec, et, vc, ctl, b, c, tout, damp, x);
+      }
+    }
+    // L2 prefetch for the slice pf_dist ahead: its rows of b and c, and the rows of tin that slice reaches first (largest distance)
+    const int lane = threadIdx.x & 31;
+    if (pf_dist > 0 && s + pf_dist < nsl && lane < 8) {
+      const size_t far = ((size_t)(s + pf_dist)) * 32;
+      if (lane < 2) { if (far + lane * 16 < (size_t)A.n) prefetch_l2(b + far + lane * 16); }
+      else if (lane < 4) { if (((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) && far + (lane - 2) * 16 < (size_t)A.n) prefetch_l2(c + far + (lane - 2) * 16); }
+      else if (lane < 7) { if (far + st.maxd + (lane - 4) * 16 < (size_t)A.n) prefetch_l2(tin + far + st.maxd + (lane - 4) * 16); }
+      else if (FLAGS & SF_TOUT) prefetch_l2(vclass + far);
+    }
+  }
+  if (FLAGS & SF_NORM) {
+    __shared__ double sm[SPMV_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double v = nrm;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      v = lane < SPMV_THREADS / 32 ? sm[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) partials[blockIdx.x] = v;
     }
   }
 }
@@ -465,7 +613,7 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) k_smooth_tma(SellView A
       const double *__restrict__ trow = tin + r;
       if (f_cpo < 0) {
         if (f_cpo != d_cpo) {                 // new distance table: one coalesced load, then kept in registers (slices share tables)
-          const int dreg = __ldg(A.col + ~f_cpo + lane);      // the column array ends with 32 spare words
+          const int dreg = __ldg(A.col + UG_COLTAB(f_cpo) + lane);      // the column array ends with 32 spare words
 #pragma unroll
           for (int j = 0; j < 32; j++) dtab[j] = __shfl_sync(0xffffffffu, dreg, j);
           d_cpo = f_cpo;
@@ -688,6 +836,15 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *ti
     }
     CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], ctx->halo_stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
+  } else if (BS == 1 && (A->sten.w == 15 || A->sten.w == 27) && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
+    // most slices carry one stencil: the variant with the stencil in the constant bank (same arithmetic, a third of the instructions)
+    const Prefetch pf = make_prefetch(ctx, A, BS);
+    if (A->sten.w == 15)
+      k_smooth_sten<FLAGS, 15><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr,
+                                                                          pf.dist, (L->n + 31) / 32);
+    else
+      k_smooth_sten<FLAGS, 27><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr,
+                                                                          pf.dist, (L->n + 31) / 32);
   } else {
     k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
                                                                       make_prefetch(ctx, A, BS), nullptr, 0, nullptr);

@@ -440,6 +440,7 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
     SellMat m;
     UG_TRY(synth_sell<GEN_A>(ctx, sp, L.d_part, L.d_part, n, &m));
     UG_TRY(sell_update_diag(ctx, &m));
+    UG_TRY(sell_share_values(ctx, &m));
     L.mats[A] = m;
     if (l > 0) {
       Level &Lc = ctx->lev[l - 1];

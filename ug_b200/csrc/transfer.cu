@@ -89,7 +89,7 @@ __device__ __forceinline__ void tr_head(const SellView &T, const uint32_t *__res
     h.wp[k] = T.val + sp[k] + lane;
     h.cp8[k] = T.vcode + sp[k] + lane;
     const bool uni = cp[k] < 0;
-    h.ci[k] = ColIter{uni ? T.col + ~cp[k] : T.col + cp[k] + lane, uni ? 1 : 32, uni ? rr : 0};
+    h.ci[k] = ColIter{uni ? T.col + UG_COLTAB(cp[k]) : T.col + cp[k] + lane, uni ? 1 : 32, uni ? rr : 0};
     h.maxl = max(h.maxl, h.len[k]);
   }
 }

@@ -15,6 +15,14 @@
 //    A slice is "uniform" when entry j of all its rows has the same distance to the row's own index -- the case
 //    of every slice of interior rows of a structured or uniformly refined grid.  col_ptr[s] < 0 marks the uniform
 //    form (bitwise complement of the offset).  The decoded indices are identical, only fewer bytes cross HBM.
+//  * values of uniform slices can be shared the same way (sell.cu sell_share_values, matrices only): when, in addition, entry j
+//    of all rows of the slice holds the same value (block) -- every slice of interior rows of a constant-coefficient operator
+//    on a structured or uniformly refined grid -- the slice reads its values from a table vt[] (one block per slice column)
+//    that slices with bit-identical value vectors share.  The code word of a uniform slice packs both offsets:
+//      ~col_ptr[s] = column-table offset (low 32 bits) | (value-table offset + 1) << 32 (0: explicit values)
+//    The explicit val[] array stays complete (the ILU/LU setup, uggpu_mat_get and the schedule builders read it); only the
+//    SpMV-type kernels take the table, i.e. the bytes that cross HBM per sweep shrink, not the footprint.  Lossless: the
+//    decoded doubles are the stored ones bit for bit, verified on the device when the tables are built.
 #ifndef UGGPU_INTERNAL_H
 #define UGGPU_INTERNAL_H
 
@@ -27,6 +35,20 @@
 #include "uggpu.h"
 
 #define SLICE 32
+// decoding of a uniform slice's code word cp = col_ptr[s] < 0
+#define UG_COLTAB(cp) ((int64_t)((~(cp)) & 0xffffffffll))          // offset of the distance table in col[]
+#define UG_VALTAB(cp) ((int64_t)((~(cp)) >> 32) - 1)               // offset of the shared value table in vt[]; -1: explicit values
+
+// The dominant stencil of a scalar matrix: the (column distances, values) pair that most slices share (sell_share_values).
+// Passed to the stencil variant of the smoothing kernel BY VALUE: the tables then live in the kernel's constant bank and, with
+// the loop over the slice columns unrolled, every distance and value is an immediate operand -- no load, no shuffle.
+struct Sten {
+  long long code;          // col_ptr[s] of the slices that use it
+  int w;                   // slice columns (0: the matrix has no dominant stencil)
+  int maxd;                // largest column distance (rows first touched through it: prefetch target)
+  long long dbytes[32];    // column distance * sizeof(double)
+  double v[32];
+};
 
 struct SellMat {
   int      n = 0;          // rows
@@ -47,6 +69,12 @@ struct SellMat {
   double  *vtable = nullptr;      // [256]
   int      nvals = 0;
   double  *val = nullptr;         // [padded*bb]
+  double  *vt = nullptr;          // [vt_len] shared value tables of uniform slices (sell_share_values), else nullptr
+  int64_t  vt_len = 0;
+  int64_t  vshared_slices = 0;
+  Sten     sten = {0, 0, 0, {0}, {0.0}};   // scalar matrices: the dominant stencil, when more than half of the slices use it
+  int64_t  sten_slices = 0;
+  int64_t  val_entries = -1;      // entries whose values a pass fetches from HBM: true entries of explicit slices + the distinct tables (-1: nnz)
   double  *diag = nullptr;        // [nslices*32*bb] copy of entry 0 of every row (the diagonal block), same planar slice layout as val with width 1:
                                   // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
                                   // fused into the restriction) stream it instead of touching one column of every slice of val.  Matrices only (not P, R).
@@ -58,7 +86,7 @@ struct SellMat {
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
   // compulsory bytes of one pass over the stored matrix (values + column words), the "z*W" term of SURVEY.md 8(d) for this format
-  double entry_bytes() const { return (vcode ? 1.0 : 8.0) * (double)nnz * bb + 4.0 * (double)col_words; }
+  double entry_bytes() const { return (vcode ? 1.0 : 8.0) * (double)(val_entries >= 0 ? val_entries : nnz) * bb + 4.0 * (double)col_words; }
 };
 
 struct SellView {          // what a kernel needs (passed by value)
@@ -72,8 +100,9 @@ struct SellView {          // what a kernel needs (passed by value)
   const double *diag;
   const uint8_t *vcode;      // transfer stencils with a value table (else nullptr)
   const double *vtable;
+  const double *vt;          // shared value tables of uniform slices (else nullptr)
 };
-static inline SellView view(const SellMat &m) { return SellView{m.n, m.fixed_w, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag, m.vcode, m.vtable}; }
+static inline SellView view(const SellMat &m) { return SellView{m.n, m.fixed_w, m.slice_ptr, m.col_ptr, m.rowlen, m.col, m.val, m.diag, m.vcode, m.vtable, m.vt}; }
 
 #ifdef __CUDACC__
 // entry offset of slice s (and its width): computed for fixed-width matrices -- one dependent load less per row
@@ -84,7 +113,7 @@ struct ColIter { const int32_t *p; int stride; int base; };
 __device__ __forceinline__ ColIter col_iter(const SellView &A, int r)
 {
   const int64_t cp = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
-  if (cp < 0) return ColIter{A.col + ~cp, 1, r};
+  if (cp < 0) return ColIter{A.col + UG_COLTAB(cp), 1, r};
   return ColIter{A.col + cp + (r & 31), 32, 0};
 }
 __device__ __forceinline__ int col_at(const ColIter &ci, int j) { return __ldg(ci.p + (size_t)j * ci.stride) + ci.base; }
@@ -186,7 +215,7 @@ __device__ __forceinline__ PfState pf_begin(const SellView &A, int r, const Pref
   }
   if (pf.dist > 0 && st.slice < pf.nsl) {
     st.sp = A.fixed_w ? (int64_t)st.slice * 32 * A.fixed_w : __ldg(A.slice_ptr + st.slice);
-    if (pf.mode & 2) st.cp = (A.fixed_w && A.col_ptr == A.slice_ptr) ? st.sp : __ldg(A.col_ptr + st.slice);
+    if ((pf.mode & 2) || A.vt) st.cp = (A.fixed_w && A.col_ptr == A.slice_ptr) ? st.sp : __ldg(A.col_ptr + st.slice);
   }
   return st;
 }
@@ -196,7 +225,7 @@ __device__ __forceinline__ void pf_end(const SellView &A, const PfState &st, con
 {
   if (st.sp < 0) return;
   const int lane = threadIdx.x & 31;
-  if (pf.mode & 1) {
+  if ((pf.mode & 1) && !(A.vt && st.cp < 0 && UG_VALTAB(st.cp) >= 0)) {      // a slice with shared values has no value stream
     const int64_t o = st.sp * BB * (int64_t)sizeof(double);
     for (int l = lane; l < pf.val_lines; l += 32)
       if (o + (int64_t)l * 128 < pf.val_bytes) prefetch_l2(reinterpret_cast<const char *>(A.val) + o + (int64_t)l * 128);
@@ -315,6 +344,9 @@ int sell_compress_cols(uggpu_ctx *ctx, SellMat *m);
 int sell_update_diag(uggpu_ctx *ctx, SellMat *m);
 // scalar-entry matrices with at most 256 distinct stored values get a one-byte code per entry + a table (lossless); no-op otherwise
 int sell_compress_values(uggpu_ctx *ctx, SellMat *m);
+// matrices: uniform slices whose rows also hold identical values share value tables (lossless; the explicit values stay); drop = forget them
+int sell_share_values(uggpu_ctx *ctx, SellMat *m);
+int sell_drop_shared_values(uggpu_ctx *ctx, SellMat *m);
 
 // ---- kernels used across files --------------------------------------------------------------------------
 struct Damp { double a[UGGPU_MAX_BS]; };
