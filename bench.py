@@ -327,10 +327,14 @@ def our_arm(args):
     if os.path.exists(tpath):        # ncu capture of the default workload only
         tj = json.load(open(tpath))
         if tj.get("workload") == {"kind": args.kind, "cells": cells, "top": top} and world == 1:
-            traffic = tj.get("k_smooth_k_dram_bytes_per_launch")
+            traffic = tj.get("dominant_kernel_dram_bytes_per_launch", tj.get("k_smooth_k_dram_bytes_per_launch"))
     # SURVEY.md 8(d) counts 4 bytes of column index per entry; the stored format fetches fewer (compressed column words)
     nnz_top, words_top = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A)), int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
     vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables)
+    sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if bs == 1 and not os.environ.get("UGGPU_NO_STENCIL") else 0
+    sten_w = round(nnz_top / max(ctx.level_n(top), 1))
+    smooth_kernel = (f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)" if sten_top > 0 and sten_w in (15, 27)
+                     else f"k_smooth_k<{bs},*> (fused smoothing step, finest level)")
     survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
     achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     total_alg = sum(v["alg_bytes"] for v in prof.values())
@@ -350,13 +354,13 @@ def our_arm(args):
                    "cache": "inputs larger than L2 (the finest matrix alone is tens of GB per sweep)",
                    "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3),
                    "defect": [first, hist[-1]] if hist else None},
-        "roofline": {"bound": "hbm", "kernel": f"k_smooth_k<{bs},*> (fused smoothing step, finest level)" if args.smoother == "jac" else
+        "roofline": {"bound": "hbm", "kernel": smooth_kernel if args.smoother == "jac" else
                      f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
                      "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
                      "bytes_model": "as stored: 8 B per value fetched (slices of identical rows share value tables), compressed column words (DESIGN.md 2-3), vectors once",
-                     "value_entries_per_entry": vals_top / max(nnz_top, 1),
+                     "value_entries_per_entry": vals_top / max(nnz_top, 1), "stencil_slices_frac": sten_top / max((ctx.level_n(top) + 31) // 32, 1),
                      "achieved_survey_model": achieved_survey, "column_words_per_entry": words_top / max(nnz_top, 1),
                      "share_of_step": dom["ms"] / ms,
                      "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
