@@ -351,7 +351,7 @@ def our_arm(args):
                    "parallelism": f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + NCCL halo copies, "
                                   f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
                    "halo_exchanges_total": exchanges,
-                   "cache": "inputs larger than L2 (the finest matrix alone is tens of GB per sweep)",
+                   "cache": "inputs larger than L2 (every sweep over the finest level streams several GB; each of its vectors alone is 1 GB)",
                    "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3),
                    "defect": [first, hist[-1]] if hist else None},
         "roofline": {"bound": "hbm", "kernel": smooth_kernel if args.smoother == "jac" else
