@@ -12,5 +12,5 @@ PY
 }
 for v in "$@"; do
   lib=$PWD/ug_b200/lib/libuggpu_$v.so; [ "$v" = base ] && lib=$PWD/ug_b200/lib/libuggpu.so
-  UGGPU_LIB=$lib timeout 300 python bench.py --no-cpu --steps 4 --e2e-steps 1 $EXTRA > $out/${tag}_$v.json 2>&1; summ $out/${tag}_$v.json $v
+  UGGPU_LIB=$lib timeout 300 python bench.py --no-cpu --steps 3 --e2e-steps 1 $EXTRA > $out/${tag}_$v.json 2>&1; summ $out/${tag}_$v.json $v
 done
