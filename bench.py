@@ -331,10 +331,14 @@ def our_arm(args):
     # SURVEY.md 8(d) counts 4 bytes of column index per entry; the stored format fetches fewer (compressed column words)
     nnz_top, words_top = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A)), int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
     vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables)
-    sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if bs == 1 and not os.environ.get("UGGPU_NO_STENCIL") else 0
+    sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if not os.environ.get("UGGPU_NO_STENCIL") else 0
     sten_w = round(nnz_top / max(ctx.level_n(top), 1))
-    smooth_kernel = (f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)" if sten_top > 0 and sten_w in (15, 27)
-                     else f"k_smooth_k<{bs},*> (fused smoothing step, finest level)")
+    if sten_top > 0 and bs == 1 and sten_w in (15, 27):
+        smooth_kernel = f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)"
+    elif sten_top > 0 and bs == 3:
+        smooth_kernel = "k_smooth_sten3<*> (fused smoothing step, 3x3-block stencil variant, finest level)"
+    else:
+        smooth_kernel = f"k_smooth_k<{bs},*> (fused smoothing step, finest level)"
     survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
     achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     total_alg = sum(v["alg_bytes"] for v in prof.values())

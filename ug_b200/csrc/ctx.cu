@@ -348,7 +348,7 @@ extern "C" int64_t uggpu_mat_val_entries(uggpu_ctx *ctx, int level, int mat)
 extern "C" int64_t uggpu_mat_stencil_slices(uggpu_ctx *ctx, int level, int mat)
 {
   SellMat *m = get_mat(ctx, level, mat);
-  return m ? (m->sten.w > 0 ? m->sten_slices : 0) : -1;
+  return m ? ((m->sten.w > 0 || m->sten3) ? m->sten_slices : 0) : -1;
 }
 
 extern "C" int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat)

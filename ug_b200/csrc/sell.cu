@@ -329,6 +329,7 @@ int sell_drop_shared_values(uggpu_ctx *ctx, SellMat *m)
   if (m->vt) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); UG_TRY(dfree(ctx, m->vt, (size_t)m->vt_len)); }
   m->vt_len = 0; m->vshared_slices = 0; m->val_entries = -1;
   m->sten.w = 0; m->sten_slices = 0;
+  delete m->sten3; m->sten3 = nullptr;
   return 0;
 }
 
@@ -397,7 +398,7 @@ int sell_share_values(uggpu_ctx *ctx, SellMat *m)
     dfree(ctx, m->col_ptr, nsl);
     m->col_ptr = d_cp; m->vt = vt; m->vt_len = voff; m->vshared_slices = shared; m->val_entries = entries;
     // scalar matrices: the code word most slices carry = the dominant stencil (kernel-parameter tables of the stencil kernel, spmv.cu)
-    if (m->bb == 1) {
+    if (m->bb == 1 || m->bb == 9) {
       std::map<int64_t, int64_t> freq;
       for (size_t s = 0; s < nsl; s++) if (flag[s]) freq[ncp[s]]++;
       int64_t best = 0, bestn = 0;
@@ -405,7 +406,22 @@ int sell_share_values(uggpu_ctx *ctx, SellMat *m)
       size_t s0 = 0;
       while (s0 < nsl && ncp[s0] != best) s0++;
       const int64_t w = s0 < nsl ? (sp[s0 + 1] - sp[s0]) >> 5 : 0;
-      if (bestn * 2 > (int64_t)nsl && w >= 1 && w <= 32) {
+      const char *mf = getenv("UGGPU_STENCIL_MIN_FRAC");          // tests: let a smaller share of the slices count as dominant
+      const double minfrac = mf ? atof(mf) : 0.5;
+      if (m->bb == 9) {
+        if ((double)bestn > minfrac * (double)nsl && w == 27) {
+          int32_t dist[27];
+          Sten3 *s3 = new Sten3();
+          memset(s3, 0, sizeof *s3);
+          cudaMemcpyAsync(dist, m->col + UG_COLTAB(best), sizeof(int32_t) * 27, cudaMemcpyDeviceToHost, st);
+          cudaMemcpyAsync(s3->v, vt + UG_VALTAB(best), sizeof(double) * 27 * 9, cudaMemcpyDeviceToHost, st);
+          if (cudaStreamSynchronize(st) == cudaSuccess) {
+            s3->code = best; s3->w = 27; s3->maxd = 0;
+            for (int j = 0; j < 27; j++) { s3->dbytes[j] = (long long)dist[j] * 24; if (dist[j] > s3->maxd) s3->maxd = dist[j]; }
+            m->sten3 = s3; m->sten_slices = bestn;
+          } else delete s3;
+        }
+      } else if ((double)bestn > minfrac * (double)nsl && w >= 1 && w <= 32) {
         int32_t dist[32]; double vals[32];
         cudaMemcpyAsync(dist, m->col + UG_COLTAB(best), sizeof(int32_t) * w, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(vals, vt + UG_VALTAB(best), sizeof(double) * w, cudaMemcpyDeviceToHost, st);
@@ -539,6 +555,7 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   if (m->vcode) dfree(ctx, m->vcode, (size_t)m->padded);
   if (m->vtable) dfree(ctx, m->vtable, 256);
   if (m->vt) dfree(ctx, m->vt, (size_t)m->vt_len);
+  delete m->sten3;
   if (m->bnd_list) dfree(ctx, m->bnd_list, (size_t)(m->n_bnd > 0 ? m->n_bnd : 1));
   if (m->col_ptr != m->slice_ptr) dfree(ctx, m->col_ptr, nsl);
   dfree(ctx, m->slice_ptr, nsl + 1);

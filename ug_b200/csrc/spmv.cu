@@ -518,6 +518,121 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MINBLOCKS) k_smooth_sten(co
   }
 }
 
+// ... and for 3x3 blocks (Q1 hexahedra, 27 block columns): the generic kernel needs 156 registers for block rows (19 % occupancy),
+// which was fine while every thread streamed 2 KB of values per row, but leaves the SM idle once the values come from a shared
+// table.  With the 27 distances and 243 values as constant-bank operands a row is 81 gathers + 243 multiply-adds in straight-line
+// code.  Same sums in the same order as row_product_t (per entry and component i: acc = m_i0*w_0; acc += m_i1*w_1; acc += m_i2*w_2;
+// s_i += acc), same epilogue as k_smooth_k.
+#ifndef SPMV_STEN3_MINBLOCKS
+#define SPMV_STEN3_MINBLOCKS 8
+#endif
+template <int FLAGS>
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_STEN3_MINBLOCKS) k_smooth_sten3(const __grid_constant__ Sten3 st, SellView A, const uint8_t *__restrict__ vclass,
+                                                                                     const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b,
+                                                                                     double *__restrict__ c, double *__restrict__ tout, Damp damp, double *__restrict__ x,
+                                                                                     double *__restrict__ partials, int *err, int pf_dist, int nsl)
+{
+  constexpr int BS = 3, BB = 9;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5;
+  const bool active = r < A.n;
+  double nrm[BS] = {0.0, 0.0, 0.0};
+  if (s < nsl) {                                               // whole warps
+    const long long cpo = __ldg(A.col_ptr + s);
+    const int len = active ? (int)A.rowlen[r] : 0;
+    double sum[BS], dg[BB];
+    if (cpo == st.code && __all_sync(0xffffffffu, len == 27)) {
+      const char *yb = reinterpret_cast<const char *>(tin + (size_t)r * BS);
+#pragma unroll
+      for (int i = 0; i < BS; i++) sum[i] = 0.0;
+#pragma unroll
+      for (int k = 0; k < BB; k++) dg[k] = st.v[k];
+#pragma unroll
+      for (int j = 0; j < 27; j++) {
+        const double *yp = reinterpret_cast<const double *>(yb + st.dbytes[j]);
+        const double w0 = __ldg(yp), w1 = __ldg(yp + 1), w2 = __ldg(yp + 2);
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double acc = st.v[j * BB + i * BS] * w0;
+          acc = acc + st.v[j * BB + i * BS + 1] * w1;
+          acc = acc + st.v[j * BB + i * BS + 2] * w2;
+          sum[i] += acc;
+        }
+      }
+    } else {
+      row_product<BS>(A, r, active, tin, sum, dg);
+    }
+    if (active) {
+      double bn[BS];
+#pragma unroll
+      for (int i = 0; i < BS; i++) {
+        const size_t k = (size_t)r * BS + i;
+        bn[i] = b[k] - sum[i];
+        b[k] = bn[i];
+      }
+      if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          const size_t k = (size_t)r * BS + i;
+          double cn;
+          if (FLAGS & SF_CADD) cn = c[k] + tin[k];
+          else if (FLAGS & SF_CSET) cn = 0.0 + tin[k];
+          else cn = c[k];
+          if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
+          if (FLAGS & SF_XADD) x[k] = x[k] + cn;
+        }
+      }
+      if (FLAGS & SF_TOUT) {
+        double sol[BS];
+        if (vclass[r] < 3) {
+#pragma unroll
+          for (int i = 0; i < BS; i++) sol[i] = 0.0;
+        } else if (solve_small_block<BS>(dg, bn, sol)) {
+          atomicExch(err, UGGPU_SMALL_DIAG);
+#pragma unroll
+          for (int i = 0; i < BS; i++) sol[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) tout[(size_t)r * BS + i] = sol[i] * damp.a[i];
+      }
+      if (FLAGS & SF_NORM) {
+        if (ctl[r] & UGGPU_CTL_NEW_DEFECT) {
+#pragma unroll
+          for (int i = 0; i < BS; i++) nrm[i] = bn[i] * bn[i];
+        }
+      }
+    }
+    // L2 prefetch for the slice pf_dist ahead: its rows of b and c (6 lines each) and the rows of tin first reached through the largest distance
+    const int lane = threadIdx.x & 31;
+    if (pf_dist > 0 && s + pf_dist < nsl && lane < 19) {
+      const size_t far = ((size_t)(s + pf_dist)) * 32 * BS;
+      const size_t nn = (size_t)A.n * BS;
+      if (lane < 6) { if (far + lane * 16 < nn) prefetch_l2(b + far + lane * 16); }
+      else if (lane < 12) { if (((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) && far + (lane - 6) * 16 < nn) prefetch_l2(c + far + (lane - 6) * 16); }
+      else { const size_t o = far + (size_t)st.maxd * BS + (lane - 12) * 16; if (o < nn) prefetch_l2(tin + o); }
+    }
+  }
+  if (FLAGS & SF_NORM) {
+    __shared__ double sm[SPMV_THREADS / 32][UGGPU_MAX_BS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      double v = nrm[i];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) sm[w][i] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) {
+        double v = lane < SPMV_THREADS / 32 ? sm[lane][i] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) partials[(size_t)blockIdx.x * BS + i] = v;
+      }
+    }
+  }
+}
+
 // ---- fused smoothing step, asynchronously staged through shared memory ----------------------------------------------
 // Same arithmetic as k_smooth_k, scalar rows.  The thread-per-row kernel above keeps every byte of the matrix stream in
 // registers while it is in flight and runs out of outstanding loads long before it runs out of HBM bandwidth (ncu: 59 %
@@ -845,6 +960,11 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *ti
     else
       k_smooth_sten<FLAGS, 27><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr,
                                                                           pf.dist, (L->n + 31) / 32);
+  } else if (BS == 3 && A->sten3 && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
+    // the same for 3x3 blocks with the 27-column stencil of Q1 hexahedra (pf distance as for vector-only slices)
+    const Prefetch pf = make_prefetch(ctx, A, BS);
+    k_smooth_sten3<FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(*A->sten3, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                     pf.dist, (L->n + 31) / 32);
   } else {
     k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
                                                                       make_prefetch(ctx, A, BS), nullptr, 0, nullptr);

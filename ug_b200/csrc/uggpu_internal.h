@@ -50,6 +50,14 @@ struct Sten {
   double v[32];
 };
 
+// ... and of a matrix of 3x3 blocks (Q1 hexahedra: 27 block columns): 27 distances + 243 values = 2.2 KB of kernel parameters
+struct Sten3 {
+  long long code;
+  int w, maxd;
+  long long dbytes[27];    // column distance * 3 * sizeof(double)
+  double v[27 * 9];        // row-major 3x3 blocks in slice-column order
+};
+
 struct SellMat {
   int      n = 0;          // rows
   int      bb = 1;         // doubles per entry (bs*bs for A, 1 for transfer weights)
@@ -74,6 +82,7 @@ struct SellMat {
   int64_t  vshared_slices = 0;
   Sten     sten = {0, 0, 0, {0}, {0.0}};   // scalar matrices: the dominant stencil, when more than half of the slices use it
   int64_t  sten_slices = 0;
+  Sten3   *sten3 = nullptr;       // 3x3-block matrices: the dominant stencil (host heap, owned by the matrix), else nullptr
   int64_t  val_entries = -1;      // entries whose values a pass fetches from HBM: true entries of explicit slices + the distinct tables (-1: nnz)
   double  *diag = nullptr;        // [nslices*32*bb] copy of entry 0 of every row (the diagonal block), same planar slice layout as val with width 1:
                                   // component k of row r at diag[((r>>5)*bb + k)*32 + (r&31)].  Kernels that need only Diag(A) (l_jac, the Jacobi start
