@@ -1,4 +1,4 @@
-// gs.cu -- the Gauss-Seidel family of np/algebra/ugiter.cc on the device:
+// gs.cu -- the Gauss-Seidel family and the ILU smoother of np/algebra/ugiter.cc on the device:
 //   l_lgs :412  v = (D+L)^-1 d        l_ugs :735  v = (D+U)^-1 d        l_lsor :1343 / l_usor :1563  the same with relaxation
 // and the smoother classes built on them (np/procs/iter.cc: gs :1039, sgs :1392, sor :4744/:4786).
 //
@@ -12,10 +12,14 @@
 //   * a SECOND copy of the triangle, SELL-32 again, with the rows permuted into level order (levels padded to whole
 //     slices) and each row holding [diagonal block, entries of the solved side in list order]: a warp reads a level's rows
 //     with the same coalesced 128/256-byte loads as the SpMV kernels; column indices keep the original numbering.
-// The solve is ONE persistent kernel: warps take slices in schedule order from a ticket counter, wait until the previous
-// level's slice count is complete (one acquire poll per warp; the matrix lines of the slice are pulled into L2 meanwhile),
-// do their 32 rows, publish.  Tickets are handed out in order, so every slice a warp waits for is owned by a running warp:
-// no cooperative launch is needed and there is no deadlock; a wait that exceeds 20 s sets the device error word instead.
+// The solve is ONE persistent, cooperatively launched kernel per sweep with a static slice assignment (warp w owns slices w, w + W,
+// ...); a slice waits for the slices its rows read from (point-to-point completion words) or, on schedules with more than 32
+// dependencies per slice, for the whole previous level (per-SM counters + mailboxes) -- see "the solve" below.  A wait that exceeds
+// 20 s sets the device error word instead of hanging.
+//
+// ILU (second half of this file): uggpu_dmatcopy / uggpu_l_ilubthdecomp / uggpu_l_luiter = class `ilu` (np/procs/iter.cc:5385-5525):
+// the decomposition runs left-looking on the dependency levels of the lower triangle, one launch per level; l_luiter is two more
+// modes of the solve kernel.
 #include <cub/device/device_radix_sort.cuh>       // before uggpu_internal.h: its SLICE macro is an identifier inside cub
 #include <cub/device/device_scan.cuh>
 
