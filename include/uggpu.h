@@ -221,6 +221,15 @@ int uggpu_restrict(uggpu_ctx*, int level, int to, int from, const double *damp /
 /* StandardInterpolateCorrection(GRID_ON_LEVEL(level), to, from, damp): level-1 -> fine `level` */
 int uggpu_interpolate_correction(uggpu_ctx*, int level, int to, int from, const double *damp);
 
+/* ---- Galerkin coarse-grid operator, np/np.h:540, np/algebra/transgrid.cc:1575 ------------------------------
+ * AssembleGalerkinByMatrix(GRID_ON_LEVEL(level), A, 0) after dmatset(level-1, level-1, ALL_VECTORS, A, 0.0), i.e. what `npcheck $G`
+ * does (np/algebra/npcheck.cc:375-379): matrix A of level-1 := P^T A_level P on the interpolation stencils of `level`, every
+ * coarse entry receiving the reference's terms in the reference's order ((m*im)*jm over the fine rows in list order, their entries
+ * in list order, the interpolation entries of the neighbour in list order) -- bit-identical values.  The product must stay on the
+ * pattern A already has on level-1 (true on nested geometric hierarchies); where the reference would create connections this
+ * call fails with UGGPU_ERROR.  One GPU only. */
+int uggpu_galerkin(uggpu_ctx*, int level, int A);
+
 /* ---- multigrid cycle, np/procs/iter.cc:7741-7949 Lmgc ------------------------------------------------ */
 /* Base solver hook: called with the stream drained when the recursion reaches baselevel.  It must
  * turn the defect b into (correction c, updated defect b) on that level exactly like

@@ -38,4 +38,10 @@ mkdir -p $G
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --smoother ilu --beta 0.1 --damp 0.8 --cycles 5 --lean --dump $G/ilu_hex3d_bs3_r2.ugh --ops --solve > /dev/null
 ./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --smoother ilu --damp 1.0 --cycles 6 --lean --dump $G/ilu_tet3d_adapt.ugh --ops --solve > /dev/null
 ./_ref/ugoracle2 --grid quad --refine 3 --smoother ilu --beta 0.5 --damp 1.0 --cycles 4 --lean --dump $G/ilu_quad2d_r3.ugh --ops --solve > /dev/null
+# ---- Galerkin coarse-grid operators: AssembleGalerkinByMatrix on the stored interpolation matrices after dmatset(coarse, 0)
+# (what `npcheck $G` does), cascaded from the top level down; pattern + values of every coarse level.  Last record group of these dumps.
+./_ref/ugoracle3 --grid tet --refine 3 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_tet3d_r3.ugh --solve > /dev/null
+./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_hex3d_bs3_r2.ugh --solve > /dev/null
+./_ref/ugoracle2 --grid tri --refine 3 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_tri2d_r3.ugh --solve > /dev/null
+./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_tet3d_adapt.ugh --solve > /dev/null
 ls -la $G

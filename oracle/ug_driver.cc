@@ -99,6 +99,7 @@ struct Opt {
   int barrier_n = 0, barrier_id = 0;
   bool ops = false, solve = false, timeit = false, quiet = true;
   bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
+  bool galerkin = false;                // --galerkin (with --imat): Galerkin coarse-grid operators by AssembleGalerkinByMatrix, cascaded from the top level down
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
 };
 
@@ -629,6 +630,25 @@ static void time_reference(const Opt &o)
          DIM, BS, top + 1, n * BS, nnz, its, tcyc, n * BS / tcyc, best_mm, best_dot, lr.last_defect[0]);
 }
 
+// Galerkin coarse-grid operators: per level what `npcheck $G` does (np/algebra/npcheck.cc:375-379) -- dmatset(coarse, 0),
+// AssembleGalerkinByMatrix(fine grid, A, 0) (np/algebra/transgrid.cc:1575) on the stored interpolation matrices -- cascaded from the
+// top level down, so level l-1 is built from the Galerkin matrix of level l.  Connections the product needs and the coarse pattern
+// lacks are created by the reference (CreateExtraConnection: second place of both row lists); the dump holds the resulting
+// pattern and values of every coarse level in the canonical entry order.  Last record group of a dump: the matrices stay changed.
+static void dump_galerkin(const Opt &o)
+{
+  (void)o;
+  int top = TOPLEVEL(mg);
+  restore_problem();
+  for (int l = top; l >= 1; l--) {
+    if (dmatset(mg, l - 1, l - 1, ALL_VECTORS, mA, 0.0) != NUM_OK) { fprintf(stderr, "dmatset failed\n"); exit(11); }
+    if (AssembleGalerkinByMatrix(GRID_ON_LEVEL(mg, l), mA, 0) != NUM_OK) { fprintf(stderr, "AssembleGalerkinByMatrix failed\n"); exit(11); }
+    gpuls::FlatLevel f;
+    if (gpuls::FlattenFlags(mg, l - 1, vx, f) || gpuls::FlattenMatrix(mg, l - 1, mA, f)) { fprintf(stderr, "FlattenMatrix(galerkin) failed\n"); exit(11); }
+    D.i32(L("galerkin/rowptr", l - 1), f.rowptr); D.i32(L("galerkin/col", l - 1), f.col); D.f64(L("galerkin/val", l - 1), f.val);
+  }
+}
+
 #ifdef WITH_GPULS
 static int run_gpu(const Opt &o);
 #endif
@@ -651,6 +671,7 @@ int main(int argc, char **argv)
     else if (a == "--smoother") o.smoother = nxt(); else if (a == "--baselevel") o.baselevel = atoi(nxt().c_str());
     else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
     else if (a == "--beta") o.beta = atof(nxt().c_str());
+    else if (a == "--galerkin") o.galerkin = true;
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;
@@ -669,6 +690,7 @@ int main(int argc, char **argv)
   for (int l = 0; l <= top; l++) printf("%s%d", l ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
   printf("] build_s=%.2f\n", t1 - t0);
   if (o.smoother != "jac" && o.smoother != "gs" && o.smoother != "sgs" && o.smoother != "sor" && o.smoother != "ilu") { fprintf(stderr, "unknown smoother %s\n", o.smoother.c_str()); return 1; }
+  if (o.galerkin && !o.imat) { fprintf(stderr, "--galerkin needs --imat (the stored interpolation matrices)\n"); return 1; }
   if (o.imat)     // the interpolation matrices the $M mode works on (transgrid.cc:2363); the format reserves them ($I)
     for (int l = 1; l <= top; l++)
       if (CreateStandardNodeRestProl(GRID_ON_LEVEL(mg, l), BS) != NUM_OK) { fprintf(stderr, "CreateStandardNodeRestProl failed\n"); return 1; }
@@ -680,6 +702,7 @@ int main(int argc, char **argv)
     if (o.ops) dump_ops(o);
     if (o.solve) dump_solve(o);
     if (o.solve && !o.lean) dump_krylov(o);
+    if (o.galerkin) dump_galerkin(o);
     D.close();
   }
   if (o.timeit) time_reference(o);

@@ -476,6 +476,52 @@ int ugport_l_luiter(const ugport_level *L, const double *lval, double *v, const 
   return 0;
 }
 
+/* ---- Galerkin coarse-grid operator ---------------------------------------------------------------------------
+ * AssembleGalerkinByMatrix np/algebra/transgrid.cc:1575-1700 with symmetric = 0, after dmatset(coarse, 0) as `npcheck $G` calls it
+ * (npcheck.cc:375-379): coarse += P^T A P on the stored interpolation matrices, accumulated in the reference's traversal order --
+ * fine rows v in list order, their entries m = (v,w) in list order, the interpolation entries im of v in VISTART order, those jm
+ * of w in VISTART order: coarse(iv,jv) += (m * im) * jm (scalar :1601-1627); blocks :1629-1700: sum over k,l of
+ * (IM[i][k] * M[k][l]) * JM[j][l] with the c*I interpolation blocks written out (their zeros take part in the sums), then
+ * coarse(iv,jv)[i][j] += sum.  `fine` / `coarse`: patterns, P of the fine level in IMAT order (dumps written with --imat);
+ * fine_val: the fine matrix' values; coarse_val[nnz_c*bs*bs] receives the result.  The reference creates connections the coarse
+ * pattern lacks (CreateExtraConnection); on nested geometric hierarchies the product stays on the pattern, and this restatement
+ * returns 2 instead of growing it (pattern growth unpinned: no dump exercises it). */
+int ugport_galerkin(const ugport_level *fine, const ugport_level *coarse, const double *fine_val, double *coarse_val)
+{
+  int bs = fine->bs, bb = bs * bs;
+  memset(coarse_val, 0, sizeof(double) * (size_t)coarse->rowptr[coarse->n] * bb);       /* dmatset(level-1, A, 0.0) */
+  for (int v = 0; v < fine->n; v++)
+    for (int e = fine->rowptr[v]; e < fine->rowptr[v + 1]; e++) {
+      int w = fine->col[e];
+      const double *M = fine_val + (size_t)e * bb;
+      for (int ie = fine->p_rowptr[v]; ie < fine->p_rowptr[v + 1]; ie++) {
+        int iv = fine->p_col[ie];
+        for (int je = fine->p_rowptr[w]; je < fine->p_rowptr[w + 1]; je++) {
+          int jv = fine->p_col[je];
+          int cm = csr_find(coarse, iv, jv);
+          if (cm < 0) return 2;
+          if (bs == 1) {
+            double fac = M[0] * fine->p_w[ie];                                        /* :1609, hoisted out of the jm loop there too */
+            coarse_val[cm] += fac * fine->p_w[je];
+            continue;
+          }
+          double IM[9], JM[9];
+          for (int a = 0; a < bb; a++) { IM[a] = 0.0; JM[a] = 0.0; }
+          for (int a = 0; a < bs; a++) { IM[a * bs + a] = fine->p_w[ie]; JM[a * bs + a] = fine->p_w[je]; }
+          double *C = coarse_val + (size_t)cm * bb;
+          for (int i = 0; i < bs; i++)
+            for (int j = 0; j < bs; j++) {
+              double sum = 0.0;
+              for (int k = 0; k < bs; k++)
+                for (int l = 0; l < bs; l++) sum += IM[i * bs + k] * M[k * bs + l] * JM[j * bs + l];
+              C[i * bs + j] += sum;
+            }
+        }
+      }
+    }
+  return 0;
+}
+
 void ugport_base_free(double *lu)
 {
   lu_fac *F = (lu_fac *)lu;

@@ -208,6 +208,16 @@ class PortBackend:
     def l_luiter(self, level, v, d):
         return self.L.ugport_l_luiter(self._lp(level), _dp(self._ilu[level][1]), _dp(self._v(v, level)), _dp(self._v(d, level)))
 
+    def galerkin(self, level, fine_val):
+        """AssembleGalerkinByMatrix on GRID_ON_LEVEL(level): values of the Galerkin matrix of level-1 (its own pattern) from the
+        fine values `fine_val` (pattern of `level`)."""
+        lc = self.h.levels[level - 1]
+        fv = np.ascontiguousarray(fine_val, dtype=np.float64)
+        out = np.zeros(len(lc.col) * lc.bs * lc.bs)
+        err = self.L.ugport_galerkin(self._lp(level), self._lp(level - 1), _dp(fv), _dp(out))
+        assert err == 0, err
+        return out
+
     def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
         return self.L.ugport_smooth(self._lp(level), SMOOTHERS[kind], _dp(self._v(x, level)), _dp(self._v(b, level)),
                                     self._vs(damp), _dp(self._v(tmp, level)))

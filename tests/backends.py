@@ -108,6 +108,16 @@ class GpuBackend:
     def l_luiter(self, level, v, d, L="__L"):
         return self.ctx.L.uggpu_l_luiter(self.ctx.h, level, self._v(v), self.ctx.handle(L), self._v(d))
 
+    def galerkin(self, level, fine_val=None):
+        """uggpu_galerkin: A of level-1 := P^T A_level P (AssembleGalerkinByMatrix after dmatset 0); returns its values.  fine_val is
+        ignored: the device already holds the fine matrix (the cascade leaves the Galerkin matrix of the level above there)."""
+        self.ctx.call("uggpu_galerkin", level, self.A)
+        lc = self.h.levels[level - 1]
+        rowptr = np.zeros(lc.n + 1, np.int32); col = np.zeros(lc.col.size, np.int32); val = np.zeros(lc.col.size * lc.bs * lc.bs)
+        self.ctx.call("uggpu_mat_get", level - 1, self.A, capi._p(rowptr), capi._p(col), capi._p(val))
+        assert np.array_equal(rowptr, lc.rowptr) and np.array_equal(col, lc.col)
+        return val
+
     def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
         t = self.ctx.handle("__L") if kind == "ilu" else self._v(tmp)        # ilu: the decomposition made by ilu_decomp
         return self.ctx.L.uggpu_smooth(self.ctx.h, level, capi.SMOOTHERS[kind], self._v(x), self._v(b), self.A, capi._vs(damp), t)

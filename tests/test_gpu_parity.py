@@ -64,3 +64,33 @@ def test_gpu_krylov(gpu_backend, golden):
         pytest.skip("dump without Krylov records")
     n = replay_krylov(gpu_backend, golden, exact=False, vec_tol=1e-10, red_tol=1e-9)
     assert n > 20
+
+
+def test_gpu_galerkin_bitexact(golden):
+    """uggpu_galerkin against AssembleGalerkinByMatrix of the reference (transgrid.cc:1575), cascaded from the top level down like
+    the dump: every value of every Galerkin coarse-level matrix bit for bit; afterwards a product with the new coarse matrix
+    equals the port's (the derived storage forms -- diagonal array, shared value tables -- follow the new values)."""
+    d = golden.raw
+    if "L0/galerkin/val" not in d:
+        pytest.skip("dump without Galerkin records")
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    be = GpuBackend(golden)
+    for l in range(golden.top, 0, -1):
+        val = be.galerkin(l)
+        ref = d[f"L{l-1}/galerkin/val"]
+        assert np.array_equal(val, ref), (l, int(np.count_nonzero(val != ref)), ref.size)
+    # the coarse matrices now in use: x = A y on level top-1 against the port working on the dumped Galerkin values
+    l = golden.top - 1
+    lv = golden.levels[l]
+    y = np.round(np.random.default_rng(3).standard_normal(lv.n * lv.bs) * 1024) / 1024
+    be.put(l, "y", y); be.put(l, "x", np.zeros_like(y))
+    be.dmatmul(l, l, 0, 0, "x", "y")
+    got = be.get(l, "x")
+    be.close()
+    import copy
+    h2 = copy.copy(golden); h2.levels = list(golden.levels); h2.levels[l] = copy.copy(lv); h2.levels[l].val = d[f"L{l}/galerkin/val"]
+    port = PortBackend(h2)
+    port.put(l, "y", y); port.put(l, "x", np.zeros_like(y))
+    port.dmatmul(l, l, 0, 0, "x", "y")
+    assert np.array_equal(got, port.get(l, "x"))

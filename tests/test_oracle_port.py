@@ -35,6 +35,23 @@ def test_port_krylov_bitexact(golden):
     assert n > 20
 
 
+def test_port_galerkin_bitexact(golden):
+    """AssembleGalerkinByMatrix (transgrid.cc:1575), cascaded from the top level down like the dump: every value of every Galerkin
+    coarse-level matrix bit for bit; the product stays on the coarse pattern of these nested hierarchies."""
+    d = golden.raw
+    if "L0/galerkin/val" not in d:
+        pytest.skip("dump without Galerkin records")
+    be = PortBackend(golden)
+    val = golden.levels[golden.top].val
+    for l in range(golden.top, 0, -1):
+        lc = golden.levels[l - 1]
+        assert np.array_equal(d[f"L{l-1}/galerkin/rowptr"], lc.rowptr) and np.array_equal(d[f"L{l-1}/galerkin/col"], lc.col)
+        val = be.galerkin(l, val)
+        ref = d[f"L{l-1}/galerkin/val"]
+        assert np.array_equal(val, ref), (l, int(np.count_nonzero(val != ref)), ref.size)
+        assert np.count_nonzero(val) > 0
+
+
 def test_golden_invariants(golden):
     """Invariants the reference's own checkers assert (np/algebra/npcheck.cc:118-154)."""
     for l, lv in enumerate(golden.levels):

@@ -1,0 +1,187 @@
+// galerkin.cu -- Galerkin coarse-grid operator: AssembleGalerkinByMatrix np/algebra/transgrid.cc:1575-1700
+// (symmetric = 0) after dmatset(coarse, 0), the way `npcheck $G` calls it (np/algebra/npcheck.cc:375-379):
+//     A_{l-1} = P^T A_l P     on the interpolation stencils of level l, accumulated in the reference's order.
+//
+// The reference scatters: fine rows v in list order, their entries m = (v,w) in list order, the interpolation entries im of v, those
+// jm of w:  coarse(iv,jv) += (m * im) * jm.  A coarse entry therefore receives its terms ordered by (v, position of m in row v,
+// position of jm in the interpolation row of w) -- im is unique per (v, iv).  Here ONE THREAD PER COARSE ROW gathers them in that
+// order: the fine rows that interpolate from iv (the transpose of P, built once per call by a stable radix sort of (coarse, fine)
+// pairs, so they come ascending), for each its matrix row, for each entry the interpolation row of the neighbour.  No atomics, no
+// reduction tree: the same additions in the same order as the sequential loop -- bit-identical values.  Blocks follow :1629-1700:
+// per (i,j) the sum over k,l of (IM[i][k] * M[k][l]) * JM[j][l] with the c*I interpolation blocks written out (their zeros take part).
+// The product must stay on the coarse pattern (it does on nested geometric hierarchies); the reference would create the missing
+// connections, this implementation reports them (UGGPU_ERROR).  A setup operation: rows are gathered uncoalesced.
+#include <cub/device/device_radix_sort.cuh>       // before uggpu_internal.h (its SLICE macro)
+#include <cub/device/device_scan.cuh>
+
+#include "uggpu_internal.h"
+
+__device__ __forceinline__ double sell_weight(const SellView &T, int r, int j)
+{
+  const int64_t idx = slice_off(T, r >> 5) + (int64_t)j * 32 + (r & 31);
+  return T.vcode ? T.vtable[T.vcode[idx]] : T.val[idx];
+}
+
+__global__ void k_gal_len(int n, const uint16_t *__restrict__ rowlen, int64_t *__restrict__ len)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n) len[r] = r < n ? rowlen[r] : 0;
+}
+
+// (coarse column, fine row) of every interpolation entry, rows ascending; cnt[c] = entries of coarse vector c
+__global__ void k_gal_pairs(SellView P, const int64_t *__restrict__ prp, int32_t *__restrict__ key, int32_t *__restrict__ val, int *__restrict__ cnt)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= P.n) return;
+  const int len = P.rowlen[v];
+  const ColIter ci = col_iter(P, v);
+  for (int j = 0; j < len; j++) {
+    const int c = col_at(ci, j);
+    key[prp[v] + j] = c; val[prp[v] + j] = v;
+    atomicAdd(&cnt[c], 1);
+  }
+}
+
+__global__ void k_gal_cnt64(int n, const int *__restrict__ cnt, int64_t *__restrict__ out)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n) out[r] = r < n ? cnt[r] : 0;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, SellView Af, const double *__restrict__ fval, SellView P,
+                                                  const int64_t *__restrict__ tptr, const int32_t *__restrict__ tfine, int *err)
+{
+  constexpr int BB = BS * BS;
+  const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= Ac.n) return;
+  const int lenc = Ac.rowlen[iv];
+  const ColIter cic = col_iter(Ac, iv);
+  double *cr = cval + slice_off(Ac, iv >> 5) * BB + (iv & 31);        // component k of entry t of this row: cr[(t*BB + k)*32]
+  for (int t = 0; t < lenc; t++)
+    for (int k = 0; k < BB; k++) cr[((size_t)t * BB + k) * 32] = 0.0;  // dmatset(level-1, A, 0.0)
+  for (int64_t q = tptr[iv]; q < tptr[iv + 1]; q++) {
+    const int v = tfine[q];
+    // im = the interpolation entry (v, iv)
+    const int lenp = P.rowlen[v];
+    const ColIter cip = col_iter(P, v);
+    double wim = 0.0;
+    for (int j = 0; j < lenp; j++) if (col_at(cip, j) == iv) { wim = sell_weight(P, v, j); break; }
+    const int lenf = Af.rowlen[v];
+    const ColIter cif = col_iter(Af, v);
+    const double *fr = fval + slice_off(Af, v >> 5) * BB + (v & 31);
+    for (int e = 0; e < lenf; e++) {
+      const int w = col_at(cif, e);
+      double M[BB];
+#pragma unroll
+      for (int k = 0; k < BB; k++) M[k] = fr[((size_t)e * BB + k) * 32];
+      const int lenw = P.rowlen[w];
+      const ColIter ciw = col_iter(P, w);
+      for (int j = 0; j < lenw; j++) {
+        const int jv = col_at(ciw, j);
+        const double wjm = sell_weight(P, w, j);
+        int t = -1;                                                     // GetMatrix(iv, jv)
+        for (int u = 0; u < lenc; u++) if (col_at(cic, u) == jv) { t = u; break; }
+        if (t < 0) { atomicExch(err, UGGPU_ERROR); continue; }          // the reference would create the connection
+        if (BS == 1) {
+          const double fac = M[0] * wim;
+          const double p = fac * wjm;
+          cr[(size_t)t * 32] = cr[(size_t)t * 32] + p;
+        } else {
+#pragma unroll
+          for (int i = 0; i < BS; i++)
+#pragma unroll
+            for (int jj = 0; jj < BS; jj++) {
+              double sum = 0.0;
+#pragma unroll
+              for (int k = 0; k < BS; k++)
+#pragma unroll
+                for (int l = 0; l < BS; l++) {
+                  const double a = (k == i ? wim : 0.0) * M[k * BS + l];
+                  const double p = a * (l == jj ? wjm : 0.0);
+                  sum += p;
+                }
+              cr[((size_t)t * BB + i * BS + jj) * 32] = cr[((size_t)t * BB + i * BS + jj) * 32] + sum;
+            }
+        }
+      }
+    }
+  }
+}
+
+extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
+{
+  Level *L = get_level(ctx, level);
+  Level *C = get_level(ctx, level - 1);
+  if (!L || !C) return UGGPU_NO_COARSER_GRID;
+  SellMat *Af = get_mat(ctx, level, A), *Ac = get_mat(ctx, level - 1, A);
+  if (!Af || !Ac) return UGGPU_DESC_MISMATCH;
+  if (!L->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "level %d has no interpolation stencil", level);
+  if (ctx->comm && (L->partitioned || C->partitioned)) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin runs on one GPU (level %d is partitioned)", level);
+  if (L->n == 0 || C->n == 0) return 0;
+  if (L->bs < 1 || L->bs > 3 || C->bs != L->bs) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "uggpu_galerkin: block size %d", L->bs);
+  cudaStream_t st = ctx->stream;
+  const int nf = L->n, nc = C->n;
+  const int64_t zp = L->P.nnz;
+  int64_t *len = nullptr, *prp = nullptr, *tptr = nullptr;
+  int32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *tfine = nullptr;
+  int *cnt = nullptr;
+  void *tmp = nullptr; size_t tmp_bytes = 0, tb2 = 0, tb3 = 0;
+  const size_t nmax = (size_t)(nf > nc ? nf : nc) + 1, zz = (size_t)(zp > 0 ? zp : 1);
+  int rc = 0;
+#define GT(expr) do { if (!rc) rc = (expr); } while (0)
+#define GC(expr) do { if (!rc) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) rc = uggpu_fail(UGGPU_CUDA_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); } } while (0)
+  GT(dalloc(ctx, &len, nmax)); GT(dalloc(ctx, &prp, nmax)); GT(dalloc(ctx, &tptr, (size_t)nc + 1));
+  GT(dalloc(ctx, &key, zz)); GT(dalloc(ctx, &val, zz)); GT(dalloc(ctx, &key2, zz)); GT(dalloc(ctx, &tfine, zz)); GT(dalloc(ctx, &cnt, (size_t)nc));
+  if (!rc) {
+    int bits = 1;
+    while ((1ll << bits) < (long long)nc && bits < 31) bits++;
+    GC(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, prp, nf + 1, st));
+    GC(cub::DeviceScan::ExclusiveSum(nullptr, tb2, len, tptr, nc + 1, st));
+    GC(cub::DeviceRadixSort::SortPairs(nullptr, tb3, key, key2, val, tfine, (int)zp, 0, bits, st));
+    if (tb2 > tmp_bytes) tmp_bytes = tb2;
+    if (tb3 > tmp_bytes) tmp_bytes = tb3;
+    GT(dev_alloc(ctx, &tmp, tmp_bytes ? tmp_bytes : 1));
+    // rows of P -> offsets; (coarse, fine) pairs in row order; a stable sort by the coarse index leaves the fine rows ascending
+    if (!rc) { k_gal_len<<<(nf + 256) / 256, 256, 0, st>>>(nf, L->P.rowlen, len); ctx->launches++; }
+    GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, prp, nf + 1, st));
+    GC(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)nc, st));
+    if (!rc) { k_gal_pairs<<<(nf + 255) / 256, 256, 0, st>>>(view(L->P), prp, key, val, cnt); ctx->launches++; }
+    if (zp > 0) GC(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, val, tfine, (int)zp, 0, bits, st));
+    if (!rc) { k_gal_cnt64<<<(nc + 256) / 256, 256, 0, st>>>(nc, cnt, len); ctx->launches++; }
+    GC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, tptr, nc + 1, st));
+    // the coarse values are about to change: nothing derived from them may survive
+    GT(sell_drop_shared_values(ctx, Ac));
+    GT(sell_free_schedules(ctx, Ac));
+    if (!rc) {
+      const int blocks = (nc + 127) / 128;
+      const SellView Acv = view(*Ac), Afv = view(*Af), Pv = view(L->P);
+      switch (L->bs) {
+        case 1: k_galerkin<1><<<blocks, 128, 0, st>>>(Acv, Ac->val, Afv, Af->val, Pv, tptr, tfine, ctx->derr); break;
+        case 2: k_galerkin<2><<<blocks, 128, 0, st>>>(Acv, Ac->val, Afv, Af->val, Pv, tptr, tfine, ctx->derr); break;
+        default: k_galerkin<3><<<blocks, 128, 0, st>>>(Acv, Ac->val, Afv, Af->val, Pv, tptr, tfine, ctx->derr); break;
+      }
+      ctx->launches++;
+      GC(cudaGetLastError());
+    }
+    if (!rc) {
+      rc = check_device_error(ctx);
+      if (rc) rc = uggpu_fail(UGGPU_ERROR, "uggpu_galerkin: the product P^T A P of level %d leaves the pattern of level %d (the reference would create the connections; not supported)", level, level - 1);
+    }
+    GT(sell_update_diag(ctx, Ac));
+    GT(sell_share_values(ctx, Ac));
+    cudaStreamSynchronize(st);
+  }
+#undef GT
+#undef GC
+  if (tmp) dev_free(ctx, tmp, tmp_bytes ? tmp_bytes : 1);
+  if (len) dfree(ctx, len, nmax);
+  if (prp) dfree(ctx, prp, nmax);
+  if (tptr) dfree(ctx, tptr, (size_t)nc + 1);
+  if (key) dfree(ctx, key, zz);
+  if (val) dfree(ctx, val, zz);
+  if (key2) dfree(ctx, key2, zz);
+  if (tfine) dfree(ctx, tfine, zz);
+  if (cnt) dfree(ctx, cnt, (size_t)nc);
+  return rc;
+}
