@@ -224,6 +224,17 @@ def our_arm(args):
     ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
     sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1, "ilu": 1.0}[args.smoother]
     cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=sm_damp, fused=1, smoother=args.smoother)
+    galerkin_ms = None
+    if args.galerkin:      # setup operation, outside the timed steps: A_{l-1} := P^T A_l P cascaded from the top level down (uggpu_galerkin)
+        if world > 1:
+            raise SystemExit("bench.py: --galerkin runs on one GPU")
+        galerkin_ms = []
+        for l in range(top, 0, -1):
+            ctx.sync()
+            tg = time.perf_counter()
+            ctx.call("uggpu_galerkin", l, A)
+            ctx.sync()
+            galerkin_ms.append(round((time.perf_counter() - tg) * 1e3, 3))
     ctx.sync()
     t_pre = time.perf_counter()
     ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
@@ -356,7 +367,7 @@ def our_arm(args):
                                   f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
                    "halo_exchanges_total": exchanges,
                    "cache": "inputs larger than L2 (every sweep over the finest level streams several GB; each of its vectors alone is 1 GB)",
-                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3),
+                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3), **({"galerkin_ms_top_down": galerkin_ms} if galerkin_ms is not None else {}),
                    "defect": [first, hist[-1]] if hist else None},
         "roofline": {"bound": "hbm", "kernel": smooth_kernel if args.smoother == "jac" else
                      f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)", "achieved": achieved, "peak": peak,
@@ -407,6 +418,9 @@ def main():
                     help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")
     ap.add_argument("--smoother", default="jac", choices=["jac", "gs", "sgs", "sor", "ilu"],
                     help="smoother class of the cycle: jac = BASELINE configs (default); gs / sgs / sor / ilu: Gauss-Seidel family and ILU (SURVEY.md 8f.2, one GPU)")
+    ap.add_argument("--galerkin", action="store_true",
+                    help="replace the coarse-level matrices by the Galerkin products P^T A P (uggpu_galerkin, SURVEY.md 8f.3) before the cycle "
+                         "and report the time per level in config.galerkin_ms_top_down")
     ap.add_argument("--replicate-below", type=int, default=300000,
                     help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()
