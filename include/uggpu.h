@@ -320,6 +320,12 @@ int uggpu_comm_destroy(uggpu_ctx *ctx);
 int uggpu_comm_size(uggpu_ctx *ctx);
 int uggpu_comm_rank(uggpu_ctx *ctx);
 int64_t uggpu_comm_exchanges(uggpu_ctx *ctx);                 /* halo exchanges issued so far                        */
+/* ModelP vector consistency, np/algebra/ugblas.cc:398 l_vector_consistent, :1035 l_vector_collect, :740 l_ghostvector_consistent
+ * (SURVEY.md 8 a13).  Rows are owned by exactly one rank (owner computes, ghost COLUMNS at the tail of every vector), so the sums
+ * over border copies of the first two have nothing to add; the copy of the owners' values into the neighbours' ghost copies is
+ * what every entry point does by itself before a kernel reads ghost columns.  The same exchange, explicitly (peer-memory windows
+ * over NVLink, or ncclSend/ncclRecv): no-op on one GPU and on levels every rank holds completely. */
+int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x);
 /* As uggpu_synth_hierarchy on a px*py*pz rank array (element partition into equal boxes of base cells = RCB of
  * parallel/dddif/lbrcb.cc:250 on a structured grid; sons inherit, lbrcb.cc:376; shared vectors are owned by the lowest
  * rank, priority.cc:200).  This rank generates the rows it owns plus ghost columns.  Levels with at most

@@ -423,3 +423,16 @@ extern "C" int uggpu_part_local_index(int dim, int cx, int cy, int cz, int px, i
   if (!box_has(g.ext, xx)) return -1;
   return part_local_index(g, xx);
 }
+
+// ModelP vector consistency.  With owner-computes storage every vector entry is held by exactly one rank, so the
+// sums over border copies of l_vector_consistent (np/algebra/ugblas.cc:398) and l_vector_collect (:1035) have nothing to add up;
+// what remains of the protocol is the copy of the owners' values into the other ranks' ghost copies, l_ghostvector_consistent
+// (:740).  Every entry point does it itself before a kernel reads ghost columns; this is the same exchange for callers that want
+// it explicitly (e.g. after uggpu_vec_upload of an iterate).  No-op on one GPU and on levels every rank holds completely.
+extern "C" int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x)
+{
+  if (!get_level(ctx, level)) return UGGPU_ERROR;
+  double *xp = get_vec(ctx, level, x);
+  if (!xp) return UGGPU_DESC_MISMATCH;
+  return halo_exchange(ctx, level, xp);
+}
