@@ -324,6 +324,25 @@ def our_arm(args):
         e2e_s = float(t.item())
     clocks = sampler.stop() if sampler else None
     dev_bytes = ctx.device_bytes()
+    # BASELINE.json's second figure, "SpMV HBM GB/s vs peak": the plain dmatmul_minus (c -= A x) on the finest level, timed by the
+    # library's per-kernel events after everything else (c is work space: every cycle starts by overwriting it)
+    spmv = None
+    if world == 1:
+        try:
+            ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
+            ctx.sync()
+            ctx.call("uggpu_prof_enable", 1)
+            for _ in range(5):
+                ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
+            ctx.sync()
+            c2, m2, b2 = C.c_int64(), C.c_double(), C.c_double()
+            ctx.call("uggpu_prof_summary", 6, top, C.byref(c2), C.byref(m2), C.byref(b2))
+            ctx.call("uggpu_prof_enable", 0)
+            if c2.value > 0 and m2.value > 0:
+                spmv = {"kernel": f"k_dmatmul_k<{bs},2> (x -= A y, finest level)", "launches": int(c2.value), "avg_ms": m2.value / c2.value,
+                        "alg_bytes_per_launch": b2.value / c2.value, "GBps": b2.value / (m2.value * 1e-3) / 1e9}
+        except Exception as e:          # a reported figure, never a reason to lose the bench line
+            spmv = {"error": str(e)[:200]}
 
     if rank != 0:
         return 0
@@ -386,6 +405,7 @@ def our_arm(args):
                 "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
         "gpu_launches": launches,
         "clocks": clocks,
+        "spmv": spmv,
     }
     if world == 1 and not args.no_cpu:
         r = run_reference_cpu(args.cpu_refine, 5, args.cpu_replicas)
