@@ -2,17 +2,23 @@
 """bench.py -- V(2,2)-cycle throughput of the gpuls hot path on B200 (BASELINE.json metric).
 
 One "step" = one iteration of the linear solver `ls` with `lmgc` V(2,2) damped-Jacobi as Iter, i.e. exactly the body
-of LinearSolver's loop (np/procs/ls.cc:693-708): c = 0; c = Lmgc(b) (b updated to the new defect); x += c;
-||b||_2 -- on a synthetic 3D P1 Poisson hierarchy (BASELINE.json configs[1]: unit cube, tetrahedra, base 4x4x4 cells,
-7 uniform refinements = 8 levels, 513^3 = 135 005 697 fine unknowns).
+of LinearSolver's loop (np/procs/ls.cc:693-708): c = 0; c = Lmgc(b) (b updated to the new defect); x += c; ||b||_2.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU; torchrun for N > 1)
     python bench.py --impl reference [...]                        the unmodified reference on the host CPU (oracle/_ref)
 
+Workloads:
+  N = 1   C2: 3D P1 Poisson, unit cube, base 4x4x4 cells, 8 levels, 513^3 = 135 005 697 fine unknowns.
+  N >= 2  C3 verbatim, a FIXED global problem ("scaling": "strong"): base 8x8x6 cells, 8 levels, 1025 x 1025 x 769 =
+          807 930 625 fine unknowns, partitioned into boxes of base cells over 2x1x1 / 2x2x1 / 2x2x2 GPUs (UG's RCB element
+          partition on a structured grid).  `--weak` gives every GPU a C2-sized box instead; the weak figure is also
+          reported as the extra key `weak` of the default run.
 Prints ONE JSON line (rank 0).  `value` = fine unknowns * K / device time of K steps with everything resident in HBM;
 `e2e` = the same through the C-ABI with HOST vectors (x, b uploaded and downloaded inside the timed region, as
 NP_LINEAR_SOLVER::Solver does with UG's VECTOR lists); `roofline` = the dominant kernel (fused smoothing step on the
-finest level) timed with CUDA events around each of its launches inside the timed region.
+finest level) timed with CUDA events around each of its launches inside the timed region.  Further keys: the same cycle on the
+GENERAL storage path (no shared value tables, no stencil kernels) and on a VARYING-coefficient operator, Q1 Poisson and 3x3-block
+elasticity, the Galerkin product, the Krylov solvers, a multi-GPU parity check against one GPU (`mgpu_parity`, N >= 2).
 """
 from __future__ import annotations
 
@@ -20,6 +26,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -30,14 +37,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "vcycle_unknowns_per_s"
 UNIT = "unknowns/s"
+ARRAYS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+WHAT = {"p1": "3D P1 Poisson, Kuhn tetrahedra (15-point rows)", "q1": "3D Q1 Poisson, hexahedra (27-point rows)",
+        "elasticity": "3D Q1 linear elasticity (3x3 blocks, 27 block entries per row), hexahedra",
+        "p1var": "3D P1 diffusion with a smoothly VARYING coefficient (no two rows share values), Kuhn tetrahedra"}
+SMOOTHER_TXT = {"jac": "Jacobi damp 0.6", "gs": "Gauss-Seidel damp 1.0", "sgs": "symmetric Gauss-Seidel damp 1.0", "sor": "SOR omega 1.1",
+                "ilu": "ILU(0) beta 0 damp 1.0"}
 
 
-def workload_name(cells, top, n, kind="p1", smoother="jac"):
-    what = {"p1": "3D P1 Poisson, unit cube, Kuhn tetrahedra", "q1": "3D Q1 Poisson, unit cube, hexahedra (27-point rows)",
-            "elasticity": "3D Q1 linear elasticity (3x3 blocks, 27 block entries per row), unit cube, hexahedra"}[kind]
-    return (f"{what}, base {cells}x{cells}x{cells} cells, {top + 1} levels, "
-            f"{n} fine unknowns, V(2,2) " + {"jac": f"{'block-' if kind == 'elasticity' else ''}Jacobi damp 0.6", "gs": "Gauss-Seidel damp 1.0",
-                                             "sgs": "symmetric Gauss-Seidel damp 1.0", "sor": "SOR omega 1.1", "ilu": "ILU(0) beta 0 damp 1.0"}[smoother] + ", base solver ls+lu")
+def workload_name(kind, cells, top, n_global, smoother="jac", P=(1, 1, 1)):
+    nn = [c * 2 ** top + 1 for c in cells]
+    part = "" if P == (1, 1, 1) else f", partitioned into {P[0]}x{P[1]}x{P[2]} boxes of base cells (one per GPU)"
+    note = " (the Kuhn hierarchy has 15 connections per row; UG's own tetrahedron rule gives 14.6 on average, DESIGN.md 4)" if kind in ("p1", "p1var") else ""
+    return (f"{WHAT[kind]}, box of {cells[0]}x{cells[1]}x{cells[2]} base cells, {top + 1} levels, {nn[0]}x{nn[1]}x{nn[2]} nodes = "
+            f"{n_global} fine unknowns{part}, V(2,2) {'block-' if kind == 'elasticity' else ''}{SMOOTHER_TXT[smoother]}, base solver ls+lu{note}")
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -109,6 +122,34 @@ def run_port_cpu(cells: int, top: int, cycles: int):
     return {"kind": "port", "cores": 1, "levels": top + 1, "unknowns": n, "cycles": its, "s_per_cycle": dt / its, "vcycle_unknowns_per_s": n * its / dt}
 
 
+def equal_size_inside_ug(refine: int, cycles: int):
+    """The gpuls numprocs INSIDE the unmodified UG (oracle/_ref/ugoracle3 --gpu: PreProcess flattens the VECTOR/MATRIX lists, Solver
+    uploads x and b, runs the cycles on the device, scatters x, b, c back into the VVALUEs) next to UG's own CPU numprocs on the SAME
+    hierarchy in the same process: wall time of NP_LINEAR_SOLVER::Solver on both sides."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ugoracle3")
+    lib = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
+    if not os.path.exists(exe):
+        return None
+    out = subprocess.run([exe, "--grid", "tet", "--refine", str(refine), "--damp", "0.6", "--cycles", str(cycles), "--gpu", lib, "--nokrylov"],
+                         capture_output=True, text=True, timeout=900)
+    n = None
+    m = re.search(r"n=\[([0-9,]+)\]", out.stdout)
+    if m:
+        n = int(m.group(1).split(",")[-1])
+    for line in out.stdout.splitlines():
+        if line.startswith(("PASS", "FAIL")) and "device base solver" in line:
+            mg, mc = re.search(r"t_gpu=([0-9.eE+-]+)s", line), re.search(r"t_cpu=([0-9.eE+-]+)s", line)
+            me = re.search(r"relerr x=([0-9.eE+-]+)", line)
+            if mg and mc and n:
+                tg, tc = float(mg.group(1)), float(mc.group(1))
+                return {"unknowns": n, "cycles": cycles, "gpu_numprocs_inside_ug_s": tg, "cpu_numprocs_s": tc, "ratio": tc / tg if tg > 0 else None,
+                        "gpu_unknowns_per_s": n * cycles / tg if tg > 0 else None, "cpu_unknowns_per_s": n * cycles / tc if tc > 0 else None,
+                        "parity": line.split(" ", 1)[0], "relerr_x": float(me.group(1)) if me else None,
+                        "what": "wall time of NP_LINEAR_SOLVER::Solver: gpuls+gpulmgc+gpujac+gputransfer (device base solver; x, b up, x, b, c down through "
+                                "the VECTOR lists inside the call) vs ls+lmgc+jac+transfer, same UG hierarchy, same process, 1 host core"}
+    return {"error": (out.stdout[-300:] + out.stderr[-300:])}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -120,6 +161,7 @@ def reference_arm(args):
         r = run_port_cpu(1, 5, cycles)
         kind = "port"
     n = r["unknowns"]
+    nn = round(n ** (1 / 3))
     sample = (f"{'UG 3.12.1 ls+lmgc+jac+transfer' if kind == 'reference' else 'oracle/ugport.c'}: {r['cycles']} V(2,2) cycles on a "
               f"{r.get('levels', '?')}-level unit-cube tet hierarchy with {n} fine unknowns (largest the host builds in ~10 s), "
               f"{r['cores']} concurrent single-threaded replica(s), throughputs added")
@@ -127,8 +169,10 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["vcycle_unknowns_per_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["cycles"], "warmup": 0, "ms_per_step": r["s_per_cycle"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.cells, args.top, (args.cells * 2 ** args.top + 1) ** 3),
-                   "measured_on": sample},
+        "config": {"workload": (f"3D P1 Poisson, unit cube, tetrahedra (UG's own refinement), {r.get('levels', '?')} levels, {nn}x{nn}x{nn} nodes = {n} fine unknowns "
+                                f"per replica x {r['cores']} replicas, V(2,2) Jacobi damp 0.6, base solver ls+lu -- the SIZE THE HOST CAN BUILD, not the GPU arm's "
+                                f"problem (UG's grid manager needs ~2.5 kB per unknown: 513^3 would take ~350 GB)"),
+                   "same_size_as_gpu_arm": False, "measured_on": sample},
         "cpu_baseline": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": r["vcycle_unknowns_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -180,233 +224,404 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def our_arm(args):
-    import numpy as np
-    import torch
-    from ug_b200 import capi
+KINDS = {"smooth": 0, "jac": 1, "restrict": 2, "interpolate": 3, "vecop": 4, "reduce": 5, "dmatmul": 6, "base": 7, "trisolve": 8, "halo": 9, "allreduce": 10}
 
+
+class Env:
+    """Environment switches of libuggpu.so (read with getenv at set-up / launch time) for the duration of one workload."""
+
+    def __init__(self, env):
+        self.env, self.old = env or {}, {}
+
+    def __enter__(self):
+        for k, v in self.env.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure(spec, rt):
+    """Builds the hierarchy of `spec` on all ranks, times spec['steps'] solver iterations, returns the figures (same dict on every
+    rank as far as rank 0 needs them).  rt = (rank, world, local, torch, dist)."""
+    import numpy as np
+    from ug_b200 import capi, mgpu
+    rank, world, local, torch, dist = rt
+    kind, cells, top, P = spec["kind"], spec["cells"], spec["top"], spec["P"]
+    steps, warmup = spec["steps"], spec["warmup"]
+    smoother = spec.get("smoother", "jac")
+    peak, peak_src = peak_hbm()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with Env(spec.get("env")):
+        ctx = capi.Context(local)
+        if world > 1:
+            mgpu.init_comm(ctx, rank, world)
+        A = ctx.handle("A")
+        t0 = time.perf_counter()
+        ctx.call("uggpu_synth_hierarchy_part", mgpu.KINDS[kind], cells[0], cells[1], cells[2], top, A, P[0], P[1], P[2], rank, C.c_int64(spec.get("replicate_below", 300000)))
+        bs = ctx.level_bs(top)
+        n = ctx.level_n(top) * bs                      # unknowns (UG counts vector components), this rank
+        n_global = int(ctx.L.uggpu_level_n_global(ctx.h, top)) * bs
+        for name in ("x", "b", "c"):
+            for l in range(top + 1):
+                ctx.alloc(l, name)
+        ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
+        sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1, "ilu": 1.0}[smoother]
+        cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=sm_damp, fused=1, smoother=smoother)
+        out = {"kind": kind, "n_global": n_global, "n_rank0": n, "bs": bs}
+        if spec.get("galerkin"):      # setup operation, outside the timed steps: A_{l-1} := P^T A_l P cascaded from the top level down (uggpu_galerkin)
+            gms = []
+            for l in range(top, 0, -1):
+                ctx.sync()
+                tg = time.perf_counter()
+                ctx.call("uggpu_galerkin", l, A)
+                ctx.sync()
+                gms.append(round((time.perf_counter() - tg) * 1e3, 3))
+            out["galerkin_ms_top_down"] = gms
+            nf, zf = ctx.level_n(top), int(ctx.L.uggpu_mat_nnz(ctx.h, top, A))
+            nc, zc = ctx.level_n(top - 1), int(ctx.L.uggpu_mat_nnz(ctx.h, top - 1, A))
+            zp = int(ctx.L.uggpu_transfer_nnz(ctx.h, top, 0))
+            # compulsory bytes of the finest product: fine matrix once (12 B per entry), P twice (gathered rows), coarse matrix written
+            gbytes = 12.0 * zf * bs * bs + 2 * 12.0 * zp + 12.0 * zc * bs * bs + 4.0 * (nf + nc)
+            out["galerkin_finest"] = {"ms": gms[0], "alg_bytes": gbytes, "GBps": gbytes / (gms[0] * 1e-3) / 1e9, "frac": gbytes / (gms[0] * 1e-3) / 1e9 / peak}
+        ctx.sync()
+        t_pre = time.perf_counter()
+        ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
+        ctx.sync()
+        out["preprocess_s"] = round(time.perf_counter() - t_pre, 3)      # LmgcPreProcess: base-level LU, Gauss-Seidel schedules / ILU decompositions
+        out["setup_s"] = round(time.perf_counter() - t0, 2)
+        X, B, Cc = ctx.handle("x"), ctx.handle("b"), ctx.handle("c")
+        res = capi.LResult()
+        ctx.call("uggpu_ls_defect", 0, top, X, B, A)
+        ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
+        first = res.last_defect[0]
+        absl, red = capi._vs([1e-300]), capi._vs([1e-300])
+
+        def step(k=1):
+            ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, X, B, A, Cc, k, absl, red, C.byref(res), None)
+
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+        for _ in range(warmup):
+            step()
+        hist = []
+        barrier()
+        sampler = ClockSampler(local) if (rank == 0 and spec.get("clocks")) else None
+        ctx.call("uggpu_prof_enable", 1)
+        launches0 = ctx.launch_count()
+        exch0 = int(ctx.L.uggpu_comm_exchanges(ctx.h))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+            hist.append(res.last_defect[0])
+        e1.record(stream)
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+        ms_events = ms
+        out["launches"] = ctx.launch_count() - launches0
+        out["halo_exchanges_per_step"] = (int(ctx.L.uggpu_comm_exchanges(ctx.h)) - exch0) / steps
+        prof = {}
+        cnt, kms, kby = C.c_int64(), C.c_double(), C.c_double()
+        for name, k in KINDS.items():
+            ctx.call("uggpu_prof_summary", k, -1, C.byref(cnt), C.byref(kms), C.byref(kby))
+            prof[name] = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+        domk = 0 if smoother == "jac" else 6      # the fused smoothing step (Jacobi) / the defect update dmatmul_minus (Gauss-Seidel family), finest level
+        ctx.call("uggpu_prof_summary", domk, top, C.byref(cnt), C.byref(kms), C.byref(kby))
+        dom = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+        ctx.call("uggpu_prof_summary", 8, top, C.byref(cnt), C.byref(kms), C.byref(kby))
+        tri = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
+        ctx.call("uggpu_prof_enable", 0)
+        # the K timed steps proper: without the per-kernel events (two cudaEventRecord around every launch are what a user does not have)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+        out["ms_per_step_with_kernel_events"] = ms_events / steps
+        out["ms"] = ms
+        out["ms_per_step"] = ms / steps
+        out["value"] = n_global * steps / (ms * 1e-3)
+        out["kernels"] = prof
+        out["kernel_sum_ms_per_step"] = sum(v["ms"] for v in prof.values()) / steps
+        out["defect"] = [first, hist[-1]] if hist else None
+        out["transport"] = ctx.halo_transport() if world > 1 else "none (one GPU)"
+        out["device_bytes"] = ctx.device_bytes()
+
+        # roofline of the dominant kernel -----------------------------------------------------------------------------
+        nrows_top = ctx.level_n(top)
+        nnz_top, words_top = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A)), int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
+        vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables, DESIGN.md 2)
+        sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if not os.environ.get("UGGPU_NO_STENCIL") else 0
+        sten_w = round(nnz_top / max(nrows_top, 1))
+        if sten_top > 0 and bs == 1 and sten_w in (15, 27):
+            smooth_kernel = f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)"
+        elif sten_top > 0 and bs == 3:
+            smooth_kernel = "k_smooth_sten3<*> (fused smoothing step, 3x3-block stencil variant, finest level)"
+        else:
+            smooth_kernel = f"k_smooth_k<{bs},*> (fused smoothing step, finest level)"
+        achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+        # SURVEY.md 8(d) counts 8 b^2 + 4 bytes per entry; the stored format fetches fewer (compressed column words, shared value tables)
+        survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
+        achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+        total_alg = sum(v["alg_bytes"] for v in prof.values())
+        out["roofline"] = {"bound": "hbm", "kernel": smooth_kernel if smoother == "jac" else f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)",
+                           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                           "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
+                           "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
+                           "bytes_model": "as stored: 8 B per value fetched (slices of identical rows share value tables), compressed column words (DESIGN.md 2-3), vectors once",
+                           "value_entries_per_entry": vals_top / max(nnz_top, 1), "stencil_slices_frac": sten_top / max((nrows_top + 31) // 32, 1),
+                           "achieved_survey_model": achieved_survey, "frac_survey_model": achieved_survey / peak,
+                           "survey_model": "SURVEY.md 8(d): 8 b^2 + 4 B per matrix entry whatever the storage; above 1 means the matrix stream no longer crosses HBM",
+                           "column_words_per_entry": words_top / max(nnz_top, 1), "share_of_step": dom["ms"] / ms_events,
+                           "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak}
+        out["trisolve_finest"] = ({"launches": tri["launches"], "avg_ms": tri["ms"] / max(tri["launches"], 1),
+                                   "GBps": tri["alg_bytes"] / (tri["ms"] * 1e-3) / 1e9 if tri["ms"] > 0 else 0.0} if smoother != "jac" else None)
+
+        # ---- end to end: host vectors in, host vectors out, every step -------------------------------------------------
+        if spec.get("e2e_steps", 0) > 0:
+            xh = torch.zeros(n, dtype=torch.float64).pin_memory()      # n counts components: the vectors hold n doubles
+            bh = torch.empty(n, dtype=torch.float64).pin_memory()
+            ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
+            ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
+
+            def e2e_step(k=1):
+                # b first (the cycle starts with it); x follows on the copy stream and hides behind the cycle, whose last kernel
+                # is the first to touch it
+                ctx.call("uggpu_vec_upload", top, B, C.c_void_p(bh.data_ptr()))
+                ctx.call("uggpu_vec_upload_async", top, X, C.c_void_p(xh.data_ptr()))
+                ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
+                step(k)
+                ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
+                ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
+
+            e2e_step()
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(spec["e2e_steps"]):
+                e2e_step()
+            barrier()
+            e2e_s = allmax((time.perf_counter() - t1) / spec["e2e_steps"])
+            out["e2e"] = {"value": n_global / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": (16 * n + 8) * world,
+                          "ms_per_step": e2e_s * 1e3, "steps": spec["e2e_steps"]}
+            # what NP_LINEAR_SOLVER::Solver does: x, b up once, k cycles on the device, x, b down once
+            kk = spec.get("e2e_solve_cycles", 10)
+            barrier()
+            t1 = time.perf_counter()
+            e2e_step(kk)
+            barrier()
+            es = allmax(time.perf_counter() - t1)
+            out["e2e_solve"] = {"value": n_global * kk / es, "unit": UNIT, "cycles": kk, "ms_per_cycle": es * 1e3 / kk, "ms_total": es * 1e3,
+                                "h2d_bytes": 16 * n * world, "d2h_bytes": (16 * n + 8) * world,
+                                "what": "one solve as the gpuls numproc runs it: x, b host->device once, k cycles resident, x, b device->host once"}
+        if sampler:
+            out["clocks"] = sampler.stop()
+
+        # BASELINE.json's second figure, "SpMV HBM GB/s vs peak": the plain dmatmul_minus (c -= A x) on the finest level, timed by the
+        # library's per-kernel events after everything else (c is work space: every cycle starts by overwriting it)
+        if spec.get("spmv"):
+            try:
+                ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
+                ctx.sync()
+                ctx.call("uggpu_prof_enable", 1)
+                for _ in range(5):
+                    ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
+                ctx.sync()
+                c2, m2, b2 = C.c_int64(), C.c_double(), C.c_double()
+                ctx.call("uggpu_prof_summary", 6, top, C.byref(c2), C.byref(m2), C.byref(b2))
+                ctx.call("uggpu_prof_enable", 0)
+                if c2.value > 0 and m2.value > 0:
+                    gb = b2.value / (m2.value * 1e-3) / 1e9
+                    extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * c2.value
+                    out["spmv"] = {"kernel": (f"k_dmatmul_sten<2,{sten_w}>" if (sten_top > 0 and bs == 1 and sten_w in (15, 27)) else f"k_dmatmul_k<{bs},2>") + " (x -= A y, finest level)",
+                                   "launches": int(c2.value), "avg_ms": m2.value / c2.value, "alg_bytes_per_launch": b2.value / c2.value, "GBps": gb, "frac": gb / peak,
+                                   "GBps_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9, "frac_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9 / peak}
+            except Exception as e:          # a reported figure, never a reason to lose the bench line
+                out["spmv"] = {"error": str(e)[:200]}
+
+        # Krylov accelerators around the cycle (SURVEY.md 8f.1): time per iteration, resident
+        if spec.get("krylov"):
+            try:
+                kr = {}
+                for l in range(top + 1):
+                    for name in ("p", "t2", "r", "v", "s", "q"):
+                        ctx.alloc(l, name)
+                for solver in ("cg", "bcgs"):
+                    ctx.call("uggpu_dset", 0, top, 0, X, C.c_double(0.0))
+                    ctx.call("uggpu_synth_rhs", top, B)
+                    ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
+                    d0 = res.last_defect[0]
+                    its = 4
+                    barrier()
+                    t1 = time.perf_counter()
+                    if solver == "cg":
+                        ctx.call("uggpu_cg_solve", C.byref(cfg), 0, top, X, B, A, Cc, ctx.handle("p"), ctx.handle("t2"), its, absl, red, C.byref(res), None)
+                    else:
+                        work = (C.c_int * 6)(*[ctx.handle(nm) for nm in ("r", "p", "v", "s", "t2", "q")])
+                        ctx.call("uggpu_bcgs_solve", C.byref(cfg), 0, top, X, B, A, work, capi._vs([1.0]), 0, its, absl, red, C.byref(res), None)
+                    barrier()
+                    dt = allmax(time.perf_counter() - t1)
+                    nit = max(int(res.number_of_linear_iterations), 1)
+                    kr[solver] = {"iterations": nit, "ms_per_iteration": dt * 1e3 / nit, "cycles_per_iteration": 1, "defect": [d0, res.last_defect[0]],
+                                  "unknowns_per_s": n_global * nit / dt}
+                out["krylov"] = kr
+            except Exception as e:
+                out["krylov"] = {"error": str(e)[:200]}
+        ctx.close()
+    return out
+
+
+def brief(m, keys=("value", "ms_per_step", "n_global", "launches", "kernel_sum_ms_per_step", "defect", "device_bytes", "setup_s", "transport", "halo_exchanges_per_step")):
+    """What an extra workload contributes to the JSON line."""
+    r = {k: m[k] for k in keys if k in m}
+    rf = m["roofline"]
+    r["dominant_kernel"] = {k: rf[k] for k in ("kernel", "avg_ms", "achieved", "frac", "achieved_survey_model", "frac_survey_model", "alg_bytes_per_launch", "value_entries_per_entry",
+                                               "column_words_per_entry", "cycle_frac")}
+    r["kernels_ms_per_step"] = {k: round(v["ms"] / max(m.get("steps", 1), 1), 4) for k, v in m["kernels"].items() if v["ms"] > 0}
+    for k in ("galerkin_ms_top_down", "galerkin_finest", "spmv", "krylov"):
+        if k in m:
+            r[k] = m[k]
+    return r
+
+
+def our_arm(args):
+    import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the gpuls path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    cells, top = args.cells, args.top
-    ctx = capi.Context(local)
-    A = ctx.handle("A")
-    t0 = time.perf_counter()
-    # weak scaling: every GPU gets a box of cells^3 base cells (513^3-type fine grid per GPU); the rank array follows
-    # UG's RCB of a structured grid (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2)
-    P = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
+    P = ARRAYS.get(world)
     if P is None:
         raise SystemExit(f"bench.py: unsupported GPU count {world} (1, 2, 4 or 8)")
-    if world > 1:
-        import torch.distributed as dist
-        idbuf = (C.c_char * 128)()
-        if rank == 0:
-            ctx.call_noctx("uggpu_comm_unique_id", idbuf)
-        t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        ctx.call("uggpu_comm_init", world, rank, C.c_char_p(bytes(t.cpu().tolist())))
-    kind = {"p1": capi.SYNTH_P1_SIMPLEX, "q1": capi.SYNTH_Q1_POISSON, "elasticity": capi.SYNTH_Q1_ELASTICITY}[args.kind]
-    ctx.call("uggpu_synth_hierarchy_part", kind, cells * P[0], cells * P[1], cells * P[2], top, A,
-             P[0], P[1], P[2], rank, C.c_int64(args.replicate_below))
-    bs = ctx.level_bs(top)
-    n = ctx.level_n(top) * bs                      # unknowns (UG counts vector components), this rank
-    n_global = int(ctx.L.uggpu_level_n_global(ctx.h, top)) * bs
-    for name in ("x", "b", "c"):
-        for l in range(top + 1):
-            ctx.alloc(l, name)
-    ctx.call("uggpu_synth_rhs", top, ctx.handle("b"))
-    sm_damp = {"jac": 0.6, "gs": 1.0, "sgs": 1.0, "sor": 1.1, "ilu": 1.0}[args.smoother]
-    cfg = ctx.lmgc_cfg(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=sm_damp, fused=1, smoother=args.smoother)
-    galerkin_ms = None
-    if args.galerkin:      # setup operation, outside the timed steps: A_{l-1} := P^T A_l P cascaded from the top level down (uggpu_galerkin)
-        if world > 1:
-            raise SystemExit("bench.py: --galerkin runs on one GPU")
-        galerkin_ms = []
-        for l in range(top, 0, -1):
-            ctx.sync()
-            tg = time.perf_counter()
-            ctx.call("uggpu_galerkin", l, A)
-            ctx.sync()
-            galerkin_ms.append(round((time.perf_counter() - tg) * 1e3, 3))
-    ctx.sync()
-    t_pre = time.perf_counter()
-    ctx.call("uggpu_lmgc_preprocess", C.byref(cfg), top, A)
-    ctx.sync()
-    preprocess_s = time.perf_counter() - t_pre      # LmgcPreProcess: base-level LU, Gauss-Seidel schedules / ILU decompositions of all levels
-    setup_s = time.perf_counter() - t0
-    X, B, Cc = ctx.handle("x"), ctx.handle("b"), ctx.handle("c")
-    res = capi.LResult()
-    ctx.call("uggpu_ls_defect", 0, top, X, B, A)
-    ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
-    first = res.last_defect[0]
-    absl, red = capi._vs([1e-300]), capi._vs([1e-300])
+    rt = (rank, world, local, torch, dist)
+    from ug_b200 import mgpu
 
-    def step():
-        ctx.call("uggpu_ls_solve", C.byref(cfg), 0, top, X, B, A, Cc, 1, absl, red, C.byref(res), None)
+    # ---- multi-GPU parity, before anything is timed: the partitioned solve must be the one-GPU solve bit for bit ------------------
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = [mgpu.parity_check(rank, world, local, kind=k, top=t, fused=f) for k, t, f in (("p1", 5, 1), ("p1", 4, 0), ("q1", 4, 1), ("elasticity", 4, 1))]
+        if not all(p["ok"] for p in parity):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "mgpu_parity": parity}))
+            return 3
 
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    # ---- the headline workload ----------------------------------------------------------------------------------------------------
+    strong = world > 1 and not args.weak and args.kind == "p1" and args.cells == 4 and args.top == 7
+    if strong:
+        cells = (8, 8, 6)                                   # C3 verbatim: a fixed global problem over 2 / 4 / 8 GPUs
+    elif world > 1:
+        cells = (args.cells * P[0], args.cells * P[1], args.cells * P[2])
+    else:
+        cells = (args.cells,) * 3
+    steps = args.steps
+    main = dict(kind=args.kind, cells=cells, top=args.top, P=P, steps=steps, warmup=args.warmup, smoother=args.smoother, e2e_steps=args.e2e_steps,
+                clocks=True, spmv=True, galerkin=args.galerkin, replicate_below=args.replicate_below, krylov=args.krylov)
+    m = measure(main, rt)
+    m["steps"] = steps
+    extras = {}
+    xs, xw = max(3, min(5, steps)), 3
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    hist = []
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    ctx.call("uggpu_prof_enable", 1)
-    launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-        hist.append(res.last_defect[0])
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - launches0
-    # per-kernel event times of the timed region
-    prof = {}
-    kinds = {"smooth": 0, "jac": 1, "restrict": 2, "interpolate": 3, "vecop": 4, "reduce": 5, "dmatmul": 6, "base": 7, "trisolve": 8}
-    cnt, kms, kby = C.c_int64(), C.c_double(), C.c_double()
-    for name, k in kinds.items():
-        ctx.call("uggpu_prof_summary", k, -1, C.byref(cnt), C.byref(kms), C.byref(kby))
-        prof[name] = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
-    # dominant kernel: the fused smoothing step (Jacobi) / the defect update dmatmul_minus (Gauss-Seidel family), finest level
-    ctx.call("uggpu_prof_summary", 0 if args.smoother == "jac" else 6, top, C.byref(cnt), C.byref(kms), C.byref(kby))
-    dom = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
-    ctx.call("uggpu_prof_summary", 8, top, C.byref(cnt), C.byref(kms), C.byref(kby))
-    tri = {"launches": cnt.value, "ms": kms.value, "alg_bytes": kby.value}
-    ctx.call("uggpu_prof_enable", 0)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-
-    # ---- end to end: host vectors in, host vectors out, every step -------------------------------------------------
-    xh = torch.zeros(n, dtype=torch.float64).pin_memory()      # n counts components: the vectors hold n doubles
-    bh = torch.empty(n, dtype=torch.float64).pin_memory()
-    ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
-    ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
-
-    def e2e_step():
-        # b first (the cycle starts with it); x follows on the copy stream and hides behind the cycle, whose last kernel
-        # is the first to touch it
-        ctx.call("uggpu_vec_upload", top, B, C.c_void_p(bh.data_ptr()))
-        ctx.call("uggpu_vec_upload_async", top, X, C.c_void_p(xh.data_ptr()))
-        ctx.call("uggpu_ls_residuum", 0, top, B, C.byref(res))
-        step()
-        ctx.call("uggpu_vec_download", top, X, C.c_void_p(xh.data_ptr()))
-        ctx.call("uggpu_vec_download", top, B, C.c_void_p(bh.data_ptr()))
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    clocks = sampler.stop() if sampler else None
-    dev_bytes = ctx.device_bytes()
-    # BASELINE.json's second figure, "SpMV HBM GB/s vs peak": the plain dmatmul_minus (c -= A x) on the finest level, timed by the
-    # library's per-kernel events after everything else (c is work space: every cycle starts by overwriting it)
-    spmv = None
-    if world == 1:
+    def extra(name, **kw):
+        spec = dict(kind="p1", cells=cells, top=args.top, P=P, steps=xs, warmup=xw, replicate_below=args.replicate_below)
+        spec.update(kw)
         try:
-            ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
-            ctx.sync()
-            ctx.call("uggpu_prof_enable", 1)
-            for _ in range(5):
-                ctx.call("uggpu_dmatmul_minus", top, top, 0, Cc, A, X)
-            ctx.sync()
-            c2, m2, b2 = C.c_int64(), C.c_double(), C.c_double()
-            ctx.call("uggpu_prof_summary", 6, top, C.byref(c2), C.byref(m2), C.byref(b2))
-            ctx.call("uggpu_prof_enable", 0)
-            if c2.value > 0 and m2.value > 0:
-                spmv = {"kernel": f"k_dmatmul_k<{bs},2> (x -= A y, finest level)", "launches": int(c2.value), "avg_ms": m2.value / c2.value,
-                        "alg_bytes_per_launch": b2.value / c2.value, "GBps": b2.value / (m2.value * 1e-3) / 1e9}
-        except Exception as e:          # a reported figure, never a reason to lose the bench line
-            spmv = {"error": str(e)[:200]}
+            r = measure(spec, rt)
+            r["steps"] = spec["steps"]
+            extras[name] = brief(r)
+            extras[name]["workload"] = workload_name(spec["kind"], spec["cells"], spec["top"], r["n_global"], spec.get("smoother", "jac"), P)
+            if spec.get("env"):
+                extras[name]["env"] = spec["env"]
+        except Exception as e:          # an extra figure is never a reason to lose the bench line
+            extras[name] = {"error": str(e)[:300]}
+
+    if not args.no_extras and args.kind == "p1" and args.smoother == "jac":
+        if world == 1:
+            # the same workload on the general storage path: what an unstructured / variable-coefficient matrix gets
+            extra("shared_tables_generic_kernel", env={"UGGPU_NO_STENCIL": "1"})
+            extra("general_path", env={"UGGPU_NO_SHARED_VALUES": "1", "UGGPU_NO_STENCIL": "1"}, spmv=True)
+            extra("varying_coefficient", kind="p1var", spmv=True)
+            extra("q1_poisson", kind="q1")
+            extra("elasticity_3x3", kind="elasticity", top=args.top - 1)
+            extra("galerkin", galerkin=True, steps=3)
+            extra("krylov", krylov=True, steps=3)
+        else:
+            c4 = (4, 4, 4)
+            extra("q1_poisson_strong", kind="q1", cells=c4)
+            extra("elasticity_3x3_strong", kind="elasticity", cells=c4, top=args.top - 1)
+            extra("varying_coefficient_strong", kind="p1var", cells=c4)
+            if strong:
+                extra("weak", cells=(4 * P[0], 4 * P[1], 4 * P[2]))
 
     if rank != 0:
         return 0
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):        # ncu capture of the default workload only
-        tj = json.load(open(tpath))
-        if tj.get("workload") == {"kind": args.kind, "cells": cells, "top": top} and world == 1:
-            traffic = tj.get("dominant_kernel_dram_bytes_per_launch", tj.get("k_smooth_k_dram_bytes_per_launch"))
-    # SURVEY.md 8(d) counts 4 bytes of column index per entry; the stored format fetches fewer (compressed column words)
-    nnz_top, words_top = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A)), int(ctx.L.uggpu_mat_col_words(ctx.h, top, A))
-    vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables)
-    sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if not os.environ.get("UGGPU_NO_STENCIL") else 0
-    sten_w = round(nnz_top / max(ctx.level_n(top), 1))
-    if sten_top > 0 and bs == 1 and sten_w in (15, 27):
-        smooth_kernel = f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)"
-    elif sten_top > 0 and bs == 3:
-        smooth_kernel = "k_smooth_sten3<*> (fused smoothing step, 3x3-block stencil variant, finest level)"
-    else:
-        smooth_kernel = f"k_smooth_k<{bs},*> (fused smoothing step, finest level)"
-    survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
-    achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-    total_alg = sum(v["alg_bytes"] for v in prof.values())
-    n_total = n_global
-    value = n_total * args.steps / (ms * 1e-3)
-    exchanges = int(ctx.L.uggpu_comm_exchanges(ctx.h))
+    n_total = m["n_global"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(cells, top, n, args.kind, args.smoother) if world == 1 else
-                   (f"3D P1 Poisson, box of {P[0]}x{P[1]}x{P[2]} unit cubes (one per GPU), Kuhn tetrahedra, base {cells * P[0]}x{cells * P[1]}x{cells * P[2]} cells, "
-                    f"{top + 1} levels, {n_global} fine unknowns ({n} on rank 0), V(2,2) Jacobi damp 0.6, base solver ls+lu"),
-                   "parallelism": f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + NCCL halo copies, "
-                                  f"levels <= {args.replicate_below} rows replicated" if world > 1 else "dp1",
-                   "halo_exchanges_total": exchanges,
-                   "cache": "inputs larger than L2 (every sweep over the finest level streams several GB; each of its vectors alone is 1 GB)",
-                   "schedule": "fused", "device_bytes": dev_bytes, "setup_s": round(setup_s, 2), "preprocess_s": round(preprocess_s, 3), **({"galerkin_ms_top_down": galerkin_ms} if galerkin_ms is not None else {}),
-                   "defect": [first, hist[-1]] if hist else None},
-        "roofline": {"bound": "hbm", "kernel": smooth_kernel if args.smoother == "jac" else
-                     f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
-                     "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
-                     "bytes_model": "as stored: 8 B per value fetched (slices of identical rows share value tables), compressed column words (DESIGN.md 2-3), vectors once",
-                     "value_entries_per_entry": vals_top / max(nnz_top, 1), "stencil_slices_frac": sten_top / max((ctx.level_n(top) + 31) // 32, 1),
-                     "achieved_survey_model": achieved_survey, "column_words_per_entry": words_top / max(nnz_top, 1),
-                     "share_of_step": dom["ms"] / ms,
-                     "cycle_alg_GBps": total_alg / (ms * 1e-3) / 1e9, "cycle_frac": total_alg / (ms * 1e-3) / 1e9 / peak},
-        "kernels": prof,
-        "trisolve_finest": {"launches": tri["launches"], "avg_ms": tri["ms"] / max(tri["launches"], 1),
-                            "GBps": tri["alg_bytes"] / (tri["ms"] * 1e-3) / 1e9 if tri["ms"] > 0 else 0.0} if args.smoother != "jac" else None,
-        "e2e": {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": (16 * n + 8) * world,
-                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "spmv": spmv,
+        "config": {"workload": workload_name(args.kind, cells, args.top, n_total, args.smoother, P),
+                   "parallelism": (f"dp{world}: element partition into {P[0]}x{P[1]}x{P[2]} boxes, owner-computes rows + ghost columns, halo transport: {m['transport']}, "
+                                   f"levels <= {args.replicate_below} rows held completely by every rank" if world > 1 else "dp1"),
+                   "scaling_note": ("strong: the global problem (SURVEY.md C3) is the same at N = 2, 4, 8; N = 1 runs C2 (135 M unknowns: C3 does not fit one GPU), so "
+                                    "efficiency against N = 1 compares per-GPU throughput" if strong else
+                                    ("weak: every GPU holds a C2-sized box" if world > 1 else "one GPU")),
+                   "halo_exchanges_per_step": m["halo_exchanges_per_step"], "halo_transport": m["transport"],
+                   "cache": "inputs larger than L2 (every sweep over the finest level streams several GB; each of its vectors alone is >= 0.8 GB)",
+                   "schedule": "fused", "device_bytes": m["device_bytes"], "setup_s": m["setup_s"], "preprocess_s": m["preprocess_s"],
+                   "ms_per_step_with_kernel_events": m.get("ms_per_step_with_kernel_events"), "kernel_sum_ms_per_step": m["kernel_sum_ms_per_step"],
+                   **({"galerkin_ms_top_down": m["galerkin_ms_top_down"], "galerkin_finest": m["galerkin_finest"]} if "galerkin_ms_top_down" in m else {}),
+                   "defect": m["defect"]},
+        "roofline": m["roofline"],
+        "kernels": m["kernels"],
+        "trisolve_finest": m["trisolve_finest"],
+        "e2e": m.get("e2e"),
+        "e2e_solve": m.get("e2e_solve"),
+        "gpu_launches": m["launches"],
+        "clocks": m.get("clocks"),
+        "spmv": m.get("spmv"),
     }
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1:        # ncu capture of the default workload only
+        tj = json.load(open(tpath))
+        if tj.get("workload") == {"kind": args.kind, "cells": args.cells, "top": args.top}:
+            line["roofline"]["traffic"] = tj.get("dominant_kernel_dram_bytes_per_launch", tj.get("k_smooth_k_dram_bytes_per_launch"))
+    if "krylov" in m:
+        line["krylov"] = m["krylov"]
+    if parity is not None:
+        line["mgpu_parity"] = {"ok": True, "x_bitexact": all(p["x_bitexact"] for p in parity), "b_bitexact": all(p["b_bitexact"] for p in parity),
+                               "hist_relerr": max(p["hist_relerr"] for p in parity), "cases": parity}
+    line.update(extras)
     if world == 1 and not args.no_cpu:
         r = run_reference_cpu(args.cpu_refine, 5, args.cpu_replicas)
         kind = "reference"
@@ -417,8 +632,12 @@ def our_arm(args):
                                 "sample": f"{r['cycles']} V(2,2) cycles, {r['unknowns']} fine unknowns, "
                                           + (f"unmodified UG 3.12.1 numprocs (oracle/_ref/ugoracle3), {r['cores']} concurrent single-threaded "
                                              f"replicas (UG's only parallel mode is MPI), throughputs added" if kind == "reference" else "oracle/ugport.c")}
+        if not args.no_extras:
+            try:
+                line["equal_size_inside_ug"] = equal_size_inside_ug(args.cpu_refine, 5)
+            except Exception as e:
+                line["equal_size_inside_ug"] = {"error": str(e)[:200]}
     print(json.dumps(line))
-    ctx.close()
     return 0
 
 
@@ -428,19 +647,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells", type=int, default=4, help="base cells per direction")
+    ap.add_argument("--cells", type=int, default=4, help="base cells per direction (N >= 2 with the defaults: SURVEY.md C3, 8x8x6)")
     ap.add_argument("--top", type=int, default=7, help="number of uniform refinements (levels - 1)")
+    ap.add_argument("--weak", action="store_true", help="N >= 2: every GPU gets a box of cells^3 base cells instead of the fixed C3 problem")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-refine", type=int, default=6, help="refinements of the host-side reference run (6 -> 274 625 unknowns)")
     ap.add_argument("--cpu-replicas", type=int, default=0, help="concurrent single-threaded reference replicas (0 = one per host core, memory permitting)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity"],
-                    help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6)")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no general-path / Q1 / elasticity / Galerkin / Krylov / weak lines)")
+    ap.add_argument("--no-parity", action="store_true", help="N >= 2: skip the parity check against one GPU")
+    ap.add_argument("--kind", default="p1", choices=["p1", "q1", "elasticity", "p1var"],
+                    help="p1: BASELINE configs[1] (default); q1 / elasticity: Q1 cubes, scalar / 3x3 blocks (configs[3]; use --top 6); p1var: varying coefficient")
     ap.add_argument("--smoother", default="jac", choices=["jac", "gs", "sgs", "sor", "ilu"],
                     help="smoother class of the cycle: jac = BASELINE configs (default); gs / sgs / sor / ilu: Gauss-Seidel family and ILU (SURVEY.md 8f.2, one GPU)")
     ap.add_argument("--galerkin", action="store_true",
                     help="replace the coarse-level matrices by the Galerkin products P^T A P (uggpu_galerkin, SURVEY.md 8f.3) before the cycle "
                          "and report the time per level in config.galerkin_ms_top_down")
+    ap.add_argument("--krylov", action="store_true", help="also time cg and bcgs around the cycle on the headline workload")
     ap.add_argument("--replicate-below", type=int, default=300000,
                     help="multi-GPU: levels with at most this many rows are held completely by every rank (coarse-level gather)")
     args = ap.parse_args()

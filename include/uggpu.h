@@ -82,6 +82,8 @@ int64_t uggpu_device_bytes(uggpu_ctx *ctx);
 #define UGGPU_K_DMATMUL     6
 #define UGGPU_K_BASE        7
 #define UGGPU_K_TRISOLVE    8   /* level-scheduled triangular solve of the Gauss-Seidel family */
+#define UGGPU_K_HALO        9   /* stand-alone halo exchange of a partitioned level (pushes fused into a producing kernel are part of that kernel) */
+#define UGGPU_K_ALLREDUCE  10   /* ncclAllReduce of norm / dot partial sums and of the gathered coarse defect */
 int uggpu_prof_enable(uggpu_ctx *ctx, int on);   /* also clears the records */
 int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes);
 
@@ -301,6 +303,9 @@ int uggpu_bcgs_solve(uggpu_ctx*, const uggpu_lmgc_cfg*, int bl, int level, int x
 #define UGGPU_SYNTH_P1_SIMPLEX    0   /* P1 Poisson on Kuhn triangles (nz = 0) / tetrahedra, scalar          */
 #define UGGPU_SYNTH_Q1_POISSON    1   /* Q1 Poisson on cubes, scalar, 27-point rows                          */
 #define UGGPU_SYNTH_Q1_ELASTICITY 2   /* Q1 linear elasticity on cubes, 3x3 blocks (E = 1, nu = 0.3)         */
+#define UGGPU_SYNTH_P1_VARCOEF    3   /* as P1_SIMPLEX with a smoothly VARYING diffusion coefficient per edge: no two rows share
+                                         their values, so neither shared value tables nor the stencil kernels apply -- the
+                                         explicit (general) path of every kernel, at size                                 */
 /* Structured nx*ny*nz cubic cells on level 0 of the unit square (nz = 0) or cube, uniformly refined `top` times.
  * Creates levels 0..top with matrix handle A, the per-row flags of a uniformly refined UG multigrid, Dirichlet
  * identity rows (VECSKIP) on the whole boundary and the standard P/R; sets FULLREFINELEVEL = top. */
@@ -320,6 +325,15 @@ int uggpu_comm_destroy(uggpu_ctx *ctx);
 int uggpu_comm_size(uggpu_ctx *ctx);
 int uggpu_comm_rank(uggpu_ctx *ctx);
 int64_t uggpu_comm_exchanges(uggpu_ctx *ctx);                 /* halo exchanges issued so far                        */
+/* how the halo exchanges of this context travel: 0 no communicator / nothing exchanged yet, 1 ncclSend/ncclRecv,
+ * 2 peer-memory windows (CUDA IPC): one push + one wait/unpack kernel per exchange, 3 peer-memory ghost rows: the neighbours'
+ * vectors are mapped (CUDA IPC) and interface rows are stored straight into their ghost rows -- by the producing kernel's
+ * epilogue in the fused cycle, by one small kernel otherwise -- with one flag wait at the head of the consuming kernel */
+#define UGGPU_TRANSPORT_NONE   0
+#define UGGPU_TRANSPORT_NCCL   1
+#define UGGPU_TRANSPORT_WINDOW 2
+#define UGGPU_TRANSPORT_GHOST  3
+int uggpu_comm_transport(uggpu_ctx *ctx);
 /* ModelP vector consistency, np/algebra/ugblas.cc:398 l_vector_consistent, :1035 l_vector_collect, :740 l_ghostvector_consistent
  * (SURVEY.md 8 a13).  Rows are owned by exactly one rank (owner computes, ghost COLUMNS at the tail of every vector), so the sums
  * over border copies of the first two have nothing to add; the copy of the owners' values into the neighbours' ghost copies is

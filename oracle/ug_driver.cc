@@ -97,7 +97,7 @@ struct Opt {
   double beta = 0.0;                    // ilu $beta (iter.cc:5415): diagonal modification of l_ilubthdecomp
   int baselevel = 0;                    // lmgc $b
   int barrier_n = 0, barrier_id = 0;
-  bool ops = false, solve = false, timeit = false, quiet = true;
+  bool ops = false, solve = false, timeit = false, quiet = true, nokrylov = false;
   bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
   bool galerkin = false;                // --galerkin (with --imat): Galerkin coarse-grid operators by AssembleGalerkinByMatrix, cascaded from the top level down
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
@@ -672,6 +672,7 @@ int main(int argc, char **argv)
     else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
     else if (a == "--beta") o.beta = atof(nxt().c_str());
     else if (a == "--galerkin") o.galerkin = true;
+    else if (a == "--nokrylov") o.nokrylov = true;       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;
@@ -780,7 +781,7 @@ static int run_gpu(const Opt &o)
   }
   // 3. Krylov accelerators: the reference's `cg` / `bcgs` around its own lmgc against gpucg / gpubcgs around gpulmgc
   //    (device-resident).  Step lengths come from parallel sums on the device: agreement to rounding (1e-9), not bitwise.
-  {
+  if (!o.nokrylov) {
     const char *cpu_cls[2] = {"cg", "bcgs"}, *gpu_cls[2] = {"gpucg", "gpubcgs"};
     const int its[2] = {6, 4};
     for (int w = 0; w < 2; w++) {

@@ -74,8 +74,8 @@ def test_synth_equals_reference_hierarchy(name, dim, kind):
     ctx.close()
 
 
-@pytest.mark.parametrize("cells,dim,top,kind", [(2, 3, 3, 0), (1, 3, 4, 0), (3, 2, 4, 0), (2, 3, 3, 1), (1, 3, 3, 2), (3, 3, 2, 2)],
-                         ids=["P1-3d-17^3", "P1-3d-17^3-base1", "P1-2d-49^2", "Q1-17^3", "elast-9^3", "elast-13^3"])
+@pytest.mark.parametrize("cells,dim,top,kind", [(2, 3, 3, 0), (1, 3, 4, 0), (3, 2, 4, 0), (2, 3, 3, 1), (1, 3, 3, 2), (3, 3, 2, 2), (2, 3, 4, 3), (3, 2, 4, 3)],
+                         ids=["P1-3d-17^3", "P1-3d-17^3-base1", "P1-2d-49^2", "Q1-17^3", "elast-9^3", "elast-13^3", "P1-varcoef-33^3", "P1-varcoef-2d-49^2"])
 def test_synth_solve_bitexact_vs_port(cells, dim, top, kind, monkeypatch, tma_rows):
     monkeypatch.setenv("UGGPU_TMA", "1"); monkeypatch.setenv("UGGPU_TMA_MIN_ROWS", tma_rows)     # "0": every scalar level runs the bulk-copy staged smoothing kernel
     from backends import GpuBackend

@@ -19,7 +19,7 @@ HEADER = os.path.join(ROOT, "include", "uggpu.h")
 MAX_BS = 3
 ALL_VECTORS = 0
 ON_SURFACE = -1
-SYNTH_P1_SIMPLEX, SYNTH_Q1_POISSON, SYNTH_Q1_ELASTICITY = 0, 1, 2
+SYNTH_P1_SIMPLEX, SYNTH_Q1_POISSON, SYNTH_Q1_ELASTICITY, SYNTH_P1_VARCOEF = 0, 1, 2, 3
 
 
 class UggpuError(RuntimeError):
@@ -192,6 +192,10 @@ class Context:
         p = C.c_void_p()
         self.call("uggpu_stream", C.byref(p))
         return p.value or 0
+
+    def halo_transport(self) -> str:
+        return {0: "none", 1: "nccl send/recv", 2: "peer-memory windows (CUDA IPC, push + unpack kernels)",
+                3: "peer-memory ghost rows (CUDA IPC, pushes fused into the producing kernels)"}.get(int(self.L.uggpu_comm_transport(self.h)), "?")
 
     def sync(self): self.call("uggpu_sync")
     def launch_count(self) -> int: return int(self.L.uggpu_launch_count(self.h))

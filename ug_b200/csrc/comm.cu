@@ -15,7 +15,9 @@
 #include <nccl.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace {
@@ -34,27 +36,37 @@ struct Nccl {
 } nccl;
 
 #define P2P_MAX_RANKS 32
-#define P2P_FLAG_BYTES 512                // flags[rank] (8 bytes each) at the start of every window allocation
+#define P2P_FLAG_BYTES 1024               // flag block at the start of every window allocation: per rank [started, landed, window seq, spare] (8 bytes each)
+#define P2P_FLAG_WORDS 4
 
-// One receive window per rank, opened by its neighbours with CUDA IPC: the halo exchange of a partitioned level is then
-//   k_halo_push         my interface rows -> straight into the neighbours' windows over NVLink (peer stores), then one
-//                       release store of the exchange number into each neighbour's flag word;
-//   k_halo_wait_unpack  wait until every neighbour's number has arrived, copy the window into the ghost rows of the vector.
-// No NCCL call, no staging on the sender.  Two window halves alternate: a sender can only be one exchange ahead of a
-// receiver (it needs the receiver's flag of exchange e before it starts e+1), so half (e & 1) is free again at e+2.
+// Three transports for the halo copy of a partitioned level (UGGPU_HALO = ghost | window | nccl; default ghost, falling back to
+// nccl when CUDA IPC is unavailable on any rank):
+//   ghost   the neighbours' copies of the vector are mapped with CUDA IPC (one handle exchange per (level, vector), on first use) and
+//           interface rows are stored straight into their ghost rows: by the epilogue of the kernel that computes them in the fused
+//           cycle (HaloK, uggpu_internal.h), by ONE small kernel (k_halo_xchg) otherwise.  No staging, no unpack.
+//   window  round 1: one receive window per rank; k_halo_push writes the interface rows into the neighbours' windows, k_halo_wait_unpack
+//           copies the window into the ghost rows.  Two kernels per exchange; kept for A/B runs.
+//   nccl    pack kernel + ncclSend/ncclRecv group.
+enum { MODE_NCCL = 1, MODE_WINDOW = 2, MODE_GHOST = 3 };
+
 struct Peer { unsigned char *base = nullptr; int64_t half = 0; };
+struct Opened { int rank; cudaIpcMemHandle_t h; void *ptr; };
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   double *sendbuf = nullptr;
   size_t sendbuf_cap = 0;
   int64_t exchanges = 0, allreduces = 0;
-  // peer-memory path
-  bool p2p_tried = false, p2p = false;
-  unsigned char *win = nullptr; size_t win_bytes = 0; int64_t half = 0;   // my window: flags, then 2 * half doubles
+  // peer-memory paths
+  bool p2p_tried = false;
+  int mode = MODE_NCCL;
+  unsigned char *win = nullptr; size_t win_bytes = 0; int64_t half = 0;   // my window: flag block, then (window transport) 2 * half doubles
   Peer peers[P2P_MAX_RANKS];
-  unsigned long long seq = 0;
+  unsigned long long seq = 0;            // window transport: exchanges
+  unsigned long long kseq = 0;           // ghost transport: comm kernels
   unsigned int *push_counter = nullptr;
+  std::vector<Opened> opened;            // vectors of other ranks mapped into this process
+  std::vector<std::pair<void *, size_t>> graveyard;   // my vectors that other ranks have mapped: freed with the communicator
 };
 
 int load_nccl()
@@ -73,6 +85,17 @@ int load_nccl()
   return 0;
 }
 }  // namespace
+
+struct GhostMap { double **d_peer = nullptr; double *h_peer[HALO_MAX_NB]; };
+struct LevelHalo {
+  HaloDev h_dev;
+  HaloDev *d_dev = nullptr;
+  uint32_t *snd_bits = nullptr; int32_t *snd_first = nullptr, *srow_ptr = nullptr; uint32_t *snd_ent = nullptr;
+  size_t nsl = 0, n_rows = 0, n_ent = 0;
+  std::vector<int> peer_recv_off;        // where my rows start in neighbour k's ghost region
+  std::map<double *, GhostMap> maps;
+};
+
 
 #define NCCL_TRY(expr)                                                                                                       \
   do {                                                                                                                       \
@@ -104,14 +127,43 @@ extern "C" int uggpu_comm_init(uggpu_ctx *ctx, int nranks, int rank, const void 
   return 0;
 }
 
+static void level_halo_free(uggpu_ctx *ctx, Level *L)
+{
+  LevelHalo *H = L->halo;
+  if (!H) return;
+  for (auto &kv : H->maps) if (kv.second.d_peer) { double **p = kv.second.d_peer; dfree(ctx, p, (size_t)HALO_MAX_NB); }
+  if (H->d_dev) dfree(ctx, H->d_dev, 1);
+  if (H->snd_bits) dfree(ctx, H->snd_bits, H->nsl + 1);
+  if (H->snd_first) dfree(ctx, H->snd_first, H->nsl + 1);
+  if (H->srow_ptr) dfree(ctx, H->srow_ptr, H->n_rows + 1);
+  if (H->snd_ent) dfree(ctx, H->snd_ent, H->n_ent + 1);
+  delete H;
+  L->halo = nullptr;
+}
+
+// Drops everything that was derived from the set of partitioned levels (window, mapped flag blocks, per-level tables): the next exchange
+// sets it up again for the levels that exist then.  Collective in effect: all ranks change their hierarchies together.
+static int p2p_reset(uggpu_ctx *ctx, Comm *c)
+{
+  if (!c->p2p_tried) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  for (int l = 0; l < UGGPU_MAX_LEVELS; l++) level_halo_free(ctx, &ctx->lev[l]);
+  for (int q = 0; q < P2P_MAX_RANKS; q++) if (c->peers[q].base) { cudaIpcCloseMemHandle(c->peers[q].base); c->peers[q] = Peer(); }
+  if (c->win) { c->graveyard.push_back({c->win, c->win_bytes}); c->win = nullptr; }     // neighbours may still have it mapped
+  c->p2p_tried = false;
+  c->mode = MODE_NCCL;
+  return 0;
+}
+
 extern "C" int uggpu_comm_destroy(uggpu_ctx *ctx)
 {
   if (!ctx || !ctx->comm) return 0;
   Comm *c = (Comm *)ctx->comm;
   cudaStreamSynchronize(ctx->stream);
+  p2p_reset(ctx, c);
   if (c->sendbuf) dfree(ctx, c->sendbuf, c->sendbuf_cap);
-  for (int q = 0; q < P2P_MAX_RANKS; q++) if (c->peers[q].base) cudaIpcCloseMemHandle(c->peers[q].base);
-  if (c->win) dfree(ctx, c->win, c->win_bytes);
+  for (auto &o : c->opened) cudaIpcCloseMemHandle(o.ptr);
+  for (auto &g : c->graveyard) dev_free(ctx, g.first, g.second);
   if (c->push_counter) dfree(ctx, c->push_counter, 1);
   if (c->comm) nccl.CommDestroy(c->comm);
   delete c;
@@ -122,15 +174,36 @@ extern "C" int uggpu_comm_destroy(uggpu_ctx *ctx)
 extern "C" int uggpu_comm_size(uggpu_ctx *ctx) { return ctx && ctx->comm ? ((Comm *)ctx->comm)->nranks : 1; }
 extern "C" int uggpu_comm_rank(uggpu_ctx *ctx) { return ctx && ctx->comm ? ((Comm *)ctx->comm)->rank : 0; }
 extern "C" int64_t uggpu_comm_exchanges(uggpu_ctx *ctx) { return ctx && ctx->comm ? ((Comm *)ctx->comm)->exchanges : 0; }
+extern "C" int uggpu_comm_transport(uggpu_ctx *ctx)
+{
+  if (!ctx || !ctx->comm) return UGGPU_TRANSPORT_NONE;
+  Comm *c = (Comm *)ctx->comm;
+  return c->p2p_tried ? c->mode : UGGPU_TRANSPORT_NONE;
+}
 
 int level_free_part(uggpu_ctx *ctx, Level *L)
 {
+  if (ctx->comm && (L->partitioned || L->halo)) p2p_reset(ctx, (Comm *)ctx->comm);
   if (L->d_part) dfree(ctx, L->d_part, 1);
   if (L->d_send_idx) dfree(ctx, L->d_send_idx, (size_t)L->send_total);
   delete L->part;
   L->part = nullptr;
   L->send_total = 0;
   return 0;
+}
+
+// A vector of a partitioned level is released: when other ranks have it mapped (ghost transport) its memory must outlive their
+// mappings -- it is parked until the communicator goes.  Returns true when the caller must NOT free it.
+bool halo_vec_release(uggpu_ctx *ctx, Level *L, double *p, size_t bytes)
+{
+  if (!ctx->comm || !L->halo) return false;
+  auto it = L->halo->maps.find(p);
+  if (it == L->halo->maps.end()) return false;
+  if (it->second.d_peer) { double **d = it->second.d_peer; dfree(ctx, d, (size_t)HALO_MAX_NB); }
+  L->halo->maps.erase(it);
+  if (L->last_pushed == p) L->last_pushed = nullptr;
+  ((Comm *)ctx->comm)->graveyard.push_back({p, bytes});
+  return true;
 }
 
 __global__ void k_halo_pack(int total, int bs, const int32_t *__restrict__ idx, const double *__restrict__ v, double *__restrict__ buf)
@@ -141,7 +214,7 @@ __global__ void k_halo_pack(int total, int bs, const int32_t *__restrict__ idx, 
   buf[i] = v[(size_t)idx[e] * bs + c];
 }
 
-// ---- peer-memory halo exchange ---------------------------------------------------------------------------------------------
+// ---- window transport ------------------------------------------------------------------------------------------------------
 struct PushArgs {
   int nnb, bs, parity;
   unsigned long long seq;
@@ -200,32 +273,90 @@ __global__ void k_halo_wait_unpack(WaitArgs a, const double *__restrict__ win, d
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) ghost[i] = win[i];
 }
 
-// Allocates my window, exchanges the IPC handles with ncclAllGather, opens the neighbours' windows.  Collective: every rank
-// calls it at its first halo exchange.  All ranks agree on the outcome (all-reduce of the success flags); on failure the
-// NCCL send/recv path stays in use.
+// ---- ghost transport, the stand-alone exchange ---------------------------------------------------------------------------------
+// One kernel: block 0 publishes `started = g`; every block waits until all neighbours have started kernel g (their reads of the ghost
+// rows about to be overwritten are done), stores its share of the interface rows into the neighbours' ghost rows; the last block to
+// finish publishes `landed = g` and waits for the neighbours' `landed = g`, so the kernel ends when MY ghost rows are complete.
+struct XchgArgs {
+  int nnb, bs;
+  int send_off[HALO_MAX_NB + 1];
+  double *dst[HALO_MAX_NB];                  // neighbour k's ghost rows of the vector, at my first row there
+};
+
+__global__ void __launch_bounds__(256) k_halo_xchg(XchgArgs a, const HaloDev *__restrict__ dev, unsigned long long g, int total, const int32_t *__restrict__ idx,
+                                                   const double *__restrict__ v, unsigned int *counter, int *err)
+{
+  if (blockIdx.x == 0) halo_publish_dev(dev, g, 0);
+  if (threadIdx.x < 32) halo_wait_dev(dev, g, 0, err);
+  __syncthreads();
+  const int n = total * a.bs;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = i / a.bs, cpt = i - e * a.bs;
+    int k = 0;
+    while (e >= a.send_off[k + 1]) k++;
+    a.dst[k][(size_t)(e - a.send_off[k]) * a.bs + cpt] = v[(size_t)idx[e] * a.bs + cpt];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    halo_publish_dev(dev, g, 1);
+    if (threadIdx.x < 32) halo_wait_dev(dev, g, 1, err);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// flag[s] bit 0: a row of slice s has an entry in a ghost column (column index >= n_owned); bit 1: a row of slice s is pushed
+__global__ void k_comm_flag(SellView A, int n_owned, const uint32_t *__restrict__ snd_bits, uint8_t *__restrict__ flag)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((r & ~31) >= A.n) return;
+  bool ghost = false;
+  if (r < A.n && n_owned >= 0) {
+    const int len = A.rowlen[r];
+    const ColIter ci = col_iter(A, r);
+    for (int j = 0; j < len; j++) if (col_at(ci, j) >= n_owned) ghost = true;
+  }
+  ghost = __any_sync(0xffffffffu, ghost);
+  if ((threadIdx.x & 31) == 0) flag[r >> 5] = (ghost ? 1 : 0) | ((snd_bits && snd_bits[r >> 5]) ? 2 : 0);
+}
+
+static bool level_comm(const uggpu_ctx *ctx, const Level *L) { return ctx->comm && L->exists && L->partitioned && L->nnb > 0; }
+
+// Collective, at the first halo operation after the set of partitioned levels changed: chooses the transport, allocates my flag block
+// (+ window), exchanges the IPC handles with ncclAllGather, maps the flag blocks of all ranks that are a neighbour on some level.
+// All ranks agree on the outcome (all-reduce of the success flags); on failure the NCCL send/recv path stays in use.
 static int p2p_setup(uggpu_ctx *ctx, Comm *c)
 {
   c->p2p_tried = true;
   const char *mode = getenv("UGGPU_HALO");
-  int want = !(mode && strcmp(mode, "nccl") == 0) && c->nranks <= P2P_MAX_RANKS;
+  int want = MODE_GHOST;
+  if (mode && strcmp(mode, "nccl") == 0) want = MODE_NCCL;
+  else if (mode && strcmp(mode, "window") == 0) want = MODE_WINDOW;
+  if (c->nranks > P2P_MAX_RANKS) want = MODE_NCCL;
   int64_t half = 0;
-  const PartGrid *gany = nullptr;
+  bool nb[P2P_MAX_RANKS] = {false};
+  bool any = false;
   for (int l = 0; l < UGGPU_MAX_LEVELS; l++) {
     Level &L = ctx->lev[l];
-    if (!L.exists || !L.partitioned || !L.part) continue;
-    gany = L.part;
+    if (!level_comm(ctx, &L)) continue;
+    any = true;
+    for (int k = 0; k < L.nnb; k++) if (L.nb_rank[k] >= 0 && L.nb_rank[k] < P2P_MAX_RANKS) nb[L.nb_rank[k]] = true;
     int64_t h = (int64_t)L.nghost * L.bs;
     if (h > half) half = h;
   }
   half = (half + 31) & ~(int64_t)31;
+  if (want != MODE_WINDOW) half = 0;
   struct Info { cudaIpcMemHandle_t h; int64_t half; int64_t ok; };
   static_assert(sizeof(Info) == 80, "Info layout");
   Info mine;
   memset(&mine, 0, sizeof mine);
   mine.half = half; mine.ok = 0;
-  if (want && gany) {
+  if (want != MODE_NCCL) {
     c->win_bytes = P2P_FLAG_BYTES + 2 * (size_t)half * sizeof(double);
-    if (dev_alloc(ctx, (void **)&c->win, c->win_bytes) == 0 && dalloc(ctx, &c->push_counter, 1) == 0) {
+    if (dev_alloc(ctx, (void **)&c->win, c->win_bytes) == 0 && (c->push_counter || dalloc(ctx, &c->push_counter, 1) == 0)) {
       cudaMemsetAsync(c->win, 0, c->win_bytes, ctx->stream);
       cudaMemsetAsync(c->push_counter, 0, sizeof(unsigned int), ctx->stream);
       if (cudaIpcGetMemHandle(&mine.h, c->win) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
@@ -242,9 +373,9 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   int ok = mine.ok ? 1 : 0;
   for (int q = 0; q < c->nranks; q++) if (!all[q].ok) ok = 0;
-  if (ok && gany) {
-    for (int k = 0; k < gany->nnb && ok; k++) {
-      const int q = gany->nb_rank[k];
+  if (ok && any) {
+    for (int q = 0; q < c->nranks && ok; q++) {
+      if (!nb[q] || q == c->rank) continue;
       void *ptr = nullptr;
       if (cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
       c->peers[q].base = (unsigned char *)ptr;
@@ -257,46 +388,247 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
   NCCL_TRY(nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&h_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  c->p2p = h_ok == (double)c->nranks;
+  c->mode = (h_ok == (double)c->nranks) ? want : MODE_NCCL;
   dfree(ctx, d_send, 1); dfree(ctx, d_recv, (size_t)c->nranks);
   if (getenv("UGGPU_HALO_VERBOSE") && c->rank == 0)
-    fprintf(stderr, "uggpu: halo exchange over %s (%d ranks, window %lld doubles per half)\n", c->p2p ? "peer memory (CUDA IPC)" : "NCCL send/recv", c->nranks, (long long)half);
+    fprintf(stderr, "uggpu: halo exchange over %s (%d ranks, window %lld doubles per half)\n",
+            c->mode == MODE_GHOST ? "peer-memory ghost rows (CUDA IPC)" : c->mode == MODE_WINDOW ? "peer-memory windows (CUDA IPC)" : "NCCL send/recv", c->nranks, (long long)half);
   return 0;
+}
+
+// Collective, once per partitioned level: every rank publishes its interface description (neighbour ranks, receive offsets, send
+// counts); from the neighbours' tables follow the places of my rows in their ghost regions.  Then the device tables of the level:
+// the flag words, and the send map (row -> (neighbour, index in its ghost region)) used by the kernels that push.
+static int level_halo_setup(uggpu_ctx *ctx, Comm *c, Level *L)
+{
+  if (L->halo) return 0;
+  if (L->nnb > HALO_MAX_NB) return uggpu_fail(UGGPU_ERROR, "halo: %d neighbours on one level (at most %d)", L->nnb, HALO_MAX_NB);
+  struct Tab { int32_t nnb, pad; int32_t rank[HALO_MAX_NB], recv_off[HALO_MAX_NB + 1], send_cnt[HALO_MAX_NB]; int32_t fill; };
+  Tab mine;
+  memset(&mine, 0, sizeof mine);
+  mine.nnb = L->nnb;
+  for (int k = 0; k < L->nnb; k++) { mine.rank[k] = L->nb_rank[k]; mine.recv_off[k] = L->nb_recv_off[k]; mine.send_cnt[k] = L->nb_send_off[k + 1] - L->nb_send_off[k]; }
+  mine.recv_off[L->nnb] = L->nb_recv_off[L->nnb];
+  Tab *d_send = nullptr, *d_recv = nullptr;
+  UG_TRY(dalloc(ctx, &d_send, 1));
+  UG_TRY(dalloc(ctx, &d_recv, (size_t)c->nranks));
+  CUDA_TRY(cudaMemcpyAsync(d_send, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(nccl.AllGather(d_send, d_recv, sizeof(Tab), ncclChar, c->comm, ctx->stream));
+  std::vector<Tab> all((size_t)c->nranks);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_recv, sizeof(Tab) * c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, d_send, 1); dfree(ctx, d_recv, (size_t)c->nranks);
+  LevelHalo *H = new LevelHalo();
+  memset(&H->h_dev, 0, sizeof H->h_dev);
+  for (int k = 0; k < L->nnb; k++) {
+    const int q = L->nb_rank[k];
+    if (q < 0 || q >= c->nranks || q == c->rank) { delete H; return uggpu_fail(UGGPU_ERROR, "halo: bad neighbour rank %d", q); }
+    const Tab &t = all[q];
+    int kk = -1;
+    for (int j = 0; j < t.nnb; j++) if (t.rank[j] == c->rank) kk = j;
+    if (kk < 0) { delete H; return uggpu_fail(UGGPU_ERROR, "halo: rank %d does not list rank %d as a neighbour", q, c->rank); }
+    if (t.recv_off[kk + 1] - t.recv_off[kk] != mine.send_cnt[k] || t.send_cnt[kk] != mine.recv_off[k + 1] - mine.recv_off[k]) {
+      delete H;
+      return uggpu_fail(UGGPU_ERROR, "halo: interface sizes of ranks %d and %d differ", c->rank, q);
+    }
+    H->peer_recv_off.push_back(t.recv_off[kk]);
+  }
+  L->halo = H;
+  L->peer_recv_off = H->peer_recv_off;
+  if (c->mode != MODE_GHOST) return 0;
+  // flag words
+  HaloDev &D = H->h_dev;
+  D.nnb = L->nnb;
+  for (int k = 0; k < L->nnb; k++) {
+    const int q = L->nb_rank[k];
+    if (!c->peers[q].base) return uggpu_fail(UGGPU_ERROR, "halo: the flag block of rank %d is not mapped", q);
+    D.my_flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + (size_t)q * P2P_FLAG_WORDS;
+    D.peer_flag[k] = reinterpret_cast<unsigned long long *>(c->peers[q].base) + (size_t)c->rank * P2P_FLAG_WORDS;
+  }
+  // send map: rows ascending, per row its (neighbour, destination) pairs
+  std::vector<int32_t> idx((size_t)L->send_total);
+  if (L->send_total) CUDA_TRY(cudaMemcpyAsync(idx.data(), L->d_send_idx, sizeof(int32_t) * idx.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::pair<int32_t, uint32_t>> ent;
+  ent.reserve(idx.size());
+  for (int k = 0; k < L->nnb; k++)
+    for (int e = L->nb_send_off[k]; e < L->nb_send_off[k + 1]; e++) {
+      const int64_t dst = (int64_t)H->peer_recv_off[k] + (e - L->nb_send_off[k]);
+      if (dst >= (1 << 27) || idx[e] < 0 || idx[e] >= L->n) return uggpu_fail(UGGPU_ERROR, "halo: send list entry out of range");
+      ent.push_back({idx[e], ((uint32_t)k << 27) | (uint32_t)dst});
+    }
+  std::stable_sort(ent.begin(), ent.end(), [](const std::pair<int32_t, uint32_t> &a, const std::pair<int32_t, uint32_t> &b) { return a.first < b.first; });
+  const size_t nsl = ((size_t)L->n + 31) / 32;
+  std::vector<uint32_t> bits(nsl + 1, 0u), ents;
+  std::vector<int32_t> first(nsl + 1, 0), rptr;
+  ents.reserve(ent.size());
+  int32_t rows = 0;
+  for (size_t i = 0; i < ent.size();) {
+    const int32_t r = ent[i].first;
+    bits[(size_t)r >> 5] |= 1u << (r & 31);
+    rptr.push_back((int32_t)ents.size());
+    for (; i < ent.size() && ent[i].first == r; i++) ents.push_back(ent[i].second);
+    rows++;
+  }
+  rptr.push_back((int32_t)ents.size());
+  { int32_t acc = 0; for (size_t s = 0; s < nsl; s++) { first[s] = acc; acc += __builtin_popcount(bits[s]); } first[nsl] = acc; }
+  H->nsl = nsl; H->n_rows = (size_t)rows; H->n_ent = ents.size();
+  UG_TRY(dalloc(ctx, &H->snd_bits, nsl + 1)); UG_TRY(dalloc(ctx, &H->snd_first, nsl + 1));
+  UG_TRY(dalloc(ctx, &H->srow_ptr, H->n_rows + 1)); UG_TRY(dalloc(ctx, &H->snd_ent, H->n_ent + 1));
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(cudaMemcpyAsync(H->snd_bits, bits.data(), sizeof(uint32_t) * (nsl + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(H->snd_first, first.data(), sizeof(int32_t) * (nsl + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(H->srow_ptr, rptr.data(), sizeof(int32_t) * rptr.size(), cudaMemcpyHostToDevice, st));
+  if (!ents.empty()) CUDA_TRY(cudaMemcpyAsync(H->snd_ent, ents.data(), sizeof(uint32_t) * ents.size(), cudaMemcpyHostToDevice, st));
+  D.snd_bits = H->snd_bits; D.snd_first = H->snd_first; D.srow_ptr = H->srow_ptr; D.snd_ent = H->snd_ent;
+  UG_TRY(dalloc(ctx, &H->d_dev, 1));
+  CUDA_TRY(cudaMemcpyAsync(H->d_dev, &D, sizeof(HaloDev), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// The neighbours' copies of vector v of level L (ghost transport).  Collective on first use of a (level, vector) pair: all ranks
+// exchange the IPC handle of their copy, every rank maps its neighbours'.  h_peer[k] / d_peer[k] = neighbour k's ghost region of the
+// vector at the place where MY rows start.
+typedef int (*GetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
+static int ghost_map(uggpu_ctx *ctx, Comm *c, Level *L, double *v, GhostMap **out)
+{
+  LevelHalo *H = L->halo;
+  auto it = H->maps.find(v);
+  if (it != H->maps.end()) { *out = &it->second; return 0; }
+  struct Info { cudaIpcMemHandle_t h; int64_t offset; int64_t own; int64_t ok; };
+  static_assert(sizeof(Info) == 88, "Info layout");
+  Info mine;
+  memset(&mine, 0, sizeof mine);
+  mine.own = (int64_t)L->n * L->bs;
+  {
+    static GetAddressRangeFn range = nullptr;
+    if (!range) {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) range = (GetAddressRangeFn)fn; else cudaGetLastError();
+    }
+    unsigned long long base = 0; size_t size = 0;
+    if (range && range(&base, &size, (unsigned long long)(uintptr_t)v) == 0 && cudaIpcGetMemHandle(&mine.h, v) == cudaSuccess) {
+      mine.offset = (int64_t)((unsigned long long)(uintptr_t)v - base);
+      mine.ok = 1;
+    } else cudaGetLastError();
+  }
+  Info *d_send = nullptr, *d_recv = nullptr;
+  UG_TRY(dalloc(ctx, &d_send, 1));
+  UG_TRY(dalloc(ctx, &d_recv, (size_t)c->nranks));
+  CUDA_TRY(cudaMemcpyAsync(d_send, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(nccl.AllGather(d_send, d_recv, sizeof(Info), ncclChar, c->comm, ctx->stream));
+  std::vector<Info> all((size_t)c->nranks);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_recv, sizeof(Info) * c->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, d_send, 1); dfree(ctx, d_recv, (size_t)c->nranks);
+  for (int q = 0; q < c->nranks; q++) if (!all[q].ok) return uggpu_fail(UGGPU_CUDA_ERROR, "halo: rank %d cannot export a vector of level %d (CUDA IPC)", q, (int)(L - ctx->lev));
+  GhostMap gm;
+  for (int k = 0; k < L->nnb; k++) {
+    const int q = L->nb_rank[k];
+    void *ptr = nullptr;
+    for (auto &o : c->opened) if (o.rank == q && memcmp(&o.h, &all[q].h, sizeof(cudaIpcMemHandle_t)) == 0) ptr = o.ptr;
+    if (!ptr) {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); return uggpu_fail(UGGPU_CUDA_ERROR, "halo: cannot map a vector of rank %d: %s", q, cudaGetErrorString(e)); }
+      c->opened.push_back(Opened{q, all[q].h, ptr});
+    }
+    gm.h_peer[k] = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ptr) + all[q].offset) + all[q].own + (size_t)H->peer_recv_off[k] * L->bs;
+  }
+  UG_TRY(dalloc(ctx, &gm.d_peer, (size_t)HALO_MAX_NB));
+  if (L->nnb) CUDA_TRY(cudaMemcpyAsync(gm.d_peer, gm.h_peer, sizeof(double *) * L->nnb, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  auto ins = H->maps.insert({v, gm});
+  *out = &ins.first->second;
+  return 0;
+}
+
+static int halo_ready(uggpu_ctx *ctx, Comm *c, Level *L)
+{
+  if (!c->p2p_tried) UG_TRY(p2p_setup(ctx, c));
+  if (!L->halo) UG_TRY(level_halo_setup(ctx, c, L));
+  return 0;
+}
+
+bool halo_fused_available(uggpu_ctx *ctx, int level)
+{
+  Level *L = &ctx->lev[level];
+  if (!level_comm(ctx, L)) return false;
+  Comm *c = (Comm *)ctx->comm;
+  if (halo_ready(ctx, c, L)) return false;
+  return c->mode == MODE_GHOST;
 }
 
 int halo_exchange(uggpu_ctx *ctx, int level, double *v);
 
-// push: my interface rows into the neighbours' windows + the release of the exchange number (on the compute stream);
+// slices of M (rows on `RL`, columns index vectors of `CL` or nullptr) that read ghost columns / hold rows to push
+static int halo_comm_flag(uggpu_ctx *ctx, Level *RL, Level *CL, SellMat *M)
+{
+  if (M->comm_flag) return 0;
+  const size_t nsl = ((size_t)M->n + 31) / 32;
+  UG_TRY(dalloc(ctx, &M->comm_flag, nsl + 1));
+  const bool cpart = CL && level_comm(ctx, CL), rpart = level_comm(ctx, RL) && RL->halo && RL->halo->snd_bits && RL->n == M->n;
+  if (nsl)
+    k_comm_flag<<<(int)((nsl * 32 + 255) / 256), 256, 0, ctx->stream>>>(view(*M), cpart ? CL->n : -1, rpart ? RL->halo->snd_bits : nullptr, M->comm_flag);
+  KCHECK(ctx);
+  return 0;
+}
+
+int halo_prepare(uggpu_ctx *ctx, int row_level, int col_level, SellMat *M, double *operand, const HaloPlan *hp, HaloK *hk)
+{
+  *hk = halo_none();
+  Level *RL = &ctx->lev[row_level], *CL = col_level >= 0 ? &ctx->lev[col_level] : nullptr;
+  const bool rpart = level_comm(ctx, RL), cpart = CL && level_comm(ctx, CL);
+  if (!rpart && !cpart) return 0;
+  Comm *c = (Comm *)ctx->comm;
+  if (rpart) UG_TRY(halo_ready(ctx, c, RL));
+  if (cpart) UG_TRY(halo_ready(ctx, c, CL));
+  if (c->mode != MODE_GHOST || getenv("UGGPU_NO_FUSED_HALO")) {
+    if (cpart && operand) return halo_exchange(ctx, col_level, operand);
+    return 0;
+  }
+  const bool ready = hp && hp->operand_ready && cpart && CL->last_pushed == operand;
+  if (cpart && operand && !ready) UG_TRY(halo_exchange(ctx, col_level, operand));
+  double *push = (hp && hp->push && rpart && hp->push_level == row_level) ? hp->push : nullptr;
+  if (!cpart && !push) return 0;                  // nothing to wait for, nothing to push
+  UG_TRY(halo_comm_flag(ctx, RL, CL, M));
+  hk->flag = M->comm_flag;
+  hk->cdev = cpart ? CL->halo->d_dev : nullptr;
+  if (push) {
+    GhostMap *gm = nullptr;
+    UG_TRY(ghost_map(ctx, c, RL, push, &gm));
+    hk->pdev = RL->halo->d_dev;
+    hk->peer = gm->d_peer;
+    RL->last_pushed = push;
+    c->exchanges++;
+  }
+  hk->g = ++c->kseq;
+  hk->err = ctx->derr;
+  return 0;
+}
+
+// window transport -- push: my interface rows into the neighbours' windows + the release of the exchange number (on the compute stream);
 // wait: poll my flag words and copy my window into the ghost rows of v (on `st`, which must be ordered behind the push).
 static int halo_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v, bool do_push, bool do_wait, cudaStream_t wait_stream)
 {
-  const PartGrid &g = *L->part;
-  const int bs = L->bs;
-  if (L->peer_recv_off.empty()) {       // where my rows land in each neighbour's window: its receive offset for me on this level
-    int cells[3];
-    for (int d = 0; d < 3; d++) cells[d] = d < g.dim ? g.nn[d] - 1 : 0;
-    for (int k = 0; k < g.nnb; k++) {
-      PartGrid nb;
-      if (part_make(&nb, g.dim, cells, g.P, g.nb_rank[k], 0)) return uggpu_fail(UGGPU_ERROR, "halo: cannot rebuild the partition of rank %d", g.nb_rank[k]);
-      int kk = -1;
-      for (int j = 0; j < nb.nnb; j++) if (nb.nb_rank[j] == g.rank) kk = j;
-      if (kk < 0) return uggpu_fail(UGGPU_ERROR, "halo: rank %d does not list rank %d as a neighbour", g.nb_rank[k], g.rank);
-      if (nb.nb_recv_off[kk + 1] - nb.nb_recv_off[kk] != g.nb_send_off[k + 1] - g.nb_send_off[k])
-        return uggpu_fail(UGGPU_ERROR, "halo: interface sizes of ranks %d and %d differ", g.rank, g.nb_rank[k]);
-      L->peer_recv_off.push_back(nb.nb_recv_off[kk]);
-    }
-  }
+  const int bs = L->bs, nnb = L->nnb;
+  const int64_t need = (int64_t)L->nghost * bs;
+  if (need > c->half) return uggpu_fail(UGGPU_ERROR, "halo: level needs %lld window doubles, the window holds %lld", (long long)need, (long long)c->half);
   if (do_push) ++c->seq;
   const unsigned long long seq = c->seq;
   const int parity = (int)(seq & 1ull);
   if (do_push) {
     PushArgs pa;
-    pa.nnb = g.nnb; pa.bs = bs; pa.parity = parity; pa.seq = seq;
-    for (int k = 0; k <= g.nnb; k++) pa.send_off[k] = g.nb_send_off[k];
-    for (int k = 0; k < g.nnb; k++) {
-      const Peer &p = c->peers[g.nb_rank[k]];
+    pa.nnb = nnb; pa.bs = bs; pa.parity = parity; pa.seq = seq;
+    for (int k = 0; k <= nnb; k++) pa.send_off[k] = L->nb_send_off[k];
+    for (int k = 0; k < nnb; k++) {
+      const Peer &p = c->peers[L->nb_rank[k]];
+      const int64_t cnt = (int64_t)(L->nb_send_off[k + 1] - L->nb_send_off[k]);
+      if (!p.base || ((int64_t)L->peer_recv_off[k] + cnt) * bs > p.half)
+        return uggpu_fail(UGGPU_ERROR, "halo: the window of rank %d is not mapped or too small for level %d", L->nb_rank[k], (int)(L - ctx->lev));
       pa.dst[k] = reinterpret_cast<double *>(p.base + P2P_FLAG_BYTES) + (size_t)parity * p.half + (size_t)L->peer_recv_off[k] * bs;
-      pa.flag[k] = reinterpret_cast<unsigned long long *>(p.base) + c->rank;
+      pa.flag[k] = reinterpret_cast<unsigned long long *>(p.base) + (size_t)c->rank * P2P_FLAG_WORDS + 2;
     }
     const int tot = L->send_total * bs;
     int pb = (tot + 255) / 256;
@@ -307,8 +639,8 @@ static int halo_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v, bool do_push, 
   }
   if (do_wait) {
     WaitArgs wa;
-    wa.nnb = g.nnb; wa.seq = seq;
-    for (int k = 0; k < g.nnb; k++) wa.flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + g.nb_rank[k];
+    wa.nnb = nnb; wa.seq = seq;
+    for (int k = 0; k < nnb; k++) wa.flag[k] = reinterpret_cast<const unsigned long long *>(c->win) + (size_t)L->nb_rank[k] * P2P_FLAG_WORDS + 2;
     const size_t cnt = (size_t)L->nghost * bs;
     int wb = (int)((cnt + 255) / 256);
     if (wb > ctx->sm_count) wb = ctx->sm_count;        // every block polls: keep them all resident
@@ -321,25 +653,18 @@ static int halo_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v, bool do_push, 
   return 0;
 }
 
-static int halo_exchange_p2p(uggpu_ctx *ctx, Comm *c, Level *L, double *v) { return halo_p2p(ctx, c, L, v, true, true, ctx->stream); }
-
-// Split exchange for kernels that overlap it with their interior rows (spmv.cu k_smooth_step): halo_begin pushes on the compute
-// stream and returns 1 when the second half may run on another stream (peer-memory path on a partitioned level), 0 when there is
-// nothing to exchange, and does the whole exchange itself (returning 0) on the NCCL path.  halo_finish waits + unpacks on `st`;
-// the caller orders `st` behind the push (event) and the compute stream behind `st` afterwards.
+// Split exchange for kernels that overlap it with their interior rows (spmv.cu k_smooth_step, UGGPU_OVERLAP=1 with the window
+// transport): halo_begin pushes on the compute stream and returns 1 when the second half may run on another stream, 0 when there is
+// nothing to exchange, and does the whole exchange itself (returning 0) on the other transports.
 int halo_begin(uggpu_ctx *ctx, int level, double *v, int *split)
 {
   *split = 0;
   Level *L = &ctx->lev[level];
-  if (!ctx->comm || !L->partitioned || !L->part || L->part->nnb == 0) return 0;
+  if (!level_comm(ctx, L)) return 0;
   Comm *c = (Comm *)ctx->comm;
-  if (!c->p2p_tried) UG_TRY(p2p_setup(ctx, c));
-  // opt-in (UGGPU_OVERLAP=1): measured SLOWER than the plain exchange on the weak-scaling bench (2 GPUs, 513^3 per GPU: 33.1 vs
-  // 29.6 ms per cycle) -- an exchange costs ~25 us next to a 4 ms kernel, while the interface slices of an x-split (every 16th
-  // slice of the lexicographic order) run far below the bandwidth of the contiguous sweep.  Kept parity-tested for partitions
-  // whose interfaces are contiguous in the row order.
+  UG_TRY(halo_ready(ctx, c, L));
   static const bool overlap = getenv("UGGPU_OVERLAP") != nullptr;
-  if (!c->p2p || !overlap) return halo_exchange(ctx, level, v);
+  if (c->mode != MODE_WINDOW || !overlap) return halo_exchange(ctx, level, v);
   UG_TRY(halo_p2p(ctx, c, L, v, true, false, ctx->stream));
   *split = 1;
   return 0;
@@ -355,12 +680,29 @@ int halo_finish(uggpu_ctx *ctx, int level, double *v, cudaStream_t st)
 int halo_exchange(uggpu_ctx *ctx, int level, double *v)
 {
   Level *L = &ctx->lev[level];
-  if (!ctx->comm || !L->partitioned || !L->part || L->part->nnb == 0) return 0;
+  if (!level_comm(ctx, L)) return 0;
   Comm *c = (Comm *)ctx->comm;
-  if (!c->p2p_tried) UG_TRY(p2p_setup(ctx, c));
-  if (c->p2p) return halo_exchange_p2p(ctx, c, L, v);
-  const PartGrid &g = *L->part;
+  UG_TRY(halo_ready(ctx, c, L));
   const int bs = L->bs;
+  ProfScope ps(ctx, UGGPU_K_HALO, level, 16.0 * bs * (double)L->send_total);
+  if (c->mode == MODE_GHOST) {
+    GhostMap *gm = nullptr;
+    UG_TRY(ghost_map(ctx, c, L, v, &gm));
+    XchgArgs xa;
+    xa.nnb = L->nnb; xa.bs = bs;
+    for (int k = 0; k <= L->nnb; k++) xa.send_off[k] = L->nb_send_off[k];
+    for (int k = 0; k < L->nnb; k++) xa.dst[k] = gm->h_peer[k];
+    const int tot = L->send_total * bs;
+    int pb = (tot + 255) / 256;
+    if (pb > 4 * ctx->sm_count) pb = 4 * ctx->sm_count;      // every block waits: all of them resident
+    if (pb < 1) pb = 1;
+    k_halo_xchg<<<pb, 256, 0, ctx->stream>>>(xa, L->halo->d_dev, ++c->kseq, L->send_total, L->d_send_idx, v, c->push_counter, ctx->derr);
+    KCHECK(ctx);
+    L->last_pushed = nullptr;
+    c->exchanges++;
+    return 0;
+  }
+  if (c->mode == MODE_WINDOW) return halo_p2p(ctx, c, L, v, true, true, ctx->stream);
   size_t need = (size_t)L->send_total * bs;
   if (need > c->sendbuf_cap) {
     if (c->sendbuf) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); UG_TRY(dfree(ctx, c->sendbuf, c->sendbuf_cap)); }
@@ -373,10 +715,10 @@ int halo_exchange(uggpu_ctx *ctx, int level, double *v)
     KCHECK(ctx);
   }
   NCCL_TRY(nccl.GroupStart());
-  for (int k = 0; k < g.nnb; k++) {
-    int ns = g.nb_send_off[k + 1] - g.nb_send_off[k], nr = g.nb_recv_off[k + 1] - g.nb_recv_off[k];
-    if (ns > 0) NCCL_TRY(nccl.Send(c->sendbuf + (size_t)g.nb_send_off[k] * bs, (size_t)ns * bs, ncclDouble, g.nb_rank[k], c->comm, ctx->stream));
-    if (nr > 0) NCCL_TRY(nccl.Recv(v + ((size_t)L->n + g.nb_recv_off[k]) * bs, (size_t)nr * bs, ncclDouble, g.nb_rank[k], c->comm, ctx->stream));
+  for (int k = 0; k < L->nnb; k++) {
+    int ns = L->nb_send_off[k + 1] - L->nb_send_off[k], nr = L->nb_recv_off[k + 1] - L->nb_recv_off[k];
+    if (ns > 0) NCCL_TRY(nccl.Send(c->sendbuf + (size_t)L->nb_send_off[k] * bs, (size_t)ns * bs, ncclDouble, L->nb_rank[k], c->comm, ctx->stream));
+    if (nr > 0) NCCL_TRY(nccl.Recv(v + ((size_t)L->n + L->nb_recv_off[k]) * bs, (size_t)nr * bs, ncclDouble, L->nb_rank[k], c->comm, ctx->stream));
   }
   NCCL_TRY(nccl.GroupEnd());
   c->exchanges++;
@@ -388,6 +730,7 @@ int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count)
   if (!ctx->comm) return 0;
   Comm *c = (Comm *)ctx->comm;
   if (c->nranks == 1 || count == 0) return 0;
+  ProfScope ps(ctx, UGGPU_K_ALLREDUCE, -2, 16.0 * (double)count);
   NCCL_TRY(nccl.AllReduce(dptr, dptr, count, ncclDouble, ncclSum, c->comm, ctx->stream));
   c->allreduces++;
   return 0;

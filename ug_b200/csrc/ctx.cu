@@ -253,7 +253,7 @@ extern "C" int uggpu_level_destroy(uggpu_ctx *ctx, int level)
   for (auto &kv : L->mats) sell_free(ctx, &kv.second);
   for (auto &kv : L->pending) { cudaEventSynchronize(kv.second); cudaEventDestroy(kv.second); }
   L->pending.clear();
-  for (auto &kv : L->vecs) { double *p = kv.second; dfree(ctx, p, vec_count(L)); }
+  for (auto &kv : L->vecs) { double *p = kv.second; if (!halo_vec_release(ctx, L, p, (vec_count(L) ? vec_count(L) : 2) * sizeof(double))) dfree(ctx, p, vec_count(L)); }
   level_free_part(ctx, L);
   sell_free(ctx, &L->P);
   sell_free(ctx, &L->R);
@@ -425,7 +425,7 @@ extern "C" int uggpu_vec_free(uggpu_ctx *ctx, int level, int vec)
   UG_TRY(vec_wait(ctx, level, vec));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   double *p = it->second;
-  UG_TRY(dfree(ctx, p, vec_count(L)));
+  if (!halo_vec_release(ctx, L, p, (vec_count(L) ? vec_count(L) : 2) * sizeof(double))) UG_TRY(dfree(ctx, p, vec_count(L)));
   L->vecs.erase(it);
   return 0;
 }

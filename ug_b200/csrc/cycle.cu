@@ -287,6 +287,115 @@ __global__ void __launch_bounds__(32) k_lu_solve_lists_block(int N, LuProg F, Lu
   for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
 }
 
+// ---- the whole base-level solve in ONE kernel -------------------------------------------------------------------------------------
+// `ls $I lu` around l_luiter: LinearResiduum, then per iteration v = (LU)^-1 b; b -= A v; c += v; LinearResiduum; convergence test
+// (ls.cc:637-749).  One CTA: warp 0 runs the list-ordered sweeps above, all threads the defect update (one thread per row, the row's
+// terms in VSTART->MNEXT order like k_dmatmul_k) and the norms.  The defect lives in shared memory for the duration.  No host round
+// trip: the cycle's stream is never drained in the middle (the host-driven loop base_solve_host read two norms back per cycle).
+struct BaseArgs { int N, n, maxit; double abslimit, reduction; };
+
+template <int BS>
+__device__ __forceinline__ void base_norm(const double *bsh, const uint8_t *__restrict__ ctl, int n, double *red, double *out)
+{
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  double acc[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) acc[i] = 0.0;
+  for (int r = tid; r < n; r += blockDim.x)
+    if (ctl[r] & UGGPU_CTL_NEW_DEFECT) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) acc[i] += bsh[r * BS + i] * bsh[r * BS + i];
+    }
+#pragma unroll
+  for (int i = 0; i < BS; i++) {
+    double v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[w * BS + i] = v;
+  }
+  __syncthreads();
+  if (tid < BS) {
+    double v = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) v += red[k * BS + tid];
+    out[tid] = sqrt(v);
+  }
+  __syncthreads();
+}
+
+template <int BS>
+__global__ void __launch_bounds__(LU_THREADS) k_base_solve(SellView A, LuProg F, LuProg B, const double *__restrict__ dinv, const uint8_t *__restrict__ ctl,
+                                                           double *__restrict__ c, double *__restrict__ b, BaseArgs a)
+{
+  extern __shared__ double smem_base[];
+  double *vs = smem_base, *prod = vs + LU_MAX_N, *bsh = prod + LU_MAX_N, *red = bsh + LU_MAX_N, *nrm = red + 32 * BS, *reach = nrm + BS;
+  __shared__ int stop;
+  constexpr int BB = BS * BS;
+  const int tid = threadIdx.x, N = a.N;
+  for (int i = tid; i < N; i += blockDim.x) bsh[i] = b[i];
+  __syncthreads();
+  base_norm<BS>(bsh, ctl, a.n, red, nrm);
+  if (tid == 0) {
+    bool below = true;                                   // sc_cmp(first, abslimit) npscan.cc:1027
+    for (int i = 0; i < BS; i++) {
+      if (fabs(nrm[i]) >= fabs(a.abslimit)) below = false;
+      reach[i] = nrm[i] * a.reduction;
+      if (reach[i] == 0.0) reach[i] = a.reduction;       // ls.cc:663-667
+    }
+    stop = below ? 1 : 0;
+  }
+  __syncthreads();
+  if (stop) return;
+  for (int it = 0; it < a.maxit; it++) {
+    if (tid < 32) {
+      for (int i = tid; i < N; i += 32) vs[i] = 0.0;     // rows with VCLASS < ACTIVE_CLASS stay 0 (ugiter.cc:4488)
+      __syncwarp();
+      if (BS == 1) { lu_sweep<false>(F, bsh, vs, prod); lu_sweep<true>(B, dinv, vs, prod); }
+      else { lu_sweep_block<BS, false>(F, bsh, dinv, vs, prod); lu_sweep_block<BS, true>(B, bsh, dinv, vs, prod); }
+    }
+    __syncthreads();
+    // b -= A v (dmatmul_minus, all rows), c += v
+    for (int r = tid; (r & ~31) < a.n; r += blockDim.x) {
+      if (r < a.n) {
+        const int lane = r & 31;
+        const int64_t sp = slice_off(A, r >> 5);
+        const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : A.col_ptr[r >> 5];
+        const int len = (int)A.rowlen[r];
+        const double *tp = (cpo < 0 && A.vt && UG_VALTAB(cpo) >= 0) ? A.vt + UG_VALTAB(cpo) : nullptr;
+        const double *vp = A.val + sp * BB + lane;
+        const ColIter ci = col_iter(A, r);
+        double sm[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i++) sm[i] = 0.0;
+        for (int j = 0; j < len; j++) {
+          const int cc = col_at(ci, j);
+          double m[BB];
+#pragma unroll
+          for (int k = 0; k < BB; k++) m[k] = tp ? tp[(size_t)j * BB + k] : vp[((size_t)j * BB + k) * 32];
+#pragma unroll
+          for (int i = 0; i < BS; i++) {
+            double acc = m[i * BS] * vs[cc * BS];
+#pragma unroll
+            for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * vs[cc * BS + q];
+            sm[i] += acc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < BS; i++) bsh[r * BS + i] = bsh[r * BS + i] - sm[i];
+      }
+    }
+    for (int i = tid; i < N; i += blockDim.x) c[i] = c[i] + vs[i];
+    __syncthreads();
+    base_norm<BS>(bsh, ctl, a.n, red, nrm);
+    if (tid == 0) {
+      bool b1 = true, b2 = true;
+      for (int i = 0; i < BS; i++) { if (fabs(nrm[i]) >= fabs(a.abslimit)) b1 = false; if (fabs(nrm[i]) >= fabs(reach[i])) b2 = false; }
+      stop = (b1 || b2) ? 1 : 0;
+    }
+    __syncthreads();
+    if (stop) break;
+  }
+  for (int i = tid; i < N; i += blockDim.x) b[i] = bsh[i];
+}
+
 int level_free_lu(uggpu_ctx *ctx, Level *L)
 {
   const size_t bbf = (size_t)(L->bs > 0 ? L->bs * L->bs : 1), nrow = (size_t)(L->bs > 0 ? L->luN / L->bs : L->luN);
@@ -493,6 +602,24 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   double *cp = get_vec(ctx, level, c), *bp = get_vec(ctx, level, b), *cc = get_vec(ctx, level, UGGPU_VEC_TMP_C);
   if (!cp || !bp || !cc) return UGGPU_DESC_MISMATCH;
   if (L->n == 0) return 0;
+  // the whole loop on the device (one CTA) when the level is held completely and the list-ordered factors exist
+  if (L->lu_lo_ptr && !(ctx->comm && L->partitioned) && !getenv("UGGPU_BASE_HOST_LOOP")) {
+    const LuProg F{L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, L->lu_active}, B{L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_active};
+    const BaseArgs ba{L->luN, L->n, cfg->base_maxit, cfg->base_abslimit, cfg->base_reduction};
+    SellMat *M = get_mat(ctx, level, A);
+    if (!M) return UGGPU_DESC_MISMATCH;
+    const size_t smem = sizeof(double) * (3 * LU_MAX_N + 32 * UGGPU_MAX_BS + 2 * UGGPU_MAX_BS);
+    // per device and cheap: set on every call (a process may drive several devices)
+    if (bs == 1) CUDA_TRY(cudaFuncSetAttribute(k_base_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (bs == 2) CUDA_TRY(cudaFuncSetAttribute(k_base_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CUDA_TRY(cudaFuncSetAttribute(k_base_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
+    if (bs == 1) k_base_solve<1><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
+    else if (bs == 2) k_base_solve<2><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
+    else k_base_solve<3><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
+    KCHECK(ctx);
+    return 0;
+  }
   double first[UGGPU_MAX_BS], last[UGGPU_MAX_BS], reach[UGGPU_MAX_BS], absl[UGGPU_MAX_BS];
   UG_TRY(level_norm(ctx, level, 1, bp, last));
   for (int i = 0; i < bs; i++) {
@@ -559,7 +686,11 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
 static inline bool use_fused(const uggpu_lmgc_cfg *cfg) { return cfg->fused && cfg->smoother == UGGPU_SM_JAC; }
 
 // t_ready: the temporary cfg->t of this level already holds damp * Diag(A)^-1 b (written by the restriction above)
-static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf)
+// push_c: the caller interpolates this level's correction next -- on a partitioned level (multi-GPU, peer-memory ghost rows) the last
+// kernel stores the interface rows of c into the neighbours' ghost rows.  The same holds for every producer -> consumer pair of the
+// schedule (HaloPlan): the kernel that computes a vector pushes the rows the next kernel's ghost columns need, and the next kernel
+// waits for its neighbours at its own head -- no exchange kernels in between.
+static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf, bool push_c = false)
 {
   if (level <= cfg->baselevel) return base_solve(ctx, cfg, level, c, b, A);
   Level *L = get_level(ctx, level);
@@ -575,12 +706,16 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   // x is only touched by the last smoothing step: an upload of it that is still in flight (uggpu_vec_upload_async) overlaps the cycle
   if (top) { xp = get_vec_lazy(ctx, level, tf->x); if (!xp) return UGGPU_DESC_MISMATCH; }
   double *cur = tA, *oth = tB;
+  const bool part = halo_fused_available(ctx, level), cpart = halo_fused_available(ctx, level - 1);
+  auto plan = [&](bool ready, double *push, int push_level) { return HaloPlan{ready, push, push_level}; };
 
   if (cfg->nu1 > 0) {
-    if (!t_ready) UG_TRY(k_jac(ctx, level, A, cur, bp, sd));
+    if (!t_ready) { const HaloPlan hp = plan(false, part ? cur : nullptr, level); UG_TRY(k_jac(ctx, level, A, cur, bp, sd, &hp)); }
     for (int i = 0; i < cfg->nu1; i++) {
-      int flags = (c_zero ? SF_CSET : SF_CADD) | (i < cfg->nu1 - 1 ? SF_TOUT : 0);
-      UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, nullptr, 0));
+      const bool lastpre = i == cfg->nu1 - 1;
+      int flags = (c_zero ? SF_CSET : SF_CADD) | (!lastpre ? SF_TOUT : 0);
+      const HaloPlan hp = plan(true, part ? (lastpre ? bp : oth) : nullptr, level);       // the last pre-smoothing step hands b to the restriction
+      UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, nullptr, 0, &hp));
       c_zero = false;
       double *sw = cur; cur = oth; oth = sw;
     }
@@ -592,17 +727,22 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     if (!bc || !cc || !tc) return UGGPU_DESC_MISMATCH;
     // not across the gather level of a multi-GPU hierarchy: there the coarse defect is complete only after the all-reduce
     const bool fuse = lc > cfg->baselevel && cfg->nu1 > 0 && !(ctx->comm && L->partitioned && !ctx->lev[lc].partitioned);
-    UG_TRY(k_restrict(ctx, level, bc, bp, one, fuse, A, tc, cc, sd));
+    {
+      const HaloPlan hp = plan(cfg->nu1 > 0, cpart && lc > cfg->baselevel ? (fuse ? tc : bc) : nullptr, lc);
+      UG_TRY(k_restrict(ctx, level, bc, bp, one, fuse, A, tc, cc, sd, &hp));
+    }
     if (!fuse) UG_TRY(k_vec_op(ctx, lc, 0, VOP_SET, cc, nullptr, Damp{{0.0, 0.0, 0.0}}));   // dset(c,0) iter.cc:7873
-    for (int g = 0; g < cfg->gamma; g++) UG_TRY(lmgc_fused(ctx, cfg, lc, c, b, A, fuse && g == 0, nullptr));
-    UG_TRY(k_interpolate(ctx, level, tA, cc, cd));
+    for (int g = 0; g < cfg->gamma; g++) UG_TRY(lmgc_fused(ctx, cfg, lc, c, b, A, fuse && g == 0, nullptr, g == cfg->gamma - 1));
+    const HaloPlan hp = plan(true, part ? tA : nullptr, level);
+    UG_TRY(k_interpolate(ctx, level, tA, cc, cd, &hp));
   }
   // c += t ; b -= A t ; first post-smoothing correction
   {
     const bool last = cfg->nu2 == 0;
     int flags = (c_zero ? SF_CSET : SF_CADD) | (last ? 0 : SF_TOUT);
     if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
-    UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0));
+    const HaloPlan hp = plan(true, part ? (last ? (push_c ? cp : nullptr) : tB) : nullptr, level);
+    UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0, &hp));
     c_zero = false;
     cur = tB; oth = tA;
   }
@@ -610,7 +750,8 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     const bool last = i == cfg->nu2 - 1;
     int flags = SF_CADD | (last ? 0 : SF_TOUT);
     if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
-    UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0));
+    const HaloPlan hp = plan(true, part ? (last ? (push_c ? cp : nullptr) : oth) : nullptr, level);
+    UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0, &hp));
     double *sw = cur; cur = oth; oth = sw;
   }
   return 0;

@@ -144,6 +144,44 @@ __device__ __forceinline__ void row_product(const SellView &A, int r, bool live,
   } else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);
 }
 
+// The same row product for the slices of a partitioned level that read GHOST columns (multi-GPU, HaloK): the ghost rows of y are
+// written by other GPUs while this kernel runs -- they are complete once the warp has passed halo_wait, but a line that holds the
+// last owned rows AND the first ghost rows may already sit in this SM's L1 from another warp's gathers.  Every gather therefore
+// bypasses L1 (ld.global.cg: L2 is where peer writes land).  Same terms, same order.  Few slices take it: not inlined.
+template <int BS>
+__device__ __noinline__ void row_product_ghost(const SellView &A, int r, bool live, const double *y, double *s, double *dg)
+{
+  constexpr int BB = BS * BS;
+  const int lane = r & 31;
+  const int64_t sp = slice_off(A, r >> 5);
+  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : A.col_ptr[r >> 5];
+  const int len = live ? (int)A.rowlen[r] : 0;
+  const double *tp = (cpo < 0 && A.vt && UG_VALTAB(cpo) >= 0) ? A.vt + UG_VALTAB(cpo) : nullptr;
+  const double *vp = A.val + sp * BB + lane;
+  const ColIter ci = col_iter(A, r);
+  for (int i = 0; i < BS; i++) s[i] = 0.0;
+  for (int k = 0; k < BB; k++) dg[k] = 0.0;
+  for (int j = 0; j < len; j++) {
+    const int c = col_at(ci, j);
+    double m[BB], w[BS];
+#pragma unroll
+    for (int k = 0; k < BB; k++) m[k] = tp ? __ldg(tp + (size_t)j * BB + k) : __ldg(vp + ((size_t)j * BB + k) * 32);
+#pragma unroll
+    for (int i = 0; i < BS; i++) w[i] = __ldcg(y + (size_t)c * BS + i);
+    if (j == 0) {
+#pragma unroll
+      for (int k = 0; k < BB; k++) dg[k] = m[k];
+    }
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      double acc = m[i * BS] * w[0];
+#pragma unroll
+      for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * w[q];
+      s[i] += acc;
+    }
+  }
+}
+
 // SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
 template <int BS>
 __device__ __forceinline__ int solve_small_block(const double (&mat)[BS * BS], const double (&rhs)[BS], double (&sol)[BS])
@@ -193,6 +231,44 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_dmatmul_k(SellView A, uint8_t 
   }
 }
 
+// Stencil variant (scalar rows), the dmatmul counterpart of k_smooth_sten below: on a matrix whose slices mostly carry ONE
+// (distance, value) table pair the tables arrive as a kernel parameter (constant bank), W is a template parameter, and a slice of
+// full-width rows with that code word runs the unrolled, predicate-free loop; every other slice takes row_product.  Same sums in
+// the same order as k_dmatmul_k.
+template <int OP, int W>
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_MINBLOCKS) k_dmatmul_sten(const __grid_constant__ Sten st, SellView A, uint8_t bit, const uint8_t *__restrict__ ctl,
+                                                                               double *__restrict__ x, const double *__restrict__ y, int pf_dist, int nsl)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5;
+  if (s >= nsl) return;                                         // whole warps
+  const bool live = r < A.n && (!bit || (ctl[r] & bit));
+  const long long cpo = __ldg(A.col_ptr + s);
+  const int len = r < A.n ? (int)A.rowlen[r] : 0;
+  if (cpo == st.code && __all_sync(0xffffffffu, len == W)) {
+    const double xo = (OP != 0 && live) ? x[r] : 0.0;
+    const char *yb = reinterpret_cast<const char *>(y + r);
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+      const double yv = __ldg(reinterpret_cast<const double *>(yb + st.dbytes[j]));
+      const double p = st.v[j] * yv;
+      sum += p;
+    }
+    if (live) x[r] = OP == 0 ? sum : (OP == 1 ? xo + sum : xo - sum);
+  } else {
+    double s1[1], d1[1];
+    row_product<1>(A, r, live, y, s1, d1);
+    if (live) x[r] = OP == 0 ? s1[0] : (OP == 1 ? x[r] + s1[0] : x[r] - s1[0]);
+  }
+  const int lane = threadIdx.x & 31;
+  if (pf_dist > 0 && s + pf_dist < nsl && lane < 5) {           // L2 prefetch: the far slice's rows of x and the rows of y it reaches first
+    const size_t far = ((size_t)(s + pf_dist)) * 32;
+    if (lane < 2) { if (OP != 0 && far + lane * 16 < (size_t)A.n) prefetch_l2(x + far + lane * 16); }
+    else if (far + st.maxd + (lane - 2) * 16 < (size_t)A.n) prefetch_l2(y + far + st.maxd + (lane - 2) * 16);
+  }
+}
+
 template <int BS>
 static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, int rowmode, double *x, const double *y)
 {
@@ -203,6 +279,15 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   const double nb = 8.0 * BS * L->n;
   ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
   const Prefetch pf = make_prefetch(ctx, A, BS);
+  if (BS == 1 && (A->sten.w == 15 || A->sten.w == 27) && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
+    const int nsl = (L->n + 31) / 32;
+#define DS(OPV, WV) k_dmatmul_sten<OPV, WV><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, v, bit, L->ctl, x, y, pf.dist, nsl)
+    if (A->sten.w == 15) { if (op == 0) DS(0, 15); else if (op == 1) DS(1, 15); else DS(2, 15); }
+    else { if (op == 0) DS(0, 27); else if (op == 1) DS(1, 27); else DS(2, 27); }
+#undef DS
+    KCHECK(ctx);
+    return 0;
+  }
   if (op == 0) k_dmatmul_k<BS, 0><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
   else if (op == 1) k_dmatmul_k<BS, 1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
   else k_dmatmul_k<BS, 2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(v, bit, L->ctl, x, y, pf);
@@ -244,10 +329,15 @@ extern "C" int uggpu_dmatmul_minus(uggpu_ctx *c, int fl, int tl, int mode, int x
 // of the row, i.e. the first 32-wide column of the slice: a coalesced read.
 template <int BS>
 __global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_t *__restrict__ vclass, double *__restrict__ v, const double *__restrict__ d, Damp damp, int *err,
-                                                        Prefetch pf)
+                                                        Prefetch pf, HaloK hk)
 {
   constexpr int BB = BS * BS;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t cf = 0;
+  if (hk.flag) {                                        // multi-GPU: this launch pushes v's interface rows into the neighbours' ghost rows
+    halo_publish(hk);
+    if ((r & ~31) < A.n) { cf = hk.flag[r >> 5]; if (cf & 2) halo_wait(hk); }
+  }
   if (r >= A.n) return;
   const int lane = r & 31;
   if (pf.dist > 0 && (r >> 5) + pf.dist < pf.nsl) {     // every stream of this kernel is direct-indexed: touch the far slice's lines now
@@ -269,23 +359,28 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_
     for (int i = 0; i < BS; i++) rhs[i] = d[(size_t)r * BS + i];
     if (solve_small_block<BS>(m, rhs, sol)) { atomicExch(err, UGGPU_SMALL_DIAG); return; }
   }
+  double pv[BS];
 #pragma unroll
-  for (int i = 0; i < BS; i++) v[(size_t)r * BS + i] = sol[i] * damp.a[i];
+  for (int i = 0; i < BS; i++) { pv[i] = sol[i] * damp.a[i]; v[(size_t)r * BS + i] = pv[i]; }
+  if ((cf & 2) && hk.peer) halo_push_row<BS>(hk, r, pv);
 }
 
-int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp)
+int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp)
 {
   Level *L = get_level(ctx, level);
   SellMat *M = get_mat(ctx, level, A);
   if (!L || !M) return UGGPU_DESC_MISMATCH;
-  if (L->n == 0) return 0;
+  HaloK hk = halo_none();
+  if (hp && hp->push) UG_TRY(halo_prepare(ctx, level, -1, M, nullptr, hp, &hk));
+  if (L->n == 0 && !hk.flag) return 0;
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
+  if (blocks < 1) blocks = 1;
   SellView vw = view(*M);
   ProfScope ps(ctx, UGGPU_K_JAC, level, (double)L->n * (8.0 * L->bs * L->bs + 16.0 * L->bs));
   switch (L->bs) {
-    case 1: k_jac_k<1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
-    case 2: k_jac_k<2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
-    default: k_jac_k<3><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs)); break;
+    case 1: k_jac_k<1><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs), hk); break;
+    case 2: k_jac_k<2><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs), hk); break;
+    default: k_jac_k<3><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(vw, L->vclass, v, d, damp, ctx->derr, make_prefetch(ctx, M, L->bs), hk); break;
   }
   KCHECK(ctx);
   return 0;
@@ -327,11 +422,73 @@ extern "C" int uggpu_jac_smooth(uggpu_ctx *ctx, int level, int x, int b, int A, 
 // per-call path, so fused and unfused results are bit-identical.  tout must not alias tin (other rows gather tin).
 // scalar rows: at most 32 registers, so that 2048 threads are resident per SM (the variant with the norm partials took 40 without
 // the bound: 75 % occupancy, 4.69 instead of ~4.2 ms on the finest level)
+// A slice of a partitioned level that reads ghost columns or holds rows to push (multi-GPU, HaloK): wait for the neighbours, the row
+// product with L1-bypassing gathers where ghost columns occur, the step's updates, the push.  Same arithmetic as the kernels' own
+// rows.  Kept out of line so that the registers of the smoothing kernels are those of their fast paths.
 template <int BS, int FLAGS>
-__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? SPMV_MINBLOCKS : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+__device__ __noinline__ void smooth_comm_rows(SellView A, int r, int cf, HaloK hk, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+                                              const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int *err, double *nrm)
+{
+  halo_wait(hk);
+  const bool active = r < A.n;
+  double s[BS], dg[BS * BS];
+  if (cf & 1) row_product_ghost<BS>(A, r, active, tin, s, dg);
+  else row_product<BS>(A, r, active, tin, s, dg);
+#pragma unroll
+  for (int i = 0; i < BS; i++) nrm[i] = 0.0;
+  if (!active) return;
+  double bn[BS], pv[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) {
+    const size_t k = (size_t)r * BS + i;
+    bn[i] = b[k] - s[i];
+    b[k] = bn[i];
+    pv[i] = bn[i];
+  }
+  if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      const size_t k = (size_t)r * BS + i;
+      double cn;
+      if (FLAGS & SF_CADD) cn = c[k] + tin[k];
+      else if (FLAGS & SF_CSET) cn = 0.0 + tin[k];
+      else cn = c[k];
+      if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
+      if (FLAGS & SF_XADD) x[k] = x[k] + cn;
+      if (hk.sel == HALO_PUSH_C) pv[i] = cn;
+    }
+  }
+  if (FLAGS & SF_TOUT) {
+    double sol[BS];
+    if (vclass[r] < 3) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) sol[i] = 0.0;
+    } else if (solve_small_block<BS>(dg, bn, sol)) {
+      atomicExch(err, UGGPU_SMALL_DIAG);
+#pragma unroll
+      for (int i = 0; i < BS; i++) sol[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      const double tv = sol[i] * damp.a[i];
+      tout[(size_t)r * BS + i] = tv;
+      if (hk.sel == HALO_PUSH_TOUT) pv[i] = tv;
+    }
+  }
+  if ((cf & 2) && hk.peer) halo_push_row<BS>(hk, r, pv);
+  if (FLAGS & SF_NORM) {
+    if (ctl[r] & UGGPU_CTL_NEW_DEFECT) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) nrm[i] = bn[i] * bn[i];
+    }
+  }
+}
+
+template <int BS, int FLAGS, bool COMM = false>
+__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? (COMM ? SPMV_MINBLOCKS * 3 / 4 : SPMV_MINBLOCKS) : 1) k_smooth_k(SellView A, const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
                                                            const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                            double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err,
-                                                           Prefetch pf, const int32_t *__restrict__ list, int nlist, const uint8_t *__restrict__ skip_slice)
+                                                           Prefetch pf, const int32_t *__restrict__ list, int nlist, const uint8_t *__restrict__ skip_slice, HaloK hk)
 {
   // Multi-GPU overlap (launch_smooth2): the INTERIOR launch covers the whole grid and skips the slices flagged in skip_slice (a
   // direct-indexed byte per slice: no extra hop in the row's chain of loads); the INTERFACE launch works on the slices list[w].
@@ -339,10 +496,25 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? SPMV_MINBLOCKS : 1) k_
   if (list) { const int w = r >> 5; r = w < nlist ? list[w] * 32 + (threadIdx.x & 31) : A.n + 32; }
   if (skip_slice && (r & ~31) < A.n && skip_slice[r >> 5]) r = A.n + 32;
   bool active = r < A.n;
+  // Multi-GPU, peer-memory ghost rows (HaloK, uggpu_internal.h): block 0 tells the neighbours that this kernel has started; the warps
+  // whose slice reads ghost columns or holds rows to push wait until all neighbours have started it, too
+  // (COMM instantiation; the other one is the single-GPU kernel unchanged)
+  uint8_t cf = 0;
+  if (COMM && hk.flag) {
+    halo_publish(hk);
+    if ((r & ~31) < A.n) cf = hk.flag[r >> 5];
+  }
   const PfState pfs = pf_begin(A, r, pf);      // software prefetch into L2 (uggpu_internal.h): requested now, issued at the end
   double nrm[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
+  if (COMM && cf) {
+    double gn[BS];
+    smooth_comm_rows<BS, FLAGS>(A, r, cf, hk, vclass, ctl, tin, b, c, tout, damp, x, err, gn);
+#pragma unroll
+    for (int i = 0; i < BS; i++) nrm[i] = gn[i];
+    active = false;                            // done
+  }
   double s[BS], dg[BS * BS];
   // scalar rows: the row's own entries of b, c, tin are requested first, so that their (HBM or L2) round trip runs next to the gathers
   double eb = 0.0, ec = 0.0, et = 0.0;
@@ -351,7 +523,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? SPMV_MINBLOCKS : 1) k_
     if ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ec = c[r];
     if (FLAGS & (SF_CADD | SF_CSET)) et = tin[r];
   }
-  if ((r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
+  if (!(COMM && cf) && (r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
   if (active) {
     double bn[BS];
 #pragma unroll
@@ -454,20 +626,28 @@ __device__ __forceinline__ double smooth_tail(int r, double sum, double dg, doub
   return 0.0;
 }
 
-template <int FLAGS, int W>
+template <int FLAGS, int W, bool COMM = false>
 __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MINBLOCKS) k_smooth_sten(const __grid_constant__ Sten st, SellView A, const uint8_t *__restrict__ vclass,
                                                                               const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b,
                                                                               double *__restrict__ c, double *__restrict__ tout, double damp, double *__restrict__ x,
-                                                                              double *__restrict__ partials, int *err, int pf_dist, int nsl)
+                                                                              double *__restrict__ partials, int *err, int pf_dist, int nsl, HaloK hk)
 {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = r >> 5;
   const bool active = r < A.n;
   double nrm = 0.0;
+  if (COMM && hk.flag) halo_publish(hk);
   if (s < nsl) {                                               // whole warps
     const long long cpo = __ldg(A.col_ptr + s);
     const int len = active ? (int)A.rowlen[r] : 0;
-    if (cpo == st.code && __all_sync(0xffffffffu, len == W)) {
+    // multi-GPU (HaloK, COMM instantiation): slices that read ghost columns or hold rows to push wait for the neighbours and take the careful path
+    const uint8_t cf = (COMM && hk.flag) ? hk.flag[s] : (uint8_t)0;
+    if (COMM && cf) {
+      double gn[1];
+      Damp dd; dd.a[0] = damp; dd.a[1] = dd.a[2] = 1.0;
+      smooth_comm_rows<1, FLAGS>(A, r, cf, hk, vclass, ctl, tin, b, c, tout, dd, x, err, gn);
+      nrm = gn[0];
+    } else if (cpo == st.code && __all_sync(0xffffffffu, len == W)) {
       // the row's own entries first: their round trip runs next to the gathers
       const double eb = b[r];
       const double ec = ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ? c[r] : 0.0;
@@ -526,22 +706,31 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_MINBLOCKS) k_smooth_sten(co
 #ifndef SPMV_STEN3_MINBLOCKS
 #define SPMV_STEN3_MINBLOCKS 8
 #endif
-template <int FLAGS>
+template <int FLAGS, bool COMM = false>
 __global__ void __launch_bounds__(SPMV_THREADS, SPMV_STEN3_MINBLOCKS) k_smooth_sten3(const __grid_constant__ Sten3 st, SellView A, const uint8_t *__restrict__ vclass,
                                                                                      const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b,
                                                                                      double *__restrict__ c, double *__restrict__ tout, Damp damp, double *__restrict__ x,
-                                                                                     double *__restrict__ partials, int *err, int pf_dist, int nsl)
+                                                                                     double *__restrict__ partials, int *err, int pf_dist, int nsl, HaloK hk)
 {
   constexpr int BS = 3, BB = 9;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = r >> 5;
   const bool active = r < A.n;
   double nrm[BS] = {0.0, 0.0, 0.0};
+  if (COMM && hk.flag) halo_publish(hk);
   if (s < nsl) {                                               // whole warps
     const long long cpo = __ldg(A.col_ptr + s);
     const int len = active ? (int)A.rowlen[r] : 0;
     double sum[BS], dg[BB];
-    if (cpo == st.code && __all_sync(0xffffffffu, len == 27)) {
+    const uint8_t cf = (COMM && hk.flag) ? hk.flag[s] : (uint8_t)0;      // multi-GPU (HaloK): ghost columns / rows to push in this slice
+    bool work = active;
+    if (COMM && cf) {
+      double gn[BS];
+      smooth_comm_rows<BS, FLAGS>(A, r, cf, hk, vclass, ctl, tin, b, c, tout, damp, x, err, gn);
+#pragma unroll
+      for (int i = 0; i < BS; i++) nrm[i] = gn[i];
+      work = false;
+    } else if (cpo == st.code && __all_sync(0xffffffffu, len == 27)) {
       const char *yb = reinterpret_cast<const char *>(tin + (size_t)r * BS);
 #pragma unroll
       for (int i = 0; i < BS; i++) sum[i] = 0.0;
@@ -562,7 +751,7 @@ __global__ void __launch_bounds__(SPMV_THREADS, SPMV_STEN3_MINBLOCKS) k_smooth_s
     } else {
       row_product<BS>(A, r, active, tin, sum, dg);
     }
-    if (active) {
+    if (work) {
       double bn[BS];
 #pragma unroll
       for (int i = 0; i < BS; i++) {
@@ -907,11 +1096,12 @@ static bool tma_geometry(uggpu_ctx *ctx, const Level *L, const SellMat *A, int *
 // computed by the same code on the same operands as in one launch: results do not change.
 template <int BS, int FLAGS>
 static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
-                          int level, int split)
+                          int level, int split, const HaloK &hk)
 {
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
+  if (blocks < 1) blocks = 1;
   int tgrid = 0, twarps = 0; size_t tsmem = 0;
-  const bool tma = !split && BS == 1 && tma_geometry(ctx, L, A, &tgrid, &twarps, &tsmem);
+  const bool tma = !split && !hk.flag && BS == 1 && tma_geometry(ctx, L, A, &tgrid, &twarps, &tsmem);
   constexpr int WPB = SPMV_THREADS / 32;
   int bi = 0, bb = 0;
   if (split) {
@@ -939,14 +1129,14 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *ti
     const Prefetch pf = make_prefetch(ctx, A, BS);
     CUDA_TRY(cudaEventRecord(ctx->halo_ev[0], ctx->stream));                  // behind the push of halo_begin
     if (bi > 0) {
-      k_smooth_k<BS, FLAGS><<<bi, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf, nullptr, 0, A->bnd_flag);
+      k_smooth_k<BS, FLAGS><<<bi, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf, nullptr, 0, A->bnd_flag, halo_none());
       KCHECK(ctx);
     }
     CUDA_TRY(cudaStreamWaitEvent(ctx->halo_stream, ctx->halo_ev[0], 0));
     UG_TRY(halo_finish(ctx, level, const_cast<double *>(tin), ctx->halo_stream));
     if (bb > 0) {
       k_smooth_k<BS, FLAGS><<<bb, SPMV_THREADS, 0, ctx->halo_stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x,
-                                                                        (FLAGS & SF_NORM) ? ctx->partials + (size_t)bi * BS : ctx->partials, ctx->derr, pf, A->bnd_list, A->n_bnd, nullptr);
+                                                                        (FLAGS & SF_NORM) ? ctx->partials + (size_t)bi * BS : ctx->partials, ctx->derr, pf, A->bnd_list, A->n_bnd, nullptr, halo_none());
       ctx->launches++;
     }
     CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], ctx->halo_stream));
@@ -954,20 +1144,27 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *ti
   } else if (BS == 1 && (A->sten.w == 15 || A->sten.w == 27) && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
     // most slices carry one stencil: the variant with the stencil in the constant bank (same arithmetic, a third of the instructions)
     const Prefetch pf = make_prefetch(ctx, A, BS);
-    if (A->sten.w == 15)
-      k_smooth_sten<FLAGS, 15><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr,
-                                                                          pf.dist, (L->n + 31) / 32);
-    else
-      k_smooth_sten<FLAGS, 27><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, ctx->derr,
-                                                                          pf.dist, (L->n + 31) / 32);
+#define STEN_LAUNCH(WV, CV) k_smooth_sten<FLAGS, WV, CV><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, \
+                                                                                                   ctx->partials, ctx->derr, pf.dist, (L->n + 31) / 32, hk)
+    if (A->sten.w == 15) { if (hk.flag) STEN_LAUNCH(15, true); else STEN_LAUNCH(15, false); }
+    else { if (hk.flag) STEN_LAUNCH(27, true); else STEN_LAUNCH(27, false); }
+#undef STEN_LAUNCH
   } else if (BS == 3 && A->sten3 && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
     // the same for 3x3 blocks with the 27-column stencil of Q1 hexahedra (pf distance as for vector-only slices)
     const Prefetch pf = make_prefetch(ctx, A, BS);
-    k_smooth_sten3<FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(*A->sten3, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
-                                                                     pf.dist, (L->n + 31) / 32);
+    if (hk.flag)
+      k_smooth_sten3<FLAGS, true><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(*A->sten3, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                           pf.dist, (L->n + 31) / 32, hk);
+    else
+      k_smooth_sten3<FLAGS, false><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(*A->sten3, view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                            pf.dist, (L->n + 31) / 32, hk);
   } else {
-    k_smooth_k<BS, FLAGS><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
-                                                                      make_prefetch(ctx, A, BS), nullptr, 0, nullptr);
+    if (hk.flag)
+      k_smooth_k<BS, FLAGS, true><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                              make_prefetch(ctx, A, BS), nullptr, 0, nullptr, hk);
+    else
+      k_smooth_k<BS, FLAGS, false><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(view(*A), L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr,
+                                                                               make_prefetch(ctx, A, BS), nullptr, 0, nullptr, hk);
   }
   KCHECK(ctx);
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)blocks, norm_slot, (int)(L - ctx->lev)));
@@ -976,9 +1173,9 @@ static int launch_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *ti
 
 template <int BS>
 static int launch_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
-                         int level, int split)
+                         int level, int split, const HaloK &hk)
 {
-#define SM_CASE(F) case F: return launch_smooth2<BS, F>(ctx, L, A, tin, b, c, tout, damp, x, norm_slot, level, split)
+#define SM_CASE(F) case F: return launch_smooth2<BS, F>(ctx, L, A, tin, b, c, tout, damp, x, norm_slot, level, split, hk)
   switch (flags) {
     SM_CASE(0);
     SM_CASE(SF_CADD);
@@ -998,20 +1195,30 @@ static int launch_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const 
   return uggpu_fail(UGGPU_ERROR, "smooth step: unsupported flag combination %d", flags);
 }
 
-int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot)
+int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
+                  const HaloPlan *hp)
 {
   Level *L = get_level(ctx, level);
   SellMat *M = get_mat(ctx, level, A);
   if (!L || !M) return UGGPU_DESC_MISMATCH;
-  if (L->n == 0) return 0;
   if ((flags & SF_TOUT) && tout == tin) return uggpu_fail(UGGPU_ERROR, "smooth step: tout aliases tin");
-  // ghost columns of the correction (no-op on one GPU); on the peer-memory path only the push happens here and the kernel's
-  // interior slices overlap the rest of the exchange
+  // Ghost columns of the correction (no-op on one GPU).  Peer-memory ghost rows: the kernel itself waits for the neighbours and stores the
+  // interface rows of the vector it produces into their ghost rows (hk); window transport with UGGPU_OVERLAP: only the push happens here
+  // and the kernel's interior slices overlap the rest of the exchange; otherwise the operand is exchanged before the launch.
   int split = 0;
-  UG_TRY(halo_begin(ctx, level, const_cast<double *>(tin), &split));
+  HaloK hk = halo_none();
+  if (halo_fused_available(ctx, level)) {
+    UG_TRY(halo_prepare(ctx, level, level, M, const_cast<double *>(tin), hp, &hk));
+    if (hk.peer) {
+      hk.sel = hp->push == tout ? HALO_PUSH_TOUT : (hp->push == b ? HALO_PUSH_B : (hp->push == c ? HALO_PUSH_C : HALO_PUSH_NONE));
+      if (hk.sel == HALO_PUSH_NONE || (hk.sel == HALO_PUSH_TOUT && !(flags & SF_TOUT)) || (hk.sel == HALO_PUSH_C && !(flags & (SF_CADD | SF_CSET))))
+        return uggpu_fail(UGGPU_ERROR, "smooth step: the vector to push is not produced by this step");
+    }
+  } else UG_TRY(halo_begin(ctx, level, const_cast<double *>(tin), &split));
+  if (L->n == 0 && !hk.flag) return 0;
   switch (L->bs) {
-    case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
-    case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
-    default: return launch_smooth<3>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split);
+    case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split, hk);
+    case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split, hk);
+    default: return launch_smooth<3>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split, hk);
   }
 }

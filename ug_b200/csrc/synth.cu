@@ -39,6 +39,7 @@ struct SynthParams {
   int bs;           // components per node
   double hpow;      // h^(dim-2): scale of the stiffness entries
   double hvol;      // h^dim
+  double hhalf;     // h / 2 (edge midpoints, UGGPU_SYNTH_P1_VARCOEF)
 };
 
 __device__ __forceinline__ bool in_grid(const int (&nn)[3], const int (&x)[3]) { return x[0] >= 0 && x[0] < nn[0] && x[1] >= 0 && x[1] < nn[1] && x[2] >= 0 && x[2] < nn[2]; }
@@ -64,15 +65,31 @@ struct RowGen {
   double w[SYNTH_MAXROW];      // scalar value of the entry (simplex matrix rows, P and R rows)
 };
 
+__device__ __forceinline__ bool is_simplex(int kind) { return kind == UGGPU_SYNTH_P1_SIMPLEX || kind == UGGPU_SYNTH_P1_VARCOEF; }
+
+// UGGPU_SYNTH_P1_VARCOEF: diffusion coefficient on the edge x--y, a smooth function of the edge midpoint in physical coordinates
+// (1 <= kappa < 2.2; symmetric in x and y; the same doubles on every rank and level-independent as a field): -div(kappa grad u)
+// in the two-point-flux form on the axis edges of the Kuhn mesh.  No two rows of a slice share their values.
+__device__ __forceinline__ double edge_kappa(const SynthParams &sp, const int (&x)[3], const int (&y)[3])
+{
+  const double u = (double)(x[0] + y[0]) * sp.hhalf, v = (double)(x[1] + y[1]) * sp.hhalf, w = (double)(x[2] + y[2]) * sp.hhalf;
+  double k = 1.0 + 0.9 * (u * (1.0 - u));
+  k = k + 0.7 * (v * v);
+  k = k + 0.5 * (u * w);
+  return k;
+}
+
 // one row of the P1 simplex matrix
 __device__ void simplex_row(const SynthParams &sp, const PartGrid &g, int r, RowGen &rg)
 {
   int x[3];
   part_row_coords(g, r, x);
   const bool bnd = on_boundary(g, x);
+  const bool var = sp.kind == UGGPU_SYNTH_P1_VARCOEF;
   int len = 0;
   rg.cols[len] = r; rg.w[len] = bnd ? 1.0 : 2.0 * sp.dim * sp.hpow; len++;
   const int nd = sp.dim == 3 ? 7 : 3;
+  double dsum = 0.0;
   for (int k = 0; k < nd; k++) {
     const int *d = sp.dim == 3 ? c_kuhn3[k] : c_kuhn2[k];
     const bool axis = (d[0] + d[1] + d[2]) == 1;
@@ -80,10 +97,13 @@ __device__ void simplex_row(const SynthParams &sp, const PartGrid &g, int r, Row
       int y[3] = {x[0] + sgn * d[0], x[1] + sgn * d[1], x[2] + sgn * d[2]};
       if (!in_grid(g.nn, y)) continue;
       rg.cols[len] = part_local_index(g, y);
-      rg.w[len] = (bnd || !axis) ? 0.0 : -sp.hpow;
+      double w = (bnd || !axis) ? 0.0 : -sp.hpow;
+      if (var && w != 0.0) { const double kw = edge_kappa(sp, x, y) * sp.hpow; w = -kw; dsum += kw; }
+      rg.w[len] = w;
       len++;
     }
   }
+  if (var && !bnd) rg.w[0] = dsum;
   rg.len = len;
 }
 
@@ -151,7 +171,7 @@ __device__ void p_row(const SynthParams &sp, const PartGrid &g, const PartGrid &
     rg.cols[0] = part_local_index(gc, X); rg.w[0] = 1.0; rg.len = 1;
     return;
   }
-  if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) {
+  if (is_simplex(sp.kind)) {
     int a[3] = {(x[0] - p[0]) >> 1, (x[1] - p[1]) >> 1, (x[2] - p[2]) >> 1};
     int b[3] = {(x[0] + p[0]) >> 1, (x[1] + p[1]) >> 1, (x[2] + p[2]) >> 1};
     rg.cols[0] = part_local_index(gc, a); rg.w[0] = 0.5;
@@ -185,7 +205,7 @@ __device__ void r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &
   for (int qz = z0; qz <= z1; qz++)
     for (int qy = -1; qy <= 1; qy++)
       for (int qx = -1; qx <= 1; qx++) {
-        if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) {
+        if (is_simplex(sp.kind)) {
           const bool nonneg = qx >= 0 && qy >= 0 && qz >= 0, nonpos = qx <= 0 && qy <= 0 && qz <= 0;
           if (!nonneg && !nonpos) continue;
         }
@@ -193,7 +213,7 @@ __device__ void r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &
         if (!in_grid(g.nn, y)) continue;
         const int nq = (qx != 0) + (qy != 0) + (qz != 0);
         rg.cols[len] = part_local_index(g, y);
-        rg.w[len] = sp.kind == UGGPU_SYNTH_P1_SIMPLEX ? (nq ? 0.5 : 1.0) : (nq == 0 ? 1.0 : (nq == 1 ? 0.5 : (nq == 2 ? 0.25 : 0.125)));
+        rg.w[len] = is_simplex(sp.kind) ? (nq ? 0.5 : 1.0) : (nq == 0 ? 1.0 : (nq == 1 ? 0.5 : (nq == 2 ? 0.25 : 0.125)));
         len++;
       }
   rg.len = len;
@@ -204,7 +224,7 @@ enum { GEN_A = 0, GEN_P = 1, GEN_R = 2 };
 template <int WHICH>
 __device__ __forceinline__ void gen_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, RowGen &rg)
 {
-  if (WHICH == GEN_A) { if (sp.kind == UGGPU_SYNTH_P1_SIMPLEX) simplex_row(sp, g, r, rg); else hex_row(sp, g, r, rg); }
+  if (WHICH == GEN_A) { if (is_simplex(sp.kind)) simplex_row(sp, g, r, rg); else hex_row(sp, g, r, rg); }
   else if (WHICH == GEN_P) p_row(sp, g, gc, r, rg);
   else r_row(sp, g, gc, r, rg);
 }
@@ -232,7 +252,7 @@ __global__ void k_synth_fill(SynthParams sp, const PartGrid *__restrict__ g, con
   RowGen rg;
   rg.len = 0;
   if (r < n) gen_row<WHICH>(sp, *g, *gc, r, rg);
-  const bool blocks = WHICH == GEN_A && sp.kind != UGGPU_SYNTH_P1_SIMPLEX;
+  const bool blocks = WHICH == GEN_A && !is_simplex(sp.kind);
   const int bb = blocks ? sp.bs * sp.bs : 1;
   int x[3] = {0, 0, 0};
   if (blocks && r < n) part_row_coords(*g, r, x);
@@ -380,6 +400,7 @@ static SynthParams make_params(const SynthInfo &si, int level)
   double h = 1.0 / (double)(si.cells[0] << level);
   p.hpow = si.dim == 3 ? h : 1.0;
   p.hvol = si.dim == 3 ? h * h * h : h * h;
+  p.hhalf = 0.5 * h;
   return p;
 }
 
@@ -387,9 +408,10 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
                                           int px, int py, int pz, int rank, int64_t replicate_below)
 {
   if (!ctx) return uggpu_fail(UGGPU_ERROR, "null context");
-  if (kind != UGGPU_SYNTH_P1_SIMPLEX && kind != UGGPU_SYNTH_Q1_POISSON && kind != UGGPU_SYNTH_Q1_ELASTICITY)
+  if (kind != UGGPU_SYNTH_P1_SIMPLEX && kind != UGGPU_SYNTH_Q1_POISSON && kind != UGGPU_SYNTH_Q1_ELASTICITY && kind != UGGPU_SYNTH_P1_VARCOEF)
     return uggpu_fail(UGGPU_ERROR, "synthetic kind %d not implemented", kind);
-  if (kind != UGGPU_SYNTH_P1_SIMPLEX && nz <= 0) return uggpu_fail(UGGPU_ERROR, "Q1 hierarchies are generated in 3D only");
+  const bool simplex = kind == UGGPU_SYNTH_P1_SIMPLEX || kind == UGGPU_SYNTH_P1_VARCOEF;
+  if (!simplex && nz <= 0) return uggpu_fail(UGGPU_ERROR, "Q1 hierarchies are generated in 3D only");
   if (nx < 1 || ny < 1 || nz < 0 || top < 0 || top >= UGGPU_MAX_LEVELS) return uggpu_fail(UGGPU_ERROR, "bad synthetic grid %dx%dx%d top %d", nx, ny, nz, top);
   const int dim = nz > 0 ? 3 : 2;
   if (px < 1 || py < 1 || pz < 1 || (dim == 2 && pz != 1)) return uggpu_fail(UGGPU_ERROR, "bad rank array %dx%dx%d", px, py, pz);
@@ -401,7 +423,7 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
   si.kind = kind; si.dim = dim; si.cells[0] = nx; si.cells[1] = ny; si.cells[2] = nz; si.top = top;
   const int P[3] = {px, py, pz};
   const int bs = kind == UGGPU_SYNTH_Q1_ELASTICITY ? 3 : 1;
-  if (kind != UGGPU_SYNTH_P1_SIMPLEX) {
+  if (!simplex) {
     std::vector<double> ke((size_t)(8 * bs) * (8 * bs));
     hex_element_matrix(bs, ke.data());
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_ke, ke.data(), ke.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -425,6 +447,10 @@ extern "C" int uggpu_synth_hierarchy_part(uggpu_ctx *ctx, int kind, int nx, int 
     UG_TRY(dalloc(ctx, &L.d_part, 1));
     CUDA_TRY(cudaMemcpyAsync(L.d_part, pg, sizeof(PartGrid), cudaMemcpyHostToDevice, ctx->stream));
     if (L.partitioned) {
+      L.nnb = pg->nnb;
+      L.nb_rank.assign(pg->nb_rank, pg->nb_rank + pg->nnb);
+      L.nb_send_off.assign(pg->nb_send_off, pg->nb_send_off + pg->nnb + 1);
+      L.nb_recv_off.assign(pg->nb_recv_off, pg->nb_recv_off + pg->nnb + 1);
       L.send_total = pg->nb_send_off[pg->nnb];
       UG_TRY(dalloc(ctx, &L.d_send_idx, (size_t)L.send_total));
       if (L.send_total > 0) {

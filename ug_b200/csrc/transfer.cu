@@ -112,11 +112,14 @@ template <int BS, bool FUSE, int K>
 __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uint8_t *__restrict__ vnclass_c, const uint32_t *__restrict__ skip_c,
                                                            double *__restrict__ to, const double *__restrict__ from, Damp damp,
                                                            SellView Ac, const uint8_t *__restrict__ vclass_c, double *__restrict__ tout, double *__restrict__ czero,
-                                                           Damp sdamp, int *err, Prefetch pf)
+                                                           Damp sdamp, int *err, Prefetch pf, HaloK hk)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (hk.flag) halo_publish(hk);                        // multi-GPU (HaloK, uggpu_internal.h; K == 1): ghost rows of the fine defect are read, coarse rows pushed
   if (warp * K * 32 >= R.n) return;
+  const uint8_t cf = hk.flag ? hk.flag[warp] : (uint8_t)0;
+  if (cf) halo_wait(hk);
   TrHead<K> h;
   tr_head<K>(R, skip_c, warp, lane, h);
   int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 #pragma unroll
     for (int k = 0; k < K; k++)
 #pragma unroll
-      for (int i = 0; i < BS; i++) v[k][i] = from[(size_t)f[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
+      for (int i = 0; i < BS; i++) v[k][i] = (cf & 1) ? __ldcg(from + (size_t)f[k] * BS + i) : from[(size_t)f[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
 #pragma unroll
     for (int k = 0; k < K; k++) {
       if (j < len[k]) {
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 #pragma unroll
     for (int i = 0; i < BS; i++) to[(size_t)r[k] * BS + i] = tr[k][i];
     if (!early) restrict_prefetch<FUSE>(R, r[k], pf, vnclass_c, skip_c, vclass_c);
+    if ((cf & 2) && hk.peer && hk.sel == HALO_PUSH_B) halo_push_row<BS>(hk, r[k], tr[k]);
     if (FUSE) {
       constexpr int BB = BS * BS;
       double sol[BS];
@@ -197,11 +201,14 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
           }
         }
       }
+      double tv[BS];
 #pragma unroll
       for (int i = 0; i < BS; i++) {
-        tout[(size_t)r[k] * BS + i] = sol[i] * sdamp.a[i];
+        tv[i] = sol[i] * sdamp.a[i];
+        tout[(size_t)r[k] * BS + i] = tv[i];
         czero[(size_t)r[k] * BS + i] = 0.0;
       }
+      if ((cf & 2) && hk.peer && hk.sel == HALO_PUSH_TOUT) halo_push_row<BS>(hk, r[k], tv);
     }
   }
 }
@@ -210,11 +217,14 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 // VECSKIP bit set stay 0 (:272-285).
 template <int BS, int K>
 __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 1 && K == 1) ? 8 : 1)) k_interpolate_k(SellView P, const uint32_t *__restrict__ skip_f, double *__restrict__ to,
-                                                              const double *__restrict__ from, Damp damp, Prefetch pf)
+                                                              const double *__restrict__ from, Damp damp, Prefetch pf, HaloK hk)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (hk.flag) halo_publish(hk);                        // multi-GPU (HaloK; K == 1): ghost rows of the coarse correction are read, fine rows pushed
   if (warp * K * 32 >= P.n) return;
+  const uint8_t cf = hk.flag ? hk.flag[warp] : (uint8_t)0;
+  if (cf) halo_wait(hk);
   const bool early = P.fixed_w != 0 && (pf.mode & 64);       // kernel-uniform; opt-in (UGGPU_PF_MODE bit 6): measured equal to touching the lines at the end (1.71 vs 1.74 ms)
   if (early) {
 #pragma unroll
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
 #pragma unroll
     for (int k = 0; k < K; k++)
 #pragma unroll
-      for (int i = 0; i < BS; i++) v[k][i] = from[(size_t)c[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
+      for (int i = 0; i < BS; i++) v[k][i] = (cf & 1) ? __ldcg(from + (size_t)c[k] * BS + i) : from[(size_t)c[k] * BS + i];      // rows that are done re-read entry 0 (discarded)
 #pragma unroll
     for (int k = 0; k < K; k++) {
       if (j < len[k]) {
@@ -260,6 +270,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
     if (r[k] >= P.n) continue;
 #pragma unroll
     for (int i = 0; i < BS; i++) to[(size_t)r[k] * BS + i] = tr[k][i];
+    if ((cf & 2) && hk.peer) halo_push_row<BS>(hk, r[k], tr[k]);
     if (!early && tr_prefetch(P, r[k], pf)) pf_rows<4>(skip_f, PfState{0, -1, (r[k] >> 5) + pf.dist}, pf);
   }
 }
@@ -292,19 +303,26 @@ extern "C" int uggpu_transfer_set_mode(uggpu_ctx *ctx, int level, int mode)
   return 0;
 }
 
-int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in, bool fuse, int A, double *tout, double *czero, Damp sdamp)
+int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in, bool fuse, int A, double *tout, double *czero, Damp sdamp,
+               const HaloPlan *hp)
 {
   Level *F = get_level(ctx, level);
   Level *C = get_level(ctx, level - 1);
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->R.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
-  if (C->n == 0) return 0;
   // IMAT mode: sums without the damping (1.0 * x is exact), the finished rows scaled afterwards
   const bool post = F->transfer_mode == UGGPU_TRANSFER_IMAT && !damp_is_one(damp_in, F->bs);
   if (post && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start with a damped IMAT restriction");
   const Damp damp = F->transfer_mode == UGGPU_TRANSFER_IMAT ? mkdamp(nullptr, 0) : damp_in;
-  // partitioned fine level: the coarse rows this rank owns gather from fine ghost rows too
-  UG_TRY(halo_exchange(ctx, level, const_cast<double *>(from)));
+  // partitioned fine level: the coarse rows this rank owns gather from fine ghost rows too.  Peer-memory ghost rows: the kernel waits for
+  // the neighbours itself and pushes the coarse rows it produces (hk); otherwise the fine defect is exchanged before the launch.
+  HaloK hk = halo_none();
+  UG_TRY(halo_prepare(ctx, level - 1, level, &F->R, const_cast<double *>(from), hp, &hk));
+  if (hk.peer) {
+    hk.sel = (fuse && hp->push == tout) ? HALO_PUSH_TOUT : (hp->push == to ? HALO_PUSH_B : HALO_PUSH_NONE);
+    if (hk.sel == HALO_PUSH_NONE) return uggpu_fail(UGGPU_ERROR, "restrict: the vector to push is not produced by this call");
+  }
+  if (C->n == 0 && !hk.flag) return 0;
   const bool gather = ctx->comm && F->partitioned && !C->partitioned;   // first completely held (replicated) level
   if (gather && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start not possible across the gather level");
   SellView Rv = view(F->R);
@@ -320,11 +338,12 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
 #define RS(BSV, KV)                                                                                                                    \
   {                                                                                                                                    \
     const Prefetch pf = make_prefetch(ctx, &F->R, F->bs, KV);                                                                          \
-    const int blocks = tr_blocks<KV>(C->n);                                                                                            \
-    if (fuse) k_restrict_k<BSV, true, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
-    else k_restrict_k<BSV, false, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf); \
+    const int blocks = tr_blocks<KV>(C->n > 0 ? C->n : 1);                                                                             \
+    if (fuse) k_restrict_k<BSV, true, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf, hk); \
+    else k_restrict_k<BSV, false, KV><<<blocks, TR_THREADS, 0, ctx->stream>>>(Rv, C->vnclass, C->skip, to, from, damp, Av, C->vclass, tout, czero, sdamp, ctx->derr, pf, hk); \
   }
-  static const int kenv = getenv("UGGPU_TR_K_RESTRICT") ? atoi(getenv("UGGPU_TR_K_RESTRICT")) : TR_K_RESTRICT;     // A/B switch
+  static const int kenv0 = getenv("UGGPU_TR_K_RESTRICT") ? atoi(getenv("UGGPU_TR_K_RESTRICT")) : TR_K_RESTRICT;     // A/B switch
+  const int kenv = hk.flag ? 1 : kenv0;                  // the comm-aware path is the one-slice-per-warp kernel
   switch (F->bs) {
     case 1: if (kenv >= 4) RS(1, 4) else if (kenv >= 2) RS(1, 2) else RS(1, 1) break;
     case 2: RS(2, 1); break;
@@ -347,20 +366,24 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   return 0;
 }
 
-int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in)
+int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp_in, const HaloPlan *hp)
 {
   Level *F = get_level(ctx, level);
   Level *C = get_level(ctx, level - 1);
   if (!F || !C) return UGGPU_NO_COARSER_GRID;
   if (!F->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "no transfer stencils on level %d (uggpu_transfer_set)", level);
-  if (F->n == 0) return 0;
   // IMAT mode (InterpolateCorrectionByMatrix_General transgrid.cc:1331,1385): sums without the damping, then dscalx on all rows
   const bool post = F->transfer_mode == UGGPU_TRANSFER_IMAT && !damp_is_one(damp_in, F->bs);
   const Damp damp = F->transfer_mode == UGGPU_TRANSFER_IMAT ? mkdamp(nullptr, 0) : damp_in;
-  UG_TRY(halo_exchange(ctx, level - 1, const_cast<double *>(from)));   // coarse ghost values (no-op if the coarse level is replicated)
+  // coarse ghost values (nothing to do if the coarse level is replicated); peer-memory ghost rows: see k_restrict
+  HaloK hk = halo_none();
+  UG_TRY(halo_prepare(ctx, level, level - 1, &F->P, const_cast<double *>(from), hp, &hk));
+  if (hk.peer && hp->push != to) return uggpu_fail(UGGPU_ERROR, "interpolate: the vector to push is not produced by this call");
+  if (F->n == 0 && !hk.flag) return 0;
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
-#define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV))
-  static const int kenv = getenv("UGGPU_TR_K_INTERP") ? atoi(getenv("UGGPU_TR_K_INTERP")) : TR_K_INTERP;     // A/B switch
+#define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n > 0 ? F->n : 1), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV), hk)
+  static const int kenv0 = getenv("UGGPU_TR_K_INTERP") ? atoi(getenv("UGGPU_TR_K_INTERP")) : TR_K_INTERP;     // A/B switch
+  const int kenv = hk.flag ? 1 : kenv0;
   switch (F->bs) {
     case 1: if (kenv >= 4) IP(1, 4); else if (kenv >= 2) IP(1, 2); else IP(1, 1); break;
     case 2: if (kenv >= 2) IP(2, 2); else IP(2, 1); break;

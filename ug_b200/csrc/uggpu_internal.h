@@ -91,6 +91,7 @@ struct SellMat {
   // multi-GPU overlap (spmv.cu): bnd_flag[s] = 1 / bnd_list = the slices with a row that references a ghost column; built on first use
   uint8_t *bnd_flag = nullptr;
   int32_t *bnd_list = nullptr;
+  uint8_t *comm_flag = nullptr;   // [slices] HaloK::flag of launches over this matrix' rows (comm.cu halo_comm_flag): bit 0 ghost columns, bit 1 rows to push
   int n_int = -1, n_bnd = 0;
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
   int64_t  col_words = 0;         // column words a pass over the matrix fetches from HBM: true entries of explicit slices + the distinct distance tables
@@ -128,6 +129,98 @@ __device__ __forceinline__ ColIter col_iter(const SellView &A, int r)
 __device__ __forceinline__ int col_at(const ColIter &ci, int j) { return __ldg(ci.p + (size_t)j * ci.stride) + ci.base; }
 #endif
 
+// ---- multi-GPU halo, peer-memory ghost rows (comm.cu) ----------------------------------------------------------------
+// Every kernel that reads ghost columns or produces a vector whose interface rows the neighbours need is a "comm kernel".  All ranks
+// launch the same comm kernels in the same order and number them g = 1, 2, ... (Comm::kseq).  At its head block 0 publishes g into the
+// `started` word it owns in every neighbour's flag block; the warps whose slice reads ghost columns or holds rows to push wait until
+// every neighbour's `started` word has reached g -- then everything the neighbours launched before kernel g is complete: their pushes
+// have landed in my ghost rows, and their reads of the ghost rows I am about to overwrite are done.  Rows to push are stored straight
+// into the ghost rows of the neighbours' copy of the same vector (mapped with CUDA IPC), by the kernel that computes them.
+#define HALO_MAX_NB 26
+struct HaloDev {                                         // device-resident tables of one partitioned level
+  int nnb;
+  const unsigned long long *my_flag[HALO_MAX_NB];        // neighbour k's words in MY flag block: [0] started, [1] landed
+  unsigned long long *peer_flag[HALO_MAX_NB];            // my words in neighbour k's flag block (peer memory)
+  const uint32_t *snd_bits;                              // [slices] lanes whose row goes to at least one neighbour
+  const int32_t *snd_first;                              // [slices] number of send rows in the slices before this one
+  const int32_t *srow_ptr;                               // [send rows + 1] -> snd_ent
+  const uint32_t *snd_ent;                               // (neighbour index << 27) | row index in that neighbour's ghost region
+};
+struct HaloK {                                           // kernel parameter; flag == nullptr: not a comm launch
+  const uint8_t *flag;                                   // per slice of the kernel's rows: bit 0 reads ghost columns, bit 1 holds rows to push
+  const HaloDev *cdev, *pdev;                            // level whose ghost rows are read / level whose rows are pushed (either may be nullptr)
+  unsigned long long g;                                  // number of this comm kernel
+  double *const *peer;                                   // [pdev->nnb] the neighbours' ghost regions of the vector this kernel produces; nullptr: no push
+  int *err;
+  int sel;                                               // smoothing step: which of its results is pushed (HALO_PUSH_*)
+};
+enum { HALO_PUSH_NONE = 0, HALO_PUSH_TOUT = 1, HALO_PUSH_B = 2, HALO_PUSH_C = 3 };
+static inline HaloK halo_none() { return HaloK{nullptr, nullptr, nullptr, 0ull, nullptr, nullptr, 0}; }
+// what the caller of a comm-aware kernel knows about the exchange around it (cycle.cu: the fused schedule)
+struct HaloPlan {
+  bool operand_ready;      // the ghost rows of the kernel's operand were pushed by the kernel that produced it: no exchange before this launch
+  double *push;            // vector this launch produces whose interface rows the next kernel's ghost columns need (nullptr: none)
+  int push_level;          // its level
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void halo_publish_dev(const HaloDev *d, unsigned long long g, int word)
+{
+  if ((int)threadIdx.x < d->nnb) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d->peer_flag[threadIdx.x] + word), "l"(g) : "memory");
+  }
+}
+// block 0 of a comm kernel: "everything this rank launched before kernel g is complete"
+__device__ __forceinline__ void halo_publish(const HaloK &h)
+{
+  if (blockIdx.x != 0) return;
+  if (h.cdev) halo_publish_dev(h.cdev, h.g, 0);
+  if (h.pdev && h.pdev != h.cdev) halo_publish_dev(h.pdev, h.g, 0);
+}
+__device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long long g, int word, int *err)
+{
+  const int lane = threadIdx.x & 31;
+  if (lane < d->nnb) {
+    unsigned long long t0 = 0, t1, got;
+    for (int it = 0;; it++) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(d->my_flag[lane] + word) : "memory");
+      if (got >= g) break;
+      if (it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      if ((it & 63) == 63) {
+        if (*reinterpret_cast<volatile int *>(err)) break;                 // an earlier wait already failed: do not wait again
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) { atomicExch(err, UGGPU_CUDA_ERROR); break; }   // 10 s: report instead of hanging the GPU
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+// a warp whose slice reads ghost columns or holds rows to push (whole warp)
+__device__ __forceinline__ void halo_wait(const HaloK &h)
+{
+  if (h.cdev) halo_wait_dev(h.cdev, h.g, 0, h.err);
+  if (h.pdev && h.pdev != h.cdev) halo_wait_dev(h.pdev, h.g, 0, h.err);
+}
+// row r of the produced vector -> the ghost rows of the neighbours that hold a copy of it
+template <int BS>
+__device__ __forceinline__ void halo_push_row(const HaloK &h, int r, const double (&v)[BS])
+{
+  const HaloDev *d = h.pdev;
+  const uint32_t bits = d->snd_bits[r >> 5];
+  const int lane = r & 31;
+  if (!((bits >> lane) & 1u)) return;
+  const int i = d->snd_first[r >> 5] + __popc(bits & ((1u << lane) - 1u));
+  for (int e = d->srow_ptr[i]; e < d->srow_ptr[i + 1]; e++) {
+    const uint32_t ent = d->snd_ent[e];
+    double *dst = h.peer[ent >> 27] + (size_t)(ent & 0x7ffffffu) * BS;
+#pragma unroll
+    for (int q = 0; q < BS; q++) dst[q] = v[q];
+  }
+}
+#endif
+
 struct Level {
   bool exists = false;
   int n = 0, bs = 0;
@@ -154,6 +247,12 @@ struct Level {
   int32_t *d_send_idx = nullptr;        // owned rows to pack, grouped by neighbour (PartGrid::nb_send_off)
   int send_total = 0;
   std::vector<int> peer_recv_off;       // per neighbour: where my rows start in ITS ghost region (peer-memory halo exchange, comm.cu)
+  // the level's interface lists in the form every transport uses (filled by the synthetic generator from PartGrid, or by
+  // uggpu_level_set_partition from the caller's lists): neighbour ranks, send list offsets into d_send_idx, receive offsets into my ghost rows
+  int nnb = 0;
+  std::vector<int> nb_rank, nb_send_off, nb_recv_off;
+  struct LevelHalo *halo = nullptr;     // comm.cu: peer-memory ghost rows (tables, mapped neighbour vectors)
+  double *last_pushed = nullptr;        // vector whose interface rows the last producing kernel stored into the neighbours' ghost rows
 };
 
 struct uggpu_ctx {
@@ -377,18 +476,28 @@ enum { RED_DOT, RED_NRM2 };
 
 // smoother step flags (spmv.cu, DESIGN.md "fused kernels")
 enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16 };
+// hp (may be nullptr): what the fused schedule knows about the exchanges around the launch (HaloPlan); without it every launch
+// exchanges its operand's ghost rows itself and pushes nothing
 int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout,
-                  Damp damp, double *x, int norm_slot);
-int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp);   // v = damp * Diag(A)^-1 d (class-masked)
+                  Damp damp, double *x, int norm_slot, const HaloPlan *hp = nullptr);
+int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp = nullptr);   // v = damp * Diag(A)^-1 d (class-masked)
 // transfer.cu: fine `level` -> level-1; with fuse: also tout = sdamp*Diag(A_{level-1})^-1 to, czero = 0 on level-1
-int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp);
-int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp);
+int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp,
+               const HaloPlan *hp = nullptr);
+int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, const HaloPlan *hp = nullptr);
 // comm.cu: all are no-ops (return 0) when the context has no communicator or the level is not partitioned
+// Prepares a comm-aware launch over the rows of matrix M (rows on `row_level`; its columns index vectors of `col_level`, whose ghost rows
+// the launch reads -- -1: none): exchanges the operand's ghost rows first unless the plan says its producer pushed them, registers the
+// vector to push, numbers the launch.  *hk stays halo_none() when the peer-memory ghost transport does not apply (one GPU, levels held
+// completely, IPC unavailable: then the operand has been exchanged through the window / NCCL path and nothing is pushed).
+int halo_prepare(uggpu_ctx *ctx, int row_level, int col_level, SellMat *M, double *operand, const HaloPlan *hp, HaloK *hk);
+bool halo_fused_available(uggpu_ctx *ctx, int level);                    // the peer-memory ghost transport is (or can be) used on this level
 int halo_exchange(uggpu_ctx *ctx, int level, double *v);                 // owned values -> the neighbours' ghost rows of v
 int halo_begin(uggpu_ctx *ctx, int level, double *v, int *split);        // push only; *split = 1: finish with halo_finish on another stream
 int halo_finish(uggpu_ctx *ctx, int level, double *v, cudaStream_t st);  // wait + unpack on st
 int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count);           // in place, on the context's stream
 int level_free_part(uggpu_ctx *ctx, Level *L);
+bool halo_vec_release(uggpu_ctx *ctx, Level *L, double *p, size_t bytes);   // true: other ranks have the vector mapped, it is parked, do not free it
 int level_free_lu(uggpu_ctx *ctx, Level *L);                              // cycle.cu: the base-level factorisation
 static inline size_t vec_count(const Level *L) { return ((size_t)L->n + (size_t)L->nghost) * (size_t)L->bs; }
 // internal temporary vector handles (never visible through the C-ABI callers' handle space)
