@@ -369,6 +369,13 @@ def measure(spec, rt):
         out["value"] = n_global * steps / (ms * 1e-3)
         out["kernels"] = prof
         out["kernel_sum_ms_per_step"] = sum(v["ms"] for v in prof.values()) / steps
+        if world > 1:      # every rank's view (rank 0's is `kernels`): a rank that waits for a slower neighbour shows it in halo / allreduce / the comm kernels
+            mine = {k: round(v["ms"] / steps, 3) for k, v in prof.items() if v["ms"] > 0}
+            mine["dominant_avg_ms"] = round(dom["ms"] / max(dom["launches"], 1), 4)
+            mine["rows"] = ctx.level_n(top)
+            allr = [None] * world
+            dist.all_gather_object(allr, mine)
+            out["per_rank_kernels_ms_per_step"] = allr
         out["defect"] = [first, hist[-1]] if hist else None
         out["transport"] = ctx.halo_transport() if world > 1 else "none (one GPU)"
         out["device_bytes"] = ctx.device_bytes()
@@ -607,6 +614,7 @@ def our_arm(args):
         "trisolve_finest": m["trisolve_finest"],
         "e2e": m.get("e2e"),
         "e2e_solve": m.get("e2e_solve"),
+        "per_rank_kernels_ms_per_step": m.get("per_rank_kernels_ms_per_step"),
         "gpu_launches": m["launches"],
         "clocks": m.get("clocks"),
         "spmv": m.get("spmv"),

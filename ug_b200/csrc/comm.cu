@@ -65,6 +65,7 @@ struct Comm {
   unsigned long long seq = 0;            // window transport: exchanges
   unsigned long long kseq = 0;           // ghost transport: comm kernels
   unsigned int *push_counter = nullptr;
+  unsigned long long *go = nullptr;      // ghost transport: the local go words of the comm kernels (HaloK::go)
   std::vector<Opened> opened;            // vectors of other ranks mapped into this process
   std::vector<std::pair<void *, size_t>> graveyard;   // my vectors that other ranks have mapped: freed with the communicator
 };
@@ -165,6 +166,7 @@ extern "C" int uggpu_comm_destroy(uggpu_ctx *ctx)
   for (auto &o : c->opened) cudaIpcCloseMemHandle(o.ptr);
   for (auto &g : c->graveyard) dev_free(ctx, g.first, g.second);
   if (c->push_counter) dfree(ctx, c->push_counter, 1);
+  if (c->go) dfree(ctx, c->go, (size_t)HALO_GO_SLOTS * 16);
   if (c->comm) nccl.CommDestroy(c->comm);
   delete c;
   ctx->comm = nullptr;
@@ -605,6 +607,11 @@ int halo_prepare(uggpu_ctx *ctx, int row_level, int col_level, SellMat *M, doubl
   }
   hk->g = ++c->kseq;
   hk->err = ctx->derr;
+  if (!c->go) {
+    UG_TRY(dalloc(ctx, &c->go, (size_t)HALO_GO_SLOTS * 16));
+    CUDA_TRY(cudaMemsetAsync(c->go, 0, sizeof(unsigned long long) * HALO_GO_SLOTS * 16, ctx->stream));
+  }
+  hk->go = c->go;
   return 0;
 }
 

@@ -153,9 +153,11 @@ struct HaloK {                                           // kernel parameter; fl
   double *const *peer;                                   // [pdev->nnb] the neighbours' ghost regions of the vector this kernel produces; nullptr: no push
   int *err;
   int sel;                                               // smoothing step: which of its results is pushed (HALO_PUSH_*)
+  unsigned long long *go;                                // [HALO_GO_SLOTS * 16] local "all neighbours have started kernel g" words, one 128-byte line per SM
 };
+#define HALO_GO_SLOTS 256
 enum { HALO_PUSH_NONE = 0, HALO_PUSH_TOUT = 1, HALO_PUSH_B = 2, HALO_PUSH_C = 3 };
-static inline HaloK halo_none() { return HaloK{nullptr, nullptr, nullptr, 0ull, nullptr, nullptr, 0}; }
+static inline HaloK halo_none() { return HaloK{nullptr, nullptr, nullptr, 0ull, nullptr, nullptr, 0, nullptr}; }
 // what the caller of a comm-aware kernel knows about the exchange around it (cycle.cu: the fused schedule)
 struct HaloPlan {
   bool operand_ready;      // the ghost rows of the kernel's operand were pushed by the kernel that produced it: no exchange before this launch
@@ -171,14 +173,23 @@ __device__ __forceinline__ void halo_publish_dev(const HaloDev *d, unsigned long
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d->peer_flag[threadIdx.x] + word), "l"(g) : "memory");
   }
 }
-// block 0 of a comm kernel: "everything this rank launched before kernel g is complete"
+__device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long long g, int word, int *err);
+// Block 0 of a comm kernel: "everything this rank launched before kernel g is complete" goes to the neighbours; then its first warp
+// is the WATCHER: it waits for the neighbours' words and raises the local go words, one per SM.  The comm warps poll only their SM's
+// go word -- hundreds of thousands of warps polling the neighbours' words themselves serialise on one L2 address (measured: +1 ms per
+// launch on a 4*10^8-row level).
 __device__ __forceinline__ void halo_publish(const HaloK &h)
 {
   if (blockIdx.x != 0) return;
   if (h.cdev) halo_publish_dev(h.cdev, h.g, 0);
   if (h.pdev && h.pdev != h.cdev) halo_publish_dev(h.pdev, h.g, 0);
+  if (threadIdx.x < 32) {
+    if (h.cdev) halo_wait_dev(h.cdev, h.g, 0, h.err);
+    if (h.pdev && h.pdev != h.cdev) halo_wait_dev(h.pdev, h.g, 0, h.err);
+    for (int s = threadIdx.x; s < HALO_GO_SLOTS; s += 32) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(h.go + (size_t)s * 16), "l"(h.g) : "memory");
+  }
 }
-__device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long long g, int word, int *err)
+__device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long long g, int word, int *err)      // one warp
 {
   const int lane = threadIdx.x & 31;
   if (lane < d->nnb) {
@@ -197,11 +208,27 @@ __device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long lo
   }
   __syncwarp();
 }
-// a warp whose slice reads ghost columns or holds rows to push (whole warp)
+// a warp whose slice reads ghost columns or holds rows to push (whole warp): wait for this SM's go word
 __device__ __forceinline__ void halo_wait(const HaloK &h)
 {
-  if (h.cdev) halo_wait_dev(h.cdev, h.g, 0, h.err);
-  if (h.pdev && h.pdev != h.cdev) halo_wait_dev(h.pdev, h.g, 0, h.err);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long *w = h.go + (size_t)(smid & (HALO_GO_SLOTS - 1)) * 16;
+    unsigned long long t0 = 0, t1, got;
+    for (int it = 0;; it++) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(w) : "memory");
+      if (got >= h.g) break;
+      if (it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      if ((it & 63) == 63) {
+        if (*reinterpret_cast<volatile int *>(h.err)) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 12000000000ull) { atomicExch(h.err, UGGPU_CUDA_ERROR); break; }
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncwarp();
 }
 // row r of the produced vector -> the ghost rows of the neighbours that hold a copy of it
 template <int BS>
