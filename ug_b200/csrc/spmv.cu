@@ -35,7 +35,12 @@
 // coalesced load per slice) and the loop broadcasts it with a shuffle, so the gather addresses do not depend on a load.
 // VSHARED (uniform slices only): the slice's values come from a shared table, one block per slice column (sell.cu
 // sell_share_values) -- a warp-uniform, L1-resident load instead of 256 bytes of HBM stream per component and column.
-template <int BS, bool UNIFORM, bool VSHARED = false>
+// CG: the gathers bypass L1 (ld.global.cg) -- slices of a partitioned level that read GHOST columns (multi-GPU, HaloK): the ghost rows of
+// y are written by other GPUs while the kernel runs; they are complete once the warp has passed halo_wait, but a line that holds the last
+// owned rows AND the first ghost rows may already sit in this SM's L1 from another warp's gathers.  L2 is where peer writes land.
+template <bool CG> __device__ __forceinline__ double gather_ld(const double *p) { return CG ? __ldcg(p) : *p; }
+
+template <int BS, bool UNIFORM, bool VSHARED = false, bool CG = false>
 __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len, int64_t cpo, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
   constexpr int BB = BS * BS;
@@ -63,7 +68,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
         for (int k = 0; k < BB; k++) m[k] = __ldg(tp + (size_t)j * BB + k);
 #pragma unroll
-        for (int i = 0; i < BS; i++) wv[i] = y[(size_t)c * BS + i];
+        for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i);
         if (j == 0) {
 #pragma unroll
           for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -91,7 +96,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
           for (int k = 0; k < BB; k++) m[k] = VSHARED ? __ldg(tp + (size_t)j * BB + k) : __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-          for (int i = 0; i < BS; i++) wv[i] = y[(size_t)c * BS + i];
+          for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i);
           if (j == 0) {
 #pragma unroll
             for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -115,7 +120,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
       for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-      for (int i = 0; i < BS; i++) w[i] = y[(size_t)c * BS + i];
+      for (int i = 0; i < BS; i++) w[i] = gather_ld<CG>(y + (size_t)c * BS + i);
       if (j == 0) {
 #pragma unroll
         for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -133,53 +138,29 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 
 // Must be entered by whole warps whose slice exists ((r & ~31) < A.n): the uniform form shuffles across the slice.
 // Rows with live == false (beyond n, or masked out by the caller) contribute nothing and get s = 0.
-template <int BS>
+// the two direct-indexed loads every row starts with (code word of the slice, row length)
+__device__ __forceinline__ void row_head(const SellView &A, int r, bool live, int64_t &cpo, int &len)
+{
+  cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
+  len = live ? (int)A.rowlen[r] : 0;
+}
+template <int BS, bool CG = false>
+__device__ __forceinline__ void row_product_h(const SellView &A, int r, int64_t cpo, int len, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
+{
+  if (cpo < 0) {
+    if (A.vt && UG_VALTAB(cpo) >= 0) row_product_t<BS, true, true, CG>(A, r, len, cpo, y, s, dg);
+    else row_product_t<BS, true, false, CG>(A, r, len, cpo, y, s, dg);
+  } else row_product_t<BS, false, false, CG>(A, r, len, cpo, y, s, dg);
+}
+template <int BS, bool CG = false>
 __device__ __forceinline__ void row_product(const SellView &A, int r, bool live, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
   const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? (int64_t)(r >> 5) * 32 * A.fixed_w : A.col_ptr[r >> 5];
   const int len = live ? (int)A.rowlen[r] : 0;
   if (cpo < 0) {
-    if (A.vt && UG_VALTAB(cpo) >= 0) row_product_t<BS, true, true>(A, r, len, cpo, y, s, dg);
-    else row_product_t<BS, true>(A, r, len, cpo, y, s, dg);
-  } else row_product_t<BS, false>(A, r, len, cpo, y, s, dg);
-}
-
-// The same row product for the slices of a partitioned level that read GHOST columns (multi-GPU, HaloK): the ghost rows of y are
-// written by other GPUs while this kernel runs -- they are complete once the warp has passed halo_wait, but a line that holds the
-// last owned rows AND the first ghost rows may already sit in this SM's L1 from another warp's gathers.  Every gather therefore
-// bypasses L1 (ld.global.cg: L2 is where peer writes land).  Same terms, same order.  Few slices take it: not inlined.
-template <int BS>
-__device__ __noinline__ void row_product_ghost(const SellView &A, int r, bool live, const double *y, double *s, double *dg)
-{
-  constexpr int BB = BS * BS;
-  const int lane = r & 31;
-  const int64_t sp = slice_off(A, r >> 5);
-  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : A.col_ptr[r >> 5];
-  const int len = live ? (int)A.rowlen[r] : 0;
-  const double *tp = (cpo < 0 && A.vt && UG_VALTAB(cpo) >= 0) ? A.vt + UG_VALTAB(cpo) : nullptr;
-  const double *vp = A.val + sp * BB + lane;
-  const ColIter ci = col_iter(A, r);
-  for (int i = 0; i < BS; i++) s[i] = 0.0;
-  for (int k = 0; k < BB; k++) dg[k] = 0.0;
-  for (int j = 0; j < len; j++) {
-    const int c = col_at(ci, j);
-    double m[BB], w[BS];
-#pragma unroll
-    for (int k = 0; k < BB; k++) m[k] = tp ? __ldg(tp + (size_t)j * BB + k) : __ldg(vp + ((size_t)j * BB + k) * 32);
-#pragma unroll
-    for (int i = 0; i < BS; i++) w[i] = __ldcg(y + (size_t)c * BS + i);
-    if (j == 0) {
-#pragma unroll
-      for (int k = 0; k < BB; k++) dg[k] = m[k];
-    }
-#pragma unroll
-    for (int i = 0; i < BS; i++) {
-      double acc = m[i * BS] * w[0];
-#pragma unroll
-      for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * w[q];
-      s[i] += acc;
-    }
-  }
+    if (A.vt && UG_VALTAB(cpo) >= 0) row_product_t<BS, true, true, CG>(A, r, len, cpo, y, s, dg);
+    else row_product_t<BS, true, false, CG>(A, r, len, cpo, y, s, dg);
+  } else row_product_t<BS, false, false, CG>(A, r, len, cpo, y, s, dg);
 }
 
 // SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
@@ -336,33 +317,40 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_
   uint8_t cf = 0;
   if (hk.flag) {                                        // multi-GPU: this launch pushes v's interface rows into the neighbours' ghost rows
     halo_publish(hk);
-    if ((r & ~31) < A.n) { cf = hk.flag[r >> 5]; if (cf & 2) halo_wait(hk); }
+    if ((r & ~31) < A.n) cf = hk.flag[r >> 5];          // used at the end only: the row's own loads do not wait for it
   }
-  if (r >= A.n) return;
+  if ((r & ~31) >= A.n) return;                         // whole warps from here on
+  const bool live = r < A.n;
   const int lane = r & 31;
-  if (pf.dist > 0 && (r >> 5) + pf.dist < pf.nsl) {     // every stream of this kernel is direct-indexed: touch the far slice's lines now
+  if (live && pf.dist > 0 && (r >> 5) + pf.dist < pf.nsl) {     // every stream of this kernel is direct-indexed: touch the far slice's lines now
     const PfState far{0, -1, (r >> 5) + pf.dist};
     if (lane < 2 * BB) prefetch_l2(reinterpret_cast<const char *>(A.diag) + ((size_t)far.slice * 32 * BB) * sizeof(double) + (size_t)lane * 128);
     pf_vec<BS>(d, far, pf);
     pf_rows<1>(vclass, far, pf);
   }
   double sol[BS];
-  if (vclass[r] < 3) {
+  bool ok = live;
+  if (live) {
+    if (vclass[r] < 3) {
 #pragma unroll
-    for (int i = 0; i < BS; i++) sol[i] = 0.0;
-  } else {
-    const double *__restrict__ vp = A.diag + ((size_t)(r >> 5) * BB) * 32 + lane;
-    double m[BB], rhs[BS];
+      for (int i = 0; i < BS; i++) sol[i] = 0.0;
+    } else {
+      const double *__restrict__ vp = A.diag + ((size_t)(r >> 5) * BB) * 32 + lane;
+      double m[BB], rhs[BS];
 #pragma unroll
-    for (int k = 0; k < BB; k++) m[k] = vp[(size_t)k * 32];
+      for (int k = 0; k < BB; k++) m[k] = vp[(size_t)k * 32];
 #pragma unroll
-    for (int i = 0; i < BS; i++) rhs[i] = d[(size_t)r * BS + i];
-    if (solve_small_block<BS>(m, rhs, sol)) { atomicExch(err, UGGPU_SMALL_DIAG); return; }
+      for (int i = 0; i < BS; i++) rhs[i] = d[(size_t)r * BS + i];
+      if (solve_small_block<BS>(m, rhs, sol)) { atomicExch(err, UGGPU_SMALL_DIAG); ok = false; }
+    }
   }
+  const bool push = (cf & 2) && hk.peer;
+  if (push) halo_wait(hk);                              // the neighbours' reads of the ghost rows about to be overwritten are done
+  if (!ok) return;
   double pv[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) { pv[i] = sol[i] * damp.a[i]; v[(size_t)r * BS + i] = pv[i]; }
-  if ((cf & 2) && hk.peer) halo_push_row<BS>(hk, r, pv);
+  if (push) halo_push_row<BS>(hk, r, pv);
 }
 
 int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp)
@@ -432,7 +420,7 @@ __device__ __noinline__ void smooth_comm_rows(SellView A, int r, int cf, HaloK h
   halo_wait(hk);
   const bool active = r < A.n;
   double s[BS], dg[BS * BS];
-  if (cf & 1) row_product_ghost<BS>(A, r, active, tin, s, dg);
+  if (cf & 1) row_product<BS, true>(A, r, active, tin, s, dg);
   else row_product<BS>(A, r, active, tin, s, dg);
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
@@ -505,6 +493,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? (COMM ? SPMV_MINBLOCKS
     if ((r & ~31) < A.n) cf = hk.flag[r >> 5];
   }
   const PfState pfs = pf_begin(A, r, pf);      // software prefetch into L2 (uggpu_internal.h): requested now, issued at the end
+  int64_t h_cpo = 0; int h_len = 0;            // COMM: the row's first loads leave together with the flag byte, not behind the branch on it
+  if (COMM && (r & ~31) < A.n) row_head(A, r, active, h_cpo, h_len);
   double nrm[BS];
 #pragma unroll
   for (int i = 0; i < BS; i++) nrm[i] = 0.0;
@@ -523,7 +513,8 @@ __global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? (COMM ? SPMV_MINBLOCKS
     if ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ec = c[r];
     if (FLAGS & (SF_CADD | SF_CSET)) et = tin[r];
   }
-  if (!(COMM && cf) && (r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
+  if (COMM) { if (!cf && (r & ~31) < A.n) row_product_h<BS>(A, r, h_cpo, h_len, tin, s, dg); }
+  else if ((r & ~31) < A.n) row_product<BS>(A, r, active, tin, s, dg);
   if (active) {
     double bn[BS];
 #pragma unroll

@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
   if (hk.flag) halo_publish(hk);                        // multi-GPU (HaloK, uggpu_internal.h; K == 1): ghost rows of the fine defect are read, coarse rows pushed
   if (warp * K * 32 >= R.n) return;
   const uint8_t cf = hk.flag ? hk.flag[warp] : (uint8_t)0;
-  if (cf) halo_wait(hk);
   TrHead<K> h;
   tr_head<K>(R, skip_c, warp, lane, h);
+  if (cf) halo_wait(hk);                                // behind the head's loads (stencil data, not ghost data): no extra round trip for the other warps
   int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci;
   const int maxl = h.maxl;
   const bool early = false;       // measured (513^3, B200): touching the far lines when the warp ENDS 1.14 ms, when it starts 1.63 ms
@@ -224,7 +224,6 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
   if (hk.flag) halo_publish(hk);                        // multi-GPU (HaloK; K == 1): ghost rows of the coarse correction are read, fine rows pushed
   if (warp * K * 32 >= P.n) return;
   const uint8_t cf = hk.flag ? hk.flag[warp] : (uint8_t)0;
-  if (cf) halo_wait(hk);
   const bool early = P.fixed_w != 0 && (pf.mode & 64);       // kernel-uniform; opt-in (UGGPU_PF_MODE bit 6): measured equal to touching the lines at the end (1.71 vs 1.74 ms)
   if (early) {
 #pragma unroll
@@ -235,6 +234,7 @@ __global__ void __launch_bounds__(TR_THREADS, (BS == 1 && K >= 4) ? 4 : ((BS == 
   }
   TrHead<K> h;
   tr_head<K>(P, skip_f, warp, lane, h);
+  if (cf) halo_wait(hk);                                // behind the head's loads (stencil data, not ghost data)
   int (&r)[K] = h.r; int (&len)[K] = h.len; uint32_t (&skip)[K] = h.skip; ColIter (&ci)[K] = h.ci;
   const int maxl = h.maxl;
   double tr[K][BS];
