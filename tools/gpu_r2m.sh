@@ -24,5 +24,8 @@ for v in "$@"; do
     xchg) run xchg UGGPU_NO_FUSED_HALO=1;;
     window) run window UGGPU_HALO=window;;
     nccl) run nccl UGGPU_HALO=nccl;;
+    nopush) run nopush UGGPU_DBG_HALO=256;;
+    nowait) run nowait UGGPU_DBG_HALO=512;;
+    neither) run neither UGGPU_DBG_HALO=768;;
   esac
 done

@@ -128,8 +128,21 @@ extern "C" int uggpu_comm_init(uggpu_ctx *ctx, int nranks, int rank, const void 
   return 0;
 }
 
+const uint32_t *halo_snd_bits(const Level *L) { return L->halo ? L->halo->snd_bits : nullptr; }
+
+static void mat_comm_free(uggpu_ctx *ctx, SellMat *m)
+{
+  if (m->comm_flag) dfree(ctx, m->comm_flag, ((size_t)(m->n > 0 ? m->n : 0) + 31) / 32 + 1);
+  if (m->x_comm) stx_free(ctx, m);
+}
+
 static void level_halo_free(uggpu_ctx *ctx, Level *L)
 {
+  // what was derived from the send lists: per-slice flags and exception-row lists of the level's matrices
+  for (auto &kv : L->mats) mat_comm_free(ctx, &kv.second);
+  mat_comm_free(ctx, &L->P);
+  mat_comm_free(ctx, &L->R);
+  L->last_pushed = nullptr;
   LevelHalo *H = L->halo;
   if (!H) return;
   for (auto &kv : H->maps) if (kv.second.d_peer) { double **p = kv.second.d_peer; dfree(ctx, p, (size_t)HALO_MAX_NB); }

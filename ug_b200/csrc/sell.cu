@@ -329,6 +329,7 @@ int sell_drop_shared_values(uggpu_ctx *ctx, SellMat *m)
   if (m->vt) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); UG_TRY(dfree(ctx, m->vt, (size_t)m->vt_len)); }
   m->vt_len = 0; m->vshared_slices = 0; m->val_entries = -1;
   m->sten.w = 0; m->sten_slices = 0;
+  stx_free(ctx, m);
   delete m->sten3; m->sten3 = nullptr;
   return 0;
 }
@@ -552,6 +553,8 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   UG_TRY(sell_free_schedules(ctx, m));
   if (m->bnd_flag) dfree(ctx, m->bnd_flag, nsl);
+  if (m->comm_flag) dfree(ctx, m->comm_flag, nsl + 1);
+  stx_free(ctx, m);
   if (m->vcode) dfree(ctx, m->vcode, (size_t)m->padded);
   if (m->vtable) dfree(ctx, m->vtable, 256);
   if (m->vt) dfree(ctx, m->vt, (size_t)m->vt_len);

@@ -38,7 +38,7 @@
 // CG: the gathers bypass L1 (ld.global.cg) -- slices of a partitioned level that read GHOST columns (multi-GPU, HaloK): the ghost rows of
 // y are written by other GPUs while the kernel runs; they are complete once the warp has passed halo_wait, but a line that holds the last
 // owned rows AND the first ghost rows may already sit in this SM's L1 from another warp's gathers.  L2 is where peer writes land.
-template <bool CG> __device__ __forceinline__ double gather_ld(const double *p) { return CG ? __ldcg(p) : *p; }
+template <bool CG> __device__ __forceinline__ double gather_ld(const double *p, bool ghost) { return (CG && ghost) ? __ldcg(p) : *p; }
 
 template <int BS, bool UNIFORM, bool VSHARED = false, bool CG = false>
 __device__ __forceinline__ void row_product_t(const SellView &A, int r, int len, int64_t cpo, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
@@ -68,7 +68,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
         for (int k = 0; k < BB; k++) m[k] = __ldg(tp + (size_t)j * BB + k);
 #pragma unroll
-        for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i);
+        for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i, c >= A.n);
         if (j == 0) {
 #pragma unroll
           for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -96,7 +96,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
           for (int k = 0; k < BB; k++) m[k] = VSHARED ? __ldg(tp + (size_t)j * BB + k) : __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-          for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i);
+          for (int i = 0; i < BS; i++) wv[i] = gather_ld<CG>(y + (size_t)c * BS + i, c >= A.n);
           if (j == 0) {
 #pragma unroll
             for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -120,7 +120,7 @@ SPMV_PRAGMA(unroll SPMV_UNROLL_U)
 #pragma unroll
       for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-      for (int i = 0; i < BS; i++) w[i] = gather_ld<CG>(y + (size_t)c * BS + i);
+      for (int i = 0; i < BS; i++) w[i] = gather_ld<CG>(y + (size_t)c * BS + i, c >= A.n);
       if (j == 0) {
 #pragma unroll
         for (int k = 0; k < BB; k++) dg[k] = m[k];
@@ -161,32 +161,6 @@ __device__ __forceinline__ void row_product(const SellView &A, int r, bool live,
     if (A.vt && UG_VALTAB(cpo) >= 0) row_product_t<BS, true, true, CG>(A, r, len, cpo, y, s, dg);
     else row_product_t<BS, true, false, CG>(A, r, len, cpo, y, s, dg);
   } else row_product_t<BS, false, false, CG>(A, r, len, cpo, y, s, dg);
-}
-
-// SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
-template <int BS>
-__device__ __forceinline__ int solve_small_block(const double (&mat)[BS * BS], const double (&rhs)[BS], double (&sol)[BS])
-{
-  if (BS == 1) { sol[0] = rhs[0] / mat[0]; return 0; }
-  if (BS == 2) {
-    double det = mat[0] * mat[3 % (BS * BS)] - mat[1 % (BS * BS)] * mat[2 % (BS * BS)];
-    if (det == 0.0) return 1;
-    det = 1.0 / det;
-    sol[0] = (rhs[0] * mat[3 % (BS * BS)] - rhs[1 % BS] * mat[1 % (BS * BS)]) * det;
-    sol[1 % BS] = (rhs[1 % BS] * mat[0] - rhs[0] * mat[2 % (BS * BS)]) * det;
-    return 0;
-  }
-  // n == 3 (indices wrapped with % only to keep the BS<3 instantiations well-formed)
-  constexpr int BB = BS * BS;
-  double M3div0 = mat[3 % BB] / mat[0];
-  double M6div0 = mat[6 % BB] / mat[0];
-  double aux = (mat[7 % BB] - M6div0 * mat[1 % BB]) / (mat[4 % BB] - M3div0 * mat[1 % BB]);
-  sol[2 % BS] = (rhs[2 % BS] - M6div0 * rhs[0] - aux * (rhs[1 % BS] - M3div0 * rhs[0]))
-                / (mat[8 % BB] - M6div0 * mat[2 % BB] - aux * (mat[5 % BB] - M3div0 * mat[2 % BB]));
-  sol[1 % BS] = (rhs[1 % BS] - mat[3 % BB] / mat[0] * rhs[0] - (mat[5 % BB] - M3div0 * mat[2 % BB]) * sol[2 % BS])
-                / (mat[4 % BB] - M3div0 * mat[1 % BB]);
-  sol[0] = (rhs[0] - mat[1 % BB] * sol[1 % BS] - mat[2 % BB] * sol[2 % BS]) / mat[0];
-  return 0;
 }
 
 // ---- dmatmul family ---------------------------------------------------------------------------------------------
@@ -260,6 +234,11 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   const double nb = 8.0 * BS * L->n;
   ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
   const Prefetch pf = make_prefetch(ctx, A, BS);
+  {
+    int done = 0;
+    UG_TRY(stx_dmatmul(ctx, L, const_cast<SellMat *>(A), op, bit, x, y, &done));
+    if (done) return 0;
+  }
   if (BS == 1 && (A->sten.w == 15 || A->sten.w == 27) && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
     const int nsl = (L->n + 31) / 32;
 #define DS(OPV, WV) k_dmatmul_sten<OPV, WV><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, v, bit, L->ctl, x, y, pf.dist, nsl)
@@ -353,6 +332,26 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_jac_k(SellView A, const uint8_
   if (push) halo_push_row<BS>(hk, r, pv);
 }
 
+// Timing experiment on ONE GPU (UGGPU_DBG_FAKE_COMM = 1: all-zero flags; 2: every 16th slice flagged "ghost columns + rows to push", waits
+// and stores switched off): the comm instantiations of the kernels without a second GPU.  Results are unchanged.
+__global__ void k_fake_flags(size_t n, int mode, uint8_t *f) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) f[i] = (mode >= 2 && (i & 15) == 15) ? 3 : 0; }
+static int fake_comm(uggpu_ctx *ctx, Level *L, HaloK *hk)
+{
+  static uint8_t *flags = nullptr; static size_t cap = 0; static int built_mode = -1;
+  static unsigned long long *go = nullptr;
+  const int mode = atoi(getenv("UGGPU_DBG_FAKE_COMM"));
+  const size_t need = ((size_t)L->n + 31) / 32 + 1;
+  if (!go) { CUDA_TRY(cudaMalloc(&go, HALO_GO_SLOTS * 128)); CUDA_TRY(cudaMemset(go, 0, HALO_GO_SLOTS * 128)); }
+  if (need > cap || mode != built_mode) {
+    if (need > cap) { if (flags) cudaFree(flags); CUDA_TRY(cudaMalloc(&flags, need)); cap = need; }
+    k_fake_flags<<<(int)((cap + 255) / 256), 256, 0, ctx->stream>>>(cap, mode, flags);
+    built_mode = mode;
+  }
+  hk->flag = flags; hk->err = ctx->derr; hk->go = go; hk->sel = HALO_DBG_NOPUSH | HALO_DBG_NOWAIT | HALO_PUSH_B;
+  hk->peer = mode >= 2 ? reinterpret_cast<double *const *>(go) : nullptr;
+  return 0;
+}
+
 int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp)
 {
   Level *L = get_level(ctx, level);
@@ -360,6 +359,8 @@ int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp dam
   if (!L || !M) return UGGPU_DESC_MISMATCH;
   HaloK hk = halo_none();
   if (hp && hp->push) UG_TRY(halo_prepare(ctx, level, -1, M, nullptr, hp, &hk));
+  if (hk.flag && getenv("UGGPU_DBG_HALO")) hk.sel |= atoi(getenv("UGGPU_DBG_HALO"));
+  if (!hk.flag && getenv("UGGPU_DBG_FAKE_COMM")) UG_TRY(fake_comm(ctx, L, &hk));
   if (L->n == 0 && !hk.flag) return 0;
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   if (blocks < 1) blocks = 1;
@@ -443,7 +444,7 @@ __device__ __noinline__ void smooth_comm_rows(SellView A, int r, int cf, HaloK h
       else cn = c[k];
       if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
       if (FLAGS & SF_XADD) x[k] = x[k] + cn;
-      if (hk.sel == HALO_PUSH_C) pv[i] = cn;
+      if ((hk.sel & 255) == HALO_PUSH_C) pv[i] = cn;
     }
   }
   if (FLAGS & SF_TOUT) {
@@ -460,7 +461,7 @@ __device__ __noinline__ void smooth_comm_rows(SellView A, int r, int cf, HaloK h
     for (int i = 0; i < BS; i++) {
       const double tv = sol[i] * damp.a[i];
       tout[(size_t)r * BS + i] = tv;
-      if (hk.sel == HALO_PUSH_TOUT) pv[i] = tv;
+      if ((hk.sel & 255) == HALO_PUSH_TOUT) pv[i] = tv;
     }
   }
   if ((cf & 2) && hk.peer) halo_push_row<BS>(hk, r, pv);
@@ -1202,11 +1203,17 @@ int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin
     UG_TRY(halo_prepare(ctx, level, level, M, const_cast<double *>(tin), hp, &hk));
     if (hk.peer) {
       hk.sel = hp->push == tout ? HALO_PUSH_TOUT : (hp->push == b ? HALO_PUSH_B : (hp->push == c ? HALO_PUSH_C : HALO_PUSH_NONE));
-      if (hk.sel == HALO_PUSH_NONE || (hk.sel == HALO_PUSH_TOUT && !(flags & SF_TOUT)) || (hk.sel == HALO_PUSH_C && !(flags & (SF_CADD | SF_CSET))))
+      if (hk.sel == HALO_PUSH_NONE || ((hk.sel & 255) == HALO_PUSH_TOUT && !(flags & SF_TOUT)) || ((hk.sel & 255) == HALO_PUSH_C && !(flags & (SF_CADD | SF_CSET))))
         return uggpu_fail(UGGPU_ERROR, "smooth step: the vector to push is not produced by this step");
     }
   } else UG_TRY(halo_begin(ctx, level, const_cast<double *>(tin), &split));
+  if (!hk.flag && getenv("UGGPU_DBG_FAKE_COMM")) UG_TRY(fake_comm(ctx, L, &hk));
   if (L->n == 0 && !hk.flag) return 0;
+  if (!split) {       // matrices with a dominant stencil, large levels: stencil rows and exception rows as two kernels (stx.cu)
+    int done = 0;
+    UG_TRY(stx_smooth(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, hk, &done));
+    if (done) return 0;
+  }
   switch (L->bs) {
     case 1: return launch_smooth<1>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split, hk);
     case 2: return launch_smooth<2>(ctx, L, M, flags, tin, b, c, tout, damp, x, norm_slot, level, split, hk);

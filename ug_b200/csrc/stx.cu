@@ -1,0 +1,501 @@
+// stx.cu -- "stencil rows + exception rows": the SpMV-type kernels of a matrix with a dominant stencil as TWO kernels.
+//
+// spmv.cu's stencil kernels (k_smooth_sten, k_dmatmul_sten) decide per SLICE: a slice whose 32 rows all carry the dominant stencil runs
+// the unrolled constant-bank loop, every other slice -- one Dirichlet row is enough -- the generic row product, which lives four to
+// five times as long (a chain of dependent loads: code word -> column words -> gathers).  On a uniformly refined grid those slices
+// are few but not rare (7 % at 513^3, 28 % at 129^3; on the upper half of an x-split twice as many as on the lower one, which is what
+// made the ranks of a partitioned run unequal), and being latency-bound they cost their share several times over.
+//
+// Here the decision is per ROW.  Bit l of xmask[s] says that row 32 s + l is EXACTLY the stencil: same length, same column distances,
+// bit-identical values, no ghost column, nothing to push to another GPU.  Kernel 1 (k_*_stx) handles those rows -- one 4-byte mask per
+// warp is all it reads of the matrix -- and nothing else: no code word, no row length, no slow path, no communication.  Kernel 2
+// (k_*_xrows) takes the compact ascending list of all other rows, one thread per row with the generic product on the SELL arrays: 32
+// exception rows per warp instead of one or two.  Both kernels perform, for every row, the same operations on the same operands in
+// the same order as the one-kernel forms (canonical VSTART->MNEXT order): results are bit-identical (tests: UGGPU_NO_STX=1 A/B, port).
+//
+// Multi-GPU (peer-memory ghost rows, HaloK): rows with ghost columns and rows whose result a neighbour needs are exception rows, so
+// kernel 1 never waits and never stores remotely; kernel 2 runs NEXT to it on a second stream, waits for the neighbours (one go word
+// per SM), gathers ghost columns past L1, and pushes -- the interface rows of an x-split, one per grid line in the row order, sit in
+// neighbouring lanes of the exception list, so their remote stores share sectors.
+#include "uggpu_internal.h"
+
+#include <cstdlib>
+#include <vector>
+
+#define STX_THREADS 128
+#define STX_MINBLOCKS (2048 / STX_THREADS)
+#define STX_MIN_ROWS 65536          // smaller levels are launch-bound: one kernel (spmv.cu) is better than two
+
+// ---- which rows are exactly the stencil ---------------------------------------------------------------------------------------------
+template <int BS, class STEN>
+__global__ void k_stx_rowmask(const __grid_constant__ STEN st, SellView A, int n_owned, const uint32_t *__restrict__ snd_bits, uint32_t *__restrict__ xmask)
+{
+  constexpr int BB = BS * BS;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((r & ~31) >= A.n) return;
+  const int lane = r & 31;
+  bool match = r < A.n && (int)A.rowlen[r < A.n ? r : 0] == st.w;
+  if (match) {
+    const int64_t sp = slice_off(A, r >> 5);
+    const double *vp = A.val + sp * BB + lane;
+    const ColIter ci = col_iter(A, r);
+    for (int j = 0; j < st.w && match; j++) {
+      const int c = col_at(ci, j);
+      if ((long long)(c - r) * (long long)(BS * sizeof(double)) != st.dbytes[j] || c < 0 || c >= n_owned) match = false;
+      for (int k = 0; k < BB && match; k++)
+        if (__double_as_longlong(vp[((size_t)j * BB + k) * 32]) != __double_as_longlong(st.v[j * BB + k])) match = false;
+    }
+    if (snd_bits && ((snd_bits[r >> 5] >> lane) & 1u)) match = false;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, match);
+  if (lane == 0) xmask[r >> 5] = m;
+}
+
+int stx_free(uggpu_ctx *ctx, SellMat *m)
+{
+  const size_t nsl = ((size_t)(m->n > 0 ? m->n : 0) + 31) / 32;
+  if (m->xmask) dfree(ctx, m->xmask, nsl + 1);
+  if (m->xrows) dfree(ctx, m->xrows, (size_t)(m->nx > 0 ? m->nx : 0) + 1);
+  m->nx = -1; m->x_comm = 0;
+  return 0;
+}
+
+// builds xmask / xrows of A (rows of level L); comm: ghost columns and rows to push are exceptions (peer-memory ghost transport)
+static int stx_ensure(uggpu_ctx *ctx, Level *L, SellMat *A, bool comm)
+{
+  if (A->xmask && A->x_comm == (comm ? 1 : 0)) return 0;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  UG_TRY(stx_free(ctx, A));
+  const size_t nsl = ((size_t)A->n + 31) / 32;
+  UG_TRY(dalloc(ctx, &A->xmask, nsl + 1));
+  const uint32_t *snd = nullptr;
+  if (comm) {
+    if (!L->halo) return uggpu_fail(UGGPU_ERROR, "stx: the level's halo tables are not set up");
+    snd = halo_snd_bits(L);      // rows to push (comm.cu)
+  }
+  const int blocks = (int)((nsl * 32 + 255) / 256);
+  if (A->bb == 1) k_stx_rowmask<1, Sten><<<blocks, 256, 0, ctx->stream>>>(A->sten, view(*A), L->n, snd, A->xmask);
+  else k_stx_rowmask<3, Sten3><<<blocks, 256, 0, ctx->stream>>>(*A->sten3, view(*A), L->n, snd, A->xmask);
+  KCHECK(ctx);
+  std::vector<uint32_t> mask(nsl);
+  CUDA_TRY(cudaMemcpyAsync(mask.data(), A->xmask, sizeof(uint32_t) * nsl, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<int32_t> rows;
+  for (size_t s = 0; s < nsl; s++) {
+    const uint32_t m = mask[s];
+    if (m == 0xffffffffu) continue;
+    for (int l = 0; l < 32; l++) {
+      const int64_t r = (int64_t)s * 32 + l;
+      if (r < A->n && !((m >> l) & 1u)) rows.push_back((int32_t)r);
+    }
+  }
+  A->nx = (int)rows.size();
+  UG_TRY(dalloc(ctx, &A->xrows, rows.size() + 1));
+  if (!rows.empty()) CUDA_TRY(cudaMemcpyAsync(A->xrows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  A->x_comm = comm ? 1 : 0;
+  return 0;
+}
+
+// ---- the generic product of ONE row on the SELL arrays, per lane (no warp cooperation: the lanes of a warp hold rows of different slices) ----
+// CG: ghost columns (index >= A.n) are gathered past L1 (see spmv.cu gather_ld)
+template <int BS, bool CG>
+__device__ __forceinline__ void row_product_lane(const SellView &A, int r, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
+{
+  constexpr int BB = BS * BS;
+  const int sl = r >> 5, lane = r & 31;
+  const int64_t sp = slice_off(A, sl);
+  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : __ldg(A.col_ptr + sl);
+  const int len = (int)A.rowlen[r];
+  const bool uni = cpo < 0;
+  const int32_t *__restrict__ cp = uni ? A.col + UG_COLTAB(cpo) : A.col + cpo + lane;
+  const int cstride = uni ? 1 : 32, cbase = uni ? r : 0;
+  const bool vsh = uni && A.vt && UG_VALTAB(cpo) >= 0;
+  const double *__restrict__ vp = vsh ? A.vt + UG_VALTAB(cpo) : A.val + sp * BB + lane;
+  const int vstride = vsh ? 1 : 32;
+#pragma unroll
+  for (int i = 0; i < BS; i++) s[i] = 0.0;
+#pragma unroll
+  for (int k = 0; k < BB; k++) dg[k] = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < len; j++) {
+    const int c = __ldg(cp + (size_t)j * cstride) + cbase;
+    double m[BB], w[BS];
+#pragma unroll
+    for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * vstride);
+#pragma unroll
+    for (int i = 0; i < BS; i++) w[i] = (CG && c >= A.n) ? __ldcg(y + (size_t)c * BS + i) : y[(size_t)c * BS + i];
+    if (j == 0) {
+#pragma unroll
+      for (int k = 0; k < BB; k++) dg[k] = m[k];
+    }
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      double acc = m[i * BS] * w[0];
+#pragma unroll
+      for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * w[q];
+      s[i] += acc;
+    }
+  }
+}
+
+// the smoothing step's updates of one row (the same statements as spmv.cu k_smooth_k); returns the norm contributions
+template <int BS, int FLAGS>
+__device__ __forceinline__ void smooth_row_tail(int r, const double (&s)[BS], const double (&dg)[BS * BS], const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl,
+                                                const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c, double *__restrict__ tout, const Damp &damp,
+                                                double *__restrict__ x, int *err, int sel, double (&pv)[BS], double (&nrm)[BS])
+{
+  double bn[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) {
+    const size_t k = (size_t)r * BS + i;
+    bn[i] = b[k] - s[i];
+    b[k] = bn[i];
+    pv[i] = bn[i];
+  }
+  if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      const size_t k = (size_t)r * BS + i;
+      double cn;
+      if (FLAGS & SF_CADD) cn = c[k] + tin[k];
+      else if (FLAGS & SF_CSET) cn = 0.0 + tin[k];
+      else cn = c[k];
+      if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
+      if (FLAGS & SF_XADD) x[k] = x[k] + cn;
+      if ((sel & 255) == HALO_PUSH_C) pv[i] = cn;
+    }
+  }
+  if (FLAGS & SF_TOUT) {
+    double sol[BS];
+    if (vclass[r] < 3) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) sol[i] = 0.0;
+    } else if (solve_small_block<BS>(dg, bn, sol)) {
+      atomicExch(err, UGGPU_SMALL_DIAG);
+#pragma unroll
+      for (int i = 0; i < BS; i++) sol[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      const double tv = sol[i] * damp.a[i];
+      tout[(size_t)r * BS + i] = tv;
+      if ((sel & 255) == HALO_PUSH_TOUT) pv[i] = tv;
+    }
+  }
+  if (FLAGS & SF_NORM) {
+    if (ctl[r] & UGGPU_CTL_NEW_DEFECT) {
+#pragma unroll
+      for (int i = 0; i < BS; i++) nrm[i] = bn[i] * bn[i];
+    }
+  }
+}
+
+template <int BS, int THREADS>
+__device__ __forceinline__ void block_norm_partials(const double (&nrm)[BS], double *__restrict__ partials)
+{
+  __shared__ double sm[THREADS / 32][UGGPU_MAX_BS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < BS; i++) {
+    double v = nrm[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w][i] = v;
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      double v = lane < THREADS / 32 ? sm[lane][i] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) partials[(size_t)blockIdx.x * BS + i] = v;
+    }
+  }
+}
+
+// ---- kernel 1, scalar rows: the rows that are exactly the stencil ---------------------------------------------------------------------
+template <int FLAGS, int W>
+__global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_smooth_stx(const __grid_constant__ Sten st, int n, const uint32_t *__restrict__ xmask,
+                                                                            const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl, const double *__restrict__ tin,
+                                                                            double *__restrict__ b, double *__restrict__ c, double *__restrict__ tout, double damp,
+                                                                            double *__restrict__ x, double *__restrict__ partials, int pf_dist, int nsl)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5, lane = threadIdx.x & 31;
+  double nrm = 0.0;
+  if (s < nsl) {                                               // whole warps
+    const uint32_t m = __ldg(xmask + s);
+    if ((m >> lane) & 1u) {
+      // the row's own entries first: their round trip runs next to the gathers
+      const double eb = b[r];
+      const double ec = ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ? c[r] : 0.0;
+      const double et = (FLAGS & (SF_CADD | SF_CSET)) ? tin[r] : 0.0;
+      const uint8_t vc = (FLAGS & SF_TOUT) ? vclass[r] : (uint8_t)3;
+      const char *yb = reinterpret_cast<const char *>(tin + r);
+      double sum = 0.0;
+#pragma unroll
+      for (int j = 0; j < W; j++) {
+        const double y = __ldg(reinterpret_cast<const double *>(yb + st.dbytes[j]));
+        const double p = st.v[j] * y;
+        sum += p;
+      }
+      const double bn = eb - sum;
+      b[r] = bn;
+      if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
+        double cn;
+        if (FLAGS & SF_CADD) cn = ec + et;
+        else if (FLAGS & SF_CSET) cn = 0.0 + et;
+        else cn = ec;
+        if (FLAGS & (SF_CADD | SF_CSET)) c[r] = cn;
+        if (FLAGS & SF_XADD) x[r] = x[r] + cn;
+      }
+      if (FLAGS & SF_TOUT) {
+        const double sol = vc < 3 ? 0.0 : bn / st.v[0];          // l_jac: 0 below ACTIVE_CLASS (ugiter.cc:300)
+        tout[r] = sol * damp;
+      }
+      if (FLAGS & SF_NORM) { if (ctl[r] & UGGPU_CTL_NEW_DEFECT) nrm = bn * bn; }
+    }
+    // L2 prefetch for the slice pf_dist ahead: its rows of b and c, the rows of tin that slice reaches first (largest distance), its mask
+    if (pf_dist > 0 && s + pf_dist < nsl && lane < 9) {
+      const size_t far = ((size_t)(s + pf_dist)) * 32;
+      if (lane < 2) { if (far + lane * 16 < (size_t)n) prefetch_l2(b + far + lane * 16); }
+      else if (lane < 4) { if (((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) && far + (lane - 2) * 16 < (size_t)n) prefetch_l2(c + far + (lane - 2) * 16); }
+      else if (lane < 7) { if (far + st.maxd + (lane - 4) * 16 < (size_t)n) prefetch_l2(tin + far + st.maxd + (lane - 4) * 16); }
+      else if (lane == 7) { if (FLAGS & SF_TOUT) prefetch_l2(vclass + far); }
+      else prefetch_l2(xmask + s + pf_dist);
+    }
+  }
+  if (FLAGS & SF_NORM) { const double na[1] = {nrm}; block_norm_partials<1, STX_THREADS>(na, partials); }
+}
+
+// ... and 3x3 blocks (27 block columns)
+#ifndef STX3_MINBLOCKS
+#define STX3_MINBLOCKS 8
+#endif
+template <int FLAGS>
+__global__ void __launch_bounds__(STX_THREADS, STX3_MINBLOCKS) k_smooth_stx3(const __grid_constant__ Sten3 st, int n, const uint32_t *__restrict__ xmask,
+                                                                             const uint8_t *__restrict__ vclass, const uint8_t *__restrict__ ctl, const double *__restrict__ tin,
+                                                                             double *__restrict__ b, double *__restrict__ c, double *__restrict__ tout, Damp damp,
+                                                                             double *__restrict__ x, double *__restrict__ partials, int *err, int pf_dist, int nsl)
+{
+  constexpr int BS = 3, BB = 9;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5, lane = threadIdx.x & 31;
+  double nrm[BS] = {0.0, 0.0, 0.0};
+  if (s < nsl) {
+    const uint32_t m = __ldg(xmask + s);
+    if ((m >> lane) & 1u) {
+      double sum[BS], dg[BB], pv[BS];
+      const char *yb = reinterpret_cast<const char *>(tin + (size_t)r * BS);
+#pragma unroll
+      for (int i = 0; i < BS; i++) sum[i] = 0.0;
+#pragma unroll
+      for (int k = 0; k < BB; k++) dg[k] = st.v[k];
+#pragma unroll
+      for (int j = 0; j < 27; j++) {
+        const double *yp = reinterpret_cast<const double *>(yb + st.dbytes[j]);
+        const double w0 = __ldg(yp), w1 = __ldg(yp + 1), w2 = __ldg(yp + 2);
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double acc = st.v[j * BB + i * BS] * w0;
+          acc = acc + st.v[j * BB + i * BS + 1] * w1;
+          acc = acc + st.v[j * BB + i * BS + 2] * w2;
+          sum[i] += acc;
+        }
+      }
+      smooth_row_tail<BS, FLAGS>(r, sum, dg, vclass, ctl, tin, b, c, tout, damp, x, err, 0, pv, nrm);
+    }
+    if (pf_dist > 0 && s + pf_dist < nsl && lane < 20) {
+      const size_t far = ((size_t)(s + pf_dist)) * 32 * BS;
+      const size_t nn = (size_t)n * BS;
+      if (lane < 6) { if (far + lane * 16 < nn) prefetch_l2(b + far + lane * 16); }
+      else if (lane < 12) { if (((FLAGS & SF_CADD) || ((FLAGS & SF_XADD) && !(FLAGS & SF_CSET))) && far + (lane - 6) * 16 < nn) prefetch_l2(c + far + (lane - 6) * 16); }
+      else if (lane < 19) { const size_t o = far + (size_t)st.maxd * BS + (lane - 12) * 16; if (o < nn) prefetch_l2(tin + o); }
+      else prefetch_l2(xmask + s + pf_dist);
+    }
+  }
+  if (FLAGS & SF_NORM) block_norm_partials<BS, STX_THREADS>(nrm, partials);
+}
+
+// ---- kernel 2: the exception rows, one thread per row ----------------------------------------------------------------------------------
+// COMM (multi-GPU, HaloK): block 0 publishes / watches, every warp waits for this SM's go word before it gathers ghost columns or pushes
+template <int BS, int FLAGS, bool COMM>
+__global__ void __launch_bounds__(STX_THREADS) k_smooth_xrows(SellView A, const int32_t *__restrict__ xrows, int nx, const uint8_t *__restrict__ vclass,
+                                                              const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
+                                                              double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err, HaloK hk)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < nx;
+  const int r = live ? __ldg(xrows + i) : 0;
+  if (COMM) { halo_publish(hk); halo_wait(hk); }
+  double nrm[BS];
+#pragma unroll
+  for (int q = 0; q < BS; q++) nrm[q] = 0.0;
+  if (live) {
+    double s[BS], dg[BS * BS], pv[BS];
+    row_product_lane<BS, COMM>(A, r, tin, s, dg);
+    smooth_row_tail<BS, FLAGS>(r, s, dg, vclass, ctl, tin, b, c, tout, damp, x, err, COMM ? hk.sel : 0, pv, nrm);
+    if (COMM && hk.peer) halo_push_row<BS>(hk, r, pv);
+  }
+  if (FLAGS & SF_NORM) block_norm_partials<BS, STX_THREADS>(nrm, partials);
+}
+
+// ---- dmatmul family ---------------------------------------------------------------------------------------------------------------------
+template <int OP, int W>
+__global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_dmatmul_stx(const __grid_constant__ Sten st, int n, const uint32_t *__restrict__ xmask, uint8_t bit,
+                                                                             const uint8_t *__restrict__ ctl, double *__restrict__ x, const double *__restrict__ y, int pf_dist, int nsl)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = r >> 5, lane = threadIdx.x & 31;
+  if (s >= nsl) return;
+  const uint32_t m = __ldg(xmask + s);
+  if (((m >> lane) & 1u) && (!bit || (ctl[r] & bit))) {
+    const double xo = OP != 0 ? x[r] : 0.0;
+    const char *yb = reinterpret_cast<const char *>(y + r);
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+      const double yv = __ldg(reinterpret_cast<const double *>(yb + st.dbytes[j]));
+      const double p = st.v[j] * yv;
+      sum += p;
+    }
+    x[r] = OP == 0 ? sum : (OP == 1 ? xo + sum : xo - sum);
+  }
+  if (pf_dist > 0 && s + pf_dist < nsl && lane < 6) {
+    const size_t far = ((size_t)(s + pf_dist)) * 32;
+    if (lane < 2) { if (OP != 0 && far + lane * 16 < (size_t)n) prefetch_l2(x + far + lane * 16); }
+    else if (lane < 5) { if (far + st.maxd + (lane - 2) * 16 < (size_t)n) prefetch_l2(y + far + st.maxd + (lane - 2) * 16); }
+    else prefetch_l2(xmask + s + pf_dist);
+  }
+}
+
+template <int BS, int OP>
+__global__ void __launch_bounds__(STX_THREADS) k_dmatmul_xrows(SellView A, const int32_t *__restrict__ xrows, int nx, uint8_t bit, const uint8_t *__restrict__ ctl,
+                                                               double *__restrict__ x, const double *__restrict__ y)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx) return;
+  const int r = __ldg(xrows + i);
+  if (bit && !(ctl[r] & bit)) return;
+  double s[BS], dg[BS * BS];
+  row_product_lane<BS, false>(A, r, y, s, dg);
+#pragma unroll
+  for (int q = 0; q < BS; q++) {
+    const size_t k = (size_t)r * BS + q;
+    if (OP == 0) x[k] = (BS == 1) ? s[q] : 0.0 + s[q];
+    else if (OP == 1) x[k] = x[k] + s[q];
+    else x[k] = x[k] - s[q];
+  }
+}
+
+// ---- launches ---------------------------------------------------------------------------------------------------------------------------
+static bool stx_applies(const Level *L, const SellMat *A)
+{
+  if (getenv("UGGPU_NO_STX") || getenv("UGGPU_NO_STENCIL")) return false;
+  const char *mr = getenv("UGGPU_STX_MIN_ROWS");
+  if (L->n < (mr ? atoi(mr) : STX_MIN_ROWS)) return false;
+  if (A->col_ptr == A->slice_ptr) return false;
+  if (L->bs == 1) return A->bb == 1 && (A->sten.w == 15 || A->sten.w == 27);
+  return L->bs == 3 && A->bb == 9 && A->sten3 != nullptr;
+}
+
+template <int BS, int FLAGS>
+static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot, const HaloK &hk)
+{
+  const int nsl = (L->n + 31) / 32;
+  const int blocks = (L->n + STX_THREADS - 1) / STX_THREADS;
+  const int xblocks = (A->nx + STX_THREADS - 1) / STX_THREADS > 0 ? (A->nx + STX_THREADS - 1) / STX_THREADS : 1;
+  if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)(blocks + xblocks) * BS));
+  const double nb = 8.0 * BS * L->n;
+  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + 3.0 * nb
+               + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
+  Prefetch pf = make_prefetch(ctx, A, BS);
+  // the exception rows run next to the stencil rows: on the second stream when they have to wait for other GPUs, else behind them
+  cudaStream_t xs = ctx->stream;
+  if (hk.flag) {
+    if (!ctx->halo_stream) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_TRY(cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, hi));
+      for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&ctx->halo_ev[i], cudaEventDisableTiming));
+    }
+    xs = ctx->halo_stream;
+    CUDA_TRY(cudaEventRecord(ctx->halo_ev[0], ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(xs, ctx->halo_ev[0], 0));
+  }
+  double *xpart = ctx->partials + (size_t)blocks * BS;
+  if (hk.flag) k_smooth_xrows<BS, FLAGS, true><<<xblocks, STX_THREADS, 0, xs>>>(view(*A), A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
+  else if (A->nx > 0 || (FLAGS & SF_NORM)) k_smooth_xrows<BS, FLAGS, false><<<xblocks, STX_THREADS, 0, xs>>>(view(*A), A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
+  KCHECK(ctx);
+  if (BS == 1) {
+    if (A->sten.w == 15) k_smooth_stx<FLAGS, 15><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl);
+    else k_smooth_stx<FLAGS, 27><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl);
+  } else {
+    k_smooth_stx3<FLAGS><<<blocks, STX_THREADS, 0, ctx->stream>>>(*A->sten3, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf.dist, nsl);
+  }
+  KCHECK(ctx);
+  if (hk.flag) {
+    CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], xs));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
+  }
+  if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)(blocks + xblocks), norm_slot, (int)(L - ctx->lev)));
+  return 0;
+}
+
+template <int BS>
+static int stx_smooth1(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot, const HaloK &hk)
+{
+#define SM_CASE(F) case F: return stx_smooth2<BS, F>(ctx, L, A, tin, b, c, tout, damp, x, norm_slot, hk)
+  switch (flags) {
+    SM_CASE(0);
+    SM_CASE(SF_CADD);
+    SM_CASE(SF_CSET);
+    SM_CASE(SF_TOUT);
+    SM_CASE(SF_CADD | SF_TOUT);
+    SM_CASE(SF_CSET | SF_TOUT);
+    SM_CASE(SF_CADD | SF_XADD | SF_NORM);
+    SM_CASE(SF_CSET | SF_XADD | SF_NORM);
+    SM_CASE(SF_CADD | SF_XADD);
+    SM_CASE(SF_CSET | SF_XADD);
+    SM_CASE(SF_CADD | SF_NORM);
+    SM_CASE(SF_CSET | SF_NORM);
+    SM_CASE(SF_NORM);
+  }
+#undef SM_CASE
+  return uggpu_fail(UGGPU_ERROR, "smooth step: unsupported flag combination %d", flags);
+}
+
+int stx_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
+               const HaloK &hk, int *done)
+{
+  *done = 0;
+  if (!stx_applies(L, A)) return 0;
+  UG_TRY(stx_ensure(ctx, L, A, hk.flag != nullptr));
+  *done = 1;
+  if (L->bs == 1) return stx_smooth1<1>(ctx, L, A, flags, tin, b, c, tout, damp, x, norm_slot, hk);
+  return stx_smooth1<3>(ctx, L, A, flags, tin, b, c, tout, damp, x, norm_slot, hk);
+}
+
+int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, double *x, const double *y, int *done)
+{
+  *done = 0;
+  if (L->bs != 1 || !stx_applies(L, A)) return 0;
+  // the mask built for the comm form (ghost columns and rows to push are exceptions) serves as well: exception rows are computed generically
+  if (!A->xmask) UG_TRY(stx_ensure(ctx, L, A, false));
+  *done = 1;
+  const int nsl = (L->n + 31) / 32;
+  const int blocks = (L->n + STX_THREADS - 1) / STX_THREADS, xblocks = (A->nx + STX_THREADS - 1) / STX_THREADS;
+  const Prefetch pf = make_prefetch(ctx, A, 1);
+#define DS(OPV, WV) k_dmatmul_stx<OPV, WV><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, bit, L->ctl, x, y, pf.dist, nsl)
+  if (A->sten.w == 15) { if (op == 0) DS(0, 15); else if (op == 1) DS(1, 15); else DS(2, 15); }
+  else { if (op == 0) DS(0, 27); else if (op == 1) DS(1, 27); else DS(2, 27); }
+#undef DS
+  KCHECK(ctx);
+  if (xblocks > 0) {
+    if (op == 0) k_dmatmul_xrows<1, 0><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
+    else if (op == 1) k_dmatmul_xrows<1, 1><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
+    else k_dmatmul_xrows<1, 2><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
+    KCHECK(ctx);
+  }
+  return 0;
+}

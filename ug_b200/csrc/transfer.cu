@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
 #pragma unroll
     for (int i = 0; i < BS; i++) to[(size_t)r[k] * BS + i] = tr[k][i];
     if (!early) restrict_prefetch<FUSE>(R, r[k], pf, vnclass_c, skip_c, vclass_c);
-    if ((cf & 2) && hk.peer && hk.sel == HALO_PUSH_B) halo_push_row<BS>(hk, r[k], tr[k]);
+    if ((cf & 2) && hk.peer && (hk.sel & 255) == HALO_PUSH_B) halo_push_row<BS>(hk, r[k], tr[k]);
     if (FUSE) {
       constexpr int BB = BS * BS;
       double sol[BS];
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_restrict_k(SellView R, const uin
         tout[(size_t)r[k] * BS + i] = tv[i];
         czero[(size_t)r[k] * BS + i] = 0.0;
       }
-      if ((cf & 2) && hk.peer && hk.sel == HALO_PUSH_TOUT) halo_push_row<BS>(hk, r[k], tv);
+      if ((cf & 2) && hk.peer && (hk.sel & 255) == HALO_PUSH_TOUT) halo_push_row<BS>(hk, r[k], tv);
     }
   }
 }
@@ -322,6 +322,7 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
     hk.sel = (fuse && hp->push == tout) ? HALO_PUSH_TOUT : (hp->push == to ? HALO_PUSH_B : HALO_PUSH_NONE);
     if (hk.sel == HALO_PUSH_NONE) return uggpu_fail(UGGPU_ERROR, "restrict: the vector to push is not produced by this call");
   }
+  if (hk.flag && getenv("UGGPU_DBG_HALO")) hk.sel |= atoi(getenv("UGGPU_DBG_HALO"));
   if (C->n == 0 && !hk.flag) return 0;
   const bool gather = ctx->comm && F->partitioned && !C->partitioned;   // first completely held (replicated) level
   if (gather && fuse) return uggpu_fail(UGGPU_ERROR, "restrict: fused Jacobi start not possible across the gather level");
@@ -379,6 +380,7 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
   HaloK hk = halo_none();
   UG_TRY(halo_prepare(ctx, level, level - 1, &F->P, const_cast<double *>(from), hp, &hk));
   if (hk.peer && hp->push != to) return uggpu_fail(UGGPU_ERROR, "interpolate: the vector to push is not produced by this call");
+  if (hk.flag && getenv("UGGPU_DBG_HALO")) hk.sel |= atoi(getenv("UGGPU_DBG_HALO"));
   if (F->n == 0 && !hk.flag) return 0;
   ProfScope ps(ctx, UGGPU_K_INTERPOLATE, level, F->P.entry_bytes() + 4.0 * (F->n + 1.0) + 8.0 * F->bs * ((double)F->n + C->n));
 #define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n > 0 ? F->n : 1), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV), hk)

@@ -91,6 +91,11 @@ struct SellMat {
   // multi-GPU overlap (spmv.cu): bnd_flag[s] = 1 / bnd_list = the slices with a row that references a ghost column; built on first use
   uint8_t *bnd_flag = nullptr;
   int32_t *bnd_list = nullptr;
+  // stencil rows + exception rows (stx.cu): bit l of xmask[s] = row 32 s + l is exactly the dominant stencil (distances, values, no ghost column, nothing to
+  // push); xrows = all other rows, ascending.  Built on first use; x_comm: built with the multi-GPU exceptions (ghost columns, rows to push)
+  uint32_t *xmask = nullptr;
+  int32_t *xrows = nullptr;
+  int nx = -1, x_comm = 0;
   uint8_t *comm_flag = nullptr;   // [slices] HaloK::flag of launches over this matrix' rows (comm.cu halo_comm_flag): bit 0 ghost columns, bit 1 rows to push
   int n_int = -1, n_bnd = 0;
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
@@ -156,6 +161,8 @@ struct HaloK {                                           // kernel parameter; fl
   unsigned long long *go;                                // [HALO_GO_SLOTS * 16] local "all neighbours have started kernel g" words, one 128-byte line per SM
 };
 #define HALO_GO_SLOTS 256
+#define HALO_DBG_NOPUSH 256     // timing experiments only (UGGPU_DBG_HALO): bits of HaloK::sel that switch the stores / the waits off
+#define HALO_DBG_NOWAIT 512
 enum { HALO_PUSH_NONE = 0, HALO_PUSH_TOUT = 1, HALO_PUSH_B = 2, HALO_PUSH_C = 3 };
 static inline HaloK halo_none() { return HaloK{nullptr, nullptr, nullptr, 0ull, nullptr, nullptr, 0, nullptr}; }
 // what the caller of a comm-aware kernel knows about the exchange around it (cycle.cu: the fused schedule)
@@ -211,6 +218,7 @@ __device__ __forceinline__ void halo_wait_dev(const HaloDev *d, unsigned long lo
 // a warp whose slice reads ghost columns or holds rows to push (whole warp): wait for this SM's go word
 __device__ __forceinline__ void halo_wait(const HaloK &h)
 {
+  if (h.sel & HALO_DBG_NOWAIT) return;
   if ((threadIdx.x & 31) == 0) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -234,6 +242,7 @@ __device__ __forceinline__ void halo_wait(const HaloK &h)
 template <int BS>
 __device__ __forceinline__ void halo_push_row(const HaloK &h, int r, const double (&v)[BS])
 {
+  if (h.sel & HALO_DBG_NOPUSH) return;
   const HaloDev *d = h.pdev;
   const uint32_t bits = d->snd_bits[r >> 5];
   const int lane = r & 31;
@@ -419,6 +428,32 @@ __device__ __forceinline__ int invert_small_block(const double *mat, double *inv
   return 0;
 }
 
+// SolveSmallBlock (block.cc:104-142), n = 1,2,3.  Returns non-zero for a singular 2x2 block.
+template <int BS>
+__device__ __forceinline__ int solve_small_block(const double (&mat)[BS * BS], const double (&rhs)[BS], double (&sol)[BS])
+{
+  if (BS == 1) { sol[0] = rhs[0] / mat[0]; return 0; }
+  if (BS == 2) {
+    double det = mat[0] * mat[3 % (BS * BS)] - mat[1 % (BS * BS)] * mat[2 % (BS * BS)];
+    if (det == 0.0) return 1;
+    det = 1.0 / det;
+    sol[0] = (rhs[0] * mat[3 % (BS * BS)] - rhs[1 % BS] * mat[1 % (BS * BS)]) * det;
+    sol[1 % BS] = (rhs[1 % BS] * mat[0] - rhs[0] * mat[2 % (BS * BS)]) * det;
+    return 0;
+  }
+  // n == 3 (indices wrapped with % only to keep the BS<3 instantiations well-formed)
+  constexpr int BB = BS * BS;
+  double M3div0 = mat[3 % BB] / mat[0];
+  double M6div0 = mat[6 % BB] / mat[0];
+  double aux = (mat[7 % BB] - M6div0 * mat[1 % BB]) / (mat[4 % BB] - M3div0 * mat[1 % BB]);
+  sol[2 % BS] = (rhs[2 % BS] - M6div0 * rhs[0] - aux * (rhs[1 % BS] - M3div0 * rhs[0]))
+                / (mat[8 % BB] - M6div0 * mat[2 % BB] - aux * (mat[5 % BB] - M3div0 * mat[2 % BB]));
+  sol[1 % BS] = (rhs[1 % BS] - mat[3 % BB] / mat[0] * rhs[0] - (mat[5 % BB] - M3div0 * mat[2 % BB]) * sol[2 % BS])
+                / (mat[4 % BB] - M3div0 * mat[1 % BB]);
+  sol[0] = (rhs[0] - mat[1 % BB] * sol[1 % BS] - mat[2 % BB] * sol[2 % BS]) / mat[0];
+  return 0;
+}
+
 // C = A * B for bs x bs blocks with the reference's summation (sum = 0; sum += a*b, ugiter.cc:3814-3822); returns true if C == 0
 template <int BS>
 __device__ __host__ __forceinline__ bool block_mul(const double *a, const double *b, double *c)
@@ -507,7 +542,14 @@ enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16 };
 // exchanges its operand's ghost rows itself and pushes nothing
 int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout,
                   Damp damp, double *x, int norm_slot, const HaloPlan *hp = nullptr);
-int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp = nullptr);   // v = damp * Diag(A)^-1 d (class-masked)
+int k_jac(uggpu_ctx *ctx, int level, int A, double *v, const double *d, Damp damp, const HaloPlan *hp = nullptr);
+// stx.cu: the smoothing step / dmatmul of a matrix with a dominant stencil as TWO kernels -- all rows that are exactly the stencil, and the
+// compact list of all other rows (boundary rows, rows with ghost columns, rows to push).  *done = 0: not applicable, the caller takes its own kernels.
+int stx_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot,
+               const HaloK &hk, int *done);
+int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, double *x, const double *y, int *done);
+int stx_free(uggpu_ctx *ctx, SellMat *m);
+const uint32_t *halo_snd_bits(const Level *L);   // comm.cu: per slice, the lanes whose row is pushed to a neighbour (nullptr: no tables)   // v = damp * Diag(A)^-1 d (class-masked)
 // transfer.cu: fine `level` -> level-1; with fuse: also tout = sdamp*Diag(A_{level-1})^-1 to, czero = 0 on level-1
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp,
                const HaloPlan *hp = nullptr);
