@@ -25,7 +25,7 @@ def describe(dim, cells, P, rank):
     rc = L.uggpu_part_describe(dim, cells[0], cells[1], cells[2], P[0], P[1], P[2], rank, out, len(out))
     assert rc == 0, L.uggpu_last_error()
     o = np.array(out[:], dtype=np.int64)
-    d = {"own": (o[0:3].copy(), o[3:6].copy()), "n_own": int(o[6]), "n_ghost": int(o[7]), "nb": []}
+    d = {"own": (o[0:3].copy(), o[3:6].copy()), "n_own": int(o[6]), "n_ghost": int(o[7]), "pitch": (int(o[9]), int(o[10])), "nb": []}
     for k in range(int(o[8])):
         q = o[16 + 16 * k: 32 + 16 * k]
         d["nb"].append({"rank": int(q[0]), "ns": int(q[1]), "nr": int(q[2]), "send": (q[3:6].copy(), q[6:9].copy()),
@@ -55,7 +55,11 @@ def test_partition_consistency(dim, cells, P):
         lo, hi = d["own"]
         assert np.all(owner[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]] == -1)
         owner[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]] = r
-        assert d["n_own"] == np.prod(hi - lo)
+        # the owned box is numbered with odd pitches in all but the slowest direction (part.h: no power-of-two strides); the gaps are dummy rows
+        ext = hi - lo
+        want = [int(ext[k]) + (1 if (k < dim - 1 and ext[k] > 1 and ext[k] % 2 == 0) else 0) for k in range(2)]
+        assert list(d["pitch"]) == want
+        assert d["n_own"] == want[0] * want[1] * ext[2]
     assert np.all(owner >= 0)
     # a node on a cut plane belongs to the lower rank (priority.cc:200-222: master = lowest rank)
     if P[0] > 1:
@@ -72,10 +76,12 @@ def test_partition_consistency(dim, cells, P):
             assert nb["ns"] == back[0]["nr"] == len(box_nodes(nb["send"]))
             for x in box_nodes(nb["recv"]):
                 assert owner[x[2], x[1], x[0]] == q
-        # local numbering: owned rows first (lexicographic in the owned box), ghosts after, grouped by owner, gap-free
+        # local numbering: owned rows first (lexicographic in the owned box with its pitches), ghosts after, grouped by owner, gap-free
         seen = set()
-        for i, x in enumerate(box_nodes(d["own"])):
-            assert local_index(dim, cells, P, r, x) == i
+        lo = d["own"][0]
+        for x in box_nodes(d["own"]):
+            i = (x[0] - lo[0]) + d["pitch"][0] * ((x[1] - lo[1]) + d["pitch"][1] * (x[2] - lo[2]))
+            assert local_index(dim, cells, P, r, x) == i and i < d["n_own"]
             seen.add(i)
         off = d["n_own"]
         for nb in d["nb"]:
@@ -83,7 +89,7 @@ def test_partition_consistency(dim, cells, P):
                 assert local_index(dim, cells, P, r, x) == off + i
                 seen.add(off + i)
             off += nb["nr"]
-        assert off == d["n_own"] + d["n_ghost"] and len(seen) == off
+        assert off == d["n_own"] + d["n_ghost"] and len(seen) == len(box_nodes(d["own"])) + d["n_ghost"]
         # every stencil neighbour (Kuhn directions and their negatives) of an owned node is owned or a ghost
         dirs = [v for v in itertools.product((0, 1), repeat=3) if any(v) and (dim == 3 or v[2] == 0)]
         lo, hi = d["own"]
@@ -115,7 +121,8 @@ def _worker(rank, world, port, dim, cells, P, q):
         gid = lambda x: x[0] + nn[0] * (x[1] + nn[1] * x[2])
         v = torch.full((d["n_own"] + d["n_ghost"],), -1.0, dtype=torch.float64)
         own = box_nodes(d["own"])
-        v[:d["n_own"]] = torch.tensor([float(gid(x)) for x in own], dtype=torch.float64)
+        v[:d["n_own"]] = 0.0               # dummy rows of the padded numbering stay 0
+        v[torch.tensor([local_index(dim, cells, P, rank, x) for x in own], dtype=torch.long)] = torch.tensor([float(gid(x)) for x in own], dtype=torch.float64)
         # pack (k_halo_pack), grouped send/recv into the ghost tail (comm.cu halo_exchange)
         reqs, off = [], d["n_own"]
         bufs = []

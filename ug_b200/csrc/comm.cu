@@ -757,7 +757,7 @@ int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count)
 }
 
 // ---- host-only description of the partition (no GPU needed): used by the CPU tests of the multi-rank logic ------------------
-// out[0..5] own lo/hi, out[6] n_own, out[7] n_ghost, out[8] nnb; then per neighbour k (stride 16 from out[16]):
+// out[0..5] own lo/hi, out[6] n_own (rows incl. the dummy rows of the padded numbering), out[7] n_ghost, out[8] nnb, out[9..10] pitches; then per neighbour k (stride 16 from out[16]):
 // rank, send count, recv count, send box lo/hi (6), recv box lo/hi (6)
 extern "C" int uggpu_part_describe(int dim, int cx, int cy, int cz, int px, int py, int pz, int rank, int32_t *out, int cap)
 {
@@ -766,7 +766,7 @@ extern "C" int uggpu_part_describe(int dim, int cx, int cy, int cz, int px, int 
   if (part_make(&g, dim, cells, P, rank, 0)) return uggpu_fail(UGGPU_ERROR, "cells %dx%dx%d do not divide over %dx%dx%d ranks", cx, cy, cz, px, py, pz);
   if (cap < 16 + 16 * g.nnb) return uggpu_fail(UGGPU_ERROR, "output too small");
   for (int d = 0; d < 3; d++) { out[d] = g.own.lo[d]; out[3 + d] = g.own.hi[d]; }
-  out[6] = g.n_own; out[7] = g.n_ghost; out[8] = g.nnb;
+  out[6] = g.n_own; out[7] = g.n_ghost; out[8] = g.nnb; out[9] = g.pitch[0]; out[10] = g.pitch[1];
   for (int k = 0; k < g.nnb; k++) {
     int32_t *o = out + 16 + 16 * k;
     o[0] = g.nb_rank[k]; o[1] = g.nb_send_off[k + 1] - g.nb_send_off[k]; o[2] = g.nb_recv_off[k + 1] - g.nb_recv_off[k];

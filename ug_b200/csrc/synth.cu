@@ -83,7 +83,7 @@ __device__ __forceinline__ double edge_kappa(const SynthParams &sp, const int (&
 __device__ void simplex_row(const SynthParams &sp, const PartGrid &g, int r, RowGen &rg)
 {
   int x[3];
-  part_row_coords(g, r, x);
+  if (!part_row_coords(g, r, x)) { rg.len = 0; return; }      // dummy row of the padded numbering (part.h): empty
   const bool bnd = on_boundary(g, x);
   const bool var = sp.kind == UGGPU_SYNTH_P1_VARCOEF;
   int len = 0;
@@ -111,7 +111,7 @@ __device__ void simplex_row(const SynthParams &sp, const PartGrid &g, int r, Row
 __device__ void hex_row(const SynthParams &sp, const PartGrid &g, int r, RowGen &rg)
 {
   int x[3];
-  part_row_coords(g, r, x);
+  if (!part_row_coords(g, r, x)) { rg.len = 0; return; }
   int len = 0;
   rg.cols[len] = r; rg.code[len] = 13; len++;
   for (int qz = -1; qz <= 1; qz++)
@@ -163,7 +163,7 @@ __device__ void hex_block(const SynthParams &sp, const PartGrid &g, const int (&
 __device__ void p_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int r, RowGen &rg)
 {
   int x[3];
-  part_row_coords(g, r, x);
+  if (!part_row_coords(g, r, x)) { rg.len = 0; return; }
   const int p[3] = {x[0] & 1, x[1] & 1, x[2] & 1};
   const int np = p[0] + p[1] + p[2];
   if (np == 0) {
@@ -197,8 +197,8 @@ __device__ void p_row(const SynthParams &sp, const PartGrid &g, const PartGrid &
 __device__ void r_row(const SynthParams &sp, const PartGrid &g, const PartGrid &gc, int R, RowGen &rg)
 {
   int X[3];
-  part_row_coords(gc, R, X);
   rg.len = 0;
+  if (!part_row_coords(gc, R, X)) return;
   if (!g.replicated && gc.replicated && !box_has(gc.own, X)) return;
   int len = 0;
   const int z0 = sp.dim == 3 ? -1 : 0, z1 = sp.dim == 3 ? 1 : 0;
@@ -255,7 +255,7 @@ __global__ void k_synth_fill(SynthParams sp, const PartGrid *__restrict__ g, con
   const bool blocks = WHICH == GEN_A && !is_simplex(sp.kind);
   const int bb = blocks ? sp.bs * sp.bs : 1;
   int x[3] = {0, 0, 0};
-  if (blocks && r < n) part_row_coords(*g, r, x);
+  if (blocks && r < n) (void)part_row_coords(*g, r, x);
   const int64_t spt = slice_ptr[s];
   const int w = (int)((slice_ptr[s + 1] - spt) >> 5);
   const int padcol = r < n ? r : 0;
@@ -273,7 +273,7 @@ __global__ void k_synth_flags(const PartGrid *__restrict__ g, int n, int bs, boo
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
-  part_row_coords(*g, r, x);
+  if (!part_row_coords(*g, r, x)) { vclass[r] = 0; vnclass[r] = 0; ctl[r] = 0; skip[r] = (1u << bs) - 1u; return; }      // dummy row: inert
   vclass[r] = 3;
   vnclass[r] = top ? 0 : 3;
   ctl[r] = top ? (UGGPU_CTL_NEW_DEFECT | UGGPU_CTL_FINE_GRID_DOF) : UGGPU_CTL_NEW_DEFECT;
@@ -286,8 +286,7 @@ __global__ void k_synth_rhs(SynthParams sp, const PartGrid *__restrict__ g, int 
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
-  part_row_coords(*g, r, x);
-  const bool bnd = on_boundary(*g, x);
+  const bool bnd = !part_row_coords(*g, r, x) || on_boundary(*g, x);      // dummy rows: 0
   for (int i = 0; i < sp.bs; i++) {
     double v = 0.0;
     if (!bnd) { if (sp.bs == 1) v = sp.hvol; else if (i == sp.bs - 1) v = -sp.hvol; }
@@ -301,7 +300,7 @@ __global__ void k_synth_gids(const PartGrid *__restrict__ g, int n, int64_t *ids
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int x[3];
-  part_row_coords(*g, r, x);
+  if (!part_row_coords(*g, r, x)) { ids[r] = -1; return; }      // dummy row of the padded numbering
   ids[r] = (int64_t)x[0] + (int64_t)g->nn[0] * ((int64_t)x[1] + (int64_t)g->nn[1] * x[2]);
 }
 
@@ -314,7 +313,7 @@ __global__ void k_synth_sendidx(const PartGrid *__restrict__ g, int total, int32
   while (i >= g->nb_send_off[k + 1]) k++;
   int x[3];
   box_unlex(g->nb_send[k], i - g->nb_send_off[k], x);
-  idx[i] = box_lex(g->own, x);
+  idx[i] = part_own_lex(*g, x);
 }
 
 template <int WHICH>

@@ -83,8 +83,12 @@ def parity_check(rank, world, local, kind="p1", top=5, fused=1, base=2, cycles=6
     ng = (cells[0] * 2 ** top + 1) * (cells[1] * 2 ** top + 1) * (cells[2] * 2 ** top + 1)
     if rank == 0:
         xg, bg, cnt = np.zeros((ng, bs)), np.zeros((ng, bs)), np.zeros(ng, int)
+        dummy_ok = True
         for i, xx, bb in zip(ids_all, x_all, b_all):
-            xg[i] = xx.reshape(-1, bs); bg[i] = bb.reshape(-1, bs); cnt[i] += 1
+            real = i >= 0                  # ids -1: dummy rows of the padded local numbering (part.h): must stay 0
+            xx, bb = xx.reshape(-1, bs), bb.reshape(-1, bs)
+            dummy_ok = dummy_ok and not np.any(xx[~real]) and not np.any(bb[~real])
+            xg[i[real]] = xx[real]; bg[i[real]] = bb[real]; np.add.at(cnt, i[real], 1)
         one = capi.Context(local)
         one.call("uggpu_synth_hierarchy", KINDS[kind], cells[0], cells[1], cells[2], top, one.handle("A"))
         first1, hist1 = _solve(one, top, cycles, fused)
@@ -93,7 +97,7 @@ def parity_check(rank, world, local, kind="p1", top=5, fused=1, base=2, cycles=6
         xe, be = bool(np.array_equal(xg, x1)), bool(np.array_equal(bg, b1))
         herr = float(max(np.max(np.abs(hist - hist1) / hist1), np.max(np.abs(first - first1) / first1)))
         conv = bool(hist[-1] < 0.05 * hist[bs - 1])
-        ok = bool(np.all(cnt == 1)) and xe and be and herr <= 1e-12 and conv
+        ok = bool(np.all(cnt == 1)) and dummy_ok and xe and be and herr <= 1e-12 and conv
         out = torch.tensor([1.0 if ok else 0.0, 1.0 if xe else 0.0, 1.0 if be else 0.0, herr, hist[bs - 1], hist[-1]], dtype=torch.float64, device="cuda")
     dist.broadcast(out, 0)
     o = out.cpu().tolist()
