@@ -537,7 +537,8 @@ def our_arm(args):
     # ---- multi-GPU parity, before anything is timed: the partitioned solve must be the one-GPU solve bit for bit ------------------
     parity = None
     if world > 1 and not args.no_parity:
-        parity = [mgpu.parity_check(rank, world, local, kind=k, top=t, fused=f) for k, t, f in (("p1", 5, 1), ("p1", 4, 0), ("q1", 4, 1), ("elasticity", 4, 1))]
+        parity = [mgpu.parity_check(rank, world, local, kind=k, top=t, fused=f, small_levels=sm)
+                  for k, t, f, sm in (("p1", 5, 1, True), ("p1", 5, 1, False), ("p1", 4, 0, False), ("q1", 4, 1, True), ("elasticity", 4, 1, True))]
         if not all(p["ok"] for p in parity):
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "mgpu_parity": parity}))

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ug_b200 import mgpu  # noqa: E402
 
-CASES = [("p1", 5, 1), ("p1", 5, 0), ("q1", 4, 1), ("elasticity", 4, 1), ("elasticity", 3, 0), ("p1var", 4, 1)]
+CASES = [("p1", 5, 1, True), ("p1", 5, 1, False), ("p1", 5, 0, False), ("q1", 4, 1, True), ("elasticity", 4, 1, True), ("elasticity", 3, 0, False), ("p1var", 4, 1, False)]
 
 
 def main():
@@ -22,9 +22,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok_all = True
-    for kind, top, fused in CASES:
+    for kind, top, fused, small in CASES:
         r = mgpu.parity_check(rank, world, local, kind=kind, top=int(os.environ.get("MGPU_TOP", top)), fused=fused,
-                              replicate_below=int(os.environ.get("MGPU_REPL", "5000")))
+                              replicate_below=int(os.environ.get("MGPU_REPL", "5000")), small_levels=small)
         if rank == 0:
             print(f"MGPU-CHECK {'PASS' if r['ok'] else 'FAIL'} " + json.dumps(r), flush=True)
         ok_all = ok_all and r["ok"]

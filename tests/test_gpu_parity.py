@@ -19,6 +19,9 @@ def gpu_backend(golden, request, monkeypatch):
     if fused == 2:      # fused schedule with the bulk-copy (TMA) staged smoothing kernel forced onto every scalar level
         monkeypatch.setenv("UGGPU_TMA", "1"); monkeypatch.setenv("UGGPU_TMA_MIN_ROWS", "0")
         fused = 1
+    if fused == 3:      # fused schedule; the row-class transfer (trc.cu) and the stencil-rows / exception-rows kernels (stx.cu) tried on every level, however small
+        monkeypatch.setenv("UGGPU_TRC_MIN_ROWS", "1"); monkeypatch.setenv("UGGPU_STX_MIN_ROWS", "1"); monkeypatch.setenv("UGGPU_STENCIL_MIN_FRAC", "0.05")
+        fused = 1
     be = GpuBackend(golden, fused=fused)
     yield be
     be.close()
@@ -38,6 +41,7 @@ def test_pattern_roundtrip_bitexact(golden):
     be.close()
 
 
+@pytest.mark.parametrize("gpu_backend", [1, 3], indirect=True, ids=["default", "row-forms-everywhere"])
 def test_gpu_ops_bitexact(gpu_backend, golden):
     if not has(golden, "ops"):
         pytest.skip("dump without per-call records")
@@ -45,7 +49,7 @@ def test_gpu_ops_bitexact(gpu_backend, golden):
     assert n > 10
 
 
-@pytest.mark.parametrize("gpu_backend", [0, 1, 2], indirect=True, ids=["per-call", "fused", "fused-tma"])
+@pytest.mark.parametrize("gpu_backend", [0, 1, 2, 3], indirect=True, ids=["per-call", "fused", "fused-tma", "fused-row-forms-everywhere"])
 def test_gpu_cycle_and_solve(gpu_backend, golden):
     if not has(golden, "solve"):
         pytest.skip("dump without solve records")

@@ -18,4 +18,4 @@ def test_partitioned_solve_equals_single_gpu():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith("MGPU-CHECK")]
-    assert out.returncode == 0 and len(lines) == 6 and all("PASS" in l for l in lines), out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0 and len(lines) == 7 and all("PASS" in l for l in lines), out.stdout[-3000:] + out.stderr[-3000:]

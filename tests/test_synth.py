@@ -366,7 +366,7 @@ def test_stencil_smoothing_kernel_bitexact_vs_port(monkeypatch, kind, top, minfr
     assert sten[0] == 0 and sten[1] == 0, sten                        # ... and the small levels keep the generic kernel
     cfg = dict(nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6)
     out = []
-    for name in ("stencil", "slice-stencil", "generic", "per-call", "port"):
+    for name in ("stencil", "slice-stencil", "generic", "no-row-classes", "per-call", "port"):
         # stencil: stencil rows + exception rows as two kernels (stx.cu); slice-stencil: the one-kernel form that decides per slice (UGGPU_NO_STX=1)
         if name == "generic":
             monkeypatch.setenv("UGGPU_NO_STENCIL", "1")
@@ -376,6 +376,10 @@ def test_stencil_smoothing_kernel_bitexact_vs_port(monkeypatch, kind, top, minfr
             monkeypatch.setenv("UGGPU_NO_STX", "1")
         else:
             monkeypatch.delenv("UGGPU_NO_STX", raising=False)
+        if name == "no-row-classes":       # transfer.cu's general kernels instead of the row-class form (trc.cu)
+            monkeypatch.setenv("UGGPU_NO_TRC", "1")
+        else:
+            monkeypatch.delenv("UGGPU_NO_TRC", raising=False)
         be = PortBackend(hier) if name == "port" else GpuBackend(hier, fused=0 if name == "per-call" else 1)
         for l, lv in enumerate(hier.levels):
             be.put(l, "x", np.zeros(lv.n * lv.bs)); be.put(l, "b", rhs if l == top else np.zeros(lv.n * lv.bs))

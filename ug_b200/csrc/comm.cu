@@ -134,6 +134,7 @@ static void mat_comm_free(uggpu_ctx *ctx, SellMat *m)
 {
   if (m->comm_flag) dfree(ctx, m->comm_flag, ((size_t)(m->n > 0 ? m->n : 0) + 31) / 32 + 1);
   if (m->x_comm) stx_free(ctx, m);
+  trc_free_comm(ctx, m);
 }
 
 static void level_halo_free(uggpu_ctx *ctx, Level *L)

@@ -555,6 +555,7 @@ int sell_free(uggpu_ctx *ctx, SellMat *m)
   if (m->bnd_flag) dfree(ctx, m->bnd_flag, nsl);
   if (m->comm_flag) dfree(ctx, m->comm_flag, nsl + 1);
   stx_free(ctx, m);
+  trc_free(ctx, m);
   if (m->vcode) dfree(ctx, m->vcode, (size_t)m->padded);
   if (m->vtable) dfree(ctx, m->vtable, 256);
   if (m->vt) dfree(ctx, m->vt, (size_t)m->vt_len);

@@ -24,7 +24,7 @@
 
 #define STX_THREADS 128
 #define STX_MINBLOCKS (2048 / STX_THREADS)
-#define STX_MIN_ROWS 65536          // smaller levels are launch-bound: one kernel (spmv.cu) is better than two
+#define STX_MIN_ROWS (1 << 20)      // smaller levels are launch-bound: one kernel (spmv.cu) is better than two
 
 // ---- which rows are exactly the stencil ---------------------------------------------------------------------------------------------
 template <int BS, class STEN>
@@ -410,9 +410,11 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
   ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + 3.0 * nb
                + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
   Prefetch pf = make_prefetch(ctx, A, BS);
-  // the exception rows run next to the stencil rows: on the second stream when they have to wait for other GPUs, else behind them
+  // the exception rows run NEXT to the stencil rows on a second stream: a small latency-bound kernel (1-2 % of the rows, a chain of
+  // dependent loads per row) that would otherwise leave the GPU half empty for its whole duration -- and, multi-GPU, the one that waits
+  const bool side = hk.flag || !getenv("UGGPU_STX_SAME_STREAM");
   cudaStream_t xs = ctx->stream;
-  if (hk.flag) {
+  if (side) {
     if (!ctx->halo_stream) {
       int lo = 0, hi = 0;
       CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -434,7 +436,7 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
     k_smooth_stx3<FLAGS><<<blocks, STX_THREADS, 0, ctx->stream>>>(*A->sten3, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf.dist, nsl);
   }
   KCHECK(ctx);
-  if (hk.flag) {
+  if (side) {
     CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], xs));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
   }

@@ -345,13 +345,17 @@ int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp d
   }
   static const int kenv0 = getenv("UGGPU_TR_K_RESTRICT") ? atoi(getenv("UGGPU_TR_K_RESTRICT")) : TR_K_RESTRICT;     // A/B switch
   const int kenv = hk.flag ? 1 : kenv0;                  // the comm-aware path is the one-slice-per-warp kernel
-  switch (F->bs) {
-    case 1: if (kenv >= 4) RS(1, 4) else if (kenv >= 2) RS(1, 2) else RS(1, 1) break;
-    case 2: RS(2, 1); break;
-    default: RS(3, 1); break;
+  int by_class = 0;                                      // rows by class (trc.cu) where the stencil's rows repeat a few shapes
+  UG_TRY(trc_restrict(ctx, F, C, to, from, damp, fuse, fuse ? get_mat(ctx, level - 1, A) : nullptr, tout, czero, sdamp, hk, &by_class));
+  if (!by_class) {
+    switch (F->bs) {
+      case 1: if (kenv >= 4) RS(1, 4) else if (kenv >= 2) RS(1, 2) else RS(1, 1) break;
+      case 2: RS(2, 1); break;
+      default: RS(3, 1); break;
+    }
+    KCHECK(ctx);
   }
 #undef RS
-  KCHECK(ctx);
   // every rank filled only the rows of the coarse nodes it would own (the others are 0): summing the disjoint parts
   // is the gather of the coarse defect onto every rank (agglomeration)
   if (gather) UG_TRY(allreduce_sum(ctx, to, (size_t)C->n * C->bs));
@@ -386,13 +390,17 @@ int k_interpolate(uggpu_ctx *ctx, int level, double *to, const double *from, Dam
 #define IP(BSV, KV) k_interpolate_k<BSV, KV><<<tr_blocks<KV>(F->n > 0 ? F->n : 1), TR_THREADS, 0, ctx->stream>>>(view(F->P), F->skip, to, from, damp, make_prefetch(ctx, &F->P, F->bs, KV), hk)
   static const int kenv0 = getenv("UGGPU_TR_K_INTERP") ? atoi(getenv("UGGPU_TR_K_INTERP")) : TR_K_INTERP;     // A/B switch
   const int kenv = hk.flag ? 1 : kenv0;
-  switch (F->bs) {
-    case 1: if (kenv >= 4) IP(1, 4); else if (kenv >= 2) IP(1, 2); else IP(1, 1); break;
-    case 2: if (kenv >= 2) IP(2, 2); else IP(2, 1); break;
-    default: if (kenv >= 2) IP(3, 2); else IP(3, 1); break;
+  int by_class = 0;                                      // rows by class (trc.cu)
+  UG_TRY(trc_interpolate(ctx, F, C, to, from, damp, hk, &by_class));
+  if (!by_class) {
+    switch (F->bs) {
+      case 1: if (kenv >= 4) IP(1, 4); else if (kenv >= 2) IP(1, 2); else IP(1, 1); break;
+      case 2: if (kenv >= 2) IP(2, 2); else IP(2, 1); break;
+      default: if (kenv >= 2) IP(3, 2); else IP(3, 1); break;
+    }
+    KCHECK(ctx);
   }
 #undef IP
-  KCHECK(ctx);
   if (post) UG_TRY(k_vec_op(ctx, level, 0, VOP_SCALX, to, nullptr, damp_in));
   return 0;
 }

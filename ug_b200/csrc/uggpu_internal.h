@@ -96,6 +96,7 @@ struct SellMat {
   uint32_t *xmask = nullptr;
   int32_t *xrows = nullptr;
   int nx = -1, x_comm = 0;
+  struct TrcData *trc = nullptr;  // transfer stencils: rows by class (trc.cu), built on first use
   uint8_t *comm_flag = nullptr;   // [slices] HaloK::flag of launches over this matrix' rows (comm.cu halo_comm_flag): bit 0 ghost columns, bit 1 rows to push
   int n_int = -1, n_bnd = 0;
   struct TriSched *tri[2] = {nullptr, nullptr};   // Gauss-Seidel schedules (gs.cu): lower / upper triangle in dependency-level order, built on demand
@@ -549,6 +550,13 @@ int stx_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *ti
                const HaloK &hk, int *done);
 int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, double *x, const double *y, int *done);
 int stx_free(uggpu_ctx *ctx, SellMat *m);
+// trc.cu: restriction / interpolation on stencils whose rows fall into a few classes (base column + class byte per row), exception rows as a
+// second kernel.  *done = 0: not applicable, the caller launches transfer.cu's kernels.
+int trc_interpolate(uggpu_ctx *ctx, Level *F, Level *C, double *to, const double *from, Damp damp, const HaloK &hk, int *done);
+int trc_restrict(uggpu_ctx *ctx, Level *F, Level *C, double *to, const double *from, Damp damp, bool fuse, const SellMat *Ac, double *tout, double *czero, Damp sdamp,
+                 const HaloK &hk, int *done);
+int trc_free(uggpu_ctx *ctx, SellMat *m);
+int trc_free_comm(uggpu_ctx *ctx, SellMat *m);       // only if it was built with the multi-GPU exceptions
 const uint32_t *halo_snd_bits(const Level *L);   // comm.cu: per slice, the lanes whose row is pushed to a neighbour (nullptr: no tables)   // v = damp * Diag(A)^-1 d (class-masked)
 // transfer.cu: fine `level` -> level-1; with fuse: also tout = sdamp*Diag(A_{level-1})^-1 to, czero = 0 on level-1
 int k_restrict(uggpu_ctx *ctx, int level, double *to, const double *from, Damp damp, bool fuse, int A, double *tout, double *czero, Damp sdamp,

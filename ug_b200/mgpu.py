@@ -48,8 +48,27 @@ def _solve(ctx, top, cycles, fused):
     return np.array([res.first_defect[i] for i in range(bs)]), hist
 
 
-def parity_check(rank, world, local, kind="p1", top=5, fused=1, base=2, cycles=6, replicate_below=5000):
-    """Returns a dict (the same on every rank) with ok, x_bitexact, b_bitexact, hist_relerr and what was run."""
+def parity_check(rank, world, local, kind="p1", top=5, fused=1, base=2, cycles=6, replicate_below=5000, small_levels=False):
+    """Returns a dict (the same on every rank) with ok, x_bitexact, b_bitexact, hist_relerr and what was run.
+    small_levels: the two-kernel row forms (stx.cu, trc.cu: stencil / class rows + exception rows, the multi-GPU work in the exception
+    kernels) also on levels below their size thresholds, so that a small test hierarchy takes the code paths of the bench."""
+    import os
+    import torch
+    import torch.distributed as dist
+    saved = {k: os.environ.get(k) for k in ("UGGPU_STX_MIN_ROWS", "UGGPU_TRC_MIN_ROWS")}
+    if small_levels:
+        os.environ["UGGPU_STX_MIN_ROWS"] = "2000"; os.environ["UGGPU_TRC_MIN_ROWS"] = "500"
+    try:
+        return _parity_check(rank, world, local, kind, top, fused, base, cycles, replicate_below, small_levels)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _parity_check(rank, world, local, kind, top, fused, base, cycles, replicate_below, small_levels):
     import torch
     import torch.distributed as dist
     P = ARRAYS[world]
@@ -103,5 +122,5 @@ def parity_check(rank, world, local, kind="p1", top=5, fused=1, base=2, cycles=6
     o = out.cpu().tolist()
     return {"ok": o[0] == 1.0, "x_bitexact": o[1] == 1.0, "b_bitexact": o[2] == 1.0, "hist_relerr": o[3], "defect": [o[4], o[5]], "kind": kind,
             "ranks": world, "array": list(P), "fused": fused, "unknowns": ng * bs, "partitioned_levels": nparts, "levels": top + 1,
-            "halo_exchanges": exch, "transport": transport, "cycles": cycles,
+            "halo_exchanges": exch, "transport": transport, "cycles": cycles, "row_forms_on_small_levels": bool(small_levels),
             "against": "the same solve on ONE GPU (rank 0), itself pinned bit-exactly to the oracle by tests/test_synth.py"}
