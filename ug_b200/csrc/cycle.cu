@@ -287,12 +287,85 @@ __global__ void __launch_bounds__(32) k_lu_solve_lists_block(int N, LuProg F, Lu
   for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
 }
 
+// ---- triangular sweeps with all threads: every row adds ITS terms in list order, rows overlap as far as their dependencies allow ----------
+// The one-warp sweeps above finish a row before they start the next: 2 x (active rows) x (entries per row) dependent additions, 0.9 ms
+// for the 567-row base level of the 1025 x 1025 x 769 hierarchy.  A row's sum is sequential by definition (the reference's order), but
+// different rows are independent up to the values they read: thread k takes program row k, walks its list in order and waits at an
+// entry only until the row it reads is published (flag word per row in shared memory, epoch-stamped).  The entry that reads the
+// preceding row sits at the END of a list (original connections follow the fill-in, gm/algebra.cc:1051-1078), so most of a row's sum is
+// formed while its predecessors are still busy.  Progress: dependencies point to earlier program rows, every thread takes its rows in
+// program order, the earliest unfinished row never waits; a bounded spin reports through the error word instead of hanging.
+#define LUP_SPIN_MAX (1 << 22)
+__device__ __forceinline__ bool lup_wait(volatile int *flag, int c, int epoch, int *err)
+{
+  for (int it = 0; flag[c] != epoch; it++)
+    if (it > LUP_SPIN_MAX) { atomicExch(err, UGGPU_ERROR); return false; }
+  __threadfence_block();
+  return true;
+}
+
+template <int BS, bool BACKWARD>
+__device__ __forceinline__ void lu_sweep_par(const LuProg P, const double *rhs /* forward: d */, const double *__restrict__ dinv, volatile double *vs, volatile int *flag,
+                                             int epoch, int *err)
+{
+  constexpr int BB = BS * BS;
+  for (int k = threadIdx.x; k < P.n; k += blockDim.x) {
+    const int row = P.row[k], o = P.ptr[k], cnt = P.ptr[k + 1] - o;
+    for (int e = o; e < o + cnt; e += 16) {                 // the row's list into L1 before the walk starts
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.col + e));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.val + (size_t)e * BB));
+      if (BB > 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.val + (size_t)e * BB + 16 * BB / 2));
+    }
+    double acc[BS];
+#pragma unroll
+    for (int i = 0; i < BS; i++) acc[i] = 0.0;
+    bool ok = true;
+    for (int e = o; e < o + cnt && ok; e++) {
+      const int c = P.col[e];
+      ok = lup_wait(flag, c, epoch, err);
+      if (BS == 1) {
+        acc[0] += P.val[e] * vs[c];
+      } else {
+        const double *m = P.val + (size_t)e * BB;
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double t = m[i * BS] * vs[c * BS];
+#pragma unroll
+          for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * vs[c * BS + q];
+          acc[i] += t;
+        }
+      }
+    }
+    if (BACKWARD) {
+      if (BS == 1) vs[row] = (vs[row] - acc[0]) * dinv[k];
+      else {
+        double sv[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i++) sv[i] = vs[row * BS + i] - acc[i];
+        const double *inv = dinv + (size_t)k * BB;
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = 0; j < BS; j++) sum += inv[i * BS + j] * sv[j];
+          vs[row * BS + i] = sum;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < BS; i++) vs[row * BS + i] = rhs[row * BS + i] - acc[i];
+    }
+    __threadfence_block();
+    flag[row] = epoch;
+  }
+}
+
 // ---- the whole base-level solve in ONE kernel -------------------------------------------------------------------------------------
 // `ls $I lu` around l_luiter: LinearResiduum, then per iteration v = (LU)^-1 b; b -= A v; c += v; LinearResiduum; convergence test
 // (ls.cc:637-749).  One CTA: warp 0 runs the list-ordered sweeps above, all threads the defect update (one thread per row, the row's
 // terms in VSTART->MNEXT order like k_dmatmul_k) and the norms.  The defect lives in shared memory for the duration.  No host round
 // trip: the cycle's stream is never drained in the middle (the host-driven loop base_solve_host read two norms back per cycle).
-struct BaseArgs { int N, n, maxit; double abslimit, reduction; };
+struct BaseArgs { int N, n, maxit; double abslimit, reduction; int par; };
 
 template <int BS>
 __device__ __forceinline__ void base_norm(const double *bsh, const uint8_t *__restrict__ ctl, int n, double *red, double *out)
@@ -323,10 +396,11 @@ __device__ __forceinline__ void base_norm(const double *bsh, const uint8_t *__re
 
 template <int BS>
 __global__ void __launch_bounds__(LU_THREADS) k_base_solve(SellView A, LuProg F, LuProg B, const double *__restrict__ dinv, const uint8_t *__restrict__ ctl,
-                                                           double *__restrict__ c, double *__restrict__ b, BaseArgs a)
+                                                           double *__restrict__ c, double *__restrict__ b, BaseArgs a, int *err)
 {
   extern __shared__ double smem_base[];
   double *vs = smem_base, *prod = vs + LU_MAX_N, *bsh = prod + LU_MAX_N, *red = bsh + LU_MAX_N, *nrm = red + 32 * BS, *reach = nrm + BS;
+  int *flag = reinterpret_cast<int *>(prod);             // parallel sweeps: one epoch word per row (the one-warp sweeps use the array for products)
   __shared__ int stop;
   constexpr int BB = BS * BS;
   const int tid = threadIdx.x, N = a.N;
@@ -345,8 +419,15 @@ __global__ void __launch_bounds__(LU_THREADS) k_base_solve(SellView A, LuProg F,
   __syncthreads();
   if (stop) return;
   for (int it = 0; it < a.maxit; it++) {
-    if (tid < 32) {
-      for (int i = tid; i < N; i += 32) vs[i] = 0.0;     // rows with VCLASS < ACTIVE_CLASS stay 0 (ugiter.cc:4488)
+    if (a.par) {
+      for (int i = tid; i < N; i += blockDim.x) vs[i] = 0.0;     // rows with VCLASS < ACTIVE_CLASS stay 0 (ugiter.cc:4488)
+      if (it == 0) for (int i = tid; i < a.n; i += blockDim.x) flag[i] = 0;
+      __syncthreads();
+      lu_sweep_par<BS, false>(F, bsh, dinv, vs, flag, 2 * it + 1, err);
+      __syncthreads();
+      lu_sweep_par<BS, true>(B, bsh, dinv, vs, flag, 2 * it + 2, err);
+    } else if (tid < 32) {
+      for (int i = tid; i < N; i += 32) vs[i] = 0.0;
       __syncwarp();
       if (BS == 1) { lu_sweep<false>(F, bsh, vs, prod); lu_sweep<true>(B, dinv, vs, prod); }
       else { lu_sweep_block<BS, false>(F, bsh, dinv, vs, prod); lu_sweep_block<BS, true>(B, bsh, dinv, vs, prod); }
@@ -605,7 +686,7 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   // the whole loop on the device (one CTA) when the level is held completely and the list-ordered factors exist
   if (L->lu_lo_ptr && !(ctx->comm && L->partitioned) && !getenv("UGGPU_BASE_HOST_LOOP")) {
     const LuProg F{L->lu_lo_row, L->lu_lo_ptr, L->lu_lo_col, L->lu_lo_val, L->lu_active}, B{L->lu_up_row, L->lu_up_ptr, L->lu_up_col, L->lu_up_val, L->lu_active};
-    const BaseArgs ba{L->luN, L->n, cfg->base_maxit, cfg->base_abslimit, cfg->base_reduction};
+    const BaseArgs ba{L->luN, L->n, cfg->base_maxit, cfg->base_abslimit, cfg->base_reduction, getenv("UGGPU_LU_ONE_WARP") ? 0 : 1};
     SellMat *M = get_mat(ctx, level, A);
     if (!M) return UGGPU_DESC_MISMATCH;
     const size_t smem = sizeof(double) * (3 * LU_MAX_N + 32 * UGGPU_MAX_BS + 2 * UGGPU_MAX_BS);
@@ -614,9 +695,9 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     else if (bs == 2) CUDA_TRY(cudaFuncSetAttribute(k_base_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CUDA_TRY(cudaFuncSetAttribute(k_base_solve<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(ctx, UGGPU_K_BASE, level, 8.0 * L->luN * L->luN);
-    if (bs == 1) k_base_solve<1><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
-    else if (bs == 2) k_base_solve<2><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
-    else k_base_solve<3><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba);
+    if (bs == 1) k_base_solve<1><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba, ctx->derr);
+    else if (bs == 2) k_base_solve<2><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba, ctx->derr);
+    else k_base_solve<3><<<1, LU_THREADS, smem, ctx->stream>>>(view(*M), F, B, L->lu_dinv, L->ctl, cp, bp, ba, ctx->derr);
     KCHECK(ctx);
     return 0;
   }
