@@ -287,76 +287,94 @@ __global__ void __launch_bounds__(32) k_lu_solve_lists_block(int N, LuProg F, Lu
   for (int i = threadIdx.x; i < N; i += 32) v[i] = vs[i];
 }
 
-// ---- triangular sweeps with all threads: every row adds ITS terms in list order, rows overlap as far as their dependencies allow ----------
+// ---- triangular sweeps with all warps: every row adds ITS terms in list order, rows overlap as far as their dependencies allow ----------
 // The one-warp sweeps above finish a row before they start the next: 2 x (active rows) x (entries per row) dependent additions, 0.9 ms
 // for the 567-row base level of the 1025 x 1025 x 769 hierarchy.  A row's sum is sequential by definition (the reference's order), but
-// different rows are independent up to the values they read: thread k takes program row k, walks its list in order and waits at an
-// entry only until the row it reads is published (flag word per row in shared memory, epoch-stamped).  The entry that reads the
-// preceding row sits at the END of a list (original connections follow the fill-in, gm/algebra.cc:1051-1078), so most of a row's sum is
-// formed while its predecessors are still busy.  Progress: dependencies point to earlier program rows, every thread takes its rows in
-// program order, the earliest unfinished row never waits; a bounded spin reports through the error word instead of hanging.
-#define LUP_SPIN_MAX (1 << 22)
-__device__ __forceinline__ bool lup_wait(volatile int *flag, int c, int epoch, int *err)
-{
-  for (int it = 0; flag[c] != epoch; it++)
-    if (it > LUP_SPIN_MAX) { atomicExch(err, UGGPU_ERROR); return false; }
-  __threadfence_block();
-  return true;
-}
-
+// different rows are independent up to the values they read.  Warp w takes the program rows w, w + W, ...; a row's list is walked in
+// chunks: the lanes wait TOGETHER until the rows their 32 entries read are published (an epoch word per row in shared memory), form
+// the products, lane 0 adds them in list order.  The last chunk holds only the last LUW_TAIL entries: the entry that reads the preceding
+// row sits near the END of a list (original connections follow the fill-in, gm/algebra.cc:1051-1078), so almost all of a row's sum is
+// formed while its predecessors are still busy, and what remains on the critical path is a hand-over and a few additions per row.
+// (Measured and rejected: one THREAD per row with per-lane waits -- lanes of a warp waiting for one another: 4.5 x slower than one warp.)
+// Progress: dependencies point to earlier program rows and every warp takes its rows in program order, so the earliest unfinished row
+// never waits; a bounded spin reports through the error word instead of hanging.
+#define LUW_TAIL 8
+#define LUW_SPIN_MAX (1 << 22)
 template <int BS, bool BACKWARD>
-__device__ __forceinline__ void lu_sweep_par(const LuProg P, const double *rhs /* forward: d */, const double *__restrict__ dinv, volatile double *vs, volatile int *flag,
-                                             int epoch, int *err)
+__device__ __forceinline__ void lu_sweep_warps(const LuProg P, const double *rhs /* forward: d */, const double *__restrict__ dinv, volatile double *vs, volatile int *flag,
+                                               int epoch, double *pbuf_all, int *err)
 {
   constexpr int BB = BS * BS;
-  for (int k = threadIdx.x; k < P.n; k += blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  volatile double *pbuf = pbuf_all + (size_t)warp * 32 * BS;
+  for (int k = warp; k < P.n; k += nw) {
     const int row = P.row[k], o = P.ptr[k], cnt = P.ptr[k + 1] - o;
-    for (int e = o; e < o + cnt; e += 16) {                 // the row's list into L1 before the walk starts
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.col + e));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(P.val + (size_t)e * BB));
-      if (BB > 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.val + (size_t)e * BB + 16 * BB / 2));
-    }
+    const int head = cnt > LUW_TAIL ? cnt - LUW_TAIL : 0;
     double acc[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) acc[i] = 0.0;
-    bool ok = true;
-    for (int e = o; e < o + cnt && ok; e++) {
-      const int c = P.col[e];
-      ok = lup_wait(flag, c, epoch, err);
-      if (BS == 1) {
-        acc[0] += P.val[e] * vs[c];
+    int a = 0;
+    while (a < cnt) {
+      const int b = a < head ? (a + 32 < head ? a + 32 : head) : cnt;
+      const bool have = a + lane < b;
+      const int e = o + a + lane;
+      const int c = have ? P.col[e] : 0;
+      double m[BB];
+      if (have) {
+#pragma unroll
+        for (int q = 0; q < BB; q++) m[q] = P.val[(size_t)e * BB + q];
+      }
+      for (int it = 0; !__all_sync(0xffffffffu, !have || flag[c] == epoch); it++)
+        if (it > LUW_SPIN_MAX) { if (lane == 0) atomicExch(err, UGGPU_ERROR); break; }
+      __threadfence_block();
+      if (have) {
+        if (BS == 1) pbuf[lane] = m[0] * vs[c];
+        else {
+#pragma unroll
+          for (int i = 0; i < BS; i++) {
+            double t = m[i * BS] * vs[c * BS];
+#pragma unroll
+            for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * vs[c * BS + q];
+            pbuf[lane * BS + i] = t;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        for (int kk = 0; kk < b - a; kk++) {
+#pragma unroll
+          for (int i = 0; i < BS; i++) acc[i] += pbuf[kk * BS + i];
+        }
+      }
+      __syncwarp();
+      a = b;
+    }
+    if (lane == 0) {
+      if (BACKWARD) {
+        if (BS == 1) vs[row] = (vs[row] - acc[0]) * dinv[k];
+        else {
+          double sv[BS], out[BS];
+#pragma unroll
+          for (int i = 0; i < BS; i++) sv[i] = vs[row * BS + i] - acc[i];
+          const double *inv = dinv + (size_t)k * BB;
+#pragma unroll
+          for (int i = 0; i < BS; i++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < BS; j++) sum += inv[i * BS + j] * sv[j];
+            out[i] = sum;
+          }
+#pragma unroll
+          for (int i = 0; i < BS; i++) vs[row * BS + i] = out[i];
+        }
       } else {
-        const double *m = P.val + (size_t)e * BB;
 #pragma unroll
-        for (int i = 0; i < BS; i++) {
-          double t = m[i * BS] * vs[c * BS];
-#pragma unroll
-          for (int q = 1; q < BS; q++) t = t + m[i * BS + q] * vs[c * BS + q];
-          acc[i] += t;
-        }
+        for (int i = 0; i < BS; i++) vs[row * BS + i] = rhs[row * BS + i] - acc[i];
       }
+      __threadfence_block();
+      flag[row] = epoch;
     }
-    if (BACKWARD) {
-      if (BS == 1) vs[row] = (vs[row] - acc[0]) * dinv[k];
-      else {
-        double sv[BS];
-#pragma unroll
-        for (int i = 0; i < BS; i++) sv[i] = vs[row * BS + i] - acc[i];
-        const double *inv = dinv + (size_t)k * BB;
-#pragma unroll
-        for (int i = 0; i < BS; i++) {
-          double sum = 0.0;
-#pragma unroll
-          for (int j = 0; j < BS; j++) sum += inv[i * BS + j] * sv[j];
-          vs[row * BS + i] = sum;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < BS; i++) vs[row * BS + i] = rhs[row * BS + i] - acc[i];
-    }
-    __threadfence_block();
-    flag[row] = epoch;
+    __syncwarp();
   }
 }
 
@@ -400,7 +418,8 @@ __global__ void __launch_bounds__(LU_THREADS) k_base_solve(SellView A, LuProg F,
 {
   extern __shared__ double smem_base[];
   double *vs = smem_base, *prod = vs + LU_MAX_N, *bsh = prod + LU_MAX_N, *red = bsh + LU_MAX_N, *nrm = red + 32 * BS, *reach = nrm + BS;
-  int *flag = reinterpret_cast<int *>(prod);             // parallel sweeps: one epoch word per row (the one-warp sweeps use the array for products)
+  int *flag = reinterpret_cast<int *>(prod);             // all-warp sweeps: one epoch word per row (the one-warp sweeps use the array for products)
+  double *pbuf = reach + BS;                             // ... and 32 * BS products per warp
   __shared__ int stop;
   constexpr int BB = BS * BS;
   const int tid = threadIdx.x, N = a.N;
@@ -423,9 +442,9 @@ __global__ void __launch_bounds__(LU_THREADS) k_base_solve(SellView A, LuProg F,
       for (int i = tid; i < N; i += blockDim.x) vs[i] = 0.0;     // rows with VCLASS < ACTIVE_CLASS stay 0 (ugiter.cc:4488)
       if (it == 0) for (int i = tid; i < a.n; i += blockDim.x) flag[i] = 0;
       __syncthreads();
-      lu_sweep_par<BS, false>(F, bsh, dinv, vs, flag, 2 * it + 1, err);
+      lu_sweep_warps<BS, false>(F, bsh, dinv, vs, flag, 2 * it + 1, pbuf, err);
       __syncthreads();
-      lu_sweep_par<BS, true>(B, bsh, dinv, vs, flag, 2 * it + 2, err);
+      lu_sweep_warps<BS, true>(B, bsh, dinv, vs, flag, 2 * it + 2, pbuf, err);
     } else if (tid < 32) {
       for (int i = tid; i < N; i += 32) vs[i] = 0.0;
       __syncwarp();
@@ -689,7 +708,7 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     const BaseArgs ba{L->luN, L->n, cfg->base_maxit, cfg->base_abslimit, cfg->base_reduction, getenv("UGGPU_LU_ONE_WARP") ? 0 : 1};
     SellMat *M = get_mat(ctx, level, A);
     if (!M) return UGGPU_DESC_MISMATCH;
-    const size_t smem = sizeof(double) * (3 * LU_MAX_N + 32 * UGGPU_MAX_BS + 2 * UGGPU_MAX_BS);
+    const size_t smem = sizeof(double) * (3 * LU_MAX_N + 32 * UGGPU_MAX_BS + 2 * UGGPU_MAX_BS + (LU_THREADS / 32) * 32 * UGGPU_MAX_BS);
     // per device and cheap: set on every call (a process may drive several devices)
     if (bs == 1) CUDA_TRY(cudaFuncSetAttribute(k_base_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else if (bs == 2) CUDA_TRY(cudaFuncSetAttribute(k_base_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
