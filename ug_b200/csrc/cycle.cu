@@ -310,17 +310,38 @@ __device__ __forceinline__ void lu_sweep_warps(const LuProg P, const double *rhs
   for (int k = warp; k < P.n; k += nw) {
     const int row = P.row[k], o = P.ptr[k], cnt = P.ptr[k + 1] - o;
     const int head = cnt > LUW_TAIL ? cnt - LUW_TAIL : 0;
+    // what the END of the row needs is requested first: the tail chunk's entries, the right-hand side / inverse diagonal
+    const bool thave = head + lane < cnt;
+    const int tc = thave ? P.col[o + head + lane] : 0;
+    double tm[BB], fin[BB];
+    if (thave) {
+#pragma unroll
+      for (int q = 0; q < BB; q++) tm[q] = P.val[(size_t)(o + head + lane) * BB + q];
+    }
+    if (lane == 0) {
+      if (BACKWARD) {
+#pragma unroll
+        for (int q = 0; q < BB; q++) fin[q] = dinv[(size_t)k * BB + q];
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; i++) fin[i] = rhs[row * BS + i];
+      }
+    }
     double acc[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) acc[i] = 0.0;
     int a = 0;
     while (a < cnt) {
-      const int b = a < head ? (a + 32 < head ? a + 32 : head) : cnt;
+      const bool tail = a >= head;
+      const int b = tail ? cnt : (a + 32 < head ? a + 32 : head);
       const bool have = a + lane < b;
       const int e = o + a + lane;
-      const int c = have ? P.col[e] : 0;
+      const int c = tail ? tc : (have ? P.col[e] : 0);
       double m[BB];
-      if (have) {
+      if (tail) {
+#pragma unroll
+        for (int q = 0; q < BB; q++) m[q] = tm[q];
+      } else if (have) {
 #pragma unroll
         for (int q = 0; q < BB; q++) m[q] = P.val[(size_t)e * BB + q];
       }
@@ -351,17 +372,16 @@ __device__ __forceinline__ void lu_sweep_warps(const LuProg P, const double *rhs
     }
     if (lane == 0) {
       if (BACKWARD) {
-        if (BS == 1) vs[row] = (vs[row] - acc[0]) * dinv[k];
+        if (BS == 1) vs[row] = (vs[row] - acc[0]) * fin[0];
         else {
           double sv[BS], out[BS];
 #pragma unroll
           for (int i = 0; i < BS; i++) sv[i] = vs[row * BS + i] - acc[i];
-          const double *inv = dinv + (size_t)k * BB;
 #pragma unroll
           for (int i = 0; i < BS; i++) {
             double sum = 0.0;
 #pragma unroll
-            for (int j = 0; j < BS; j++) sum += inv[i * BS + j] * sv[j];
+            for (int j = 0; j < BS; j++) sum += fin[i * BS + j] * sv[j];
             out[i] = sum;
           }
 #pragma unroll
@@ -369,7 +389,7 @@ __device__ __forceinline__ void lu_sweep_warps(const LuProg P, const double *rhs
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < BS; i++) vs[row * BS + i] = rhs[row * BS + i] - acc[i];
+        for (int i = 0; i < BS; i++) vs[row * BS + i] = fin[i] - acc[i];
       }
       __threadfence_block();
       flag[row] = epoch;
