@@ -163,7 +163,7 @@ static int p2p_reset(uggpu_ctx *ctx, Comm *c)
   if (!c->p2p_tried) return 0;
   cudaStreamSynchronize(ctx->stream);
   for (int l = 0; l < UGGPU_MAX_LEVELS; l++) level_halo_free(ctx, &ctx->lev[l]);
-  for (int q = 0; q < P2P_MAX_RANKS; q++) if (c->peers[q].base) { cudaIpcCloseMemHandle(c->peers[q].base); c->peers[q] = Peer(); }
+  for (int q = 0; q < P2P_MAX_RANKS; q++) c->peers[q] = Peer();      // the mappings stay in c->opened until the communicator goes
   if (c->win) { c->graveyard.push_back({c->win, c->win_bytes}); c->win = nullptr; }     // neighbours may still have it mapped
   c->p2p_tried = false;
   c->mode = MODE_NCCL;
@@ -339,6 +339,23 @@ __global__ void k_comm_flag(SellView A, int n_owned, const uint32_t *__restrict_
   if ((threadIdx.x & 31) == 0) flag[r >> 5] = (ghost ? 1 : 0) | ((snd_bits && snd_bits[r >> 5]) ? 2 : 0);
 }
 
+// offset of a device pointer inside the allocation its IPC handle stands for (cudaMalloc packs small allocations into shared blocks; the
+// handle of such a pointer is the block's, and the importer gets the block's base)
+typedef int (*GetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
+static bool ipc_offset(const void *p, int64_t *offset)
+{
+  static GetAddressRangeFn range = nullptr;
+  if (!range) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) range = (GetAddressRangeFn)fn; else cudaGetLastError();
+  }
+  unsigned long long base = 0; size_t size = 0;
+  if (!range || range(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return false;
+  *offset = (int64_t)((unsigned long long)(uintptr_t)p - base);
+  return true;
+}
+
 static bool level_comm(const uggpu_ctx *ctx, const Level *L) { return ctx->comm && L->exists && L->partitioned && L->nnb > 0; }
 
 // Collective, at the first halo operation after the set of partitioned levels changed: chooses the transport, allocates my flag block
@@ -365,8 +382,8 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
   }
   half = (half + 31) & ~(int64_t)31;
   if (want != MODE_WINDOW) half = 0;
-  struct Info { cudaIpcMemHandle_t h; int64_t half; int64_t ok; };
-  static_assert(sizeof(Info) == 80, "Info layout");
+  struct Info { cudaIpcMemHandle_t h; int64_t half; int64_t ok; int64_t offset; };
+  static_assert(sizeof(Info) == 88, "Info layout");
   Info mine;
   memset(&mine, 0, sizeof mine);
   mine.half = half; mine.ok = 0;
@@ -375,7 +392,7 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
     if (dev_alloc(ctx, (void **)&c->win, c->win_bytes) == 0 && (c->push_counter || dalloc(ctx, &c->push_counter, 1) == 0)) {
       cudaMemsetAsync(c->win, 0, c->win_bytes, ctx->stream);
       cudaMemsetAsync(c->push_counter, 0, sizeof(unsigned int), ctx->stream);
-      if (cudaIpcGetMemHandle(&mine.h, c->win) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
+      if (ipc_offset(c->win, &mine.offset) && cudaIpcGetMemHandle(&mine.h, c->win) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
     }
   }
   c->half = half;
@@ -393,8 +410,12 @@ static int p2p_setup(uggpu_ctx *ctx, Comm *c)
     for (int q = 0; q < c->nranks && ok; q++) {
       if (!nb[q] || q == c->rank) continue;
       void *ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-      c->peers[q].base = (unsigned char *)ptr;
+      for (auto &o : c->opened) if (o.rank == q && memcmp(&o.h, &all[q].h, sizeof(cudaIpcMemHandle_t)) == 0) ptr = o.ptr;
+      if (!ptr) {
+        if (cudaIpcOpenMemHandle(&ptr, all[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->opened.push_back(Opened{q, all[q].h, ptr});
+      }
+      c->peers[q].base = (unsigned char *)ptr + all[q].offset;
       c->peers[q].half = all[q].half;
     }
   }
@@ -506,7 +527,6 @@ static int level_halo_setup(uggpu_ctx *ctx, Comm *c, Level *L)
 // The neighbours' copies of vector v of level L (ghost transport).  Collective on first use of a (level, vector) pair: all ranks
 // exchange the IPC handle of their copy, every rank maps its neighbours'.  h_peer[k] / d_peer[k] = neighbour k's ghost region of the
 // vector at the place where MY rows start.
-typedef int (*GetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
 static int ghost_map(uggpu_ctx *ctx, Comm *c, Level *L, double *v, GhostMap **out)
 {
   LevelHalo *H = L->halo;
@@ -517,19 +537,7 @@ static int ghost_map(uggpu_ctx *ctx, Comm *c, Level *L, double *v, GhostMap **ou
   Info mine;
   memset(&mine, 0, sizeof mine);
   mine.own = (int64_t)L->n * L->bs;
-  {
-    static GetAddressRangeFn range = nullptr;
-    if (!range) {
-      void *fn = nullptr;
-      cudaDriverEntryPointQueryResult qr;
-      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) range = (GetAddressRangeFn)fn; else cudaGetLastError();
-    }
-    unsigned long long base = 0; size_t size = 0;
-    if (range && range(&base, &size, (unsigned long long)(uintptr_t)v) == 0 && cudaIpcGetMemHandle(&mine.h, v) == cudaSuccess) {
-      mine.offset = (int64_t)((unsigned long long)(uintptr_t)v - base);
-      mine.ok = 1;
-    } else cudaGetLastError();
-  }
+  if (ipc_offset(v, &mine.offset) && cudaIpcGetMemHandle(&mine.h, v) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
   Info *d_send = nullptr, *d_recv = nullptr;
   UG_TRY(dalloc(ctx, &d_send, 1));
   UG_TRY(dalloc(ctx, &d_recv, (size_t)c->nranks));
