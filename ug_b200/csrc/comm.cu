@@ -490,7 +490,7 @@ static int level_halo_setup(uggpu_ctx *ctx, Comm *c, Level *L)
   ent.reserve(idx.size());
   for (int k = 0; k < L->nnb; k++)
     for (int e = L->nb_send_off[k]; e < L->nb_send_off[k + 1]; e++) {
-      const int64_t dst = (int64_t)H->peer_recv_off[k] + (e - L->nb_send_off[k]);
+      const int64_t dst = e - L->nb_send_off[k];      // relative to the place of my rows in neighbour k's ghost region (GhostMap::h_peer[k] points there)
       if (dst >= (1 << 27) || idx[e] < 0 || idx[e] >= L->n) return uggpu_fail(UGGPU_ERROR, "halo: send list entry out of range");
       ent.push_back({idx[e], ((uint32_t)k << 27) | (uint32_t)dst});
     }
