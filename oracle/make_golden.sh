@@ -16,6 +16,10 @@ mkdir -p $G
 ./_ref/ugoracle3 --grid hex  --bs 3 --refine 2 --damp 0.6 --cycles 10 --dump $G/c4_hex3d_bs3_r2.ugh --ops --solve > /dev/null
 # C5 family: adaptively refined tets (2 uniform + 2 local refinements): partial levels, classes < 3
 ./_ref/ugoracle3 --grid tet  --refine 2 --adapt 2 --damp 0.6 --cycles 10 --dump $G/c5_tet3d_adapt.ugh --ops --solve > /dev/null
+# 2x2 blocks (plane elasticity): Cramer's rule of SolveSmallBlock (block.cc:119), the b = 2 paths of every kernel; Q1 quads with the
+# per-call records + solve + Krylov, P1 triangles with sgs as smoother
+./_ref/ugoracle2 --grid quad --bs 2 --refine 3 --damp 0.7 --cycles 8 --dump $G/c4_quad2d_bs2_r3.ugh --ops --solve > /dev/null
+./_ref/ugoracle2 --grid tri --bs 2 --refine 3 --damp 0.7 --cycles 6 --lean --smoother sgs --dump $G/sgs_tri2d_bs2_r3.ugh --ops --solve > /dev/null
 # quads with scalar unknowns (Q1 in 2D), W-cycle
 ./_ref/ugoracle2 --grid quad --refine 3 --damp 0.8 --gamma 2 --cycles 6 --dump $G/q1_quad2d_r3_w.ugh --ops --solve > /dev/null
 # ---- Gauss-Seidel family as smoother: reference classes gs / sgs / sor inside lmgc.  --lean: hierarchy + the

@@ -31,9 +31,22 @@ CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "ilu", "--beta", "0.25", "--damp", "0.9", "--cycles", "5"]),
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--smoother", "ilu", "--beta", "0.1", "--damp", "0.8", "--cycles", "4"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--smoother", "ilu", "--damp", "1.0", "--cycles", "5"]),
+    # 2x2 blocks (plane elasticity)
+    ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "4", "--damp", "0.7", "--cycles", "6"]),
+    # ---- at size: the storage forms that only switch on for large levels (fixed-width layout, L2 prefetch, multi-block reductions,
+    # the stencil-rows / exception-rows kernels, the row-class transfer) against the REFERENCE ITSELF, not only against the port.
+    # --nokrylov: the four ls / lmgc mixes only (the reference's own cg / bcgs runs at this size take minutes of CPU time)
+    ("ugoracle3", ["--grid", "tet", "--refine", "5", "--damp", "0.6", "--cycles", "5", "--nokrylov"]),                 # 33^3 = 35 937 unknowns
+    ("ugoracle3", ["--grid", "tet", "--refine", "6", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),                 # 65^3 = 274 625 unknowns
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "4", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),      # 17^3 nodes x 3
+    ("ugoracle3", ["--grid", "hex", "--refine", "5", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),                 # Q1 Poisson 33^3: 27-point rows
+    ("ugoracle2", ["--grid", "tri", "--refine", "6", "--damp", "0.8", "--cycles", "6"]),                               # C1 verbatim: 65^2 = 4 225 unknowns, 7 levels
+    ("ugoracle2", ["--grid", "tri", "--refine", "9", "--damp", "0.8", "--cycles", "4", "--nokrylov"]),                 # 513^2 = 263 169 unknowns
+    ("ugoracle3", ["--grid", "tet", "--refine", "4", "--adapt", "2", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),   # adaptive on 17^3
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
-       "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu"]
+       "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu", "quad-bs2", "tet-r5-33^3", "tet-r6-65^3", "hex-bs3-r4", "hex-q1-r5-33^3", "tri-r6-C1", "tri-r9-513^2",
+       "tet-r4-adaptive"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)
@@ -41,8 +54,8 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     path = os.path.join(ROOT, "oracle", "_ref", exe)
     if not os.path.exists(path):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
-    out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    assert sum(l.startswith("PASS") for l in lines) == 6, lines      # 4 ls/lmgc mixes + gpucg + gpubcgs
+    assert sum(l.startswith("PASS") for l in lines) == (4 if "--nokrylov" in args else 6), lines      # 4 ls/lmgc mixes [+ gpucg + gpubcgs]
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -529,7 +529,7 @@ int level_free_lu(uggpu_ctx *ctx, Level *L)
   if (L->lu_up_col) dfree(ctx, L->lu_up_col, (size_t)L->lu_up_nnz + 1);
   if (L->lu_lo_val) dfree(ctx, L->lu_lo_val, ((size_t)L->lu_lo_nnz + 1) * bbf);
   if (L->lu_up_val) dfree(ctx, L->lu_up_val, ((size_t)L->lu_up_nnz + 1) * bbf);
-  L->luN = 0; L->luA = -1; L->lu_lo_nnz = L->lu_up_nnz = L->lu_active = 0;
+  L->luN = 0; L->luA = -1; L->luGen = -1; L->lu_lo_nnz = L->lu_up_nnz = L->lu_active = 0;
   return 0;
 }
 
@@ -664,6 +664,7 @@ extern "C" int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, 
     if (N > LU_MAX_N) return uggpu_fail(UGGPU_OUT_OF_MEM, "base level has %d unknowns; the device LU handles at most %d (use a coarser base level or a host base solver)", N, LU_MAX_N);
     UG_TRY(level_free_lu(ctx, L));
     L->luN = N; L->luA = A;
+    { SellMat *M0 = get_mat(ctx, bl, A); L->luGen = M0 ? M0->gen : -1; }
     UG_TRY(dalloc(ctx, &L->lu, (size_t)N * N));
     if (N > 0) {
       CUDA_TRY(cudaMemsetAsync(L->lu, 0, (size_t)N * N * sizeof(double), ctx->stream));
@@ -718,6 +719,12 @@ static int base_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   Level *L = get_level(ctx, level);
   if (!L) return UGGPU_ERROR;
   if (!L->lu || L->luA != A) return uggpu_fail(UGGPU_ERROR, "base level %d not factored: call uggpu_lmgc_preprocess first", level);
+  {
+    SellMat *M0 = get_mat(ctx, level, A);
+    if (M0 && M0->gen != L->luGen)
+      return uggpu_fail(UGGPU_ERROR, "base level %d: the matrix values changed after the factorisation (uggpu_mat_set_values / uggpu_galerkin / uggpu_dmatcopy): "
+                                     "call uggpu_lmgc_preprocess again", level);
+  }
   int bs = L->bs;
   double *cp = get_vec(ctx, level, c), *bp = get_vec(ctx, level, b), *cc = get_vec(ctx, level, UGGPU_VEC_TMP_C);
   if (!cp || !bp || !cc) return UGGPU_DESC_MISMATCH;

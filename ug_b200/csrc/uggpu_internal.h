@@ -96,6 +96,7 @@ struct SellMat {
   uint32_t *xmask = nullptr;
   int32_t *xrows = nullptr;
   int nx = -1, x_comm = 0;
+  int64_t  gen = 0;               // value generation: bumped whenever the values change (sell_update_diag); what was derived from them (base-level LU) checks it
   struct TrcData *trc = nullptr;  // transfer stencils: rows by class (trc.cu), built on first use
   uint8_t *comm_flag = nullptr;   // [slices] HaloK::flag of launches over this matrix' rows (comm.cu halo_comm_flag): bit 0 ghost columns, bit 1 rows to push
   int n_int = -1, n_bnd = 0;
@@ -271,6 +272,7 @@ struct Level {
   // base-level dense LU (column-major, inverse diagonal stored), built by uggpu_lmgc_preprocess
   double *lu = nullptr;
   int luN = 0, luA = -1;
+  int64_t luGen = -1;            // value generation of the matrix the factorisation was made from
   // scalar levels: the rows' lower / upper entries in the order of UG's matrix lists after l_lrdecomp's fill-in (cycle.cu lu_lists)
   int32_t *lu_lo_ptr = nullptr, *lu_lo_col = nullptr, *lu_up_ptr = nullptr, *lu_up_col = nullptr, *lu_lo_row = nullptr, *lu_up_row = nullptr;
   double *lu_lo_val = nullptr, *lu_up_val = nullptr, *lu_dinv = nullptr;

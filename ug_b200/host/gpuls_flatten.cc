@@ -32,6 +32,15 @@ int NodeComps(const VECDATA_DESC *vd)
   return VD_NCMPS_IN_TYPE(vd, t0);
 }
 
+// 0-based row numbers in list order.  Every Flatten* function numbers the grids it reads ITSELF: VINDEX is a scratch field that any host
+// numproc may renumber between two calls (l_setindex of the reference is 1-based and is called by the host lu / gs / ilu PreProcess).
+static int Renumber(GRID *g)
+{
+  int n = 0;
+  for (VECTOR *v = FIRSTVECTOR(g); v != NULL; v = SUCCVC(v)) VINDEX(v) = n++;
+  return n;
+}
+
 int FlattenFlags(MULTIGRID *mg, int level, const VECDATA_DESC *x, FlatLevel &out)
 {
   GRID *g = GRID_ON_LEVEL(mg, level);
@@ -66,6 +75,7 @@ int FlattenMatrix(MULTIGRID *mg, int level, const MATDATA_DESC *A, FlatLevel &ou
 {
   GRID *g = GRID_ON_LEVEL(mg, level);
   if (g == NULL || out.n <= 0) return 1;
+  if (Renumber(g) != out.n) return 1;
   VECTOR *v0 = FIRSTVECTOR(g);
   int t0 = VTYPE(v0);
   int bs = out.bs, bb = bs * bs;
@@ -119,6 +129,7 @@ int FlattenTransfer(MULTIGRID *mg, int level, FlatLevel &out)
   GRID *cg = GRID_ON_LEVEL(mg, level - 1);
   if (fg == NULL || cg == NULL) return 1;
   int nf = out.n, nc = NVEC(cg);
+  if (Renumber(fg) != nf || Renumber(cg) != nc) return 1;
 
   // P rows are indexed by vector row; build per-node first (one node per nodal vector).
   std::vector<int32_t> pcnt(nf, 0);
@@ -194,6 +205,7 @@ int FlattenTransferIMAT(MULTIGRID *mg, int level, FlatLevel &out)
   GRID *fg = GRID_ON_LEVEL(mg, level), *cg = GRID_ON_LEVEL(mg, level - 1);
   if (fg == NULL || cg == NULL) return 2;
   const int nf = out.n, nc = NVEC(cg), bs = out.bs;
+  if (Renumber(fg) != nf || Renumber(cg) != nc) return 2;
   out.p_rowptr.assign(nf + 1, 0);
   out.p_col.clear(); out.p_w.clear();
   out.node_row.clear();

@@ -83,6 +83,8 @@ struct Mirror {
   const VECDATA_DESC *xdesc = nullptr;
   std::vector<gpuls::FlatLevel> fl;
   std::vector<char> have_level, have_transfer;
+  std::vector<const MATDATA_DESC *> level_A;     // what have_level[] refers to
+  std::vector<const VECDATA_DESC *> level_x;
   std::map<const void *, int> handles;
   std::vector<double> buf;
 
@@ -120,6 +122,8 @@ Mirror *Acquire(MULTIGRID *mg)
     m.fl.assign(MAXLEVEL, gpuls::FlatLevel());
     m.have_level.assign(MAXLEVEL, 0);
     m.have_transfer.assign(MAXLEVEL, 0);
+    m.level_A.assign(MAXLEVEL, (const MATDATA_DESC *)NULL);
+    m.level_x.assign(MAXLEVEL, (const VECDATA_DESC *)NULL);
     m.handles.clear();
   }
   m.refs++;
@@ -141,10 +145,32 @@ Mirror *Find(MULTIGRID *mg)
   return it == g_mirrors.end() ? NULL : &it->second;
 }
 
+// A PreProcess failed somewhere inside a bracket: the numprocs above it return their error without a PostProcess, so their mirror
+// references would never be given back and the NEXT solve would find a mirror that still claims to hold the (then reassembled) matrix.
+// The mirror is therefore dropped as a whole -- device context, uploaded levels, all references; the next PreProcess starts clean.
+void Destroy(MULTIGRID *mg)
+{
+  auto it = g_mirrors.find(mg);
+  if (it == g_mirrors.end()) return;
+  if (it->second.ctx) api.uggpu_ctx_destroy(it->second.ctx);
+  g_mirrors.erase(it);
+}
+
+// the mirror a numproc acquired in its PreProcess, if it still exists (Destroy after a failed PreProcess removes it)
+Mirror *Live(Mirror *held, MULTIGRID *mg)
+{
+  Mirror *m = Find(mg);
+  return (held != NULL && m == held) ? m : NULL;
+}
+#define PRE_FAIL(np_, result_) do { Destroy(NP_MG(theNP)); (np_)->m = NULL; NP_RETURN(1, result_); } while (0)
+#define PRE_FAIL_JAC(np_, result_) do { (np_)->acquired = 0; PRE_FAIL(np_, result_); } while (0)
+
 // flatten + upload matrix A and the row flags of `level` (once per PreProcess bracket)
 int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC *A)
 {
-  if (m->have_level[level]) return 0;
+  // one upload per PreProcess bracket and (level, A, x): another matrix or vector descriptor on the same level is flattened again
+  if (m->have_level[level] && m->level_A[level] == A && m->level_x[level] == x) return 0;
+  if (m->have_level[level]) { m->have_level[level] = 0; m->have_transfer[level] = 0; if (level + 1 < MAXLEVEL) m->have_transfer[level + 1] = 0; }
   gpuls::FlatLevel &f = m->fl[level];
   if (gpuls::FlattenFlags(m->mg, level, x, f)) { UserWriteF("gpuls: level %d is not a pure nodal vector format\n", level); return 1; }
   if (f.bs > UGGPU_MAX_BS) { UserWriteF("gpuls: %d components per vector exceed UGGPU_MAX_BS\n", f.bs); return 1; }
@@ -156,6 +182,7 @@ int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC 
   DEV(uggpu_mat_set(m->ctx, level, m->handle(A), f.rowptr.data(), f.col.data(), f.val.data()));
   DEV(uggpu_set_fullrefinelevel(m->ctx, FULLREFINELEVEL(m->mg)));
   m->have_level[level] = 1;
+  m->level_A[level] = A; m->level_x[level] = x;
   return 0;
 }
 
@@ -243,20 +270,20 @@ INT GpuJacPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b
   if (m == NULL) NP_RETURN(1, result[0]);
   np->m = m;
   np->acquired++;
-  if (EnsureLevel(np->m, level, x, A)) NP_RETURN(1, result[0]);
+  if (EnsureLevel(np->m, level, x, A)) PRE_FAIL_JAC(np, result[0]);
   if (np->kind == UGGPU_SM_ILU) {
     // ILUPreProcess iter.cc:5444-5476: L = copy of A (AllocMDFromMD + dmatcopy), l_ilubthdecomp(L, beta, no threshold)
     double beta[UGGPU_MAX_BS];
     for (int i = 0; i < UGGPU_MAX_BS; i++) beta[i] = i < m->bs ? np->beta[i] : 0.0;
     np->L_handle = m->handle(&np->L_handle);
-    if (api.uggpu_dmatcopy(m->ctx, level, level, UGGPU_ALL_VECTORS, np->L_handle, m->handle(A))) NP_RETURN(dev_fail("uggpu_dmatcopy"), result[0]);
+    if (api.uggpu_dmatcopy(m->ctx, level, level, UGGPU_ALL_VECTORS, np->L_handle, m->handle(A))) { dev_fail("uggpu_dmatcopy"); PRE_FAIL_JAC(np, result[0]); }
     if (api.uggpu_l_ilubthdecomp(m->ctx, level, np->L_handle, beta)) {
       PrintErrorMessage('E', "GpuIluPreProcess", "decomposition failed");      // iter.cc:5470
-      NP_RETURN(dev_fail("uggpu_l_ilubthdecomp"), result[0]);
+      { dev_fail("uggpu_l_ilubthdecomp"); PRE_FAIL_JAC(np, result[0]); }
     }
   } else if (np->kind != UGGPU_SM_JAC) {
     // l_setindex (iter.cc:1027): rows are numbered in list order by the flattening; the device builds its level schedule
-    if (api.uggpu_gs_preprocess(m->ctx, level, m->handle(A))) NP_RETURN(dev_fail("uggpu_gs_preprocess"), result[0]);
+    if (api.uggpu_gs_preprocess(m->ctx, level, m->handle(A))) { dev_fail("uggpu_gs_preprocess"); PRE_FAIL_JAC(np, result[0]); }
     np->t_handle = m->handle(&np->t_handle);
   }
   *baselevel = level;                                                      // iter.cc:908
@@ -268,7 +295,7 @@ INT GpuJacIter(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATD
 {
   NP_GPUJAC *np = (NP_GPUJAC *)theNP;
   NPIT_A(theNP) = A; NPIT_c(theNP) = x; NPIT_b(theNP) = b;
-  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
   if (m == NULL || !m->have_level[level]) { UserWriteF("%s: Iter without PreProcess\n", SmootherName(np->kind)); NP_RETURN(1, result[0]); }
   double damp[UGGPU_MAX_BS];
   VsToArray(np->damp, m->bs, damp);
@@ -347,8 +374,8 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
   np->m = Acquire(NP_MG(theNP));
   if (np->m == NULL) NP_RETURN(1, result[0]);
   np->fl = *fl; np->tl = tl;
-  for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) NP_RETURN(1, result[0]);
-  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) NP_RETURN(1, result[0]);
+  for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
+  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) PRE_FAIL(np, result[0]);
   return 0;
 }
 
@@ -356,7 +383,7 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
 INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
-  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
   if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: RestrictDefect without PreProcess (or level < 1: matrix-dependent transfer is not on the GPU path)\n"); NP_RETURN(1, result[0]); }
   double d[UGGPU_MAX_BS];
   VsToArray(damp, m->bs, d);
@@ -372,7 +399,7 @@ INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_D
 INT GpuInterpolateCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
-  Mirror *m = np->m ? np->m : Find(NP_MG(theNP));
+  Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
   if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: InterpolateCorrection without PreProcess\n"); NP_RETURN(1, result[0]); }
   double d[UGGPU_MAX_BS];
   VsToArray(damp, m->bs, d);
@@ -549,23 +576,23 @@ INT GpuLmgcPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
   if (np->m == NULL) NP_RETURN(1, result[0]);
   np->level = level;
   // same order as LmgcPreProcess iter.cc:7714-7738
-  if ((*np->Transfer->PreProcess)(np->Transfer, &(np->baselevel), level, x, b, A, result)) REP_ERR_RETURN(1);
+  if ((*np->Transfer->PreProcess)(np->Transfer, &(np->baselevel), level, x, b, A, result)) PRE_FAIL(np, result[0]);
   for (int i = np->baselevel + 1; i <= level; i++)
-    if ((*np->PreSmooth->PreProcess)(np->PreSmooth, i, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+    if ((*np->PreSmooth->PreProcess)(np->PreSmooth, i, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   if (np->PreSmooth != np->PostSmooth)
     for (int i = np->baselevel + 1; i <= level; i++)
-      if ((*np->PostSmooth->PreProcess)(np->PostSmooth, i, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+      if ((*np->PostSmooth->PreProcess)(np->PostSmooth, i, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   *baselevel = MIN(np->baselevel, level);
   if (!np->devbase && np->BaseSolver->PreProcess != NULL)
-    if ((*np->BaseSolver->PreProcess)(np->BaseSolver, *baselevel, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+    if ((*np->BaseSolver->PreProcess)(np->BaseSolver, *baselevel, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   if (((NP_GPUJAC *)np->PreSmooth)->damp[0] != ((NP_GPUJAC *)np->PostSmooth)->damp[0]) {
     UserWrite("gpulmgc: pre and post smoother must use the same damping\n");
-    NP_RETURN(1, result[0]);
+    PRE_FAIL(np, result[0]);
   }
   np->t_handle = np->m->handle(&np->t);      // the temporary np->t of Lmgc (iter.cc:7810) lives on the device only
   uggpu_lmgc_cfg cfg;
   FillCfg(np, &cfg);
-  if (api.uggpu_lmgc_preprocess(np->m->ctx, &cfg, level, np->m->handle(A))) NP_RETURN(dev_fail("uggpu_lmgc_preprocess"), result[0]);
+  if (api.uggpu_lmgc_preprocess(np->m->ctx, &cfg, level, np->m->handle(A))) { dev_fail("uggpu_lmgc_preprocess"); PRE_FAIL(np, result[0]); }
   return 0;
 }
 
@@ -575,7 +602,7 @@ INT GpuLmgcIter(NP_ITER *theNP, INT level, VECDATA_DESC *c, VECDATA_DESC *b, MAT
 {
   NP_GPULMGC *np = (NP_GPULMGC *)theNP;
   NPIT_A(theNP) = A; NPIT_c(theNP) = c; NPIT_b(theNP) = b;
-  Mirror *m = np->m;
+  Mirror *m = Live(np->m, NP_MG(theNP));
   if (m == NULL) { UserWrite("gpulmgc: Iter without PreProcess\n"); NP_RETURN(1, result[0]); }
   np->cur_c = c; np->cur_b = b; np->cur_A = A;
   uggpu_lmgc_cfg cfg;
@@ -687,18 +714,18 @@ INT GpuLsPreProcess(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA
   NPLS_A(theNP) = A; NPLS_x(theNP) = x; NPLS_b(theNP) = b;
   np->m = Acquire(NP_MG(theNP));
   if (np->m == NULL) NP_RETURN(1, result[0]);
-  if ((*np->Iter->PreProcess)(np->Iter, level, x, b, A, baselevel, result)) REP_ERR_RETURN(1);
+  if ((*np->Iter->PreProcess)(np->Iter, level, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   np->baselevel = MIN(*baselevel, level);
   // ON_SURFACE loops touch levels FULLREFINELEVEL..level
   for (int l = MIN(np->baselevel, (INT)FULLREFINELEVEL(NP_MG(theNP))); l <= level; l++)
-    if (EnsureLevel(np->m, l, x, A)) NP_RETURN(1, result[0]);
+    if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
   return 0;
 }
 
 INT GpuLsDefect(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
 {
   NP_GPULS *np = (NP_GPULS *)theNP;
-  Mirror *m = np->m;
+  Mirror *m = Live(np->m, NP_MG(theNP));
   if (m == NULL) { UserWrite("gpuls: Defect without PreProcess\n"); NP_RETURN(1, result[0]); }
   const int bl = MIN(FULLREFINELEVEL(NP_MG(theNP)), MAX(0, np->baselevel));   // ls.cc:570
   const int fr = MIN((INT)FULLREFINELEVEL(NP_MG(theNP)), level);
@@ -713,7 +740,7 @@ INT GpuLsDefect(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
 INT GpuLsResiduum(NP_LINEAR_SOLVER *theNP, INT bl, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, LRESULT *lresult)
 {
   NP_GPULS *np = (NP_GPULS *)theNP;
-  Mirror *m = np->m;
+  Mirror *m = Live(np->m, NP_MG(theNP));
   if (m == NULL) { UserWrite("gpuls: Residuum without PreProcess\n"); NP_RETURN(1, lresult->error_code); }
   const int fr = MIN((INT)FULLREFINELEVEL(NP_MG(theNP)), level);
   for (int l = fr; l <= level; l++)
@@ -730,7 +757,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
 {
   NP_GPULS *np = (NP_GPULS *)theNP;
   NP_GPULMGC *mgc = (NP_GPULMGC *)np->Iter;
-  Mirror *m = np->m;
+  Mirror *m = Live(np->m, NP_MG(theNP));
   INT PrintID = 0;
   char text[DISPLAY_WIDTH + 4];
   if (m == NULL || mgc->m == NULL) { UserWrite("gpuls: Solver without PreProcess\n"); NP_RETURN(1, lresult->error_code); }
