@@ -538,7 +538,7 @@ __global__ void k_sell_diag(int n, int bb, const int64_t *__restrict__ slice_ptr
 
 int sell_update_diag(uggpu_ctx *ctx, SellMat *m)
 {
-  m->gen++;                      // called after every change of the values
+  m->gen = ++ctx->value_gen;     // called after every change of the values
 
   if (m->n <= 0) return 0;
   const size_t nsl = (size_t)(m->n + 31) / 32;

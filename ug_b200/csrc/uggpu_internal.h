@@ -304,6 +304,7 @@ struct uggpu_ctx {
   int fullrefinelevel = 0;
   int64_t launches = 0;
   int64_t bytes = 0;
+  int64_t value_gen = 0;       // source of SellMat::gen (unique per context, so a re-created matrix never repeats a number)
   // reduction scratch
   double *partials = nullptr;  size_t partials_cap = 0;   // device
   double *dres = nullptr;                                  // device results [UGGPU_MAX_LEVELS*4*UGGPU_MAX_BS]
