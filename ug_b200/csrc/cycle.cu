@@ -783,6 +783,11 @@ struct TopFuse {       // work of the enclosing LinearSolver iteration folded in
   bool c_zero = false; // c is known to be 0 on entry (dset ls.cc:695 skipped)
   bool norm = false;   // accumulate ||b||^2 over NEW_DEFECT rows of `level` into result slot 0
   bool done_x = false, done_norm = false;
+  // another cycle follows (LinearSolver's loop): the last smoothing step also writes the damped Jacobi correction of the NEW defect, which
+  // is what the next cycle starts with (l_jac + dscalx of its first smoothing step) -- the Jacobi pass over the top level at the start
+  // of every cycle but the first disappears.  next_t: where it was written (0: not done, 1: cfg->t, 2: the second temporary)
+  bool want_t = false;
+  int next_t = 0;
 };
 
 static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A)
@@ -817,7 +822,7 @@ static inline bool use_fused(const uggpu_lmgc_cfg *cfg) { return cfg->fused && c
 // kernel stores the interface rows of c into the neighbours' ghost rows.  The same holds for every producer -> consumer pair of the
 // schedule (HaloPlan): the kernel that computes a vector pushes the rows the next kernel's ghost columns need, and the next kernel
 // waits for its neighbours at its own head -- no exchange kernels in between.
-static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf, bool push_c = false)
+static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int c, int b, int A, bool t_ready, TopFuse *tf, bool push_c = false, int t_buf = 1)
 {
   if (level <= cfg->baselevel) return base_solve(ctx, cfg, level, c, b, A);
   Level *L = get_level(ctx, level);
@@ -833,6 +838,7 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   // x is only touched by the last smoothing step: an upload of it that is still in flight (uggpu_vec_upload_async) overlaps the cycle
   if (top) { xp = get_vec_lazy(ctx, level, tf->x); if (!xp) return UGGPU_DESC_MISMATCH; }
   double *cur = tA, *oth = tB;
+  if (t_ready && t_buf == 2) { cur = tB; oth = tA; }      // the previous cycle's last step left the correction in the second temporary
   const bool part = halo_fused_available(ctx, level), cpart = halo_fused_available(ctx, level - 1);
   auto plan = [&](bool ready, double *push, int push_level) { return HaloPlan{ready, push, push_level}; };
 
@@ -869,8 +875,12 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   {
     const bool last = cfg->nu2 == 0;
     int flags = (c_zero ? SF_CSET : SF_CADD) | (last ? 0 : SF_TOUT);
-    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
-    const HaloPlan hp = plan(true, part ? (last ? (push_c ? cp : nullptr) : tB) : nullptr, level);
+    bool nt = false;
+    if (last && top) {
+      flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x));
+      if (tf->want_t && tf->norm && cfg->nu1 > 0) { flags |= SF_TOUT; tf->next_t = 2; nt = true; }
+    }
+    const HaloPlan hp = plan(true, part ? (last ? (nt ? tB : (push_c ? cp : nullptr)) : tB) : nullptr, level);
     UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0, &hp));
     c_zero = false;
     cur = tB; oth = tA;
@@ -878,8 +888,12 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   for (int i = 0; i < cfg->nu2; i++) {
     const bool last = i == cfg->nu2 - 1;
     int flags = SF_CADD | (last ? 0 : SF_TOUT);
-    if (last && top) { flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x)); }
-    const HaloPlan hp = plan(true, part ? (last ? (push_c ? cp : nullptr) : oth) : nullptr, level);
+    bool nt = false;
+    if (last && top) {
+      flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x));
+      if (tf->want_t && tf->norm && cfg->nu1 > 0) { flags |= SF_TOUT; tf->next_t = oth == tA ? 1 : 2; nt = true; }
+    }
+    const HaloPlan hp = plan(true, part ? (last ? (nt ? oth : (push_c ? cp : nullptr)) : oth) : nullptr, level);
     UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0, &hp));
     double *sw = cur; cur = oth; oth = sw;
   }
@@ -942,12 +956,15 @@ extern "C" int uggpu_ls_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
   if (sc_cmp(res->last_defect, abslimit, bs)) { res->converged = 1; return 0; }
   const Damp none = mkdamp(nullptr, 0);
   const bool surface_is_top = ctx->fullrefinelevel >= level;   // no lower-level terms in the ON_SURFACE norm
+  int next_t = 0;                                              // the previous iteration's last kernel left the next Jacobi correction there (TopFuse)
   for (int it = 0; it < maxiter; it++) {
     bool done_x = false, done_norm = false;
     if (use_fused(cfg) && level > cfg->baselevel) {
       TopFuse tf;
       tf.level = level; tf.x = x; tf.c_zero = true; tf.norm = surface_is_top;
-      UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, false, &tf));
+      tf.want_t = it + 1 < maxiter && !getenv("UGGPU_NO_NEXT_T");
+      UG_TRY(lmgc_fused(ctx, cfg, level, c, b, A, next_t != 0, &tf, false, next_t ? next_t : 1));
+      next_t = tf.next_t;
       done_x = tf.done_x; done_norm = tf.done_norm;
     } else {
       UG_TRY(uggpu_dset(ctx, level, level, UGGPU_ALL_VECTORS, c, 0.0));     // ls.cc:695

@@ -1177,6 +1177,8 @@ static int launch_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const 
     SM_CASE(SF_CSET | SF_TOUT);
     SM_CASE(SF_CADD | SF_XADD | SF_NORM);
     SM_CASE(SF_CSET | SF_XADD | SF_NORM);
+    SM_CASE(SF_CADD | SF_XADD | SF_NORM | SF_TOUT);      // last step of a cycle that another cycle follows (cycle.cu TopFuse::want_t)
+    SM_CASE(SF_CSET | SF_XADD | SF_NORM | SF_TOUT);
     SM_CASE(SF_CADD | SF_XADD);
     SM_CASE(SF_CSET | SF_XADD);
     SM_CASE(SF_CADD | SF_NORM);

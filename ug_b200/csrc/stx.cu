@@ -19,6 +19,7 @@
 // neighbouring lanes of the exception list, so their remote stores share sectors.
 #include "uggpu_internal.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -51,9 +52,39 @@ __global__ void k_stx_rowmask(const __grid_constant__ STEN st, SellView A, int n
   if (lane == 0) xmask[r >> 5] = m;
 }
 
+// copies the entries of the exception rows into the packed form (one thread per list position)
+template <int BS>
+__global__ void k_stx_pack(SellView A, const int32_t *__restrict__ xrows, int nx, const int64_t *__restrict__ xs_ptr, uint16_t *__restrict__ xs_len,
+                           int32_t *__restrict__ xs_col, double *__restrict__ xs_val)
+{
+  constexpr int BB = BS * BS;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx) return;
+  const int r = xrows[i], sl = r >> 5, lane = r & 31, pl = i & 31;
+  const int64_t sp = slice_off(A, sl);
+  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : A.col_ptr[sl];
+  const int len = (int)A.rowlen[r];
+  const bool uni = cpo < 0;
+  const int32_t *cp = uni ? A.col + UG_COLTAB(cpo) : A.col + cpo + lane;
+  const int cstride = uni ? 1 : 32, cbase = uni ? r : 0;
+  const double *vp = A.val + sp * BB + lane;          // the explicit values are always complete
+  const int64_t o = xs_ptr[i >> 5];
+  xs_len[i] = (uint16_t)len;
+  for (int j = 0; j < len; j++) {
+    xs_col[o + (int64_t)j * 32 + pl] = cp[(size_t)j * cstride] + cbase;
+    for (int k = 0; k < BB; k++) xs_val[(o + (int64_t)j * 32) * BB + (int64_t)k * 32 + pl] = vp[((size_t)j * BB + k) * 32];
+  }
+}
+
 int stx_free(uggpu_ctx *ctx, SellMat *m)
 {
   const size_t nsl = ((size_t)(m->n > 0 ? m->n : 0) + 31) / 32;
+  const size_t nxs = ((size_t)(m->nx > 0 ? m->nx : 0) + 31) / 32;
+  if (m->xs_ptr) dfree(ctx, m->xs_ptr, nxs + 1);
+  if (m->xs_len) dfree(ctx, m->xs_len, nxs * 32 + 1);
+  if (m->xs_col) dfree(ctx, m->xs_col, (size_t)m->xs_entries + 1);
+  if (m->xs_val) dfree(ctx, m->xs_val, (size_t)m->xs_entries * m->bb + 1);
+  m->xs_entries = 0;
   if (m->xmask) dfree(ctx, m->xmask, nsl + 1);
   if (m->xrows) dfree(ctx, m->xrows, (size_t)(m->nx > 0 ? m->nx : 0) + 1);
   m->nx = -1; m->x_comm = 0;
@@ -92,49 +123,71 @@ static int stx_ensure(uggpu_ctx *ctx, Level *L, SellMat *A, bool comm)
   A->nx = (int)rows.size();
   UG_TRY(dalloc(ctx, &A->xrows, rows.size() + 1));
   if (!rows.empty()) CUDA_TRY(cudaMemcpyAsync(A->xrows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // packed copy of the exception rows' entries: widths per group of 32 list positions from the row lengths
+  std::vector<uint16_t> rl((size_t)A->n);
+  if (A->n) CUDA_TRY(cudaMemcpyAsync(rl.data(), A->rowlen, sizeof(uint16_t) * rl.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const size_t nxs = (rows.size() + 31) / 32;
+  std::vector<int64_t> xp(nxs + 1, 0);
+  for (size_t g = 0; g < nxs; g++) {
+    int w = 0;
+    for (size_t i = g * 32; i < rows.size() && i < g * 32 + 32; i++) w = std::max(w, (int)rl[(size_t)rows[i]]);
+    xp[g + 1] = xp[g] + (int64_t)w * 32;
+  }
+  A->xs_entries = xp[nxs];
+  UG_TRY(dalloc(ctx, &A->xs_ptr, nxs + 1));
+  UG_TRY(dalloc(ctx, &A->xs_len, nxs * 32 + 1));
+  UG_TRY(dalloc(ctx, &A->xs_col, (size_t)A->xs_entries + 1));
+  UG_TRY(dalloc(ctx, &A->xs_val, (size_t)A->xs_entries * A->bb + 1));
+  CUDA_TRY(cudaMemcpyAsync(A->xs_ptr, xp.data(), sizeof(int64_t) * (nxs + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(A->xs_len, 0, sizeof(uint16_t) * (nxs * 32 + 1), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(A->xs_col, 0, sizeof(int32_t) * ((size_t)A->xs_entries + 1), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(A->xs_val, 0, sizeof(double) * ((size_t)A->xs_entries * A->bb + 1), ctx->stream));
+  if (A->nx > 0) {
+    const int pb = (A->nx + 255) / 256;
+    if (A->bb == 1) k_stx_pack<1><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
+    else k_stx_pack<3><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
+    KCHECK(ctx);
+  }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   A->x_comm = comm ? 1 : 0;
   return 0;
 }
 
-// ---- the generic product of ONE row on the SELL arrays, per lane (no warp cooperation: the lanes of a warp hold rows of different slices) ----
-// CG: ghost columns (index >= A.n) are gathered past L1 (see spmv.cu gather_ld)
+// ---- the product of list position i on the packed copy of the exception rows (coalesced: entry j of the warp's 32 rows is contiguous) ----
+// CG: ghost columns (index >= n_owned) are gathered past L1 (see spmv.cu gather_ld)
+struct XPack { const int64_t *ptr; const uint16_t *len; const int32_t *col; const double *val; };
 template <int BS, bool CG>
-__device__ __forceinline__ void row_product_lane(const SellView &A, int r, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
+__device__ __forceinline__ void row_product_packed(const XPack &X, int i, int n_owned, const double *__restrict__ y, double (&s)[BS], double (&dg)[BS * BS])
 {
   constexpr int BB = BS * BS;
-  const int sl = r >> 5, lane = r & 31;
-  const int64_t sp = slice_off(A, sl);
-  const int64_t cpo = (A.fixed_w && A.col_ptr == A.slice_ptr) ? sp : __ldg(A.col_ptr + sl);
-  const int len = (int)A.rowlen[r];
-  const bool uni = cpo < 0;
-  const int32_t *__restrict__ cp = uni ? A.col + UG_COLTAB(cpo) : A.col + cpo + lane;
-  const int cstride = uni ? 1 : 32, cbase = uni ? r : 0;
-  const bool vsh = uni && A.vt && UG_VALTAB(cpo) >= 0;
-  const double *__restrict__ vp = vsh ? A.vt + UG_VALTAB(cpo) : A.val + sp * BB + lane;
-  const int vstride = vsh ? 1 : 32;
+  const int pl = i & 31;
+  const int64_t o = __ldg(X.ptr + (i >> 5));
+  const int len = (int)X.len[i];
+  const int32_t *__restrict__ cp = X.col + o + pl;
+  const double *__restrict__ vp = X.val + o * BB + pl;
 #pragma unroll
-  for (int i = 0; i < BS; i++) s[i] = 0.0;
+  for (int q = 0; q < BS; q++) s[q] = 0.0;
 #pragma unroll
   for (int k = 0; k < BB; k++) dg[k] = 0.0;
 #pragma unroll 4
   for (int j = 0; j < len; j++) {
-    const int c = __ldg(cp + (size_t)j * cstride) + cbase;
+    const int c = __ldg(cp + (size_t)j * 32);
     double m[BB], w[BS];
 #pragma unroll
-    for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * vstride);
+    for (int k = 0; k < BB; k++) m[k] = __ldg(vp + ((size_t)j * BB + k) * 32);
 #pragma unroll
-    for (int i = 0; i < BS; i++) w[i] = (CG && c >= A.n) ? __ldcg(y + (size_t)c * BS + i) : y[(size_t)c * BS + i];
+    for (int q = 0; q < BS; q++) w[q] = (CG && c >= n_owned) ? __ldcg(y + (size_t)c * BS + q) : y[(size_t)c * BS + q];
     if (j == 0) {
 #pragma unroll
       for (int k = 0; k < BB; k++) dg[k] = m[k];
     }
 #pragma unroll
-    for (int i = 0; i < BS; i++) {
-      double acc = m[i * BS] * w[0];
+    for (int q = 0; q < BS; q++) {
+      double acc = m[q * BS] * w[0];
 #pragma unroll
-      for (int q = 1; q < BS; q++) acc = acc + m[i * BS + q] * w[q];
-      s[i] += acc;
+      for (int t = 1; t < BS; t++) acc = acc + m[q * BS + t] * w[t];
+      s[q] += acc;
     }
   }
 }
@@ -320,7 +373,7 @@ __global__ void __launch_bounds__(STX_THREADS, STX3_MINBLOCKS) k_smooth_stx3(con
 // ---- kernel 2: the exception rows, one thread per row ----------------------------------------------------------------------------------
 // COMM (multi-GPU, HaloK): block 0 publishes / watches, every warp waits for this SM's go word before it gathers ghost columns or pushes
 template <int BS, int FLAGS, bool COMM>
-__global__ void __launch_bounds__(STX_THREADS) k_smooth_xrows(SellView A, const int32_t *__restrict__ xrows, int nx, const uint8_t *__restrict__ vclass,
+__global__ void __launch_bounds__(STX_THREADS) k_smooth_xrows(XPack X, int n_owned, const int32_t *__restrict__ xrows, int nx, const uint8_t *__restrict__ vclass,
                                                               const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                               double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err, HaloK hk)
 {
@@ -333,7 +386,7 @@ __global__ void __launch_bounds__(STX_THREADS) k_smooth_xrows(SellView A, const 
   for (int q = 0; q < BS; q++) nrm[q] = 0.0;
   if (live) {
     double s[BS], dg[BS * BS], pv[BS];
-    row_product_lane<BS, COMM>(A, r, tin, s, dg);
+    row_product_packed<BS, COMM>(X, i, n_owned, tin, s, dg);
     smooth_row_tail<BS, FLAGS>(r, s, dg, vclass, ctl, tin, b, c, tout, damp, x, err, COMM ? hk.sel : 0, pv, nrm);
     if (COMM && hk.peer) halo_push_row<BS>(hk, r, pv);
   }
@@ -370,7 +423,7 @@ __global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_dmatmul_stx(cons
 }
 
 template <int BS, int OP>
-__global__ void __launch_bounds__(STX_THREADS) k_dmatmul_xrows(SellView A, const int32_t *__restrict__ xrows, int nx, uint8_t bit, const uint8_t *__restrict__ ctl,
+__global__ void __launch_bounds__(STX_THREADS) k_dmatmul_xrows(XPack X, int n_owned, const int32_t *__restrict__ xrows, int nx, uint8_t bit, const uint8_t *__restrict__ ctl,
                                                                double *__restrict__ x, const double *__restrict__ y)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +431,7 @@ __global__ void __launch_bounds__(STX_THREADS) k_dmatmul_xrows(SellView A, const
   const int r = __ldg(xrows + i);
   if (bit && !(ctl[r] & bit)) return;
   double s[BS], dg[BS * BS];
-  row_product_lane<BS, false>(A, r, y, s, dg);
+  row_product_packed<BS, false>(X, i, n_owned, y, s, dg);
 #pragma unroll
   for (int q = 0; q < BS; q++) {
     const size_t k = (size_t)r * BS + q;
@@ -426,8 +479,9 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
     CUDA_TRY(cudaStreamWaitEvent(xs, ctx->halo_ev[0], 0));
   }
   double *xpart = ctx->partials + (size_t)blocks * BS;
-  if (hk.flag) k_smooth_xrows<BS, FLAGS, true><<<xblocks, STX_THREADS, 0, xs>>>(view(*A), A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
-  else if (A->nx > 0 || (FLAGS & SF_NORM)) k_smooth_xrows<BS, FLAGS, false><<<xblocks, STX_THREADS, 0, xs>>>(view(*A), A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
+  const XPack X{A->xs_ptr, A->xs_len, A->xs_col, A->xs_val};
+  if (hk.flag) k_smooth_xrows<BS, FLAGS, true><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
+  else if (A->nx > 0 || (FLAGS & SF_NORM)) k_smooth_xrows<BS, FLAGS, false><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
   KCHECK(ctx);
   if (BS == 1) {
     if (A->sten.w == 15) k_smooth_stx<FLAGS, 15><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl);
@@ -457,6 +511,8 @@ static int stx_smooth1(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const do
     SM_CASE(SF_CSET | SF_TOUT);
     SM_CASE(SF_CADD | SF_XADD | SF_NORM);
     SM_CASE(SF_CSET | SF_XADD | SF_NORM);
+    SM_CASE(SF_CADD | SF_XADD | SF_NORM | SF_TOUT);      // last step of a cycle that another cycle follows (cycle.cu TopFuse::want_t)
+    SM_CASE(SF_CSET | SF_XADD | SF_NORM | SF_TOUT);
     SM_CASE(SF_CADD | SF_XADD);
     SM_CASE(SF_CSET | SF_XADD);
     SM_CASE(SF_CADD | SF_NORM);
@@ -494,9 +550,10 @@ int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, doubl
 #undef DS
   KCHECK(ctx);
   if (xblocks > 0) {
-    if (op == 0) k_dmatmul_xrows<1, 0><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
-    else if (op == 1) k_dmatmul_xrows<1, 1><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
-    else k_dmatmul_xrows<1, 2><<<xblocks, STX_THREADS, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, bit, L->ctl, x, y);
+    const XPack X{A->xs_ptr, A->xs_len, A->xs_col, A->xs_val};
+    if (op == 0) k_dmatmul_xrows<1, 0><<<xblocks, STX_THREADS, 0, ctx->stream>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
+    else if (op == 1) k_dmatmul_xrows<1, 1><<<xblocks, STX_THREADS, 0, ctx->stream>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
+    else k_dmatmul_xrows<1, 2><<<xblocks, STX_THREADS, 0, ctx->stream>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
     KCHECK(ctx);
   }
   return 0;

@@ -96,6 +96,10 @@ struct SellMat {
   uint32_t *xmask = nullptr;
   int32_t *xrows = nullptr;
   int nx = -1, x_comm = 0;
+  // ... and the exception rows' entries once more, packed: SELL-32 over the LIST (entry j of list position i at xs_ptr[i >> 5] + 32 j + (i & 31),
+  // explicit columns, explicit values) -- gathering them from the matrix' own slices costs a 32-byte sector per 4- or 8-byte entry
+  int64_t *xs_ptr = nullptr; uint16_t *xs_len = nullptr; int32_t *xs_col = nullptr; double *xs_val = nullptr;
+  int64_t xs_entries = 0;
   int64_t  gen = 0;               // value generation: bumped whenever the values change (sell_update_diag); what was derived from them (base-level LU) checks it
   struct TrcData *trc = nullptr;  // transfer stencils: rows by class (trc.cu), built on first use
   uint8_t *comm_flag = nullptr;   // [slices] HaloK::flag of launches over this matrix' rows (comm.cu halo_comm_flag): bit 0 ghost columns, bit 1 rows to push
