@@ -232,13 +232,18 @@ static int launch_dmatmul(uggpu_ctx *ctx, Level *L, const SellMat *A, int op, in
   int blocks = (L->n + SPMV_THREADS - 1) / SPMV_THREADS;
   SellView v = view(*A);
   const double nb = 8.0 * BS * L->n;
-  ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
-  const Prefetch pf = make_prefetch(ctx, A, BS);
   {
+    // matrices with a dominant stencil, large levels: stencil rows and exception rows as two kernels (stx.cu); their byte model differs
+    const double mb = stx_matrix_bytes(L, A);
     int done = 0;
-    UG_TRY(stx_dmatmul(ctx, L, const_cast<SellMat *>(A), op, bit, x, y, &done));
+    if (mb >= 0) {
+      ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), mb + (op == 0 ? 2.0 : 3.0) * nb);
+      UG_TRY(stx_dmatmul(ctx, L, const_cast<SellMat *>(A), op, bit, x, y, &done));
+    } else UG_TRY(stx_dmatmul(ctx, L, const_cast<SellMat *>(A), op, bit, x, y, &done));      // first use: builds the row mask (not timed)
     if (done) return 0;
   }
+  ProfScope ps(ctx, UGGPU_K_DMATMUL, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + (op == 0 ? 2.0 : 3.0) * nb);
+  const Prefetch pf = make_prefetch(ctx, A, BS);
   if (BS == 1 && (A->sten.w == 15 || A->sten.w == 27) && A->col_ptr != A->slice_ptr && !getenv("UGGPU_NO_STENCIL")) {
     const int nsl = (L->n + 31) / 32;
 #define DS(OPV, WV) k_dmatmul_sten<OPV, WV><<<blocks, SPMV_THREADS, 0, ctx->stream>>>(A->sten, v, bit, L->ctl, x, y, pf.dist, nsl)

@@ -452,6 +452,14 @@ static bool stx_applies(const Level *L, const SellMat *A)
   return L->bs == 3 && A->bb == 9 && A->sten3 != nullptr;
 }
 
+// bytes of MATRIX data one pass of the kernel pair fetches: the row mask, and the packed copy of the exception rows (values, columns, list,
+// lengths) -- the stencil rows read nothing else of the matrix.  < 0: the pair does not apply to this matrix (yet)
+double stx_matrix_bytes(const Level *L, const SellMat *A)
+{
+  if (!stx_applies(L, A) || !A->xmask) return -1.0;
+  return 4.0 * ((L->n + 31) / 32) + (double)A->xs_entries * (8.0 * A->bb + 4.0) + 6.0 * (double)(A->nx > 0 ? A->nx : 0);
+}
+
 template <int BS, int FLAGS>
 static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot, const HaloK &hk)
 {
@@ -460,7 +468,8 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
   const int xblocks = (A->nx + STX_THREADS - 1) / STX_THREADS > 0 ? (A->nx + STX_THREADS - 1) / STX_THREADS : 1;
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)(blocks + xblocks) * BS));
   const double nb = 8.0 * BS * L->n;
-  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), A->entry_bytes() + 4.0 * (L->n + 1.0) + 3.0 * nb
+  // algorithmic bytes: what the pair reads of the matrix (mask + packed exception rows), the gathered operand once, b read + write, c, tout, x
+  ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), stx_matrix_bytes(L, A) + 3.0 * nb
                + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
   Prefetch pf = make_prefetch(ctx, A, BS);
   // the exception rows run NEXT to the stencil rows on a second stream: a small latency-bound kernel (1-2 % of the rows, a chain of

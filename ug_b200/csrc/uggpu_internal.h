@@ -557,6 +557,7 @@ int stx_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *ti
                const HaloK &hk, int *done);
 int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, double *x, const double *y, int *done);
 int stx_free(uggpu_ctx *ctx, SellMat *m);
+double stx_matrix_bytes(const Level *L, const SellMat *A);   // matrix bytes one pass of the stx kernel pair fetches (< 0: not applicable / not built)
 // trc.cu: restriction / interpolation on stencils whose rows fall into a few classes (base column + class byte per row), exception rows as a
 // second kernel.  *done = 0: not applicable, the caller launches transfer.cu's kernels.
 int trc_interpolate(uggpu_ctx *ctx, Level *F, Level *C, double *to, const double *from, Damp damp, const HaloK &hk, int *done);
