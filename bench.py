@@ -387,22 +387,27 @@ def measure(spec, rt):
         vals_top = int(ctx.L.uggpu_mat_val_entries(ctx.h, top, A))      # entries whose values a sweep fetches (shared value tables)
         sten_top = int(ctx.L.uggpu_mat_stencil_slices(ctx.h, top, A)) if not os.environ.get("UGGPU_NO_STENCIL") else 0
         sten_w = round(nnz_top / max(nrows_top, 1))
+        stx = not os.environ.get("UGGPU_NO_STX") and nrows_top >= (1 << 20)
         if sten_top > 0 and bs == 1 and sten_w in (15, 27):
-            smooth_kernel = f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)"
+            smooth_kernel = (f"k_smooth_stx<*,{sten_w}> + k_smooth_xrows (fused smoothing step: rows that are exactly the stencil + the packed exception rows, two kernels side by side, finest level)"
+                             if stx else f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)")
         elif sten_top > 0 and bs == 3:
-            smooth_kernel = "k_smooth_sten3<*> (fused smoothing step, 3x3-block stencil variant, finest level)"
+            smooth_kernel = ("k_smooth_stx3<*> + k_smooth_xrows<3,*> (fused smoothing step, 3x3 blocks: stencil rows + packed exception rows, finest level)"
+                             if stx else "k_smooth_sten3<*> (fused smoothing step, 3x3-block stencil variant, finest level)")
         else:
             smooth_kernel = f"k_smooth_k<{bs},*> (fused smoothing step, finest level)"
         achieved = dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-        # SURVEY.md 8(d) counts 8 b^2 + 4 bytes per entry; the stored format fetches fewer (compressed column words, shared value tables)
-        survey_extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * dom["launches"]
+        # SURVEY.md 8(d) counts (8 b^2 + 4) bytes per entry + 4 (n + 1); the stored form fetches what uggpu_mat_pass_bytes says
+        pass_bytes = float(ctx.L.uggpu_mat_pass_bytes(ctx.h, top, A))
+        survey_extra = ((8.0 * bs * bs + 4.0) * nnz_top + 4.0 * (nrows_top + 1) - pass_bytes) * dom["launches"]
         achieved_survey = (dom["alg_bytes"] + survey_extra) / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
         total_alg = sum(v["alg_bytes"] for v in prof.values())
         out["roofline"] = {"bound": "hbm", "kernel": smooth_kernel if smoother == "jac" else f"k_dmatmul_k<{bs},2> (defect update of the smoothing step, finest level)",
                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                            "launches": dom["launches"], "avg_ms": dom["ms"] / max(dom["launches"], 1),
                            "alg_bytes_per_launch": dom["alg_bytes"] / max(dom["launches"], 1),
-                           "bytes_model": "as stored: 8 B per value fetched (slices of identical rows share value tables), compressed column words (DESIGN.md 2-3), vectors once",
+                           "bytes_model": "as stored: the matrix bytes a pass fetches (uggpu_mat_pass_bytes: row mask + packed exception rows for stencil matrices; values + compressed column words otherwise, DESIGN.md 2-3) + every vector once",
+                           "matrix_bytes_per_pass": pass_bytes,
                            "value_entries_per_entry": vals_top / max(nnz_top, 1), "stencil_slices_frac": sten_top / max((nrows_top + 31) // 32, 1),
                            "achieved_survey_model": achieved_survey, "frac_survey_model": achieved_survey / peak,
                            "survey_model": "SURVEY.md 8(d): 8 b^2 + 4 B per matrix entry whatever the storage; above 1 means the matrix stream no longer crosses HBM",
@@ -465,8 +470,8 @@ def measure(spec, rt):
                 ctx.call("uggpu_prof_enable", 0)
                 if c2.value > 0 and m2.value > 0:
                     gb = b2.value / (m2.value * 1e-3) / 1e9
-                    extra = (4.0 * (nnz_top - words_top) + 8.0 * bs * bs * (nnz_top - vals_top)) * c2.value
-                    out["spmv"] = {"kernel": (f"k_dmatmul_sten<2,{sten_w}>" if (sten_top > 0 and bs == 1 and sten_w in (15, 27)) else f"k_dmatmul_k<{bs},2>") + " (x -= A y, finest level)",
+                    extra = ((8.0 * bs * bs + 4.0) * nnz_top + 4.0 * (nrows_top + 1) - pass_bytes) * c2.value
+                    out["spmv"] = {"kernel": ((f"k_dmatmul_stx<2,{sten_w}> + k_dmatmul_xrows" if stx else f"k_dmatmul_sten<2,{sten_w}>") if (sten_top > 0 and bs == 1 and sten_w in (15, 27)) else f"k_dmatmul_k<{bs},2>") + " (x -= A y, finest level)",
                                    "launches": int(c2.value), "avg_ms": m2.value / c2.value, "alg_bytes_per_launch": b2.value / c2.value, "GBps": gb, "frac": gb / peak,
                                    "GBps_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9, "frac_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9 / peak}
             except Exception as e:          # a reported figure, never a reason to lose the bench line

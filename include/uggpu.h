@@ -119,6 +119,10 @@ int64_t uggpu_mat_val_entries(uggpu_ctx *ctx, int level, int mat);
  * more than half of the slices; 0 when there is none.  Such matrices run the stencil variant of the fused smoothing kernel
  * (tables in the kernel's constant bank; same arithmetic, same results; UGGPU_NO_STENCIL=1 switches it off). */
 int64_t uggpu_mat_stencil_slices(uggpu_ctx *ctx, int level, int mat);
+/* Bytes of MATRIX data one SpMV-type pass over the matrix fetches from HBM in its current storage form (values that are read, column
+ * words, row lengths / slice offsets; for matrices served by the stencil-rows / exception-rows kernels: the row mask and the packed
+ * exception rows).  What the roofline figures count for the matrix; SURVEY.md 8(d)'s model is (8 b^2 + 4) * nnz + 4 (n + 1). */
+double uggpu_mat_pass_bytes(uggpu_ctx *ctx, int level, int mat);
 int uggpu_mat_free(uggpu_ctx *ctx, int level, int mat);
 /* Standard (geometric) transfer stencils between `level` and level-1 (np/algebra/transgrid.cc:117-336):
  * P: p_rowptr[n_fine+1], p_col (coarse row), p_w (GNs weight, zeros dropped, corner order);
@@ -346,6 +350,17 @@ int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x);
  * `replicate_below` rows (and level 0) are held completely by every rank. */
 int uggpu_synth_hierarchy_part(uggpu_ctx*, int kind, int nx, int ny, int nz, int top, int A,
                                int px, int py, int pz, int rank, int64_t replicate_below);
+/* A partition the CALLER supplies -- what a ModelP application knows from DDD: the vectors this rank is master of
+ * (parallel/dddif/priority.cc:200-222) are the level's rows (uggpu_level_create with n = their number), the border / ghost copies it
+ * reads become n_ghost ghost rows at the tail of every vector, addressed by column indices >= n in uggpu_mat_set / uggpu_transfer_set.
+ * Ghost row recv_off[k] + j is the copy of the j-th row neighbour nb_rank[k] sends; send_idx[send_off[k] .. send_off[k+1]) are the owned
+ * rows neighbour k needs, in the order of ITS ghost rows (both sides enumerate an interface in the same order, the role of the sorted
+ * interface lists of parallel/ddd/if/ifcreate.cc:155-203).  Call after uggpu_level_create, before any vector of the level exists, on
+ * every rank (ranks without a neighbour on the level pass nnb = 0).  Replaces l_vector_consistent / l_ghostvector_consistent
+ * (np/algebra/ugblas.cc:398, :740) for the hot path: the entry points exchange what they read.  ug_b200/partition.py derives the
+ * lists from a UG hierarchy with the reference's own rules (RCB of the element centres lbrcb.cc:250-330, inheritance :376). */
+int uggpu_level_set_partition(uggpu_ctx *ctx, int level, int n_ghost, int64_t n_global, int nnb, const int32_t *nb_rank,
+                              const int32_t *send_off /* [nnb+1] */, const int32_t *send_idx, const int32_t *recv_off /* [nnb+1] */);
 int64_t uggpu_level_n_global(uggpu_ctx *ctx, int level);      /* rows of the level over all ranks                    */
 int uggpu_level_is_partitioned(uggpu_ctx *ctx, int level);
 int uggpu_synth_global_ids(uggpu_ctx *ctx, int level, int64_t *ids /* [uggpu_level_n] */);

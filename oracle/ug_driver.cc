@@ -97,7 +97,7 @@ struct Opt {
   double beta = 0.0;                    // ilu $beta (iter.cc:5415): diagonal modification of l_ilubthdecomp
   int baselevel = 0;                    // lmgc $b
   int barrier_n = 0, barrier_id = 0;
-  bool ops = false, solve = false, timeit = false, quiet = true, nokrylov = false;
+  bool ops = false, solve = false, timeit = false, quiet = true, nokrylov = false, elems = false;
   bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
   bool galerkin = false;                // --galerkin (with --imat): Galerkin coarse-grid operators by AssembleGalerkinByMatrix, cascaded from the top level down
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
@@ -350,8 +350,22 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
       D.i32(L("node_row", l), f.node_row);
     }
     dumpvec("rhs", vb, l);
+    if (o.elems) {
+      // elements in list order: the rows of their corner vectors, and the position of the father element in the list of the level below
+      // (-1 on level 0) -- what parallel/dddif/lbrcb.cc works on (centres of mass of the level-0 elements, sons inherit)
+      GRID *g = GRID_ON_LEVEL(mg, l);
+      std::vector<int32_t> eptr(1, 0), enodes, efather;
+      std::map<ELEMENT *, int> pos;
+      if (l > 0) { int k = 0; for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l - 1)); e; e = SUCCE(e)) pos[e] = k++; }
+      for (ELEMENT *e = FIRSTELEMENT(g); e; e = SUCCE(e)) {
+        for (int i = 0; i < CORNERS_OF_ELEM(e); i++) enodes.push_back((int32_t)VINDEX(NVECTOR(CORNER(e, i))));
+        eptr.push_back((int32_t)enodes.size());
+        efather.push_back(l > 0 && EFATHER(e) ? pos[EFATHER(e)] : -1);
+      }
+      D.i32(L("elem_ptr", l), eptr); D.i32(L("elem_nodes", l), enodes); D.i32(L("elem_father", l), efather);
+    }
     // vertex coordinates in row order (lets tests relate UG's ordering to the synthetic generator)
-    if (o.lean) continue;
+    if (o.lean && !o.elems) continue;
     std::vector<double> xyz((size_t)f.n * DIM);
     for (NODE *n = FIRSTNODE(GRID_ON_LEVEL(mg, l)); n; n = SUCCN(n))
       for (int d = 0; d < DIM; d++) xyz[(size_t)VINDEX(NVECTOR(n)) * DIM + d] = CVECT(MYVERTEX(n))[d];
@@ -672,7 +686,8 @@ int main(int argc, char **argv)
     else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
     else if (a == "--beta") o.beta = atof(nxt().c_str());
     else if (a == "--galerkin") o.galerkin = true;
-    else if (a == "--nokrylov") o.nokrylov = true;       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
+    else if (a == "--nokrylov") o.nokrylov = true;
+    else if (a == "--elems") o.elems = true;             // dump the elements (corner rows, fathers): input of the element partition (ug_b200/partition.py)       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
   int ac = 1; char *av0 = argv[0]; char **av = &av0;

@@ -66,6 +66,7 @@ def lib():
         L.uggpu_last_error.restype = C.c_char_p
         for name in ("uggpu_launch_count", "uggpu_device_bytes", "uggpu_mat_nnz", "uggpu_mat_padded_nnz", "uggpu_transfer_nnz", "uggpu_mat_col_words", "uggpu_mat_val_entries", "uggpu_mat_stencil_slices"):
             getattr(L, name).restype = C.c_int64
+        L.uggpu_mat_pass_bytes.restype = C.c_double
         L.uggpu_dset.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.uggpu_dscal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.uggpu_daxpy.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
@@ -142,6 +143,23 @@ class Context:
                 if "transfer_mode" in hier.raw:          # dumps written with `transfer $M` (oracle/ug_driver.cc --imat)
                     self.call("uggpu_transfer_set_mode", l, int(hier.raw["transfer_mode"][0]))
         self.call("uggpu_set_fullrefinelevel", int(hier.fullrefinelevel))
+
+    def upload_local_levels(self, levels, fullrefinelevel: int, bs: int, A: str = "A"):
+        """One rank's part of a partitioned hierarchy (ug_b200.partition.split): levels, partitions, flags, matrices, transfer stencils."""
+        a = self.handle(A)
+        i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        for l, lv in enumerate(levels):
+            self.call("uggpu_level_create", l, int(lv.n), int(bs))
+            if lv.partitioned:
+                self.call("uggpu_level_set_partition", l, int(lv.n_ghost), C.c_int64(int(lv.n_global)), int(lv.nb_rank.size), _p(i32(lv.nb_rank)),
+                          _p(i32(lv.send_off)), _p(i32(lv.send_idx)), _p(i32(lv.recv_off)))
+            self.call("uggpu_level_set_flags", l, _p(np.ascontiguousarray(lv.vclass)), _p(np.ascontiguousarray(lv.vnclass)),
+                      _p(np.ascontiguousarray(lv.ctl)), _p(np.ascontiguousarray(lv.skip)))
+            self.call("uggpu_mat_set", l, a, _p(i32(lv.rowptr)), _p(i32(lv.col)), _p(np.ascontiguousarray(lv.val, dtype=np.float64)))
+            if l > 0:
+                self.call("uggpu_transfer_set", l, _p(i32(lv.p_rowptr)), _p(i32(lv.p_col)), _p(np.ascontiguousarray(lv.p_w, dtype=np.float64)),
+                          _p(i32(lv.r_rowptr)), _p(i32(lv.r_col)), _p(np.ascontiguousarray(lv.r_w, dtype=np.float64)))
+        self.call("uggpu_set_fullrefinelevel", int(fullrefinelevel))
 
     def download_hierarchy(self, top: int, A: str = "A"):
         """Canonical CSR/flags/stencils of levels 0..top back on the host (ug_b200.hierarchy.Hierarchy)."""

@@ -356,7 +356,9 @@ static bool ipc_offset(const void *p, int64_t *offset)
   return true;
 }
 
-static bool level_comm(const uggpu_ctx *ctx, const Level *L) { return ctx->comm && L->exists && L->partitioned && L->nnb > 0; }
+// A partitioned level takes part in the exchanges even when THIS rank has no neighbour on it (the numbering of the comm kernels and the
+// collective set-up steps must stay the same on all ranks)
+static bool level_comm(const uggpu_ctx *ctx, const Level *L) { return ctx->comm && L->exists && L->partitioned; }
 
 // Collective, at the first halo operation after the set of partitioned levels changed: chooses the transport, allocates my flag block
 // (+ window), exchanges the IPC handles with ncclAllGather, maps the flag blocks of all ranks that are a neighbour on some level.
@@ -762,6 +764,50 @@ int allreduce_sum(uggpu_ctx *ctx, double *dptr, size_t count)
   ProfScope ps(ctx, UGGPU_K_ALLREDUCE, -2, 16.0 * (double)count);
   NCCL_TRY(nccl.AllReduce(dptr, dptr, count, ncclDouble, ncclSum, c->comm, ctx->stream));
   c->allreduces++;
+  return 0;
+}
+
+// ---- a partition the CALLER supplies (SURVEY.md 8 a13 / e): what a ModelP application knows from DDD ----------------------------------------
+// The level was created with n = the rows this rank OWNS (master vectors, parallel/dddif/priority.cc:200-222); its vectors get n_ghost more
+// rows at the tail, and column indices >= n in the level's matrices and transfer stencils address them.  Ghost row recv_off[k] + j is
+// the copy of the j-th row neighbour nb_rank[k] sends; send_idx[send_off[k] .. send_off[k+1]) are my rows neighbour k needs, in the order
+// of ITS ghost rows -- both sides enumerate an interface in the same order (the role of the sorted interface lists of
+// parallel/ddd/if/ifcreate.cc:155-203).  Call it after uggpu_level_create and before the first vector of the level exists.  From then on
+// every entry point behaves as on the synthetic partitions: halo copies in front of (or fused into) the kernels that read ghost columns,
+// global sums in the reductions.  Levels every rank holds completely are simply not given a partition.
+extern "C" int uggpu_level_set_partition(uggpu_ctx *ctx, int level, int n_ghost, int64_t n_global, int nnb, const int32_t *nb_rank,
+                                         const int32_t *send_off, const int32_t *send_idx, const int32_t *recv_off)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (!ctx->comm) return uggpu_fail(UGGPU_ERROR, "uggpu_level_set_partition needs uggpu_comm_init first");
+  if (!L->vecs.empty()) return uggpu_fail(UGGPU_ERROR, "level %d already has vectors: set the partition right after uggpu_level_create", level);
+  if (n_ghost < 0 || nnb < 0 || nnb > HALO_MAX_NB || (nnb > 0 && (!nb_rank || !send_off || !recv_off)))
+    return uggpu_fail(UGGPU_ERROR, "bad partition description (n_ghost %d, %d neighbours, at most %d)", n_ghost, nnb, HALO_MAX_NB);
+  Comm *c = (Comm *)ctx->comm;
+  if (nnb > 0 && (send_off[0] != 0 || recv_off[0] != 0 || recv_off[nnb] != n_ghost)) return uggpu_fail(UGGPU_ERROR, "partition: offsets must start at 0 and recv_off must end at n_ghost");
+  for (int k = 0; k < nnb; k++) {
+    if (nb_rank[k] < 0 || nb_rank[k] >= c->nranks || nb_rank[k] == c->rank) return uggpu_fail(UGGPU_ERROR, "partition: bad neighbour rank %d", nb_rank[k]);
+    if (send_off[k + 1] < send_off[k] || recv_off[k + 1] < recv_off[k]) return uggpu_fail(UGGPU_ERROR, "partition: offsets must not decrease");
+  }
+  const int total = nnb > 0 ? send_off[nnb] : 0;
+  if (total > 0 && !send_idx) return uggpu_fail(UGGPU_ERROR, "partition: send_idx missing");
+  for (int e = 0; e < total; e++) if (send_idx[e] < 0 || send_idx[e] >= L->n) return uggpu_fail(UGGPU_ERROR, "partition: send_idx[%d] = %d is not an owned row", e, send_idx[e]);
+  UG_TRY(level_free_part(ctx, L));
+  L->partitioned = true;
+  L->nghost = n_ghost;
+  L->n_global = n_global;
+  L->nnb = nnb;
+  L->nb_rank.assign(nb_rank, nb_rank + nnb);
+  L->nb_send_off.assign(send_off, send_off + nnb + (nnb > 0 ? 1 : 0));
+  L->nb_recv_off.assign(recv_off, recv_off + nnb + (nnb > 0 ? 1 : 0));
+  if (nnb == 0) { L->nb_send_off.assign(1, 0); L->nb_recv_off.assign(1, 0); }
+  L->send_total = total;
+  UG_TRY(dalloc(ctx, &L->d_send_idx, (size_t)total));
+  if (total > 0) {
+    CUDA_TRY(cudaMemcpyAsync(L->d_send_idx, send_idx, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   return 0;
 }
 

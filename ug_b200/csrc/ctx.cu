@@ -351,6 +351,15 @@ extern "C" int64_t uggpu_mat_stencil_slices(uggpu_ctx *ctx, int level, int mat)
   return m ? ((m->sten.w > 0 || m->sten3) ? m->sten_slices : 0) : -1;
 }
 
+extern "C" double uggpu_mat_pass_bytes(uggpu_ctx *ctx, int level, int mat)
+{
+  Level *L = get_level(ctx, level);
+  SellMat *m = get_mat(ctx, level, mat);
+  if (!L || !m) return -1.0;
+  const double sb = stx_matrix_bytes(L, m);
+  return sb >= 0 ? sb : m->entry_bytes() + 4.0 * (L->n + 1.0);
+}
+
 extern "C" int64_t uggpu_mat_padded_nnz(uggpu_ctx *ctx, int level, int mat)
 {
   SellMat *m = get_mat(ctx, level, mat);

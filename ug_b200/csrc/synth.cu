@@ -503,7 +503,7 @@ extern "C" int64_t uggpu_level_n_global(uggpu_ctx *ctx, int level)
 {
   Level *L = get_level(ctx, level);
   if (!L) return -1;
-  return L->part ? L->n_global : (int64_t)L->n;
+  return L->n_global > 0 ? L->n_global : (int64_t)L->n;
 }
 
 extern "C" int uggpu_level_is_partitioned(uggpu_ctx *ctx, int level)
