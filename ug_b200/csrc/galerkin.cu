@@ -48,6 +48,7 @@ __global__ void k_gal_cnt64(int n, const int *__restrict__ cnt, int64_t *__restr
   if (r <= n) out[r] = r < n ? cnt[r] : 0;
 }
 
+#define GAL_ACC 32
 template <int BS>
 __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, SellView Af, const double *__restrict__ fval, SellView P,
                                                   const int64_t *__restrict__ tptr, const int32_t *__restrict__ tfine, int *err)
@@ -58,8 +59,21 @@ __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, Sel
   const int lenc = Ac.rowlen[iv];
   const ColIter cic = col_iter(Ac, iv);
   double *cr = cval + slice_off(Ac, iv >> 5) * BB + (iv & 31);        // component k of entry t of this row: cr[(t*BB + k)*32]
-  for (int t = 0; t < lenc; t++)
-    for (int k = 0; k < BB; k++) cr[((size_t)t * BB + k) * 32] = 0.0;  // dmatset(level-1, A, 0.0)
+  // Rows of up to GAL_ACC entries accumulate in a thread-private array (the same additions in the same order; one store per entry at the
+  // end) and keep their column indices there, too: the first version read-modify-wrote the coarse values in HBM for every one of the
+  // ~430 terms of a coarse row (186 ms on the finest level of the 513^3 hierarchy)
+  const bool local = lenc <= GAL_ACC;
+  double acc[GAL_ACC * BB];
+  int ccol[GAL_ACC];
+  if (local) {
+    for (int t = 0; t < lenc; t++) {
+      ccol[t] = col_at(cic, t);
+      for (int k = 0; k < BB; k++) acc[t * BB + k] = 0.0;
+    }
+  } else {
+    for (int t = 0; t < lenc; t++)
+      for (int k = 0; k < BB; k++) cr[((size_t)t * BB + k) * 32] = 0.0;  // dmatset(level-1, A, 0.0)
+  }
   for (int64_t q = tptr[iv]; q < tptr[iv + 1]; q++) {
     const int v = tfine[q];
     // im = the interpolation entry (v, iv)
@@ -81,12 +95,14 @@ __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, Sel
         const int jv = col_at(ciw, j);
         const double wjm = sell_weight(P, w, j);
         int t = -1;                                                     // GetMatrix(iv, jv)
-        for (int u = 0; u < lenc; u++) if (col_at(cic, u) == jv) { t = u; break; }
+        if (local) { for (int u = 0; u < lenc; u++) if (ccol[u] == jv) { t = u; break; } }
+        else { for (int u = 0; u < lenc; u++) if (col_at(cic, u) == jv) { t = u; break; } }
         if (t < 0) { atomicExch(err, UGGPU_ERROR); continue; }          // the reference would create the connection
         if (BS == 1) {
           const double fac = M[0] * wim;
           const double p = fac * wjm;
-          cr[(size_t)t * 32] = cr[(size_t)t * 32] + p;
+          if (local) acc[t] = acc[t] + p;
+          else cr[(size_t)t * 32] = cr[(size_t)t * 32] + p;
         } else {
 #pragma unroll
           for (int i = 0; i < BS; i++)
@@ -101,12 +117,16 @@ __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, Sel
                   const double p = a * (l == jj ? wjm : 0.0);
                   sum += p;
                 }
-              cr[((size_t)t * BB + i * BS + jj) * 32] = cr[((size_t)t * BB + i * BS + jj) * 32] + sum;
+              if (local) acc[t * BB + i * BS + jj] = acc[t * BB + i * BS + jj] + sum;
+              else cr[((size_t)t * BB + i * BS + jj) * 32] = cr[((size_t)t * BB + i * BS + jj) * 32] + sum;
             }
         }
       }
     }
   }
+  if (local)
+    for (int t = 0; t < lenc; t++)
+      for (int k = 0; k < BB; k++) cr[((size_t)t * BB + k) * 32] = acc[t * BB + k];
 }
 
 extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
