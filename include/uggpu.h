@@ -84,6 +84,7 @@ int64_t uggpu_device_bytes(uggpu_ctx *ctx);
 #define UGGPU_K_TRISOLVE    8   /* level-scheduled triangular solve of the Gauss-Seidel family */
 #define UGGPU_K_HALO        9   /* stand-alone halo exchange of a partitioned level (pushes fused into a producing kernel are part of that kernel) */
 #define UGGPU_K_ALLREDUCE  10   /* ncclAllReduce of norm / dot partial sums and of the gathered coarse defect */
+#define UGGPU_K_ASSEMBLE   11   /* element-loop assembly of one level (uggpu_assemble) */
 int uggpu_prof_enable(uggpu_ctx *ctx, int on);   /* also clears the records */
 int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes);
 
@@ -103,6 +104,8 @@ int uggpu_level_get_flags(uggpu_ctx *ctx, int level, uint8_t *vclass, uint8_t *v
 int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, const int32_t *col,
                   const double *val);
 int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const double *val);
+/* pattern only, all values 0 (what creatematrix + dmatset(A, 0) leave): the matrix a device-side assembly fills */
+int uggpu_mat_set_pattern(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, const int32_t *col);
 int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val);
 int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat);
 /* entries actually stored on the device (SELL-32 slices padded to their longest row) */
@@ -235,6 +238,32 @@ int uggpu_interpolate_correction(uggpu_ctx*, int level, int to, int from, const 
  * pattern A already has on level-1 (true on nested geometric hierarchies); where the reference would create connections this
  * call fails with UGGPU_ERROR.  One GPU only. */
 int uggpu_galerkin(uggpu_ctx*, int level, int A);
+
+/* ---- element-loop assembly on the device, np/procs/assemble.h:225 NP_LOCAL_ASSEMBLE, np/procs/assemble.cc:657 ------
+ * One level of LocalAssemble (assemble.cc:671-697) followed by that level's share of NPLocalAssemblePostMatrix (:624): b = 0, A = 0,
+ * VECSKIP cleared; for the elements in list order the local defect and the local matrix (summed over the quadrature points) are added
+ * to the vectors' / connections' values (GetElementVVMPtrs np/udm/disctools.cc:1113: corner order, components row-major per block
+ * pair); VECSKIP := skip (SetElementDirichletFlags :1763 -- which components are Dirichlet is the application's decision); then
+ * AssembleDirichletBoundary (disctools.cc:1837): for every component with its skip bit set  b = x, the row of the diagonal block becomes
+ * the unit row and the row of every other block of the vector 0.  x is only read (the caller has set its Dirichlet values, the job of
+ * AssembleLocal in the reference).  The element kernel -- application code in UG -- is built in:
+ *   UGGPU_FE_POISSON     bs = 1:   int coef_e grad(phi_i).grad(phi_j),  rhs int source[0] phi_i
+ *   UGGPU_FE_ELASTICITY  bs = dim: isotropic linear elasticity (E, nu; lambda = E nu / ((1+nu)(1-2nu)), mu = E / (2(1+nu))), scaled by coef_e
+ * on simplices (dim+1 corners, centroid rule) and tensor elements (2^dim corners in UG's corner numbering, 2-point Gauss per direction).
+ * elem_ptr[nelem+1] / elem_row: rows of the elements' corner vectors in CORNER order, elements in FIRSTELEMENT->SUCCE order; coef[nelem]
+ * (NULL: 1); coord[n*dim] by row; skip[n] (NULL: none); host pointers.  Matrix A must exist with its pattern (uggpu_mat_set /
+ * uggpu_mat_set_pattern), vectors x and b must exist.  Every value receives the reference's terms in the reference's order (one thread
+ * per row gathers its elements in list order): bit-identical to the sequential scatter loop.  One GPU only. */
+#define UGGPU_FE_POISSON    0
+#define UGGPU_FE_ELASTICITY 1
+typedef struct uggpu_fe_cfg {
+  int    problem;                    /* UGGPU_FE_*                                   */
+  int    dim;                        /* 2 | 3                                        */
+  double E, nu;                      /* elasticity                                   */
+  double source[UGGPU_MAX_BS];       /* right-hand side density per component        */
+} uggpu_fe_cfg;
+int uggpu_assemble(uggpu_ctx*, int level, int x, int b, int A, const uggpu_fe_cfg *cfg, int64_t nelem, const int64_t *elem_ptr,
+                   const int32_t *elem_row, const double *coef, const double *coord, const uint32_t *skip);
 
 /* ---- multigrid cycle, np/procs/iter.cc:7741-7949 Lmgc ------------------------------------------------ */
 /* Base solver hook: called with the stream drained when the recursion reaches baselevel.  It must

@@ -48,4 +48,14 @@ mkdir -p $G
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_hex3d_bs3_r2.ugh --solve > /dev/null
 ./_ref/ugoracle2 --grid tri --refine 3 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_tri2d_r3.ugh --solve > /dev/null
 ./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --imat --galerkin --lean --cycles 2 --dump $G/galerkin_tet3d_adapt.ugh --solve > /dev/null
+# ---- element-loop assembly: the reference's LocalAssemble (np/procs/assemble.cc:657) + AssembleDirichletBoundary with the
+# element kernel of ug_driver.cc's class `fe` (diffusion with a coefficient per element / linear elasticity, Dirichlet values g(x) != 0):
+# elements, coordinates, coefficients, and what the loop leaves on every level (matrix values, rhs, sol, VECSKIP).  Tets, hexes (scalar and
+# 3x3 blocks), adaptively refined tets (rows of up to 42 entries), triangles, quads with 2x2 blocks
+./_ref/ugoracle3 --grid tet --refine 3 --lean --assemble --dump $G/asm_tet3d_r3.ugh > /dev/null
+./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --lean --assemble --dump $G/asm_hex3d_bs3_r2.ugh > /dev/null
+./_ref/ugoracle3 --grid hex --refine 3 --lean --assemble --dump $G/asm_hex3d_r3.ugh > /dev/null
+./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --lean --assemble --dump $G/asm_tet3d_adapt.ugh > /dev/null
+./_ref/ugoracle2 --grid tri --refine 4 --lean --assemble --dump $G/asm_tri2d_r4.ugh > /dev/null
+./_ref/ugoracle2 --grid quad --bs 2 --refine 3 --lean --assemble --dump $G/asm_quad2d_bs2_r3.ugh > /dev/null
 ls -la $G

@@ -41,6 +41,8 @@
 #include "transgrid.h"
 #include "ugdevices.h"
 #include "refine.h"
+#include "assemble.h"
+#include "disctools.h"
 
 #include "gpuls_flatten.h"
 #ifdef WITH_GPULS
@@ -100,6 +102,7 @@ struct Opt {
   bool ops = false, solve = false, timeit = false, quiet = true, nokrylov = false, elems = false;
   bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
   bool galerkin = false;                // --galerkin (with --imat): Galerkin coarse-grid operators by AssembleGalerkinByMatrix, cascaded from the top level down
+  bool assemble = false;                // --assemble: run the reference's LocalAssemble (np/procs/assemble.cc:657) with the element kernel below and dump what it leaves
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
 };
 
@@ -264,6 +267,129 @@ static void assemble(void)
         for (int i = 0; i < BS; i++) MVALUE(VSTART(v), MD_MCMP_OF_RT_CT(mA, t0, t0, i * BS + i)) = 1.0;
       }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Element-loop assembly through the reference's own NP_LOCAL_ASSEMBLE machinery: np/procs/assemble.cc:657-706
+// LocalAssemble (dset / dmatset / CLEAR_VECSKIP, elements in list order, GetElementVVMPtrs np/udm/disctools.cc:1113, `+=` of the local
+// defect and matrix, SetElementDirichletFlags :1763 on boundary elements) and :624 NPLocalAssemblePostMatrix (AssembleDirichletBoundary
+// disctools.cc:1837 on every level).  UG leaves the element kernel to the application (AssembleLocal); class `fe` below is that
+// application: P1 / Q1 diffusion with one coefficient per element, or isotropic linear elasticity, source term, Dirichlet values g(x)
+// on the whole boundary.  The local matrix is summed over the quadrature points first and added to the global one once per element
+// (assemble() above adds every quadrature term directly; for simplices -- one point -- the two agree to the bit when the coefficient is 1).
+// assemble.cc:606-731 defines these four WITHOUT the namespace prefix its header declares them with: the library exports them in the
+// global namespace, so they are declared (and called) there
+INT NPLocalAssembleInit(NP_LOCAL_ASSEMBLE *, INT, char **);
+INT NPLocalAssembleDisplay(NP_LOCAL_ASSEMBLE *);
+INT NPLocalAssembleConstruct(NP_ASSEMBLE *);
+INT NPLocalAssemblePostMatrix(NP_LOCAL_ASSEMBLE *, INT, VECDATA_DESC *, VECDATA_DESC *, MATDATA_DESC *, INT *);
+static void restore_problem(void);
+static DOUBLE fe_sol[24], fe_def[24], fe_mat[24 * 24];
+static INT fe_vecskip[24];
+static const double fe_E = 1.0, fe_nu = 0.3;
+
+static double fe_coef(ELEMENT *e)
+{
+  int nc = CORNERS_OF_ELEM(e);
+  double c[3] = {0, 0, 0};
+  for (int i = 0; i < nc; i++) for (int d = 0; d < DIM; d++) c[d] += CVECT(MYVERTEX(CORNER(e, i)))[d];
+  for (int d = 0; d < DIM; d++) c[d] /= nc;
+  return 1.0 + 0.5 * c[0] + 0.25 * c[1] * c[1] + (DIM == 3 ? 0.125 * c[2] : 0.0);
+}
+static void fe_source(double *f) { for (int a = 0; a < BS; a++) f[a] = 0.0; if (BS == 1) f[0] = 1.0; else f[BS - 1] = -1.0; }
+static double fe_dirichlet(const double *x, int a) { return (a + 1) * (0.25 * x[0] - 0.5 * x[1] + (DIM == 3 ? 0.125 * x[2] : 0.0)); }
+
+static INT FEPreProcess(NP_LOCAL_ASSEMBLE *, INT, VECDATA_DESC *, VECDATA_DESC *, MATDATA_DESC *, DOUBLE **sol, DOUBLE **def, DOUBLE **mat, INT **vecskip, INT *)
+{
+  *sol = fe_sol; *def = fe_def; *mat = fe_mat; *vecskip = fe_vecskip;
+  return 0;
+}
+
+static INT FEAssembleLocal(ELEMENT *e, INT *result)
+{
+  const int nc = CORNERS_OF_ELEM(e), m = nc * BS;
+  if (nc != DIM + 1 && nc != (1 << DIM)) { result[0] = __LINE__; return 1; }
+  const double lam = fe_E * fe_nu / ((1 + fe_nu) * (1 - 2 * fe_nu)), mu = fe_E / (2 * (1 + fe_nu));
+  QP qp[8];
+  const int nq = element_qps(e, qp);
+  const double kappa = fe_coef(e);
+  double f[3]; fe_source(f);
+  for (int q = 0; q < nq; q++) {
+    const double wk = kappa * qp[q].w;
+    for (int i = 0; i < nc; i++) {
+      const double wn = qp[q].w * qp[q].N[i];
+      for (int a = 0; a < BS; a++) fe_def[i * BS + a] += wn * f[a];
+    }
+    for (int i = 0; i < nc; i++)
+      for (int j = 0; j < nc; j++) {
+        const double *gi = qp[q].G[i], *gj = qp[q].G[j];
+        double dot = 0; for (int d = 0; d < DIM; d++) dot += gi[d] * gj[d];
+        if (BS == 1) fe_mat[i * m + j] += wk * dot;
+        else
+          for (int a = 0; a < BS; a++) for (int b = 0; b < BS; b++) {
+            double k = lam * gi[a] * gj[b] + mu * gi[b] * gj[a] + ((a == b) ? mu * dot : 0.0);
+            fe_mat[(i * BS + a) * m + j * BS + b] += wk * k;
+          }
+      }
+  }
+  if (OBJT(e) == BEOBJ)
+    for (int i = 0; i < nc; i++)
+      if (OBJT(MYVERTEX(CORNER(e, i))) == BVOBJ)
+        for (int a = 0; a < BS; a++) { fe_vecskip[i * BS + a] = 1; fe_sol[i * BS + a] = fe_dirichlet(CVECT(MYVERTEX(CORNER(e, i))), a); }
+  return 0;
+}
+
+static INT FEInit(NP_BASE *theNP, INT argc, char **argv) { return ::NPLocalAssembleInit((NP_LOCAL_ASSEMBLE *)theNP, argc, argv); }
+static INT FEDisplay(NP_BASE *theNP) { return ::NPLocalAssembleDisplay((NP_LOCAL_ASSEMBLE *)theNP); }
+static INT FEConstruct(NP_BASE *theNP)
+{
+  theNP->Init = FEInit; theNP->Display = FEDisplay; theNP->Execute = NPAssembleExecute;
+  NP_LOCAL_ASSEMBLE *la = (NP_LOCAL_ASSEMBLE *)theNP;
+  ::NPLocalAssembleConstruct(&la->assemble);
+  la->PreProcess = FEPreProcess; la->AssembleLocal = FEAssembleLocal; la->AssembleLocalDefect = NULL; la->AssembleLocalMatrix = NULL;
+  la->PostMatrix = ::NPLocalAssemblePostMatrix; la->PostProcess = NULL;
+  return 0;
+}
+
+// what the reference's LocalAssemble leaves on every level: matrix values (canonical entry order), right-hand side, solution (random
+// values, g(x) on the boundary), VECSKIP, and the per-element coefficients the element kernel used.  The elements and coordinates are
+// in the hierarchy part of the dump (--assemble implies --elems).  Afterwards the problem of the other records is restored.
+static void run_fe_assemble(const char *cls)
+{
+  static int made = 0;
+  int top = TOPLEVEL(mg);
+  INT result = 0;
+  if (!made && CreateClass(ASSEMBLE_CLASS_NAME ".fe", sizeof(NP_LOCAL_ASSEMBLE), FEConstruct)) { fprintf(stderr, "CreateClass fe failed\n"); exit(12); }
+  made = 1;
+  char nm[32]; snprintf(nm, sizeof nm, "ass_%s", cls);
+  cmd("npcreate %s $c %s", nm, cls);
+  cmd("npinit %s $A MAT $x sol $b rhs", nm);
+  NP_ASSEMBLE *ass = (NP_ASSEMBLE *)GetNumProcByName(mg, nm, ASSEMBLE_CLASS_NAME);
+  if (!ass) { fprintf(stderr, "numproc %s not found\n", nm); exit(12); }
+  for (int l = 0; l <= top; l++) fill_lcg(vx, l, 7);
+  if ((*ass->PreProcess)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: PreProcess failed (%d)\n", cls, (int)result); exit(12); }
+  if ((*ass->Assemble)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: Assemble failed (%d)\n", cls, (int)result); exit(12); }
+  if ((*ass->PostProcess)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: PostProcess failed (%d)\n", cls, (int)result); exit(12); }
+}
+
+static void dump_assemble(const Opt &o)
+{
+  (void)o;
+  int top = TOPLEVEL(mg);
+  run_fe_assemble("fe");
+  D.scalar_d("asm/E", fe_E); D.scalar_d("asm/nu", fe_nu);
+  { double f[3]; fe_source(f); D.rec("asm/source", 1, f, BS, 8); }
+  for (int l = 0; l <= top; l++) {
+    gpuls::FlatLevel f;
+    if (gpuls::FlattenFlags(mg, l, vx, f) || gpuls::FlattenMatrix(mg, l, mA, f)) { fprintf(stderr, "FlattenMatrix(assemble) failed\n"); exit(12); }
+    D.f64(L("asm/val", l), f.val); D.u32(L("asm/skip", l), f.skip);
+    dumpvec("asm/rhs", vb, l); dumpvec("asm/sol", vx, l);
+    std::vector<double> coef;
+    for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l)); e; e = SUCCE(e)) coef.push_back(fe_coef(e));
+    D.f64(L("asm/coef", l), coef);
+  }
+  restore_problem();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,6 +812,7 @@ int main(int argc, char **argv)
     else if (a == "--lean") o.lean = true; else if (a == "--imat") o.imat = true;
     else if (a == "--beta") o.beta = atof(nxt().c_str());
     else if (a == "--galerkin") o.galerkin = true;
+    else if (a == "--assemble") { o.assemble = true; o.elems = true; }
     else if (a == "--nokrylov") o.nokrylov = true;
     else if (a == "--elems") o.elems = true;             // dump the elements (corner rows, fathers): input of the element partition (ug_b200/partition.py)       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
@@ -718,6 +845,7 @@ int main(int argc, char **argv)
     if (o.ops) dump_ops(o);
     if (o.solve) dump_solve(o);
     if (o.solve && !o.lean) dump_krylov(o);
+    if (o.assemble) dump_assemble(o);
     if (o.galerkin) dump_galerkin(o);
     D.close();
   }

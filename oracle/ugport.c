@@ -880,3 +880,118 @@ int ugport_bcgs_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int
   ugport_base_free(lu);
   return nit;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------------------
+ * Element-loop assembly: one level of LocalAssemble np/procs/assemble.cc:671-697 + that level's share of
+ * NPLocalAssemblePostMatrix :624 (AssembleDirichletBoundary np/udm/disctools.cc:1837), sequential scatter loop like the reference,
+ * with the element kernel of oracle/ug_driver.cc's class `fe` (UG leaves AssembleLocal to the application): simplices with the
+ * centroid rule, tensor elements with 2-point Gauss, local matrix summed over the quadrature points, then added once per element. */
+static double fe_det_inv(int dim, double J[3][3], double Ji[3][3])
+{
+  if (dim == 2) {
+    double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    Ji[0][0] = J[1][1] / det; Ji[0][1] = -J[0][1] / det; Ji[1][0] = -J[1][0] / det; Ji[1][1] = J[0][0] / det;
+    return det;
+  }
+  double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det; Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+  Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  return det;
+}
+
+typedef struct { double w, N[8], G[8][3]; } fe_qpt;
+
+static int fe_element_qps(int dim, int nc, double X[8][3], fe_qpt *qp)
+{
+  static const int LOC[8][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1}};   /* UG's corner numbering */
+  double J[3][3], Ji[3][3];
+  if (nc == dim + 1) {
+    for (int d = 0; d < dim; d++) for (int k = 0; k < dim; k++) J[k][d] = X[k + 1][d] - X[0][d];
+    double det = fe_det_inv(dim, J, Ji);
+    qp[0].w = fabs(det) / ((dim == 3) ? 6.0 : 2.0);
+    for (int i = 0; i < nc; i++) qp[0].N[i] = 1.0 / nc;
+    for (int d = 0; d < dim; d++) {
+      double s = 0;
+      for (int k = 0; k < dim; k++) { qp[0].G[k + 1][d] = Ji[d][k]; s += Ji[d][k]; }
+      qp[0].G[0][d] = -s;
+    }
+    return 1;
+  }
+  const double g[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+  int nq = 0;
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < ((dim == 3) ? 2 : 1); c++) {
+    double xi[3] = {g[a], g[b], g[c]}, dN[8][3];
+    for (int i = 0; i < nc; i++) {
+      double f[3], df[3];
+      for (int d = 0; d < dim; d++) { f[d] = LOC[i][d] ? xi[d] : 1.0 - xi[d]; df[d] = LOC[i][d] ? 1.0 : -1.0; }
+      qp[nq].N[i] = 1.0;
+      for (int d = 0; d < dim; d++) qp[nq].N[i] *= f[d];
+      for (int d = 0; d < dim; d++) { dN[i][d] = df[d]; for (int e = 0; e < dim; e++) if (e != d) dN[i][d] *= f[e]; }
+    }
+    for (int k = 0; k < dim; k++) for (int d = 0; d < dim; d++) { J[k][d] = 0; for (int i = 0; i < nc; i++) J[k][d] += dN[i][k] * X[i][d]; }
+    double det = fe_det_inv(dim, J, Ji);
+    qp[nq].w = fabs(det) / ((dim == 3) ? 8.0 : 4.0);
+    for (int i = 0; i < nc; i++) for (int d = 0; d < dim; d++) { double s = 0; for (int k = 0; k < dim; k++) s += Ji[d][k] * dN[i][k]; qp[nq].G[i][d] = s; }
+    nq++;
+  }
+  return nq;
+}
+
+int ugport_assemble(const ugport_level *L, const ugport_fe *fe, int64_t nelem, const int64_t *elem_ptr, const int32_t *elem_row,
+                    const double *coef, const double *coord, const uint32_t *skip, const double *x, double *val, double *b)
+{
+  const int n = L->n, bs = L->bs, bb = bs * bs, dim = fe->dim;
+  const double lam = fe->E * fe->nu / ((1 + fe->nu) * (1 - 2 * fe->nu)), mu = fe->E / (2 * (1 + fe->nu));
+  for (int64_t i = 0; i < (int64_t)n * bs; i++) b[i] = 0.0;                           /* dset(b, 0) */
+  for (int64_t i = 0; i < (int64_t)L->rowptr[n] * bb; i++) val[i] = 0.0;             /* dmatset(A, 0) */
+  for (int64_t e = 0; e < nelem; e++) {
+    const int32_t *er = elem_row + elem_ptr[e];
+    const int nc = (int)(elem_ptr[e + 1] - elem_ptr[e]), m = nc * bs;
+    if (nc != dim + 1 && nc != (1 << dim)) return 1;
+    double X[8][3], def[24], mat[24 * 24];
+    fe_qpt qp[8];
+    for (int i = 0; i < nc; i++) for (int d = 0; d < dim; d++) X[i][d] = coord[(size_t)er[i] * dim + d];
+    const int nq = fe_element_qps(dim, nc, X, qp);
+    const double kappa = coef ? coef[e] : 1.0;
+    for (int i = 0; i < m; i++) def[i] = 0.0;
+    for (int i = 0; i < m * m; i++) mat[i] = 0.0;
+    for (int q = 0; q < nq; q++) {
+      const double wk = kappa * qp[q].w;
+      for (int i = 0; i < nc; i++) {
+        const double wn = qp[q].w * qp[q].N[i];
+        for (int a = 0; a < bs; a++) def[i * bs + a] += wn * fe->source[a];
+      }
+      for (int i = 0; i < nc; i++)
+        for (int j = 0; j < nc; j++) {
+          const double *gi = qp[q].G[i], *gj = qp[q].G[j];
+          double dot = 0; for (int d = 0; d < dim; d++) dot += gi[d] * gj[d];
+          if (bs == 1) mat[i * m + j] += wk * dot;
+          else
+            for (int a = 0; a < bs; a++) for (int c = 0; c < bs; c++) {
+              double k = lam * gi[a] * gj[c] + mu * gi[c] * gj[a] + ((a == c) ? mu * dot : 0.0);
+              mat[(i * bs + a) * m + j * bs + c] += wk * k;
+            }
+        }
+    }
+    for (int i = 0; i < nc; i++) for (int a = 0; a < bs; a++) b[(size_t)er[i] * bs + a] += def[i * bs + a];
+    for (int i = 0; i < nc; i++)
+      for (int j = 0; j < nc; j++) {
+        int64_t t = -1;
+        for (int64_t u = L->rowptr[er[i]]; u < L->rowptr[er[i] + 1]; u++) if (L->col[u] == er[j]) { t = u; break; }
+        if (t < 0) return 3;                                                         /* GetElementVVMPtrs: -3 */
+        for (int a = 0; a < bs; a++) for (int c = 0; c < bs; c++) val[t * bb + a * bs + c] += mat[(i * bs + a) * m + j * bs + c];
+      }
+  }
+  for (int r = 0; r < n; r++)                                                         /* AssembleDirichletBoundary */
+    for (int a = 0; a < bs; a++)
+      if (skip && (skip[r] & (1u << a))) {
+        b[(size_t)r * bs + a] = x[(size_t)r * bs + a];
+        for (int64_t u = L->rowptr[r]; u < L->rowptr[r + 1]; u++)
+          for (int c = 0; c < bs; c++) val[u * bb + a * bs + c] = (u == L->rowptr[r] && c == a) ? 1.0 : 0.0;
+      }
+  return 0;
+}

@@ -35,6 +35,10 @@ class _Cfg(C.Structure):
                 ("smoother", C.c_int), ("imat", C.c_int)]
 
 
+class _Fe(C.Structure):
+    _fields_ = [("problem", C.c_int), ("dim", C.c_int), ("E", C.c_double), ("nu", C.c_double), ("source", C.c_double * MAX_BS)]
+
+
 SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3, "ilu": 4}
 
 
@@ -217,6 +221,20 @@ class PortBackend:
         err = self.L.ugport_galerkin(self._lp(level), self._lp(level - 1), _dp(fv), _dp(out))
         assert err == 0, err
         return out
+
+    def assemble(self, level, fe, elem_ptr, elem_row, coef, coord, skip, x):
+        """One level of LocalAssemble + AssembleDirichletBoundary (assemble.cc:657, disctools.cc:1837): returns (val, b)."""
+        lv = self.h.levels[level]
+        cfg = _Fe(fe["problem"], fe["dim"], fe["E"], fe["nu"], (C.c_double * MAX_BS)(*(list(fe["source"]) + [0.0] * MAX_BS)[:MAX_BS]))
+        ep = np.ascontiguousarray(elem_ptr, dtype=np.int64); er = np.ascontiguousarray(elem_row, dtype=np.int32)
+        cf = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        xy = np.ascontiguousarray(coord, dtype=np.float64); sk = np.ascontiguousarray(skip, dtype=np.uint32)
+        xx = np.ascontiguousarray(x, dtype=np.float64)
+        val = np.zeros(len(lv.col) * lv.bs * lv.bs); b = np.zeros(lv.n * lv.bs)
+        self.L.ugport_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        err = self.L.ugport_assemble(C.addressof(self.levels[level]), C.addressof(cfg), len(ep) - 1, _p(ep), _p(er), _p(cf), _p(xy), _p(sk), _p(xx), _p(val), _p(b))
+        assert err == 0, err
+        return val, b
 
     def smooth(self, level, kind, x, b, damp, tmp="__sgs"):
         return self.L.ugport_smooth(self._lp(level), SMOOTHERS[kind], _dp(self._v(x, level)), _dp(self._v(b, level)),

@@ -98,3 +98,45 @@ def test_gpu_galerkin_bitexact(golden):
     port.put(l, "y", y); port.put(l, "x", np.zeros_like(y))
     port.dmatmul(l, l, 0, 0, "x", "y")
     assert np.array_equal(got, port.get(l, "x"))
+
+
+def test_gpu_assemble_bitexact(golden):
+    """uggpu_assemble against the reference's LocalAssemble + AssembleDirichletBoundary (np/procs/assemble.cc:657,
+    np/udm/disctools.cc:1837; dumps written by `ug_driver --assemble`): matrix values, right-hand side and VECSKIP of every level bit
+    for bit -- into a matrix created from the pattern alone (uggpu_mat_set_pattern) -- and a product with the assembled matrix equals
+    the port's on the dumped values (diagonal array and shared tables follow the new values)."""
+    d = golden.raw
+    if "L0/asm/val" not in d:
+        pytest.skip("dump without assembly records")
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    from test_oracle_port import fe_of
+    from ug_b200 import capi
+    be = GpuBackend(golden)
+    ctx = be.ctx
+    for l, lv in enumerate(golden.levels):
+        g = lambda k: d[f"L{l}/{k}"]
+        ctx.call("uggpu_mat_set_pattern", l, ctx.handle("K"), capi._p(np.ascontiguousarray(lv.rowptr)), capi._p(np.ascontiguousarray(lv.col)))
+        be.put(l, "x", g("asm/sol")); be.put(l, "b", np.full(lv.n * lv.bs, 7.0))
+        ctx.assemble(l, "x", "b", "K", fe_of(golden), g("elem_ptr"), g("elem_nodes"), g("asm/coef"), g("xyz"), g("asm/skip"))
+        val = ctx.mat_values(l, "K", lv.col.size)
+        ref = g("asm/val")
+        assert np.array_equal(val, ref), (l, int(np.count_nonzero(val != ref)), ref.size)
+        assert np.array_equal(be.get(l, "b"), g("asm/rhs")), l
+        assert np.array_equal(be.get(l, "x"), g("asm/sol")), l
+        skip = np.zeros(lv.n, np.uint32)
+        ctx.call("uggpu_level_get_flags", l, None, None, None, capi._p(skip))
+        assert np.array_equal(skip, g("asm/skip"))
+    l = golden.top
+    lv = golden.levels[l]
+    y = np.round(np.random.default_rng(5).standard_normal(lv.n * lv.bs) * 1024) / 1024
+    be.put(l, "y", y); be.put(l, "z", np.zeros_like(y))
+    ctx.call("uggpu_dmatmul", l, l, 0, ctx.handle("z"), ctx.handle("K"), ctx.handle("y"))
+    got = be.get(l, "z")
+    be.close()
+    import copy
+    h2 = copy.copy(golden); h2.levels = list(golden.levels); h2.levels[l] = copy.copy(lv); h2.levels[l].val = d[f"L{l}/asm/val"]
+    port = PortBackend(h2)
+    port.put(l, "y", y); port.put(l, "z", np.zeros_like(y))
+    port.dmatmul(l, l, 0, 0, "z", "y")
+    assert np.array_equal(got, port.get(l, "z"))

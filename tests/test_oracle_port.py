@@ -52,6 +52,27 @@ def test_port_galerkin_bitexact(golden):
         assert np.count_nonzero(val) > 0
 
 
+def fe_of(golden):
+    d = golden.raw
+    return dict(problem=0 if golden.bs == 1 else 1, dim=golden.dim, E=float(d["asm/E"][0]), nu=float(d["asm/nu"][0]), source=list(d["asm/source"]))
+
+
+def test_port_assemble_bitexact(golden):
+    """Element-loop assembly against what the reference's LocalAssemble (np/procs/assemble.cc:657) and
+    AssembleDirichletBoundary (np/udm/disctools.cc:1837) leave with the element kernel of oracle/ug_driver.cc's class `fe`: every
+    matrix value and the right-hand side of every level, bit for bit."""
+    d = golden.raw
+    if "L0/asm/val" not in d:
+        pytest.skip("dump without assembly records")
+    be = PortBackend(golden)
+    for l in range(golden.top + 1):
+        g = lambda k: d[f"L{l}/{k}"]
+        val, b = be.assemble(l, fe_of(golden), g("elem_ptr"), g("elem_nodes"), g("asm/coef"), g("xyz"), g("asm/skip"), g("asm/sol"))
+        assert np.array_equal(val, g("asm/val")), (l, int(np.count_nonzero(val != g("asm/val"))))
+        assert np.array_equal(b, g("asm/rhs")), l
+        assert np.count_nonzero(g("asm/skip")) > 0 and np.count_nonzero(b) > 0
+
+
 def test_golden_invariants(golden):
     """Invariants the reference's own checkers assert (np/algebra/npcheck.cc:118-154)."""
     for l, lv in enumerate(golden.levels):

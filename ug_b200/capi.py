@@ -40,6 +40,10 @@ class LmgcCfg(C.Structure):
 SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3, "ilu": 4}       # UGGPU_SM_*
 
 
+class FeCfg(C.Structure):               # uggpu_fe_cfg
+    _fields_ = [("problem", C.c_int), ("dim", C.c_int), ("E", C.c_double), ("nu", C.c_double), ("source", C.c_double * MAX_BS)]
+
+
 class LResult(C.Structure):
     _fields_ = [("error_code", C.c_int), ("converged", C.c_int), ("number_of_linear_iterations", C.c_int),
                 ("first_defect", C.c_double * MAX_BS), ("last_defect", C.c_double * MAX_BS)]
@@ -214,6 +218,22 @@ class Context:
     def halo_transport(self) -> str:
         return {0: "none", 1: "nccl send/recv", 2: "peer-memory windows (CUDA IPC, push + unpack kernels)",
                 3: "peer-memory ghost rows (CUDA IPC, pushes fused into the producing kernels)"}.get(int(self.L.uggpu_comm_transport(self.h)), "?")
+
+    def assemble(self, level: int, x: str, b: str, A: str, fe: dict, elem_ptr, elem_row, coef, coord, skip):
+        """uggpu_assemble: one level of LocalAssemble + AssembleDirichletBoundary on the device (fe: problem, dim, E, nu, source)."""
+        cfg = FeCfg(int(fe["problem"]), int(fe["dim"]), float(fe.get("E", 1.0)), float(fe.get("nu", 0.3)),
+                    (C.c_double * MAX_BS)(*(list(fe["source"]) + [0.0] * MAX_BS)[:MAX_BS]))
+        ep = np.ascontiguousarray(elem_ptr, dtype=np.int64); er = np.ascontiguousarray(elem_row, dtype=np.int32)
+        cf = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
+        xy = np.ascontiguousarray(coord, dtype=np.float64)
+        sk = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint32)
+        self.call("uggpu_assemble", level, self.handle(x), self.handle(b), self.handle(A), C.byref(cfg), C.c_int64(len(ep) - 1), _p(ep), _p(er), _p(cf), _p(xy), _p(sk))
+
+    def mat_values(self, level: int, A: str, nnz: int) -> np.ndarray:
+        bs = self.level_bs(level)
+        val = np.zeros(nnz * bs * bs)
+        self.call("uggpu_mat_get", level, self.handle(A), None, None, _p(val))
+        return val
 
     def sync(self): self.call("uggpu_sync")
     def launch_count(self) -> int: return int(self.L.uggpu_launch_count(self.h))

@@ -311,6 +311,20 @@ extern "C" int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *
   return 0;
 }
 
+extern "C" int uggpu_mat_set_pattern(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, const int32_t *col)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  if (!rowptr || !col) return uggpu_fail(UGGPU_ERROR, "uggpu_mat_set_pattern: null array");
+  auto it = L->mats.find(mat);
+  if (it != L->mats.end()) { UG_TRY(sell_free(ctx, &it->second)); L->mats.erase(it); }
+  SellMat m;
+  UG_TRY(sell_from_host_csr(ctx, L->n, L->bs * L->bs, rowptr, col, nullptr, &m));     // val == nullptr: zeros
+  UG_TRY(sell_update_diag(ctx, &m));
+  L->mats[mat] = m;
+  return 0;
+}
+
 extern "C" int uggpu_mat_set_values(uggpu_ctx *ctx, int level, int mat, const double *val)
 {
   SellMat *m = get_mat(ctx, level, mat);

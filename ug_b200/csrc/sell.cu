@@ -670,7 +670,8 @@ int sell_from_host_csr(uggpu_ctx *ctx, int n, int bb, const int32_t *rowptr, con
   CUDA_TRY(cudaMemcpyAsync(d_rp, rp.data(), ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (nnz) {
     CUDA_TRY(cudaMemcpyAsync(d_col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nnz * bb * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (val) CUDA_TRY(cudaMemcpyAsync(d_val, val, (size_t)nnz * bb * sizeof(double), cudaMemcpyHostToDevice, st));
+    else CUDA_TRY(cudaMemsetAsync(d_val, 0, (size_t)nnz * bb * sizeof(double), st));        // pattern only
   }
   int rc = sell_from_device_csr(ctx, n, bb, d_rp, d_col, d_val, out);
   CUDA_TRY(cudaStreamSynchronize(st));
