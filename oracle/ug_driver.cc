@@ -355,7 +355,7 @@ static INT FEConstruct(NP_BASE *theNP)
 // what the reference's LocalAssemble leaves on every level: matrix values (canonical entry order), right-hand side, solution (random
 // values, g(x) on the boundary), VECSKIP, and the per-element coefficients the element kernel used.  The elements and coordinates are
 // in the hierarchy part of the dump (--assemble implies --elems).  Afterwards the problem of the other records is restored.
-static void run_fe_assemble(const char *cls)
+static NP_ASSEMBLE *run_fe_assemble(const char *cls, bool keep_open = false)
 {
   static int made = 0;
   int top = TOPLEVEL(mg);
@@ -363,14 +363,20 @@ static void run_fe_assemble(const char *cls)
   if (!made && CreateClass(ASSEMBLE_CLASS_NAME ".fe", sizeof(NP_LOCAL_ASSEMBLE), FEConstruct)) { fprintf(stderr, "CreateClass fe failed\n"); exit(12); }
   made = 1;
   char nm[32]; snprintf(nm, sizeof nm, "ass_%s", cls);
-  cmd("npcreate %s $c %s", nm, cls);
-  cmd("npinit %s $A MAT $x sol $b rhs", nm);
   NP_ASSEMBLE *ass = (NP_ASSEMBLE *)GetNumProcByName(mg, nm, ASSEMBLE_CLASS_NAME);
+  if (!ass) {
+    cmd("npcreate %s $c %s", nm, cls);
+    if (strcmp(cls, "fe") == 0) cmd("npinit %s $A MAT $x sol $b rhs", nm);
+    else if (BS == 1) cmd("npinit %s $A MAT $x sol $b rhs $P poisson $f 1", nm);
+    else cmd("npinit %s $A MAT $x sol $b rhs $P elasticity $E %.17g $nu %.17g $f %s-1", nm, fe_E, fe_nu, BS == 3 ? "0 0 " : "0 ");
+    ass = (NP_ASSEMBLE *)GetNumProcByName(mg, nm, ASSEMBLE_CLASS_NAME);
+  }
   if (!ass) { fprintf(stderr, "numproc %s not found\n", nm); exit(12); }
   for (int l = 0; l <= top; l++) fill_lcg(vx, l, 7);
   if ((*ass->PreProcess)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: PreProcess failed (%d)\n", cls, (int)result); exit(12); }
   if ((*ass->Assemble)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: Assemble failed (%d)\n", cls, (int)result); exit(12); }
-  if ((*ass->PostProcess)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: PostProcess failed (%d)\n", cls, (int)result); exit(12); }
+  if (!keep_open && (*ass->PostProcess)(ass, top, vx, vb, mA, &result)) { fprintf(stderr, "%s: PostProcess failed (%d)\n", cls, (int)result); exit(12); }
+  return ass;
 }
 
 static void dump_assemble(const Opt &o)
@@ -964,6 +970,67 @@ static int run_gpu(const Opt &o)
              ex, eb, tm[1], tm[0]);
       if (!ok) fails++;
     }
+  }
+  // 4. assemble.gpufe against the reference's NP_LOCAL_ASSEMBLE loop with the same element kernel (class `fe` above): every MVALUE,
+  //    the right-hand side, x (Dirichlet values) and VECSKIP of every level bit for bit; then a gpuls solve INSIDE gpufe's bracket
+  //    (the matrix never crosses PCIe as values) against the CPU solve of the same assembled problem
+  if (o.assemble) {
+    struct Snap { std::vector<double> val, b, x; std::vector<uint32_t> skip; };
+    auto snap = [&](std::vector<Snap> &out) {
+      out.assign(top + 1, Snap());
+      for (int l = 0; l <= top; l++) {
+        gpuls::FlatLevel f;
+        if (gpuls::FlattenFlags(mg, l, vx, f) || gpuls::FlattenMatrix(mg, l, mA, f)) { fprintf(stderr, "flatten failed\n"); exit(12); }
+        out[l].val = f.val; out[l].skip = f.skip; out[l].b = gather(vb, l); out[l].x = gather(vx, l);
+      }
+    };
+    std::vector<Snap> ref, got;
+    run_fe_assemble("fe");
+    snap(ref);
+    cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", o.cycles);
+    memset(&lr, 0, sizeof lr);
+    (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+    (*ls->Defect)(ls, top, vx, vb, mA, &result);
+    (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
+    (*ls->Solver)(ls, top, vx, vb, mA, abslimit, red, &lr);
+    (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
+    std::vector<std::vector<double> > xs(top + 1);
+    for (int l = 0; l <= top; l++) xs[l] = gather(vx, l);
+    LRESULT lr_ref = lr;
+    // wipe what the device run has to produce
+    for (int l = 0; l <= top; l++) {
+      dmatset(mg, l, l, ALL_VECTORS, mA, -7.0); dset(mg, l, l, ALL_VECTORS, vb, -7.0);
+      for (VECTOR *v = FIRSTVECTOR(GRID_ON_LEVEL(mg, l)); v; v = SUCCVC(v)) VECSKIP(v) = 0;
+    }
+    gpuls::SetFEData(fe_coef, fe_dirichlet);
+    NP_ASSEMBLE *gass = run_fe_assemble("gpufe", true);
+    snap(got);
+    size_t bad = 0, cnt = 0;
+    for (int l = 0; l <= top; l++) {
+      for (size_t i = 0; i < ref[l].val.size(); i++, cnt++) if (memcmp(&ref[l].val[i], &got[l].val[i], 8)) bad++;
+      for (size_t i = 0; i < ref[l].b.size(); i++, cnt++) if (memcmp(&ref[l].b[i], &got[l].b[i], 8) || memcmp(&ref[l].x[i], &got[l].x[i], 8)) bad++;
+      for (size_t i = 0; i < ref[l].skip.size(); i++, cnt++) if (ref[l].skip[i] != got[l].skip[i]) bad++;
+    }
+    printf("%s gpufe vs fe (NP_LOCAL_ASSEMBLE): %zu of %zu values differ (matrix, rhs, sol, VECSKIP on %d levels)\n", bad ? "FAIL" : "PASS", bad, cnt, top + 1);
+    if (bad) fails++;
+    NP_LINEAR_SOLVER *g = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "g1mgs", LINEAR_SOLVER_CLASS_NAME);
+    memset(&lr, 0, sizeof lr);
+    if (!g || (*g->PreProcess)(g, top, vx, vb, mA, &bl, &result)) { printf("FAIL gpuls inside the gpufe bracket: PreProcess\n"); fails++; }
+    else {
+      (*g->Defect)(g, top, vx, vb, mA, &result);
+      (*g->Residuum)(g, bl, top, vx, vb, mA, &lr);
+      int rc = (*g->Solver)(g, top, vx, vb, mA, abslimit, red, &lr);
+      (*g->PostProcess)(g, top, vx, vb, mA, &result);
+      double ex = 0;
+      for (int l = 0; l <= top; l++) ex = fmax(ex, maxrel(xs[l], gather(vx, l)));
+      double ed = fabs(lr.last_defect[0] - lr_ref.last_defect[0]) / lr_ref.last_defect[0];
+      bool ok = !rc && ex <= 1e-12 && ed <= 1e-12 && lr.number_of_linear_iterations == lr_ref.number_of_linear_iterations;
+      printf("%s gpuls+gpulmgc inside the gpufe bracket (matrix assembled on the device, no value upload): its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e\n",
+             ok ? "PASS" : "FAIL", (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_ref.last_defect[0], ex);
+      if (!ok) fails++;
+    }
+    (*gass->PostProcess)(gass, top, vx, vb, mA, &result);
+    restore_problem();
   }
   printf("gpuls drop-in: %d failure(s)\n", fails);
   return fails ? 10 : 0;

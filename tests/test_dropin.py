@@ -43,10 +43,18 @@ CASES = [
     ("ugoracle2", ["--grid", "tri", "--refine", "6", "--damp", "0.8", "--cycles", "6"]),                               # C1 verbatim: 65^2 = 4 225 unknowns, 7 levels
     ("ugoracle2", ["--grid", "tri", "--refine", "9", "--damp", "0.8", "--cycles", "4", "--nokrylov"]),                 # 513^2 = 263 169 unknowns
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--adapt", "2", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),   # adaptive on 17^3
+    # ---- assemble.gpufe against the reference's NP_LOCAL_ASSEMBLE loop (np/procs/assemble.cc:657) with the same element
+    # kernel: MVALUEs, rhs, Dirichlet values and VECSKIP of every level bit for bit, then gpuls inside gpufe's bracket vs the CPU solve
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--damp", "0.6", "--cycles", "5", "--nokrylov", "--assemble"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),
+    ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "3", "--damp", "0.7", "--cycles", "4", "--nokrylov", "--assemble"]),
+    ("ugoracle3", ["--grid", "hex", "--refine", "4", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),     # Q1 17^3
+    ("ugoracle3", ["--grid", "tet", "--refine", "5", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),     # 33^3
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
        "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu", "quad-bs2", "tet-r5-33^3", "tet-r6-65^3", "hex-bs3-r4", "hex-q1-r5-33^3", "tri-r6-C1", "tri-r9-513^2",
-       "tet-r4-adaptive"]
+       "tet-r4-adaptive", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "assemble-hex-q1-r4", "assemble-tet-r5-33^3"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)
@@ -57,5 +65,6 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    assert sum(l.startswith("PASS") for l in lines) == (4 if "--nokrylov" in args else 6), lines      # 4 ls/lmgc mixes [+ gpucg + gpubcgs]
+    want = (4 if "--nokrylov" in args else 6) + (2 if "--assemble" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket]
+    assert sum(l.startswith("PASS") for l in lines) == want, lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -119,6 +119,60 @@ int FlattenMatrixValues(MULTIGRID *mg, int level, const MATDATA_DESC *A, std::ve
   return 0;
 }
 
+int ScatterMatrixValues(MULTIGRID *mg, int level, const MATDATA_DESC *A, const std::vector<double> &val, int bs)
+{
+  GRID *g = GRID_ON_LEVEL(mg, level);
+  if (g == NULL) return 1;
+  VECTOR *v0 = FIRSTVECTOR(g);
+  int bb = bs * bs;
+  SHORT comp[MAX_SINGLE_MAT_COMP];
+  if (BlockComps(A, VTYPE(v0), bs, comp)) return 3;
+  size_t e = 0;
+  for (VECTOR *v = v0; v != NULL; v = SUCCVC(v))
+    for (MATRIX *m = VSTART(v); m != NULL; m = MNEXT(m), e++) {
+      if ((e + 1) * bb > val.size()) return 5;
+      for (int k = 0; k < bb; k++) MVALUE(m, comp[k]) = val[e * bb + k];
+    }
+  return 0;
+}
+
+int ScatterSkip(MULTIGRID *mg, int level, const std::vector<uint32_t> &skip)
+{
+  GRID *g = GRID_ON_LEVEL(mg, level);
+  if (g == NULL) return 1;
+  size_t r = 0;
+  for (VECTOR *v = FIRSTVECTOR(g); v != NULL; v = SUCCVC(v), r++) {
+    if (r >= skip.size()) return 5;
+    VECSKIP(v) = skip[r];
+  }
+  return 0;
+}
+
+int FlattenElements(MULTIGRID *mg, int level, std::vector<int64_t> &elem_ptr, std::vector<int32_t> &elem_row, std::vector<double> &coord,
+                    std::vector<uint32_t> &dirichlet_skip, int bs)
+{
+  GRID *g = GRID_ON_LEVEL(mg, level);
+  if (g == NULL) return 1;
+  const int n = NVEC(g);
+  elem_ptr.assign(1, 0); elem_row.clear();
+  coord.assign((size_t)n * DIM, 0.0);
+  dirichlet_skip.assign((size_t)n, 0u);
+  for (NODE *nd = FIRSTNODE(g); nd != NULL; nd = SUCCN(nd)) {
+    const int r = (int)VINDEX(NVECTOR(nd));
+    if (r < 0 || r >= n) return 2;
+    for (int d = 0; d < DIM; d++) coord[(size_t)r * DIM + d] = CVECT(MYVERTEX(nd))[d];
+  }
+  for (ELEMENT *e = FIRSTELEMENT(g); e != NULL; e = SUCCE(e)) {
+    for (int i = 0; i < CORNERS_OF_ELEM(e); i++) {
+      const int r = (int)VINDEX(NVECTOR(CORNER(e, i)));
+      elem_row.push_back((int32_t)r);
+      if (OBJT(e) == BEOBJ && OBJT(MYVERTEX(CORNER(e, i))) == BVOBJ) dirichlet_skip[r] = (1u << bs) - 1u;
+    }
+    elem_ptr.push_back((int64_t)elem_row.size());
+  }
+  return 0;
+}
+
 // Standard transfer stencils, mirroring the per-node logic of
 // StandardIntCorNodeVector (transgrid.cc:269-307) for P and
 // StandardRestrictNodeVector (transgrid.cc:150-189) for R.

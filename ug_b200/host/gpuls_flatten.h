@@ -53,6 +53,16 @@ int FlattenTransfer(NS_DIM_PREFIX MULTIGRID *mg, int level, FlatLevel &out);
 // 8 when a vector has CRITBITs set.
 int FlattenTransferIMAT(NS_DIM_PREFIX MULTIGRID *mg, int level, FlatLevel &out);
 
+// Device-side assembly: the elements of `level` in FIRSTELEMENT->SUCCE order with the rows (VINDEX, FlattenFlags
+// first) of their corner vectors in CORNER order, the vertex coordinates by row, and the VECSKIP words the element loop of
+// np/procs/assemble.cc:657 would leave when every component of a boundary vertex met in a boundary element is Dirichlet
+// (SetElementDirichletFlags, np/udm/disctools.cc:1763).
+int FlattenElements(NS_DIM_PREFIX MULTIGRID *mg, int level, std::vector<int64_t> &elem_ptr, std::vector<int32_t> &elem_row, std::vector<double> &coord,
+                    std::vector<uint32_t> &dirichlet_skip, int bs);
+// inverse of FlattenMatrixValues / of the skip part of FlattenFlags: device results back into MVALUEs / VECSKIP
+int ScatterMatrixValues(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PREFIX MATDATA_DESC *A, const std::vector<double> &val, int bs);
+int ScatterSkip(NS_DIM_PREFIX MULTIGRID *mg, int level, const std::vector<uint32_t> &skip);
+
 // VVALUE gather/scatter in list order: host[r*bs+i] <-> VVALUE(v, VD_CMP_OF_TYPE(vd,VTYPE(v),i))
 void GatherVector(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PREFIX VECDATA_DESC *vd, int bs, double *host);
 void ScatterVector(NS_DIM_PREFIX MULTIGRID *mg, int level, const NS_DIM_PREFIX VECDATA_DESC *vd, int bs, const double *host);

@@ -27,6 +27,7 @@
 #include "iter.h"
 #include "ls.h"
 #include "transfer.h"
+#include "assemble.h"
 #include "ugdevices.h"
 #include "ugstruct.h"
 #include "misc.h"
@@ -42,7 +43,7 @@ USING_UG_NAMESPACES
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
   X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
-  X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp)
+  X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags)
 
 namespace {
 struct Api {
@@ -864,7 +865,142 @@ INT GpuLsConstructKind(NP_BASE *theNP, INT kind)
   return 0;
 }
 
+
+// =========================================================================================================================
+// assemble.gpufe  (reference interface: NP_ASSEMBLE np/procs/assemble.h:178-210; the loop it replaces: LocalAssemble
+// np/procs/assemble.cc:657-706 and NPLocalAssemblePostMatrix :624 of NP_LOCAL_ASSEMBLE)
+// The element kernel, which UG leaves to the application's AssembleLocal, is the device library's built-in one (uggpu_assemble).
+// Assemble(level) does what LocalAssemble does -- levels 0..level -- and leaves the same MVALUEs, right-hand side, Dirichlet values
+// of x and VECSKIP words in UG's data structures, bit for bit; the device copies stay valid for a solver whose PreProcess runs
+// inside this numproc's PreProcess/PostProcess bracket (no second upload of the matrix).
+// =========================================================================================================================
+gpuls::ElemCoefFn g_fe_coef = NULL;
+gpuls::DirichletFn g_fe_dirichlet = NULL;
+
+struct NP_GPUFE {
+  NP_ASSEMBLE ass;
+  INT problem;          // UGGPU_FE_*
+  DOUBLE E, nu;
+  DOUBLE source[UGGPU_MAX_BS];
+  Mirror *m;
+};
+
+INT GpuFeInit(NP_BASE *theNP, INT argc, char **argv)
+{
+  NP_GPUFE *np = (NP_GPUFE *)theNP;
+  char buf[64];
+  np->problem = UGGPU_FE_POISSON;
+  if (ReadArgvChar("P", buf, argc, argv) == 0) {
+    if (strcmp(buf, "elasticity") == 0) np->problem = UGGPU_FE_ELASTICITY;
+    else if (strcmp(buf, "poisson") != 0) { PrintErrorMessageF('E', "GpuFeInit", "unknown problem '%s' (poisson | elasticity)", buf); return NP_NOT_ACTIVE; }
+  }
+  if (ReadArgvDOUBLE("E", &np->E, argc, argv)) np->E = 1.0;
+  if (ReadArgvDOUBLE("nu", &np->nu, argc, argv)) np->nu = 0.3;
+  for (int i = 0; i < UGGPU_MAX_BS; i++) np->source[i] = 0.0;
+  np->source[0] = 1.0;
+  for (int i = 0; i < argc; i++)
+    if (argv[i][0] == 'f') {
+      double f[3] = {0, 0, 0};
+      char opt[32];
+      int k = sscanf(argv[i], "%31s %lf %lf %lf", opt, &f[0], &f[1], &f[2]);
+      if (k >= 2 && strcmp(opt, "f") == 0) for (int j = 0; j < UGGPU_MAX_BS; j++) np->source[j] = j < k - 1 ? f[j] : 0.0;
+    }
+  return NPAssembleInit(theNP, argc, argv);
+}
+
+INT GpuFeDisplay(NP_BASE *theNP)
+{
+  NP_GPUFE *np = (NP_GPUFE *)theNP;
+  NPAssembleDisplay(theNP);
+  UserWrite("configuration parameters:\n");
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "P", np->problem == UGGPU_FE_ELASTICITY ? "elasticity" : "poisson");
+  UserWriteF(DISPLAY_NP_FORMAT_SF, "E", (float)np->E);
+  UserWriteF(DISPLAY_NP_FORMAT_SF, "nu", (float)np->nu);
+  UserWriteF(DISPLAY_NP_FORMAT_SS, "device", "B200 via libuggpu");
+  return 0;
+}
+
+INT GpuFePreProcess(NP_ASSEMBLE *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUFE *np = (NP_GPUFE *)theNP;
+  np->m = Acquire(NP_MG(theNP));
+  if (np->m == NULL) NP_RETURN(1, result[0]);
+  return 0;
+}
+
+INT GpuFeAssemble(NP_ASSEMBLE *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUFE *np = (NP_GPUFE *)theNP;
+  MULTIGRID *mg = NP_MG(theNP);
+  Mirror *m = np->m ? Live(np->m, mg) : NULL;
+  if (m == NULL) { UserWrite("gpufe: Assemble without PreProcess\n"); NP_RETURN(1, result[0]); }
+  std::vector<int64_t> eptr; std::vector<int32_t> erow; std::vector<double> coord, coef, val; std::vector<uint32_t> skip;
+  for (int l = 0; l <= level; l++) {
+    UserWriteF(" [%d:", l);                                                     // assemble.cc:672
+    gpuls::FlatLevel &f = m->fl[l];
+    // the pattern (connections) is the grid manager's; values and VECSKIP are about to be replaced
+    if (gpuls::FlattenFlags(mg, l, x, f)) { UserWriteF("gpufe: level %d is not a pure nodal vector format\n", l); NP_RETURN(1, result[0]); }
+    if (f.bs > UGGPU_MAX_BS) NP_RETURN(1, result[0]);
+    if (gpuls::FlattenMatrix(mg, l, A, f)) { UserWrite("gpufe: cannot flatten the matrix pattern\n"); NP_RETURN(1, result[0]); }
+    if (gpuls::FlattenElements(mg, l, eptr, erow, coord, skip, f.bs)) NP_RETURN(1, result[0]);
+    m->bs = f.bs; m->xdesc = x;
+    m->have_level[l] = 0; m->have_transfer[l] = 0; if (l + 1 < MAXLEVEL) m->have_transfer[l + 1] = 0;
+    if (api.uggpu_level_create(m->ctx, l, f.n, f.bs)) NP_RETURN(dev_fail("uggpu_level_create"), result[0]);
+    if (api.uggpu_level_set_flags(m->ctx, l, f.vclass.data(), f.vnclass.data(), f.ctl.data(), NULL)) NP_RETURN(dev_fail("uggpu_level_set_flags"), result[0]);
+    if (api.uggpu_mat_set_pattern(m->ctx, l, m->handle(A), f.rowptr.data(), f.col.data())) NP_RETURN(dev_fail("uggpu_mat_set_pattern"), result[0]);
+    // the application's part of AssembleLocal: coefficients, Dirichlet values of x on the boundary vertices
+    const size_t nelem = eptr.size() - 1;
+    coef.clear();
+    if (g_fe_coef) { coef.reserve(nelem); for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l)); e != NULL; e = SUCCE(e)) coef.push_back((*g_fe_coef)(e)); }
+    m->buf.resize((size_t)f.n * f.bs + 1);
+    gpuls::GatherVector(mg, l, x, f.bs, m->buf.data());
+    for (int r = 0; r < f.n; r++)
+      for (int a = 0; a < f.bs; a++)
+        if (skip[r] & (1u << a)) m->buf[(size_t)r * f.bs + a] = g_fe_dirichlet ? (*g_fe_dirichlet)(&coord[(size_t)r * DIM], a) : 0.0;
+    if (api.uggpu_vec_upload(m->ctx, l, m->handle(x), m->buf.data())) NP_RETURN(dev_fail("uggpu_vec_upload"), result[0]);
+    gpuls::ScatterVector(mg, l, x, f.bs, m->buf.data());                        // `*sptr[i] = sol[i]`, assemble.cc:692
+    if (api.uggpu_vec_alloc(m->ctx, l, m->handle(b))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+    uggpu_fe_cfg cfg;
+    cfg.problem = (int)np->problem; cfg.dim = DIM; cfg.E = np->E; cfg.nu = np->nu;
+    for (int a = 0; a < UGGPU_MAX_BS; a++) cfg.source[a] = np->source[a];
+    if (api.uggpu_assemble(m->ctx, l, m->handle(x), m->handle(b), m->handle(A), &cfg, (int64_t)nelem, eptr.data(), erow.data(),
+                           coef.empty() ? NULL : coef.data(), coord.data(), skip.data())) NP_RETURN(dev_fail("uggpu_assemble"), result[0]);
+    // results into UG's data structures: MVALUEs, right-hand side, VECSKIP
+    val.assign(f.val.size(), 0.0);
+    if (api.uggpu_mat_get(m->ctx, l, m->handle(A), NULL, NULL, val.data())) NP_RETURN(dev_fail("uggpu_mat_get"), result[0]);
+    if (gpuls::ScatterMatrixValues(mg, l, A, val, f.bs) || gpuls::ScatterSkip(mg, l, skip)) NP_RETURN(1, result[0]);
+    f.val = val; f.skip = skip;
+    if (Download(m, l, b)) NP_RETURN(1, result[0]);
+    if (api.uggpu_set_fullrefinelevel(m->ctx, FULLREFINELEVEL(mg))) NP_RETURN(dev_fail("uggpu_set_fullrefinelevel"), result[0]);
+    m->have_level[l] = 1; m->level_A[l] = A; m->level_x[l] = x;                 // a solver inside the bracket finds the matrix on the device
+    UserWrite("a]");
+  }
+  UserWrite(" [d]\n");
+  return 0;
+}
+
+INT GpuFePostProcess(NP_ASSEMBLE *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUFE *np = (NP_GPUFE *)theNP;
+  if (np->m != NULL) { if (Live(np->m, NP_MG(theNP))) Release(NP_MG(theNP)); np->m = NULL; }
+  return 0;
+}
+
+INT GpuFeConstruct(NP_BASE *theNP)
+{
+  theNP->Init = GpuFeInit;
+  theNP->Display = GpuFeDisplay;
+  theNP->Execute = NPAssembleExecute;
+  NP_ASSEMBLE *np = (NP_ASSEMBLE *)theNP;
+  np->PreProcess = GpuFePreProcess;
+  np->Assemble = GpuFeAssemble;
+  np->PostProcess = GpuFePostProcess;
+  return 0;
+}
+
 }  // namespace
+
+void gpuls::SetFEData(gpuls::ElemCoefFn coef, gpuls::DirichletFn dirichlet) { g_fe_coef = coef; g_fe_dirichlet = dirichlet; }
 
 INT NS_DIM_PREFIX InitGpuLS(void)
 {
@@ -878,5 +1014,6 @@ INT NS_DIM_PREFIX InitGpuLS(void)
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpuls", sizeof(NP_GPULS), GpuLsConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpucg", sizeof(NP_GPULS), GpuCgConstruct)) REP_ERR_RETURN(__LINE__);
   if (CreateClass(LINEAR_SOLVER_CLASS_NAME ".gpubcgs", sizeof(NP_GPULS), GpuBcgsConstruct)) REP_ERR_RETURN(__LINE__);
+  if (CreateClass(ASSEMBLE_CLASS_NAME ".gpufe", sizeof(NP_GPUFE), GpuFeConstruct)) REP_ERR_RETURN(__LINE__);
   return 0;
 }

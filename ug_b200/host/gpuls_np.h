@@ -9,6 +9,9 @@
 //   iter.gpulmgc                   NP_ITER                      iter.lmgc         iter.cc:7613-7980
 //   linear_solver.gpuls            NP_LINEAR_SOLVER (ls.h:79)   linear_solver.ls  ls.cc:539-905
 //   linear_solver.gpucg / gpubcgs  NP_LINEAR_SOLVER             linear_solver.cg / bcgs  ls.cc:939-1160, 1750-2062
+//   assemble.gpufe                 NP_ASSEMBLE (assemble.h:178) the element loop of NP_LOCAL_ASSEMBLE: LocalAssemble assemble.cc:657-706 +
+//                                                               NPLocalAssemblePostMatrix :624, with a built-in P1/Q1 element kernel
+//                                                               ($P poisson|elasticity $E $nu $f <source per component>)
 //
 // Same option letters as the CPU classes ($A $x $b $c $damp $S $T $n1 $n2 $g $b $t $m $I $red $abslimit $display),
 // plus on gpulmgc: $devbase (solve the base level on the device instead of calling the BaseSolver numproc) and
@@ -24,6 +27,11 @@ namespace gpuls {
 // dlopen()s libuggpu.so (path may be NULL: $UGGPU_LIB, then "libuggpu.so" on the loader path). 0 = ok.
 int LoadDeviceLibrary(const char *path);
 const char *LastLoadError();
+// assemble.gpufe: the application's data for the built-in element kernel -- one coefficient per element (NULL: 1) and the Dirichlet
+// value of component `comp` at a boundary vertex (NULL: 0).  In UG both live inside the application's AssembleLocal.
+typedef double (*ElemCoefFn)(NS_DIM_PREFIX ELEMENT *e);
+typedef double (*DirichletFn)(const double *pos, int comp);
+void SetFEData(ElemCoefFn coef, DirichletFn dirichlet);
 }
 
 START_UGDIM_NAMESPACE
