@@ -509,6 +509,82 @@ def measure(spec, rt):
     return out
 
 
+def kuhn_elements(nx, ny, nz):
+    """Rows of the corner vectors of the 6 Kuhn tetrahedra (diagonal 0-6, UG's hexahedron corner numbering) of every cube of a structured
+    nx*ny*nz-cell grid with lexicographic rows (x fastest) -- the mesh uggpu_synth_hierarchy assembles analytically -- in cube order."""
+    import numpy as np
+    NX, NY = nx + 1, ny + 1
+    i, j, k = np.meshgrid(np.arange(nx, dtype=np.int64), np.arange(ny, dtype=np.int64), np.arange(nz, dtype=np.int64), indexing="ij")
+    base = (i + NX * (j + NY * k)).transpose(2, 1, 0).ravel()
+    off = np.array([0, 1, 1 + NX, NX, NX * NY, 1 + NX * NY, 1 + NX + NX * NY, NX + NX * NY], dtype=np.int64)
+    tets = np.array([[0, 1, 2, 6], [0, 2, 3, 6], [0, 3, 7, 6], [0, 7, 4, 6], [0, 4, 5, 6], [0, 5, 1, 6]])
+    er = (base[:, None, None] + off[tets][None, :, :]).astype(np.int32).reshape(-1)
+    return np.arange(0, er.size + 1, 4, dtype=np.int64), er
+
+
+def assemble_bench(local, cells, top):
+    """SURVEY.md 8f.4 at size: uggpu_assemble (the element loop of np/procs/assemble.cc:657 + AssembleDirichletBoundary) on the finest level
+    of the synthetic P1 hierarchy from its element list, into a second matrix with the same pattern; kernel time from CUDA events
+    (uggpu_prof), compared entry by entry with the matrix the generator wrote analytically.  A setup operation, outside the timed steps."""
+    import numpy as np
+    from ug_b200 import capi, mgpu
+    peak, _ = peak_hbm()
+    ctx = capi.Context(local)
+    try:
+        A = ctx.handle("A")
+        ctx.call("uggpu_synth_hierarchy", mgpu.KINDS["p1"], cells[0], cells[1], cells[2], top, A)
+        n = ctx.level_n(top)
+        nn = [c * 2 ** top + 1 for c in cells]
+        assert n == nn[0] * nn[1] * nn[2]
+        t0 = time.perf_counter()
+        ep, er = kuhn_elements(nn[0] - 1, nn[1] - 1, nn[2] - 1)
+        h = 1.0 / (nn[0] - 1)
+        z, y, x = np.meshgrid(np.arange(nn[2]), np.arange(nn[1]), np.arange(nn[0]), indexing="ij")
+        coord = np.stack([x.ravel() * h, y.ravel() * h, z.ravel() * h], axis=1).astype(np.float64)
+        bnd = ((x == 0) | (x == nn[0] - 1) | (y == 0) | (y == nn[1] - 1) | (z == 0) | (z == nn[2] - 1)).ravel()
+        skip = bnd.astype(np.uint32)
+        del x, y, z
+        host_s = time.perf_counter() - t0
+        nnz = int(ctx.L.uggpu_mat_nnz(ctx.h, top, A))
+        rowptr = np.zeros(n + 1, np.int32); col = np.zeros(nnz, np.int32); val = np.zeros(nnz)
+        ctx.call("uggpu_mat_get", top, A, capi._p(rowptr), capi._p(col), capi._p(val))
+        K = ctx.handle("K")
+        ctx.call("uggpu_mat_set_pattern", top, K, capi._p(rowptr), capi._p(col))
+        ctx.alloc(top, "x"); ctx.alloc(top, "b"); ctx.alloc(top, "b0")
+        ctx.call("uggpu_dset", top, top, 0, ctx.handle("x"), 0.0)
+        ctx.call("uggpu_synth_rhs", top, ctx.handle("b0"))
+        fe = dict(problem=0, dim=3, E=1.0, nu=0.3, source=[1.0])
+        ms = []
+        for rep in range(3):
+            ctx.call("uggpu_prof_enable", 1)
+            t1 = time.perf_counter()
+            ctx.assemble(top, "x", "b", "K", fe, ep, er, None, coord, skip)
+            ctx.sync()
+            call_ms = (time.perf_counter() - t1) * 1e3
+            launches, kms, byt = C.c_int64(0), C.c_double(0), C.c_double(0)
+            ctx.call("uggpu_prof_summary", 11, top, C.byref(launches), C.byref(kms), C.byref(byt))
+            ctx.call("uggpu_prof_enable", 0)
+            ms.append((kms.value, call_ms))
+        kval = ctx.mat_values(top, "K", nnz)
+        b, b0 = ctx.get(top, "b"), ctx.get(top, "b0")
+        scale = float(np.abs(val).max())
+        nelem = ep.size - 1
+        # compulsory bytes: the element list once (16 B per tetrahedron) + 4 corner coordinates per element (96 B, gathered) + the matrix
+        # written once (12 B per entry as stored explicitly) + rhs, x, skip
+        alg = 16.0 * nelem + 96.0 * nelem + 8.0 * nnz + 4.0 * nnz + 20.0 * n
+        best = min(m[0] for m in ms)
+        return {"workload": f"P1 Poisson, {nn[0]}x{nn[1]}x{nn[2]} nodes = {n} rows, {nelem} Kuhn tetrahedra, {nnz} matrix entries",
+                "kernel_ms": round(best, 3), "call_ms_with_uploads_and_sort": round(min(m[1] for m in ms), 1), "host_element_list_s": round(host_s, 2),
+                "elements_per_s": nelem / (best * 1e-3), "alg_bytes": alg, "GBps": alg / (best * 1e-3) / 1e9, "frac": alg / (best * 1e-3) / 1e9 / peak,
+                "max_abs_diff_vs_generator_matrix_rel": float(np.abs(kval - val).max() / scale), "entries_bit_identical_frac": float(np.mean(kval == val)),
+                "rhs_max_abs_diff_rel": float(np.abs(b - b0).max() / np.abs(b0).max()),
+                "parity": "bit-exact against the reference's NP_LOCAL_ASSEMBLE loop on 6 hierarchies (tests/test_gpu_parity.py::test_gpu_assemble_bitexact, "
+                          "tests/test_dropin.py assemble-*); here: agreement with the generator's analytic stencil"}
+    finally:
+        ctx.close()
+
+
+
 def brief(m, keys=("value", "ms_per_step", "n_global", "launches", "kernel_sum_ms_per_step", "defect", "device_bytes", "setup_s", "transport", "halo_exchanges_per_step")):
     """What an extra workload contributes to the JSON line."""
     r = {k: m[k] for k in keys if k in m}
@@ -589,6 +665,10 @@ def our_arm(args):
             extra("elasticity_3x3", kind="elasticity", top=args.top - 1)
             extra("galerkin", galerkin=True, steps=3)
             extra("krylov", krylov=True, steps=3)
+            try:
+                extras["assemble"] = assemble_bench(local, (args.cells,) * 3, args.top - 1)
+            except Exception as e:
+                extras["assemble"] = {"error": str(e)[:300]}
         else:
             c4 = (4, 4, 4)
             extra("q1_poisson_strong", kind="q1", cells=c4)
