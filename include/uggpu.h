@@ -265,6 +265,31 @@ typedef struct uggpu_fe_cfg {
 int uggpu_assemble(uggpu_ctx*, int level, int x, int b, int A, const uggpu_fe_cfg *cfg, int64_t nelem, const int64_t *elem_ptr,
                    const int32_t *elem_row, const double *coef, const double *coord, const uint32_t *skip);
 
+/* ---- savedata / loaddata for device vectors, np/udm/data_io.cc:650 SaveData / :408 LoadData -----------------------------
+ * The reference's data files: a header (np/udm/dio.cc:338 Write_DT_General; DIO_GENERAL np/udm/dio.h) and one record per NODE, in the
+ * order of the node IDs over all levels, holding the components of the saved VECDATA_DESCs side by side; modes "asc" and "bin"
+ * (low/bio.cc; "xdr" is not offered).  Files written here are byte-identical to the reference's and either side reads the other's.
+ * The caller supplies what only the grid manager knows: for node ID i the level id_level[i] and the row id_row[i] of its vector, and the
+ * header fields.  uggpu_savedata gathers the vectors `vec[0..nvd)` of all levels on the device into file order, copies the body down
+ * once and writes it; uggpu_loaddata parses a file, uploads the body once and scatters it into vec[0..nvd) (vec[i] < 0, or fewer
+ * descriptors than the file holds: those values are skipped, data_io.cc:515-523; component counts must match, :521).
+ * uggpu_data_write / uggpu_data_read are the host-only halves (format only, no device): data[nnode * sum(ncomp)] in file order. */
+typedef struct uggpu_data_general {      /* DIO_GENERAL, np/udm/dio.h                                                        */
+  const char *ident;                     /* string variable :IDENTIFICATION ("---" when unset, data_io.cc:750)               */
+  const char *mgfile;                    /* multigrid file the data belongs to ("saved_without_mg", data_io.cc:747)          */
+  double time, dt, ndt;                  /* -1 when the file carries no time step number (data_io.cc:758-762)                */
+  int    nparfiles, me, magic_cookie;    /* procs, me, MG_MAGIC_COOKIE(theMG)                                                */
+} uggpu_data_general;
+int uggpu_data_write(const char *filename, const char *type /* "asc" | "bin" */, const uggpu_data_general *g, int nvd, const int *ncomp,
+                     const char *const *vdname, const char *const *compnames, int64_t nnode, const double *data);
+/* data == NULL: header only.  g->ident / g->mgfile point into storage that stays valid until the next call on the same thread. */
+int uggpu_data_read(const char *filename, uggpu_data_general *g, int *nvd, int *ncomp /* [ncomp_cap] or NULL */, int ncomp_cap,
+                    int64_t *ndata, double *data, int64_t data_cap);
+int uggpu_savedata(uggpu_ctx *ctx, const char *filename, const char *type, const uggpu_data_general *g, int nvd, const int *vec,
+                   const char *const *vdname, const char *const *compnames, int64_t nnode, const int32_t *id_level, const int32_t *id_row);
+int uggpu_loaddata(uggpu_ctx *ctx, const char *filename, int nvd, const int *vec, int64_t nnode, const int32_t *id_level,
+                   const int32_t *id_row, uggpu_data_general *general_out /* or NULL */);
+
 /* ---- multigrid cycle, np/procs/iter.cc:7741-7949 Lmgc ------------------------------------------------ */
 /* Base solver hook: called with the stream drained when the recursion reaches baselevel.  It must
  * turn the defect b into (correction c, updated defect b) on that level exactly like

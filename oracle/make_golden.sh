@@ -58,4 +58,9 @@ mkdir -p $G
 ./_ref/ugoracle3 --grid tet --refine 2 --adapt 2 --lean --assemble --dump $G/asm_tet3d_adapt.ugh > /dev/null
 ./_ref/ugoracle2 --grid tri --refine 4 --lean --assemble --dump $G/asm_tri2d_r4.ugh > /dev/null
 ./_ref/ugoracle2 --grid quad --bs 2 --refine 3 --lean --assemble --dump $G/asm_quad2d_bs2_r3.ugh > /dev/null
+# ---- savedata / loaddata: files written by the reference's SaveData (np/udm/data_io.cc:650, without a multigrid file, modes bin and
+# asc) embedded as byte records, the node-ID order of their bodies, the vectors they were written from
+./_ref/ugoracle3 --grid tet --refine 2 --lean --savedata /tmp/ugsd_golden_t --dump $G/savedata_tet3d_r2.ugh > /dev/null
+./_ref/ugoracle2 --grid quad --bs 2 --refine 2 --lean --savedata /tmp/ugsd_golden_q --dump $G/savedata_quad2d_bs2_r2.ugh > /dev/null
+./_ref/ugoracle3 --grid tet --refine 1 --adapt 2 --lean --savedata /tmp/ugsd_golden_a --dump $G/savedata_tet3d_adapt.ugh > /dev/null
 ls -la $G

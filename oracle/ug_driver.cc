@@ -21,6 +21,7 @@
 #include <cstring>
 #include <cmath>
 #include <ctime>
+#include <unistd.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -43,6 +44,7 @@
 #include "refine.h"
 #include "assemble.h"
 #include "disctools.h"
+#include "data_io.h"
 
 #include "gpuls_flatten.h"
 #ifdef WITH_GPULS
@@ -102,6 +104,7 @@ struct Opt {
   bool ops = false, solve = false, timeit = false, quiet = true, nokrylov = false, elems = false;
   bool imat = false;                    // transfer $M: RestrictByMatrix / InterpolateCorrectionByMatrix on stored interpolation matrices
   bool galerkin = false;                // --galerkin (with --imat): Galerkin coarse-grid operators by AssembleGalerkinByMatrix, cascaded from the top level down
+  std::string savedata;
   bool assemble = false;                // --assemble: run the reference's LocalAssemble (np/procs/assemble.cc:657) with the element kernel below and dump what it leaves
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
 };
@@ -395,6 +398,51 @@ static void dump_assemble(const Opt &o)
     for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l)); e; e = SUCCE(e)) coef.push_back(fe_coef(e));
     D.f64(L("asm/coef", l), coef);
   }
+  restore_problem();
+}
+
+
+// savedata / loaddata: the reference's SaveData (np/udm/data_io.cc:650) writes vectors `sol` and `rhs` (seeded values) of all
+// levels without a multigrid file, in binary and ASCII mode; the dump records the node-ID order the file body follows.
+static void dump_savedata(const Opt &o)
+{
+  int top = TOPLEVEL(mg);
+  for (int l = 0; l <= top; l++) { fill_lcg(vx, l, 11); fill_lcg(vb, l, 12); }
+  VECDATA_DESC *vds[2] = {vx, vb};
+  // Built with UG_USE_SYSTEM_HEAP (oracle/Makefile) the multigrid heap is a stub of MIN_HEAP_SIZE bytes (gm/ugm.cc:3165) while every
+  // allocation is a malloc; SaveData / LoadData size their buffers from `size - used` of that stub (data_io.cc:886, :570) and give up.
+  // The size FIELD is raised for the duration of the calls -- no reference source is touched, the buffers still come from malloc.
+  const MEM heap_size_field = MGHEAP(mg)->size;
+  MGHEAP(mg)->size = MGHEAP(mg)->used + (MEM)(1u << 30);
+  EVALUES *ev[2] = {NULL, NULL}; EVECTOR *evec[2] = {NULL, NULL};
+  for (const char *type : {"bin", "asc"}) {
+    std::string name = o.savedata;
+    if (SaveData(mg, (char *)name.c_str(), 1, 1, (char *)type, -1, 0.0, 0.0, 0.0, 2, vds, ev, evec, NULL)) { fprintf(stderr, "SaveData(%s) failed\n", type); exit(13); }
+  }
+  MGHEAP(mg)->size = heap_size_field;
+  for (const char *type : {"bin", "asc"}) {           // the files themselves travel inside the dump
+    std::string path = o.savedata + ".ug.data." + type;
+    std::vector<uint8_t> bytes;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); exit(13); }
+    for (int c; (c = fgetc(f)) != EOF;) bytes.push_back((uint8_t)c);
+    fclose(f);
+    D.u8(std::string("savedata/file_") + type, bytes);
+    remove(path.c_str());
+  }
+  std::vector<int32_t> idl, idr;
+  int nn = 0;
+  for (int l = 0; l <= top; l++) nn += NN(GRID_ON_LEVEL(mg, l));
+  idl.assign(nn, -1); idr.assign(nn, -1);
+  for (int l = 0; l <= top; l++) {
+    gpuls::FlatLevel f;
+    if (gpuls::FlattenFlags(mg, l, vx, f)) exit(13);
+    for (NODE *n = PFIRSTNODE(GRID_ON_LEVEL(mg, l)); n; n = SUCCN(n)) { idl[ID(n)] = l; idr[ID(n)] = VINDEX(NVECTOR(n)); }
+    dumpvec("savedata/sol", vx, l); dumpvec("savedata/rhs", vb, l);
+  }
+  D.i32("savedata/id_level", idl); D.i32("savedata/id_row", idr);
+  D.scalar_i("savedata/magic_cookie", MG_MAGIC_COOKIE(mg));
+  { std::vector<uint8_t> cn; for (int j = 0; j < BS; j++) cn.push_back((uint8_t)vx->compNames[j]); D.u8("savedata/compnames", cn); }
   restore_problem();
 }
 
@@ -819,6 +867,7 @@ int main(int argc, char **argv)
     else if (a == "--beta") o.beta = atof(nxt().c_str());
     else if (a == "--galerkin") o.galerkin = true;
     else if (a == "--assemble") { o.assemble = true; o.elems = true; }
+    else if (a == "--savedata") o.savedata = nxt();      // prefix of the data files the reference's SaveData writes (np/udm/data_io.cc:650)
     else if (a == "--nokrylov") o.nokrylov = true;
     else if (a == "--elems") o.elems = true;             // dump the elements (corner rows, fathers): input of the element partition (ug_b200/partition.py)       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
@@ -852,6 +901,7 @@ int main(int argc, char **argv)
     if (o.solve) dump_solve(o);
     if (o.solve && !o.lean) dump_krylov(o);
     if (o.assemble) dump_assemble(o);
+    if (!o.savedata.empty()) dump_savedata(o);
     if (o.galerkin) dump_galerkin(o);
     D.close();
   }
@@ -1028,6 +1078,43 @@ static int run_gpu(const Opt &o)
       printf("%s gpuls+gpulmgc inside the gpufe bracket (matrix assembled on the device, no value upload): its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e\n",
              ok ? "PASS" : "FAIL", (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_ref.last_defect[0], ex);
       if (!ok) fails++;
+    }
+    // savedata / loaddata on the device mirror against the reference's SaveData (np/udm/data_io.cc:650): (a) the device copies of sol and
+    // rhs -> file, bytes equal to the file the reference writes from the VVALUEs; (b) a file the reference wrote from OTHER values -> device
+    // vectors (gpuls::LoadData) -> file again (gpuls::SaveData): bytes equal to the file that was loaded
+    {
+      VECDATA_DESC *vds[2] = {vx, vb};
+      EVALUES *ev[2] = {NULL, NULL}; EVECTOR *evec[2] = {NULL, NULL};
+      char base[64]; snprintf(base, sizeof base, "/tmp/ugsd_%d", (int)getpid());
+      std::string ref1 = std::string(base) + "_ref1", dev1 = std::string(base) + "_dev1", ref2 = std::string(base) + "_ref2", dev2 = std::string(base) + "_dev2";
+      auto bytes = [](const std::string &p) { std::vector<char> b; FILE *f = fopen(p.c_str(), "rb"); if (f) { for (int c; (c = fgetc(f)) != EOF;) b.push_back((char)c); fclose(f); } return b; };
+      const MEM heap_size_field = MGHEAP(mg)->size;
+      int bad_io = 0;
+      for (const char *type : {"bin", "asc"}) {
+        for (int l = 0; l <= top; l++) { Snap &s0 = got[l]; gpuls::ScatterVector(mg, l, vx, BS, s0.x.data()); gpuls::ScatterVector(mg, l, vb, BS, s0.b.data()); }
+        MGHEAP(mg)->size = MGHEAP(mg)->used + (MEM)(1u << 30);
+        int e1 = SaveData(mg, (char *)ref1.c_str(), 1, 1, (char *)type, -1, 0.0, 0.0, 0.0, 2, vds, ev, evec, NULL);
+        for (int l = 0; l <= top; l++) { fill_lcg(vx, l, 21); fill_lcg(vb, l, 22); }
+        int e2 = SaveData(mg, (char *)ref2.c_str(), 1, 1, (char *)type, -1, 0.0, 0.0, 0.0, 2, vds, ev, evec, NULL);
+        MGHEAP(mg)->size = heap_size_field;
+        int e3 = gpuls::SaveData(mg, dev1.c_str(), type, -1, 0.0, 0.0, 0.0, 2, vds);
+        std::string sfx = std::string(".ug.data.") + type;
+        std::vector<char> r1 = bytes(ref1 + sfx), d1 = bytes(dev1 + sfx), r2 = bytes(ref2 + sfx);
+        bool ok1 = !e1 && !e3 && !r1.empty() && r1 == d1;
+        printf("%s savedata %s from the device mirror: %zu bytes, %s the reference's file\n", ok1 ? "PASS" : "FAIL", type, d1.size(), ok1 ? "identical to" : "DIFFERENT from");
+        bool ok2 = false;
+        if (!e2 && !gpuls::LoadData(mg, ref2.c_str(), type, -1, 2, vds) && !gpuls::SaveData(mg, dev2.c_str(), type, -1, 0.0, 0.0, 0.0, 2, vds)) {
+          std::vector<char> d2 = bytes(dev2 + sfx);
+          ok2 = !r2.empty() && r2 == d2 && r2 != r1;
+        }
+        printf("%s loaddata %s into the device mirror, saved again: %s the loaded file\n", ok2 ? "PASS" : "FAIL", type, ok2 ? "identical to" : "DIFFERENT from");
+        if (!ok1) bad_io++;
+        if (!ok2) bad_io++;
+        // the device copies go back to the values of (a) for the next mode
+        if (strcmp(type, "bin") == 0 && gpuls::LoadData(mg, ref1.c_str(), "bin", -1, 2, vds)) bad_io++;
+        for (const std::string &p : {ref1, dev1, ref2, dev2}) remove((p + sfx).c_str());
+      }
+      fails += bad_io;
     }
     (*gass->PostProcess)(gass, top, vx, vb, mA, &result);
     restore_problem();

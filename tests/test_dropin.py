@@ -65,6 +65,6 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    want = (4 if "--nokrylov" in args else 6) + (2 if "--assemble" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket]
+    want = (4 if "--nokrylov" in args else 6) + (6 if "--assemble" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket, savedata / loaddata bin + asc]
     assert sum(l.startswith("PASS") for l in lines) == want, lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -43,7 +43,8 @@ USING_UG_NAMESPACES
   X(uggpu_mat_set) X(uggpu_transfer_set) X(uggpu_vec_alloc) X(uggpu_vec_upload) X(uggpu_vec_download) X(uggpu_jac_smooth)                       \
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
   X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
-  X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags)
+  X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags) \
+  X(uggpu_savedata) X(uggpu_loaddata)
 
 namespace {
 struct Api {
@@ -999,6 +1000,79 @@ INT GpuFeConstruct(NP_BASE *theNP)
 }
 
 }  // namespace
+
+// ---- savedata / loaddata on the device mirror (gpuls_np.h) ---------------------------------------------------------------------------
+namespace {
+// node ID -> (level, row) after RenumberMultiGrid, the order of the file body (data_io.cc:906-925); rows = list positions, as uploaded
+int NodeMap(MULTIGRID *mg, std::vector<int32_t> &idl, std::vector<int32_t> &idr)
+{
+  if (RenumberMultiGrid(mg, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0) != GM_OK) { UserWrite("ERROR: cannot renumber multigrid\n"); return 1; }   // data_io.cc:675
+  int nn = 0;
+  for (int l = 0; l <= TOPLEVEL(mg); l++) nn += NN(GRID_ON_LEVEL(mg, l));
+  idl.assign(nn, -1); idr.assign(nn, -1);
+  for (int l = 0; l <= TOPLEVEL(mg); l++) {
+    GRID *g = GRID_ON_LEVEL(mg, l);
+    int r = 0;
+    for (VECTOR *v = FIRSTVECTOR(g); v != NULL; v = SUCCVC(v)) VINDEX(v) = r++;
+    for (NODE *n = PFIRSTNODE(g); n != NULL; n = SUCCN(n)) {
+      const int id = ID(n);
+      if (id < 0 || id >= nn || idl[id] >= 0) { UserWrite("internal ERROR: id is out of range\n"); return 1; }                                  // data_io.cc:546
+      idl[id] = l; idr[id] = (int32_t)VINDEX(NVECTOR(n));
+    }
+  }
+  return 0;
+}
+std::string DataFileName(const char *name, const char *type, int number)
+{
+  std::string f = name;
+  if (number != -1) { char b[16]; snprintf(b, sizeof b, ".%06d", number); f += b; }                                                              // data_io.cc:722
+  return f + ".ug.data." + type;
+}
+}
+
+int gpuls::SaveData(MULTIGRID *mg, const char *name, const char *type, int number, double time, double dt, double ndt, int n, VECDATA_DESC **vds)
+{
+  Mirror *m = Find(mg);
+  if (m == NULL || n < 1 || n > 100) { UserWrite("gpuls::SaveData: no device mirror (call inside a PreProcess/PostProcess bracket)\n"); return 1; }
+  std::vector<int32_t> idl, idr;
+  if (NodeMap(mg, idl, idr)) return 1;
+  std::vector<int> vec(n);
+  std::vector<std::string> names(n), comps(n);
+  std::vector<const char *> np(n), cp(n);
+  for (int i = 0; i < n; i++) {
+    if (vds[i] == NULL) { UserWrite("gpuls::SaveData: eval procs are not offered\n"); return 1; }
+    const int nc = gpuls::NodeComps(vds[i]);
+    if (nc <= 0) { PrintErrorMessageF('E', "SaveData", "vd mismatch for io (no %d)", i); return 1; }                                            // data_io.cc:707
+    vec[i] = m->handle(vds[i]);
+    names[i] = ENVITEM_NAME(vds[i]);
+    for (int j = 0; j < nc; j++) comps[i] += vds[i]->compNames[j];
+    np[i] = names[i].c_str(); cp[i] = comps[i].c_str();
+  }
+  uggpu_data_general g;
+  char *ident = GetStringVar(":IDENTIFICATION");
+  g.ident = ident ? ident : "---";
+  g.mgfile = "saved_without_mg";
+  g.time = number != -1 ? time : -1.0; g.dt = number != -1 ? dt : -1.0; g.ndt = number != -1 ? ndt : -1.0;
+  g.nparfiles = 1; g.me = 0; g.magic_cookie = MG_MAGIC_COOKIE(mg);
+  const std::string file = DataFileName(name, type, number);
+  if (api.uggpu_savedata(m->ctx, file.c_str(), type, &g, n, vec.data(), np.data(), cp.data(), (int64_t)idl.size(), idl.data(), idr.data())) return dev_fail("uggpu_savedata");
+  return 0;
+}
+
+int gpuls::LoadData(MULTIGRID *mg, const char *name, const char *type, int number, int n, VECDATA_DESC **vds)
+{
+  Mirror *m = Find(mg);
+  if (m == NULL || n < 1 || n > 100) { UserWrite("gpuls::LoadData: no device mirror (call inside a PreProcess/PostProcess bracket)\n"); return 1; }
+  std::vector<int32_t> idl, idr;
+  if (NodeMap(mg, idl, idr)) return 1;
+  std::vector<int> vec(n);
+  for (int i = 0; i < n; i++) vec[i] = vds[i] ? m->handle(vds[i]) : -1;
+  uggpu_data_general g;
+  const std::string file = DataFileName(name, type, number);
+  if (api.uggpu_loaddata(m->ctx, file.c_str(), n, vec.data(), (int64_t)idl.size(), idl.data(), idr.data(), &g)) return dev_fail("uggpu_loaddata");
+  if (SetStringValue(":IO:TIME", g.time) || SetStringValue(":IO:DT", g.dt) || SetStringValue(":IO:NDT", g.ndt)) return 1;                       // data_io.cc:500-502
+  return 0;
+}
 
 void gpuls::SetFEData(gpuls::ElemCoefFn coef, gpuls::DirichletFn dirichlet) { g_fe_coef = coef; g_fe_dirichlet = dirichlet; }
 

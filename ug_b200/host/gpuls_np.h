@@ -32,6 +32,13 @@ const char *LastLoadError();
 typedef double (*ElemCoefFn)(NS_DIM_PREFIX ELEMENT *e);
 typedef double (*DirichletFn)(const double *pos, int comp);
 void SetFEData(ElemCoefFn coef, DirichletFn dirichlet);
+// savedata / loaddata for DEVICE vectors (reference: SaveData np/udm/data_io.cc:650 with save_without_mg, LoadData :408; the commands
+// `savedata` / `loaddata` of ui/commands.cc call those).  Valid inside a PreProcess/PostProcess bracket of a gpuls numproc, i.e. while the
+// device mirror of `mg` holds the vectors: the values are taken from / written to the device copies, the VVALUEs are not touched.  Files
+// are byte-identical to the reference's.  type: "asc" | "bin"; number = -1: no time step suffix.  0 = ok.
+int SaveData(NS_DIM_PREFIX MULTIGRID *mg, const char *name, const char *type, int number, double time, double dt, double ndt, int n,
+             NS_DIM_PREFIX VECDATA_DESC **vds);
+int LoadData(NS_DIM_PREFIX MULTIGRID *mg, const char *name, const char *type, int number, int n, NS_DIM_PREFIX VECDATA_DESC **vds);
 }
 
 START_UGDIM_NAMESPACE
