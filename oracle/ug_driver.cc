@@ -1090,8 +1090,11 @@ static int run_gpu(const Opt &o)
       auto bytes = [](const std::string &p) { std::vector<char> b; FILE *f = fopen(p.c_str(), "rb"); if (f) { for (int c; (c = fgetc(f)) != EOF;) b.push_back((char)c); fclose(f); } return b; };
       const MEM heap_size_field = MGHEAP(mg)->size;
       int bad_io = 0;
+      // after the solve above the VVALUEs of sol and rhs equal their device copies (gpuls downloads both at the end of Solver)
+      std::vector<std::vector<double> > cx(top + 1), cb(top + 1);
+      for (int l = 0; l <= top; l++) { cx[l] = gather(vx, l); cb[l] = gather(vb, l); }
       for (const char *type : {"bin", "asc"}) {
-        for (int l = 0; l <= top; l++) { Snap &s0 = got[l]; gpuls::ScatterVector(mg, l, vx, BS, s0.x.data()); gpuls::ScatterVector(mg, l, vb, BS, s0.b.data()); }
+        for (int l = 0; l <= top; l++) { gpuls::ScatterVector(mg, l, vx, BS, cx[l].data()); gpuls::ScatterVector(mg, l, vb, BS, cb[l].data()); }
         MGHEAP(mg)->size = MGHEAP(mg)->used + (MEM)(1u << 30);
         int e1 = SaveData(mg, (char *)ref1.c_str(), 1, 1, (char *)type, -1, 0.0, 0.0, 0.0, 2, vds, ev, evec, NULL);
         for (int l = 0; l <= top; l++) { fill_lcg(vx, l, 21); fill_lcg(vb, l, 22); }
