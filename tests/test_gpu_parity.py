@@ -140,3 +140,36 @@ def test_gpu_assemble_bitexact(golden):
     port.put(l, "y", y); port.put(l, "z", np.zeros_like(y))
     port.dmatmul(l, l, 0, 0, "z", "y")
     assert np.array_equal(got, port.get(l, "z"))
+
+
+def test_gpu_krylov_fused_chains_bitexact(golden, monkeypatch):
+    """cg / bcgs with the fused BLAS-1 chains (blas1.cu chain_loop: CGUpdate's calls in three passes, the bcgs updates in one pass each,
+    the residuum's partial sums inside the pass that produces the defect) against the same solvers issuing one kernel per reference call
+    (UGGPU_NO_KRYLOV_FUSION=1): iterates, defects, every work vector's effect and the defect history BIT for bit -- the chains perform
+    the same operations per entry in the same order and the reductions keep launch geometry and accumulation order."""
+    if not has(golden, "krylov"):
+        pytest.skip("dump without Krylov records")
+    from backends import GpuBackend
+    from replay import cycle_cfg
+    cfg = cycle_cfg(golden)
+    top = golden.top
+    out = {}
+    for fused in (1, 0):
+        if fused:
+            monkeypatch.delenv("UGGPU_NO_KRYLOV_FUSION", raising=False)
+        else:
+            monkeypatch.setenv("UGGPU_NO_KRYLOV_FUSION", "1")
+        be = GpuBackend(golden, fused=1)
+        res = []
+        for name in ("cg", "bcgs"):
+            for l, lv in enumerate(golden.levels):
+                be.put(l, "x", np.zeros(lv.n * lv.bs)); be.put(l, "b", lv.rhs)
+            be.ls_defect(0, top, "x", "b")
+            its, first, hist = (be.cg_solve if name == "cg" else be.bcgs_solve)(top, "x", "b", cfg, 5)
+            res.append((its, first, hist, [be.get(l, "x") for l in range(top + 1)], [be.get(l, "b") for l in range(top + 1)]))
+        out[fused] = res
+        be.close()
+    for a, b in zip(out[1], out[0]):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        for va, vb in zip(a[3] + a[4], b[3] + b[4]):
+            assert np.array_equal(va, vb)

@@ -270,6 +270,121 @@ extern "C" int uggpu_dminusadd(uggpu_ctx *c, int fl, int tl, int mode, int x, in
 extern "C" int uggpu_daxpy(uggpu_ctx *c, int fl, int tl, int mode, int x, double a, int y) { return vec_loop(c, fl, tl, mode, VOP_AXPYX, x, y, &a, true); }
 extern "C" int uggpu_daxpyx(uggpu_ctx *c, int fl, int tl, int mode, int x, const double *a, int y) { return vec_loop(c, fl, tl, mode, VOP_AXPYX, x, y, a, false); }
 
+// ---- fused chains (uggpu_internal.h CH_*) -----------------------------------------------------------------------------------------------
+struct ChainArgs { double *v[5]; double a0, a1; };
+template <int CH> struct ChainTraits { static const bool reduces = (CH == CH_ADD_DOT || CH == CH_AXPY2_NRM || CH == CH_BCGS_S); static const int nvec = CH == CH_SCAL_ADD ? 2 : (CH == CH_ADD_DOT ? 3 : (CH == CH_AXPY2_NRM ? 4 : 5)); };
+
+template <int BS, int CH>
+__global__ void __launch_bounds__(RED_THREADS) k_chain(int n, int red, uint8_t bit, const uint8_t *__restrict__ ctl, ChainArgs A, double *__restrict__ partials)
+{
+  double acc[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) acc[i] = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const bool in = red && (!bit || (ctl[r] & bit));
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+      const size_t k = (size_t)r * BS + i;
+      if (CH == CH_ADD_DOT) {
+        const double b = A.v[0][k] + A.v[1][k];
+        A.v[0][k] = b;
+        if (in) acc[i] += A.v[2][k] * b;
+      } else if (CH == CH_SCAL_ADD) {
+        double p = A.v[0][k] * A.a0;
+        p = p + A.v[1][k];
+        A.v[0][k] = p;
+      } else if (CH == CH_AXPY2_NRM) {
+        A.v[0][k] = A.v[0][k] + A.a0 * A.v[1][k];
+        const double b = A.v[2][k] + A.a1 * A.v[3][k];
+        A.v[2][k] = b;
+        if (in) acc[i] += b * b;
+      } else if (CH == CH_BCGS_P) {
+        double p = A.v[0][k] * A.a0;
+        p = p + A.v[1][k];
+        p = p + A.a1 * A.v[2][k];
+        A.v[0][k] = p; A.v[3][k] = 0.0; A.v[4][k] = p;
+      } else {   // CH_BCGS_S
+        A.v[0][k] = A.v[0][k] + A.a0 * A.v[1][k];
+        const double sv = A.v[3][k] + A.a1 * A.v[4][k];
+        A.v[2][k] = sv;
+        if (in) acc[i] += sv * sv;
+      }
+    }
+  }
+  if (ChainTraits<CH>::reduces && red) block_reduce_store<BS>(acc, partials + (size_t)blockIdx.x * BS);
+}
+
+template <int BS, int CH>
+static int launch_chain(uggpu_ctx *ctx, Level *L, int rowmode, const ChainArgs &A, int slot)
+{
+  if (L->n == 0) return 0;
+  const bool red = ChainTraits<CH>::reduces && rowmode >= 0;
+  uint8_t bit = rowmode <= 0 ? 0 : (rowmode == 1 ? UGGPU_CTL_NEW_DEFECT : UGGPU_CTL_FINE_GRID_DOF);
+  int blocks = (L->n + RED_THREADS - 1) / RED_THREADS;          // the geometry of launch_red: identical partial sums
+  int cap = ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (red) UG_TRY(ensure_partials(ctx, (size_t)blocks * BS));
+  {
+    ProfScope ps(ctx, UGGPU_K_VECOP, (int)(L - ctx->lev), 8.0 * BS * L->n * (CH == CH_ADD_DOT ? 4.0 : CH == CH_SCAL_ADD ? 3.0 : CH == CH_AXPY2_NRM ? 6.0 : CH == CH_BCGS_P ? 6.0 : 6.0));
+    k_chain<BS, CH><<<blocks, RED_THREADS, 0, ctx->stream>>>(L->n, red ? 1 : 0, bit, L->ctl, A, ctx->partials);
+    KCHECK(ctx);
+  }
+  if (red) return reduce_partials_final(ctx, BS, (size_t)blocks, slot, (int)(L - ctx->lev));
+  return 0;
+}
+
+template <int CH>
+static int chain_level(uggpu_ctx *ctx, Level *L, int rowmode, const ChainArgs &A, int slot)
+{
+  switch (L->bs) {
+    case 1: return launch_chain<1, CH>(ctx, L, rowmode, A, slot);
+    case 2: return launch_chain<2, CH>(ctx, L, rowmode, A, slot);
+    default: return launch_chain<3, CH>(ctx, L, rowmode, A, slot);
+  }
+}
+
+int chain_loop(uggpu_ctx *ctx, int fl, int tl, int chain, const int *vecs, double a0, double a1, double *sums, int *bs_out)
+{
+  std::vector<LoopItem> surf;
+  UG_TRY(surface_loop(ctx, fl, tl, UGGPU_ON_SURFACE, surf));
+  const int nvec = chain == CH_SCAL_ADD ? 2 : (chain == CH_ADD_DOT ? 3 : (chain == CH_AXPY2_NRM ? 4 : 5));
+  int bs = 1, nslots = 0;
+  // the reduction's slots follow reduce_loop: one per surface level, ascending
+  int slot_of[UGGPU_MAX_LEVELS], mode_of[UGGPU_MAX_LEVELS];
+  for (int l = 0; l < UGGPU_MAX_LEVELS; l++) { slot_of[l] = -1; mode_of[l] = -1; }
+  for (auto &it : surf) { slot_of[it.level] = nslots++; mode_of[it.level] = it.rowmode; }
+  for (int l = fl; l <= tl; l++) {
+    Level *L = get_level(ctx, l);
+    if (!L) return UGGPU_ERROR;
+    bs = L->bs;
+    ChainArgs A;
+    for (int i = 0; i < 5; i++) A.v[i] = nullptr;
+    for (int i = 0; i < nvec; i++) { A.v[i] = get_vec(ctx, l, vecs[i]); if (!A.v[i]) return UGGPU_DESC_MISMATCH; }
+    A.a0 = a0; A.a1 = a1;
+    const int rm = mode_of[l], sl = slot_of[l] < 0 ? 0 : slot_of[l];
+    switch (chain) {
+      case CH_ADD_DOT: UG_TRY(chain_level<CH_ADD_DOT>(ctx, L, rm, A, sl)); break;
+      case CH_SCAL_ADD: UG_TRY(chain_level<CH_SCAL_ADD>(ctx, L, rm, A, sl)); break;
+      case CH_AXPY2_NRM: UG_TRY(chain_level<CH_AXPY2_NRM>(ctx, L, rm, A, sl)); break;
+      case CH_BCGS_P: UG_TRY(chain_level<CH_BCGS_P>(ctx, L, rm, A, sl)); break;
+      case CH_BCGS_S: UG_TRY(chain_level<CH_BCGS_S>(ctx, L, rm, A, sl)); break;
+      default: return uggpu_fail(UGGPU_ERROR, "unknown chain %d", chain);
+    }
+  }
+  if (bs_out) *bs_out = bs;
+  if (!sums || chain == CH_SCAL_ADD || chain == CH_BCGS_P) return 0;
+  // surface levels below fl (ON_SURFACE starts at FULLREFINELEVEL whatever fl is, vecloop.ct:22): their rows are not touched by the
+  // chain's vector operations but belong to the reduction -- callers use fl <= FULLREFINELEVEL, anything else is refused
+  for (auto &it : surf) if (it.level < fl) return uggpu_fail(UGGPU_ERROR, "chain_loop: surface level %d below the first level %d", it.level, fl);
+  UG_TRY(fetch_results(ctx, nslots));
+  for (int i = 0; i < UGGPU_MAX_BS; i++) sums[i] = 0.0;
+  for (int s2 = 0; s2 < nslots; s2++)
+    for (int i = 0; i < bs; i++) sums[i] += ctx->hres[s2 * UGGPU_MAX_BS + i];
+  return 0;
+}
+
 // sums[i] = sum over the loop of x_i*y_i per component i (ddotx ugblas.cc:2946) -- host adds the per-level results in level order
 int reduce_loop(uggpu_ctx *ctx, int fl, int tl, int mode, int kind, int x, int y, double *sums /* [MAX_BS] */, int *bs_out)
 {

@@ -1024,6 +1024,10 @@ static int krylov_begin(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int l
   return 0;
 }
 
+// Fused BLAS-1 chains (blas1.cu chain_loop) in cg / bcgs: on unless UGGPU_NO_KRYLOV_FUSION is set (A/B: identical results) or the solve
+// starts above FULLREFINELEVEL (the ON_SURFACE reductions then cover levels the ALL_VECTORS operations do not)
+static bool krylov_fusion(uggpu_ctx *ctx, int bl) { return !getenv("UGGPU_NO_KRYLOV_FUSION") && bl <= ctx->fullrefinelevel; }
+
 extern "C" int uggpu_ddotw(uggpu_ctx *ctx, int fl, int tl, int mode, int x, int y, const double *w, double *a)
 {
   double s[UGGPU_MAX_BS]; int bs;
@@ -1043,11 +1047,28 @@ extern "C" int uggpu_cg_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
   const int ALL = UGGPU_ALL_VECTORS, SURF = UGGPU_ON_SURFACE;
   UG_TRY(uggpu_dset(ctx, bl, level, ALL, p, 0.0));                                  // CGPrepare
   double rho = 1.0, lambda = 0.0;
+  const bool fuse = krylov_fusion(ctx, bl);
   if (sc_cmp(res->last_defect, abslimit, bs)) { res->converged = 1; return 0; }
   for (int it = 0; it < maxiter; it++) {
     UG_TRY(uggpu_dset(ctx, level, level, ALL, c, 0.0));                             // ls.cc:695
     UG_TRY(run_cycle(ctx, cfg, level, c, b, A));
     UG_TRY(uggpu_dmatmul(ctx, bl, level, ALL, t, A, c));                            // CGUpdate :1003
+    if (fuse) {
+      // the BLAS-1 calls of CGUpdate in three passes instead of seven (same operations per entry, same partial sums: bit-identical)
+      double s3[UGGPU_MAX_BS];
+      const int v1[3] = {b, t, c};
+      UG_TRY(chain_loop(ctx, bl, level, CH_ADD_DOT, v1, 0.0, 0.0, s3, nullptr));      // dadd b t; ddot c b
+      lambda = 0.0; for (int i = 0; i < bs; i++) lambda += s3[i];
+      const int v2[2] = {p, c};
+      UG_TRY(chain_loop(ctx, bl, level, CH_SCAL_ADD, v2, lambda / rho, 0.0, nullptr, nullptr));   // dscal p; dadd p c
+      rho = lambda;
+      UG_TRY(uggpu_dmatmul(ctx, bl, level, ALL, t, A, p));
+      UG_TRY(uggpu_ddot(ctx, bl, level, SURF, t, p, &lambda));
+      if (lambda == 0.0) { res->error_code = UGGPU_ERROR; return uggpu_fail(UGGPU_ERROR, "cg: (Ap,p) = 0 in iteration %d", it); }   // :1017
+      const int v3[4] = {x, p, b, t};
+      UG_TRY(chain_loop(ctx, bl, level, CH_AXPY2_NRM, v3, rho / lambda, -rho / lambda, s3, nullptr));   // daxpy x p; daxpy b t; LinearResiduum
+      for (int i = 0; i < bs; i++) res->last_defect[i] = sqrt(s3[i]);
+    } else {
     UG_TRY(uggpu_dadd(ctx, bl, level, ALL, b, t));
     UG_TRY(uggpu_ddot(ctx, bl, level, SURF, c, b, &lambda));
     UG_TRY(uggpu_dscal(ctx, bl, level, ALL, p, lambda / rho));
@@ -1059,6 +1080,7 @@ extern "C" int uggpu_cg_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl,
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, rho / lambda, p));
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, b, -rho / lambda, t));
     UG_TRY(uggpu_ls_residuum(ctx, bl, level, b, res));
+    }
     if (history) for (int i = 0; i < bs; i++) history[it * bs + i] = res->last_defect[i];
     res->number_of_linear_iterations = it + 1;
     if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) { res->converged = 1; break; }
@@ -1080,6 +1102,7 @@ extern "C" int uggpu_bcgs_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int b
   double w2[UGGPU_MAX_BS];
   for (int i = 0; i < UGGPU_MAX_BS; i++) w2[i] = weight[i] * weight[i];             // BCGSInit :1757
   double alpha = 0.0, rho_new = 0.0, beta = 0.0, tt = 0.0, rho = 0.0, omega = 0.0;
+  const bool fuse = krylov_fusion(ctx, bl);
   int restart = 1, eq_count = 0;
   if (sc_cmp(res->last_defect, abslimit, bs)) res->converged = 1;
   for (int i = 0; i < maxiter; i++) {
@@ -1093,21 +1116,33 @@ extern "C" int uggpu_bcgs_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int b
     }
     UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, b, r, w2, &rho_new));
     if (rho != 0.0 && omega != 0.0) beta = rho_new * alpha / rho / omega;
+    if (fuse) {
+      const int v5[5] = {p, b, v, q, s};
+      UG_TRY(chain_loop(ctx, bl, level, CH_BCGS_P, v5, beta, -beta * omega, nullptr, nullptr));    // the five calls below in one pass
+    } else {
     UG_TRY(uggpu_dscal(ctx, bl, level, ALL, p, beta));
     UG_TRY(uggpu_dadd(ctx, bl, level, ALL, p, b));
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, p, -beta * omega, v));
     UG_TRY(uggpu_dset(ctx, bl, level, ALL, q, 0.0));
     UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, s, p));
+    }
     UG_TRY(run_cycle(ctx, cfg, level, q, p, A));                                    // Iter(q, p) :1944
     UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, p, s));
     UG_TRY(uggpu_dmatmul(ctx, bl, level, SURF, v, A, q));
     UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, v, r, w2, &alpha));
     if (alpha != 0.0) alpha = rho_new / alpha;
-    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, alpha, q));
     res->number_of_linear_iterations++;
+    if (fuse) {
+      double s3[UGGPU_MAX_BS];
+      const int v5[5] = {x, q, s, b, v};
+      UG_TRY(chain_loop(ctx, bl, level, CH_BCGS_S, v5, alpha, -alpha, s3, nullptr));                // daxpy x q; dcopy s b; daxpy s v; LinearResiduum(s)
+      for (int k = 0; k < bs; k++) res->last_defect[k] = sqrt(s3[k]);
+    } else {
+    UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, alpha, q));
     UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, s, b));
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, s, -alpha, v));
     UG_TRY(uggpu_ls_residuum(ctx, bl, level, s, res));
+    }
     if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) {
       UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, b, s));
       res->converged = 1;
@@ -1122,11 +1157,18 @@ extern "C" int uggpu_bcgs_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int b
     UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, t, t, w2, &tt));
     UG_TRY(uggpu_ddotw(ctx, bl, level, SURF, s, t, w2, &omega));
     if (tt != 0.0) omega /= tt;
+    rho = rho_new;
+    if (fuse) {
+      double s3[UGGPU_MAX_BS];
+      const int v5[5] = {x, q, b, s, t};
+      UG_TRY(chain_loop(ctx, bl, level, CH_BCGS_S, v5, omega, -omega, s3, nullptr));                // daxpy x q; dcopy b s; daxpy b t; LinearResiduum(b)
+      for (int k = 0; k < bs; k++) res->last_defect[k] = sqrt(s3[k]);
+    } else {
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, x, omega, q));
     UG_TRY(uggpu_dcopy(ctx, bl, level, ALL, b, s));
     UG_TRY(uggpu_daxpy(ctx, bl, level, ALL, b, -omega, t));
-    rho = rho_new;
     UG_TRY(uggpu_ls_residuum(ctx, bl, level, b, res));
+    }
     if (history) for (int k = 0; k < bs; k++) history[i * bs + k] = res->last_defect[k];
     res->number_of_linear_iterations++;
     if (sc_cmp(res->last_defect, abslimit, bs) || sc_cmp(res->last_defect, reach, bs)) { res->converged = 1; break; }

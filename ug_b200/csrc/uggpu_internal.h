@@ -543,6 +543,18 @@ int reduce_loop(uggpu_ctx *ctx, int fl, int tl, int mode, int kind, int x, int y
 
 enum { VOP_SET, VOP_COPY, VOP_SCALX, VOP_ADD, VOP_SUB, VOP_MINUSADD, VOP_AXPYX };
 enum { RED_DOT, RED_NRM2 };
+// Fused BLAS-1 chains of the Krylov solvers (blas1.cu chain_loop): several reference calls on the same rows in ONE pass, every entry
+// receiving the same operations in the same order (results bit-identical to the separate calls), optionally with the partial sums of
+// the reduction that follows (same launch geometry and accumulation order as k_red_rows, so the sums are bit-identical, too).
+enum { CH_ADD_DOT,      // v0 += v1;                                   sum v2 * v0                      (cg: dadd b t, ddot c b)
+       CH_SCAL_ADD,     // v0 = v0 * a0 + v1                                                            (cg: dscal p, dadd p c)
+       CH_AXPY2_NRM,    // v0 += a0 * v1;  v2 += a1 * v3;               sum v2 * v2                      (cg: daxpy x p, daxpy b t, residuum)
+       CH_BCGS_P,       // v0 = v0 * a0 + v1 + a1 * v2;  v3 = 0;  v4 = v0                                (bcgs: dscal p, dadd p b, daxpy p v, dset q, dcopy s p)
+       CH_BCGS_S,       // v0 += a0 * v1;  v2 = v3 + a1 * v4;           sum v2 * v2                      (bcgs: daxpy x q, dcopy s b, daxpy s v, residuum of s)
+       CH_COUNT };
+// levels fl..tl, every row (ALL_VECTORS); the reduction, if the chain has one, over the ON_SURFACE rows of those levels; sums[bs] summed
+// over the levels in level order on the host like reduce_loop
+int chain_loop(uggpu_ctx *ctx, int fl, int tl, int chain, const int *vecs, double a0, double a1, double *sums, int *bs_out);
 
 // smoother step flags (spmv.cu, DESIGN.md "fused kernels")
 enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16 };
