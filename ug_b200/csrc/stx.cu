@@ -53,8 +53,39 @@ __global__ void k_stx_rowmask(const __grid_constant__ STEN st, SellView A, int n
 }
 
 // copies the entries of the exception rows into the packed form (one thread per list position)
+// Entries whose stored value (block) is all zeros -- the off-diagonal entries of a Dirichlet row, the diagonal neighbours of the P1 Laplacian
+// on a Kuhn mesh -- are not copied into the packed rows, and the stencil kernels skip the stencil's zero coefficients (sten_nonzero).  The
+// accumulator of a row product starts at +0.0 and the sum of two doubles is -0.0 only if both are, so it is never -0.0; a product with a
+// zero coefficient is +-0.0 for every FINITE operand and adding it changes nothing: the results are bit-identical to the reference's as
+// long as the operand holds no Inf / NaN (then the reference's row turns NaN through 0 * Inf and this one does not -- the solve is lost
+// either way).  What it saves: a Dirichlet row gathered 15 operands, one 32-byte sector each, for 14 zero coefficients (690 B of DRAM
+// traffic per row, 15 % of the traffic of a smoothing step at 513^3).  UGGPU_KEEP_ZERO_ENTRIES=1 keeps every entry (A/B).
+static bool keep_zero_entries() { static int k = -1; if (k < 0) k = getenv("UGGPU_KEEP_ZERO_ENTRIES") ? 1 : 0; return k == 1; }
+
 template <int BS>
-__global__ void k_stx_pack(SellView A, const int32_t *__restrict__ xrows, int nx, const int64_t *__restrict__ xs_ptr, uint16_t *__restrict__ xs_len,
+__device__ __forceinline__ bool stx_entry_kept(const double *vp, int j, bool keep_all)
+{
+  if (keep_all || j == 0) return true;
+  for (int k = 0; k < BS * BS; k++) if (vp[((size_t)j * BS * BS + k) * 32] != 0.0) return true;
+  return false;
+}
+
+// entries the packed copy of exception row i keeps
+template <int BS>
+__global__ void k_stx_count(SellView A, const int32_t *__restrict__ xrows, int nx, int keep_all, uint16_t *__restrict__ cnt)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx) return;
+  const int r = xrows[i];
+  const double *vp = A.val + slice_off(A, r >> 5) * BS * BS + (r & 31);
+  const int len = (int)A.rowlen[r];
+  int c = 0;
+  for (int j = 0; j < len; j++) if (stx_entry_kept<BS>(vp, j, keep_all != 0)) c++;
+  cnt[i] = (uint16_t)c;
+}
+
+template <int BS>
+__global__ void k_stx_pack(SellView A, const int32_t *__restrict__ xrows, int nx, int keep_all, const int64_t *__restrict__ xs_ptr, uint16_t *__restrict__ xs_len,
                            int32_t *__restrict__ xs_col, double *__restrict__ xs_val)
 {
   constexpr int BB = BS * BS;
@@ -69,11 +100,14 @@ __global__ void k_stx_pack(SellView A, const int32_t *__restrict__ xrows, int nx
   const int cstride = uni ? 1 : 32, cbase = uni ? r : 0;
   const double *vp = A.val + sp * BB + lane;          // the explicit values are always complete
   const int64_t o = xs_ptr[i >> 5];
-  xs_len[i] = (uint16_t)len;
+  int q = 0;
   for (int j = 0; j < len; j++) {
-    xs_col[o + (int64_t)j * 32 + pl] = cp[(size_t)j * cstride] + cbase;
-    for (int k = 0; k < BB; k++) xs_val[(o + (int64_t)j * 32) * BB + (int64_t)k * 32 + pl] = vp[((size_t)j * BB + k) * 32];
+    if (!stx_entry_kept<BS>(vp, j, keep_all != 0)) continue;
+    xs_col[o + (int64_t)q * 32 + pl] = cp[(size_t)j * cstride] + cbase;
+    for (int k = 0; k < BB; k++) xs_val[(o + (int64_t)q * 32) * BB + (int64_t)k * 32 + pl] = vp[((size_t)j * BB + k) * 32];
+    q++;
   }
+  xs_len[i] = (uint16_t)q;
 }
 
 int stx_free(uggpu_ctx *ctx, SellMat *m)
@@ -123,15 +157,25 @@ static int stx_ensure(uggpu_ctx *ctx, Level *L, SellMat *A, bool comm)
   A->nx = (int)rows.size();
   UG_TRY(dalloc(ctx, &A->xrows, rows.size() + 1));
   if (!rows.empty()) CUDA_TRY(cudaMemcpyAsync(A->xrows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, ctx->stream));
-  // packed copy of the exception rows' entries: widths per group of 32 list positions from the row lengths
-  std::vector<uint16_t> rl((size_t)A->n);
-  if (A->n) CUDA_TRY(cudaMemcpyAsync(rl.data(), A->rowlen, sizeof(uint16_t) * rl.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  // packed copy of the exception rows' entries: widths per group of 32 list positions from the number of entries each row keeps
+  const int keep_all = keep_zero_entries() ? 1 : 0;
+  std::vector<uint16_t> rl(rows.size());
+  if (!rows.empty()) {
+    uint16_t *d_cnt = nullptr;
+    UG_TRY(dalloc(ctx, &d_cnt, rows.size()));
+    const int cb = (A->nx + 255) / 256;
+    if (A->bb == 1) k_stx_count<1><<<cb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, keep_all, d_cnt);
+    else k_stx_count<3><<<cb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, keep_all, d_cnt);
+    KCHECK(ctx);
+    CUDA_TRY(cudaMemcpyAsync(rl.data(), d_cnt, sizeof(uint16_t) * rl.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_cnt, rows.size());
+  }
   const size_t nxs = (rows.size() + 31) / 32;
   std::vector<int64_t> xp(nxs + 1, 0);
   for (size_t g = 0; g < nxs; g++) {
     int w = 0;
-    for (size_t i = g * 32; i < rows.size() && i < g * 32 + 32; i++) w = std::max(w, (int)rl[(size_t)rows[i]]);
+    for (size_t i = g * 32; i < rows.size() && i < g * 32 + 32; i++) w = std::max(w, (int)rl[i]);
     xp[g + 1] = xp[g] + (int64_t)w * 32;
   }
   A->xs_entries = xp[nxs];
@@ -145,8 +189,8 @@ static int stx_ensure(uggpu_ctx *ctx, Level *L, SellMat *A, bool comm)
   CUDA_TRY(cudaMemsetAsync(A->xs_val, 0, sizeof(double) * ((size_t)A->xs_entries * A->bb + 1), ctx->stream));
   if (A->nx > 0) {
     const int pb = (A->nx + 255) / 256;
-    if (A->bb == 1) k_stx_pack<1><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
-    else k_stx_pack<3><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
+    if (A->bb == 1) k_stx_pack<1><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, keep_all, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
+    else k_stx_pack<3><<<pb, 256, 0, ctx->stream>>>(view(*A), A->xrows, A->nx, keep_all, A->xs_ptr, A->xs_len, A->xs_col, A->xs_val);
     KCHECK(ctx);
   }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -377,14 +421,13 @@ __global__ void __launch_bounds__(STX_THREADS) k_smooth_xrows(XPack X, int n_own
                                                               const uint8_t *__restrict__ ctl, const double *__restrict__ tin, double *__restrict__ b, double *__restrict__ c,
                                                               double *__restrict__ tout, Damp damp, double *__restrict__ x, double *__restrict__ partials, int *err, HaloK hk)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < nx;
-  const int r = live ? __ldg(xrows + i) : 0;
   if (COMM) { halo_publish(hk); halo_wait(hk); }
   double nrm[BS];
 #pragma unroll
   for (int q = 0; q < BS; q++) nrm[q] = 0.0;
-  if (live) {
+  // one thread per row, or -- with a capped grid (stx_xgrid) -- a grid-stride loop: a narrow kernel that runs UNDER the stencil rows
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    const int r = __ldg(xrows + i);
     double s[BS], dg[BS * BS], pv[BS];
     row_product_packed<BS, COMM>(X, i, n_owned, tin, s, dg);
     smooth_row_tail<BS, FLAGS>(r, s, dg, vclass, ctl, tin, b, c, tout, damp, x, err, COMM ? hk.sel : 0, pv, nrm);
@@ -426,18 +469,18 @@ template <int BS, int OP>
 __global__ void __launch_bounds__(STX_THREADS) k_dmatmul_xrows(XPack X, int n_owned, const int32_t *__restrict__ xrows, int nx, uint8_t bit, const uint8_t *__restrict__ ctl,
                                                                double *__restrict__ x, const double *__restrict__ y)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nx) return;
-  const int r = __ldg(xrows + i);
-  if (bit && !(ctl[r] & bit)) return;
-  double s[BS], dg[BS * BS];
-  row_product_packed<BS, false>(X, i, n_owned, y, s, dg);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    const int r = __ldg(xrows + i);
+    if (bit && !(ctl[r] & bit)) continue;
+    double s[BS], dg[BS * BS];
+    row_product_packed<BS, false>(X, i, n_owned, y, s, dg);
 #pragma unroll
-  for (int q = 0; q < BS; q++) {
-    const size_t k = (size_t)r * BS + q;
-    if (OP == 0) x[k] = (BS == 1) ? s[q] : 0.0 + s[q];
-    else if (OP == 1) x[k] = x[k] + s[q];
-    else x[k] = x[k] - s[q];
+    for (int q = 0; q < BS; q++) {
+      const size_t k = (size_t)r * BS + q;
+      if (OP == 0) x[k] = (BS == 1) ? s[q] : 0.0 + s[q];
+      else if (OP == 1) x[k] = x[k] + s[q];
+      else x[k] = x[k] - s[q];
+    }
   }
 }
 
@@ -460,12 +503,58 @@ double stx_matrix_bytes(const Level *L, const SellMat *A)
   return 4.0 * ((L->n + 31) / 32) + (double)A->xs_entries * (8.0 * A->bb + 4.0) + 6.0 * (double)(A->nx > 0 ? A->nx : 0);
 }
 
+// Grid of an exception-row kernel.  Launched with one thread per row and high priority it takes the whole GPU for its duration (a chain
+// of dependent loads per row: 0.2 ms at 513^3 with the SMs nearly idle) and the stencil rows start behind it.  With UGGPU_XROWS_CTAS = k
+// CTAs per SM it is a narrow grid-stride kernel instead, resident next to the stencil-row kernel for that kernel's whole duration.
+static int stx_xgrid(const uggpu_ctx *ctx, int xblocks)
+{
+  static int k = -1;
+  if (k < 0) { const char *e = getenv("UGGPU_XROWS_CTAS"); k = e ? atoi(e) : 0; }
+  if (k <= 0) return xblocks;
+  const int cap = ctx->sm_count * k;
+  return xblocks < cap ? xblocks : cap;
+}
+
+static int stx_fork(uggpu_ctx *ctx, cudaStream_t *xs)
+{
+  if (!ctx->halo_stream) {
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&ctx->halo_ev[i], cudaEventDisableTiming));
+  }
+  *xs = ctx->halo_stream;
+  CUDA_TRY(cudaEventRecord(ctx->halo_ev[0], ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(*xs, ctx->halo_ev[0], 0));
+  return 0;
+}
+static int stx_join(uggpu_ctx *ctx, cudaStream_t xs)
+{
+  CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], xs));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
+  return 0;
+}
+
+// the stencil without its zero coefficients (entry 0, the diagonal, stays first); *w_out = number of entries kept
+static Sten sten_nonzero(const Sten &st)
+{
+  if (keep_zero_entries()) return st;
+  Sten c = st;
+  int q = 0;
+  for (int j = 0; j < st.w; j++)
+    if (j == 0 || st.v[j] != 0.0) { c.dbytes[q] = st.dbytes[j]; c.v[q] = st.v[j]; q++; }
+  for (int j = q; j < 32; j++) { c.dbytes[j] = 0; c.v[j] = 0.0; }
+  c.w = q;
+  if (q != 7 && q != 15 && q != 21 && q != 27) return st;      // widths the kernels are instantiated for (P1 Kuhn: 15 -> 7, Q1 Laplace: 27 -> 21)
+  return c;
+}
+
 template <int BS, int FLAGS>
 static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, double *b, double *c, double *tout, Damp damp, double *x, int norm_slot, const HaloK &hk)
 {
   const int nsl = (L->n + 31) / 32;
   const int blocks = (L->n + STX_THREADS - 1) / STX_THREADS;
-  const int xblocks = (A->nx + STX_THREADS - 1) / STX_THREADS > 0 ? (A->nx + STX_THREADS - 1) / STX_THREADS : 1;
+  const int xblocks = stx_xgrid(ctx, (A->nx + STX_THREADS - 1) / STX_THREADS > 0 ? (A->nx + STX_THREADS - 1) / STX_THREADS : 1);
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)(blocks + xblocks) * BS));
   const double nb = 8.0 * BS * L->n;
   // algorithmic bytes: what the pair reads of the matrix (mask + packed exception rows), the gathered operand once, b read + write, c, tout, x
@@ -476,33 +565,22 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
   // dependent loads per row) that would otherwise leave the GPU half empty for its whole duration -- and, multi-GPU, the one that waits
   const bool side = hk.flag || !getenv("UGGPU_STX_SAME_STREAM");
   cudaStream_t xs = ctx->stream;
-  if (side) {
-    if (!ctx->halo_stream) {
-      int lo = 0, hi = 0;
-      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      CUDA_TRY(cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, hi));
-      for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&ctx->halo_ev[i], cudaEventDisableTiming));
-    }
-    xs = ctx->halo_stream;
-    CUDA_TRY(cudaEventRecord(ctx->halo_ev[0], ctx->stream));
-    CUDA_TRY(cudaStreamWaitEvent(xs, ctx->halo_ev[0], 0));
-  }
+  if (side) UG_TRY(stx_fork(ctx, &xs));
   double *xpart = ctx->partials + (size_t)blocks * BS;
   const XPack X{A->xs_ptr, A->xs_len, A->xs_col, A->xs_val};
   if (hk.flag) k_smooth_xrows<BS, FLAGS, true><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
   else if (A->nx > 0 || (FLAGS & SF_NORM)) k_smooth_xrows<BS, FLAGS, false><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, L->vclass, L->ctl, tin, b, c, tout, damp, x, xpart, ctx->derr, hk);
   KCHECK(ctx);
   if (BS == 1) {
-    if (A->sten.w == 15) k_smooth_stx<FLAGS, 15><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl);
-    else k_smooth_stx<FLAGS, 27><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl);
+    const Sten st = sten_nonzero(A->sten);
+#define SX(WV) k_smooth_stx<FLAGS, WV><<<blocks, STX_THREADS, 0, ctx->stream>>>(st, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp.a[0], x, ctx->partials, pf.dist, nsl)
+    if (st.w == 7) SX(7); else if (st.w == 15) SX(15); else if (st.w == 21) SX(21); else SX(27);
+#undef SX
   } else {
     k_smooth_stx3<FLAGS><<<blocks, STX_THREADS, 0, ctx->stream>>>(*A->sten3, L->n, A->xmask, L->vclass, L->ctl, tin, b, c, tout, damp, x, ctx->partials, ctx->derr, pf.dist, nsl);
   }
   KCHECK(ctx);
-  if (side) {
-    CUDA_TRY(cudaEventRecord(ctx->halo_ev[1], xs));
-    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->halo_ev[1], 0));
-  }
+  if (side) UG_TRY(stx_join(ctx, xs));
   if (FLAGS & SF_NORM) UG_TRY(reduce_partials_final(ctx, BS, (size_t)(blocks + xblocks), norm_slot, (int)(L - ctx->lev)));
   return 0;
 }
@@ -551,14 +629,28 @@ int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, doubl
   if (!A->xmask) UG_TRY(stx_ensure(ctx, L, A, false));
   *done = 1;
   const int nsl = (L->n + 31) / 32;
-  const int blocks = (L->n + STX_THREADS - 1) / STX_THREADS, xblocks = (A->nx + STX_THREADS - 1) / STX_THREADS;
+  const int blocks = (L->n + STX_THREADS - 1) / STX_THREADS, xfull = (A->nx + STX_THREADS - 1) / STX_THREADS, xblocks = stx_xgrid(ctx, xfull);
   const Prefetch pf = make_prefetch(ctx, A, 1);
-#define DS(OPV, WV) k_dmatmul_stx<OPV, WV><<<blocks, STX_THREADS, 0, ctx->stream>>>(A->sten, L->n, A->xmask, bit, L->ctl, x, y, pf.dist, nsl)
-  if (A->sten.w == 15) { if (op == 0) DS(0, 15); else if (op == 1) DS(1, 15); else DS(2, 15); }
-  else { if (op == 0) DS(0, 27); else if (op == 1) DS(1, 27); else DS(2, 27); }
+  // a capped exception-row grid runs next to the stencil rows on the second stream (started first); otherwise behind them on the same stream
+  const bool side = xblocks > 0 && xblocks < xfull;
+  cudaStream_t xs = ctx->stream;
+  if (side) {
+    UG_TRY(stx_fork(ctx, &xs));
+    const XPack X{A->xs_ptr, A->xs_len, A->xs_col, A->xs_val};
+    if (op == 0) k_dmatmul_xrows<1, 0><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
+    else if (op == 1) k_dmatmul_xrows<1, 1><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
+    else k_dmatmul_xrows<1, 2><<<xblocks, STX_THREADS, 0, xs>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
+    KCHECK(ctx);
+  }
+  const Sten st = sten_nonzero(A->sten);
+#define DS(OPV, WV) k_dmatmul_stx<OPV, WV><<<blocks, STX_THREADS, 0, ctx->stream>>>(st, L->n, A->xmask, bit, L->ctl, x, y, pf.dist, nsl)
+#define DW(WV) { if (op == 0) DS(0, WV); else if (op == 1) DS(1, WV); else DS(2, WV); }
+  if (st.w == 7) DW(7) else if (st.w == 15) DW(15) else if (st.w == 21) DW(21) else DW(27)
+#undef DW
 #undef DS
   KCHECK(ctx);
-  if (xblocks > 0) {
+  if (side) UG_TRY(stx_join(ctx, xs));
+  else if (xblocks > 0) {
     const XPack X{A->xs_ptr, A->xs_len, A->xs_col, A->xs_val};
     if (op == 0) k_dmatmul_xrows<1, 0><<<xblocks, STX_THREADS, 0, ctx->stream>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
     else if (op == 1) k_dmatmul_xrows<1, 1><<<xblocks, STX_THREADS, 0, ctx->stream>>>(X, L->n, A->xrows, A->nx, bit, L->ctl, x, y);
