@@ -398,6 +398,13 @@ int uggpu_comm_transport(uggpu_ctx *ctx);
  * what every entry point does by itself before a kernel reads ghost columns.  The same exchange, explicitly (peer-memory windows
  * over NVLink, or ncclSend/ncclRecv): no-op on one GPU and on levels every rank holds completely. */
 int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x);
+/* ADDITIVE vectors of a caller that assembles element by element (every rank has added its elements' contributions to all vectors of those
+ * elements, also to its ghost rows): l_vector_collect (np/algebra/ugblas.cc:1035) -- the master copy gets the sum over all copies, the
+ * ghost rows 0 -- and l_vector_consistent (:398) -- every copy gets the sum.  Ghost segments travel back to their owners (ncclSend/ncclRecv),
+ * the owner adds them in the order of its neighbour list (one addition per copy; vectors with more than two copies: "up to summation
+ * order", like the reference's interface order).  No-op on one GPU and on levels every rank holds completely. */
+int uggpu_l_vector_collect(uggpu_ctx *ctx, int level, int x);
+int uggpu_l_vector_consistent(uggpu_ctx *ctx, int level, int x);
 /* As uggpu_synth_hierarchy on a px*py*pz rank array (element partition into equal boxes of base cells = RCB of
  * parallel/dddif/lbrcb.cc:250 on a structured grid; sons inherit, lbrcb.cc:376; shared vectors are owned by the lowest
  * rank, priority.cc:200).  This rank generates the rows it owns plus ghost columns.  Levels with at most

@@ -71,6 +71,57 @@ def run(name, fused, repl, rank, world, local):
     return good
 
 
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def run_collect(name, repl, rank, world, local):
+    """uggpu_l_vector_collect / uggpu_l_vector_consistent (l_vector_collect np/algebra/ugblas.cc:1035, l_vector_consistent :398): every rank
+    holds ADDITIVE values -- its own part a_q[g] on every copy (owned or ghost) of vector g it holds; values are multiples of 2^-10, so the
+    sums are exact in any order.  After collect the master copy must hold the sum over all ranks that hold a copy and the ghost rows 0;
+    after consistent every copy must hold the sum."""
+    hier = Hierarchy.from_ugh(os.path.join(GOLD, name + ".ugh"))
+    top, bs = hier.top, hier.bs
+    dimx, dimy = ARR[world]
+    owners = partition.vector_owners(hier, dimx, dimy)
+    parts = [partition.split(hier, owners, world, q, repl) for q in range(world)]
+    mine = parts[rank]
+    ctx = capi.Context(local)
+    mgpu.init_comm(ctx, rank, world)
+    ctx.upload_local_levels(mine, hier.fullrefinelevel, bs)
+    ok, checked = True, 0
+    for l, L in enumerate(mine):
+        if not L.partitioned:
+            continue
+        ng = hier.levels[l].n
+        part_of = lambda q: (np.round(np.random.default_rng(100 * l + q).standard_normal(ng * bs) * 1024) / 1024).reshape(ng, bs)
+        want = np.zeros((ng, bs))
+        for q in range(world):                       # the sum over the ranks that hold a copy of the vector
+            held = np.zeros(ng, bool); held[parts[q][l].rows] = True
+            want[held] += part_of(q)[held]
+        for fn in ("uggpu_l_vector_collect", "uggpu_l_vector_consistent"):
+            ctx.alloc(l, "v")
+            t = torch.as_tensor(_DevArray(ctx.devptr(l, "v"), (L.n + L.n_ghost) * bs), device="cuda")
+            t.copy_(torch.from_numpy(part_of(rank)[L.rows].reshape(-1)).cuda())
+            torch.cuda.synchronize()
+            ctx.call(fn, l, ctx.handle("v"))
+            ctx.sync()
+            got = t.cpu().numpy().reshape(-1, bs)
+            ok = ok and np.array_equal(got[:L.n], want[L.rows[:L.n]])
+            ghost_want = want[L.rows[L.n:]] if fn.endswith("consistent") else np.zeros((L.n_ghost, bs))
+            ok = ok and np.array_equal(got[L.n:], ghost_want)
+            checked += 1
+    ctx.close()
+    t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    good = bool(t.item() == 1.0) and checked > 0
+    if rank == 0:
+        print(f"PART-CHECK {'PASS' if good else 'FAIL'} " + json.dumps({"hierarchy": name, "ranks": world, "what": "l_vector_collect / l_vector_consistent on additive vectors",
+              "levels_checked": checked // 2, "ghosts_rank0": [int(L.n_ghost) for L in mine]}), flush=True)
+    return good
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -78,6 +129,7 @@ def main():
     ok = True
     for name, fused, repl in (("part_tet3d_r3", 1, 30), ("part_tet3d_r3", 0, 130), ("part_tet3d_adapt", 1, 30), ("part_tet3d_adapt", 0, 30)):
         ok = run(name, fused, repl, rank, world, local) and ok
+    ok = run_collect("part_hex3d_bs3_r3", 30, rank, world, local) and ok
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

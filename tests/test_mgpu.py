@@ -32,4 +32,4 @@ def test_caller_supplied_partition_of_a_ug_hierarchy():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", "29519", os.path.join(ROOT, "tests", "part_check.py")], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith("PART-CHECK")]
-    assert out.returncode == 0 and len(lines) == 4 and all("PASS" in l for l in lines), out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0 and len(lines) == 5 and all("PASS" in l for l in lines), out.stdout[-3000:] + out.stderr[-3000:]

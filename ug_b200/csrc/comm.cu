@@ -854,3 +854,81 @@ extern "C" int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x)
   if (!xp) return UGGPU_DESC_MISMATCH;
   return halo_exchange(ctx, level, xp);
 }
+
+// ---- sums over the copies of a vector: l_vector_collect (np/algebra/ugblas.cc:1035), l_vector_consistent (:398) ----------------------
+// A ModelP caller that assembles by ELEMENTS holds ADDITIVE vectors: every rank has added the contributions of its own elements to all
+// vectors of those elements -- also to the ones another rank is master of, which here are its ghost rows.  collect: the master gets the sum
+// over all copies, the other copies 0 (DDD_IFAOneway BorderVectorIF, Gather_VectorComp / Scatter_VectorComp adding, ugblas.cc:334-381);
+// consistent: every copy gets the sum (DDD_IFAExchange BorderVectorSymmIF).  With owned rows + ghost rows: every rank sends its ghost
+// segments back to their owners (ncclSend/ncclRecv, the reverse of the halo copy), the owner adds what it receives to its rows in the order
+// of its neighbour list (ascending rank) -- one addition per copy, deterministic; for vectors with more than two copies the order of the
+// additions may differ from DDD's interface order, which the reference does not fix either ("up to summation order") --
+// then the ghosts are zeroed (collect) or refreshed from the owners (consistent).  A setup-path operation (right-hand sides, iterates).
+__global__ void k_halo_add_back(int total, int bs, const int32_t *__restrict__ idx, double *__restrict__ v, const double *__restrict__ buf)
+{
+  // one thread per (send row, component); a row that goes to several neighbours appears once per neighbour: the additions of one
+  // row are done by ONE thread in list order (first occurrence), so their order is fixed
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total * bs) return;
+  const int e = i / bs, q = i - e * bs;
+  const int r = idx[e];
+  for (int f = 0; f < e; f++) if (idx[f] == r) return;          // not the first occurrence of this row (interface lists are short: setup path)
+  double acc = v[(size_t)r * bs + q];
+  for (int f = e; f < total; f++) if (idx[f] == r) acc = acc + buf[(size_t)f * bs + q];
+  v[(size_t)r * bs + q] = acc;
+}
+
+static int vector_sum_back(uggpu_ctx *ctx, int level, double *v)
+{
+  Level *L = &ctx->lev[level];
+  if (!level_comm(ctx, L)) return 0;
+  Comm *c = (Comm *)ctx->comm;
+  UG_TRY(halo_ready(ctx, c, L));
+  const int bs = L->bs;
+  const size_t need = (size_t)L->send_total * bs;
+  if (need > c->sendbuf_cap) {
+    if (c->sendbuf) { CUDA_TRY(cudaStreamSynchronize(ctx->stream)); UG_TRY(dfree(ctx, c->sendbuf, c->sendbuf_cap)); }
+    c->sendbuf_cap = need + need / 4;
+    UG_TRY(dalloc(ctx, &c->sendbuf, c->sendbuf_cap));
+  }
+  ProfScope ps(ctx, UGGPU_K_HALO, level, 16.0 * bs * (double)L->send_total);
+  NCCL_TRY(nccl.GroupStart());
+  for (int k = 0; k < L->nnb; k++) {
+    const int ns = L->nb_send_off[k + 1] - L->nb_send_off[k], nr = L->nb_recv_off[k + 1] - L->nb_recv_off[k];
+    // reverse direction: my ghost segment of neighbour k goes to k, k's copies of my rows arrive in the order of my send list for k
+    if (nr > 0) NCCL_TRY(nccl.Send(v + ((size_t)L->n + L->nb_recv_off[k]) * bs, (size_t)nr * bs, ncclDouble, L->nb_rank[k], c->comm, ctx->stream));
+    if (ns > 0) NCCL_TRY(nccl.Recv(c->sendbuf + (size_t)L->nb_send_off[k] * bs, (size_t)ns * bs, ncclDouble, L->nb_rank[k], c->comm, ctx->stream));
+  }
+  NCCL_TRY(nccl.GroupEnd());
+  if (L->send_total > 0) {
+    const int tot = L->send_total * bs;
+    k_halo_add_back<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(L->send_total, bs, L->d_send_idx, v, c->sendbuf);
+    KCHECK(ctx);
+  }
+  c->exchanges++;
+  return 0;
+}
+
+extern "C" int uggpu_l_vector_collect(uggpu_ctx *ctx, int level, int x)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  double *xp = get_vec(ctx, level, x);
+  if (!xp) return UGGPU_DESC_MISMATCH;
+  if (!level_comm(ctx, L)) return 0;
+  UG_TRY(vector_sum_back(ctx, level, xp));
+  if (L->nghost > 0) CUDA_TRY(cudaMemsetAsync(xp + (size_t)L->n * L->bs, 0, sizeof(double) * (size_t)L->nghost * L->bs, ctx->stream));
+  L->last_pushed = nullptr;
+  return 0;
+}
+
+extern "C" int uggpu_l_vector_consistent(uggpu_ctx *ctx, int level, int x)
+{
+  Level *L = get_level(ctx, level);
+  if (!L) return UGGPU_ERROR;
+  double *xp = get_vec(ctx, level, x);
+  if (!xp) return UGGPU_DESC_MISMATCH;
+  if (!level_comm(ctx, L)) return 0;
+  UG_TRY(vector_sum_back(ctx, level, xp));
+  return halo_exchange(ctx, level, xp);
+}
