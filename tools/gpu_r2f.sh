@@ -1,11 +1,7 @@
 #!/bin/bash
-out=gpurun_out; mkdir -p $out
-for v in fake1 fake2; do
-  if [ $v = fake1 ]; then export UGGPU_DBG_FAKE_COMM=1; fi; if [ $v = fake2 ]; then export UGGPU_DBG_FAKE_COMM=2; fi
-  timeout 300 python bench.py --no-extras --no-cpu --steps 10 --e2e-steps 0 > $out/r2f_$v.json 2> $out/r2f_$v.err
-  python - $out/r2f_$v.json $v <<'PY'
-import json,sys
-d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
-print(sys.argv[2], "%.2f ms/step dom %.3f ms"%(d["ms_per_step"], r["avg_ms"]), {k:round(v["ms"]/d["steps"],3) for k,v in d["kernels"].items() if v["ms"]>0})
-PY
-done
+# bash tools/gpu_r2f.sh <tag>: final state of the round -- what the driver runs (tests, smoke, bench, reference arm), the ncu launch list of the
+# bench command and one --set full capture of the dominant kernel pair on the finest level
+tag=$1; out=gpurun_out; mkdir -p $out
+bash tools/gpu_r2x.sh $tag
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras --e2e-steps 0 > $out/${tag}_launches.log 2>&1
+bash tools/gpu_r2p.sh ${tag}_stx "k_smooth_stx|k_smooth_xrows" 60 4

@@ -841,6 +841,11 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   if (t_ready && t_buf == 2) { cur = tB; oth = tA; }      // the previous cycle's last step left the correction in the second temporary
   const bool part = halo_fused_available(ctx, level), cpart = halo_fused_available(ctx, level - 1);
   auto plan = [&](bool ready, double *push, int push_level) { return HaloPlan{ready, push, push_level}; };
+  // Pairs of consecutive steps share one update of c (SF_CPREV): the first step of a pair leaves c alone, the second adds both corrections
+  // in the reference's order.  One pair at the end of the pre-smoothing, one at the end of the post-smoothing; only where both steps run in
+  // the stencil-rows / exception-rows kernels.
+  SellMat *Mc = get_mat(ctx, level, A);
+  const bool pairs = Mc && stx_handles(L, Mc) && !getenv("UGGPU_OVERLAP");
 
   if (cfg->nu1 > 0) {
     // the Jacobi start of the cycle's top level is a pure streaming kernel (measured: the flag byte of the comm form costs it 37 %): its
@@ -848,10 +853,11 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     if (!t_ready) UG_TRY(k_jac(ctx, level, A, cur, bp, sd, nullptr));
     for (int i = 0; i < cfg->nu1; i++) {
       const bool lastpre = i == cfg->nu1 - 1;
-      int flags = (c_zero ? SF_CSET : SF_CADD) | (!lastpre ? SF_TOUT : 0);
+      const bool defer = pairs && cfg->nu1 >= 2 && i == cfg->nu1 - 2, second = pairs && cfg->nu1 >= 2 && lastpre;
+      int flags = (defer ? 0 : (c_zero ? SF_CSET : SF_CADD) | (second ? SF_CPREV : 0)) | (!lastpre ? SF_TOUT : 0);
       const HaloPlan hp = plan(t_ready || i > 0, part ? (lastpre ? bp : oth) : nullptr, level);       // the last pre-smoothing step hands b to the restriction
       UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, nullptr, 0, &hp));
-      c_zero = false;
+      if (!defer) c_zero = false;
       double *sw = cur; cur = oth; oth = sw;
     }
   }
@@ -874,7 +880,8 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
   // c += t ; b -= A t ; first post-smoothing correction
   {
     const bool last = cfg->nu2 == 0;
-    int flags = (c_zero ? SF_CSET : SF_CADD) | (last ? 0 : SF_TOUT);
+    const bool defer = pairs && cfg->nu2 == 1;                  // with one post-smoothing step the pair is (this step, that step)
+    int flags = (defer ? 0 : (c_zero ? SF_CSET : SF_CADD)) | (last ? 0 : SF_TOUT);
     bool nt = false;
     if (last && top) {
       flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x));
@@ -882,12 +889,13 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     }
     const HaloPlan hp = plan(true, part ? (last ? (nt ? tB : (push_c ? cp : nullptr)) : tB) : nullptr, level);
     UG_TRY(k_smooth_step(ctx, level, A, flags, tA, bp, cp, tB, sd, xp, 0, &hp));
-    c_zero = false;
+    if (!defer) c_zero = false;
     cur = tB; oth = tA;
   }
   for (int i = 0; i < cfg->nu2; i++) {
     const bool last = i == cfg->nu2 - 1;
-    int flags = SF_CADD | (last ? 0 : SF_TOUT);
+    const bool defer = pairs && cfg->nu2 >= 2 && i == cfg->nu2 - 2, second = pairs && last;
+    int flags = (defer ? 0 : ((c_zero ? SF_CSET : SF_CADD) | (second ? SF_CPREV : 0))) | (last ? 0 : SF_TOUT);
     bool nt = false;
     if (last && top) {
       flags |= SF_XADD | (tf->norm ? SF_NORM : 0); tf->done_x = true; tf->done_norm = tf->norm; UG_TRY(vec_wait(ctx, level, tf->x));
@@ -895,6 +903,7 @@ static int lmgc_fused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int 
     }
     const HaloPlan hp = plan(true, part ? (last ? (nt ? oth : (push_c ? cp : nullptr)) : oth) : nullptr, level);
     UG_TRY(k_smooth_step(ctx, level, A, flags, cur, bp, cp, oth, sd, xp, 0, &hp));
+    if (!defer) c_zero = false;
     double *sw = cur; cur = oth; oth = sw;
   }
   return 0;

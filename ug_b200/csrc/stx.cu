@@ -255,9 +255,11 @@ __device__ __forceinline__ void smooth_row_tail(int r, const double (&s)[BS], co
     for (int i = 0; i < BS; i++) {
       const size_t k = (size_t)r * BS + i;
       double cn;
-      if (FLAGS & SF_CADD) cn = c[k] + tin[k];
-      else if (FLAGS & SF_CSET) cn = 0.0 + tin[k];
+      if (FLAGS & SF_CADD) cn = c[k];
+      else if (FLAGS & SF_CSET) cn = 0.0;
       else cn = c[k];
+      if (FLAGS & SF_CPREV) cn = cn + tout[k];                 // the previous step's correction (uggpu_internal.h SF_CPREV)
+      if (FLAGS & (SF_CADD | SF_CSET)) cn = cn + tin[k];
       if (FLAGS & (SF_CADD | SF_CSET)) c[k] = cn;
       if (FLAGS & SF_XADD) x[k] = x[k] + cn;
       if ((sel & 255) == HALO_PUSH_C) pv[i] = cn;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_smooth_stx(const
       const double eb = b[r];
       const double ec = ((FLAGS & (SF_CADD | SF_XADD)) && !(FLAGS & SF_CSET)) ? c[r] : 0.0;
       const double et = (FLAGS & (SF_CADD | SF_CSET)) ? tin[r] : 0.0;
+      const double ep = (FLAGS & SF_CPREV) ? tout[r] : 0.0;
       const uint8_t vc = (FLAGS & SF_TOUT) ? vclass[r] : (uint8_t)3;
       const char *yb = reinterpret_cast<const char *>(tin + r);
       double sum = 0.0;
@@ -340,8 +343,8 @@ __global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_smooth_stx(const
       b[r] = bn;
       if (FLAGS & (SF_CADD | SF_CSET | SF_XADD)) {
         double cn;
-        if (FLAGS & SF_CADD) cn = ec + et;
-        else if (FLAGS & SF_CSET) cn = 0.0 + et;
+        if (FLAGS & SF_CADD) cn = (FLAGS & SF_CPREV) ? (ec + ep) + et : ec + et;
+        else if (FLAGS & SF_CSET) cn = (FLAGS & SF_CPREV) ? (0.0 + ep) + et : 0.0 + et;
         else cn = ec;
         if (FLAGS & (SF_CADD | SF_CSET)) c[r] = cn;
         if (FLAGS & SF_XADD) x[r] = x[r] + cn;
@@ -495,6 +498,8 @@ static bool stx_applies(const Level *L, const SellMat *A)
   return L->bs == 3 && A->bb == 9 && A->sten3 != nullptr;
 }
 
+bool stx_handles(const Level *L, const SellMat *A) { return stx_applies(L, A) && !getenv("UGGPU_NO_CPREV"); }
+
 // bytes of MATRIX data one pass of the kernel pair fetches: the row mask, and the packed copy of the exception rows (values, columns, list,
 // lengths) -- the stencil rows read nothing else of the matrix.  < 0: the pair does not apply to this matrix (yet)
 double stx_matrix_bytes(const Level *L, const SellMat *A)
@@ -559,7 +564,8 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
   const double nb = 8.0 * BS * L->n;
   // algorithmic bytes: what the pair reads of the matrix (mask + packed exception rows), the gathered operand once, b read + write, c, tout, x
   ProfScope ps(ctx, UGGPU_K_SMOOTH, (int)(L - ctx->lev), stx_matrix_bytes(L, A) + 3.0 * nb
-               + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0));
+               + ((FLAGS & SF_CADD) ? 2.0 * nb : 0.0) + ((FLAGS & SF_CSET) ? nb : 0.0) + ((FLAGS & SF_TOUT) ? nb : 0.0) + ((FLAGS & SF_XADD) ? 2.0 * nb : 0.0)
+               + ((FLAGS & SF_CPREV) ? nb : 0.0));
   Prefetch pf = make_prefetch(ctx, A, BS);
   // the exception rows run NEXT to the stencil rows on a second stream: a small latency-bound kernel (1-2 % of the rows, a chain of
   // dependent loads per row) that would otherwise leave the GPU half empty for its whole duration -- and, multi-GPU, the one that waits
@@ -605,6 +611,19 @@ static int stx_smooth1(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const do
     SM_CASE(SF_CADD | SF_NORM);
     SM_CASE(SF_CSET | SF_NORM);
     SM_CASE(SF_NORM);
+    // the second step of a pair whose first step left c alone (SF_CPREV)
+    SM_CASE(SF_CADD | SF_CPREV);
+    SM_CASE(SF_CSET | SF_CPREV);
+    SM_CASE(SF_CADD | SF_CPREV | SF_TOUT);
+    SM_CASE(SF_CSET | SF_CPREV | SF_TOUT);
+    SM_CASE(SF_CADD | SF_CPREV | SF_XADD | SF_NORM);
+    SM_CASE(SF_CADD | SF_CPREV | SF_XADD | SF_NORM | SF_TOUT);
+    SM_CASE(SF_CADD | SF_CPREV | SF_XADD);
+    SM_CASE(SF_CADD | SF_CPREV | SF_NORM);
+    SM_CASE(SF_CSET | SF_CPREV | SF_XADD | SF_NORM);
+    SM_CASE(SF_CSET | SF_CPREV | SF_XADD | SF_NORM | SF_TOUT);
+    SM_CASE(SF_CSET | SF_CPREV | SF_XADD);
+    SM_CASE(SF_CSET | SF_CPREV | SF_NORM);
   }
 #undef SM_CASE
   return uggpu_fail(UGGPU_ERROR, "smooth step: unsupported flag combination %d", flags);

@@ -557,7 +557,13 @@ enum { CH_ADD_DOT,      // v0 += v1;                                   sum v2 * 
 int chain_loop(uggpu_ctx *ctx, int fl, int tl, int chain, const int *vecs, double a0, double a1, double *sums, int *bs_out);
 
 // smoother step flags (spmv.cu, DESIGN.md "fused kernels")
-enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16 };
+enum { SF_TOUT = 1, SF_CADD = 2, SF_CSET = 4, SF_XADD = 8, SF_NORM = 16,
+       // The step BEFORE this one left c alone (no SF_CADD / SF_CSET); this one adds both corrections, in the reference's order:
+       // c = (c + t_prev) + t_in.  t_prev is the previous step's input, which sits in the row of the buffer this step writes its output to
+       // (the two temporaries alternate) and is read by the row's own thread before it is overwritten.  Saves one read + write of c per
+       // pair of steps (16 B per row; 8 B come back as the read of t_prev).  Only the stencil-rows / exception-rows kernels (stx.cu)
+       // take it: cycle.cu asks stx_handles() before it schedules a pair.
+       SF_CPREV = 32 };
 // hp (may be nullptr): what the fused schedule knows about the exchanges around the launch (HaloPlan); without it every launch
 // exchanges its operand's ghost rows itself and pushes nothing
 int k_smooth_step(uggpu_ctx *ctx, int level, int A, int flags, const double *tin, double *b, double *c, double *tout,
@@ -569,6 +575,7 @@ int stx_smooth(uggpu_ctx *ctx, Level *L, SellMat *A, int flags, const double *ti
                const HaloK &hk, int *done);
 int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, double *x, const double *y, int *done);
 int stx_free(uggpu_ctx *ctx, SellMat *m);
+bool stx_handles(const Level *L, const SellMat *A);            // smoothing steps of this matrix go to the stx kernel pair (any flag combination of stx_smooth1)
 double stx_matrix_bytes(const Level *L, const SellMat *A);   // matrix bytes one pass of the stx kernel pair fetches (< 0: not applicable / not built)
 // trc.cu: restriction / interpolation on stencils whose rows fall into a few classes (base column + class byte per row), exception rows as a
 // second kernel.  *done = 0: not applicable, the caller launches transfer.cu's kernels.
