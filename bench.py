@@ -122,20 +122,20 @@ def run_port_cpu(cells: int, top: int, cycles: int):
     return {"kind": "port", "cores": 1, "levels": top + 1, "unknowns": n, "cycles": its, "s_per_cycle": dt / its, "vcycle_unknowns_per_s": n * its / dt}
 
 
-def equal_size_inside_ug(refine: int, cycles: int):
+def equal_size_inside_ug(refine: int, cycles: int, exe_name: str = "ugoracle3", grid_args=None, bs: int = 1):
     """The gpuls numprocs INSIDE the unmodified UG (oracle/_ref/ugoracle3 --gpu: PreProcess flattens the VECTOR/MATRIX lists, Solver
     uploads x and b, runs the cycles on the device, scatters x, b, c back into the VVALUEs) next to UG's own CPU numprocs on the SAME
     hierarchy in the same process: wall time of NP_LINEAR_SOLVER::Solver on both sides."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ugoracle3")
+    exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
     lib = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
     if not os.path.exists(exe):
         return None
-    out = subprocess.run([exe, "--grid", "tet", "--refine", str(refine), "--damp", "0.6", "--cycles", str(cycles), "--gpu", lib, "--nokrylov"],
+    out = subprocess.run([exe] + (grid_args or ["--grid", "tet", "--refine", str(refine), "--damp", "0.6"]) + ["--cycles", str(cycles), "--gpu", lib, "--nokrylov"],
                          capture_output=True, text=True, timeout=900)
     n = None
     m = re.search(r"n=\[([0-9,]+)\]", out.stdout)
     if m:
-        n = int(m.group(1).split(",")[-1])
+        n = int(m.group(1).split(",")[-1]) * bs
     for line in out.stdout.splitlines():
         if line.startswith(("PASS", "FAIL")) and "device base solver" in line:
             mg, mc = re.search(r"t_gpu=([0-9.eE+-]+)s", line), re.search(r"t_cpu=([0-9.eE+-]+)s", line)
@@ -244,6 +244,14 @@ class Env:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def nonzero_w(sten_w, kind):
+    """Nonzero coefficients of the dominant stencil of the synthetic operators (stx.cu sten_nonzero): the P1 Laplacian on a Kuhn mesh has 8
+    zero coefficients among its 15 connections (the diagonal neighbours), the Q1 Laplacian 6 among 27 (the face neighbours)."""
+    if os.environ.get("UGGPU_KEEP_ZERO_ENTRIES"):
+        return sten_w
+    return {("p1", 15): 7, ("q1", 27): 21}.get((kind, sten_w), sten_w)
 
 
 def peak_hbm():
@@ -389,7 +397,7 @@ def measure(spec, rt):
         sten_w = round(nnz_top / max(nrows_top, 1))
         stx = not os.environ.get("UGGPU_NO_STX") and nrows_top >= (1 << 20)
         if sten_top > 0 and bs == 1 and sten_w in (15, 27):
-            smooth_kernel = (f"k_smooth_stx<*,{sten_w}> + k_smooth_xrows (fused smoothing step: rows that are exactly the stencil + the packed exception rows, two kernels side by side, finest level)"
+            smooth_kernel = (f"k_smooth_stx<*,W> + k_smooth_xrows (fused smoothing step: rows that are exactly the {sten_w}-entry stencil -- the kernel runs on its nonzero coefficients, W = {nonzero_w(sten_w, kind)} -- + the packed exception rows, two kernels side by side, finest level)"
                              if stx else f"k_smooth_sten<*,{sten_w}> (fused smoothing step, stencil variant, finest level)")
         elif sten_top > 0 and bs == 3:
             smooth_kernel = ("k_smooth_stx3<*> + k_smooth_xrows<3,*> (fused smoothing step, 3x3 blocks: stencil rows + packed exception rows, finest level)"
@@ -471,7 +479,7 @@ def measure(spec, rt):
                 if c2.value > 0 and m2.value > 0:
                     gb = b2.value / (m2.value * 1e-3) / 1e9
                     extra = ((8.0 * bs * bs + 4.0) * nnz_top + 4.0 * (nrows_top + 1) - pass_bytes) * c2.value
-                    out["spmv"] = {"kernel": ((f"k_dmatmul_stx<2,{sten_w}> + k_dmatmul_xrows" if stx else f"k_dmatmul_sten<2,{sten_w}>") if (sten_top > 0 and bs == 1 and sten_w in (15, 27)) else f"k_dmatmul_k<{bs},2>") + " (x -= A y, finest level)",
+                    out["spmv"] = {"kernel": ((f"k_dmatmul_stx<2,W = {nonzero_w(sten_w, kind)} of {sten_w}> + k_dmatmul_xrows" if stx else f"k_dmatmul_sten<2,{sten_w}>") if (sten_top > 0 and bs == 1 and sten_w in (15, 27)) else f"k_dmatmul_k<{bs},2>") + " (x -= A y, finest level)",
                                    "launches": int(c2.value), "avg_ms": m2.value / c2.value, "alg_bytes_per_launch": b2.value / c2.value, "GBps": gb, "frac": gb / peak,
                                    "GBps_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9, "frac_survey_model": (b2.value + extra) / (m2.value * 1e-3) / 1e9 / peak}
             except Exception as e:          # a reported figure, never a reason to lose the bench line
@@ -732,6 +740,16 @@ def our_arm(args):
                 line["equal_size_inside_ug"] = equal_size_inside_ug(args.cpu_refine, 5)
             except Exception as e:
                 line["equal_size_inside_ug"] = {"error": str(e)[:200]}
+            # BASELINE.json's other configurations, as UG itself builds them, GPU numprocs inside UG next to the CPU numprocs: C1 verbatim (2D P1,
+            # 6 refinements, 4 225 unknowns -- launch-bound on a GPU), a C4-type hierarchy (Q1 hexahedra, 3x3 blocks) and a C5-type one
+            # (adaptively refined tetrahedra: partial levels, irregular rows) at the sizes the host builds in seconds
+            for key, exe_name, ga, bsz in (("c1_inside_ug", "ugoracle2", ["--grid", "tri", "--refine", "6", "--damp", "0.8"], 1),
+                                           ("c4_inside_ug", "ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "4", "--damp", "0.6"], 3),
+                                           ("c5_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "4", "--adapt", "2", "--damp", "0.6"], 1)):
+                try:
+                    line[key] = equal_size_inside_ug(0, 5, exe_name, ga, bsz)
+                except Exception as e:
+                    line[key] = {"error": str(e)[:200]}
     print(json.dumps(line))
     return 0
 
