@@ -312,7 +312,7 @@ __device__ __forceinline__ void block_norm_partials(const double (&nrm)[BS], dou
   }
 }
 
-struct YTile { int q, k; };                                   // slices between two passes of a warp, passes per warp (k = 1: off)
+struct YTile { int q, k, block; };                            // slices between two passes, passes (k = 1: off); block: the k slices go to the k warps of a block instead of k passes of a warp
 
 // ---- kernel 1, scalar rows: the rows that are exactly the stencil ---------------------------------------------------------------------
 template <int FLAGS, int W, int YK>
@@ -329,11 +329,13 @@ __global__ void __launch_bounds__(STX_THREADS, STX_MINBLOCKS) k_smooth_stx(const
   // for W = 7: the loop costs registers the 21- and 27-entry variants do not have under the 32-register bound (they spill: 1.58 -> 3.1 ms).
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int g0 = YK == 1 ? wg : (wg / yt.q) * yt.q * YK + wg % yt.q;
+  // YK == 1 with yt.k == 4: the same permutation spread over the four warps of a block (block j of group g: slices g*q*4 + j + q*w) --
+  // no loop, no extra registers: the form the 21- / 27-entry variants can afford
+  const int g0 = YK == 1 ? (yt.block ? ((wg >> 2) / yt.q) * yt.q * 4 + (wg >> 2) % yt.q + yt.q * (wg & 3) : wg) : (wg / yt.q) * yt.q * YK + wg % yt.q;
   double nrm = 0.0;
 #pragma unroll 1
   for (int it = 0; it < YK; it++) {
-    const int s = YK == 1 ? wg : g0 + it * yt.q;
+    const int s = YK == 1 ? g0 : g0 + it * yt.q;
     if (s >= nsl) break;                                       // whole warps
     const int r = s * 32 + lane;
     const uint32_t m = __ldg(xmask + s);
@@ -583,8 +585,10 @@ static YTile stx_ytile(const Sten &st, int nsl)
 {
   static int k = -1;
   if (k < 0) { const char *e = getenv("UGGPU_STX_YTILE"); k = e ? atoi(e) : STX_YTILE_DEFAULT; if (k < 1) k = 1; }
-  YTile yt{1, 1};
-  if (k != 4 || st.w != 7) return yt;                            // the one instantiated form (see k_smooth_stx)
+  YTile yt{1, 1, 0};
+  static int bt = -1;
+  if (bt < 0) bt = getenv("UGGPU_STX_BTILE") ? 1 : 0;
+  if (k != 4 || (st.w != 7 && !bt)) return yt;                   // W = 7: four passes per warp; other widths (UGGPU_STX_BTILE=1): four warps of a block
   long long best = 0;
   for (int j = 0; j < st.w; j++) {
     const long long d = st.dbytes[j] / (long long)sizeof(double);
@@ -592,12 +596,13 @@ static YTile stx_ytile(const Sten &st, int nsl)
   }
   const int q = (int)((best + 16) / 32);
   if (q < 1 || (long long)q * k > nsl) return yt;
-  yt.q = q; yt.k = k;
+  yt.q = q; yt.k = k; yt.block = st.w != 7;
   return yt;
 }
 static int stx_yblocks(const YTile &yt, int nsl)
 {
   const long long groups = ((long long)nsl + (long long)yt.q * yt.k - 1) / ((long long)yt.q * yt.k);
+  if (yt.block) return (int)(groups * yt.q);                     // one block (k = 4 warps = STX_THREADS / 32) per k slices
   return (int)((groups * yt.q * 32 + STX_THREADS - 1) / STX_THREADS);
 }
 
@@ -606,7 +611,7 @@ static int stx_smooth2(uggpu_ctx *ctx, Level *L, SellMat *A, const double *tin, 
 {
   const int nsl = (L->n + 31) / 32;
   const Sten stc = BS == 1 ? sten_nonzero(A->sten) : Sten();
-  const YTile yt = BS == 1 ? stx_ytile(stc, nsl) : YTile{1, 1};
+  const YTile yt = BS == 1 ? stx_ytile(stc, nsl) : YTile{1, 1, 0};
   const int blocks = BS == 1 ? stx_yblocks(yt, nsl) : (L->n + STX_THREADS - 1) / STX_THREADS;
   const int xblocks = stx_xgrid(ctx, (A->nx + STX_THREADS - 1) / STX_THREADS > 0 ? (A->nx + STX_THREADS - 1) / STX_THREADS : 1);
   if (FLAGS & SF_NORM) UG_TRY(ensure_partials(ctx, (size_t)(blocks + xblocks) * BS));
@@ -711,7 +716,8 @@ int stx_dmatmul(uggpu_ctx *ctx, Level *L, SellMat *A, int op, uint8_t bit, doubl
     KCHECK(ctx);
   }
   const Sten st = sten_nonzero(A->sten);
-  const YTile yt = stx_ytile(st, nsl);
+  YTile yt = stx_ytile(st, nsl);
+  if (yt.block) yt = YTile{1, 1, 0};                              // the block form exists in the smoothing kernel only
   const int sblocks = stx_yblocks(yt, nsl);
 #define DS(OPV, WV, YKV) k_dmatmul_stx<OPV, WV, YKV><<<sblocks, STX_THREADS, 0, ctx->stream>>>(st, L->n, A->xmask, bit, L->ctl, x, y, pf.dist, nsl, yt)
 #define DW(WV, YKV) { if (op == 0) DS(0, WV, YKV); else if (op == 1) DS(1, WV, YKV); else DS(2, WV, YKV); }
