@@ -85,6 +85,7 @@ int64_t uggpu_device_bytes(uggpu_ctx *ctx);
 #define UGGPU_K_HALO        9   /* stand-alone halo exchange of a partitioned level (pushes fused into a producing kernel are part of that kernel) */
 #define UGGPU_K_ALLREDUCE  10   /* ncclAllReduce of norm / dot partial sums and of the gathered coarse defect */
 #define UGGPU_K_ASSEMBLE   11   /* element-loop assembly of one level (uggpu_assemble) */
+#define UGGPU_K_GALERKIN   12   /* Galerkin product of one level (uggpu_galerkin: the product kernel, without the sort of the transposed stencil) */
 int uggpu_prof_enable(uggpu_ctx *ctx, int on);   /* also clears the records */
 int uggpu_prof_summary(uggpu_ctx *ctx, int kind, int level, int64_t *launches, double *ms, double *alg_bytes);
 

@@ -275,13 +275,20 @@ extern "C" int uggpu_assemble(uggpu_ctx *ctx, int level, int x, int b, int A, co
       ctx->launches++;
       GC(cudaGetLastError());
     }
+    bool launched = false;
     if (!rc) {
+      launched = true;
       rc = check_device_error(ctx);
       if (rc == UGGPU_DESC_MISMATCH) rc = uggpu_fail(UGGPU_DESC_MISMATCH, "uggpu_assemble: two corners of an element have no matrix entry on level %d (GetElementVVMPtrs -3)", level);
       else if (rc) rc = uggpu_fail(UGGPU_ERROR, "uggpu_assemble: bad element list on level %d (corner rows out of range, or an element that is neither a simplex nor a tensor element)", level);
     }
-    GT(sell_update_diag(ctx, Am));
-    GT(sell_share_values(ctx, Am));
+    // whatever the kernel reported, the values have changed: the diagonal array and the value generation follow them (nothing derived
+    // from the old values may be used with the new ones, also after a failed call)
+    if (launched) {
+      const int rc2 = sell_update_diag(ctx, Am);
+      if (!rc) rc = rc2;
+      if (!rc) rc = sell_share_values(ctx, Am);
+    }
     cudaStreamSynchronize(st);
   }
 #undef GT

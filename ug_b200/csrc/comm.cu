@@ -864,18 +864,15 @@ extern "C" int uggpu_l_ghostvector_consistent(uggpu_ctx *ctx, int level, int x)
 // of its neighbour list (ascending rank) -- one addition per copy, deterministic; for vectors with more than two copies the order of the
 // additions may differ from DDD's interface order, which the reference does not fix either ("up to summation order") --
 // then the ghosts are zeroed (collect) or refreshed from the owners (consistent).  A setup-path operation (right-hand sides, iterates).
-__global__ void k_halo_add_back(int total, int bs, const int32_t *__restrict__ idx, double *__restrict__ v, const double *__restrict__ buf)
+__global__ void k_halo_add_back(int cnt, int bs, const int32_t *__restrict__ idx, double *__restrict__ v, const double *__restrict__ buf)
 {
-  // one thread per (send row, component); a row that goes to several neighbours appears once per neighbour: the additions of one
-  // row are done by ONE thread in list order (first occurrence), so their order is fixed
+  // the copies ONE neighbour sent: its rows are distinct, so every (row, component) has one thread; the neighbours are processed by
+  // consecutive launches in list order, which fixes the order of the additions a row with several copies receives
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total * bs) return;
+  if (i >= cnt * bs) return;
   const int e = i / bs, q = i - e * bs;
-  const int r = idx[e];
-  for (int f = 0; f < e; f++) if (idx[f] == r) return;          // not the first occurrence of this row (interface lists are short: setup path)
-  double acc = v[(size_t)r * bs + q];
-  for (int f = e; f < total; f++) if (idx[f] == r) acc = acc + buf[(size_t)f * bs + q];
-  v[(size_t)r * bs + q] = acc;
+  const size_t k = (size_t)idx[e] * bs + q;
+  v[k] = v[k] + buf[(size_t)e * bs + q];
 }
 
 static int vector_sum_back(uggpu_ctx *ctx, int level, double *v)
@@ -900,9 +897,10 @@ static int vector_sum_back(uggpu_ctx *ctx, int level, double *v)
     if (ns > 0) NCCL_TRY(nccl.Recv(c->sendbuf + (size_t)L->nb_send_off[k] * bs, (size_t)ns * bs, ncclDouble, L->nb_rank[k], c->comm, ctx->stream));
   }
   NCCL_TRY(nccl.GroupEnd());
-  if (L->send_total > 0) {
-    const int tot = L->send_total * bs;
-    k_halo_add_back<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(L->send_total, bs, L->d_send_idx, v, c->sendbuf);
+  for (int k = 0; k < L->nnb; k++) {
+    const int off = L->nb_send_off[k], cnt = L->nb_send_off[k + 1] - off;
+    if (cnt <= 0) continue;
+    k_halo_add_back<<<(cnt * bs + 255) / 256, 256, 0, ctx->stream>>>(cnt, bs, L->d_send_idx + off, v, c->sendbuf + (size_t)off * bs);
     KCHECK(ctx);
   }
   c->exchanges++;

@@ -176,6 +176,7 @@ extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
     if (!rc) {
       const int blocks = (nc + 127) / 128;
       const SellView Acv = view(*Ac), Afv = view(*Af), Pv = view(L->P);
+      ProfScope ps(ctx, UGGPU_K_GALERKIN, level, 12.0 * (double)Af->nnz * Af->bb + 24.0 * (double)zp + 12.0 * (double)Ac->nnz * Ac->bb + 4.0 * ((double)nf + nc));
       switch (L->bs) {
         case 1: k_galerkin<1><<<blocks, 128, 0, st>>>(Acv, Ac->val, Afv, Af->val, Pv, tptr, tfine, ctx->derr); break;
         case 2: k_galerkin<2><<<blocks, 128, 0, st>>>(Acv, Ac->val, Afv, Af->val, Pv, tptr, tfine, ctx->derr); break;
@@ -184,12 +185,18 @@ extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
       ctx->launches++;
       GC(cudaGetLastError());
     }
+    bool launched = false;
     if (!rc) {
+      launched = true;
       rc = check_device_error(ctx);
       if (rc) rc = uggpu_fail(UGGPU_ERROR, "uggpu_galerkin: the product P^T A P of level %d leaves the pattern of level %d (the reference would create the connections; not supported)", level, level - 1);
     }
-    GT(sell_update_diag(ctx, Ac));
-    GT(sell_share_values(ctx, Ac));
+    // the coarse values have changed whatever the kernel reported: diagonal array and value generation follow them, also after a failed call
+    if (launched) {
+      const int rc2 = sell_update_diag(ctx, Ac);
+      if (!rc) rc = rc2;
+      if (!rc) rc = sell_share_values(ctx, Ac);
+    }
     cudaStreamSynchronize(st);
   }
 #undef GT
