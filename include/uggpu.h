@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define UGGPU_MAX_BS      3    /* components per vector handled by the block kernels          */
-#define UGGPU_MAX_LEVELS  32   /* MAXLEVEL, gm/gm.h                                           */
+#define UGGPU_MAX_LEVELS  64   /* 2 * MAXLEVEL (gm/gm.h): the geometric levels and, below them, the algebraic levels of an AMG transfer */
 #define UGGPU_MAX_COMP    40   /* MAX_VEC_COMP, np/udm/udm.h: length of a VEC_SCALAR          */
 
 /* loop modes, np/np.h:184-185 */

@@ -76,6 +76,19 @@ struct Dump {
 };
 static Dump D;
 
+#include <execinfo.h>
+#include <signal.h>
+// a crash inside the reference: print where (addr2line -e ugoracleN <addresses>) instead of dying silently
+static void on_crash(int sig)
+{
+  void *bt[48];
+  int n = backtrace(bt, 48);
+  fprintf(stderr, "ug_driver: signal %d inside the reference; backtrace:\n", sig);
+  backtrace_symbols_fd(bt, n, 2);
+  fflush(NULL);
+  _exit(128 + sig);
+}
+
 static void cmd(const char *fmt, ...)
 {
   char b[2048];
@@ -107,6 +120,11 @@ struct Opt {
   std::string savedata;
   bool assemble = false;                // --assemble: run the reference's LocalAssemble (np/procs/assemble.cc:657) with the element kernel below and dump what it leaves
   bool lean = false;                    // --lean: dumps without the BLAS-1/2 and transfer records, the coordinates and the Krylov runs
+  // --amg CLASS "INIT": the cycle continues below level 0 on algebraic levels built by the reference's own AMG transfer numproc
+  // (np/procs/amgtransfer.cc: classes selectionAMG / clusterAMG), attached to the transfer class with `$amg` (transfer.cc:593, :660)
+  std::string amg_class, amg_init;
+  bool collapse = false;                // --collapse: after the --refine steps the surface becomes level 0 (UG's `collapse`, gm/ugm.cc:3930): a large level 0 for the AMG
+  int refine2 = 0;                      // --refine2 K: K uniform refinements after the collapse
 };
 
 static MULTIGRID *mg;
@@ -114,7 +132,10 @@ static VECDATA_DESC *vx, *vb, *vc, *vt;
 static MATDATA_DESC *mA;
 static int BS;
 
-static std::string L(const char *what, int lev) { char b[128]; snprintf(b, sizeof b, "L%d/%s", lev, what); return b; }
+// LO: the bottom level of the multigrid while a dump is written -- 0, or negative once the algebraic levels of an AMG transfer exist
+// (--amg with $hold).  Dumps number their levels from 0: record "L<k>/..." belongs to UG's level LO + k.
+static int LO = 0;
+static std::string L(const char *what, int lev) { char b[128]; snprintf(b, sizeof b, "L%d/%s", lev - LO, what); return b; }
 
 // deterministic test vectors: k * 2^-20 from a 64-bit LCG, seed mixes level+tag
 static void fill_lcg(const VECDATA_DESC *vd, int lev, uint64_t seed)
@@ -467,6 +488,7 @@ static void build_hierarchy(const Opt &o)
 #endif
   cmd("fixcoarsegrid");
   for (int i = 0; i < o.refine; i++) cmd("refine $a");
+  if (o.collapse) { cmd("collapse"); for (int i = 0; i < o.refine2; i++) cmd("refine $a"); }
   for (int r = 0; r < o.adapt; r++) {
     for (int l = 0; l <= TOPLEVEL(mg); l++)
       for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l)); e; e = SUCCE(e)) {
@@ -494,7 +516,10 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
   else cmd("npinit %ssmooth $damp %.17g", pfx, o.damp);
   cmd("npcreate %sbaseit $c lu", pfx);           cmd("npinit %sbaseit", pfx);
   cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
-  cmd("npcreate %stransfer $c %s", pfx, transfer); cmd("npinit %stransfer%s", pfx, o.imat ? " $M" : "");
+  if (!o.amg_class.empty()) { cmd("npcreate %samgt $c %s", pfx, o.amg_class.c_str()); cmd("npinit %samgt %s", pfx, o.amg_init.c_str()); }
+  cmd("npcreate %stransfer $c %s", pfx, transfer);
+  if (!o.amg_class.empty()) cmd("npinit %stransfer%s $amg %samgt", pfx, o.imat ? " $M" : "", pfx);
+  else cmd("npinit %stransfer%s", pfx, o.imat ? " $M" : "");
   cmd("npcreate %slmgc $c %s", pfx, lmgc);
   cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel);
   cmd("npcreate %smgs $c %s", pfx, ls);
@@ -505,26 +530,30 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
 static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
 {
   int top = TOPLEVEL(mg);
-  fl.resize(top + 1);
-  D.scalar_i("dim", DIM); D.scalar_i("bs", BS); D.scalar_i("toplevel", top);
-  D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg));
+  fl.resize(top - LO + 1);
+  D.scalar_i("dim", DIM); D.scalar_i("bs", BS); D.scalar_i("toplevel", top - LO);
+  D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg) - LO);
+  D.scalar_i("bottomlevel", LO);
   D.scalar_d("damp", o.damp); D.scalar_i("nu1", o.nu1); D.scalar_i("nu2", o.nu2); D.scalar_i("gamma", o.gamma);
   D.scalar_i("baselevel", o.baselevel);
   D.scalar_i("smoother", o.smoother == "jac" ? 0 : o.smoother == "gs" ? 1 : o.smoother == "sgs" ? 2 : o.smoother == "sor" ? 3 : 4);
   if (o.smoother == "ilu") D.scalar_d("ilu_beta", o.beta);
-  for (int l = 0; l <= top; l++) {
-    if (gpuls::FlattenFlags(mg, l, vx, fl[l])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
-    if (gpuls::FlattenMatrix(mg, l, mA, fl[l])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
+  for (int l = LO; l <= top; l++) {
+    if (gpuls::FlattenFlags(mg, l, vx, fl[l - LO])) { fprintf(stderr, "FlattenFlags failed\n"); exit(6); }
+    if (gpuls::FlattenMatrix(mg, l, mA, fl[l - LO])) { fprintf(stderr, "FlattenMatrix failed\n"); exit(6); }
   }
   D.scalar_i("transfer_mode", o.imat ? 1 : 0);
-  for (int l = 1; l <= top; l++)
-    if (o.imat ? gpuls::FlattenTransferIMAT(mg, l, fl[l]) : gpuls::FlattenTransfer(mg, l, fl[l])) { fprintf(stderr, "FlattenTransfer failed\n"); exit(6); }
-  for (int l = 0; l <= top; l++) {
-    gpuls::FlatLevel &f = fl[l];
+  for (int l = LO + 1; l <= top; l++) {
+    const bool imat = o.imat || l < 1;        // levels < 1 always use the stored interpolation matrices (transfer.cc:733, :756)
+    if (imat ? gpuls::FlattenTransferIMAT(mg, l, fl[l - LO]) : gpuls::FlattenTransfer(mg, l, fl[l - LO])) { fprintf(stderr, "FlattenTransfer failed\n"); exit(6); }
+    if (LO < 0) D.scalar_i(L("transfer_mode", l), imat ? 1 : 0);
+  }
+  for (int l = LO; l <= top; l++) {
+    gpuls::FlatLevel &f = fl[l - LO];
     D.scalar_i(L("n", l), f.n);
     D.i32(L("rowptr", l), f.rowptr); D.i32(L("col", l), f.col); D.f64(L("val", l), f.val);
     D.u8(L("vclass", l), f.vclass); D.u8(L("vnclass", l), f.vnclass); D.u8(L("ctl", l), f.ctl); D.u32(L("skip", l), f.skip);
-    if (l > 0) {
+    if (l > LO) {
       D.i32(L("p_rowptr", l), f.p_rowptr); D.i32(L("p_col", l), f.p_col); D.f64(L("p_w", l), f.p_w);
       D.i32(L("r_rowptr", l), f.r_rowptr); D.i32(L("r_col", l), f.r_col); D.f64(L("r_w", l), f.r_w);
       D.i32(L("node_row", l), f.node_row);
@@ -536,7 +565,7 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
       GRID *g = GRID_ON_LEVEL(mg, l);
       std::vector<int32_t> eptr(1, 0), enodes, efather;
       std::map<ELEMENT *, int> pos;
-      if (l > 0) { int k = 0; for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l - 1)); e; e = SUCCE(e)) pos[e] = k++; }
+      if (l > LO) { int k = 0; for (ELEMENT *e = FIRSTELEMENT(GRID_ON_LEVEL(mg, l - 1)); e; e = SUCCE(e)) pos[e] = k++; }
       for (ELEMENT *e = FIRSTELEMENT(g); e; e = SUCCE(e)) {
         for (int i = 0; i < CORNERS_OF_ELEM(e); i++) enodes.push_back((int32_t)VINDEX(NVECTOR(CORNER(e, i))));
         eptr.push_back((int32_t)enodes.size());
@@ -545,7 +574,7 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
       D.i32(L("elem_ptr", l), eptr); D.i32(L("elem_nodes", l), enodes); D.i32(L("elem_father", l), efather);
     }
     // vertex coordinates in row order (lets tests relate UG's ordering to the synthetic generator)
-    if (o.lean && !o.elems) continue;
+    if ((o.lean && !o.elems) || l < 0) continue;      // algebraic levels have no nodes
     std::vector<double> xyz((size_t)f.n * DIM);
     for (NODE *n = FIRSTNODE(GRID_ON_LEVEL(mg, l)); n; n = SUCCN(n))
       for (int d = 0; d < DIM; d++) xyz[(size_t)VINDEX(NVECTOR(n)) * DIM + d] = CVECT(MYVERTEX(n))[d];
@@ -666,6 +695,10 @@ static void restore_problem(void)
 {
   // rhs and sol back to the assembled state (assemble() also rewrites the matrix: same values)
   assemble();
+  // algebraic levels: work space of the cycle only; zeroed so that every run starts from the same state
+  for (int l = LO; l < 0; l++)
+    for (VECTOR *v = FIRSTVECTOR(GRID_ON_LEVEL(mg, l)); v != NULL; v = SUCCVC(v))
+      for (int i = 0; i < BS; i++) { VVALUE(v, VD_CMP_OF_TYPE(vx, VTYPE(v), i)) = 0.0; VVALUE(v, VD_CMP_OF_TYPE(vb, VTYPE(v), i)) = 0.0; VVALUE(v, VD_CMP_OF_TYPE(vc, VTYPE(v), i)) = 0.0; VVALUE(v, VD_CMP_OF_TYPE(vt, VTYPE(v), i)) = 0.0; }
 }
 
 // one Lmgc cycle through the numproc interface + the full `ls` solve
@@ -677,9 +710,9 @@ static void dump_solve(const Opt &o)
   NP_ITER *lmgc = (NP_ITER *)GetNumProcByName(mg, "lmgc", ITER_CLASS_NAME);
   // --- a single cycle on the raw right-hand side (c = 0 on entry)
   (*lmgc->PreProcess)(lmgc, top, vx, vb, mA, &bl, &result);
-  dset(mg, 0, top, ALL_VECTORS, vc, 0.0);
+  dset(mg, LO, top, ALL_VECTORS, vc, 0.0);
   if ((*lmgc->Iter)(lmgc, top, vc, vb, mA, &result)) { fprintf(stderr, "Lmgc failed\n"); exit(9); }
-  for (int l = 0; l <= top; l++) { dumpvec("lmgc/c", vc, l); dumpvec("lmgc/b", vb, l); }
+  for (int l = LO; l <= top; l++) { dumpvec("lmgc/c", vc, l); dumpvec("lmgc/b", vb, l); }
   (*lmgc->PostProcess)(lmgc, top, vx, vb, mA, &result);
   // --- full solve, history after every iteration (maxit = cycles, limits unreachable)
   restore_problem();
@@ -689,7 +722,7 @@ static void dump_solve(const Opt &o)
   (*ls->Defect)(ls, top, vx, vb, mA, &result);
   (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
   D.rec("solve/first_defect", 1, lr.last_defect, BS, 8);
-  for (int l = 0; l <= top; l++) dumpvec("solve/b_first", vb, l);
+  for (int l = LO; l <= top; l++) dumpvec("solve/b_first", vb, l);
   (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
   // iterate one cycle at a time to record the history: maxit=1 solver calls are NOT equivalent
   // (first_defect handling), so we call Solver once with maxit=cycles and read PCR-independent
@@ -708,7 +741,7 @@ static void dump_solve(const Opt &o)
     (*ls->PostProcess)(ls, top, vx, vb, mA, &result);
     if (k == 1 || k == 2 || k == 5 || k == o.cycles) {
       char nm[64];
-      for (int l = 0; l <= top; l++) {
+      for (int l = LO; l <= top; l++) {
         snprintf(nm, sizeof nm, "solve/x_after_%d", k); dumpvec(nm, vx, l);
         snprintf(nm, sizeof nm, "solve/b_after_%d", k); dumpvec(nm, vb, l);
       }
@@ -753,7 +786,7 @@ static void dump_krylov(const Opt &o)
       nits.push_back(lr.number_of_linear_iterations);
       (*s->PostProcess)(s, top, vx, vb, mA, &result);
       if (k == 1 || k == 2 || k == K[w])
-        for (int l = 0; l <= top; l++) {
+        for (int l = LO; l <= top; l++) {
           snprintf(key, sizeof key, "%s/x_after_%d", names[w], k); dumpvec(key, vx, l);
           snprintf(key, sizeof key, "%s/b_after_%d", names[w], k); dumpvec(key, vb, l);
         }
@@ -796,7 +829,7 @@ static void time_reference(const Opt &o)
   NP_LINEAR_SOLVER *ls = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "mgs", LINEAR_SOLVER_CLASS_NAME);
   cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", o.cycles);
   LRESULT lr; memset(&lr, 0, sizeof lr);
-  (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+  if ((*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result)) { fprintf(stderr, "PreProcess of the reference's numprocs failed\n"); exit(9); }
   (*ls->Defect)(ls, top, vx, vb, mA, &result);
   (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
   VEC_SCALAR abslimit, red;
@@ -869,6 +902,8 @@ int main(int argc, char **argv)
     else if (a == "--assemble") { o.assemble = true; o.elems = true; }
     else if (a == "--savedata") o.savedata = nxt();      // prefix of the data files the reference's SaveData writes (np/udm/data_io.cc:650)
     else if (a == "--nokrylov") o.nokrylov = true;
+    else if (a == "--amg") { o.amg_class = nxt(); o.amg_init = nxt(); }
+    else if (a == "--collapse") o.collapse = true; else if (a == "--refine2") o.refine2 = atoi(nxt().c_str());
     else if (a == "--elems") o.elems = true;             // dump the elements (corner rows, fathers): input of the element partition (ug_b200/partition.py)       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
   }
@@ -876,6 +911,7 @@ int main(int argc, char **argv)
   // keep UG's banner noise out of stdout: results are printed by this driver only
   FILE *saved = stdout;
   (void)saved;
+  signal(SIGSEGV, on_crash); signal(SIGABRT, on_crash);
   if (InitUg(&ac, &av)) { fprintf(stderr, "InitUg failed\n"); return 1; }
 #ifdef WITH_GPULS
   if (!o.gpu.empty()) { if (gpuls::LoadDeviceLibrary(o.gpu.c_str())) { fprintf(stderr, "cannot load %s\n", o.gpu.c_str()); return 1; } if (InitGpuLS()) { fprintf(stderr, "InitGpuLS failed\n"); return 1; } }
@@ -894,6 +930,19 @@ int main(int argc, char **argv)
       if (CreateStandardNodeRestProl(GRID_ON_LEVEL(mg, l), BS) != NUM_OK) { fprintf(stderr, "CreateStandardNodeRestProl failed\n"); return 1; }
   make_numprocs(o, "", o.smoother.c_str(), "lmgc", "transfer", "ls", o.cycles);
   std::vector<gpuls::FlatLevel> fl;
+  if (!o.dump.empty() && !o.amg_class.empty()) {
+    // the algebraic levels must exist while the dump is written: one PreProcess / PostProcess bracket of the transfer builds them, and
+    // the AMG numproc's $hold keeps them (later brackets keep coarsening and interpolation and recompute the matrices, amgtransfer.cc:1004)
+    if (o.amg_init.find("$hold") == std::string::npos || o.ops || o.galerkin || o.assemble || !o.savedata.empty()) { fprintf(stderr, "--amg dumps need $hold and hold the hierarchy and the solve records only\n"); return 1; }
+    NP_TRANSFER *t = (NP_TRANSFER *)GetNumProcByName(mg, "transfer", TRANSFER_CLASS_NAME);
+    INT fl0 = 0, result = 0;
+    if (!t || (*t->PreProcess)(t, &fl0, top, vx, vb, mA, &result) || (*t->PostProcess)(t, &fl0, top, vx, vb, mA, &result)) { fprintf(stderr, "AMG setup failed\n"); return 1; }
+    LO = BOTTOMLEVEL(mg);
+    printf("algebraic levels: bottom=%d n=[", LO);
+    for (int l = LO; l < 0; l++) printf("%s%d", l > LO ? "," : "", (int)NVEC(GRID_ON_LEVEL(mg, l)));
+    printf("]\n");
+    restore_problem();
+  }
   if (!o.dump.empty()) {
     D.open(o.dump.c_str());
     dump_hierarchy(o, fl);
@@ -933,7 +982,7 @@ static int run_gpu(const Opt &o)
   cmd("npinit mgs $A MAT $x sol $b rhs $m %d $red 1e-30 $abslimit 1e-30 $I lmgc $display no", o.cycles);
   NP_LINEAR_SOLVER *ls = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, "mgs", LINEAR_SOLVER_CLASS_NAME);
   LRESULT lr; memset(&lr, 0, sizeof lr);
-  (*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result);
+  if ((*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result)) { printf("FAIL reference: PreProcess of the CPU numprocs\n"); return 1; }
   (*ls->Defect)(ls, top, vx, vb, mA, &result);
   (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
   double c0 = now();

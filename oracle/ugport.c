@@ -684,21 +684,26 @@ int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu,
 {
   const ugport_level *L = &lv[level];
   double one[UGPORT_MAX_BS] = {1.0, 1.0, 1.0};
-  if (level <= cfg->baselevel) { base_solve(L, cfg, lu, c[level], b[level], t[level]); return 0; }
+  if (level <= cfg->baselevel) {
+    if (cfg->base_hook) return cfg->base_hook(cfg->base_user, level, c[level], b[level]);
+    base_solve(L, cfg, lu, c[level], b[level], t[level]);
+    return 0;
+  }
   double *tmp = cfg->smoother == UGPORT_SM_SGS ? (double *)malloc(sizeof(double) * (size_t)L->n * L->bs) : NULL;
   for (int i = 0; i < cfg->nu1; i++) {
     int err = ugport_smooth(L, cfg->smoother, t[level], b[level], cfg->smooth_damp, tmp);
     if (err) { free(tmp); return err; }
     ugport_dadd(L, 0, c[level], t[level]);
   }
-  if (cfg->imat) ugport_restrict_imat(L, &lv[level - 1], b[level - 1], b[level], one);
+  const int imat = cfg->imat || level <= cfg->imat_below;
+  if (imat) ugport_restrict_imat(L, &lv[level - 1], b[level - 1], b[level], one);
   else ugport_restrict(L, &lv[level - 1], b[level - 1], b[level], one);           /* :7843, Factor_One */
   ugport_dset(&lv[level - 1], 0, c[level - 1], 0.0);                         /* :7873 */
   for (int g = 0; g < cfg->gamma; g++) {
     int err = ugport_lmgc(lv, cfg, lu, level - 1, c, b, t);
     if (err) { free(tmp); return err; }
   }
-  if (cfg->imat) ugport_interpolate_imat(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);
+  if (imat) ugport_interpolate_imat(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);
   else ugport_interpolate(L, &lv[level - 1], t[level], c[level - 1], cfg->cycle_damp);  /* :7886 */
   ugport_dadd(L, 0, c[level], t[level]);                                     /* :7903 */
   ugport_dmatmul(L, 2, 0, b[level], t[level]);                               /* :7905 */
@@ -736,7 +741,7 @@ int ugport_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int leve
 {
   int bs = lv[level].bs, bl = cfg->baselevel, it, done = 0;
   double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS];
-  double *lu = ugport_base_factor(&lv[bl]);
+  double *lu = cfg->base_hook ? NULL : ugport_base_factor(&lv[bl]);
   ugport_ls_residuum(lv, fr, bl, level, b, last);
   for (int i = 0; i < bs; i++) { first_defect[i] = last[i]; reach[i] = last[i] * reduction[i]; if (reach[i] == 0.0) reach[i] = reduction[i]; }
   if (sc_cmp(last, abslimit, bs)) { ugport_base_free(lu); return 0; }
@@ -782,7 +787,7 @@ int ugport_cg_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int l
 {
   int bs = lv[level].bs, bl = cfg->baselevel, it, done = 0;
   double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS];
-  double *lu = ugport_base_factor(&lv[bl]);
+  double *lu = cfg->base_hook ? NULL : ugport_base_factor(&lv[bl]);
   ALL_LOOP(ugport_dset(L, 0, p[l], 0.0));                                        /* CGPrepare */
   double rho = 1.0, lambda;
   ugport_ls_residuum(lv, fr, bl, level, b, last);
@@ -821,7 +826,7 @@ int ugport_bcgs_solve(const ugport_level *lv, const ugport_cfg *cfg, int fr, int
   int bs = lv[level].bs, bl = cfg->baselevel, nit = 0, eq_count = 0, restart = 1;
   double last[UGPORT_MAX_BS], reach[UGPORT_MAX_BS], old[UGPORT_MAX_BS] = {-1.0, -1.0, -1.0};
   double alpha = 0.0, rho_new = 0.0, beta = 0.0, tsq = 0.0, rho = 0.0, omega = 0.0;
-  double *lu = ugport_base_factor(&lv[bl]);
+  double *lu = cfg->base_hook ? NULL : ugport_base_factor(&lv[bl]);
   ugport_ls_residuum(lv, fr, bl, level, b, last);
   for (int i = 0; i < bs; i++) { first_defect[i] = last[i]; reach[i] = last[i] * reduction[i]; if (reach[i] == 0.0) reach[i] = reduction[i]; }
   int converged = sc_cmp(last, abslimit, bs);

@@ -32,7 +32,8 @@ class _Cfg(C.Structure):
     _fields_ = [("nu1", C.c_int), ("nu2", C.c_int), ("gamma", C.c_int), ("baselevel", C.c_int),
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
                 ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
-                ("smoother", C.c_int), ("imat", C.c_int)]
+                ("smoother", C.c_int), ("imat", C.c_int), ("imat_below", C.c_int),
+                ("base_hook", C.c_void_p), ("base_user", C.c_void_p)]
 
 
 class _Fe(C.Structure):
@@ -92,6 +93,8 @@ class PortBackend:
             arr[i] = _Level(lv.n, lv.bs, ilu=None, **fields)
         self.levels = arr
         self.imat = bool(int(hier.raw["transfer_mode"][0])) if "transfer_mode" in getattr(hier, "raw", {}) else False
+        # dumps with algebraic levels (ug_driver --amg): UG's levels < 1 always use the by-matrix transfer; the dump numbers them from 0
+        self.imat_below = -int(hier.raw["bottomlevel"][0]) if "bottomlevel" in getattr(hier, "raw", {}) else 0
         self.vec: Dict[str, List[np.ndarray]] = {}
         self._ilu: Dict[int, tuple] = {}          # level -> (beta, decomposed values)
 
@@ -241,11 +244,11 @@ class PortBackend:
                                     self._vs(damp), _dp(self._v(tmp, level)))
 
     def restrict(self, level, to, frm, damp):
-        (self.L.ugport_restrict_imat if self.imat else self.L.ugport_restrict)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level - 1)),
+        (self.L.ugport_restrict_imat if self.imat or level <= self.imat_below else self.L.ugport_restrict)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level - 1)),
                                _dp(self._v(frm, level)), self._vs(damp))
 
     def interpolate(self, level, to, frm, damp):
-        (self.L.ugport_interpolate_imat if self.imat else self.L.ugport_interpolate)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level)),
+        (self.L.ugport_interpolate_imat if self.imat or level <= self.imat_below else self.L.ugport_interpolate)(self._lp(level), self._lp(level - 1), _dp(self._v(to, level)),
                                   _dp(self._v(frm, level - 1)), self._vs(damp))
 
     # ---- cycle / solver
@@ -260,6 +263,7 @@ class PortBackend:
         c.base_abslimit = cfg.get("base_abslimit", 1e-10)
         c.smoother = SMOOTHERS[cfg.get("smoother", "jac")]
         c.imat = 1 if self.imat else 0
+        c.imat_below = self.imat_below
         if cfg.get("smoother") == "ilu":           # what LmgcPreProcess -> ILUPreProcess does on the levels above the base level
             beta = float(cfg.get("ilu_beta", 0.0))
             for l in range(c.baselevel + 1, len(self.h.levels)):

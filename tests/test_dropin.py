@@ -13,6 +13,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
 
+AMG_RS = "$strongRel 0.25 $C RugeStueben $I RugeStueben $CM Galerkin $vectLimit 20"
+AMG_VANEK = "$strongVanek 0.08 $C VanekNeuss $I Vanek $CM Galerkin $vectLimit 10"
+# averaging interpolation (the one the reference offers for systems) on a greedy independent set.  Not `$C Average`: CoarsenAverage re-links
+# the vector list of the level it coarsens and re-sorts its matrix lists (np/algebra/amgtools.cc:1330-1440), so two successive solves of the
+# reference itself run on differently ordered levels and differ in the last bits -- nothing a run-after-run comparison can be pinned on
+AMG_AVG = "$strongRel 0.25 $C Greedy $I Average $CM Galerkin"
 CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--damp", "0.6", "--cycles", "6"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--damp", "0.6", "--cycles", "6"]),
@@ -51,10 +57,17 @@ CASES = [
     ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "3", "--damp", "0.7", "--cycles", "4", "--nokrylov", "--assemble"]),
     ("ugoracle3", ["--grid", "hex", "--refine", "4", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),     # Q1 17^3
     ("ugoracle3", ["--grid", "tet", "--refine", "5", "--damp", "0.6", "--cycles", "4", "--nokrylov", "--assemble"]),     # 33^3
+    # ---- algebraic levels: `transfer $amg amgt` / `gputransfer $amg amgt` with the reference's own AMG transfer numproc
+    # (np/procs/amgtransfer.cc) building levels -1, -2, ... below a collapsed level 0 in every PreProcess; the device cycle runs on them
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS]),                          # Ruge-Stueben
+    ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),       # Vanek aggregation, one geometric level above
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--collapse", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 10"]),   # 3x3 blocks, averaging
+    ("ugoracle3", ["--grid", "tet", "--refine", "5", "--collapse", "--refine2", "1", "--cycles", "4", "--nokrylov", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),   # 65^3 on 33^3 on 4 algebraic levels
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
        "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu", "quad-bs2", "tet-r5-33^3", "tet-r6-65^3", "hex-bs3-r4", "hex-q1-r5-33^3", "tri-r6-C1", "tri-r9-513^2",
-       "tet-r4-adaptive", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "assemble-hex-q1-r4", "assemble-tet-r5-33^3"]
+       "tet-r4-adaptive", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "assemble-hex-q1-r4", "assemble-tet-r5-33^3",
+       "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-65^3-on-33^3-greedy-average"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)

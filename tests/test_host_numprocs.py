@@ -1,0 +1,64 @@
+"""Host logic of the `gpuls` numproc family on a machine WITHOUT a GPU: the drop-in cases of tests/test_dropin.py inside the unmodified
+reference (oracle/_ref/ugoracle{2,3}), with tests/standin/libuggpu_standin.so in place of libuggpu.so.  The stand-in answers the C-ABI
+calls the numprocs make with the oracle's plain-C restatement, so what is exercised here is everything ABOVE the C-ABI: flattening of
+UG's lists, level numbering (algebraic levels below 0 -> device levels), upload caching per PreProcess bracket, the base-solver
+callback, LRESULT.  Results must equal the CPU numprocs' bit for bit (the restatement is bit-exact).  The CUDA library is tested by
+the same cases in tests/test_dropin.py (`-m gpu`)."""
+import os
+import subprocess
+
+import pytest
+
+from test_dropin import AMG_AVG, AMG_RS, AMG_VANEK
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "standin", "uggpu_standin.cc")
+LIB = os.path.join(ROOT, "tests", "standin", "libuggpu_standin.so")
+
+
+@pytest.fixture(scope="module")
+def standin():
+    deps = [SRC, os.path.join(ROOT, "oracle", "ugport.c"), os.path.join(ROOT, "oracle", "ugport.h"), os.path.join(ROOT, "include", "uggpu.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        obj = LIB[:-3] + ".ugport.o"
+        inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle")]
+        subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-fPIC", "-c", deps[1], "-o", obj] + inc, check=True)
+        subprocess.run(["g++", "-std=c++14", "-O1", "-ffp-contract=off", "-fPIC", "-shared", SRC, obj, "-o", LIB, "-lm"] + inc, check=True)
+    return LIB
+
+
+CASES = [
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--damp", "0.6", "--cycles", "6"]),
+    ("ugoracle2", ["--grid", "tri", "--refine", "5", "--damp", "0.8", "--cycles", "6"]),
+    ("ugoracle2", ["--grid", "quad", "--refine", "3", "--damp", "0.8", "--gamma", "2", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "gs", "--damp", "0.9", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--smoother", "sgs", "--damp", "0.8", "--cycles", "4"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--smoother", "sor", "--damp", "1.1", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--baselevel", "2", "--damp", "0.6", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--imat", "--damp", "0.6", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "ilu", "--beta", "0.25", "--damp", "0.9", "--cycles", "5"]),
+    ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "4", "--damp", "0.7", "--cycles", "6"]),
+    # algebraic levels below level 0: `gputransfer $amg amgt` calls the reference's AMG numproc, mirrors levels -1, -2, ... as device levels
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS]),
+    ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--collapse", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 10"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),
+]
+IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat", "tet-ilu-beta",
+       "quad-bs2", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
+
+
+@pytest.mark.parametrize("exe,args", CASES, ids=IDS)
+def test_host_numprocs_against_standin(standin, exe, args):
+    path = os.path.join(ROOT, "oracle", "_ref", exe)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    out = subprocess.run([path] + args + ["--nokrylov", "--gpu", standin], capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
+    assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
+    assert sum(l.startswith("PASS") for l in lines) == 4, lines
+    # bit for bit, also with the "device" base solver (the stand-in's is the restatement of the reference's ls + lu)
+    assert all("relerr x=0.000e+00 b=0.000e+00" in l for l in lines if l.startswith("PASS")), lines
+    assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -144,7 +144,9 @@ class Context:
                 self.call("uggpu_transfer_set", l, _p(np.ascontiguousarray(lv.p_rowptr)), _p(np.ascontiguousarray(lv.p_col)),
                           _p(np.ascontiguousarray(lv.p_w)), _p(np.ascontiguousarray(lv.r_rowptr)),
                           _p(np.ascontiguousarray(lv.r_col)), _p(np.ascontiguousarray(lv.r_w)))
-                if "transfer_mode" in hier.raw:          # dumps written with `transfer $M` (oracle/ug_driver.cc --imat)
+                if f"L{l}/transfer_mode" in hier.raw:    # dumps with algebraic levels (--amg): by-matrix transfer below UG's level 1
+                    self.call("uggpu_transfer_set_mode", l, int(hier.raw[f"L{l}/transfer_mode"][0]))
+                elif "transfer_mode" in hier.raw:        # dumps written with `transfer $M` (oracle/ug_driver.cc --imat)
                     self.call("uggpu_transfer_set_mode", l, int(hier.raw["transfer_mode"][0]))
         self.call("uggpu_set_fullrefinelevel", int(hier.fullrefinelevel))
 

@@ -255,7 +255,7 @@ int FlattenTransfer(MULTIGRID *mg, int level, FlatLevel &out)
 
 int FlattenTransferIMAT(MULTIGRID *mg, int level, FlatLevel &out)
 {
-  if (level < 1) return 1;
+  if (level <= BOTTOMLEVEL(mg)) return 1;          // levels < 1: the algebraic levels of an AMG transfer (np/procs/amgtransfer.cc), same lists
   GRID *fg = GRID_ON_LEVEL(mg, level), *cg = GRID_ON_LEVEL(mg, level - 1);
   if (fg == NULL || cg == NULL) return 2;
   const int nf = out.n, nc = NVEC(cg), bs = out.bs;

@@ -89,6 +89,12 @@ struct Mirror {
   std::vector<const VECDATA_DESC *> level_x;
   std::map<const void *, int> handles;
   std::vector<double> buf;
+  // UG numbers the algebraic levels an AMG transfer builds below level 0 with negative numbers (BOTTOMLEVEL(mg) < 0,
+  // np/procs/amgtransfer.cc:737); the device library's levels start at 0.  Device level = UG level + loff; loff is 0 unless a
+  // gputransfer with $amg has built such levels (SetBottom below).  The arrays above are indexed through ix().
+  int loff = 0;
+  int dl(int level) const { return level + loff; }
+  static int ix(int level) { return level + MAXLEVEL; }
 
   int handle(const void *desc)
   {
@@ -121,12 +127,13 @@ Mirror *Acquire(MULTIGRID *mg)
     int dev = 0;
     if (const char *s = getenv("UGGPU_DEVICE")) dev = atoi(s);
     if (api.uggpu_ctx_create(dev, &m.ctx)) { dev_fail("uggpu_ctx_create"); g_mirrors.erase(mg); return NULL; }
-    m.fl.assign(MAXLEVEL, gpuls::FlatLevel());
-    m.have_level.assign(MAXLEVEL, 0);
-    m.have_transfer.assign(MAXLEVEL, 0);
-    m.level_A.assign(MAXLEVEL, (const MATDATA_DESC *)NULL);
-    m.level_x.assign(MAXLEVEL, (const VECDATA_DESC *)NULL);
+    m.fl.assign(2 * MAXLEVEL, gpuls::FlatLevel());
+    m.have_level.assign(2 * MAXLEVEL, 0);
+    m.have_transfer.assign(2 * MAXLEVEL, 0);
+    m.level_A.assign(2 * MAXLEVEL, (const MATDATA_DESC *)NULL);
+    m.level_x.assign(2 * MAXLEVEL, (const VECDATA_DESC *)NULL);
     m.handles.clear();
+    m.loff = 0;
   }
   m.refs++;
   return &m;
@@ -167,57 +174,72 @@ Mirror *Live(Mirror *held, MULTIGRID *mg)
 #define PRE_FAIL(np_, result_) do { Destroy(NP_MG(theNP)); (np_)->m = NULL; NP_RETURN(1, result_); } while (0)
 #define PRE_FAIL_JAC(np_, result_) do { (np_)->acquired = 0; PRE_FAIL(np_, result_); } while (0)
 
+// An AMG transfer has built levels down to `bottom` < 0: they become device levels 0.. and everything above moves up.  Levels that
+// were uploaded under another offset are flattened again (at most once per bracket: the AMG runs first in a transfer's PreProcess).
+void SetBottom(Mirror *m, int bottom)
+{
+  const int loff = bottom < 0 ? -bottom : 0;
+  if (loff == m->loff) return;
+  m->loff = loff;
+  std::fill(m->have_level.begin(), m->have_level.end(), 0);
+  std::fill(m->have_transfer.begin(), m->have_transfer.end(), 0);
+}
+
 // flatten + upload matrix A and the row flags of `level` (once per PreProcess bracket)
 int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC *A)
 {
   // one upload per PreProcess bracket and (level, A, x): another matrix or vector descriptor on the same level is flattened again
-  if (m->have_level[level] && m->level_A[level] == A && m->level_x[level] == x) return 0;
-  if (m->have_level[level]) { m->have_level[level] = 0; m->have_transfer[level] = 0; if (level + 1 < MAXLEVEL) m->have_transfer[level + 1] = 0; }
-  gpuls::FlatLevel &f = m->fl[level];
+  const int k = Mirror::ix(level);
+  if (level < -MAXLEVEL || level >= MAXLEVEL || m->dl(level) < 0 || m->dl(level) >= UGGPU_MAX_LEVELS) { UserWriteF("gpuls: level %d is outside the device library's range\n", level); return 1; }
+  if (m->have_level[k] && m->level_A[k] == A && m->level_x[k] == x) return 0;
+  if (m->have_level[k]) { m->have_level[k] = 0; m->have_transfer[k] = 0; if (level + 1 < MAXLEVEL) m->have_transfer[k + 1] = 0; }
+  gpuls::FlatLevel &f = m->fl[k];
   if (gpuls::FlattenFlags(m->mg, level, x, f)) { UserWriteF("gpuls: level %d is not a pure nodal vector format\n", level); return 1; }
   if (f.bs > UGGPU_MAX_BS) { UserWriteF("gpuls: %d components per vector exceed UGGPU_MAX_BS\n", f.bs); return 1; }
   if (gpuls::FlattenMatrix(m->mg, level, A, f)) { UserWrite("gpuls: cannot flatten the matrix\n"); return 1; }
   m->bs = f.bs;
   m->xdesc = x;
-  DEV(uggpu_level_create(m->ctx, level, f.n, f.bs));
-  DEV(uggpu_level_set_flags(m->ctx, level, f.vclass.data(), f.vnclass.data(), f.ctl.data(), f.skip.data()));
-  DEV(uggpu_mat_set(m->ctx, level, m->handle(A), f.rowptr.data(), f.col.data(), f.val.data()));
-  DEV(uggpu_set_fullrefinelevel(m->ctx, FULLREFINELEVEL(m->mg)));
-  m->have_level[level] = 1;
-  m->level_A[level] = A; m->level_x[level] = x;
+  DEV(uggpu_level_create(m->ctx, m->dl(level), f.n, f.bs));
+  DEV(uggpu_level_set_flags(m->ctx, m->dl(level), f.vclass.data(), f.vnclass.data(), f.ctl.data(), f.skip.data()));
+  DEV(uggpu_mat_set(m->ctx, m->dl(level), m->handle(A), f.rowptr.data(), f.col.data(), f.val.data()));
+  DEV(uggpu_set_fullrefinelevel(m->ctx, m->dl(FULLREFINELEVEL(m->mg))));
+  m->have_level[k] = 1;
+  m->level_A[k] = A; m->level_x[k] = x;
   return 0;
 }
 
 // imat: `transfer $M` -- the stencils come from the stored interpolation matrices (gpuls_flatten.h FlattenTransferIMAT)
 int EnsureTransfer(Mirror *m, int level, int imat)
 {
-  if (m->have_transfer[level] == 1 + imat) return 0;
-  if (level < 1 || !m->have_level[level] || !m->have_level[level - 1]) return 1;
-  gpuls::FlatLevel &f = m->fl[level];
+  const int k = Mirror::ix(level);
+  if (level < 1) imat = 1;       // below level 1 the reference always works on the stored interpolation matrices (transfer.cc:733, :756)
+  if (m->have_transfer[k] == 1 + imat) return 0;
+  if (level <= -MAXLEVEL || !m->have_level[k] || !m->have_level[k - 1]) return 1;
+  gpuls::FlatLevel &f = m->fl[k];
   if (int rc = imat ? gpuls::FlattenTransferIMAT(m->mg, level, f) : gpuls::FlattenTransfer(m->mg, level, f)) {
     UserWriteF("gpuls: cannot flatten the %s transfer of level %d (code %d)\n", imat ? "IMAT" : "standard", level, rc);
     return 1;
   }
-  DEV(uggpu_transfer_set(m->ctx, level, f.p_rowptr.data(), f.p_col.data(), f.p_w.data(), f.r_rowptr.data(), f.r_col.data(), f.r_w.data()));
-  DEV(uggpu_transfer_set_mode(m->ctx, level, imat ? UGGPU_TRANSFER_IMAT : UGGPU_TRANSFER_STANDARD));
-  m->have_transfer[level] = 1 + imat;
+  DEV(uggpu_transfer_set(m->ctx, m->dl(level), f.p_rowptr.data(), f.p_col.data(), f.p_w.data(), f.r_rowptr.data(), f.r_col.data(), f.r_w.data()));
+  DEV(uggpu_transfer_set_mode(m->ctx, m->dl(level), imat ? UGGPU_TRANSFER_IMAT : UGGPU_TRANSFER_STANDARD));
+  m->have_transfer[k] = 1 + imat;
   return 0;
 }
 
 int Upload(Mirror *m, int level, const VECDATA_DESC *vd)
 {
-  const gpuls::FlatLevel &f = m->fl[level];
+  const gpuls::FlatLevel &f = m->fl[Mirror::ix(level)];
   m->buf.resize((size_t)f.n * f.bs + 1);
   gpuls::GatherVector(m->mg, level, vd, f.bs, m->buf.data());
-  DEV(uggpu_vec_upload(m->ctx, level, m->handle(vd), m->buf.data()));
+  DEV(uggpu_vec_upload(m->ctx, m->dl(level), m->handle(vd), m->buf.data()));
   return 0;
 }
 
 int Download(Mirror *m, int level, const VECDATA_DESC *vd)
 {
-  const gpuls::FlatLevel &f = m->fl[level];
+  const gpuls::FlatLevel &f = m->fl[Mirror::ix(level)];
   m->buf.resize((size_t)f.n * f.bs + 1);
-  DEV(uggpu_vec_download(m->ctx, level, m->handle(vd), m->buf.data()));
+  DEV(uggpu_vec_download(m->ctx, m->dl(level), m->handle(vd), m->buf.data()));
   gpuls::ScatterVector(m->mg, level, vd, f.bs, m->buf.data());
   return 0;
 }
@@ -278,14 +300,14 @@ INT GpuJacPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b
     double beta[UGGPU_MAX_BS];
     for (int i = 0; i < UGGPU_MAX_BS; i++) beta[i] = i < m->bs ? np->beta[i] : 0.0;
     np->L_handle = m->handle(&np->L_handle);
-    if (api.uggpu_dmatcopy(m->ctx, level, level, UGGPU_ALL_VECTORS, np->L_handle, m->handle(A))) { dev_fail("uggpu_dmatcopy"); PRE_FAIL_JAC(np, result[0]); }
-    if (api.uggpu_l_ilubthdecomp(m->ctx, level, np->L_handle, beta)) {
+    if (api.uggpu_dmatcopy(m->ctx, m->dl(level), m->dl(level), UGGPU_ALL_VECTORS, np->L_handle, m->handle(A))) { dev_fail("uggpu_dmatcopy"); PRE_FAIL_JAC(np, result[0]); }
+    if (api.uggpu_l_ilubthdecomp(m->ctx, m->dl(level), np->L_handle, beta)) {
       PrintErrorMessage('E', "GpuIluPreProcess", "decomposition failed");      // iter.cc:5470
       { dev_fail("uggpu_l_ilubthdecomp"); PRE_FAIL_JAC(np, result[0]); }
     }
   } else if (np->kind != UGGPU_SM_JAC) {
     // l_setindex (iter.cc:1027): rows are numbered in list order by the flattening; the device builds its level schedule
-    if (api.uggpu_gs_preprocess(m->ctx, level, m->handle(A))) { dev_fail("uggpu_gs_preprocess"); PRE_FAIL_JAC(np, result[0]); }
+    if (api.uggpu_gs_preprocess(m->ctx, m->dl(level), m->handle(A))) { dev_fail("uggpu_gs_preprocess"); PRE_FAIL_JAC(np, result[0]); }
     np->t_handle = m->handle(&np->t_handle);
   }
   *baselevel = level;                                                      // iter.cc:908
@@ -298,15 +320,15 @@ INT GpuJacIter(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *b, MATD
   NP_GPUJAC *np = (NP_GPUJAC *)theNP;
   NPIT_A(theNP) = A; NPIT_c(theNP) = x; NPIT_b(theNP) = b;
   Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
-  if (m == NULL || !m->have_level[level]) { UserWriteF("%s: Iter without PreProcess\n", SmootherName(np->kind)); NP_RETURN(1, result[0]); }
+  if (m == NULL || !m->have_level[Mirror::ix(level)]) { UserWriteF("%s: Iter without PreProcess\n", SmootherName(np->kind)); NP_RETURN(1, result[0]); }
   double damp[UGGPU_MAX_BS];
   VsToArray(np->damp, m->bs, damp);
   if (Upload(m, level, b)) NP_RETURN(1, result[0]);
-  if (api.uggpu_vec_alloc(m->ctx, level, m->handle(x))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+  if (api.uggpu_vec_alloc(m->ctx, m->dl(level), m->handle(x))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
   if (np->kind != UGGPU_SM_JAC) {
-    if (api.uggpu_smooth(m->ctx, level, (int)np->kind, m->handle(x), m->handle(b), m->handle(A), damp, np->kind == UGGPU_SM_ILU ? np->L_handle : np->t_handle)) NP_RETURN(dev_fail("uggpu_smooth"), result[0]);
+    if (api.uggpu_smooth(m->ctx, m->dl(level), (int)np->kind, m->handle(x), m->handle(b), m->handle(A), damp, np->kind == UGGPU_SM_ILU ? np->L_handle : np->t_handle)) NP_RETURN(dev_fail("uggpu_smooth"), result[0]);
   } else
-  if (api.uggpu_jac_smooth(m->ctx, level, m->handle(x), m->handle(b), m->handle(A), damp)) NP_RETURN(dev_fail("uggpu_jac_smooth"), result[0]);
+  if (api.uggpu_jac_smooth(m->ctx, m->dl(level), m->handle(x), m->handle(b), m->handle(A), damp)) NP_RETURN(dev_fail("uggpu_jac_smooth"), result[0]);
   if (Download(m, level, x) || Download(m, level, b)) NP_RETURN(1, result[0]);
   return 0;
 }
@@ -340,19 +362,33 @@ INT GpuSorConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_S
 INT GpuIluConstruct(NP_BASE *theNP) { return GpuSmootherConstruct(theNP, UGGPU_SM_ILU); }
 
 // =========================================================================================================================
-// transfer.gputransfer  (reference: NP_STANDARD_TRANSFER transfer.cc:115-133, standard mode only)
+// transfer.gputransfer  (reference: NP_STANDARD_TRANSFER transfer.cc:115-133, standard mode, $M and $amg)
 // =========================================================================================================================
 struct NP_GPUTRANSFER {
   NP_TRANSFER transfer;
   Mirror *m;
   INT fl, tl;
   INT imat;            // $M: IMAT_MODE (transfer.cc:564-572): RestrictByMatrix / InterpolateCorrectionByMatrix
+  NP_TRANSFER *amg;    // $amg <numproc>: NP_STANDARD_TRANSFER.amg (transfer.cc:132, :593): a transfer numproc of the host -- the reference's
+                       // selectionAMG / clusterAMG (np/procs/amgtransfer.cc) -- whose PreProcess builds algebraic levels below level 0 when
+                       // the cycle's base level is <= 0 (transfer.cc:660-664).  The coarsening stays the reference's sequential host code (a setup
+                       // step); the levels it leaves (vectors, Galerkin matrices, interpolation matrices) are mirrored like any other
+                       // level and the device cycle runs on them with the by-matrix transfer, as the reference does for all levels < 1.
+  INT amg_ran;
 };
+
+INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result);
 
 INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
   np->imat = ReadArgvOption("M", argc, argv);
+  np->amg = (NP_TRANSFER *)ReadArgvNumProc(theNP->mg, "amg", TRANSFER_CLASS_NAME, argc, argv);       // transfer.cc:593
+  np->amg_ran = 0;
+  if (np->amg != NULL && (np->amg->RestrictDefect == GpuRestrictDefect || np->amg->PreProcess == NULL)) {
+    UserWrite("gputransfer: $amg must name a host transfer numproc that builds the algebraic levels (selectionAMG, clusterAMG)\n");
+    return NP_NOT_ACTIVE;
+  }
   if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("L", argc, argv) || ReadArgvOption("D", argc, argv)) {
     UserWrite("gputransfer: the standard (geometric) transfer and $M (stored interpolation matrices) are on the GPU path; $R $S $L $D are not supported\n");
     return NP_NOT_ACTIVE;
@@ -366,6 +402,7 @@ INT GpuTransferDisplay(NP_BASE *theNP)
   NPTransferDisplay((NP_TRANSFER *)theNP);
   UserWriteF(DISPLAY_NP_FORMAT_SS, "Restrict", np->imat ? "RestrictByMatrix (device)" : "StandardRestrict (device)");
   UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", np->imat ? "InterpolateCorrectionByMatrix (device)" : "StandardInterpolateCorrection (device)");
+  if (np->amg != NULL) UserWriteF(DISPLAY_NP_FORMAT_SS, "amg", ENVITEM_NAME(np->amg));
   return 0;
 }
 
@@ -375,6 +412,12 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
   np->m = Acquire(NP_MG(theNP));
   if (np->m == NULL) NP_RETURN(1, result[0]);
+  np->amg_ran = 0;
+  if (np->amg != NULL && *fl <= 0) {                                      // transfer.cc:660-664: the AMG sets *fl to the new bottom level
+    if ((*np->amg->PreProcess)(np->amg, fl, 0, x, b, A, result)) PRE_FAIL(np, result[0]);
+    np->amg_ran = 1;
+    SetBottom(np->m, *fl);
+  }
   np->fl = *fl; np->tl = tl;
   for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
   for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) PRE_FAIL(np, result[0]);
@@ -386,12 +429,12 @@ INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_D
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
   Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
-  if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: RestrictDefect without PreProcess (or level < 1: matrix-dependent transfer is not on the GPU path)\n"); NP_RETURN(1, result[0]); }
+  if (m == NULL || level <= -MAXLEVEL || level >= MAXLEVEL || !m->have_transfer[Mirror::ix(level)]) { UserWrite("gputransfer: RestrictDefect without PreProcess\n"); NP_RETURN(1, result[0]); }
   double d[UGGPU_MAX_BS];
   VsToArray(damp, m->bs, d);
   // the coarse vector is an input too: rows with VNCLASS < NEWDEF_CLASS keep their values (transgrid.cc:143-147)
   if (Upload(m, level, from) || Upload(m, level - 1, to)) NP_RETURN(1, result[0]);
-  if (api.uggpu_restrict(m->ctx, level, m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_restrict"), result[0]);
+  if (api.uggpu_restrict(m->ctx, m->dl(level), m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_restrict"), result[0]);
   if (Download(m, level - 1, to)) NP_RETURN(1, result[0]);
   result[0] = 0;
   return 0;
@@ -402,12 +445,12 @@ INT GpuInterpolateCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VE
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
   Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
-  if (level < 1 || m == NULL || !m->have_transfer[level]) { UserWrite("gputransfer: InterpolateCorrection without PreProcess\n"); NP_RETURN(1, result[0]); }
+  if (m == NULL || level <= -MAXLEVEL || level >= MAXLEVEL || !m->have_transfer[Mirror::ix(level)]) { UserWrite("gputransfer: InterpolateCorrection without PreProcess\n"); NP_RETURN(1, result[0]); }
   double d[UGGPU_MAX_BS];
   VsToArray(damp, m->bs, d);
   if (Upload(m, level - 1, from)) NP_RETURN(1, result[0]);
-  if (api.uggpu_vec_alloc(m->ctx, level, m->handle(to))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
-  if (api.uggpu_interpolate_correction(m->ctx, level, m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_interpolate_correction"), result[0]);
+  if (api.uggpu_vec_alloc(m->ctx, m->dl(level), m->handle(to))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+  if (api.uggpu_interpolate_correction(m->ctx, m->dl(level), m->handle(to), m->handle(from), d)) NP_RETURN(dev_fail("uggpu_interpolate_correction"), result[0]);
   if (Download(m, level, to)) NP_RETURN(1, result[0]);
   result[0] = 0;
   return 0;
@@ -416,8 +459,17 @@ INT GpuInterpolateCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VE
 INT GpuTransferPostProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  INT rc = 0;
+  if (np->amg != NULL && np->amg_ran && np->amg->PostProcess != NULL) {      // transfer.cc:836-838: disposes the algebraic levels (unless $hold)
+    if ((*np->amg->PostProcess)(np->amg, fl, 0, x, b, A, result)) rc = 1;
+    np->amg_ran = 0;
+    // the levels below 0 are gone from the host (or will be rebuilt by the next PreProcess): nothing uploaded for them may be reused
+    if (Mirror *m = Live(np->m, NP_MG(theNP)))
+      for (int l = -MAXLEVEL; l <= 0; l++) { m->have_level[Mirror::ix(l)] = 0; m->have_transfer[Mirror::ix(l)] = 0; if (l == 0) m->have_transfer[Mirror::ix(1)] = 0; }
+  }
   if (np->m) Release(NP_MG(theNP));
   np->m = NULL;
+  if (rc) REP_ERR_RETURN(1);
   return 0;
 }
 
@@ -539,6 +591,7 @@ int HostBaseSolver(void *user, uggpu_ctx *ctx, int level, int c, int b, int A)
     if (kv.second == c) cd = (VECDATA_DESC *)kv.first;
     if (kv.second == b) bd = (VECDATA_DESC *)kv.first;
   }
+  level -= m->loff;        // the device library's level -> UG's
   if (Download(m, level, cd) || Download(m, level, bd)) return 1;
   if ((*np->BaseSolver->Residuum)(np->BaseSolver, MIN(level, np->baselevel), level, cd, bd, np->cur_A, &lresult)) return 1;
   if ((*np->BaseSolver->Solver)(np->BaseSolver, level, cd, bd, np->cur_A, np->BaseSolver->abslimit, np->BaseSolver->reduction, &lresult)) return 1;
@@ -550,7 +603,7 @@ void FillCfg(NP_GPULMGC *np, uggpu_lmgc_cfg *cfg)
 {
   Mirror *m = np->m;
   memset(cfg, 0, sizeof *cfg);
-  cfg->nu1 = np->nu1; cfg->nu2 = np->nu2; cfg->gamma = np->gamma; cfg->baselevel = np->baselevel;
+  cfg->nu1 = np->nu1; cfg->nu2 = np->nu2; cfg->gamma = np->gamma; cfg->baselevel = m->dl(np->baselevel);
   VsToArray(((NP_GPUJAC *)np->PreSmooth)->damp, m->bs, cfg->smooth_damp);
   VsToArray(np->damp, m->bs, cfg->cycle_damp);
   cfg->t = np->t_handle;
@@ -594,7 +647,7 @@ INT GpuLmgcPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
   np->t_handle = np->m->handle(&np->t);      // the temporary np->t of Lmgc (iter.cc:7810) lives on the device only
   uggpu_lmgc_cfg cfg;
   FillCfg(np, &cfg);
-  if (api.uggpu_lmgc_preprocess(np->m->ctx, &cfg, level, np->m->handle(A))) { dev_fail("uggpu_lmgc_preprocess"); PRE_FAIL(np, result[0]); }
+  if (api.uggpu_lmgc_preprocess(np->m->ctx, &cfg, np->m->dl(level), np->m->handle(A))) { dev_fail("uggpu_lmgc_preprocess"); PRE_FAIL(np, result[0]); }
   return 0;
 }
 
@@ -612,7 +665,7 @@ INT GpuLmgcIter(NP_ITER *theNP, INT level, VECDATA_DESC *c, VECDATA_DESC *b, MAT
   const int bl = MIN(np->baselevel, level);
   for (int l = bl; l <= level; l++)
     if (Upload(m, l, c) || Upload(m, l, b)) NP_RETURN(1, result[0]);
-  if (api.uggpu_lmgc(m->ctx, &cfg, level, m->handle(c), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_lmgc"), result[0]);
+  if (api.uggpu_lmgc(m->ctx, &cfg, m->dl(level), m->handle(c), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_lmgc"), result[0]);
   for (int l = bl; l <= level; l++)
     if (Download(m, l, c) || Download(m, l, b)) NP_RETURN(1, result[0]);
   return 0;
@@ -733,7 +786,7 @@ INT GpuLsDefect(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   const int fr = MIN((INT)FULLREFINELEVEL(NP_MG(theNP)), level);
   for (int l = fr; l <= level; l++)
     if (Upload(m, l, x) || Upload(m, l, b)) NP_RETURN(1, result[0]);
-  if (api.uggpu_ls_defect(m->ctx, bl, level, m->handle(x), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_ls_defect"), result[0]);
+  if (api.uggpu_ls_defect(m->ctx, m->dl(bl), m->dl(level), m->handle(x), m->handle(b), m->handle(A))) NP_RETURN(dev_fail("uggpu_ls_defect"), result[0]);
   for (int l = fr; l <= level; l++)
     if (Download(m, l, b)) NP_RETURN(1, result[0]);
   return *result;
@@ -749,7 +802,7 @@ INT GpuLsResiduum(NP_LINEAR_SOLVER *theNP, INT bl, INT level, VECDATA_DESC *x, V
     if (Upload(m, l, b)) NP_RETURN(1, lresult->error_code);
   uggpu_lresult r;
   memset(&r, 0, sizeof r);
-  if (api.uggpu_ls_residuum(m->ctx, bl, level, m->handle(b), &r)) NP_RETURN(dev_fail("uggpu_ls_residuum"), lresult->error_code);
+  if (api.uggpu_ls_residuum(m->ctx, m->dl(bl), m->dl(level), m->handle(b), &r)) NP_RETURN(dev_fail("uggpu_ls_residuum"), lresult->error_code);
   for (int i = 0; i < m->bs; i++) lresult->last_defect[i] = r.last_defect[i];
   return 0;
 }
@@ -774,7 +827,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   // up: x and b (all cycle levels: the reference's x += c and the cycle's work vectors live on them), c = np->c
   for (int l = bl; l <= level; l++) {
     if (Upload(m, l, x) || Upload(m, l, b)) NP_RETURN(1, lresult->error_code);
-    if (api.uggpu_vec_alloc(m->ctx, l, m->handle(np->c))) NP_RETURN(dev_fail("uggpu_vec_alloc"), lresult->error_code);
+    if (api.uggpu_vec_alloc(m->ctx, m->dl(l), m->handle(np->c))) NP_RETURN(dev_fail("uggpu_vec_alloc"), lresult->error_code);
   }
   mgc->cur_c = np->c; mgc->cur_b = b; mgc->cur_A = A;
   uggpu_lmgc_cfg cfg;
@@ -788,10 +841,10 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   for (int i = 0; i < nwork; i++)          // CGPrepare / CGUpdate / BCGSPreProcess allocate these from the same pool
     if (AllocVDFromVD(NP_MG(theNP), bl, level, x, &np->w[i])) NP_RETURN(1, lresult->error_code);
   if (np->kind == GPULS_LS) {
-    if (api.uggpu_ls_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
+    if (api.uggpu_ls_solve(m->ctx, &cfg, m->dl(bl), m->dl(level), m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
       NP_RETURN(dev_fail("uggpu_ls_solve"), lresult->error_code);
   } else if (np->kind == GPULS_CG) {
-    if (api.uggpu_cg_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), m->handle(np->w[0]), m->handle(np->w[1]),
+    if (api.uggpu_cg_solve(m->ctx, &cfg, m->dl(bl), m->dl(level), m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), m->handle(np->w[0]), m->handle(np->w[1]),
                            np->maxiter, absl, red, &r, history.data()))
       NP_RETURN(dev_fail("uggpu_cg_solve"), lresult->error_code);
   } else {
@@ -799,7 +852,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
     double wgt[UGGPU_MAX_BS];
     for (int i = 0; i < 6; i++) wh[i] = m->handle(np->w[i]);
     for (int i = 0; i < UGGPU_MAX_BS; i++) wgt[i] = i < bs ? np->weight[i] : 1.0;
-    if (api.uggpu_bcgs_solve(m->ctx, &cfg, bl, level, m->handle(x), m->handle(b), m->handle(A), wh, wgt, np->restart, np->maxiter, absl, red, &r, history.data()))
+    if (api.uggpu_bcgs_solve(m->ctx, &cfg, m->dl(bl), m->dl(level), m->handle(x), m->handle(b), m->handle(A), wh, wgt, np->restart, np->maxiter, absl, red, &r, history.data()))
       NP_RETURN(dev_fail("uggpu_bcgs_solve"), lresult->error_code);
   }
   for (int i = 0; i < nwork; i++)
@@ -938,17 +991,18 @@ INT GpuFeAssemble(NP_ASSEMBLE *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
   std::vector<int64_t> eptr; std::vector<int32_t> erow; std::vector<double> coord, coef, val; std::vector<uint32_t> skip;
   for (int l = 0; l <= level; l++) {
     UserWriteF(" [%d:", l);                                                     // assemble.cc:672
-    gpuls::FlatLevel &f = m->fl[l];
+    const int k = Mirror::ix(l);
+    gpuls::FlatLevel &f = m->fl[k];
     // the pattern (connections) is the grid manager's; values and VECSKIP are about to be replaced
     if (gpuls::FlattenFlags(mg, l, x, f)) { UserWriteF("gpufe: level %d is not a pure nodal vector format\n", l); NP_RETURN(1, result[0]); }
     if (f.bs > UGGPU_MAX_BS) NP_RETURN(1, result[0]);
     if (gpuls::FlattenMatrix(mg, l, A, f)) { UserWrite("gpufe: cannot flatten the matrix pattern\n"); NP_RETURN(1, result[0]); }
     if (gpuls::FlattenElements(mg, l, eptr, erow, coord, skip, f.bs)) NP_RETURN(1, result[0]);
     m->bs = f.bs; m->xdesc = x;
-    m->have_level[l] = 0; m->have_transfer[l] = 0; if (l + 1 < MAXLEVEL) m->have_transfer[l + 1] = 0;
-    if (api.uggpu_level_create(m->ctx, l, f.n, f.bs)) NP_RETURN(dev_fail("uggpu_level_create"), result[0]);
-    if (api.uggpu_level_set_flags(m->ctx, l, f.vclass.data(), f.vnclass.data(), f.ctl.data(), NULL)) NP_RETURN(dev_fail("uggpu_level_set_flags"), result[0]);
-    if (api.uggpu_mat_set_pattern(m->ctx, l, m->handle(A), f.rowptr.data(), f.col.data())) NP_RETURN(dev_fail("uggpu_mat_set_pattern"), result[0]);
+    m->have_level[k] = 0; m->have_transfer[k] = 0; if (l + 1 < MAXLEVEL) m->have_transfer[k + 1] = 0;
+    if (api.uggpu_level_create(m->ctx, m->dl(l), f.n, f.bs)) NP_RETURN(dev_fail("uggpu_level_create"), result[0]);
+    if (api.uggpu_level_set_flags(m->ctx, m->dl(l), f.vclass.data(), f.vnclass.data(), f.ctl.data(), NULL)) NP_RETURN(dev_fail("uggpu_level_set_flags"), result[0]);
+    if (api.uggpu_mat_set_pattern(m->ctx, m->dl(l), m->handle(A), f.rowptr.data(), f.col.data())) NP_RETURN(dev_fail("uggpu_mat_set_pattern"), result[0]);
     // the application's part of AssembleLocal: coefficients, Dirichlet values of x on the boundary vertices
     const size_t nelem = eptr.size() - 1;
     coef.clear();
@@ -958,22 +1012,22 @@ INT GpuFeAssemble(NP_ASSEMBLE *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
     for (int r = 0; r < f.n; r++)
       for (int a = 0; a < f.bs; a++)
         if (skip[r] & (1u << a)) m->buf[(size_t)r * f.bs + a] = g_fe_dirichlet ? (*g_fe_dirichlet)(&coord[(size_t)r * DIM], a) : 0.0;
-    if (api.uggpu_vec_upload(m->ctx, l, m->handle(x), m->buf.data())) NP_RETURN(dev_fail("uggpu_vec_upload"), result[0]);
+    if (api.uggpu_vec_upload(m->ctx, m->dl(l), m->handle(x), m->buf.data())) NP_RETURN(dev_fail("uggpu_vec_upload"), result[0]);
     gpuls::ScatterVector(mg, l, x, f.bs, m->buf.data());                        // `*sptr[i] = sol[i]`, assemble.cc:692
-    if (api.uggpu_vec_alloc(m->ctx, l, m->handle(b))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
+    if (api.uggpu_vec_alloc(m->ctx, m->dl(l), m->handle(b))) NP_RETURN(dev_fail("uggpu_vec_alloc"), result[0]);
     uggpu_fe_cfg cfg;
     cfg.problem = (int)np->problem; cfg.dim = DIM; cfg.E = np->E; cfg.nu = np->nu;
     for (int a = 0; a < UGGPU_MAX_BS; a++) cfg.source[a] = np->source[a];
-    if (api.uggpu_assemble(m->ctx, l, m->handle(x), m->handle(b), m->handle(A), &cfg, (int64_t)nelem, eptr.data(), erow.data(),
+    if (api.uggpu_assemble(m->ctx, m->dl(l), m->handle(x), m->handle(b), m->handle(A), &cfg, (int64_t)nelem, eptr.data(), erow.data(),
                            coef.empty() ? NULL : coef.data(), coord.data(), skip.data())) NP_RETURN(dev_fail("uggpu_assemble"), result[0]);
     // results into UG's data structures: MVALUEs, right-hand side, VECSKIP
     val.assign(f.val.size(), 0.0);
-    if (api.uggpu_mat_get(m->ctx, l, m->handle(A), NULL, NULL, val.data())) NP_RETURN(dev_fail("uggpu_mat_get"), result[0]);
+    if (api.uggpu_mat_get(m->ctx, m->dl(l), m->handle(A), NULL, NULL, val.data())) NP_RETURN(dev_fail("uggpu_mat_get"), result[0]);
     if (gpuls::ScatterMatrixValues(mg, l, A, val, f.bs) || gpuls::ScatterSkip(mg, l, skip)) NP_RETURN(1, result[0]);
     f.val = val; f.skip = skip;
     if (Download(m, l, b)) NP_RETURN(1, result[0]);
-    if (api.uggpu_set_fullrefinelevel(m->ctx, FULLREFINELEVEL(mg))) NP_RETURN(dev_fail("uggpu_set_fullrefinelevel"), result[0]);
-    m->have_level[l] = 1; m->level_A[l] = A; m->level_x[l] = x;                 // a solver inside the bracket finds the matrix on the device
+    if (api.uggpu_set_fullrefinelevel(m->ctx, m->dl(FULLREFINELEVEL(mg)))) NP_RETURN(dev_fail("uggpu_set_fullrefinelevel"), result[0]);
+    m->have_level[k] = 1; m->level_A[k] = A; m->level_x[k] = x;                 // a solver inside the bracket finds the matrix on the device
     UserWrite("a]");
   }
   UserWrite(" [d]\n");
@@ -1036,6 +1090,7 @@ int gpuls::SaveData(MULTIGRID *mg, const char *name, const char *type, int numbe
   if (m == NULL || n < 1 || n > 100) { UserWrite("gpuls::SaveData: no device mirror (call inside a PreProcess/PostProcess bracket)\n"); return 1; }
   std::vector<int32_t> idl, idr;
   if (NodeMap(mg, idl, idr)) return 1;
+  for (auto &l : idl) if (l >= 0) l += m->loff;          // UG's level numbers -> the device library's
   std::vector<int> vec(n);
   std::vector<std::string> names(n), comps(n);
   std::vector<const char *> np(n), cp(n);
@@ -1065,6 +1120,7 @@ int gpuls::LoadData(MULTIGRID *mg, const char *name, const char *type, int numbe
   if (m == NULL || n < 1 || n > 100) { UserWrite("gpuls::LoadData: no device mirror (call inside a PreProcess/PostProcess bracket)\n"); return 1; }
   std::vector<int32_t> idl, idr;
   if (NodeMap(mg, idl, idr)) return 1;
+  for (auto &l : idl) if (l >= 0) l += m->loff;          // UG's level numbers -> the device library's
   std::vector<int> vec(n);
   for (int i = 0; i < n; i++) vec[i] = vds[i] ? m->handle(vds[i]) : -1;
   uggpu_data_general g;
