@@ -317,9 +317,16 @@ typedef struct uggpu_lmgc_cfg {
   int    smoother_L;                 /* ilu: matrix handle that receives the decomposition on every level above the base
                                         level (NP_SMOOTHER.L, allocated by ILUPreProcess iter.cc:5459)                  */
   double ilu_beta[UGGPU_MAX_BS];     /* ilu $beta      (iter.cc:5423)                           */
+  int    level_opt;                  /* transfer $L (transfer.cc:574): after the post-smoothing of every level above the base level the
+                                        transfer's AdaptCorrection runs (iter.cc:7944 -> transfer.cc:812 -> MinimizeLevel :488); its two
+                                        scalars are parallel sums, so with it the cycle agrees with the reference to rounding (1e-12),
+                                        not bit for bit; runs the one-kernel-per-call schedule                                     */
 } uggpu_lmgc_cfg;
 
 int uggpu_lmgc_preprocess(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int A);   /* LmgcPreProcess iter.cc:7707 */
+/* MinimizeLevel np/procs/transfer.cc:488 (the AdaptCorrection hook of `transfer $L`, :812): t = A c; a0 = (t, b); a1 = |t|^2;
+ * c *= 1 + a0/a1; b -= (a0/a1) t -- the correction scaled so that the defect is minimal along it.  t: work vector. */
+int uggpu_minimize_level(uggpu_ctx*, int level, int c, int b, int A, int t);
 int uggpu_lmgc(uggpu_ctx*, const uggpu_lmgc_cfg*, int level, int c, int b, int A); /* Lmgc          iter.cc:7741 */
 
 /* ---- linear solver, np/procs/ls.cc:562-749 ------------------------------------------------------------ */

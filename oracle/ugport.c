@@ -679,6 +679,19 @@ static void base_solve(const ugport_level *L, const ugport_cfg *cfg, const doubl
   free(cc);
 }
 
+/* np/procs/transfer.cc:488-516 */
+void ugport_minimize_level(const ugport_level *L, double *c, double *b, double *t)
+{
+  double a0 = 0.0, a1 = 0.0;
+  ugport_dmatmul(L, 0, 0, t, c);                 /* :498 dmatmul(t, A, c) */
+  ugport_ddot_acc(L, 0, t, b, &a0);              /* :504 */
+  ugport_dnrm2_acc(L, 0, t, &a1);                /* :506 dnrm2 = sqrt of the sum ... */
+  a1 = sqrt(a1);
+  a1 *= a1;                                      /* :508 ... squared again */
+  ugport_dscal(L, 0, c, 1 + a0 / a1);            /* :511 */
+  ugport_daxpy(L, 0, b, -a0 / a1, t);            /* :513 */
+}
+
 /* np/procs/iter.cc:7741-7949 */
 int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu, int level, double **c, double **b, double **t)
 {
@@ -713,6 +726,7 @@ int ugport_lmgc(const ugport_level *lv, const ugport_cfg *cfg, const double *lu,
     ugport_dadd(L, 0, c[level], t[level]);
   }
   free(tmp);
+  if (cfg->level_opt) ugport_minimize_level(L, c[level], b[level], t[level]);   /* :7944 AdaptCorrection -> transfer.cc:812 */
   return 0;
 }
 

@@ -32,7 +32,7 @@ class _Cfg(C.Structure):
     _fields_ = [("nu1", C.c_int), ("nu2", C.c_int), ("gamma", C.c_int), ("baselevel", C.c_int),
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
                 ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
-                ("smoother", C.c_int), ("imat", C.c_int), ("imat_below", C.c_int),
+                ("smoother", C.c_int), ("imat", C.c_int), ("imat_below", C.c_int), ("level_opt", C.c_int),
                 ("base_hook", C.c_void_p), ("base_user", C.c_void_p)]
 
 
@@ -264,6 +264,7 @@ class PortBackend:
         c.smoother = SMOOTHERS[cfg.get("smoother", "jac")]
         c.imat = 1 if self.imat else 0
         c.imat_below = self.imat_below
+        c.level_opt = int(cfg.get("level_opt", 0))
         if cfg.get("smoother") == "ilu":           # what LmgcPreProcess -> ILUPreProcess does on the levels above the base level
             beta = float(cfg.get("ilu_beta", 0.0))
             for l in range(c.baselevel + 1, len(self.h.levels)):

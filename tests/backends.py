@@ -135,7 +135,7 @@ class GpuBackend:
                               smooth_damp=cfg["smooth_damp"], cycle_damp=cfg.get("cycle_damp", 1.0),
                               base_maxit=cfg.get("base_maxit", 10), base_reduction=cfg.get("base_reduction", 1e-8),
                               base_abslimit=cfg.get("base_abslimit", 1e-10), fused=self.fused, t=t,
-                              smoother=cfg.get("smoother", "jac"), ilu_beta=cfg.get("ilu_beta", 0.0))
+                              smoother=cfg.get("smoother", "jac"), ilu_beta=cfg.get("ilu_beta", 0.0), level_opt=cfg.get("level_opt", 0))
         return c
 
     def lmgc(self, level, c, b, cfg, t="__t"):

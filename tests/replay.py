@@ -165,7 +165,8 @@ def cycle_cfg(hier, **over):
     cfg = dict(nu1=int(d["nu1"][0]), nu2=int(d["nu2"][0]), gamma=int(d["gamma"][0]),
                baselevel=int(d["baselevel"][0]) if "baselevel" in d else 0, smoother=smoother_of(hier),
                smooth_damp=float(d["damp"][0]), cycle_damp=1.0, base_maxit=10, base_reduction=1e-8,
-               base_abslimit=1e-10, ilu_beta=float(d["ilu_beta"][0]) if "ilu_beta" in d else 0.0)
+               base_abslimit=1e-10, ilu_beta=float(d["ilu_beta"][0]) if "ilu_beta" in d else 0.0,
+               level_opt=int(d["level_opt"][0]) if "level_opt" in d else 0)
     cfg.update(over)
     return cfg
 

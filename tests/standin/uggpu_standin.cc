@@ -109,6 +109,7 @@ void port_cfg(uggpu_ctx *c, const uggpu_lmgc_cfg *g, int level, Hook *hk, ugport
   for (int i = 0; i < UGPORT_MAX_BS; i++) { p->smooth_damp[i] = g->smooth_damp[i]; p->cycle_damp[i] = g->cycle_damp[i]; }
   p->base_maxit = g->base_maxit; p->base_reduction = g->base_reduction; p->base_abslimit = g->base_abslimit;
   p->smoother = g->smoother;
+  p->level_opt = g->level_opt;
   // by-matrix levels: all of them ($M), or the lowest ones (the algebraic levels of an AMG transfer); anything else cannot be expressed
   int below = g->baselevel;
   for (int l = g->baselevel + 1; l <= level; l++)
@@ -290,6 +291,16 @@ int uggpu_interpolate_correction(uggpu_ctx *ctx, int level, int to, int from, co
   double *tv = vec_of(ctx, level, to, true), *fv = vec_of(ctx, level - 1, from, false);
   if (!tv || !fv) return UGGPU_DESC_MISMATCH;
   (ctx->lev[level].mode == UGGPU_TRANSFER_IMAT ? ugport_interpolate_imat : ugport_interpolate)(&lv[level], &lv[level - 1], tv, fv, damp);
+  return 0;
+}
+
+int uggpu_minimize_level(uggpu_ctx *ctx, int level, int c, int b, int A, int t)
+{
+  std::vector<ugport_level> lv;
+  port_levels(ctx, A, 0, lv);
+  double *cv = vec_of(ctx, level, c, false), *bv = vec_of(ctx, level, b, false), *tv = vec_of(ctx, level, t, true);
+  if (!cv || !bv || !tv || !lv[level].val) return UGGPU_DESC_MISMATCH;
+  ugport_minimize_level(&lv[level], cv, bv, tv);
   return 0;
 }
 

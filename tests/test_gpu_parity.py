@@ -55,7 +55,10 @@ def test_gpu_cycle_and_solve(gpu_backend, golden):
         pytest.skip("dump without solve records")
     # Base levels with FREE rows (lu_* fixtures): the device follows the order of UG's matrix lists with fill-in, scalar and
     # block elimination alike (cycle.cu lu_lists) -- bit for bit.
-    n = replay_solve(gpu_backend, golden, exact=True, red_tol=1e-12)
+    # transfer $L (lopt_* fixtures): the two scalars of MinimizeLevel are parallel sums on the device, so everything downstream of them
+    # agrees to rounding (1e-11 of the largest entry), not bit for bit
+    lopt = "level_opt" in golden.raw and int(golden.raw["level_opt"][0]) != 0
+    n = replay_solve(gpu_backend, golden, exact=not lopt, vec_tol=1e-11, red_tol=1e-11 if lopt else 1e-12)
     assert n > 10
 
 

@@ -40,6 +40,8 @@ CASES = [
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--imat", "--damp", "0.6", "--cycles", "5"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--smoother", "ilu", "--beta", "0.25", "--damp", "0.9", "--cycles", "5"]),
     ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "4", "--damp", "0.7", "--cycles", "6"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--levelopt", "--damp", "0.6", "--cycles", "5"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--levelopt", "--damp", "0.6", "--cycles", "4"]),
     # algebraic levels below level 0: `gputransfer $amg amgt` calls the reference's AMG numproc, mirrors levels -1, -2, ... as device levels
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS]),
     ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),
@@ -47,7 +49,7 @@ CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat", "tet-ilu-beta",
-       "quad-bs2", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
+       "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)

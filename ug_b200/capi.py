@@ -34,7 +34,7 @@ class LmgcCfg(C.Structure):
                 ("smooth_damp", C.c_double * MAX_BS), ("cycle_damp", C.c_double * MAX_BS),
                 ("t", C.c_int), ("base_maxit", C.c_int), ("base_reduction", C.c_double), ("base_abslimit", C.c_double),
                 ("base_solver", C.c_void_p), ("base_user", C.c_void_p), ("fused", C.c_int), ("smoother", C.c_int),
-                ("smoother_L", C.c_int), ("ilu_beta", C.c_double * MAX_BS)]
+                ("smoother_L", C.c_int), ("ilu_beta", C.c_double * MAX_BS), ("level_opt", C.c_int)]
 
 
 SMOOTHERS = {"jac": 0, "gs": 1, "sgs": 2, "sor": 3, "ilu": 4}       # UGGPU_SM_*
@@ -243,7 +243,7 @@ class Context:
 
     # ---- cycle configuration
     def lmgc_cfg(self, nu1=2, nu2=2, gamma=1, baselevel=0, smooth_damp=0.6, cycle_damp=1.0, base_maxit=10,
-                 base_reduction=1e-8, base_abslimit=1e-10, fused=1, t="__t", smoother="jac", ilu_beta=0.0, smoother_L="__L") -> LmgcCfg:
+                 base_reduction=1e-8, base_abslimit=1e-10, fused=1, t="__t", smoother="jac", ilu_beta=0.0, smoother_L="__L", level_opt=0) -> LmgcCfg:
         c = LmgcCfg()
         c.nu1, c.nu2, c.gamma, c.baselevel = nu1, nu2, gamma, baselevel
         for i in range(MAX_BS):
@@ -256,6 +256,7 @@ class Context:
         c.fused = int(fused)
         c.smoother = SMOOTHERS[smoother]
         c.smoother_L = self.handle(smoother_L)
+        c.level_opt = int(level_opt)
         for i in range(MAX_BS):
             c.ilu_beta[i] = ilu_beta
         return c

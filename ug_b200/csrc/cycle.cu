@@ -811,11 +811,27 @@ static int lmgc_unfused(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, in
     UG_TRY(uggpu_smooth(ctx, level, cfg->smoother, t, b, A, cfg->smooth_damp, cfg->smoother == UGGPU_SM_ILU ? cfg->smoother_L : UGGPU_VEC_TMP_A));
     UG_TRY(uggpu_dadd(ctx, level, level, UGGPU_ALL_VECTORS, c, t));
   }
+  if (cfg->level_opt) UG_TRY(uggpu_minimize_level(ctx, level, c, b, A, t));         // :7944 AdaptCorrection (transfer $L; np->t is free again, :7942)
   return 0;
 }
 
-// the fused schedule is built on the Jacobi step; every other smoother class runs one kernel group per reference call
-static inline bool use_fused(const uggpu_lmgc_cfg *cfg) { return cfg->fused && cfg->smoother == UGGPU_SM_JAC; }
+// MinimizeLevel np/procs/transfer.cc:488-516, call for call
+extern "C" int uggpu_minimize_level(uggpu_ctx *ctx, int level, int c, int b, int A, int t)
+{
+  double a0 = 0.0, a1 = 0.0;
+  UG_TRY(uggpu_vec_alloc(ctx, level, t));
+  UG_TRY(uggpu_dmatmul(ctx, level, level, UGGPU_ALL_VECTORS, t, A, c));             // :498
+  UG_TRY(uggpu_ddot(ctx, level, level, UGGPU_ALL_VECTORS, t, b, &a0));              // :504
+  UG_TRY(uggpu_dnrm2(ctx, level, level, UGGPU_ALL_VECTORS, t, &a1));                // :506
+  a1 *= a1;                                                                          // :508 "need norm^2"
+  UG_TRY(uggpu_dscal(ctx, level, level, UGGPU_ALL_VECTORS, c, 1 + a0 / a1));        // :511
+  UG_TRY(uggpu_daxpy(ctx, level, level, UGGPU_ALL_VECTORS, b, -a0 / a1, t));        // :513
+  return 0;
+}
+
+// the fused schedule is built on the Jacobi step; every other smoother class runs one kernel group per reference call, and so does
+// the level optimisation of `transfer $L` (its scalars come back to the host between the calls)
+static inline bool use_fused(const uggpu_lmgc_cfg *cfg) { return cfg->fused && cfg->smoother == UGGPU_SM_JAC && !cfg->level_opt; }
 
 // t_ready: the temporary cfg->t of this level already holds damp * Diag(A)^-1 b (written by the restriction above)
 // push_c: the caller interpolates this level's correction next -- on a partitioned level (multi-GPU, peer-memory ghost rows) the last

@@ -44,7 +44,7 @@ USING_UG_NAMESPACES
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
   X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
   X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags) \
-  X(uggpu_savedata) X(uggpu_loaddata)
+  X(uggpu_savedata) X(uggpu_loaddata) X(uggpu_minimize_level)
 
 namespace {
 struct Api {
@@ -375,6 +375,8 @@ struct NP_GPUTRANSFER {
                        // step); the levels it leaves (vectors, Galerkin matrices, interpolation matrices) are mirrored like any other
                        // level and the device cycle runs on them with the by-matrix transfer, as the reference does for all levels < 1.
   INT amg_ran;
+  INT level;           // $L: level optimisation, AdaptCorrection = MinimizeLevel (transfer.cc:574, :812, :488)
+  VECDATA_DESC *t;     // its work vector (transfer.cc:592 $t), on the device only
 };
 
 INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result);
@@ -389,8 +391,10 @@ INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
     UserWrite("gputransfer: $amg must name a host transfer numproc that builds the algebraic levels (selectionAMG, clusterAMG)\n");
     return NP_NOT_ACTIVE;
   }
-  if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("L", argc, argv) || ReadArgvOption("D", argc, argv)) {
-    UserWrite("gputransfer: the standard (geometric) transfer and $M (stored interpolation matrices) are on the GPU path; $R $S $L $D are not supported\n");
+  np->level = ReadArgvOption("L", argc, argv);                                                        // transfer.cc:574
+  np->t = ReadArgvVecDesc(theNP->mg, "t", argc, argv);                                                // transfer.cc:592
+  if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("D", argc, argv)) {
+    UserWrite("gputransfer: the standard (geometric) transfer, $M (stored interpolation matrices), $L (level optimisation) and $amg are on the GPU path; $R $S $D are not supported\n");
     return NP_NOT_ACTIVE;
   }
   return NPTransferInit((NP_TRANSFER *)theNP, argc, argv);                // transfer.cc:593
@@ -403,6 +407,7 @@ INT GpuTransferDisplay(NP_BASE *theNP)
   UserWriteF(DISPLAY_NP_FORMAT_SS, "Restrict", np->imat ? "RestrictByMatrix (device)" : "StandardRestrict (device)");
   UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", np->imat ? "InterpolateCorrectionByMatrix (device)" : "StandardInterpolateCorrection (device)");
   if (np->amg != NULL) UserWriteF(DISPLAY_NP_FORMAT_SS, "amg", ENVITEM_NAME(np->amg));
+  UserWriteF(DISPLAY_NP_FORMAT_SI, "level", (int)np->level);
   return 0;
 }
 
@@ -456,6 +461,19 @@ INT GpuInterpolateCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VE
   return 0;
 }
 
+// AdaptCorrection transfer.cc:812 (called by Lmgc after the post-smoothing, iter.cc:7944): with $L, MinimizeLevel (:488) on c and b of `level`
+INT GpuAdaptCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *c, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  if (!np->level) return 0;
+  Mirror *m = np->m ? Live(np->m, NP_MG(theNP)) : Find(NP_MG(theNP));
+  if (m == NULL || level <= -MAXLEVEL || level >= MAXLEVEL || !m->have_level[Mirror::ix(level)]) { UserWrite("gputransfer: AdaptCorrection without PreProcess\n"); NP_RETURN(1, result[0]); }
+  if (Upload(m, level, c) || Upload(m, level, b)) NP_RETURN(1, result[0]);
+  if (api.uggpu_minimize_level(m->ctx, m->dl(level), m->handle(c), m->handle(b), m->handle(A), m->handle(&np->t))) NP_RETURN(dev_fail("uggpu_minimize_level"), result[0]);
+  if (Download(m, level, c) || Download(m, level, b)) NP_RETURN(1, result[0]);
+  return 0;
+}
+
 INT GpuTransferPostProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
@@ -486,7 +504,7 @@ INT GpuTransferConstruct(NP_BASE *theNP)
   np->RestrictDefect = GpuRestrictDefect;
   np->InterpolateNewVectors = NULL;      // nested-iteration hooks: not on the cycle path; callers test for NULL
   np->ProjectSolution = NULL;
-  np->AdaptCorrection = NULL;            // iter.cc:7944 tests for NULL
+  np->AdaptCorrection = GpuAdaptCorrection;   // does nothing without $L, like AdaptCorrection transfer.cc:812
   np->PostProcess = GpuTransferPostProcess;
   np->PostProcessProject = NULL;
   np->PostProcessSolution = NULL;
@@ -609,6 +627,7 @@ void FillCfg(NP_GPULMGC *np, uggpu_lmgc_cfg *cfg)
   cfg->t = np->t_handle;
   cfg->fused = np->unfused ? 0 : 1;
   cfg->smoother = (int)((NP_GPUJAC *)np->PreSmooth)->kind;
+  cfg->level_opt = ((NP_GPUTRANSFER *)np->Transfer)->level ? 1 : 0;          // iter.cc:7944: the transfer's AdaptCorrection inside the cycle
   if (cfg->smoother == UGGPU_SM_ILU) {
     cfg->smoother_L = ((NP_GPUJAC *)np->PreSmooth)->L_handle;
     for (int i = 0; i < UGGPU_MAX_BS; i++) cfg->ilu_beta[i] = i < m->bs ? ((NP_GPUJAC *)np->PreSmooth)->beta[i] : 0.0;
