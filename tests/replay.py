@@ -243,7 +243,8 @@ def replay_krylov(be, hier, exact=True, vec_tol=1e-10, red_tol=1e-9, floor=1e-10
                     _cmp_vec(f"L{l}/{name}/b_after_{k}", be.get(l, "b"), d[f"L{l}/{name}/b_after_{k}"], True, vec_tol)
                 else:       # the defect shrinks towards rounding level: compare on the scale of the first defect
                     gb, rb = be.get(l, "b"), d[f"L{l}/{name}/b_after_{k}"]
-                    scale = max(np.max(np.abs(d[f"L{l}/solve/b_first"])), 1e-300)
+                    # (at least the first defect of the top level: the lower levels of a dump with algebraic levels start from zero)
+                    scale = max(np.max(np.abs(d[f"L{l}/solve/b_first"])), np.max(np.abs(d[f"L{top}/solve/b_first"])), 1e-300)
                     if not np.max(np.abs(gb - rb)) <= vec_tol * scale:
                         raise Mismatch(f"L{l}/{name}/b_after_{k}: abs err {np.max(np.abs(gb - rb)):.3e} > {vec_tol:.1e} * {scale:.3e}")
                 n += 2
