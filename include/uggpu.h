@@ -235,10 +235,17 @@ int uggpu_interpolate_correction(uggpu_ctx*, int level, int to, int from, const 
  * AssembleGalerkinByMatrix(GRID_ON_LEVEL(level), A, 0) after dmatset(level-1, level-1, ALL_VECTORS, A, 0.0), i.e. what `npcheck $G`
  * does (np/algebra/npcheck.cc:375-379): matrix A of level-1 := P^T A_level P on the interpolation stencils of `level`, every
  * coarse entry receiving the reference's terms in the reference's order ((m*im)*jm over the fine rows in list order, their entries
- * in list order, the interpolation entries of the neighbour in list order) -- bit-identical values.  The product must stay on the
- * pattern A already has on level-1 (true on nested geometric hierarchies); where the reference would create connections this
- * call fails with UGGPU_ERROR.  One GPU only. */
+ * in list order, the interpolation entries of the neighbour in list order) -- bit-identical values.  Connections the product needs
+ * and level-1 lacks are created like the reference does (CreateExtraConnection, transgrid.cc:1615: second place of both rows' lists):
+ * when A does not exist on level-1 (a fresh algebraic level, np/procs/amgtransfer.cc:915) its pattern comes from the product alone,
+ * diagonal entries first; when the product leaves an existing pattern that pattern grows.  The symbolic step runs on the host
+ * (uggpu_galerkin_pattern), the numeric one on the device.  One GPU only. */
 int uggpu_galerkin(uggpu_ctx*, int level, int A);
+/* Host only (no device): the pattern of the coarse level after the product -- per row the diagonal, the connections the product creates
+ * in REVERSE order of creation (creation order = first term (iv, jv) or (jv, iv) in the reference's traversal; gm/algebra.cc:1051-1078),
+ * then the off-diagonal entries of the start pattern.  start_* == NULL: one diagonal entry per row.  out_col == NULL: row pointers only. */
+int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
+                           const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col);
 
 /* ---- element-loop assembly on the device, np/procs/assemble.h:225 NP_LOCAL_ASSEMBLE, np/procs/assemble.cc:657 ------
  * One level of LocalAssemble (assemble.cc:671-697) followed by that level's share of NPLocalAssemblePostMatrix (:624): b = 0, A = 0,

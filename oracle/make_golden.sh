@@ -64,12 +64,13 @@ mkdir -p $G
 ./_ref/ugoracle2 --grid quad --bs 2 --refine 2 --lean --savedata /tmp/ugsd_golden_q --dump $G/savedata_quad2d_bs2_r2.ugh > /dev/null
 ./_ref/ugoracle3 --grid tet --refine 1 --adapt 2 --lean --savedata /tmp/ugsd_golden_a --dump $G/savedata_tet3d_adapt.ugh > /dev/null
 # ---- algebraic levels below level 0 (the AMG side): the reference's own AMG transfer numprocs (np/procs/amgtransfer.cc: selectionAMG with
-# Ruge-Stueben coarsening and interpolation, clusterAMG with Vanek's aggregation, selectionAMG with averaging on 3x3 blocks) attached to the
+# Ruge-Stueben coarsening and interpolation, clusterAMG with Vanek's aggregation, selectionAMG with averaging interpolation on a greedy independent set for 3x3 blocks -- not `$C Average`, which re-links the vector list and
+# re-sorts the matrix lists of the level it coarsens, amgtools.cc:1330-1440) attached to the
 # transfer class with $amg build levels -1, -2, ... with Galerkin matrices under a collapsed level 0; the dumps number the levels from 0 and hold
 # the flattened hierarchy (matrices, by-matrix transfer stencils of the algebraic levels) and the solve / Krylov records on all of them
 AMG_RS='$strongRel 0.25 $C RugeStueben $I RugeStueben $CM Galerkin $vectLimit 20 $hold'
 AMG_VANEK='$strongVanek 0.08 $C VanekNeuss $I Vanek $CM Galerkin $vectLimit 10 $hold'
-AMG_AVG='$strongRel 0.25 $C Average $I Average $CM Galerkin $vectLimit 10 $hold'
+AMG_AVG='$strongRel 0.25 $C Greedy $I Average $CM Galerkin $vectLimit 10 $hold'
 ./_ref/ugoracle3 --grid tet --refine 3 --collapse --amg selectionAMG "$AMG_RS" --cycles 5 --dump $G/amg_tet3d_rs.ugh --solve > /dev/null
 ./_ref/ugoracle2 --grid tri --refine 4 --collapse --refine2 1 --amg clusterAMG "$AMG_VANEK" --cycles 5 --lean --dump $G/amg_tri2d_vanek.ugh --solve > /dev/null
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --collapse --amg selectionAMG "$AMG_AVG" --cycles 4 --lean --dump $G/amg_hex3d_bs3_avg.ugh --solve > /dev/null

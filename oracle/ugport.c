@@ -522,6 +522,56 @@ int ugport_galerkin(const ugport_level *fine, const ugport_level *coarse, const 
   return 0;
 }
 
+/* The pattern AssembleGalerkinByMatrix leaves on the coarse level when connections are missing (transgrid.cc:1615-1617, :1649-1651):
+ * CreateExtraConnection -> CreateConnection (gm/algebra.cc:969-1081) puts BOTH matrices of a new connection at the SECOND place of their
+ * rows' lists (:1051-1078), the diagonal stays first.  A row therefore ends up as: diagonal, the connections created by the product in
+ * REVERSE order of creation, then the off-diagonal entries it had before.  Creation order = order of the first term (iv, jv) or (jv, iv)
+ * in the traversal of ugport_galerkin.  start_rowptr / start_col: the pattern before the product (NULL: one diagonal entry per row, what
+ * the AMG's GenerateNewGrid creates, np/algebra/amgtools.c:538-640).  Call with out_col == NULL to get the row pointers (sizes) first.
+ * Plain dynamic rows and linear searches: test infrastructure for small levels. */
+int ugport_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
+                            const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col)
+{
+  typedef struct { int32_t *e; int n0, nnew, cap; } prow;    /* e[0..n0): the old entries, e[n0..n0+nnew): new ones in creation order */
+  prow *R = (prow *)calloc((size_t)(nc > 0 ? nc : 1), sizeof(prow));
+  for (int i = 0; i < nc; i++) {
+    int n0 = start_rowptr ? start_rowptr[i + 1] - start_rowptr[i] : 1;
+    R[i].cap = n0 + 8; R[i].n0 = n0; R[i].nnew = 0;
+    R[i].e = (int32_t *)malloc(sizeof(int32_t) * (size_t)R[i].cap);
+    if (start_rowptr) memcpy(R[i].e, start_col + start_rowptr[i], sizeof(int32_t) * (size_t)n0); else R[i].e[0] = i;
+    if (n0 < 1 || R[i].e[0] != i) { for (int k = 0; k <= i; k++) free(R[k].e); free(R); return 4; }      /* diagonal first */
+  }
+#define PUSH(row, colv) do { prow *q = &R[row]; if (q->n0 + q->nnew == q->cap) { q->cap *= 2; q->e = (int32_t *)realloc(q->e, sizeof(int32_t) * (size_t)q->cap); } \
+                             q->e[q->n0 + q->nnew++] = (colv); } while (0)
+  for (int v = 0; v < nf; v++)
+    for (int e = a_rowptr[v]; e < a_rowptr[v + 1]; e++) {
+      int w = a_col[e];
+      for (int ie = p_rowptr[v]; ie < p_rowptr[v + 1]; ie++) {
+        int iv = p_col[ie];
+        for (int je = p_rowptr[w]; je < p_rowptr[w + 1]; je++) {
+          int jv = p_col[je], have = 0;
+          const prow *q = &R[iv];
+          for (int k = 0; k < q->n0 + q->nnew; k++) if (q->e[k] == jv) { have = 1; break; }      /* GetMatrix(iv, jv) */
+          if (have) continue;
+          PUSH(iv, jv); PUSH(jv, iv);                                                           /* one CONNECTION = both directions */
+        }
+      }
+    }
+#undef PUSH
+  out_rowptr[0] = 0;
+  for (int i = 0; i < nc; i++) out_rowptr[i + 1] = out_rowptr[i] + R[i].n0 + R[i].nnew;
+  if (out_col)
+    for (int i = 0; i < nc; i++) {
+      int32_t *o = out_col + out_rowptr[i];
+      *o++ = R[i].e[0];
+      for (int k = R[i].nnew - 1; k >= 0; k--) *o++ = R[i].e[R[i].n0 + k];
+      for (int k = 1; k < R[i].n0; k++) *o++ = R[i].e[k];
+    }
+  for (int i = 0; i < nc; i++) free(R[i].e);
+  free(R);
+  return 0;
+}
+
 void ugport_base_free(double *lu)
 {
   lu_fac *F = (lu_fac *)lu;

@@ -225,6 +225,20 @@ class PortBackend:
         assert err == 0, err
         return out
 
+    def galerkin_pattern(self, level, start=None):
+        """Pattern (rowptr, col) of level-1 after AssembleGalerkinByMatrix on `level` had to create its connections; start = (rowptr, col)
+        of the coarse level before the product, None = diagonal entries only."""
+        lf, lc = self.h.levels[level], self.h.levels[level - 1]
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        ar, ac, pr, pc = i32(lf.rowptr), i32(lf.col), i32(lf.p_rowptr), i32(lf.p_col)
+        sr, sc = (i32(start[0]), i32(start[1])) if start is not None else (None, None)
+        rp = np.zeros(lc.n + 1, np.int32)
+        args = [int(lf.n), int(lc.n), _p(ar), _p(ac), _p(pr), _p(pc), _p(sr), _p(sc)]
+        assert self.L.ugport_galerkin_pattern(*args, _p(rp), None) == 0
+        col = np.zeros(int(rp[-1]), np.int32)
+        assert self.L.ugport_galerkin_pattern(*args, _p(rp), _p(col)) == 0
+        return rp, col
+
     def assemble(self, level, fe, elem_ptr, elem_row, coef, coord, skip, x):
         """One level of LocalAssemble + AssembleDirichletBoundary (assemble.cc:657, disctools.cc:1837): returns (val, b)."""
         lv = self.h.levels[level]

@@ -176,3 +176,55 @@ def test_gpu_krylov_fused_chains_bitexact(golden, monkeypatch):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         for va, vb in zip(a[3] + a[4], b[3] + b[4]):
             assert np.array_equal(va, vb)
+
+
+def test_gpu_galerkin_pattern_growth(golden):
+    """uggpu_galerkin on levels whose coarse matrix does not exist yet (the algebraic levels of the amg_* dumps, built by the reference's
+    AMG transfer with AssembleGalerkinByMatrix + CreateExtraConnection): the coarse PATTERN -- order of the rows' lists included -- and,
+    cascaded from level 0 down, every VALUE bit for bit (the dump holds the values after AssembleDirichletBoundary; the raw products are
+    compared with the port's, which the CPU suite pins against the dump).  Then a product that has to GROW an existing pattern."""
+    from test_oracle_port import amg_levels, dirichlet_rows
+    namg = amg_levels(golden)
+    if namg == 0:
+        pytest.skip("dump without algebraic levels")
+    from backends import GpuBackend
+    from oracle.ugport import PortBackend
+    from ug_b200 import capi
+    be = GpuBackend(golden)
+    port = PortBackend(golden)
+    ctx = be.ctx
+    pval = golden.levels[namg].val
+    for k in range(namg, 0, -1):
+        lc = golden.levels[k - 1]
+        ctx.call("uggpu_mat_free", k - 1, be.A)
+        val = be.galerkin(k)                       # asserts the pattern against the dump's
+        pval = port.galerkin(k, pval)
+        assert np.array_equal(val, pval), (k, int(np.count_nonzero(val != pval)), pval.size)
+        assert np.array_equal(dirichlet_rows(val, lc.rowptr, lc.skip, lc.bs), lc.val), k
+    # growth of an existing pattern: level namg-1 restarts from the diagonal and a symmetric subset of its connections
+    k = namg
+    lc = golden.levels[k - 1]
+    srp = [0]; scol = []
+    for r in range(lc.n):
+        row = lc.col[lc.rowptr[r]:lc.rowptr[r + 1]]
+        scol += [int(row[0])] + [int(c) for c in row[1:] if (r + int(c)) % 3 == 0]
+        srp.append(len(scol))
+    srp = np.array(srp, np.int32); scol = np.array(scol, np.int32)
+    ctx.call("uggpu_mat_set_pattern", k - 1, be.A, capi._p(srp), capi._p(scol))
+    ctx.call("uggpu_galerkin", k, be.A)
+    rp2, col2 = port.galerkin_pattern(k, start=(srp, scol))
+    rowptr = np.zeros(lc.n + 1, np.int32); col = np.zeros(lc.col.size, np.int32); val = np.zeros(lc.col.size * lc.bs * lc.bs)
+    ctx.call("uggpu_mat_get", k - 1, be.A, capi._p(rowptr), capi._p(col), capi._p(val))
+    assert np.array_equal(rowptr, rp2) and np.array_equal(col, col2)
+    # same values as on the reference's pattern, entry by entry (the order of a row's entries does not enter an entry's sum)
+    bb = lc.bs * lc.bs
+    ref = port.galerkin(k, golden.levels[k].val if k == namg else None).reshape(-1, bb)
+    want = {}
+    for r in range(lc.n):
+        for e in range(lc.rowptr[r], lc.rowptr[r + 1]):
+            want[(r, int(lc.col[e]))] = ref[e]
+    got = val.reshape(-1, bb)
+    for r in range(lc.n):
+        for e in range(rowptr[r], rowptr[r + 1]):
+            assert np.array_equal(got[e], want[(r, int(col[e]))]), (r, int(col[e]))
+    be.close()

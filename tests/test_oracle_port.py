@@ -97,3 +97,73 @@ def test_golden_invariants(golden):
             if l > (-int(golden.raw["bottomlevel"][0]) if "bottomlevel" in golden.raw else 0):
                 s = np.add.reduceat(lv.p_w, lv.p_rowptr[:-1])
                 assert np.allclose(s, 1.0, atol=1e-14)
+
+
+def dirichlet_rows(val, rowptr, skip, bs):
+    """What AssembleDirichletBoundary (np/udm/disctools.cc:1837) does to the matrix rows of vectors with skip bits: row j of every block
+    of the vector's row zeroed, the diagonal entry (j, j) set to 1."""
+    v = np.array(val, dtype=np.float64).reshape(-1, bs * bs)
+    for r in np.nonzero(skip)[0]:
+        for j in range(bs):
+            if (int(skip[r]) >> j) & 1:
+                v[rowptr[r]:rowptr[r + 1], j * bs:(j + 1) * bs] = 0.0
+                v[rowptr[r], j * bs + j] = 1.0
+    return v.reshape(-1)
+
+
+def amg_levels(golden):
+    return -int(golden.raw["bottomlevel"][0]) if "bottomlevel" in golden.raw else 0
+
+
+def test_port_galerkin_pattern_growth_bitexact(golden):
+    """The algebraic levels of the amg_* dumps were built by the reference's AMG transfer: every coarse matrix is AssembleGalerkinByMatrix
+    (transgrid.cc:1575) on a level that held diagonal entries only, so all its connections were created by the product
+    (CreateExtraConnection -> gm/algebra.cc:969).  The restatement must reproduce the PATTERN including the order of the rows' lists
+    (diagonal, connections in reverse order of creation) and, cascaded from level 0 down like amgtransfer.cc:812-925, every value --
+    the dump holds them after AssembleDirichletBoundary (amgtransfer.cc:1041), the cascade continues with the raw product."""
+    namg = amg_levels(golden)
+    if namg == 0:
+        pytest.skip("dump without algebraic levels")
+    be = PortBackend(golden)
+    val = golden.levels[namg].val
+    for k in range(namg, 0, -1):
+        lc = golden.levels[k - 1]
+        rp, col = be.galerkin_pattern(k)
+        assert np.array_equal(rp, lc.rowptr) and np.array_equal(col, lc.col), k
+        val = be.galerkin(k, val)
+        assert np.array_equal(dirichlet_rows(val, lc.rowptr, lc.skip, lc.bs), lc.val), k
+        # growing an EXISTING pattern: start from the diagonal and a symmetric subset of the connections -- the created ones must come
+        # right after the diagonal, the old entries keep their order at the end of the row
+        srp = [0]; scol = []
+        for r in range(lc.n):
+            row = lc.col[lc.rowptr[r]:lc.rowptr[r + 1]]
+            scol += [int(row[0])] + [int(c) for c in row[1:] if (r + int(c)) % 3 == 0]
+            srp.append(len(scol))
+        rp2, col2 = be.galerkin_pattern(k, start=(np.array(srp, np.int32), np.array(scol, np.int32)))
+        assert np.array_equal(rp2, lc.rowptr)
+        for r in range(lc.n):
+            nold = srp[r + 1] - srp[r] - 1
+            got = col2[rp2[r]:rp2[r + 1]]
+            assert got[0] == r and sorted(got) == sorted(lc.col[lc.rowptr[r]:lc.rowptr[r + 1]])
+            assert list(got[len(got) - nold:]) == scol[srp[r] + 1:srp[r + 1]]
+
+
+def test_product_galerkin_pattern_host_function(golden):
+    """uggpu_galerkin_pattern (host half of uggpu_galerkin's pattern growth; no device involved) against the reference's patterns."""
+    namg = amg_levels(golden)
+    if namg == 0:
+        pytest.skip("dump without algebraic levels")
+    import ctypes as C
+    from ug_b200 import capi
+    L = capi.lib()
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in range(namg, 0, -1):
+        lf, lc = golden.levels[k], golden.levels[k - 1]
+        ar, ac, pr, pc = i32(lf.rowptr), i32(lf.col), i32(lf.p_rowptr), i32(lf.p_col)
+        rp = np.zeros(lc.n + 1, np.int32)
+        args = [C.c_int(lf.n), C.c_int(lc.n), p(ar), p(ac), p(pr), p(pc), None, None]
+        assert L.uggpu_galerkin_pattern(*args, p(rp), None) == 0
+        col = np.zeros(int(rp[-1]), np.int32)
+        assert L.uggpu_galerkin_pattern(*args, p(rp), p(col)) == 0
+        assert np.array_equal(rp, lc.rowptr) and np.array_equal(col, lc.col), k

@@ -87,6 +87,13 @@ SellMat *get_mat(uggpu_ctx *ctx, int level, int mat)
   return &it->second;
 }
 
+SellMat *get_mat_quiet(uggpu_ctx *ctx, int level, int mat)      // nullptr without an error message when the matrix does not exist
+{
+  if (level < 0 || level >= UGGPU_MAX_LEVELS || !ctx->lev[level].exists) return nullptr;
+  auto it = ctx->lev[level].mats.find(mat);
+  return it == ctx->lev[level].mats.end() ? nullptr : &it->second;
+}
+
 // Distance rule (measured on B200, 513^3, profiles/README.md): 3/4 of the warps resident on the whole GPU, i.e. the slice a
 // warp of the next generation will start with -- but never more than ~40 MB of matrix ahead (beyond ~60 MB the prefetched
 // lines are evicted from the 126 MB L2 before they are used and the kernel gets slower than without prefetch), and off when

@@ -129,17 +129,122 @@ __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, Sel
       for (int k = 0; k < BB; k++) cr[((size_t)t * BB + k) * 32] = acc[t * BB + k];
 }
 
+// ---- pattern growth (CreateExtraConnection, transgrid.cc:1615-1617 / :1649-1651) ------------------------------------------------------
+// The SYMBOLIC half of the product runs on the host: which connections the reference creates, and where they end up in the rows' lists,
+// is decided by the order of a sequential traversal (every new connection goes to the second place of both rows, gm/algebra.cc:1051-1078).
+// A row ends up as: diagonal, the connections created by the product in reverse order of creation, its old off-diagonal entries.  The
+// NUMERIC half is the kernel above on the new pattern.  A setup step of AMG hierarchies (np/procs/amgtransfer.cc:915-925), sizes of a few
+// 10^5 rows; a device form (first-touch times of the pairs by a segmented min + sort) is the next step, DESIGN.md 9.
+#include <unordered_set>
+#include <vector>
+
+extern "C" int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
+                                      const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col)
+{
+  if (nf < 0 || nc < 0 || !a_rowptr || !a_col || !p_rowptr || !p_col || !out_rowptr) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: null argument");
+  if ((start_rowptr == nullptr) != (start_col == nullptr)) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: start pattern needs both arrays");
+  std::unordered_set<uint64_t> have;                       // directed pairs (row << 32 | column) present so far
+  std::vector<std::vector<int32_t> > created((size_t)nc);  // per row: the columns of its new connections in creation order
+  auto key = [](int32_t r, int32_t c) { return ((uint64_t)(uint32_t)r << 32) | (uint32_t)c; };
+  if (start_rowptr) {
+    have.reserve((size_t)start_rowptr[nc] * 2 + 16);
+    for (int i = 0; i < nc; i++) {
+      if (start_rowptr[i + 1] <= start_rowptr[i] || start_col[start_rowptr[i]] != i) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: row %d does not start with its diagonal entry", i);
+      for (int e = start_rowptr[i]; e < start_rowptr[i + 1]; e++) {
+        if (start_col[e] < 0 || start_col[e] >= nc) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: column out of range in row %d", i);
+        have.insert(key(i, start_col[e]));
+      }
+    }
+  } else {
+    have.reserve((size_t)nc * 16 + 16);
+    for (int i = 0; i < nc; i++) have.insert(key(i, i));
+  }
+  for (int v = 0; v < nf; v++)
+    for (int e = a_rowptr[v]; e < a_rowptr[v + 1]; e++) {
+      const int w = a_col[e];
+      if (w < 0 || w >= nf) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: fine column out of range in row %d", v);
+      for (int ie = p_rowptr[v]; ie < p_rowptr[v + 1]; ie++) {
+        const int32_t iv = p_col[ie];
+        if (iv < 0 || iv >= nc) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: interpolation column out of range in row %d", v);
+        for (int je = p_rowptr[w]; je < p_rowptr[w + 1]; je++) {
+          const int32_t jv = p_col[je];
+          if (jv < 0 || jv >= nc) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: interpolation column out of range in row %d", w);
+          if (!have.insert(key(iv, jv)).second) continue;          // GetMatrix(iv, jv) finds it
+          have.insert(key(jv, iv));                                  // one CONNECTION holds both directions
+          created[iv].push_back(jv);
+          created[jv].push_back(iv);
+        }
+      }
+    }
+  int64_t total = 0;
+  out_rowptr[0] = 0;
+  for (int i = 0; i < nc; i++) {
+    total += (start_rowptr ? start_rowptr[i + 1] - start_rowptr[i] : 1) + (int64_t)created[i].size();
+    if (total > 2147483647LL) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: more than 2^31 - 1 entries");
+    out_rowptr[i + 1] = (int32_t)total;
+  }
+  if (!out_col) return 0;
+  for (int i = 0; i < nc; i++) {
+    int32_t *o = out_col + out_rowptr[i];
+    *o++ = i;
+    for (size_t k = created[i].size(); k-- > 0;) *o++ = created[i][k];
+    if (start_rowptr) for (int e = start_rowptr[i] + 1; e < start_rowptr[i + 1]; e++) *o++ = start_col[e];
+  }
+  return 0;
+}
+
+// gives matrix A of level-1 the pattern the product needs: from its present pattern, or -- no such matrix yet -- from one diagonal entry per row
+static int galerkin_grow(uggpu_ctx *ctx, int level, int A)
+{
+  Level *L = get_level(ctx, level), *C = get_level(ctx, level - 1);
+  SellMat *Af = get_mat(ctx, level, A), *Ac = get_mat_quiet(ctx, level - 1, A);
+  if (!L || !C || !Af) return UGGPU_DESC_MISMATCH;
+  const int nf = L->n, nc = C->n;
+  std::vector<int32_t> arp((size_t)nf + 1), acol((size_t)Af->nnz + 1), prp((size_t)nf + 1), pcol((size_t)L->P.nnz + 1), srp, scol, orp((size_t)nc + 1), ocol;
+  UG_TRY(sell_to_host_csr(ctx, Af, arp.data(), acol.data(), nullptr));
+  UG_TRY(sell_to_host_csr(ctx, &L->P, prp.data(), pcol.data(), nullptr));
+  if (Ac) {
+    srp.resize((size_t)nc + 1); scol.resize((size_t)Ac->nnz + 1);
+    UG_TRY(sell_to_host_csr(ctx, Ac, srp.data(), scol.data(), nullptr));
+  }
+  UG_TRY(uggpu_galerkin_pattern(nf, nc, arp.data(), acol.data(), prp.data(), pcol.data(), Ac ? srp.data() : nullptr, Ac ? scol.data() : nullptr, orp.data(), nullptr));
+  ocol.resize((size_t)orp[nc] + 1);
+  UG_TRY(uggpu_galerkin_pattern(nf, nc, arp.data(), acol.data(), prp.data(), pcol.data(), Ac ? srp.data() : nullptr, Ac ? scol.data() : nullptr, orp.data(), ocol.data()));
+  return uggpu_mat_set_pattern(ctx, level - 1, A, orp.data(), ocol.data());      // values zero: the product writes all of them
+}
+
+static int galerkin_product(uggpu_ctx *ctx, int level, int A, bool *pattern_miss);
+
 extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
+{
+  Level *L = get_level(ctx, level);
+  Level *C = get_level(ctx, level - 1);
+  if (!L || !C) return UGGPU_NO_COARSER_GRID;
+  if (!get_mat(ctx, level, A)) return UGGPU_DESC_MISMATCH;
+  if (!L->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "level %d has no interpolation stencil", level);
+  if (ctx->comm && (L->partitioned || C->partitioned)) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin runs on one GPU (level %d is partitioned)", level);
+  if (L->n == 0 || C->n == 0) return 0;
+  if (L->bs < 1 || L->bs > 3 || C->bs != L->bs) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "uggpu_galerkin: block size %d", L->bs);
+  // a coarse level without this matrix (a fresh algebraic level, amgtransfer.cc:915): the pattern comes from the product alone
+  if (!get_mat_quiet(ctx, level - 1, A)) UG_TRY(galerkin_grow(ctx, level, A));
+  bool miss = false;
+  UG_TRY(galerkin_product(ctx, level, A, &miss));
+  if (miss) {          // the product leaves the pattern: create the connections like the reference and run it again
+    UG_TRY(galerkin_grow(ctx, level, A));
+    UG_TRY(galerkin_product(ctx, level, A, &miss));
+    if (miss) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin: the grown pattern of level %d still misses a connection", level - 1);
+  }
+  return 0;
+}
+
+static int galerkin_product(uggpu_ctx *ctx, int level, int A, bool *pattern_miss)
 {
   Level *L = get_level(ctx, level);
   Level *C = get_level(ctx, level - 1);
   if (!L || !C) return UGGPU_NO_COARSER_GRID;
   SellMat *Af = get_mat(ctx, level, A), *Ac = get_mat(ctx, level - 1, A);
   if (!Af || !Ac) return UGGPU_DESC_MISMATCH;
-  if (!L->P.valid()) return uggpu_fail(UGGPU_NO_COARSER_GRID, "level %d has no interpolation stencil", level);
-  if (ctx->comm && (L->partitioned || C->partitioned)) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin runs on one GPU (level %d is partitioned)", level);
-  if (L->n == 0 || C->n == 0) return 0;
-  if (L->bs < 1 || L->bs > 3 || C->bs != L->bs) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "uggpu_galerkin: block size %d", L->bs);
+  *pattern_miss = false;
   cudaStream_t st = ctx->stream;
   const int nf = L->n, nc = C->n;
   const int64_t zp = L->P.nnz;
@@ -189,7 +294,7 @@ extern "C" int uggpu_galerkin(uggpu_ctx *ctx, int level, int A)
     if (!rc) {
       launched = true;
       rc = check_device_error(ctx);
-      if (rc) rc = uggpu_fail(UGGPU_ERROR, "uggpu_galerkin: the product P^T A P of level %d leaves the pattern of level %d (the reference would create the connections; not supported)", level, level - 1);
+      if (rc == UGGPU_ERROR) { *pattern_miss = true; rc = 0; }      // a term without a coarse entry (the kernel's only report): the caller grows the pattern
     }
     // the coarse values have changed whatever the kernel reported: diagonal array and value generation follow them, also after a failed call
     if (launched) {

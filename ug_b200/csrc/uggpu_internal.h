@@ -500,6 +500,7 @@ double *get_vec(uggpu_ctx *ctx, int level, int vec);         // NULL + error if 
 double *get_vec_lazy(uggpu_ctx *ctx, int level, int vec);    // the pointer only: the caller calls vec_wait() before the first kernel that touches it
 int vec_wait(uggpu_ctx *ctx, int level, int vec);
 SellMat *get_mat(uggpu_ctx *ctx, int level, int mat);
+SellMat *get_mat_quiet(uggpu_ctx *ctx, int level, int mat);
 int ensure_partials(uggpu_ctx *ctx, size_t count);
 int check_device_error(uggpu_ctx *ctx);                      // sync + read the device error word
 
