@@ -752,7 +752,11 @@ def our_arm(args):
             # (adaptively refined tetrahedra: partial levels, irregular rows) at the sizes the host builds in seconds
             for key, exe_name, ga, bsz in (("c1_inside_ug", "ugoracle2", ["--grid", "tri", "--refine", "6", "--damp", "0.8"], 1),
                                            ("c4_inside_ug", "ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "4", "--damp", "0.6"], 3),
-                                           ("c5_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "4", "--adapt", "2", "--damp", "0.6"], 1)):
+                                           ("c5_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "4", "--adapt", "2", "--damp", "0.6"], 1),
+                                           # algebraic levels: 65^3 on 33^3 (collapsed to level 0) on four levels built by the reference's
+                                           # selectionAMG in every PreProcess (host, both sides); the cycle over all of them on the device vs on the host
+                                           ("amg_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "5", "--collapse", "--refine2", "1", "--damp", "0.6", "--amg", "selectionAMG",
+                                                                           "$strongRel 0.25 $C Greedy $I Average $CM Galerkin $vectLimit 40"], 1)):
                 try:
                     line[key] = equal_size_inside_ug(0, 5, exe_name, ga, bsz)
                 except Exception as e:

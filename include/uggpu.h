@@ -247,6 +247,20 @@ int uggpu_galerkin(uggpu_ctx*, int level, int A);
 int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
                            const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col);
 
+/* ---- setup of algebraic levels (the AMG side), np/procs/amgtransfer.cc:795-925 with np/algebra/amgtools.cc ---------------
+ * One pass of the reference's coarsening loop for `selectionAMG $strongRel <theta> $C RugeStueben $I RugeStueben $CM Galerkin` on scalar
+ * equations: MarkRelative (amgtools.cc:188), CoarsenRugeStueben (:684) + GenerateNewGrid (:538), IpRugeStueben (:2237), then the Galerkin
+ * matrix (uggpu_galerkin; its pattern is created by the product).  level-1 is created: flags of its vectors, by-matrix transfer stencils in
+ * the reference's list order, matrix A -- identical to the level the reference builds, bit for bit, so a cycle over it gives the
+ * reference's results.  The coarsening and the weights are computed on the host from the downloaded matrix (sequential list algorithm;
+ * uggpu_amg_rs_host is that half alone, no device involved); *n_coarse = 0 and no level when all or no vectors would be coarse (the
+ * reference's "error in coarsening").  Levels are numbered from 0: the caller places the finest level high enough.  One GPU only. */
+int uggpu_amg_coarsen_rs(uggpu_ctx*, int level, int A, double theta, int *n_coarse);
+/* coarse[n]: 1 for the vectors that become coarse points (they are numbered in list order); P in by-matrix order: p_rowptr[n+1],
+ * p_col / p_w with room for nnz + n entries.  All rows of P are empty when *n_coarse is 0 or n. */
+int uggpu_amg_rs_host(int n, const int32_t *rowptr, const int32_t *col, const double *val, const uint32_t *skip, double theta,
+                      uint8_t *coarse, int32_t *p_rowptr, int32_t *p_col, double *p_w, int *n_coarse);
+
 /* ---- element-loop assembly on the device, np/procs/assemble.h:225 NP_LOCAL_ASSEMBLE, np/procs/assemble.cc:657 ------
  * One level of LocalAssemble (assemble.cc:671-697) followed by that level's share of NPLocalAssemblePostMatrix (:624): b = 0, A = 0,
  * VECSKIP cleared; for the elements in list order the local defect and the local matrix (summed over the quadrature points) are added

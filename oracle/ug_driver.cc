@@ -536,6 +536,10 @@ static void dump_hierarchy(const Opt &o, std::vector<gpuls::FlatLevel> &fl)
   D.scalar_i("fullrefinelevel", FULLREFINELEVEL(mg) - LO);
   D.scalar_i("bottomlevel", LO);
   if (o.levelopt) D.scalar_i("level_opt", 1);
+  if (!o.amg_class.empty()) {        // which AMG built the algebraic levels: class and init string, as bytes
+    D.u8("amg/class", std::vector<uint8_t>(o.amg_class.begin(), o.amg_class.end()));
+    D.u8("amg/init", std::vector<uint8_t>(o.amg_init.begin(), o.amg_init.end()));
+  }
   D.scalar_d("damp", o.damp); D.scalar_i("nu1", o.nu1); D.scalar_i("nu2", o.nu2); D.scalar_i("gamma", o.gamma);
   D.scalar_i("baselevel", o.baselevel);
   D.scalar_i("smoother", o.smoother == "jac" ? 0 : o.smoother == "gs" ? 1 : o.smoother == "sgs" ? 2 : o.smoother == "sor" ? 3 : 4);

@@ -228,3 +228,35 @@ def test_gpu_galerkin_pattern_growth(golden):
         for e in range(rowptr[r], rowptr[r + 1]):
             assert np.array_equal(got[e], want[(r, int(col[e]))]), (r, int(col[e]))
     be.close()
+
+
+def test_gpu_amg_setup_rs(golden):
+    """uggpu_amg_coarsen_rs rebuilds every algebraic level of the amg_*_rs dumps from the level above it -- strong connections,
+    Ruge-Stueben coarsening and interpolation, Galerkin matrix with the pattern created by the product -- and must arrive at the levels
+    the reference's selectionAMG built: flags, transfer stencils (list order, weights), matrix pattern (list order) and values, all bit
+    for bit.  The solve records of the dump are then replayed on the rebuilt hierarchy."""
+    from test_oracle_port import amg_levels, is_rs
+    if not is_rs(golden):
+        pytest.skip("dump without Ruge-Stueben levels")
+    import ctypes as C
+    from backends import GpuBackend
+    be = GpuBackend(golden)
+    ctx = be.ctx
+    namg = amg_levels(golden)
+    for k in range(namg, 0, -1):
+        nc = C.c_int(0)
+        ctx.call("uggpu_amg_coarsen_rs", k, be.A, C.c_double(0.25), C.byref(nc))
+        assert nc.value == golden.levels[k - 1].n, k
+    back = ctx.download_hierarchy(golden.top)
+    for l in range(namg + 1):
+        a, b = golden.levels[l], back.levels[l]
+        for key in ("rowptr", "col", "val", "vclass", "vnclass", "ctl", "skip"):
+            if l < namg or key in ("rowptr", "col", "val"):
+                assert np.array_equal(getattr(a, key), getattr(b, key)), (l, key)
+        if 0 < l <= namg:
+            for key in ("p_rowptr", "p_col", "p_w", "r_rowptr", "r_col", "r_w"):
+                assert np.array_equal(getattr(a, key), getattr(b, key)), (l, key)
+    n = replay_solve(be, golden, exact=True, red_tol=1e-12)
+    assert n > 10
+    # below the last level the coarsening stops by itself one day: all or no vectors coarse -> no level, n_coarse = 0
+    be.close()

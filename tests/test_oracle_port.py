@@ -167,3 +167,47 @@ def test_product_galerkin_pattern_host_function(golden):
         col = np.zeros(int(rp[-1]), np.int32)
         assert L.uggpu_galerkin_pattern(*args, p(rp), p(col)) == 0
         assert np.array_equal(rp, lc.rowptr) and np.array_equal(col, lc.col), k
+
+
+def amg_config(golden):
+    """(class, init string) of the AMG transfer numproc that built the dump's algebraic levels."""
+    d = golden.raw
+    if "amg/class" not in d:
+        return None, ""
+    return bytes(d["amg/class"]).decode(), bytes(d["amg/init"]).decode()
+
+
+def is_rs(golden):
+    cls, init = amg_config(golden)
+    return cls == "selectionAMG" and "$C RugeStueben" in init and "$I RugeStueben" in init and "$strongRel 0.25" in init
+
+
+def test_product_amg_rs_host_function(golden):
+    """uggpu_amg_rs_host (MarkRelative + CoarsenRugeStueben + IpRugeStueben on the flat matrix; host half of uggpu_amg_coarsen_rs, no
+    device involved) against the levels the reference's selectionAMG built: the same coarse points and the same interpolation rows --
+    columns in the reference's list order, weights bit for bit -- on every algebraic level."""
+    if not is_rs(golden):
+        pytest.skip("dump without Ruge-Stueben levels")
+    import ctypes as C
+    from ug_b200 import capi
+    L = capi.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    namg = amg_levels(golden)
+    assert namg >= 2
+    for k in range(namg, 0, -1):
+        lf, lc = golden.levels[k], golden.levels[k - 1]
+        n, nnz = lf.n, lf.col.size
+        rp = np.ascontiguousarray(lf.rowptr, np.int32); col = np.ascontiguousarray(lf.col, np.int32)
+        val = np.ascontiguousarray(lf.val, np.float64); skip = np.ascontiguousarray(lf.skip, np.uint32)
+        coarse = np.zeros(n, np.uint8); prp = np.zeros(n + 1, np.int32); pcol = np.zeros(nnz + n, np.int32); pw = np.zeros(nnz + n)
+        nc = C.c_int(0)
+        assert L.uggpu_amg_rs_host(C.c_int(n), p(rp), p(col), p(val), p(skip), C.c_double(0.25), p(coarse), p(prp), p(pcol), p(pw), C.byref(nc)) == 0
+        assert nc.value == lc.n == int(coarse.sum()), k
+        z = int(prp[-1])
+        assert np.array_equal(prp, lf.p_rowptr) and np.array_equal(pcol[:z], lf.p_col) and np.array_equal(pw[:z], lf.p_w), k
+        # the coarse points are exactly the rows that interpolate from one vector with weight 1 and carry no skip bits' exception
+        one = np.diff(lf.p_rowptr) == 1
+        assert np.all(one[coarse == 1])
+        # flags the new level must carry (GenerateNewGrid amgtools.cc:585-600)
+        assert np.all(lc.vclass == 3) and np.array_equal(lc.vnclass, lf.vclass[coarse == 1]) and np.all(lc.ctl == 1)
+        assert np.array_equal(lc.skip, lf.skip[coarse == 1])
