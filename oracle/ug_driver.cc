@@ -123,6 +123,8 @@ struct Opt {
   // --amg CLASS "INIT": the cycle continues below level 0 on algebraic levels built by the reference's own AMG transfer numproc
   // (np/procs/amgtransfer.cc: classes selectionAMG / clusterAMG), attached to the transfer class with `$amg` (transfer.cc:593, :660)
   std::string amg_class, amg_init;
+  bool hooks = false;                   // --hooks (with --gpu): InterpolateNewVectors / ProjectSolution of transfer vs gputransfer on the same vectors
+  bool transferD = false;               // --transferD: transfer $D (AssembleDirichletBoundary on every level in the transfer's PreProcess, transfer.cc:666)
   bool levelopt = false;                // --levelopt: transfer $L, level optimisation after every level's post-smoothing (transfer.cc:574, :812, MinimizeLevel :488)
   bool collapse = false;                // --collapse: after the --refine steps the surface becomes level 0 (UG's `collapse`, gm/ugm.cc:3930): a large level 0 for the AMG
   int refine2 = 0;                      // --refine2 K: K uniform refinements after the collapse
@@ -519,8 +521,9 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
   cmd("npcreate %sbasesolver $c ls", pfx);       cmd("npinit %sbasesolver $red 1e-8 $m 10 $I %sbaseit", pfx, pfx);
   if (!o.amg_class.empty()) { cmd("npcreate %samgt $c %s", pfx, o.amg_class.c_str()); cmd("npinit %samgt %s", pfx, o.amg_init.c_str()); }
   cmd("npcreate %stransfer $c %s", pfx, transfer);
-  if (!o.amg_class.empty()) cmd("npinit %stransfer%s%s $amg %samgt", pfx, o.imat ? " $M" : "", o.levelopt ? " $L" : "", pfx);
-  else cmd("npinit %stransfer%s%s", pfx, o.imat ? " $M" : "", o.levelopt ? " $L" : "");
+  const std::string topt = std::string(o.imat ? " $M" : "") + (o.levelopt ? " $L" : "") + (o.transferD ? " $D" : "");
+  if (!o.amg_class.empty()) cmd("npinit %stransfer%s $amg %samgt", pfx, topt.c_str(), pfx);
+  else cmd("npinit %stransfer%s", pfx, topt.c_str());
   cmd("npcreate %slmgc $c %s", pfx, lmgc);
   cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel);
   cmd("npcreate %smgs $c %s", pfx, ls);
@@ -910,6 +913,7 @@ int main(int argc, char **argv)
     else if (a == "--nokrylov") o.nokrylov = true;
     else if (a == "--amg") { o.amg_class = nxt(); o.amg_init = nxt(); }
     else if (a == "--levelopt") o.levelopt = true;
+    else if (a == "--hooks") o.hooks = true; else if (a == "--transferD") o.transferD = true;
     else if (a == "--collapse") o.collapse = true; else if (a == "--refine2") o.refine2 = atoi(nxt().c_str());
     else if (a == "--elems") o.elems = true;             // dump the elements (corner rows, fathers): input of the element partition (ug_b200/partition.py)       // --gpu: only the ls/lmgc mixes (bench.py's equal-size line)
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
@@ -1043,6 +1047,29 @@ static int run_gpu(const Opt &o)
     printf("%s %s: its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e b=%.3e defect=%.3e  t_gpu=%.4fs t_cpu=%.4fs\n", ok ? "PASS" : "FAIL", c.name,
            (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_cpu.last_defect[0], ex, eb, ed, g1 - g0, c1 - c0);
     if (!ok) fails++;
+  }
+  // 2b. the nested-iteration hooks of NP_TRANSFER (transfer.h:79-166) on seeded vectors: class transfer vs class gputransfer
+  if (o.hooks) {
+    NP_TRANSFER *tc = (NP_TRANSFER *)GetNumProcByName(mg, "transfer", TRANSFER_CLASS_NAME), *tg = (NP_TRANSFER *)GetNumProcByName(mg, "g0transfer", TRANSFER_CLASS_NAME);
+    std::vector<std::vector<double> > ref[2];
+    bool okh = tc && tg && tg->InterpolateNewVectors && tg->ProjectSolution;
+    for (int side = 0; okh && side < 2; side++) {
+      NP_TRANSFER *t = side ? tg : tc;
+      for (int l = 0; l <= top; l++) fill_lcg(vx, l, 21);
+      // mark every vector of the levels above 0 as new, as a grid adaption would: the hook then interpolates all of them
+      for (int l = 1; l <= top; l++) for (VECTOR *v = FIRSTVECTOR(GRID_ON_LEVEL(mg, l)); v != NULL; v = SUCCVC(v)) SETVNEW(v, 1);
+      if ((*t->InterpolateNewVectors)(t, 0, top, vx, &result)) okh = false;
+      std::vector<std::vector<double> > got;
+      for (int l = 0; l <= top; l++) got.push_back(gather(vx, l));
+      for (int l = 0; l <= top; l++) fill_lcg(vx, l, 22);
+      if ((*t->ProjectSolution)(t, 0, top, vx, &result)) okh = false;
+      for (int l = 0; l <= top; l++) got.push_back(gather(vx, l));
+      if (side == 0) ref[0] = got; else ref[1] = got;
+    }
+    okh = okh && ref[0] == ref[1];
+    printf("%s hooks: InterpolateNewVectors / ProjectSolution of gputransfer vs transfer, %d levels, bitwise\n", okh ? "PASS" : "FAIL", top + 1);
+    if (!okh) fails++;
+    restore_problem();
   }
   // 3. Krylov accelerators: the reference's `cg` / `bcgs` around its own lmgc against gpucg / gpubcgs around gpulmgc
   //    (device-resident).  Step lengths come from parallel sums on the device: agreement to rounding (1e-9), not bitwise.

@@ -60,6 +60,8 @@ CASES = [
     # ---- transfer $L / gputransfer $L: level optimisation (MinimizeLevel, np/procs/transfer.cc:488) inside the cycle; agreement to rounding
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--levelopt", "--damp", "0.6", "--cycles", "5"]),
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--levelopt", "--damp", "0.6", "--cycles", "4"]),
+    # transfer $D (AssembleDirichletBoundary in the transfer's PreProcess) and the nested-iteration hooks InterpolateNewVectors / ProjectSolution
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--transferD", "--hooks", "--damp", "0.6", "--cycles", "4", "--nokrylov"]),
     # ---- algebraic levels: `transfer $amg amgt` / `gputransfer $amg amgt` with the reference's own AMG transfer numproc
     # (np/procs/amgtransfer.cc) building levels -1, -2, ... below a collapsed level 0 in every PreProcess; the device cycle runs on them
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS]),                          # Ruge-Stueben
@@ -70,7 +72,7 @@ CASES = [
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
        "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu", "quad-bs2", "tet-r5-33^3", "tet-r6-65^3", "hex-bs3-r4", "hex-q1-r5-33^3", "tri-r6-C1", "tri-r9-513^2",
        "tet-r4-adaptive", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "assemble-hex-q1-r4", "assemble-tet-r5-33^3",
-       "tet-r4-levelopt", "hex-bs3-levelopt",
+       "tet-r4-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks",
        "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-65^3-on-33^3-greedy-average"]
 
 
@@ -82,6 +84,6 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    want = (4 if "--nokrylov" in args else 6) + (6 if "--assemble" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket, savedata / loaddata bin + asc]
+    want = (4 if "--nokrylov" in args else 6) + (6 if "--assemble" in args else 0) + (1 if "--hooks" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket, savedata / loaddata bin + asc]
     assert sum(l.startswith("PASS") for l in lines) == want, lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -42,6 +42,8 @@ CASES = [
     ("ugoracle2", ["--grid", "quad", "--bs", "2", "--refine", "4", "--damp", "0.7", "--cycles", "6"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--levelopt", "--damp", "0.6", "--cycles", "5"]),
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--levelopt", "--damp", "0.6", "--cycles", "4"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "2", "--adapt", "2", "--transferD", "--hooks", "--damp", "0.6", "--cycles", "4"]),
+    ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--imat", "--hooks", "--damp", "0.6", "--cycles", "4"]),
     # algebraic levels below level 0: `gputransfer $amg amgt` calls the reference's AMG numproc, mirrors levels -1, -2, ... as device levels
     ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS]),
     ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),
@@ -49,7 +51,7 @@ CASES = [
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat", "tet-ilu-beta",
-       "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
+       "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks", "hex-bs3-imat-hooks", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)
@@ -60,7 +62,7 @@ def test_host_numprocs_against_standin(standin, exe, args):
     out = subprocess.run([path] + args + ["--nokrylov", "--gpu", standin], capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    assert sum(l.startswith("PASS") for l in lines) == 4, lines
+    assert sum(l.startswith("PASS") for l in lines) == 4 + (1 if "--hooks" in args else 0), lines
     # bit for bit, also with the "device" base solver (the stand-in's is the restatement of the reference's ls + lu)
-    assert all("relerr x=0.000e+00 b=0.000e+00" in l for l in lines if l.startswith("PASS")), lines
+    assert all("relerr x=0.000e+00 b=0.000e+00" in l for l in lines if l.startswith("PASS") and "hooks" not in l), lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

@@ -21,6 +21,8 @@
 #include <string>
 #include <vector>
 
+#include "np.h"
+#include "disctools.h"
 #include "numproc.h"
 #include "npscan.h"
 #include "pcr.h"
@@ -377,6 +379,7 @@ struct NP_GPUTRANSFER {
   INT amg_ran;
   INT level;           // $L: level optimisation, AdaptCorrection = MinimizeLevel (transfer.cc:574, :812, :488)
   VECDATA_DESC *t;     // its work vector (transfer.cc:592 $t), on the device only
+  INT dirichlet;       // $D [k]: AssembleDirichletBoundary on the levels in PreProcess (transfer.cc:575, :666-678)
 };
 
 INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result);
@@ -393,8 +396,9 @@ INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
   }
   np->level = ReadArgvOption("L", argc, argv);                                                        // transfer.cc:574
   np->t = ReadArgvVecDesc(theNP->mg, "t", argc, argv);                                                // transfer.cc:592
-  if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv) || ReadArgvOption("D", argc, argv)) {
-    UserWrite("gputransfer: the standard (geometric) transfer, $M (stored interpolation matrices), $L (level optimisation) and $amg are on the GPU path; $R $S $D are not supported\n");
+  np->dirichlet = ReadArgvOption("D", argc, argv);                                                    // transfer.cc:575
+  if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv)) {
+    UserWrite("gputransfer: the standard (geometric) transfer, $M (stored interpolation matrices), $L (level optimisation), $D and $amg are on the GPU path; $R $S are not supported\n");
     return NP_NOT_ACTIVE;
   }
   return NPTransferInit((NP_TRANSFER *)theNP, argc, argv);                // transfer.cc:593
@@ -422,6 +426,12 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
     if ((*np->amg->PreProcess)(np->amg, fl, 0, x, b, A, result)) PRE_FAIL(np, result[0]);
     np->amg_ran = 1;
     SetBottom(np->m, *fl);
+  }
+  if (np->dirichlet) {                                                    // transfer.cc:666-678: a host step on UG's lists, before they are flattened
+    int i = *fl;
+    if (np->dirichlet > 1) i = np->dirichlet - 1;
+    for (; i <= tl; i++)
+      if (AssembleDirichletBoundary(GRID_ON_LEVEL(NP_MG(theNP), i), A, x, b)) PRE_FAIL(np, result[0]);
   }
   np->fl = *fl; np->tl = tl;
   for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
@@ -474,6 +484,29 @@ INT GpuAdaptCorrection(NP_TRANSFER *theNP, INT level, VECDATA_DESC *c, VECDATA_D
   return 0;
 }
 
+// InterpolateNewVectors / ProjectSolution (transfer.cc:772, :792): hooks of nested iteration (nonlinear solvers, time steppers), called once per
+// grid adaption and not inside the cycle.  They act on UG's VVALUEs on the host with the reference's own functions; every entry point of the
+// gpuls classes uploads its vector arguments on entry, so no device copy can go stale.
+INT GpuInterpolateNewVectors(NP_TRANSFER *theNP, INT fl, INT tl, VECDATA_DESC *x, INT *result)
+{
+  NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
+  for (INT i = fl + 1; i <= tl; i++) {
+    result[0] = np->imat ? InterpolateNewVectorsByMatrix(GRID_ON_LEVEL(NP_MG(theNP), i), x) : StandardInterpolateNewVectors(GRID_ON_LEVEL(NP_MG(theNP), i), x);
+    if (result[0]) NP_RETURN(1, result[0]);
+  }
+  return 0;
+}
+
+INT GpuProjectSolution(NP_TRANSFER *theNP, INT fl, INT tl, VECDATA_DESC *x, INT *result)
+{
+  result[0] = 0;
+  for (INT i = tl - 1; i >= fl; i--) {
+    result[0] = StandardProject(GRID_ON_LEVEL(NP_MG(theNP), i), x, x);
+    if (result[0]) NP_RETURN(1, result[0]);
+  }
+  return 0;
+}
+
 INT GpuTransferPostProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, VECDATA_DESC *b, MATDATA_DESC *A, INT *result)
 {
   NP_GPUTRANSFER *np = (NP_GPUTRANSFER *)theNP;
@@ -502,8 +535,8 @@ INT GpuTransferConstruct(NP_BASE *theNP)
   np->PreProcessSolution = NULL;
   np->InterpolateCorrection = GpuInterpolateCorrection;
   np->RestrictDefect = GpuRestrictDefect;
-  np->InterpolateNewVectors = NULL;      // nested-iteration hooks: not on the cycle path; callers test for NULL
-  np->ProjectSolution = NULL;
+  np->InterpolateNewVectors = GpuInterpolateNewVectors;      // nested-iteration hooks: the reference's functions on the host
+  np->ProjectSolution = GpuProjectSolution;
   np->AdaptCorrection = GpuAdaptCorrection;   // does nothing without $L, like AdaptCorrection transfer.cc:812
   np->PostProcess = GpuTransferPostProcess;
   np->PostProcessProject = NULL;
