@@ -261,6 +261,14 @@ int uggpu_amg_coarsen_rs(uggpu_ctx*, int level, int A, double theta, int *n_coar
 int uggpu_amg_rs_host(int n, const int32_t *rowptr, const int32_t *col, const double *val, const uint32_t *skip, double theta,
                       uint8_t *coarse, int32_t *p_rowptr, int32_t *p_col, double *p_w, int *n_coarse);
 
+/* The same for `clusterAMG $strongVanek <theta> $C VanekNeuss $I {PiecewiseConstant | Vanek} $CM Galerkin` (scalar): MarkVanek (amgtools.cc:254),
+ * CoarsenVanek + GenerateClusters (:1960, :1864: aggregation in three passes), IpPiecewiseConstant (:3019) for smooth = 0 or IpVanek (:3041,
+ * smoothed aggregation) for smooth = 1.  One coarse vector per cluster in the order of creation.  uggpu_amg_vanek_host: cluster[n] (-1: no
+ * cluster, the vector does not interpolate), seed[n] (first n_coarse entries: the vector each cluster was started from; may be NULL). */
+int uggpu_amg_coarsen_vanek(uggpu_ctx*, int level, int A, double theta, int smooth, int *n_coarse);
+int uggpu_amg_vanek_host(int n, const int32_t *rowptr, const int32_t *col, const double *val, const uint32_t *skip, double theta, int smooth,
+                         int32_t *cluster, int32_t *seed, int32_t *p_rowptr, int32_t *p_col, double *p_w, int *n_coarse);
+
 /* ---- element-loop assembly on the device, np/procs/assemble.h:225 NP_LOCAL_ASSEMBLE, np/procs/assemble.cc:657 ------
  * One level of LocalAssemble (assemble.cc:671-697) followed by that level's share of NPLocalAssemblePostMatrix (:624): b = 0, A = 0,
  * VECSKIP cleared; for the elements in list order the local defect and the local matrix (summed over the quadrature points) are added

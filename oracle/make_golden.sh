@@ -75,6 +75,8 @@ AMG_AVG='$strongRel 0.25 $C Greedy $I Average $CM Galerkin $vectLimit 10 $hold'
 ./_ref/ugoracle2 --grid tri --refine 4 --collapse --refine2 1 --amg clusterAMG "$AMG_VANEK" --cycles 5 --lean --dump $G/amg_tri2d_vanek.ugh --solve > /dev/null
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --collapse --amg selectionAMG "$AMG_AVG" --cycles 4 --lean --dump $G/amg_hex3d_bs3_avg.ugh --solve > /dev/null
 ./_ref/ugoracle2 --grid quad --refine 4 --collapse --refine2 1 --amg selectionAMG "$AMG_RS" --cycles 5 --lean --dump $G/amg_quad2d_rs.ugh --solve > /dev/null
+# aggregation with piecewise constant interpolation in 3D (the smoothed one dereferences a NULL interpolation matrix on this grid in the reference itself)
+./_ref/ugoracle3 --grid tet --refine 3 --collapse --amg clusterAMG '$strongVanek 0.08 $C VanekNeuss $I PiecewiseConstant $CM Galerkin $vectLimit 10 $hold' --cycles 4 --lean --dump $G/amg_tet3d_vanek_pc.ugh --solve > /dev/null
 # ---- level optimisation (`transfer $L`): AdaptCorrection = MinimizeLevel (np/procs/transfer.cc:812, :488) after the post-smoothing of every level
 ./_ref/ugoracle3 --grid tet --refine 3 --levelopt --cycles 5 --lean --dump $G/lopt_tet3d_r3.ugh --solve > /dev/null
 ./_ref/ugoracle3 --grid hex --bs 3 --refine 2 --levelopt --cycles 4 --lean --dump $G/lopt_hex3d_bs3_r2.ugh --solve > /dev/null

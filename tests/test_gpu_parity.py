@@ -230,14 +230,15 @@ def test_gpu_galerkin_pattern_growth(golden):
     be.close()
 
 
-def test_gpu_amg_setup_rs(golden):
-    """uggpu_amg_coarsen_rs rebuilds every algebraic level of the amg_*_rs dumps from the level above it -- strong connections,
-    Ruge-Stueben coarsening and interpolation, Galerkin matrix with the pattern created by the product -- and must arrive at the levels
-    the reference's selectionAMG built: flags, transfer stencils (list order, weights), matrix pattern (list order) and values, all bit
-    for bit.  The solve records of the dump are then replayed on the rebuilt hierarchy."""
-    from test_oracle_port import amg_levels, is_rs
-    if not is_rs(golden):
-        pytest.skip("dump without Ruge-Stueben levels")
+def test_gpu_amg_setup(golden):
+    """uggpu_amg_coarsen_rs / uggpu_amg_coarsen_vanek rebuild every algebraic level of the Ruge-Stueben / Vanek dumps from the level above
+    it -- strong connections, coarsening and interpolation, Galerkin matrix with the pattern created by the product -- and must arrive at
+    the levels the reference's selectionAMG / clusterAMG built: flags, transfer stencils (list order, weights), matrix pattern (list
+    order) and values, all bit for bit.  The solve records of the dump are then replayed on the rebuilt hierarchy."""
+    from test_oracle_port import amg_levels, is_rs, vanek_config
+    vk = vanek_config(golden)
+    if not is_rs(golden) and vk is None:
+        pytest.skip("dump without Ruge-Stueben or Vanek levels")
     import ctypes as C
     from backends import GpuBackend
     be = GpuBackend(golden)
@@ -245,7 +246,10 @@ def test_gpu_amg_setup_rs(golden):
     namg = amg_levels(golden)
     for k in range(namg, 0, -1):
         nc = C.c_int(0)
-        ctx.call("uggpu_amg_coarsen_rs", k, be.A, C.c_double(0.25), C.byref(nc))
+        if vk is None:
+            ctx.call("uggpu_amg_coarsen_rs", k, be.A, C.c_double(0.25), C.byref(nc))
+        else:
+            ctx.call("uggpu_amg_coarsen_vanek", k, be.A, C.c_double(vk[0]), int(vk[1]), C.byref(nc))
         assert nc.value == golden.levels[k - 1].n, k
     back = ctx.download_hierarchy(golden.top)
     for l in range(namg + 1):

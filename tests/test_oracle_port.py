@@ -182,6 +182,48 @@ def is_rs(golden):
     return cls == "selectionAMG" and "$C RugeStueben" in init and "$I RugeStueben" in init and "$strongRel 0.25" in init
 
 
+def vanek_config(golden):
+    """(theta, smooth) when the dump's algebraic levels were built by clusterAMG with VanekNeuss aggregation, else None."""
+    import re
+    cls, init = amg_config(golden)
+    if cls != "clusterAMG" or "$C VanekNeuss" not in init:
+        return None
+    m = re.search(r"\$strongVanek ([0-9.eE+-]+)", init)
+    smooth = 1 if "$I Vanek" in init else (0 if "$I PiecewiseConstant" in init else None)
+    return (float(m.group(1)), smooth) if m and smooth is not None else None
+
+
+def test_product_amg_vanek_host_function(golden):
+    """uggpu_amg_vanek_host (MarkVanek + CoarsenVanek / GenerateClusters + IpVanek or IpPiecewiseConstant on the flat matrix) against the
+    levels the reference's clusterAMG built: the same clusters in the same order and the same interpolation rows -- the cluster's own entry
+    first, the smoothed ones behind it in the reference's list order, weights bit for bit."""
+    cfg = vanek_config(golden)
+    if cfg is None:
+        pytest.skip("dump without Vanek aggregation levels")
+    theta, smooth = cfg
+    import ctypes as C
+    from ug_b200 import capi
+    L = capi.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    namg = amg_levels(golden)
+    for k in range(namg, 0, -1):
+        lf, lc = golden.levels[k], golden.levels[k - 1]
+        n, nnz = lf.n, lf.col.size
+        rp = np.ascontiguousarray(lf.rowptr, np.int32); col = np.ascontiguousarray(lf.col, np.int32)
+        val = np.ascontiguousarray(lf.val, np.float64); skip = np.ascontiguousarray(lf.skip, np.uint32)
+        cluster = np.zeros(n, np.int32); seed = np.zeros(n, np.int32)
+        prp = np.zeros(n + 1, np.int32); pcol = np.zeros(nnz + n, np.int32); pw = np.zeros(nnz + n)
+        nc = C.c_int(0)
+        assert L.uggpu_amg_vanek_host(C.c_int(n), p(rp), p(col), p(val), p(skip), C.c_double(theta), C.c_int(smooth), p(cluster), p(seed),
+                                      p(prp), p(pcol), p(pw), C.byref(nc)) == 0
+        assert nc.value == lc.n, k
+        z = int(prp[-1])
+        assert np.array_equal(prp, lf.p_rowptr) and np.array_equal(pcol[:z], lf.p_col) and np.array_equal(pw[:z], lf.p_w), k
+        has = np.diff(lf.p_rowptr) > 0
+        assert np.array_equal(cluster[has], lf.p_col[lf.p_rowptr[:-1][has]]) and np.all(cluster[~has] == -1)
+        assert np.all(lc.vclass == 3) and np.array_equal(lc.vnclass, lf.vclass[seed[:lc.n]]) and np.all(lc.ctl == 1) and np.all(lc.skip == 0)
+
+
 def test_product_amg_rs_host_function(golden):
     """uggpu_amg_rs_host (MarkRelative + CoarsenRugeStueben + IpRugeStueben on the flat matrix; host half of uggpu_amg_coarsen_rs, no
     device involved) against the levels the reference's selectionAMG built: the same coarse points and the same interpolation rows --

@@ -13,6 +13,7 @@
 // A setup path: one call per level, host time ~ the reference's own.
 #include "uggpu_internal.h"
 
+#include <cmath>
 #include <vector>
 
 #define AMG_MAXNEIGHBORS 128      // np/algebra/amgtools.h:52
@@ -206,6 +207,219 @@ extern "C" int uggpu_amg_rs_host(int n, const int32_t *rowptr, const int32_t *co
   return 0;
 }
 
+// ---- clusterAMG: MarkVanek amgtools.cc:254, CoarsenVanek :1960 with GenerateClusters :1864, IpPiecewiseConstant :3019 / IpVanek :3041 ------
+// Aggregation: clusters are grown around seed vectors taken from bucket lists ordered by the number of strong connections from vectors
+// that are still free (first pass: clusters of at least 2/3 of the average neighbourhood; second: leftovers join the smallest
+// neighbouring cluster; third: the rest seeds clusters of any size).  One coarse vector per cluster, in the order of creation.
+// cluster[v] = coarse vector of v, -1 for the vectors without strong connections (Dirichlet rows): they do not interpolate;
+// seed[c] (or NULL) = the vector cluster c was started from.
+// smooth = 0: piecewise constant interpolation; 1: Vanek's smoothed aggregation (one damped Jacobi step of the filtered matrix applied to
+// the piecewise constant one; the cluster's own entry stays first in the row, the others follow in reverse order of creation).
+extern "C" int uggpu_amg_vanek_host(int n, const int32_t *rowptr, const int32_t *col, const double *val, const uint32_t *skip, double theta, int smooth,
+                                    int32_t *cluster, int32_t *seed, int32_t *p_rowptr, int32_t *p_col, double *p_w, int *n_coarse)
+{
+  if (n < 0 || !rowptr || !col || !val || !skip || !cluster || !p_rowptr || !p_col || !p_w || !n_coarse) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: null argument");
+  const int64_t nnz = rowptr[n];
+  for (int v = 0; v < n; v++)
+    if (rowptr[v + 1] <= rowptr[v] || col[rowptr[v]] != v) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: row %d does not start with its diagonal entry", v);
+  // ---- MarkVanek amgtools.cc:254-310, scalar (vcomp = 0)
+  std::vector<uint8_t> strong((size_t)nnz, 0);
+  for (int v = 0; v < n; v++) {
+    if (skip[v]) continue;
+    const double nii = fabs(val[rowptr[v]]);
+    for (int e = rowptr[v] + 1; e < rowptr[v + 1]; e++) {
+      const int w = col[e];
+      if (skip[w] != 0) continue;
+      const double njj = fabs(val[rowptr[w]]), nij = fabs(val[e]);
+      if (nij >= theta * sqrt(nii * njj)) strong[e] = 1;
+    }
+  }
+  std::vector<int32_t> adj((size_t)nnz, -1);
+  for (int v = 0; v < n; v++)
+    for (int e = rowptr[v] + 1; e < rowptr[v + 1]; e++) {
+      const int w = col[e];
+      for (int f = rowptr[w] + 1; f < rowptr[w + 1]; f++) if (col[f] == v) { adj[e] = f; break; }
+    }
+  // ---- CoarsenVanek :1960-2116
+  std::vector<uint8_t> ccoarse(n, 0);
+  std::vector<int> sin(n, 0), sout(n, 0);
+  Lists Ls(n);
+  int maxNeighbors = 0;
+  long sumStrong = 0;
+  for (int v = 0; v < n; v++) {                                   // CountStrongNeighbors :394
+    int nb = 0, ns = 0;
+    for (int e = rowptr[v] + 1; e < rowptr[v + 1]; e++) {
+      if (strong[e]) { sumStrong++; sout[col[e]]++; ns++; }
+      nb++;
+    }
+    if (nb > maxNeighbors) maxNeighbors = nb;
+    sin[v] = ns;
+  }
+  const double avNosN = n > 0 ? (double)sumStrong / (double)n : 0.0;
+  if (maxNeighbors > AMG_MAXNEIGHBORS) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: a row has %d neighbours, the coarsening handles %d (MAXNEIGHBORS)", maxNeighbors, AMG_MAXNEIGHBORS);
+  const int nU = 2 * AMG_MAXNEIGHBORS + 1;
+  std::vector<int> Ua(nU, -1), Ue(nU, -1);
+  int Da = -1, De = -1;
+  for (int v = 0; v < n; v++) {                                   // DistributeInitialList :354
+    cluster[v] = -1;
+    if (sin[v] == 0) Ls.add_end(Da, De, v);
+    else { if (sout[v] >= nU) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: bucket overflow"); Ls.add_end(Ua[sout[v]], Ue[sout[v]], v); }
+  }
+  std::vector<int> csize;                                         // VINDEX(newVect): size of the cluster
+  std::vector<int> cseed;                                         // the seed vector (its class becomes the next class of the coarse vector)
+  int err = 0;
+  auto lower_free_neighbours = [&](int m) {                       // "change the order for the neighbors": one strong connection from a free vector less
+    for (int e = rowptr[m] + 1; e < rowptr[m + 1]; e++)
+      if (strong[e]) {
+        const int v2 = col[e];
+        if (ccoarse[v2]) continue;
+        int k = sout[v2];
+        if (sin[v2] == 0 || k <= 0) { err = 1; return; }          // the reference would follow a NULL pointer here (a vector outside the bucket lists)
+        Ls.eliminate(Ua[k], Ue[k], v2);
+        sout[v2] = --k;
+        Ls.add_end(Ua[k], Ue[k], v2);
+      }
+  };
+  auto generate_clusters = [&](int minSize) {                     // GenerateClusters :1864-1958
+    if (minSize < 0) minSize = 0;
+    int i = AMG_MAXNEIGHBORS;
+    std::vector<int> members;
+    while (i >= minSize) {
+      int a;
+      while ((a = Ua[i]) != -1) {
+        members.clear();
+        Ls.eliminate(Ua[i], Ue[i], a);
+        members.push_back(a);
+        ccoarse[a] = 1;
+        for (int e = rowptr[a] + 1; e < rowptr[a + 1]; e++) {
+          const int e2 = adj[e];
+          if (e2 < 0) { err = 2; return; }
+          if (strong[e2]) {
+            const int v2 = col[e];
+            if (ccoarse[v2]) continue;                            // already belongs to a cluster
+            const int k = sout[v2];
+            Ls.eliminate(Ua[k], Ue[k], v2);
+            members.push_back(v2);
+            ccoarse[v2] = 1;
+          }
+        }
+        const int c = (int)csize.size();
+        csize.push_back((int)members.size());
+        cseed.push_back(a);
+        for (int m : members) { cluster[m] = c; lower_free_neighbours(m); if (err) return; }
+      }
+      i--;
+    }
+  };
+  generate_clusters((int)((avNosN + 1.0) * 0.66 - 1.0));
+  if (err) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: %s", err == 2 ? "G(A) is not symmetric" : "a strong connection leads to a vector without strong connections of its own");
+  for (int i = 0; i < AMG_MAXNEIGHBORS; i++) {                    // second step :2041-2096
+    int a = Ua[i];
+    while (a != -1) {
+      int minSize = 999, best = -1;
+      for (int e = rowptr[a] + 1; e < rowptr[a + 1]; e++)
+        if (strong[e]) {
+          const int v2 = col[e];
+          if (ccoarse[v2] && csize[cluster[v2]] < minSize) { minSize = csize[cluster[v2]]; best = cluster[v2]; }
+        }
+      if (best != -1) {
+        ccoarse[a] = 1;
+        lower_free_neighbours(a);
+        if (err) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: a strong connection leads to a vector without strong connections of its own");
+        Ls.eliminate(Ua[i], Ue[i], a);                            // its successor pointer stays valid
+        cluster[a] = best;
+        csize[best]++;
+      }
+      a = Ls.succ[a];
+    }
+  }
+  generate_clusters(0);                                           // third pass
+  if (err) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: %s", err == 2 ? "G(A) is not symmetric" : "a strong connection leads to a vector without strong connections of its own");
+  const int nc = (int)csize.size();
+  *n_coarse = nc;
+  if (seed) for (int c = 0; c < nc; c++) seed[c] = cseed[c];
+  // ---- interpolation
+  int64_t z = 0;
+  p_rowptr[0] = 0;
+  std::vector<int32_t> oc; std::vector<double> ow;
+  double factor = 0.0;
+  for (int v = 0; v < n; v++) {
+    if (cluster[v] < 0) {
+      if (smooth && skip[v] == 0) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: vector %d without a cluster is not a Dirichlet vector (IpVanek needs its interpolation matrix)", v);
+      p_rowptr[v + 1] = (int32_t)z; continue;
+    }
+    double own = 1.0;                                             // piecewise constant on the clusters :3019 / :3062
+    oc.clear(); ow.clear();
+    if (smooth && skip[v] == 0) {                                 // IpVanek :3066-3103: P := (I - 2/3 D_f^-1 A_strong) P, D_f the diagonal of the filtered matrix
+      double sum = val[rowptr[v]];
+      for (int e = rowptr[v] + 1; e < rowptr[v + 1]; e++)
+        if (!strong[e] && skip[col[e]] == 0) sum += val[e];
+      if (sum != 0.0) factor = 1.0 / sum;                         // BLOCK_INVERT: untouched when singular
+      factor *= -0.666666666;
+      for (int e = rowptr[v] + 1; e < rowptr[v + 1]; e++)
+        if (strong[e]) {
+          const int c2 = cluster[col[e]];
+          if (c2 < 0) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_vanek_host: strong neighbour without a cluster");
+          if (c2 == cluster[v]) { own += factor * val[e]; continue; }
+          size_t k = 0;
+          while (k < oc.size() && oc[k] != c2) k++;
+          if (k == oc.size()) { oc.push_back(c2); ow.push_back(0.0); }
+          ow[k] += factor * val[e];
+        }
+    }
+    p_col[z] = cluster[v]; p_w[z] = own; z++;
+    for (size_t k = oc.size(); k-- > 0;) { p_col[z] = oc[k]; p_w[z] = ow[k]; z++; }      // inserted right behind the cluster's entry: newest first
+    p_rowptr[v + 1] = (int32_t)z;
+  }
+  return 0;
+}
+
+// the new level on the device from the interpolation rows: vectors' flags, by-matrix transfer stencils, Galerkin matrix
+static int amg_build_level(uggpu_ctx *ctx, int level, int A, int n, int nc, const std::vector<uint8_t> &vclass, const std::vector<uint8_t> &cnclass,
+                           const std::vector<uint32_t> &cskip, const std::vector<int32_t> &prp, const std::vector<int32_t> &pcol, const std::vector<double> &pw)
+{
+  std::vector<uint8_t> cclass((size_t)nc, 3), cctl((size_t)nc, 1);      // class 3, NEW_DEFECT set, FINE_GRID_DOF clear (amgtools.cc:585-600, :1905-1909)
+  UG_TRY(uggpu_level_create(ctx, level - 1, nc, 1));
+  UG_TRY(uggpu_level_set_flags(ctx, level - 1, cclass.data(), cnclass.data(), cctl.data(), cskip.data()));
+  // R: the coarse rows list the contributions of the fine rows with VCLASS >= NEWDEF_CLASS in fine list order (RestrictByMatrix, transgrid.cc:1142)
+  std::vector<int32_t> rrp((size_t)nc + 1, 0), rcol((size_t)prp[n] + 1);
+  std::vector<double> rw((size_t)prp[n] + 1);
+  for (int v = 0; v < n; v++) if (vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) rrp[pcol[e] + 1]++;
+  for (int k = 0; k < nc; k++) rrp[k + 1] += rrp[k];
+  { std::vector<int32_t> fill(rrp.begin(), rrp.end() - 1);
+    for (int v = 0; v < n; v++) if (vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) { const int32_t pos = fill[pcol[e]]++; rcol[pos] = v; rw[pos] = pw[e]; } }
+  UG_TRY(uggpu_transfer_set(ctx, level, prp.data(), pcol.data(), pw.data(), rrp.data(), rcol.data(), rw.data()));
+  UG_TRY(uggpu_transfer_set_mode(ctx, level, UGGPU_TRANSFER_IMAT));
+  return uggpu_galerkin(ctx, level, A);             // level-1 has no matrix A yet: pattern and values come from the product
+}
+
+extern "C" int uggpu_amg_coarsen_vanek(uggpu_ctx *ctx, int level, int A, double theta, int smooth, int *n_coarse)
+{
+  Level *L = get_level(ctx, level);
+  SellMat *Af = get_mat(ctx, level, A);
+  if (!L || !Af || !n_coarse) return UGGPU_DESC_MISMATCH;
+  if (level < 1) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_coarsen_vanek: no room below level %d (levels are numbered from 0)", level);
+  if (L->bs != 1) return uggpu_fail(UGGPU_BLOCK_TOO_LARGE, "uggpu_amg_coarsen_vanek: scalar equations only (block size %d)", L->bs);
+  if (ctx->comm && L->partitioned) return uggpu_fail(UGGPU_ERROR, "uggpu_amg_coarsen_vanek runs on one GPU (level %d is partitioned)", level);
+  const int n = L->n;
+  const size_t nnz = (size_t)Af->nnz;
+  std::vector<int32_t> rp((size_t)n + 1), col(nnz + 1), prp((size_t)n + 1), pcol(nnz + (size_t)n + 1), cluster((size_t)n + 1), seed((size_t)n + 1);
+  std::vector<double> val(nnz + 1), pw(nnz + (size_t)n + 1);
+  std::vector<uint8_t> vclass((size_t)n + 1);
+  std::vector<uint32_t> skip((size_t)n + 1);
+  UG_TRY(sell_to_host_csr(ctx, Af, rp.data(), col.data(), val.data()));
+  UG_TRY(uggpu_level_get_flags(ctx, level, vclass.data(), nullptr, nullptr, skip.data()));
+  int nc = 0;
+  UG_TRY(uggpu_amg_vanek_host(n, rp.data(), col.data(), val.data(), skip.data(), theta, smooth, cluster.data(), seed.data(), prp.data(), pcol.data(), pw.data(), &nc));
+  *n_coarse = nc;
+  if (nc == 0 || nc == n) { *n_coarse = 0; return 0; }
+  // GenerateClusters :1905-1909: next class = class of the seed vector; VECSKIP of a cluster's vector is never set
+  std::vector<uint8_t> cnclass((size_t)nc);
+  std::vector<uint32_t> cskip((size_t)nc, 0u);
+  for (int c = 0; c < nc; c++) cnclass[c] = vclass[seed[c]];
+  return amg_build_level(ctx, level, A, n, nc, vclass, cnclass, cskip, prp, pcol, pw);
+}
+
 // One level: level-1 := coarsening of `level` with matrix A.  *n_coarse = 0 (and no level created) when the coarsening selects all or no
 // vectors (GenerateNewGrid's "nothing to do", the reference's "error in coarsening").
 extern "C" int uggpu_amg_coarsen_rs(uggpu_ctx *ctx, int level, int A, double theta, int *n_coarse)
@@ -228,21 +442,9 @@ extern "C" int uggpu_amg_coarsen_rs(uggpu_ctx *ctx, int level, int A, double the
   UG_TRY(uggpu_amg_rs_host(n, rp.data(), col.data(), val.data(), skip.data(), theta, coarse.data(), prp.data(), pcol.data(), pw.data(), &nc));
   *n_coarse = nc;
   if (nc == 0 || nc == n) { *n_coarse = 0; return 0; }
-  // the new level's vectors (GenerateNewGrid amgtools.cc:585-600): class 3, next class = class of the fine vector, NEW_DEFECT set,
-  // FINE_GRID_DOF clear, VECSKIP inherited
-  std::vector<uint8_t> cclass((size_t)nc, 3), cnclass((size_t)nc), cctl((size_t)nc, 1);
+  // the new level's vectors (GenerateNewGrid amgtools.cc:585-600): next class = class of the fine vector, VECSKIP inherited
+  std::vector<uint8_t> cnclass((size_t)nc);
   std::vector<uint32_t> cskip((size_t)nc);
   for (int v = 0, k = 0; v < n; v++) if (coarse[v]) { cnclass[k] = vclass[v]; cskip[k] = skip[v]; k++; }
-  UG_TRY(uggpu_level_create(ctx, level - 1, nc, 1));
-  UG_TRY(uggpu_level_set_flags(ctx, level - 1, cclass.data(), cnclass.data(), cctl.data(), cskip.data()));
-  // R: the coarse rows list the contributions of the fine rows with VCLASS >= NEWDEF_CLASS in fine list order (RestrictByMatrix, transgrid.cc:1142)
-  std::vector<int32_t> rrp((size_t)nc + 1, 0), rcol((size_t)prp[n] + 1);
-  std::vector<double> rw((size_t)prp[n] + 1);
-  for (int v = 0; v < n; v++) if (vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) rrp[pcol[e] + 1]++;
-  for (int k = 0; k < nc; k++) rrp[k + 1] += rrp[k];
-  { std::vector<int32_t> fill(rrp.begin(), rrp.end() - 1);
-    for (int v = 0; v < n; v++) if (vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) { const int32_t pos = fill[pcol[e]]++; rcol[pos] = v; rw[pos] = pw[e]; } }
-  UG_TRY(uggpu_transfer_set(ctx, level, prp.data(), pcol.data(), pw.data(), rrp.data(), rcol.data(), rw.data()));
-  UG_TRY(uggpu_transfer_set_mode(ctx, level, UGGPU_TRANSFER_IMAT));
-  return uggpu_galerkin(ctx, level, A);             // level-1 has no matrix A yet: pattern and values come from the product
+  return amg_build_level(ctx, level, A, n, nc, vclass, cnclass, cskip, prp, pcol, pw);
 }
