@@ -123,6 +123,9 @@ struct Opt {
   // --amg CLASS "INIT": the cycle continues below level 0 on algebraic levels built by the reference's own AMG transfer numproc
   // (np/procs/amgtransfer.cc: classes selectionAMG / clusterAMG), attached to the transfer class with `$amg` (transfer.cc:593, :660)
   std::string amg_class, amg_init;
+  // --gpuamg "OPTIONS": the gputransfer numprocs of the --gpu run get `$gpuamg OPTIONS` (the algebraic levels are built by the device
+  // library itself and exist on the device only) instead of `$amg amgt`; the CPU side keeps the reference's AMG numproc (--amg)
+  std::string gpuamg;
   bool hooks = false;                   // --hooks (with --gpu): InterpolateNewVectors / ProjectSolution of transfer vs gputransfer on the same vectors
   bool transferD = false;               // --transferD: transfer $D (AssembleDirichletBoundary on every level in the transfer's PreProcess, transfer.cc:666)
   bool levelopt = false;                // --levelopt: transfer $L, level optimisation after every level's post-smoothing (transfer.cc:574, :812, MinimizeLevel :488)
@@ -522,7 +525,8 @@ static void make_numprocs(const Opt &o, const char *pfx, const char *jac, const 
   if (!o.amg_class.empty()) { cmd("npcreate %samgt $c %s", pfx, o.amg_class.c_str()); cmd("npinit %samgt %s", pfx, o.amg_init.c_str()); }
   cmd("npcreate %stransfer $c %s", pfx, transfer);
   const std::string topt = std::string(o.imat ? " $M" : "") + (o.levelopt ? " $L" : "") + (o.transferD ? " $D" : "");
-  if (!o.amg_class.empty()) cmd("npinit %stransfer%s $amg %samgt", pfx, topt.c_str(), pfx);
+  if (!o.gpuamg.empty() && strcmp(transfer, "gputransfer") == 0) cmd("npinit %stransfer%s $gpuamg %s", pfx, topt.c_str(), o.gpuamg.c_str());
+  else if (!o.amg_class.empty()) cmd("npinit %stransfer%s $amg %samgt", pfx, topt.c_str(), pfx);
   else cmd("npinit %stransfer%s", pfx, topt.c_str());
   cmd("npcreate %slmgc $c %s", pfx, lmgc);
   cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel);
@@ -912,6 +916,7 @@ int main(int argc, char **argv)
     else if (a == "--savedata") o.savedata = nxt();      // prefix of the data files the reference's SaveData writes (np/udm/data_io.cc:650)
     else if (a == "--nokrylov") o.nokrylov = true;
     else if (a == "--amg") { o.amg_class = nxt(); o.amg_init = nxt(); }
+    else if (a == "--gpuamg") o.gpuamg = nxt();
     else if (a == "--levelopt") o.levelopt = true;
     else if (a == "--hooks") o.hooks = true; else if (a == "--transferD") o.transferD = true;
     else if (a == "--collapse") o.collapse = true; else if (a == "--refine2") o.refine2 = atoi(nxt().c_str());
@@ -1018,6 +1023,8 @@ static int run_gpu(const Opt &o)
   int k = 0;
   for (const Cfg &c : cfgs) {
     char pfx[16]; snprintf(pfx, sizeof pfx, "g%d", k++);
+    // algebraic levels on the device only: no host vectors there, so only the device-resident solve with the device base solver applies
+    if (!o.gpuamg.empty() && strstr(c.extra, "devbase") == NULL) continue;
     make_numprocs(o, pfx, (std::string("gpu") + o.smoother).c_str(), c.lmgc, c.transfer, c.ls, o.cycles);
     if (c.extra[0]) cmd("npinit %slmgc $S %ssmooth %ssmooth %sbasesolver $T %stransfer $n1 %d $n2 %d $g %d $b %d%s", pfx, pfx, pfx, pfx, pfx, o.nu1, o.nu2, o.gamma, o.baselevel, c.extra);
     restore_problem();

@@ -30,6 +30,19 @@ int fail(int code, const char *fmt, ...)
   g_err = b;
   return code;
 }
+}  // namespace
+
+// the host halves of the algebraic-level setup are the PRODUCT's own code (no device in them): the stand-in runs the very same coarsening
+int uggpu_fail(int code, const char *fmt, ...)
+{
+  char b[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+  g_err = b;
+  return code;
+}
+#include "../../ug_b200/csrc/amg_host.inc"
+
+namespace {
 
 struct Lev {
   bool exists = false;
@@ -302,6 +315,66 @@ int uggpu_minimize_level(uggpu_ctx *ctx, int level, int c, int b, int A, int t)
   if (!cv || !bv || !tv || !lv[level].val) return UGGPU_DESC_MISMATCH;
   ugport_minimize_level(&lv[level], cv, bv, tv);
   return 0;
+}
+
+// level-1 from the interpolation rows: flags, by-matrix stencils, Galerkin matrix (pattern: ugport_galerkin_pattern, values: ugport_galerkin)
+static int standin_build_level(uggpu_ctx *ctx, int level, int A, int nc, const std::vector<uint8_t> &cnclass, const std::vector<uint32_t> &cskip,
+                               const std::vector<int32_t> &prp, const std::vector<int32_t> &pcol, const std::vector<double> &pw)
+{
+  Lev &F = ctx->lev[level];
+  const int n = F.n;
+  std::vector<uint8_t> cclass((size_t)nc, 3), cctl((size_t)nc, 1);
+  if (uggpu_level_create(ctx, level - 1, nc, 1) || uggpu_level_set_flags(ctx, level - 1, cclass.data(), cnclass.data(), cctl.data(), cskip.data())) return UGGPU_ERROR;
+  std::vector<int32_t> rrp((size_t)nc + 1, 0), rcol((size_t)prp[n] + 1);
+  std::vector<double> rw((size_t)prp[n] + 1);
+  for (int v = 0; v < n; v++) if (F.vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) rrp[pcol[e] + 1]++;
+  for (int k = 0; k < nc; k++) rrp[k + 1] += rrp[k];
+  { std::vector<int32_t> fill(rrp.begin(), rrp.end() - 1);
+    for (int v = 0; v < n; v++) if (F.vclass[v] >= 2) for (int e = prp[v]; e < prp[v + 1]; e++) { const int32_t pos = fill[pcol[e]]++; rcol[pos] = v; rw[pos] = pw[e]; } }
+  if (uggpu_transfer_set(ctx, level, prp.data(), pcol.data(), pw.data(), rrp.data(), rcol.data(), rw.data())) return UGGPU_ERROR;
+  uggpu_transfer_set_mode(ctx, level, UGGPU_TRANSFER_IMAT);
+  std::vector<int32_t> crp((size_t)nc + 1), ccol;
+  if (ugport_galerkin_pattern(n, nc, F.rowptr.data(), F.col.data(), prp.data(), pcol.data(), nullptr, nullptr, crp.data(), nullptr)) return fail(UGGPU_ERROR, "galerkin pattern");
+  ccol.resize((size_t)crp[nc] + 1);
+  if (ugport_galerkin_pattern(n, nc, F.rowptr.data(), F.col.data(), prp.data(), pcol.data(), nullptr, nullptr, crp.data(), ccol.data())) return fail(UGGPU_ERROR, "galerkin pattern");
+  if (uggpu_mat_set_pattern(ctx, level - 1, A, crp.data(), ccol.data())) return UGGPU_ERROR;
+  std::vector<ugport_level> lv;
+  port_levels(ctx, A, 0, lv);
+  if (ugport_galerkin(&lv[level], &lv[level - 1], F.mat[A].data(), ctx->lev[level - 1].mat[A].data())) return fail(UGGPU_ERROR, "galerkin product");
+  return 0;
+}
+
+int uggpu_amg_coarsen_rs(uggpu_ctx *ctx, int level, int A, double theta, int *n_coarse)
+{
+  Lev *L = level_of(ctx, level);
+  if (!L || level < 1 || L->bs != 1 || !L->mat.count(A)) return fail(UGGPU_ERROR, "uggpu_amg_coarsen_rs: bad level");
+  const int n = L->n; const size_t nnz = L->col.size();
+  std::vector<int32_t> prp((size_t)n + 1), pcol(nnz + (size_t)n + 1);
+  std::vector<double> pw(nnz + (size_t)n + 1);
+  std::vector<uint8_t> coarse((size_t)n + 1);
+  int nc = 0;
+  if (int rc = uggpu_amg_rs_host(n, L->rowptr.data(), L->col.data(), L->mat[A].data(), L->skip.data(), theta, coarse.data(), prp.data(), pcol.data(), pw.data(), &nc)) return rc;
+  *n_coarse = nc;
+  if (nc == 0 || nc == n) { *n_coarse = 0; return 0; }
+  std::vector<uint8_t> cnclass((size_t)nc); std::vector<uint32_t> cskip((size_t)nc);
+  for (int v = 0, k = 0; v < n; v++) if (coarse[v]) { cnclass[k] = L->vclass[v]; cskip[k] = L->skip[v]; k++; }
+  return standin_build_level(ctx, level, A, nc, cnclass, cskip, prp, pcol, pw);
+}
+
+int uggpu_amg_coarsen_vanek(uggpu_ctx *ctx, int level, int A, double theta, int smooth, int *n_coarse)
+{
+  Lev *L = level_of(ctx, level);
+  if (!L || level < 1 || L->bs != 1 || !L->mat.count(A)) return fail(UGGPU_ERROR, "uggpu_amg_coarsen_vanek: bad level");
+  const int n = L->n; const size_t nnz = L->col.size();
+  std::vector<int32_t> prp((size_t)n + 1), pcol(nnz + (size_t)n + 1), cluster((size_t)n + 1), seed((size_t)n + 1);
+  std::vector<double> pw(nnz + (size_t)n + 1);
+  int nc = 0;
+  if (int rc = uggpu_amg_vanek_host(n, L->rowptr.data(), L->col.data(), L->mat[A].data(), L->skip.data(), theta, smooth, cluster.data(), seed.data(), prp.data(), pcol.data(), pw.data(), &nc)) return rc;
+  *n_coarse = nc;
+  if (nc == 0 || nc == n) { *n_coarse = 0; return 0; }
+  std::vector<uint8_t> cnclass((size_t)nc); std::vector<uint32_t> cskip((size_t)nc, 0u);
+  for (int c = 0; c < nc; c++) cnclass[c] = L->vclass[seed[c]];
+  return standin_build_level(ctx, level, A, nc, cnclass, cskip, prp, pcol, pw);
 }
 
 int uggpu_lmgc_preprocess(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int level, int A)

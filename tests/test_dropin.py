@@ -15,6 +15,7 @@ LIB = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
 
 AMG_RS = "$strongRel 0.25 $C RugeStueben $I RugeStueben $CM Galerkin $vectLimit 20"
 AMG_VANEK = "$strongVanek 0.08 $C VanekNeuss $I Vanek $CM Galerkin $vectLimit 10"
+AMG_VANEK_PC = "$strongVanek 0.08 $C VanekNeuss $I PiecewiseConstant $CM Galerkin $vectLimit 60"
 # averaging interpolation (the one the reference offers for systems) on a greedy independent set.  Not `$C Average`: CoarsenAverage re-links
 # the vector list of the level it coarsens and re-sorts its matrix lists (np/algebra/amgtools.cc:1330-1440), so two successive solves of the
 # reference itself run on differently ordered levels and differ in the last bits -- nothing a run-after-run comparison can be pinned on
@@ -68,12 +69,19 @@ CASES = [
     ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),       # Vanek aggregation, one geometric level above
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--collapse", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 10"]),   # 3x3 blocks, averaging
     ("ugoracle3", ["--grid", "tet", "--refine", "5", "--collapse", "--refine2", "1", "--cycles", "4", "--nokrylov", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),   # 65^3 on 33^3 on 4 algebraic levels
+    # ---- gputransfer $gpuamg: the algebraic levels are built by the device library itself (uggpu_amg_coarsen_rs / _vanek) and exist on the device
+    # only; the reference side runs its own AMG numproc -- same levels, same bits.  Device-resident solve with the device base solver only
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--nokrylov", "--amg", "selectionAMG", AMG_RS, "--gpuamg", "RugeStueben $theta 0.25 $vectLimit 20"]),
+    ("ugoracle2", ["--grid", "quad", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--nokrylov", "--amg", "selectionAMG", AMG_RS, "--gpuamg", "RugeStueben $vectLimit 20"]),
+    ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--nokrylov", "--amg", "clusterAMG", AMG_VANEK, "--gpuamg", "Vanek $theta 0.08 $vectLimit 10"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--nokrylov", "--amg", "clusterAMG", AMG_VANEK_PC, "--gpuamg", "VanekPC $theta 0.08 $vectLimit 60"]),
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat",
        "tet-ilu-beta", "hex-bs3-ilu-beta", "tet-adaptive-ilu", "quad-bs2", "tet-r5-33^3", "tet-r6-65^3", "hex-bs3-r4", "hex-q1-r5-33^3", "tri-r6-C1", "tri-r9-513^2",
        "tet-r4-adaptive", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "assemble-hex-q1-r4", "assemble-tet-r5-33^3",
        "tet-r4-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks",
-       "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-65^3-on-33^3-greedy-average"]
+       "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-65^3-on-33^3-greedy-average",
+       "gpuamg-tet-ruge-stueben", "gpuamg-quad-ruge-stueben-refine2", "gpuamg-tri-vanek-refine2", "gpuamg-tet-33^3-on-17^3-vanek-pc"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)
@@ -84,6 +92,8 @@ def test_gpuls_numprocs_inside_ug(exe, args):
     out = subprocess.run([path] + args + ["--gpu", LIB], capture_output=True, text=True, timeout=900)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    want = (4 if "--nokrylov" in args else 6) + (6 if "--assemble" in args else 0) + (1 if "--hooks" in args else 0)      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket, savedata / loaddata bin + asc]
+    want = (4 if "--nokrylov" in args else 6) + (6 if "--assemble" in args else 0) + (1 if "--hooks" in args else 0)
+    if "--gpuamg" in args:
+        want = 1        # the device-resident solve with the device base solver: the only mix with algebraic levels that exist on the device alone      # 4 ls/lmgc mixes [+ gpucg + gpubcgs] [+ gpufe, gpuls inside its bracket, savedata / loaddata bin + asc]
     assert sum(l.startswith("PASS") for l in lines) == want, lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

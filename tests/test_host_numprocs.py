@@ -9,7 +9,7 @@ import subprocess
 
 import pytest
 
-from test_dropin import AMG_AVG, AMG_RS, AMG_VANEK
+from test_dropin import AMG_AVG, AMG_RS, AMG_VANEK, AMG_VANEK_PC
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "standin", "uggpu_standin.cc")
@@ -49,9 +49,16 @@ CASES = [
     ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK]),
     ("ugoracle3", ["--grid", "hex", "--bs", "3", "--refine", "2", "--collapse", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 10"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "selectionAMG", AMG_AVG + " $vectLimit 40"]),
+    # ---- gputransfer $gpuamg: the algebraic levels are built by the device library itself (uggpu_amg_coarsen_rs / _vanek) and exist on the device
+    # only; the reference side runs its own AMG numproc -- same levels, same bits.  Device-resident solve with the device base solver only
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--cycles", "5", "--amg", "selectionAMG", AMG_RS, "--gpuamg", "RugeStueben $theta 0.25 $vectLimit 20"]),
+    ("ugoracle2", ["--grid", "quad", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "selectionAMG", AMG_RS, "--gpuamg", "RugeStueben $vectLimit 20"]),
+    ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK, "--gpuamg", "Vanek $theta 0.08 $vectLimit 10"]),
+    ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "clusterAMG", AMG_VANEK_PC, "--gpuamg", "VanekPC $theta 0.08 $vectLimit 60"]),
 ]
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat", "tet-ilu-beta",
-       "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks", "hex-bs3-imat-hooks", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average"]
+       "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks", "hex-bs3-imat-hooks", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average",
+       "gpuamg-tet-ruge-stueben", "gpuamg-quad-ruge-stueben-refine2", "gpuamg-tri-vanek-refine2", "gpuamg-tet-33^3-on-17^3-vanek-pc"]
 
 
 @pytest.mark.parametrize("exe,args", CASES, ids=IDS)
@@ -62,7 +69,7 @@ def test_host_numprocs_against_standin(standin, exe, args):
     out = subprocess.run([path] + args + ["--nokrylov", "--gpu", standin], capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.startswith(("PASS", "FAIL", "gpuls"))]
     assert out.returncode == 0, "\n".join(lines) + out.stderr[-2000:]
-    assert sum(l.startswith("PASS") for l in lines) == 4 + (1 if "--hooks" in args else 0), lines
+    assert sum(l.startswith("PASS") for l in lines) == (1 if "--gpuamg" in args else 4 + (1 if "--hooks" in args else 0)), lines
     # bit for bit, also with the "device" base solver (the stand-in's is the restatement of the reference's ls + lu)
     assert all("relerr x=0.000e+00 b=0.000e+00" in l for l in lines if l.startswith("PASS") and "hooks" not in l), lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"

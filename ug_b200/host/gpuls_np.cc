@@ -46,7 +46,7 @@ USING_UG_NAMESPACES
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
   X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
   X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags) \
-  X(uggpu_savedata) X(uggpu_loaddata) X(uggpu_minimize_level)
+  X(uggpu_savedata) X(uggpu_loaddata) X(uggpu_minimize_level) X(uggpu_amg_coarsen_rs) X(uggpu_amg_coarsen_vanek)
 
 namespace {
 struct Api {
@@ -193,6 +193,7 @@ int EnsureLevel(Mirror *m, int level, const VECDATA_DESC *x, const MATDATA_DESC 
   // one upload per PreProcess bracket and (level, A, x): another matrix or vector descriptor on the same level is flattened again
   const int k = Mirror::ix(level);
   if (level < -MAXLEVEL || level >= MAXLEVEL || m->dl(level) < 0 || m->dl(level) >= UGGPU_MAX_LEVELS) { UserWriteF("gpuls: level %d is outside the device library's range\n", level); return 1; }
+  if (m->have_level[k] == 2) return 0;        // built on the device (gputransfer $gpuamg): nothing to flatten
   if (m->have_level[k] && m->level_A[k] == A && m->level_x[k] == x) return 0;
   if (m->have_level[k]) { m->have_level[k] = 0; m->have_transfer[k] = 0; if (level + 1 < MAXLEVEL) m->have_transfer[k + 1] = 0; }
   gpuls::FlatLevel &f = m->fl[k];
@@ -228,8 +229,11 @@ int EnsureTransfer(Mirror *m, int level, int imat)
   return 0;
 }
 
+// have_level[] == 2: an algebraic level that exists on the device only (gputransfer $gpuamg): UG holds no vectors for it.  The cycle uses
+// such levels as work space (the restriction writes their defect, dset their correction), so "uploading" is allocating and nothing comes back.
 int Upload(Mirror *m, int level, const VECDATA_DESC *vd)
 {
+  if (m->have_level[Mirror::ix(level)] == 2) { DEV(uggpu_vec_alloc(m->ctx, m->dl(level), m->handle(vd))); return 0; }
   const gpuls::FlatLevel &f = m->fl[Mirror::ix(level)];
   m->buf.resize((size_t)f.n * f.bs + 1);
   gpuls::GatherVector(m->mg, level, vd, f.bs, m->buf.data());
@@ -239,6 +243,7 @@ int Upload(Mirror *m, int level, const VECDATA_DESC *vd)
 
 int Download(Mirror *m, int level, const VECDATA_DESC *vd)
 {
+  if (m->have_level[Mirror::ix(level)] == 2) return 0;
   const gpuls::FlatLevel &f = m->fl[Mirror::ix(level)];
   m->buf.resize((size_t)f.n * f.bs + 1);
   DEV(uggpu_vec_download(m->ctx, m->dl(level), m->handle(vd), m->buf.data()));
@@ -380,6 +385,14 @@ struct NP_GPUTRANSFER {
   INT level;           // $L: level optimisation, AdaptCorrection = MinimizeLevel (transfer.cc:574, :812, :488)
   VECDATA_DESC *t;     // its work vector (transfer.cc:592 $t), on the device only
   INT dirichlet;       // $D [k]: AssembleDirichletBoundary on the levels in PreProcess (transfer.cc:575, :666-678)
+  // $gpuamg {RugeStueben | Vanek | VanekPC}: the algebraic levels below level 0 are built by the device library itself (uggpu_amg_coarsen_rs /
+  // uggpu_amg_coarsen_vanek: the reference's selectionAMG $strongRel $C RugeStueben $I RugeStueben resp. clusterAMG $strongVanek $C VanekNeuss
+  // $I Vanek / PiecewiseConstant, $CM Galerkin, bit for bit) and exist on the device only: UG's grid manager never sees them.  $theta,
+  // $vectLimit, $levelLimit as the AMG numprocs' $strong... value, $vectLimit, $levelLimit (amgtransfer.cc:540-552, :800-812).  Needs the
+  // device-resident cycle with the device base solver (gpulmgc $devbase): there are no host vectors for a host numproc to work on.
+  INT gpuamg;          // 0 none, 1 Ruge-Stueben, 2 Vanek (smoothed aggregation), 3 Vanek with piecewise constant interpolation
+  DOUBLE theta;
+  INT vectLimit, levelLimit;
 };
 
 INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result);
@@ -397,6 +410,19 @@ INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
   np->level = ReadArgvOption("L", argc, argv);                                                        // transfer.cc:574
   np->t = ReadArgvVecDesc(theNP->mg, "t", argc, argv);                                                // transfer.cc:592
   np->dirichlet = ReadArgvOption("D", argc, argv);                                                    // transfer.cc:575
+  np->gpuamg = 0;
+  {
+    char kind[VALUELEN];
+    if (ReadArgvChar("gpuamg", kind, argc, argv) == 0) {
+      np->gpuamg = strcmp(kind, "RugeStueben") == 0 ? 1 : strcmp(kind, "Vanek") == 0 ? 2 : strcmp(kind, "VanekPC") == 0 ? 3 : 0;
+      if (np->gpuamg == 0 || np->amg != NULL) { UserWrite("gputransfer: $gpuamg {RugeStueben | Vanek | VanekPC}, not together with $amg\n"); return NP_NOT_ACTIVE; }
+    }
+    np->theta = np->gpuamg == 1 ? 0.25 : 0.08;
+    ReadArgvDOUBLE("theta", &np->theta, argc, argv);
+    np->vectLimit = 0; ReadArgvINT("vectLimit", &np->vectLimit, argc, argv);
+    np->levelLimit = -16; ReadArgvINT("levelLimit", &np->levelLimit, argc, argv);
+    if (np->levelLimit > 0 || np->levelLimit < -MAXLEVEL + 1) { UserWrite("gputransfer: $levelLimit must be in -MAXLEVEL+1..0\n"); return NP_NOT_ACTIVE; }
+  }
   if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv)) {
     UserWrite("gputransfer: the standard (geometric) transfer, $M (stored interpolation matrices), $L (level optimisation), $D and $amg are on the GPU path; $R $S are not supported\n");
     return NP_NOT_ACTIVE;
@@ -412,6 +438,12 @@ INT GpuTransferDisplay(NP_BASE *theNP)
   UserWriteF(DISPLAY_NP_FORMAT_SS, "InterpolateCor", np->imat ? "InterpolateCorrectionByMatrix (device)" : "StandardInterpolateCorrection (device)");
   if (np->amg != NULL) UserWriteF(DISPLAY_NP_FORMAT_SS, "amg", ENVITEM_NAME(np->amg));
   UserWriteF(DISPLAY_NP_FORMAT_SI, "level", (int)np->level);
+  if (np->gpuamg) {
+    UserWriteF(DISPLAY_NP_FORMAT_SS, "gpuamg", np->gpuamg == 1 ? "RugeStueben" : np->gpuamg == 2 ? "Vanek" : "VanekPC");
+    UserWriteF(DISPLAY_NP_FORMAT_SF, "theta", (float)np->theta);
+    UserWriteF(DISPLAY_NP_FORMAT_SI, "vectLimit", (int)np->vectLimit);
+    UserWriteF(DISPLAY_NP_FORMAT_SI, "levelLimit", (int)np->levelLimit);
+  }
   return 0;
 }
 
@@ -432,6 +464,35 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
     if (np->dirichlet > 1) i = np->dirichlet - 1;
     for (; i <= tl; i++)
       if (AssembleDirichletBoundary(GRID_ON_LEVEL(NP_MG(theNP), i), A, x, b)) PRE_FAIL(np, result[0]);
+  }
+  if (np->gpuamg && *fl <= 0 && np->levelLimit < 0) {
+    // room for the levels the device library may build below level 0, then the coarsening loop of AMGTransferPreProcess (amgtransfer.cc:795-925)
+    // with its $vectLimit / $levelLimit criteria; the AMG starts at level 0 like the reference's ("AMG can only be used on levels >= 0", :750)
+    Mirror *m = np->m;
+    SetBottom(m, np->levelLimit);
+    for (int l = -MAXLEVEL; l < 0; l++) { m->have_level[Mirror::ix(l)] = 0; m->have_transfer[Mirror::ix(l)] = 0; }
+    m->have_transfer[Mirror::ix(0)] = 0;
+    for (int l = 0; l <= tl; l++) if (EnsureLevel(m, l, x, A)) PRE_FAIL(np, result[0]);
+    if (m->bs != 1) { UserWrite("gputransfer: $gpuamg handles scalar equations\n"); PRE_FAIL(np, result[0]); }
+    int level = 0, nvec = m->fl[Mirror::ix(0)].n;
+    while (level > np->levelLimit) {
+      if (np->vectLimit != 0 && nvec <= np->vectLimit) break;                                     // :806
+      int nc = 0;
+      const int rc = np->gpuamg == 1 ? api.uggpu_amg_coarsen_rs(m->ctx, m->dl(level), m->handle(A), np->theta, &nc)
+                                     : api.uggpu_amg_coarsen_vanek(m->ctx, m->dl(level), m->handle(A), np->theta, np->gpuamg == 2 ? 1 : 0, &nc);
+      if (rc) { dev_fail("uggpu_amg_coarsen"); PRE_FAIL(np, result[0]); }
+      if (nc == 0) break;                                                                        // all or no vectors coarse: the coarsening has come to its end
+      m->have_level[Mirror::ix(level - 1)] = 2;
+      m->have_transfer[Mirror::ix(level)] = 2;
+      gpuls::FlatLevel &f = m->fl[Mirror::ix(level - 1)];
+      f = gpuls::FlatLevel(); f.n = nc; f.bs = 1;
+      nvec = nc;
+      level--;
+    }
+    *fl = level;
+    np->fl = *fl; np->tl = tl;
+    for (int l = 1; l <= tl; l++) if (EnsureTransfer(m, l, np->imat ? 1 : 0)) PRE_FAIL(np, result[0]);
+    return 0;
   }
   np->fl = *fl; np->tl = tl;
   for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
@@ -690,6 +751,10 @@ INT GpuLmgcPreProcess(NP_ITER *theNP, INT level, VECDATA_DESC *x, VECDATA_DESC *
     for (int i = np->baselevel + 1; i <= level; i++)
       if ((*np->PostSmooth->PreProcess)(np->PostSmooth, i, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   *baselevel = MIN(np->baselevel, level);
+  if (!np->devbase && *baselevel >= -MAXLEVEL && np->m->have_level[Mirror::ix(*baselevel)] == 2) {
+    UserWrite("gpulmgc: the base level was built on the device (gputransfer $gpuamg): a host base solver has no vectors there, use $devbase\n");
+    PRE_FAIL(np, result[0]);
+  }
   if (!np->devbase && np->BaseSolver->PreProcess != NULL)
     if ((*np->BaseSolver->PreProcess)(np->BaseSolver, *baselevel, x, b, A, baselevel, result)) PRE_FAIL(np, result[0]);
   if (((NP_GPUJAC *)np->PreSmooth)->damp[0] != ((NP_GPUJAC *)np->PostSmooth)->damp[0]) {
@@ -870,7 +935,10 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   if (m == NULL || mgc->m == NULL) { UserWrite("gpuls: Solver without PreProcess\n"); NP_RETURN(1, lresult->error_code); }
   const int bs = m->bs, bl = np->baselevel;
   for (int i = 0; i < VD_NCOMP(x); i++) { NPLS_red(theNP)[i] = reduction[i]; NPLS_abs(theNP)[i] = abslimit[i]; }
-  if (AllocVDFromVD(NP_MG(theNP), bl, level, x, &np->c)) NP_RETURN(1, lresult->error_code);   // ls.cc:662
+  // UG's descriptors can only be allocated on levels its grid manager holds: algebraic levels that exist on the device only (gputransfer
+  // $gpuamg) have no VECTORs -- their work vectors are allocated by Upload on the device
+  const int hbl = MAX(bl, (int)BOTTOMLEVEL(NP_MG(theNP)));
+  if (AllocVDFromVD(NP_MG(theNP), hbl, level, x, &np->c)) NP_RETURN(1, lresult->error_code);   // ls.cc:662
   CenterInPattern(text, DISPLAY_WIDTH, ENVITEM_NAME(np), '*', "\n");
   if (np->display > PCR_NO_DISPLAY)
     if (PreparePCR(x, np->display, text, &PrintID)) NP_RETURN(1, lresult->error_code);
@@ -891,7 +959,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
   std::vector<double> history((size_t)MAX(np->maxiter, 1) * bs, 0.0);
   const int nwork = np->kind == GPULS_CG ? 2 : (np->kind == GPULS_BCGS ? 6 : 0);
   for (int i = 0; i < nwork; i++)          // CGPrepare / CGUpdate / BCGSPreProcess allocate these from the same pool
-    if (AllocVDFromVD(NP_MG(theNP), bl, level, x, &np->w[i])) NP_RETURN(1, lresult->error_code);
+    if (AllocVDFromVD(NP_MG(theNP), hbl, level, x, &np->w[i])) NP_RETURN(1, lresult->error_code);
   if (np->kind == GPULS_LS) {
     if (api.uggpu_ls_solve(m->ctx, &cfg, m->dl(bl), m->dl(level), m->handle(x), m->handle(b), m->handle(A), m->handle(np->c), np->maxiter, absl, red, &r, history.data()))
       NP_RETURN(dev_fail("uggpu_ls_solve"), lresult->error_code);
@@ -908,7 +976,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
       NP_RETURN(dev_fail("uggpu_bcgs_solve"), lresult->error_code);
   }
   for (int i = 0; i < nwork; i++)
-    if (FreeVD(NP_MG(theNP), bl, level, np->w[i])) REP_ERR_RETURN(1);
+    if (FreeVD(NP_MG(theNP), hbl, level, np->w[i])) REP_ERR_RETURN(1);
   // down: x, b, c on every cycle level (what the CPU classes leave in the VECTORs)
   for (int l = bl; l <= level; l++)
     if (Download(m, l, x) || Download(m, l, b) || Download(m, l, np->c)) NP_RETURN(1, lresult->error_code);
@@ -936,7 +1004,7 @@ INT GpuLsSolver(NP_LINEAR_SOLVER *theNP, INT level, VECDATA_DESC *x, VECDATA_DES
     else
       UserWriteF("LS  : L=%2d N=%2d TSOLVE=%10.4g\n", level, lresult->number_of_linear_iterations, ti);
   }
-  if (FreeVD(NP_MG(theNP), bl, level, np->c)) REP_ERR_RETURN(1);
+  if (FreeVD(NP_MG(theNP), hbl, level, np->c)) REP_ERR_RETURN(1);
   return 0;
 }
 
