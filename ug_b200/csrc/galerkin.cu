@@ -135,29 +135,62 @@ __global__ void __launch_bounds__(128) k_galerkin(SellView Ac, double *cval, Sel
 // A row ends up as: diagonal, the connections created by the product in reverse order of creation, its old off-diagonal entries.  The
 // NUMERIC half is the kernel above on the new pattern.  A setup step of AMG hierarchies (np/procs/amgtransfer.cc:915-925), sizes of a few
 // 10^5 rows; a device form (first-touch times of the pairs by a segmented min + sort) is the next step, DESIGN.md 9.
-#include <unordered_set>
 #include <vector>
+
+namespace {
+// set of directed pairs (row << 32 | column): open addressing, linear probing, grows at 1/2 load.  (std::unordered_set costs ~400 ns per
+// term of the product here; this table ~30 ns.)
+struct PairSet {
+  std::vector<uint64_t> tab;
+  size_t mask = 0, count = 0;
+  explicit PairSet(size_t expect) { size_t cap = 1024; while (cap < 2 * expect + 16) cap <<= 1; tab.assign(cap, 0); mask = cap - 1; }
+  static uint64_t mix(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k; }
+  void grow()
+  {
+    std::vector<uint64_t> old;
+    old.swap(tab);
+    tab.assign(old.size() * 2, 0); mask = tab.size() - 1; count = 0;
+    for (uint64_t k : old) if (k) insert_key(k);
+  }
+  bool insert_key(uint64_t k)        // k != 0
+  {
+    size_t i = mix(k) & mask;
+    while (tab[i]) { if (tab[i] == k) return false; i = (i + 1) & mask; }
+    tab[i] = k;
+    if (++count * 2 > tab.size()) grow();
+    return true;
+  }
+  bool insert(int32_t r, int32_t c) { return insert_key((((uint64_t)(uint32_t)r << 32) | (uint32_t)c) + 1); }
+};
+}  // namespace
+
+static int galerkin_pattern_impl(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
+                                 const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col, std::vector<int32_t> *out_vec);
 
 extern "C" int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
                                       const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col)
 {
+  return galerkin_pattern_impl(nf, nc, a_rowptr, a_col, p_rowptr, p_col, start_rowptr, start_col, out_rowptr, out_col, nullptr);
+}
+
+// out_vec (internal callers): receives the columns, sized here -- one traversal instead of the two of the count-then-fill protocol
+static int galerkin_pattern_impl(int nf, int nc, const int32_t *a_rowptr, const int32_t *a_col, const int32_t *p_rowptr, const int32_t *p_col,
+                                 const int32_t *start_rowptr, const int32_t *start_col, int32_t *out_rowptr, int32_t *out_col, std::vector<int32_t> *out_vec)
+{
   if (nf < 0 || nc < 0 || !a_rowptr || !a_col || !p_rowptr || !p_col || !out_rowptr) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: null argument");
   if ((start_rowptr == nullptr) != (start_col == nullptr)) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: start pattern needs both arrays");
-  std::unordered_set<uint64_t> have;                       // directed pairs (row << 32 | column) present so far
+  PairSet have(start_rowptr ? (size_t)start_rowptr[nc] * 2 : (size_t)nc * 16);      // directed pairs present so far
   std::vector<std::vector<int32_t> > created((size_t)nc);  // per row: the columns of its new connections in creation order
-  auto key = [](int32_t r, int32_t c) { return ((uint64_t)(uint32_t)r << 32) | (uint32_t)c; };
   if (start_rowptr) {
-    have.reserve((size_t)start_rowptr[nc] * 2 + 16);
     for (int i = 0; i < nc; i++) {
       if (start_rowptr[i + 1] <= start_rowptr[i] || start_col[start_rowptr[i]] != i) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: row %d does not start with its diagonal entry", i);
       for (int e = start_rowptr[i]; e < start_rowptr[i + 1]; e++) {
         if (start_col[e] < 0 || start_col[e] >= nc) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: column out of range in row %d", i);
-        have.insert(key(i, start_col[e]));
+        have.insert(i, start_col[e]);
       }
     }
   } else {
-    have.reserve((size_t)nc * 16 + 16);
-    for (int i = 0; i < nc; i++) have.insert(key(i, i));
+    for (int i = 0; i < nc; i++) have.insert(i, i);
   }
   for (int v = 0; v < nf; v++)
     for (int e = a_rowptr[v]; e < a_rowptr[v + 1]; e++) {
@@ -169,8 +202,8 @@ extern "C" int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, c
         for (int je = p_rowptr[w]; je < p_rowptr[w + 1]; je++) {
           const int32_t jv = p_col[je];
           if (jv < 0 || jv >= nc) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: interpolation column out of range in row %d", w);
-          if (!have.insert(key(iv, jv)).second) continue;          // GetMatrix(iv, jv) finds it
-          have.insert(key(jv, iv));                                  // one CONNECTION holds both directions
+          if (iv == jv || !have.insert(iv, jv)) continue;             // GetMatrix(iv, jv) finds it (the diagonal always exists)
+          have.insert(jv, iv);                                       // one CONNECTION holds both directions
           created[iv].push_back(jv);
           created[jv].push_back(iv);
         }
@@ -183,6 +216,7 @@ extern "C" int uggpu_galerkin_pattern(int nf, int nc, const int32_t *a_rowptr, c
     if (total > 2147483647LL) return uggpu_fail(UGGPU_ERROR, "uggpu_galerkin_pattern: more than 2^31 - 1 entries");
     out_rowptr[i + 1] = (int32_t)total;
   }
+  if (out_vec) { out_vec->resize((size_t)total + 1); out_col = out_vec->data(); }
   if (!out_col) return 0;
   for (int i = 0; i < nc; i++) {
     int32_t *o = out_col + out_rowptr[i];
@@ -207,9 +241,7 @@ static int galerkin_grow(uggpu_ctx *ctx, int level, int A)
     srp.resize((size_t)nc + 1); scol.resize((size_t)Ac->nnz + 1);
     UG_TRY(sell_to_host_csr(ctx, Ac, srp.data(), scol.data(), nullptr));
   }
-  UG_TRY(uggpu_galerkin_pattern(nf, nc, arp.data(), acol.data(), prp.data(), pcol.data(), Ac ? srp.data() : nullptr, Ac ? scol.data() : nullptr, orp.data(), nullptr));
-  ocol.resize((size_t)orp[nc] + 1);
-  UG_TRY(uggpu_galerkin_pattern(nf, nc, arp.data(), acol.data(), prp.data(), pcol.data(), Ac ? srp.data() : nullptr, Ac ? scol.data() : nullptr, orp.data(), ocol.data()));
+  UG_TRY(galerkin_pattern_impl(nf, nc, arp.data(), acol.data(), prp.data(), pcol.data(), Ac ? srp.data() : nullptr, Ac ? scol.data() : nullptr, orp.data(), nullptr, &ocol));
   return uggpu_mat_set_pattern(ctx, level - 1, A, orp.data(), ocol.data());      // values zero: the product writes all of them
 }
 
