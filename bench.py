@@ -142,7 +142,9 @@ def equal_size_inside_ug(refine: int, cycles: int, exe_name: str = "ugoracle3", 
             me = re.search(r"relerr x=([0-9.eE+-]+)", line)
             if mg and mc and n:
                 tg, tc = float(mg.group(1)), float(mc.group(1))
+                pg, pc = re.search(r"pre_gpu=([0-9.eE+-]+)s", line), re.search(r"pre_cpu=([0-9.eE+-]+)s", line)
                 return {"unknowns": n, "cycles": cycles, "gpu_numprocs_inside_ug_s": tg, "cpu_numprocs_s": tc, "ratio": tc / tg if tg > 0 else None,
+                        "preprocess_gpu_s": float(pg.group(1)) if pg else None, "preprocess_cpu_s": float(pc.group(1)) if pc else None,
                         "gpu_unknowns_per_s": n * cycles / tg if tg > 0 else None, "cpu_unknowns_per_s": n * cycles / tc if tc > 0 else None,
                         "parity": line.split(" ", 1)[0], "relerr_x": float(me.group(1)) if me else None,
                         "what": "wall time of NP_LINEAR_SOLVER::Solver: gpuls+gpulmgc+gpujac+gputransfer (device base solver; x, b up, x, b, c down through "
@@ -756,7 +758,13 @@ def our_arm(args):
                                            # algebraic levels: 65^3 on 33^3 (collapsed to level 0) on four levels built by the reference's
                                            # selectionAMG in every PreProcess (host, both sides); the cycle over all of them on the device vs on the host
                                            ("amg_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "5", "--collapse", "--refine2", "1", "--damp", "0.6", "--amg", "selectionAMG",
-                                                                           "$strongRel 0.25 $C Greedy $I Average $CM Galerkin $vectLimit 40"], 1)):
+                                                                           "$strongRel 0.25 $C Greedy $I Average $CM Galerkin $vectLimit 40"], 1),
+                                           # the same size with the algebraic levels built by the device library itself (gputransfer $gpuamg VanekPC: aggregation,
+                                           # piecewise constant interpolation, Galerkin matrices; levels on the device only) against the reference's clusterAMG
+                                           # numproc on the host: preprocess_* are the PreProcess brackets, i.e. the two AMG setups
+                                           ("gpuamg_inside_ug", "ugoracle3", ["--grid", "tet", "--refine", "5", "--collapse", "--refine2", "1", "--damp", "0.6", "--amg", "clusterAMG",
+                                                                              "$strongVanek 0.08 $C VanekNeuss $I PiecewiseConstant $CM Galerkin $vectLimit 60",
+                                                                              "--gpuamg", "VanekPC $theta 0.08 $vectLimit 60"], 1)):
                 try:
                     line[key] = equal_size_inside_ug(0, 5, exe_name, ga, bsz)
                 except Exception as e:

@@ -1000,7 +1000,9 @@ static int run_gpu(const Opt &o)
   LRESULT lr; memset(&lr, 0, sizeof lr);
   double bscale = 1e-300;
   { std::vector<double> b0 = gather(vb, top); for (size_t i = 0; i < b0.size(); i++) bscale = fmax(bscale, fabs(b0[i])); }
+  const double cp0 = now();
   if ((*ls->PreProcess)(ls, top, vx, vb, mA, &bl, &result)) { printf("FAIL reference: PreProcess of the CPU numprocs\n"); return 1; }
+  const double cpre = now() - cp0;      // PreProcess: with --amg this is where the algebraic levels are built
   (*ls->Defect)(ls, top, vx, vb, mA, &result);
   (*ls->Residuum)(ls, bl, top, vx, vb, mA, &lr);
   double c0 = now();
@@ -1031,7 +1033,9 @@ static int run_gpu(const Opt &o)
     std::string name = std::string(pfx) + "mgs";
     NP_LINEAR_SOLVER *g = (NP_LINEAR_SOLVER *)GetNumProcByName(mg, name.c_str(), LINEAR_SOLVER_CLASS_NAME);
     memset(&lr, 0, sizeof lr);
+    const double gp0 = now();
     if ((*g->PreProcess)(g, top, vx, vb, mA, &bl, &result)) { printf("FAIL %s: PreProcess\n", c.name); fails++; continue; }
+    const double gpre = now() - gp0;      // flattening + upload (+ the algebraic levels: the reference's numproc on the host, or $gpuamg)
     (*g->Defect)(g, top, vx, vb, mA, &result);
     (*g->Residuum)(g, bl, top, vx, vb, mA, &lr);
     double g0 = now();
@@ -1051,8 +1055,8 @@ static int run_gpu(const Opt &o)
     // transfer $L: the two scalars of MinimizeLevel are parallel sums on the device -- agreement to rounding, like the Krylov classes
     const double tol = o.levelopt ? fmax(c.tol, 1e-11) : c.tol;
     bool ok = ex <= tol && eb <= tol && ed <= (o.levelopt ? 1e-11 : 1e-12) && lr.number_of_linear_iterations == lr_cpu.number_of_linear_iterations;
-    printf("%s %s: its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e b=%.3e defect=%.3e  t_gpu=%.4fs t_cpu=%.4fs\n", ok ? "PASS" : "FAIL", c.name,
-           (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_cpu.last_defect[0], ex, eb, ed, g1 - g0, c1 - c0);
+    printf("%s %s: its=%d last_defect=%.10e (cpu %.10e) relerr x=%.3e b=%.3e defect=%.3e  t_gpu=%.4fs t_cpu=%.4fs  pre_gpu=%.4fs pre_cpu=%.4fs\n", ok ? "PASS" : "FAIL", c.name,
+           (int)lr.number_of_linear_iterations, lr.last_defect[0], lr_cpu.last_defect[0], ex, eb, ed, g1 - g0, c1 - c0, gpre, cpre);
     if (!ok) fails++;
   }
   // 2b. the nested-iteration hooks of NP_TRANSFER (transfer.h:79-166) on seeded vectors: class transfer vs class gputransfer
