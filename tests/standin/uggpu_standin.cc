@@ -7,7 +7,7 @@
 // (tests/test_host_numprocs.py, `-m "not gpu"`).  The GPU tests run the same drop-in cases against the real library.
 //
 // Build: g++ -O1 -shared -fPIC -I include -I oracle tests/standin/uggpu_standin.cc oracle/ugport.c -o tests/standin/libuggpu_standin.so
-// (tests/test_host_numprocs.py does it).  Assembly, savedata / loaddata and partitions are not offered (calls fail).
+// (tests/test_host_numprocs.py does it).  bcgs and partitions are not offered (calls fail).
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -491,18 +491,102 @@ int uggpu_bcgs_solve(uggpu_ctx *, const uggpu_lmgc_cfg *, int, int, int, int, in
 {
   return fail(UGGPU_ERROR, "the CPU stand-in does not offer bcgs");
 }
-int uggpu_assemble(uggpu_ctx *, int, int, int, int, const uggpu_fe_cfg *, int64_t, const int64_t *, const int32_t *, const double *, const double *, const uint32_t *)
+int uggpu_assemble(uggpu_ctx *ctx, int level, int x, int b, int A, const uggpu_fe_cfg *cfg, int64_t nelem, const int64_t *elem_ptr, const int32_t *elem_row,
+                   const double *coef, const double *coord, const uint32_t *skip)
 {
-  return fail(UGGPU_ERROR, "the CPU stand-in does not offer assembly");
+  Lev *L = level_of(ctx, level);
+  if (!L || !cfg || !L->mat.count(A)) return fail(UGGPU_DESC_MISMATCH, "uggpu_assemble: level or matrix missing");
+  double *xv = vec_of(ctx, level, x, false), *bv = vec_of(ctx, level, b, true);
+  if (!xv || !bv) return UGGPU_DESC_MISMATCH;
+  std::vector<uint32_t> sk((size_t)L->n + 1, 0u);
+  if (skip) memcpy(sk.data(), skip, sizeof(uint32_t) * (size_t)L->n);
+  std::vector<double> cf;
+  if (!coef) { cf.assign((size_t)nelem + 1, 1.0); coef = cf.data(); }
+  std::vector<ugport_level> lv;
+  port_levels(ctx, A, 0, lv);
+  ugport_fe fe;
+  fe.problem = cfg->problem; fe.dim = cfg->dim; fe.E = cfg->E; fe.nu = cfg->nu;
+  for (int i = 0; i < UGPORT_MAX_BS; i++) fe.source[i] = cfg->source[i];
+  const int rc = ugport_assemble(&lv[level], &fe, nelem, elem_ptr, elem_row, coef, coord, sk.data(), xv, L->mat[A].data(), bv);
+  if (rc) return fail(rc == 3 ? UGGPU_DESC_MISMATCH : UGGPU_ERROR, "uggpu_assemble: the restatement returned %d", rc);
+  L->skip.assign(sk.begin(), sk.begin() + L->n);                    // VECSKIP := skip (SetElementDirichletFlags)
+  return 0;
 }
-int uggpu_savedata(uggpu_ctx *, const char *, const char *, const uggpu_data_general *, int, const int *, const char *const *, const char *const *, int64_t,
-                   const int32_t *, const int32_t *)
+
+// savedata / loaddata: the FORMAT halves are host-only functions of the product library (uggpu_data_write / uggpu_data_read, no device in
+// them); the stand-in borrows them from libuggpu.so next to the repository's ug_b200/lib and does the gather / scatter itself
+}  // extern "C"
+#include <dlfcn.h>
+#include <cstdlib>
+#include <climits>
+namespace {
+typedef int (*data_write_fn)(const char *, const char *, const uggpu_data_general *, int, const int *, const char *const *, const char *const *, int64_t, const double *);
+typedef int (*data_read_fn)(const char *, uggpu_data_general *, int *, int *, int, int64_t *, double *, int64_t);
+data_write_fn p_write = nullptr;
+data_read_fn p_read = nullptr;
+int bind_format_functions()
 {
-  return fail(UGGPU_ERROR, "the CPU stand-in does not offer savedata");
+  if (p_write && p_read) return 0;
+  Dl_info info;
+  if (!dladdr((void *)&bind_format_functions, &info) || !info.dli_fname) return 1;
+  char real[4096];
+  if (!realpath(info.dli_fname, real)) return 1;
+  std::string dir = real;                                            // .../tests/standin/libuggpu_standin.so
+  for (int k = 0; k < 3; k++) { size_t pos = dir.find_last_of('/'); if (pos == std::string::npos) return 1; dir.erase(pos); }
+  void *h = dlopen((dir + "/ug_b200/lib/libuggpu.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 1;
+  p_write = (data_write_fn)dlsym(h, "uggpu_data_write");
+  p_read = (data_read_fn)dlsym(h, "uggpu_data_read");
+  return (p_write && p_read) ? 0 : 1;
 }
-int uggpu_loaddata(uggpu_ctx *, const char *, int, const int *, int64_t, const int32_t *, const int32_t *, uggpu_data_general *)
+}  // namespace
+extern "C" {
+
+int uggpu_savedata(uggpu_ctx *ctx, const char *filename, const char *type, const uggpu_data_general *g, int nvd, const int *vec, const char *const *vdname,
+                   const char *const *compnames, int64_t nnode, const int32_t *id_level, const int32_t *id_row)
 {
-  return fail(UGGPU_ERROR, "the CPU stand-in does not offer loaddata");
+  if (bind_format_functions()) return fail(UGGPU_ERROR, "the CPU stand-in cannot bind uggpu_data_write / uggpu_data_read of libuggpu.so");
+  std::vector<int> ncomp(nvd);
+  int sum = 0;
+  for (int i = 0; i < nvd; i++) { ncomp[i] = (int)strlen(compnames[i]); sum += ncomp[i]; }
+  std::vector<double> body((size_t)nnode * sum + 1);
+  for (int64_t id = 0; id < nnode; id++) {
+    int o = 0;
+    for (int i = 0; i < nvd; i++) {
+      const double *v = vec_of(ctx, id_level[id], vec[i], false);
+      if (!v || ctx->lev[id_level[id]].bs != ncomp[i]) return fail(UGGPU_DESC_MISMATCH, "uggpu_savedata: vector %d on level %d", vec[i], id_level[id]);
+      for (int c = 0; c < ncomp[i]; c++) body[(size_t)id * sum + o + c] = v[(size_t)id_row[id] * ncomp[i] + c];
+      o += ncomp[i];
+    }
+  }
+  return p_write(filename, type, g, nvd, ncomp.data(), vdname, compnames, nnode, body.data());
+}
+
+int uggpu_loaddata(uggpu_ctx *ctx, const char *filename, int nvd, const int *vec, int64_t nnode, const int32_t *id_level, const int32_t *id_row, uggpu_data_general *general_out)
+{
+  if (bind_format_functions()) return fail(UGGPU_ERROR, "the CPU stand-in cannot bind uggpu_data_write / uggpu_data_read of libuggpu.so");
+  uggpu_data_general g;
+  int fnvd = 0, ncomp[64];
+  int64_t ndata = 0;
+  if (p_read(filename, &g, &fnvd, ncomp, 64, &ndata, nullptr, 0)) return fail(UGGPU_ERROR, "uggpu_loaddata: cannot read the header of %s", filename);
+  int sum = 0;
+  for (int i = 0; i < fnvd; i++) sum += ncomp[i];
+  std::vector<double> body((size_t)ndata + 1);
+  if (p_read(filename, &g, &fnvd, ncomp, 64, &ndata, body.data(), ndata)) return fail(UGGPU_ERROR, "uggpu_loaddata: cannot read %s", filename);
+  if (sum <= 0 || ndata != nnode * sum) return fail(UGGPU_ERROR, "uggpu_loaddata: %s holds %lld values, expected %lld", filename, (long long)ndata, (long long)nnode * sum);
+  for (int64_t id = 0; id < nnode; id++) {
+    int o = 0;
+    for (int i = 0; i < fnvd; i++) {
+      if (i < nvd && vec[i] >= 0) {
+        double *v = vec_of(ctx, id_level[id], vec[i], true);
+        if (!v || ctx->lev[id_level[id]].bs != ncomp[i]) return fail(UGGPU_DESC_MISMATCH, "uggpu_loaddata: vector %d on level %d", vec[i], id_level[id]);
+        for (int c = 0; c < ncomp[i]; c++) v[(size_t)id_row[id] * ncomp[i] + c] = body[(size_t)id * sum + o + c];
+      }
+      o += ncomp[i];
+    }
+  }
+  if (general_out) *general_out = g;
+  return 0;
 }
 
 }  // extern "C"
