@@ -7,7 +7,7 @@
 // (tests/test_host_numprocs.py, `-m "not gpu"`).  The GPU tests run the same drop-in cases against the real library.
 //
 // Build: g++ -O1 -shared -fPIC -I include -I oracle tests/standin/uggpu_standin.cc oracle/ugport.c -o tests/standin/libuggpu_standin.so
-// (tests/test_host_numprocs.py does it).  bcgs and partitions are not offered (calls fail).
+// (tests/test_host_numprocs.py does it).  bcgs restarts and partitions are not offered (calls fail).
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -109,10 +109,16 @@ void vec_array(uggpu_ctx *c, int h, bool create, int lo, int hi, std::vector<dou
 }
 
 struct Hook { const uggpu_lmgc_cfg *cfg; uggpu_ctx *ctx; int c, b, A; };
-int base_hook(void *user, int level, double *, double *)
+// the cycle may run on other vectors than the solver's (bcgs: Iter(q, p) and Iter(q, s)): the handles are found from the storage
+int base_hook(void *user, int level, double *c, double *b)
 {
   Hook *h = (Hook *)user;
-  return h->cfg->base_solver(h->cfg->base_user, h->ctx, level, h->c, h->b, h->A);
+  int ch = h->c, bh = h->b;
+  for (auto &kv : h->ctx->lev[level].vec) {
+    if (kv.second.data() == c) ch = kv.first;
+    if (kv.second.data() == b) bh = kv.first;
+  }
+  return h->cfg->base_solver(h->cfg->base_user, h->ctx, level, ch, bh, h->A);
 }
 // transfer modes: the port takes one flag for all levels and "by-matrix at and below level k"
 void port_cfg(uggpu_ctx *c, const uggpu_lmgc_cfg *g, int level, Hook *hk, ugport_cfg *p)
@@ -486,10 +492,35 @@ int uggpu_cg_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level,
   return 0;
 }
 
-int uggpu_bcgs_solve(uggpu_ctx *, const uggpu_lmgc_cfg *, int, int, int, int, int, const int *, const double *, int, int, const double *, const double *,
-                     uggpu_lresult *, double *)
+int uggpu_bcgs_solve(uggpu_ctx *ctx, const uggpu_lmgc_cfg *cfg, int bl, int level, int x, int b, int A, const int *work, const double *weight, int restart_every,
+                     int maxiter, const double *abslimit, const double *reduction, uggpu_lresult *res, double *history)
 {
-  return fail(UGGPU_ERROR, "the CPU stand-in does not offer bcgs");
+  (void)bl;
+  if (restart_every != 0) return fail(UGGPU_ERROR, "the CPU stand-in offers bcgs without restarts");
+  if (int rc = ilu_ready(ctx, cfg, level, A)) return rc;
+  std::vector<ugport_level> lv;
+  port_levels(ctx, A, cfg->smoother == UGGPU_SM_ILU ? cfg->smoother_L : 0, lv);
+  Hook hk = {cfg, ctx, work[5], work[1], A};
+  ugport_cfg p;
+  port_cfg(ctx, cfg, level, &hk, &p);
+  std::vector<double *> xv, bv, tv, wv[6];
+  vec_array(ctx, x, false, 0, 0, xv); vec_array(ctx, b, false, 0, 0, bv);
+  vec_array(ctx, cfg->t, true, cfg->baselevel, level, tv);
+  for (int i = 0; i < 6; i++) vec_array(ctx, work[i], true, cfg->baselevel, level, wv[i]);      // r p v s t q
+  const int bs = ctx->lev[level].bs;
+  double w2[UGPORT_MAX_BS];
+  for (int i = 0; i < UGPORT_MAX_BS; i++) w2[i] = weight[i] * weight[i];                         // BCGSInit ls.cc:1757
+  std::vector<double> hist((size_t)(maxiter > 0 ? maxiter : 1) * bs, 0.0);
+  double first[UGPORT_MAX_BS];
+  const int fr = ctx->fullrefinelevel < level ? ctx->fullrefinelevel : level;
+  const int its = ugport_bcgs_solve(lv.data(), &p, fr, level, xv.data(), bv.data(), tv.data(), wv[0].data(), wv[1].data(), wv[2].data(), wv[3].data(), wv[4].data(),
+                                    wv[5].data(), w2, maxiter, abslimit, reduction, first, hist.data());
+  if (its < 0) return fail(UGGPU_ERROR, "bcgs failed");
+  const int nhist = (its + 1) / 2;
+  if (history) memcpy(history, hist.data(), sizeof(double) * (size_t)nhist * bs);
+  finish(res, nhist, bs, first, hist.data(), abslimit, reduction);
+  res->number_of_linear_iterations = its;
+  return 0;
 }
 int uggpu_assemble(uggpu_ctx *ctx, int level, int x, int b, int A, const uggpu_fe_cfg *cfg, int64_t nelem, const int64_t *elem_ptr, const int32_t *elem_row,
                    const double *coef, const double *coord, const uint32_t *skip)
