@@ -208,6 +208,12 @@ int uggpu_mat_set(uggpu_ctx *ctx, int level, int mat, const int32_t *rowptr, con
   return 0;
 }
 
+int64_t uggpu_mat_nnz(uggpu_ctx *ctx, int level, int mat)
+{
+  Lev *L = level_of(ctx, level);
+  return (L && L->mat.count(mat)) ? (int64_t)L->col.size() : -1;
+}
+
 int uggpu_mat_get(uggpu_ctx *ctx, int level, int mat, int32_t *rowptr, int32_t *col, double *val)
 {
   Lev *L = level_of(ctx, level);

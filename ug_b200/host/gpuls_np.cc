@@ -46,7 +46,7 @@ USING_UG_NAMESPACES
   X(uggpu_restrict) X(uggpu_interpolate_correction) X(uggpu_lmgc_preprocess) X(uggpu_lmgc) X(uggpu_ls_defect) X(uggpu_ls_residuum)              \
   X(uggpu_ls_solve) X(uggpu_cg_solve) X(uggpu_bcgs_solve) X(uggpu_launch_count) X(uggpu_smooth) X(uggpu_gs_preprocess) X(uggpu_transfer_set_mode) \
   X(uggpu_dmatcopy) X(uggpu_l_ilubthdecomp) X(uggpu_assemble) X(uggpu_mat_set_pattern) X(uggpu_mat_get) X(uggpu_level_get_flags) \
-  X(uggpu_savedata) X(uggpu_loaddata) X(uggpu_minimize_level) X(uggpu_amg_coarsen_rs) X(uggpu_amg_coarsen_vanek)
+  X(uggpu_savedata) X(uggpu_loaddata) X(uggpu_minimize_level) X(uggpu_amg_coarsen_rs) X(uggpu_amg_coarsen_vanek) X(uggpu_mat_nnz)
 
 namespace {
 struct Api {
@@ -392,7 +392,8 @@ struct NP_GPUTRANSFER {
   // device-resident cycle with the device base solver (gpulmgc $devbase): there are no host vectors for a host numproc to work on.
   INT gpuamg;          // 0 none, 1 Ruge-Stueben, 2 Vanek (smoothed aggregation), 3 Vanek with piecewise constant interpolation
   DOUBLE theta;
-  INT vectLimit, levelLimit;
+  INT vectLimit, levelLimit, matLimit;
+  DOUBLE bandLimit, vRedLimit, mRedLimit;        // the AMG numprocs' other stopping criteria (amgtransfer.cc:543-550, :806-826, :1000-1012)
 };
 
 INT GpuRestrictDefect(NP_TRANSFER *theNP, INT level, VECDATA_DESC *to, VECDATA_DESC *from, MATDATA_DESC *A, VEC_SCALAR damp, INT *result);
@@ -421,6 +422,10 @@ INT GpuTransferInit(NP_BASE *theNP, INT argc, char **argv)
     ReadArgvDOUBLE("theta", &np->theta, argc, argv);
     np->vectLimit = 0; ReadArgvINT("vectLimit", &np->vectLimit, argc, argv);
     np->levelLimit = -16; ReadArgvINT("levelLimit", &np->levelLimit, argc, argv);
+    np->matLimit = 0; ReadArgvINT("matLimit", &np->matLimit, argc, argv);
+    np->bandLimit = 0.0; ReadArgvDOUBLE("bandLimit", &np->bandLimit, argc, argv);
+    np->vRedLimit = 0.0; ReadArgvDOUBLE("vRedLimit", &np->vRedLimit, argc, argv);
+    np->mRedLimit = 0.0; ReadArgvDOUBLE("mRedLimit", &np->mRedLimit, argc, argv);
     if (np->levelLimit > 0 || np->levelLimit < -MAXLEVEL + 1) { UserWrite("gputransfer: $levelLimit must be in -MAXLEVEL+1..0\n"); return NP_NOT_ACTIVE; }
   }
   if (ReadArgvOption("R", argc, argv) || ReadArgvOption("S", argc, argv)) {
@@ -443,6 +448,10 @@ INT GpuTransferDisplay(NP_BASE *theNP)
     UserWriteF(DISPLAY_NP_FORMAT_SF, "theta", (float)np->theta);
     UserWriteF(DISPLAY_NP_FORMAT_SI, "vectLimit", (int)np->vectLimit);
     UserWriteF(DISPLAY_NP_FORMAT_SI, "levelLimit", (int)np->levelLimit);
+    UserWriteF(DISPLAY_NP_FORMAT_SI, "matLimit", (int)np->matLimit);
+    UserWriteF(DISPLAY_NP_FORMAT_SF, "bandLimit", (float)np->bandLimit);
+    UserWriteF(DISPLAY_NP_FORMAT_SF, "vRedLimit", (float)np->vRedLimit);
+    UserWriteF(DISPLAY_NP_FORMAT_SF, "mRedLimit", (float)np->mRedLimit);
   }
   return 0;
 }
@@ -474,9 +483,13 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
     m->have_transfer[Mirror::ix(0)] = 0;
     for (int l = 0; l <= tl; l++) if (EnsureLevel(m, l, x, A)) PRE_FAIL(np, result[0]);
     if (m->bs != 1) { UserWrite("gputransfer: $gpuamg handles scalar equations\n"); PRE_FAIL(np, result[0]); }
+    // nMat = 2 * nCon of the reference (:802): a diagonal connection counts once, a pair of off-diagonal matrices once -> entries + vectors
     int level = 0, nvec = m->fl[Mirror::ix(0)].n;
+    double nmat = (double)m->fl[Mirror::ix(0)].col.size() + nvec;
     while (level > np->levelLimit) {
       if (np->vectLimit != 0 && nvec <= np->vectLimit) break;                                     // :806
+      if (np->matLimit != 0 && nmat <= np->matLimit) break;                                       // :813
+      if (np->bandLimit != 0.0 && nmat / (double)nvec > np->bandLimit) break;                     // :820
       int nc = 0;
       const int rc = np->gpuamg == 1 ? api.uggpu_amg_coarsen_rs(m->ctx, m->dl(level), m->handle(A), np->theta, &nc)
                                      : api.uggpu_amg_coarsen_vanek(m->ctx, m->dl(level), m->handle(A), np->theta, np->gpuamg == 2 ? 1 : 0, &nc);
@@ -486,8 +499,12 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
       m->have_transfer[Mirror::ix(level)] = 2;
       gpuls::FlatLevel &f = m->fl[Mirror::ix(level - 1)];
       f = gpuls::FlatLevel(); f.n = nc; f.bs = 1;
-      nvec = nc;
+      const double cmat = (double)api.uggpu_mat_nnz(m->ctx, m->dl(level - 1), m->handle(A)) + nc;
+      // the reduction criteria are tested AFTER the level was built, and the level stays (:1000-1012)
+      const bool stalled = (np->vRedLimit != 0.0 && (double)nc / (double)nvec > np->vRedLimit) || (np->mRedLimit != 0.0 && cmat / nmat > np->mRedLimit);
+      nvec = nc; nmat = cmat;
       level--;
+      if (stalled) break;
     }
     *fl = level;
     np->fl = *fl; np->tl = tl;
