@@ -32,3 +32,22 @@ def test_no_cpu_fallback():
     rc = L.uggpu_ctx_create(0, C.byref(h))
     assert rc != 0 and not h.value
     assert b"no CPU fallback" in L.uggpu_last_error()
+
+
+def test_host_numprocs_bind_only_exported_symbols():
+    """Every entry point the gpuls numproc family binds with dlsym (ug_b200/host/gpuls_np.cc UGGPU_FUNCS) is declared in include/uggpu.h and
+    exported by libuggpu.so -- a missing one would make every numproc refuse to load on the GPU box -- and the CPU stand-in of the test suite
+    (tests/standin) defines all of them too."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "ug_b200", "host", "gpuls_np.cc")).read()
+    m = re.search(r"#define UGGPU_FUNCS\(X\)(.*?)\n\n", src, re.S)
+    names = re.findall(r"X\((uggpu_[a-z0-9_]+)\)", m.group(1))
+    assert len(names) >= 30
+    declared = set(capi.declared_symbols())
+    lib = capi.lib()
+    standin = open(os.path.join(root, "tests", "standin", "uggpu_standin.cc")).read()
+    for n in names:
+        assert n in declared, n
+        assert hasattr(lib, n), n
+        assert re.search(r"\b" + n + r"\s*\(", standin), n
