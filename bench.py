@@ -127,7 +127,7 @@ def equal_size_inside_ug(refine: int, cycles: int, exe_name: str = "ugoracle3", 
     uploads x and b, runs the cycles on the device, scatters x, b, c back into the VVALUEs) next to UG's own CPU numprocs on the SAME
     hierarchy in the same process: wall time of NP_LINEAR_SOLVER::Solver on both sides."""
     exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
-    lib = os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")
+    lib = os.environ.get("UGGPU_BENCH_LIB") or os.path.join(ROOT, "ug_b200", "lib", "libuggpu.so")      # (override: the CPU stand-in, to test this parser without a GPU)
     if not os.path.exists(exe):
         return None
     out = subprocess.run([exe] + (grid_args or ["--grid", "tet", "--refine", str(refine), "--damp", "0.6"]) + ["--cycles", str(cycles), "--gpu", lib, "--nokrylov"],
