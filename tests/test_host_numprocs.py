@@ -62,6 +62,11 @@ CASES = [
     ("ugoracle2", ["--grid", "tri", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "5", "--amg", "clusterAMG", AMG_VANEK, "--gpuamg", "Vanek $theta 0.08 $vectLimit 10"]),
     ("ugoracle3", ["--grid", "tet", "--refine", "4", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "clusterAMG", AMG_VANEK_PC, "--gpuamg", "VanekPC $theta 0.08 $vectLimit 60"]),
 ] + [
+    # algebraic levels with the other smoother classes, the W-cycle and the level optimisation (host logic only: the CUDA kernels of these
+    # combinations run on algebraic levels in the GPU suite through the golden dumps with the Jacobi smoother)
+    ("ugoracle3", ["--grid", "tet", "--refine", "3", "--collapse", "--refine2", "1", "--cycles", "4", "--amg", "selectionAMG", AMG_RS] + extra)
+    for extra in (["--smoother", "gs", "--damp", "0.9"], ["--smoother", "ilu", "--beta", "0.25", "--damp", "0.9"], ["--levelopt"], ["--smoother", "sgs", "--damp", "0.8", "--gamma", "2"])
+] + [
     # the stopping criteria of the coarsening loop (amgtransfer.cc:806-826, :1000-1012), the same on both sides: same number of levels, same bits
     ("ugoracle2", ["--grid", "tri", "--refine", "5", "--collapse", "--cycles", "4", "--amg", "selectionAMG", "$strongRel 0.25 $C RugeStueben $I RugeStueben $CM Galerkin " + crit,
                    "--gpuamg", "RugeStueben " + crit])
@@ -70,6 +75,7 @@ CASES = [
 IDS = ["tet-r3", "tet-adaptive", "hex-bs3", "tri-r5", "quad-W", "tet-gs", "hex-bs3-sgs", "tet-adaptive-sor", "tet-baselevel2", "hex-bs3-imat", "tet-ilu-beta",
        "quad-bs2", "tet-levelopt", "hex-bs3-levelopt", "tet-adaptive-transferD-hooks", "hex-bs3-imat-hooks", "assemble-tet-r3", "assemble-hex-bs3", "assemble-tet-adaptive", "assemble-quad-bs2", "amg-tet-ruge-stueben", "amg-tri-vanek-refine2", "amg-hex-bs3-greedy-average", "amg-tet-33^3-on-17^3-greedy-average",
        "gpuamg-tet-ruge-stueben", "gpuamg-quad-ruge-stueben-refine2", "gpuamg-tri-vanek-refine2", "gpuamg-tet-33^3-on-17^3-vanek-pc",
+       "amg-gs", "amg-ilu", "amg-levelopt", "amg-sgs-W",
        "gpuamg-vRedLimit", "gpuamg-bandLimit", "gpuamg-mRedLimit", "gpuamg-matLimit", "gpuamg-levelLimit"]
 
 
