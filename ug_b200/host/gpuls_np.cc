@@ -512,8 +512,15 @@ INT GpuTransferPreProcess(NP_TRANSFER *theNP, INT *fl, INT tl, VECDATA_DESC *x, 
     return 0;
   }
   np->fl = *fl; np->tl = tl;
-  for (int l = *fl; l <= tl; l++) if (EnsureLevel(np->m, l, x, A)) PRE_FAIL(np, result[0]);
-  for (int l = *fl + 1; l <= tl; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) PRE_FAIL(np, result[0]);
+  bool bad = false;
+  for (int l = *fl; l <= tl && !bad; l++) if (EnsureLevel(np->m, l, x, A)) bad = true;
+  for (int l = *fl + 1; l <= tl && !bad; l++) if (EnsureTransfer(np->m, l, np->imat ? 1 : 0)) bad = true;
+  if (bad) {
+    // the AMG numproc's bracket is closed again (it frees the matrix descriptors of its levels and disposes them, amgtransfer.cc:1166-1200):
+    // no PostProcess will follow a failed PreProcess
+    if (np->amg_ran && np->amg->PostProcess != NULL) { INT r2 = 0; (*np->amg->PostProcess)(np->amg, fl, 0, x, b, A, &r2); np->amg_ran = 0; }
+    PRE_FAIL(np, result[0]);
+  }
   return 0;
 }
 
