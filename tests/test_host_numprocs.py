@@ -93,3 +93,18 @@ def test_host_numprocs_against_standin(standin, exe, args):
     # bit for bit, also with the "device" base solver (the stand-in's is the restatement of the reference's ls + lu)
     assert all("relerr x=0.000e+00 b=0.000e+00" in l for l in lines if l.startswith("PASS") and "relerr x=" in l and "gpufe bracket" not in l and " vs " not in l), lines
     assert lines[-1] == "gpuls drop-in: 0 failure(s)"
+
+
+def test_failed_preprocess_leaves_a_clean_state(standin):
+    """A PreProcess that fails inside the bracket ($gpuamg on a block system: scalar equations only) must fail loudly and cleanly -- message,
+    non-zero result, no crash, the mirror dropped."""
+    path = os.path.join(ROOT, "oracle", "_ref", "ugoracle3")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    args = ["--grid", "hex", "--bs", "3", "--refine", "2", "--collapse", "--cycles", "3", "--nokrylov",
+            "--amg", "selectionAMG", AMG_AVG + " $vectLimit 10", "--gpuamg", "RugeStueben"]
+    out = subprocess.run([path] + args + ["--gpu", standin], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 10, (out.returncode, out.stdout[-500:], out.stderr[-500:])            # the driver's "failures" exit code, not a signal
+    assert "gputransfer: $gpuamg handles scalar equations" in out.stdout
+    assert "FAIL gpuls+gpulmgc, device base solver: PreProcess" in out.stdout
+    assert out.stdout.strip().splitlines()[-1] == "gpuls drop-in: 1 failure(s)"
